@@ -1,0 +1,281 @@
+"""Stage-level checks of the CPU oracle against closed-form physics.
+
+The reference holds no golden vectors for `mj_step` (parity unpinned); these tests pin the
+oracle to physics that has an analytic answer so that the GPU-vs-oracle parity tests mean something.
+"""
+import numpy as np
+import pytest
+
+from gymnasium_robotics_b200.mjcf import compile_mjcf
+from oracle.oracle_sim import OracleSim
+
+G = 9.81
+
+
+def make(mjcf_file, xml):
+    return OracleSim(compile_mjcf(mjcf_file(xml)))
+
+
+FREE_BOX = """
+<mujoco><option timestep="0.002"/>
+<worldbody>
+  <body name="b" pos="0 0 1"><freejoint/><geom type="box" size="0.1 0.2 0.3" mass="2"/></body>
+</worldbody></mujoco>"""
+
+
+def test_free_fall_matches_semi_implicit_euler(mjcf_file):
+    s = make(mjcf_file, FREE_BOX)
+    n, h = 100, 0.002
+    s.step(n)
+    assert s.qvel[2] == pytest.approx(-G * h * n, rel=1e-12)
+    assert s.qpos[2] == pytest.approx(1 - G * h * h * n * (n + 1) / 2, rel=1e-12)
+    assert np.allclose(s.qpos[3:7], [1, 0, 0, 0])
+
+
+def test_free_body_torque_free_rotation_conserves_angular_momentum(mjcf_file):
+    s = make(mjcf_file, FREE_BOX.replace('timestep="0.002"', 'timestep="0.0005" gravity="0 0 0"'))
+    s.qvel[3:6] = [1.0, 2.0, 0.5]
+    m = s.model
+    I = m.body_inertia[1]
+
+    def L_world():
+        s.forward()
+        R = s.xmat[1].reshape(3, 3)
+        return R @ (I * s.qvel[3:6])  # free-joint angular velocity is in the body frame
+
+    L0 = L_world()
+    s.step(2000)
+    assert np.allclose(L_world(), L0, rtol=0, atol=2e-3 * np.linalg.norm(L0))  # first-order integrator drift
+    assert np.linalg.norm(s.qpos[3:7]) == pytest.approx(1, abs=1e-12)
+
+
+PENDULUM = """
+<mujoco><option timestep="0.0005"/>
+<worldbody>
+  <body name="p" pos="0 0 2">
+    <joint name="h" type="hinge" axis="0 1 0" pos="0 0 0"/>
+    <geom type="sphere" size="0.05" pos="0 0 -1" mass="1"/>
+  </body>
+</worldbody></mujoco>"""
+
+
+def test_pendulum_period_and_energy(mjcf_file):
+    s = make(mjcf_file, PENDULUM)
+    th0 = 0.1
+    s.qpos[0] = th0
+    I = 1.0 * 1.0 ** 2 + 0.4 * 1.0 * 0.05 ** 2  # point mass + sphere inertia
+    T = 2 * np.pi * np.sqrt(I / (1.0 * G * 1.0)) * (1 + th0 ** 2 / 16)
+    h = 0.0005
+    qs = []
+    for _ in range(int(1.5 * T / h)):
+        s.step(1)
+        qs.append(s.qpos[0])
+    qs = np.array(qs)
+    # first return to the positive maximum
+    k = np.argmax(qs[int(0.75 * T / h):]) + int(0.75 * T / h)
+    assert k * h == pytest.approx(T, rel=2e-3)
+    assert qs[k] == pytest.approx(th0, rel=5e-3)
+
+
+SPRING = """
+<mujoco><option timestep="0.001" gravity="0 0 0"/>
+<worldbody>
+  <body name="m" pos="0 0 0">
+    <joint name="s" type="slide" axis="1 0 0" stiffness="100" damping="2" armature="0.5"/>
+    <geom type="sphere" size="0.05" mass="1.5"/>
+  </body>
+</worldbody></mujoco>"""
+
+
+def test_spring_damper_implicit_damping_recurrence(mjcf_file):
+    s = make(mjcf_file, SPRING)
+    s.qpos[0] = 0.1
+    m_eff, k, b, h = 2.0, 100.0, 2.0, 0.001
+    x, v = 0.1, 0.0
+    for _ in range(500):
+        s.step(1)
+        v = v + h * (-k * x - b * v) / (m_eff + h * b)  # Euler with implicit joint damping (Appendix B step 10)
+        x = x + h * v
+        assert s.qpos[0] == pytest.approx(x, abs=1e-12)
+        assert s.qvel[0] == pytest.approx(v, abs=1e-12)
+
+
+BOX_ON_PLANE = """
+<mujoco><option timestep="0.002"/>
+<worldbody>
+  <geom name="floor" type="plane" size="1 1 1"/>
+  <body name="b" pos="0 0 0.1"><freejoint/><geom name="box" type="box" size="0.1 0.1 0.1" mass="2"/></body>
+</worldbody></mujoco>"""
+
+
+def test_box_rests_on_plane_with_weight_balanced_by_contacts(mjcf_file):
+    s = make(mjcf_file, BOX_ON_PLANE)
+    s.step(1000)
+    assert s.ncon == 4
+    assert np.abs(s.qvel).max() < 1e-6
+    assert 0.0995 < s.qpos[2] < 0.1
+    # total normal force = weight: each pyramidal contact's normal force is the sum of its 4 edge forces
+    assert s.efc("force").sum() == pytest.approx(2 * G, rel=1e-6)
+    assert np.allclose(s.qpos[3:7], [1, 0, 0, 0], atol=1e-9)
+
+
+def test_box_on_plane_static_equilibrium_penetration(mjcf_file):
+    """At rest aref = -k*imp*r must produce force mg: analytic depth from solref/solimp (Appendix B.1)."""
+    s = make(mjcf_file, BOX_ON_PLANE)
+    s.step(3000)
+    r = s.qpos[2] - 0.1  # = contact dist (negative)
+    # per-contact: 4 active edge rows, each D*(aref - J a), at rest a=0: f_edge = D*aref ; sum_edges = 4*D*aref = mg/4
+    d0, dw, width = 0.9, 0.95, 0.001
+    x = min(1.0, abs(r) / width)
+    y = 2 * x * x if x <= 0.5 else 1 - 2 * (1 - x) ** 2
+    imp = d0 + y * (dw - d0)
+    tc, dr = 0.02, 1.0
+    kk = 1.0 / (dw * dw * tc * tc * dr * dr)
+    aref = -kk * imp * r
+    invw = 1.0 / 2.0  # translational inverse weight of the free box (1/m)
+    mu = 1.0
+    R = 2 * mu * mu * ((1 - imp) / imp * (invw + mu * mu * invw))
+    total = 4 * 4 * aref / R
+    assert total == pytest.approx(2 * G, rel=1e-3)
+
+
+def test_friction_cone_stick_and_slip(mjcf_file):
+    mu = 0.5  # below the cube's tipping limit so the box slides without tumbling
+    for tilt, sticks in ((0.25, True), (1.0, False)):  # tan(theta) vs mu
+        th = np.arctan(tilt)
+        g = np.array([G * np.sin(th), 0, -G * np.cos(th)])
+        xml = BOX_ON_PLANE.replace('timestep="0.002"', f'timestep="0.002" gravity="{g[0]} {g[1]} {g[2]}"')
+        xml = xml.replace('type="plane"', f'type="plane" friction="{mu} 0.005 0.0001"').replace('type="box"', f'type="box" friction="{mu} 0.005 0.0001"')
+        s = make(mjcf_file, xml)
+        s.step(500)
+        if sticks:
+            assert abs(s.qvel[0]) < 2e-2  # soft-constraint creep only
+        else:
+            a = G * (np.sin(th) - mu * np.cos(th))
+            assert s.qvel[0] == pytest.approx(a * 1.0, rel=0.03)
+
+
+LIMIT = """
+<mujoco><option timestep="0.002"/>
+<worldbody>
+  <body name="m" pos="0 0 1">
+    <joint name="s" type="slide" axis="0 0 1" limited="true" range="-0.2 0.3"/>
+    <geom type="sphere" size="0.05" mass="1"/>
+  </body>
+</worldbody></mujoco>"""
+
+
+def test_joint_limit_holds_weight(mjcf_file):
+    s = make(mjcf_file, LIMIT)
+    s.step(2000)
+    assert -0.21 < s.qpos[0] < -0.199
+    assert abs(s.qvel[0]) < 1e-6
+    assert s.efc("force").sum() == pytest.approx(G, rel=1e-6)
+
+
+ACT = """
+<mujoco><option timestep="0.002" gravity="0 0 0"/>
+<worldbody>
+  <body name="m" pos="0 0 0">
+    <joint name="s" type="slide" axis="1 0 0" damping="20"/>
+    <geom type="sphere" size="0.05" mass="1"/>
+  </body>
+</worldbody>
+<actuator><position joint="s" kp="100" ctrllimited="true" ctrlrange="0 0.2"/></actuator>
+</mujoco>"""
+
+
+def test_position_actuator_converges_and_clamps_ctrl(mjcf_file):
+    s = make(mjcf_file, ACT)
+    s.ctrl[0] = 0.5  # outside ctrlrange: clamped to 0.2 inside the engine (Appendix C.4)
+    s.step(3000)
+    assert s.qpos[0] == pytest.approx(0.2, abs=1e-6)
+
+
+WELD = """
+<mujoco><option timestep="0.002"/>
+<worldbody>
+  <body name="mocap" mocap="true" pos="0 0 1"/>
+  <body name="b" pos="0 0 1"><freejoint/><geom type="box" size="0.05 0.05 0.05" mass="1"/></body>
+</worldbody>
+<equality><weld body1="mocap" body2="b" solref="0.02 1" solimp="0.9 0.95 0.001"/></equality>
+</mujoco>"""
+
+
+def test_weld_tracks_mocap_pose(mjcf_file):
+    s = make(mjcf_file, WELD)
+    s.mocap_pos[0] = [0.1, -0.05, 1.2]
+    q = np.array([np.cos(0.3), 0, np.sin(0.3), 0])
+    s.mocap_quat[0] = q
+    s.step(1500)
+    # soft weld: gravity sag is  m g / (k*imp/R...) -- small; orientation must match
+    assert np.allclose(s.qpos[:2], [0.1, -0.05], atol=1e-4)
+    assert s.qpos[2] == pytest.approx(1.2, abs=5e-3)
+    assert abs(abs(np.dot(s.qpos[3:7], q)) - 1) < 1e-5
+    assert np.abs(s.qvel).max() < 1e-5
+
+
+CHAIN = """
+<mujoco><option timestep="0.001"/>
+<worldbody>
+  <body name="a" pos="0 0 1">
+    <joint name="j1" type="hinge" axis="0 1 0"/>
+    <geom type="capsule" fromto="0 0 0 0.3 0 0" size="0.02" mass="1"/>
+    <body name="b" pos="0.3 0 0">
+      <joint name="j2" type="hinge" axis="0 0 1"/>
+      <geom type="box" size="0.1 0.02 0.03" pos="0.1 0 0" mass="0.7"/>
+      <body name="c" pos="0.2 0 0">
+        <joint name="j3" type="slide" axis="1 0 0"/>
+        <geom type="sphere" size="0.04" mass="0.4"/>
+      </body>
+    </body>
+  </body>
+</worldbody></mujoco>"""
+
+
+def test_total_energy_conserved_on_unconstrained_chain(mjcf_file):
+    """Exercises CRB + RNE (Coriolis/centrifugal) consistency: E = 1/2 v'Mv + sum m g z is conserved to O(h)."""
+    s = make(mjcf_file, CHAIN)
+    s.qvel[:] = [1.0, -2.0, 0.5]
+    m = s.model
+
+    def energy():
+        s.forward()
+        ke = 0.5 * s.qvel @ s.M @ s.qvel
+        # potential from body coms: xipos = xpos + xmat @ ipos
+        pe = 0.0
+        for b in range(1, m.nbody):
+            z = s.xpos[b][2] + (s.xmat[b].reshape(3, 3) @ m.body_ipos[b])[2]
+            pe += m.body_mass[b] * G * z
+        return ke + pe
+
+    e0 = energy()
+    s.step(1000)
+    assert energy() == pytest.approx(e0, abs=5e-3 * abs(e0) + 5e-3)
+
+
+def test_bias_force_matches_finite_difference_of_lagrangian(mjcf_file):
+    """qfrc_bias = C(q,v)v + g(q): check against M*qacc from the unconstrained equation using energy rate."""
+    s = make(mjcf_file, CHAIN)
+    rng = np.random.default_rng(0)
+    s.qpos[:] = rng.uniform(-0.5, 0.5, 3)
+    s.qvel[:] = rng.uniform(-1, 1, 3)
+    s.forward()
+    # power balance: d/dt (KE + PE) = 0 for the unconstrained system =>  v . (M a) + 1/2 v' Mdot v + dPE/dt = 0
+    a = s.qacc.copy()
+    M0, v = s.M.copy(), s.qvel.copy()
+    q0 = s.qpos.copy()
+    eps = 1e-6
+
+    def M_and_pe(q):
+        s.qpos[:] = q
+        s.forward()
+        mm = s.model
+        pe = sum(mm.body_mass[b] * G * (s.xpos[b][2] + (s.xmat[b].reshape(3, 3) @ mm.body_ipos[b])[2]) for b in range(1, mm.nbody))
+        return s.M.copy(), pe
+
+    Mp, pep = M_and_pe(q0 + eps * v)
+    Mm, pem = M_and_pe(q0 - eps * v)
+    Mdot = (Mp - Mm) / (2 * eps)
+    pedot = (pep - pem) / (2 * eps)
+    assert v @ M0 @ a + 0.5 * v @ Mdot @ v + pedot == pytest.approx(0, abs=1e-6)
