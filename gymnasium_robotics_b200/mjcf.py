@@ -663,7 +663,7 @@ def _dense_mass_matrix(nbody, nv, parent, mass, inertia, xipos, ximat, xmat, joi
     return M, jacs
 
 
-def compile_mjcf(path, overrides=None) -> Model:
+def compile_mjcf(path, overrides=None, mesh_mesh=False) -> Model:
     """Compile an MJCF file to the runtime :class:`Model`.
 
     ``overrides`` may carry ``{"opt": {...}, "actuator_gainprm": {name: [...]}, ...}`` for
@@ -891,6 +891,8 @@ def compile_mjcf(path, overrides=None) -> Model:
                 continue
             if g1["type"] == GEOM_PLANE and g2["type"] == GEOM_PLANE:
                 continue
+            if g1["type"] == GEOM_MESH and g2["type"] == GEOM_MESH and not mesh_mesh:
+                continue  # mesh-mesh narrow phase not restated yet (DESIGN.md "collision coverage")
             if g1["priority"] != g2["priority"]:
                 hi = g1 if g1["priority"] > g2["priority"] else g2
                 solref, solimp, fri = hi["solref"], hi["solimp"], hi["friction"]
