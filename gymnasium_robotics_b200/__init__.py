@@ -1,0 +1,49 @@
+"""gymnasium_robotics_b200: B200-native batched simulator behind the Gymnasium-Robotics env API (hot path only).
+
+Drop-in boundary mirrored from the reference registry (gymnasium_robotics/__init__.py:12-80): the same env ids and
+kwargs, constructed as batched vector envs.  `make_vec(id, num_envs=N)` works without gymnasium; when gymnasium is
+importable the ids are also registered with a `vector_entry_point` so that
+`gymnasium.make_vec(id, num_envs=N, vectorization_mode="vector_entry_point")` builds the CUDA env.
+"""
+from __future__ import annotations
+
+__version__ = "0.1.0"
+
+# id -> (task, reward_type, max_episode_steps); only the new-binding versions (-v4) of the reference are mirrored,
+# the mujoco_py (-v1) ids are out of scope
+ENV_IDS = {}
+for _task in ("FetchReach", "FetchPush", "FetchPickAndPlace"):
+    for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
+        ENV_IDS[f"{_task}{_suffix}-v4"] = dict(task=_task, reward_type=_rt, max_episode_steps=50)
+
+
+def make_vec(env_id: str, num_envs: int = 1, **kwargs):
+    """Batched replacement for `gym.make_vec(env_id, num_envs=...)` (reference ids, e.g. "FetchPickAndPlace-v4")."""
+    from .fetch import FetchVectorEnv
+
+    if env_id not in ENV_IDS:
+        raise KeyError(f"{env_id!r} is not provided by the CUDA path yet; available: {sorted(ENV_IDS)}")
+    spec = dict(ENV_IDS[env_id])
+    spec.update(kwargs)
+    return FetchVectorEnv(num_envs=num_envs, **spec)
+
+
+def _vector_entry_point(task, **kwargs):
+    from .fetch import FetchVectorEnv
+
+    return FetchVectorEnv(task=task, **kwargs)
+
+
+def register_envs():
+    """Register the ids with gymnasium (no-op when gymnasium is not installed)."""
+    try:
+        import gymnasium  # noqa: F401
+        from gymnasium.envs.registration import register, registry
+    except Exception:  # noqa: BLE001
+        return False
+    for env_id, spec in ENV_IDS.items():
+        if env_id in registry:
+            continue
+        register(id=env_id, vector_entry_point="gymnasium_robotics_b200.fetch:FetchVectorEnv",
+                 kwargs=dict(task=spec["task"], reward_type=spec["reward_type"], max_episode_steps=spec["max_episode_steps"]))
+    return True

@@ -1,0 +1,71 @@
+"""ctypes binding of the C-ABI in include/b200sim.h (the in-tree CUDA library libb200sim.so).
+
+There is deliberately no CPU fallback: if the library or a CUDA device is missing, importing callers get a loud
+error.  (The CPU restatement under oracle/ is test infrastructure and is never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sim.so")
+_LIB = None
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+
+class FetchTaskC(ctypes.Structure):
+    """b200sim_fetch_task_t"""
+    _fields_ = [(n, ctypes.c_int) for n in ("has_object", "block_gripper", "n_substeps", "reward_dense", "grip_site",
+                                             "obj_site", "frame_site", "nrobot")] + \
+               [("robot_qadr", ctypes.c_int * 16), ("robot_dadr", ctypes.c_int * 16), ("finger_qadr", ctypes.c_int * 2),
+                ("nobs", ctypes.c_int), ("distance_threshold", ctypes.c_float), ("dt", ctypes.c_float)]
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """nvcc-compile csrc/b200sim.cu for sm_100a into the in-tree libb200sim.so (cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc", "b200sim.cu")
+    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("sim_core.cuh", "fetch_task.cuh", "dmodel.h")] + \
+           [os.path.join(_HERE, "..", "include", f) for f in ("b200sim.h", "b200sim_model.h")]
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA path has no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    L.b200sim_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, vp, vp, ctypes.POINTER(FetchTaskC), ci, ci, ctypes.POINTER(vp)]
+    L.b200sim_create.restype = ci
+    L.b200sim_destroy.argtypes = [vp]
+    L.b200sim_destroy.restype = None
+    L.b200sim_last_error.argtypes = [vp]
+    L.b200sim_last_error.restype = ctypes.c_char_p
+    L.b200sim_num_envs.argtypes = [vp]
+    L.b200sim_layout.argtypes = [vp, ctypes.POINTER(ci)]
+    L.b200sim_state.argtypes = [vp]
+    L.b200sim_state.restype = vp
+    L.b200sim_step.argtypes = [vp] * 9
+    L.b200sim_refresh.argtypes = [vp] * 8
+    L.b200sim_raw_step.argtypes = [vp, ci] + [vp] * 6
+    L.b200sim_compute_reward.argtypes = [vp, vp, vp, ci, vp, vp]
+    L.b200sim_launch_count.argtypes = [vp]
+    L.b200sim_launch_count.restype = ctypes.c_long
+    L.b200sim_launch_config.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = ["b200sim_create", "b200sim_destroy", "b200sim_last_error", "b200sim_num_envs", "b200sim_layout",
+                    "b200sim_state", "b200sim_step", "b200sim_refresh", "b200sim_raw_step", "b200sim_compute_reward",
+                    "b200sim_launch_count", "b200sim_launch_config"]

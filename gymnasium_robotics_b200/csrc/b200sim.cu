@@ -1,0 +1,205 @@
+// b200sim: CUDA kernels (sm_100a) + the C-ABI of include/b200sim.h.
+//
+// One warp integrates one env for a whole env-step (all sub-steps on chip); WPB warps share one copy of the model
+// constants that a single thread stages into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier).
+// Per-env state lives in HBM as one contiguous fp32 record per env (read once, written once per step).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sim.h"
+#include "fetch_task.cuh"
+
+#ifndef B200_WPB
+#define B200_WPB 4
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restrict__ model_g, FetchTask task, int mode, int nraw,
+                                                         int N, float* __restrict__ state, const float* __restrict__ actions,
+                                                         const unsigned char* __restrict__ mask, float* __restrict__ obs,
+                                                         float* __restrict__ achieved, float* __restrict__ desired,
+                                                         float* __restrict__ reward, float* __restrict__ success,
+                                                         int* __restrict__ info) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // ---- stage the model constants: TMA 1-D bulk copy global -> shared, completion on an mbarrier
+  const int model_words = ((const DMHead*)model_g)->nwords;  // uniform scalar load
+  const uint32_t bytes = (uint32_t)model_words * 4u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+                 "l"(model_g), "r"(bytes), "r"(smem_u32(&bar))
+                 : "memory");
+  }
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done)
+                   : "r"(smem_u32(&bar))
+                   : "memory");
+    }
+  }
+  const DMHead* h = (const DMHead*)smem;
+  const int env = blockIdx.x * WPB + warp;
+  if (env >= N) return;
+  if (mask && !mask[env]) return;
+  Ctx c;
+  c.mw = smem; c.h = h; c.lane = lane;
+  c.s = (float*)(smem + model_words) + (size_t)warp * h->scr_words;
+  float a4[4] = {0, 0, 0, 0};
+  if (actions) { for (int k = 0; k < 4; k++) a4[k] = actions[(size_t)env * 4 + k]; }
+  fetch_env_step(c, task, mode, nraw, state + (size_t)env * task.st_stride, a4, obs + (size_t)env * task.nobs,
+                 achieved + (size_t)env * 3, desired + (size_t)env * 3, reward + env, success + env, info ? info + env : nullptr);
+}
+
+__global__ void reward_kernel(const float* __restrict__ ag, const float* __restrict__ dg, int M, float thr, int dense,
+                              float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float dx = ag[3 * i] - dg[3 * i], dy = ag[3 * i + 1] - dg[3 * i + 1], dz = ag[3 * i + 2] - dg[3 * i + 2];
+  float d = sqrtf(dx * dx + dy * dy + dz * dz);
+  out[i] = dense ? -d : -(d > thr ? 1.f : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct b200sim {
+  int N = 0, device = 0;
+  std::vector<uint8_t> blob;
+  b200_model_view view;
+  std::vector<uint32_t> model_host;
+  uint32_t* model_dev = nullptr;
+  FetchTask task;
+  float* state = nullptr;
+  size_t smem_bytes = 0;
+  int blocks = 0;
+  long launches = 0;
+  std::string err;
+};
+
+static std::string g_err;
+
+static int fail(b200sim* h, const std::string& msg, int code) {
+  if (h) h->err = msg; else g_err = msg;
+  return code;
+}
+
+#define CUDA_OK(call)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) return fail(h, std::string(#call) + ": " + cudaGetErrorString(e_), -100 - (int)e_); \
+  } while (0)
+
+extern "C" {
+
+int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data, const float* ref,
+                   const b200sim_fetch_task_t* task, int num_envs, int device, b200sim_t** out) {
+  b200sim* h = nullptr;
+  if (!model_blob || !task || !out || num_envs <= 0) return fail(nullptr, "b200sim_create: bad arguments", -1);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(nullptr, "b200sim_create: no CUDA device (the CUDA path has no CPU fallback)", -2);
+  h = new b200sim;
+  h->N = num_envs; h->device = device;
+  h->blob.assign((const uint8_t*)model_blob, (const uint8_t*)model_blob + nbytes);
+  if (b200_model_parse(h->blob.data(), nbytes, &h->view) != 0) { delete h; return fail(nullptr, "b200sim_create: not a model blob", -3); }
+  float r[3] = {0, 0, 0};
+  if (ref) { r[0] = ref[0]; r[1] = ref[1]; r[2] = ref[2]; }
+  std::string err;
+  if (dm_build(h->view, eq_data, r, h->model_host, err) != 0) { delete h; return fail(nullptr, "b200sim_create: " + err, -4); }
+  const DMHead* dh = (const DMHead*)h->model_host.data();
+  FetchTask& t = h->task;
+  memset(&t, 0, sizeof(t));
+  t.has_object = task->has_object; t.block_gripper = task->block_gripper; t.n_substeps = task->n_substeps;
+  t.reward_dense = task->reward_dense; t.grip_site = task->grip_site; t.obj_site = task->obj_site; t.frame_site = task->frame_site;
+  t.nrobot = task->nrobot;
+  if (t.nrobot < 2 || t.nrobot > FETCH_MAX_ROBOT_JNT) { delete h; return fail(nullptr, "b200sim_create: bad nrobot", -5); }
+  for (int i = 0; i < 16; i++) { t.robot_qadr[i] = task->robot_qadr[i]; t.robot_dadr[i] = task->robot_dadr[i]; }
+  t.finger_qadr[0] = task->finger_qadr[0]; t.finger_qadr[1] = task->finger_qadr[1];
+  t.nobs = task->nobs; t.distance_threshold = task->distance_threshold; t.dt = task->dt;
+  if (dh->nmocap != 1) { delete h; return fail(nullptr, "b200sim_create: Fetch task needs exactly one mocap body", -6); }
+  int o = 0;
+  t.st_qpos = o; o += dh->nq; t.st_qvel = o; o += dh->nv; t.st_warm = o; o += dh->nv; t.st_ctrl = o; o += dh->nu;
+  t.st_mocap = o; o += 7; t.st_pose = o; o += 7; t.st_goal = o; o += 3;
+  t.st_stride = (o + 3) & ~3;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, "b200sim_create: cudaSetDevice failed", -7); }
+  h->smem_bytes = ((size_t)dh->nwords + (size_t)B200_WPB * dh->scr_words) * 4;
+  h->blocks = (num_envs + B200_WPB - 1) / B200_WPB;
+  cudaError_t e = cudaFuncSetAttribute(fetch_kernel<B200_WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e != cudaSuccess) { std::string m = std::string("cudaFuncSetAttribute(smem=") + std::to_string(h->smem_bytes) + "): " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
+  if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, (size_t)num_envs * t.st_stride * 4) != cudaSuccess) {
+    delete h; return fail(nullptr, "b200sim_create: cudaMalloc failed", -9);
+  }
+  cudaMemcpy(h->model_dev, h->model_host.data(), h->model_host.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(h->state, 0, (size_t)num_envs * t.st_stride * 4);
+  *out = h;
+  return 0;
+}
+
+void b200sim_destroy(b200sim_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->model_dev) cudaFree(h->model_dev);
+  if (h->state) cudaFree(h->state);
+  delete h;
+}
+
+const char* b200sim_last_error(const b200sim_t* h) { return h ? h->err.c_str() : g_err.c_str(); }
+int b200sim_num_envs(const b200sim_t* h) { return h->N; }
+int b200sim_layout(const b200sim_t* h, int* out) {
+  const FetchTask& t = h->task;
+  out[B200SIM_ST_QPOS] = t.st_qpos; out[B200SIM_ST_QVEL] = t.st_qvel; out[B200SIM_ST_WARM] = t.st_warm; out[B200SIM_ST_CTRL] = t.st_ctrl;
+  out[B200SIM_ST_MOCAP] = t.st_mocap; out[B200SIM_ST_POSE] = t.st_pose; out[B200SIM_ST_GOAL] = t.st_goal; out[B200SIM_ST_STRIDE] = t.st_stride;
+  return 0;
+}
+float* b200sim_state(b200sim_t* h) { return h->state; }
+long b200sim_launch_count(const b200sim_t* h) { return h->launches; }
+int b200sim_launch_config(const b200sim_t* h, int* smem_bytes, int* envs_per_block, int* blocks) {
+  if (smem_bytes) *smem_bytes = (int)h->smem_bytes;
+  if (envs_per_block) *envs_per_block = B200_WPB;
+  if (blocks) *blocks = h->blocks;
+  return 0;
+}
+
+static int launch(b200sim* h, int mode, int nraw, const float* actions, const unsigned char* mask, float* obs, float* achieved,
+                  float* desired, float* reward, float* success, int* info, void* stream) {
+  if (!obs || !achieved || !desired || !reward || !success) return fail(h, "output pointers must not be NULL", -1);
+  CUDA_OK(cudaSetDevice(h->device));
+  fetch_kernel<B200_WPB><<<h->blocks, B200_WPB * 32, h->smem_bytes, (cudaStream_t)stream>>>(
+      h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int b200sim_step(b200sim_t* h, const float* actions, float* obs, float* achieved, float* desired, float* reward, float* success,
+                 int* info, void* stream) {
+  if (!actions) return fail(h, "b200sim_step: actions is NULL", -1);
+  return launch(h, MODE_STEP, 0, actions, nullptr, obs, achieved, desired, reward, success, info, stream);
+}
+int b200sim_refresh(b200sim_t* h, const unsigned char* mask, float* obs, float* achieved, float* desired, float* reward,
+                    float* success, void* stream) {
+  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+}
+int b200sim_raw_step(b200sim_t* h, int nstep, float* obs, float* achieved, float* desired, float* reward, float* success,
+                     void* stream) {
+  return launch(h, MODE_RAW, nstep, nullptr, nullptr, obs, achieved, desired, reward, success, nullptr, stream);
+}
+int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const float* desired, int M, float* out, void* stream) {
+  if (M <= 0) return 0;
+  cudaSetDevice(h->device);
+  reward_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(achieved, desired, M, h->task.distance_threshold, h->task.reward_dense, out);
+  const_cast<b200sim*>(h)->launches++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// Device model: the fp32 constant tables one thread block stages into shared memory, and the per-env
+// scratch layout.  Built on the host from the fp64 blob (include/b200sim_model.h) by dm_build().
+//
+// Replaces the `mujoco.MjModel` object of the reference (gymnasium_robotics/envs/robot_env.py:293).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <string>
+
+#include "../../include/b200sim_model.h"
+
+#define DM_MAX_BODY 32   // one lane per body / 32-bit body masks
+#define DM_MAX_NV 32     // 32-bit dof masks
+#define DM_NCON_MAX 16   // contacts kept per env per sub-step
+#define DM_NDOFROW_MAX 16
+#define DM_NGROUP_MAX 8
+#define DM_NCAND_MAX 32
+#define DM_NWELD_MAX 1
+
+// (name, words-per-element, kind) ; kind selects the element count
+#define DM_ARRAYS(X) \
+  X(body_parent, 1, nb) X(body_jntadr, 1, nb) X(body_jntnum, 1, nb) X(body_dofadr, 1, nb) X(body_dofnum, 1, nb) \
+  X(body_mocapid, 1, nb) X(body_ancdof, 1, nb) X(body_sub, 1, nb) X(body_pos, 3, nb) X(body_quat, 4, nb) \
+  X(body_ipos, 3, nb) X(body_iquat, 4, nb) X(body_mass, 1, nb) X(body_inertia, 3, nb) \
+  X(jnt_type, 1, njnt) X(jnt_body, 1, njnt) X(jnt_qposadr, 1, njnt) X(jnt_dofadr, 1, njnt) X(jnt_limited, 1, njnt) \
+  X(jnt_pos, 3, njnt) X(jnt_axis, 3, njnt) X(jnt_range, 2, njnt) X(jnt_margin, 1, njnt) X(jnt_stiffness, 1, njnt) \
+  X(jnt_solref, 2, njnt) X(jnt_solimp, 5, njnt) X(jnt_qpos0, 1, njnt) X(jnt_qspring, 1, njnt) \
+  X(dof_body, 1, nv) X(dof_jnt, 1, nv) X(dof_anc, 1, nv) X(dof_pre, 1, nv) X(dof_armature, 1, nv) \
+  X(dof_damping, 1, nv) X(dof_frictionloss, 1, nv) X(dof_invweight0, 1, nv) \
+  X(geom_type, 1, ngeom) X(geom_body, 1, ngeom) X(geom_pos, 3, ngeom) X(geom_quat, 4, ngeom) X(geom_size, 3, ngeom) \
+  X(geom_rbound, 1, ngeom) \
+  X(pair_geom1, 1, npair) X(pair_geom2, 1, npair) X(pair_condim, 1, npair) X(pair_friction, 3, npair) \
+  X(pair_margin, 1, npair) X(pair_gap, 1, npair) X(pair_solref, 2, npair) X(pair_solimp, 5, npair) X(pair_invweight, 2, npair) \
+  X(site_body, 1, nsite) X(site_pos, 3, nsite) X(site_quat, 4, nsite) \
+  X(act_trnid, 1, nu) X(act_ctrllimited, 1, nu) X(act_forcelimited, 1, nu) X(act_gear, 1, nu) X(act_gain, 1, nu) \
+  X(act_bias, 3, nu) X(act_ctrlrange, 2, nu) X(act_forcerange, 2, nu) \
+  X(eq_type, 1, neq) X(eq_obj1, 1, neq) X(eq_obj2, 1, neq) X(eq_active, 1, neq) X(eq_data, 11, neq) X(eq_solref, 2, neq) \
+  X(eq_solimp, 5, neq) X(eq_invweight, 2, neq) \
+  X(mocap_body, 1, nmocap)
+
+// per-env scratch arrays (name, words expression)
+#define DM_SCRATCH(X) \
+  X(qpos, nq) X(qvel, nv) X(qacc, nv) X(warm, nv) X(ctrl, nu) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) \
+  X(xpos, 3 * nb) X(xquat, 4 * nb) X(xmat, 9 * nb) X(kinA, 8 * nb) X(kinB, 8 * nb) \
+  X(cinert, 10 * nb) X(cdof, 6 * nv) X(cvel, 6 * nb) X(b6, 6 * nb) X(d6, 6 * nv) \
+  X(M, nv * (nv + 1) / 2) X(H, nv * (nv + 1) / 2) \
+  X(fsmooth, nv) X(fcon, nv) X(grad, nv) X(search, nv) X(Ma, nv) X(Mv, nv) X(tmpv, nv) \
+  X(geom_xpos, 3 * ngeom) \
+  X(con, DM_NCON_MAX * CON_WORDS) X(dofrow, DM_NDOFROW_MAX * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
+  X(group, DM_NGROUP_MAX * GRP_WORDS) X(cand, DM_NCAND_MAX) X(counters, 8) X(red, 8)
+
+// contact record layout (words)
+enum { C_R = 0 /*pos - ref*/, C_FRAME = 3, C_DIST = 12, C_MU = 13 /*5*/, C_D = 18, C_B = 19, C_KIR = 20, C_U = 21 /*6*/,
+       C_JV = 27 /*6*/, C_C0 = 33 /*6*/, C_F = 39 /*6*/, C_DIM = 45, C_BA = 46, C_BB = 47, C_GRP = 48, C_PAIR = 49,
+       C_MARGIN = 50, CON_WORDS = 52 };
+// dof row: limit / frictionloss / joint equality
+enum { DR_DOF = 0, DR_COEF = 1, DR_DOF2 = 2, DR_COEF2 = 3, DR_TYPE = 4, DR_D = 5, DR_R = 6, DR_FLOSS = 7, DR_AREF = 8,
+       DR_JAR = 9, DR_JV = 10, DR_B = 11, DR_KIR = 12, DR_WORDS = 14 };
+// weld: 6 rows, each w[6]; then D[6], B[6], KIR[6], jar[6], jv[6], bodies, group
+enum { W_W = 0, W_D = 36, W_B = 42, W_KIR = 48, W_JAR = 54, W_JV = 60, W_BA = 66, W_BB = 67, W_GRP = 68, WELD_WORDS = 70 };
+// group: K[21] + bodies
+enum { G_K = 0, G_BA = 21, G_BB = 22, GRP_WORDS = 24 };
+enum { ROWT_EQ = 0, ROWT_FRICTION = 1, ROWT_LIMIT = 2 };
+enum { CNT_NCON = 0, CNT_NDR = 1, CNT_NGRP = 2, CNT_NCAND = 3, CNT_NWELD = 4, CNT_ITERS = 5, CNT_OVERFLOW = 6 };
+
+struct DMHead {
+  int nb, njnt, nq, nv, nu, ngeom, nsite, nmocap, neq, npair;
+  int nwords;      // size of the model buffer (header included) in 4-byte words
+  int scr_words;   // per-env scratch size in words
+  int iterations, ls_iterations, integrator, any_damping, kin_iters, pad0;
+  float timestep, gravity[3], tolerance, impratio, meaninertia, ls_tolerance, ref[3];
+#define X(name, w, kind) int o_##name;
+  DM_ARRAYS(X)
+#undef X
+#define X(name, words) int s_##name;
+  DM_SCRATCH(X)
+#undef X
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-side builder
+static inline uint32_t f2w(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+static inline int dm_build(const b200_model_view& m, const double* eq_data_override, const float ref[3],
+                           std::vector<uint32_t>& buf, std::string& err) {
+  DMHead h;
+  memset(&h, 0, sizeof(h));
+  h.nb = m.nbody; h.njnt = m.njnt; h.nq = m.nq; h.nv = m.nv; h.nu = m.nu; h.ngeom = m.ngeom; h.nsite = m.nsite;
+  h.nmocap = m.nmocap; h.neq = m.neq; h.npair = m.npair;
+  if (h.nb > DM_MAX_BODY) { err = "model has more than 32 runtime bodies"; return -1; }
+  if (h.nv > DM_MAX_NV) { err = "model has more than 32 dofs"; return -1; }
+  if (m.ntendon > 0) { err = "tendons are not supported by the CUDA path yet"; return -1; }
+  int nweld = 0;
+  for (int e = 0; e < m.neq; e++) if (m.eq_type[e] == B200_EQ_WELD) nweld++;
+  if (nweld > DM_NWELD_MAX) { err = "too many weld constraints"; return -1; }
+  h.iterations = m.opt_int[B200_OPTI_ITERATIONS]; h.ls_iterations = m.opt_int[B200_OPTI_LS_ITERATIONS];
+  h.integrator = m.opt_int[B200_OPTI_INTEGRATOR];
+  if (h.integrator != B200_INT_EULER) { err = "only the Euler integrator is implemented on the CUDA path"; return -1; }
+  h.timestep = (float)m.opt[B200_OPT_TIMESTEP];
+  for (int k = 0; k < 3; k++) { h.gravity[k] = (float)m.opt[B200_OPT_GRAVITY + k]; h.ref[k] = ref[k]; }
+  h.tolerance = (float)m.opt[B200_OPT_TOLERANCE]; h.impratio = (float)m.opt[B200_OPT_IMPRATIO];
+  h.meaninertia = (float)m.opt[B200_OPT_MEANINERTIA]; h.ls_tolerance = (float)m.opt[B200_OPT_LS_TOLERANCE];
+  for (int d = 0; d < m.nv; d++) if (m.dof_damping[d] > 0) h.any_damping = 1;
+  // offsets
+  int nb = h.nb, njnt = h.njnt, nq = h.nq, nv = h.nv, nu = h.nu, ngeom = h.ngeom, nsite = h.nsite, nmocap = h.nmocap,
+      neq = h.neq, npair = h.npair;
+  int off = (int)((sizeof(DMHead) + 3) / 4);
+#define X(name, w, kind) h.o_##name = off; off += (w) * (kind);
+  DM_ARRAYS(X)
+#undef X
+  off = (off + 3) & ~3;  // 16-byte multiple for the bulk copy
+  h.nwords = off;
+  int so = 0;
+#define X(name, words) h.s_##name = so; so += (words); so = (so + 1) & ~1;
+  DM_SCRATCH(X)
+#undef X
+  h.scr_words = (so + 3) & ~3;
+  (void)nq;
+  buf.assign(h.nwords, 0);
+  auto F = [&](int o, int i, double v) { buf[o + i] = f2w((float)v); };
+  auto I = [&](int o, int i, int v) { buf[o + i] = (uint32_t)v; };
+  // masks
+  std::vector<uint32_t> anc(nv, 0), pre(nv, 0), bodyanc(nb, 0), sub(nb, 0);
+  for (int d = 0; d < nv; d++) {
+    int p = m.dof_parent[d];
+    anc[d] = (p >= 0 ? anc[p] : 0u) | (1u << d);
+  }
+  for (int b = 1; b < nb; b++) {
+    // dofs of this body and of all ancestors
+    int a = b;
+    while (a > 0 && m.body_dofnum[a] == 0) a = m.body_parent[a];
+    bodyanc[b] = a > 0 ? anc[m.body_dofadr[a] + m.body_dofnum[a] - 1] : 0u;
+  }
+  for (int b = nb - 1; b >= 0; b--) {
+    sub[b] |= 1u << b;
+    if (b > 0) sub[m.body_parent[b]] |= sub[b];
+  }
+  for (int d = 0; d < nv; d++) {
+    int b = m.dof_body[d], j = m.dof_jnt[d];
+    uint32_t mask = bodyanc[m.body_parent[b]];  // all dofs of ancestor bodies
+    // earlier dofs of the same body: every earlier joint of the body; for a free joint's rotational dofs only the
+    // three translational dofs (body-fixed axes: no rot-rot terms, see DESIGN.md "velocity products")
+    for (int e = m.body_dofadr[b]; e < d; e++) {
+      if (m.dof_jnt[e] != j) mask |= 1u << e;
+      else if (m.jnt_type[j] == B200_JNT_FREE && d - m.jnt_dofadr[j] >= 3 && e - m.jnt_dofadr[j] < 3) mask |= 1u << e;
+    }
+    pre[d] = mask;
+  }
+  {
+    int maxdepth = 1;
+    std::vector<int> depth(nb, 0);
+    for (int b = 1; b < nb; b++) { depth[b] = depth[m.body_parent[b]] + 1; if (depth[b] > maxdepth) maxdepth = depth[b]; }
+    h.kin_iters = 0;
+    while ((1 << h.kin_iters) < maxdepth) h.kin_iters++;
+  }
+  for (int b = 0; b < nb; b++) {
+    I(h.o_body_parent, b, m.body_parent[b]); I(h.o_body_jntadr, b, m.body_jntadr[b]); I(h.o_body_jntnum, b, m.body_jntnum[b]);
+    I(h.o_body_dofadr, b, m.body_dofadr[b]); I(h.o_body_dofnum, b, m.body_dofnum[b]); I(h.o_body_mocapid, b, m.body_mocapid[b]);
+    buf[h.o_body_ancdof + b] = bodyanc[b]; buf[h.o_body_sub + b] = sub[b];
+    for (int k = 0; k < 3; k++) { F(h.o_body_pos, 3 * b + k, m.body_pos[3 * b + k]); F(h.o_body_ipos, 3 * b + k, m.body_ipos[3 * b + k]);
+      F(h.o_body_inertia, 3 * b + k, m.body_inertia[3 * b + k]); }
+    for (int k = 0; k < 4; k++) { F(h.o_body_quat, 4 * b + k, m.body_quat[4 * b + k]); F(h.o_body_iquat, 4 * b + k, m.body_iquat[4 * b + k]); }
+    F(h.o_body_mass, b, m.body_mass[b]);
+  }
+  for (int j = 0; j < njnt; j++) {
+    if (m.jnt_type[j] == B200_JNT_BALL) { err = "ball joints are not supported"; return -1; }
+    I(h.o_jnt_type, j, m.jnt_type[j]); I(h.o_jnt_body, j, m.jnt_body[j]); I(h.o_jnt_qposadr, j, m.jnt_qposadr[j]);
+    I(h.o_jnt_dofadr, j, m.jnt_dofadr[j]); I(h.o_jnt_limited, j, m.jnt_limited[j]);
+    for (int k = 0; k < 3; k++) { F(h.o_jnt_pos, 3 * j + k, m.jnt_pos[3 * j + k]); F(h.o_jnt_axis, 3 * j + k, m.jnt_axis[3 * j + k]); }
+    for (int k = 0; k < 2; k++) { F(h.o_jnt_range, 2 * j + k, m.jnt_range[2 * j + k]); F(h.o_jnt_solref, 2 * j + k, m.jnt_solref[2 * j + k]); }
+    for (int k = 0; k < 5; k++) F(h.o_jnt_solimp, 5 * j + k, m.jnt_solimp[5 * j + k]);
+    F(h.o_jnt_margin, j, m.jnt_margin[j]); F(h.o_jnt_stiffness, j, m.jnt_stiffness[j]);
+    F(h.o_jnt_qpos0, j, m.qpos0[m.jnt_qposadr[j]]); F(h.o_jnt_qspring, j, m.qpos_spring[m.jnt_qposadr[j]]);
+    if (m.jnt_type[j] == B200_JNT_FREE && m.body_jntnum[m.jnt_body[j]] != 1) { err = "free joint must be the only joint of its body"; return -1; }
+  }
+  for (int d = 0; d < nv; d++) {
+    I(h.o_dof_body, d, m.dof_body[d]); I(h.o_dof_jnt, d, m.dof_jnt[d]); buf[h.o_dof_anc + d] = anc[d]; buf[h.o_dof_pre + d] = pre[d];
+    F(h.o_dof_armature, d, m.dof_armature[d]); F(h.o_dof_damping, d, m.dof_damping[d]);
+    F(h.o_dof_frictionloss, d, m.dof_frictionloss[d]); F(h.o_dof_invweight0, d, m.dof_invweight0[d]);
+    if (m.dof_frictionloss[d] > 0) { err = "frictionloss rows are not supported by the CUDA path yet"; return -1; }
+  }
+  for (int g = 0; g < ngeom; g++) {
+    I(h.o_geom_type, g, m.geom_type[g]); I(h.o_geom_body, g, m.geom_body[g]);
+    for (int k = 0; k < 3; k++) { F(h.o_geom_pos, 3 * g + k, m.geom_pos[3 * g + k]); F(h.o_geom_size, 3 * g + k, m.geom_size[3 * g + k]); }
+    for (int k = 0; k < 4; k++) F(h.o_geom_quat, 4 * g + k, m.geom_quat[4 * g + k]);
+    F(h.o_geom_rbound, g, m.geom_rbound[g]);
+  }
+  for (int p = 0; p < npair; p++) {
+    I(h.o_pair_geom1, p, m.pair_geom1[p]); I(h.o_pair_geom2, p, m.pair_geom2[p]); I(h.o_pair_condim, p, m.pair_condim[p]);
+    int t1 = m.geom_type[m.pair_geom1[p]], t2 = m.geom_type[m.pair_geom2[p]];
+    bool ok = (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_BOX) || (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX);
+    if (!ok) { err = "collision pair type not supported by the CUDA path yet (only plane-box, box-box)"; return -1; }
+    F(h.o_pair_friction, 3 * p + 0, m.pair_friction[5 * p + 0]); F(h.o_pair_friction, 3 * p + 1, m.pair_friction[5 * p + 2]);
+    F(h.o_pair_friction, 3 * p + 2, m.pair_friction[5 * p + 3]);
+    F(h.o_pair_margin, p, m.pair_margin[p]); F(h.o_pair_gap, p, m.pair_gap[p]);
+    for (int k = 0; k < 2; k++) { F(h.o_pair_solref, 2 * p + k, m.pair_solref[2 * p + k]); F(h.o_pair_invweight, 2 * p + k, m.pair_invweight[2 * p + k]); }
+    for (int k = 0; k < 5; k++) F(h.o_pair_solimp, 5 * p + k, m.pair_solimp[5 * p + k]);
+  }
+  for (int s = 0; s < nsite; s++) {
+    I(h.o_site_body, s, m.site_body[s]);
+    for (int k = 0; k < 3; k++) F(h.o_site_pos, 3 * s + k, m.site_pos[3 * s + k]);
+    for (int k = 0; k < 4; k++) F(h.o_site_quat, 4 * s + k, m.site_quat[4 * s + k]);
+  }
+  for (int a = 0; a < nu; a++) {
+    I(h.o_act_trnid, a, m.act_trnid[a]); I(h.o_act_ctrllimited, a, m.act_ctrllimited[a]); I(h.o_act_forcelimited, a, m.act_forcelimited[a]);
+    F(h.o_act_gear, a, m.act_gear[a]); F(h.o_act_gain, a, m.act_gainprm[3 * a]);
+    for (int k = 0; k < 3; k++) F(h.o_act_bias, 3 * a + k, m.act_biasprm[3 * a + k]);
+    for (int k = 0; k < 2; k++) { F(h.o_act_ctrlrange, 2 * a + k, m.act_ctrlrange[2 * a + k]); F(h.o_act_forcerange, 2 * a + k, m.act_forcerange[2 * a + k]); }
+  }
+  for (int e = 0; e < neq; e++) {
+    if (m.eq_type[e] != B200_EQ_WELD) { err = "only weld equalities are supported by the CUDA path yet"; return -1; }
+    I(h.o_eq_type, e, m.eq_type[e]); I(h.o_eq_obj1, e, m.eq_obj1[e]); I(h.o_eq_obj2, e, m.eq_obj2[e]); I(h.o_eq_active, e, m.eq_active[e]);
+    const double* data = eq_data_override ? eq_data_override + 11 * e : m.eq_data + 11 * e;
+    for (int k = 0; k < 11; k++) F(h.o_eq_data, 11 * e + k, data[k]);
+    for (int k = 0; k < 2; k++) { F(h.o_eq_solref, 2 * e + k, m.eq_solref[2 * e + k]); F(h.o_eq_invweight, 2 * e + k, m.eq_invweight[2 * e + k]); }
+    for (int k = 0; k < 5; k++) F(h.o_eq_solimp, 5 * e + k, m.eq_solimp[5 * e + k]);
+  }
+  for (int i = 0; i < nmocap; i++) I(h.o_mocap_body, i, m.mocap_body[i]);
+  memcpy(buf.data(), &h, sizeof(h));
+  return 0;
+}

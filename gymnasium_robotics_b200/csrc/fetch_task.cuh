@@ -1,0 +1,144 @@
+// Fetch task layer executed inside the step kernel: action application, sub-step loop, observation, reward.
+// Restates (batched, fp32) the per-step Python of the reference:
+//   BaseRobotEnv.step                 gymnasium_robotics/envs/robot_env.py:114-152
+//   MujocoFetchEnv._set_action        envs/fetch/fetch_env.py:85-105, 305-310 ; utils/mujoco_utils.py:34-71, 83-107
+//   MujocoFetchEnv._step_callback     envs/fetch/fetch_env.py:295-303
+//   generate_mujoco_observations      envs/fetch/fetch_env.py:312-360 ; rotations.mat2euler utils/rotations.py:162-184
+//   compute_reward / _is_success      envs/fetch/fetch_env.py:74-80, 168-170
+#pragma once
+#include "sim_core.cuh"
+
+#define FETCH_MAX_ROBOT_JNT 16
+
+struct FetchTask {
+  int has_object, block_gripper, n_substeps, reward_dense;
+  int grip_site, obj_site, frame_site;  // "robot0:grip", "object0", body frame of robot0:gripper_link
+  int nrobot;
+  int robot_qadr[FETCH_MAX_ROBOT_JNT], robot_dadr[FETCH_MAX_ROBOT_JNT];
+  int finger_qadr[2];
+  int nobs;
+  float distance_threshold, dt;
+  // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(3)
+  int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride;
+};
+
+enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
+
+HD void site_pose(const Ctx& c, int site, float* pos, float* quat) {
+  int b = MI(site_body)[site];
+  float t[3];
+  mulmv(t, SF(xmat) + 9 * b, MF(site_pos) + 3 * site);
+  for (int k = 0; k < 3; k++) pos[k] = SF(xpos)[3 * b + k] + t[k];
+  if (quat) qmul(quat, SF(xquat) + 4 * b, MF(site_quat) + 4 * site);
+}
+
+HD void load_state(const Ctx& c, const FetchTask& t, const float* st) {
+  const DMHead* h = c.h;
+  LANES(i, h->nq) SF(qpos)[i] = st[t.st_qpos + i];
+  LANES(i, h->nv) { SF(qvel)[i] = st[t.st_qvel + i]; SF(warm)[i] = st[t.st_warm + i]; }
+  LANES(i, h->nu) SF(ctrl)[i] = st[t.st_ctrl + i];
+  LANES(i, 3 * h->nmocap) SF(mocap_pos)[i] = st[t.st_mocap + i];
+  LANES(i, 4 * h->nmocap) SF(mocap_quat)[i] = st[t.st_mocap + 3 + i];
+  if (c.lane == 0) { SI(counters)[CNT_ITERS] = 0; SI(counters)[CNT_OVERFLOW] = 0; }
+  SYNC();
+}
+
+HD void store_state(const Ctx& c, const FetchTask& t, float* st) {
+  const DMHead* h = c.h;
+  LANES(i, h->nq) st[t.st_qpos + i] = SF(qpos)[i];
+  LANES(i, h->nv) { st[t.st_qvel + i] = SF(qvel)[i]; st[t.st_warm + i] = SF(warm)[i]; }
+  LANES(i, h->nu) st[t.st_ctrl + i] = SF(ctrl)[i];
+  LANES(i, 3 * h->nmocap) st[t.st_mocap + i] = SF(mocap_pos)[i];
+  LANES(i, 4 * h->nmocap) st[t.st_mocap + 3 + i] = SF(mocap_quat)[i];
+  if (c.lane == 0) {
+    float p[3], q[4];
+    site_pose(c, t.frame_site, p, q);  // data.xpos / data.xquat of the welded body as of the last forward pass
+    for (int k = 0; k < 3; k++) st[t.st_pose + k] = p[k];
+    for (int k = 0; k < 4; k++) st[t.st_pose + 3 + k] = q[k];
+  }
+}
+
+HD void site_vel(const Ctx& c, int site, const float* pos, float* velp, float* velr) {
+  const float* V = SF(cvel) + 6 * MI(site_body)[site];
+  float r[3] = {pos[0] - c.h->ref[0], pos[1] - c.h->ref[1], pos[2] - c.h->ref[2]}, t[3];
+  cross3(t, V, r);
+  velp[0] = V[3] + t[0]; velp[1] = V[4] + t[1]; velp[2] = V[5] + t[2];
+  if (velr) { velr[0] = V[0]; velr[1] = V[1]; velr[2] = V[2]; }
+}
+
+HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float* obs, float* achieved, float* desired,
+                      float* reward, float* success) {
+  pass_V(c, SF(qvel), SF(cvel));  // site velocities: Jacobian of the last forward pass times the current qvel
+  if (c.lane == 0) {
+    float grip[3], gvel[3], o[32];
+    int n = 0;
+    site_pose(c, t.grip_site, grip, nullptr);
+    site_vel(c, t.grip_site, grip, gvel, nullptr);
+    for (int k = 0; k < 3; k++) gvel[k] *= t.dt;
+    for (int k = 0; k < 3; k++) o[n++] = grip[k];
+    float ag[3] = {grip[0], grip[1], grip[2]};
+    const float* gs_q = SF(qpos);
+    const float* gs_v = SF(qvel);
+    float gstate[2] = {gs_q[t.robot_qadr[t.nrobot - 2]], gs_q[t.robot_qadr[t.nrobot - 1]]};
+    float gv[2] = {gs_v[t.robot_dadr[t.nrobot - 2]] * t.dt, gs_v[t.robot_dadr[t.nrobot - 1]] * t.dt};
+    if (t.has_object) {
+      float op[3], oq[4], m[9], vp[3], vr[3];
+      site_pose(c, t.obj_site, op, oq);
+      q2mat(m, oq);
+      site_vel(c, t.obj_site, op, vp, vr);
+      for (int k = 0; k < 3; k++) o[n++] = op[k];
+      for (int k = 0; k < 3; k++) o[n++] = op[k] - grip[k];
+      o[n++] = gstate[0]; o[n++] = gstate[1];
+      // mat2euler
+      float cy = sqrtf(m[8] * m[8] + m[5] * m[5]);
+      float ex, ey, ez;
+      if (cy > 8.8817841970012523e-16f) { ez = -atan2f(m[1], m[0]); ey = -atan2f(-m[2], cy); ex = -atan2f(m[5], m[8]); }
+      else { ez = -atan2f(-m[3], m[4]); ey = -atan2f(-m[2], cy); ex = 0.f; }
+      o[n++] = ex; o[n++] = ey; o[n++] = ez;
+      for (int k = 0; k < 3; k++) o[n++] = vp[k] * t.dt - gvel[k];
+      for (int k = 0; k < 3; k++) o[n++] = vr[k] * t.dt;
+      for (int k = 0; k < 3; k++) ag[k] = op[k];
+    } else { o[n++] = gstate[0]; o[n++] = gstate[1]; }
+    for (int k = 0; k < 3; k++) o[n++] = gvel[k];
+    o[n++] = gv[0]; o[n++] = gv[1];
+    for (int k = 0; k < n; k++) obs[k] = o[k];
+    float d2 = 0;
+    for (int k = 0; k < 3; k++) { achieved[k] = ag[k]; desired[k] = goal[k]; float e = ag[k] - goal[k]; d2 += e * e; }
+    float d = sqrtf(d2);
+    *reward = t.reward_dense ? -d : -(d > t.distance_threshold ? 1.f : 0.f);
+    *success = d < t.distance_threshold ? 1.f : 0.f;
+  }
+}
+
+// one env, one warp.  `st` is this env's state record; outputs are this env's rows.
+HD void fetch_env_step(const Ctx& c, const FetchTask& t, int mode, int nraw, float* st, const float* action, float* obs,
+                       float* achieved, float* desired, float* reward, float* success, int* iters_out) {
+  const DMHead* h = c.h;
+  load_state(c, t, st);
+  if (mode == MODE_STEP) {
+    // _set_action: clip, scale, mocap <- last forward pose of the welded body + delta, position actuators relative
+    float a[4];
+    for (int k = 0; k < 4; k++) a[k] = fminf(fmaxf(action[k], -1.f), 1.f);
+    if (c.lane == 0) {
+      for (int k = 0; k < 3; k++) SF(mocap_pos)[k] = st[t.st_pose + k] + 0.05f * a[k];
+      const float rot[4] = {1.f, 0.f, 1.f, 0.f};
+      for (int k = 0; k < 4; k++) SF(mocap_quat)[k] = st[t.st_pose + 3 + k] + rot[k];
+      float g = t.block_gripper ? 0.f : a[3];
+      for (int i = 0; i < h->nu; i++) SF(ctrl)[i] = SF(qpos)[MI(jnt_qposadr)[MI(act_trnid)[i]]] + g;
+    }
+    SYNC();
+  }
+  int nsub = mode == MODE_STEP ? t.n_substeps : (mode == MODE_RAW ? nraw : 0);
+  for (int s = 0; s < nsub; s++) { forward(c); euler_step(c); }
+  if (mode == MODE_REFRESH || (mode == MODE_STEP && t.block_gripper) || nsub == 0) {
+    if (mode == MODE_STEP && t.block_gripper) {
+      if (c.lane == 0) { SF(qpos)[t.finger_qadr[0]] = 0.f; SF(qpos)[t.finger_qadr[1]] = 0.f; }
+      SYNC();
+    }
+    kinematics(c);
+    com_quantities(c);
+  }
+  fetch_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
+  store_state(c, t, st);
+  if (iters_out && c.lane == 0) *iters_out = SI(counters)[CNT_ITERS] | (SI(counters)[CNT_OVERFLOW] << 16);
+}

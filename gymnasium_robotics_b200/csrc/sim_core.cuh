@@ -1,0 +1,1237 @@
+// b200sim physics core: one warp integrates one env.  Hand-written for sm_100a; the same source compiles on the
+// host with WARP_W == 1 for the test-only emulation harness in tests/hostsim (never part of the product library).
+//
+// Replaces `mujoco.mj_step(model, data, nstep=n_substeps)` (reference: gymnasium_robotics/envs/robot_env.py:340-341)
+// for the model features listed in DESIGN.md.  Formulation (differs from the oracle on purpose):
+//   * spatial quantities are expressed about one fixed world point `ref` (not per-tree subtree coms);
+//   * kinematics by pointer jumping over the body tree (log depth);
+//   * tree recursions (CRB, velocities, RNE, J*v, J^T f) via ancestor / subtree bit masks, no sequential passes;
+//   * constraint Jacobian is never materialised: each base row is a spatial 6-vector `w` plus a body pair, pyramid
+//     edges are combinations of a contact's base rows, and H = M + J^T D J is assembled from per-body-pair 6x6 blocks;
+//   * dense packed Cholesky for H and for (M + h*B).
+#pragma once
+#include "dmodel.h"
+
+#ifdef __CUDACC__
+#define HD __device__ __forceinline__
+#define HDN __device__ __noinline__
+#define WARP_W 32
+#define SYNC() __syncwarp()
+#else
+#define HD static inline
+#define HDN static
+#define WARP_W 1
+#define SYNC() do { } while (0)
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+#endif
+
+#define B200_MINVAL 1e-15f
+#define B200_MINIMP 0.0001f
+#define B200_MAXIMP 0.9999f
+
+struct Ctx {
+  const uint32_t* mw;  // model words (shared memory)
+  const DMHead* h;
+  float* s;            // this env's scratch (shared memory)
+  int lane;
+};
+#define MI(name) ((const int*)(c.mw + c.h->o_##name))
+#define MU(name) ((const uint32_t*)(c.mw + c.h->o_##name))
+#define MF(name) ((const float*)(c.mw + c.h->o_##name))
+#define SF(name) (c.s + c.h->s_##name)
+#define SI(name) ((int*)(c.s + c.h->s_##name))
+#define LANES(i, n) for (int i = c.lane; i < (n); i += WARP_W)
+
+// ---------------------------------------------------------------------------------------------------------------
+// warp helpers
+HD float wsum(float v) {
+#ifdef __CUDACC__
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+HD float wmax(float v) {
+#ifdef __CUDACC__
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+  return v;
+}
+HD int wsumi(int v) {
+#ifdef __CUDACC__
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+// exclusive prefix sum of v over lanes; *total = sum
+HD int wexscan(int v, int lane, int* total) {
+#ifdef __CUDACC__
+  int x = v;
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  *total = __shfl_sync(0xffffffffu, x, 31);
+  return x - v;
+#else
+  (void)lane; *total = v; return 0;
+#endif
+}
+HD int ffs_pop(uint32_t& m) {  // index of lowest set bit, and clear it
+#ifdef __CUDACC__
+  int b = __ffs(m) - 1;
+#else
+  int b = __builtin_ctz(m);
+#endif
+  m &= m - 1;
+  return b;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small math
+HD float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+HD void cross3(float* r, const float* a, const float* b) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+HD float dot6(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5]; }
+HD void qmul(float* r, const float* a, const float* b) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+HD void qnormalize(float* q) {
+  float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < 1e-12f) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  float inv = 1.0f / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+HD void q2mat(float* m, const float* q) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+HD void qrot(float* r, const float* q, const float* v) {  // r = R(q) v
+  float t[3], u[3] = {q[1], q[2], q[3]};
+  cross3(t, u, v);
+  t[0] = 2 * t[0]; t[1] = 2 * t[1]; t[2] = 2 * t[2];
+  float c2[3];
+  cross3(c2, u, t);
+  r[0] = v[0] + q[0] * t[0] + c2[0]; r[1] = v[1] + q[0] * t[1] + c2[1]; r[2] = v[2] + q[0] * t[2] + c2[2];
+}
+HD void mulmv(float* r, const float* m, const float* v) {
+  float x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+HD void mulmtv(float* r, const float* m, const float* v) {
+  float x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2], z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+HD void cross_motion(float* r, const float* v, const float* s) {
+  float a[3], b[3], cc[3];
+  cross3(a, v, s); cross3(b, v, s + 3); cross3(cc, v + 3, s);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = b[0] + cc[0]; r[4] = b[1] + cc[1]; r[5] = b[2] + cc[2];
+}
+HD void cross_force(float* r, const float* v, const float* f) {
+  float a[3], b[3], cc[3];
+  cross3(a, v, f); cross3(b, v + 3, f + 3); cross3(cc, v, f + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = cc[0]; r[4] = cc[1]; r[5] = cc[2];
+}
+HD void mul_inert(float* res, const float* I, const float* v) {  // 10-number inertia about `ref`
+  const float* mo = I + 6;
+  float t[3];
+  res[0] = I[0] * v[0] + I[3] * v[1] + I[4] * v[2];
+  res[1] = I[3] * v[0] + I[1] * v[1] + I[5] * v[2];
+  res[2] = I[4] * v[0] + I[5] * v[1] + I[2] * v[2];
+  cross3(t, mo, v + 3);
+  res[0] += t[0]; res[1] += t[1]; res[2] += t[2];
+  cross3(t, v, mo);
+  res[3] = I[9] * v[3] + t[0]; res[4] = I[9] * v[4] + t[1]; res[5] = I[9] * v[5] + t[2];
+}
+HD int pidx(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j + 1)) / 2 + i; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1. kinematics (pointer jumping)
+HD void kinematics(const Ctx& c) {
+  const DMHead* h = c.h;
+  int nb = h->nb;
+  float *A = SF(kinA), *B = SF(kinB);
+  const float *qpos = SF(qpos);
+  LANES(b, nb) {
+    float lp[3] = {0, 0, 0}, lq[4] = {1, 0, 0, 0};
+    int anc = 0;
+    if (b > 0) {
+      anc = MI(body_parent)[b];
+      int mid = MI(body_mocapid)[b], jn = MI(body_jntnum)[b], ja = MI(body_jntadr)[b];
+      if (mid >= 0) {
+        for (int k = 0; k < 3; k++) lp[k] = SF(mocap_pos)[3 * mid + k];
+        for (int k = 0; k < 4; k++) lq[k] = SF(mocap_quat)[4 * mid + k];
+        qnormalize(lq);
+      } else if (jn == 1 && MI(jnt_type)[ja] == B200_JNT_FREE) {
+        int a = MI(jnt_qposadr)[ja];
+        for (int k = 0; k < 3; k++) lp[k] = qpos[a + k];
+        for (int k = 0; k < 4; k++) lq[k] = qpos[a + 3 + k];
+        qnormalize(lq);
+      } else {
+        for (int k = 0; k < 3; k++) lp[k] = MF(body_pos)[3 * b + k];
+        for (int k = 0; k < 4; k++) lq[k] = MF(body_quat)[4 * b + k];
+        for (int j = ja; j < ja + jn; j++) {
+          const float* jp = MF(jnt_pos) + 3 * j;
+          const float* jax = MF(jnt_axis) + 3 * j;
+          float dq = qpos[MI(jnt_qposadr)[j]] - MF(jnt_qpos0)[j];
+          if (MI(jnt_type)[j] == B200_JNT_SLIDE) {
+            float ax[3];
+            qrot(ax, lq, jax);
+            lp[0] += ax[0] * dq; lp[1] += ax[1] * dq; lp[2] += ax[2] * dq;
+          } else {
+            float anc_l[3], t[3], ql[4], nq[4], sn, cs;
+#ifdef __CUDACC__
+            sincosf(0.5f * dq, &sn, &cs);
+#else
+            sn = sinf(0.5f * dq); cs = cosf(0.5f * dq);
+#endif
+            qrot(t, lq, jp);
+            anc_l[0] = lp[0] + t[0]; anc_l[1] = lp[1] + t[1]; anc_l[2] = lp[2] + t[2];
+            ql[0] = cs; ql[1] = jax[0] * sn; ql[2] = jax[1] * sn; ql[3] = jax[2] * sn;
+            qmul(nq, lq, ql);
+            lq[0] = nq[0]; lq[1] = nq[1]; lq[2] = nq[2]; lq[3] = nq[3];
+            qrot(t, lq, jp);
+            lp[0] = anc_l[0] - t[0]; lp[1] = anc_l[1] - t[1]; lp[2] = anc_l[2] - t[2];
+          }
+        }
+      }
+    }
+    float* o = A + 8 * b;
+    o[0] = lp[0]; o[1] = lp[1]; o[2] = lp[2]; o[3] = lq[0]; o[4] = lq[1]; o[5] = lq[2]; o[6] = lq[3];
+    ((int*)o)[7] = anc;
+  }
+  SYNC();
+  for (int it = 0; it < h->kin_iters; it++) {
+    LANES(b, nb) {
+      const float* me = A + 8 * b;
+      float* o = B + 8 * b;
+      int anc = ((const int*)me)[7];
+      if (anc != 0) {
+        const float* pa = A + 8 * anc;
+        float t[3], q[4];
+        qrot(t, pa + 3, me);
+        qmul(q, pa + 3, me + 3);
+        o[0] = pa[0] + t[0]; o[1] = pa[1] + t[1]; o[2] = pa[2] + t[2];
+        o[3] = q[0]; o[4] = q[1]; o[5] = q[2]; o[6] = q[3];
+        ((int*)o)[7] = ((const int*)pa)[7];
+      } else {
+        for (int k = 0; k < 7; k++) o[k] = me[k];
+        ((int*)o)[7] = 0;
+      }
+    }
+    SYNC();
+    float* t = A; A = B; B = t;
+  }
+  LANES(b, nb) {
+    const float* me = A + 8 * b;
+    float q[4] = {me[3], me[4], me[5], me[6]};
+    qnormalize(q);
+    float* xp = SF(xpos) + 3 * b;
+    float* xq = SF(xquat) + 4 * b;
+    xp[0] = me[0]; xp[1] = me[1]; xp[2] = me[2];
+    xq[0] = q[0]; xq[1] = q[1]; xq[2] = q[2]; xq[3] = q[3];
+    q2mat(SF(xmat) + 9 * b, q);
+  }
+  SYNC();
+}
+
+// 2. spatial inertias and motion axes about `ref`; geom centres
+HD void com_quantities(const Ctx& c) {
+  const DMHead* h = c.h;
+  const float* ref = h->ref;
+  LANES(b, h->nb) {
+    float* ci = SF(cinert) + 10 * b;
+    if (b == 0) { for (int k = 0; k < 10; k++) ci[k] = 0; continue; }
+    const float* R = SF(xmat) + 9 * b;
+    float ip[3], r[3], iq[4], Ri[9];
+    mulmv(ip, R, MF(body_ipos) + 3 * b);
+    for (int k = 0; k < 3; k++) r[k] = SF(xpos)[3 * b + k] + ip[k] - ref[k];
+    qmul(iq, SF(xquat) + 4 * b, MF(body_iquat) + 4 * b);
+    q2mat(Ri, iq);
+    const float* d = MF(body_inertia) + 3 * b;
+    float mass = MF(body_mass)[b];
+    float I00 = Ri[0] * d[0] * Ri[0] + Ri[1] * d[1] * Ri[1] + Ri[2] * d[2] * Ri[2];
+    float I11 = Ri[3] * d[0] * Ri[3] + Ri[4] * d[1] * Ri[4] + Ri[5] * d[2] * Ri[5];
+    float I22 = Ri[6] * d[0] * Ri[6] + Ri[7] * d[1] * Ri[7] + Ri[8] * d[2] * Ri[8];
+    float I01 = Ri[0] * d[0] * Ri[3] + Ri[1] * d[1] * Ri[4] + Ri[2] * d[2] * Ri[5];
+    float I02 = Ri[0] * d[0] * Ri[6] + Ri[1] * d[1] * Ri[7] + Ri[2] * d[2] * Ri[8];
+    float I12 = Ri[3] * d[0] * Ri[6] + Ri[4] * d[1] * Ri[7] + Ri[5] * d[2] * Ri[8];
+    float rr = dot3(r, r);
+    ci[0] = I00 + mass * (rr - r[0] * r[0]); ci[1] = I11 + mass * (rr - r[1] * r[1]); ci[2] = I22 + mass * (rr - r[2] * r[2]);
+    ci[3] = I01 - mass * r[0] * r[1]; ci[4] = I02 - mass * r[0] * r[2]; ci[5] = I12 - mass * r[1] * r[2];
+    ci[6] = mass * r[0]; ci[7] = mass * r[1]; ci[8] = mass * r[2]; ci[9] = mass;
+  }
+  LANES(j, h->njnt) {
+    int b = MI(jnt_body)[j], d = MI(jnt_dofadr)[j], t = MI(jnt_type)[j];
+    const float* R = SF(xmat) + 9 * b;
+    const float* xp = SF(xpos) + 3 * b;
+    float* cd = SF(cdof) + 6 * d;
+    if (t == B200_JNT_FREE) {
+      float off[3] = {ref[0] - xp[0], ref[1] - xp[1], ref[2] - xp[2]};
+      for (int k = 0; k < 3; k++) { for (int a = 0; a < 6; a++) cd[6 * k + a] = 0; cd[6 * k + 3 + k] = 1; }
+      for (int k = 0; k < 3; k++) {
+        float ax[3] = {R[k], R[3 + k], R[6 + k]};
+        float* o = cd + 6 * (3 + k);
+        o[0] = ax[0]; o[1] = ax[1]; o[2] = ax[2];
+        cross3(o + 3, ax, off);
+      }
+    } else {
+      float ax[3];
+      mulmv(ax, R, MF(jnt_axis) + 3 * j);
+      if (t == B200_JNT_SLIDE) { cd[0] = cd[1] = cd[2] = 0; cd[3] = ax[0]; cd[4] = ax[1]; cd[5] = ax[2]; }
+      else {
+        float jp[3], off[3];
+        mulmv(jp, R, MF(jnt_pos) + 3 * j);
+        for (int k = 0; k < 3; k++) off[k] = ref[k] - (xp[k] + jp[k]);
+        cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+        cross3(cd + 3, ax, off);
+      }
+    }
+  }
+  LANES(g, h->ngeom) {
+    int b = MI(geom_body)[g];
+    float t[3];
+    mulmv(t, SF(xmat) + 9 * b, MF(geom_pos) + 3 * g);
+    for (int k = 0; k < 3; k++) SF(geom_xpos)[3 * g + k] = SF(xpos)[3 * b + k] + t[k];
+  }
+  SYNC();
+}
+
+// 4. mass matrix, packed lower triangle
+HD void mass_matrix(const Ctx& c) {
+  const DMHead* h = c.h;
+  int nv = h->nv, nM = nv * (nv + 1) / 2;
+  float* M = SF(M);
+  LANES(i, nM) M[i] = 0;
+  SYNC();
+  LANES(i, nv) {
+    float crb[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t sub = MU(body_sub)[MI(dof_body)[i]];
+    while (sub) { int b = ffs_pop(sub); const float* ci = SF(cinert) + 10 * b; for (int k = 0; k < 10; k++) crb[k] += ci[k]; }
+    float buf[6];
+    mul_inert(buf, crb, SF(cdof) + 6 * i);
+    uint32_t anc = MU(dof_anc)[i];
+    int row = i * (i + 1) / 2;
+    while (anc) { int j = ffs_pop(anc); M[row + j] = dot6(SF(cdof) + 6 * j, buf); }
+    M[row + i] += MF(dof_armature)[i];
+  }
+  SYNC();
+}
+
+// velocity pass: b6[b] = sum_{j in ancdof(b)} cdof_j * vec_j
+HD void pass_V(const Ctx& c, const float* vec, float* out) {
+  LANES(b, c.h->nb) {
+    float v[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t m = MU(body_ancdof)[b];
+    while (m) { int j = ffs_pop(m); const float* cd = SF(cdof) + 6 * j; float q = vec[j]; for (int k = 0; k < 6; k++) v[k] += cd[k] * q; }
+    for (int k = 0; k < 6; k++) out[6 * b + k] = v[k];
+  }
+  SYNC();
+}
+
+// 7. smooth forces: fsmooth = passive - bias + actuation
+HD void smooth_forces(const Ctx& c) {
+  const DMHead* h = c.h;
+  int nv = h->nv, nb = h->nb;
+  const float *qvel = SF(qvel), *qpos = SF(qpos);
+  pass_V(c, qvel, SF(cvel));
+  LANES(j, nv) {
+    float vp[6] = {0, 0, 0, 0, 0, 0}, vj[6];
+    uint32_t m = MU(dof_pre)[j];
+    while (m) { int i = ffs_pop(m); const float* cd = SF(cdof) + 6 * i; float q = qvel[i]; for (int k = 0; k < 6; k++) vp[k] += cd[k] * q; }
+    for (int k = 0; k < 6; k++) vj[k] = SF(cdof)[6 * j + k] * qvel[j];
+    cross_motion(SF(d6) + 6 * j, vp, vj);
+  }
+  SYNC();
+  LANES(b, nb) {
+    float* f = SF(b6) + 6 * b;
+    if (b == 0) { for (int k = 0; k < 6; k++) f[k] = 0; continue; }
+    float a[6] = {0, 0, 0, -h->gravity[0], -h->gravity[1], -h->gravity[2]};
+    uint32_t m = MU(body_ancdof)[b];
+    while (m) { int j = ffs_pop(m); const float* d = SF(d6) + 6 * j; for (int k = 0; k < 6; k++) a[k] += d[k]; }
+    float Ia[6], Iv[6], x[6];
+    mul_inert(Ia, SF(cinert) + 10 * b, a);
+    mul_inert(Iv, SF(cinert) + 10 * b, SF(cvel) + 6 * b);
+    cross_force(x, SF(cvel) + 6 * b, Iv);
+    for (int k = 0; k < 6; k++) f[k] = Ia[k] + x[k];
+  }
+  SYNC();
+  LANES(j, nv) {
+    float fs[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t sub = MU(body_sub)[MI(dof_body)[j]];
+    while (sub) { int b = ffs_pop(sub); const float* f = SF(b6) + 6 * b; for (int k = 0; k < 6; k++) fs[k] += f[k]; }
+    float bias = dot6(SF(cdof) + 6 * j, fs);
+    float f = -MF(dof_damping)[j] * qvel[j] - bias;
+    int jn = MI(dof_jnt)[j];
+    if (MI(jnt_type)[jn] != B200_JNT_FREE) {
+      float st = MF(jnt_stiffness)[jn];
+      if (st != 0) f -= st * (qpos[MI(jnt_qposadr)[jn]] - MF(jnt_qspring)[jn]);
+      for (int a = 0; a < h->nu; a++) {
+        if (MI(act_trnid)[a] != jn) continue;
+        float ct = SF(ctrl)[a];
+        if (MI(act_ctrllimited)[a]) ct = fminf(fmaxf(ct, MF(act_ctrlrange)[2 * a]), MF(act_ctrlrange)[2 * a + 1]);
+        float gear = MF(act_gear)[a];
+        float len = gear * qpos[MI(jnt_qposadr)[jn]], vel = gear * qvel[j];
+        const float* bp = MF(act_bias) + 3 * a;
+        float af = MF(act_gain)[a] * ct + bp[0] + bp[1] * len + bp[2] * vel;
+        if (MI(act_forcelimited)[a]) af = fminf(fmaxf(af, MF(act_forcerange)[2 * a]), MF(act_forcerange)[2 * a + 1]);
+        f += gear * af;
+      }
+    }
+    SF(fsmooth)[j] = f;
+  }
+  SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 5. collision (plane-box, box-box; same decision logic as oracle/oracle.c, fp32)
+struct ContactOut { float pos[4][3]; float dist[4]; float n[3]; int cnt; };
+
+HD void geom_pose(const Ctx& c, int g, float* pos, float* mat) {
+  int b = MI(geom_body)[g];
+  float q[4];
+  qmul(q, SF(xquat) + 4 * b, MF(geom_quat) + 4 * g);
+  q2mat(mat, q);
+  pos[0] = SF(geom_xpos)[3 * g]; pos[1] = SF(geom_xpos)[3 * g + 1]; pos[2] = SF(geom_xpos)[3 * g + 2];
+}
+
+HD void collide_plane_box(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
+  float pp[3], pm[9], bp[3], bm[9];
+  geom_pose(c, g1, pp, pm); geom_pose(c, g2, bp, bm);
+  const float* sz = MF(geom_size) + 3 * g2;
+  float n[3] = {pm[2], pm[5], pm[8]}, dif[3] = {bp[0] - pp[0], bp[1] - pp[1], bp[2] - pp[2]};
+  float dist0 = dot3(dif, n);
+  o.cnt = 0; o.n[0] = n[0]; o.n[1] = n[1]; o.n[2] = n[2];
+  for (int i = 0; i < 8; i++) {
+    float loc[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]}, vec[3];
+    mulmv(vec, bm, loc);
+    float ld = dot3(n, vec);
+    if (dist0 + ld > margin || ld > 0 || o.cnt >= 4) continue;
+    float d = dist0 + ld;
+    int k = o.cnt++;
+    o.dist[k] = d;
+    for (int a = 0; a < 3; a++) o.pos[k][a] = bp[a] + vec[a] - n[a] * d * 0.5f;
+  }
+}
+
+HD int clip_poly(const float (*in)[2], int n, float (*out)[2], int axis, float bound, float sign) {
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    const float* a = in[i];
+    const float* b = in[(i + 1 == n) ? 0 : i + 1];
+    float da = sign * a[axis] - bound, db = sign * b[axis] - bound;
+    if (da <= 0) { out[k][0] = a[0]; out[k][1] = a[1]; k++; }
+    if ((da < 0 && db > 0) || (da > 0 && db < 0)) {
+      float t = da / (da - db);
+      out[k][0] = a[0] + t * (b[0] - a[0]); out[k][1] = a[1] + t * (b[1] - a[1]); k++;
+    }
+  }
+  return k;
+}
+
+HDN void collide_box_box(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
+  float pa[3], Ra[9], pb[3], Rb[9];
+  geom_pose(c, g1, pa, Ra); geom_pose(c, g2, pb, Rb);
+  const float* ha = MF(geom_size) + 3 * g1;
+  const float* hb = MF(geom_size) + 3 * g2;
+  o.cnt = 0;
+  float d[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]}, da[3], db[3];
+  mulmtv(da, Ra, d); mulmtv(db, Rb, d);
+  float C[3][3], Q[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) { C[i][j] = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j]; Q[i][j] = fabsf(C[i][j]); }
+  float best = -1e30f, bestsign = 1; int code = -1;
+  for (int i = 0; i < 3; i++) {
+    float sep = fabsf(da[i]) - (ha[i] + hb[0] * Q[i][0] + hb[1] * Q[i][1] + hb[2] * Q[i][2]);
+    if (sep > margin) return;
+    if (sep > best) { best = sep; code = i; bestsign = da[i] < 0 ? -1.f : 1.f; }
+  }
+  for (int j = 0; j < 3; j++) {
+    float sep = fabsf(db[j]) - (hb[j] + ha[0] * Q[0][j] + ha[1] * Q[1][j] + ha[2] * Q[2][j]);
+    if (sep > margin) return;
+    if (sep > best) { best = sep; code = 3 + j; bestsign = db[j] < 0 ? -1.f : 1.f; }
+  }
+  float ebest = -1e30f; int ecode = -1; float eaxis[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      float ai[3] = {Ra[i], Ra[3 + i], Ra[6 + i]}, bj[3] = {Rb[j], Rb[3 + j], Rb[6 + j]}, ax[3];
+      cross3(ax, ai, bj);
+      float l = sqrtf(dot3(ax, ax));
+      if (l < 1e-6f) continue;
+      float il = 1.0f / l;
+      ax[0] *= il; ax[1] *= il; ax[2] *= il;
+      float ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) {
+        float ak[3] = {Ra[k], Ra[3 + k], Ra[6 + k]}, bk[3] = {Rb[k], Rb[3 + k], Rb[6 + k]};
+        ra += ha[k] * fabsf(dot3(ak, ax)); rb += hb[k] * fabsf(dot3(bk, ax));
+      }
+      float dd = dot3(d, ax), sep = fabsf(dd) - (ra + rb);
+      if (sep > margin) return;
+      if (sep > ebest) { ebest = sep; ecode = 3 * i + j; float sg = dd < 0 ? -1.f : 1.f; eaxis[0] = sg * ax[0]; eaxis[1] = sg * ax[1]; eaxis[2] = sg * ax[2]; }
+    }
+  if (ecode >= 0 && ebest > best + 1e-3f * (fabsf(best) + 1e-3f) && ebest > 0.95f * best && ebest > best) {
+    int i = ecode / 3, j = ecode % 3;
+    float n[3] = {eaxis[0], eaxis[1], eaxis[2]};
+    float ea[3] = {Ra[i], Ra[3 + i], Ra[6 + i]}, eb[3] = {Rb[j], Rb[3 + j], Rb[6 + j]};
+    float PA[3] = {pa[0], pa[1], pa[2]}, PB[3] = {pb[0], pb[1], pb[2]};
+    for (int k = 0; k < 3; k++) {
+      float ak[3] = {Ra[k], Ra[3 + k], Ra[6 + k]}, bk[3] = {Rb[k], Rb[3 + k], Rb[6 + k]};
+      if (k != i) { float sg = (dot3(n, ak) > 0 ? 1.f : -1.f) * ha[k]; PA[0] += ak[0] * sg; PA[1] += ak[1] * sg; PA[2] += ak[2] * sg; }
+      if (k != j) { float sg = (dot3(n, bk) > 0 ? -1.f : 1.f) * hb[k]; PB[0] += bk[0] * sg; PB[1] += bk[1] * sg; PB[2] += bk[2] * sg; }
+    }
+    float w[3] = {PA[0] - PB[0], PA[1] - PB[1], PA[2] - PB[2]};
+    float b = dot3(ea, eb), dd = dot3(ea, w), e = dot3(eb, w), den = 1 - b * b;
+    float sp = den > 1e-12f ? (b * e - dd) / den : 0, tp = den > 1e-12f ? (e - b * dd) / den : 0;
+    sp = fminf(fmaxf(sp, -ha[i]), ha[i]); tp = fminf(fmaxf(tp, -hb[j]), hb[j]);
+    o.cnt = 1; o.dist[0] = ebest; o.n[0] = n[0]; o.n[1] = n[1]; o.n[2] = n[2];
+    for (int k = 0; k < 3; k++) o.pos[0][k] = 0.5f * (PA[k] + ea[k] * sp + PB[k] + eb[k] * tp);
+    return;
+  }
+  const float *pr, *Rr, *pi, *Ri; const float *hr, *hi; int ax; float sgn; int flip;
+  if (code < 3) { pr = pa; Rr = Ra; pi = pb; Ri = Rb; hr = ha; hi = hb; ax = code; sgn = bestsign; flip = 0; }
+  else { pr = pb; Rr = Rb; pi = pa; Ri = Ra; hr = hb; hi = ha; ax = code - 3; sgn = -bestsign; flip = 1; }
+  float nr[3] = {Rr[ax] * sgn, Rr[3 + ax] * sgn, Rr[6 + ax] * sgn};
+  float nloc[3];
+  mulmtv(nloc, Ri, nr);
+  int iax = 0; float bestd = -1;
+  for (int k = 0; k < 3; k++) if (fabsf(nloc[k]) > bestd) { bestd = fabsf(nloc[k]); iax = k; }
+  float isgn = nloc[iax] > 0 ? -1.f : 1.f;
+  int u = (iax + 1) % 3, v = (iax + 2) % 3, ru = (ax + 1) % 3, rv = (ax + 2) % 3;
+  float au[3] = {Rr[ru], Rr[3 + ru], Rr[6 + ru]}, av[3] = {Rr[rv], Rr[3 + rv], Rr[6 + rv]};
+  float fc[3] = {pi[0] + Ri[iax] * isgn * hi[iax], pi[1] + Ri[3 + iax] * isgn * hi[iax], pi[2] + Ri[6 + iax] * isgn * hi[iax]};
+  float iu[3] = {Ri[u], Ri[3 + u], Ri[6 + u]}, iv[3] = {Ri[v], Ri[3 + v], Ri[6 + v]};
+  float poly[8][2], tmp[8][2], zc[4];
+  for (int k = 0; k < 4; k++) {
+    float su = (k == 0 || k == 3) ? 1.f : -1.f, sv = (k < 2) ? 1.f : -1.f;
+    float rel[3];
+    for (int a = 0; a < 3; a++) rel[a] = fc[a] + iu[a] * su * hi[u] + iv[a] * sv * hi[v] - pr[a];
+    poly[k][0] = dot3(rel, au); poly[k][1] = dot3(rel, av);
+    zc[k] = dot3(rel, nr) - hr[ax];
+  }
+  float h0, hx, hy;
+  {
+    float x0 = poly[0][0], y0 = poly[0][1], x1 = poly[1][0], y1 = poly[1][1], x3 = poly[3][0], y3 = poly[3][1];
+    float z0 = zc[0], z1 = zc[1], z3 = zc[3];
+    float det = (x1 - x0) * (y3 - y0) - (x3 - x0) * (y1 - y0);
+    if (fabsf(det) < 1e-14f) { hx = hy = 0; h0 = z0; }
+    else {
+      hx = ((z1 - z0) * (y3 - y0) - (z3 - z0) * (y1 - y0)) / det;
+      hy = ((x1 - x0) * (z3 - z0) - (x3 - x0) * (z1 - z0)) / det;
+      h0 = z0 - hx * x0 - hy * y0;
+    }
+  }
+  int n = 4;
+  n = clip_poly(poly, n, tmp, 0, hr[ru], 1.f);
+  n = clip_poly(tmp, n, poly, 0, hr[ru], -1.f);
+  n = clip_poly(poly, n, tmp, 1, hr[rv], 1.f);
+  n = clip_poly(tmp, n, poly, 1, hr[rv], -1.f);
+  float cand[8][3]; int nc = 0;
+  for (int k = 0; k < n && k < 8; k++) {
+    float z = h0 + hx * poly[k][0] + hy * poly[k][1];
+    if (z > margin) continue;
+    cand[nc][0] = poly[k][0]; cand[nc][1] = poly[k][1]; cand[nc][2] = z; nc++;
+  }
+  if (nc == 0) return;
+  int sel[4], ns = 0;
+  if (nc <= 4) { for (int k = 0; k < nc; k++) sel[ns++] = k; }
+  else {
+    int i0 = 0;
+    for (int k = 1; k < nc; k++) if (cand[k][2] < cand[i0][2]) i0 = k;
+    int i1 = -1; float bd = -1;
+    for (int k = 0; k < nc; k++) { float dx = cand[k][0] - cand[i0][0], dy = cand[k][1] - cand[i0][1], q = dx * dx + dy * dy; if (k != i0 && q > bd) { bd = q; i1 = k; } }
+    float ex = cand[i1][0] - cand[i0][0], ey = cand[i1][1] - cand[i0][1];
+    int i2 = -1, i3 = -1; float bp = 0, bn = 0;
+    for (int k = 0; k < nc; k++) {
+      if (k == i0 || k == i1) continue;
+      float cr = ex * (cand[k][1] - cand[i0][1]) - ey * (cand[k][0] - cand[i0][0]);
+      if (cr > bp) { bp = cr; i2 = k; }
+      if (cr < bn) { bn = cr; i3 = k; }
+    }
+    sel[ns++] = i0; sel[ns++] = i1;
+    if (i2 >= 0) sel[ns++] = i2;
+    if (i3 >= 0) sel[ns++] = i3;
+    for (int a = 0; a < ns; a++) for (int b = a + 1; b < ns; b++) if (sel[b] < sel[a]) { int t = sel[a]; sel[a] = sel[b]; sel[b] = t; }
+  }
+  float fs = flip ? -1.f : 1.f;
+  o.n[0] = fs * nr[0]; o.n[1] = fs * nr[1]; o.n[2] = fs * nr[2];
+  o.cnt = ns;
+  for (int k = 0; k < ns; k++) {
+    const float* cd = cand[sel[k]];
+    o.dist[k] = cd[2];
+    for (int a = 0; a < 3; a++) o.pos[k][a] = pr[a] + au[a] * cd[0] + av[a] * cd[1] + nr[a] * (hr[ax] + 0.5f * cd[2]);
+  }
+}
+
+HD void make_frame(float* f) {
+  float n = sqrtf(dot3(f, f)), inv = n > 1e-12f ? 1.0f / n : 0.f;
+  f[0] *= inv; f[1] *= inv; f[2] *= inv;
+  float* y = f + 3;
+  y[0] = y[1] = y[2] = 0;
+  if (f[1] < 0.5f && f[1] > -0.5f) y[1] = 1; else y[2] = 1;
+  float d = dot3(f, y);
+  y[0] -= f[0] * d; y[1] -= f[1] * d; y[2] -= f[2] * d;
+  float ny = 1.0f / sqrtf(dot3(y, y));
+  y[0] *= ny; y[1] *= ny; y[2] *= ny;
+  cross3(f + 6, f, y);
+}
+
+HD void collision(const Ctx& c) {
+  const DMHead* h = c.h;
+  int* cnt = SI(counters);
+  int* cand = SI(cand);
+  if (c.lane == 0) { cnt[CNT_NCON] = 0; cnt[CNT_NCAND] = 0; }
+  SYNC();
+  // broad phase: lanes over the static pair list, ordered compaction
+  for (int base = 0; base < h->npair; base += WARP_W) {
+    int p = base + c.lane;
+    bool hit = false;
+    if (p < h->npair) {
+      int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
+      float margin = MF(pair_margin)[p];
+      const float *x1 = SF(geom_xpos) + 3 * g1, *x2 = SF(geom_xpos) + 3 * g2;
+      float dif[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
+      if (MI(geom_type)[g1] == B200_GEOM_PLANE) {
+        int b = MI(geom_body)[g1];
+        float q[4], m[9];
+        qmul(q, SF(xquat) + 4 * b, MF(geom_quat) + 4 * g1);
+        q2mat(m, q);
+        float n[3] = {m[2], m[5], m[8]};
+        hit = dot3(dif, n) <= margin + MF(geom_rbound)[g2];
+      } else {
+        float bound = margin + MF(geom_rbound)[g1] + MF(geom_rbound)[g2];
+        hit = dot3(dif, dif) <= bound * bound;
+      }
+    }
+    int total, slot = wexscan(hit ? 1 : 0, c.lane, &total);
+    int basec = cnt[CNT_NCAND];
+    SYNC();
+    if (hit && basec + slot < DM_NCAND_MAX) cand[basec + slot] = p;
+    if (c.lane == 0) { int nn = basec + total; if (nn > DM_NCAND_MAX) { nn = DM_NCAND_MAX; cnt[CNT_OVERFLOW] |= 1; } cnt[CNT_NCAND] = nn; }
+    SYNC();
+  }
+  // narrow phase: one lane per candidate pair (lock-step over identical pair types in the common case)
+  int ncand = cnt[CNT_NCAND];
+  for (int base = 0; base < ncand; base += WARP_W) {
+    int ci = base + c.lane;
+    ContactOut o;
+    o.cnt = 0;
+    int p = -1;
+    if (ci < ncand) {
+      p = cand[ci];
+      int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
+      float margin = MF(pair_margin)[p];
+      if (MI(geom_type)[g1] == B200_GEOM_PLANE) collide_plane_box(c, g1, g2, margin, o);
+      else collide_box_box(c, g1, g2, margin, o);
+      // contacts beyond the gap are not turned into constraints
+      float inc = margin - MF(pair_gap)[p];
+      int k2 = 0;
+      for (int k = 0; k < o.cnt; k++) if (o.dist[k] < inc) { if (k2 != k) { o.dist[k2] = o.dist[k]; for (int a = 0; a < 3; a++) o.pos[k2][a] = o.pos[k][a]; } k2++; }
+      o.cnt = k2;
+    }
+    int total, slot = wexscan(o.cnt, c.lane, &total);
+    int basec = cnt[CNT_NCON];
+    SYNC();
+    for (int k = 0; k < o.cnt; k++) {
+      int id = basec + slot + k;
+      if (id >= DM_NCON_MAX) break;
+      float* cr = SF(con) + id * CON_WORDS;
+      for (int a = 0; a < 3; a++) { cr[C_R + a] = o.pos[k][a] - h->ref[a]; cr[C_FRAME + a] = o.n[a]; }
+      make_frame(cr + C_FRAME);
+      cr[C_DIST] = o.dist[k];
+      const float* fr = MF(pair_friction) + 3 * p;
+      cr[C_MU] = fr[0]; cr[C_MU + 1] = fr[0]; cr[C_MU + 2] = fr[1]; cr[C_MU + 3] = fr[2]; cr[C_MU + 4] = fr[2];
+      int* ci2 = (int*)cr;
+      ci2[C_DIM] = MI(pair_condim)[p];
+      ci2[C_BA] = MI(geom_body)[MI(pair_geom1)[p]]; ci2[C_BB] = MI(geom_body)[MI(pair_geom2)[p]];
+      ci2[C_PAIR] = p;
+      cr[C_MARGIN] = MF(pair_margin)[p] - MF(pair_gap)[p];
+    }
+    if (c.lane == 0) { int nn = basec + total; if (nn > DM_NCON_MAX) { nn = DM_NCON_MAX; cnt[CNT_OVERFLOW] |= 2; } cnt[CNT_NCON] = nn; }
+    SYNC();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 6. constraint rows
+HD float impedance(const float* solimp, float pos, float margin) {
+  float d0 = fminf(fmaxf(solimp[0], B200_MINIMP), B200_MAXIMP), d1 = fminf(fmaxf(solimp[1], B200_MINIMP), B200_MAXIMP);
+  float width = fmaxf(solimp[2], 0.f), mid = fminf(fmaxf(solimp[3], B200_MINIMP), B200_MAXIMP), power = fmaxf(solimp[4], 1.f);
+  if (d0 == d1 || width <= B200_MINVAL) return 0.5f * (d0 + d1);
+  float x = fabsf((pos - margin) / width);
+  if (x >= 1) return d1;
+  if (x <= 0) return d0;
+  float y;
+  if (power == 1) y = x;
+  else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+  else y = x <= mid ? powf(x, power) / powf(mid, power - 1) : 1 - powf(1 - x, power) / powf(1 - mid, power - 1);
+  return d0 + y * (d1 - d0);
+}
+// K and B of the reference acceleration (refsafe), given solref and dmax = solimp[1]
+HD void ref_kb(const Ctx& c, const float* solref, float dmax_in, float* K, float* B) {
+  float dmax = fminf(fmaxf(dmax_in, B200_MINIMP), B200_MAXIMP);
+  if (solref[0] > 0) {
+    float tc = fmaxf(solref[0], 2 * c.h->timestep), dr = solref[1];
+    *K = 1.0f / fmaxf(dmax * dmax * tc * tc * dr * dr, B200_MINVAL);
+    *B = 2.0f / fmaxf(dmax * tc, B200_MINVAL);
+  } else { *K = -solref[0] / (dmax * dmax); *B = -solref[1] / dmax; }
+}
+
+// spatial vector of contact base row k (about ref): k<3 translational along frame row k, k>=3 rotational about frame row k-3
+HD void con_w(const float* cr, int k, float* w) {
+  if (k < 3) { const float* f = cr + C_FRAME + 3 * k; cross3(w, cr + C_R, f); w[3] = f[0]; w[4] = f[1]; w[5] = f[2]; }
+  else { const float* f = cr + C_FRAME + 3 * (k - 3); w[0] = f[0]; w[1] = f[1]; w[2] = f[2]; w[3] = w[4] = w[5] = 0; }
+}
+
+HD int find_group(const Ctx& c, int ba, int bb) {  // lane 0 only
+  int* cnt = SI(counters);
+  for (int g = 0; g < cnt[CNT_NGRP]; g++) {
+    const int* gi = (const int*)(SF(group) + g * GRP_WORDS);
+    if (gi[G_BA] == ba && gi[G_BB] == bb) return g;
+  }
+  if (cnt[CNT_NGRP] >= DM_NGROUP_MAX) { cnt[CNT_OVERFLOW] |= 4; return DM_NGROUP_MAX - 1; }
+  int g = cnt[CNT_NGRP]++;
+  int* gi = (int*)(SF(group) + g * GRP_WORDS);
+  gi[G_BA] = ba; gi[G_BB] = bb;
+  return g;
+}
+
+HD void make_constraint(const Ctx& c) {
+  const DMHead* h = c.h;
+  int* cnt = SI(counters);
+  if (c.lane == 0) { cnt[CNT_NDR] = 0; cnt[CNT_NGRP] = 0; cnt[CNT_NWELD] = 0; }
+  SYNC();
+  // weld equalities (lane 0; at most DM_NWELD_MAX)
+  if (c.lane == 0) {
+    for (int e = 0; e < h->neq; e++) {
+      if (!MI(eq_active)[e] || MI(eq_type)[e] != B200_EQ_WELD) continue;
+      float* wr = SF(weld) + cnt[CNT_NWELD] * WELD_WORDS;
+      const float* data = MF(eq_data) + 11 * e;
+      int s1 = MI(eq_obj1)[e], s2 = MI(eq_obj2)[e], b1 = 0, b2 = 0;
+      float p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0}, q1[4] = {1, 0, 0, 0}, q2[4] = {1, 0, 0, 0}, t[3];
+      if (s1 >= 0) { b1 = MI(site_body)[s1]; qmul(q1, SF(xquat) + 4 * b1, MF(site_quat) + 4 * s1); mulmv(t, SF(xmat) + 9 * b1, MF(site_pos) + 3 * s1); for (int k = 0; k < 3; k++) p1[k] = SF(xpos)[3 * b1 + k] + t[k]; }
+      if (s2 >= 0) { b2 = MI(site_body)[s2]; qmul(q2, SF(xquat) + 4 * b2, MF(site_quat) + 4 * s2); mulmv(t, SF(xmat) + 9 * b2, MF(site_pos) + 3 * s2); for (int k = 0; k < 3; k++) p2[k] = SF(xpos)[3 * b2 + k] + t[k]; }
+      qrot(t, q1, data + 3); for (int k = 0; k < 3; k++) p1[k] += t[k];
+      qrot(t, q2, data + 0); for (int k = 0; k < 3; k++) p2[k] += t[k];
+      float cpos[6], ts = data[10];
+      for (int k = 0; k < 3; k++) cpos[k] = p1[k] - p2[k];
+      float quat[4], quat1[4] = {q2[0], -q2[1], -q2[2], -q2[3]}, quat2[4];
+      qmul(quat, q1, data + 6);
+      qmul(quat2, quat1, quat);
+      cpos[3] = ts * quat2[1]; cpos[4] = ts * quat2[2]; cpos[5] = ts * quat2[3];
+      // rows: J = J(body1 at p1) - J(body2 at p2).  Both points coincide up to the residual, and only one side carries
+      // dofs when the other is a mocap body; we evaluate both sides with their own lever arms through (A=b2, B=b1).
+      // translational rows about the point of the moving side
+      const float* pm = (b1 > 0 && MU(body_ancdof)[b1]) ? p1 : p2;
+      float r[3] = {pm[0] - h->ref[0], pm[1] - h->ref[1], pm[2] - h->ref[2]};
+      for (int k = 0; k < 3; k++) {
+        float e3[3] = {k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
+        float* w = wr + W_W + 6 * k;
+        cross3(w, r, e3); w[3] = e3[0]; w[4] = e3[1]; w[5] = e3[2];
+      }
+      for (int a = 0; a < 3; a++) {  // column a of the 3x3 map (relative angular velocity -> residual rate)
+        float qa[4] = {0, a == 0 ? 1.f : 0.f, a == 1 ? 1.f : 0.f, a == 2 ? 1.f : 0.f}, t1[4], t2[4];
+        qmul(t1, quat1, qa); qmul(t2, t1, quat);
+        for (int k = 0; k < 3; k++) { float* w = wr + W_W + 6 * (3 + k); w[a] = 0.5f * ts * t2[1 + k]; w[3 + a] = 0; }
+      }
+      float K, Bc;
+      ref_kb(c, MF(eq_solref) + 2 * e, MF(eq_solimp)[5 * e + 1], &K, &Bc);
+      for (int k = 0; k < 6; k++) {
+        float imp = impedance(MF(eq_solimp) + 5 * e, cpos[k], 0.f);
+        float R = fmaxf((1 - imp) / imp * MF(eq_invweight)[2 * e + (k < 3 ? 0 : 1)], B200_MINVAL);
+        wr[W_D + k] = 1.0f / R; wr[W_B + k] = Bc; wr[W_KIR + k] = K * imp * cpos[k];
+      }
+      int* wi = (int*)wr;
+      wi[W_BA] = b2; wi[W_BB] = b1;  // row value = w . (V[b1] - V[b2])
+      wi[W_GRP] = find_group(c, b2, b1);
+      cnt[CNT_NWELD]++;
+    }
+  }
+  SYNC();
+  // contacts: impedance and regulariser in parallel; body-pair groups assigned in order by lane 0
+  LANES(i, cnt[CNT_NCON]) {
+    float* cr = SF(con) + i * CON_WORDS;
+    int* ci = (int*)cr;
+    int p = ci[C_PAIR], dim = ci[C_DIM];
+    float imp = impedance(MF(pair_solimp) + 5 * p, cr[C_DIST], cr[C_MARGIN]);
+    float K, Bc;
+    ref_kb(c, MF(pair_solref) + 2 * p, MF(pair_solimp)[5 * p + 1], &K, &Bc);
+    float tran = MF(pair_invweight)[2 * p], mu0 = cr[C_MU];
+    float R;
+    if (dim == 1) R = fmaxf((1 - imp) / imp * tran, B200_MINVAL);
+    else {
+      float R0 = fmaxf((1 - imp) / imp * (tran + mu0 * mu0 * tran), B200_MINVAL);
+      float mu = mu0 * rsqrtf(h->impratio);
+      R = fmaxf(2 * mu * mu * R0, B200_MINVAL);
+    }
+    cr[C_D] = 1.0f / R; cr[C_B] = Bc; cr[C_KIR] = K * imp * (cr[C_DIST] - cr[C_MARGIN]);
+  }
+  if (c.lane == 0) {
+    for (int i = 0; i < cnt[CNT_NCON]; i++) {
+      int* ci = (int*)(SF(con) + i * CON_WORDS);
+      ci[C_GRP] = find_group(c, ci[C_BA], ci[C_BB]);
+    }
+  }
+  SYNC();
+  // joint limits -> dof rows (ordered compaction over joints, lower side first)
+  for (int base = 0; base < h->njnt; base += WARP_W) {
+    int j = base + c.lane;
+    int nrow = 0; float dist[2] = {0, 0}; float sgn[2] = {0, 0};
+    if (j < h->njnt && MI(jnt_limited)[j] && MI(jnt_type)[j] != B200_JNT_FREE) {
+      float q = SF(qpos)[MI(jnt_qposadr)[j]], margin = MF(jnt_margin)[j];
+      float dl = q - MF(jnt_range)[2 * j], du = MF(jnt_range)[2 * j + 1] - q;
+      if (dl < margin) { dist[nrow] = dl; sgn[nrow] = 1.f; nrow++; }
+      if (du < margin) { dist[nrow] = du; sgn[nrow] = -1.f; nrow++; }
+    }
+    int total, slot = wexscan(nrow, c.lane, &total);
+    int basec = cnt[CNT_NDR];
+    SYNC();
+    for (int k = 0; k < nrow; k++) {
+      int id = basec + slot + k;
+      if (id >= DM_NDOFROW_MAX) break;
+      float* dr = SF(dofrow) + id * DR_WORDS;
+      int* di = (int*)dr;
+      int d = MI(jnt_dofadr)[j];
+      float margin = MF(jnt_margin)[j];
+      float imp = impedance(MF(jnt_solimp) + 5 * j, dist[k], margin);
+      float K, Bc;
+      ref_kb(c, MF(jnt_solref) + 2 * j, MF(jnt_solimp)[5 * j + 1], &K, &Bc);
+      float R = fmaxf((1 - imp) / imp * MF(dof_invweight0)[d], B200_MINVAL);
+      di[DR_DOF] = d; dr[DR_COEF] = sgn[k]; di[DR_DOF2] = -1; dr[DR_COEF2] = 0; di[DR_TYPE] = ROWT_LIMIT;
+      dr[DR_D] = 1.0f / R; dr[DR_R] = R; dr[DR_FLOSS] = 0; dr[DR_B] = Bc; dr[DR_KIR] = K * imp * (dist[k] - margin);
+    }
+    if (c.lane == 0) { int nn = basec + total; if (nn > DM_NDOFROW_MAX) { nn = DM_NDOFROW_MAX; cnt[CNT_OVERFLOW] |= 8; } cnt[CNT_NDR] = nn; }
+    SYNC();
+  }
+}
+
+// rows <- J * vec (+ optional scaling into the aref constants).  mode 0: C0 = B*(J qvel) + KIR ; mode 1: U = J a + C0 ; mode 2: JV = J s
+enum { RV_C0 = 0, RV_U = 1, RV_JV = 2 };
+HD void rows_from_vec(const Ctx& c, const float* vec, int mode) {
+  const int* cnt = SI(counters);
+  pass_V(c, vec, SF(b6));
+  const float* V = SF(b6);
+  LANES(i, cnt[CNT_NCON]) {
+    float* cr = SF(con) + i * CON_WORDS;
+    const int* ci = (const int*)cr;
+    int dim = ci[C_DIM], nbase = dim == 1 ? 1 : dim;
+    float dV[6];
+    for (int k = 0; k < 6; k++) dV[k] = V[6 * ci[C_BB] + k] - V[6 * ci[C_BA] + k];
+    for (int k = 0; k < nbase; k++) {
+      float w[6];
+      con_w(cr, k, w);
+      float val = dot6(w, dV);
+      if (mode == RV_C0) cr[C_C0 + k] = cr[C_B] * val + (k == 0 ? cr[C_KIR] : 0.f);
+      else if (mode == RV_U) cr[C_U + k] = val + cr[C_C0 + k];
+      else cr[C_JV + k] = val;
+    }
+  }
+  LANES(i, cnt[CNT_NWELD] * 6) {
+    float* wr = SF(weld) + (i / 6) * WELD_WORDS;
+    const int* wi = (const int*)wr;
+    int k = i % 6;
+    float dV[6];
+    for (int a = 0; a < 6; a++) dV[a] = V[6 * wi[W_BB] + a] - V[6 * wi[W_BA] + a];
+    float val = dot6(wr + W_W + 6 * k, dV);
+    if (mode == RV_C0) wr[W_KIR + k] = wr[W_B + k] * val + wr[W_KIR + k];  // KIR becomes the full constant c0
+    else if (mode == RV_U) wr[W_JAR + k] = val + wr[W_KIR + k];
+    else wr[W_JV + k] = val;
+  }
+  LANES(i, cnt[CNT_NDR]) {
+    float* dr = SF(dofrow) + i * DR_WORDS;
+    const int* di = (const int*)dr;
+    float val = dr[DR_COEF] * vec[di[DR_DOF]];
+    if (di[DR_DOF2] >= 0) val += dr[DR_COEF2] * vec[di[DR_DOF2]];
+    if (mode == RV_C0) dr[DR_AREF] = dr[DR_B] * val + dr[DR_KIR];  // c0
+    else if (mode == RV_U) dr[DR_JAR] = val + dr[DR_AREF];
+    else dr[DR_JV] = val;
+  }
+  SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 8. Newton solver pieces
+// pyramid forces of a contact from its base-row values U; writes base-row generalized forces F; returns the cost
+HD float contact_forces(float* cr, int dim) {
+  float D = cr[C_D], un = cr[C_U], cost = 0;
+  if (dim == 1) { float f = un < 0 ? -D * un : 0.f; cr[C_F] = f; return un < 0 ? 0.5f * D * un * un : 0.f; }
+  float Fn = 0;
+  for (int k = 1; k < dim; k++) {
+    float mu = cr[C_MU + k - 1], uk = cr[C_U + k];
+    float xp = un + mu * uk, xm = un - mu * uk;
+    float fp = xp < 0 ? -D * xp : 0.f, fm = xm < 0 ? -D * xm : 0.f;
+    if (xp < 0) cost += 0.5f * D * xp * xp;
+    if (xm < 0) cost += 0.5f * D * xm * xm;
+    Fn += fp + fm;
+    cr[C_F + k] = mu * (fp - fm);
+  }
+  cr[C_F] = Fn;
+  return cost;
+}
+
+// forces for all rows at the current U; returns the total constraint cost (all lanes get the sum)
+HD float update_forces(const Ctx& c) {
+  const int* cnt = SI(counters);
+  float cost = 0;
+  LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; cost += contact_forces(cr, ((const int*)cr)[C_DIM]); }
+  LANES(i, cnt[CNT_NWELD] * 6) {
+    float* wr = SF(weld) + (i / 6) * WELD_WORDS;
+    int k = i % 6;
+    float x = wr[W_JAR + k], D = wr[W_D + k];
+    cost += 0.5f * D * x * x;
+  }
+  LANES(i, cnt[CNT_NDR]) {
+    const float* dr = SF(dofrow) + i * DR_WORDS;
+    float x = dr[DR_JAR];
+    if (x < 0) cost += 0.5f * dr[DR_D] * x * x;
+  }
+  SYNC();
+  return wsum(cost);
+}
+
+// fcon = J^T f from the stored base-row forces
+HD void pass_F(const Ctx& c, float* out) {
+  const DMHead* h = c.h;
+  const int* cnt = SI(counters);
+  int ncon = cnt[CNT_NCON], nweld = cnt[CNT_NWELD], ndr = cnt[CNT_NDR];
+  LANES(b, h->nb) {
+    float F[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < ncon; i++) {
+      const float* cr = SF(con) + i * CON_WORDS;
+      const int* ci = (const int*)cr;
+      float sg = ci[C_BB] == b ? 1.f : (ci[C_BA] == b ? -1.f : 0.f);
+      if (sg == 0.f) continue;
+      int dim = ci[C_DIM], nbase = dim == 1 ? 1 : dim;
+      for (int k = 0; k < nbase; k++) { float w[6]; con_w(cr, k, w); float f = sg * cr[C_F + k]; for (int a = 0; a < 6; a++) F[a] += f * w[a]; }
+    }
+    for (int i = 0; i < nweld; i++) {
+      const float* wr = SF(weld) + i * WELD_WORDS;
+      const int* wi = (const int*)wr;
+      float sg = wi[W_BB] == b ? 1.f : (wi[W_BA] == b ? -1.f : 0.f);
+      if (sg == 0.f) continue;
+      for (int k = 0; k < 6; k++) { float f = -sg * wr[W_D + k] * wr[W_JAR + k]; const float* w = wr + W_W + 6 * k; for (int a = 0; a < 6; a++) F[a] += f * w[a]; }
+    }
+    for (int a = 0; a < 6; a++) SF(b6)[6 * b + a] = F[a];
+  }
+  SYNC();
+  LANES(j, h->nv) {
+    float fs[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t sub = MU(body_sub)[MI(dof_body)[j]];
+    while (sub) { int b = ffs_pop(sub); const float* f = SF(b6) + 6 * b; for (int k = 0; k < 6; k++) fs[k] += f[k]; }
+    float q = dot6(SF(cdof) + 6 * j, fs);
+    for (int i = 0; i < ndr; i++) {
+      const float* dr = SF(dofrow) + i * DR_WORDS;
+      const int* di = (const int*)dr;
+      float x = dr[DR_JAR];
+      float f = x < 0 ? -dr[DR_D] * x : 0.f;
+      if (di[DR_DOF] == j) q += dr[DR_COEF] * f;
+      if (di[DR_DOF2] == j) q += dr[DR_COEF2] * f;
+    }
+    out[j] = q;
+  }
+  SYNC();
+}
+
+HD void mulM(const Ctx& c, const float* v, float* out) {
+  int nv = c.h->nv;
+  const float* M = SF(M);
+  LANES(i, nv) {
+    float a = 0;
+    for (int j = 0; j < nv; j++) a += M[pidx(i, j)] * v[j];
+    out[i] = a;
+  }
+  SYNC();
+}
+
+// H = M + sum_g S_g^T K_g S_g  (+ dof rows on the diagonal blocks)
+HD void build_H(const Ctx& c) {
+  const DMHead* h = c.h;
+  const int* cnt = SI(counters);
+  int nv = h->nv, nM = nv * (nv + 1) / 2, ncon = cnt[CNT_NCON], nweld = cnt[CNT_NWELD], ngrp = cnt[CNT_NGRP], ndr = cnt[CNT_NDR];
+  float* H = SF(H);
+  LANES(i, nM) H[i] = SF(M)[i];
+  // K blocks: lane e < 21 owns packed entry e of every group's 6x6
+  for (int g = 0; g < ngrp; g++) {
+    float* K = SF(group) + g * GRP_WORDS + G_K;
+    LANES(e, 21) {
+      int r = 0; while ((r + 1) * (r + 2) / 2 <= e) r++;
+      int s = e - r * (r + 1) / 2;
+      float acc = 0;
+      for (int i = 0; i < ncon; i++) {
+        const float* cr = SF(con) + i * CON_WORDS;
+        const int* ci = (const int*)cr;
+        if (ci[C_GRP] != g) continue;
+        int dim = ci[C_DIM];
+        float D = cr[C_D], un = cr[C_U], wn[6];
+        con_w(cr, 0, wn);
+        if (dim == 1) { if (un < 0) acc += D * wn[r] * wn[s]; continue; }
+        float Wnn = 0;
+        for (int k = 1; k < dim; k++) {
+          float mu = cr[C_MU + k - 1], uk = cr[C_U + k];
+          float ap = (un + mu * uk) < 0 ? 1.f : 0.f, am = (un - mu * uk) < 0 ? 1.f : 0.f;
+          if (ap + am == 0.f) continue;
+          float wk[6];
+          con_w(cr, k, wk);
+          Wnn += ap + am;
+          float Wnk = mu * (ap - am), Wkk = mu * mu * (ap + am);
+          acc += D * (Wnk * (wn[r] * wk[s] + wk[r] * wn[s]) + Wkk * wk[r] * wk[s]);
+        }
+        acc += D * Wnn * wn[r] * wn[s];
+      }
+      for (int i = 0; i < nweld; i++) {
+        const float* wr = SF(weld) + i * WELD_WORDS;
+        if (((const int*)wr)[W_GRP] != g) continue;
+        for (int k = 0; k < 6; k++) acc += wr[W_D + k] * wr[W_W + 6 * k + r] * wr[W_W + 6 * k + s];
+      }
+      K[e] = acc;
+    }
+  }
+  SYNC();
+  // y_i = K cdof_i for dofs in the group's chains, then H_ij += sigma_i sigma_j cdof_j . y_i
+  for (int g = 0; g < ngrp; g++) {
+    const float* K = SF(group) + g * GRP_WORDS + G_K;
+    const int* gi = (const int*)(SF(group) + g * GRP_WORDS);
+    uint32_t ma = MU(body_ancdof)[gi[G_BA]], mb = MU(body_ancdof)[gi[G_BB]];
+    uint32_t S = ma ^ mb;
+    LANES(i, nv) {
+      if (!((S >> i) & 1u)) continue;
+      const float* cd = SF(cdof) + 6 * i;
+      float* y = SF(d6) + 6 * i;
+      for (int r = 0; r < 6; r++) {
+        float a = 0;
+        for (int s2 = 0; s2 < 6; s2++) a += K[pidx(r, s2)] * cd[s2];
+        y[r] = a;
+      }
+    }
+    SYNC();
+    LANES(i, nv) {
+      if (!((S >> i) & 1u)) continue;
+      float si = ((mb >> i) & 1u) ? 1.f : -1.f;
+      const float* y = SF(d6) + 6 * i;
+      int row = i * (i + 1) / 2;
+      uint32_t m2 = S & ((2u << i) - 1u);  // j <= i
+      while (m2) {
+        int j = ffs_pop(m2);
+        float sj = ((mb >> j) & 1u) ? 1.f : -1.f;
+        H[row + j] += si * sj * dot6(SF(cdof) + 6 * j, y);
+      }
+    }
+    SYNC();
+  }
+  // dof rows (active ones)
+  if (c.lane == 0) {
+    for (int i = 0; i < ndr; i++) {
+      const float* dr = SF(dofrow) + i * DR_WORDS;
+      const int* di = (const int*)dr;
+      if (!(dr[DR_JAR] < 0)) continue;
+      int d1 = di[DR_DOF], d2 = di[DR_DOF2];
+      H[pidx(d1, d1)] += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF];
+      if (d2 >= 0) { H[pidx(d2, d2)] += dr[DR_D] * dr[DR_COEF2] * dr[DR_COEF2]; H[pidx(d1, d2)] += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF2]; }
+    }
+  }
+  SYNC();
+}
+
+// in-place packed Cholesky H = L L^T, one lane per row
+HD void cholesky(const Ctx& c, float* H) {
+  int n = c.h->nv;
+  for (int k = 0; k < n; k++) {
+    float hkk = H[k * (k + 1) / 2 + k];
+    float d = sqrtf(fmaxf(hkk, 1e-30f)), inv = 1.0f / d;
+    SYNC();
+    LANES(i, n) { if (i == k) H[i * (i + 1) / 2 + k] = d; else if (i > k) H[i * (i + 1) / 2 + k] *= inv; }
+    SYNC();
+    LANES(i, n) {
+      if (i <= k) continue;
+      int row = i * (i + 1) / 2;
+      float lik = H[row + k];
+      for (int j = k + 1; j <= i; j++) H[row + j] -= lik * H[j * (j + 1) / 2 + k];
+    }
+    SYNC();
+  }
+}
+// x <- (L L^T)^-1 x
+HD void chol_solve(const Ctx& c, const float* L, float* x) {
+  int n = c.h->nv;
+  for (int k = 0; k < n; k++) {
+    if (c.lane == (k % WARP_W)) x[k] = x[k] / L[k * (k + 1) / 2 + k];
+    SYNC();
+    float xk = x[k];
+    LANES(i, n) if (i > k) x[i] -= L[i * (i + 1) / 2 + k] * xk;
+    SYNC();
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    if (c.lane == (k % WARP_W)) x[k] = x[k] / L[k * (k + 1) / 2 + k];
+    SYNC();
+    float xk = x[k];
+    LANES(i, k) x[i] -= L[k * (k + 1) / 2 + i] * xk;
+    SYNC();
+  }
+}
+
+// line-search evaluation: cost(alpha) - gauss constant, first and second derivative
+HD void ls_eval(const Ctx& c, float alpha, float g1, float g2, float* out) {
+  const int* cnt = SI(counters);
+  float cost = 0, d1 = 0, d2 = 0;
+  LANES(i, cnt[CNT_NCON]) {
+    const float* cr = SF(con) + i * CON_WORDS;
+    int dim = ((const int*)cr)[C_DIM];
+    float D = cr[C_D], un = cr[C_U] + alpha * cr[C_JV], vn = cr[C_JV];
+    if (dim == 1) { if (un < 0) { cost += 0.5f * D * un * un; d1 += D * un * vn; d2 += D * vn * vn; } continue; }
+    for (int k = 1; k < dim; k++) {
+      float mu = cr[C_MU + k - 1], uk = cr[C_U + k] + alpha * cr[C_JV + k], vk = cr[C_JV + k];
+      float xp = un + mu * uk, vp = vn + mu * vk, xm = un - mu * uk, vm = vn - mu * vk;
+      if (xp < 0) { cost += 0.5f * D * xp * xp; d1 += D * xp * vp; d2 += D * vp * vp; }
+      if (xm < 0) { cost += 0.5f * D * xm * xm; d1 += D * xm * vm; d2 += D * vm * vm; }
+    }
+  }
+  LANES(i, cnt[CNT_NWELD] * 6) {
+    const float* wr = SF(weld) + (i / 6) * WELD_WORDS;
+    int k = i % 6;
+    float D = wr[W_D + k], v = wr[W_JV + k], x = wr[W_JAR + k] + alpha * v;
+    cost += 0.5f * D * x * x; d1 += D * x * v; d2 += D * v * v;
+  }
+  LANES(i, cnt[CNT_NDR]) {
+    const float* dr = SF(dofrow) + i * DR_WORDS;
+    float D = dr[DR_D], v = dr[DR_JV], x = dr[DR_JAR] + alpha * v;
+    if (x < 0) { cost += 0.5f * D * x * x; d1 += D * x * v; d2 += D * v * v; }
+  }
+  out[0] = wsum(cost) + alpha * g1 + alpha * alpha * g2;
+  out[1] = wsum(d1) + g1 + 2 * alpha * g2;
+  out[2] = wsum(d2) + 2 * g2;
+}
+
+// returns alpha; *improve = cost(0) - cost(alpha)
+HD float linesearch(const Ctx& c, float g1, float g2, float gtol, int maxit, float* improve) {
+  float p0[3], p[3];
+  ls_eval(c, 0.f, g1, g2, p0);
+  *improve = 0;
+  if (p0[1] >= 0 || p0[2] <= 0) return 0.f;
+  gtol = fmaxf(gtol, 1e-5f * fabsf(p0[1]));  // single-precision floor on the derivative test
+  float lo = 0, hi = -1, alpha = -p0[1] / p0[2], best = 0, bestcost = p0[0];
+  for (int it = 0; it < maxit; it++) {
+    ls_eval(c, alpha, g1, g2, p);
+    if (p[0] <= bestcost) { bestcost = p[0]; best = alpha; }
+    if (fabsf(p[1]) < gtol) break;
+    if (p[1] < 0) lo = alpha; else hi = alpha;
+    float next = alpha - p[1] / p[2];
+    if (hi > 0 && (next <= lo || next >= hi)) next = 0.5f * (lo + hi);
+    if (next == alpha) break;
+    alpha = next;
+  }
+  *improve = p0[0] - bestcost;
+  return best;
+}
+
+HD void solve_newton(const Ctx& c) {
+  const DMHead* h = c.h;
+  int nv = h->nv;
+  int* cnt = SI(counters);
+  float *a = SF(qacc), *Ma = SF(Ma), *Mv = SF(Mv), *grad = SF(grad), *search = SF(search), *fs = SF(fsmooth), *fcon = SF(fcon);
+  float scale = 1.0f / (h->meaninertia * (float)(nv > 1 ? nv : 1));
+  LANES(i, nv) a[i] = SF(warm)[i];
+  SYNC();
+  rows_from_vec(c, SF(qvel), RV_C0);
+  mulM(c, a, Ma);
+  rows_from_vec(c, a, RV_U);
+  float improvement = 0;
+  int iter = 0;
+  // single-precision floor for the convergence tests (fp64 reference uses `tolerance` directly)
+  float tol = fmaxf(h->tolerance, 1e-6f);
+  for (;; iter++) {
+    update_forces(c);
+    pass_F(c, fcon);
+    float g2sum = 0, f2sum = 0;
+    LANES(i, nv) {
+      float g = Ma[i] - fs[i] - fcon[i], f = fabsf(Ma[i]) + fabsf(fs[i]) + fabsf(fcon[i]);
+      grad[i] = g; g2sum += g * g; f2sum += f * f;
+    }
+    SYNC();
+    float gnorm = sqrtf(wsum(g2sum)), fnorm = sqrtf(wsum(f2sum));
+#if defined(B200_DEBUG_SOLVER) && !defined(__CUDACC__)
+    printf("  iter %d gnorm %.3e fnorm %.3e improvement %.3e\n", iter, gnorm, fnorm, improvement);
+#endif
+    // single-precision floor: the gradient cannot be resolved below ~eps32 * (|M a| + |f_smooth| + |f_constraint|)
+    if (gnorm < 2e-6f * fnorm) break;
+    if (iter > 0 && (scale * improvement < tol || scale * gnorm < tol)) break;
+    if (iter >= h->iterations || iter >= 12) break;
+    build_H(c);
+    cholesky(c, SF(H));
+    LANES(i, nv) search[i] = -grad[i];
+    SYNC();
+    chol_solve(c, SF(H), search);
+    mulM(c, search, Mv);
+    rows_from_vec(c, search, RV_JV);
+    float q1 = 0, q2 = 0, sn = 0;
+    LANES(i, nv) { q1 += search[i] * (Ma[i] - fs[i]); q2 += 0.5f * search[i] * Mv[i]; sn += search[i] * search[i]; }
+    q1 = wsum(q1); q2 = wsum(q2); sn = sqrtf(wsum(sn));
+    if (sn < 1e-20f) break;
+    float gtol = h->tolerance * h->ls_tolerance * sn / scale;
+    float alpha = linesearch(c, q1, q2, gtol, h->ls_iterations < 20 ? h->ls_iterations : 20, &improvement);
+    if (alpha == 0.f) break;
+    LANES(i, nv) { a[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+    LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 6; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
+    LANES(i, cnt[CNT_NWELD] * 6) { float* wr = SF(weld) + (i / 6) * WELD_WORDS; wr[W_JAR + i % 6] += alpha * wr[W_JV + i % 6]; }
+    LANES(i, cnt[CNT_NDR]) { float* dr = SF(dofrow) + i * DR_WORDS; dr[DR_JAR] += alpha * dr[DR_JV]; }
+    SYNC();
+  }
+  if (c.lane == 0) cnt[CNT_ITERS] += iter;
+  SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward dynamics (mj_forward) and one Euler sub-step
+HD void forward(const Ctx& c) {
+  kinematics(c);
+  com_quantities(c);
+  mass_matrix(c);
+  collision(c);
+  make_constraint(c);
+  smooth_forces(c);
+  solve_newton(c);
+}
+
+HD void euler_step(const Ctx& c) {
+  const DMHead* h = c.h;
+  int nv = h->nv, nM = nv * (nv + 1) / 2;
+  float hh = h->timestep;
+  float* H = SF(H);
+  float* x = SF(tmpv);
+  LANES(i, nv) SF(warm)[i] = SF(qacc)[i];
+  if (h->any_damping) {
+    LANES(i, nM) H[i] = SF(M)[i];
+    SYNC();
+    LANES(i, nv) { H[i * (i + 1) / 2 + i] += hh * MF(dof_damping)[i]; x[i] = SF(fsmooth)[i] + SF(fcon)[i]; }
+    SYNC();
+    cholesky(c, H);
+    chol_solve(c, H, x);
+  } else {
+    LANES(i, nv) x[i] = SF(qacc)[i];
+    SYNC();
+  }
+  LANES(i, nv) SF(qvel)[i] += hh * x[i];
+  SYNC();
+  LANES(j, h->njnt) {
+    int a = MI(jnt_qposadr)[j], d = MI(jnt_dofadr)[j];
+    float* qpos = SF(qpos);
+    const float* qvel = SF(qvel);
+    if (MI(jnt_type)[j] == B200_JNT_FREE) {
+      for (int k = 0; k < 3; k++) qpos[a + k] += hh * qvel[d + k];
+      float w[3] = {qvel[d + 3], qvel[d + 4], qvel[d + 5]};
+      float n = sqrtf(dot3(w, w));
+      float q[4] = {qpos[a + 3], qpos[a + 4], qpos[a + 5], qpos[a + 6]};
+      if (n > 0) {
+        float ang = 0.5f * n * hh, sn = sinf(ang), cs = cosf(ang), inv = 1.0f / n;
+        float dq[4] = {cs, w[0] * inv * sn, w[1] * inv * sn, w[2] * inv * sn}, nq[4];
+        qmul(nq, q, dq);
+        q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
+      }
+      qnormalize(q);
+      qpos[a + 3] = q[0]; qpos[a + 4] = q[1]; qpos[a + 5] = q[2]; qpos[a + 6] = q[3];
+    } else qpos[a] += hh * qvel[d];
+  }
+  SYNC();
+}

@@ -1,0 +1,374 @@
+"""Batched Fetch environments (`gym.vector.VectorEnv`-style) on the b200sim CUDA path.
+
+Host-side mirror of the reference's Fetch stack, batched over `num_envs`:
+  * task tables              envs/fetch/{reach,push,pick_and_place}.py ctor kwargs (e.g. pick_and_place.py:139-162)
+  * construction/_env_setup  envs/fetch/fetch_env.py:404-428, envs/robot_env.py:292-303
+  * reset/_reset_sim/_sample_goal   envs/robot_env.py:154-186, envs/fetch/fetch_env.py:375-402, 153-166
+  * step                     envs/robot_env.py:114-152  (runs entirely inside one CUDA kernel, csrc/fetch_task.cuh)
+  * compute_reward/_is_success      envs/fetch/fetch_env.py:74-80, 168-170
+  * TimeLimit (max_episode_steps=50) and vector autoreset as gymnasium's wrappers/vector envs do.
+All per-step arithmetic happens on the GPU; this file only owns reset-time sampling and bookkeeping.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .mjcf import EQ_WELD, JNT_FREE
+from .models import load_model
+from .spaces import Box, Dict as DictSpace, batch_space
+
+FETCH_TASKS = {
+    "FetchReach": dict(model="fetch_reach", has_object=False, block_gripper=True, gripper_extra_height=0.2,
+                       target_in_the_air=True, target_offset=0.0, obj_range=0.15, target_range=0.15, distance_threshold=0.05,
+                       initial_qpos={"robot0:slide0": 0.4049, "robot0:slide1": 0.48, "robot0:slide2": 0.0}),
+    "FetchPush": dict(model="fetch_push", has_object=True, block_gripper=True, gripper_extra_height=0.0,
+                      target_in_the_air=False, target_offset=0.0, obj_range=0.15, target_range=0.15, distance_threshold=0.05,
+                      initial_qpos={"robot0:slide0": 0.405, "robot0:slide1": 0.48, "robot0:slide2": 0.0,
+                                    "object0:joint": [1.25, 0.53, 0.4, 1.0, 0.0, 0.0, 0.0]}),
+    "FetchPickAndPlace": dict(model="fetch_pick_and_place", has_object=True, block_gripper=False, gripper_extra_height=0.2,
+                              target_in_the_air=True, target_offset=0.0, obj_range=0.15, target_range=0.15,
+                              distance_threshold=0.05,
+                              initial_qpos={"robot0:slide0": 0.405, "robot0:slide1": 0.48, "robot0:slide2": 0.0,
+                                            "object0:joint": [1.25, 0.53, 0.4, 1.0, 0.0, 0.0, 0.0]}),
+}
+N_SUBSTEPS = 20
+REF_POINT = (1.0, 0.75, 0.4)  # fixed world point the device spatial algebra is expressed about
+
+
+def make_task_struct(model, cfg, reward_type, n_substeps=N_SUBSTEPS):
+    t = _lib.FetchTaskC()
+    t.has_object, t.block_gripper = int(cfg["has_object"]), int(cfg["block_gripper"])
+    t.n_substeps, t.reward_dense = n_substeps, int(reward_type == "dense")
+    t.grip_site = model.site_id("robot0:grip")
+    t.obj_site = model.site_id("object0") if cfg["has_object"] else -1
+    t.frame_site = model.frame_site("robot0:gripper_link")
+    robot = [j for j, n in enumerate(model.names["joint"]) if n.startswith("robot")]
+    t.nrobot = len(robot)
+    for i, j in enumerate(robot):
+        t.robot_qadr[i], t.robot_dadr[i] = int(model.jnt_qposadr[j]), int(model.jnt_dofadr[j])
+    t.finger_qadr[0] = int(model.jnt_qposadr[model.joint_id("robot0:l_gripper_finger_joint")])
+    t.finger_qadr[1] = int(model.jnt_qposadr[model.joint_id("robot0:r_gripper_finger_joint")])
+    t.nobs = 25 if cfg["has_object"] else 10
+    t.distance_threshold = float(cfg["distance_threshold"])
+    t.dt = float(model.opt[0] * n_substeps)
+    return t
+
+
+def welded_eq_data(model):
+    """utils/mujoco_utils.py:74-80 reset_mocap_welds, applied to the model constants before upload."""
+    eq = np.array(model.eq_data, dtype=np.float64).reshape(-1, 11).copy()
+    for i in range(model.neq):
+        if model.eq_type[i] == EQ_WELD:
+            eq[i, :7] = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+    return eq
+
+
+class _DevArray:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class CudaBackend:
+    """Thin owner of a `b200sim_t` handle; all arguments are torch CUDA tensors passed as raw device pointers."""
+
+    def __init__(self, model, eq_data, task, num_envs, device):
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200sim needs a CUDA device: there is no CPU fallback on the product path")
+        self.device = torch.device(device)
+        self.L = _lib.lib()
+        blob = model.to_blob()
+        h = ctypes.c_void_p()
+        ref = np.asarray(REF_POINT, dtype=np.float32)
+        eq = np.ascontiguousarray(eq_data, dtype=np.float64)
+        rc = self.L.b200sim_create(blob, len(blob), eq.ctypes.data, ref.ctypes.data, ctypes.byref(task), num_envs,
+                                   self.device.index or 0, ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"b200sim_create failed ({rc}): {self.L.b200sim_last_error(None).decode()}")
+        self.h = h
+        self.num_envs, self.nobs = num_envs, task.nobs
+        lay = (ctypes.c_int * 8)()
+        self.L.b200sim_layout(h, lay)
+        self.layout = dict(zip(("qpos", "qvel", "warm", "ctrl", "mocap", "pose", "goal", "stride"), list(lay)))
+        self.state = torch.as_tensor(_DevArray(self.L.b200sim_state(h), (num_envs, self.layout["stride"])), device=self.device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.state = None
+            self.L.b200sim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"b200sim call failed ({rc}): {self.L.b200sim_last_error(self.h).decode()}")
+
+    def new_outputs(self):
+        n, d = self.num_envs, self.device
+        return dict(obs=torch.empty((n, self.nobs), dtype=torch.float32, device=d),
+                    achieved=torch.empty((n, 3), dtype=torch.float32, device=d),
+                    desired=torch.empty((n, 3), dtype=torch.float32, device=d),
+                    reward=torch.empty(n, dtype=torch.float32, device=d), success=torch.empty(n, dtype=torch.float32, device=d))
+
+    def _ptrs(self, out):
+        return [out[k].data_ptr() for k in ("obs", "achieved", "desired", "reward", "success")]
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def step(self, actions, out, info=None):
+        assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape == (self.num_envs, 4)
+        self._check(self.L.b200sim_step(self.h, actions.data_ptr(), *self._ptrs(out), info.data_ptr() if info is not None else None, self._stream()))
+
+    def refresh(self, mask, out):
+        self._check(self.L.b200sim_refresh(self.h, mask.data_ptr() if mask is not None else None, *self._ptrs(out), self._stream()))
+
+    def raw_step(self, nstep, out):
+        self._check(self.L.b200sim_raw_step(self.h, int(nstep), *self._ptrs(out), self._stream()))
+
+    def compute_reward(self, ag, dg):
+        ag = ag.to(self.device, torch.float32).contiguous().reshape(-1, 3)
+        dg = dg.to(self.device, torch.float32).contiguous().reshape(-1, 3)
+        out = torch.empty(ag.shape[0], dtype=torch.float32, device=self.device)
+        self._check(self.L.b200sim_compute_reward(self.h, ag.data_ptr(), dg.data_ptr(), ag.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    @property
+    def launches(self):
+        return int(self.L.b200sim_launch_count(self.h))
+
+
+class FetchVectorEnv:
+    """`gym.make_vec("FetchPickAndPlace-v4", num_envs=N)` replacement.  Observations, rewards and flags are torch
+    tensors on `device` (float32 / bool) with a leading `num_envs` axis."""
+
+    metadata = {"render_modes": [], "render_fps": 25, "autoreset_mode": "next_step"}
+
+    def __init__(self, task: str = "FetchPickAndPlace", num_envs: int = 1, reward_type: str = "sparse",
+                 max_episode_steps: Optional[int] = 50, device="cuda:0", rng_mode: str = "auto",
+                 autoreset_mode: str = "next_step", n_substeps: int = N_SUBSTEPS, backend_factory=None, **kwargs):
+        if task not in FETCH_TASKS:
+            raise KeyError(f"unknown Fetch task {task!r}")
+        if reward_type not in ("sparse", "dense"):
+            raise ValueError("reward_type must be 'sparse' or 'dense'")
+        if autoreset_mode not in ("next_step", "same_step", "disabled"):
+            raise ValueError("autoreset_mode must be next_step, same_step or disabled")
+        if kwargs.get("render_mode") is not None:
+            raise NotImplementedError("rendering is out of scope for the batched CUDA path")
+        cfg = dict(FETCH_TASKS[task])
+        self.task_name, self.cfg, self.reward_type = task, cfg, reward_type
+        self.num_envs, self.max_episode_steps, self.autoreset_mode = int(num_envs), max_episode_steps, autoreset_mode
+        self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
+        self.n_substeps = n_substeps
+        self.model = load_model(cfg["model"])
+        self.task = make_task_struct(self.model, cfg, reward_type, n_substeps)
+        eq = welded_eq_data(self.model)
+        factory = backend_factory or CudaBackend
+        self.backend = factory(self.model, eq, self.task, self.num_envs, device)
+        self.device = self.backend.device
+        self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
+            if self.rng_mode == "numpy" else None
+        self._gen = torch.Generator(device=self.device)
+        self._gen.seed()
+        lay = self.backend.layout
+        self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", self.model.nq), ("qvel", self.model.nv), ("warm", self.model.nv),
+                                                              ("ctrl", self.model.nu), ("mocap", 7), ("pose", 7), ("goal", 3))}
+        self.dt = float(self.model.opt[0] * n_substeps)
+        nobs = self.task.nobs
+        self.single_action_space = Box(-1.0, 1.0, shape=(4,), dtype=np.float32)
+        self.single_observation_space = DictSpace(dict(
+            desired_goal=Box(-np.inf, np.inf, shape=(3,), dtype=np.float64),
+            achieved_goal=Box(-np.inf, np.inf, shape=(3,), dtype=np.float64),
+            observation=Box(-np.inf, np.inf, shape=(nobs,), dtype=np.float64)))
+        self.action_space = batch_space(self.single_action_space, self.num_envs)
+        self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        self._env_setup()
+        self.closed = False
+
+    # ------------------------------------------------------------------ construction
+    def _env_setup(self):
+        """envs/fetch/fetch_env.py:404-428 run once for every env in lock-step (all envs are identical here)."""
+        m, st, sl = self.model, self.backend.state, self._sl
+        qpos = np.array(m.qpos0, dtype=np.float64)
+        for name, value in self.cfg["initial_qpos"].items():
+            j = m.joint_id(name)
+            a = int(m.jnt_qposadr[j])
+            n = 7 if m.jnt_type[j] == JNT_FREE else 1
+            qpos[a:a + n] = value
+        st.zero_()
+        st[:, sl["qpos"]] = torch.as_tensor(qpos, dtype=torch.float32, device=self.device)
+        st[:, sl["mocap"]] = torch.tensor([0, 0, 0, 1, 0, 0, 0], dtype=torch.float32, device=self.device)
+        out = self.backend.new_outputs()
+        self.backend.refresh(None, out)  # mj_forward
+        grip = out["obs"][:, 0:3]
+        target = grip + torch.tensor([-0.498, 0.005, -0.431 + self.cfg["gripper_extra_height"]], dtype=torch.float32, device=self.device)
+        st[:, sl["mocap"]] = torch.cat([target, torch.tensor([1.0, 0.0, 1.0, 0.0], device=self.device).expand(self.num_envs, 4)], dim=1)
+        self.backend.raw_step(10 * self.n_substeps, out)  # 10 x mj_step(nstep=n_substeps)
+        # site positions as of the last forward pass (the reference reads data.site_xpos without a new mj_forward)
+        self.initial_gripper_xpos = out["obs"][0, 0:3].clone()
+        self.height_offset = float(out["obs"][0, 5]) if self.cfg["has_object"] else None
+        self.initial_qpos = st[0, sl["qpos"]].clone()
+        self.initial_qvel = st[0, sl["qvel"]].clone()
+        self._mocap_rest = torch.tensor([0, 0, 0, 1, 0, 0, 0], dtype=torch.float32, device=self.device)
+        self._obj_qadr = int(m.jnt_qposadr[m.joint_id("object0:joint")]) if self.cfg["has_object"] else -1
+        self._last = out
+
+    # ------------------------------------------------------------------ sampling
+    def _sample_reset(self, idx):
+        """Object start position (fetch_env.py:386-399) and goal (fetch_env.py:153-166) for the envs in `idx`."""
+        cfg, n = self.cfg, idx.numel()
+        g0 = self.initial_gripper_xpos
+        off = cfg["target_offset"]
+        if self.rng_mode == "numpy":
+            g0n = g0.double().cpu().numpy()
+            obj = np.zeros((n, 2))
+            goals = np.zeros((n, 3))
+            for k, i in enumerate(idx.tolist()):
+                rng = self._np_rngs[i]
+                if cfg["has_object"]:
+                    xy = g0n[:2]
+                    while np.linalg.norm(xy - g0n[:2]) < 0.1:
+                        xy = g0n[:2] + rng.uniform(-cfg["obj_range"], cfg["obj_range"], size=2)
+                    obj[k] = xy
+                    goal = g0n[:3] + rng.uniform(-cfg["target_range"], cfg["target_range"], size=3)
+                    goal += off
+                    goal[2] = self.height_offset
+                    if cfg["target_in_the_air"] and rng.uniform() < 0.5:
+                        goal[2] += rng.uniform(0, 0.45)
+                else:
+                    goal = g0n[:3] + rng.uniform(-cfg["target_range"], cfg["target_range"], size=3)
+                goals[k] = goal
+            return (torch.as_tensor(obj, dtype=torch.float32, device=self.device) if cfg["has_object"] else None,
+                    torch.as_tensor(goals, dtype=torch.float32, device=self.device))
+        # device RNG (Philox): same distributions, different stream
+        u = lambda *s: torch.rand(*s, generator=self._gen, device=self.device)
+        obj = None
+        if cfg["has_object"]:
+            obj = g0[:2] + (u(n, 2) * 2 - 1) * cfg["obj_range"]
+            bad = torch.linalg.norm(obj - g0[:2], dim=1) < 0.1
+            while bool(bad.any()):
+                nb = int(bad.sum())
+                obj[bad] = g0[:2] + (u(nb, 2) * 2 - 1) * cfg["obj_range"]
+                bad = torch.linalg.norm(obj - g0[:2], dim=1) < 0.1
+        goals = g0[:3] + (u(n, 3) * 2 - 1) * cfg["target_range"]
+        if cfg["has_object"]:
+            goals = goals + torch.as_tensor(off, dtype=torch.float32, device=self.device)
+            goals[:, 2] = self.height_offset
+            if cfg["target_in_the_air"]:
+                air = u(n) < 0.5
+                goals[:, 2] += torch.where(air, u(n) * 0.45, torch.zeros(n, device=self.device))
+        return obj, goals
+
+    def _reset_envs(self, mask, out):
+        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        if idx.numel() == 0:
+            return
+        st, sl = self.backend.state, self._sl
+        obj, goals = self._sample_reset(idx)
+        rec = torch.zeros((idx.numel(), st.shape[1]), dtype=torch.float32, device=self.device)  # mj_resetData
+        rec[:, sl["qpos"]] = self.initial_qpos
+        rec[:, sl["qvel"]] = self.initial_qvel
+        rec[:, sl["mocap"]] = self._mocap_rest
+        if obj is not None:
+            rec[:, self._sl["qpos"].start + self._obj_qadr: self._sl["qpos"].start + self._obj_qadr + 2] = obj
+        rec[:, sl["goal"]] = goals
+        st[idx] = rec
+        self._elapsed[idx] = 0
+        self.backend.refresh(mask.to(torch.uint8), out)  # mj_forward + _get_obs for the reset envs
+
+    # ------------------------------------------------------------------ gymnasium API
+    def _obs_dict(self, out):
+        return {"observation": out["obs"], "achieved_goal": out["achieved"], "desired_goal": out["desired"]}
+
+    def reset(self, *, seed=None, options=None):
+        if seed is not None:
+            seeds = [seed + i for i in range(self.num_envs)] if isinstance(seed, (int, np.integer)) else list(seed)
+            if self.rng_mode == "numpy":
+                self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(s))) for s in seeds]
+            self._gen.manual_seed(int(seeds[0]))
+        out = self.backend.new_outputs()
+        mask = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        self._reset_envs(mask, out)
+        self._needs_reset.zero_()
+        self._last = out
+        return self._obs_dict(out), {}
+
+    def step(self, actions):
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
+        if tuple(actions.shape) != (self.num_envs, 4):
+            raise ValueError("Action dimension mismatch")
+        actions = actions.to(self.device, torch.float32, non_blocking=True).contiguous()
+        out = self.backend.new_outputs()
+        self.backend.step(actions, out)  # clip + _set_action + n_substeps x mj_step + _get_obs + reward, one kernel
+        self._elapsed += 1
+        reward, success = out["reward"], out["success"]
+        terminated = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)  # robot_env.py:106-112
+        info = {"is_success": success}
+        if self.autoreset_mode == "next_step" and bool(self._needs_reset.any()):
+            # envs that finished on the previous call are reset now; their action is ignored (gymnasium NEXT_STEP)
+            pre = self._needs_reset.clone()
+            self._reset_envs(pre, out)
+            reward = torch.where(pre, torch.zeros_like(reward), reward)
+            out["reward"] = reward
+            info["is_success"] = torch.where(pre, torch.zeros_like(success), success)
+            self._needs_reset.zero_()
+        truncated = (self._elapsed >= self.max_episode_steps) if self.max_episode_steps is not None else torch.zeros_like(terminated)
+        done = truncated | terminated
+        if self.autoreset_mode == "next_step":
+            self._needs_reset = done
+        elif self.autoreset_mode == "same_step" and bool(done.any()):
+            info["final_obs"] = {k: v.clone() for k, v in self._obs_dict(out).items()}
+            info["_final_obs"] = done.clone()
+            self._reset_envs(done, out)
+        info["_is_success"] = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        self._last = out
+        return self._obs_dict(out), reward, terminated, truncated, info
+
+    # GoalEnv API (core.py:45-114), batched; accepts numpy or torch, any leading shape
+    def compute_reward(self, achieved_goal, desired_goal, info=None):
+        is_np = not torch.is_tensor(achieved_goal)
+        ag = torch.as_tensor(np.asarray(achieved_goal)) if is_np else achieved_goal
+        dg = torch.as_tensor(np.asarray(desired_goal)) if not torch.is_tensor(desired_goal) else desired_goal
+        lead = ag.shape[:-1]
+        r = self.backend.compute_reward(ag, dg).reshape(lead)
+        if is_np:
+            r = r.cpu().numpy()
+            return r.astype(np.float32) if self.reward_type == "sparse" else r.astype(np.float64)
+        return r
+
+    def compute_terminated(self, achieved_goal, desired_goal, info=None):
+        return False
+
+    def compute_truncated(self, achieved_goal, desired_goal, info=None):
+        return False
+
+    # state access (checkpoint / parity injection), SURVEY.md section 5
+    def get_state(self):
+        return self.backend.state.clone(), self._elapsed.clone()
+
+    def set_state(self, state, elapsed=None):
+        self.backend.state.copy_(state)
+        if elapsed is not None:
+            self._elapsed.copy_(elapsed)
+        out = self.backend.new_outputs()
+        self.backend.refresh(None, out)
+        self._last = out
+        return self._obs_dict(out)
+
+    def close(self):
+        if not getattr(self, "closed", True):
+            self.backend.close()
+            self.closed = True

@@ -1,0 +1,49 @@
+"""Compiled model store.
+
+The reference's MJCF/STL assets are not redistributed; `build_models()` compiles them (when the reference checkout is
+present, i.e. in the build container) into constant-table blobs under ``gymnasium_robotics_b200/models/`` which are
+what ships and what the GPU box loads (``/root/reference`` does not exist there).
+"""
+from __future__ import annotations
+
+import os
+
+from .mjcf import Model, compile_mjcf
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MODEL_DIR = os.path.join(_HERE, "models")
+REFERENCE_ASSETS = os.environ.get("B200SIM_REFERENCE_ASSETS", "/root/reference/gymnasium_robotics/envs/assets")
+
+# model name -> MJCF path relative to the reference's assets directory
+MODEL_SOURCES = {
+    "fetch_reach": "fetch/reach.xml",
+    "fetch_push": "fetch/push.xml",
+    "fetch_pick_and_place": "fetch/pick_and_place.xml",
+}
+
+
+def build_models(force: bool = False):
+    """(Re)compile every model blob from the reference's assets, if they are available."""
+    if not os.path.isdir(REFERENCE_ASSETS):
+        return []
+    os.makedirs(MODEL_DIR, exist_ok=True)
+    built = []
+    for name, rel in MODEL_SOURCES.items():
+        out = os.path.join(MODEL_DIR, name + ".b200m")
+        if os.path.exists(out) and not force:
+            continue
+        blob = compile_mjcf(os.path.join(REFERENCE_ASSETS, rel)).to_blob()
+        with open(out, "wb") as f:
+            f.write(blob)
+        built.append(out)
+    return built
+
+
+def load_model(name: str) -> Model:
+    path = os.path.join(MODEL_DIR, name + ".b200m")
+    if not os.path.exists(path):
+        build_models()
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"compiled model {path} is missing and the reference assets are not available to build it")
+    with open(path, "rb") as f:
+        return Model.from_blob(f.read())

@@ -1,0 +1,73 @@
+/* b200sim C-ABI: the drop-in boundary of the CUDA path.
+ *
+ * The reference crosses into native code through the pybind11 module `mujoco`
+ * (gymnasium_robotics/envs/robot_env.py:293-294 MjModel/MjData, :341 mj_step, fetch_env.py:303,401 mj_forward,
+ * utils/mujoco_utils.py:115,125 mj_jacSite).  Those per-env, per-call entry points are replaced by the batched
+ * entry points below: one call advances every env by one `step()` of the reference
+ * (BaseRobotEnv.step, robot_env.py:114-152) entirely on the GPU.
+ *
+ * Conventions: opaque handle, int error codes (0 = ok), no exceptions, no torch types.  Every `float*`/`int*`
+ * argument of step/refresh/raw_step is a DEVICE pointer owned by the caller ([N, dim] row-major, fp32); the
+ * library owns the persistent per-env state.  Calls are asynchronous and ordered on `stream` (a cudaStream_t,
+ * NULL = default stream).  `b200sim_last_error` returns a static or handle-owned string.
+ */
+#ifndef B200SIM_H
+#define B200SIM_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200sim b200sim_t;
+
+/* Task constants of the Fetch family (reference: envs/fetch/fetch_env.py:29-69 ctor args, resolved to ids). */
+typedef struct b200sim_fetch_task {
+  int has_object, block_gripper, n_substeps, reward_dense;
+  int grip_site, obj_site, frame_site; /* site ids: "robot0:grip", "object0", frame of body robot0:gripper_link */
+  int nrobot;                          /* joints whose name starts with "robot" (utils/mujoco_utils.py:23-31) */
+  int robot_qadr[16], robot_dadr[16];
+  int finger_qadr[2];                  /* qpos addresses zeroed by _step_callback when block_gripper */
+  int nobs;
+  float distance_threshold, dt;
+} b200sim_fetch_task_t;
+
+/* indices into the layout array returned by b200sim_layout (offsets in floats inside one env's state record) */
+enum { B200SIM_ST_QPOS = 0, B200SIM_ST_QVEL, B200SIM_ST_WARM, B200SIM_ST_CTRL, B200SIM_ST_MOCAP, B200SIM_ST_POSE,
+       B200SIM_ST_GOAL, B200SIM_ST_STRIDE, B200SIM_ST_COUNT };
+
+/* model_blob: include/b200sim_model.h format.  eq_data: optional [neq*11] override of the model's equality data
+ * (the reference rewrites it after load: utils/mujoco_utils.py:74-80).  ref: fixed world point the spatial algebra is
+ * expressed about.  Replaces MjModel.from_xml_path + MjData (robot_env.py:293-294). */
+int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data, const float* ref,
+                   const b200sim_fetch_task_t* task, int num_envs, int device, b200sim_t** out);
+void b200sim_destroy(b200sim_t* h);
+const char* b200sim_last_error(const b200sim_t* h);
+
+int b200sim_num_envs(const b200sim_t* h);
+int b200sim_layout(const b200sim_t* h, int* out /* [B200SIM_ST_COUNT] */);
+/* device pointer to the [num_envs, stride] fp32 state records (qpos|qvel|qacc_warmstart|ctrl|mocap|pose|goal) --
+ * the hook for reset, parity injection and checkpointing (reference: data.qpos/qvel views, robot_env.py:301-315). */
+float* b200sim_state(b200sim_t* h);
+
+/* One env.step() for every env: clip + _set_action + n_substeps x mj_step + _step_callback + _get_obs + reward.
+ * info (optional, [N] int32): low 16 bits = Newton iterations spent, bit 16.. = capacity-overflow flags. */
+int b200sim_step(b200sim_t* h, const float* actions, float* obs, float* achieved, float* desired, float* reward,
+                 float* success, int* info, void* stream);
+/* mj_forward-style refresh of derived quantities + observation for envs with mask[i] != 0 (mask NULL = all);
+ * used after reset writes new state records (reference: fetch_env.py:375-402 _reset_sim -> mj_forward, _get_obs). */
+int b200sim_refresh(b200sim_t* h, const unsigned char* mask, float* obs, float* achieved, float* desired, float* reward,
+                    float* success, void* stream);
+/* nstep raw mj_step calls with the ctrl / mocap currently in the state records (reference: fetch_env.py:419-420). */
+int b200sim_raw_step(b200sim_t* h, int nstep, float* obs, float* achieved, float* desired, float* reward, float* success,
+                     void* stream);
+/* GoalEnv.compute_reward on M (achieved, desired) pairs, device pointers (reference: fetch_env.py:74-80). */
+int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const float* desired, int M, float* out, void* stream);
+/* number of kernel launches issued through this handle so far */
+long b200sim_launch_count(const b200sim_t* h);
+/* shared-memory bytes per block and warps (envs) per block chosen at create time */
+int b200sim_launch_config(const b200sim_t* h, int* smem_bytes, int* envs_per_block, int* blocks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,115 @@
+"""Test-only ctypes wrapper for the host emulation (WARP_W == 1) of the CUDA physics core.  See hostsim.cpp."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = None
+
+
+class FetchTaskC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("has_object", "block_gripper", "n_substeps", "reward_dense", "grip_site",
+                                             "obj_site", "frame_site", "nrobot")] + \
+               [("robot_qadr", ctypes.c_int * 16), ("robot_dadr", ctypes.c_int * 16), ("finger_qadr", ctypes.c_int * 2),
+                ("nobs", ctypes.c_int), ("distance_threshold", ctypes.c_float), ("dt", ctypes.c_float)] + \
+               [(n, ctypes.c_int) for n in ("st_qpos", "st_qvel", "st_warm", "st_ctrl", "st_mocap", "st_pose", "st_goal",
+                                             "st_stride")]
+
+
+def build(force=False):
+    out = os.path.join(_HERE, "libhostsim.so")
+    srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_ROOT, "gymnasium_robotics_b200", "csrc", f)
+                                                   for f in ("sim_core.cuh", "dmodel.h", "fetch_task.cuh")] + \
+           [os.path.join(_ROOT, "include", "b200sim_model.h")]
+    if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function", "-o", out, srcs[0]])
+    return out
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build())
+        L.hostsim_create.restype = ctypes.c_void_p
+        L.hostsim_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        L.hostsim_scratch.restype = ctypes.POINTER(ctypes.c_float)
+        L.hostsim_scratch.argtypes = [ctypes.c_void_p]
+        for f in ("hostsim_destroy", "hostsim_forward", "hostsim_kinematics"):
+            getattr(L, f).argtypes = [ctypes.c_void_p]
+            getattr(L, f).restype = None
+        L.hostsim_step.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.hostsim_step.restype = None
+        L.hostsim_offset.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.hostsim_scr_words.argtypes = [ctypes.c_void_p]
+        L.hostsim_env_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
+        assert L.hostsim_task_size() == ctypes.sizeof(FetchTaskC)
+        _LIB = L
+    return _LIB
+
+
+class HostSim:
+    """fp32 single-env emulation of the kernel; arrays are views into the emulated shared-memory scratch."""
+
+    def __init__(self, model, eq_data=None, ref=(1.0, 0.75, 0.4)):
+        self.model = model
+        blob = model.to_blob()
+        L = lib()
+        self._L = L
+        eq = np.ascontiguousarray(eq_data, dtype=np.float64) if eq_data is not None else None
+        r = np.asarray(ref, dtype=np.float32)
+        self._h = L.hostsim_create(blob, len(blob), eq.ctypes.data if eq is not None else None, r.ctypes.data)
+        if not self._h:
+            raise RuntimeError("hostsim_create failed")
+        n = L.hostsim_scr_words(self._h)
+        self.scratch = np.ctypeslib.as_array(L.hostsim_scratch(self._h), shape=(n,))
+        self.ref = r.astype(np.float64)
+
+    def arr(self, name, count, dtype=np.float32):
+        o = self._L.hostsim_offset(self._h, name.encode())
+        assert o >= 0, name
+        v = self.scratch[o:o + count]
+        return v if dtype == np.float32 else v.view(dtype)
+
+    def __getattr__(self, k):
+        m = self.__dict__["model"]
+        sizes = {"qpos": m.nq, "qvel": m.nv, "qacc": m.nv, "warm": m.nv, "ctrl": m.nu, "mocap_pos": 3 * m.nmocap,
+                 "mocap_quat": 4 * m.nmocap, "xpos": 3 * m.nbody, "xquat": 4 * m.nbody, "xmat": 9 * m.nbody,
+                 "fsmooth": m.nv, "fcon": m.nv, "M": m.nv * (m.nv + 1) // 2, "cdof": 6 * m.nv, "cinert": 10 * m.nbody}
+        if k in sizes:
+            return self.arr(k, sizes[k])
+        raise AttributeError(k)
+
+    def counters(self):
+        return self.arr("counters", 8, np.int32)
+
+    def dense_M(self):
+        nv = self.model.nv
+        P = self.M
+        M = np.zeros((nv, nv))
+        for i in range(nv):
+            for j in range(i + 1):
+                M[i, j] = M[j, i] = P[i * (i + 1) // 2 + j]
+        return M
+
+    def kinematics(self):
+        self._L.hostsim_kinematics(self._h)
+
+    def forward(self):
+        self._L.hostsim_forward(self._h)
+
+    def step(self, n=1):
+        self._L.hostsim_step(self._h, int(n))
+
+    def env_step(self, task, mode, nraw, st, action, nobs):
+        obs = np.zeros(nobs, dtype=np.float32)
+        ag, dg = np.zeros(3, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        rew, suc = np.zeros(1, dtype=np.float32), np.zeros(1, dtype=np.float32)
+        a = np.ascontiguousarray(action, dtype=np.float32)
+        it = self._L.hostsim_env_step(self._h, ctypes.byref(task), mode, nraw, st.ctypes.data, a.ctypes.data, obs.ctypes.data,
+                                      ag.ctypes.data, dg.ctypes.data, rew.ctypes.data, suc.ctypes.data)
+        return obs, ag, dg, float(rew[0]), float(suc[0]), it

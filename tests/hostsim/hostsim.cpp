@@ -1,0 +1,52 @@
+// TEST-ONLY host emulation of the CUDA physics core: compiles gymnasium_robotics_b200/csrc/sim_core.cuh with
+// WARP_W == 1 (one "lane" runs every strided loop) so the fp32 kernel arithmetic can be compared with the fp64 oracle
+// on a machine without a GPU.  Never linked into the product library; the product path is CUDA only.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <string>
+#include "../../gymnasium_robotics_b200/csrc/fetch_task.cuh"
+
+struct HostSim {
+  std::vector<uint8_t> blob;
+  b200_model_view view;
+  std::vector<uint32_t> model;
+  std::vector<float> scratch;
+  Ctx ctx;
+  std::string err;
+};
+
+extern "C" {
+void* hostsim_create(const void* blob, size_t n, const double* eq_data, const float* ref) {
+  HostSim* s = new HostSim;
+  s->blob.assign((const uint8_t*)blob, (const uint8_t*)blob + n);
+  if (b200_model_parse(s->blob.data(), n, &s->view) != 0) { delete s; return nullptr; }
+  if (dm_build(s->view, eq_data, ref, s->model, s->err) != 0) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); delete s; return nullptr; }
+  const DMHead* h = (const DMHead*)s->model.data();
+  s->scratch.assign(h->scr_words, 0.f);
+  s->ctx.mw = s->model.data(); s->ctx.h = h; s->ctx.s = s->scratch.data(); s->ctx.lane = 0;
+  return s;
+}
+void hostsim_destroy(void* p) { delete (HostSim*)p; }
+float* hostsim_scratch(void* p) { return ((HostSim*)p)->scratch.data(); }
+int hostsim_scr_words(void* p) { return ((HostSim*)p)->ctx.h->scr_words; }
+int hostsim_offset(void* p, const char* name) {
+  const DMHead* h = ((HostSim*)p)->ctx.h;
+#define X(nm, words) if (strcmp(name, #nm) == 0) return h->s_##nm;
+  DM_SCRATCH(X)
+#undef X
+  return -1;
+}
+void hostsim_forward(void* p) { forward(((HostSim*)p)->ctx); }
+void hostsim_step(void* p, int n) { for (int i = 0; i < n; i++) { forward(((HostSim*)p)->ctx); euler_step(((HostSim*)p)->ctx); } }
+void hostsim_kinematics(void* p) { kinematics(((HostSim*)p)->ctx); com_quantities(((HostSim*)p)->ctx); mass_matrix(((HostSim*)p)->ctx); }
+int hostsim_task_size() { return (int)sizeof(FetchTask); }
+int hostsim_env_step(void* p, const FetchTask* t, int mode, int nraw, float* st, const float* action, float* obs, float* achieved,
+                     float* desired, float* reward, float* success) {
+  int it = 0;
+  fetch_env_step(((HostSim*)p)->ctx, *t, mode, nraw, st, action, obs, achieved, desired, reward, success, &it);
+  return it;
+}
+}
+extern "C" int hostsim_model_words(void* p) { return ((HostSim*)p)->ctx.h->nwords; }

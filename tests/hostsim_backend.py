@@ -1,0 +1,65 @@
+"""CPU test backend for FetchVectorEnv: drives the WARP_W == 1 host emulation of the kernel source, one env at a time.
+Lets the `-m "not gpu"` suite cover the host logic (reset sampling, autoreset, TimeLimit, spaces) and the kernel
+arithmetic without a GPU.  Test infrastructure only."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from tests.hostsim import FetchTaskC as HostTaskC, HostSim
+
+
+class HostSimBackend:
+    def __init__(self, model, eq_data, task, num_envs, device):
+        from gymnasium_robotics_b200.fetch import REF_POINT
+
+        self.device = torch.device("cpu")
+        self.num_envs, self.nobs = num_envs, task.nobs
+        self.sim = HostSim(model, eq_data=eq_data, ref=REF_POINT)
+        t = HostTaskC()
+        for name, _ in task._fields_:
+            setattr(t, name, getattr(task, name))
+        o = 0
+        lay = {}
+        for k, n in (("qpos", model.nq), ("qvel", model.nv), ("warm", model.nv), ("ctrl", model.nu), ("mocap", 7), ("pose", 7), ("goal", 3)):
+            lay[k] = o
+            o += n
+        lay["stride"] = (o + 3) & ~3
+        for k in ("qpos", "qvel", "warm", "ctrl", "mocap", "pose", "goal", "stride"):
+            setattr(t, "st_" + k, lay[k])
+        self.task, self.layout = t, lay
+        self.state = torch.zeros((num_envs, lay["stride"]), dtype=torch.float32)
+        self.launches = 0
+
+    def close(self):
+        pass
+
+    def new_outputs(self):
+        n = self.num_envs
+        return dict(obs=torch.zeros((n, self.nobs)), achieved=torch.zeros((n, 3)), desired=torch.zeros((n, 3)),
+                    reward=torch.zeros(n), success=torch.zeros(n))
+
+    def _run(self, mode, nraw, actions, mask, out):
+        st = self.state.numpy()
+        for i in range(self.num_envs):
+            if mask is not None and not bool(mask[i]):
+                continue
+            a = actions[i].numpy() if actions is not None else np.zeros(4, dtype=np.float32)
+            obs, ag, dg, rew, suc, _ = self.sim.env_step(self.task, mode, nraw, st[i], a, self.nobs)
+            out["obs"][i] = torch.from_numpy(obs); out["achieved"][i] = torch.from_numpy(ag); out["desired"][i] = torch.from_numpy(dg)
+            out["reward"][i] = rew; out["success"][i] = suc
+        self.launches += 1
+
+    def step(self, actions, out, info=None):
+        self._run(0, 0, actions, None, out)
+
+    def refresh(self, mask, out):
+        self._run(1, 0, None, mask, out)
+
+    def raw_step(self, nstep, out):
+        self._run(2, nstep, None, None, out)
+
+    def compute_reward(self, ag, dg):
+        ag = ag.to(torch.float32).reshape(-1, 3); dg = dg.to(torch.float32).reshape(-1, 3)
+        d = torch.sqrt(((ag - dg) ** 2).sum(-1))
+        return -d if self.task.reward_dense else -(d > self.task.distance_threshold).to(torch.float32)

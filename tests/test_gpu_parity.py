@@ -1,0 +1,160 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI, against the fp64 CPU
+oracle on identical inputs.  Tolerances (fp32 kernel vs fp64 oracle):
+  * one env-step (20 sub-steps) from an identical injected state: |obs_gpu - obs_oracle| <= 2e-4 absolute
+    (positions in m, scaled velocities, euler angles in rad);
+  * rewards / success flags: exact, given the same achieved/desired goals;
+  * same-seed runs on the same GPU: bit-identical.
+The physics oracle itself is "parity unpinned" w.r.t. MuJoCo (see oracle/oracle.c header).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+OBS_TOL = 2e-4
+
+
+def _mk(task, n, **kw):
+    from gymnasium_robotics_b200.fetch import FetchVectorEnv
+
+    return FetchVectorEnv(task, num_envs=n, device="cuda:0", **kw)
+
+
+@pytest.mark.parametrize("task", ["FetchReach", "FetchPush", "FetchPickAndPlace"])
+def test_env_setup_matches_oracle(task):
+    from tests.parity_util import oracle_env_from_model
+
+    env = _mk(task, 4, rng_mode="numpy")
+    orc = oracle_env_from_model(task, env.model)
+    assert np.allclose(env.initial_gripper_xpos.double().cpu().numpy(), orc.initial_gripper_xpos, atol=1e-4)
+    assert np.allclose(env.initial_qpos.double().cpu().numpy(), orc.initial_qpos, atol=2e-4)
+    if env.height_offset is not None:
+        assert env.height_offset == pytest.approx(orc.height_offset, abs=1e-5)
+    env.close()
+
+
+@pytest.mark.parametrize("task", ["FetchReach", "FetchPush", "FetchPickAndPlace"])
+def test_step_parity_from_identical_state(task):
+    """Config 1/2 of BASELINE.json: per-step comparison from identical (qpos, qvel, warmstart, ctrl, mocap, goal)."""
+    from tests.parity_util import inject_oracle_state, oracle_env_from_model
+
+    n = 8
+    env = _mk(task, n, rng_mode="numpy")
+    env.reset(seed=100)
+    oracles = [oracle_env_from_model(task, env.model) for _ in range(n)]
+    rng = np.random.default_rng(7)
+    for i, o in enumerate(oracles):
+        o.reset(seed=100 + i)
+    worst = 0.0
+    for step in range(12):
+        inject_oracle_state(env, oracles)
+        a = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        if step >= 6:  # drive the gripper down towards the table/object to exercise contacts
+            a[:, 2] = -1.0
+            a[:, 3] = -1.0 if step % 2 else 1.0
+        o, r, term, trunc, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            got = o["observation"][i].double().cpu().numpy()
+            err = np.abs(got - oo["observation"]).max()
+            worst = max(worst, err)
+            assert err < OBS_TOL, f"step {step} env {i}: obs err {err}"
+            assert np.abs(o["achieved_goal"][i].double().cpu().numpy() - oo["achieved_goal"]).max() < OBS_TOL
+            # reward/success must agree unless the distance sits within tolerance of the threshold
+            d = np.linalg.norm(oo["achieved_goal"] - oo["desired_goal"])
+            if abs(d - 0.05) > 5e-4:
+                assert float(r[i]) == float(orr) and float(info["is_success"][i]) == float(oi["is_success"])
+    print(f"{task}: worst single-step obs error {worst:.2e}")
+    env.close()
+
+
+def test_free_running_rollout_tracks_oracle():
+    """50 free-running env-steps (no re-injection) on the contact-free FetchReach task stay within 1e-3."""
+    from tests.parity_util import oracle_env_from_model
+
+    env = _mk("FetchReach", 2, rng_mode="numpy")
+    obs, _ = env.reset(seed=3)
+    orc = oracle_env_from_model("FetchReach", env.model)
+    oo, _ = orc.reset(seed=3)
+    assert np.abs(obs["desired_goal"][0].double().cpu().numpy() - oo["desired_goal"]).max() < 1e-6  # same PCG64 stream
+    rng = np.random.default_rng(0)
+    for _ in range(49):
+        a = rng.uniform(-1, 1, (2, 4)).astype(np.float32)
+        o, r, *_ = env.step(torch.as_tensor(a))
+        oo, *_ = orc.step(a[0].astype(np.float64))
+        assert np.abs(o["observation"][0].double().cpu().numpy() - oo["observation"]).max() < 1e-3
+    env.close()
+
+
+def test_reward_and_success_bit_exact_given_goals():
+    """fetch_env.py:74-80, 168-170 on 1e5 random pairs: exact equality with the numpy restatement in fp32 inputs."""
+    env = _mk("FetchPickAndPlace", 2)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ag = torch.rand((100000, 3), generator=g, device="cuda") * 0.2
+    dg = torch.rand((100000, 3), generator=g, device="cuda") * 0.2
+    r = env.compute_reward(ag, dg, {})
+    d = np.sqrt(((ag.cpu().numpy().astype(np.float32) - dg.cpu().numpy().astype(np.float32)) ** 2).sum(-1, dtype=np.float32))
+    near = np.abs(d - 0.05) < 1e-6
+    want = -(d > np.float32(0.05)).astype(np.float32)
+    assert np.array_equal(r.cpu().numpy()[~near], want[~near])
+    rn = env.compute_reward(ag.cpu().numpy()[:10], dg.cpu().numpy()[:10], {})
+    assert rn.dtype == np.float32 and rn.shape == (10,)
+    env.close()
+
+
+def test_same_seed_determinism_bitwise():
+    """tests/test_envs.py:62-117 of the reference: two instances, same seed, same actions => identical outputs."""
+    outs = []
+    for _ in range(2):
+        env = _mk("FetchPickAndPlace", 64, rng_mode="torch")
+        env.reset(seed=11)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        acc = []
+        for _ in range(20):
+            a = torch.rand((64, 4), generator=g, device="cuda") * 2 - 1
+            o, r, te, tr, info = env.step(a)
+            acc.append(torch.cat([o["observation"], o["achieved_goal"], o["desired_goal"], r[:, None]], dim=1).clone())
+        outs.append(torch.stack(acc))
+        env.close()
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 2 size (4096 envs): finite outputs, identical envs stay bit-identical (lock-step invariance),
+    GoalEnv reward invariant (core.py:61-62), TimeLimit truncation at 50, autoreset restores the initial state."""
+    n = 4096
+    env = _mk("FetchPickAndPlace", n, rng_mode="torch", autoreset_mode="same_step")
+    obs, _ = env.reset(seed=0)
+    st, _ = env.get_state()
+    st[:] = st[0]  # every env gets env 0's state and goal
+    env.set_state(st)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(50):
+        a = (torch.rand((1, 4), generator=g, device="cuda") * 2 - 1).expand(n, 4).contiguous()
+        o, r, te, tr, info = env.step(a)
+        assert torch.isfinite(o["observation"]).all()
+        if t < 49:
+            assert torch.equal(o["observation"], o["observation"][0:1].expand_as(o["observation"]))
+            rr = env.compute_reward(o["achieved_goal"], o["desired_goal"], {})
+            assert torch.equal(rr, r)
+            assert not bool(tr.any())
+    assert bool(tr.all()) and not bool(te.any())
+    # same-step autoreset: robot joints back at the initial configuration (tests/test_envs.py:175-231 of the reference)
+    st2, el = env.get_state()
+    lay = env.backend.layout
+    q = st2[:, lay["qpos"]:lay["qpos"] + env.model.nq]
+    assert torch.allclose(q[:, :15], env.initial_qpos[:15].expand(n, 15))
+    assert int(el.max()) == 0
+    env.close()
+
+
+def test_missing_device_is_loud():
+    from gymnasium_robotics_b200 import _lib
+
+    L = _lib.lib()
+    import ctypes
+
+    h = ctypes.c_void_p()
+    rc = L.b200sim_create(None, 0, None, None, None, 1, 0, ctypes.byref(h))
+    assert rc != 0 and b"bad arguments" in L.b200sim_last_error(None)
