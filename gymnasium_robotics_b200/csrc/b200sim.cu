@@ -17,7 +17,7 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int WPB>
+template <int WPB, int NVP>
 __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restrict__ model_g, FetchTask task, int mode, int nraw,
                                                          int N, float* __restrict__ state, const float* __restrict__ actions,
                                                          const unsigned char* __restrict__ mask, float* __restrict__ obs,
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
   c.s = (float*)(smem + model_words) + (size_t)warp * h->scr_words;
   float a4[4] = {0, 0, 0, 0};
   if (actions) { for (int k = 0; k < 4; k++) a4[k] = actions[(size_t)env * 4 + k]; }
-  fetch_env_step(c, task, mode, nraw, state + (size_t)env * task.st_stride, a4, obs + (size_t)env * task.nobs,
+  fetch_env_step<NVP>(c, task, mode, nraw, state + (size_t)env * task.st_stride, a4, obs + (size_t)env * task.nobs,
                  achieved + (size_t)env * 3, desired + (size_t)env * 3, reward + env, success + env, info ? info + env : nullptr);
 }
 
@@ -84,6 +84,7 @@ struct b200sim {
   size_t smem_bytes = 0;
   int blocks = 0;
   long launches = 0;
+  int nvp = 32;
   std::string err;
 };
 
@@ -134,7 +135,11 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, "b200sim_create: cudaSetDevice failed", -7); }
   h->smem_bytes = ((size_t)dh->nwords + (size_t)B200_WPB * dh->scr_words) * 4;
   h->blocks = (num_envs + B200_WPB - 1) / B200_WPB;
-  cudaError_t e = cudaFuncSetAttribute(fetch_kernel<B200_WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  h->nvp = dh->nv <= 16 ? 16 : (dh->nv <= 24 ? 24 : 32);
+  cudaError_t e = cudaSuccess;
+  if (h->nvp == 16) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  else if (h->nvp == 24) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  else e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e != cudaSuccess) { std::string m = std::string("cudaFuncSetAttribute(smem=") + std::to_string(h->smem_bytes) + "): " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
   if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, (size_t)num_envs * t.st_stride * 4) != cudaSuccess) {
     delete h; return fail(nullptr, "b200sim_create: cudaMalloc failed", -9);
@@ -174,8 +179,11 @@ static int launch(b200sim* h, int mode, int nraw, const float* actions, const un
                   float* desired, float* reward, float* success, int* info, void* stream) {
   if (!obs || !achieved || !desired || !reward || !success) return fail(h, "output pointers must not be NULL", -1);
   CUDA_OK(cudaSetDevice(h->device));
-  fetch_kernel<B200_WPB><<<h->blocks, B200_WPB * 32, h->smem_bytes, (cudaStream_t)stream>>>(
-      h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info);
+#define B200_LAUNCH(NVP_)                                                                                   \
+  fetch_kernel<B200_WPB, NVP_><<<h->blocks, B200_WPB * 32, h->smem_bytes, (cudaStream_t)stream>>>(          \
+      h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info)
+  if (h->nvp == 16) B200_LAUNCH(16); else if (h->nvp == 24) B200_LAUNCH(24); else B200_LAUNCH(32);
+#undef B200_LAUNCH
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

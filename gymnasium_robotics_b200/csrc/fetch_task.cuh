@@ -111,6 +111,7 @@ HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float
 }
 
 // one env, one warp.  `st` is this env's state record; outputs are this env's rows.
+template <int NVP>
 HD void fetch_env_step(const Ctx& c, const FetchTask& t, int mode, int nraw, float* st, const float* action, float* obs,
                        float* achieved, float* desired, float* reward, float* success, int* iters_out) {
   const DMHead* h = c.h;
@@ -129,7 +130,7 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, int mode, int nraw, flo
     SYNC();
   }
   int nsub = mode == MODE_STEP ? t.n_substeps : (mode == MODE_RAW ? nraw : 0);
-  for (int s = 0; s < nsub; s++) { forward(c); euler_step(c); }
+  for (int s = 0; s < nsub; s++) { forward<NVP>(c); euler_step<NVP>(c); }
   if (mode == MODE_REFRESH || (mode == MODE_STEP && t.block_gripper) || nsub == 0) {
     if (mode == MODE_STEP && t.block_gripper) {
       if (c.lane == 0) { SF(qpos)[t.finger_qadr[0]] = 0.f; SF(qpos)[t.finger_qadr[1]] = 0.f; }

@@ -15,11 +15,13 @@
 #ifdef __CUDACC__
 #define HD __device__ __forceinline__
 #define HDN __device__ __noinline__
+#define STAGE __device__ __noinline__  // pipeline stages are real calls: keeps the kernel inside the instruction caches
 #define WARP_W 32
 #define SYNC() __syncwarp()
 #else
 #define HD static inline
 #define HDN static
+#define STAGE static
 #define WARP_W 1
 #define SYNC() do { } while (0)
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
@@ -151,7 +153,7 @@ HD int pidx(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j + 1)
 
 // ---------------------------------------------------------------------------------------------------------------
 // 1. kinematics (pointer jumping)
-HD void kinematics(const Ctx& c) {
+STAGE void kinematics(const Ctx c) {
   const DMHead* h = c.h;
   int nb = h->nb;
   float *A = SF(kinA), *B = SF(kinB);
@@ -240,7 +242,7 @@ HD void kinematics(const Ctx& c) {
 }
 
 // 2. spatial inertias and motion axes about `ref`; geom centres
-HD void com_quantities(const Ctx& c) {
+STAGE void com_quantities(const Ctx c) {
   const DMHead* h = c.h;
   const float* ref = h->ref;
   LANES(b, h->nb) {
@@ -302,7 +304,7 @@ HD void com_quantities(const Ctx& c) {
 }
 
 // 4. mass matrix, packed lower triangle
-HD void mass_matrix(const Ctx& c) {
+STAGE void mass_matrix(const Ctx c) {
   const DMHead* h = c.h;
   int nv = h->nv, nM = nv * (nv + 1) / 2;
   float* M = SF(M);
@@ -323,7 +325,7 @@ HD void mass_matrix(const Ctx& c) {
 }
 
 // velocity pass: b6[b] = sum_{j in ancdof(b)} cdof_j * vec_j
-HD void pass_V(const Ctx& c, const float* vec, float* out) {
+STAGE void pass_V(const Ctx c, const float* vec, float* out) {
   LANES(b, c.h->nb) {
     float v[6] = {0, 0, 0, 0, 0, 0};
     uint32_t m = MU(body_ancdof)[b];
@@ -334,7 +336,7 @@ HD void pass_V(const Ctx& c, const float* vec, float* out) {
 }
 
 // 7. smooth forces: fsmooth = passive - bias + actuation
-HD void smooth_forces(const Ctx& c) {
+STAGE void smooth_forces(const Ctx c) {
   const DMHead* h = c.h;
   int nv = h->nv, nb = h->nb;
   const float *qvel = SF(qvel), *qpos = SF(qpos);
@@ -579,7 +581,7 @@ HD void make_frame(float* f) {
   cross3(f + 6, f, y);
 }
 
-HD void collision(const Ctx& c) {
+STAGE void collision(const Ctx c) {
   const DMHead* h = c.h;
   int* cnt = SI(counters);
   int* cand = SI(cand);
@@ -699,7 +701,7 @@ HD int find_group(const Ctx& c, int ba, int bb) {  // lane 0 only
   return g;
 }
 
-HD void make_constraint(const Ctx& c) {
+STAGE void make_constraint(const Ctx c) {
   const DMHead* h = c.h;
   int* cnt = SI(counters);
   if (c.lane == 0) { cnt[CNT_NDR] = 0; cnt[CNT_NGRP] = 0; cnt[CNT_NWELD] = 0; }
@@ -810,7 +812,7 @@ HD void make_constraint(const Ctx& c) {
 
 // rows <- J * vec (+ optional scaling into the aref constants).  mode 0: C0 = B*(J qvel) + KIR ; mode 1: U = J a + C0 ; mode 2: JV = J s
 enum { RV_C0 = 0, RV_U = 1, RV_JV = 2 };
-HD void rows_from_vec(const Ctx& c, const float* vec, int mode) {
+STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
   const int* cnt = SI(counters);
   pass_V(c, vec, SF(b6));
   const float* V = SF(b6);
@@ -873,7 +875,7 @@ HD float contact_forces(float* cr, int dim) {
 }
 
 // forces for all rows at the current U; returns the total constraint cost (all lanes get the sum)
-HD float update_forces(const Ctx& c) {
+STAGE float update_forces(const Ctx c) {
   const int* cnt = SI(counters);
   float cost = 0;
   LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; cost += contact_forces(cr, ((const int*)cr)[C_DIM]); }
@@ -893,7 +895,7 @@ HD float update_forces(const Ctx& c) {
 }
 
 // fcon = J^T f from the stored base-row forces
-HD void pass_F(const Ctx& c, float* out) {
+STAGE void pass_F(const Ctx c, float* out) {
   const DMHead* h = c.h;
   const int* cnt = SI(counters);
   int ncon = cnt[CNT_NCON], nweld = cnt[CNT_NWELD], ndr = cnt[CNT_NDR];
@@ -935,7 +937,7 @@ HD void pass_F(const Ctx& c, float* out) {
   SYNC();
 }
 
-HD void mulM(const Ctx& c, const float* v, float* out) {
+STAGE void mulM(const Ctx c, const float* v, float* out) {
   int nv = c.h->nv;
   const float* M = SF(M);
   LANES(i, nv) {
@@ -947,7 +949,7 @@ HD void mulM(const Ctx& c, const float* v, float* out) {
 }
 
 // H = M + sum_g S_g^T K_g S_g  (+ dof rows on the diagonal blocks)
-HD void build_H(const Ctx& c) {
+STAGE void build_H(const Ctx c) {
   const DMHead* h = c.h;
   const int* cnt = SI(counters);
   int nv = h->nv, nM = nv * (nv + 1) / 2, ncon = cnt[CNT_NCON], nweld = cnt[CNT_NWELD], ngrp = cnt[CNT_NGRP], ndr = cnt[CNT_NDR];
@@ -1036,7 +1038,7 @@ HD void build_H(const Ctx& c) {
 }
 
 // in-place packed Cholesky H = L L^T, one lane per row
-HD void cholesky(const Ctx& c, float* H) {
+STAGE void cholesky(const Ctx c, float* H) {
   int n = c.h->nv;
   for (int k = 0; k < n; k++) {
     float hkk = H[k * (k + 1) / 2 + k];
@@ -1054,7 +1056,7 @@ HD void cholesky(const Ctx& c, float* H) {
   }
 }
 // x <- (L L^T)^-1 x
-HD void chol_solve(const Ctx& c, const float* L, float* x) {
+STAGE void chol_solve(const Ctx c, const float* L, float* x) {
   int n = c.h->nv;
   for (int k = 0; k < n; k++) {
     if (c.lane == (k % WARP_W)) x[k] = x[k] / L[k * (k + 1) / 2 + k];
@@ -1072,8 +1074,64 @@ HD void chol_solve(const Ctx& c, const float* L, float* x) {
   }
 }
 
+// x <- (A + hh*diag(dadd))^-1 x for the packed SPD matrix A.  CUDA: register-resident right-looking Cholesky, lane i owns
+// the full symmetric row i (lower part ends up as L, the frozen upper part gives L^T), columns travel by warp shuffle;
+// NVP is nv padded to a compile-time size (identity padding).  Host emulation: the shared-memory routines above.
+#ifdef __CUDACC__
+template <int NVP>
+__device__ __noinline__ void spd_solve(const Ctx c, const float* A, const float* dadd, float hh, float* x, float* scratchH) {
+  (void)scratchH;
+  const int nv = c.h->nv, i = c.lane;
+  const unsigned FULL = 0xffffffffu;
+  float h[NVP];
+  const int rowi = i * (i + 1) / 2;
+#pragma unroll
+  for (int j = 0; j < NVP; j++) {
+    float v = (i == j) ? 1.f : 0.f;
+    if (i < nv && j < nv) v = (j <= i) ? A[rowi + j] : A[j * (j + 1) / 2 + i];
+    if (dadd != nullptr && i == j && i < nv) v += hh * dadd[i];
+    h[j] = v;
+  }
+  float b = (i < nv) ? x[i] : 0.f;
+  float dinv = 1.f;
+#pragma unroll
+  for (int k = 0; k < NVP; k++) {
+    float hkk = __shfl_sync(FULL, h[k], k);
+    float inv = rsqrtf(fmaxf(hkk, 1e-30f));
+    float lik = (i > k) ? h[k] * inv : 0.f;
+    if (i == k) dinv = inv;
+    h[k] = (i > k) ? lik : h[k];
+#pragma unroll
+    for (int j = k + 1; j < NVP; j++) { float ljk = __shfl_sync(FULL, lik, j); h[j] = fmaf(-lik, ljk, h[j]); }
+  }
+#pragma unroll
+  for (int k = 0; k < NVP; k++) {  // L y = b
+    float yk = __shfl_sync(FULL, b * dinv, k);
+    b = (i > k) ? fmaf(-h[k], yk, b) : ((i == k) ? yk : b);
+  }
+  float sacc = 0.f, z = 0.f;
+#pragma unroll
+  for (int k = NVP - 1; k >= 0; k--) {  // L^T z = y, with l_kj = h_j[k] * dinv_j for k > j
+    float zk = __shfl_sync(FULL, (b - dinv * sacc) * dinv, k);
+    if (i < k) sacc = fmaf(h[k], zk, sacc);
+    if (i == k) z = zk;
+  }
+  if (i < nv) x[i] = z;
+  __syncwarp();
+}
+#else
+template <int NVP>
+static inline void spd_solve(const Ctx& c, const float* A, const float* dadd, float hh, float* x, float* scratchH) {
+  int nv = c.h->nv, nM = nv * (nv + 1) / 2;
+  for (int i = 0; i < nM; i++) scratchH[i] = A[i];
+  if (dadd) for (int i = 0; i < nv; i++) scratchH[i * (i + 1) / 2 + i] += hh * dadd[i];
+  cholesky(c, scratchH);
+  chol_solve(c, scratchH, x);
+}
+#endif
+
 // line-search evaluation: cost(alpha) - gauss constant, first and second derivative
-HD void ls_eval(const Ctx& c, float alpha, float g1, float g2, float* out) {
+STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
   const int* cnt = SI(counters);
   float cost = 0, d1 = 0, d2 = 0;
   LANES(i, cnt[CNT_NCON]) {
@@ -1105,7 +1163,7 @@ HD void ls_eval(const Ctx& c, float alpha, float g1, float g2, float* out) {
 }
 
 // returns alpha; *improve = cost(0) - cost(alpha)
-HD float linesearch(const Ctx& c, float g1, float g2, float gtol, int maxit, float* improve) {
+STAGE float linesearch(const Ctx c, float g1, float g2, float gtol, int maxit, float* improve) {
   float p0[3], p[3];
   ls_eval(c, 0.f, g1, g2, p0);
   *improve = 0;
@@ -1126,7 +1184,8 @@ HD float linesearch(const Ctx& c, float g1, float g2, float gtol, int maxit, flo
   return best;
 }
 
-HD void solve_newton(const Ctx& c) {
+template <int NVP>
+STAGE void solve_newton(const Ctx c) {
   const DMHead* h = c.h;
   int nv = h->nv;
   int* cnt = SI(counters);
@@ -1159,10 +1218,9 @@ HD void solve_newton(const Ctx& c) {
     if (iter > 0 && (scale * improvement < tol || scale * gnorm < tol)) break;
     if (iter >= h->iterations || iter >= 12) break;
     build_H(c);
-    cholesky(c, SF(H));
     LANES(i, nv) search[i] = -grad[i];
     SYNC();
-    chol_solve(c, SF(H), search);
+    spd_solve<NVP>(c, SF(H), nullptr, 0.f, search, SF(H));
     mulM(c, search, Mv);
     rows_from_vec(c, search, RV_JV);
     float q1 = 0, q2 = 0, sn = 0;
@@ -1184,30 +1242,29 @@ HD void solve_newton(const Ctx& c) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward dynamics (mj_forward) and one Euler sub-step
-HD void forward(const Ctx& c) {
+template <int NVP>
+STAGE void forward(const Ctx c) {
   kinematics(c);
   com_quantities(c);
   mass_matrix(c);
   collision(c);
   make_constraint(c);
   smooth_forces(c);
-  solve_newton(c);
+  solve_newton<NVP>(c);
 }
 
-HD void euler_step(const Ctx& c) {
+template <int NVP>
+STAGE void euler_step(const Ctx c) {
   const DMHead* h = c.h;
-  int nv = h->nv, nM = nv * (nv + 1) / 2;
+  int nv = h->nv;
   float hh = h->timestep;
   float* H = SF(H);
   float* x = SF(tmpv);
   LANES(i, nv) SF(warm)[i] = SF(qacc)[i];
   if (h->any_damping) {
-    LANES(i, nM) H[i] = SF(M)[i];
+    LANES(i, nv) x[i] = SF(fsmooth)[i] + SF(fcon)[i];
     SYNC();
-    LANES(i, nv) { H[i * (i + 1) / 2 + i] += hh * MF(dof_damping)[i]; x[i] = SF(fsmooth)[i] + SF(fcon)[i]; }
-    SYNC();
-    cholesky(c, H);
-    chol_solve(c, H, x);
+    spd_solve<NVP>(c, SF(M), MF(dof_damping), hh, x, H);
   } else {
     LANES(i, nv) x[i] = SF(qacc)[i];
     SYNC();

@@ -31,9 +31,14 @@ def oracle_state_record(env, orc):
 
 
 def inject_oracle_state(env, oracles):
-    recs = np.stack([oracle_state_record(env, o) for o in oracles])
-    env.backend.state.copy_(torch.as_tensor(recs, dtype=torch.float32))
-    return env.set_state(env.backend.state.clone())
+    recs = torch.as_tensor(np.stack([oracle_state_record(env, o) for o in oracles]), dtype=torch.float32)
+    env.backend.state.copy_(recs)
+    obs = env.set_state(env.backend.state.clone())
+    # set_state refreshes derived data, which re-anchors the stored "pose of the welded body as of the last forward
+    # pass" to the injected qpos; the oracle's value is one sub-step stale: restore it
+    lay = env.backend.layout
+    env.backend.state[:, lay["pose"]:lay["pose"] + 7] = recs[:, lay["pose"]:lay["pose"] + 7].to(env.backend.state.device)
+    return obs
 
 
 def oracle_obs_vector(obs):
