@@ -52,15 +52,15 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
   }
   const DMHead* h = (const DMHead*)smem;
   const int env = blockIdx.x * WPB + warp;
-  if (env >= N) return;
-  if (mask && !mask[env]) return;
+  const bool active = env < N && !(mask && !mask[env]);  // warp-uniform
   Ctx c;
   c.mw = smem; c.h = h; c.lane = lane;
   c.s = (float*)(smem + model_words) + (size_t)warp * h->scr_words;
   float a4[4] = {0, 0, 0, 0};
-  if (actions) { for (int k = 0; k < 4; k++) a4[k] = actions[(size_t)env * 4 + k]; }
-  fetch_env_step<NVP>(c, task, mode, nraw, state + (size_t)env * task.st_stride, a4, obs + (size_t)env * task.nobs,
-                 achieved + (size_t)env * 3, desired + (size_t)env * 3, reward + env, success + env, info ? info + env : nullptr);
+  const size_t e = active ? (size_t)env : 0;
+  if (actions && active) { for (int k = 0; k < 4; k++) a4[k] = actions[e * 4 + k]; }
+  fetch_env_step<NVP>(c, task, active, mode, nraw, state + e * task.st_stride, a4, obs + e * task.nobs, achieved + e * 3,
+                      desired + e * 3, reward + e, success + e, info ? info + e : nullptr);
 }
 
 __global__ void reward_kernel(const float* __restrict__ ag, const float* __restrict__ dg, int M, float thr, int dense,

@@ -110,27 +110,34 @@ HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float
   }
 }
 
-// one env, one warp.  `st` is this env's state record; outputs are this env's rows.
+// one env, one warp.  `st` is this env's state record; outputs are this env's rows.  `active` is warp-uniform: idle
+// warps run the same control flow (for the block-wide alignment barriers) but touch no memory.
 template <int NVP>
-HD void fetch_env_step(const Ctx& c, const FetchTask& t, int mode, int nraw, float* st, const float* action, float* obs,
+HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, int nraw, float* st, const float* action, float* obs,
                        float* achieved, float* desired, float* reward, float* success, int* iters_out) {
   const DMHead* h = c.h;
-  load_state(c, t, st);
-  if (mode == MODE_STEP) {
-    // _set_action: clip, scale, mocap <- last forward pose of the welded body + delta, position actuators relative
-    float a[4];
-    for (int k = 0; k < 4; k++) a[k] = fminf(fmaxf(action[k], -1.f), 1.f);
-    if (c.lane == 0) {
-      for (int k = 0; k < 3; k++) SF(mocap_pos)[k] = st[t.st_pose + k] + 0.05f * a[k];
-      const float rot[4] = {1.f, 0.f, 1.f, 0.f};
-      for (int k = 0; k < 4; k++) SF(mocap_quat)[k] = st[t.st_pose + 3 + k] + rot[k];
-      float g = t.block_gripper ? 0.f : a[3];
-      for (int i = 0; i < h->nu; i++) SF(ctrl)[i] = SF(qpos)[MI(jnt_qposadr)[MI(act_trnid)[i]]] + g;
+  if (active) {
+    load_state(c, t, st);
+    if (mode == MODE_STEP) {
+      // _set_action: clip, scale, mocap <- last forward pose of the welded body + delta, position actuators relative
+      float a[4];
+      for (int k = 0; k < 4; k++) a[k] = fminf(fmaxf(action[k], -1.f), 1.f);
+      if (c.lane == 0) {
+        for (int k = 0; k < 3; k++) SF(mocap_pos)[k] = st[t.st_pose + k] + 0.05f * a[k];
+        const float rot[4] = {1.f, 0.f, 1.f, 0.f};
+        for (int k = 0; k < 4; k++) SF(mocap_quat)[k] = st[t.st_pose + 3 + k] + rot[k];
+        float g = t.block_gripper ? 0.f : a[3];
+        for (int i = 0; i < h->nu; i++) SF(ctrl)[i] = SF(qpos)[MI(jnt_qposadr)[MI(act_trnid)[i]]] + g;
+      }
+      SYNC();
     }
-    SYNC();
   }
   int nsub = mode == MODE_STEP ? t.n_substeps : (mode == MODE_RAW ? nraw : 0);
-  for (int s = 0; s < nsub; s++) { forward<NVP>(c); euler_step<NVP>(c); }
+  for (int s = 0; s < nsub; s++) {
+    forward<NVP>(c, active);
+    if (active) euler_step<NVP>(c);
+  }
+  if (!active) return;
   if (mode == MODE_REFRESH || (mode == MODE_STEP && t.block_gripper) || nsub == 0) {
     if (mode == MODE_STEP && t.block_gripper) {
       if (c.lane == 0) { SF(qpos)[t.finger_qadr[0]] = 0.f; SF(qpos)[t.finger_qadr[1]] = 0.f; }

@@ -16,14 +16,28 @@
 #define HD __device__ __forceinline__
 #define HDN __device__ __noinline__
 #define STAGE __device__ __noinline__  // pipeline stages are real calls: keeps the kernel inside the instruction caches
+#define ASSUME_SHARED_PTR(p) __builtin_assume(__isShared(p))
+#define ASSUME_SHARED(c) do { __builtin_assume(__isShared((c).s)); __builtin_assume(__isShared((c).mw)); __builtin_assume(__isShared((c).h)); } while (0)
 #define WARP_W 32
 #define SYNC() __syncwarp()
+// block-wide alignment points: keep the warps of a block inside the same code window (instruction-cache locality)
+#ifdef B200_BLOCK_ALIGN
+#define ALIGN() __syncthreads()
+#define ALIGN_OR(p) __syncthreads_or(p)
+#else
+#define ALIGN() do { } while (0)
+#define ALIGN_OR(p) (p)
+#endif
 #else
 #define HD static inline
 #define HDN static
 #define STAGE static
+#define ASSUME_SHARED(c) do { } while (0)
+#define ASSUME_SHARED_PTR(p) do { } while (0)
 #define WARP_W 1
 #define SYNC() do { } while (0)
+#define ALIGN() do { } while (0)
+#define ALIGN_OR(p) (p)
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #endif
 
@@ -154,6 +168,7 @@ HD int pidx(int i, int j) { return i >= j ? (i * (i + 1)) / 2 + j : (j * (j + 1)
 // ---------------------------------------------------------------------------------------------------------------
 // 1. kinematics (pointer jumping)
 STAGE void kinematics(const Ctx c) {
+  ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int nb = h->nb;
   float *A = SF(kinA), *B = SF(kinB);
@@ -243,6 +258,7 @@ STAGE void kinematics(const Ctx c) {
 
 // 2. spatial inertias and motion axes about `ref`; geom centres
 STAGE void com_quantities(const Ctx c) {
+  ASSUME_SHARED(c);
   const DMHead* h = c.h;
   const float* ref = h->ref;
   LANES(b, h->nb) {
@@ -305,6 +321,7 @@ STAGE void com_quantities(const Ctx c) {
 
 // 4. mass matrix, packed lower triangle
 STAGE void mass_matrix(const Ctx c) {
+  ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int nv = h->nv, nM = nv * (nv + 1) / 2;
   float* M = SF(M);
@@ -326,6 +343,8 @@ STAGE void mass_matrix(const Ctx c) {
 
 // velocity pass: b6[b] = sum_{j in ancdof(b)} cdof_j * vec_j
 STAGE void pass_V(const Ctx c, const float* vec, float* out) {
+  ASSUME_SHARED(c);
+  ASSUME_SHARED_PTR(vec); ASSUME_SHARED_PTR(out);
   LANES(b, c.h->nb) {
     float v[6] = {0, 0, 0, 0, 0, 0};
     uint32_t m = MU(body_ancdof)[b];
@@ -337,6 +356,7 @@ STAGE void pass_V(const Ctx c, const float* vec, float* out) {
 
 // 7. smooth forces: fsmooth = passive - bias + actuation
 STAGE void smooth_forces(const Ctx c) {
+  ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int nv = h->nv, nb = h->nb;
   const float *qvel = SF(qvel), *qpos = SF(qpos);
@@ -435,7 +455,8 @@ HD int clip_poly(const float (*in)[2], int n, float (*out)[2], int axis, float b
   return k;
 }
 
-HDN void collide_box_box(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
+HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
+  ASSUME_SHARED(c);
   float pa[3], Ra[9], pb[3], Rb[9];
   geom_pose(c, g1, pa, Ra); geom_pose(c, g2, pb, Rb);
   const float* ha = MF(geom_size) + 3 * g1;
@@ -582,6 +603,7 @@ HD void make_frame(float* f) {
 }
 
 STAGE void collision(const Ctx c) {
+  ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int* cnt = SI(counters);
   int* cand = SI(cand);
@@ -659,7 +681,8 @@ STAGE void collision(const Ctx c) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // 6. constraint rows
-HD float impedance(const float* solimp, float pos, float margin) {
+HDN float impedance(const float* solimp, float pos, float margin) {
+  ASSUME_SHARED_PTR(solimp);
   float d0 = fminf(fmaxf(solimp[0], B200_MINIMP), B200_MAXIMP), d1 = fminf(fmaxf(solimp[1], B200_MINIMP), B200_MAXIMP);
   float width = fmaxf(solimp[2], 0.f), mid = fminf(fmaxf(solimp[3], B200_MINIMP), B200_MAXIMP), power = fmaxf(solimp[4], 1.f);
   if (d0 == d1 || width <= B200_MINVAL) return 0.5f * (d0 + d1);
@@ -702,6 +725,7 @@ HD int find_group(const Ctx& c, int ba, int bb) {  // lane 0 only
 }
 
 STAGE void make_constraint(const Ctx c) {
+  ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int* cnt = SI(counters);
   if (c.lane == 0) { cnt[CNT_NDR] = 0; cnt[CNT_NGRP] = 0; cnt[CNT_NWELD] = 0; }
@@ -813,6 +837,8 @@ STAGE void make_constraint(const Ctx c) {
 // rows <- J * vec (+ optional scaling into the aref constants).  mode 0: C0 = B*(J qvel) + KIR ; mode 1: U = J a + C0 ; mode 2: JV = J s
 enum { RV_C0 = 0, RV_U = 1, RV_JV = 2 };
 STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
+  ASSUME_SHARED(c);
+  ASSUME_SHARED_PTR(vec);
   const int* cnt = SI(counters);
   pass_V(c, vec, SF(b6));
   const float* V = SF(b6);
@@ -876,6 +902,7 @@ HD float contact_forces(float* cr, int dim) {
 
 // forces for all rows at the current U; returns the total constraint cost (all lanes get the sum)
 STAGE float update_forces(const Ctx c) {
+  ASSUME_SHARED(c);
   const int* cnt = SI(counters);
   float cost = 0;
   LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; cost += contact_forces(cr, ((const int*)cr)[C_DIM]); }
@@ -896,6 +923,8 @@ STAGE float update_forces(const Ctx c) {
 
 // fcon = J^T f from the stored base-row forces
 STAGE void pass_F(const Ctx c, float* out) {
+  ASSUME_SHARED(c);
+  ASSUME_SHARED_PTR(out);
   const DMHead* h = c.h;
   const int* cnt = SI(counters);
   int ncon = cnt[CNT_NCON], nweld = cnt[CNT_NWELD], ndr = cnt[CNT_NDR];
@@ -938,6 +967,8 @@ STAGE void pass_F(const Ctx c, float* out) {
 }
 
 STAGE void mulM(const Ctx c, const float* v, float* out) {
+  ASSUME_SHARED(c);
+  ASSUME_SHARED_PTR(v); ASSUME_SHARED_PTR(out);
   int nv = c.h->nv;
   const float* M = SF(M);
   LANES(i, nv) {
@@ -950,6 +981,7 @@ STAGE void mulM(const Ctx c, const float* v, float* out) {
 
 // H = M + sum_g S_g^T K_g S_g  (+ dof rows on the diagonal blocks)
 STAGE void build_H(const Ctx c) {
+  ASSUME_SHARED(c);
   const DMHead* h = c.h;
   const int* cnt = SI(counters);
   int nv = h->nv, nM = nv * (nv + 1) / 2, ncon = cnt[CNT_NCON], nweld = cnt[CNT_NWELD], ngrp = cnt[CNT_NGRP], ndr = cnt[CNT_NDR];
@@ -1039,6 +1071,7 @@ STAGE void build_H(const Ctx c) {
 
 // in-place packed Cholesky H = L L^T, one lane per row
 STAGE void cholesky(const Ctx c, float* H) {
+  ASSUME_SHARED(c);
   int n = c.h->nv;
   for (int k = 0; k < n; k++) {
     float hkk = H[k * (k + 1) / 2 + k];
@@ -1057,6 +1090,7 @@ STAGE void cholesky(const Ctx c, float* H) {
 }
 // x <- (L L^T)^-1 x
 STAGE void chol_solve(const Ctx c, const float* L, float* x) {
+  ASSUME_SHARED(c);
   int n = c.h->nv;
   for (int k = 0; k < n; k++) {
     if (c.lane == (k % WARP_W)) x[k] = x[k] / L[k * (k + 1) / 2 + k];
@@ -1080,26 +1114,38 @@ STAGE void chol_solve(const Ctx c, const float* L, float* x) {
 #ifdef __CUDACC__
 template <int NVP>
 __device__ __noinline__ void spd_solve(const Ctx c, const float* A, const float* dadd, float hh, float* x, float* scratchH) {
+  ASSUME_SHARED(c);
+  __builtin_assume(__isShared(A)); __builtin_assume(__isShared(x)); if (dadd) __builtin_assume(__isShared(dadd));
   (void)scratchH;
   const int nv = c.h->nv, i = c.lane;
   const unsigned FULL = 0xffffffffu;
   float h[NVP];
   const int rowi = i * (i + 1) / 2;
+  const bool live = i < nv;
+  // branch-free loads (clamped index + select) so the warp stays converged for the shuffles below
 #pragma unroll
   for (int j = 0; j < NVP; j++) {
-    float v = (i == j) ? 1.f : 0.f;
-    if (i < nv && j < nv) v = (j <= i) ? A[rowi + j] : A[j * (j + 1) / 2 + i];
-    if (dadd != nullptr && i == j && i < nv) v += hh * dadd[i];
+    const bool in = live && j < nv;
+    int idx = (j <= i) ? rowi + j : j * (j + 1) / 2 + i;
+    idx = in ? idx : 0;
+    float v = A[idx];
+    v = in ? v : ((i == j) ? 1.f : 0.f);
     h[j] = v;
   }
-  float b = (i < nv) ? x[i] : 0.f;
+  if (dadd != nullptr) {
+    float dd = hh * dadd[live ? i : 0];
+#pragma unroll
+    for (int j = 0; j < NVP; j++) h[j] += (live && i == j) ? dd : 0.f;
+  }
+  float b = x[live ? i : 0];
+  b = live ? b : 0.f;
   float dinv = 1.f;
 #pragma unroll
   for (int k = 0; k < NVP; k++) {
     float hkk = __shfl_sync(FULL, h[k], k);
     float inv = rsqrtf(fmaxf(hkk, 1e-30f));
     float lik = (i > k) ? h[k] * inv : 0.f;
-    if (i == k) dinv = inv;
+    dinv = (i == k) ? inv : dinv;
     h[k] = (i > k) ? lik : h[k];
 #pragma unroll
     for (int j = k + 1; j < NVP; j++) { float ljk = __shfl_sync(FULL, lik, j); h[j] = fmaf(-lik, ljk, h[j]); }
@@ -1107,14 +1153,16 @@ __device__ __noinline__ void spd_solve(const Ctx c, const float* A, const float*
 #pragma unroll
   for (int k = 0; k < NVP; k++) {  // L y = b
     float yk = __shfl_sync(FULL, b * dinv, k);
-    b = (i > k) ? fmaf(-h[k], yk, b) : ((i == k) ? yk : b);
+    float bn = fmaf(-h[k], yk, b);
+    b = (i > k) ? bn : ((i == k) ? yk : b);
   }
   float sacc = 0.f, z = 0.f;
 #pragma unroll
   for (int k = NVP - 1; k >= 0; k--) {  // L^T z = y, with l_kj = h_j[k] * dinv_j for k > j
     float zk = __shfl_sync(FULL, (b - dinv * sacc) * dinv, k);
-    if (i < k) sacc = fmaf(h[k], zk, sacc);
-    if (i == k) z = zk;
+    float sn = fmaf(h[k], zk, sacc);
+    sacc = (i < k) ? sn : sacc;
+    z = (i == k) ? zk : z;
   }
   if (i < nv) x[i] = z;
   __syncwarp();
@@ -1132,6 +1180,7 @@ static inline void spd_solve(const Ctx& c, const float* A, const float* dadd, fl
 
 // line-search evaluation: cost(alpha) - gauss constant, first and second derivative
 STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
+  ASSUME_SHARED(c);
   const int* cnt = SI(counters);
   float cost = 0, d1 = 0, d2 = 0;
   LANES(i, cnt[CNT_NCON]) {
@@ -1164,6 +1213,7 @@ STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
 
 // returns alpha; *improve = cost(0) - cost(alpha)
 STAGE float linesearch(const Ctx c, float g1, float g2, float gtol, int maxit, float* improve) {
+  ASSUME_SHARED(c);
   float p0[3], p[3];
   ls_eval(c, 0.f, g1, g2, p0);
   *improve = 0;
@@ -1184,77 +1234,110 @@ STAGE float linesearch(const Ctx c, float g1, float g2, float gtol, int maxit, f
   return best;
 }
 
+// Newton solver, split so that the iteration loop can be driven block-uniformly (see forward()).
+STAGE void newton_begin(const Ctx c) {
+  ASSUME_SHARED(c);
+  int nv = c.h->nv;
+  LANES(i, nv) SF(qacc)[i] = SF(warm)[i];
+  SYNC();
+  rows_from_vec(c, SF(qvel), RV_C0);
+  mulM(c, SF(qacc), SF(Ma));
+  rows_from_vec(c, SF(qacc), RV_U);
+}
+
+// forces, gradient and the convergence tests at the current point; returns 1 when the solver is finished
+STAGE int newton_check(const Ctx c, int iter, float improvement) {
+  ASSUME_SHARED(c);
+  const DMHead* h = c.h;
+  int nv = h->nv;
+  float *Ma = SF(Ma), *grad = SF(grad), *fs = SF(fsmooth), *fcon = SF(fcon);
+  float scale = 1.0f / (h->meaninertia * (float)(nv > 1 ? nv : 1));
+  float tol = fmaxf(h->tolerance, 1e-6f);  // single-precision floor for the convergence tests
+  update_forces(c);
+  pass_F(c, fcon);
+  float g2sum = 0, f2sum = 0;
+  LANES(i, nv) {
+    float g = Ma[i] - fs[i] - fcon[i], f = fabsf(Ma[i]) + fabsf(fs[i]) + fabsf(fcon[i]);
+    grad[i] = g; g2sum += g * g; f2sum += f * f;
+  }
+  SYNC();
+  float gnorm = sqrtf(wsum(g2sum)), fnorm = sqrtf(wsum(f2sum));
+#if defined(B200_DEBUG_SOLVER) && !defined(__CUDACC__)
+  printf("  iter %d gnorm %.3e fnorm %.3e improvement %.3e\n", iter, gnorm, fnorm, improvement);
+#endif
+  // single-precision floor: the gradient cannot be resolved below ~eps32 * (|M a| + |f_smooth| + |f_constraint|)
+  if (gnorm < 2e-6f * fnorm) return 1;
+  if (iter > 0 && (scale * improvement < tol || scale * gnorm < tol)) return 1;
+  if (iter >= h->iterations || iter >= 12) return 1;
+  return 0;
+}
+
+// Newton direction; returns 0 if the direction vanished
 template <int NVP>
-STAGE void solve_newton(const Ctx c) {
+STAGE void newton_direction(const Ctx c) {
+  ASSUME_SHARED(c);
+  int nv = c.h->nv;
+  build_H(c);
+  LANES(i, nv) SF(search)[i] = -SF(grad)[i];
+  SYNC();
+  spd_solve<NVP>(c, SF(H), nullptr, 0.f, SF(search), SF(H));
+}
+
+// exact line search and move; returns 1 when the solver must stop (no progress possible), *improvement updated
+STAGE int newton_move(const Ctx c, float* improvement) {
+  ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int nv = h->nv;
   int* cnt = SI(counters);
-  float *a = SF(qacc), *Ma = SF(Ma), *Mv = SF(Mv), *grad = SF(grad), *search = SF(search), *fs = SF(fsmooth), *fcon = SF(fcon);
+  float *a = SF(qacc), *Ma = SF(Ma), *Mv = SF(Mv), *search = SF(search), *fs = SF(fsmooth);
   float scale = 1.0f / (h->meaninertia * (float)(nv > 1 ? nv : 1));
-  LANES(i, nv) a[i] = SF(warm)[i];
+  mulM(c, search, Mv);
+  rows_from_vec(c, search, RV_JV);
+  float q1 = 0, q2 = 0, sn = 0;
+  LANES(i, nv) { q1 += search[i] * (Ma[i] - fs[i]); q2 += 0.5f * search[i] * Mv[i]; sn += search[i] * search[i]; }
+  q1 = wsum(q1); q2 = wsum(q2); sn = sqrtf(wsum(sn));
+  if (sn < 1e-20f) return 1;
+  float gtol = h->tolerance * h->ls_tolerance * sn / scale;
+  float alpha = linesearch(c, q1, q2, gtol, h->ls_iterations < 20 ? h->ls_iterations : 20, improvement);
+  if (alpha == 0.f) return 1;
+  LANES(i, nv) { a[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+  LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 6; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
+  LANES(i, cnt[CNT_NWELD] * 6) { float* wr = SF(weld) + (i / 6) * WELD_WORDS; wr[W_JAR + i % 6] += alpha * wr[W_JV + i % 6]; }
+  LANES(i, cnt[CNT_NDR]) { float* dr = SF(dofrow) + i * DR_WORDS; dr[DR_JAR] += alpha * dr[DR_JV]; }
   SYNC();
-  rows_from_vec(c, SF(qvel), RV_C0);
-  mulM(c, a, Ma);
-  rows_from_vec(c, a, RV_U);
-  float improvement = 0;
-  int iter = 0;
-  // single-precision floor for the convergence tests (fp64 reference uses `tolerance` directly)
-  float tol = fmaxf(h->tolerance, 1e-6f);
-  for (;; iter++) {
-    update_forces(c);
-    pass_F(c, fcon);
-    float g2sum = 0, f2sum = 0;
-    LANES(i, nv) {
-      float g = Ma[i] - fs[i] - fcon[i], f = fabsf(Ma[i]) + fabsf(fs[i]) + fabsf(fcon[i]);
-      grad[i] = g; g2sum += g * g; f2sum += f * f;
-    }
-    SYNC();
-    float gnorm = sqrtf(wsum(g2sum)), fnorm = sqrtf(wsum(f2sum));
-#if defined(B200_DEBUG_SOLVER) && !defined(__CUDACC__)
-    printf("  iter %d gnorm %.3e fnorm %.3e improvement %.3e\n", iter, gnorm, fnorm, improvement);
-#endif
-    // single-precision floor: the gradient cannot be resolved below ~eps32 * (|M a| + |f_smooth| + |f_constraint|)
-    if (gnorm < 2e-6f * fnorm) break;
-    if (iter > 0 && (scale * improvement < tol || scale * gnorm < tol)) break;
-    if (iter >= h->iterations || iter >= 12) break;
-    build_H(c);
-    LANES(i, nv) search[i] = -grad[i];
-    SYNC();
-    spd_solve<NVP>(c, SF(H), nullptr, 0.f, search, SF(H));
-    mulM(c, search, Mv);
-    rows_from_vec(c, search, RV_JV);
-    float q1 = 0, q2 = 0, sn = 0;
-    LANES(i, nv) { q1 += search[i] * (Ma[i] - fs[i]); q2 += 0.5f * search[i] * Mv[i]; sn += search[i] * search[i]; }
-    q1 = wsum(q1); q2 = wsum(q2); sn = sqrtf(wsum(sn));
-    if (sn < 1e-20f) break;
-    float gtol = h->tolerance * h->ls_tolerance * sn / scale;
-    float alpha = linesearch(c, q1, q2, gtol, h->ls_iterations < 20 ? h->ls_iterations : 20, &improvement);
-    if (alpha == 0.f) break;
-    LANES(i, nv) { a[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
-    LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 6; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
-    LANES(i, cnt[CNT_NWELD] * 6) { float* wr = SF(weld) + (i / 6) * WELD_WORDS; wr[W_JAR + i % 6] += alpha * wr[W_JV + i % 6]; }
-    LANES(i, cnt[CNT_NDR]) { float* dr = SF(dofrow) + i * DR_WORDS; dr[DR_JAR] += alpha * dr[DR_JV]; }
-    SYNC();
-  }
-  if (c.lane == 0) cnt[CNT_ITERS] += iter;
-  SYNC();
+  if (c.lane == 0) cnt[CNT_ITERS] += 1;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward dynamics (mj_forward) and one Euler sub-step
+// One forward pass.  `active` is warp-uniform; idle warps (no env, or masked out) only take part in the block-wide
+// alignment barriers, so every warp of the block executes the same barrier sequence.  The Newton loop runs until every
+// warp of the block has converged (converged warps idle through the remaining rounds).
 template <int NVP>
-STAGE void forward(const Ctx c) {
-  kinematics(c);
-  com_quantities(c);
-  mass_matrix(c);
-  collision(c);
-  make_constraint(c);
-  smooth_forces(c);
-  solve_newton<NVP>(c);
+HD void forward(const Ctx c, bool active) {
+  ALIGN();
+  if (active) { kinematics(c); com_quantities(c); mass_matrix(c); }
+  ALIGN();
+  if (active) collision(c);
+  ALIGN();
+  if (active) { make_constraint(c); smooth_forces(c); newton_begin(c); }
+  int done = active ? 0 : 1;
+  float improvement = 0;
+  for (int iter = 0;; iter++) {
+    ALIGN();
+    if (!done) done = newton_check(c, iter, improvement);
+    if (!ALIGN_OR(!done)) break;
+    if (!done) newton_direction<NVP>(c);
+    ALIGN();
+    if (!done) done = newton_move(c, &improvement) ? 2 : 0;
+    // a warp that stopped in newton_move still needs forces consistent with its final point: they are (no move made)
+  }
 }
 
 template <int NVP>
 STAGE void euler_step(const Ctx c) {
+  ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int nv = h->nv;
   float hh = h->timestep;

@@ -38,14 +38,14 @@ int hostsim_offset(void* p, const char* name) {
 #undef X
   return -1;
 }
-void hostsim_forward(void* p) { forward<32>(((HostSim*)p)->ctx); }
-void hostsim_step(void* p, int n) { for (int i = 0; i < n; i++) { forward<32>(((HostSim*)p)->ctx); euler_step<32>(((HostSim*)p)->ctx); } }
+void hostsim_forward(void* p) { forward<32>(((HostSim*)p)->ctx, true); }
+void hostsim_step(void* p, int n) { for (int i = 0; i < n; i++) { forward<32>(((HostSim*)p)->ctx, true); euler_step<32>(((HostSim*)p)->ctx); } }
 void hostsim_kinematics(void* p) { kinematics(((HostSim*)p)->ctx); com_quantities(((HostSim*)p)->ctx); mass_matrix(((HostSim*)p)->ctx); }
 int hostsim_task_size() { return (int)sizeof(FetchTask); }
 int hostsim_env_step(void* p, const FetchTask* t, int mode, int nraw, float* st, const float* action, float* obs, float* achieved,
                      float* desired, float* reward, float* success) {
   int it = 0;
-  fetch_env_step<32>(((HostSim*)p)->ctx, *t, mode, nraw, st, action, obs, achieved, desired, reward, success, &it);
+  fetch_env_step<32>(((HostSim*)p)->ctx, *t, true, mode, nraw, st, action, obs, achieved, desired, reward, success, &it);
   return it;
 }
 }
