@@ -68,7 +68,7 @@ def run_reference(args, quiet=False):
     import numpy as np
 
     cores = max(1, os.cpu_count() or 1)
-    per = max(1, args.sample_envs // cores)
+    per = max(1, max(args.sample_envs, 16 * cores) // cores)  # >= 16 envs per worker so IPC does not dominate
     nenv = per * cores
     ctx = mp.get_context("fork")
     pools = [ctx.Pool(1, initializer=_worker_init, initargs=(per, 1000 * w)) for w in range(cores)]

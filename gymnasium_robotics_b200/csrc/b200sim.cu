@@ -12,7 +12,7 @@
 #include "fetch_task.cuh"
 
 #ifndef B200_WPB
-#define B200_WPB 4
+#define B200_WPB 14
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -1,0 +1,31 @@
+"""Env-level data parallelism across GPUs: contiguous env-index ranges per rank, no data-path
+collective; an optional gather of the per-step outputs to one rank.  Works with any torch.distributed backend
+(NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def local_env_range(num_envs_total: int, rank: int, world_size: int):
+    """Rank r owns [r*n, (r+1)*n) with n = ceil(N / world); the last rank may own fewer."""
+    n = -(-num_envs_total // world_size)
+    lo = min(rank * n, num_envs_total)
+    return lo, min(lo + n, num_envs_total)
+
+
+def env_seeds(seed0: int, rank: int, world_size: int, num_envs_total: int):
+    """Seeds `seed0 + global env index`, so results do not depend on the world size."""
+    lo, hi = local_env_range(num_envs_total, rank, world_size)
+    return list(range(seed0 + lo, seed0 + hi))
+
+
+def gather_step_outputs(obs: dict, reward: torch.Tensor, dst: int = 0):
+    """all_gather `observation | achieved_goal | desired_goal | reward` rows (equal local sizes) and return the
+    [world*n, dim] tensor on every rank (rank `dst` is the consumer)."""
+    packed = torch.cat([obs["observation"], obs["achieved_goal"], obs["desired_goal"], reward[:, None]], dim=1).contiguous()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return packed
+    out = torch.empty((dist.get_world_size() * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed)
+    return out

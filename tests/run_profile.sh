@@ -1,0 +1,11 @@
+#!/bin/bash
+# GPU-box recipe for the committed profile summaries (see profiles/README.md).  Usage: bash tests/run_profile.sh <tag>
+tag=${1:-r1}
+mkdir -p gpurun_out
+# 1. every launch with its device time (shares, not absolutes)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv \
+    python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_${tag}.log 2>&1
+# 2. the step kernel, full set, once
+ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 10 -c 1 -o gpurun_out/prof_${tag} \
+    python tests/prof_step.py 4096 12 > gpurun_out/ncu_${tag}.log 2>&1
+tail -2 gpurun_out/ncu_${tag}.log

@@ -1,0 +1,132 @@
+"""Host logic of FetchVectorEnv on CPU: the kernel source runs through the WARP_W == 1 emulation backend
+(tests/hostsim_backend.py), so reset sampling, seeding, TimeLimit, autoreset and the GoalEnv contract are covered
+without a GPU -- and the emulated kernel arithmetic is compared with the fp64 oracle env along the way."""
+import numpy as np
+import pytest
+import torch
+
+from gymnasium_robotics_b200.fetch import FetchVectorEnv
+from tests.hostsim_backend import HostSimBackend
+from tests.parity_util import inject_oracle_state, oracle_env_from_model
+
+
+def mk(task="FetchPickAndPlace", n=2, **kw):
+    return FetchVectorEnv(task, num_envs=n, backend_factory=HostSimBackend, **kw)
+
+
+@pytest.fixture(scope="module")
+def pnp():
+    return mk("FetchPickAndPlace", 3, rng_mode="numpy")
+
+
+def test_spaces_and_shapes(pnp):
+    obs, info = pnp.reset(seed=1)
+    assert info == {}
+    assert obs["observation"].shape == (3, 25) and obs["achieved_goal"].shape == (3, 3) and obs["desired_goal"].shape == (3, 3)
+    assert pnp.single_action_space.shape == (4,) and pnp.single_action_space.dtype == np.float32
+    assert pnp.single_observation_space["observation"].shape == (25,)
+    assert pnp.action_space.shape == (3, 4)
+    o, r, te, tr, inf = pnp.step(np.zeros((3, 4), dtype=np.float32))
+    assert r.shape == (3,) and te.dtype == torch.bool and tr.dtype == torch.bool and "is_success" in inf
+    with pytest.raises(ValueError, match="Action dimension mismatch"):  # robot_env.py:129-130
+        pnp.step(np.zeros((3, 5), dtype=np.float32))
+
+
+def test_initial_state_matches_oracle_and_published_value(pnp):
+    orc = oracle_env_from_model("FetchPickAndPlace", pnp.model)
+    assert np.allclose(pnp.initial_gripper_xpos.double().numpy(), orc.initial_gripper_xpos, atol=2e-5)
+    # gripper rest position quoted by the reference's own docs/tests era (remembered public value)
+    assert np.allclose(orc.initial_gripper_xpos, [1.3419, 0.7491, 0.5347], atol=5e-4)
+    assert pnp.height_offset == pytest.approx(orc.height_offset, abs=2e-6)
+
+
+def test_reset_sampling_follows_the_reference_rng_stream(pnp):
+    """numpy mode: env i is seeded seed+i with Generator(PCG64(SeedSequence)) and draws in the reference's order
+    (fetch_env.py:386-399 then :153-166), so goals/object starts equal the oracle env's for the same seed."""
+    obs, _ = pnp.reset(seed=40)
+    for i in range(3):
+        orc = oracle_env_from_model("FetchPickAndPlace", pnp.model)
+        oo, _ = orc.reset(seed=40 + i)
+        assert np.allclose(obs["desired_goal"][i].double().numpy(), oo["desired_goal"], atol=1e-6)
+        assert np.allclose(obs["achieved_goal"][i].double().numpy(), oo["achieved_goal"], atol=2e-5)
+        assert np.allclose(obs["observation"][i].double().numpy(), oo["observation"], atol=5e-5)
+    # reset-state invariant of the reference (tests/test_envs.py:175-231): qpos == initial_qpos except object xy
+    st, _ = pnp.get_state()
+    q = st[:, :22]
+    assert torch.equal(q[:, :15], pnp.initial_qpos[:15].expand(3, 15)) and torch.equal(q[:, 17:], pnp.initial_qpos[17:].expand(3, 5))
+    assert torch.count_nonzero(st[:, 22:22 + 21] - pnp.initial_qvel) == 0
+
+
+def test_same_seed_determinism():
+    outs = []
+    for _ in range(2):
+        env = mk("FetchPush", 2, rng_mode="numpy")
+        env.reset(seed=5)
+        rng = np.random.default_rng(0)
+        acc = []
+        for _ in range(6):
+            o, r, *_ = env.step(rng.uniform(-1, 1, (2, 4)).astype(np.float32))
+            acc.append(torch.cat([o["observation"], o["desired_goal"], r[:, None]], 1))
+        outs.append(torch.stack(acc))
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_step_tracks_oracle_and_reward_contract(pnp):
+    pnp.reset(seed=9)
+    oracles = [oracle_env_from_model("FetchPickAndPlace", pnp.model) for _ in range(3)]
+    for i, o in enumerate(oracles):
+        o.reset(seed=9 + i)
+    rng = np.random.default_rng(3)
+    for _ in range(4):
+        inject_oracle_state(pnp, oracles)
+        a = rng.uniform(-1, 1, (3, 4)).astype(np.float32)
+        o, r, te, tr, info = pnp.step(a)
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            assert np.abs(o["observation"][i].double().numpy() - oo["observation"]).max() < 2e-4
+            assert float(r[i]) == float(orr)
+        # GoalEnv invariant (core.py:61-62)
+        assert torch.equal(pnp.compute_reward(o["achieved_goal"], o["desired_goal"], {}), r)
+        rn = pnp.compute_reward(o["achieved_goal"].numpy(), o["desired_goal"].numpy(), {})
+        assert rn.dtype == np.float32 and np.array_equal(rn, r.numpy())
+
+
+def test_timelimit_and_next_step_autoreset():
+    env = mk("FetchReach", 2, rng_mode="numpy", max_episode_steps=3)
+    env.reset(seed=0)
+    a = np.full((2, 4), 0.5, dtype=np.float32)
+    for t in range(3):
+        o, r, te, tr, info = env.step(a)
+        assert not bool(te.any()) and bool(tr.all()) == (t == 2)
+    moved = o["observation"].clone()
+    o2, r2, te2, tr2, info2 = env.step(a)  # NEXT_STEP: this call resets, action ignored, reward 0
+    assert not bool(tr2.any()) and torch.count_nonzero(r2) == 0
+    assert torch.allclose(o2["observation"][:, :3], env.initial_gripper_xpos.expand(2, 3), atol=1e-4)
+    assert not torch.allclose(o2["observation"], moved)
+    o3, *_ = env.step(a)
+    assert int(env._elapsed.max()) == 1
+
+
+def test_same_step_autoreset_reports_final_obs():
+    env = mk("FetchReach", 2, rng_mode="torch", autoreset_mode="same_step", max_episode_steps=2)
+    env.reset(seed=0)
+    a = np.full((2, 4), 1.0, dtype=np.float32)
+    env.step(a)
+    o, r, te, tr, info = env.step(a)
+    assert bool(tr.all()) and "final_obs" in info and bool(info["_final_obs"].all())
+    assert not torch.allclose(info["final_obs"]["observation"], o["observation"])
+    assert torch.allclose(o["observation"][:, :3], env.initial_gripper_xpos.expand(2, 3), atol=1e-4)
+
+
+def test_dense_reward_and_registry():
+    import gymnasium_robotics_b200 as pkg
+
+    assert set(pkg.ENV_IDS) >= {"FetchReach-v4", "FetchPickAndPlace-v4", "FetchPickAndPlaceDense-v4", "FetchPush-v4"}
+    assert pkg.ENV_IDS["FetchPickAndPlace-v4"]["max_episode_steps"] == 50  # reference __init__.py:47-52
+    env = pkg.make_vec("FetchReachDense-v4", num_envs=1, backend_factory=HostSimBackend, rng_mode="numpy")
+    obs, _ = env.reset(seed=2)
+    o, r, *_ = env.step(np.zeros((1, 4), dtype=np.float32))
+    d = torch.linalg.norm(o["achieved_goal"] - o["desired_goal"], dim=1)
+    assert torch.allclose(r, -d)
+    with pytest.raises(KeyError):
+        pkg.make_vec("HandReach-v3", num_envs=1)
