@@ -14,8 +14,8 @@
 #define DM_MAX_BODY 32   // one lane per body / 32-bit body masks
 #define DM_MAX_NV 32     // 32-bit dof masks
 #define DM_NCON_MAX 16   // contacts kept per env per sub-step
-#define DM_NDOFROW_MAX 16
-#define DM_NGROUP_MAX 8
+#define DM_NDOFROW_MAX 12
+#define DM_NGROUP_MAX 10
 #define DM_NCAND_MAX 32
 #define DM_NWELD_MAX 1
 
@@ -51,17 +51,18 @@
   X(con, DM_NCON_MAX * CON_WORDS) X(dofrow, DM_NDOFROW_MAX * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
   X(group, DM_NGROUP_MAX * GRP_WORDS) X(cand, DM_NCAND_MAX) X(counters, 8) X(red, 8)
 
-// contact record layout (words)
-enum { C_R = 0 /*pos - ref*/, C_FRAME = 3, C_DIST = 12, C_MU = 13 /*5*/, C_D = 18, C_B = 19, C_KIR = 20, C_U = 21 /*6*/,
-       C_JV = 27 /*6*/, C_C0 = 33 /*6*/, C_F = 39 /*6*/, C_DIM = 45, C_BA = 46, C_BB = 47, C_GRP = 48, C_PAIR = 49,
-       C_MARGIN = 50, CON_WORDS = 52 };
+// contact record layout (words): up to 4 base rows (normal, two tangents, torsion); W holds the spatial row vectors of
+// the three translational rows (about `ref`), the torsional row is (W0[3:6], 0)
+enum { C_W = 0 /*18*/, C_DIST = 18, C_MU = 19 /*slide, torsion, roll*/, C_D = 22, C_B = 23, C_KIR = 24, C_C0 = 25 /*4*/,
+       C_U = 29 /*4*/, C_JV = 33 /*4*/, C_F = 37 /*4*/, C_DIM = 41, C_GRP = 42, C_PAIR = 43, C_MARGIN = 44, CON_WORDS = 46 };
 // dof row: limit / frictionloss / joint equality
 enum { DR_DOF = 0, DR_COEF = 1, DR_DOF2 = 2, DR_COEF2 = 3, DR_TYPE = 4, DR_D = 5, DR_R = 6, DR_FLOSS = 7, DR_AREF = 8,
        DR_JAR = 9, DR_JV = 10, DR_B = 11, DR_KIR = 12, DR_WORDS = 14 };
 // weld: 6 rows, each w[6]; then D[6], B[6], KIR[6], jar[6], jv[6], bodies, group
-enum { W_W = 0, W_D = 36, W_B = 42, W_KIR = 48, W_JAR = 54, W_JV = 60, W_BA = 66, W_BB = 67, W_GRP = 68, WELD_WORDS = 70 };
-// group: K[21] + bodies
-enum { G_K = 0, G_BA = 21, G_BB = 22, GRP_WORDS = 24 };
+enum { W_W = 0, W_D = 36, W_B = 42, W_KIR = 48, W_JAR = 54, W_JV = 60, W_GRP = 66, WELD_WORDS = 68 };
+// group = one geom pair in contact (its contacts are contiguous) or one weld: 6x6 block K, bodies, contact range,
+// dof mask S = anc(A) xor anc(B) with sign mask (bit set: dof on the B side), per-group delta-velocity and force
+enum { G_K = 0, G_BA = 21, G_BB = 22, G_START = 23, G_COUNT = 24, G_MASK = 25, G_SIGN = 26, G_DV = 27, G_F = 33, GRP_WORDS = 40 };
 enum { ROWT_EQ = 0, ROWT_FRICTION = 1, ROWT_LIMIT = 2 };
 enum { CNT_NCON = 0, CNT_NDR = 1, CNT_NGRP = 2, CNT_NCAND = 3, CNT_NWELD = 4, CNT_ITERS = 5, CNT_OVERFLOW = 6 };
 
@@ -192,6 +193,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     int t1 = m.geom_type[m.pair_geom1[p]], t2 = m.geom_type[m.pair_geom2[p]];
     bool ok = (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_BOX) || (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX);
     if (!ok) { err = "collision pair type not supported by the CUDA path yet (only plane-box, box-box)"; return -1; }
+    if (m.pair_condim[p] != 1 && m.pair_condim[p] != 3 && m.pair_condim[p] != 4) { err = "condim must be 1, 3 or 4 on the CUDA path"; return -1; }
     F(h.o_pair_friction, 3 * p + 0, m.pair_friction[5 * p + 0]); F(h.o_pair_friction, 3 * p + 1, m.pair_friction[5 * p + 2]);
     F(h.o_pair_friction, 3 * p + 2, m.pair_friction[5 * p + 3]);
     F(h.o_pair_margin, p, m.pair_margin[p]); F(h.o_pair_gap, p, m.pair_gap[p]);

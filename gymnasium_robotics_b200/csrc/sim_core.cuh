@@ -607,7 +607,7 @@ STAGE void collision(const Ctx c) {
   const DMHead* h = c.h;
   int* cnt = SI(counters);
   int* cand = SI(cand);
-  if (c.lane == 0) { cnt[CNT_NCON] = 0; cnt[CNT_NCAND] = 0; }
+  if (c.lane == 0) { cnt[CNT_NCON] = 0; cnt[CNT_NCAND] = 0; cnt[CNT_NGRP] = 0; }
   SYNC();
   // broad phase: lanes over the static pair list, ordered compaction
   for (int base = 0; base < h->npair; base += WARP_W) {
@@ -657,24 +657,41 @@ STAGE void collision(const Ctx c) {
       o.cnt = k2;
     }
     int total, slot = wexscan(o.cnt, c.lane, &total);
-    int basec = cnt[CNT_NCON];
+    int gtotal, gslot = wexscan(o.cnt > 0 ? 1 : 0, c.lane, &gtotal);
+    int basec = cnt[CNT_NCON], baseg = cnt[CNT_NGRP];
     SYNC();
+    int kept = 0;
+    int gid = baseg + gslot;
     for (int k = 0; k < o.cnt; k++) {
       int id = basec + slot + k;
-      if (id >= DM_NCON_MAX) break;
+      if (id >= DM_NCON_MAX || gid >= DM_NGROUP_MAX - DM_NWELD_MAX) break;
       float* cr = SF(con) + id * CON_WORDS;
-      for (int a = 0; a < 3; a++) { cr[C_R + a] = o.pos[k][a] - h->ref[a]; cr[C_FRAME + a] = o.n[a]; }
-      make_frame(cr + C_FRAME);
+      float fr9[9] = {o.n[0], o.n[1], o.n[2], 0, 0, 0, 0, 0, 0};
+      make_frame(fr9);
+      float r[3] = {o.pos[k][0] - h->ref[0], o.pos[k][1] - h->ref[1], o.pos[k][2] - h->ref[2]};
+      for (int a = 0; a < 3; a++) { float* w = cr + C_W + 6 * a; cross3(w, r, fr9 + 3 * a); w[3] = fr9[3 * a]; w[4] = fr9[3 * a + 1]; w[5] = fr9[3 * a + 2]; }
       cr[C_DIST] = o.dist[k];
       const float* fr = MF(pair_friction) + 3 * p;
-      cr[C_MU] = fr[0]; cr[C_MU + 1] = fr[0]; cr[C_MU + 2] = fr[1]; cr[C_MU + 3] = fr[2]; cr[C_MU + 4] = fr[2];
+      cr[C_MU] = fr[0]; cr[C_MU + 1] = fr[1]; cr[C_MU + 2] = fr[2];
       int* ci2 = (int*)cr;
       ci2[C_DIM] = MI(pair_condim)[p];
-      ci2[C_BA] = MI(geom_body)[MI(pair_geom1)[p]]; ci2[C_BB] = MI(geom_body)[MI(pair_geom2)[p]];
+      ci2[C_GRP] = gid;
       ci2[C_PAIR] = p;
       cr[C_MARGIN] = MF(pair_margin)[p] - MF(pair_gap)[p];
+      kept++;
     }
-    if (c.lane == 0) { int nn = basec + total; if (nn > DM_NCON_MAX) { nn = DM_NCON_MAX; cnt[CNT_OVERFLOW] |= 2; } cnt[CNT_NCON] = nn; }
+    if (o.cnt > 0 && gid < DM_NGROUP_MAX - DM_NWELD_MAX) {
+      int* gi = (int*)(SF(group) + gid * GRP_WORDS);
+      int ba = MI(geom_body)[MI(pair_geom1)[p]], bb = MI(geom_body)[MI(pair_geom2)[p]];
+      uint32_t ma = MU(body_ancdof)[ba], mb = MU(body_ancdof)[bb];
+      gi[G_BA] = ba; gi[G_BB] = bb; gi[G_START] = basec + slot; gi[G_COUNT] = kept;
+      ((uint32_t*)gi)[G_MASK] = ma ^ mb; ((uint32_t*)gi)[G_SIGN] = mb;
+    }
+    if (c.lane == 0) {
+      int nn = basec + total; if (nn > DM_NCON_MAX) { nn = DM_NCON_MAX; cnt[CNT_OVERFLOW] |= 2; }
+      int ng = baseg + gtotal; if (ng > DM_NGROUP_MAX - DM_NWELD_MAX) { ng = DM_NGROUP_MAX - DM_NWELD_MAX; cnt[CNT_OVERFLOW] |= 4; }
+      cnt[CNT_NCON] = nn; cnt[CNT_NGRP] = ng;
+    }
     SYNC();
   }
 }
@@ -705,30 +722,18 @@ HD void ref_kb(const Ctx& c, const float* solref, float dmax_in, float* K, float
   } else { *K = -solref[0] / (dmax * dmax); *B = -solref[1] / dmax; }
 }
 
-// spatial vector of contact base row k (about ref): k<3 translational along frame row k, k>=3 rotational about frame row k-3
+// spatial vector of contact base row k (about ref): k<3 translational rows are cached in C_W, k==3 is the torsional row
 HD void con_w(const float* cr, int k, float* w) {
-  if (k < 3) { const float* f = cr + C_FRAME + 3 * k; cross3(w, cr + C_R, f); w[3] = f[0]; w[4] = f[1]; w[5] = f[2]; }
-  else { const float* f = cr + C_FRAME + 3 * (k - 3); w[0] = f[0]; w[1] = f[1]; w[2] = f[2]; w[3] = w[4] = w[5] = 0; }
+  if (k < 3) { const float* s = cr + C_W + 6 * k; w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = s[3]; w[4] = s[4]; w[5] = s[5]; }
+  else { w[0] = cr[C_W + 3]; w[1] = cr[C_W + 4]; w[2] = cr[C_W + 5]; w[3] = w[4] = w[5] = 0; }
 }
-
-HD int find_group(const Ctx& c, int ba, int bb) {  // lane 0 only
-  int* cnt = SI(counters);
-  for (int g = 0; g < cnt[CNT_NGRP]; g++) {
-    const int* gi = (const int*)(SF(group) + g * GRP_WORDS);
-    if (gi[G_BA] == ba && gi[G_BB] == bb) return g;
-  }
-  if (cnt[CNT_NGRP] >= DM_NGROUP_MAX) { cnt[CNT_OVERFLOW] |= 4; return DM_NGROUP_MAX - 1; }
-  int g = cnt[CNT_NGRP]++;
-  int* gi = (int*)(SF(group) + g * GRP_WORDS);
-  gi[G_BA] = ba; gi[G_BB] = bb;
-  return g;
-}
+HD float con_mu(const float* cr, int k) { return k < 3 ? cr[C_MU] : cr[C_MU + 1]; }  // base row k >= 1
 
 STAGE void make_constraint(const Ctx c) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int* cnt = SI(counters);
-  if (c.lane == 0) { cnt[CNT_NDR] = 0; cnt[CNT_NGRP] = 0; cnt[CNT_NWELD] = 0; }
+  if (c.lane == 0) { cnt[CNT_NDR] = 0; cnt[CNT_NWELD] = 0; }
   SYNC();
   // weld equalities (lane 0; at most DM_NWELD_MAX)
   if (c.lane == 0) {
@@ -771,8 +776,12 @@ STAGE void make_constraint(const Ctx c) {
         wr[W_D + k] = 1.0f / R; wr[W_B + k] = Bc; wr[W_KIR + k] = K * imp * cpos[k];
       }
       int* wi = (int*)wr;
-      wi[W_BA] = b2; wi[W_BB] = b1;  // row value = w . (V[b1] - V[b2])
-      wi[W_GRP] = find_group(c, b2, b1);
+      int gid = cnt[CNT_NGRP]++;  // one group per weld; row value = w . (V[b1] - V[b2]) => A = b2, B = b1
+      wi[W_GRP] = gid;
+      int* gi = (int*)(SF(group) + gid * GRP_WORDS);
+      uint32_t ma = MU(body_ancdof)[b2], mb = MU(body_ancdof)[b1];
+      gi[G_BA] = b2; gi[G_BB] = b1; gi[G_START] = 0; gi[G_COUNT] = 0;
+      ((uint32_t*)gi)[G_MASK] = ma ^ mb; ((uint32_t*)gi)[G_SIGN] = mb;
       cnt[CNT_NWELD]++;
     }
   }
@@ -785,7 +794,7 @@ STAGE void make_constraint(const Ctx c) {
     float imp = impedance(MF(pair_solimp) + 5 * p, cr[C_DIST], cr[C_MARGIN]);
     float K, Bc;
     ref_kb(c, MF(pair_solref) + 2 * p, MF(pair_solimp)[5 * p + 1], &K, &Bc);
-    float tran = MF(pair_invweight)[2 * p], mu0 = cr[C_MU];
+    float tran = MF(pair_invweight)[2 * p], mu0 = cr[C_MU];  // sliding friction
     float R;
     if (dim == 1) R = fmaxf((1 - imp) / imp * tran, B200_MINVAL);
     else {
@@ -795,13 +804,6 @@ STAGE void make_constraint(const Ctx c) {
     }
     cr[C_D] = 1.0f / R; cr[C_B] = Bc; cr[C_KIR] = K * imp * (cr[C_DIST] - cr[C_MARGIN]);
   }
-  if (c.lane == 0) {
-    for (int i = 0; i < cnt[CNT_NCON]; i++) {
-      int* ci = (int*)(SF(con) + i * CON_WORDS);
-      ci[C_GRP] = find_group(c, ci[C_BA], ci[C_BB]);
-    }
-  }
-  SYNC();
   // joint limits -> dof rows (ordered compaction over joints, lower side first)
   for (int base = 0; base < h->njnt; base += WARP_W) {
     int j = base + c.lane;
@@ -840,14 +842,22 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
   ASSUME_SHARED(c);
   ASSUME_SHARED_PTR(vec);
   const int* cnt = SI(counters);
-  pass_V(c, vec, SF(b6));
-  const float* V = SF(b6);
+  int ngrp = cnt[CNT_NGRP];
+  // per-group relative spatial velocity dV_g = sum_{j in S_g} sigma_gj cdof_j vec_j  (lane = (group, component))
+  LANES(idx, ngrp * 6) {
+    int g = idx / 6, a = idx - 6 * g;
+    float* gr = SF(group) + g * GRP_WORDS;
+    uint32_t S = ((const uint32_t*)gr)[G_MASK], sg = ((const uint32_t*)gr)[G_SIGN];
+    float acc = 0;
+    while (S) { int j = ffs_pop(S); float t = SF(cdof)[6 * j + a] * vec[j]; acc += ((sg >> j) & 1u) ? t : -t; }
+    gr[G_DV + a] = acc;
+  }
+  SYNC();
   LANES(i, cnt[CNT_NCON]) {
     float* cr = SF(con) + i * CON_WORDS;
     const int* ci = (const int*)cr;
     int dim = ci[C_DIM], nbase = dim == 1 ? 1 : dim;
-    float dV[6];
-    for (int k = 0; k < 6; k++) dV[k] = V[6 * ci[C_BB] + k] - V[6 * ci[C_BA] + k];
+    const float* dV = SF(group) + ci[C_GRP] * GRP_WORDS + G_DV;
     for (int k = 0; k < nbase; k++) {
       float w[6];
       con_w(cr, k, w);
@@ -859,10 +869,8 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
   }
   LANES(i, cnt[CNT_NWELD] * 6) {
     float* wr = SF(weld) + (i / 6) * WELD_WORDS;
-    const int* wi = (const int*)wr;
     int k = i % 6;
-    float dV[6];
-    for (int a = 0; a < 6; a++) dV[a] = V[6 * wi[W_BB] + a] - V[6 * wi[W_BA] + a];
+    const float* dV = SF(group) + ((const int*)wr)[W_GRP] * GRP_WORDS + G_DV;
     float val = dot6(wr + W_W + 6 * k, dV);
     if (mode == RV_C0) wr[W_KIR + k] = wr[W_B + k] * val + wr[W_KIR + k];  // KIR becomes the full constant c0
     else if (mode == RV_U) wr[W_JAR + k] = val + wr[W_KIR + k];
@@ -888,7 +896,7 @@ HD float contact_forces(float* cr, int dim) {
   if (dim == 1) { float f = un < 0 ? -D * un : 0.f; cr[C_F] = f; return un < 0 ? 0.5f * D * un * un : 0.f; }
   float Fn = 0;
   for (int k = 1; k < dim; k++) {
-    float mu = cr[C_MU + k - 1], uk = cr[C_U + k];
+    float mu = con_mu(cr, k), uk = cr[C_U + k];
     float xp = un + mu * uk, xm = un - mu * uk;
     float fp = xp < 0 ? -D * xp : 0.f, fm = xm < 0 ? -D * xm : 0.f;
     if (xp < 0) cost += 0.5f * D * xp * xp;
@@ -921,38 +929,43 @@ STAGE float update_forces(const Ctx c) {
   return wsum(cost);
 }
 
-// fcon = J^T f from the stored base-row forces
+// fcon = J^T f from the stored base-row forces: per-group spatial force, then one 6-dot per (dof, group)
 STAGE void pass_F(const Ctx c, float* out) {
   ASSUME_SHARED(c);
   ASSUME_SHARED_PTR(out);
   const DMHead* h = c.h;
   const int* cnt = SI(counters);
-  int ncon = cnt[CNT_NCON], nweld = cnt[CNT_NWELD], ndr = cnt[CNT_NDR];
-  LANES(b, h->nb) {
-    float F[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < ncon; i++) {
+  int ngrp = cnt[CNT_NGRP], nweld = cnt[CNT_NWELD], ndr = cnt[CNT_NDR];
+  LANES(idx, ngrp * 6) {
+    int g = idx / 6, a = idx - 6 * g;
+    float* gr = SF(group) + g * GRP_WORDS;
+    const int* gi = (const int*)gr;
+    float acc = 0;
+    for (int i = gi[G_START]; i < gi[G_START] + gi[G_COUNT]; i++) {
       const float* cr = SF(con) + i * CON_WORDS;
-      const int* ci = (const int*)cr;
-      float sg = ci[C_BB] == b ? 1.f : (ci[C_BA] == b ? -1.f : 0.f);
-      if (sg == 0.f) continue;
-      int dim = ci[C_DIM], nbase = dim == 1 ? 1 : dim;
-      for (int k = 0; k < nbase; k++) { float w[6]; con_w(cr, k, w); float f = sg * cr[C_F + k]; for (int a = 0; a < 6; a++) F[a] += f * w[a]; }
+      int dim = ((const int*)cr)[C_DIM];
+      acc += cr[C_F] * cr[C_W + a];
+      if (dim > 1) acc += cr[C_F + 1] * cr[C_W + 6 + a] + cr[C_F + 2] * cr[C_W + 12 + a];
+      if (dim > 3 && a < 3) acc += cr[C_F + 3] * cr[C_W + 3 + a];
     }
     for (int i = 0; i < nweld; i++) {
       const float* wr = SF(weld) + i * WELD_WORDS;
-      const int* wi = (const int*)wr;
-      float sg = wi[W_BB] == b ? 1.f : (wi[W_BA] == b ? -1.f : 0.f);
-      if (sg == 0.f) continue;
-      for (int k = 0; k < 6; k++) { float f = -sg * wr[W_D + k] * wr[W_JAR + k]; const float* w = wr + W_W + 6 * k; for (int a = 0; a < 6; a++) F[a] += f * w[a]; }
+      if (((const int*)wr)[W_GRP] != g) continue;
+      for (int k = 0; k < 6; k++) acc -= wr[W_D + k] * wr[W_JAR + k] * wr[W_W + 6 * k + a];
     }
-    for (int a = 0; a < 6; a++) SF(b6)[6 * b + a] = F[a];
+    gr[G_F + a] = acc;
   }
   SYNC();
   LANES(j, h->nv) {
-    float fs[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t sub = MU(body_sub)[MI(dof_body)[j]];
-    while (sub) { int b = ffs_pop(sub); const float* f = SF(b6) + 6 * b; for (int k = 0; k < 6; k++) fs[k] += f[k]; }
-    float q = dot6(SF(cdof) + 6 * j, fs);
+    float q = 0;
+    const float* cd = SF(cdof) + 6 * j;
+    for (int g = 0; g < ngrp; g++) {
+      const float* gr = SF(group) + g * GRP_WORDS;
+      uint32_t S = ((const uint32_t*)gr)[G_MASK];
+      if (!((S >> j) & 1u)) continue;
+      float d = dot6(cd, gr + G_F);
+      q += ((((const uint32_t*)gr)[G_SIGN] >> j) & 1u) ? d : -d;
+    }
     for (int i = 0; i < ndr; i++) {
       const float* dr = SF(dofrow) + i * DR_WORDS;
       const int* di = (const int*)dr;
@@ -984,36 +997,36 @@ STAGE void build_H(const Ctx c) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
   const int* cnt = SI(counters);
-  int nv = h->nv, nM = nv * (nv + 1) / 2, ncon = cnt[CNT_NCON], nweld = cnt[CNT_NWELD], ngrp = cnt[CNT_NGRP], ndr = cnt[CNT_NDR];
+  int nv = h->nv, nM = nv * (nv + 1) / 2, nweld = cnt[CNT_NWELD], ngrp = cnt[CNT_NGRP], ndr = cnt[CNT_NDR];
   float* H = SF(H);
   LANES(i, nM) H[i] = SF(M)[i];
   // K blocks: lane e < 21 owns packed entry e of every group's 6x6
   for (int g = 0; g < ngrp; g++) {
     float* K = SF(group) + g * GRP_WORDS + G_K;
+    const int* gi = (const int*)(SF(group) + g * GRP_WORDS);
     LANES(e, 21) {
       int r = 0; while ((r + 1) * (r + 2) / 2 <= e) r++;
       int s = e - r * (r + 1) / 2;
       float acc = 0;
-      for (int i = 0; i < ncon; i++) {
+      for (int i = gi[G_START]; i < gi[G_START] + gi[G_COUNT]; i++) {
         const float* cr = SF(con) + i * CON_WORDS;
-        const int* ci = (const int*)cr;
-        if (ci[C_GRP] != g) continue;
-        int dim = ci[C_DIM];
-        float D = cr[C_D], un = cr[C_U], wn[6];
-        con_w(cr, 0, wn);
-        if (dim == 1) { if (un < 0) acc += D * wn[r] * wn[s]; continue; }
+        int dim = ((const int*)cr)[C_DIM];
+        float D = cr[C_D], un = cr[C_U];
+        float wnr = cr[C_W + r], wns = cr[C_W + s];
+        if (dim == 1) { if (un < 0) acc += D * wnr * wns; continue; }
         float Wnn = 0;
         for (int k = 1; k < dim; k++) {
-          float mu = cr[C_MU + k - 1], uk = cr[C_U + k];
+          float mu = con_mu(cr, k), uk = cr[C_U + k];
           float ap = (un + mu * uk) < 0 ? 1.f : 0.f, am = (un - mu * uk) < 0 ? 1.f : 0.f;
           if (ap + am == 0.f) continue;
-          float wk[6];
-          con_w(cr, k, wk);
+          float wkr, wks;
+          if (k < 3) { wkr = cr[C_W + 6 * k + r]; wks = cr[C_W + 6 * k + s]; }
+          else { wkr = r < 3 ? cr[C_W + 3 + r] : 0.f; wks = s < 3 ? cr[C_W + 3 + s] : 0.f; }
           Wnn += ap + am;
           float Wnk = mu * (ap - am), Wkk = mu * mu * (ap + am);
-          acc += D * (Wnk * (wn[r] * wk[s] + wk[r] * wn[s]) + Wkk * wk[r] * wk[s]);
+          acc += D * (Wnk * (wnr * wks + wkr * wns) + Wkk * wkr * wks);
         }
-        acc += D * Wnn * wn[r] * wn[s];
+        acc += D * Wnn * wnr * wns;
       }
       for (int i = 0; i < nweld; i++) {
         const float* wr = SF(weld) + i * WELD_WORDS;
@@ -1027,9 +1040,8 @@ STAGE void build_H(const Ctx c) {
   // y_i = K cdof_i for dofs in the group's chains, then H_ij += sigma_i sigma_j cdof_j . y_i
   for (int g = 0; g < ngrp; g++) {
     const float* K = SF(group) + g * GRP_WORDS + G_K;
-    const int* gi = (const int*)(SF(group) + g * GRP_WORDS);
-    uint32_t ma = MU(body_ancdof)[gi[G_BA]], mb = MU(body_ancdof)[gi[G_BB]];
-    uint32_t S = ma ^ mb;
+    const uint32_t* gu = (const uint32_t*)(SF(group) + g * GRP_WORDS);
+    uint32_t S = gu[G_MASK], mb = gu[G_SIGN];
     LANES(i, nv) {
       if (!((S >> i) & 1u)) continue;
       const float* cd = SF(cdof) + 6 * i;
@@ -1189,7 +1201,7 @@ STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
     float D = cr[C_D], un = cr[C_U] + alpha * cr[C_JV], vn = cr[C_JV];
     if (dim == 1) { if (un < 0) { cost += 0.5f * D * un * un; d1 += D * un * vn; d2 += D * vn * vn; } continue; }
     for (int k = 1; k < dim; k++) {
-      float mu = cr[C_MU + k - 1], uk = cr[C_U + k] + alpha * cr[C_JV + k], vk = cr[C_JV + k];
+      float mu = con_mu(cr, k), uk = cr[C_U + k] + alpha * cr[C_JV + k], vk = cr[C_JV + k];
       float xp = un + mu * uk, vp = vn + mu * vk, xm = un - mu * uk, vm = vn - mu * vk;
       if (xp < 0) { cost += 0.5f * D * xp * xp; d1 += D * xp * vp; d2 += D * vp * vp; }
       if (xm < 0) { cost += 0.5f * D * xm * xm; d1 += D * xm * vm; d2 += D * vm * vm; }
@@ -1301,7 +1313,7 @@ STAGE int newton_move(const Ctx c, float* improvement) {
   float alpha = linesearch(c, q1, q2, gtol, h->ls_iterations < 20 ? h->ls_iterations : 20, improvement);
   if (alpha == 0.f) return 1;
   LANES(i, nv) { a[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
-  LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 6; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
+  LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 4; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
   LANES(i, cnt[CNT_NWELD] * 6) { float* wr = SF(weld) + (i / 6) * WELD_WORDS; wr[W_JAR + i % 6] += alpha * wr[W_JV + i % 6]; }
   LANES(i, cnt[CNT_NDR]) { float* dr = SF(dofrow) + i * DR_WORDS; dr[DR_JAR] += alpha * dr[DR_JV]; }
   SYNC();
