@@ -12,7 +12,7 @@
 #include "fetch_task.cuh"
 
 #ifndef B200_WPB
-#define B200_WPB 14
+#define B200_WPB 16
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,10 +135,10 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, "b200sim_create: cudaSetDevice failed", -7); }
   h->smem_bytes = ((size_t)dh->nwords + (size_t)B200_WPB * dh->scr_words) * 4;
   h->blocks = (num_envs + B200_WPB - 1) / B200_WPB;
-  h->nvp = dh->nv <= 16 ? 16 : (dh->nv <= 24 ? 24 : 32);
+  h->nvp = dh->nv == 15 ? 15 : (dh->nv == 21 ? 21 : 32);  // exact sizes for the Fetch models, padded otherwise
   cudaError_t e = cudaSuccess;
-  if (h->nvp == 16) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-  else if (h->nvp == 24) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (h->nvp == 15) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  else if (h->nvp == 21) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   else e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e != cudaSuccess) { std::string m = std::string("cudaFuncSetAttribute(smem=") + std::to_string(h->smem_bytes) + "): " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
   if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, (size_t)num_envs * t.st_stride * 4) != cudaSuccess) {
@@ -182,7 +182,7 @@ static int launch(b200sim* h, int mode, int nraw, const float* actions, const un
 #define B200_LAUNCH(NVP_)                                                                                   \
   fetch_kernel<B200_WPB, NVP_><<<h->blocks, B200_WPB * 32, h->smem_bytes, (cudaStream_t)stream>>>(          \
       h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info)
-  if (h->nvp == 16) B200_LAUNCH(16); else if (h->nvp == 24) B200_LAUNCH(24); else B200_LAUNCH(32);
+  if (h->nvp == 15) B200_LAUNCH(15); else if (h->nvp == 21) B200_LAUNCH(21); else B200_LAUNCH(32);
 #undef B200_LAUNCH
   h->launches++;
   CUDA_OK(cudaGetLastError());

@@ -135,6 +135,7 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   int nsub = mode == MODE_STEP ? t.n_substeps : (mode == MODE_RAW ? nraw : 0);
   for (int s = 0; s < nsub; s++) {
     forward<NVP>(c, active);
+    ALIGN_AT(4);
     if (active) euler_step<NVP>(c);
   }
   if (!active) return;

@@ -1289,7 +1289,6 @@ template <int NVP>
 STAGE void newton_direction(const Ctx c) {
   ASSUME_SHARED(c);
   int nv = c.h->nv;
-  build_H(c);
   LANES(i, nv) SF(search)[i] = -SF(grad)[i];
   SYNC();
   spd_solve<NVP>(c, SF(H), nullptr, 0.f, SF(search), SF(H));
@@ -1326,25 +1325,47 @@ STAGE int newton_move(const Ctx c, float* improvement) {
 // One forward pass.  `active` is warp-uniform; idle warps (no env, or masked out) only take part in the block-wide
 // alignment barriers, so every warp of the block executes the same barrier sequence.  The Newton loop runs until every
 // warp of the block has converged (converged warps idle through the remaining rounds).
+#ifndef B200_ALIGN_LEVEL
+#define B200_ALIGN_LEVEL 3
+#endif
+#define ALIGN_AT(level) do { if (B200_ALIGN_LEVEL >= (level)) ALIGN(); } while (0)
 template <int NVP>
 HD void forward(const Ctx c, bool active) {
-  ALIGN();
-  if (active) { kinematics(c); com_quantities(c); mass_matrix(c); }
-  ALIGN();
+  ALIGN_AT(1);
+  if (active) kinematics(c);
+  ALIGN_AT(4);
+  if (active) { com_quantities(c); mass_matrix(c); }
+  ALIGN_AT(2);
   if (active) collision(c);
-  ALIGN();
-  if (active) { make_constraint(c); smooth_forces(c); newton_begin(c); }
+  ALIGN_AT(2);
+  if (active) make_constraint(c);
+  ALIGN_AT(4);
+  if (active) smooth_forces(c);
+  ALIGN_AT(4);
+  if (active) newton_begin(c);
   int done = active ? 0 : 1;
   float improvement = 0;
+#if B200_ALIGN_LEVEL >= 3
   for (int iter = 0;; iter++) {
     ALIGN();
     if (!done) done = newton_check(c, iter, improvement);
     if (!ALIGN_OR(!done)) break;
+    if (!done) build_H(c);
+    ALIGN_AT(4);
     if (!done) newton_direction<NVP>(c);
     ALIGN();
     if (!done) done = newton_move(c, &improvement) ? 2 : 0;
-    // a warp that stopped in newton_move still needs forces consistent with its final point: they are (no move made)
   }
+#else
+  ALIGN_AT(2);
+  for (int iter = 0; !done; iter++) {
+    done = newton_check(c, iter, improvement);
+    if (done) break;
+    build_H(c);
+    newton_direction<NVP>(c);
+    done = newton_move(c, &improvement) ? 2 : 0;
+  }
+#endif
 }
 
 template <int NVP>
