@@ -12,7 +12,10 @@
 #include "fetch_task.cuh"
 
 #ifndef B200_WPB
-#define B200_WPB 16
+#define B200_WPB 28
+#endif
+#ifdef B200_BLOCK_ALIGN
+static_assert(B200_WPB % B200_AG == 0, "warps per block must be a multiple of the alignment group size");
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -28,7 +31,7 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
   __shared__ __align__(8) unsigned long long bar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // ---- stage the model constants: TMA 1-D bulk copy global -> shared, completion on an mbarrier
-  const int model_words = ((const DMHead*)model_g)->nwords;  // uniform scalar load
+  const int model_words = ((const DMHead*)model_g)->hot_words;  // header + HOT arrays (uniform scalar load)
   const uint32_t bytes = (uint32_t)model_words * 4u;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
   const int env = blockIdx.x * WPB + warp;
   const bool active = env < N && !(mask && !mask[env]);  // warp-uniform
   Ctx c;
-  c.mw = smem; c.h = h; c.lane = lane;
+  c.mg = model_g; c.mw = smem; c.h = h; c.lane = lane;
   c.s = (float*)(smem + model_words) + (size_t)warp * h->scr_words;
   float a4[4] = {0, 0, 0, 0};
   const size_t e = active ? (size_t)env : 0;
@@ -133,7 +136,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   t.st_mocap = o; o += 7; t.st_pose = o; o += 7; t.st_goal = o; o += 3;
   t.st_stride = (o + 3) & ~3;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, "b200sim_create: cudaSetDevice failed", -7); }
-  h->smem_bytes = ((size_t)dh->nwords + (size_t)B200_WPB * dh->scr_words) * 4;
+  h->smem_bytes = ((size_t)dh->hot_words + (size_t)B200_WPB * dh->scr_words) * 4;
   h->blocks = (num_envs + B200_WPB - 1) / B200_WPB;
   h->nvp = dh->nv == 15 ? 15 : (dh->nv == 21 ? 21 : 32);  // exact sizes for the Fetch models, padded otherwise
   cudaError_t e = cudaSuccess;

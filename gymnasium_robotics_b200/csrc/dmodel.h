@@ -14,13 +14,14 @@
 #define DM_MAX_BODY 32   // one lane per body / 32-bit body masks
 #define DM_MAX_NV 32     // 32-bit dof masks
 #define DM_NCON_MAX 16   // contacts kept per env per sub-step
-#define DM_NDOFROW_MAX 12
+#define DM_NDOFROW_MAX 8
 #define DM_NGROUP_MAX 10
 #define DM_NCAND_MAX 32
 #define DM_NWELD_MAX 1
 
-// (name, words-per-element, kind) ; kind selects the element count
-#define DM_ARRAYS(X) \
+// (name, words-per-element, kind) ; kind selects the element count.  HOT arrays are staged into shared memory by every
+// block; COLD arrays (per-pair contact parameters, read only when a contact is created) stay in global memory.
+#define DM_ARRAYS_HOT(X) \
   X(body_parent, 1, nb) X(body_jntadr, 1, nb) X(body_jntnum, 1, nb) X(body_dofadr, 1, nb) X(body_dofnum, 1, nb) \
   X(body_mocapid, 1, nb) X(body_ancdof, 1, nb) X(body_sub, 1, nb) X(body_pos, 3, nb) X(body_quat, 4, nb) \
   X(body_ipos, 3, nb) X(body_iquat, 4, nb) X(body_mass, 1, nb) X(body_inertia, 3, nb) \
@@ -31,44 +32,47 @@
   X(dof_damping, 1, nv) X(dof_frictionloss, 1, nv) X(dof_invweight0, 1, nv) \
   X(geom_type, 1, ngeom) X(geom_body, 1, ngeom) X(geom_pos, 3, ngeom) X(geom_quat, 4, ngeom) X(geom_size, 3, ngeom) \
   X(geom_rbound, 1, ngeom) \
-  X(pair_geom1, 1, npair) X(pair_geom2, 1, npair) X(pair_condim, 1, npair) X(pair_friction, 3, npair) \
-  X(pair_margin, 1, npair) X(pair_gap, 1, npair) X(pair_solref, 2, npair) X(pair_solimp, 5, npair) X(pair_invweight, 2, npair) \
+  X(pair_geom1, 1, npair) X(pair_geom2, 1, npair) X(pair_margin, 1, npair) \
   X(site_body, 1, nsite) X(site_pos, 3, nsite) X(site_quat, 4, nsite) \
   X(act_trnid, 1, nu) X(act_ctrllimited, 1, nu) X(act_forcelimited, 1, nu) X(act_gear, 1, nu) X(act_gain, 1, nu) \
   X(act_bias, 3, nu) X(act_ctrlrange, 2, nu) X(act_forcerange, 2, nu) \
   X(eq_type, 1, neq) X(eq_obj1, 1, neq) X(eq_obj2, 1, neq) X(eq_active, 1, neq) X(eq_data, 11, neq) X(eq_solref, 2, neq) \
   X(eq_solimp, 5, neq) X(eq_invweight, 2, neq) \
   X(mocap_body, 1, nmocap)
+#define DM_ARRAYS_COLD(X) \
+  X(pair_condim, 1, npair) X(pair_friction, 3, npair) X(pair_gap, 1, npair) X(pair_solref, 2, npair) \
+  X(pair_solimp, 5, npair) X(pair_invweight, 2, npair)
+#define DM_ARRAYS(X) DM_ARRAYS_HOT(X) DM_ARRAYS_COLD(X)
 
-// per-env scratch arrays (name, words expression)
-#define DM_SCRATCH(X) \
-  X(qpos, nq) X(qvel, nv) X(qacc, nv) X(warm, nv) X(ctrl, nu) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) \
-  X(xpos, 3 * nb) X(xquat, 4 * nb) X(xmat, 9 * nb) X(kinA, 8 * nb) X(kinB, 8 * nb) \
-  X(cinert, 10 * nb) X(cdof, 6 * nv) X(cvel, 6 * nb) X(b6, 6 * nb) X(d6, 6 * nv) \
-  X(M, nv * (nv + 1) / 2) X(H, nv * (nv + 1) / 2) \
-  X(fsmooth, nv) X(fcon, nv) X(grad, nv) X(search, nv) X(Ma, nv) X(Mv, nv) X(tmpv, nv) \
-  X(geom_xpos, 3 * ngeom) \
+// per-env scratch that lives for the whole sub-step (name, words expression)
+#define DM_SCRATCH_PERSIST(X) \
+  X(qpos, nq) X(qvel, nv) X(qacc, nv) X(ctrl, nu) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) \
+  X(xpos, 3 * nb) X(xquat, 4 * nb) X(cdof, 6 * nv) X(M, nv * (nv + 1) / 2) X(fsmooth, nv) X(fcon, nv) \
   X(con, DM_NCON_MAX * CON_WORDS) X(dofrow, DM_NDOFROW_MAX * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
-  X(group, DM_NGROUP_MAX * GRP_WORDS) X(cand, DM_NCAND_MAX) X(counters, 8) X(red, 8)
+  X(group, DM_NGROUP_MAX * GRP_WORDS) X(counters, 8)
+// time-shared region `uni`: kinematics {kinA, kinB} -> dynamics {cinert, b6, d6, geom_xpos, cand} -> solver {H, d6, grad,
+// search, Ma, Mv} -> observation {cvel}.  d6 keeps one offset in both phases that use it.
+#define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
+#define DM_SCRATCH(X) DM_SCRATCH_PERSIST(X)
 
-// contact record layout (words): up to 4 base rows (normal, two tangents, torsion); W holds the spatial row vectors of
-// the three translational rows (about `ref`), the torsional row is (W0[3:6], 0)
-enum { C_W = 0 /*18*/, C_DIST = 18, C_MU = 19 /*slide, torsion, roll*/, C_D = 22, C_B = 23, C_KIR = 24, C_C0 = 25 /*4*/,
-       C_U = 29 /*4*/, C_JV = 33 /*4*/, C_F = 37 /*4*/, C_DIM = 41, C_GRP = 42, C_PAIR = 43, C_MARGIN = 44, CON_WORDS = 46 };
-// dof row: limit / frictionloss / joint equality
-enum { DR_DOF = 0, DR_COEF = 1, DR_DOF2 = 2, DR_COEF2 = 3, DR_TYPE = 4, DR_D = 5, DR_R = 6, DR_FLOSS = 7, DR_AREF = 8,
-       DR_JAR = 9, DR_JV = 10, DR_B = 11, DR_KIR = 12, DR_WORDS = 14 };
-// weld: 6 rows, each w[6]; then D[6], B[6], KIR[6], jar[6], jv[6], bodies, group
-enum { W_W = 0, W_D = 36, W_B = 42, W_KIR = 48, W_JAR = 54, W_JV = 60, W_GRP = 66, WELD_WORDS = 68 };
-// group = one geom pair in contact (its contacts are contiguous) or one weld: 6x6 block K, bodies, contact range,
-// dof mask S = anc(A) xor anc(B) with sign mask (bit set: dof on the B side), per-group delta-velocity and force
-enum { G_K = 0, G_BA = 21, G_BB = 22, G_START = 23, G_COUNT = 24, G_MASK = 25, G_SIGN = 26, G_DV = 27, G_F = 33, GRP_WORDS = 40 };
+// contact record (words): up to 4 base rows (normal, two tangents, torsion).  W = spatial vectors of the three
+// translational rows about `ref`; the torsional row is (W0[3:6], 0).  During row set-up JV[0] holds B of the reference
+// acceleration and U holds K*imp*r (normal row) / 0; afterwards U = J a - aref and JV = J search.
+enum { C_W = 0 /*18*/, C_MU = 18 /*slide, torsion*/, C_D = 20, C_U = 21 /*4*/, C_JV = 25 /*4*/, C_DIMGRP = 29, CON_WORDS = 30 };
+// dof row (joint limit; later frictionloss / joint equality): JAR holds K*imp*r and JV holds B during set-up
+enum { DR_DOF = 0, DR_COEF = 1, DR_D = 2, DR_JAR = 3, DR_JV = 4, DR_DOF2 = 5, DR_COEF2 = 6, DR_WORDS = 8 };
+// weld: 6 rows w[6]; D[6], JAR[6] (K*imp*r during set-up), JV[6], B (one value), group
+enum { W_W = 0, W_D = 36, W_JAR = 42, W_JV = 48, W_B = 54, W_GRP = 55, WELD_WORDS = 56 };
+// group = one geom pair in contact (its contacts are contiguous) or one weld: 6x6 block K, contact range, dof mask
+// S = anc(A) xor anc(B) with sign mask (bit set: dof on the B side), and a 6-vector used for dV (J*v) and F (J^T f)
+enum { G_K = 0, G_START = 21, G_COUNT = 22, G_MASK = 23, G_SIGN = 24, G_V = 25, GRP_WORDS = 32 };
 enum { ROWT_EQ = 0, ROWT_FRICTION = 1, ROWT_LIMIT = 2 };
 enum { CNT_NCON = 0, CNT_NDR = 1, CNT_NGRP = 2, CNT_NCAND = 3, CNT_NWELD = 4, CNT_ITERS = 5, CNT_OVERFLOW = 6 };
 
 struct DMHead {
   int nb, njnt, nq, nv, nu, ngeom, nsite, nmocap, neq, npair;
   int nwords;      // size of the model buffer (header included) in 4-byte words
+  int hot_words;   // leading part staged into shared memory (header + HOT arrays)
   int scr_words;   // per-env scratch size in words
   int iterations, ls_iterations, integrator, any_damping, kin_iters, pad0;
   float timestep, gravity[3], tolerance, impratio, meaninertia, ls_tolerance, ref[3];
@@ -76,7 +80,10 @@ struct DMHead {
   DM_ARRAYS(X)
 #undef X
 #define X(name, words) int s_##name;
-  DM_SCRATCH(X)
+  DM_SCRATCH_PERSIST(X)
+#undef X
+#define X(name) int s_##name;
+  DM_SCRATCH_UNION(X)
 #undef X
 };
 
@@ -109,14 +116,32 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
       neq = h.neq, npair = h.npair;
   int off = (int)((sizeof(DMHead) + 3) / 4);
 #define X(name, w, kind) h.o_##name = off; off += (w) * (kind);
-  DM_ARRAYS(X)
+  DM_ARRAYS_HOT(X)
 #undef X
   off = (off + 3) & ~3;  // 16-byte multiple for the bulk copy
+  h.hot_words = off;
+#define X(name, w, kind) h.o_##name = off; off += (w) * (kind);
+  DM_ARRAYS_COLD(X)
+#undef X
+  off = (off + 3) & ~3;
   h.nwords = off;
   int so = 0;
 #define X(name, words) h.s_##name = so; so += (words); so = (so + 1) & ~1;
-  DM_SCRATCH(X)
+  DM_SCRATCH_PERSIST(X)
 #undef X
+  {
+    int nM = nv * (nv + 1) / 2, u = so;
+    int d6off = 16 * nb > nM ? 16 * nb : nM;
+    d6off = (d6off + 1) & ~1;
+    h.s_kinA = u; h.s_kinB = u + 8 * nb;
+    h.s_cinert = u; h.s_b6 = u + 10 * nb; h.s_d6 = u + d6off;
+    int after = u + d6off + 6 * nv;
+    h.s_geom_xpos = after; h.s_cand = after + 3 * ngeom;
+    h.s_H = u; h.s_grad = after; h.s_search = after + nv; h.s_Ma = after + 2 * nv; h.s_Mv = after + 3 * nv;
+    h.s_cvel = u;
+    int endA = after + 3 * ngeom + DM_NCAND_MAX, endB = after + 4 * nv;
+    so = endA > endB ? endA : endB;
+  }
   h.scr_words = (so + 3) & ~3;
   (void)nq;
   buf.assign(h.nwords, 0);

@@ -27,7 +27,7 @@ enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
 HD void site_pose(const Ctx& c, int site, float* pos, float* quat) {
   int b = MI(site_body)[site];
   float t[3];
-  mulmv(t, SF(xmat) + 9 * b, MF(site_pos) + 3 * site);
+  qrot(t, SF(xquat) + 4 * b, MF(site_pos) + 3 * site);
   for (int k = 0; k < 3; k++) pos[k] = SF(xpos)[3 * b + k] + t[k];
   if (quat) qmul(quat, SF(xquat) + 4 * b, MF(site_quat) + 4 * site);
 }
@@ -35,7 +35,7 @@ HD void site_pose(const Ctx& c, int site, float* pos, float* quat) {
 HD void load_state(const Ctx& c, const FetchTask& t, const float* st) {
   const DMHead* h = c.h;
   LANES(i, h->nq) SF(qpos)[i] = st[t.st_qpos + i];
-  LANES(i, h->nv) { SF(qvel)[i] = st[t.st_qvel + i]; SF(warm)[i] = st[t.st_warm + i]; }
+  LANES(i, h->nv) { SF(qvel)[i] = st[t.st_qvel + i]; SF(qacc)[i] = st[t.st_warm + i]; }  // qacc doubles as the warm start
   LANES(i, h->nu) SF(ctrl)[i] = st[t.st_ctrl + i];
   LANES(i, 3 * h->nmocap) SF(mocap_pos)[i] = st[t.st_mocap + i];
   LANES(i, 4 * h->nmocap) SF(mocap_quat)[i] = st[t.st_mocap + 3 + i];
@@ -46,7 +46,7 @@ HD void load_state(const Ctx& c, const FetchTask& t, const float* st) {
 HD void store_state(const Ctx& c, const FetchTask& t, float* st) {
   const DMHead* h = c.h;
   LANES(i, h->nq) st[t.st_qpos + i] = SF(qpos)[i];
-  LANES(i, h->nv) { st[t.st_qvel + i] = SF(qvel)[i]; st[t.st_warm + i] = SF(warm)[i]; }
+  LANES(i, h->nv) { st[t.st_qvel + i] = SF(qvel)[i]; st[t.st_warm + i] = SF(qacc)[i]; }
   LANES(i, h->nu) st[t.st_ctrl + i] = SF(ctrl)[i];
   LANES(i, 3 * h->nmocap) st[t.st_mocap + i] = SF(mocap_pos)[i];
   LANES(i, 4 * h->nmocap) st[t.st_mocap + 3 + i] = SF(mocap_quat)[i];

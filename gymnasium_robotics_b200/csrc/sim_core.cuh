@@ -22,8 +22,18 @@
 #define SYNC() __syncwarp()
 // block-wide alignment points: keep the warps of a block inside the same code window (instruction-cache locality)
 #ifdef B200_BLOCK_ALIGN
-#define ALIGN() __syncthreads()
-#define ALIGN_OR(p) __syncthreads_or(p)
+// the warps of a block form alignment groups of B200_AG warps; each group has its own named barrier
+#ifndef B200_AG
+#define B200_AG 14
+#endif
+__device__ __forceinline__ void b200_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ int b200_bar_or(int id, int nthreads, int pred) {
+  int r;
+  asm volatile("{\n .reg .pred p, q;\n setp.ne.s32 p, %3, 0;\n bar.red.or.pred q, %1, %2, p;\n selp.s32 %0, 1, 0, q;\n}" : "=r"(r) : "r"(id), "r"(nthreads), "r"(pred) : "memory");
+  return r;
+}
+#define ALIGN() b200_bar(1 + (int)(threadIdx.x >> 5) / B200_AG, B200_AG * 32)
+#define ALIGN_OR(p) b200_bar_or(1 + (int)(threadIdx.x >> 5) / B200_AG, B200_AG * 32, (p))
 #else
 #define ALIGN() do { } while (0)
 #define ALIGN_OR(p) (p)
@@ -46,7 +56,8 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define B200_MAXIMP 0.9999f
 
 struct Ctx {
-  const uint32_t* mw;  // model words (shared memory)
+  const uint32_t* mg;  // whole model buffer in global memory (COLD arrays are read from here)
+  const uint32_t* mw;  // header + HOT arrays staged in shared memory
   const DMHead* h;
   float* s;            // this env's scratch (shared memory)
   int lane;
@@ -54,6 +65,8 @@ struct Ctx {
 #define MI(name) ((const int*)(c.mw + c.h->o_##name))
 #define MU(name) ((const uint32_t*)(c.mw + c.h->o_##name))
 #define MF(name) ((const float*)(c.mw + c.h->o_##name))
+#define GI(name) ((const int*)(c.mg + c.h->o_##name))
+#define GF(name) ((const float*)(c.mg + c.h->o_##name))
 #define SF(name) (c.s + c.h->s_##name)
 #define SI(name) ((int*)(c.s + c.h->s_##name))
 #define LANES(i, n) for (int i = c.lane; i < (n); i += WARP_W)
@@ -251,7 +264,6 @@ STAGE void kinematics(const Ctx c) {
     float* xq = SF(xquat) + 4 * b;
     xp[0] = me[0]; xp[1] = me[1]; xp[2] = me[2];
     xq[0] = q[0]; xq[1] = q[1]; xq[2] = q[2]; xq[3] = q[3];
-    q2mat(SF(xmat) + 9 * b, q);
   }
   SYNC();
 }
@@ -264,9 +276,8 @@ STAGE void com_quantities(const Ctx c) {
   LANES(b, h->nb) {
     float* ci = SF(cinert) + 10 * b;
     if (b == 0) { for (int k = 0; k < 10; k++) ci[k] = 0; continue; }
-    const float* R = SF(xmat) + 9 * b;
     float ip[3], r[3], iq[4], Ri[9];
-    mulmv(ip, R, MF(body_ipos) + 3 * b);
+    qrot(ip, SF(xquat) + 4 * b, MF(body_ipos) + 3 * b);
     for (int k = 0; k < 3; k++) r[k] = SF(xpos)[3 * b + k] + ip[k] - ref[k];
     qmul(iq, SF(xquat) + 4 * b, MF(body_iquat) + 4 * b);
     q2mat(Ri, iq);
@@ -285,7 +296,8 @@ STAGE void com_quantities(const Ctx c) {
   }
   LANES(j, h->njnt) {
     int b = MI(jnt_body)[j], d = MI(jnt_dofadr)[j], t = MI(jnt_type)[j];
-    const float* R = SF(xmat) + 9 * b;
+    float R[9];
+    q2mat(R, SF(xquat) + 4 * b);
     const float* xp = SF(xpos) + 3 * b;
     float* cd = SF(cdof) + 6 * d;
     if (t == B200_JNT_FREE) {
@@ -313,7 +325,7 @@ STAGE void com_quantities(const Ctx c) {
   LANES(g, h->ngeom) {
     int b = MI(geom_body)[g];
     float t[3];
-    mulmv(t, SF(xmat) + 9 * b, MF(geom_pos) + 3 * g);
+    qrot(t, SF(xquat) + 4 * b, MF(geom_pos) + 3 * g);
     for (int k = 0; k < 3; k++) SF(geom_xpos)[3 * g + k] = SF(xpos)[3 * b + k] + t[k];
   }
   SYNC();
@@ -360,7 +372,6 @@ STAGE void smooth_forces(const Ctx c) {
   const DMHead* h = c.h;
   int nv = h->nv, nb = h->nb;
   const float *qvel = SF(qvel), *qpos = SF(qpos);
-  pass_V(c, qvel, SF(cvel));
   LANES(j, nv) {
     float vp[6] = {0, 0, 0, 0, 0, 0}, vj[6];
     uint32_t m = MU(dof_pre)[j];
@@ -373,12 +384,19 @@ STAGE void smooth_forces(const Ctx c) {
     float* f = SF(b6) + 6 * b;
     if (b == 0) { for (int k = 0; k < 6; k++) f[k] = 0; continue; }
     float a[6] = {0, 0, 0, -h->gravity[0], -h->gravity[1], -h->gravity[2]};
+    float v[6] = {0, 0, 0, 0, 0, 0};  // spatial velocity of this body (kept in registers)
     uint32_t m = MU(body_ancdof)[b];
-    while (m) { int j = ffs_pop(m); const float* d = SF(d6) + 6 * j; for (int k = 0; k < 6; k++) a[k] += d[k]; }
+    while (m) {
+      int j = ffs_pop(m);
+      const float* d = SF(d6) + 6 * j;
+      const float* cd = SF(cdof) + 6 * j;
+      float q = qvel[j];
+      for (int k = 0; k < 6; k++) { a[k] += d[k]; v[k] += cd[k] * q; }
+    }
     float Ia[6], Iv[6], x[6];
     mul_inert(Ia, SF(cinert) + 10 * b, a);
-    mul_inert(Iv, SF(cinert) + 10 * b, SF(cvel) + 6 * b);
-    cross_force(x, SF(cvel) + 6 * b, Iv);
+    mul_inert(Iv, SF(cinert) + 10 * b, v);
+    cross_force(x, v, Iv);
     for (int k = 0; k < 6; k++) f[k] = Ia[k] + x[k];
   }
   SYNC();
@@ -407,6 +425,30 @@ STAGE void smooth_forces(const Ctx c) {
     SF(fsmooth)[j] = f;
   }
   SYNC();
+}
+
+// impedance and reference-acceleration constants of the soft-constraint model (used when rows are created)
+HDN float impedance(const float* solimp, float pos, float margin) {
+  float d0 = fminf(fmaxf(solimp[0], B200_MINIMP), B200_MAXIMP), d1 = fminf(fmaxf(solimp[1], B200_MINIMP), B200_MAXIMP);
+  float width = fmaxf(solimp[2], 0.f), mid = fminf(fmaxf(solimp[3], B200_MINIMP), B200_MAXIMP), power = fmaxf(solimp[4], 1.f);
+  if (d0 == d1 || width <= B200_MINVAL) return 0.5f * (d0 + d1);
+  float x = fabsf((pos - margin) / width);
+  if (x >= 1) return d1;
+  if (x <= 0) return d0;
+  float y;
+  if (power == 1) y = x;
+  else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+  else y = x <= mid ? powf(x, power) / powf(mid, power - 1) : 1 - powf(1 - x, power) / powf(1 - mid, power - 1);
+  return d0 + y * (d1 - d0);
+}
+// K and B of the reference acceleration (refsafe), given solref and dmax = solimp[1]
+HD void ref_kb(const Ctx& c, const float* solref, float dmax_in, float* K, float* B) {
+  float dmax = fminf(fmaxf(dmax_in, B200_MINIMP), B200_MAXIMP);
+  if (solref[0] > 0) {
+    float tc = fmaxf(solref[0], 2 * c.h->timestep), dr = solref[1];
+    *K = 1.0f / fmaxf(dmax * dmax * tc * tc * dr * dr, B200_MINVAL);
+    *B = 2.0f / fmaxf(dmax * tc, B200_MINVAL);
+  } else { *K = -solref[0] / (dmax * dmax); *B = -solref[1] / dmax; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -651,7 +693,7 @@ STAGE void collision(const Ctx c) {
       if (MI(geom_type)[g1] == B200_GEOM_PLANE) collide_plane_box(c, g1, g2, margin, o);
       else collide_box_box(c, g1, g2, margin, o);
       // contacts beyond the gap are not turned into constraints
-      float inc = margin - MF(pair_gap)[p];
+      float inc = margin - GF(pair_gap)[p];
       int k2 = 0;
       for (int k = 0; k < o.cnt; k++) if (o.dist[k] < inc) { if (k2 != k) { o.dist[k2] = o.dist[k]; for (int a = 0; a < 3; a++) o.pos[k2][a] = o.pos[k][a]; } k2++; }
       o.cnt = k2;
@@ -670,21 +712,36 @@ STAGE void collision(const Ctx c) {
       make_frame(fr9);
       float r[3] = {o.pos[k][0] - h->ref[0], o.pos[k][1] - h->ref[1], o.pos[k][2] - h->ref[2]};
       for (int a = 0; a < 3; a++) { float* w = cr + C_W + 6 * a; cross3(w, r, fr9 + 3 * a); w[3] = fr9[3 * a]; w[4] = fr9[3 * a + 1]; w[5] = fr9[3 * a + 2]; }
-      cr[C_DIST] = o.dist[k];
-      const float* fr = MF(pair_friction) + 3 * p;
-      cr[C_MU] = fr[0]; cr[C_MU + 1] = fr[1]; cr[C_MU + 2] = fr[2];
-      int* ci2 = (int*)cr;
-      ci2[C_DIM] = MI(pair_condim)[p];
-      ci2[C_GRP] = gid;
-      ci2[C_PAIR] = p;
-      cr[C_MARGIN] = MF(pair_margin)[p] - MF(pair_gap)[p];
+      const float* fr = GF(pair_friction) + 3 * p;
+      int dim = GI(pair_condim)[p];
+      float mu0 = fr[0];
+      cr[C_MU] = mu0; cr[C_MU + 1] = fr[1];
+      // impedance, regulariser (shared by all pyramid edges of the contact) and reference-acceleration constants
+      float incl = MF(pair_margin)[p] - GF(pair_gap)[p];
+      float solimp[5] = {GF(pair_solimp)[5 * p], GF(pair_solimp)[5 * p + 1], GF(pair_solimp)[5 * p + 2], GF(pair_solimp)[5 * p + 3], GF(pair_solimp)[5 * p + 4]};
+      float solref[2] = {GF(pair_solref)[2 * p], GF(pair_solref)[2 * p + 1]};
+      float imp = impedance(solimp, o.dist[k], incl);
+      float K, Bc;
+      ref_kb(c, solref, solimp[1], &K, &Bc);
+      float tran = GF(pair_invweight)[2 * p];
+      float R;
+      if (dim == 1) R = fmaxf((1 - imp) / imp * tran, B200_MINVAL);
+      else {
+        float R0 = fmaxf((1 - imp) / imp * (tran + mu0 * mu0 * tran), B200_MINVAL);
+        float mu = mu0 * rsqrtf(h->impratio);
+        R = fmaxf(2 * mu * mu * R0, B200_MINVAL);
+      }
+      cr[C_D] = 1.0f / R;
+      cr[C_U] = K * imp * (o.dist[k] - incl); cr[C_U + 1] = 0; cr[C_U + 2] = 0; cr[C_U + 3] = 0;
+      cr[C_JV] = Bc;
+      ((int*)cr)[C_DIMGRP] = dim | (gid << 8);
       kept++;
     }
     if (o.cnt > 0 && gid < DM_NGROUP_MAX - DM_NWELD_MAX) {
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
       int ba = MI(geom_body)[MI(pair_geom1)[p]], bb = MI(geom_body)[MI(pair_geom2)[p]];
       uint32_t ma = MU(body_ancdof)[ba], mb = MU(body_ancdof)[bb];
-      gi[G_BA] = ba; gi[G_BB] = bb; gi[G_START] = basec + slot; gi[G_COUNT] = kept;
+      gi[G_START] = basec + slot; gi[G_COUNT] = kept;
       ((uint32_t*)gi)[G_MASK] = ma ^ mb; ((uint32_t*)gi)[G_SIGN] = mb;
     }
     if (c.lane == 0) {
@@ -698,36 +755,14 @@ STAGE void collision(const Ctx c) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // 6. constraint rows
-HDN float impedance(const float* solimp, float pos, float margin) {
-  ASSUME_SHARED_PTR(solimp);
-  float d0 = fminf(fmaxf(solimp[0], B200_MINIMP), B200_MAXIMP), d1 = fminf(fmaxf(solimp[1], B200_MINIMP), B200_MAXIMP);
-  float width = fmaxf(solimp[2], 0.f), mid = fminf(fmaxf(solimp[3], B200_MINIMP), B200_MAXIMP), power = fmaxf(solimp[4], 1.f);
-  if (d0 == d1 || width <= B200_MINVAL) return 0.5f * (d0 + d1);
-  float x = fabsf((pos - margin) / width);
-  if (x >= 1) return d1;
-  if (x <= 0) return d0;
-  float y;
-  if (power == 1) y = x;
-  else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
-  else y = x <= mid ? powf(x, power) / powf(mid, power - 1) : 1 - powf(1 - x, power) / powf(1 - mid, power - 1);
-  return d0 + y * (d1 - d0);
-}
-// K and B of the reference acceleration (refsafe), given solref and dmax = solimp[1]
-HD void ref_kb(const Ctx& c, const float* solref, float dmax_in, float* K, float* B) {
-  float dmax = fminf(fmaxf(dmax_in, B200_MINIMP), B200_MAXIMP);
-  if (solref[0] > 0) {
-    float tc = fmaxf(solref[0], 2 * c.h->timestep), dr = solref[1];
-    *K = 1.0f / fmaxf(dmax * dmax * tc * tc * dr * dr, B200_MINVAL);
-    *B = 2.0f / fmaxf(dmax * tc, B200_MINVAL);
-  } else { *K = -solref[0] / (dmax * dmax); *B = -solref[1] / dmax; }
-}
-
 // spatial vector of contact base row k (about ref): k<3 translational rows are cached in C_W, k==3 is the torsional row
 HD void con_w(const float* cr, int k, float* w) {
   if (k < 3) { const float* s = cr + C_W + 6 * k; w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = s[3]; w[4] = s[4]; w[5] = s[5]; }
   else { w[0] = cr[C_W + 3]; w[1] = cr[C_W + 4]; w[2] = cr[C_W + 5]; w[3] = w[4] = w[5] = 0; }
 }
 HD float con_mu(const float* cr, int k) { return k < 3 ? cr[C_MU] : cr[C_MU + 1]; }  // base row k >= 1
+HD int con_dim(const float* cr) { return ((const int*)cr)[C_DIMGRP] & 0xff; }
+HD int con_grp(const float* cr) { return ((const int*)cr)[C_DIMGRP] >> 8; }
 
 STAGE void make_constraint(const Ctx c) {
   ASSUME_SHARED(c);
@@ -743,8 +778,8 @@ STAGE void make_constraint(const Ctx c) {
       const float* data = MF(eq_data) + 11 * e;
       int s1 = MI(eq_obj1)[e], s2 = MI(eq_obj2)[e], b1 = 0, b2 = 0;
       float p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0}, q1[4] = {1, 0, 0, 0}, q2[4] = {1, 0, 0, 0}, t[3];
-      if (s1 >= 0) { b1 = MI(site_body)[s1]; qmul(q1, SF(xquat) + 4 * b1, MF(site_quat) + 4 * s1); mulmv(t, SF(xmat) + 9 * b1, MF(site_pos) + 3 * s1); for (int k = 0; k < 3; k++) p1[k] = SF(xpos)[3 * b1 + k] + t[k]; }
-      if (s2 >= 0) { b2 = MI(site_body)[s2]; qmul(q2, SF(xquat) + 4 * b2, MF(site_quat) + 4 * s2); mulmv(t, SF(xmat) + 9 * b2, MF(site_pos) + 3 * s2); for (int k = 0; k < 3; k++) p2[k] = SF(xpos)[3 * b2 + k] + t[k]; }
+      if (s1 >= 0) { b1 = MI(site_body)[s1]; qmul(q1, SF(xquat) + 4 * b1, MF(site_quat) + 4 * s1); qrot(t, SF(xquat) + 4 * b1, MF(site_pos) + 3 * s1); for (int k = 0; k < 3; k++) p1[k] = SF(xpos)[3 * b1 + k] + t[k]; }
+      if (s2 >= 0) { b2 = MI(site_body)[s2]; qmul(q2, SF(xquat) + 4 * b2, MF(site_quat) + 4 * s2); qrot(t, SF(xquat) + 4 * b2, MF(site_pos) + 3 * s2); for (int k = 0; k < 3; k++) p2[k] = SF(xpos)[3 * b2 + k] + t[k]; }
       qrot(t, q1, data + 3); for (int k = 0; k < 3; k++) p1[k] += t[k];
       qrot(t, q2, data + 0); for (int k = 0; k < 3; k++) p2[k] += t[k];
       float cpos[6], ts = data[10];
@@ -753,9 +788,7 @@ STAGE void make_constraint(const Ctx c) {
       qmul(quat, q1, data + 6);
       qmul(quat2, quat1, quat);
       cpos[3] = ts * quat2[1]; cpos[4] = ts * quat2[2]; cpos[5] = ts * quat2[3];
-      // rows: J = J(body1 at p1) - J(body2 at p2).  Both points coincide up to the residual, and only one side carries
-      // dofs when the other is a mocap body; we evaluate both sides with their own lever arms through (A=b2, B=b1).
-      // translational rows about the point of the moving side
+      // rows: J = J(body1 at p1) - J(body2 at p2); translational rows about the anchor of the side that carries dofs
       const float* pm = (b1 > 0 && MU(body_ancdof)[b1]) ? p1 : p2;
       float r[3] = {pm[0] - h->ref[0], pm[1] - h->ref[1], pm[2] - h->ref[2]};
       for (int k = 0; k < 3; k++) {
@@ -773,37 +806,19 @@ STAGE void make_constraint(const Ctx c) {
       for (int k = 0; k < 6; k++) {
         float imp = impedance(MF(eq_solimp) + 5 * e, cpos[k], 0.f);
         float R = fmaxf((1 - imp) / imp * MF(eq_invweight)[2 * e + (k < 3 ? 0 : 1)], B200_MINVAL);
-        wr[W_D + k] = 1.0f / R; wr[W_B + k] = Bc; wr[W_KIR + k] = K * imp * cpos[k];
+        wr[W_D + k] = 1.0f / R; wr[W_JAR + k] = K * imp * cpos[k];
       }
-      int* wi = (int*)wr;
+      wr[W_B] = Bc;
       int gid = cnt[CNT_NGRP]++;  // one group per weld; row value = w . (V[b1] - V[b2]) => A = b2, B = b1
-      wi[W_GRP] = gid;
+      ((int*)wr)[W_GRP] = gid;
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
       uint32_t ma = MU(body_ancdof)[b2], mb = MU(body_ancdof)[b1];
-      gi[G_BA] = b2; gi[G_BB] = b1; gi[G_START] = 0; gi[G_COUNT] = 0;
+      gi[G_START] = 0; gi[G_COUNT] = 0;
       ((uint32_t*)gi)[G_MASK] = ma ^ mb; ((uint32_t*)gi)[G_SIGN] = mb;
       cnt[CNT_NWELD]++;
     }
   }
   SYNC();
-  // contacts: impedance and regulariser in parallel; body-pair groups assigned in order by lane 0
-  LANES(i, cnt[CNT_NCON]) {
-    float* cr = SF(con) + i * CON_WORDS;
-    int* ci = (int*)cr;
-    int p = ci[C_PAIR], dim = ci[C_DIM];
-    float imp = impedance(MF(pair_solimp) + 5 * p, cr[C_DIST], cr[C_MARGIN]);
-    float K, Bc;
-    ref_kb(c, MF(pair_solref) + 2 * p, MF(pair_solimp)[5 * p + 1], &K, &Bc);
-    float tran = MF(pair_invweight)[2 * p], mu0 = cr[C_MU];  // sliding friction
-    float R;
-    if (dim == 1) R = fmaxf((1 - imp) / imp * tran, B200_MINVAL);
-    else {
-      float R0 = fmaxf((1 - imp) / imp * (tran + mu0 * mu0 * tran), B200_MINVAL);
-      float mu = mu0 * rsqrtf(h->impratio);
-      R = fmaxf(2 * mu * mu * R0, B200_MINVAL);
-    }
-    cr[C_D] = 1.0f / R; cr[C_B] = Bc; cr[C_KIR] = K * imp * (cr[C_DIST] - cr[C_MARGIN]);
-  }
   // joint limits -> dof rows (ordered compaction over joints, lower side first)
   for (int base = 0; base < h->njnt; base += WARP_W) {
     int j = base + c.lane;
@@ -828,16 +843,16 @@ STAGE void make_constraint(const Ctx c) {
       float K, Bc;
       ref_kb(c, MF(jnt_solref) + 2 * j, MF(jnt_solimp)[5 * j + 1], &K, &Bc);
       float R = fmaxf((1 - imp) / imp * MF(dof_invweight0)[d], B200_MINVAL);
-      di[DR_DOF] = d; dr[DR_COEF] = sgn[k]; di[DR_DOF2] = -1; dr[DR_COEF2] = 0; di[DR_TYPE] = ROWT_LIMIT;
-      dr[DR_D] = 1.0f / R; dr[DR_R] = R; dr[DR_FLOSS] = 0; dr[DR_B] = Bc; dr[DR_KIR] = K * imp * (dist[k] - margin);
+      di[DR_DOF] = d; dr[DR_COEF] = sgn[k]; di[DR_DOF2] = -1; dr[DR_COEF2] = 0;
+      dr[DR_D] = 1.0f / R; dr[DR_JAR] = K * imp * (dist[k] - margin); dr[DR_JV] = Bc;
     }
     if (c.lane == 0) { int nn = basec + total; if (nn > DM_NDOFROW_MAX) { nn = DM_NDOFROW_MAX; cnt[CNT_OVERFLOW] |= 8; } cnt[CNT_NDR] = nn; }
     SYNC();
   }
 }
 
-// rows <- J * vec (+ optional scaling into the aref constants).  mode 0: C0 = B*(J qvel) + KIR ; mode 1: U = J a + C0 ; mode 2: JV = J s
-enum { RV_C0 = 0, RV_U = 1, RV_JV = 2 };
+// rows <- J * vec.  RV_C0: row = B * (J qvel) + row (row holds K*imp*r; B in the JV slot) ; RV_ADD: row += J a ; RV_JV: JV = J s
+enum { RV_C0 = 0, RV_ADD = 1, RV_JV = 2 };
 STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
   ASSUME_SHARED(c);
   ASSUME_SHARED_PTR(vec);
@@ -850,30 +865,30 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
     uint32_t S = ((const uint32_t*)gr)[G_MASK], sg = ((const uint32_t*)gr)[G_SIGN];
     float acc = 0;
     while (S) { int j = ffs_pop(S); float t = SF(cdof)[6 * j + a] * vec[j]; acc += ((sg >> j) & 1u) ? t : -t; }
-    gr[G_DV + a] = acc;
+    gr[G_V + a] = acc;
   }
   SYNC();
   LANES(i, cnt[CNT_NCON]) {
     float* cr = SF(con) + i * CON_WORDS;
-    const int* ci = (const int*)cr;
-    int dim = ci[C_DIM], nbase = dim == 1 ? 1 : dim;
-    const float* dV = SF(group) + ci[C_GRP] * GRP_WORDS + G_DV;
+    int dim = con_dim(cr), nbase = dim == 1 ? 1 : dim;
+    const float* dV = SF(group) + con_grp(cr) * GRP_WORDS + G_V;
+    float Bc = cr[C_JV];
     for (int k = 0; k < nbase; k++) {
       float w[6];
       con_w(cr, k, w);
       float val = dot6(w, dV);
-      if (mode == RV_C0) cr[C_C0 + k] = cr[C_B] * val + (k == 0 ? cr[C_KIR] : 0.f);
-      else if (mode == RV_U) cr[C_U + k] = val + cr[C_C0 + k];
+      if (mode == RV_C0) cr[C_U + k] += Bc * val;
+      else if (mode == RV_ADD) cr[C_U + k] += val;
       else cr[C_JV + k] = val;
     }
   }
   LANES(i, cnt[CNT_NWELD] * 6) {
     float* wr = SF(weld) + (i / 6) * WELD_WORDS;
     int k = i % 6;
-    const float* dV = SF(group) + ((const int*)wr)[W_GRP] * GRP_WORDS + G_DV;
+    const float* dV = SF(group) + ((const int*)wr)[W_GRP] * GRP_WORDS + G_V;
     float val = dot6(wr + W_W + 6 * k, dV);
-    if (mode == RV_C0) wr[W_KIR + k] = wr[W_B + k] * val + wr[W_KIR + k];  // KIR becomes the full constant c0
-    else if (mode == RV_U) wr[W_JAR + k] = val + wr[W_KIR + k];
+    if (mode == RV_C0) wr[W_JAR + k] += wr[W_B] * val;
+    else if (mode == RV_ADD) wr[W_JAR + k] += val;
     else wr[W_JV + k] = val;
   }
   LANES(i, cnt[CNT_NDR]) {
@@ -881,8 +896,8 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
     const int* di = (const int*)dr;
     float val = dr[DR_COEF] * vec[di[DR_DOF]];
     if (di[DR_DOF2] >= 0) val += dr[DR_COEF2] * vec[di[DR_DOF2]];
-    if (mode == RV_C0) dr[DR_AREF] = dr[DR_B] * val + dr[DR_KIR];  // c0
-    else if (mode == RV_U) dr[DR_JAR] = val + dr[DR_AREF];
+    if (mode == RV_C0) dr[DR_JAR] += dr[DR_JV] * val;
+    else if (mode == RV_ADD) dr[DR_JAR] += val;
     else dr[DR_JV] = val;
   }
   SYNC();
@@ -890,43 +905,18 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // 8. Newton solver pieces
-// pyramid forces of a contact from its base-row values U; writes base-row generalized forces F; returns the cost
-HD float contact_forces(float* cr, int dim) {
-  float D = cr[C_D], un = cr[C_U], cost = 0;
-  if (dim == 1) { float f = un < 0 ? -D * un : 0.f; cr[C_F] = f; return un < 0 ? 0.5f * D * un * un : 0.f; }
-  float Fn = 0;
+// base-row generalized forces of a contact from its base-row values U (pyramid edges f = -D * min(0, u_n +- mu u_k))
+HD void contact_base_forces(const float* cr, int dim, float* F) {
+  float D = cr[C_D], un = cr[C_U];
+  F[0] = F[1] = F[2] = F[3] = 0;
+  if (dim == 1) { F[0] = un < 0 ? -D * un : 0.f; return; }
   for (int k = 1; k < dim; k++) {
     float mu = con_mu(cr, k), uk = cr[C_U + k];
     float xp = un + mu * uk, xm = un - mu * uk;
     float fp = xp < 0 ? -D * xp : 0.f, fm = xm < 0 ? -D * xm : 0.f;
-    if (xp < 0) cost += 0.5f * D * xp * xp;
-    if (xm < 0) cost += 0.5f * D * xm * xm;
-    Fn += fp + fm;
-    cr[C_F + k] = mu * (fp - fm);
+    F[0] += fp + fm;
+    F[k] = mu * (fp - fm);
   }
-  cr[C_F] = Fn;
-  return cost;
-}
-
-// forces for all rows at the current U; returns the total constraint cost (all lanes get the sum)
-STAGE float update_forces(const Ctx c) {
-  ASSUME_SHARED(c);
-  const int* cnt = SI(counters);
-  float cost = 0;
-  LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; cost += contact_forces(cr, ((const int*)cr)[C_DIM]); }
-  LANES(i, cnt[CNT_NWELD] * 6) {
-    float* wr = SF(weld) + (i / 6) * WELD_WORDS;
-    int k = i % 6;
-    float x = wr[W_JAR + k], D = wr[W_D + k];
-    cost += 0.5f * D * x * x;
-  }
-  LANES(i, cnt[CNT_NDR]) {
-    const float* dr = SF(dofrow) + i * DR_WORDS;
-    float x = dr[DR_JAR];
-    if (x < 0) cost += 0.5f * dr[DR_D] * x * x;
-  }
-  SYNC();
-  return wsum(cost);
 }
 
 // fcon = J^T f from the stored base-row forces: per-group spatial force, then one 6-dot per (dof, group)
@@ -943,17 +933,19 @@ STAGE void pass_F(const Ctx c, float* out) {
     float acc = 0;
     for (int i = gi[G_START]; i < gi[G_START] + gi[G_COUNT]; i++) {
       const float* cr = SF(con) + i * CON_WORDS;
-      int dim = ((const int*)cr)[C_DIM];
-      acc += cr[C_F] * cr[C_W + a];
-      if (dim > 1) acc += cr[C_F + 1] * cr[C_W + 6 + a] + cr[C_F + 2] * cr[C_W + 12 + a];
-      if (dim > 3 && a < 3) acc += cr[C_F + 3] * cr[C_W + 3 + a];
+      int dim = con_dim(cr);
+      float F[4];
+      contact_base_forces(cr, dim, F);
+      acc += F[0] * cr[C_W + a];
+      if (dim > 1) acc += F[1] * cr[C_W + 6 + a] + F[2] * cr[C_W + 12 + a];
+      if (dim > 3 && a < 3) acc += F[3] * cr[C_W + 3 + a];
     }
     for (int i = 0; i < nweld; i++) {
       const float* wr = SF(weld) + i * WELD_WORDS;
       if (((const int*)wr)[W_GRP] != g) continue;
       for (int k = 0; k < 6; k++) acc -= wr[W_D + k] * wr[W_JAR + k] * wr[W_W + 6 * k + a];
     }
-    gr[G_F + a] = acc;
+    gr[G_V + a] = acc;
   }
   SYNC();
   LANES(j, h->nv) {
@@ -963,7 +955,7 @@ STAGE void pass_F(const Ctx c, float* out) {
       const float* gr = SF(group) + g * GRP_WORDS;
       uint32_t S = ((const uint32_t*)gr)[G_MASK];
       if (!((S >> j) & 1u)) continue;
-      float d = dot6(cd, gr + G_F);
+      float d = dot6(cd, gr + G_V);
       q += ((((const uint32_t*)gr)[G_SIGN] >> j) & 1u) ? d : -d;
     }
     for (int i = 0; i < ndr; i++) {
@@ -1010,7 +1002,7 @@ STAGE void build_H(const Ctx c) {
       float acc = 0;
       for (int i = gi[G_START]; i < gi[G_START] + gi[G_COUNT]; i++) {
         const float* cr = SF(con) + i * CON_WORDS;
-        int dim = ((const int*)cr)[C_DIM];
+        int dim = con_dim(cr);
         float D = cr[C_D], un = cr[C_U];
         float wnr = cr[C_W + r], wns = cr[C_W + s];
         if (dim == 1) { if (un < 0) acc += D * wnr * wns; continue; }
@@ -1197,7 +1189,7 @@ STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
   float cost = 0, d1 = 0, d2 = 0;
   LANES(i, cnt[CNT_NCON]) {
     const float* cr = SF(con) + i * CON_WORDS;
-    int dim = ((const int*)cr)[C_DIM];
+    int dim = con_dim(cr);
     float D = cr[C_D], un = cr[C_U] + alpha * cr[C_JV], vn = cr[C_JV];
     if (dim == 1) { if (un < 0) { cost += 0.5f * D * un * un; d1 += D * un * vn; d2 += D * vn * vn; } continue; }
     for (int k = 1; k < dim; k++) {
@@ -1249,12 +1241,10 @@ STAGE float linesearch(const Ctx c, float g1, float g2, float gtol, int maxit, f
 // Newton solver, split so that the iteration loop can be driven block-uniformly (see forward()).
 STAGE void newton_begin(const Ctx c) {
   ASSUME_SHARED(c);
-  int nv = c.h->nv;
-  LANES(i, nv) SF(qacc)[i] = SF(warm)[i];
-  SYNC();
+  // qacc holds the warm start (previous sub-step's solution); rows become J a - aref = J a + B (J qvel) + K imp r
   rows_from_vec(c, SF(qvel), RV_C0);
   mulM(c, SF(qacc), SF(Ma));
-  rows_from_vec(c, SF(qacc), RV_U);
+  rows_from_vec(c, SF(qacc), RV_ADD);
 }
 
 // forces, gradient and the convergence tests at the current point; returns 1 when the solver is finished
@@ -1265,7 +1255,6 @@ STAGE int newton_check(const Ctx c, int iter, float improvement) {
   float *Ma = SF(Ma), *grad = SF(grad), *fs = SF(fsmooth), *fcon = SF(fcon);
   float scale = 1.0f / (h->meaninertia * (float)(nv > 1 ? nv : 1));
   float tol = fmaxf(h->tolerance, 1e-6f);  // single-precision floor for the convergence tests
-  update_forces(c);
   pass_F(c, fcon);
   float g2sum = 0, f2sum = 0;
   LANES(i, nv) {
@@ -1375,8 +1364,7 @@ STAGE void euler_step(const Ctx c) {
   int nv = h->nv;
   float hh = h->timestep;
   float* H = SF(H);
-  float* x = SF(tmpv);
-  LANES(i, nv) SF(warm)[i] = SF(qacc)[i];
+  float* x = SF(search);  // qacc itself is next sub-step's warm start
   if (h->any_damping) {
     LANES(i, nv) x[i] = SF(fsmooth)[i] + SF(fcon)[i];
     SYNC();

@@ -77,8 +77,8 @@ class HostSim:
 
     def __getattr__(self, k):
         m = self.__dict__["model"]
-        sizes = {"qpos": m.nq, "qvel": m.nv, "qacc": m.nv, "warm": m.nv, "ctrl": m.nu, "mocap_pos": 3 * m.nmocap,
-                 "mocap_quat": 4 * m.nmocap, "xpos": 3 * m.nbody, "xquat": 4 * m.nbody, "xmat": 9 * m.nbody,
+        sizes = {"qpos": m.nq, "qvel": m.nv, "qacc": m.nv, "ctrl": m.nu, "mocap_pos": 3 * m.nmocap,
+                 "mocap_quat": 4 * m.nmocap, "xpos": 3 * m.nbody, "xquat": 4 * m.nbody,
                  "fsmooth": m.nv, "fcon": m.nv, "M": m.nv * (m.nv + 1) // 2, "cdof": 6 * m.nv, "cinert": 10 * m.nbody}
         if k in sizes:
             return self.arr(k, sizes[k])

@@ -25,7 +25,7 @@ void* hostsim_create(const void* blob, size_t n, const double* eq_data, const fl
   if (dm_build(s->view, eq_data, ref, s->model, s->err) != 0) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); delete s; return nullptr; }
   const DMHead* h = (const DMHead*)s->model.data();
   s->scratch.assign(h->scr_words, 0.f);
-  s->ctx.mw = s->model.data(); s->ctx.h = h; s->ctx.s = s->scratch.data(); s->ctx.lane = 0;
+  s->ctx.mg = s->model.data(); s->ctx.mw = s->model.data(); s->ctx.h = h; s->ctx.s = s->scratch.data(); s->ctx.lane = 0;
   return s;
 }
 void hostsim_destroy(void* p) { delete (HostSim*)p; }
@@ -34,7 +34,10 @@ int hostsim_scr_words(void* p) { return ((HostSim*)p)->ctx.h->scr_words; }
 int hostsim_offset(void* p, const char* name) {
   const DMHead* h = ((HostSim*)p)->ctx.h;
 #define X(nm, words) if (strcmp(name, #nm) == 0) return h->s_##nm;
-  DM_SCRATCH(X)
+  DM_SCRATCH_PERSIST(X)
+#undef X
+#define X(nm) if (strcmp(name, #nm) == 0) return h->s_##nm;
+  DM_SCRATCH_UNION(X)
 #undef X
   return -1;
 }

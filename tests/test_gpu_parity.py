@@ -82,7 +82,7 @@ def test_free_running_rollout_tracks_oracle():
     obs, _ = env.reset(seed=3)
     orc = oracle_env_from_model("FetchReach", env.model)
     oo, _ = orc.reset(seed=3)
-    assert np.abs(obs["desired_goal"][0].double().cpu().numpy() - oo["desired_goal"]).max() < 1e-6  # same PCG64 stream
+    assert np.abs(obs["desired_goal"][0].double().cpu().numpy() - oo["desired_goal"]).max() < 1e-5  # same PCG64 stream (offset by the fp32 rest pose)
     rng = np.random.default_rng(0)
     for _ in range(49):
         a = rng.uniform(-1, 1, (2, 4)).astype(np.float32)
