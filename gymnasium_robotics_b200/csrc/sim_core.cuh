@@ -24,7 +24,7 @@
 #ifdef B200_BLOCK_ALIGN
 // the warps of a block form alignment groups of B200_AG warps; each group has its own named barrier
 #ifndef B200_AG
-#define B200_AG 14
+#define B200_AG 28
 #endif
 __device__ __forceinline__ void b200_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ int b200_bar_or(int id, int nthreads, int pred) {
@@ -1141,8 +1141,8 @@ __device__ __noinline__ void spd_solve(const Ctx c, const float* A, const float*
 #pragma unroll
     for (int j = 0; j < NVP; j++) h[j] += (live && i == j) ? dd : 0.f;
   }
-  float b = x[live ? i : 0];
-  b = live ? b : 0.f;
+  float b = 0.f;
+  if (live) b = x[i];  // predicated load: idle lanes never touch x
   float dinv = 1.f;
 #pragma unroll
   for (int k = 0; k < NVP; k++) {
@@ -1168,6 +1168,7 @@ __device__ __noinline__ void spd_solve(const Ctx c, const float* A, const float*
     sacc = (i < k) ? sn : sacc;
     z = (i == k) ? zk : z;
   }
+  __syncwarp();
   if (i < nv) x[i] = z;
   __syncwarp();
 }
