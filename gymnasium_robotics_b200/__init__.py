@@ -15,16 +15,26 @@ ENV_IDS = {}
 for _task in ("FetchReach", "FetchPush", "FetchPickAndPlace"):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
         ENV_IDS[f"{_task}{_suffix}-v4"] = dict(task=_task, reward_type=_rt, max_episode_steps=50)
+# AntMaze: the reference registers v3/v4/v5 x sparse/dense (__init__.py:839-958); v5 (Gymnasium Ant-v5) is mirrored
+for _maze, _steps in (("UMaze", 700), ("Open", 700), ("Open_Diverse_G", 700), ("Open_Diverse_GR", 700), ("Medium", 1000),
+                      ("Medium_Diverse_G", 1000), ("Medium_Diverse_GR", 1000), ("Large", 1000), ("Large_Diverse_G", 1000),
+                      ("Large_Diverse_GR", 1000)):
+    for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
+        ENV_IDS[f"AntMaze_{_maze}{_suffix}-v5"] = dict(maze=_maze, reward_type=_rt, max_episode_steps=_steps)
 
 
 def make_vec(env_id: str, num_envs: int = 1, **kwargs):
     """Batched replacement for `gym.make_vec(env_id, num_envs=...)` (reference ids, e.g. "FetchPickAndPlace-v4")."""
-    from .fetch import FetchVectorEnv
-
     if env_id not in ENV_IDS:
         raise KeyError(f"{env_id!r} is not provided by the CUDA path yet; available: {sorted(ENV_IDS)}")
     spec = dict(ENV_IDS[env_id])
     spec.update(kwargs)
+    if "maze" in spec:
+        from .maze import AntMazeVectorEnv
+
+        return AntMazeVectorEnv(num_envs=num_envs, **spec)
+    from .fetch import FetchVectorEnv
+
     return FetchVectorEnv(num_envs=num_envs, **spec)
 
 
@@ -44,6 +54,6 @@ def register_envs():
     for env_id, spec in ENV_IDS.items():
         if env_id in registry:
             continue
-        register(id=env_id, vector_entry_point="gymnasium_robotics_b200.fetch:FetchVectorEnv",
-                 kwargs=dict(task=spec["task"], reward_type=spec["reward_type"], max_episode_steps=spec["max_episode_steps"]))
+        ep = "gymnasium_robotics_b200.maze:AntMazeVectorEnv" if "maze" in spec else "gymnasium_robotics_b200.fetch:FetchVectorEnv"
+        register(id=env_id, vector_entry_point=ep, kwargs=dict(spec))
     return True

@@ -59,20 +59,22 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
   Ctx c;
   c.mg = model_g; c.mw = smem; c.h = h; c.lane = lane;
   c.s = (float*)(smem + model_words) + (size_t)warp * h->scr_words;
-  float a4[4] = {0, 0, 0, 0};
+  float act[TASK_MAX_ACT] = {0, 0, 0, 0, 0, 0, 0, 0};
   const size_t e = active ? (size_t)env : 0;
-  if (actions && active) { for (int k = 0; k < 4; k++) a4[k] = actions[e * 4 + k]; }
-  fetch_env_step<NVP>(c, task, active, mode, nraw, state + e * task.st_stride, a4, obs + e * task.nobs, achieved + e * 3,
-                      desired + e * 3, reward + e, success + e, info ? info + e : nullptr);
+  if (actions && active) { for (int k = 0; k < TASK_MAX_ACT; k++) if (k < task.nact) act[k] = actions[e * task.nact + k]; }
+  fetch_env_step<NVP>(c, task, active, mode, nraw, state + e * task.st_stride, act, obs + e * task.nobs, achieved + e * task.ngoal,
+                      desired + e * task.ngoal, reward + e, success + e, info ? info + e : nullptr);
 }
 
-__global__ void reward_kernel(const float* __restrict__ ag, const float* __restrict__ dg, int M, float thr, int dense,
-                              float* __restrict__ out) {
+__global__ void reward_kernel(const float* __restrict__ ag, const float* __restrict__ dg, int M, int ngoal, int kind, float thr,
+                              float radius, int dense, float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
-  float dx = ag[3 * i] - dg[3 * i], dy = ag[3 * i + 1] - dg[3 * i + 1], dz = ag[3 * i + 2] - dg[3 * i + 2];
-  float d = sqrtf(dx * dx + dy * dy + dz * dz);
-  out[i] = dense ? -d : -(d > thr ? 1.f : 0.f);
+  float d2 = 0;
+  for (int k = 0; k < ngoal; k++) { float e = ag[ngoal * i + k] - dg[ngoal * i + k]; d2 += e * e; }
+  float d = sqrtf(d2);
+  if (kind == TASK_FETCH) out[i] = dense ? -d : -(d > thr ? 1.f : 0.f);   // fetch_env.py:74-80
+  else out[i] = dense ? expf(-d) : (d <= radius ? 1.f : 0.f);               // maze_v4.py:381-388
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -126,22 +128,27 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   t.has_object = task->has_object; t.block_gripper = task->block_gripper; t.n_substeps = task->n_substeps;
   t.reward_dense = task->reward_dense; t.grip_site = task->grip_site; t.obj_site = task->obj_site; t.frame_site = task->frame_site;
   t.nrobot = task->nrobot;
-  if (t.nrobot < 2 || t.nrobot > FETCH_MAX_ROBOT_JNT) { delete h; return fail(nullptr, "b200sim_create: bad nrobot", -5); }
+  if (task->kind == TASK_FETCH && (t.nrobot < 2 || t.nrobot > FETCH_MAX_ROBOT_JNT)) { delete h; return fail(nullptr, "b200sim_create: bad nrobot", -5); }
   for (int i = 0; i < 16; i++) { t.robot_qadr[i] = task->robot_qadr[i]; t.robot_dadr[i] = task->robot_dadr[i]; }
   t.finger_qadr[0] = task->finger_qadr[0]; t.finger_qadr[1] = task->finger_qadr[1];
   t.nobs = task->nobs; t.distance_threshold = task->distance_threshold; t.dt = task->dt;
-  if (dh->nmocap != 1) { delete h; return fail(nullptr, "b200sim_create: Fetch task needs exactly one mocap body", -6); }
+  t.kind = task->kind; t.nact = task->nact; t.ngoal = task->ngoal; t.success_radius = task->success_radius;
+  if (t.kind == TASK_FETCH) { t.nact = 4; t.ngoal = 3; }
+  if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
+  if (t.kind == TASK_FETCH && dh->nmocap != 1) { delete h; return fail(nullptr, "b200sim_create: Fetch task needs exactly one mocap body", -6); }
+  if (t.kind == TASK_ANTMAZE && (t.nact != dh->nu || t.nact > TASK_MAX_ACT || t.ngoal != 2 || t.nobs != dh->nq - 2 + dh->nv)) { delete h; return fail(nullptr, "b200sim_create: inconsistent AntMaze task", -6); }
   int o = 0;
   t.st_qpos = o; o += dh->nq; t.st_qvel = o; o += dh->nv; t.st_warm = o; o += dh->nv; t.st_ctrl = o; o += dh->nu;
-  t.st_mocap = o; o += 7; t.st_pose = o; o += 7; t.st_goal = o; o += 3;
+  t.st_mocap = o; o += 7 * dh->nmocap; t.st_pose = o; o += (t.kind == TASK_FETCH ? 7 : 0); t.st_goal = o; o += t.ngoal;
   t.st_stride = (o + 3) & ~3;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, "b200sim_create: cudaSetDevice failed", -7); }
   h->smem_bytes = ((size_t)dh->hot_words + (size_t)B200_WPB * dh->scr_words) * 4;
   h->blocks = (num_envs + B200_WPB - 1) / B200_WPB;
-  h->nvp = dh->nv == 15 ? 15 : (dh->nv == 21 ? 21 : 32);  // exact sizes for the Fetch models, padded otherwise
+  h->nvp = dh->nv == 15 ? 15 : (dh->nv == 21 ? 21 : (dh->nv == 14 ? 14 : 32));  // exact sizes for the in-scope models, padded otherwise
   cudaError_t e = cudaSuccess;
   if (h->nvp == 15) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   else if (h->nvp == 21) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  else if (h->nvp == 14) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   else e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e != cudaSuccess) { std::string m = std::string("cudaFuncSetAttribute(smem=") + std::to_string(h->smem_bytes) + "): " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
   if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, (size_t)num_envs * t.st_stride * 4) != cudaSuccess) {
@@ -185,7 +192,7 @@ static int launch(b200sim* h, int mode, int nraw, const float* actions, const un
 #define B200_LAUNCH(NVP_)                                                                                   \
   fetch_kernel<B200_WPB, NVP_><<<h->blocks, B200_WPB * 32, h->smem_bytes, (cudaStream_t)stream>>>(          \
       h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info)
-  if (h->nvp == 15) B200_LAUNCH(15); else if (h->nvp == 21) B200_LAUNCH(21); else B200_LAUNCH(32);
+  if (h->nvp == 15) B200_LAUNCH(15); else if (h->nvp == 21) B200_LAUNCH(21); else if (h->nvp == 14) B200_LAUNCH(14); else B200_LAUNCH(32);
 #undef B200_LAUNCH
   h->launches++;
   CUDA_OK(cudaGetLastError());
@@ -208,7 +215,8 @@ int b200sim_raw_step(b200sim_t* h, int nstep, float* obs, float* achieved, float
 int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const float* desired, int M, float* out, void* stream) {
   if (M <= 0) return 0;
   cudaSetDevice(h->device);
-  reward_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(achieved, desired, M, h->task.distance_threshold, h->task.reward_dense, out);
+  reward_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(achieved, desired, M, h->task.ngoal, h->task.kind, h->task.distance_threshold,
+                                                                  h->task.success_radius, h->task.reward_dense, out);
   const_cast<b200sim*>(h)->launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -13,9 +13,7 @@
 
 #define DM_MAX_BODY 32   // one lane per body / 32-bit body masks
 #define DM_MAX_NV 32     // 32-bit dof masks
-#define DM_NCON_MAX 16   // contacts kept per env per sub-step
 #define DM_NDOFROW_MAX 8
-#define DM_NGROUP_MAX 10
 #define DM_NCAND_MAX 32
 #define DM_NWELD_MAX 1
 
@@ -38,7 +36,7 @@
   X(act_bias, 3, nu) X(act_ctrlrange, 2, nu) X(act_forcerange, 2, nu) \
   X(eq_type, 1, neq) X(eq_obj1, 1, neq) X(eq_obj2, 1, neq) X(eq_active, 1, neq) X(eq_data, 11, neq) X(eq_solref, 2, neq) \
   X(eq_solimp, 5, neq) X(eq_invweight, 2, neq) \
-  X(mocap_body, 1, nmocap)
+  X(mocap_body, 1, nmocap) X(grid_walls, 1, ngridw)
 #define DM_ARRAYS_COLD(X) \
   X(pair_condim, 1, npair) X(pair_friction, 3, npair) X(pair_gap, 1, npair) X(pair_solref, 2, npair) \
   X(pair_solimp, 5, npair) X(pair_invweight, 2, npair)
@@ -48,8 +46,9 @@
 #define DM_SCRATCH_PERSIST(X) \
   X(qpos, nq) X(qvel, nv) X(qacc, nv) X(ctrl, nu) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) \
   X(xpos, 3 * nb) X(xquat, 4 * nb) X(cdof, 6 * nv) X(M, nv * (nv + 1) / 2) X(fsmooth, nv) X(fcon, nv) \
-  X(con, DM_NCON_MAX * CON_WORDS) X(dofrow, DM_NDOFROW_MAX * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
-  X(group, DM_NGROUP_MAX * GRP_WORDS) X(counters, 8)
+  X(rk_q0, nrkq) X(rk_v0, nrkv) X(rk_dx, nrkv) X(rk_df, nrkv) \
+  X(con, ncon_max * CON_WORDS) X(dofrow, DM_NDOFROW_MAX * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
+  X(group, ngrp_max * GRP_WORDS) X(counters, 8)
 // time-shared region `uni`: kinematics {kinA, kinB} -> dynamics {cinert, b6, d6, geom_xpos, cand} -> solver {H, d6, grad,
 // search, Ma, Mv} -> observation {cvel}.  d6 keeps one offset in both phases that use it.
 #define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
@@ -74,7 +73,9 @@ struct DMHead {
   int nwords;      // size of the model buffer (header included) in 4-byte words
   int hot_words;   // leading part staged into shared memory (header + HOT arrays)
   int scr_words;   // per-env scratch size in words
-  int iterations, ls_iterations, integrator, any_damping, kin_iters, pad0;
+  int iterations, ls_iterations, integrator, any_damping, kin_iters, ncon_max, ngrp_max, pad2;
+  int grid_len, grid_wid, ngridw, pad1;   // maze wall grid (0 x 0 when the model has none)
+  float grid_scale, grid_top, grid_xc, grid_yc;  // cell size, wall top height, map centre offsets
   float timestep, gravity[3], tolerance, impratio, meaninertia, ls_tolerance, ref[3];
 #define X(name, w, kind) int o_##name;
   DM_ARRAYS(X)
@@ -95,8 +96,34 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
                            std::vector<uint32_t>& buf, std::string& err) {
   DMHead h;
   memset(&h, 0, sizeof(h));
-  h.nb = m.nbody; h.njnt = m.njnt; h.nq = m.nq; h.nv = m.nv; h.nu = m.nu; h.ngeom = m.ngeom; h.nsite = m.nsite;
-  h.nmocap = m.nmocap; h.neq = m.neq; h.npair = m.npair;
+  h.nb = m.nbody; h.njnt = m.njnt; h.nq = m.nq; h.nv = m.nv; h.nu = m.nu; h.nsite = m.nsite;
+  h.nmocap = m.nmocap; h.neq = m.neq;
+  // pair list on the device: ordinary pairs, plus one grid pair (geom2 = -1) per geom that can touch maze walls
+  std::vector<int> psrc;       // source pair index in the blob
+  std::vector<int> pgrid;      // 1 = grid pair
+  {
+    std::vector<char> seen(m.ngeom, 0);
+    for (int p = 0; p < m.npair; p++) {
+      bool isgrid = m.n_pair_grid == m.npair && m.pair_grid[p];
+      if (!isgrid) { psrc.push_back(p); pgrid.push_back(0); }
+      else if (!seen[m.pair_geom1[p]]) { seen[m.pair_geom1[p]] = 1; psrc.push_back(p); pgrid.push_back(1); }
+    }
+  }
+  h.npair = (int)psrc.size();
+  std::vector<int> gmap(m.ngeom, -1), gsrc;
+  for (size_t p = 0; p < psrc.size(); p++) {
+    int ga = m.pair_geom1[psrc[p]], gb = m.pair_geom2[psrc[p]];
+    if (gmap[ga] < 0) { gmap[ga] = (int)gsrc.size(); gsrc.push_back(ga); }
+    if (!pgrid[p] && gmap[gb] < 0) { gmap[gb] = (int)gsrc.size(); gsrc.push_back(gb); }
+  }
+  h.ngeom = (int)gsrc.size();
+  if (m.n_grid_dims >= 2 && m.grid_dims[0] > 0) {
+    h.grid_len = m.grid_dims[0]; h.grid_wid = m.grid_dims[1]; h.ngridw = (h.grid_len * h.grid_wid + 31) / 32;
+    h.grid_scale = (float)m.grid_param[0]; h.grid_top = (float)(m.grid_param[1] * m.grid_param[0]);
+    h.grid_xc = (float)m.grid_param[2]; h.grid_yc = (float)m.grid_param[3];
+  }
+  h.ncon_max = m.nmocap > 0 ? 16 : 20;   // contacts kept per env per sub-step
+  h.ngrp_max = m.nmocap > 0 ? 10 : 14;   // geom pairs in contact (+ welds) per env per sub-step
   if (h.nb > DM_MAX_BODY) { err = "model has more than 32 runtime bodies"; return -1; }
   if (h.nv > DM_MAX_NV) { err = "model has more than 32 dofs"; return -1; }
   if (m.ntendon > 0) { err = "tendons are not supported by the CUDA path yet"; return -1; }
@@ -105,7 +132,6 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   if (nweld > DM_NWELD_MAX) { err = "too many weld constraints"; return -1; }
   h.iterations = m.opt_int[B200_OPTI_ITERATIONS]; h.ls_iterations = m.opt_int[B200_OPTI_LS_ITERATIONS];
   h.integrator = m.opt_int[B200_OPTI_INTEGRATOR];
-  if (h.integrator != B200_INT_EULER) { err = "only the Euler integrator is implemented on the CUDA path"; return -1; }
   h.timestep = (float)m.opt[B200_OPT_TIMESTEP];
   for (int k = 0; k < 3; k++) { h.gravity[k] = (float)m.opt[B200_OPT_GRAVITY + k]; h.ref[k] = ref[k]; }
   h.tolerance = (float)m.opt[B200_OPT_TOLERANCE]; h.impratio = (float)m.opt[B200_OPT_IMPRATIO];
@@ -113,7 +139,8 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   for (int d = 0; d < m.nv; d++) if (m.dof_damping[d] > 0) h.any_damping = 1;
   // offsets
   int nb = h.nb, njnt = h.njnt, nq = h.nq, nv = h.nv, nu = h.nu, ngeom = h.ngeom, nsite = h.nsite, nmocap = h.nmocap,
-      neq = h.neq, npair = h.npair;
+      neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max;
+  int nrkq = h.integrator == B200_INT_RK4 ? nq : 0, nrkv = h.integrator == B200_INT_RK4 ? nv : 0;
   int off = (int)((sizeof(DMHead) + 3) / 4);
 #define X(name, w, kind) h.o_##name = off; off += (w) * (kind);
   DM_ARRAYS_HOT(X)
@@ -208,23 +235,27 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     if (m.dof_frictionloss[d] > 0) { err = "frictionloss rows are not supported by the CUDA path yet"; return -1; }
   }
   for (int g = 0; g < ngeom; g++) {
-    I(h.o_geom_type, g, m.geom_type[g]); I(h.o_geom_body, g, m.geom_body[g]);
-    for (int k = 0; k < 3; k++) { F(h.o_geom_pos, 3 * g + k, m.geom_pos[3 * g + k]); F(h.o_geom_size, 3 * g + k, m.geom_size[3 * g + k]); }
-    for (int k = 0; k < 4; k++) F(h.o_geom_quat, 4 * g + k, m.geom_quat[4 * g + k]);
-    F(h.o_geom_rbound, g, m.geom_rbound[g]);
+    int sg = gsrc[g];
+    I(h.o_geom_type, g, m.geom_type[sg]); I(h.o_geom_body, g, m.geom_body[sg]);
+    for (int k = 0; k < 3; k++) { F(h.o_geom_pos, 3 * g + k, m.geom_pos[3 * sg + k]); F(h.o_geom_size, 3 * g + k, m.geom_size[3 * sg + k]); }
+    for (int k = 0; k < 4; k++) F(h.o_geom_quat, 4 * g + k, m.geom_quat[4 * sg + k]);
+    F(h.o_geom_rbound, g, m.geom_rbound[sg]);
   }
   for (int p = 0; p < npair; p++) {
-    I(h.o_pair_geom1, p, m.pair_geom1[p]); I(h.o_pair_geom2, p, m.pair_geom2[p]); I(h.o_pair_condim, p, m.pair_condim[p]);
-    int t1 = m.geom_type[m.pair_geom1[p]], t2 = m.geom_type[m.pair_geom2[p]];
-    bool ok = (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_BOX) || (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX);
-    if (!ok) { err = "collision pair type not supported by the CUDA path yet (only plane-box, box-box)"; return -1; }
-    if (m.pair_condim[p] != 1 && m.pair_condim[p] != 3 && m.pair_condim[p] != 4) { err = "condim must be 1, 3 or 4 on the CUDA path"; return -1; }
-    F(h.o_pair_friction, 3 * p + 0, m.pair_friction[5 * p + 0]); F(h.o_pair_friction, 3 * p + 1, m.pair_friction[5 * p + 2]);
-    F(h.o_pair_friction, 3 * p + 2, m.pair_friction[5 * p + 3]);
-    F(h.o_pair_margin, p, m.pair_margin[p]); F(h.o_pair_gap, p, m.pair_gap[p]);
-    for (int k = 0; k < 2; k++) { F(h.o_pair_solref, 2 * p + k, m.pair_solref[2 * p + k]); F(h.o_pair_invweight, 2 * p + k, m.pair_invweight[2 * p + k]); }
-    for (int k = 0; k < 5; k++) F(h.o_pair_solimp, 5 * p + k, m.pair_solimp[5 * p + k]);
+    int sp = psrc[p];
+    I(h.o_pair_geom1, p, gmap[m.pair_geom1[sp]]); I(h.o_pair_geom2, p, pgrid[p] ? -1 : gmap[m.pair_geom2[sp]]); I(h.o_pair_condim, p, m.pair_condim[sp]);
+    int t1 = m.geom_type[m.pair_geom1[sp]], t2 = m.geom_type[m.pair_geom2[sp]];
+    bool ok = (t1 == B200_GEOM_PLANE && (t2 == B200_GEOM_BOX || t2 == B200_GEOM_SPHERE || t2 == B200_GEOM_CAPSULE)) ||
+              (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) || ((t1 == B200_GEOM_SPHERE || t1 == B200_GEOM_CAPSULE) && t2 == B200_GEOM_BOX);
+    if (!ok) { err = "collision pair type not supported by the CUDA path yet"; return -1; }
+    if (m.pair_condim[sp] != 1 && m.pair_condim[sp] != 3 && m.pair_condim[sp] != 4) { err = "condim must be 1, 3 or 4 on the CUDA path"; return -1; }
+    F(h.o_pair_friction, 3 * p + 0, m.pair_friction[5 * sp + 0]); F(h.o_pair_friction, 3 * p + 1, m.pair_friction[5 * sp + 2]);
+    F(h.o_pair_friction, 3 * p + 2, m.pair_friction[5 * sp + 3]);
+    F(h.o_pair_margin, p, m.pair_margin[sp]); F(h.o_pair_gap, p, m.pair_gap[sp]);
+    for (int k = 0; k < 2; k++) { F(h.o_pair_solref, 2 * p + k, m.pair_solref[2 * sp + k]); F(h.o_pair_invweight, 2 * p + k, m.pair_invweight[2 * sp + k]); }
+    for (int k = 0; k < 5; k++) F(h.o_pair_solimp, 5 * p + k, m.pair_solimp[5 * sp + k]);
   }
+  for (int i = 0; i < h.grid_len * h.grid_wid; i++) if (m.grid_walls[i]) buf[h.o_grid_walls + i / 32] |= 1u << (i % 32);
   for (int s = 0; s < nsite; s++) {
     I(h.o_site_body, s, m.site_body[s]);
     for (int k = 0; k < 3; k++) F(h.o_site_pos, 3 * s + k, m.site_pos[3 * s + k]);

@@ -18,9 +18,14 @@ struct FetchTask {
   int finger_qadr[2];
   int nobs;
   float distance_threshold, dt;
-  // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(3)
+  // task family (TASK_FETCH / TASK_ANTMAZE), action and goal widths, maze success radius
+  int kind, nact, ngoal;
+  float success_radius;
+  // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(ngoal)
   int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride;
 };
+enum { TASK_FETCH = 0, TASK_ANTMAZE = 1 };
+#define TASK_MAX_ACT 8
 
 enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
 
@@ -50,7 +55,7 @@ HD void store_state(const Ctx& c, const FetchTask& t, float* st) {
   LANES(i, h->nu) st[t.st_ctrl + i] = SF(ctrl)[i];
   LANES(i, 3 * h->nmocap) st[t.st_mocap + i] = SF(mocap_pos)[i];
   LANES(i, 4 * h->nmocap) st[t.st_mocap + 3 + i] = SF(mocap_quat)[i];
-  if (c.lane == 0) {
+  if (c.lane == 0 && t.kind == TASK_FETCH) {
     float p[3], q[4];
     site_pose(c, t.frame_site, p, q);  // data.xpos / data.xquat of the welded body as of the last forward pass
     for (int k = 0; k < 3; k++) st[t.st_pose + k] = p[k];
@@ -110,6 +115,22 @@ HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float
   }
 }
 
+// AntMaze: obs = ant qpos[2:] | qvel, achieved = qpos[:2]; reward exp(-d) (dense) or d <= r (sparse)
+// (reference: envs/maze/ant_maze_v5.py:295-320, envs/maze/maze_v4.py:381-398)
+HD void antmaze_observe(const Ctx& c, const FetchTask& t, const float* goal, float* obs, float* achieved, float* desired,
+                        float* reward, float* success) {
+  const DMHead* h = c.h;
+  LANES(i, h->nq - 2) obs[i] = SF(qpos)[2 + i];
+  LANES(i, h->nv) obs[h->nq - 2 + i] = SF(qvel)[i];
+  if (c.lane == 0) {
+    float dx = SF(qpos)[0] - goal[0], dy = SF(qpos)[1] - goal[1];
+    float d = sqrtf(dx * dx + dy * dy);
+    achieved[0] = SF(qpos)[0]; achieved[1] = SF(qpos)[1]; desired[0] = goal[0]; desired[1] = goal[1];
+    *reward = t.reward_dense ? expf(-d) : (d <= t.success_radius ? 1.f : 0.f);
+    *success = d <= t.success_radius ? 1.f : 0.f;
+  }
+}
+
 // one env, one warp.  `st` is this env's state record; outputs are this env's rows.  `active` is warp-uniform: idle
 // warps run the same control flow (for the block-wide alignment barriers) but touch no memory.
 template <int NVP>
@@ -118,7 +139,7 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   const DMHead* h = c.h;
   if (active) {
     load_state(c, t, st);
-    if (mode == MODE_STEP) {
+    if (mode == MODE_STEP && t.kind == TASK_FETCH) {
       // _set_action: clip, scale, mocap <- last forward pose of the welded body + delta, position actuators relative
       float a[4];
       for (int k = 0; k < 4; k++) a[k] = fminf(fmaxf(action[k], -1.f), 1.f);
@@ -130,24 +151,33 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
         for (int i = 0; i < h->nu; i++) SF(ctrl)[i] = SF(qpos)[MI(jnt_qposadr)[MI(act_trnid)[i]]] + g;
       }
       SYNC();
+    } else if (mode == MODE_STEP) {
+      // do_simulation(action, frame_skip): ctrl = action (clamped to ctrlrange inside the actuation stage)
+      LANES(i, h->nu) SF(ctrl)[i] = action[i];
+      SYNC();
     }
   }
   int nsub = mode == MODE_STEP ? t.n_substeps : (mode == MODE_RAW ? nraw : 0);
   for (int s = 0; s < nsub; s++) {
     forward<NVP>(c, active);
     ALIGN_AT(4);
-    if (active) euler_step<NVP>(c);
+    if (h->integrator == B200_INT_RK4) rk4_substep<NVP>(c, active);
+    else if (active) euler_step<NVP>(c);
   }
   if (!active) return;
-  if (mode == MODE_REFRESH || (mode == MODE_STEP && t.block_gripper) || nsub == 0) {
-    if (mode == MODE_STEP && t.block_gripper) {
-      if (c.lane == 0) { SF(qpos)[t.finger_qadr[0]] = 0.f; SF(qpos)[t.finger_qadr[1]] = 0.f; }
-      SYNC();
+  if (t.kind == TASK_FETCH) {
+    if (mode == MODE_REFRESH || (mode == MODE_STEP && t.block_gripper) || nsub == 0) {
+      if (mode == MODE_STEP && t.block_gripper) {
+        if (c.lane == 0) { SF(qpos)[t.finger_qadr[0]] = 0.f; SF(qpos)[t.finger_qadr[1]] = 0.f; }
+        SYNC();
+      }
+      kinematics(c);
+      com_quantities(c);
     }
-    kinematics(c);
-    com_quantities(c);
+    fetch_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
+  } else {
+    antmaze_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   }
-  fetch_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   store_state(c, t, st);
   if (iters_out && c.lane == 0) *iters_out = SI(counters)[CNT_ITERS] | (SI(counters)[CNT_OVERFLOW] << 16);
 }

@@ -453,7 +453,7 @@ HD void ref_kb(const Ctx& c, const float* solref, float dmax_in, float* K, float
 
 // ---------------------------------------------------------------------------------------------------------------
 // 5. collision (plane-box, box-box; same decision logic as oracle/oracle.c, fp32)
-struct ContactOut { float pos[4][3]; float dist[4]; float n[3]; int cnt; };
+struct ContactOut { float pos[4][3]; float nrm[4][3]; float dist[4]; int cnt; };
 
 HD void geom_pose(const Ctx& c, int g, float* pos, float* mat) {
   int b = MI(geom_body)[g];
@@ -469,7 +469,7 @@ HD void collide_plane_box(const Ctx& c, int g1, int g2, float margin, ContactOut
   const float* sz = MF(geom_size) + 3 * g2;
   float n[3] = {pm[2], pm[5], pm[8]}, dif[3] = {bp[0] - pp[0], bp[1] - pp[1], bp[2] - pp[2]};
   float dist0 = dot3(dif, n);
-  o.cnt = 0; o.n[0] = n[0]; o.n[1] = n[1]; o.n[2] = n[2];
+  o.cnt = 0;
   for (int i = 0; i < 8; i++) {
     float loc[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]}, vec[3];
     mulmv(vec, bm, loc);
@@ -478,7 +478,7 @@ HD void collide_plane_box(const Ctx& c, int g1, int g2, float margin, ContactOut
     float d = dist0 + ld;
     int k = o.cnt++;
     o.dist[k] = d;
-    for (int a = 0; a < 3; a++) o.pos[k][a] = bp[a] + vec[a] - n[a] * d * 0.5f;
+    for (int a = 0; a < 3; a++) { o.pos[k][a] = bp[a] + vec[a] - n[a] * d * 0.5f; o.nrm[k][a] = n[a]; }
   }
 }
 
@@ -552,7 +552,7 @@ HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& 
     float b = dot3(ea, eb), dd = dot3(ea, w), e = dot3(eb, w), den = 1 - b * b;
     float sp = den > 1e-12f ? (b * e - dd) / den : 0, tp = den > 1e-12f ? (e - b * dd) / den : 0;
     sp = fminf(fmaxf(sp, -ha[i]), ha[i]); tp = fminf(fmaxf(tp, -hb[j]), hb[j]);
-    o.cnt = 1; o.dist[0] = ebest; o.n[0] = n[0]; o.n[1] = n[1]; o.n[2] = n[2];
+    o.cnt = 1; o.dist[0] = ebest; o.nrm[0][0] = n[0]; o.nrm[0][1] = n[1]; o.nrm[0][2] = n[2];
     for (int k = 0; k < 3; k++) o.pos[0][k] = 0.5f * (PA[k] + ea[k] * sp + PB[k] + eb[k] * tp);
     return;
   }
@@ -622,13 +622,130 @@ HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& 
     for (int a = 0; a < ns; a++) for (int b = a + 1; b < ns; b++) if (sel[b] < sel[a]) { int t = sel[a]; sel[a] = sel[b]; sel[b] = t; }
   }
   float fs = flip ? -1.f : 1.f;
-  o.n[0] = fs * nr[0]; o.n[1] = fs * nr[1]; o.n[2] = fs * nr[2];
   o.cnt = ns;
   for (int k = 0; k < ns; k++) {
     const float* cd = cand[sel[k]];
     o.dist[k] = cd[2];
+    o.nrm[k][0] = fs * nr[0]; o.nrm[k][1] = fs * nr[1]; o.nrm[k][2] = fs * nr[2];
     for (int a = 0; a < 3; a++) o.pos[k][a] = pr[a] + au[a] * cd[0] + av[a] * cd[1] + nr[a] * (hr[ax] + 0.5f * cd[2]);
   }
+}
+
+// ---- sphere / capsule against planes and boxes (same decision logic as oracle/oracle.c)
+HD void collide_plane_sphere(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
+  float pp[3], pm[9];
+  geom_pose(c, g1, pp, pm);
+  const float* ce = SF(geom_xpos) + 3 * g2;
+  float n[3] = {pm[2], pm[5], pm[8]}, dif[3] = {ce[0] - pp[0], ce[1] - pp[1], ce[2] - pp[2]};
+  float r = MF(geom_size)[3 * g2], d = dot3(dif, n) - r;
+  o.cnt = 0;
+  if (d > margin) return;
+  o.cnt = 1; o.dist[0] = d;
+  for (int a = 0; a < 3; a++) { o.pos[0][a] = ce[a] - n[a] * (r + 0.5f * d); o.nrm[0][a] = n[a]; }
+}
+HD void collide_plane_capsule(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
+  float pp[3], pm[9], cp[3], cm[9];
+  geom_pose(c, g1, pp, pm); geom_pose(c, g2, cp, cm);
+  float n[3] = {pm[2], pm[5], pm[8]}, ax[3] = {cm[2], cm[5], cm[8]};
+  float r = MF(geom_size)[3 * g2], hl = MF(geom_size)[3 * g2 + 1];
+  o.cnt = 0;
+  for (int side = -1; side <= 1; side += 2) {
+    float e[3] = {cp[0] + ax[0] * side * hl, cp[1] + ax[1] * side * hl, cp[2] + ax[2] * side * hl};
+    float dif[3] = {e[0] - pp[0], e[1] - pp[1], e[2] - pp[2]};
+    float d = dot3(dif, n) - r;
+    if (d > margin) continue;
+    int k = o.cnt++;
+    o.dist[k] = d;
+    for (int a = 0; a < 3; a++) { o.pos[k][a] = e[a] - n[a] * (r + 0.5f * d); o.nrm[k][a] = n[a]; }
+  }
+}
+// signed distance from p to the surface of a box (pose bp/bm, half sizes h); normal points from the surface towards p
+HD float point_box(const float* p, const float* bp, const float* bm, const float* h, float* closest, float* normal) {
+  float rel[3] = {p[0] - bp[0], p[1] - bp[1], p[2] - bp[2]}, loc[3], q[3];
+  mulmtv(loc, bm, rel);
+  bool inside = true;
+  for (int k = 0; k < 3; k++) { q[k] = fminf(fmaxf(loc[k], -h[k]), h[k]); if (q[k] != loc[k]) inside = false; }
+  float nl[3] = {0, 0, 0}, dist;
+  if (!inside) {
+    float d[3] = {loc[0] - q[0], loc[1] - q[1], loc[2] - q[2]};
+    dist = sqrtf(dot3(d, d));
+    float inv = 1.0f / dist;
+    nl[0] = d[0] * inv; nl[1] = d[1] * inv; nl[2] = d[2] * inv;
+  } else {
+    int ax = 0; float best = 1e30f;
+    for (int k = 0; k < 3; k++) { float pen = h[k] - fabsf(loc[k]); if (pen < best) { best = pen; ax = k; } }
+    dist = -best;
+    float sg = loc[ax] < 0 ? -1.f : 1.f;
+    if (ax == 0) { nl[0] = sg; q[0] = sg * h[0]; } else if (ax == 1) { nl[1] = sg; q[1] = sg * h[1]; } else { nl[2] = sg; q[2] = sg * h[2]; }
+  }
+  mulmv(closest, bm, q);
+  closest[0] += bp[0]; closest[1] += bp[1]; closest[2] += bp[2];
+  mulmv(normal, bm, nl);
+  return dist;
+}
+HD void sphere_box_contact(const float* center, float r, const float* bp, const float* bm, const float* bh, float margin, ContactOut& o) {
+  if (o.cnt >= 4) return;
+  float closest[3], nrm[3];
+  float d = point_box(center, bp, bm, bh, closest, nrm) - r;
+  if (d > margin) return;
+  int k = o.cnt++;
+  o.dist[k] = d;
+  for (int a = 0; a < 3; a++) { o.nrm[k][a] = -nrm[a]; o.pos[k][a] = closest[a] + nrm[a] * 0.5f * d; }
+}
+HDN void capsule_box_contacts(const float* cp, const float* ax, float r, float hl, const float* bp, const float* bm, const float* bh,
+                              float margin, ContactOut& o) {
+  float e0[3] = {cp[0] - ax[0] * hl, cp[1] - ax[1] * hl, cp[2] - ax[2] * hl}, e1[3] = {cp[0] + ax[0] * hl, cp[1] + ax[1] * hl, cp[2] + ax[2] * hl};
+  float cl[3], nn[3];
+  float d0 = point_box(e0, bp, bm, bh, cl, nn) - r, d1 = point_box(e1, bp, bm, bh, cl, nn) - r;
+  if (d0 <= margin && d1 <= margin) {
+    sphere_box_contact(e0, r, bp, bm, bh, margin, o);
+    sphere_box_contact(e1, r, bp, bm, bh, margin, o);
+    return;
+  }
+  const float gr = 0.6180339887498949f;
+  float lo = -hl, hi = hl, x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo), p[3];
+  for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * x1;
+  float f1 = point_box(p, bp, bm, bh, cl, nn);
+  for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * x2;
+  float f2 = point_box(p, bp, bm, bh, cl, nn);
+  for (int it = 0; it < 24; it++) {
+    if (f1 < f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * x1; f1 = point_box(p, bp, bm, bh, cl, nn); }
+    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * x2; f2 = point_box(p, bp, bm, bh, cl, nn); }
+  }
+  float t = 0.5f * (lo + hi);
+  for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * t;
+  sphere_box_contact(p, r, bp, bm, bh, margin, o);
+}
+// sphere or capsule geom g1 against box geom g2, or (g2 < 0) against the maze wall cells around it
+HD void collide_round_box(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
+  const DMHead* h = c.h;
+  o.cnt = 0;
+  float cp[3], cm[9];
+  geom_pose(c, g1, cp, cm);
+  bool capsule = MI(geom_type)[g1] == B200_GEOM_CAPSULE;
+  float r = MF(geom_size)[3 * g1], hl = MF(geom_size)[3 * g1 + 1], ax[3] = {cm[2], cm[5], cm[8]};
+  if (g2 >= 0) {
+    float bp[3], bm[9];
+    geom_pose(c, g2, bp, bm);
+    if (capsule) capsule_box_contacts(cp, ax, r, hl, bp, bm, MF(geom_size) + 3 * g2, margin, o);
+    else sphere_box_contact(cp, r, bp, bm, MF(geom_size) + 3 * g2, margin, o);
+    return;
+  }
+  float reach = MF(geom_rbound)[g1] + margin, s = h->grid_scale;
+  if (cp[2] - reach > h->grid_top) return;
+  int j0 = (int)floorf((cp[0] - reach + h->grid_xc) / s), j1 = (int)floorf((cp[0] + reach + h->grid_xc) / s);
+  int i0 = (int)floorf((h->grid_yc - (cp[1] + reach)) / s), i1 = (int)floorf((h->grid_yc - (cp[1] - reach)) / s);
+  const float idm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  float bh[3] = {0.5f * s, 0.5f * s, 0.5f * h->grid_top};
+  for (int i = i0; i <= i1; i++)
+    for (int j = j0; j <= j1; j++) {
+      if (i < 0 || j < 0 || i >= h->grid_len || j >= h->grid_wid) continue;
+      int bit = i * h->grid_wid + j;
+      if (!((MU(grid_walls)[bit >> 5] >> (bit & 31)) & 1u)) continue;
+      float bp[3] = {(j + 0.5f) * s - h->grid_xc, h->grid_yc - (i + 0.5f) * s, 0.5f * h->grid_top};
+      if (capsule) capsule_box_contacts(cp, ax, r, hl, bp, idm, bh, margin, o);
+      else sphere_box_contact(cp, r, bp, idm, bh, margin, o);
+    }
 }
 
 HD void make_frame(float* f) {
@@ -660,7 +777,21 @@ STAGE void collision(const Ctx c) {
       float margin = MF(pair_margin)[p];
       const float *x1 = SF(geom_xpos) + 3 * g1, *x2 = SF(geom_xpos) + 3 * g2;
       float dif[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
-      if (MI(geom_type)[g1] == B200_GEOM_PLANE) {
+      if (g2 < 0) {
+        // maze walls: any wall cell within reach of the geom's bounding sphere?
+        float reach = MF(geom_rbound)[g1] + margin, s = h->grid_scale;
+        const float* x = SF(geom_xpos) + 3 * g1;
+        if (x[2] - reach <= h->grid_top) {
+          int j0 = (int)floorf((x[0] - reach + h->grid_xc) / s), j1 = (int)floorf((x[0] + reach + h->grid_xc) / s);
+          int i0 = (int)floorf((h->grid_yc - (x[1] + reach)) / s), i1 = (int)floorf((h->grid_yc - (x[1] - reach)) / s);
+          for (int i = i0; i <= i1; i++)
+            for (int j = j0; j <= j1; j++) {
+              if (i < 0 || j < 0 || i >= h->grid_len || j >= h->grid_wid) continue;
+              int bit = i * h->grid_wid + j;
+              if ((MU(grid_walls)[bit >> 5] >> (bit & 31)) & 1u) hit = true;
+            }
+        }
+      } else if (MI(geom_type)[g1] == B200_GEOM_PLANE) {
         int b = MI(geom_body)[g1];
         float q[4], m[9];
         qmul(q, SF(xquat) + 4 * b, MF(geom_quat) + 4 * g1);
@@ -690,12 +821,17 @@ STAGE void collision(const Ctx c) {
       p = cand[ci];
       int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
       float margin = MF(pair_margin)[p];
-      if (MI(geom_type)[g1] == B200_GEOM_PLANE) collide_plane_box(c, g1, g2, margin, o);
-      else collide_box_box(c, g1, g2, margin, o);
+      int t1 = MI(geom_type)[g1], t2 = g2 < 0 ? B200_GEOM_BOX : MI(geom_type)[g2];
+      if (t1 == B200_GEOM_PLANE) {
+        if (t2 == B200_GEOM_BOX) collide_plane_box(c, g1, g2, margin, o);
+        else if (t2 == B200_GEOM_SPHERE) collide_plane_sphere(c, g1, g2, margin, o);
+        else collide_plane_capsule(c, g1, g2, margin, o);
+      } else if (t1 == B200_GEOM_BOX) collide_box_box(c, g1, g2, margin, o);
+      else collide_round_box(c, g1, g2, margin, o);
       // contacts beyond the gap are not turned into constraints
       float inc = margin - GF(pair_gap)[p];
       int k2 = 0;
-      for (int k = 0; k < o.cnt; k++) if (o.dist[k] < inc) { if (k2 != k) { o.dist[k2] = o.dist[k]; for (int a = 0; a < 3; a++) o.pos[k2][a] = o.pos[k][a]; } k2++; }
+      for (int k = 0; k < o.cnt; k++) if (o.dist[k] < inc) { if (k2 != k) { o.dist[k2] = o.dist[k]; for (int a = 0; a < 3; a++) { o.pos[k2][a] = o.pos[k][a]; o.nrm[k2][a] = o.nrm[k][a]; } } k2++; }
       o.cnt = k2;
     }
     int total, slot = wexscan(o.cnt, c.lane, &total);
@@ -706,9 +842,9 @@ STAGE void collision(const Ctx c) {
     int gid = baseg + gslot;
     for (int k = 0; k < o.cnt; k++) {
       int id = basec + slot + k;
-      if (id >= DM_NCON_MAX || gid >= DM_NGROUP_MAX - DM_NWELD_MAX) break;
+      if (id >= h->ncon_max || gid >= h->ngrp_max - DM_NWELD_MAX) break;
       float* cr = SF(con) + id * CON_WORDS;
-      float fr9[9] = {o.n[0], o.n[1], o.n[2], 0, 0, 0, 0, 0, 0};
+      float fr9[9] = {o.nrm[k][0], o.nrm[k][1], o.nrm[k][2], 0, 0, 0, 0, 0, 0};
       make_frame(fr9);
       float r[3] = {o.pos[k][0] - h->ref[0], o.pos[k][1] - h->ref[1], o.pos[k][2] - h->ref[2]};
       for (int a = 0; a < 3; a++) { float* w = cr + C_W + 6 * a; cross3(w, r, fr9 + 3 * a); w[3] = fr9[3 * a]; w[4] = fr9[3 * a + 1]; w[5] = fr9[3 * a + 2]; }
@@ -737,16 +873,16 @@ STAGE void collision(const Ctx c) {
       ((int*)cr)[C_DIMGRP] = dim | (gid << 8);
       kept++;
     }
-    if (o.cnt > 0 && gid < DM_NGROUP_MAX - DM_NWELD_MAX) {
+    if (o.cnt > 0 && gid < h->ngrp_max - DM_NWELD_MAX) {
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
-      int ba = MI(geom_body)[MI(pair_geom1)[p]], bb = MI(geom_body)[MI(pair_geom2)[p]];
+      int ba = MI(geom_body)[MI(pair_geom1)[p]], bb = MI(pair_geom2)[p] < 0 ? 0 : MI(geom_body)[MI(pair_geom2)[p]];
       uint32_t ma = MU(body_ancdof)[ba], mb = MU(body_ancdof)[bb];
       gi[G_START] = basec + slot; gi[G_COUNT] = kept;
       ((uint32_t*)gi)[G_MASK] = ma ^ mb; ((uint32_t*)gi)[G_SIGN] = mb;
     }
     if (c.lane == 0) {
-      int nn = basec + total; if (nn > DM_NCON_MAX) { nn = DM_NCON_MAX; cnt[CNT_OVERFLOW] |= 2; }
-      int ng = baseg + gtotal; if (ng > DM_NGROUP_MAX - DM_NWELD_MAX) { ng = DM_NGROUP_MAX - DM_NWELD_MAX; cnt[CNT_OVERFLOW] |= 4; }
+      int nn = basec + total; if (nn > h->ncon_max) { nn = h->ncon_max; cnt[CNT_OVERFLOW] |= 2; }
+      int ng = baseg + gtotal; if (ng > h->ngrp_max - DM_NWELD_MAX) { ng = h->ngrp_max - DM_NWELD_MAX; cnt[CNT_OVERFLOW] |= 4; }
       cnt[CNT_NCON] = nn; cnt[CNT_NGRP] = ng;
     }
     SYNC();
@@ -1358,6 +1494,31 @@ HD void forward(const Ctx c, bool active) {
 #endif
 }
 
+// qpos <- qpos (+) dt * vel  (free-joint quaternions on the manifold)
+STAGE void integrate_pos(const Ctx c, float* qpos, const float* qvel, float hh) {
+  ASSUME_SHARED(c);
+  ASSUME_SHARED_PTR(qpos); ASSUME_SHARED_PTR(qvel);
+  const DMHead* h = c.h;
+  LANES(j, h->njnt) {
+    int a = MI(jnt_qposadr)[j], d = MI(jnt_dofadr)[j];
+    if (MI(jnt_type)[j] == B200_JNT_FREE) {
+      for (int k = 0; k < 3; k++) qpos[a + k] += hh * qvel[d + k];
+      float w[3] = {qvel[d + 3], qvel[d + 4], qvel[d + 5]};
+      float n = sqrtf(dot3(w, w));
+      float q[4] = {qpos[a + 3], qpos[a + 4], qpos[a + 5], qpos[a + 6]};
+      if (n > 0) {
+        float ang = 0.5f * n * hh, sn = sinf(ang), cs = cosf(ang), inv = 1.0f / n;
+        float dq[4] = {cs, w[0] * inv * sn, w[1] * inv * sn, w[2] * inv * sn}, nq[4];
+        qmul(nq, q, dq);
+        q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
+      }
+      qnormalize(q);
+      qpos[a + 3] = q[0]; qpos[a + 4] = q[1]; qpos[a + 5] = q[2]; qpos[a + 6] = q[3];
+    } else qpos[a] += hh * qvel[d];
+  }
+  SYNC();
+}
+
 template <int NVP>
 STAGE void euler_step(const Ctx c) {
   ASSUME_SHARED(c);
@@ -1376,24 +1537,42 @@ STAGE void euler_step(const Ctx c) {
   }
   LANES(i, nv) SF(qvel)[i] += hh * x[i];
   SYNC();
-  LANES(j, h->njnt) {
-    int a = MI(jnt_qposadr)[j], d = MI(jnt_dofadr)[j];
-    float* qpos = SF(qpos);
-    const float* qvel = SF(qvel);
-    if (MI(jnt_type)[j] == B200_JNT_FREE) {
-      for (int k = 0; k < 3; k++) qpos[a + k] += hh * qvel[d + k];
-      float w[3] = {qvel[d + 3], qvel[d + 4], qvel[d + 5]};
-      float n = sqrtf(dot3(w, w));
-      float q[4] = {qpos[a + 3], qpos[a + 4], qpos[a + 5], qpos[a + 6]};
-      if (n > 0) {
-        float ang = 0.5f * n * hh, sn = sinf(ang), cs = cosf(ang), inv = 1.0f / n;
-        float dq[4] = {cs, w[0] * inv * sn, w[1] * inv * sn, w[2] * inv * sn}, nq[4];
-        qmul(nq, q, dq);
-        q[0] = nq[0]; q[1] = nq[1]; q[2] = nq[2]; q[3] = nq[3];
-      }
-      qnormalize(q);
-      qpos[a + 3] = q[0]; qpos[a + 4] = q[1]; qpos[a + 5] = q[2]; qpos[a + 6] = q[3];
-    } else qpos[a] += hh * qvel[d];
+  integrate_pos(c, SF(qpos), SF(qvel), hh);
+}
+
+// one classical RK4 sub-step over (qpos, qvel), ctrl held constant, one forward pass per stage, no implicit damping
+// (reference: `integrator="RK4"` of the Ant model, gymnasium_robotics/envs/mujoco/assets/ant.xml:3).  The first
+// stage's forward pass has already been done by the caller.
+template <int NVP>
+HD void rk4_substep(const Ctx c, bool active) {
+  const DMHead* h = c.h;
+  const int nv = h->nv, nq = h->nq;
+  const float hh = h->timestep;
+  const float A[3] = {0.5f, 0.5f, 1.0f}, B[4] = {1.0f / 6, 1.0f / 3, 1.0f / 3, 1.0f / 6};
+  if (active) {
+    LANES(i, nq) SF(rk_q0)[i] = SF(qpos)[i];
+    LANES(i, nv) { SF(rk_v0)[i] = SF(qvel)[i]; SF(rk_dx)[i] = B[0] * SF(qvel)[i]; SF(rk_df)[i] = B[0] * SF(qacc)[i]; }
+    SYNC();
   }
-  SYNC();
+  for (int st = 1; st < 4; st++) {
+    if (active) {
+      float a = A[st - 1] * hh;
+      LANES(i, nq) SF(qpos)[i] = SF(rk_q0)[i];
+      SYNC();
+      integrate_pos(c, SF(qpos), SF(qvel), a);           // X_{st-1} is the current qvel
+      LANES(i, nv) SF(qvel)[i] = SF(rk_v0)[i] + a * SF(qacc)[i];
+      SYNC();
+    }
+    forward<NVP>(c, active);
+    if (active) {
+      LANES(i, nv) { SF(rk_dx)[i] += B[st] * SF(qvel)[i]; SF(rk_df)[i] += B[st] * SF(qacc)[i]; }
+      SYNC();
+    }
+  }
+  if (active) {
+    LANES(i, nq) SF(qpos)[i] = SF(rk_q0)[i];
+    LANES(i, nv) SF(qvel)[i] = SF(rk_v0)[i] + hh * SF(rk_df)[i];
+    SYNC();
+    integrate_pos(c, SF(qpos), SF(rk_dx), hh);
+  }
 }

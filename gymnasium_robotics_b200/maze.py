@@ -1,0 +1,306 @@
+"""Batched AntMaze environments (v5) on the b200sim CUDA path.
+
+Host-side mirror of the reference's maze stack, batched over `num_envs`:
+  * map tables               envs/maze/maps.py:52-135 (data), ids/kwargs/max_episode_steps __init__.py:839-958
+  * Maze grid math           envs/maze/maze_v4.py:135-146 (cell<->xy), :148-242 (goal/reset cell collection)
+  * MazeEnv.reset / noise / update_goal     envs/maze/maze_v4.py:276-297, 299-379, 400-418
+  * AntMazeEnv ctor/reset/step/_get_obs     envs/maze/ant_maze_v5.py:221-320 (inner AntEnv [ext]: frame_skip 5, RK4)
+  * compute_reward / compute_terminated     envs/maze/maze_v4.py:381-398
+The per-step arithmetic (5 RK4 sub-steps, observation, reward, success) runs inside one CUDA kernel launch.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .fetch import CudaBackend
+from .models import load_model
+from .spaces import Box, Dict as DictSpace, batch_space
+
+R, G, C = "r", "g", "c"
+MAPS = {
+    "Open": [[1, 1, 1, 1, 1, 1, 1], [1, 0, 0, 0, 0, 0, 1], [1, 0, 0, 0, 0, 0, 1], [1, 0, 0, 0, 0, 0, 1], [1, 1, 1, 1, 1, 1, 1]],
+    "Open_Diverse_G": [[1, 1, 1, 1, 1, 1, 1], [1, R, G, G, G, G, 1], [1, G, G, G, G, G, 1], [1, G, G, G, G, G, 1], [1, 1, 1, 1, 1, 1, 1]],
+    "Open_Diverse_GR": [[1, 1, 1, 1, 1, 1, 1], [1, C, C, C, C, C, 1], [1, C, C, C, C, C, 1], [1, C, C, C, C, C, 1], [1, 1, 1, 1, 1, 1, 1]],
+    "UMaze": [[1, 1, 1, 1, 1], [1, 0, 0, 0, 1], [1, 1, 1, 0, 1], [1, 0, 0, 0, 1], [1, 1, 1, 1, 1]],
+    "Medium": [[1, 1, 1, 1, 1, 1, 1, 1], [1, 0, 0, 1, 1, 0, 0, 1], [1, 0, 0, 1, 0, 0, 0, 1], [1, 1, 0, 0, 0, 1, 1, 1],
+               [1, 0, 0, 1, 0, 0, 0, 1], [1, 0, 1, 0, 0, 1, 0, 1], [1, 0, 0, 0, 1, 0, 0, 1], [1, 1, 1, 1, 1, 1, 1, 1]],
+    "Medium_Diverse_G": [[1, 1, 1, 1, 1, 1, 1, 1], [1, R, 0, 1, 1, 0, 0, 1], [1, 0, 0, 1, 0, 0, G, 1], [1, 1, 0, 0, 0, 1, 1, 1],
+                         [1, 0, 0, 1, 0, 0, 0, 1], [1, G, 1, 0, 0, 1, 0, 1], [1, 0, 0, 0, 1, G, 0, 1], [1, 1, 1, 1, 1, 1, 1, 1]],
+    "Medium_Diverse_GR": [[1, 1, 1, 1, 1, 1, 1, 1], [1, C, 0, 1, 1, 0, 0, 1], [1, 0, 0, 1, 0, 0, C, 1], [1, 1, 0, 0, 0, 1, 1, 1],
+                          [1, 0, 0, 1, 0, 0, 0, 1], [1, C, 1, 0, 0, 1, 0, 1], [1, 0, 0, 0, 1, C, 0, 1], [1, 1, 1, 1, 1, 1, 1, 1]],
+    "Large": [[1] * 12, [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 1], [1, 0, 1, 1, 0, 1, 0, 1, 0, 1, 0, 1], [1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 1],
+              [1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1], [1, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0, 1], [1, 1, 0, 1, 0, 1, 0, 1, 0, 1, 1, 1],
+              [1, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1], [1] * 12],
+    "Large_Diverse_G": [[1] * 12, [1, R, 0, 0, 0, 1, G, 0, 0, 0, 0, 1], [1, 0, 1, 1, 0, 1, 0, 1, 0, 1, 0, 1], [1, 0, 0, 0, 0, G, 0, 1, 0, 0, G, 1],
+                        [1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1], [1, 0, G, 1, 0, 1, 0, 0, 0, 0, 0, 1], [1, 1, 0, 1, 0, 1, 0, 1, 0, 1, 1, 1],
+                        [1, 0, 0, 1, G, 0, G, 1, 0, G, 0, 1], [1] * 12],
+    "Large_Diverse_GR": [[1] * 12, [1, C, 0, 0, 0, 1, C, 0, 0, 0, 0, 1], [1, 0, 1, 1, 0, 1, 0, 1, 0, 1, 0, 1], [1, 0, 0, 0, 0, C, 0, 1, 0, 0, C, 1],
+                         [1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1], [1, 0, C, 1, 0, 1, 0, 0, 0, 0, 0, 1], [1, 1, 0, 1, 0, 1, 0, 1, 0, 1, 1, 1],
+                         [1, 0, 0, 1, C, 0, C, 1, 0, C, 0, 1], [1] * 12],
+}
+# wall layout -> compiled physics model (the diverse variants only relabel free cells)
+MAP_MODEL = {k: "antmaze_" + k.split("_")[0].lower() for k in MAPS}
+MAX_EPISODE_STEPS = {k: (700 if k.startswith(("Open", "UMaze")) else 1000) for k in MAPS}
+SCALING, HEIGHT, NOISE, SUCCESS_RADIUS, FRAME_SKIP = 4.0, 0.5, 0.25, 0.45, 5
+
+
+class MazeCells:
+    """Cell bookkeeping of `Maze` (maze_v4.py:26-242) without the XML part."""
+
+    def __init__(self, maze_map, scaling=SCALING):
+        self.maze_map, self.scaling = maze_map, scaling
+        self.length, self.width = len(maze_map), len(maze_map[0])
+        self.x_center, self.y_center = self.width / 2 * scaling, self.length / 2 * scaling
+        goals, resets, combined, empty = [], [], [], []
+        for i in range(self.length):
+            for j in range(self.width):
+                cell, xy = maze_map[i][j], self.cell_rowcol_to_xy((i, j))
+                if cell == R:
+                    resets.append(xy)
+                elif cell == G:
+                    goals.append(xy)
+                elif cell == C:
+                    combined.append(xy)
+                elif cell == 0:
+                    empty.append(xy)
+        if not goals and not resets and not combined:
+            combined = empty
+        elif not resets and not combined:
+            resets = empty
+        elif not goals and not combined:
+            goals = empty
+        self.goal_locations = np.array(goals + combined)
+        self.reset_locations = np.array(resets + combined)
+
+    def cell_rowcol_to_xy(self, rowcol):
+        return np.array([(rowcol[1] + 0.5) * self.scaling - self.x_center, self.y_center - (rowcol[0] + 0.5) * self.scaling])
+
+    def cell_xy_to_rowcol(self, xy):
+        return np.array([math.floor((self.y_center - xy[1]) / self.scaling), math.floor((xy[0] + self.x_center) / self.scaling)])
+
+
+def make_antmaze_task(model, reward_type):
+    t = _lib.FetchTaskC()
+    t.kind, t.nact, t.ngoal = 1, int(model.nu), 2
+    t.n_substeps, t.reward_dense = FRAME_SKIP, int(reward_type == "dense")
+    t.nobs = int(model.nq - 2 + model.nv)
+    t.success_radius = SUCCESS_RADIUS
+    t.dt = float(model.opt[0] * FRAME_SKIP)
+    return t
+
+
+class _AntBackend(CudaBackend):
+    """CudaBackend with AntMaze output widths (goal dim 2, action dim 8)."""
+
+    def new_outputs(self):
+        n, d = self.num_envs, self.device
+        return dict(obs=torch.empty((n, self.nobs), dtype=torch.float32, device=d),
+                    achieved=torch.empty((n, 2), dtype=torch.float32, device=d), desired=torch.empty((n, 2), dtype=torch.float32, device=d),
+                    reward=torch.empty(n, dtype=torch.float32, device=d), success=torch.empty(n, dtype=torch.float32, device=d))
+
+    def step(self, actions, out, info=None):
+        assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape[0] == self.num_envs
+        self._check(self.L.b200sim_step(self.h, actions.data_ptr(), *self._ptrs(out), info.data_ptr() if info is not None else None, self._stream()))
+
+    def compute_reward(self, ag, dg):
+        ag = ag.to(self.device, torch.float32).contiguous().reshape(-1, 2)
+        dg = dg.to(self.device, torch.float32).contiguous().reshape(-1, 2)
+        out = torch.empty(ag.shape[0], dtype=torch.float32, device=self.device)
+        self._check(self.L.b200sim_compute_reward(self.h, ag.data_ptr(), dg.data_ptr(), ag.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+
+class AntMazeVectorEnv:
+    """`gym.make_vec("AntMaze_Large-v5", num_envs=N)` replacement (torch CUDA tensors, leading `num_envs` axis)."""
+
+    metadata = {"render_modes": [], "render_fps": 50, "autoreset_mode": "next_step"}
+
+    def __init__(self, maze: str = "Large", num_envs: int = 1, reward_type: str = "sparse", continuing_task: bool = True,
+                 reset_target: bool = False, max_episode_steps: Optional[int] = None, device="cuda:0", rng_mode: str = "auto",
+                 autoreset_mode: str = "next_step", backend_factory=None, **kwargs):
+        if maze not in MAPS:
+            raise KeyError(f"unknown maze {maze!r}")
+        if reward_type not in ("sparse", "dense"):
+            raise ValueError("reward_type must be 'sparse' or 'dense'")
+        if kwargs.get("render_mode") is not None:
+            raise NotImplementedError("rendering is out of scope for the batched CUDA path")
+        self.maze_name, self.reward_type = maze, reward_type
+        self.continuing_task, self.reset_target = continuing_task, reset_target
+        self.num_envs, self.autoreset_mode = int(num_envs), autoreset_mode
+        self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
+        self.max_episode_steps = MAX_EPISODE_STEPS[maze] if max_episode_steps is None else max_episode_steps
+        self.cells = MazeCells(MAPS[maze])
+        self.model = load_model(MAP_MODEL[maze])
+        self.task = make_antmaze_task(self.model, reward_type)
+        factory = backend_factory or _AntBackend
+        self.backend = factory(self.model, np.zeros((0, 11)), self.task, self.num_envs, device)
+        self.device = self.backend.device
+        self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)]
+        self._gen = torch.Generator(device=self.device)
+        self._gen.seed()
+        lay, m = self.backend.layout, self.model
+        self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", m.nq), ("qvel", m.nv), ("warm", m.nv), ("ctrl", m.nu), ("goal", 2))}
+        nobs = self.task.nobs
+        self.single_action_space = Box(-1.0, 1.0, shape=(m.nu,), dtype=np.float32)
+        self.single_observation_space = DictSpace(dict(
+            observation=Box(-np.inf, np.inf, shape=(nobs,), dtype=np.float64),
+            achieved_goal=Box(-np.inf, np.inf, shape=(2,), dtype=np.float64),
+            desired_goal=Box(-np.inf, np.inf, shape=(2,), dtype=np.float64)))
+        self.action_space = batch_space(self.single_action_space, self.num_envs)
+        self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+        self.init_qpos = torch.as_tensor(np.array(m.qpos0), dtype=torch.float32, device=self.device)
+        self._goal_loc = torch.as_tensor(self.cells.goal_locations, dtype=torch.float32, device=self.device)
+        self._reset_loc = torch.as_tensor(self.cells.reset_locations, dtype=torch.float32, device=self.device)
+        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        self.dt = float(m.opt[0] * FRAME_SKIP)
+        self.closed = False
+
+    # ------------------------------------------------------------------ sampling (MazeEnv.reset, maze_v4.py:299-358)
+    def _noise_np(self, rng, xy):
+        nx = rng.uniform(low=-NOISE, high=NOISE) * SCALING
+        ny = rng.uniform(low=-NOISE, high=NOISE) * SCALING
+        return np.array([xy[0] + nx, xy[1] + ny])
+
+    def _sample_np(self, i, options):
+        rng, cells = self._np_rngs[i], self.cells
+        options = options or {}
+        if options.get("goal_cell") is not None:
+            gc = options["goal_cell"]
+            assert cells.length > gc[0] and cells.width > gc[1] and cells.maze_map[gc[0]][gc[1]] != 1, f"Goal can't be placed in a wall cell, {gc}"
+            goal = cells.cell_rowcol_to_xy(gc)
+        else:
+            goal = cells.goal_locations[rng.integers(low=0, high=len(cells.goal_locations))].copy()
+        goal = self._noise_np(rng, goal)
+        if options.get("reset_cell") is not None:
+            rc = options["reset_cell"]
+            assert cells.length > rc[0] and cells.width > rc[1] and cells.maze_map[rc[0]][rc[1]] != 1, f"Reset can't be placed in a wall cell, {rc}"
+            pos = cells.cell_rowcol_to_xy(rc)
+        else:
+            pos = goal.copy()
+            while np.linalg.norm(pos - goal) <= 0.5 * SCALING:
+                pos = cells.reset_locations[rng.integers(low=0, high=len(cells.reset_locations))].copy()
+        return goal, self._noise_np(rng, pos)
+
+    def _sample(self, idx, options=None):
+        n = idx.numel()
+        if self.rng_mode == "numpy" or options:
+            gs, ps = zip(*[self._sample_np(i, options) for i in idx.tolist()])
+            return (torch.as_tensor(np.array(gs), dtype=torch.float32, device=self.device),
+                    torch.as_tensor(np.array(ps), dtype=torch.float32, device=self.device))
+        u = lambda *s: torch.rand(*s, generator=self._gen, device=self.device)
+        ri = lambda hi, k: torch.randint(0, hi, (k,), generator=self._gen, device=self.device)
+        goal = self._goal_loc[ri(len(self._goal_loc), n)] + (u(n, 2) * 2 - 1) * NOISE * SCALING
+        pos = self._reset_loc[ri(len(self._reset_loc), n)]
+        bad = torch.linalg.norm(pos - goal, dim=1) <= 0.5 * SCALING
+        while bool(bad.any()):
+            pos[bad] = self._reset_loc[ri(len(self._reset_loc), int(bad.sum()))]
+            bad = torch.linalg.norm(pos - goal, dim=1) <= 0.5 * SCALING
+        return goal, pos + (u(n, 2) * 2 - 1) * NOISE * SCALING
+
+    def _reset_envs(self, mask, out, options=None):
+        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        if idx.numel() == 0:
+            return
+        st, sl = self.backend.state, self._sl
+        goal, pos = self._sample(idx, options)
+        rec = torch.zeros((idx.numel(), st.shape[1]), dtype=torch.float32, device=self.device)
+        rec[:, sl["qpos"]] = self.init_qpos          # ant_env.init_qpos with [:2] = reset_pos (ant_maze_v5.py:285)
+        rec[:, sl["qpos"].start: sl["qpos"].start + 2] = pos
+        rec[:, sl["goal"]] = goal
+        st[idx] = rec
+        self._elapsed[idx] = 0
+        self.backend.refresh(mask.to(torch.uint8), out)
+
+    # ------------------------------------------------------------------ gymnasium API
+    def _obs_dict(self, out):
+        return {"observation": out["obs"], "achieved_goal": out["achieved"], "desired_goal": out["desired"]}
+
+    def reset(self, *, seed=None, options=None):
+        if seed is not None:
+            seeds = [seed + i for i in range(self.num_envs)] if isinstance(seed, (int, np.integer)) else list(seed)
+            self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(s))) for s in seeds]
+            self._gen.manual_seed(int(seeds[0]))
+        out = self.backend.new_outputs()
+        self._reset_envs(torch.ones(self.num_envs, dtype=torch.bool, device=self.device), out, options)
+        self._needs_reset.zero_()
+        return self._obs_dict(out), {"success": out["success"] > 0}
+
+    def step(self, actions):
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
+        if tuple(actions.shape) != (self.num_envs, self.model.nu):
+            raise ValueError("Action dimension mismatch")
+        actions = actions.to(self.device, torch.float32, non_blocking=True).contiguous()
+        out = self.backend.new_outputs()
+        self.backend.step(actions, out)
+        self._elapsed += 1
+        reward, success = out["reward"], out["success"] > 0
+        terminated = torch.zeros_like(success) if self.continuing_task else success.clone()  # maze_v4.py:390-398
+        info = {"success": success}
+        if self.autoreset_mode == "next_step" and bool(self._needs_reset.any()):
+            pre = self._needs_reset.clone()
+            self._reset_envs(pre, out)
+            reward = torch.where(pre, torch.zeros_like(reward), reward)
+            out["reward"] = reward
+            terminated = terminated & ~pre
+            self._needs_reset.zero_()
+        if self.continuing_task and self.reset_target and len(self.cells.goal_locations) > 1 and bool(success.any()):
+            self._update_goal(success, out)  # maze_v4.py:400-418
+        truncated = (self._elapsed >= self.max_episode_steps) if self.max_episode_steps is not None else torch.zeros_like(terminated)
+        done = truncated | terminated
+        if self.autoreset_mode == "next_step":
+            self._needs_reset = done
+        elif self.autoreset_mode == "same_step" and bool(done.any()):
+            info["final_obs"] = {k: v.clone() for k, v in self._obs_dict(out).items()}
+            info["_final_obs"] = done.clone()
+            self._reset_envs(done, out)
+        return self._obs_dict(out), reward, terminated, truncated, info
+
+    def _update_goal(self, success, out):
+        idx = torch.nonzero(success, as_tuple=False).flatten()
+        st, sl = self.backend.state, self._sl
+        for i in idx.tolist():
+            ag = out["achieved"][i].double().cpu().numpy()
+            goal = st[i, sl["goal"]].double().cpu().numpy()
+            rng = self._np_rngs[i]
+            while np.linalg.norm(ag - goal) <= SUCCESS_RADIUS:
+                goal = self._noise_np(rng, self.cells.goal_locations[rng.integers(low=0, high=len(self.cells.goal_locations))].copy())
+            st[i, sl["goal"]] = torch.as_tensor(goal, dtype=torch.float32, device=self.device)
+
+    def compute_reward(self, achieved_goal, desired_goal, info=None):
+        is_np = not torch.is_tensor(achieved_goal)
+        ag = torch.as_tensor(np.asarray(achieved_goal)) if is_np else achieved_goal
+        dg = torch.as_tensor(np.asarray(desired_goal)) if not torch.is_tensor(desired_goal) else desired_goal
+        r = self.backend.compute_reward(ag, dg).reshape(ag.shape[:-1])
+        return r.cpu().numpy().astype(np.float64) if is_np else r
+
+    def compute_terminated(self, achieved_goal, desired_goal, info=None):
+        if not self.continuing_task:
+            return bool(np.linalg.norm(np.asarray(achieved_goal) - np.asarray(desired_goal)) <= SUCCESS_RADIUS)
+        return False
+
+    def compute_truncated(self, achieved_goal, desired_goal, info=None):
+        return False
+
+    def get_state(self):
+        return self.backend.state.clone(), self._elapsed.clone()
+
+    def set_state(self, state, elapsed=None):
+        self.backend.state.copy_(state)
+        if elapsed is not None:
+            self._elapsed.copy_(elapsed)
+        out = self.backend.new_outputs()
+        self.backend.refresh(None, out)
+        return self._obs_dict(out)
+
+    def close(self):
+        if not getattr(self, "closed", True):
+            self.backend.close()
+            self.closed = True

@@ -36,7 +36,7 @@ EQ_CONNECT, EQ_WELD, EQ_JOINT = 0, 1, 2
 INT_EULER, INT_RK4 = 0, 1
 MINVAL = 1e-15
 BLOB_MAGIC = 0x4D303242  # "B20M"
-BLOB_VERSION = 3
+BLOB_VERSION = 4
 
 
 # --------------------------------------------------------------------------------------
@@ -228,10 +228,14 @@ _DEFAULT_TAGS = ("geom", "joint", "site", "position", "motor", "general", "veloc
 
 
 class _Parser:
-    def __init__(self, path, overrides=None):
+    def __init__(self, path, overrides=None, root=None):
         self.path = os.path.abspath(path)
         self.dir = os.path.dirname(self.path)
-        self.root = self._load(self.path)
+        if root is not None:
+            self.root = root
+            self._expand_includes(self.root, self.dir)
+        else:
+            self.root = self._load(self.path)
         self.compiler = {"angle": "degree", "eulerseq": "xyz", "meshdir": "", "inertiafromgeom": "auto",
                          "autolimits": "true", "coordinate": "local"}
         self.defaults = {"main": {t: {} for t in _DEFAULT_TAGS}}
@@ -502,7 +506,8 @@ class Model:
                   "body_mocapid", "body_rootid", "jnt_type", "jnt_body", "jnt_qposadr", "jnt_dofadr", "jnt_limited",
                   "dof_body", "dof_jnt", "dof_parent", "geom_type", "geom_body", "pair_geom1", "pair_geom2", "pair_condim",
                   "site_body", "act_trnid", "act_ctrllimited", "act_forcelimited", "eq_type", "eq_obj1", "eq_obj2",
-                  "eq_active", "mocap_body", "ten_adr", "ten_num", "ten_limited", "wrap_dof", "sensor_site", "sensor_body"]
+                  "eq_active", "mocap_body", "ten_adr", "ten_num", "ten_limited", "wrap_dof", "sensor_site", "sensor_body",
+                  "pair_grid", "grid_dims", "grid_walls"]
     FLT_FIELDS = ["opt", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "jnt_pos",
                   "jnt_axis", "jnt_range", "jnt_margin", "jnt_stiffness", "jnt_solref", "jnt_solimp", "qpos0",
                   "qpos_spring", "dof_armature", "dof_damping", "dof_frictionloss", "dof_invweight0", "dof_solref_fri",
@@ -510,7 +515,7 @@ class Model:
                   "geom_size", "geom_rbound", "pair_friction", "pair_margin", "pair_gap", "pair_solref", "pair_solimp",
                   "pair_invweight", "site_pos", "site_quat", "act_gear", "act_gainprm", "act_biasprm", "act_ctrlrange",
                   "act_forcerange", "eq_data", "eq_solref", "eq_solimp", "eq_invweight", "ten_range", "ten_margin",
-                  "ten_solref", "ten_solimp", "ten_invweight0", "wrap_coef", "sensor_size", "key_qpos"]
+                  "ten_solref", "ten_solimp", "ten_invweight0", "wrap_coef", "sensor_size", "key_qpos", "grid_param"]
 
     def __init__(self):
         self.names = {}
@@ -663,13 +668,36 @@ def _dense_mass_matrix(nbody, nv, parent, mass, inertia, xipos, ximat, xmat, joi
     return M, jacs
 
 
-def compile_mjcf(path, overrides=None, mesh_mesh=False) -> Model:
+def make_maze_xml(agent_xml_path, maze_map, maze_size_scaling, maze_height):
+    """MJCF tree of an agent placed in a maze: restates the geometry part of `Maze.make_maze`
+    (gymnasium_robotics/envs/maze/maze_v4.py:148-242): one static box per wall cell, centred grid, target site."""
+    tree = ET.parse(agent_xml_path)
+    root = tree.getroot()
+    worldbody = root.find(".//worldbody")
+    length, width = len(maze_map), len(maze_map[0])
+    xc, yc = width / 2 * maze_size_scaling, length / 2 * maze_size_scaling
+    for i in range(length):
+        for j in range(width):
+            if maze_map[i][j] == 1:
+                x = (j + 0.5) * maze_size_scaling - xc
+                y = yc - (i + 0.5) * maze_size_scaling
+                ET.SubElement(worldbody, "geom", name=f"block_{i}_{j}", pos=f"{x} {y} {maze_height / 2 * maze_size_scaling}",
+                              size=f"{0.5 * maze_size_scaling} {0.5 * maze_size_scaling} {maze_height / 2 * maze_size_scaling}",
+                              type="box", contype="1", conaffinity="1")
+    ET.SubElement(worldbody, "site", name="target", pos=f"0 0 {maze_height / 2 * maze_size_scaling}",
+                  size=f"{0.2 * maze_size_scaling}", type="sphere")
+    grid = dict(length=length, width=width, scaling=float(maze_size_scaling), height=float(maze_height),
+                walls=[[1 if maze_map[i][j] == 1 else 0 for j in range(width)] for i in range(length)])
+    return root, grid
+
+
+def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None) -> Model:
     """Compile an MJCF file to the runtime :class:`Model`.
 
     ``overrides`` may carry ``{"opt": {...}, "actuator_gainprm": {name: [...]}, ...}`` for
     constructor-time edits the reference performs on the loaded model.
     """
-    P = _Parser(path, overrides)
+    P = _Parser(path, overrides, root=root)
     F = P.parse()
     nb = len(F.bodies)
     name2body = {b["name"]: i for i, b in enumerate(F.bodies)}
@@ -925,6 +953,15 @@ def compile_mjcf(path, overrides=None, mesh_mesh=False) -> Model:
                  floats(pr.get("solref"), 2, None) if pr.get("solref") else 0.5 * (g1["solref"] + g2["solref"]),
                  floats(pr.get("solimp"), 5, [0.9, 0.95, 0.001, 0.5, 2]) if pr.get("solimp") else 0.5 * (g1["solimp"] + g2["solimp"]))
     m.pair_geom1, m.pair_geom2, m.pair_condim = (np.array(x, dtype=np.int32) for x in (P1, P2, PC))
+    # maze walls: pairs whose second geom is a wall block can be served by a grid lookup instead of the pair list
+    gnames = [F.geoms[g]["name"] for g in gkeep]
+    m.pair_grid = np.array([1 if (grid is not None and gnames[b].startswith("block_")) else 0 for b in P2], dtype=np.int32)
+    if grid is not None:
+        m.grid_dims = np.array([grid["length"], grid["width"]], dtype=np.int32)
+        m.grid_walls = np.array(grid["walls"], dtype=np.int32).ravel()
+        m.grid_param = np.array([grid["scaling"], grid["height"], grid["width"] / 2 * grid["scaling"], grid["length"] / 2 * grid["scaling"]])
+    else:
+        m.grid_dims, m.grid_walls, m.grid_param = np.zeros(2, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(4)
     m.pair_friction = np.array(PF).reshape(-1, 5)
     m.pair_margin, m.pair_gap = np.array(PM), np.array(PG)
     m.pair_solref, m.pair_solimp, m.pair_invweight = np.array(PSR).reshape(-1, 2), np.array(PSI).reshape(-1, 5), np.array(PIW).reshape(-1, 2)

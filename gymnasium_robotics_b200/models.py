@@ -22,6 +22,11 @@ MODEL_SOURCES = {
 }
 
 
+# maze models: in-tree legacy twin of Gymnasium's ant.xml (Gymnasium itself is un-vendored) + generated wall boxes
+ANT_XML = "../mujoco/assets/ant.xml"
+MAZE_MODELS = {"antmaze_open": "Open", "antmaze_umaze": "UMaze", "antmaze_medium": "Medium", "antmaze_large": "Large"}
+
+
 def build_models(force: bool = False):
     """(Re)compile every model blob from the reference's assets, if they are available."""
     if not os.path.isdir(REFERENCE_ASSETS):
@@ -35,6 +40,18 @@ def build_models(force: bool = False):
         blob = compile_mjcf(os.path.join(REFERENCE_ASSETS, rel)).to_blob()
         with open(out, "wb") as f:
             f.write(blob)
+        built.append(out)
+    from .maze import HEIGHT, MAPS, SCALING
+    from .mjcf import make_maze_xml
+
+    ant = os.path.normpath(os.path.join(REFERENCE_ASSETS, ANT_XML))
+    for name, key in MAZE_MODELS.items():
+        out = os.path.join(MODEL_DIR, name + ".b200m")
+        if os.path.exists(out) and not force:
+            continue
+        root, grid = make_maze_xml(ant, MAPS[key], SCALING, HEIGHT)
+        with open(out, "wb") as f:
+            f.write(compile_mjcf(ant, root=root, grid=grid).to_blob())
         built.append(out)
     return built
 

@@ -29,6 +29,10 @@ typedef struct b200sim_fetch_task {
   int finger_qadr[2];                  /* qpos addresses zeroed by _step_callback when block_gripper */
   int nobs;
   float distance_threshold, dt;
+  /* task family: 0 = Fetch (fields above), 1 = AntMaze (envs/maze/ant_maze_v5.py: ctrl = action, obs = qpos[2:]|qvel,
+   * goal = xy; uses nobs, n_substeps (= frame_skip), reward_dense, nact, ngoal, success_radius) */
+  int kind, nact, ngoal;
+  float success_radius;
 } b200sim_fetch_task_t;
 
 /* indices into the layout array returned by b200sim_layout (offsets in floats inside one env's state record) */

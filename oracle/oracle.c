@@ -722,6 +722,80 @@ static void collide_box_box(oracle_sim* s, int pair, real margin) {
   }
 }
 
+/* ---- sphere / capsule vs box (own formulation): closest point on the box to a point, in the box frame */
+static real point_box(const real* p, const real* bp, const real* bm, const double* h, real* closest, real* normal) {
+  /* returns signed distance from p to the box surface; normal points from the box surface towards p */
+  real rel[3], loc[3], q[3];
+  sub3(rel, p, bp);
+  mulmatTvec3(loc, bm, rel);
+  int inside = 1;
+  for (int k = 0; k < 3; k++) { q[k] = loc[k] < -h[k] ? -h[k] : (loc[k] > h[k] ? h[k] : loc[k]); if (q[k] != loc[k]) inside = 0; }
+  real nl[3] = {0, 0, 0}, dist;
+  if (!inside) {
+    real d[3] = {loc[0] - q[0], loc[1] - q[1], loc[2] - q[2]};
+    dist = norm3(d);
+    nl[0] = d[0] / dist; nl[1] = d[1] / dist; nl[2] = d[2] / dist;
+  } else {
+    int ax = 0; real best = 1e300;
+    for (int k = 0; k < 3; k++) { real pen = h[k] - fabs(loc[k]); if (pen < best) { best = pen; ax = k; } }
+    dist = -best;
+    nl[ax] = loc[ax] < 0 ? -1 : 1;
+    q[ax] = nl[ax] * h[ax];
+  }
+  mulmatvec3(closest, bm, q); add3(closest, closest, bp);
+  mulmatvec3(normal, bm, nl);
+  return dist;
+}
+
+static void sphere_box_contact(oracle_sim* s, int pair, const real* center, real r, int gbox, real margin) {
+  const b200_model_view* m = &s->m;
+  real closest[3], nrm[3];
+  real d = point_box(center, s->geom_xpos + 3 * gbox, s->geom_xmat + 9 * gbox, m->geom_size + 3 * gbox, closest, nrm) - r;
+  if (d > margin) return;
+  /* contact normal from geom1 (sphere/capsule) to geom2 (box) = -nrm ; position midway between the two surfaces */
+  real n[3] = {-nrm[0], -nrm[1], -nrm[2]}, pos[3];
+  copy3(pos, closest);
+  addscl3(pos, nrm, 0.5 * d);
+  add_contact(s, pair, d, pos, n);
+}
+
+static void collide_sphere_box(oracle_sim* s, int pair, real margin) {
+  const b200_model_view* m = &s->m;
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  sphere_box_contact(s, pair, s->geom_xpos + 3 * g1, m->geom_size[3 * g1], g2, margin);
+}
+
+/* capsule (geom1) vs box (geom2): both end spheres if both are within the margin, else the sphere at the point of the
+ * segment closest to the box (golden-section search on the convex distance function) */
+static void collide_capsule_box(oracle_sim* s, int pair, real margin) {
+  const b200_model_view* m = &s->m;
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  const real *c = s->geom_xpos + 3 * g1, *cm = s->geom_xmat + 9 * g1;
+  real ax[3] = {cm[2], cm[5], cm[8]}, r = m->geom_size[3 * g1], h = m->geom_size[3 * g1 + 1];
+  const real *bp = s->geom_xpos + 3 * g2, *bm = s->geom_xmat + 9 * g2;
+  const double* bh = m->geom_size + 3 * g2;
+  real e0[3], e1[3], cl[3], nn[3];
+  copy3(e0, c); addscl3(e0, ax, -h);
+  copy3(e1, c); addscl3(e1, ax, h);
+  real d0 = point_box(e0, bp, bm, bh, cl, nn) - r, d1 = point_box(e1, bp, bm, bh, cl, nn) - r;
+  if (d0 <= margin && d1 <= margin) {
+    sphere_box_contact(s, pair, e0, r, g2, margin);
+    sphere_box_contact(s, pair, e1, r, g2, margin);
+    return;
+  }
+  const real gr = 0.6180339887498949;
+  real lo = -h, hi = h, x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo), p[3];
+  copy3(p, c); addscl3(p, ax, x1); real f1 = point_box(p, bp, bm, bh, cl, nn);
+  copy3(p, c); addscl3(p, ax, x2); real f2 = point_box(p, bp, bm, bh, cl, nn);
+  for (int it = 0; it < 24; it++) {
+    if (f1 < f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); copy3(p, c); addscl3(p, ax, x1); f1 = point_box(p, bp, bm, bh, cl, nn); }
+    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); copy3(p, c); addscl3(p, ax, x2); f2 = point_box(p, bp, bm, bh, cl, nn); }
+  }
+  real t = 0.5 * (lo + hi);
+  copy3(p, c); addscl3(p, ax, t);
+  sphere_box_contact(s, pair, p, r, g2, margin);
+}
+
 static void collision(oracle_sim* s) {
   const b200_model_view* m = &s->m;
   s->ncon = 0;
@@ -745,6 +819,8 @@ static void collision(oracle_sim* s) {
     else if (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_SPHERE) collide_plane_sphere(s, p, margin);
     else if (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_CAPSULE) collide_plane_capsule(s, p, margin);
     else if (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) collide_box_box(s, p, margin);
+    else if (t1 == B200_GEOM_SPHERE && t2 == B200_GEOM_BOX) collide_sphere_box(s, p, margin);
+    else if (t1 == B200_GEOM_CAPSULE && t2 == B200_GEOM_BOX) collide_capsule_box(s, p, margin);
     /* other pair types: not yet restated (DESIGN.md lists them) */
   }
 }

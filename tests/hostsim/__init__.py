@@ -16,7 +16,8 @@ class FetchTaskC(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ("has_object", "block_gripper", "n_substeps", "reward_dense", "grip_site",
                                              "obj_site", "frame_site", "nrobot")] + \
                [("robot_qadr", ctypes.c_int * 16), ("robot_dadr", ctypes.c_int * 16), ("finger_qadr", ctypes.c_int * 2),
-                ("nobs", ctypes.c_int), ("distance_threshold", ctypes.c_float), ("dt", ctypes.c_float)] + \
+                ("nobs", ctypes.c_int), ("distance_threshold", ctypes.c_float), ("dt", ctypes.c_float),
+                ("kind", ctypes.c_int), ("nact", ctypes.c_int), ("ngoal", ctypes.c_int), ("success_radius", ctypes.c_float)] + \
                [(n, ctypes.c_int) for n in ("st_qpos", "st_qvel", "st_warm", "st_ctrl", "st_mocap", "st_pose", "st_goal",
                                              "st_stride")]
 
@@ -105,11 +106,12 @@ class HostSim:
     def step(self, n=1):
         self._L.hostsim_step(self._h, int(n))
 
-    def env_step(self, task, mode, nraw, st, action, nobs):
+    def env_step(self, task, mode, nraw, st, action, nobs, ngoal=3):
         obs = np.zeros(nobs, dtype=np.float32)
-        ag, dg = np.zeros(3, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        ag, dg = np.zeros(ngoal, dtype=np.float32), np.zeros(ngoal, dtype=np.float32)
         rew, suc = np.zeros(1, dtype=np.float32), np.zeros(1, dtype=np.float32)
-        a = np.ascontiguousarray(action, dtype=np.float32)
+        a = np.zeros(8, dtype=np.float32)
+        a[:len(action)] = action
         it = self._L.hostsim_env_step(self._h, ctypes.byref(task), mode, nraw, st.ctypes.data, a.ctypes.data, obs.ctypes.data,
                                       ag.ctypes.data, dg.ctypes.data, rew.ctypes.data, suc.ctypes.data)
         return obs, ag, dg, float(rew[0]), float(suc[0]), it

@@ -21,7 +21,12 @@ class HostSimBackend:
             setattr(t, name, getattr(task, name))
         o = 0
         lay = {}
-        for k, n in (("qpos", model.nq), ("qvel", model.nv), ("warm", model.nv), ("ctrl", model.nu), ("mocap", 7), ("pose", 7), ("goal", 3)):
+        fetch = task.kind == 0
+        if fetch:
+            t.nact, t.ngoal = 4, 3
+        self.ngoal, self.nact = int(t.ngoal), int(t.nact)
+        for k, n in (("qpos", model.nq), ("qvel", model.nv), ("warm", model.nv), ("ctrl", model.nu), ("mocap", 7 * model.nmocap),
+                     ("pose", 7 if fetch else 0), ("goal", self.ngoal)):
             lay[k] = o
             o += n
         lay["stride"] = (o + 3) & ~3
@@ -36,7 +41,7 @@ class HostSimBackend:
 
     def new_outputs(self):
         n = self.num_envs
-        return dict(obs=torch.zeros((n, self.nobs)), achieved=torch.zeros((n, 3)), desired=torch.zeros((n, 3)),
+        return dict(obs=torch.zeros((n, self.nobs)), achieved=torch.zeros((n, self.ngoal)), desired=torch.zeros((n, self.ngoal)),
                     reward=torch.zeros(n), success=torch.zeros(n))
 
     def _run(self, mode, nraw, actions, mask, out):
@@ -44,8 +49,8 @@ class HostSimBackend:
         for i in range(self.num_envs):
             if mask is not None and not bool(mask[i]):
                 continue
-            a = actions[i].numpy() if actions is not None else np.zeros(4, dtype=np.float32)
-            obs, ag, dg, rew, suc, _ = self.sim.env_step(self.task, mode, nraw, st[i], a, self.nobs)
+            a = actions[i].numpy() if actions is not None else np.zeros(self.nact, dtype=np.float32)
+            obs, ag, dg, rew, suc, _ = self.sim.env_step(self.task, mode, nraw, st[i], a, self.nobs, self.ngoal)
             out["obs"][i] = torch.from_numpy(obs); out["achieved"][i] = torch.from_numpy(ag); out["desired"][i] = torch.from_numpy(dg)
             out["reward"][i] = rew; out["success"][i] = suc
         self.launches += 1
@@ -60,6 +65,8 @@ class HostSimBackend:
         self._run(2, nstep, None, None, out)
 
     def compute_reward(self, ag, dg):
-        ag = ag.to(torch.float32).reshape(-1, 3); dg = dg.to(torch.float32).reshape(-1, 3)
+        ag = ag.to(torch.float32).reshape(-1, self.ngoal); dg = dg.to(torch.float32).reshape(-1, self.ngoal)
         d = torch.sqrt(((ag - dg) ** 2).sum(-1))
+        if self.task.kind == 1:
+            return torch.exp(-d) if self.task.reward_dense else (d <= self.task.success_radius).to(torch.float32)
         return -d if self.task.reward_dense else -(d > self.task.distance_threshold).to(torch.float32)
