@@ -11,12 +11,9 @@
 #include "../../include/b200sim.h"
 #include "fetch_task.cuh"
 
-#ifndef B200_WPB
-#define B200_WPB 28
-#endif
-#ifdef B200_BLOCK_ALIGN
-static_assert(B200_WPB % B200_AG == 0, "warps per block must be a multiple of the alignment group size");
-#endif
+// warps (= envs) per block: 28 fills an SM in one wave at 4096 envs per GPU; smaller batches use smaller blocks so
+// that every SM still gets work (e.g. the 1024-env shards of BASELINE config 4)
+#define B200_WPB_MAX 28
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -78,6 +75,8 @@ __global__ void reward_kernel(const float* __restrict__ ag, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+#define B200_FOR_ALL_VARIANTS(X) X(7, 14) X(7, 15) X(7, 21) X(14, 14) X(14, 15) X(14, 21) X(28, 14) X(28, 15) X(28, 21)
+
 struct b200sim {
   int N = 0, device = 0;
   std::vector<uint8_t> blob;
@@ -89,7 +88,7 @@ struct b200sim {
   size_t smem_bytes = 0;
   int blocks = 0;
   long launches = 0;
-  int nvp = 32;
+  int nvp = 32, wpb = B200_WPB_MAX;
   std::string err;
 };
 
@@ -142,14 +141,17 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   t.st_mocap = o; o += 7 * dh->nmocap; t.st_pose = o; o += (t.kind == TASK_FETCH ? 7 : 0); t.st_goal = o; o += t.ngoal;
   t.st_stride = (o + 3) & ~3;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, "b200sim_create: cudaSetDevice failed", -7); }
-  h->smem_bytes = ((size_t)dh->hot_words + (size_t)B200_WPB * dh->scr_words) * 4;
-  h->blocks = (num_envs + B200_WPB - 1) / B200_WPB;
-  h->nvp = dh->nv == 15 ? 15 : (dh->nv == 21 ? 21 : (dh->nv == 14 ? 14 : 32));  // exact sizes for the in-scope models, padded otherwise
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+  h->wpb = (num_envs + nsm - 1) / nsm <= 7 ? 7 : ((num_envs + nsm - 1) / nsm <= 14 ? 14 : 28);
+  h->smem_bytes = ((size_t)dh->hot_words + (size_t)h->wpb * dh->scr_words) * 4;
+  h->blocks = (num_envs + h->wpb - 1) / h->wpb;
+  h->nvp = dh->nv == 15 ? 15 : (dh->nv == 21 ? 21 : (dh->nv == 14 ? 14 : 0));  // exact sizes of the in-scope models
+  if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for this nv (14, 15, 21 are built)", -8); }
   cudaError_t e = cudaSuccess;
-  if (h->nvp == 15) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-  else if (h->nvp == 21) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-  else if (h->nvp == 14) e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-  else e = cudaFuncSetAttribute(fetch_kernel<B200_WPB, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+#define B200_SETATTR(W, V) if (h->wpb == W && h->nvp == V) e = cudaFuncSetAttribute(fetch_kernel<W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  B200_FOR_ALL_VARIANTS(B200_SETATTR)
+#undef B200_SETATTR
   if (e != cudaSuccess) { std::string m = std::string("cudaFuncSetAttribute(smem=") + std::to_string(h->smem_bytes) + "): " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
   if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, (size_t)num_envs * t.st_stride * 4) != cudaSuccess) {
     delete h; return fail(nullptr, "b200sim_create: cudaMalloc failed", -9);
@@ -180,7 +182,7 @@ float* b200sim_state(b200sim_t* h) { return h->state; }
 long b200sim_launch_count(const b200sim_t* h) { return h->launches; }
 int b200sim_launch_config(const b200sim_t* h, int* smem_bytes, int* envs_per_block, int* blocks) {
   if (smem_bytes) *smem_bytes = (int)h->smem_bytes;
-  if (envs_per_block) *envs_per_block = B200_WPB;
+  if (envs_per_block) *envs_per_block = h->wpb;
   if (blocks) *blocks = h->blocks;
   return 0;
 }
@@ -189,10 +191,11 @@ static int launch(b200sim* h, int mode, int nraw, const float* actions, const un
                   float* desired, float* reward, float* success, int* info, void* stream) {
   if (!obs || !achieved || !desired || !reward || !success) return fail(h, "output pointers must not be NULL", -1);
   CUDA_OK(cudaSetDevice(h->device));
-#define B200_LAUNCH(NVP_)                                                                                   \
-  fetch_kernel<B200_WPB, NVP_><<<h->blocks, B200_WPB * 32, h->smem_bytes, (cudaStream_t)stream>>>(          \
-      h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info)
-  if (h->nvp == 15) B200_LAUNCH(15); else if (h->nvp == 21) B200_LAUNCH(21); else if (h->nvp == 14) B200_LAUNCH(14); else B200_LAUNCH(32);
+#define B200_LAUNCH(W, V)                                                                                   \
+  if (h->wpb == W && h->nvp == V)                                                                                \
+    fetch_kernel<W, V><<<h->blocks, W * 32, h->smem_bytes, (cudaStream_t)stream>>>(                              \
+        h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info);
+  B200_FOR_ALL_VARIANTS(B200_LAUNCH)
 #undef B200_LAUNCH
   h->launches++;
   CUDA_OK(cudaGetLastError());

@@ -22,18 +22,9 @@
 #define SYNC() __syncwarp()
 // block-wide alignment points: keep the warps of a block inside the same code window (instruction-cache locality)
 #ifdef B200_BLOCK_ALIGN
-// the warps of a block form alignment groups of B200_AG warps; each group has its own named barrier
-#ifndef B200_AG
-#define B200_AG 28
-#endif
-__device__ __forceinline__ void b200_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ int b200_bar_or(int id, int nthreads, int pred) {
-  int r;
-  asm volatile("{\n .reg .pred p, q;\n setp.ne.s32 p, %3, 0;\n bar.red.or.pred q, %1, %2, p;\n selp.s32 %0, 1, 0, q;\n}" : "=r"(r) : "r"(id), "r"(nthreads), "r"(pred) : "memory");
-  return r;
-}
-#define ALIGN() b200_bar(1 + (int)(threadIdx.x >> 5) / B200_AG, B200_AG * 32)
-#define ALIGN_OR(p) b200_bar_or(1 + (int)(threadIdx.x >> 5) / B200_AG, B200_AG * 32, (p))
+// the alignment group is the whole block
+#define ALIGN() __syncthreads()
+#define ALIGN_OR(p) __syncthreads_or(p)
 #else
 #define ALIGN() do { } while (0)
 #define ALIGN_OR(p) (p)
