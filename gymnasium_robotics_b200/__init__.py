@@ -21,6 +21,12 @@ for _maze, _steps in (("UMaze", 700), ("Open", 700), ("Open_Diverse_G", 700), ("
                       ("Large_Diverse_GR", 1000)):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
         ENV_IDS[f"AntMaze_{_maze}{_suffix}-v5"] = dict(maze=_maze, reward_type=_rt, max_episode_steps=_steps)
+# PointMaze-v3 (__init__.py:960-1080)
+for _maze, _steps in (("UMaze", 300), ("Open", 300), ("Open_Diverse_G", 300), ("Open_Diverse_GR", 300), ("Medium", 600),
+                      ("Medium_Diverse_G", 600), ("Medium_Diverse_GR", 600), ("Large", 800), ("Large_Diverse_G", 800),
+                      ("Large_Diverse_GR", 800)):
+    for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
+        ENV_IDS[f"PointMaze_{_maze}{_suffix}-v3"] = dict(maze=_maze, agent="point", reward_type=_rt, max_episode_steps=_steps)
 
 
 def make_vec(env_id: str, num_envs: int = 1, **kwargs):
@@ -30,9 +36,9 @@ def make_vec(env_id: str, num_envs: int = 1, **kwargs):
     spec = dict(ENV_IDS[env_id])
     spec.update(kwargs)
     if "maze" in spec:
-        from .maze import AntMazeVectorEnv
+        from .maze import MazeVectorEnv
 
-        return AntMazeVectorEnv(num_envs=num_envs, **spec)
+        return MazeVectorEnv(num_envs=num_envs, **spec)
     from .fetch import FetchVectorEnv
 
     return FetchVectorEnv(num_envs=num_envs, **spec)
@@ -54,6 +60,6 @@ def register_envs():
     for env_id, spec in ENV_IDS.items():
         if env_id in registry:
             continue
-        ep = "gymnasium_robotics_b200.maze:AntMazeVectorEnv" if "maze" in spec else "gymnasium_robotics_b200.fetch:FetchVectorEnv"
+        ep = "gymnasium_robotics_b200.maze:MazeVectorEnv" if "maze" in spec else "gymnasium_robotics_b200.fetch:FetchVectorEnv"
         register(id=env_id, vector_entry_point=ep, kwargs=dict(spec))
     return True

@@ -23,7 +23,8 @@ class FetchTaskC(ctypes.Structure):
                                              "obj_site", "frame_site", "nrobot")] + \
                [("robot_qadr", ctypes.c_int * 16), ("robot_dadr", ctypes.c_int * 16), ("finger_qadr", ctypes.c_int * 2),
                 ("nobs", ctypes.c_int), ("distance_threshold", ctypes.c_float), ("dt", ctypes.c_float),
-                ("kind", ctypes.c_int), ("nact", ctypes.c_int), ("ngoal", ctypes.c_int), ("success_radius", ctypes.c_float)]
+                ("kind", ctypes.c_int), ("nact", ctypes.c_int), ("ngoal", ctypes.c_int), ("success_radius", ctypes.c_float),
+                ("obs_qpos_start", ctypes.c_int), ("vel_clip", ctypes.c_float)]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

@@ -132,10 +132,11 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   t.finger_qadr[0] = task->finger_qadr[0]; t.finger_qadr[1] = task->finger_qadr[1];
   t.nobs = task->nobs; t.distance_threshold = task->distance_threshold; t.dt = task->dt;
   t.kind = task->kind; t.nact = task->nact; t.ngoal = task->ngoal; t.success_radius = task->success_radius;
+  t.obs_qpos_start = task->obs_qpos_start; t.vel_clip = task->vel_clip;
   if (t.kind == TASK_FETCH) { t.nact = 4; t.ngoal = 3; }
   if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
   if (t.kind == TASK_FETCH && dh->nmocap != 1) { delete h; return fail(nullptr, "b200sim_create: Fetch task needs exactly one mocap body", -6); }
-  if (t.kind == TASK_ANTMAZE && (t.nact != dh->nu || t.nact > TASK_MAX_ACT || t.ngoal != 2 || t.nobs != dh->nq - 2 + dh->nv)) { delete h; return fail(nullptr, "b200sim_create: inconsistent AntMaze task", -6); }
+  if (t.kind == TASK_ANTMAZE && (t.nact != dh->nu || t.nact > TASK_MAX_ACT || t.ngoal != 2 || t.nobs != dh->nq - t.obs_qpos_start + dh->nv)) { delete h; return fail(nullptr, "b200sim_create: inconsistent AntMaze task", -6); }
   int o = 0;
   t.st_qpos = o; o += dh->nq; t.st_qvel = o; o += dh->nv; t.st_warm = o; o += dh->nv; t.st_ctrl = o; o += dh->nu;
   t.st_mocap = o; o += 7 * dh->nmocap; t.st_pose = o; o += (t.kind == TASK_FETCH ? 7 : 0); t.st_goal = o; o += t.ngoal;
@@ -146,8 +147,8 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   h->wpb = (num_envs + nsm - 1) / nsm <= 7 ? 7 : ((num_envs + nsm - 1) / nsm <= 14 ? 14 : 28);
   h->smem_bytes = ((size_t)dh->hot_words + (size_t)h->wpb * dh->scr_words) * 4;
   h->blocks = (num_envs + h->wpb - 1) / h->wpb;
-  h->nvp = dh->nv == 15 ? 15 : (dh->nv == 21 ? 21 : (dh->nv == 14 ? 14 : 0));  // exact sizes of the in-scope models
-  if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for this nv (14, 15, 21 are built)", -8); }
+  h->nvp = dh->nv <= 14 ? 14 : (dh->nv == 15 ? 15 : (dh->nv <= 21 ? 21 : 0));  // smallest built size >= nv (identity padding)
+  if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for nv > 21 yet", -8); }
   cudaError_t e = cudaSuccess;
 #define B200_SETATTR(W, V) if (h->wpb == W && h->nvp == V) e = cudaFuncSetAttribute(fetch_kernel<W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   B200_FOR_ALL_VARIANTS(B200_SETATTR)

@@ -21,10 +21,12 @@ struct FetchTask {
   // task family (TASK_FETCH / TASK_ANTMAZE), action and goal widths, maze success radius
   int kind, nact, ngoal;
   float success_radius;
+  int obs_qpos_start;   // maze tasks: first qpos entry that is part of `observation` (Ant 2, Point 0)
+  float vel_clip;       // maze tasks: |qvel| clip applied before stepping (Point 5.0, 0 = none)
   // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(ngoal)
   int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride;
 };
-enum { TASK_FETCH = 0, TASK_ANTMAZE = 1 };
+enum { TASK_FETCH = 0, TASK_ANTMAZE = 1 };  // TASK_ANTMAZE covers both maze agents (Ant, Point)
 #define TASK_MAX_ACT 8
 
 enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
@@ -120,8 +122,9 @@ HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float
 HD void antmaze_observe(const Ctx& c, const FetchTask& t, const float* goal, float* obs, float* achieved, float* desired,
                         float* reward, float* success) {
   const DMHead* h = c.h;
-  LANES(i, h->nq - 2) obs[i] = SF(qpos)[2 + i];
-  LANES(i, h->nv) obs[h->nq - 2 + i] = SF(qvel)[i];
+  const int q0 = t.obs_qpos_start;
+  LANES(i, h->nq - q0) obs[i] = SF(qpos)[q0 + i];
+  LANES(i, h->nv) obs[h->nq - q0 + i] = SF(qvel)[i];
   if (c.lane == 0) {
     float dx = SF(qpos)[0] - goal[0], dy = SF(qpos)[1] - goal[1];
     float d = sqrtf(dx * dx + dy * dy);
@@ -152,8 +155,13 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
       }
       SYNC();
     } else if (mode == MODE_STEP) {
-      // do_simulation(action, frame_skip): ctrl = action (clamped to ctrlrange inside the actuation stage)
+      // do_simulation(action, frame_skip): ctrl = action (clamped to ctrlrange inside the actuation stage);
+      // PointEnv.step first clips the action and the velocity (envs/maze/point.py:52-77)
       LANES(i, h->nu) SF(ctrl)[i] = action[i];
+      if (t.vel_clip > 0) {
+        LANES(i, h->nu) SF(ctrl)[i] = fminf(fmaxf(action[i], -1.f), 1.f);
+        LANES(i, h->nv) SF(qvel)[i] = fminf(fmaxf(SF(qvel)[i], -t.vel_clip), t.vel_clip);
+      }
       SYNC();
     }
   }

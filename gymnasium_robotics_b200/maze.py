@@ -1,10 +1,11 @@
-"""Batched AntMaze environments (v5) on the b200sim CUDA path.
+"""Batched AntMaze (v5) and PointMaze (v3) environments on the b200sim CUDA path.
 
 Host-side mirror of the reference's maze stack, batched over `num_envs`:
   * map tables               envs/maze/maps.py:52-135 (data), ids/kwargs/max_episode_steps __init__.py:839-958
   * Maze grid math           envs/maze/maze_v4.py:135-146 (cell<->xy), :148-242 (goal/reset cell collection)
   * MazeEnv.reset / noise / update_goal     envs/maze/maze_v4.py:276-297, 299-379, 400-418
   * AntMazeEnv ctor/reset/step/_get_obs     envs/maze/ant_maze_v5.py:221-320 (inner AntEnv [ext]: frame_skip 5, RK4)
+  * PointMazeEnv / PointEnv                 envs/maze/point_maze.py:316-434, envs/maze/point.py:22-77 (frame_skip 1, Euler)
   * compute_reward / compute_terminated     envs/maze/maze_v4.py:381-398
 The per-step arithmetic (5 RK4 sub-steps, observation, reward, success) runs inside one CUDA kernel launch.
 """
@@ -44,9 +45,20 @@ MAPS = {
                          [1, 0, 0, 1, C, 0, C, 1, 0, C, 0, 1], [1] * 12],
 }
 # wall layout -> compiled physics model (the diverse variants only relabel free cells)
-MAP_MODEL = {k: "antmaze_" + k.split("_")[0].lower() for k in MAPS}
-MAX_EPISODE_STEPS = {k: (700 if k.startswith(("Open", "UMaze")) else 1000) for k in MAPS}
-SCALING, HEIGHT, NOISE, SUCCESS_RADIUS, FRAME_SKIP = 4.0, 0.5, 0.25, 0.45, 5
+NOISE, SUCCESS_RADIUS = 0.25, 0.45
+# per agent: maze_size_scaling, maze_height, frame_skip, first qpos entry in `observation`, velocity clip, episode lengths
+AGENTS = {
+    "ant": dict(scaling=4.0, height=0.5, frame_skip=5, obs_qpos_start=2, vel_clip=0.0, fps=50,
+                steps={k: (700 if k.startswith(("Open", "UMaze")) else 1000) for k in MAPS}),     # __init__.py:839-958
+    "point": dict(scaling=1.0, height=0.4, frame_skip=1, obs_qpos_start=0, vel_clip=5.0, fps=100,
+                  steps={k: (300 if k.startswith(("Open", "UMaze")) else (600 if k.startswith("Medium") else 800)) for k in MAPS}),  # :960-1080
+}
+SCALING, HEIGHT, FRAME_SKIP = AGENTS["ant"]["scaling"], AGENTS["ant"]["height"], AGENTS["ant"]["frame_skip"]
+
+
+def model_name(agent, maze):
+    """wall layout -> compiled physics model (the diverse variants only relabel free cells)"""
+    return f"{agent}maze_" + maze.split("_")[0].lower()
 
 
 class MazeCells:
@@ -84,14 +96,20 @@ class MazeCells:
         return np.array([math.floor((self.y_center - xy[1]) / self.scaling), math.floor((xy[0] + self.x_center) / self.scaling)])
 
 
-def make_antmaze_task(model, reward_type):
+def make_maze_task(model, reward_type, agent="ant"):
+    cfg = AGENTS[agent]
     t = _lib.FetchTaskC()
     t.kind, t.nact, t.ngoal = 1, int(model.nu), 2
-    t.n_substeps, t.reward_dense = FRAME_SKIP, int(reward_type == "dense")
-    t.nobs = int(model.nq - 2 + model.nv)
+    t.n_substeps, t.reward_dense = cfg["frame_skip"], int(reward_type == "dense")
+    t.obs_qpos_start, t.vel_clip = cfg["obs_qpos_start"], cfg["vel_clip"]
+    t.nobs = int(model.nq - cfg["obs_qpos_start"] + model.nv)
     t.success_radius = SUCCESS_RADIUS
-    t.dt = float(model.opt[0] * FRAME_SKIP)
+    t.dt = float(model.opt[0] * cfg["frame_skip"])
     return t
+
+
+def make_antmaze_task(model, reward_type):
+    return make_maze_task(model, reward_type, "ant")
 
 
 class _AntBackend(CudaBackend):
@@ -115,15 +133,19 @@ class _AntBackend(CudaBackend):
         return out
 
 
-class AntMazeVectorEnv:
-    """`gym.make_vec("AntMaze_Large-v5", num_envs=N)` replacement (torch CUDA tensors, leading `num_envs` axis)."""
+class MazeVectorEnv:
+    """`gym.make_vec("AntMaze_Large-v5" | "PointMaze_UMaze-v3", num_envs=N)` replacement (torch CUDA tensors, leading
+    `num_envs` axis).  `maze_map` may be a name from `MAPS` or (for the point agent's tests) an explicit cell list."""
 
     metadata = {"render_modes": [], "render_fps": 50, "autoreset_mode": "next_step"}
+    AGENT = "ant"
 
-    def __init__(self, maze: str = "Large", num_envs: int = 1, reward_type: str = "sparse", continuing_task: bool = True,
+    def __init__(self, maze="Large", num_envs: int = 1, reward_type: str = "sparse", continuing_task: bool = True,
                  reset_target: bool = False, max_episode_steps: Optional[int] = None, device="cuda:0", rng_mode: str = "auto",
-                 autoreset_mode: str = "next_step", backend_factory=None, **kwargs):
-        if maze not in MAPS:
+                 autoreset_mode: str = "next_step", backend_factory=None, agent: Optional[str] = None, model=None, **kwargs):
+        self.agent = agent or self.AGENT
+        cfg = AGENTS[self.agent]
+        if isinstance(maze, str) and maze not in MAPS:
             raise KeyError(f"unknown maze {maze!r}")
         if reward_type not in ("sparse", "dense"):
             raise ValueError("reward_type must be 'sparse' or 'dense'")
@@ -133,10 +155,15 @@ class AntMazeVectorEnv:
         self.continuing_task, self.reset_target = continuing_task, reset_target
         self.num_envs, self.autoreset_mode = int(num_envs), autoreset_mode
         self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
-        self.max_episode_steps = MAX_EPISODE_STEPS[maze] if max_episode_steps is None else max_episode_steps
-        self.cells = MazeCells(MAPS[maze])
-        self.model = load_model(MAP_MODEL[maze])
-        self.task = make_antmaze_task(self.model, reward_type)
+        self.scaling, self.frame_skip = cfg["scaling"], cfg["frame_skip"]
+        self.metadata["render_fps"] = cfg["fps"]
+        named = isinstance(maze, str)
+        self.max_episode_steps = (cfg["steps"][maze] if named else None) if max_episode_steps is None else max_episode_steps
+        self.cells = MazeCells(MAPS[maze] if named else maze, cfg["scaling"])
+        if model is None and not named:
+            raise ValueError("an explicit maze map needs its compiled `model` (see models.compile_maze_model)")
+        self.model = model if model is not None else load_model(model_name(self.agent, maze))
+        self.task = make_maze_task(self.model, reward_type, self.agent)
         factory = backend_factory or _AntBackend
         self.backend = factory(self.model, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device
@@ -159,13 +186,13 @@ class AntMazeVectorEnv:
         self._reset_loc = torch.as_tensor(self.cells.reset_locations, dtype=torch.float32, device=self.device)
         self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
-        self.dt = float(m.opt[0] * FRAME_SKIP)
+        self.dt = float(m.opt[0] * self.frame_skip)
         self.closed = False
 
     # ------------------------------------------------------------------ sampling (MazeEnv.reset, maze_v4.py:299-358)
     def _noise_np(self, rng, xy):
-        nx = rng.uniform(low=-NOISE, high=NOISE) * SCALING
-        ny = rng.uniform(low=-NOISE, high=NOISE) * SCALING
+        nx = rng.uniform(low=-NOISE, high=NOISE) * self.scaling
+        ny = rng.uniform(low=-NOISE, high=NOISE) * self.scaling
         return np.array([xy[0] + nx, xy[1] + ny])
 
     def _sample_np(self, i, options):
@@ -184,25 +211,25 @@ class AntMazeVectorEnv:
             pos = cells.cell_rowcol_to_xy(rc)
         else:
             pos = goal.copy()
-            while np.linalg.norm(pos - goal) <= 0.5 * SCALING:
+            while np.linalg.norm(pos - goal) <= 0.5 * self.scaling:
                 pos = cells.reset_locations[rng.integers(low=0, high=len(cells.reset_locations))].copy()
         return goal, self._noise_np(rng, pos)
 
     def _sample(self, idx, options=None):
         n = idx.numel()
-        if self.rng_mode == "numpy" or options:
+        if self.rng_mode == "numpy" or options:  # explicit cells always go through the reference-ordered numpy path
             gs, ps = zip(*[self._sample_np(i, options) for i in idx.tolist()])
             return (torch.as_tensor(np.array(gs), dtype=torch.float32, device=self.device),
                     torch.as_tensor(np.array(ps), dtype=torch.float32, device=self.device))
         u = lambda *s: torch.rand(*s, generator=self._gen, device=self.device)
         ri = lambda hi, k: torch.randint(0, hi, (k,), generator=self._gen, device=self.device)
-        goal = self._goal_loc[ri(len(self._goal_loc), n)] + (u(n, 2) * 2 - 1) * NOISE * SCALING
+        goal = self._goal_loc[ri(len(self._goal_loc), n)] + (u(n, 2) * 2 - 1) * NOISE * self.scaling
         pos = self._reset_loc[ri(len(self._reset_loc), n)]
-        bad = torch.linalg.norm(pos - goal, dim=1) <= 0.5 * SCALING
+        bad = torch.linalg.norm(pos - goal, dim=1) <= 0.5 * self.scaling
         while bool(bad.any()):
             pos[bad] = self._reset_loc[ri(len(self._reset_loc), int(bad.sum()))]
-            bad = torch.linalg.norm(pos - goal, dim=1) <= 0.5 * SCALING
-        return goal, pos + (u(n, 2) * 2 - 1) * NOISE * SCALING
+            bad = torch.linalg.norm(pos - goal, dim=1) <= 0.5 * self.scaling
+        return goal, pos + (u(n, 2) * 2 - 1) * NOISE * self.scaling
 
     def _reset_envs(self, mask, out, options=None):
         idx = torch.nonzero(mask, as_tuple=False).flatten()
@@ -304,3 +331,11 @@ class AntMazeVectorEnv:
         if not getattr(self, "closed", True):
             self.backend.close()
             self.closed = True
+
+
+class AntMazeVectorEnv(MazeVectorEnv):
+    AGENT = "ant"
+
+
+class PointMazeVectorEnv(MazeVectorEnv):
+    AGENT = "point"

@@ -24,7 +24,18 @@ MODEL_SOURCES = {
 
 # maze models: in-tree legacy twin of Gymnasium's ant.xml (Gymnasium itself is un-vendored) + generated wall boxes
 ANT_XML = "../mujoco/assets/ant.xml"
-MAZE_MODELS = {"antmaze_open": "Open", "antmaze_umaze": "UMaze", "antmaze_medium": "Medium", "antmaze_large": "Large"}
+POINT_XML = "point/point.xml"
+MAZE_MODELS = {f"{a}maze_{k.lower()}": (a, k) for a in ("ant", "point") for k in ("Open", "UMaze", "Medium", "Large")}
+
+
+def compile_maze_model(agent, maze_map):
+    """Compile agent + maze walls (restating Maze.make_maze, maze_v4.py:148-242); needs the reference assets."""
+    from .maze import AGENTS
+    from .mjcf import make_maze_xml
+
+    xml = os.path.normpath(os.path.join(REFERENCE_ASSETS, ANT_XML if agent == "ant" else POINT_XML))
+    root, grid = make_maze_xml(xml, maze_map, AGENTS[agent]["scaling"], AGENTS[agent]["height"])
+    return compile_mjcf(xml, root=root, grid=grid)
 
 
 def build_models(force: bool = False):
@@ -41,17 +52,14 @@ def build_models(force: bool = False):
         with open(out, "wb") as f:
             f.write(blob)
         built.append(out)
-    from .maze import HEIGHT, MAPS, SCALING
-    from .mjcf import make_maze_xml
+    from .maze import MAPS
 
-    ant = os.path.normpath(os.path.join(REFERENCE_ASSETS, ANT_XML))
-    for name, key in MAZE_MODELS.items():
+    for name, (agent, key) in MAZE_MODELS.items():
         out = os.path.join(MODEL_DIR, name + ".b200m")
         if os.path.exists(out) and not force:
             continue
-        root, grid = make_maze_xml(ant, MAPS[key], SCALING, HEIGHT)
         with open(out, "wb") as f:
-            f.write(compile_mjcf(ant, root=root, grid=grid).to_blob())
+            f.write(compile_maze_model(agent, MAPS[key]).to_blob())
         built.append(out)
     return built
 

@@ -33,6 +33,8 @@ typedef struct b200sim_fetch_task {
    * goal = xy; uses nobs, n_substeps (= frame_skip), reward_dense, nact, ngoal, success_radius) */
   int kind, nact, ngoal;
   float success_radius;
+  int obs_qpos_start;   /* maze: first qpos entry inside `observation` (ant_maze_v5.py:312-320: 2; point_maze.py:404-410: 0) */
+  float vel_clip;       /* maze: |qvel| clip before stepping (envs/maze/point.py:73-77: 5.0; 0 = none) */
 } b200sim_fetch_task_t;
 
 /* indices into the layout array returned by b200sim_layout (offsets in floats inside one env's state record) */

@@ -234,3 +234,51 @@ def test_antmaze_shard_size_batch_properties():
         assert not bool(walls[i, j].any())
         assert not bool(te.any()) and not bool(tr.any())
     env.close()
+
+
+# ------------------------------------------------------------------------------------------------ PointMaze
+def test_pointmaze_reference_known_answers_on_gpu():
+    """The reference's only numeric known answers (tests/envs/maze/test_point_maze.py:20-45) through the C-ABI on the GPU."""
+    import json
+    import os
+
+    from gymnasium_robotics_b200.maze import PointMazeVectorEnv
+    from gymnasium_robotics_b200.mjcf import Model
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    model = Model.from_blob(open(os.path.join(here, "golden", "pointmaze_4x4.b200m"), "rb").read())
+    for c in json.load(open(os.path.join(here, "golden", "maze_known_answers.json"))):
+        env = PointMazeVectorEnv(c["maze_map"], num_envs=3, model=model, device="cuda:0", rng_mode="numpy")
+        obs, info = env.reset(seed=[c["seed"]] * 3, options=c["options"])
+        if "reset_pos" in c["expect"]:
+            np.testing.assert_almost_equal(np.array(c["expect"]["reset_pos"] + [0, 0]), obs["observation"][0].double().cpu().numpy(), decimal=c["decimal"])
+        if "goal" in c["expect"]:
+            np.testing.assert_almost_equal(np.array(c["expect"]["goal"]), obs["desired_goal"][2].double().cpu().numpy(), decimal=c["decimal"])
+        env.close()
+
+
+def test_pointmaze_rollout_tracks_oracle():
+    from gymnasium_robotics_b200.maze import MAPS, PointMazeVectorEnv
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.point_maze_env import OraclePointMazeEnv
+
+    env = PointMazeVectorEnv("Medium", num_envs=4, device="cuda:0", rng_mode="numpy")
+    obs, _ = env.reset(seed=11)
+    model = load_model("pointmaze_medium")
+    oracles = [OraclePointMazeEnv(MAPS["Medium"], model) for _ in range(4)]
+    for i, o in enumerate(oracles):
+        o.reset(seed=11 + i)
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for _ in range(200):
+        a = rng.uniform(-1.5, 1.5, (4, 2)).astype(np.float32)
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, *_ = orc.step(a[i].astype(np.float64))
+            worst = max(worst, np.abs(o["observation"][i].double().cpu().numpy() - oo["observation"]).max())
+            d = np.linalg.norm(oo["achieved_goal"] - oo["desired_goal"])
+            if abs(d - 0.45) > 1e-3:
+                assert float(r[i]) == float(orr) and bool(info["success"][i]) == (d <= 0.45)
+    print(f"PointMaze free-running 200 steps: worst {worst:.2e}")
+    assert worst < 2e-3
+    env.close()
