@@ -25,6 +25,11 @@ sys.path.insert(0, ROOT)
 TASK, ENV_ID, ENVS_PER_GPU = "FetchPickAndPlace", "FetchPickAndPlace-v4", 4096
 # algorithmic HBM bytes per env-step: state read+write, action, obs/goals/reward/flags written
 B_ALG = 2 * 4 * (22 + 2 * 21 + 2 + 7 + 3 + 1) + 4 * 4 + 4 * (25 + 2 * 3) + 10
+# other workloads (BASELINE.json configs): name -> (env id, action dim, sub-steps, algorithmic bytes per env-step, default envs/GPU)
+WORKLOADS = {
+    "fetch_pick_and_place": ("FetchPickAndPlace-v4", 4, 20, B_ALG, 4096),
+    "antmaze_large": ("AntMaze_Large-v5", 8, 5, 2 * 4 * (15 + 28 + 0 + 0 + 2 + 1) + 32 + 124 + 10, 1024),  # config 4: 8192 envs over 8 GPUs
+}
 
 
 def measured_peaks():
@@ -148,11 +153,17 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
-    n = args.envs_per_gpu
-    env = FetchVectorEnv(TASK, num_envs=n, device=dev, rng_mode="torch", autoreset_mode="same_step")
+    env_id, nact, nsub, b_alg, default_n = WORKLOADS[args.workload]
+    n = args.envs_per_gpu or default_n
+    if args.workload == "fetch_pick_and_place":
+        env = FetchVectorEnv(TASK, num_envs=n, device=dev, rng_mode="torch", autoreset_mode="same_step")
+    else:
+        import gymnasium_robotics_b200 as grb
+
+        env = grb.make_vec(env_id, num_envs=n, device=dev, rng_mode="torch", autoreset_mode="same_step")
     env.reset(seed=1000 * rank)  # seeds seed0 + global env index would need numpy streams; device RNG is per rank
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    tape = torch.rand((64, n, 4), generator=g, device=dev) * 2 - 1  # pre-generated action tape (RNG outside the timed region)
+    tape = torch.rand((64, n, nact), generator=g, device=dev) * 2 - 1  # pre-generated action tape (RNG outside the timed region)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > L2 (126 MB)
 
     def barrier():
@@ -192,13 +203,14 @@ def run_ours(args):
     # ---- end to end through the public API with HOST buffers: pinned actions H2D, results D2H, every step
     host_tape = [tape[k].cpu().pin_memory() for k in range(8)]
     nobs = env.task.nobs
+    ngoal = 3 if args.workload == "fetch_pick_and_place" else 2
     host_out = {"observation": torch.empty((n, nobs), dtype=torch.float32).pin_memory(),
-                "achieved_goal": torch.empty((n, 3), dtype=torch.float32).pin_memory(),
-                "desired_goal": torch.empty((n, 3), dtype=torch.float32).pin_memory(),
+                "achieved_goal": torch.empty((n, ngoal), dtype=torch.float32).pin_memory(),
+                "desired_goal": torch.empty((n, ngoal), dtype=torch.float32).pin_memory(),
                 "reward": torch.empty(n, dtype=torch.float32).pin_memory(),
                 "truncated": torch.empty(n, dtype=torch.bool).pin_memory(), "terminated": torch.empty(n, dtype=torch.bool).pin_memory(),
                 "is_success": torch.empty(n, dtype=torch.float32).pin_memory()}
-    h2d = n * 4 * 4
+    h2d = n * nact * 4
     d2h = sum(v.numel() * v.element_size() for v in host_out.values())
 
     def e2e_step(k):
@@ -209,7 +221,7 @@ def run_ours(args):
         host_out["reward"].copy_(r, non_blocking=True)
         host_out["terminated"].copy_(te, non_blocking=True)
         host_out["truncated"].copy_(tr, non_blocking=True)
-        host_out["is_success"].copy_(info["is_success"], non_blocking=True)
+        host_out["is_success"].copy_((info["is_success"] if "is_success" in info else info["success"]).to(torch.float32), non_blocking=True)
         torch.cuda.synchronize(dev)
 
     for k in range(args.warmup):
@@ -223,6 +235,8 @@ def run_ours(args):
         e2e_step(k)
         e2e_s += time.perf_counter() - t0
     barrier()
+    if os.environ.get("B200SIM_BENCH_DEBUG"):
+        print(f"[rank {rank}] ms/step {ms / args.steps:.3f} kernel {kms:.3f} e2e {e2e_s * 1e3 / args.steps:.3f}", file=sys.stderr)
     t = torch.tensor([ms, e2e_s * 1e3, kms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -232,13 +246,13 @@ def run_ours(args):
     e2e_value = total_envs * args.steps / (e2e_ms / 1e3)
     if rank == 0:
         peak, how = measured_peaks()
-        achieved = B_ALG * n / (kms / 1e3) / 1e9
+        achieved = b_alg * n / (kms / 1e3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.workload == "fetch_pick_and_place":
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "fetch_pick_and_place":
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "20", "--warmup", "2"]
             try:
                 outp = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
@@ -248,11 +262,11 @@ def run_ours(args):
         line = {"metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{ENV_ID}, {n} envs/GPU, 20 sub-steps/env-step, random actions U(-1,1), TimeLimit 50, "
+                "config": {"workload": f"{env_id}, {n} envs/GPU, {nsub} sub-steps/env-step, random actions U(-1,1), TimeLimit, "
                                        "same-step autoreset", "envs_per_gpu": n, "l2": "flushed between timed iterations (256 MB fill)",
                            "parallelism": f"env-sharded x{world}, no data-path collective"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": how, "algorithmic_bytes_per_env_step": B_ALG,
+                             "traffic": traffic, "peak_source": how, "algorithmic_bytes_per_env_step": b_alg,
                              "kernel_ms": kms,
                              "note": "path is FP32-issue/latency bound (SURVEY.md 0.4, 8d); HBM fraction is reported because the metric asks for it"},
                 "cpu_baseline": cpu,
@@ -271,7 +285,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--workload", default="fetch_pick_and_place", choices=sorted(WORKLOADS))
     ap.add_argument("--sample-envs", type=int, default=256, help="envs per step of the CPU arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
