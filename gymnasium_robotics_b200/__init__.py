@@ -27,6 +27,11 @@ for _maze, _steps in (("UMaze", 300), ("Open", 300), ("Open_Diverse_G", 300), ("
                       ("Large_Diverse_GR", 800)):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
         ENV_IDS[f"PointMaze_{_maze}{_suffix}-v3"] = dict(maze=_maze, agent="point", reward_type=_rt, max_episode_steps=_steps)
+# Shadow-Hand block manipulation, new-binding ids (-v1; __init__.py:105-395); touch-sensor variants are "next"
+for _task in ("HandManipulateBlockRotateZ", "HandManipulateBlockRotateParallel", "HandManipulateBlockRotateXYZ",
+              "HandManipulateBlockFull", "HandManipulateBlock"):
+    for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
+        ENV_IDS[f"{_task}{_suffix}-v1"] = dict(hand_task=_task, reward_type=_rt, max_episode_steps=100)
 
 
 def make_vec(env_id: str, num_envs: int = 1, **kwargs):
@@ -39,6 +44,10 @@ def make_vec(env_id: str, num_envs: int = 1, **kwargs):
         from .maze import MazeVectorEnv
 
         return MazeVectorEnv(num_envs=num_envs, **spec)
+    if "hand_task" in spec:
+        from .hand import HandVectorEnv
+
+        return HandVectorEnv(task=spec.pop("hand_task"), num_envs=num_envs, **spec)
     from .fetch import FetchVectorEnv
 
     return FetchVectorEnv(num_envs=num_envs, **spec)
@@ -60,6 +69,10 @@ def register_envs():
     for env_id, spec in ENV_IDS.items():
         if env_id in registry:
             continue
-        ep = "gymnasium_robotics_b200.maze:MazeVectorEnv" if "maze" in spec else "gymnasium_robotics_b200.fetch:FetchVectorEnv"
-        register(id=env_id, vector_entry_point=ep, kwargs=dict(spec))
+        ep = "gymnasium_robotics_b200.maze:MazeVectorEnv" if "maze" in spec else \
+            ("gymnasium_robotics_b200.hand:make_hand_vec" if "hand_task" in spec else "gymnasium_robotics_b200.fetch:FetchVectorEnv")
+        kw = dict(spec)
+        if "hand_task" in kw:
+            kw["task"] = kw.pop("hand_task")
+        register(id=env_id, vector_entry_point=ep, kwargs=kw)
     return True

@@ -24,7 +24,9 @@ class FetchTaskC(ctypes.Structure):
                [("robot_qadr", ctypes.c_int * 16), ("robot_dadr", ctypes.c_int * 16), ("finger_qadr", ctypes.c_int * 2),
                 ("nobs", ctypes.c_int), ("distance_threshold", ctypes.c_float), ("dt", ctypes.c_float),
                 ("kind", ctypes.c_int), ("nact", ctypes.c_int), ("ngoal", ctypes.c_int), ("success_radius", ctypes.c_float),
-                ("obs_qpos_start", ctypes.c_int), ("vel_clip", ctypes.c_float)]
+                ("obs_qpos_start", ctypes.c_int), ("vel_clip", ctypes.c_float),
+                ("obj_qadr", ctypes.c_int), ("obj_dadr", ctypes.c_int), ("goal_flags", ctypes.c_int),
+                ("rotation_threshold", ctypes.c_float)]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -61,6 +63,7 @@ def lib():
     L.b200sim_step.argtypes = [vp] * 9
     L.b200sim_refresh.argtypes = [vp] * 8
     L.b200sim_raw_step.argtypes = [vp, ci] + [vp] * 6
+    L.b200sim_raw_step_masked.argtypes = [vp, vp, ci] + [vp] * 6
     L.b200sim_compute_reward.argtypes = [vp, vp, vp, ci, vp, vp]
     L.b200sim_launch_count.argtypes = [vp]
     L.b200sim_launch_count.restype = ctypes.c_long
@@ -70,5 +73,5 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["b200sim_create", "b200sim_destroy", "b200sim_last_error", "b200sim_num_envs", "b200sim_layout",
-                    "b200sim_state", "b200sim_step", "b200sim_refresh", "b200sim_raw_step", "b200sim_compute_reward",
+                    "b200sim_state", "b200sim_step", "b200sim_refresh", "b200sim_raw_step", "b200sim_raw_step_masked", "b200sim_compute_reward",
                     "b200sim_launch_count", "b200sim_launch_config"]

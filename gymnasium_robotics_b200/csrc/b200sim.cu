@@ -56,17 +56,22 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
   Ctx c;
   c.mg = model_g; c.mw = smem; c.h = h; c.lane = lane;
   c.s = (float*)(smem + model_words) + (size_t)warp * h->scr_words;
-  float act[TASK_MAX_ACT] = {0, 0, 0, 0, 0, 0, 0, 0};
   const size_t e = active ? (size_t)env : 0;
-  if (actions && active) { for (int k = 0; k < TASK_MAX_ACT; k++) if (k < task.nact) act[k] = actions[e * task.nact + k]; }
+  const float* act = actions ? actions + e * task.nact : nullptr;  // only dereferenced in MODE_STEP by active warps
   fetch_env_step<NVP>(c, task, active, mode, nraw, state + e * task.st_stride, act, obs + e * task.nobs, achieved + e * task.ngoal,
                       desired + e * task.ngoal, reward + e, success + e, info ? info + e : nullptr);
 }
 
 __global__ void reward_kernel(const float* __restrict__ ag, const float* __restrict__ dg, int M, int ngoal, int kind, float thr,
-                              float radius, int dense, float* __restrict__ out) {
+                              float radius, int dense, FetchTask task, float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
+  if (kind == TASK_HAND) {   // manipulate.py:120-128
+    float dp, dr;
+    hand_goal_distance(task, ag + 7 * i, dg + 7 * i, &dp, &dr);
+    out[i] = hand_reward(task, dp, dr, nullptr);
+    return;
+  }
   float d2 = 0;
   for (int k = 0; k < ngoal; k++) { float e = ag[ngoal * i + k] - dg[ngoal * i + k]; d2 += e * e; }
   float d = sqrtf(d2);
@@ -75,7 +80,8 @@ __global__ void reward_kernel(const float* __restrict__ ag, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-#define B200_FOR_ALL_VARIANTS(X) X(7, 14) X(7, 15) X(7, 21) X(14, 14) X(14, 15) X(14, 21) X(28, 14) X(28, 15) X(28, 21)
+#define B200_FOR_ALL_VARIANTS(X) X(7, 14) X(7, 15) X(7, 21) X(14, 14) X(14, 15) X(14, 21) X(28, 14) X(28, 15) X(28, 21) \
+  X(7, 30) X(14, 30)
 
 struct b200sim {
   int N = 0, device = 0;
@@ -133,10 +139,13 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   t.nobs = task->nobs; t.distance_threshold = task->distance_threshold; t.dt = task->dt;
   t.kind = task->kind; t.nact = task->nact; t.ngoal = task->ngoal; t.success_radius = task->success_radius;
   t.obs_qpos_start = task->obs_qpos_start; t.vel_clip = task->vel_clip;
+  t.obj_qadr = task->obj_qadr; t.obj_dadr = task->obj_dadr; t.goal_flags = task->goal_flags; t.rotation_threshold = task->rotation_threshold;
   if (t.kind == TASK_FETCH) { t.nact = 4; t.ngoal = 3; }
-  if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
+  if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE && t.kind != TASK_HAND) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
+  if (t.kind == TASK_HAND && (t.nact != dh->nu || t.ngoal != 7 || t.obj_qadr != dh->nq - 7 || t.obj_dadr != dh->nv - 6 ||
+                              t.nobs != t.obj_qadr + dh->nv + 7)) { delete h; return fail(nullptr, "b200sim_create: inconsistent Hand task", -6); }
   if (t.kind == TASK_FETCH && dh->nmocap != 1) { delete h; return fail(nullptr, "b200sim_create: Fetch task needs exactly one mocap body", -6); }
-  if (t.kind == TASK_ANTMAZE && (t.nact != dh->nu || t.nact > TASK_MAX_ACT || t.ngoal != 2 || t.nobs != dh->nq - t.obs_qpos_start + dh->nv)) { delete h; return fail(nullptr, "b200sim_create: inconsistent AntMaze task", -6); }
+  if (t.kind == TASK_ANTMAZE && (t.nact != dh->nu || t.ngoal != 2 || t.nobs != dh->nq - t.obs_qpos_start + dh->nv)) { delete h; return fail(nullptr, "b200sim_create: inconsistent AntMaze task", -6); }
   int o = 0;
   t.st_qpos = o; o += dh->nq; t.st_qvel = o; o += dh->nv; t.st_warm = o; o += dh->nv; t.st_ctrl = o; o += dh->nu;
   t.st_mocap = o; o += 7 * dh->nmocap; t.st_pose = o; o += (t.kind == TASK_FETCH ? 7 : 0); t.st_goal = o; o += t.ngoal;
@@ -145,10 +154,11 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
   h->wpb = (num_envs + nsm - 1) / nsm <= 7 ? 7 : ((num_envs + nsm - 1) / nsm <= 14 ? 14 : 28);
+  h->nvp = dh->nv <= 14 ? 14 : (dh->nv == 15 ? 15 : (dh->nv <= 21 ? 21 : (dh->nv <= 30 ? 30 : 0)));  // smallest built size >= nv (identity padding)
+  if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for nv > 30 yet", -8); }
+  if (h->nvp == 30 && h->wpb > 14) h->wpb = 14;  // the large models' scratch does not fit 28 envs per block
   h->smem_bytes = ((size_t)dh->hot_words + (size_t)h->wpb * dh->scr_words) * 4;
   h->blocks = (num_envs + h->wpb - 1) / h->wpb;
-  h->nvp = dh->nv <= 14 ? 14 : (dh->nv == 15 ? 15 : (dh->nv <= 21 ? 21 : 0));  // smallest built size >= nv (identity padding)
-  if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for nv > 21 yet", -8); }
   cudaError_t e = cudaSuccess;
 #define B200_SETATTR(W, V) if (h->wpb == W && h->nvp == V) e = cudaFuncSetAttribute(fetch_kernel<W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   B200_FOR_ALL_VARIANTS(B200_SETATTR)
@@ -212,6 +222,10 @@ int b200sim_refresh(b200sim_t* h, const unsigned char* mask, float* obs, float* 
                     float* success, void* stream) {
   return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
 }
+int b200sim_raw_step_masked(b200sim_t* h, const unsigned char* mask, int nstep, float* obs, float* achieved, float* desired,
+                            float* reward, float* success, void* stream) {
+  return launch(h, MODE_RAW, nstep, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+}
 int b200sim_raw_step(b200sim_t* h, int nstep, float* obs, float* achieved, float* desired, float* reward, float* success,
                      void* stream) {
   return launch(h, MODE_RAW, nstep, nullptr, nullptr, obs, achieved, desired, reward, success, nullptr, stream);
@@ -220,7 +234,7 @@ int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const floa
   if (M <= 0) return 0;
   cudaSetDevice(h->device);
   reward_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(achieved, desired, M, h->task.ngoal, h->task.kind, h->task.distance_threshold,
-                                                                  h->task.success_radius, h->task.reward_dense, out);
+                                                                  h->task.success_radius, h->task.reward_dense, h->task, out);
   const_cast<b200sim*>(h)->launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -13,7 +13,7 @@
 
 #define DM_MAX_BODY 32   // one lane per body / 32-bit body masks
 #define DM_MAX_NV 32     // 32-bit dof masks
-#define DM_NDOFROW_MAX 8
+#define DM_NDOFROW_MIN 8
 #define DM_NCAND_MAX 32
 #define DM_NWELD_MAX 1
 
@@ -36,10 +36,13 @@
   X(act_bias, 3, nu) X(act_ctrlrange, 2, nu) X(act_forcerange, 2, nu) \
   X(eq_type, 1, neq) X(eq_obj1, 1, neq) X(eq_obj2, 1, neq) X(eq_active, 1, neq) X(eq_data, 11, neq) X(eq_solref, 2, neq) \
   X(eq_solimp, 5, neq) X(eq_invweight, 2, neq) \
-  X(mocap_body, 1, nmocap) X(grid_walls, 1, ngridw)
+  X(mocap_body, 1, nmocap) X(grid_walls, 1, ngridw) \
+  X(dof_fricD, 1, nfric) X(dof_fricB, 1, nfric) \
+  X(ten_dof, 2, nten) X(ten_qadr, 2, nten) X(ten_coef, 2, nten) X(ten_range, 2, nten) X(ten_margin, 1, nten)
 #define DM_ARRAYS_COLD(X) \
   X(pair_condim, 1, npair) X(pair_friction, 3, npair) X(pair_gap, 1, npair) X(pair_solref, 2, npair) \
-  X(pair_solimp, 5, npair) X(pair_invweight, 2, npair)
+  X(pair_solimp, 5, npair) X(pair_invweight, 2, npair) \
+  X(ten_solref, 2, nten) X(ten_solimp, 5, nten) X(ten_invweight, 1, nten)
 #define DM_ARRAYS(X) DM_ARRAYS_HOT(X) DM_ARRAYS_COLD(X)
 
 // per-env scratch that lives for the whole sub-step (name, words expression)
@@ -47,8 +50,8 @@
   X(qpos, nq) X(qvel, nv) X(qacc, nv) X(ctrl, nu) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) \
   X(xpos, 3 * nb) X(xquat, 4 * nb) X(cdof, 6 * nv) X(M, nv * (nv + 1) / 2) X(fsmooth, nv) X(fcon, nv) \
   X(rk_q0, nrkq) X(rk_v0, nrkv) X(rk_dx, nrkv) X(rk_df, nrkv) \
-  X(con, ncon_max * CON_WORDS) X(dofrow, DM_NDOFROW_MAX * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
-  X(group, ngrp_max * GRP_WORDS) X(counters, 8)
+  X(con, ncon_max * CON_WORDS) X(dofrow, ndr_max * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
+  X(group, ngrp_max * GRP_WORDS) X(counters, 8) X(fric, 2 * nfric)
 // time-shared region `uni`: kinematics {kinA, kinB} -> dynamics {cinert, b6, d6, geom_xpos, cand} -> solver {H, d6, grad,
 // search, Ma, Mv} -> observation {cvel}.  d6 keeps one offset in both phases that use it.
 #define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
@@ -58,7 +61,10 @@
 // translational rows about `ref`; the torsional row is (W0[3:6], 0).  During row set-up JV[0] holds B of the reference
 // acceleration and U holds K*imp*r (normal row) / 0; afterwards U = J a - aref and JV = J search.
 enum { C_W = 0 /*18*/, C_MU = 18 /*slide, torsion*/, C_D = 20, C_U = 21 /*4*/, C_JV = 25 /*4*/, C_DIMGRP = 29, CON_WORDS = 30 };
-// dof row (joint limit; later frictionloss / joint equality): JAR holds K*imp*r and JV holds B during set-up
+// dof row (joint limit or fixed-tendon limit over <= 2 dofs): JAR holds K*imp*r and JV holds B during set-up.
+// Dof frictionloss rows are always present, one per dof, with constant D and B: they live in the per-dof arrays
+// `fric` (FR_JAR, FR_JV) instead of generic rows.
+enum { FR_JAR = 0, FR_JV = 1 };
 enum { DR_DOF = 0, DR_COEF = 1, DR_D = 2, DR_JAR = 3, DR_JV = 4, DR_DOF2 = 5, DR_COEF2 = 6, DR_WORDS = 8 };
 // weld: 6 rows w[6]; D[6], JAR[6] (K*imp*r during set-up), JV[6], B (one value), group
 enum { W_W = 0, W_D = 36, W_JAR = 42, W_JV = 48, W_B = 54, W_GRP = 55, WELD_WORDS = 56 };
@@ -73,7 +79,8 @@ struct DMHead {
   int nwords;      // size of the model buffer (header included) in 4-byte words
   int hot_words;   // leading part staged into shared memory (header + HOT arrays)
   int scr_words;   // per-env scratch size in words
-  int iterations, ls_iterations, integrator, any_damping, kin_iters, ncon_max, ngrp_max, pad2;
+  int iterations, ls_iterations, integrator, any_damping, kin_iters, ncon_max, ngrp_max, ndr_max;
+  int nten, nfric, pad3, pad4;   // limited fixed tendons; nfric = nv when any dof has frictionloss, else 0
   int grid_len, grid_wid, ngridw, pad1;   // maze wall grid (0 x 0 when the model has none)
   float grid_scale, grid_top, grid_xc, grid_yc;  // cell size, wall top height, map centre offsets
   float timestep, gravity[3], tolerance, impratio, meaninertia, ls_tolerance, ref[3];
@@ -126,7 +133,20 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   h.ngrp_max = m.nmocap > 0 ? 10 : 14;   // geom pairs in contact (+ welds) per env per sub-step
   if (h.nb > DM_MAX_BODY) { err = "model has more than 32 runtime bodies"; return -1; }
   if (h.nv > DM_MAX_NV) { err = "model has more than 32 dofs"; return -1; }
-  if (m.ntendon > 0) { err = "tendons are not supported by the CUDA path yet"; return -1; }
+  std::vector<int> tsrc;   // limited fixed tendons (unlimited ones have no effect without springs)
+  for (int t = 0; t < m.ntendon; t++) {
+    if (!m.ten_limited[t]) continue;
+    if (m.ten_num[t] < 1 || m.ten_num[t] > 2) { err = "fixed tendons over more than 2 joints are not supported by the CUDA path"; return -1; }
+    tsrc.push_back(t);
+  }
+  h.nten = (int)tsrc.size();
+  for (int d = 0; d < m.nv; d++) if (m.dof_frictionloss[d] > 0) h.nfric = m.nv;
+  {
+    int nlim = 0;
+    for (int j = 0; j < m.njnt; j++) if (m.jnt_limited[j] && m.jnt_type[j] != B200_JNT_FREE) nlim++;
+    int want = nlim + h.nten;   // at most one side of every limit can be active at a time
+    h.ndr_max = want < DM_NDOFROW_MIN ? DM_NDOFROW_MIN : (want > 48 ? 48 : want);
+  }
   int nweld = 0;
   for (int e = 0; e < m.neq; e++) if (m.eq_type[e] == B200_EQ_WELD) nweld++;
   if (nweld > DM_NWELD_MAX) { err = "too many weld constraints"; return -1; }
@@ -139,7 +159,8 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   for (int d = 0; d < m.nv; d++) if (m.dof_damping[d] > 0) h.any_damping = 1;
   // offsets
   int nb = h.nb, njnt = h.njnt, nq = h.nq, nv = h.nv, nu = h.nu, ngeom = h.ngeom, nsite = h.nsite, nmocap = h.nmocap,
-      neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max;
+      neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max, ndr_max = h.ndr_max,
+      nten = h.nten, nfric = h.nfric;
   int nrkq = h.integrator == B200_INT_RK4 ? nq : 0, nrkv = h.integrator == B200_INT_RK4 ? nv : 0;
   int off = (int)((sizeof(DMHead) + 3) / 4);
 #define X(name, w, kind) h.o_##name = off; off += (w) * (kind);
@@ -232,7 +253,29 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     I(h.o_dof_body, d, m.dof_body[d]); I(h.o_dof_jnt, d, m.dof_jnt[d]); buf[h.o_dof_anc + d] = anc[d]; buf[h.o_dof_pre + d] = pre[d];
     F(h.o_dof_armature, d, m.dof_armature[d]); F(h.o_dof_damping, d, m.dof_damping[d]);
     F(h.o_dof_frictionloss, d, m.dof_frictionloss[d]); F(h.o_dof_invweight0, d, m.dof_invweight0[d]);
-    if (m.dof_frictionloss[d] > 0) { err = "frictionloss rows are not supported by the CUDA path yet"; return -1; }
+    if (nfric) {
+      // constant row parameters of the dof-friction constraint (pos = 0, margin = 0): D = 1/R, B of the reference acceleration
+      double fl = m.dof_frictionloss[d];
+      const double* si = m.dof_solimp_fri + 5 * d; const double* sr = m.dof_solref_fri + 2 * d;
+      double d0 = fmin(fmax(si[0], 0.0001), 0.9999), d1 = fmin(fmax(si[1], 0.0001), 0.9999), width = fmax(si[2], 0.0);
+      double imp = (d0 == d1 || width <= 1e-15) ? 0.5 * (d0 + d1) : d0;   // x = |pos - margin| / width = 0
+      double R = fmax((1 - imp) / imp * m.dof_invweight0[d], 1e-15);
+      double B = sr[0] > 0 ? 2.0 / fmax(d1 * fmax(sr[0], 2 * m.opt[B200_OPT_TIMESTEP]), 1e-15) : -sr[1] / d1;
+      F(h.o_dof_fricD, d, fl > 0 ? 1.0 / R : 0.0); F(h.o_dof_fricB, d, B);
+    }
+  }
+  for (int t = 0; t < nten; t++) {
+    int st = tsrc[t], adr = m.ten_adr[st];
+    for (int k = 0; k < 2; k++) {
+      bool has = k < m.ten_num[st];
+      int d = has ? m.wrap_dof[adr + k] : -1;
+      if (has && m.jnt_type[m.dof_jnt[d]] == B200_JNT_FREE) { err = "tendon over a free joint"; return -1; }
+      I(h.o_ten_dof, 2 * t + k, d); I(h.o_ten_qadr, 2 * t + k, has ? m.jnt_qposadr[m.dof_jnt[d]] : 0);
+      F(h.o_ten_coef, 2 * t + k, has ? m.wrap_coef[adr + k] : 0.0);
+      F(h.o_ten_range, 2 * t + k, m.ten_range[2 * st + k]); F(h.o_ten_solref, 2 * t + k, m.ten_solref[2 * st + k]);
+    }
+    F(h.o_ten_margin, t, m.ten_margin[st]); F(h.o_ten_invweight, t, m.ten_invweight0[st]);
+    for (int k = 0; k < 5; k++) F(h.o_ten_solimp, 5 * t + k, m.ten_solimp[5 * st + k]);
   }
   for (int g = 0; g < ngeom; g++) {
     int sg = gsrc[g];
@@ -245,8 +288,9 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     int sp = psrc[p];
     I(h.o_pair_geom1, p, gmap[m.pair_geom1[sp]]); I(h.o_pair_geom2, p, pgrid[p] ? -1 : gmap[m.pair_geom2[sp]]); I(h.o_pair_condim, p, m.pair_condim[sp]);
     int t1 = m.geom_type[m.pair_geom1[sp]], t2 = m.geom_type[m.pair_geom2[sp]];
-    bool ok = (t1 == B200_GEOM_PLANE && (t2 == B200_GEOM_BOX || t2 == B200_GEOM_SPHERE || t2 == B200_GEOM_CAPSULE)) ||
-              (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) || ((t1 == B200_GEOM_SPHERE || t1 == B200_GEOM_CAPSULE) && t2 == B200_GEOM_BOX);
+    bool r1 = t1 == B200_GEOM_SPHERE || t1 == B200_GEOM_CAPSULE, r2 = t2 == B200_GEOM_SPHERE || t2 == B200_GEOM_CAPSULE;
+    bool ok = (t1 == B200_GEOM_PLANE && (t2 == B200_GEOM_BOX || r2)) || (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) ||
+              (r1 && t2 == B200_GEOM_BOX) || (r1 && r2);
     if (!ok) { err = "collision pair type not supported by the CUDA path yet"; return -1; }
     if (m.pair_condim[sp] != 1 && m.pair_condim[sp] != 3 && m.pair_condim[sp] != 4) { err = "condim must be 1, 3 or 4 on the CUDA path"; return -1; }
     F(h.o_pair_friction, 3 * p + 0, m.pair_friction[5 * sp + 0]); F(h.o_pair_friction, 3 * p + 1, m.pair_friction[5 * sp + 2]);

@@ -23,11 +23,14 @@ struct FetchTask {
   float success_radius;
   int obs_qpos_start;   // maze tasks: first qpos entry that is part of `observation` (Ant 2, Point 0)
   float vel_clip;       // maze tasks: |qvel| clip applied before stepping (Point 5.0, 0 = none)
+  // hand manipulation tasks: object free joint addresses, which goal parts count, rotation threshold
+  int obj_qadr, obj_dadr, goal_flags;
+  float rotation_threshold;
   // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(ngoal)
   int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride;
 };
-enum { TASK_FETCH = 0, TASK_ANTMAZE = 1 };  // TASK_ANTMAZE covers both maze agents (Ant, Point)
-#define TASK_MAX_ACT 8
+enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2 };  // TASK_ANTMAZE covers both maze agents (Ant, Point)
+enum { GOAL_USE_POS = 1, GOAL_USE_ROT = 2 };
 
 enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
 
@@ -134,6 +137,38 @@ HD void antmaze_observe(const Ctx& c, const FetchTask& t, const float* goal, flo
   }
 }
 
+// Shadow-hand block manipulation: obs = robot qpos | robot qvel | object qvel | object qpos, achieved = object qpos (7)
+// (reference: envs/shadow_dexterous_hand/manipulate.py:298-314, :88-138)
+HD void hand_goal_distance(const FetchTask& t, const float* a, const float* g, float* d_pos, float* d_rot) {
+  *d_pos = 0.f; *d_rot = 0.f;
+  if (t.goal_flags & GOAL_USE_POS) { float e[3] = {a[0] - g[0], a[1] - g[1], a[2] - g[2]}; *d_pos = sqrtf(dot3(e, e)); }
+  if (t.goal_flags & GOAL_USE_ROT) {
+    // w component of a * conj(g)
+    float w = a[3] * g[3] + a[4] * g[4] + a[5] * g[5] + a[6] * g[6];
+    *d_rot = 2.f * acosf(fminf(fmaxf(w, -1.f), 1.f));
+  }
+}
+HD float hand_reward(const FetchTask& t, float d_pos, float d_rot, float* success) {
+  float s = (d_pos < t.distance_threshold ? 1.f : 0.f) * (d_rot < t.rotation_threshold ? 1.f : 0.f);
+  if (success) *success = s;
+  return t.reward_dense ? -(10.f * d_pos + d_rot) : s - 1.f;
+}
+HD void hand_observe(const Ctx& c, const FetchTask& t, const float* goal, float* obs, float* achieved, float* desired,
+                     float* reward, float* success) {
+  const DMHead* h = c.h;
+  const int nrq = t.obj_qadr, nrv = t.obj_dadr;  // robot joints come first, the object's free joint last
+  LANES(i, nrq) obs[i] = SF(qpos)[i];
+  LANES(i, nrv) obs[nrq + i] = SF(qvel)[i];
+  LANES(i, 6) obs[nrq + nrv + i] = SF(qvel)[nrv + i];
+  LANES(i, 7) { float v = SF(qpos)[nrq + i]; obs[nrq + nrv + 6 + i] = v; achieved[i] = v; desired[i] = goal[i]; }
+  if (c.lane == 0) {
+    float dp, dr;
+    hand_goal_distance(t, SF(qpos) + nrq, goal, &dp, &dr);
+    *reward = hand_reward(t, dp, dr, success);
+  }
+  (void)h;
+}
+
 // one env, one warp.  `st` is this env's state record; outputs are this env's rows.  `active` is warp-uniform: idle
 // warps run the same control flow (for the block-wide alignment barriers) but touch no memory.
 template <int NVP>
@@ -142,7 +177,15 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   const DMHead* h = c.h;
   if (active) {
     load_state(c, t, st);
-    if (mode == MODE_STEP && t.kind == TASK_FETCH) {
+    if (mode == MODE_STEP && t.kind == TASK_HAND) {
+      // MujocoHandEnv._set_action (hand_env.py:42-61, absolute control): ctrl = centre + clip(a) * half range, clipped
+      LANES(i, h->nu) {
+        float lo = MF(act_ctrlrange)[2 * i], hi = MF(act_ctrlrange)[2 * i + 1];
+        float a = fminf(fmaxf(action[i], -1.f), 1.f);
+        SF(ctrl)[i] = fminf(fmaxf(0.5f * (hi + lo) + a * (0.5f * (hi - lo)), lo), hi);
+      }
+      SYNC();
+    } else if (mode == MODE_STEP && t.kind == TASK_FETCH) {
       // _set_action: clip, scale, mocap <- last forward pose of the welded body + delta, position actuators relative
       float a[4];
       for (int k = 0; k < 4; k++) a[k] = fminf(fmaxf(action[k], -1.f), 1.f);
@@ -183,6 +226,8 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
       com_quantities(c);
     }
     fetch_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
+  } else if (t.kind == TASK_HAND) {
+    hand_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   } else {
     antmaze_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   }

@@ -739,6 +739,41 @@ HD void collide_round_box(const Ctx& c, int g1, int g2, float margin, ContactOut
     }
 }
 
+// sphere/capsule against sphere/capsule: closest points of the two axis segments, then a sphere-sphere contact
+// (same decision logic as oracle/oracle.c collide_round_round)
+HD void collide_round_round(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
+  o.cnt = 0;
+  float p1[3], m1[9], p2[3], m2[9];
+  geom_pose(c, g1, p1, m1); geom_pose(c, g2, p2, m2);
+  float a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]};
+  float r1 = MF(geom_size)[3 * g1], r2 = MF(geom_size)[3 * g2];
+  float h1 = MI(geom_type)[g1] == B200_GEOM_CAPSULE ? MF(geom_size)[3 * g1 + 1] : 0.f;
+  float h2 = MI(geom_type)[g2] == B200_GEOM_CAPSULE ? MF(geom_size)[3 * g2 + 1] : 0.f;
+  float w[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+  float b = dot3(a1, a2), d = dot3(a1, w), e = dot3(a2, w), den = 1 - b * b, sp = 0, tp = 0;
+  if (h1 <= 0 && h2 <= 0) { sp = 0; tp = 0; }
+  else if (h1 <= 0) { sp = 0; tp = e; }
+  else if (h2 <= 0) { tp = 0; sp = -d; }
+  else if (den > 1e-9f) {
+    sp = fminf(fmaxf((b * e - d) / den, -h1), h1);
+    tp = e + b * sp;
+    if (tp < -h2) { tp = -h2; sp = b * tp - d; }
+    else if (tp > h2) { tp = h2; sp = b * tp - d; }
+  } else {
+    float mid2 = -d, lo = fmaxf(mid2 - h2, -h1), hi = fminf(mid2 + h2, h1);
+    sp = lo > hi ? (mid2 < 0 ? -h1 : h1) : 0.5f * (lo + hi);
+    tp = e + b * sp;
+  }
+  sp = fminf(fmaxf(sp, -h1), h1); tp = fminf(fmaxf(tp, -h2), h2);
+  float q1[3], n[3];
+  for (int k = 0; k < 3; k++) { q1[k] = p1[k] + a1[k] * sp; n[k] = p2[k] + a2[k] * tp - q1[k]; }
+  float len = sqrtf(dot3(n, n)), dist = len - r1 - r2;
+  if (dist > margin) return;
+  if (len < 1e-12f) { n[0] = 0; n[1] = 0; n[2] = 1; } else { float il = 1.0f / len; n[0] *= il; n[1] *= il; n[2] *= il; }
+  o.cnt = 1; o.dist[0] = dist;
+  for (int k = 0; k < 3; k++) { o.nrm[0][k] = n[k]; o.pos[0][k] = q1[k] + n[k] * (r1 + 0.5f * dist); }
+}
+
 HD void make_frame(float* f) {
   float n = sqrtf(dot3(f, f)), inv = n > 1e-12f ? 1.0f / n : 0.f;
   f[0] *= inv; f[1] *= inv; f[2] *= inv;
@@ -818,7 +853,8 @@ STAGE void collision(const Ctx c) {
         else if (t2 == B200_GEOM_SPHERE) collide_plane_sphere(c, g1, g2, margin, o);
         else collide_plane_capsule(c, g1, g2, margin, o);
       } else if (t1 == B200_GEOM_BOX) collide_box_box(c, g1, g2, margin, o);
-      else collide_round_box(c, g1, g2, margin, o);
+      else if (t2 == B200_GEOM_BOX) collide_round_box(c, g1, g2, margin, o);
+      else collide_round_round(c, g1, g2, margin, o);
       // contacts beyond the gap are not turned into constraints
       float inc = margin - GF(pair_gap)[p];
       int k2 = 0;
@@ -961,7 +997,7 @@ STAGE void make_constraint(const Ctx c) {
     SYNC();
     for (int k = 0; k < nrow; k++) {
       int id = basec + slot + k;
-      if (id >= DM_NDOFROW_MAX) break;
+      if (id >= h->ndr_max) break;
       float* dr = SF(dofrow) + id * DR_WORDS;
       int* di = (int*)dr;
       int d = MI(jnt_dofadr)[j];
@@ -973,9 +1009,46 @@ STAGE void make_constraint(const Ctx c) {
       di[DR_DOF] = d; dr[DR_COEF] = sgn[k]; di[DR_DOF2] = -1; dr[DR_COEF2] = 0;
       dr[DR_D] = 1.0f / R; dr[DR_JAR] = K * imp * (dist[k] - margin); dr[DR_JV] = Bc;
     }
-    if (c.lane == 0) { int nn = basec + total; if (nn > DM_NDOFROW_MAX) { nn = DM_NDOFROW_MAX; cnt[CNT_OVERFLOW] |= 8; } cnt[CNT_NDR] = nn; }
+    if (c.lane == 0) { int nn = basec + total; if (nn > h->ndr_max) { nn = h->ndr_max; cnt[CNT_OVERFLOW] |= 8; } cnt[CNT_NDR] = nn; }
     SYNC();
   }
+  // limits of fixed tendons (length = sum coef * qpos over <= 2 joints) -> dof rows, lower side first
+  for (int base = 0; base < h->nten; base += WARP_W) {
+    int t = base + c.lane;
+    int nrow = 0; float dist[2] = {0, 0}; float sgn[2] = {0, 0};
+    if (t < h->nten) {
+      float len = MF(ten_coef)[2 * t] * SF(qpos)[MI(ten_qadr)[2 * t]];
+      if (MI(ten_dof)[2 * t + 1] >= 0) len += MF(ten_coef)[2 * t + 1] * SF(qpos)[MI(ten_qadr)[2 * t + 1]];
+      float margin = MF(ten_margin)[t];
+      float dl = len - MF(ten_range)[2 * t], du = MF(ten_range)[2 * t + 1] - len;
+      if (dl < margin) { dist[nrow] = dl; sgn[nrow] = 1.f; nrow++; }
+      if (du < margin) { dist[nrow] = du; sgn[nrow] = -1.f; nrow++; }
+    }
+    int total, slot = wexscan(nrow, c.lane, &total);
+    int basec = cnt[CNT_NDR];
+    SYNC();
+    for (int k = 0; k < nrow; k++) {
+      int id = basec + slot + k;
+      if (id >= h->ndr_max) break;
+      float* dr = SF(dofrow) + id * DR_WORDS;
+      int* di = (int*)dr;
+      float margin = MF(ten_margin)[t];
+      float solimp[5] = {GF(ten_solimp)[5 * t], GF(ten_solimp)[5 * t + 1], GF(ten_solimp)[5 * t + 2], GF(ten_solimp)[5 * t + 3], GF(ten_solimp)[5 * t + 4]};
+      float solref[2] = {GF(ten_solref)[2 * t], GF(ten_solref)[2 * t + 1]};
+      float imp = impedance(solimp, dist[k], margin);
+      float K, Bc;
+      ref_kb(c, solref, solimp[1], &K, &Bc);
+      float R = fmaxf((1 - imp) / imp * GF(ten_invweight)[t], B200_MINVAL);
+      di[DR_DOF] = MI(ten_dof)[2 * t]; dr[DR_COEF] = sgn[k] * MF(ten_coef)[2 * t];
+      di[DR_DOF2] = MI(ten_dof)[2 * t + 1]; dr[DR_COEF2] = sgn[k] * MF(ten_coef)[2 * t + 1];
+      dr[DR_D] = 1.0f / R; dr[DR_JAR] = K * imp * (dist[k] - margin); dr[DR_JV] = Bc;
+    }
+    if (c.lane == 0) { int nn = basec + total; if (nn > h->ndr_max) { nn = h->ndr_max; cnt[CNT_OVERFLOW] |= 8; } cnt[CNT_NDR] = nn; }
+    SYNC();
+  }
+  // dof frictionloss rows: position residual 0, so the row value starts at 0
+  LANES(d, h->nfric) SF(fric)[d] = 0.f;
+  SYNC();
 }
 
 // rows <- J * vec.  RV_C0: row = B * (J qvel) + row (row holds K*imp*r; B in the JV slot) ; RV_ADD: row += J a ; RV_JV: JV = J s
@@ -1026,6 +1099,12 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
     if (mode == RV_C0) dr[DR_JAR] += dr[DR_JV] * val;
     else if (mode == RV_ADD) dr[DR_JAR] += val;
     else dr[DR_JV] = val;
+  }
+  LANES(d, c.h->nfric) {
+    float* fr = SF(fric);
+    if (mode == RV_C0) fr[d] += MF(dof_fricB)[d] * vec[d];
+    else if (mode == RV_ADD) fr[d] += vec[d];
+    else fr[c.h->nfric + d] = vec[d];
   }
   SYNC();
 }
@@ -1092,6 +1171,11 @@ STAGE void pass_F(const Ctx c, float* out) {
       float f = x < 0 ? -dr[DR_D] * x : 0.f;
       if (di[DR_DOF] == j) q += dr[DR_COEF] * f;
       if (di[DR_DOF2] == j) q += dr[DR_COEF2] * f;
+    }
+    if (h->nfric) {
+      // Huber-type friction row: force -D x clamped to +-frictionloss
+      float fl = MF(dof_frictionloss)[j];
+      q += fminf(fmaxf(-MF(dof_fricD)[j] * SF(fric)[j], -fl), fl);
     }
     out[j] = q;
   }
@@ -1186,6 +1270,12 @@ STAGE void build_H(const Ctx c) {
     }
     SYNC();
   }
+  // dof friction rows in their quadratic zone (|x| < R * frictionloss)
+  LANES(d, h->nfric) {
+    float D = MF(dof_fricD)[d], x = SF(fric)[d];
+    if (D > 0 && fabsf(x) * D < MF(dof_frictionloss)[d]) H[d * (d + 1) / 2 + d] += D;
+  }
+  SYNC();
   // dof rows (active ones)
   if (c.lane == 0) {
     for (int i = 0; i < ndr; i++) {
@@ -1338,6 +1428,15 @@ STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
     float D = dr[DR_D], v = dr[DR_JV], x = dr[DR_JAR] + alpha * v;
     if (x < 0) { cost += 0.5f * D * x * x; d1 += D * x * v; d2 += D * v * v; }
   }
+  LANES(d, c.h->nfric) {
+    float D = MF(dof_fricD)[d];
+    if (D > 0) {
+      float fl = MF(dof_frictionloss)[d], v = SF(fric)[c.h->nfric + d], x = SF(fric)[d] + alpha * v, Rf = fl / D;
+      if (x <= -Rf) { cost += fl * (-0.5f * Rf - x); d1 -= fl * v; }
+      else if (x >= Rf) { cost += fl * (-0.5f * Rf + x); d1 += fl * v; }
+      else { cost += 0.5f * D * x * x; d1 += D * x * v; d2 += D * v * v; }
+    }
+  }
   out[0] = wsum(cost) + alpha * g1 + alpha * alpha * g2;
   out[1] = wsum(d1) + g1 + 2 * alpha * g2;
   out[2] = wsum(d2) + 2 * g2;
@@ -1432,6 +1531,7 @@ STAGE int newton_move(const Ctx c, float* improvement) {
   LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 4; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
   LANES(i, cnt[CNT_NWELD] * 6) { float* wr = SF(weld) + (i / 6) * WELD_WORDS; wr[W_JAR + i % 6] += alpha * wr[W_JV + i % 6]; }
   LANES(i, cnt[CNT_NDR]) { float* dr = SF(dofrow) + i * DR_WORDS; dr[DR_JAR] += alpha * dr[DR_JV]; }
+  LANES(d, h->nfric) SF(fric)[d] += alpha * SF(fric)[h->nfric + d];
   SYNC();
   if (c.lane == 0) cnt[CNT_ITERS] += 1;
   return 0;

@@ -83,7 +83,7 @@ class CudaBackend:
         self.L = _lib.lib()
         blob = model.to_blob()
         h = ctypes.c_void_p()
-        ref = np.asarray(REF_POINT, dtype=np.float32)
+        ref = np.asarray(getattr(self, "REF", REF_POINT), dtype=np.float32)
         eq = np.ascontiguousarray(eq_data, dtype=np.float64)
         rc = self.L.b200sim_create(blob, len(blob), eq.ctypes.data, ref.ctypes.data, ctypes.byref(task), num_envs,
                                    self.device.index or 0, ctypes.byref(h))
@@ -91,6 +91,7 @@ class CudaBackend:
             raise RuntimeError(f"b200sim_create failed ({rc}): {self.L.b200sim_last_error(None).decode()}")
         self.h = h
         self.num_envs, self.nobs = num_envs, task.nobs
+        self.ngoal, self.nact = (3, 4) if task.kind == 0 else (task.ngoal, task.nact)
         lay = (ctypes.c_int * 8)()
         self.L.b200sim_layout(h, lay)
         self.layout = dict(zip(("qpos", "qvel", "warm", "ctrl", "mocap", "pose", "goal", "stride"), list(lay)))
@@ -115,8 +116,8 @@ class CudaBackend:
     def new_outputs(self):
         n, d = self.num_envs, self.device
         return dict(obs=torch.empty((n, self.nobs), dtype=torch.float32, device=d),
-                    achieved=torch.empty((n, 3), dtype=torch.float32, device=d),
-                    desired=torch.empty((n, 3), dtype=torch.float32, device=d),
+                    achieved=torch.empty((n, self.ngoal), dtype=torch.float32, device=d),
+                    desired=torch.empty((n, self.ngoal), dtype=torch.float32, device=d),
                     reward=torch.empty(n, dtype=torch.float32, device=d), success=torch.empty(n, dtype=torch.float32, device=d))
 
     def _ptrs(self, out):
@@ -126,18 +127,21 @@ class CudaBackend:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def step(self, actions, out, info=None):
-        assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape == (self.num_envs, 4)
+        assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape == (self.num_envs, self.nact)
         self._check(self.L.b200sim_step(self.h, actions.data_ptr(), *self._ptrs(out), info.data_ptr() if info is not None else None, self._stream()))
 
     def refresh(self, mask, out):
         self._check(self.L.b200sim_refresh(self.h, mask.data_ptr() if mask is not None else None, *self._ptrs(out), self._stream()))
 
-    def raw_step(self, nstep, out):
-        self._check(self.L.b200sim_raw_step(self.h, int(nstep), *self._ptrs(out), self._stream()))
+    def raw_step(self, nstep, out, mask=None):
+        if mask is None:
+            self._check(self.L.b200sim_raw_step(self.h, int(nstep), *self._ptrs(out), self._stream()))
+        else:
+            self._check(self.L.b200sim_raw_step_masked(self.h, mask.data_ptr(), int(nstep), *self._ptrs(out), self._stream()))
 
     def compute_reward(self, ag, dg):
-        ag = ag.to(self.device, torch.float32).contiguous().reshape(-1, 3)
-        dg = dg.to(self.device, torch.float32).contiguous().reshape(-1, 3)
+        ag = ag.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)
+        dg = dg.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)
         out = torch.empty(ag.shape[0], dtype=torch.float32, device=self.device)
         self._check(self.L.b200sim_compute_reward(self.h, ag.data_ptr(), dg.data_ptr(), ag.shape[0], out.data_ptr(), self._stream()))
         return out
@@ -308,7 +312,7 @@ class FetchVectorEnv:
     def step(self, actions):
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
-        if tuple(actions.shape) != (self.num_envs, 4):
+        if tuple(actions.shape) != (self.num_envs, self.single_action_space.shape[0]):
             raise ValueError("Action dimension mismatch")
         actions = actions.to(self.device, torch.float32, non_blocking=True).contiguous()
         out = self.backend.new_outputs()

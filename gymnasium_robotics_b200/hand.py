@@ -1,0 +1,259 @@
+"""Batched Shadow-Hand block manipulation envs on the CUDA simulator: the vector-env replacement for
+`gym.make_vec("HandManipulateBlockRotateXYZ-v1", num_envs=N)` and its Z / Parallel / Full siblings.
+
+Mirrors (batched) the reference's Python around the hot path:
+  * MujocoHandEnv._set_action                 envs/shadow_dexterous_hand/hand_env.py:42-61   (inside the step kernel)
+  * MujocoManipulateEnv._get_obs / reward      envs/shadow_dexterous_hand/manipulate.py:88-138, 298-314 (inside the kernel)
+  * MujocoManipulateEnv._reset_sim             manipulate.py:154-224 : randomised object pose, 10 x 20 settle sub-steps
+                                               with zero action, retry while the block is not on the palm
+  * MujocoManipulateEnv._sample_goal           manipulate.py:226-279
+  * BaseRobotEnv.reset/step                    envs/robot_env.py:114-186 ; TimeLimit(100) of the registry (__init__.py:274-284)
+The visual-only `target` free body of manipulate_block.xml is not simulated (it is contype 0, written only by
+`_render_callback` and never observed), so nq = 24 + 7 and nv = 24 + 6.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import rotations
+from ._lib import FetchTaskC
+from .fetch import CudaBackend, FetchVectorEnv, N_SUBSTEPS
+from .models import load_model
+from .spaces import Box, Dict as DictSpace, batch_space
+
+# target_position / target_rotation of the registered ids (__init__.py:105-395); TARGET_POSITION_RANGE manipulate_block.py:226
+HAND_TASKS = {
+    "HandManipulateBlockRotateZ": dict(target_position="ignore", target_rotation="z"),
+    "HandManipulateBlockRotateParallel": dict(target_position="ignore", target_rotation="parallel"),
+    "HandManipulateBlockRotateXYZ": dict(target_position="ignore", target_rotation="xyz"),
+    "HandManipulateBlockFull": dict(target_position="random", target_rotation="xyz"),
+    "HandManipulateBlock": dict(target_position="random", target_rotation="xyz"),
+}
+TARGET_POSITION_RANGE = np.array([(-0.04, 0.04), (-0.06, 0.02), (0.0, 0.06)])
+HAND_REF_POINT = (1.0, 0.9, 0.2)   # fixed world point of the spatial algebra: inside the hand's workspace
+GOAL_USE_POS, GOAL_USE_ROT = 1, 2
+
+
+def make_hand_task(model, target_position, target_rotation, reward_type, distance_threshold, rotation_threshold, n_substeps):
+    """b200sim_fetch_task_t for kind 2 (ids resolved the way MujocoModelNames would, utils/mujoco_utils.py:327-469)."""
+    m = model
+    jobj = m.joint_id("object:joint")
+    robot = [j for j, n in enumerate(m.names["joint"]) if n.startswith("robot")]
+    assert robot == list(range(len(robot))) and jobj == len(robot), "robot joints must precede the object's free joint"
+    t = FetchTaskC()
+    t.kind, t.nact, t.ngoal = 2, int(m.nu), 7
+    t.n_substeps, t.reward_dense = int(n_substeps), int(reward_type == "dense")
+    t.obj_qadr, t.obj_dadr = int(m.jnt_qposadr[jobj]), int(m.jnt_dofadr[jobj])
+    t.nobs = t.obj_qadr + int(m.nv) + 7
+    t.goal_flags = (GOAL_USE_POS if target_position != "ignore" else 0) | (GOAL_USE_ROT if target_rotation != "ignore" else 0)
+    t.distance_threshold, t.rotation_threshold = float(distance_threshold), float(rotation_threshold)
+    t.dt = float(m.opt[0] * n_substeps)
+    return t
+
+
+class _HandBackend(CudaBackend):
+    REF = HAND_REF_POINT
+
+
+class HandVectorEnv(FetchVectorEnv):
+    """Observations, rewards and flags are float32 / bool torch tensors on `device` with a leading `num_envs` axis."""
+
+    metadata = {"render_modes": [], "render_fps": 25, "autoreset_mode": "next_step"}
+
+    def __init__(self, task: str = "HandManipulateBlockRotateXYZ", num_envs: int = 1, reward_type: str = "sparse",
+                 max_episode_steps: Optional[int] = 100, device="cuda:0", rng_mode: str = "auto", autoreset_mode: str = "next_step",
+                 n_substeps: int = N_SUBSTEPS, backend_factory=None, target_position=None, target_rotation=None,
+                 randomize_initial_position=True, randomize_initial_rotation=True, distance_threshold=0.01,
+                 rotation_threshold=0.1, relative_control=False, model=None, **kwargs):
+        if task not in HAND_TASKS:
+            raise KeyError(f"unknown Hand task {task!r}")
+        if reward_type not in ("sparse", "dense"):
+            raise ValueError("reward_type must be 'sparse' or 'dense'")
+        if autoreset_mode not in ("next_step", "same_step", "disabled"):
+            raise ValueError("autoreset_mode must be next_step, same_step or disabled")
+        if kwargs.get("render_mode") is not None:
+            raise NotImplementedError("rendering is out of scope for the batched CUDA path")
+        if relative_control:
+            # hand_env.py:47-57 calls data.get_joint_qpos, which the new mujoco bindings lack: dead code for the -v1 ids
+            raise NotImplementedError("relative_control is not available in the reference's -v1 envs either")
+        cfg = dict(HAND_TASKS[task])
+        self.target_position = target_position or cfg["target_position"]
+        self.target_rotation = target_rotation or cfg["target_rotation"]
+        assert self.target_position in ("ignore", "fixed", "random")
+        assert self.target_rotation in ("ignore", "fixed", "xyz", "z", "parallel")
+        self.randomize_initial_position, self.randomize_initial_rotation = randomize_initial_position, randomize_initial_rotation
+        self.distance_threshold, self.rotation_threshold = distance_threshold, rotation_threshold
+        self.task_name, self.cfg, self.reward_type = task, cfg, reward_type
+        self.num_envs, self.max_episode_steps, self.autoreset_mode = int(num_envs), max_episode_steps, autoreset_mode
+        self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
+        self.n_substeps = n_substeps
+        self.model = model if model is not None else load_model("hand_block")
+        m = self.model
+        self.task = make_hand_task(m, self.target_position, self.target_rotation, reward_type, distance_threshold,
+                                   rotation_threshold, n_substeps)
+        factory = backend_factory or _HandBackend
+        self.backend = factory(m, np.zeros((0, 11)), self.task, self.num_envs, device)
+        self.device = self.backend.device
+        self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
+            if self.rng_mode == "numpy" else None
+        self._gen = torch.Generator(device=self.device)
+        self._gen.seed()
+        lay = self.backend.layout
+        self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", m.nq), ("qvel", m.nv), ("warm", m.nv), ("ctrl", m.nu), ("goal", 7))}
+        self._obj = slice(lay["qpos"] + self.task.obj_qadr, lay["qpos"] + self.task.obj_qadr + 7)
+        self.dt = float(m.opt[0] * n_substeps)
+        nobs = self.task.nobs
+        self.single_action_space = Box(-1.0, 1.0, shape=(int(m.nu),), dtype=np.float32)
+        self.single_observation_space = DictSpace(dict(
+            desired_goal=Box(-np.inf, np.inf, shape=(7,), dtype=np.float64),
+            achieved_goal=Box(-np.inf, np.inf, shape=(7,), dtype=np.float64),
+            observation=Box(-np.inf, np.inf, shape=(nobs,), dtype=np.float64)))
+        self.action_space = batch_space(self.single_action_space, self.num_envs)
+        self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        # robot_env.py:301-303 after _env_setup with initial_qpos = {} (manipulate.py:148-151)
+        self.initial_qpos = torch.as_tensor(np.array(m.qpos0), dtype=torch.float32, device=self.device)
+        self.initial_qvel = torch.zeros(m.nv, dtype=torch.float32, device=self.device)
+        cr = np.asarray(m.act_ctrlrange, dtype=np.float64).reshape(-1, 2)
+        self._ctrl_center = torch.as_tensor((cr[:, 0] + cr[:, 1]) / 2.0, dtype=torch.float32, device=self.device)  # _set_action(zeros)
+        self._parallel_np = rotations.parallel_quats()
+        self._parallel = torch.as_tensor(np.array(self._parallel_np), dtype=torch.float32, device=self.device)
+        self._range = torch.as_tensor(TARGET_POSITION_RANGE, dtype=torch.float32, device=self.device)
+        self.reset_attempts = 0   # total settle passes run by resets (>= number of resets; diagnostics)
+        self._last = None
+        self.closed = False
+
+    # ------------------------------------------------------------------ sampling
+    @staticmethod
+    def _quat_mul_t(a, b):
+        aw, ax, ay, az = a.unbind(-1)
+        bw, bx, by, bz = b.unbind(-1)
+        return torch.stack([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                            aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw], dim=-1)
+
+    def _angle_axis_t(self, n, axis_mode):
+        """Random (angle, axis) quaternion batch on the device RNG: angle ~ U(-pi, pi); axis = z or U(-1, 1)^3 normalised."""
+        u = lambda *s: torch.rand(*s, generator=self._gen, device=self.device)
+        angle = (u(n) * 2 - 1) * np.pi
+        if axis_mode == "z":
+            axis = torch.tensor([0.0, 0.0, 1.0], device=self.device).expand(n, 3)
+        else:
+            axis = u(n, 3) * 2 - 1
+            axis = axis / torch.linalg.norm(axis, dim=1, keepdim=True)
+        q = torch.cat([torch.cos(angle / 2).unsqueeze(1), torch.sin(angle / 2).unsqueeze(1) * axis], dim=1)
+        return q / torch.linalg.norm(q, dim=1, keepdim=True)
+
+    def _sample_initial_pose(self, idx):
+        """manipulate.py:171-208: object start pose for the envs in `idx` -> float32 [n, 7]."""
+        n = idx.numel()
+        q0 = self.initial_qpos[self.task.obj_qadr:self.task.obj_qadr + 7]
+        if self.rng_mode == "numpy":
+            out = np.zeros((n, 7))
+            q0n = q0.double().cpu().numpy()
+            for k, i in enumerate(idx.tolist()):
+                rng = self._np_rngs[i]
+                pos, quat = q0n[:3].copy(), q0n[3:].copy()
+                if self.randomize_initial_rotation:
+                    if self.target_rotation == "z":
+                        off = rotations.quat_from_angle_and_axis(rng.uniform(-np.pi, np.pi), np.array([0.0, 0.0, 1.0]))
+                        quat = rotations.quat_mul(quat, off)
+                    elif self.target_rotation == "parallel":
+                        z = rotations.quat_from_angle_and_axis(rng.uniform(-np.pi, np.pi), np.array([0.0, 0.0, 1.0]))
+                        par = self._parallel_np[rng.integers(24)]
+                        quat = rotations.quat_mul(quat, rotations.quat_mul(z, par))
+                    elif self.target_rotation in ("xyz", "ignore"):
+                        angle = rng.uniform(-np.pi, np.pi)
+                        quat = rotations.quat_mul(quat, rotations.quat_from_angle_and_axis(angle, rng.uniform(-1.0, 1.0, size=3)))
+                if self.randomize_initial_position and self.target_position != "fixed":
+                    pos = pos + rng.normal(size=3, scale=0.005)
+                out[k, :3], out[k, 3:] = pos, quat / np.linalg.norm(quat)
+            return torch.as_tensor(out, dtype=torch.float32, device=self.device)
+        pos, quat = q0[:3].expand(n, 3).clone(), q0[3:].expand(n, 4).clone()
+        if self.randomize_initial_rotation:
+            if self.target_rotation == "z":
+                quat = self._quat_mul_t(quat, self._angle_axis_t(n, "z"))
+            elif self.target_rotation == "parallel":
+                z = self._angle_axis_t(n, "z")
+                par = self._parallel[torch.randint(0, 24, (n,), generator=self._gen, device=self.device)]
+                quat = self._quat_mul_t(quat, self._quat_mul_t(z, par))
+            elif self.target_rotation in ("xyz", "ignore"):
+                quat = self._quat_mul_t(quat, self._angle_axis_t(n, "xyz"))
+        if self.randomize_initial_position and self.target_position != "fixed":
+            pos = pos + 0.005 * torch.randn(n, 3, generator=self._gen, device=self.device)
+        return torch.cat([pos, quat / torch.linalg.norm(quat, dim=1, keepdim=True)], dim=1)
+
+    def _sample_goals(self, idx, obj):
+        """manipulate.py:226-279 given the settled object pose `obj` [n, 7]."""
+        n = idx.numel()
+        if self.rng_mode == "numpy":
+            objn = obj.double().cpu().numpy()
+            goals = np.zeros((n, 7))
+            for k, i in enumerate(idx.tolist()):
+                rng = self._np_rngs[i]
+                pos = objn[k, :3].copy()
+                if self.target_position == "random":
+                    pos = pos + rng.uniform(TARGET_POSITION_RANGE[:, 0], TARGET_POSITION_RANGE[:, 1])
+                if self.target_rotation == "z":
+                    quat = rotations.quat_from_angle_and_axis(rng.uniform(-np.pi, np.pi), np.array([0.0, 0.0, 1.0]))
+                elif self.target_rotation == "parallel":
+                    quat = rotations.quat_from_angle_and_axis(rng.uniform(-np.pi, np.pi), np.array([0.0, 0.0, 1.0]))
+                    quat = rotations.quat_mul(quat, self._parallel_np[rng.integers(24)])
+                elif self.target_rotation == "xyz":
+                    angle = rng.uniform(-np.pi, np.pi)
+                    quat = rotations.quat_from_angle_and_axis(angle, rng.uniform(-1.0, 1.0, size=3))
+                else:
+                    quat = objn[k, 3:].copy()
+                goals[k, :3], goals[k, 3:] = pos, quat / np.linalg.norm(quat)
+            return torch.as_tensor(goals, dtype=torch.float32, device=self.device)
+        pos = obj[:, :3].clone()
+        if self.target_position == "random":
+            u = torch.rand(n, 3, generator=self._gen, device=self.device)
+            pos = pos + self._range[:, 0] + u * (self._range[:, 1] - self._range[:, 0])
+        if self.target_rotation == "z":
+            quat = self._angle_axis_t(n, "z")
+        elif self.target_rotation == "parallel":
+            quat = self._angle_axis_t(n, "z")
+            quat = self._quat_mul_t(quat, self._parallel[torch.randint(0, 24, (n,), generator=self._gen, device=self.device)])
+        elif self.target_rotation == "xyz":
+            quat = self._angle_axis_t(n, "xyz")
+        else:
+            quat = obj[:, 3:].clone()
+        return torch.cat([pos, quat / torch.linalg.norm(quat, dim=1, keepdim=True)], dim=1)
+
+    def _reset_envs(self, mask, out):
+        """BaseRobotEnv.reset (robot_env.py:154-186): retry `_reset_sim` until the block rests on the palm, then sample
+        the goal.  Every attempt settles the pending envs together with one masked raw-step launch (10 x 20 sub-steps)."""
+        idx_all = torch.nonzero(mask, as_tuple=False).flatten()
+        if idx_all.numel() == 0:
+            return
+        st, sl = self.backend.state, self._sl
+        pending = mask.clone()
+        for attempt in range(100):
+            idx = torch.nonzero(pending, as_tuple=False).flatten()
+            if idx.numel() == 0:
+                break
+            rec = torch.zeros((idx.numel(), st.shape[1]), dtype=torch.float32, device=self.device)  # time, qpos, qvel reset
+            rec[:, sl["qpos"]] = self.initial_qpos
+            rec[:, sl["qvel"]] = self.initial_qvel
+            rec[:, self._obj] = self._sample_initial_pose(idx)
+            rec[:, sl["ctrl"]] = self._ctrl_center          # _set_action(np.zeros(20))
+            rec[:, sl["goal"]] = st[idx][:, sl["goal"]]
+            st[idx] = rec
+            self.backend.raw_step(10 * self.n_substeps, out, mask=pending.to(torch.uint8))
+            self.reset_attempts += 1
+            on_palm = st[:, self._obj.start + 2] > 0.04     # site "object:center" sits at the body origin
+            pending = pending & ~on_palm
+        else:
+            raise RuntimeError("hand reset did not settle on the palm within 100 attempts")
+        st[idx_all, sl["goal"]] = self._sample_goals(idx_all, st[idx_all][:, self._obj])
+        self._elapsed[idx_all] = 0
+        self.backend.refresh(mask.to(torch.uint8), out)  # mj_forward + _get_obs for the reset envs
+
+
+def make_hand_vec(task, **kwargs):
+    return HandVectorEnv(task=task, **kwargs)

@@ -242,6 +242,13 @@ class _Parser:
         self.default_parent = {"main": None}
         self.full = Full()
         self.overrides = overrides or {}
+        # bodies removed before compilation (e.g. the Hand's decoupled, unobserved visual `target` free body)
+        drop = set(self.overrides.get("drop_bodies", ()))
+        if drop:
+            for parent in list(self.root.iter()):
+                for ch in list(parent):
+                    if ch.tag == "body" and ch.get("name") in drop:
+                        parent.remove(ch)
 
     # -- xml loading with <include>
     def _load(self, path):

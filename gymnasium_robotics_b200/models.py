@@ -19,7 +19,10 @@ MODEL_SOURCES = {
     "fetch_reach": "fetch/reach.xml",
     "fetch_push": "fetch/push.xml",
     "fetch_pick_and_place": "fetch/pick_and_place.xml",
+    "hand_block": "hand/manipulate_block.xml",
 }
+# compile-time edits: the Hand's visual-only `target` free body (contype 0, never observed) is not simulated
+MODEL_OVERRIDES = {"hand_block": {"drop_bodies": ["target"]}}
 
 
 # maze models: in-tree legacy twin of Gymnasium's ant.xml (Gymnasium itself is un-vendored) + generated wall boxes
@@ -48,7 +51,7 @@ def build_models(force: bool = False):
         out = os.path.join(MODEL_DIR, name + ".b200m")
         if os.path.exists(out) and not force:
             continue
-        blob = compile_mjcf(os.path.join(REFERENCE_ASSETS, rel)).to_blob()
+        blob = compile_mjcf(os.path.join(REFERENCE_ASSETS, rel), overrides=MODEL_OVERRIDES.get(name)).to_blob()
         with open(out, "wb") as f:
             f.write(blob)
         built.append(out)

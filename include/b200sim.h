@@ -35,6 +35,11 @@ typedef struct b200sim_fetch_task {
   float success_radius;
   int obs_qpos_start;   /* maze: first qpos entry inside `observation` (ant_maze_v5.py:312-320: 2; point_maze.py:404-410: 0) */
   float vel_clip;       /* maze: |qvel| clip before stepping (envs/maze/point.py:73-77: 5.0; 0 = none) */
+  /* kind 2 = Shadow-hand manipulation (envs/shadow_dexterous_hand/hand_env.py:42-61 absolute control, manipulate.py:88-138,
+   * 298-314): nact = 20, ngoal = 7, obs = robot qpos | robot qvel | object qvel | object qpos; obj_qadr / obj_dadr = qpos /
+   * dof address of "object:joint" (must be the last joint); goal_flags bit 0: position counts, bit 1: rotation counts */
+  int obj_qadr, obj_dadr, goal_flags;
+  float rotation_threshold;
 } b200sim_fetch_task_t;
 
 /* indices into the layout array returned by b200sim_layout (offsets in floats inside one env's state record) */
@@ -66,6 +71,10 @@ int b200sim_refresh(b200sim_t* h, const unsigned char* mask, float* obs, float* 
 /* nstep raw mj_step calls with the ctrl / mocap currently in the state records (reference: fetch_env.py:419-420). */
 int b200sim_raw_step(b200sim_t* h, int nstep, float* obs, float* achieved, float* desired, float* reward, float* success,
                      void* stream);
+/* the same for envs with mask[i] != 0 only (mask NULL = all): the settle phase of a partial reset
+ * (reference: envs/shadow_dexterous_hand/manipulate.py:213-222, 10 x mj_step(nstep=n_substeps) inside _reset_sim). */
+int b200sim_raw_step_masked(b200sim_t* h, const unsigned char* mask, int nstep, float* obs, float* achieved, float* desired,
+                            float* reward, float* success, void* stream);
 /* GoalEnv.compute_reward on M (achieved, desired) pairs, device pointers (reference: fetch_env.py:74-80). */
 int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const float* desired, int M, float* out, void* stream);
 /* number of kernel launches issued through this handle so far */

@@ -796,6 +796,55 @@ static void collide_capsule_box(oracle_sim* s, int pair, real margin) {
   sphere_box_contact(s, pair, p, r, g2, margin);
 }
 
+/* sphere/capsule (geom1) vs sphere/capsule (geom2): closest points of the two axis segments (a sphere is a segment of
+ * zero length), then a sphere-sphere contact there.  Parallel overlapping segments give one contact at the middle of
+ * the overlap. */
+static void segment_closest(const real* p1, const real* a1, real h1, const real* p2, const real* a2, real h2, real* s_out, real* t_out) {
+  real w[3];
+  sub3(w, p1, p2);
+  real b = dot3(a1, a2), d = dot3(a1, w), e = dot3(a2, w), den = 1 - b * b, sp, tp;
+  if (h1 <= 0 && h2 <= 0) { *s_out = 0; *t_out = 0; return; }
+  if (h1 <= 0) { sp = 0; tp = e; }
+  else if (h2 <= 0) { tp = 0; sp = -d; }
+  else if (den > 1e-9) {
+    sp = (b * e - d) / den;
+    if (sp < -h1) sp = -h1; if (sp > h1) sp = h1;
+    tp = e + b * sp;
+    if (tp < -h2) { tp = -h2; sp = b * tp - d; }
+    else if (tp > h2) { tp = h2; sp = b * tp - d; }
+  } else {
+    /* parallel: interval of segment 1 (in its own coordinate) facing segment 2 */
+    real mid2 = -d, /* centre of segment 2 projected on axis 1, relative to p1 */ lo = mid2 - h2, hi = mid2 + h2;
+    if (lo < -h1) lo = -h1; if (hi > h1) hi = h1;
+    if (lo > hi) sp = mid2 < 0 ? -h1 : h1; else sp = 0.5 * (lo + hi);
+    tp = e + b * sp;
+  }
+  if (sp < -h1) sp = -h1; if (sp > h1) sp = h1;
+  if (tp < -h2) tp = -h2; if (tp > h2) tp = h2;
+  *s_out = sp; *t_out = tp;
+}
+static void collide_round_round(oracle_sim* s, int pair, real margin) {
+  const b200_model_view* m = &s->m;
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  const real *c1 = s->geom_xpos + 3 * g1, *m1 = s->geom_xmat + 9 * g1, *c2 = s->geom_xpos + 3 * g2, *m2 = s->geom_xmat + 9 * g2;
+  real a1[3] = {m1[2], m1[5], m1[8]}, a2[3] = {m2[2], m2[5], m2[8]};
+  real r1 = m->geom_size[3 * g1], r2 = m->geom_size[3 * g2];
+  real h1 = m->geom_type[g1] == B200_GEOM_CAPSULE ? m->geom_size[3 * g1 + 1] : 0;
+  real h2 = m->geom_type[g2] == B200_GEOM_CAPSULE ? m->geom_size[3 * g2 + 1] : 0;
+  real sp, tp, q1[3], q2[3], n[3];
+  segment_closest(c1, a1, h1, c2, a2, h2, &sp, &tp);
+  copy3(q1, c1); addscl3(q1, a1, sp);
+  copy3(q2, c2); addscl3(q2, a2, tp);
+  sub3(n, q2, q1);
+  real len = sqrt(dot3(n, n)), d = len - r1 - r2;
+  if (d > margin) return;
+  if (len < 1e-12) { n[0] = 0; n[1] = 0; n[2] = 1; } else { n[0] /= len; n[1] /= len; n[2] /= len; }
+  real pos[3];
+  copy3(pos, q1);
+  addscl3(pos, n, r1 + 0.5 * d);
+  add_contact(s, pair, d, pos, n);
+}
+
 static void collision(oracle_sim* s) {
   const b200_model_view* m = &s->m;
   s->ncon = 0;
@@ -821,6 +870,8 @@ static void collision(oracle_sim* s) {
     else if (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) collide_box_box(s, p, margin);
     else if (t1 == B200_GEOM_SPHERE && t2 == B200_GEOM_BOX) collide_sphere_box(s, p, margin);
     else if (t1 == B200_GEOM_CAPSULE && t2 == B200_GEOM_BOX) collide_capsule_box(s, p, margin);
+    else if ((t1 == B200_GEOM_SPHERE || t1 == B200_GEOM_CAPSULE) && (t2 == B200_GEOM_SPHERE || t2 == B200_GEOM_CAPSULE))
+      collide_round_round(s, p, margin);
     /* other pair types: not yet restated (DESIGN.md lists them) */
   }
 }

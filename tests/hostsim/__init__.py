@@ -18,7 +18,9 @@ class FetchTaskC(ctypes.Structure):
                [("robot_qadr", ctypes.c_int * 16), ("robot_dadr", ctypes.c_int * 16), ("finger_qadr", ctypes.c_int * 2),
                 ("nobs", ctypes.c_int), ("distance_threshold", ctypes.c_float), ("dt", ctypes.c_float),
                 ("kind", ctypes.c_int), ("nact", ctypes.c_int), ("ngoal", ctypes.c_int), ("success_radius", ctypes.c_float),
-                ("obs_qpos_start", ctypes.c_int), ("vel_clip", ctypes.c_float)] + \
+                ("obs_qpos_start", ctypes.c_int), ("vel_clip", ctypes.c_float),
+                ("obj_qadr", ctypes.c_int), ("obj_dadr", ctypes.c_int), ("goal_flags", ctypes.c_int),
+                ("rotation_threshold", ctypes.c_float)] + \
                [(n, ctypes.c_int) for n in ("st_qpos", "st_qvel", "st_warm", "st_ctrl", "st_mocap", "st_pose", "st_goal",
                                              "st_stride")]
 
@@ -111,7 +113,7 @@ class HostSim:
         obs = np.zeros(nobs, dtype=np.float32)
         ag, dg = np.zeros(ngoal, dtype=np.float32), np.zeros(ngoal, dtype=np.float32)
         rew, suc = np.zeros(1, dtype=np.float32), np.zeros(1, dtype=np.float32)
-        a = np.zeros(8, dtype=np.float32)
+        a = np.zeros(max(32, len(action)), dtype=np.float32)
         a[:len(action)] = action
         it = self._L.hostsim_env_step(self._h, ctypes.byref(task), mode, nraw, st.ctypes.data, a.ctypes.data, obs.ctypes.data,
                                       ag.ctypes.data, dg.ctypes.data, rew.ctypes.data, suc.ctypes.data)

@@ -15,7 +15,7 @@ class HostSimBackend:
 
         self.device = torch.device("cpu")
         self.num_envs, self.nobs = num_envs, task.nobs
-        self.sim = HostSim(model, eq_data=eq_data, ref=REF_POINT)
+        self.sim = HostSim(model, eq_data=eq_data if len(eq_data) else None, ref=getattr(self, "REF", REF_POINT))
         t = HostTaskC()
         for name, _ in task._fields_:
             setattr(t, name, getattr(task, name))
@@ -61,11 +61,17 @@ class HostSimBackend:
     def refresh(self, mask, out):
         self._run(1, 0, None, mask, out)
 
-    def raw_step(self, nstep, out):
-        self._run(2, nstep, None, None, out)
+    def raw_step(self, nstep, out, mask=None):
+        self._run(2, nstep, None, mask, out)
 
     def compute_reward(self, ag, dg):
         ag = ag.to(torch.float32).reshape(-1, self.ngoal); dg = dg.to(torch.float32).reshape(-1, self.ngoal)
+        if self.task.kind == 2:  # same arithmetic as the kernel's hand_goal_distance / hand_reward (fetch_task.cuh)
+            t = self.task
+            dp = torch.sqrt(((ag[:, :3] - dg[:, :3]) ** 2).sum(-1)) if t.goal_flags & 1 else torch.zeros(ag.shape[0])
+            dr = 2 * torch.acos(torch.clamp((ag[:, 3:] * dg[:, 3:]).sum(-1), -1, 1)) if t.goal_flags & 2 else torch.zeros(ag.shape[0])
+            suc = (dp < t.distance_threshold).to(torch.float32) * (dr < t.rotation_threshold).to(torch.float32)
+            return -(10 * dp + dr) if t.reward_dense else suc - 1
         d = torch.sqrt(((ag - dg) ** 2).sum(-1))
         if self.task.kind == 1:
             return torch.exp(-d) if self.task.reward_dense else (d <= self.task.success_radius).to(torch.float32)

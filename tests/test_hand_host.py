@@ -1,0 +1,100 @@
+"""HandVectorEnv (host logic + the kernel source emulated with WARP_W == 1) against the oracle restatement of the
+reference's MujocoHandBlockEnv.  CPU only; the GPU parity proper is in tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+import gymnasium_robotics_b200 as pkg
+from gymnasium_robotics_b200.hand import HandVectorEnv, HAND_REF_POINT
+from gymnasium_robotics_b200.models import load_model
+from oracle.hand_env import OracleHandBlockEnv
+from tests.hostsim_backend import HostSimBackend
+
+
+class HandHostBackend(HostSimBackend):
+    REF = HAND_REF_POINT
+
+
+def make(task="HandManipulateBlockRotateXYZ", n=1, **kw):
+    return HandVectorEnv(task, num_envs=n, backend_factory=HandHostBackend, rng_mode="numpy", **kw)
+
+
+def test_spaces_and_ids():
+    env = pkg.make_vec("HandManipulateBlockRotateXYZ-v1", num_envs=2, backend_factory=HandHostBackend, rng_mode="numpy")
+    assert env.single_action_space.shape == (20,)
+    assert env.single_observation_space["observation"].shape == (61,)
+    assert env.single_observation_space["achieved_goal"].shape == (7,)
+    assert env.max_episode_steps == 100
+    obs, info = env.reset(seed=3)
+    assert obs["observation"].shape == (2, 61) and obs["desired_goal"].shape == (2, 7)
+    with pytest.raises(ValueError):
+        env.step(np.zeros((2, 4), dtype=np.float32))
+    assert "HandManipulateBlockDense-v1" in pkg.ENV_IDS and "HandManipulateBlockRotateParallel-v1" in pkg.ENV_IDS
+
+
+@pytest.mark.parametrize("task,kw", [("HandManipulateBlockRotateXYZ", dict(target_position="ignore", target_rotation="xyz")),
+                                     ("HandManipulateBlockFull", dict(target_position="random", target_rotation="xyz")),
+                                     ("HandManipulateBlockRotateParallel", dict(target_position="ignore", target_rotation="parallel"))])
+def test_reset_matches_oracle_sampling(task, kw):
+    """Same seed -> same RNG draws (numpy PCG64 parity mode): identical goal; settled state within fp32 tolerance."""
+    model = load_model("hand_block")
+    env = make(task)
+    orc = OracleHandBlockEnv(model=model, **kw)
+    obs, _ = env.reset(seed=11)
+    oobs, _ = orc.reset(seed=11)
+    g, og = obs["desired_goal"][0].double().numpy(), oobs["desired_goal"]
+    np.testing.assert_allclose(g[3:], og[3:], atol=2e-6)          # rotation goal: pure RNG + quaternion algebra
+    np.testing.assert_allclose(g[:3], og[:3], atol=2e-3)          # position goal rides on the settled block position
+    a, oa = obs["achieved_goal"][0].double().numpy(), oobs["achieved_goal"]
+    np.testing.assert_allclose(a[:3], oa[:3], atol=2e-3)
+    assert a[2] > 0.04 and oa[2] > 0.04
+    # robot joints after the 200 settle sub-steps
+    np.testing.assert_allclose(obs["observation"][0, :24].double().numpy(), oobs["observation"][:24], atol=5e-3)
+
+
+def test_step_tracks_oracle_from_injected_state():
+    """Free-running env steps from identical state: fp32 kernel arithmetic vs the fp64 oracle."""
+    model = load_model("hand_block")
+    env = make()
+    orc = OracleHandBlockEnv(model=model)
+    env.reset(seed=5)
+    orc.reset(seed=5)
+    lay, m = env.backend.layout, model
+    rec = np.zeros(lay["stride"])
+    s = orc.sim
+    rec[lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+    rec[lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+    rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+    rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+    rec[lay["goal"]:lay["goal"] + 7] = orc.goal
+    env.set_state(torch.as_tensor(rec[None], dtype=torch.float32))
+    rng = np.random.default_rng(0)
+    for k in range(3):
+        a = rng.uniform(-1, 1, size=20)
+        obs, rew, term, trunc, info = env.step(a[None].astype(np.float32))
+        oobs, orew, _, _, oinfo = orc.step(a)
+        o, oo = obs["observation"][0].double().numpy(), oobs["observation"]
+        # joint angles and block pose; velocities are looser (contact forces on a 70 g block)
+        np.testing.assert_allclose(o[:24], oo[:24], atol=2e-3)
+        np.testing.assert_allclose(o[54:57], oo[54:57], atol=2e-3)
+        assert float(rew[0]) == float(orew)
+        assert float(info["is_success"][0]) == float(oinfo["is_success"])
+    assert not bool(term.any()) and not bool(trunc.any())
+
+
+def test_compute_reward_matches_oracle():
+    model = load_model("hand_block")
+    rng = np.random.default_rng(1)
+    ag, dg = rng.normal(size=(64, 7)), rng.normal(size=(64, 7))
+    ag[:, 3:] /= np.linalg.norm(ag[:, 3:], axis=1, keepdims=True)
+    dg[:, 3:] /= np.linalg.norm(dg[:, 3:], axis=1, keepdims=True)
+    dg[:8] = ag[:8]                       # exact successes
+    dg[8:16, :3] = ag[8:16, :3] + 0.004   # near the 0.01 m threshold
+    for task, kw in (("HandManipulateBlockRotateXYZ", dict(target_position="ignore", target_rotation="xyz")),
+                     ("HandManipulateBlockFull", dict(target_position="random", target_rotation="xyz"))):
+        for rt in ("sparse", "dense"):
+            env = make(task, reward_type=rt)
+            orc = OracleHandBlockEnv(model=model, reward_type=rt, **kw)
+            r = env.compute_reward(ag, dg, {})
+            ro = orc.compute_reward(ag, dg, {})
+            np.testing.assert_allclose(r, ro, atol=2e-3 if rt == "dense" else 0)

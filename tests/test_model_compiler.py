@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from gymnasium_robotics_b200.mjcf import Model, compile_mjcf
-from gymnasium_robotics_b200.models import MODEL_DIR, MODEL_SOURCES, REFERENCE_ASSETS, load_model
+from gymnasium_robotics_b200.models import MODEL_DIR, MODEL_OVERRIDES, MODEL_SOURCES, REFERENCE_ASSETS, load_model
 
 
 def test_committed_blobs_load_and_have_expected_sizes():
@@ -28,7 +28,7 @@ def test_blob_round_trip_is_lossless():
 @pytest.mark.needs_reference
 def test_committed_blobs_match_a_fresh_compile():
     for name, rel in MODEL_SOURCES.items():
-        fresh = compile_mjcf(os.path.join(REFERENCE_ASSETS, rel)).to_blob()
+        fresh = compile_mjcf(os.path.join(REFERENCE_ASSETS, rel), overrides=MODEL_OVERRIDES.get(name)).to_blob()
         assert open(os.path.join(MODEL_DIR, name + ".b200m"), "rb").read() == fresh, name
 
 

@@ -217,6 +217,7 @@ def test_weld_tracks_mocap_pose(mjcf_file):
 
 CHAIN = """
 <mujoco><option timestep="0.001"/>
+<default><geom contype="0" conaffinity="0"/></default>
 <worldbody>
   <body name="a" pos="0 0 1">
     <joint name="j1" type="hinge" axis="0 1 0"/>
