@@ -28,6 +28,11 @@ B_ALG = 2 * 4 * (22 + 2 * 21 + 2 + 7 + 3 + 1) + 4 * 4 + 4 * (25 + 2 * 3) + 10
 # other workloads (BASELINE.json configs): name -> (env id, action dim, sub-steps, algorithmic bytes per env-step, default envs/GPU)
 WORKLOADS = {
     "fetch_pick_and_place": ("FetchPickAndPlace-v4", 4, 20, B_ALG, 4096),
+    # config 3 (plain 61-dim observation; nq = 31, nv = 30 without the visual-only target body)
+    "hand_block": ("HandManipulateBlockRotateXYZ-v1", 20, 20, 2 * 4 * (31 + 60 + 20 + 0 + 7 + 1) + 80 + 4 * (61 + 14) + 10, 2048),
+    # config 3 as named: 24 DoF + 92 touch sensors (153-dim observation)
+    "hand_block_touch": ("HandManipulateBlockRotateXYZ_ContinuousTouchSensors-v1", 20, 20,
+                         2 * 4 * (31 + 60 + 20 + 0 + 7 + 1) + 80 + 4 * (153 + 14) + 10, 2048),
     "antmaze_large": ("AntMaze_Large-v5", 8, 5, 2 * 4 * (15 + 28 + 0 + 0 + 2 + 1) + 32 + 124 + 10, 1024),  # config 4: 8192 envs over 8 GPUs
 }
 
@@ -203,7 +208,7 @@ def run_ours(args):
     # ---- end to end through the public API with HOST buffers: pinned actions H2D, results D2H, every step
     host_tape = [tape[k].cpu().pin_memory() for k in range(8)]
     nobs = env.task.nobs
-    ngoal = 3 if args.workload == "fetch_pick_and_place" else 2
+    ngoal = env.backend.ngoal
     host_out = {"observation": torch.empty((n, nobs), dtype=torch.float32).pin_memory(),
                 "achieved_goal": torch.empty((n, ngoal), dtype=torch.float32).pin_memory(),
                 "desired_goal": torch.empty((n, ngoal), dtype=torch.float32).pin_memory(),

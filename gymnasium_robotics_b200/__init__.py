@@ -32,6 +32,11 @@ for _task in ("HandManipulateBlockRotateZ", "HandManipulateBlockRotateParallel",
               "HandManipulateBlockFull", "HandManipulateBlock"):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
         ENV_IDS[f"{_task}{_suffix}-v1"] = dict(hand_task=_task, reward_type=_rt, max_episode_steps=100)
+        # 92 touch sensors appended to the observation (__init__.py:122-170 and siblings)
+        ENV_IDS[f"{_task}_BooleanTouchSensors{_suffix}-v1"] = dict(hand_task=_task, reward_type=_rt, max_episode_steps=100,
+                                                                  touch_get_obs="boolean")
+        ENV_IDS[f"{_task}_ContinuousTouchSensors{_suffix}-v1"] = dict(hand_task=_task, reward_type=_rt, max_episode_steps=100,
+                                                                     touch_get_obs="sensordata")
 
 
 def make_vec(env_id: str, num_envs: int = 1, **kwargs):

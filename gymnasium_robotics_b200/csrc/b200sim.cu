@@ -5,6 +5,7 @@
 // Per-env state lives in HBM as one contiguous fp32 record per env (read once, written once per step).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -140,10 +141,12 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   t.kind = task->kind; t.nact = task->nact; t.ngoal = task->ngoal; t.success_radius = task->success_radius;
   t.obs_qpos_start = task->obs_qpos_start; t.vel_clip = task->vel_clip;
   t.obj_qadr = task->obj_qadr; t.obj_dadr = task->obj_dadr; t.goal_flags = task->goal_flags; t.rotation_threshold = task->rotation_threshold;
+  t.touch_mode = task->touch_mode;
   if (t.kind == TASK_FETCH) { t.nact = 4; t.ngoal = 3; }
   if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE && t.kind != TASK_HAND) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
   if (t.kind == TASK_HAND && (t.nact != dh->nu || t.ngoal != 7 || t.obj_qadr != dh->nq - 7 || t.obj_dadr != dh->nv - 6 ||
-                              t.nobs != t.obj_qadr + dh->nv + 7)) { delete h; return fail(nullptr, "b200sim_create: inconsistent Hand task", -6); }
+                              t.touch_mode < 0 || t.touch_mode > 3 || (t.touch_mode && dh->nsensor == 0) ||
+                              t.nobs != t.obj_qadr + dh->nv + 7 + (t.touch_mode ? dh->nsensor : 0))) { delete h; return fail(nullptr, "b200sim_create: inconsistent Hand task", -6); }
   if (t.kind == TASK_FETCH && dh->nmocap != 1) { delete h; return fail(nullptr, "b200sim_create: Fetch task needs exactly one mocap body", -6); }
   if (t.kind == TASK_ANTMAZE && (t.nact != dh->nu || t.ngoal != 2 || t.nobs != dh->nq - t.obs_qpos_start + dh->nv)) { delete h; return fail(nullptr, "b200sim_create: inconsistent AntMaze task", -6); }
   int o = 0;
@@ -156,7 +159,9 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   h->wpb = (num_envs + nsm - 1) / nsm <= 7 ? 7 : ((num_envs + nsm - 1) / nsm <= 14 ? 14 : 28);
   h->nvp = dh->nv <= 14 ? 14 : (dh->nv == 15 ? 15 : (dh->nv <= 21 ? 21 : (dh->nv <= 30 ? 30 : 0)));  // smallest built size >= nv (identity padding)
   if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for nv > 30 yet", -8); }
+  if (dh->nv <= 21 && (dh->nten > 0 || dh->nfric > 0 || dh->nsensor > 0 || dh->any_round_pair)) h->nvp = 30;  // hand features live in the NVP = 30 build
   if (h->nvp == 30 && h->wpb > 14) h->wpb = 14;  // the large models' scratch does not fit 28 envs per block
+  if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 14 || (w == 28 && h->nvp != 30)) h->wpb = w; }  // experiments
   h->smem_bytes = ((size_t)dh->hot_words + (size_t)h->wpb * dh->scr_words) * 4;
   h->blocks = (num_envs + h->wpb - 1) / h->wpb;
   cudaError_t e = cudaSuccess;

@@ -14,7 +14,7 @@
 #define DM_MAX_BODY 32   // one lane per body / 32-bit body masks
 #define DM_MAX_NV 32     // 32-bit dof masks
 #define DM_NDOFROW_MIN 8
-#define DM_NCAND_MAX 32
+#define DM_NCAND_MAX 96   // broad-phase candidate slots (one byte each: pair index < 256)
 #define DM_NWELD_MAX 1
 
 // (name, words-per-element, kind) ; kind selects the element count.  HOT arrays are staged into shared memory by every
@@ -42,7 +42,8 @@
 #define DM_ARRAYS_COLD(X) \
   X(pair_condim, 1, npair) X(pair_friction, 3, npair) X(pair_gap, 1, npair) X(pair_solref, 2, npair) \
   X(pair_solimp, 5, npair) X(pair_invweight, 2, npair) \
-  X(ten_solref, 2, nten) X(ten_solimp, 5, nten) X(ten_invweight, 1, nten)
+  X(ten_solref, 2, nten) X(ten_solimp, 5, nten) X(ten_invweight, 1, nten) \
+  X(sensor_site, 1, nsensor) X(sensor_body, 1, nsensor) X(sensor_type, 1, nsensor) X(sensor_size, 3, nsensor)
 #define DM_ARRAYS(X) DM_ARRAYS_HOT(X) DM_ARRAYS_COLD(X)
 
 // per-env scratch that lives for the whole sub-step (name, words expression)
@@ -51,7 +52,7 @@
   X(xpos, 3 * nb) X(xquat, 4 * nb) X(cdof, 6 * nv) X(M, nv * (nv + 1) / 2) X(fsmooth, nv) X(fcon, nv) \
   X(rk_q0, nrkq) X(rk_v0, nrkv) X(rk_dx, nrkv) X(rk_df, nrkv) \
   X(con, ncon_max * CON_WORDS) X(dofrow, ndr_max * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
-  X(group, ngrp_max * GRP_WORDS) X(counters, 8) X(fric, 2 * nfric)
+  X(group, ngrp_max * GRP_WORDS) X(counters, 8) X(fric, 2 * nfric) X(conx, ncx * CX_WORDS)
 // time-shared region `uni`: kinematics {kinA, kinB} -> dynamics {cinert, b6, d6, geom_xpos, cand} -> solver {H, d6, grad,
 // search, Ma, Mv} -> observation {cvel}.  d6 keeps one offset in both phases that use it.
 #define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
@@ -65,6 +66,8 @@ enum { C_W = 0 /*18*/, C_MU = 18 /*slide, torsion*/, C_D = 20, C_U = 21 /*4*/, C
 // Dof frictionloss rows are always present, one per dof, with constant D and B: they live in the per-dof arrays
 // `fric` (FR_JAR, FR_JV) instead of generic rows.
 enum { FR_JAR = 0, FR_JV = 1 };
+// contact extras kept only by models with touch sensors: world position and pair index
+enum { CX_POS = 0, CX_PAIR = 3, CX_WORDS = 4 };
 enum { DR_DOF = 0, DR_COEF = 1, DR_D = 2, DR_JAR = 3, DR_JV = 4, DR_DOF2 = 5, DR_COEF2 = 6, DR_WORDS = 8 };
 // weld: 6 rows w[6]; D[6], JAR[6] (K*imp*r during set-up), JV[6], B (one value), group
 enum { W_W = 0, W_D = 36, W_JAR = 42, W_JV = 48, W_B = 54, W_GRP = 55, WELD_WORDS = 56 };
@@ -80,8 +83,8 @@ struct DMHead {
   int hot_words;   // leading part staged into shared memory (header + HOT arrays)
   int scr_words;   // per-env scratch size in words
   int iterations, ls_iterations, integrator, any_damping, kin_iters, ncon_max, ngrp_max, ndr_max;
-  int nten, nfric, pad3, pad4;   // limited fixed tendons; nfric = nv when any dof has frictionloss, else 0
-  int grid_len, grid_wid, ngridw, pad1;   // maze wall grid (0 x 0 when the model has none)
+  int nten, nfric, ncand_max, nsensor;   // nsensor: touch sensors (site volume + body)   // limited fixed tendons; nfric = nv when any dof has frictionloss, else 0
+  int grid_len, grid_wid, ngridw, any_round_pair;   // maze wall grid (0 x 0 when the model has none)
   float grid_scale, grid_top, grid_xc, grid_yc;  // cell size, wall top height, map centre offsets
   float timestep, gravity[3], tolerance, impratio, meaninertia, ls_tolerance, ref[3];
 #define X(name, w, kind) int o_##name;
@@ -129,6 +132,10 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     h.grid_scale = (float)m.grid_param[0]; h.grid_top = (float)(m.grid_param[1] * m.grid_param[0]);
     h.grid_xc = (float)m.grid_param[2]; h.grid_yc = (float)m.grid_param[3];
   }
+  h.nsensor = m.nsensor;
+  if (m.nsensor > 0 && m.n_sensor_type != m.nsensor) { err = "model blob lacks sensor_type"; return -1; }
+  h.ncand_max = DM_NCAND_MAX;
+  if (h.npair > 255) { err = "more than 255 candidate geom pairs"; return -1; }
   h.ncon_max = m.nmocap > 0 ? 16 : 20;   // contacts kept per env per sub-step
   h.ngrp_max = m.nmocap > 0 ? 10 : 14;   // geom pairs in contact (+ welds) per env per sub-step
   if (h.nb > DM_MAX_BODY) { err = "model has more than 32 runtime bodies"; return -1; }
@@ -145,7 +152,9 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     int nlim = 0;
     for (int j = 0; j < m.njnt; j++) if (m.jnt_limited[j] && m.jnt_type[j] != B200_JNT_FREE) nlim++;
     int want = nlim + h.nten;   // at most one side of every limit can be active at a time
-    h.ndr_max = want < DM_NDOFROW_MIN ? DM_NDOFROW_MIN : (want > 48 ? 48 : want);
+    // models with tendon-coupled, friction-loaded joints (the Shadow hand) sit at many limits at once; the arm / legged
+    // models keep the small table that lets 28 envs share one thread block
+    h.ndr_max = (h.nten > 0 || h.nfric > 0) ? (want < DM_NDOFROW_MIN ? DM_NDOFROW_MIN : (want > 48 ? 48 : want)) : DM_NDOFROW_MIN;
   }
   int nweld = 0;
   for (int e = 0; e < m.neq; e++) if (m.eq_type[e] == B200_EQ_WELD) nweld++;
@@ -160,7 +169,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   // offsets
   int nb = h.nb, njnt = h.njnt, nq = h.nq, nv = h.nv, nu = h.nu, ngeom = h.ngeom, nsite = h.nsite, nmocap = h.nmocap,
       neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max, ndr_max = h.ndr_max,
-      nten = h.nten, nfric = h.nfric;
+      nten = h.nten, nfric = h.nfric, nsensor = h.nsensor, ncx = h.nsensor > 0 ? h.ncon_max : 0;
   int nrkq = h.integrator == B200_INT_RK4 ? nq : 0, nrkv = h.integrator == B200_INT_RK4 ? nv : 0;
   int off = (int)((sizeof(DMHead) + 3) / 4);
 #define X(name, w, kind) h.o_##name = off; off += (w) * (kind);
@@ -187,7 +196,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     h.s_geom_xpos = after; h.s_cand = after + 3 * ngeom;
     h.s_H = u; h.s_grad = after; h.s_search = after + nv; h.s_Ma = after + 2 * nv; h.s_Mv = after + 3 * nv;
     h.s_cvel = u;
-    int endA = after + 3 * ngeom + DM_NCAND_MAX, endB = after + 4 * nv;
+    int endA = after + 3 * ngeom + h.ncand_max / 4, endB = after + 4 * nv;
     so = endA > endB ? endA : endB;
   }
   h.scr_words = (so + 3) & ~3;
@@ -291,6 +300,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     bool r1 = t1 == B200_GEOM_SPHERE || t1 == B200_GEOM_CAPSULE, r2 = t2 == B200_GEOM_SPHERE || t2 == B200_GEOM_CAPSULE;
     bool ok = (t1 == B200_GEOM_PLANE && (t2 == B200_GEOM_BOX || r2)) || (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) ||
               (r1 && t2 == B200_GEOM_BOX) || (r1 && r2);
+    if (r1 && r2) h.any_round_pair = 1;
     if (!ok) { err = "collision pair type not supported by the CUDA path yet"; return -1; }
     if (m.pair_condim[sp] != 1 && m.pair_condim[sp] != 3 && m.pair_condim[sp] != 4) { err = "condim must be 1, 3 or 4 on the CUDA path"; return -1; }
     F(h.o_pair_friction, 3 * p + 0, m.pair_friction[5 * sp + 0]); F(h.o_pair_friction, 3 * p + 1, m.pair_friction[5 * sp + 2]);
@@ -298,6 +308,10 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     F(h.o_pair_margin, p, m.pair_margin[sp]); F(h.o_pair_gap, p, m.pair_gap[sp]);
     for (int k = 0; k < 2; k++) { F(h.o_pair_solref, 2 * p + k, m.pair_solref[2 * sp + k]); F(h.o_pair_invweight, 2 * p + k, m.pair_invweight[2 * sp + k]); }
     for (int k = 0; k < 5; k++) F(h.o_pair_solimp, 5 * p + k, m.pair_solimp[5 * sp + k]);
+  }
+  for (int k = 0; k < nsensor; k++) {
+    I(h.o_sensor_site, k, m.sensor_site[k]); I(h.o_sensor_body, k, m.sensor_body[k]); I(h.o_sensor_type, k, m.sensor_type[k]);
+    for (int a = 0; a < 3; a++) F(h.o_sensor_size, 3 * k + a, m.sensor_size[3 * k + a]);
   }
   for (int i = 0; i < h.grid_len * h.grid_wid; i++) if (m.grid_walls[i]) buf[h.o_grid_walls + i / 32] |= 1u << (i % 32);
   for (int s = 0; s < nsite; s++) {

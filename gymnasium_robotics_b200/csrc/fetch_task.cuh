@@ -26,6 +26,7 @@ struct FetchTask {
   // hand manipulation tasks: object free joint addresses, which goal parts count, rotation threshold
   int obj_qadr, obj_dadr, goal_flags;
   float rotation_threshold;
+  int touch_mode;       // 0 = no touch observation, 1 = sensordata, 2 = boolean, 3 = log(x + 1)
   // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(ngoal)
   int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride;
 };
@@ -169,6 +170,55 @@ HD void hand_observe(const Ctx& c, const FetchTask& t, const float* goal, float*
   (void)h;
 }
 
+// Touch sensors as of the last forward pass (public MuJoCo semantics, restated in oracle/oracle.c `sensors`): sum of the
+// normal forces of the contacts that involve the sensor's body and whose ray from the contact point along the contact
+// normal (flipped when the sensor's body is the second one) hits the site volume.  Appended to the observation by
+// MujocoManipulateTouchSensorsEnv._get_obs (envs/shadow_dexterous_hand/manipulate_touch_sensors.py:107-138).
+HD bool ray_hits_site(int type, const float* size, const float* p, const float* d) {
+  if (type == B200_GEOM_SPHERE) {
+    float r = size[0], b = dot3(p, d), cc = dot3(p, p) - r * r;
+    if (cc <= 0) return true;
+    return b * b - cc >= 0 && -b >= 0;
+  }
+  float t0 = 0, t1 = 1e30f;
+  for (int k = 0; k < 3; k++) {
+    if (fabsf(d[k]) < 1e-12f) { if (fabsf(p[k]) > size[k]) return false; continue; }
+    float a = (-size[k] - p[k]) / d[k], b = (size[k] - p[k]) / d[k];
+    if (a > b) { float t = a; a = b; b = t; }
+    t0 = fmaxf(t0, a); t1 = fminf(t1, b);
+    if (t0 > t1) return false;
+  }
+  return true;
+}
+HD void touch_observe(const Ctx& c, const FetchTask& t, float* out) {
+  const DMHead* h = c.h;
+  const int ncon = SI(counters)[CNT_NCON];
+  LANES(k, h->nsensor) {
+    int site = GI(sensor_site)[k], body = GI(sensor_body)[k], type = GI(sensor_type)[k];
+    float size[3] = {GF(sensor_size)[3 * k], GF(sensor_size)[3 * k + 1], GF(sensor_size)[3 * k + 2]};
+    float total = 0.f, sp[3], sq[4];
+    bool posed = false;
+    for (int i = 0; i < ncon; i++) {
+      const float* cr = SF(con) + i * CON_WORDS;
+      const float* cx = SF(conx) + i * CX_WORDS;
+      int p = ((const int*)cx)[CX_PAIR];
+      int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
+      int b1 = MI(geom_body)[g1], b2 = g2 < 0 ? 0 : MI(geom_body)[g2];
+      if (b1 != body && b2 != body) continue;
+      float F[4];
+      contact_base_forces(cr, con_dim(cr), F);
+      if (!(F[0] > 0)) continue;
+      if (!posed) { site_pose(c, site, sp, sq); posed = true; }
+      float rel[3] = {cx[CX_POS] - sp[0], cx[CX_POS + 1] - sp[1], cx[CX_POS + 2] - sp[2]};
+      float sg = b2 == body ? -1.f : 1.f, dir[3] = {sg * cr[C_W + 3], sg * cr[C_W + 4], sg * cr[C_W + 5]};  // contact normal
+      float qc[4] = {sq[0], -sq[1], -sq[2], -sq[3]}, loc[3], dl[3];
+      qrot(loc, qc, rel); qrot(dl, qc, dir);
+      if (ray_hits_site(type, size, loc, dl)) total += F[0];
+    }
+    out[k] = t.touch_mode == 2 ? (total > 0.f ? 1.f : 0.f) : (t.touch_mode == 3 ? logf(total + 1.f) : total);
+  }
+}
+
 // one env, one warp.  `st` is this env's state record; outputs are this env's rows.  `active` is warp-uniform: idle
 // warps run the same control flow (for the block-wide alignment barriers) but touch no memory.
 template <int NVP>
@@ -177,7 +227,7 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   const DMHead* h = c.h;
   if (active) {
     load_state(c, t, st);
-    if (mode == MODE_STEP && t.kind == TASK_HAND) {
+    if (NVP >= 30 && mode == MODE_STEP && t.kind == TASK_HAND) {
       // MujocoHandEnv._set_action (hand_env.py:42-61, absolute control): ctrl = centre + clip(a) * half range, clipped
       LANES(i, h->nu) {
         float lo = MF(act_ctrlrange)[2 * i], hi = MF(act_ctrlrange)[2 * i + 1];
@@ -215,6 +265,13 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
     if (h->integrator == B200_INT_RK4) rk4_substep<NVP>(c, active);
     else if (active) euler_step<NVP>(c);
   }
+  // touch sensors read the contacts and forces of the last forward pass: a refresh (no sub-step) runs one first,
+  // block-uniformly (forward() contains the block-wide alignment barriers); the warm start is left untouched
+  const bool touch_fwd = NVP >= 30 && t.kind == TASK_HAND && t.touch_mode != 0 && nsub == 0;
+  if (touch_fwd) {
+    forward<NVP>(c, active);
+    if (active) { LANES(i, h->nv) SF(qacc)[i] = st[t.st_warm + i]; SYNC(); }
+  }
   if (!active) return;
   if (t.kind == TASK_FETCH) {
     if (mode == MODE_REFRESH || (mode == MODE_STEP && t.block_gripper) || nsub == 0) {
@@ -226,8 +283,9 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
       com_quantities(c);
     }
     fetch_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
-  } else if (t.kind == TASK_HAND) {
+  } else if (NVP >= 30 && t.kind == TASK_HAND) {
     hand_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
+    if (t.touch_mode) touch_observe(c, t, obs + t.obj_qadr + h->nv + 7);
   } else {
     antmaze_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   }

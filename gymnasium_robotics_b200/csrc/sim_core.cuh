@@ -741,7 +741,8 @@ HD void collide_round_box(const Ctx& c, int g1, int g2, float margin, ContactOut
 
 // sphere/capsule against sphere/capsule: closest points of the two axis segments, then a sphere-sphere contact
 // (same decision logic as oracle/oracle.c collide_round_round)
-HD void collide_round_round(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
+HDN void collide_round_round(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
+  ASSUME_SHARED(c);
   o.cnt = 0;
   float p1[3], m1[9], p2[3], m2[9];
   geom_pose(c, g1, p1, m1); geom_pose(c, g2, p2, m2);
@@ -787,11 +788,14 @@ HD void make_frame(float* f) {
   cross3(f + 6, f, y);
 }
 
+// HF: model family with hand features (frictionloss rows, tendon limits, round-round pairs, touch sensors); compiled out
+// of the other kernel instantiations to keep their instruction stream short
+template <bool HF>
 STAGE void collision(const Ctx c) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int* cnt = SI(counters);
-  int* cand = SI(cand);
+  unsigned char* cand = (unsigned char*)SI(cand);
   if (c.lane == 0) { cnt[CNT_NCON] = 0; cnt[CNT_NCAND] = 0; cnt[CNT_NGRP] = 0; }
   SYNC();
   // broad phase: lanes over the static pair list, ordered compaction
@@ -832,8 +836,8 @@ STAGE void collision(const Ctx c) {
     int total, slot = wexscan(hit ? 1 : 0, c.lane, &total);
     int basec = cnt[CNT_NCAND];
     SYNC();
-    if (hit && basec + slot < DM_NCAND_MAX) cand[basec + slot] = p;
-    if (c.lane == 0) { int nn = basec + total; if (nn > DM_NCAND_MAX) { nn = DM_NCAND_MAX; cnt[CNT_OVERFLOW] |= 1; } cnt[CNT_NCAND] = nn; }
+    if (hit && basec + slot < h->ncand_max) cand[basec + slot] = (unsigned char)p;
+    if (c.lane == 0) { int nn = basec + total; if (nn > h->ncand_max) { nn = h->ncand_max; cnt[CNT_OVERFLOW] |= 1; } cnt[CNT_NCAND] = nn; }
     SYNC();
   }
   // narrow phase: one lane per candidate pair (lock-step over identical pair types in the common case)
@@ -854,7 +858,7 @@ STAGE void collision(const Ctx c) {
         else collide_plane_capsule(c, g1, g2, margin, o);
       } else if (t1 == B200_GEOM_BOX) collide_box_box(c, g1, g2, margin, o);
       else if (t2 == B200_GEOM_BOX) collide_round_box(c, g1, g2, margin, o);
-      else collide_round_round(c, g1, g2, margin, o);
+      else if (HF) collide_round_round(c, g1, g2, margin, o);
       // contacts beyond the gap are not turned into constraints
       float inc = margin - GF(pair_gap)[p];
       int k2 = 0;
@@ -898,6 +902,11 @@ STAGE void collision(const Ctx c) {
       cr[C_U] = K * imp * (o.dist[k] - incl); cr[C_U + 1] = 0; cr[C_U + 2] = 0; cr[C_U + 3] = 0;
       cr[C_JV] = Bc;
       ((int*)cr)[C_DIMGRP] = dim | (gid << 8);
+      if (HF && h->nsensor > 0) {
+        float* cx = SF(conx) + id * CX_WORDS;
+        cx[CX_POS] = o.pos[k][0]; cx[CX_POS + 1] = o.pos[k][1]; cx[CX_POS + 2] = o.pos[k][2];
+        ((int*)cx)[CX_PAIR] = p;
+      }
       kept++;
     }
     if (o.cnt > 0 && gid < h->ngrp_max - DM_NWELD_MAX) {
@@ -927,6 +936,7 @@ HD float con_mu(const float* cr, int k) { return k < 3 ? cr[C_MU] : cr[C_MU + 1]
 HD int con_dim(const float* cr) { return ((const int*)cr)[C_DIMGRP] & 0xff; }
 HD int con_grp(const float* cr) { return ((const int*)cr)[C_DIMGRP] >> 8; }
 
+template <bool HF>
 STAGE void make_constraint(const Ctx c) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
@@ -1013,7 +1023,7 @@ STAGE void make_constraint(const Ctx c) {
     SYNC();
   }
   // limits of fixed tendons (length = sum coef * qpos over <= 2 joints) -> dof rows, lower side first
-  for (int base = 0; base < h->nten; base += WARP_W) {
+  if (HF) for (int base = 0; base < h->nten; base += WARP_W) {
     int t = base + c.lane;
     int nrow = 0; float dist[2] = {0, 0}; float sgn[2] = {0, 0};
     if (t < h->nten) {
@@ -1047,12 +1057,12 @@ STAGE void make_constraint(const Ctx c) {
     SYNC();
   }
   // dof frictionloss rows: position residual 0, so the row value starts at 0
-  LANES(d, h->nfric) SF(fric)[d] = 0.f;
-  SYNC();
+  if (HF) { LANES(d, h->nfric) SF(fric)[d] = 0.f; SYNC(); }
 }
 
 // rows <- J * vec.  RV_C0: row = B * (J qvel) + row (row holds K*imp*r; B in the JV slot) ; RV_ADD: row += J a ; RV_JV: JV = J s
 enum { RV_C0 = 0, RV_ADD = 1, RV_JV = 2 };
+template <bool HF>
 STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
   ASSUME_SHARED(c);
   ASSUME_SHARED_PTR(vec);
@@ -1100,7 +1110,7 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
     else if (mode == RV_ADD) dr[DR_JAR] += val;
     else dr[DR_JV] = val;
   }
-  LANES(d, c.h->nfric) {
+  if (HF) LANES(d, c.h->nfric) {
     float* fr = SF(fric);
     if (mode == RV_C0) fr[d] += MF(dof_fricB)[d] * vec[d];
     else if (mode == RV_ADD) fr[d] += vec[d];
@@ -1126,6 +1136,7 @@ HD void contact_base_forces(const float* cr, int dim, float* F) {
 }
 
 // fcon = J^T f from the stored base-row forces: per-group spatial force, then one 6-dot per (dof, group)
+template <bool HF>
 STAGE void pass_F(const Ctx c, float* out) {
   ASSUME_SHARED(c);
   ASSUME_SHARED_PTR(out);
@@ -1172,7 +1183,7 @@ STAGE void pass_F(const Ctx c, float* out) {
       if (di[DR_DOF] == j) q += dr[DR_COEF] * f;
       if (di[DR_DOF2] == j) q += dr[DR_COEF2] * f;
     }
-    if (h->nfric) {
+    if (HF && h->nfric) {
       // Huber-type friction row: force -D x clamped to +-frictionloss
       float fl = MF(dof_frictionloss)[j];
       q += fminf(fmaxf(-MF(dof_fricD)[j] * SF(fric)[j], -fl), fl);
@@ -1196,6 +1207,7 @@ STAGE void mulM(const Ctx c, const float* v, float* out) {
 }
 
 // H = M + sum_g S_g^T K_g S_g  (+ dof rows on the diagonal blocks)
+template <bool HF>
 STAGE void build_H(const Ctx c) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
@@ -1271,11 +1283,13 @@ STAGE void build_H(const Ctx c) {
     SYNC();
   }
   // dof friction rows in their quadratic zone (|x| < R * frictionloss)
-  LANES(d, h->nfric) {
-    float D = MF(dof_fricD)[d], x = SF(fric)[d];
-    if (D > 0 && fabsf(x) * D < MF(dof_frictionloss)[d]) H[d * (d + 1) / 2 + d] += D;
+  if (HF) {
+    LANES(d, h->nfric) {
+      float D = MF(dof_fricD)[d], x = SF(fric)[d];
+      if (D > 0 && fabsf(x) * D < MF(dof_frictionloss)[d]) H[d * (d + 1) / 2 + d] += D;
+    }
+    SYNC();
   }
-  SYNC();
   // dof rows (active ones)
   if (c.lane == 0) {
     for (int i = 0; i < ndr; i++) {
@@ -1401,6 +1415,7 @@ static inline void spd_solve(const Ctx& c, const float* A, const float* dadd, fl
 #endif
 
 // line-search evaluation: cost(alpha) - gauss constant, first and second derivative
+template <bool HF>
 STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
   ASSUME_SHARED(c);
   const int* cnt = SI(counters);
@@ -1428,7 +1443,7 @@ STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
     float D = dr[DR_D], v = dr[DR_JV], x = dr[DR_JAR] + alpha * v;
     if (x < 0) { cost += 0.5f * D * x * x; d1 += D * x * v; d2 += D * v * v; }
   }
-  LANES(d, c.h->nfric) {
+  if (HF) LANES(d, c.h->nfric) {
     float D = MF(dof_fricD)[d];
     if (D > 0) {
       float fl = MF(dof_frictionloss)[d], v = SF(fric)[c.h->nfric + d], x = SF(fric)[d] + alpha * v, Rf = fl / D;
@@ -1443,16 +1458,17 @@ STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
 }
 
 // returns alpha; *improve = cost(0) - cost(alpha)
+template <bool HF>
 STAGE float linesearch(const Ctx c, float g1, float g2, float gtol, int maxit, float* improve) {
   ASSUME_SHARED(c);
   float p0[3], p[3];
-  ls_eval(c, 0.f, g1, g2, p0);
+  ls_eval<HF>(c, 0.f, g1, g2, p0);
   *improve = 0;
   if (p0[1] >= 0 || p0[2] <= 0) return 0.f;
   gtol = fmaxf(gtol, 1e-5f * fabsf(p0[1]));  // single-precision floor on the derivative test
   float lo = 0, hi = -1, alpha = -p0[1] / p0[2], best = 0, bestcost = p0[0];
   for (int it = 0; it < maxit; it++) {
-    ls_eval(c, alpha, g1, g2, p);
+    ls_eval<HF>(c, alpha, g1, g2, p);
     if (p[0] <= bestcost) { bestcost = p[0]; best = alpha; }
     if (fabsf(p[1]) < gtol) break;
     if (p[1] < 0) lo = alpha; else hi = alpha;
@@ -1466,15 +1482,17 @@ STAGE float linesearch(const Ctx c, float g1, float g2, float gtol, int maxit, f
 }
 
 // Newton solver, split so that the iteration loop can be driven block-uniformly (see forward()).
+template <bool HF>
 STAGE void newton_begin(const Ctx c) {
   ASSUME_SHARED(c);
   // qacc holds the warm start (previous sub-step's solution); rows become J a - aref = J a + B (J qvel) + K imp r
-  rows_from_vec(c, SF(qvel), RV_C0);
+  rows_from_vec<HF>(c, SF(qvel), RV_C0);
   mulM(c, SF(qacc), SF(Ma));
-  rows_from_vec(c, SF(qacc), RV_ADD);
+  rows_from_vec<HF>(c, SF(qacc), RV_ADD);
 }
 
 // forces, gradient and the convergence tests at the current point; returns 1 when the solver is finished
+template <bool HF>
 STAGE int newton_check(const Ctx c, int iter, float improvement) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
@@ -1482,7 +1500,7 @@ STAGE int newton_check(const Ctx c, int iter, float improvement) {
   float *Ma = SF(Ma), *grad = SF(grad), *fs = SF(fsmooth), *fcon = SF(fcon);
   float scale = 1.0f / (h->meaninertia * (float)(nv > 1 ? nv : 1));
   float tol = fmaxf(h->tolerance, 1e-6f);  // single-precision floor for the convergence tests
-  pass_F(c, fcon);
+  pass_F<HF>(c, fcon);
   float g2sum = 0, f2sum = 0;
   LANES(i, nv) {
     float g = Ma[i] - fs[i] - fcon[i], f = fabsf(Ma[i]) + fabsf(fs[i]) + fabsf(fcon[i]);
@@ -1511,6 +1529,7 @@ STAGE void newton_direction(const Ctx c) {
 }
 
 // exact line search and move; returns 1 when the solver must stop (no progress possible), *improvement updated
+template <bool HF>
 STAGE int newton_move(const Ctx c, float* improvement) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
@@ -1519,19 +1538,19 @@ STAGE int newton_move(const Ctx c, float* improvement) {
   float *a = SF(qacc), *Ma = SF(Ma), *Mv = SF(Mv), *search = SF(search), *fs = SF(fsmooth);
   float scale = 1.0f / (h->meaninertia * (float)(nv > 1 ? nv : 1));
   mulM(c, search, Mv);
-  rows_from_vec(c, search, RV_JV);
+  rows_from_vec<HF>(c, search, RV_JV);
   float q1 = 0, q2 = 0, sn = 0;
   LANES(i, nv) { q1 += search[i] * (Ma[i] - fs[i]); q2 += 0.5f * search[i] * Mv[i]; sn += search[i] * search[i]; }
   q1 = wsum(q1); q2 = wsum(q2); sn = sqrtf(wsum(sn));
   if (sn < 1e-20f) return 1;
   float gtol = h->tolerance * h->ls_tolerance * sn / scale;
-  float alpha = linesearch(c, q1, q2, gtol, h->ls_iterations < 20 ? h->ls_iterations : 20, improvement);
+  float alpha = linesearch<HF>(c, q1, q2, gtol, h->ls_iterations < 20 ? h->ls_iterations : 20, improvement);
   if (alpha == 0.f) return 1;
   LANES(i, nv) { a[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
   LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 4; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
   LANES(i, cnt[CNT_NWELD] * 6) { float* wr = SF(weld) + (i / 6) * WELD_WORDS; wr[W_JAR + i % 6] += alpha * wr[W_JV + i % 6]; }
   LANES(i, cnt[CNT_NDR]) { float* dr = SF(dofrow) + i * DR_WORDS; dr[DR_JAR] += alpha * dr[DR_JV]; }
-  LANES(d, h->nfric) SF(fric)[d] += alpha * SF(fric)[h->nfric + d];
+  if (HF) LANES(d, h->nfric) SF(fric)[d] += alpha * SF(fric)[h->nfric + d];
   SYNC();
   if (c.lane == 0) cnt[CNT_ITERS] += 1;
   return 0;
@@ -1548,39 +1567,40 @@ STAGE int newton_move(const Ctx c, float* improvement) {
 #define ALIGN_AT(level) do { if (B200_ALIGN_LEVEL >= (level)) ALIGN(); } while (0)
 template <int NVP>
 HD void forward(const Ctx c, bool active) {
+  constexpr bool HF = NVP >= 30;
   ALIGN_AT(1);
   if (active) kinematics(c);
   ALIGN_AT(4);
   if (active) { com_quantities(c); mass_matrix(c); }
   ALIGN_AT(2);
-  if (active) collision(c);
+  if (active) collision<HF>(c);
   ALIGN_AT(2);
-  if (active) make_constraint(c);
+  if (active) make_constraint<HF>(c);
   ALIGN_AT(4);
   if (active) smooth_forces(c);
   ALIGN_AT(4);
-  if (active) newton_begin(c);
+  if (active) newton_begin<HF>(c);
   int done = active ? 0 : 1;
   float improvement = 0;
 #if B200_ALIGN_LEVEL >= 3
   for (int iter = 0;; iter++) {
     ALIGN();
-    if (!done) done = newton_check(c, iter, improvement);
+    if (!done) done = newton_check<HF>(c, iter, improvement);
     if (!ALIGN_OR(!done)) break;
-    if (!done) build_H(c);
+    if (!done) build_H<HF>(c);
     ALIGN_AT(4);
     if (!done) newton_direction<NVP>(c);
     ALIGN();
-    if (!done) done = newton_move(c, &improvement) ? 2 : 0;
+    if (!done) done = newton_move<HF>(c, &improvement) ? 2 : 0;
   }
 #else
   ALIGN_AT(2);
   for (int iter = 0; !done; iter++) {
-    done = newton_check(c, iter, improvement);
+    done = newton_check<HF>(c, iter, improvement);
     if (done) break;
-    build_H(c);
+    build_H<HF>(c);
     newton_direction<NVP>(c);
-    done = newton_move(c, &improvement) ? 2 : 0;
+    done = newton_move<HF>(c, &improvement) ? 2 : 0;
   }
 #endif
 }

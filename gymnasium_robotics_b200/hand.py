@@ -37,7 +37,11 @@ HAND_REF_POINT = (1.0, 0.9, 0.2)   # fixed world point of the spatial algebra: i
 GOAL_USE_POS, GOAL_USE_ROT = 1, 2
 
 
-def make_hand_task(model, target_position, target_rotation, reward_type, distance_threshold, rotation_threshold, n_substeps):
+TOUCH_MODES = {"off": 0, "sensordata": 1, "boolean": 2, "log": 3}   # manipulate_touch_sensors.py:30-40 touch_get_obs
+
+
+def make_hand_task(model, target_position, target_rotation, reward_type, distance_threshold, rotation_threshold, n_substeps,
+                   touch_get_obs=None):
     """b200sim_fetch_task_t for kind 2 (ids resolved the way MujocoModelNames would, utils/mujoco_utils.py:327-469)."""
     m = model
     jobj = m.joint_id("object:joint")
@@ -47,7 +51,8 @@ def make_hand_task(model, target_position, target_rotation, reward_type, distanc
     t.kind, t.nact, t.ngoal = 2, int(m.nu), 7
     t.n_substeps, t.reward_dense = int(n_substeps), int(reward_type == "dense")
     t.obj_qadr, t.obj_dadr = int(m.jnt_qposadr[jobj]), int(m.jnt_dofadr[jobj])
-    t.nobs = t.obj_qadr + int(m.nv) + 7
+    t.touch_mode = TOUCH_MODES.get(touch_get_obs, 0) if touch_get_obs is not None else 0
+    t.nobs = t.obj_qadr + int(m.nv) + 7 + (int(m.nsensor) if t.touch_mode else 0)
     t.goal_flags = (GOAL_USE_POS if target_position != "ignore" else 0) | (GOAL_USE_ROT if target_rotation != "ignore" else 0)
     t.distance_threshold, t.rotation_threshold = float(distance_threshold), float(rotation_threshold)
     t.dt = float(m.opt[0] * n_substeps)
@@ -67,7 +72,8 @@ class HandVectorEnv(FetchVectorEnv):
                  max_episode_steps: Optional[int] = 100, device="cuda:0", rng_mode: str = "auto", autoreset_mode: str = "next_step",
                  n_substeps: int = N_SUBSTEPS, backend_factory=None, target_position=None, target_rotation=None,
                  randomize_initial_position=True, randomize_initial_rotation=True, distance_threshold=0.01,
-                 rotation_threshold=0.1, relative_control=False, model=None, **kwargs):
+                 rotation_threshold=0.1, relative_control=False, model=None, touch_get_obs=None,
+                 touch_visualisation="on_touch", **kwargs):
         if task not in HAND_TASKS:
             raise KeyError(f"unknown Hand task {task!r}")
         if reward_type not in ("sparse", "dense"):
@@ -90,10 +96,13 @@ class HandVectorEnv(FetchVectorEnv):
         self.num_envs, self.max_episode_steps, self.autoreset_mode = int(num_envs), max_episode_steps, autoreset_mode
         self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
         self.n_substeps = n_substeps
-        self.model = model if model is not None else load_model("hand_block")
+        # touch_get_obs is None for the plain ids; the *TouchSensors ids pass "boolean" / "sensordata" (or "log" / "off"):
+        # they use the model with the 92 touch sites (manipulate_block_touch_sensors.py:72-92)
+        self.touch_get_obs = touch_get_obs
+        self.model = model if model is not None else load_model("hand_block" if touch_get_obs is None else "hand_block_touch")
         m = self.model
         self.task = make_hand_task(m, self.target_position, self.target_rotation, reward_type, distance_threshold,
-                                   rotation_threshold, n_substeps)
+                                   rotation_threshold, n_substeps, touch_get_obs)
         factory = backend_factory or _HandBackend
         self.backend = factory(m, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device

@@ -36,7 +36,7 @@ EQ_CONNECT, EQ_WELD, EQ_JOINT = 0, 1, 2
 INT_EULER, INT_RK4 = 0, 1
 MINVAL = 1e-15
 BLOB_MAGIC = 0x4D303242  # "B20M"
-BLOB_VERSION = 4
+BLOB_VERSION = 5
 
 
 # --------------------------------------------------------------------------------------
@@ -513,7 +513,7 @@ class Model:
                   "body_mocapid", "body_rootid", "jnt_type", "jnt_body", "jnt_qposadr", "jnt_dofadr", "jnt_limited",
                   "dof_body", "dof_jnt", "dof_parent", "geom_type", "geom_body", "pair_geom1", "pair_geom2", "pair_condim",
                   "site_body", "act_trnid", "act_ctrllimited", "act_forcelimited", "eq_type", "eq_obj1", "eq_obj2",
-                  "eq_active", "mocap_body", "ten_adr", "ten_num", "ten_limited", "wrap_dof", "sensor_site", "sensor_body",
+                  "eq_active", "mocap_body", "ten_adr", "ten_num", "ten_limited", "wrap_dof", "sensor_site", "sensor_body", "sensor_type",
                   "pair_grid", "grid_dims", "grid_walls"]
     FLT_FIELDS = ["opt", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "jnt_pos",
                   "jnt_axis", "jnt_range", "jnt_margin", "jnt_stiffness", "jnt_solref", "jnt_solimp", "qpos0",
@@ -1050,13 +1050,18 @@ def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None) ->
     m.wrap_dof, m.wrap_coef = np.array(wd, dtype=np.int32), np.array(wc)
 
     # touch sensors (site volume + body), others ignored
-    ss, sbod, ssz = [], [], []
+    ss, sbod, ssz, sty = [], [], [], []
     sname = {s["name"]: i for i, s in enumerate(F.sites)}
+    sensor_prefix = (overrides or {}).get("sensor_prefix")   # keep only the sensors an env reads (e.g. "robot0:TS_")
     for S in F.sensors:
-        if S["type"] == "touch":
+        if S["type"] == "touch" and (sensor_prefix is None or S.get("name", "").startswith(sensor_prefix)):
             si = sname[S["site"]]
             ss.append(si); sbod.append(rt_of[F.sites[si]["body"]]); ssz.append(F.sites[si]["size"])
+            sty.append(GEOM_NAMES[F.sites[si]["type"]])
+            if sty[-1] not in (GEOM_NAMES["sphere"], GEOM_NAMES["box"]):
+                raise NotImplementedError("touch sensor sites must be spheres or boxes")
     m.sensor_site, m.sensor_body, m.sensor_size = np.array(ss, dtype=np.int32), np.array(sbod, dtype=np.int32), np.array(ssz).reshape(-1, 3)
+    m.sensor_type = np.array(sty, dtype=np.int32)
     m.key_qpos = np.zeros(0)
 
     o = F.opt

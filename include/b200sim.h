@@ -40,6 +40,9 @@ typedef struct b200sim_fetch_task {
    * dof address of "object:joint" (must be the last joint); goal_flags bit 0: position counts, bit 1: rotation counts */
   int obj_qadr, obj_dadr, goal_flags;
   float rotation_threshold;
+  /* touch observation appended after the 61 base entries (manipulate_touch_sensors.py:107-138): 0 = none,
+   * 1 = sensordata, 2 = boolean, 3 = log(x + 1); one value per touch sensor of the model */
+  int touch_mode;
 } b200sim_fetch_task_t;
 
 /* indices into the layout array returned by b200sim_layout (offsets in floats inside one env's state record) */

@@ -15,7 +15,7 @@
 #include <stddef.h>
 
 #define B200M_MAGIC 0x4D303242u
-#define B200M_VERSION 4u
+#define B200M_VERSION 5u
 
 enum { B200_JNT_FREE = 0, B200_JNT_BALL = 1, B200_JNT_SLIDE = 2, B200_JNT_HINGE = 3 };
 enum { B200_GEOM_PLANE = 0, B200_GEOM_HFIELD = 1, B200_GEOM_SPHERE = 2, B200_GEOM_CAPSULE = 3,
@@ -37,7 +37,7 @@ enum { B200_OPTI_ITERATIONS = 0, B200_OPTI_LS_ITERATIONS = 1, B200_OPTI_INTEGRAT
   X(body_mocapid) X(body_rootid) X(jnt_type) X(jnt_body) X(jnt_qposadr) X(jnt_dofadr) X(jnt_limited) \
   X(dof_body) X(dof_jnt) X(dof_parent) X(geom_type) X(geom_body) X(pair_geom1) X(pair_geom2) X(pair_condim) \
   X(site_body) X(act_trnid) X(act_ctrllimited) X(act_forcelimited) X(eq_type) X(eq_obj1) X(eq_obj2) \
-  X(eq_active) X(mocap_body) X(ten_adr) X(ten_num) X(ten_limited) X(wrap_dof) X(sensor_site) X(sensor_body) \
+  X(eq_active) X(mocap_body) X(ten_adr) X(ten_num) X(ten_limited) X(wrap_dof) X(sensor_site) X(sensor_body) X(sensor_type) \
   X(pair_grid) X(grid_dims) X(grid_walls)
 
 #define B200M_FLT_FIELDS(X) \

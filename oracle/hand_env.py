@@ -19,13 +19,13 @@ TARGET_POSITION_RANGE = np.array([(-0.04, 0.04), (-0.06, 0.02), (0.0, 0.06)])  #
 
 
 def compile_hand_model(assets_dir="/root/reference/gymnasium_robotics/envs/assets", xml=HAND_BLOCK_XML):
-    return compile_mjcf(f"{assets_dir}/{xml}", overrides={"drop_bodies": ["target"]})
+    return compile_mjcf(f"{assets_dir}/{xml}", overrides={"drop_bodies": ["target"], "sensor_prefix": "robot0:TS_"})
 
 
 class OracleHandBlockEnv:
     def __init__(self, target_position="ignore", target_rotation="xyz", reward_type="sparse", model=None,
                  randomize_initial_position=True, randomize_initial_rotation=True, distance_threshold=0.01,
-                 rotation_threshold=0.1, n_substeps=20):
+                 rotation_threshold=0.1, n_substeps=20, touch_get_obs=None):
         # manipulate.py:24-85 (ctor), manipulate_block.py:214-230
         self.target_position, self.target_rotation = target_position, target_rotation
         self.target_position_range = TARGET_POSITION_RANGE
@@ -34,9 +34,11 @@ class OracleHandBlockEnv:
         self.randomize_initial_rotation = randomize_initial_rotation
         self.distance_threshold, self.rotation_threshold = distance_threshold, rotation_threshold
         self.reward_type, self.n_substeps = reward_type, n_substeps
+        self.touch_get_obs = touch_get_obs  # manipulate_touch_sensors.py:10-64 (None = plain env without touch observation)
         assert target_position in ("ignore", "fixed", "random")
         assert target_rotation in ("ignore", "fixed", "xyz", "z", "parallel")
-        self.model = model if model is not None else compile_hand_model()
+        self.model = model if model is not None else compile_hand_model(
+            xml=HAND_BLOCK_XML if touch_get_obs is None else "hand/manipulate_block_touch_sensors.xml")
         self.sim = OracleSim(self.model)
         m = self.model
         self._robot_joints = [j for j, n in enumerate(m.names["joint"]) if n.startswith("robot")]
@@ -89,7 +91,14 @@ class OracleHandBlockEnv:
         robot_qvel = np.array([s.qvel[m.jnt_dofadr[j]] for j in self._robot_joints])
         object_qvel = s.qvel[self._obj_v:self._obj_v + 6]
         achieved = self._get_achieved_goal()
-        return {"observation": np.concatenate([robot_qpos, robot_qvel, object_qvel, achieved]),
+        touch = np.zeros(0)  # manipulate_touch_sensors.py:107-138; all touch sensors of this model are "robot0:TS_*"
+        if self.touch_get_obs == "sensordata":
+            touch = s.sensordata.copy()
+        elif self.touch_get_obs == "boolean":
+            touch = (s.sensordata > 0.0).astype(np.float64)
+        elif self.touch_get_obs == "log":
+            touch = np.log(s.sensordata + 1.0)
+        return {"observation": np.concatenate([robot_qpos, robot_qvel, object_qvel, achieved, touch]),
                 "achieved_goal": achieved.copy(), "desired_goal": self.goal.copy()}
 
     def step(self, action):  # robot_env.py:114-152

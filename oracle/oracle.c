@@ -1309,23 +1309,48 @@ static void solve_newton(oracle_sim* s) {
 #undef MULJ
 }
 
-/* 9. touch sensors: sum of normal forces of contacts on the sensor's body whose point lies in the site volume */
+/* 9. touch sensors (public MuJoCo semantics): sum of the normal forces of the active contacts that involve the sensor's
+ * body and whose ray -- from the contact point along the contact normal, flipped when the sensor's body is the second
+ * body -- hits the site volume (always true for a contact point inside the volume).  Site shapes: sphere, box. */
+static int ray_hits_site(int type, const double* size, const real* p, const real* d) { /* p, d in the site frame */
+  if (type == B200_GEOM_SPHERE) {
+    real r = size[0], b = dot3(p, d), c = dot3(p, p) - r * r;
+    if (c <= 0) return 1;              /* starts inside */
+    real disc = b * b - c;
+    return disc >= 0 && -b >= 0;       /* nearest root t = -b - sqrt(disc) >= 0 when the ray points at the sphere */
+  }
+  /* box: slab test for t >= 0 */
+  real t0 = 0, t1 = 1e30;
+  for (int k = 0; k < 3; k++) {
+    if (fabs(d[k]) < 1e-12) { if (fabs(p[k]) > size[k]) return 0; continue; }
+    real a = (-size[k] - p[k]) / d[k], b = (size[k] - p[k]) / d[k];
+    if (a > b) { real t = a; a = b; b = t; }
+    if (a > t0) t0 = a;
+    if (b < t1) t1 = b;
+    if (t0 > t1) return 0;
+  }
+  return 1;
+}
 static void sensors(oracle_sim* s) {
   const b200_model_view* m = &s->m;
   for (int k = 0; k < m->nsensor; k++) {
     int site = m->sensor_site[k], body = m->sensor_body[k];
+    int type = m->n_sensor_type == m->nsensor ? m->sensor_type[k] : B200_GEOM_BOX;
     real total = 0;
     for (int c = 0; c < s->ncon; c++) {
       Contact* con = &s->con[c];
       if (con->efc_address < 0 || (con->body1 != body && con->body2 != body)) continue;
-      real rel[3], loc[3];
-      sub3(rel, con->pos, s->site_xpos + 3 * site);
-      mulmatTvec3(loc, s->site_xmat + 9 * site, rel);
-      const double* sz = m->sensor_size + 3 * k;
-      if (fabs(loc[0]) > sz[0] || fabs(loc[1]) > sz[1] || fabs(loc[2]) > sz[2]) continue; /* box-shaped site volume */
       int nrow = con->dim == 1 ? 1 : 2 * (con->dim - 1);
       real fn = 0;
       for (int r = 0; r < nrow; r++) fn += s->efc_force[con->efc_address + r];
+      if (fn <= 0) continue;
+      real rel[3], loc[3], dir[3], dl[3];
+      sub3(rel, con->pos, s->site_xpos + 3 * site);
+      mulmatTvec3(loc, s->site_xmat + 9 * site, rel);
+      real sg = con->body2 == body ? -1 : 1;
+      for (int a = 0; a < 3; a++) dir[a] = sg * con->frame[a];
+      mulmatTvec3(dl, s->site_xmat + 9 * site, dir);
+      if (!ray_hits_site(type, m->sensor_size + 3 * k, loc, dl)) continue;
       total += fn;
     }
     s->sensordata[k] = total;

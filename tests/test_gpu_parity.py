@@ -282,3 +282,135 @@ def test_pointmaze_rollout_tracks_oracle():
     print(f"PointMaze free-running 200 steps: worst {worst:.2e}")
     assert worst < 2e-3
     env.close()
+
+
+# ------------------------------------------------------------------------------------------------ Shadow Hand (config 3)
+def _mk_hand(task, n, **kw):
+    from gymnasium_robotics_b200.hand import HandVectorEnv
+
+    return HandVectorEnv(task, num_envs=n, device="cuda:0", **kw)
+
+
+def test_hand_reset_and_step_parity():
+    """HandManipulateBlockRotateXYZ-v1: reset (same PCG64 draws, 200 settle sub-steps) and env-steps from injected
+    oracle states.  Tolerances: goal rotation 2e-6 (RNG + quaternion algebra only); joint angles / block position 2e-3
+    per env-step (contact forces on the 70 g block amplify fp32 geometry round-off)."""
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.hand_env import OracleHandBlockEnv
+
+    n = 6
+    model = load_model("hand_block")
+    env = _mk_hand("HandManipulateBlockRotateXYZ", n, rng_mode="numpy")
+    obs, _ = env.reset(seed=40)
+    oracles = [OracleHandBlockEnv(model=model) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=40 + i)
+        g = obs["desired_goal"][i].double().cpu().numpy()
+        assert np.abs(g[3:] - oo["desired_goal"][3:]).max() < 2e-6
+        a = obs["achieved_goal"][i].double().cpu().numpy()
+        assert a[2] > 0.04 and np.abs(a[:3] - oo["achieved_goal"][:3]).max() < 5e-3
+    lay, m = env.backend.layout, model
+    rng = np.random.default_rng(4)
+    errs = []
+    for step in range(10):
+        rec = np.zeros((n, lay["stride"]))
+        for i, o in enumerate(oracles):
+            s = o.sim
+            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+            rec[i, lay["goal"]:lay["goal"] + 7] = o.goal
+        env.set_state(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
+        info_bits = torch.zeros(n, dtype=torch.int32, device="cuda")
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            got = o["observation"][i].double().cpu().numpy()
+            assert np.isfinite(got).all()
+            errs.append(max(np.abs(got[:24] - oo["observation"][:24]).max(), np.abs(got[54:57] - oo["observation"][54:57]).max()))
+            assert float(r[i]) == float(orr) and float(info["is_success"][i]) == float(oi["is_success"])
+    errs = np.array(errs)
+    print(f"Hand: median {np.median(errs):.2e} p90 {np.quantile(errs, 0.9):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < 2e-4 and np.mean(errs < 2e-3) >= 0.9 and errs.max() < 0.1
+    env.close()
+
+
+def test_hand_full_size_batch_properties():
+    """BASELINE config 3 size (2048 envs): finite outputs, unit block quaternions, lock-step invariance of identical envs,
+    GoalEnv reward invariant, no capacity overflow flags, TimeLimit at 100 + same-step autoreset puts the block back on
+    the palm with the hand at its initial configuration before the settle phase."""
+    n = 2048
+    env = _mk_hand("HandManipulateBlockRotateXYZ", n, rng_mode="torch", autoreset_mode="same_step")
+    obs, _ = env.reset(seed=0)
+    assert bool((obs["achieved_goal"][:, 2] > 0.04).all())
+    st, _ = env.get_state()
+    st[: n // 2] = st[0]
+    env.set_state(st)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    out = env.backend.new_outputs()
+    info_bits = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for t in range(100):
+        a = torch.rand((n, 20), generator=g, device="cuda") * 2 - 1
+        a[: n // 2] = a[0]
+        if t == 50:  # one raw backend step with the info word: Newton iterations and overflow flags
+            env.backend.step(a.contiguous(), out, info_bits)
+            env._elapsed += 1
+            assert int((info_bits >> 16).max()) == 0, "contact / row capacity overflow"
+            continue
+        o, r, te, tr, info = env.step(a)
+        assert torch.isfinite(o["observation"]).all()
+        if t < 99:
+            assert torch.equal(o["observation"][: n // 2], o["observation"][0:1].expand(n // 2, -1))
+            assert torch.equal(env.compute_reward(o["achieved_goal"], o["desired_goal"], {}), r)
+            qn = torch.linalg.norm(o["achieved_goal"][:, 3:], dim=1)
+            assert bool(((qn - 1).abs() < 1e-4).all())
+            assert not bool(tr.any())
+    assert bool(tr.all()) and not bool(te.any())
+    assert bool((o["achieved_goal"][:, 2] > 0.04).all())   # after the same-step reset
+    assert int(env._elapsed.max()) == 0
+    env.close()
+
+
+def test_hand_touch_sensors_parity():
+    """HandManipulateBlockRotateXYZ_ContinuousTouchSensors-v1 (BASELINE config 3: 24 DoF + 92 touch sensors): the same
+    sensors fire as in the oracle after reset and after env-steps from injected states; forces within 5 % of the scale."""
+    import gymnasium_robotics_b200 as pkg
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.hand_env import OracleHandBlockEnv
+
+    n = 4
+    model = load_model("hand_block_touch")
+    env = pkg.make_vec("HandManipulateBlockRotateXYZ_ContinuousTouchSensors-v1", num_envs=n, device="cuda:0", rng_mode="numpy")
+    assert env.single_observation_space["observation"].shape == (153,)
+    obs, _ = env.reset(seed=60)
+    oracles = [OracleHandBlockEnv(model=model, touch_get_obs="sensordata") for _ in range(n)]
+    lay, m = env.backend.layout, model
+    rng = np.random.default_rng(6)
+    agree, total = 0, 0
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=60 + i)
+        t, ot = obs["observation"][i, 61:].double().cpu().numpy(), oo["observation"][61:]
+        assert ot.sum() > 0.3 and abs(t.sum() - ot.sum()) < 0.1 * ot.sum()   # the block's weight is carried by the hand
+    for step in range(6):
+        rec = np.zeros((n, lay["stride"]))
+        for i, o in enumerate(oracles):
+            s = o.sim
+            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+            rec[i, lay["goal"]:lay["goal"] + 7] = o.goal
+        env.set_state(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, *_ = orc.step(a[i].astype(np.float64))
+            t, ot = o["observation"][i, 61:].double().cpu().numpy(), oo["observation"][61:]
+            assert np.isfinite(t).all() and (t >= 0).all()
+            total += 1
+            agree += int(np.abs(t - ot).max() <= 0.05 * max(1.0, ot.max()))
+    print(f"Hand touch: {agree}/{total} env-steps with all 92 sensors within 5 % of the force scale")
+    assert agree >= 0.8 * total
+    env.close()

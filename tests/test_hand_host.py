@@ -98,3 +98,38 @@ def test_compute_reward_matches_oracle():
             r = env.compute_reward(ag, dg, {})
             ro = orc.compute_reward(ag, dg, {})
             np.testing.assert_allclose(r, ro, atol=2e-3 if rt == "dense" else 0)
+
+
+def test_touch_sensor_observation_tracks_oracle():
+    """HandManipulateBlockRotateXYZ_ContinuousTouchSensors-v1 / _BooleanTouchSensors-v1: 92 extra observation entries."""
+    model = load_model("hand_block_touch")
+    assert model.nsensor == 92
+    env = pkg.make_vec("HandManipulateBlockRotateXYZ_ContinuousTouchSensors-v1", num_envs=1, backend_factory=HandHostBackend,
+                       rng_mode="numpy")
+    envb = pkg.make_vec("HandManipulateBlockRotateXYZ_BooleanTouchSensors-v1", num_envs=1, backend_factory=HandHostBackend,
+                        rng_mode="numpy")
+    assert env.single_observation_space["observation"].shape == (153,)
+    orc = OracleHandBlockEnv(model=model, touch_get_obs="sensordata")
+    obs, _ = env.reset(seed=2)
+    obsb, _ = envb.reset(seed=2)
+    oobs, _ = orc.reset(seed=2)
+    t, tb, ot = obs["observation"][0, 61:].double().numpy(), obsb["observation"][0, 61:].double().numpy(), oobs["observation"][61:]
+    assert ot.shape == (92,) and ot.sum() > 0.3   # the 70 g block rests on the hand: about m g = 0.69 N of normal force
+    # the same sensors fire; forces agree to a few percent (fp32 contact geometry, see DESIGN.md)
+    assert set(np.nonzero(t > 1e-3)[0]) == set(np.nonzero(ot > 1e-3)[0])
+    np.testing.assert_allclose(t, ot, atol=0.03 * max(1.0, ot.max()))
+    assert np.array_equal(tb, (t > 0).astype(np.float64))
+    # one step with identical state: touch values follow
+    lay, m, s = env.backend.layout, model, orc.sim
+    rec = np.zeros(lay["stride"])
+    rec[lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+    rec[lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+    rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+    rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+    rec[lay["goal"]:lay["goal"] + 7] = orc.goal
+    env.set_state(torch.as_tensor(rec[None], dtype=torch.float32))
+    a = np.random.default_rng(3).uniform(-1, 1, 20)
+    obs, *_ = env.step(a[None].astype(np.float32))
+    oobs, *_ = orc.step(a)
+    t, ot = obs["observation"][0, 61:].double().numpy(), oobs["observation"][61:]
+    np.testing.assert_allclose(t, ot, atol=0.05 * max(1.0, ot.max()))
