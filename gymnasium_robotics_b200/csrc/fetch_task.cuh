@@ -225,6 +225,7 @@ template <int NVP>
 HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, int nraw, float* st, const float* action, float* obs,
                        float* achieved, float* desired, float* reward, float* success, int* iters_out) {
   const DMHead* h = c.h;
+  constexpr int kAlign = ALIGN_LEVEL_FOR(NVP);
   if (active) {
     load_state(c, t, st);
     if (NVP >= 30 && mode == MODE_STEP && t.kind == TASK_HAND) {

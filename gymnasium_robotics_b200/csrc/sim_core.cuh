@@ -1564,10 +1564,13 @@ STAGE int newton_move(const Ctx c, float* improvement) {
 #ifndef B200_ALIGN_LEVEL
 #define B200_ALIGN_LEVEL 3
 #endif
-#define ALIGN_AT(level) do { if (B200_ALIGN_LEVEL >= (level)) ALIGN(); } while (0)
+// alignment density per kernel build: the hand build (NVP = 30, 14 warps per block) gains from the finest level
+#define ALIGN_LEVEL_FOR(NVP) ((NVP) >= 30 ? 4 : B200_ALIGN_LEVEL)
+#define ALIGN_AT(level) do { if (kAlign >= (level)) ALIGN(); } while (0)
 template <int NVP>
 HD void forward(const Ctx c, bool active) {
   constexpr bool HF = NVP >= 30;
+  constexpr int kAlign = ALIGN_LEVEL_FOR(NVP);
   ALIGN_AT(1);
   if (active) kinematics(c);
   ALIGN_AT(4);
@@ -1582,7 +1585,7 @@ HD void forward(const Ctx c, bool active) {
   if (active) newton_begin<HF>(c);
   int done = active ? 0 : 1;
   float improvement = 0;
-#if B200_ALIGN_LEVEL >= 3
+  if (kAlign >= 3) {
   for (int iter = 0;; iter++) {
     ALIGN();
     if (!done) done = newton_check<HF>(c, iter, improvement);
@@ -1593,7 +1596,7 @@ HD void forward(const Ctx c, bool active) {
     ALIGN();
     if (!done) done = newton_move<HF>(c, &improvement) ? 2 : 0;
   }
-#else
+  } else {
   ALIGN_AT(2);
   for (int iter = 0; !done; iter++) {
     done = newton_check<HF>(c, iter, improvement);
@@ -1602,7 +1605,7 @@ HD void forward(const Ctx c, bool active) {
     newton_direction<NVP>(c);
     done = newton_move<HF>(c, &improvement) ? 2 : 0;
   }
-#endif
+  }
 }
 
 // qpos <- qpos (+) dt * vel  (free-joint quaternions on the manifold)
