@@ -37,6 +37,9 @@ for _task in ("HandManipulateBlockRotateZ", "HandManipulateBlockRotateParallel",
                                                                   touch_get_obs="boolean")
         ENV_IDS[f"{_task}_ContinuousTouchSensors{_suffix}-v1"] = dict(hand_task=_task, reward_type=_rt, max_episode_steps=100,
                                                                      touch_get_obs="sensordata")
+# HandReach, new-binding version (__init__.py:90-95)
+for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
+    ENV_IDS[f"HandReach{_suffix}-v3"] = dict(hand_task="HandReach", reward_type=_rt, max_episode_steps=50)
 
 
 def make_vec(env_id: str, num_envs: int = 1, **kwargs):
@@ -50,9 +53,9 @@ def make_vec(env_id: str, num_envs: int = 1, **kwargs):
 
         return MazeVectorEnv(num_envs=num_envs, **spec)
     if "hand_task" in spec:
-        from .hand import HandVectorEnv
+        from .hand import make_hand_vec
 
-        return HandVectorEnv(task=spec.pop("hand_task"), num_envs=num_envs, **spec)
+        return make_hand_vec(spec.pop("hand_task"), num_envs=num_envs, **spec)
     from .fetch import FetchVectorEnv
 
     return FetchVectorEnv(num_envs=num_envs, **spec)

@@ -76,7 +76,7 @@ __global__ void reward_kernel(const float* __restrict__ ag, const float* __restr
   float d2 = 0;
   for (int k = 0; k < ngoal; k++) { float e = ag[ngoal * i + k] - dg[ngoal * i + k]; d2 += e * e; }
   float d = sqrtf(d2);
-  if (kind == TASK_FETCH) out[i] = dense ? -d : -(d > thr ? 1.f : 0.f);   // fetch_env.py:74-80
+  if (kind == TASK_FETCH || kind == TASK_HAND_REACH) out[i] = dense ? -d : -(d > thr ? 1.f : 0.f);   // fetch_env.py:74-80, reach.py:88-93
   else out[i] = dense ? expf(-d) : (d <= radius ? 1.f : 0.f);               // maze_v4.py:381-388
 }
 
@@ -142,13 +142,19 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   t.obs_qpos_start = task->obs_qpos_start; t.vel_clip = task->vel_clip;
   t.obj_qadr = task->obj_qadr; t.obj_dadr = task->obj_dadr; t.goal_flags = task->goal_flags; t.rotation_threshold = task->rotation_threshold;
   t.touch_mode = task->touch_mode;
+  for (int k = 0; k < 5; k++) t.tip_site[k] = task->tip_site[k];
   if (t.kind == TASK_FETCH) { t.nact = 4; t.ngoal = 3; }
-  if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE && t.kind != TASK_HAND) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
+  if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE && t.kind != TASK_HAND && t.kind != TASK_HAND_REACH) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
   if (t.kind == TASK_HAND && (t.nact != dh->nu || t.ngoal != 7 || t.obj_qadr != dh->nq - 7 || t.obj_dadr != dh->nv - 6 ||
                               t.touch_mode < 0 || t.touch_mode > 3 || (t.touch_mode && dh->nsensor == 0) ||
                               t.nobs != t.obj_qadr + dh->nv + 7 + (t.touch_mode ? dh->nsensor : 0))) { delete h; return fail(nullptr, "b200sim_create: inconsistent Hand task", -6); }
   if (t.kind == TASK_FETCH && dh->nmocap != 1) { delete h; return fail(nullptr, "b200sim_create: Fetch task needs exactly one mocap body", -6); }
   if (t.kind == TASK_ANTMAZE && (t.nact != dh->nu || t.ngoal != 2 || t.nobs != dh->nq - t.obs_qpos_start + dh->nv)) { delete h; return fail(nullptr, "b200sim_create: inconsistent AntMaze task", -6); }
+  if (t.kind == TASK_HAND_REACH) {
+    bool ok = t.nact == dh->nu && t.ngoal == 15 && t.nobs == dh->nq + dh->nv + 15;
+    for (int k = 0; k < 5; k++) ok = ok && t.tip_site[k] >= 0 && t.tip_site[k] < dh->nsite;
+    if (!ok) { delete h; return fail(nullptr, "b200sim_create: inconsistent HandReach task", -6); }
+  }
   int o = 0;
   t.st_qpos = o; o += dh->nq; t.st_qvel = o; o += dh->nv; t.st_warm = o; o += dh->nv; t.st_ctrl = o; o += dh->nu;
   t.st_mocap = o; o += 7 * dh->nmocap; t.st_pose = o; o += (t.kind == TASK_FETCH ? 7 : 0); t.st_goal = o; o += t.ngoal;
@@ -159,6 +165,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   h->wpb = (num_envs + nsm - 1) / nsm <= 7 ? 7 : ((num_envs + nsm - 1) / nsm <= 14 ? 14 : 28);
   h->nvp = dh->nv <= 14 ? 14 : (dh->nv == 15 ? 15 : (dh->nv <= 21 ? 21 : (dh->nv <= 30 ? 30 : 0)));  // smallest built size >= nv (identity padding)
   if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for nv > 30 yet", -8); }
+  if (t.kind == TASK_HAND || t.kind == TASK_HAND_REACH) h->nvp = 30;  // the hand task code is compiled into this build only
   if (dh->nv <= 21 && (dh->nten > 0 || dh->nfric > 0 || dh->nsensor > 0 || dh->any_round_pair)) h->nvp = 30;  // hand features live in the NVP = 30 build
   if (h->nvp == 30 && h->wpb > 14) h->wpb = 14;  // the large models' scratch does not fit 28 envs per block
   if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 14 || (w == 28 && h->nvp != 30)) h->wpb = w; }  // experiments

@@ -27,10 +27,11 @@ struct FetchTask {
   int obj_qadr, obj_dadr, goal_flags;
   float rotation_threshold;
   int touch_mode;       // 0 = no touch observation, 1 = sensordata, 2 = boolean, 3 = log(x + 1)
+  int tip_site[5];      // HandReach: fingertip sites "robot0:S_{ff,mf,rf,lf,th}tip"
   // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(ngoal)
   int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride;
 };
-enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2 };  // TASK_ANTMAZE covers both maze agents (Ant, Point)
+enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2, TASK_HAND_REACH = 3 };  // TASK_ANTMAZE covers both maze agents (Ant, Point)
 enum { GOAL_USE_POS = 1, GOAL_USE_ROT = 2 };
 
 enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
@@ -170,6 +171,30 @@ HD void hand_observe(const Ctx& c, const FetchTask& t, const float* goal, float*
   (void)h;
 }
 
+// HandReach: obs = robot qpos | robot qvel | 5 fingertip site positions (as of the last forward pass), which are also the
+// achieved goal; reward / success on the 15-dim distance (reference: envs/shadow_dexterous_hand/reach.py:88-130, 284-300)
+HD void reach_observe(const Ctx& c, const FetchTask& t, const float* goal, float* obs, float* achieved, float* desired,
+                      float* reward, float* success) {
+  const DMHead* h = c.h;
+  LANES(i, h->nq) obs[i] = SF(qpos)[i];
+  LANES(i, h->nv) obs[h->nq + i] = SF(qvel)[i];
+  float d2 = 0.f;
+  LANES(k, 5) {
+    float p[3];
+    site_pose(c, t.tip_site[k], p, nullptr);
+    for (int a = 0; a < 3; a++) {
+      obs[h->nq + h->nv + 3 * k + a] = p[a]; achieved[3 * k + a] = p[a]; desired[3 * k + a] = goal[3 * k + a];
+      float e = p[a] - goal[3 * k + a];
+      d2 += e * e;
+    }
+  }
+  float d = sqrtf(wsum(d2));
+  if (c.lane == 0) {
+    *reward = t.reward_dense ? -d : -(d > t.distance_threshold ? 1.f : 0.f);
+    *success = d < t.distance_threshold ? 1.f : 0.f;
+  }
+}
+
 // Touch sensors as of the last forward pass (public MuJoCo semantics, restated in oracle/oracle.c `sensors`): sum of the
 // normal forces of the contacts that involve the sensor's body and whose ray from the contact point along the contact
 // normal (flipped when the sensor's body is the second one) hits the site volume.  Appended to the observation by
@@ -228,7 +253,7 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   constexpr int kAlign = ALIGN_LEVEL_FOR(NVP);
   if (active) {
     load_state(c, t, st);
-    if (NVP >= 30 && mode == MODE_STEP && t.kind == TASK_HAND) {
+    if (NVP >= 30 && mode == MODE_STEP && (t.kind == TASK_HAND || t.kind == TASK_HAND_REACH)) {
       // MujocoHandEnv._set_action (hand_env.py:42-61, absolute control): ctrl = centre + clip(a) * half range, clipped
       LANES(i, h->nu) {
         float lo = MF(act_ctrlrange)[2 * i], hi = MF(act_ctrlrange)[2 * i + 1];
@@ -284,6 +309,9 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
       com_quantities(c);
     }
     fetch_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
+  } else if (NVP >= 30 && t.kind == TASK_HAND_REACH) {
+    if (nsub == 0) kinematics(c);   // refresh after a reset: site positions of the new state
+    reach_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   } else if (NVP >= 30 && t.kind == TASK_HAND) {
     hand_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
     if (t.touch_mode) touch_observe(c, t, obs + t.obj_qadr + h->nv + 7);

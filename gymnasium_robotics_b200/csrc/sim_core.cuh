@@ -1290,8 +1290,24 @@ STAGE void build_H(const Ctx c) {
     }
     SYNC();
   }
-  // dof rows (active ones)
-  if (c.lane == 0) {
+  if (HF) {
+    // dof rows (active ones): lane = dof; a row over (d1, d2) adds to the two diagonals and to the entry (max, min),
+    // which the lane of the larger dof owns
+    LANES(j, nv) {
+      float diag = 0.f;
+      for (int i = 0; i < ndr; i++) {
+        const float* dr = SF(dofrow) + i * DR_WORDS;
+        const int* di = (const int*)dr;
+        if (!(dr[DR_JAR] < 0)) continue;
+        int d1 = di[DR_DOF], d2 = di[DR_DOF2];
+        if (d1 == j) diag += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF];
+        if (d2 == j) diag += dr[DR_D] * dr[DR_COEF2] * dr[DR_COEF2];
+        if (d2 >= 0 && (d1 > d2 ? d1 : d2) == j) H[j * (j + 1) / 2 + (d1 > d2 ? d2 : d1)] += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF2];
+      }
+      H[j * (j + 1) / 2 + j] += diag;
+    }
+  } else if (c.lane == 0) {
+    // few limit rows (arm / legged models): one lane walks them
     for (int i = 0; i < ndr; i++) {
       const float* dr = SF(dofrow) + i * DR_WORDS;
       const int* di = (const int*)dr;

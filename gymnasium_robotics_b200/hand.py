@@ -264,5 +264,165 @@ class HandVectorEnv(FetchVectorEnv):
         self.backend.refresh(mask.to(torch.uint8), out)  # mj_forward + _get_obs for the reset envs
 
 
+
+
+# ---------------------------------------------------------------------------------------------------------------- HandReach
+FINGERTIP_SITE_NAMES = ["robot0:S_fftip", "robot0:S_mftip", "robot0:S_rftip", "robot0:S_lftip", "robot0:S_thtip"]  # reach.py:8-14
+# reach.py:15-40 DEFAULT_INITIAL_QPOS (joint order of the model)
+REACH_INITIAL_QPOS = {
+    "robot0:WRJ1": -0.16514339750464327, "robot0:WRJ0": -0.31973286565062153, "robot0:FFJ3": 0.14340512546557435,
+    "robot0:FFJ2": 0.32028208333591573, "robot0:FFJ1": 0.7126053607727917, "robot0:FFJ0": 0.6705281001412586,
+    "robot0:MFJ3": 0.000246444303701037, "robot0:MFJ2": 0.3152655251085491, "robot0:MFJ1": 0.7659800313729842,
+    "robot0:MFJ0": 0.7323156897425923, "robot0:RFJ3": 0.00038520700007378114, "robot0:RFJ2": 0.36743546201985233,
+    "robot0:RFJ1": 0.7119514095008576, "robot0:RFJ0": 0.6699446327514138, "robot0:LFJ4": 0.0525442258033891,
+    "robot0:LFJ3": -0.13615534724474673, "robot0:LFJ2": 0.39872030433433003, "robot0:LFJ1": 0.7415570009679252,
+    "robot0:LFJ0": 0.704096378652974, "robot0:THJ4": 0.003673823825070126, "robot0:THJ3": 0.5506291436028695,
+    "robot0:THJ2": -0.014515151997119306, "robot0:THJ1": -0.0015229223564485414, "robot0:THJ0": -0.7894883021600622,
+}
+
+
+def body_xpos(model, qpos, body_name):
+    """World position of a body frame for hinge/slide chains (host-side forward kinematics over the compiled tables;
+    the reference reads `data.xpos[body]` after `mj_forward`, reach.py:292-296)."""
+    m = model
+    b = m.names["body_map"][body_name]
+    chain = []
+    while b > 0:
+        chain.append(b)
+        b = int(m.body_parent[b])
+    pos, quat = np.zeros(3), np.array([1.0, 0.0, 0.0, 0.0])
+    bpos, bquat = np.asarray(m.body_pos).reshape(-1, 3), np.asarray(m.body_quat).reshape(-1, 4)
+    jpos, jaxis = np.asarray(m.jnt_pos).reshape(-1, 3), np.asarray(m.jnt_axis).reshape(-1, 3)
+    rot = lambda q, v: rotations.quat2mat(q) @ v
+    for b in reversed(chain):
+        pos = pos + rot(quat, bpos[b])
+        quat = rotations.quat_mul(quat, bquat[b])
+        for j in range(int(m.body_jntadr[b]), int(m.body_jntadr[b]) + int(m.body_jntnum[b])):
+            dq = qpos[int(m.jnt_qposadr[j])] - m.qpos0[int(m.jnt_qposadr[j])]
+            if int(m.jnt_type[j]) == 2:   # slide
+                pos = pos + rot(quat, jaxis[j]) * dq
+            else:                         # hinge about the joint anchor
+                anchor = pos + rot(quat, jpos[j])
+                quat = rotations.quat_mul(quat, rotations.quat_from_angle_and_axis(dq, jaxis[j].copy()))
+                pos = anchor - rot(quat, jpos[j])
+    return pos
+
+
+class HandReachVectorEnv(FetchVectorEnv):
+    """`gym.make_vec("HandReach-v3", num_envs=N)` replacement (envs/shadow_dexterous_hand/reach.py, MujocoHandReachEnv)."""
+
+    metadata = {"render_modes": [], "render_fps": 25, "autoreset_mode": "next_step"}
+
+    def __init__(self, num_envs: int = 1, reward_type: str = "sparse", max_episode_steps: Optional[int] = 50, device="cuda:0",
+                 rng_mode: str = "auto", autoreset_mode: str = "next_step", n_substeps: int = N_SUBSTEPS, backend_factory=None,
+                 distance_threshold=0.01, relative_control=False, initial_qpos=None, model=None, **kwargs):
+        if reward_type not in ("sparse", "dense"):
+            raise ValueError("reward_type must be 'sparse' or 'dense'")
+        if autoreset_mode not in ("next_step", "same_step", "disabled"):
+            raise ValueError("autoreset_mode must be next_step, same_step or disabled")
+        if kwargs.get("render_mode") is not None:
+            raise NotImplementedError("rendering is out of scope for the batched CUDA path")
+        if relative_control:
+            raise NotImplementedError("relative_control is not available in the reference's new-binding envs either")
+        self.task_name, self.reward_type, self.distance_threshold = "HandReach", reward_type, distance_threshold
+        self.num_envs, self.max_episode_steps, self.autoreset_mode = int(num_envs), max_episode_steps, autoreset_mode
+        self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
+        self.n_substeps = n_substeps
+        self.model = model if model is not None else load_model("hand_reach")
+        m = self.model
+        t = FetchTaskC()
+        t.kind, t.nact, t.ngoal = 3, int(m.nu), 15
+        t.n_substeps, t.reward_dense = int(n_substeps), int(reward_type == "dense")
+        t.nobs = int(m.nq) + int(m.nv) + 15
+        t.distance_threshold, t.dt = float(distance_threshold), float(m.opt[0] * n_substeps)
+        for k, name in enumerate(FINGERTIP_SITE_NAMES):
+            t.tip_site[k] = m.site_id(name)
+        self.task = t
+        factory = backend_factory or _HandBackend
+        self.backend = factory(m, np.zeros((0, 11)), t, self.num_envs, device)
+        self.device = self.backend.device
+        self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
+            if self.rng_mode == "numpy" else None
+        self._gen = torch.Generator(device=self.device)
+        self._gen.seed()
+        lay = self.backend.layout
+        self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", m.nq), ("qvel", m.nv), ("warm", m.nv), ("ctrl", m.nu), ("goal", 15))}
+        self.dt = float(m.opt[0] * n_substeps)
+        self.single_action_space = Box(-1.0, 1.0, shape=(int(m.nu),), dtype=np.float32)
+        self.single_observation_space = DictSpace(dict(
+            desired_goal=Box(-np.inf, np.inf, shape=(15,), dtype=np.float64),
+            achieved_goal=Box(-np.inf, np.inf, shape=(15,), dtype=np.float64),
+            observation=Box(-np.inf, np.inf, shape=(t.nobs,), dtype=np.float64)))
+        self.action_space = batch_space(self.single_action_space, self.num_envs)
+        self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        # _env_setup (reach.py:286-296): initial joint angles, mj_forward, initial fingertip positions and palm position
+        q0 = np.array(m.qpos0, dtype=np.float64)
+        for name, value in (initial_qpos or REACH_INITIAL_QPOS).items():
+            q0[int(m.jnt_qposadr[m.joint_id(name)])] = value
+        self.initial_qpos = torch.as_tensor(q0, dtype=torch.float32, device=self.device)
+        self.initial_qvel = torch.zeros(m.nv, dtype=torch.float32, device=self.device)
+        st = self.backend.state
+        st.zero_()
+        st[:, self._sl["qpos"]] = self.initial_qpos
+        out = self.backend.new_outputs()
+        self.backend.refresh(None, out)
+        self.initial_goal = out["achieved"][0].clone()
+        self.palm_xpos = body_xpos(m, q0, "robot0:palm")
+        self._last = out
+        self.closed = False
+
+    def _sample_goals(self, idx):
+        """reach.py:95-121."""
+        n = idx.numel()
+        init = self.initial_goal.double().cpu().numpy().reshape(5, 3)
+        if self.rng_mode == "numpy":
+            goals = np.zeros((n, 15))
+            finger_names = [name for name in FINGERTIP_SITE_NAMES if name != "robot0:S_thtip"]
+            for k, i in enumerate(idx.tolist()):
+                rng = self._np_rngs[i]
+                finger_idx = FINGERTIP_SITE_NAMES.index(rng.choice(finger_names))
+                meeting = self.palm_xpos + np.array([0.0, -0.09, 0.05])
+                meeting = meeting + rng.normal(scale=0.005, size=3)
+                goal = init.copy()
+                for j in (4, finger_idx):
+                    d = meeting - goal[j]
+                    goal[j] = meeting - 0.005 * d / np.linalg.norm(d)
+                if rng.uniform() < 0.1:
+                    goal = init.copy()
+                goals[k] = goal.flatten()
+            return torch.as_tensor(goals, dtype=torch.float32, device=self.device)
+        dev = self.device
+        init_t = self.initial_goal.reshape(5, 3)
+        finger = torch.randint(0, 4, (n,), generator=self._gen, device=dev)
+        meeting = torch.as_tensor(self.palm_xpos + np.array([0.0, -0.09, 0.05]), dtype=torch.float32, device=dev) \
+            + 0.005 * torch.randn(n, 3, generator=self._gen, device=dev)
+        goal = init_t.expand(n, 5, 3).clone()
+        ar = torch.arange(n, device=dev)
+        for sel in (torch.full((n,), 4, device=dev, dtype=torch.long), finger):
+            d = meeting - goal[ar, sel]
+            goal[ar, sel] = meeting - 0.005 * d / torch.linalg.norm(d, dim=1, keepdim=True)
+        keep = torch.rand(n, generator=self._gen, device=dev) < 0.1
+        goal[keep] = init_t
+        return goal.reshape(n, 15)
+
+    def _reset_envs(self, mask, out):
+        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        if idx.numel() == 0:
+            return
+        st, sl = self.backend.state, self._sl
+        rec = torch.zeros((idx.numel(), st.shape[1]), dtype=torch.float32, device=self.device)  # mj_resetData (robot_env.py:305-316)
+        rec[:, sl["qpos"]] = self.initial_qpos
+        rec[:, sl["qvel"]] = self.initial_qvel
+        rec[:, sl["goal"]] = self._sample_goals(idx)
+        st[idx] = rec
+        self._elapsed[idx] = 0
+        self.backend.refresh(mask.to(torch.uint8), out)  # mj_forward + _get_obs
+
+
 def make_hand_vec(task, **kwargs):
+    if task == "HandReach":
+        return HandReachVectorEnv(**kwargs)
     return HandVectorEnv(task=task, **kwargs)

@@ -43,6 +43,9 @@ typedef struct b200sim_fetch_task {
   /* touch observation appended after the 61 base entries (manipulate_touch_sensors.py:107-138): 0 = none,
    * 1 = sensordata, 2 = boolean, 3 = log(x + 1); one value per touch sensor of the model */
   int touch_mode;
+  /* kind 3 = HandReach (envs/shadow_dexterous_hand/reach.py): same control as kind 2, obs = robot qpos | robot qvel |
+   * 5 fingertip site positions = achieved goal (ngoal = 15), Fetch-style distance reward with distance_threshold */
+  int tip_site[5];
 } b200sim_fetch_task_t;
 
 /* indices into the layout array returned by b200sim_layout (offsets in floats inside one env's state record) */

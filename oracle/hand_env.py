@@ -174,3 +174,87 @@ class OracleHandBlockEnv:
             did = self._reset_sim()
         self.goal = self._sample_goal().copy()
         return self._get_obs(), {}
+
+
+# ---------------------------------------------------------------------------------------------------------------- HandReach
+class OracleHandReachEnv:
+    """envs/shadow_dexterous_hand/reach.py (MujocoHandReachEnv) + hand_env.py + robot_env.py, on the oracle simulator."""
+
+    def __init__(self, reward_type="sparse", model=None, distance_threshold=0.01, n_substeps=20, initial_qpos=None):
+        from gymnasium_robotics_b200.hand import FINGERTIP_SITE_NAMES, REACH_INITIAL_QPOS
+
+        self.site_names = FINGERTIP_SITE_NAMES
+        self.distance_threshold, self.reward_type, self.n_substeps = distance_threshold, reward_type, n_substeps
+        self.model = model if model is not None else compile_mjcf(
+            "/root/reference/gymnasium_robotics/envs/assets/hand/reach.xml", overrides={"sensor_prefix": "robot0:TS_"})
+        self.sim = OracleSim(self.model)
+        m, s = self.model, self.sim
+        self._tips = [m.site_id(n) for n in self.site_names]
+        self._robot_joints = [j for j, n in enumerate(m.names["joint"]) if n.startswith("robot")]
+        self.goal = np.zeros(0)
+        self.np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(None)))
+        # _env_setup, reach.py:286-296
+        for name, value in (initial_qpos or REACH_INITIAL_QPOS).items():
+            s.qpos[m.jnt_qposadr[m.joint_id(name)]] = value
+        s.forward()
+        self.initial_goal = self._get_achieved_goal().copy()
+        self.palm_xpos = s.xpos[m.names["body_map"]["robot0:palm"]].copy()
+        self.initial_time = float(s.time[0])
+        self.initial_qpos, self.initial_qvel = s.qpos.copy(), s.qvel.copy()
+
+    def _get_achieved_goal(self):  # reach.py:278-283
+        return np.array([self.sim.site_xpos[i] for i in self._tips]).flatten()
+
+    def compute_reward(self, achieved_goal, goal, info):  # reach.py:88-93
+        d = np.linalg.norm(np.asarray(achieved_goal) - np.asarray(goal), axis=-1)
+        return -(d > self.distance_threshold).astype(np.float32) if self.reward_type == "sparse" else -d
+
+    def _is_success(self, achieved_goal, desired_goal):  # reach.py:123-125
+        d = np.linalg.norm(np.asarray(achieved_goal) - np.asarray(desired_goal), axis=-1)
+        return (d < self.distance_threshold).astype(np.float32)
+
+    _set_action = OracleHandBlockEnv._set_action
+
+    def _get_obs(self):  # reach.py:298-310
+        m, s = self.model, self.sim
+        robot_qpos = np.array([s.qpos[m.jnt_qposadr[j]] for j in self._robot_joints])
+        robot_qvel = np.array([s.qvel[m.jnt_dofadr[j]] for j in self._robot_joints])
+        achieved = self._get_achieved_goal()
+        return {"observation": np.concatenate([robot_qpos, robot_qvel, achieved]), "achieved_goal": achieved.copy(),
+                "desired_goal": self.goal.copy()}
+
+    def _sample_goal(self):  # reach.py:95-121
+        rng = self.np_random
+        finger_names = [n for n in self.site_names if n != "robot0:S_thtip"]
+        finger_name = rng.choice(finger_names)
+        thumb_idx, finger_idx = self.site_names.index("robot0:S_thtip"), self.site_names.index(finger_name)
+        meeting_pos = self.palm_xpos + np.array([0.0, -0.09, 0.05])
+        meeting_pos = meeting_pos + rng.normal(scale=0.005, size=meeting_pos.shape)
+        goal = self.initial_goal.copy().reshape(-1, 3)
+        for idx in (thumb_idx, finger_idx):
+            offset_direction = meeting_pos - goal[idx]
+            offset_direction /= np.linalg.norm(offset_direction)
+            goal[idx] = meeting_pos - 0.005 * offset_direction
+        if rng.uniform() < 0.1:
+            goal = self.initial_goal.copy()
+        return goal.flatten()
+
+    def step(self, action):  # robot_env.py:114-152
+        action = np.clip(np.asarray(action, dtype=np.float64), -1.0, 1.0)
+        self._set_action(action)
+        self.sim.step(self.n_substeps)
+        obs = self._get_obs()
+        info = {"is_success": self._is_success(obs["achieved_goal"], self.goal)}
+        return obs, self.compute_reward(obs["achieved_goal"], self.goal, info), False, False, info
+
+    def reset(self, seed=None):  # robot_env.py:154-186, 305-316
+        if seed is not None:
+            self.np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        s = self.sim
+        s.reset_data()
+        s.time[0] = self.initial_time
+        s.qpos[:] = self.initial_qpos
+        s.qvel[:] = self.initial_qvel
+        s.forward()
+        self.goal = self._sample_goal().copy()
+        return self._get_obs(), {}

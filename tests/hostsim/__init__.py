@@ -20,7 +20,7 @@ class FetchTaskC(ctypes.Structure):
                 ("kind", ctypes.c_int), ("nact", ctypes.c_int), ("ngoal", ctypes.c_int), ("success_radius", ctypes.c_float),
                 ("obs_qpos_start", ctypes.c_int), ("vel_clip", ctypes.c_float),
                 ("obj_qadr", ctypes.c_int), ("obj_dadr", ctypes.c_int), ("goal_flags", ctypes.c_int),
-                ("rotation_threshold", ctypes.c_float), ("touch_mode", ctypes.c_int)] + \
+                ("rotation_threshold", ctypes.c_float), ("touch_mode", ctypes.c_int), ("tip_site", ctypes.c_int * 5)] + \
                [(n, ctypes.c_int) for n in ("st_qpos", "st_qvel", "st_warm", "st_ctrl", "st_mocap", "st_pose", "st_goal",
                                              "st_stride")]
 

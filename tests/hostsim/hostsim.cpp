@@ -53,3 +53,4 @@ int hostsim_env_step(void* p, const FetchTask* t, int mode, int nraw, float* st,
 }
 }
 extern "C" int hostsim_model_words(void* p) { return ((HostSim*)p)->ctx.h->nwords; }
+extern "C" int hostsim_hot_words(void* p) { return ((HostSim*)p)->ctx.h->hot_words; }

@@ -414,3 +414,44 @@ def test_hand_touch_sensors_parity():
     print(f"Hand touch: {agree}/{total} env-steps with all 92 sensors within 5 % of the force scale")
     assert agree >= 0.8 * total
     env.close()
+
+
+def test_hand_reach_parity():
+    """HandReach-v3 on the GPU: same goals as the oracle for the same seeds, env-steps from injected states within 2e-4 on
+    the fingertip positions (achieved goal), rewards / success exact."""
+    import gymnasium_robotics_b200 as pkg
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.hand_env import OracleHandReachEnv
+
+    n = 4
+    model = load_model("hand_reach")
+    env = pkg.make_vec("HandReach-v3", num_envs=n, device="cuda:0", rng_mode="numpy")
+    obs, _ = env.reset(seed=70)
+    oracles = [OracleHandReachEnv(model=model) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=70 + i)
+        assert np.abs(obs["desired_goal"][i].double().cpu().numpy() - oo["desired_goal"]).max() < 2e-6
+        assert np.abs(obs["observation"][i].double().cpu().numpy() - oo["observation"]).max() < 2e-6
+    lay, m = env.backend.layout, model
+    rng = np.random.default_rng(7)
+    errs = []
+    for step in range(8):
+        rec = np.zeros((n, lay["stride"]))
+        for i, o in enumerate(oracles):
+            s = o.sim
+            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+            rec[i, lay["goal"]:lay["goal"] + 15] = o.goal
+        env.set_state(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            errs.append(np.abs(o["achieved_goal"][i].double().cpu().numpy() - oo["achieved_goal"]).max())
+            assert float(r[i]) == float(orr) and float(info["is_success"][i]) == float(oi["is_success"])
+    errs = np.array(errs)
+    print(f"HandReach: median {np.median(errs):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < 2e-5 and errs.max() < 2e-4
+    env.close()

@@ -133,3 +133,34 @@ def test_touch_sensor_observation_tracks_oracle():
     oobs, *_ = orc.step(a)
     t, ot = obs["observation"][0, 61:].double().numpy(), oobs["observation"][61:]
     np.testing.assert_allclose(t, ot, atol=0.05 * max(1.0, ot.max()))
+
+
+def test_hand_reach_matches_oracle():
+    """HandReach-v3: construction (initial fingertip goal, palm position by host FK), goal sampling with the reference's
+    draw order, and env-steps from identical state."""
+    from gymnasium_robotics_b200.hand import HandReachVectorEnv
+    from oracle.hand_env import OracleHandReachEnv
+
+    model = load_model("hand_reach")
+    env = pkg.make_vec("HandReach-v3", num_envs=2, backend_factory=HandHostBackend, rng_mode="numpy")
+    assert isinstance(env, HandReachVectorEnv) and env.max_episode_steps == 50
+    assert env.single_observation_space["observation"].shape == (63,) and env.single_action_space.shape == (20,)
+    orc = OracleHandReachEnv(model=model)
+    np.testing.assert_allclose(env.palm_xpos, orc.palm_xpos, atol=1e-12)
+    np.testing.assert_allclose(env.initial_goal.double().numpy(), orc.initial_goal, atol=2e-6)
+    for seed in (0, 1, 2, 3):   # covers both branches of the 10 % "keep the initial pose" draw over the seeds
+        obs, _ = env.reset(seed=seed)
+        oobs, _ = orc.reset(seed=seed)
+        np.testing.assert_allclose(obs["desired_goal"][0].double().numpy(), oobs["desired_goal"], atol=2e-6)
+        np.testing.assert_allclose(obs["observation"][0].double().numpy(), oobs["observation"], atol=2e-6)
+    rng = np.random.default_rng(0)
+    for k in range(4):
+        a = rng.uniform(-1, 1, size=(2, 20)).astype(np.float32)
+        a[1] = a[0]
+        obs, rew, term, trunc, info = env.step(a)
+        oobs, orew, _, _, oinfo = orc.step(a[0].astype(np.float64))
+        np.testing.assert_allclose(obs["observation"][0].double().numpy(), oobs["observation"], atol=2e-3)
+        np.testing.assert_allclose(obs["achieved_goal"][0].double().numpy(), oobs["achieved_goal"], atol=2e-4)
+        assert float(rew[0]) == float(orew) and float(info["is_success"][0]) == float(oinfo["is_success"])
+    r = env.compute_reward(obs["achieved_goal"], obs["desired_goal"], {})
+    assert torch.equal(r, rew)
