@@ -16,6 +16,16 @@
 // that every SM still gets work (e.g. the 1024-env shards of BASELINE config 4)
 #define B200_WPB_MAX 28
 
+#ifdef B200_STAGE_TIMING
+__device__ unsigned long long g_stage_cycles[TM_COUNT];
+extern "C" int b200sim_debug_stage_cycles(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_stage_cycles, sizeof(unsigned long long) * TM_COUNT);
+  if (reset) { unsigned long long z[TM_COUNT] = {0}; cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z)); }
+  return TM_COUNT;
+}
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int WPB, int NVP>
@@ -55,12 +65,26 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
   const int env = blockIdx.x * WPB + warp;
   const bool active = env < N && !(mask && !mask[env]);  // warp-uniform
   Ctx c;
+#ifdef B200_STAGE_TIMING
+  long long tim[TM_COUNT];
+  for (int k = 0; k < TM_COUNT; k++) tim[k] = 0;
+  c.tim = tim;
+  const long long t_begin = clock64();
+#endif
   c.mg = model_g; c.mw = smem; c.h = h; c.lane = lane;
   c.s = (float*)(smem + model_words) + (size_t)warp * h->scr_words;
   const size_t e = active ? (size_t)env : 0;
   const float* act = actions ? actions + e * task.nact : nullptr;  // only dereferenced in MODE_STEP by active warps
   fetch_env_step<NVP>(c, task, active, mode, nraw, state + e * task.st_stride, act, obs + e * task.nobs, achieved + e * task.ngoal,
                       desired + e * task.ngoal, reward + e, success + e, info ? info + e : nullptr);
+#ifdef B200_STAGE_TIMING
+  if (lane == 0 && active) {
+    long long sum = 0;
+    for (int k = 0; k < TM_COUNT; k++) if (k != TM_OTHER) sum += tim[k];
+    tim[TM_OTHER] = clock64() - t_begin - sum;
+    for (int k = 0; k < TM_COUNT; k++) atomicAdd(&g_stage_cycles[k], (unsigned long long)tim[k]);
+  }
+#endif
 }
 
 __global__ void reward_kernel(const float* __restrict__ ag, const float* __restrict__ dg, int M, int ngoal, int kind, float thr,

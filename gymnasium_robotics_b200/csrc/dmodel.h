@@ -83,6 +83,7 @@ struct DMHead {
   int hot_words;   // leading part staged into shared memory (header + HOT arrays)
   int scr_words;   // per-env scratch size in words
   int iterations, ls_iterations, integrator, any_damping, kin_iters, ncon_max, ngrp_max, ndr_max;
+  int edges_per_con, pad5, pad6, pad7;   // pyramid edges of the widest contact (2 * (condim - 1)): line-search edge slots
   int nten, nfric, ncand_max, nsensor;   // nsensor: touch sensors (site volume + body)   // limited fixed tendons; nfric = nv when any dof has frictionloss, else 0
   int grid_len, grid_wid, ngridw, any_round_pair;   // maze wall grid (0 x 0 when the model has none)
   float grid_scale, grid_top, grid_xc, grid_yc;  // cell size, wall top height, map centre offsets
@@ -120,6 +121,11 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     }
   }
   h.npair = (int)psrc.size();
+  h.edges_per_con = 1;
+  for (size_t p = 0; p < psrc.size(); p++) {
+    int cd = m.pair_condim[psrc[p]], ne = cd == 1 ? 1 : 2 * (cd - 1);
+    if (ne > h.edges_per_con) h.edges_per_con = ne;
+  }
   std::vector<int> gmap(m.ngeom, -1), gsrc;
   for (size_t p = 0; p < psrc.size(); p++) {
     int ga = m.pair_geom1[psrc[p]], gb = m.pair_geom2[psrc[p]];
@@ -189,6 +195,9 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   {
     int nM = nv * (nv + 1) / 2, u = so;
     int d6off = 16 * nb > nM ? 16 * nb : nM;
+    // the line-search edge list (x0, v, D per edge slot) overlays H and d6 after the direction solve
+    int need = 3 * (h.edges_per_con * ncon_max + 6 * DM_NWELD_MAX + ndr_max) - 6 * nv;
+    if (need > d6off) d6off = need;
     d6off = (d6off + 1) & ~1;
     h.s_kinA = u; h.s_kinB = u + 8 * nb;
     h.s_cinert = u; h.s_b6 = u + 10 * nb; h.s_d6 = u + d6off;
@@ -301,6 +310,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     bool ok = (t1 == B200_GEOM_PLANE && (t2 == B200_GEOM_BOX || r2)) || (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) ||
               (r1 && t2 == B200_GEOM_BOX) || (r1 && r2);
     if (r1 && r2) h.any_round_pair = 1;
+
     if (!ok) { err = "collision pair type not supported by the CUDA path yet"; return -1; }
     if (m.pair_condim[sp] != 1 && m.pair_condim[sp] != 3 && m.pair_condim[sp] != 4) { err = "condim must be 1, 3 or 4 on the CUDA path"; return -1; }
     F(h.o_pair_friction, 3 * p + 0, m.pair_friction[5 * sp + 0]); F(h.o_pair_friction, 3 * p + 1, m.pair_friction[5 * sp + 2]);
@@ -309,6 +319,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     for (int k = 0; k < 2; k++) { F(h.o_pair_solref, 2 * p + k, m.pair_solref[2 * sp + k]); F(h.o_pair_invweight, 2 * p + k, m.pair_invweight[2 * sp + k]); }
     for (int k = 0; k < 5; k++) F(h.o_pair_solimp, 5 * p + k, m.pair_solimp[5 * sp + k]);
   }
+  if (3 * (h.edges_per_con * ncon_max + 6 * DM_NWELD_MAX + ndr_max) > h.s_grad - h.s_H) { err = "line-search edge list does not fit the solver scratch"; return -1; }
   for (int k = 0; k < nsensor; k++) {
     I(h.o_sensor_site, k, m.sensor_site[k]); I(h.o_sensor_body, k, m.sensor_body[k]); I(h.o_sensor_type, k, m.sensor_type[k]);
     for (int a = 0; a < 3; a++) F(h.o_sensor_size, 3 * k + a, m.sensor_size[3 * k + a]);

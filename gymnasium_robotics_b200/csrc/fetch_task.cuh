@@ -287,9 +287,11 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   int nsub = mode == MODE_STEP ? t.n_substeps : (mode == MODE_RAW ? nraw : 0);
   for (int s = 0; s < nsub; s++) {
     forward<NVP>(c, active);
-    ALIGN_AT(4);
+    TIC();
+    ALIGN_AT(4); TOC(TM_BARRIER);
     if (h->integrator == B200_INT_RK4) rk4_substep<NVP>(c, active);
     else if (active) euler_step<NVP>(c);
+    TOC(TM_INTEG);
   }
   // touch sensors read the contacts and forces of the last forward pass: a refresh (no sub-step) runs one first,
   // block-uniformly (forward() contains the block-wide alignment barriers); the warm start is left untouched

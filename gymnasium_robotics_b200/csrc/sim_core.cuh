@@ -52,7 +52,18 @@ struct Ctx {
   const DMHead* h;
   float* s;            // this env's scratch (shared memory)
   int lane;
+#ifdef B200_STAGE_TIMING
+  long long* tim;      // experiments only: per-thread cycle counters per stage
+#endif
 };
+#ifdef B200_STAGE_TIMING
+enum { TM_KIN = 0, TM_COM_M, TM_COLL, TM_CONSTR, TM_SMOOTH, TM_NBEGIN, TM_NCHECK, TM_BUILDH, TM_NDIR, TM_NMOVE, TM_INTEG, TM_BARRIER, TM_OTHER, TM_COUNT };
+#define TIC() long long t0_ = clock64()
+#define TOC(k) do { long long t1_ = clock64(); c.tim[k] += t1_ - t0_; t0_ = t1_; } while (0)
+#else
+#define TIC() do { } while (0)
+#define TOC(k) do { } while (0)
+#endif
 #define MI(name) ((const int*)(c.mw + c.h->o_##name))
 #define MU(name) ((const uint32_t*)(c.mw + c.h->o_##name))
 #define MF(name) ((const float*)(c.mw + c.h->o_##name))
@@ -1143,6 +1154,14 @@ STAGE void pass_F(const Ctx c, float* out) {
   const DMHead* h = c.h;
   const int* cnt = SI(counters);
   int ngrp = cnt[CNT_NGRP], nweld = cnt[CNT_NWELD], ndr = cnt[CNT_NDR];
+  // base-row forces once per contact (parked in the JV slots, which are rewritten by the next J * search product)
+  LANES(i, cnt[CNT_NCON]) {
+    float* cr = SF(con) + i * CON_WORDS;
+    float F[4];
+    contact_base_forces(cr, con_dim(cr), F);
+    cr[C_JV] = F[0]; cr[C_JV + 1] = F[1]; cr[C_JV + 2] = F[2]; cr[C_JV + 3] = F[3];
+  }
+  SYNC();
   LANES(idx, ngrp * 6) {
     int g = idx / 6, a = idx - 6 * g;
     float* gr = SF(group) + g * GRP_WORDS;
@@ -1151,8 +1170,7 @@ STAGE void pass_F(const Ctx c, float* out) {
     for (int i = gi[G_START]; i < gi[G_START] + gi[G_COUNT]; i++) {
       const float* cr = SF(con) + i * CON_WORDS;
       int dim = con_dim(cr);
-      float F[4];
-      contact_base_forces(cr, dim, F);
+      const float* F = cr + C_JV;
       acc += F[0] * cr[C_W + a];
       if (dim > 1) acc += F[1] * cr[C_W + 6 + a] + F[2] * cr[C_W + 12 + a];
       if (dim > 3 && a < 3) acc += F[3] * cr[C_W + 3 + a];
@@ -1430,34 +1448,55 @@ static inline void spd_solve(const Ctx& c, const float* A, const float* dadd, fl
 }
 #endif
 
-// line-search evaluation: cost(alpha) - gauss constant, first and second derivative
+// Line search over a flat edge list.  ls_edges() expands every constraint row into (x0, v, D) triples once per Newton
+// move -- pyramid edges of a contact are x = u_n +- mu u_k -- into the scratch that H and d6 occupied before the direction
+// solve; ls_eval() then walks the triples with all 32 lanes.  D < 0 marks a two-sided (equality) row, D == 0 an empty slot.
 template <bool HF>
-STAGE void ls_eval(const Ctx c, float alpha, float g1, float g2, float* out) {
+STAGE int ls_edges(const Ctx c) {
   ASSUME_SHARED(c);
+  const DMHead* h = c.h;
   const int* cnt = SI(counters);
-  float cost = 0, d1 = 0, d2 = 0;
-  LANES(i, cnt[CNT_NCON]) {
+  const int epc = h->edges_per_con, ncon = cnt[CNT_NCON], nweld6 = cnt[CNT_NWELD] * 6, ndr = cnt[CNT_NDR];
+  float* E = SF(H);
+  LANES(i, ncon) {
     const float* cr = SF(con) + i * CON_WORDS;
+    float* e = E + 3 * epc * i;
     int dim = con_dim(cr);
-    float D = cr[C_D], un = cr[C_U] + alpha * cr[C_JV], vn = cr[C_JV];
-    if (dim == 1) { if (un < 0) { cost += 0.5f * D * un * un; d1 += D * un * vn; d2 += D * vn * vn; } continue; }
-    for (int k = 1; k < dim; k++) {
-      float mu = con_mu(cr, k), uk = cr[C_U + k] + alpha * cr[C_JV + k], vk = cr[C_JV + k];
-      float xp = un + mu * uk, vp = vn + mu * vk, xm = un - mu * uk, vm = vn - mu * vk;
-      if (xp < 0) { cost += 0.5f * D * xp * xp; d1 += D * xp * vp; d2 += D * vp * vp; }
-      if (xm < 0) { cost += 0.5f * D * xm * xm; d1 += D * xm * vm; d2 += D * vm * vm; }
+    float D = cr[C_D], un = cr[C_U], vn = cr[C_JV];
+    int ne = 0;
+    if (dim == 1) { e[0] = un; e[1] = vn; e[2] = D; ne = 1; }
+    else for (int k = 1; k < dim; k++) {
+      float mu = con_mu(cr, k), uk = mu * cr[C_U + k], vk = mu * cr[C_JV + k];
+      e[3 * ne] = un + uk; e[3 * ne + 1] = vn + vk; e[3 * ne + 2] = D; ne++;
+      e[3 * ne] = un - uk; e[3 * ne + 1] = vn - vk; e[3 * ne + 2] = D; ne++;
     }
+    for (; ne < epc; ne++) e[3 * ne + 2] = 0.f;
   }
-  LANES(i, cnt[CNT_NWELD] * 6) {
+  float* W = E + 3 * epc * ncon;
+  LANES(i, nweld6) {
     const float* wr = SF(weld) + (i / 6) * WELD_WORDS;
     int k = i % 6;
-    float D = wr[W_D + k], v = wr[W_JV + k], x = wr[W_JAR + k] + alpha * v;
-    cost += 0.5f * D * x * x; d1 += D * x * v; d2 += D * v * v;
+    W[3 * i] = wr[W_JAR + k]; W[3 * i + 1] = wr[W_JV + k]; W[3 * i + 2] = -wr[W_D + k];
   }
-  LANES(i, cnt[CNT_NDR]) {
+  float* R = W + 3 * nweld6;
+  LANES(i, ndr) {
     const float* dr = SF(dofrow) + i * DR_WORDS;
-    float D = dr[DR_D], v = dr[DR_JV], x = dr[DR_JAR] + alpha * v;
-    if (x < 0) { cost += 0.5f * D * x * x; d1 += D * x * v; d2 += D * v * v; }
+    R[3 * i] = dr[DR_JAR]; R[3 * i + 1] = dr[DR_JV]; R[3 * i + 2] = dr[DR_D];
+  }
+  SYNC();
+  return epc * ncon + nweld6 + ndr;
+}
+
+// cost(alpha) - gauss constant, first and second derivative
+template <bool HF>
+STAGE void ls_eval(const Ctx c, int nedge, float alpha, float g1, float g2, float* out) {
+  ASSUME_SHARED(c);
+  float cost = 0, d1 = 0, d2 = 0;
+  const float* E = SF(H);
+  LANES(i, nedge) {
+    float x0 = E[3 * i], v = E[3 * i + 1], D = E[3 * i + 2];
+    float x = fmaf(alpha, v, x0), Da = fabsf(D);
+    if (D < 0 || (x < 0 && D > 0)) { float dx = Da * x; cost = fmaf(0.5f * dx, x, cost); d1 = fmaf(dx, v, d1); d2 = fmaf(Da * v, v, d2); }
   }
   if (HF) LANES(d, c.h->nfric) {
     float D = MF(dof_fricD)[d];
@@ -1478,13 +1517,14 @@ template <bool HF>
 STAGE float linesearch(const Ctx c, float g1, float g2, float gtol, int maxit, float* improve) {
   ASSUME_SHARED(c);
   float p0[3], p[3];
-  ls_eval<HF>(c, 0.f, g1, g2, p0);
+  const int nedge = ls_edges<HF>(c);
+  ls_eval<HF>(c, nedge, 0.f, g1, g2, p0);
   *improve = 0;
   if (p0[1] >= 0 || p0[2] <= 0) return 0.f;
   gtol = fmaxf(gtol, 1e-5f * fabsf(p0[1]));  // single-precision floor on the derivative test
   float lo = 0, hi = -1, alpha = -p0[1] / p0[2], best = 0, bestcost = p0[0];
   for (int it = 0; it < maxit; it++) {
-    ls_eval<HF>(c, alpha, g1, g2, p);
+    ls_eval<HF>(c, nedge, alpha, g1, g2, p);
     if (p[0] <= bestcost) { bestcost = p[0]; best = alpha; }
     if (fabsf(p[1]) < gtol) break;
     if (p[1] < 0) lo = alpha; else hi = alpha;
@@ -1587,40 +1627,46 @@ template <int NVP>
 HD void forward(const Ctx c, bool active) {
   constexpr bool HF = NVP >= 30;
   constexpr int kAlign = ALIGN_LEVEL_FOR(NVP);
-  ALIGN_AT(1);
+  TIC();
+  ALIGN_AT(1); TOC(TM_BARRIER);
   if (active) kinematics(c);
-  ALIGN_AT(4);
+  TOC(TM_KIN); ALIGN_AT(4); TOC(TM_BARRIER);
   if (active) { com_quantities(c); mass_matrix(c); }
-  ALIGN_AT(2);
+  TOC(TM_COM_M); ALIGN_AT(2); TOC(TM_BARRIER);
   if (active) collision<HF>(c);
-  ALIGN_AT(2);
+  TOC(TM_COLL); ALIGN_AT(2); TOC(TM_BARRIER);
   if (active) make_constraint<HF>(c);
-  ALIGN_AT(4);
+  TOC(TM_CONSTR); ALIGN_AT(4); TOC(TM_BARRIER);
   if (active) smooth_forces(c);
-  ALIGN_AT(4);
+  TOC(TM_SMOOTH); ALIGN_AT(4); TOC(TM_BARRIER);
   if (active) newton_begin<HF>(c);
+  TOC(TM_NBEGIN);
   int done = active ? 0 : 1;
   float improvement = 0;
   if (kAlign >= 3) {
-  for (int iter = 0;; iter++) {
-    ALIGN();
-    if (!done) done = newton_check<HF>(c, iter, improvement);
-    if (!ALIGN_OR(!done)) break;
-    if (!done) build_H<HF>(c);
-    ALIGN_AT(4);
-    if (!done) newton_direction<NVP>(c);
-    ALIGN();
-    if (!done) done = newton_move<HF>(c, &improvement) ? 2 : 0;
-  }
+    for (int iter = 0;; iter++) {
+      ALIGN(); TOC(TM_BARRIER);
+      if (!done) done = newton_check<HF>(c, iter, improvement);
+      TOC(TM_NCHECK);
+      bool more = ALIGN_OR(!done);
+      TOC(TM_BARRIER);
+      if (!more) break;
+      if (!done) build_H<HF>(c);
+      TOC(TM_BUILDH); ALIGN_AT(4); TOC(TM_BARRIER);
+      if (!done) newton_direction<NVP>(c);
+      TOC(TM_NDIR); ALIGN(); TOC(TM_BARRIER);
+      if (!done) done = newton_move<HF>(c, &improvement) ? 2 : 0;
+      TOC(TM_NMOVE);
+    }
   } else {
-  ALIGN_AT(2);
-  for (int iter = 0; !done; iter++) {
-    done = newton_check<HF>(c, iter, improvement);
-    if (done) break;
-    build_H<HF>(c);
-    newton_direction<NVP>(c);
-    done = newton_move<HF>(c, &improvement) ? 2 : 0;
-  }
+    ALIGN_AT(2);
+    for (int iter = 0; !done; iter++) {
+      done = newton_check<HF>(c, iter, improvement);
+      if (done) break;
+      build_H<HF>(c);
+      newton_direction<NVP>(c);
+      done = newton_move<HF>(c, &improvement) ? 2 : 0;
+    }
   }
 }
 
