@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
 #ifdef B200_STAGE_TIMING
   if (lane == 0 && active) {
     long long sum = 0;
-    for (int k = 0; k < TM_COUNT; k++) if (k != TM_OTHER) sum += tim[k];
+    for (int k = 0; k < TM_OTHER; k++) sum += tim[k];
     tim[TM_OTHER] = clock64() - t_begin - sum;
     for (int k = 0; k < TM_COUNT; k++) atomicAdd(&g_stage_cycles[k], (unsigned long long)tim[k]);
   }

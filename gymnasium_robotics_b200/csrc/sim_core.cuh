@@ -57,7 +57,7 @@ struct Ctx {
 #endif
 };
 #ifdef B200_STAGE_TIMING
-enum { TM_KIN = 0, TM_COM_M, TM_COLL, TM_CONSTR, TM_SMOOTH, TM_NBEGIN, TM_NCHECK, TM_BUILDH, TM_NDIR, TM_NMOVE, TM_INTEG, TM_BARRIER, TM_OTHER, TM_COUNT };
+enum { TM_KIN = 0, TM_COM_M, TM_COLL, TM_CONSTR, TM_SMOOTH, TM_NBEGIN, TM_NCHECK, TM_BUILDH, TM_NDIR, TM_NMOVE, TM_INTEG, TM_BARRIER, TM_OTHER, TM_MV_MULM, TM_MV_ROWS, TM_MV_LS, TM_CK_PASSF, TM_MV_UPD, TM_COUNT };
 #define TIC() long long t0_ = clock64()
 #define TOC(k) do { long long t1_ = clock64(); c.tim[k] += t1_ - t0_; t0_ = t1_; } while (0)
 #else
@@ -1556,7 +1556,9 @@ STAGE int newton_check(const Ctx c, int iter, float improvement) {
   float *Ma = SF(Ma), *grad = SF(grad), *fs = SF(fsmooth), *fcon = SF(fcon);
   float scale = 1.0f / (h->meaninertia * (float)(nv > 1 ? nv : 1));
   float tol = fmaxf(h->tolerance, 1e-6f);  // single-precision floor for the convergence tests
+  TIC();
   pass_F<HF>(c, fcon);
+  TOC(TM_CK_PASSF);
   float g2sum = 0, f2sum = 0;
   LANES(i, nv) {
     float g = Ma[i] - fs[i] - fcon[i], f = fabsf(Ma[i]) + fabsf(fs[i]) + fabsf(fcon[i]);
@@ -1593,14 +1595,19 @@ STAGE int newton_move(const Ctx c, float* improvement) {
   int* cnt = SI(counters);
   float *a = SF(qacc), *Ma = SF(Ma), *Mv = SF(Mv), *search = SF(search), *fs = SF(fsmooth);
   float scale = 1.0f / (h->meaninertia * (float)(nv > 1 ? nv : 1));
+  TIC();
   mulM(c, search, Mv);
+  TOC(TM_MV_MULM);
   rows_from_vec<HF>(c, search, RV_JV);
+  TOC(TM_MV_ROWS);
   float q1 = 0, q2 = 0, sn = 0;
   LANES(i, nv) { q1 += search[i] * (Ma[i] - fs[i]); q2 += 0.5f * search[i] * Mv[i]; sn += search[i] * search[i]; }
   q1 = wsum(q1); q2 = wsum(q2); sn = sqrtf(wsum(sn));
   if (sn < 1e-20f) return 1;
   float gtol = h->tolerance * h->ls_tolerance * sn / scale;
+  TOC(TM_MV_ROWS);
   float alpha = linesearch<HF>(c, q1, q2, gtol, h->ls_iterations < 20 ? h->ls_iterations : 20, improvement);
+  TOC(TM_MV_LS);
   if (alpha == 0.f) return 1;
   LANES(i, nv) { a[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
   LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 4; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
@@ -1609,6 +1616,7 @@ STAGE int newton_move(const Ctx c, float* improvement) {
   if (HF) LANES(d, h->nfric) SF(fric)[d] += alpha * SF(fric)[h->nfric + d];
   SYNC();
   if (c.lane == 0) cnt[CNT_ITERS] += 1;
+  TOC(TM_MV_UPD);
   return 0;
 }
 

@@ -306,6 +306,7 @@ class FetchVectorEnv:
         mask = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
         self._reset_envs(mask, out)
         self._needs_reset.zero_()
+        self._elapsed_ub, self._pending_reset = 0, False
         self._last = out
         return self._obs_dict(out), {}
 
@@ -318,25 +319,35 @@ class FetchVectorEnv:
         out = self.backend.new_outputs()
         self.backend.step(actions, out)  # clip + _set_action + n_substeps x mj_step + _get_obs + reward, one kernel
         self._elapsed += 1
+        self._elapsed_ub = getattr(self, "_elapsed_ub", 0) + 1   # host-side upper bound of max(_elapsed): no sync on most steps
         reward, success = out["reward"], out["success"]
         terminated = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)  # robot_env.py:106-112
         info = {"is_success": success}
-        if self.autoreset_mode == "next_step" and bool(self._needs_reset.any()):
-            # envs that finished on the previous call are reset now; their action is ignored (gymnasium NEXT_STEP)
-            pre = self._needs_reset.clone()
-            self._reset_envs(pre, out)
-            reward = torch.where(pre, torch.zeros_like(reward), reward)
-            out["reward"] = reward
-            info["is_success"] = torch.where(pre, torch.zeros_like(success), success)
-            self._needs_reset.zero_()
-        truncated = (self._elapsed >= self.max_episode_steps) if self.max_episode_steps is not None else torch.zeros_like(terminated)
+        if self.autoreset_mode == "next_step" and getattr(self, "_pending_reset", False):
+            self._pending_reset = False
+            if bool(self._needs_reset.any()):
+                # envs that finished on the previous call are reset now; their action is ignored (gymnasium NEXT_STEP)
+                pre = self._needs_reset.clone()
+                self._reset_envs(pre, out)
+                reward = torch.where(pre, torch.zeros_like(reward), reward)
+                out["reward"] = reward
+                info["is_success"] = torch.where(pre, torch.zeros_like(success), success)
+                self._needs_reset.zero_()
+                self._elapsed_ub = int(self._elapsed.max())
+        # TimeLimit: the device counters are only compared (and the host only synchronises) once the bound says an env may be due
+        may_truncate = self.max_episode_steps is not None and self._elapsed_ub >= self.max_episode_steps
+        truncated = (self._elapsed >= self.max_episode_steps) if may_truncate else torch.zeros_like(terminated)
         done = truncated | terminated
-        if self.autoreset_mode == "next_step":
-            self._needs_reset = done
-        elif self.autoreset_mode == "same_step" and bool(done.any()):
-            info["final_obs"] = {k: v.clone() for k, v in self._obs_dict(out).items()}
-            info["_final_obs"] = done.clone()
-            self._reset_envs(done, out)
+        if may_truncate:
+            if self.autoreset_mode == "next_step":
+                self._needs_reset = done
+                self._pending_reset = True
+            elif self.autoreset_mode == "same_step":
+                if bool(done.any()):
+                    info["final_obs"] = {k: v.clone() for k, v in self._obs_dict(out).items()}
+                    info["_final_obs"] = done.clone()
+                    self._reset_envs(done, out)
+                self._elapsed_ub = int(self._elapsed.max())
         info["_is_success"] = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
         self._last = out
         return self._obs_dict(out), reward, terminated, truncated, info
@@ -367,6 +378,7 @@ class FetchVectorEnv:
         self.backend.state.copy_(state)
         if elapsed is not None:
             self._elapsed.copy_(elapsed)
+        self._elapsed_ub = int(self._elapsed.max())
         out = self.backend.new_outputs()
         self.backend.refresh(None, out)
         self._last = out

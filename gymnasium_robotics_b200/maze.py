@@ -257,6 +257,7 @@ class MazeVectorEnv:
         out = self.backend.new_outputs()
         self._reset_envs(torch.ones(self.num_envs, dtype=torch.bool, device=self.device), out, options)
         self._needs_reset.zero_()
+        self._elapsed_ub, self._pending_reset = 0, False
         return self._obs_dict(out), {"success": out["success"] > 0}
 
     def step(self, actions):
@@ -268,26 +269,38 @@ class MazeVectorEnv:
         out = self.backend.new_outputs()
         self.backend.step(actions, out)
         self._elapsed += 1
+        self._elapsed_ub = getattr(self, "_elapsed_ub", 0) + 1   # host-side upper bound of max(_elapsed)
         reward, success = out["reward"], out["success"] > 0
         terminated = torch.zeros_like(success) if self.continuing_task else success.clone()  # maze_v4.py:390-398
         info = {"success": success}
-        if self.autoreset_mode == "next_step" and bool(self._needs_reset.any()):
-            pre = self._needs_reset.clone()
-            self._reset_envs(pre, out)
-            reward = torch.where(pre, torch.zeros_like(reward), reward)
-            out["reward"] = reward
-            terminated = terminated & ~pre
-            self._needs_reset.zero_()
+        # a continuing task can only end by TimeLimit: then the host knows from its step counter when a check is due and
+        # does not synchronise with the device on the other steps
+        lazy = self.continuing_task
+        if self.autoreset_mode == "next_step" and (not lazy or getattr(self, "_pending_reset", True)):
+            self._pending_reset = False
+            if bool(self._needs_reset.any()):
+                pre = self._needs_reset.clone()
+                self._reset_envs(pre, out)
+                reward = torch.where(pre, torch.zeros_like(reward), reward)
+                out["reward"] = reward
+                terminated = terminated & ~pre
+                self._needs_reset.zero_()
+                self._elapsed_ub = int(self._elapsed.max())
         if self.continuing_task and self.reset_target and len(self.cells.goal_locations) > 1 and bool(success.any()):
             self._update_goal(success, out)  # maze_v4.py:400-418
-        truncated = (self._elapsed >= self.max_episode_steps) if self.max_episode_steps is not None else torch.zeros_like(terminated)
+        may_truncate = self.max_episode_steps is not None and (not lazy or self._elapsed_ub >= self.max_episode_steps)
+        truncated = (self._elapsed >= self.max_episode_steps) if may_truncate else torch.zeros_like(terminated)
         done = truncated | terminated
-        if self.autoreset_mode == "next_step":
-            self._needs_reset = done
-        elif self.autoreset_mode == "same_step" and bool(done.any()):
-            info["final_obs"] = {k: v.clone() for k, v in self._obs_dict(out).items()}
-            info["_final_obs"] = done.clone()
-            self._reset_envs(done, out)
+        if may_truncate or not lazy:
+            if self.autoreset_mode == "next_step":
+                self._needs_reset = done
+                self._pending_reset = True
+            elif self.autoreset_mode == "same_step":
+                if bool(done.any()):
+                    info["final_obs"] = {k: v.clone() for k, v in self._obs_dict(out).items()}
+                    info["_final_obs"] = done.clone()
+                    self._reset_envs(done, out)
+                self._elapsed_ub = int(self._elapsed.max())
         return self._obs_dict(out), reward, terminated, truncated, info
 
     def _update_goal(self, success, out):
@@ -323,6 +336,7 @@ class MazeVectorEnv:
         self.backend.state.copy_(state)
         if elapsed is not None:
             self._elapsed.copy_(elapsed)
+        self._elapsed_ub = int(self._elapsed.max())
         out = self.backend.new_outputs()
         self.backend.refresh(None, out)
         return self._obs_dict(out)

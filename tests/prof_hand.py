@@ -6,7 +6,8 @@ from gymnasium_robotics_b200.hand import HandVectorEnv
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
-env = HandVectorEnv("HandManipulateBlockRotateXYZ", num_envs=n, rng_mode="torch", autoreset_mode="same_step")
+touch = "sensordata" if len(sys.argv) > 3 and sys.argv[3] == "touch" else None
+env = HandVectorEnv("HandManipulateBlockRotateXYZ", num_envs=n, rng_mode="torch", autoreset_mode="same_step", touch_get_obs=touch)
 env.reset(seed=0)
 g = torch.Generator(device="cuda").manual_seed(1234)
 info = torch.zeros(n, dtype=torch.int32, device="cuda")

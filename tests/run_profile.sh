@@ -9,3 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 10 -c 1 -o gpurun_out/prof_${tag} \
     python tests/prof_step.py 4096 12 > gpurun_out/ncu_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_${tag}.log
+# 3. the Shadow-Hand build of the step kernel (BASELINE config 3: 2048 envs, 92 touch sensors)
+ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 6 -c 1 -o gpurun_out/prof_hand_${tag} \
+    python tests/prof_hand.py 2048 8 touch > gpurun_out/ncu_hand_${tag}.log 2>&1
+tail -2 gpurun_out/ncu_hand_${tag}.log

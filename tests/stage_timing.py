@@ -5,7 +5,8 @@ from gymnasium_robotics_b200 import _lib
 from gymnasium_robotics_b200.fetch import FetchVectorEnv
 from gymnasium_robotics_b200.hand import HandVectorEnv
 NAMES = ["kinematics", "com+mass_matrix", "collision", "make_constraint", "smooth_forces", "newton_begin", "newton_check", "build_H",
-         "newton_direction", "newton_move", "integrate", "barrier wait", "other (load/observe/store)"]
+         "newton_direction", "newton_move", "integrate", "barrier wait", "other (load/observe/store)", "  (newton_move: M*search)", "  (newton_move: J*search + dots)", "  (newton_move: line search)",
+         "  (newton_check: J^T f)", "  (newton_move: update)"]
 L = _lib.lib()
 for which in sys.argv[1:] or ["fetch", "hand"]:
     if which == "fetch":
@@ -18,11 +19,11 @@ for which in sys.argv[1:] or ["fetch", "hand"]:
     g = torch.Generator(device="cuda").manual_seed(1)
     tape = torch.rand((16, n, nact), generator=g, device="cuda") * 2 - 1
     for k in range(5): env.step(tape[k])
-    out = (ctypes.c_ulonglong * 16)()
+    out = (ctypes.c_ulonglong * 32)()
     L.b200sim_debug_stage_cycles(out, 1)
     for k in range(10): env.step(tape[k])
     cnt = L.b200sim_debug_stage_cycles(out, 1)
-    tot = sum(out[:cnt])
+    tot = sum(out[:13])
     print(f"== {which}: cycles per env-step per warp {tot / (10 * n):.0f}")
     for k in range(cnt):
         print(f"  {NAMES[k]:28s} {100 * out[k] / tot:5.1f}%")

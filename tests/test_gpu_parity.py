@@ -357,6 +357,7 @@ def test_hand_full_size_batch_properties():
         if t == 50:  # one raw backend step with the info word: Newton iterations and overflow flags
             env.backend.step(a.contiguous(), out, info_bits)
             env._elapsed += 1
+            env._elapsed_ub += 1
             assert int((info_bits >> 16).max()) == 0, "contact / row capacity overflow"
             continue
         o, r, te, tr, info = env.step(a)
