@@ -883,41 +883,15 @@ STAGE void collision(const Ctx c) {
     int kept = 0;
     int gid = baseg + gslot;
     for (int k = 0; k < o.cnt; k++) {
+      // raw contact (position, normal, distance, pair) parked in its record; finalised by one lane per contact below
       int id = basec + slot + k;
       if (id >= h->ncon_max || gid >= h->ngrp_max - DM_NWELD_MAX) break;
       float* cr = SF(con) + id * CON_WORDS;
-      float fr9[9] = {o.nrm[k][0], o.nrm[k][1], o.nrm[k][2], 0, 0, 0, 0, 0, 0};
-      make_frame(fr9);
-      float r[3] = {o.pos[k][0] - h->ref[0], o.pos[k][1] - h->ref[1], o.pos[k][2] - h->ref[2]};
-      for (int a = 0; a < 3; a++) { float* w = cr + C_W + 6 * a; cross3(w, r, fr9 + 3 * a); w[3] = fr9[3 * a]; w[4] = fr9[3 * a + 1]; w[5] = fr9[3 * a + 2]; }
-      const float* fr = GF(pair_friction) + 3 * p;
-      int dim = GI(pair_condim)[p];
-      float mu0 = fr[0];
-      cr[C_MU] = mu0; cr[C_MU + 1] = fr[1];
-      // impedance, regulariser (shared by all pyramid edges of the contact) and reference-acceleration constants
-      float incl = MF(pair_margin)[p] - GF(pair_gap)[p];
-      float solimp[5] = {GF(pair_solimp)[5 * p], GF(pair_solimp)[5 * p + 1], GF(pair_solimp)[5 * p + 2], GF(pair_solimp)[5 * p + 3], GF(pair_solimp)[5 * p + 4]};
-      float solref[2] = {GF(pair_solref)[2 * p], GF(pair_solref)[2 * p + 1]};
-      float imp = impedance(solimp, o.dist[k], incl);
-      float K, Bc;
-      ref_kb(c, solref, solimp[1], &K, &Bc);
-      float tran = GF(pair_invweight)[2 * p];
-      float R;
-      if (dim == 1) R = fmaxf((1 - imp) / imp * tran, B200_MINVAL);
-      else {
-        float R0 = fmaxf((1 - imp) / imp * (tran + mu0 * mu0 * tran), B200_MINVAL);
-        float mu = mu0 * rsqrtf(h->impratio);
-        R = fmaxf(2 * mu * mu * R0, B200_MINVAL);
-      }
-      cr[C_D] = 1.0f / R;
-      cr[C_U] = K * imp * (o.dist[k] - incl); cr[C_U + 1] = 0; cr[C_U + 2] = 0; cr[C_U + 3] = 0;
-      cr[C_JV] = Bc;
-      ((int*)cr)[C_DIMGRP] = dim | (gid << 8);
-      if (HF && h->nsensor > 0) {
-        float* cx = SF(conx) + id * CX_WORDS;
-        cx[CX_POS] = o.pos[k][0]; cx[CX_POS + 1] = o.pos[k][1]; cx[CX_POS + 2] = o.pos[k][2];
-        ((int*)cx)[CX_PAIR] = p;
-      }
+      cr[0] = o.pos[k][0]; cr[1] = o.pos[k][1]; cr[2] = o.pos[k][2];
+      cr[3] = o.nrm[k][0]; cr[4] = o.nrm[k][1]; cr[5] = o.nrm[k][2];
+      cr[6] = o.dist[k];
+      ((int*)cr)[7] = p;
+      ((int*)cr)[C_DIMGRP] = gid << 8;
       kept++;
     }
     if (o.cnt > 0 && gid < h->ngrp_max - DM_NWELD_MAX) {
@@ -934,6 +908,45 @@ STAGE void collision(const Ctx c) {
     }
     SYNC();
   }
+  // contact records: frame, spatial row vectors about `ref`, friction, impedance / regulariser / reference-acceleration
+  // constants -- one lane per contact
+  LANES(id, cnt[CNT_NCON]) {
+    float* cr = SF(con) + id * CON_WORDS;
+    const float pos[3] = {cr[0], cr[1], cr[2]}, dist = cr[6];
+    float fr9[9] = {cr[3], cr[4], cr[5], 0, 0, 0, 0, 0, 0};
+    const int p = ((const int*)cr)[7], gid8 = ((const int*)cr)[C_DIMGRP];
+    make_frame(fr9);
+    float r[3] = {pos[0] - h->ref[0], pos[1] - h->ref[1], pos[2] - h->ref[2]};
+    for (int a = 0; a < 3; a++) { float* w = cr + C_W + 6 * a; cross3(w, r, fr9 + 3 * a); w[3] = fr9[3 * a]; w[4] = fr9[3 * a + 1]; w[5] = fr9[3 * a + 2]; }
+    const float* fr = GF(pair_friction) + 3 * p;
+    int dim = GI(pair_condim)[p];
+    float mu0 = fr[0];
+    cr[C_MU] = mu0; cr[C_MU + 1] = fr[1];
+    float incl = MF(pair_margin)[p] - GF(pair_gap)[p];
+    float solimp[5] = {GF(pair_solimp)[5 * p], GF(pair_solimp)[5 * p + 1], GF(pair_solimp)[5 * p + 2], GF(pair_solimp)[5 * p + 3], GF(pair_solimp)[5 * p + 4]};
+    float solref[2] = {GF(pair_solref)[2 * p], GF(pair_solref)[2 * p + 1]};
+    float imp = impedance(solimp, dist, incl);
+    float K, Bc;
+    ref_kb(c, solref, solimp[1], &K, &Bc);
+    float tran = GF(pair_invweight)[2 * p];
+    float R;
+    if (dim == 1) R = fmaxf((1 - imp) / imp * tran, B200_MINVAL);
+    else {
+      float R0 = fmaxf((1 - imp) / imp * (tran + mu0 * mu0 * tran), B200_MINVAL);
+      float mu = mu0 * rsqrtf(h->impratio);
+      R = fmaxf(2 * mu * mu * R0, B200_MINVAL);
+    }
+    cr[C_D] = 1.0f / R;
+    cr[C_U] = K * imp * (dist - incl); cr[C_U + 1] = 0; cr[C_U + 2] = 0; cr[C_U + 3] = 0;
+    cr[C_JV] = Bc;
+    ((int*)cr)[C_DIMGRP] = dim | gid8;
+    if (HF && h->nsensor > 0) {
+      float* cx = SF(conx) + id * CX_WORDS;
+      cx[CX_POS] = pos[0]; cx[CX_POS + 1] = pos[1]; cx[CX_POS + 2] = pos[2];
+      ((int*)cx)[CX_PAIR] = p;
+    }
+  }
+  SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
