@@ -29,7 +29,8 @@ for _maze, _steps in (("UMaze", 300), ("Open", 300), ("Open_Diverse_G", 300), ("
         ENV_IDS[f"PointMaze_{_maze}{_suffix}-v3"] = dict(maze=_maze, agent="point", reward_type=_rt, max_episode_steps=_steps)
 # Shadow-Hand block manipulation, new-binding ids (-v1; __init__.py:105-395); touch-sensor variants are "next"
 for _task in ("HandManipulateBlockRotateZ", "HandManipulateBlockRotateParallel", "HandManipulateBlockRotateXYZ",
-              "HandManipulateBlockFull", "HandManipulateBlock"):
+              "HandManipulateBlockFull", "HandManipulateBlock", "HandManipulatePenRotate", "HandManipulatePenFull",
+              "HandManipulatePen"):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
         ENV_IDS[f"{_task}{_suffix}-v1"] = dict(hand_task=_task, reward_type=_rt, max_episode_steps=100)
         # 92 touch sensors appended to the observation (__init__.py:122-170 and siblings)

@@ -32,7 +32,7 @@ struct FetchTask {
   int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride;
 };
 enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2, TASK_HAND_REACH = 3 };  // TASK_ANTMAZE covers both maze agents (Ant, Point)
-enum { GOAL_USE_POS = 1, GOAL_USE_ROT = 2 };
+enum { GOAL_USE_POS = 1, GOAL_USE_ROT = 2, GOAL_IGNORE_Z = 4 };
 
 enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
 
@@ -139,14 +139,44 @@ HD void antmaze_observe(const Ctx& c, const FetchTask& t, const float* goal, flo
   }
 }
 
+HD void quat_to_euler(const float* q, float* e) {
+  float n = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  float m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (n > 2.220446e-16f) {
+    float sc = 2.0f / n, w = q[0], x = q[1], y = q[2], z = q[3];
+    m[0] = 1 - sc * (y * y + z * z); m[1] = sc * (x * y - w * z); m[2] = sc * (x * z + w * y);
+    m[3] = sc * (x * y + w * z); m[4] = 1 - sc * (x * x + z * z); m[5] = sc * (y * z - w * x);
+    m[6] = sc * (x * z - w * y); m[7] = sc * (y * z + w * x); m[8] = 1 - sc * (x * x + y * y);
+  }
+  float cy = sqrtf(m[8] * m[8] + m[5] * m[5]);
+  if (cy > 8.8817841970012523e-16f) { e[2] = -atan2f(m[1], m[0]); e[1] = -atan2f(-m[2], cy); e[0] = -atan2f(m[5], m[8]); }
+  else { e[2] = -atan2f(-m[3], m[4]); e[1] = -atan2f(-m[2], cy); e[0] = 0.f; }
+}
+HD void euler_to_quat(const float* e, float* q) {
+  float ai = 0.5f * e[2], aj = -0.5f * e[1], ak = 0.5f * e[0];
+  float si = sinf(ai), sj = sinf(aj), sk = sinf(ak), ci = cosf(ai), cj = cosf(aj), ck = cosf(ak);
+  float cc = ci * ck, cs = ci * sk, sc = si * ck, ss = si * sk;
+  q[0] = cj * cc + sj * ss; q[3] = cj * sc - sj * cs; q[2] = -(cj * ss + sj * cc); q[1] = cj * cs - sj * sc;
+}
+
 // Shadow-hand block manipulation: obs = robot qpos | robot qvel | object qvel | object qpos, achieved = object qpos (7)
 // (reference: envs/shadow_dexterous_hand/manipulate.py:298-314, :88-138)
 HD void hand_goal_distance(const FetchTask& t, const float* a, const float* g, float* d_pos, float* d_rot) {
   *d_pos = 0.f; *d_rot = 0.f;
   if (t.goal_flags & GOAL_USE_POS) { float e[3] = {a[0] - g[0], a[1] - g[1], a[2] - g[2]}; *d_pos = sqrtf(dot3(e, e)); }
   if (t.goal_flags & GOAL_USE_ROT) {
-    // w component of a * conj(g)
-    float w = a[3] * g[3] + a[4] * g[4] + a[5] * g[5] + a[6] * g[6];
+    float qa[4] = {a[3], a[4], a[5], a[6]};
+    if (t.goal_flags & GOAL_IGNORE_Z) {
+      // ignore_z_target_rotation (manipulate.py:97-106; the pen): both quaternions to Euler angles (R = Rx Ry Rz,
+      // utils/rotations.py:162-184, 245-271), the achieved z angle replaced by the goal's, back to a quaternion (:140-159)
+      float ea[3], eb[3];
+      quat_to_euler(a + 3, ea);
+      quat_to_euler(g + 3, eb);
+      ea[2] = eb[2];
+      euler_to_quat(ea, qa);
+    }
+    // w component of qa * conj(g)
+    float w = qa[0] * g[3] + qa[1] * g[4] + qa[2] * g[5] + qa[3] * g[6];
     *d_rot = 2.f * acosf(fminf(fmaxf(w, -1.f), 1.f));
   }
 }

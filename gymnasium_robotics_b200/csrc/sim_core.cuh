@@ -716,7 +716,32 @@ HDN void capsule_box_contacts(const float* cp, const float* ax, float r, float h
   }
   float t = 0.5f * (lo + hi);
   for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * t;
-  sphere_box_contact(p, r, bp, bm, bh, margin, o);
+  float fmin = point_box(p, bp, bm, bh, cl, nn);
+  if (fmin - r > margin) return;
+  // flat zone {f <= fmin + tol} of the convex distance function: a capsule lying (nearly) parallel on a face gets one
+  // contact at each end of the zone instead of one at an arbitrary point of it (same rule as oracle/oracle.c)
+  const float tol = 2e-5f;
+  float tz[2];
+  for (int side = 0; side < 2; side++) {
+    float out = side ? hl : -hl, in = t;
+    for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * out;
+    if (point_box(p, bp, bm, bh, cl, nn) <= fmin + tol) in = out;
+    else for (int it = 0; it < 14; it++) {
+      float mid = 0.5f * (out + in);
+      for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * mid;
+      if (point_box(p, bp, bm, bh, cl, nn) <= fmin + tol) in = mid; else out = mid;
+    }
+    tz[side] = in;
+  }
+  if (tz[1] - tz[0] > r) {
+    for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * tz[0];
+    sphere_box_contact(p, r, bp, bm, bh, margin, o);
+    for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * tz[1];
+    sphere_box_contact(p, r, bp, bm, bh, margin, o);
+  } else {
+    for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * t;
+    sphere_box_contact(p, r, bp, bm, bh, margin, o);
+  }
 }
 // sphere or capsule geom g1 against box geom g2, or (g2 < 0) against the maze wall cells around it
 HD void collide_round_box(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {

@@ -31,17 +31,25 @@ HAND_TASKS = {
     "HandManipulateBlockRotateXYZ": dict(target_position="ignore", target_rotation="xyz"),
     "HandManipulateBlockFull": dict(target_position="random", target_rotation="xyz"),
     "HandManipulateBlock": dict(target_position="random", target_rotation="xyz"),
+    # the pen (manipulate_pen.py:216-235: no initial rotation randomisation, z rotation ignored, 5 cm position threshold;
+    # ids __init__.py:651-780)
+    "HandManipulatePenRotate": dict(target_position="ignore", target_rotation="xyz", model="hand_pen", touch_model="hand_pen_touch",
+                                    randomize_initial_rotation=False, ignore_z_target_rotation=True, distance_threshold=0.05),
+    "HandManipulatePenFull": dict(target_position="random", target_rotation="xyz", model="hand_pen", touch_model="hand_pen_touch",
+                                  randomize_initial_rotation=False, ignore_z_target_rotation=True, distance_threshold=0.05),
+    "HandManipulatePen": dict(target_position="random", target_rotation="xyz", model="hand_pen", touch_model="hand_pen_touch",
+                              randomize_initial_rotation=False, ignore_z_target_rotation=True, distance_threshold=0.05),
 }
 TARGET_POSITION_RANGE = np.array([(-0.04, 0.04), (-0.06, 0.02), (0.0, 0.06)])
 HAND_REF_POINT = (1.0, 0.9, 0.2)   # fixed world point of the spatial algebra: inside the hand's workspace
-GOAL_USE_POS, GOAL_USE_ROT = 1, 2
+GOAL_USE_POS, GOAL_USE_ROT, GOAL_IGNORE_Z = 1, 2, 4
 
 
 TOUCH_MODES = {"off": 0, "sensordata": 1, "boolean": 2, "log": 3}   # manipulate_touch_sensors.py:30-40 touch_get_obs
 
 
 def make_hand_task(model, target_position, target_rotation, reward_type, distance_threshold, rotation_threshold, n_substeps,
-                   touch_get_obs=None):
+                   touch_get_obs=None, ignore_z_target_rotation=False):
     """b200sim_fetch_task_t for kind 2 (ids resolved the way MujocoModelNames would, utils/mujoco_utils.py:327-469)."""
     m = model
     jobj = m.joint_id("object:joint")
@@ -53,7 +61,8 @@ def make_hand_task(model, target_position, target_rotation, reward_type, distanc
     t.obj_qadr, t.obj_dadr = int(m.jnt_qposadr[jobj]), int(m.jnt_dofadr[jobj])
     t.touch_mode = TOUCH_MODES.get(touch_get_obs, 0) if touch_get_obs is not None else 0
     t.nobs = t.obj_qadr + int(m.nv) + 7 + (int(m.nsensor) if t.touch_mode else 0)
-    t.goal_flags = (GOAL_USE_POS if target_position != "ignore" else 0) | (GOAL_USE_ROT if target_rotation != "ignore" else 0)
+    t.goal_flags = (GOAL_USE_POS if target_position != "ignore" else 0) | (GOAL_USE_ROT if target_rotation != "ignore" else 0) | \
+        (GOAL_IGNORE_Z if ignore_z_target_rotation else 0)
     t.distance_threshold, t.rotation_threshold = float(distance_threshold), float(rotation_threshold)
     t.dt = float(m.opt[0] * n_substeps)
     return t
@@ -71,9 +80,9 @@ class HandVectorEnv(FetchVectorEnv):
     def __init__(self, task: str = "HandManipulateBlockRotateXYZ", num_envs: int = 1, reward_type: str = "sparse",
                  max_episode_steps: Optional[int] = 100, device="cuda:0", rng_mode: str = "auto", autoreset_mode: str = "next_step",
                  n_substeps: int = N_SUBSTEPS, backend_factory=None, target_position=None, target_rotation=None,
-                 randomize_initial_position=True, randomize_initial_rotation=True, distance_threshold=0.01,
+                 randomize_initial_position=True, randomize_initial_rotation=None, distance_threshold=None,
                  rotation_threshold=0.1, relative_control=False, model=None, touch_get_obs=None,
-                 touch_visualisation="on_touch", **kwargs):
+                 touch_visualisation="on_touch", ignore_z_target_rotation=None, **kwargs):
         if task not in HAND_TASKS:
             raise KeyError(f"unknown Hand task {task!r}")
         if reward_type not in ("sparse", "dense"):
@@ -86,6 +95,11 @@ class HandVectorEnv(FetchVectorEnv):
             # hand_env.py:47-57 calls data.get_joint_qpos, which the new mujoco bindings lack: dead code for the -v1 ids
             raise NotImplementedError("relative_control is not available in the reference's -v1 envs either")
         cfg = dict(HAND_TASKS[task])
+        # per-object defaults of the reference's env classes (block: manipulate.py:24-40; pen: manipulate_pen.py:216-235)
+        randomize_initial_rotation = cfg.get("randomize_initial_rotation", True) if randomize_initial_rotation is None else randomize_initial_rotation
+        distance_threshold = cfg.get("distance_threshold", 0.01) if distance_threshold is None else distance_threshold
+        ignore_z_target_rotation = cfg.get("ignore_z_target_rotation", False) if ignore_z_target_rotation is None else ignore_z_target_rotation
+        self.ignore_z_target_rotation = ignore_z_target_rotation
         self.target_position = target_position or cfg["target_position"]
         self.target_rotation = target_rotation or cfg["target_rotation"]
         assert self.target_position in ("ignore", "fixed", "random")
@@ -99,10 +113,11 @@ class HandVectorEnv(FetchVectorEnv):
         # touch_get_obs is None for the plain ids; the *TouchSensors ids pass "boolean" / "sensordata" (or "log" / "off"):
         # they use the model with the 92 touch sites (manipulate_block_touch_sensors.py:72-92)
         self.touch_get_obs = touch_get_obs
-        self.model = model if model is not None else load_model("hand_block" if touch_get_obs is None else "hand_block_touch")
+        self.model = model if model is not None else load_model(
+            cfg.get("model", "hand_block") if touch_get_obs is None else cfg.get("touch_model", "hand_block_touch"))
         m = self.model
         self.task = make_hand_task(m, self.target_position, self.target_rotation, reward_type, distance_threshold,
-                                   rotation_threshold, n_substeps, touch_get_obs)
+                                   rotation_threshold, n_substeps, touch_get_obs, ignore_z_target_rotation)
         factory = backend_factory or _HandBackend
         self.backend = factory(m, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device

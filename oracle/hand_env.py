@@ -25,7 +25,7 @@ def compile_hand_model(assets_dir="/root/reference/gymnasium_robotics/envs/asset
 class OracleHandBlockEnv:
     def __init__(self, target_position="ignore", target_rotation="xyz", reward_type="sparse", model=None,
                  randomize_initial_position=True, randomize_initial_rotation=True, distance_threshold=0.01,
-                 rotation_threshold=0.1, n_substeps=20, touch_get_obs=None):
+                 rotation_threshold=0.1, n_substeps=20, touch_get_obs=None, ignore_z_target_rotation=False):
         # manipulate.py:24-85 (ctor), manipulate_block.py:214-230
         self.target_position, self.target_rotation = target_position, target_rotation
         self.target_position_range = TARGET_POSITION_RANGE
@@ -35,6 +35,7 @@ class OracleHandBlockEnv:
         self.distance_threshold, self.rotation_threshold = distance_threshold, rotation_threshold
         self.reward_type, self.n_substeps = reward_type, n_substeps
         self.touch_get_obs = touch_get_obs  # manipulate_touch_sensors.py:10-64 (None = plain env without touch observation)
+        self.ignore_z_target_rotation = ignore_z_target_rotation  # True for the pen (manipulate_pen.py:231)
         assert target_position in ("ignore", "fixed", "random")
         assert target_rotation in ("ignore", "fixed", "xyz", "z", "parallel")
         self.model = model if model is not None else compile_hand_model(
@@ -53,14 +54,19 @@ class OracleHandBlockEnv:
         self.initial_qvel = self.sim.qvel.copy()
 
     # ------------------------------------------------------------------ GoalEnv API
-    def _goal_distance(self, goal_a, goal_b):  # manipulate.py:88-115 (ignore_z_target_rotation = False for the block)
+    def _goal_distance(self, goal_a, goal_b):  # manipulate.py:88-115
         goal_a, goal_b = np.asarray(goal_a, dtype=np.float64), np.asarray(goal_b, dtype=np.float64)
         d_pos = np.zeros_like(goal_a[..., 0])
         d_rot = np.zeros_like(goal_b[..., 0])
         if self.target_position != "ignore":
             d_pos = np.linalg.norm(goal_a[..., :3] - goal_b[..., :3], axis=-1)
         if self.target_rotation != "ignore":
-            quat_diff = rotations.quat_mul(goal_a[..., 3:], rotations.quat_conjugate(goal_b[..., 3:]))
+            quat_a, quat_b = goal_a[..., 3:], goal_b[..., 3:]
+            if self.ignore_z_target_rotation:
+                euler_a, euler_b = rotations.quat2euler(quat_a), rotations.quat2euler(quat_b)
+                euler_a[..., 2] = euler_b[..., 2]   # the reference indexes [2] (1-D goals); batched goals use the last axis here
+                quat_a = rotations.euler2quat(euler_a)
+            quat_diff = rotations.quat_mul(quat_a, rotations.quat_conjugate(quat_b))
             d_rot = 2 * np.arccos(np.clip(quat_diff[..., 0], -1.0, 1.0))
         return d_pos, d_rot
 

@@ -793,7 +793,27 @@ static void collide_capsule_box(oracle_sim* s, int pair, real margin) {
   }
   real t = 0.5 * (lo + hi);
   copy3(p, c); addscl3(p, ax, t);
-  sphere_box_contact(s, pair, p, r, g2, margin);
+  real fmin = point_box(p, bp, bm, bh, cl, nn);
+  if (fmin - r > margin) return;
+  /* flat zone {f <= fmin + tol} of the convex distance function: a capsule lying (nearly) parallel on a face gets one
+   * contact at each end of the zone instead of one at an arbitrary point of it */
+  const real tol = 2e-5;
+  real ta = t, tb = t, a0 = -h, b0 = h;
+  copy3(p, c); addscl3(p, ax, a0);
+  if (point_box(p, bp, bm, bh, cl, nn) <= fmin + tol) ta = a0;
+  else { real in = t; for (int it = 0; it < 14; it++) { real mid = 0.5 * (a0 + in); copy3(p, c); addscl3(p, ax, mid);
+      if (point_box(p, bp, bm, bh, cl, nn) <= fmin + tol) in = mid; else a0 = mid; } ta = in; }
+  copy3(p, c); addscl3(p, ax, b0);
+  if (point_box(p, bp, bm, bh, cl, nn) <= fmin + tol) tb = b0;
+  else { real in = t; for (int it = 0; it < 14; it++) { real mid = 0.5 * (b0 + in); copy3(p, c); addscl3(p, ax, mid);
+      if (point_box(p, bp, bm, bh, cl, nn) <= fmin + tol) in = mid; else b0 = mid; } tb = in; }
+  if (tb - ta > r) {
+    copy3(p, c); addscl3(p, ax, ta); sphere_box_contact(s, pair, p, r, g2, margin);
+    copy3(p, c); addscl3(p, ax, tb); sphere_box_contact(s, pair, p, r, g2, margin);
+  } else {
+    copy3(p, c); addscl3(p, ax, t);
+    sphere_box_contact(s, pair, p, r, g2, margin);
+  }
 }
 
 /* sphere/capsule (geom1) vs sphere/capsule (geom2): closest points of the two axis segments (a sphere is a segment of

@@ -69,7 +69,13 @@ class HostSimBackend:
         if self.task.kind == 2:  # same arithmetic as the kernel's hand_goal_distance / hand_reward (fetch_task.cuh)
             t = self.task
             dp = torch.sqrt(((ag[:, :3] - dg[:, :3]) ** 2).sum(-1)) if t.goal_flags & 1 else torch.zeros(ag.shape[0])
-            dr = 2 * torch.acos(torch.clamp((ag[:, 3:] * dg[:, 3:]).sum(-1), -1, 1)) if t.goal_flags & 2 else torch.zeros(ag.shape[0])
+            qa = ag[:, 3:]
+            if t.goal_flags & 4:   # ignore_z_target_rotation (the pen)
+                from gymnasium_robotics_b200 import rotations as R
+                ea, eb = R.quat2euler(qa.double().numpy()), R.quat2euler(dg[:, 3:].double().numpy())
+                ea[:, 2] = eb[:, 2]
+                qa = torch.as_tensor(R.euler2quat(ea), dtype=torch.float32)
+            dr = 2 * torch.acos(torch.clamp((qa * dg[:, 3:]).sum(-1), -1, 1)) if t.goal_flags & 2 else torch.zeros(ag.shape[0])
             suc = (dp < t.distance_threshold).to(torch.float32) * (dr < t.rotation_threshold).to(torch.float32)
             return -(10 * dp + dr) if t.reward_dense else suc - 1
         d = torch.sqrt(((ag - dg) ** 2).sum(-1))

@@ -164,3 +164,59 @@ def test_hand_reach_matches_oracle():
         assert float(rew[0]) == float(orew) and float(info["is_success"][0]) == float(oinfo["is_success"])
     r = env.compute_reward(obs["achieved_goal"], obs["desired_goal"], {})
     assert torch.equal(r, rew)
+
+
+def test_pen_env_matches_oracle():
+    """HandManipulatePen*-v1: capsule object, no initial rotation randomisation, z rotation ignored in the goal distance,
+    5 cm position threshold (manipulate_pen.py:216-235)."""
+    model = load_model("hand_pen")
+    env = pkg.make_vec("HandManipulatePenRotate-v1", num_envs=1, backend_factory=HandHostBackend, rng_mode="numpy")
+    assert env.ignore_z_target_rotation and env.distance_threshold == 0.05 and not env.randomize_initial_rotation
+    orc = OracleHandBlockEnv(model=model, target_position="ignore", target_rotation="xyz", randomize_initial_rotation=False,
+                             ignore_z_target_rotation=True, distance_threshold=0.05)
+    obs, _ = env.reset(seed=21)
+    oobs, _ = orc.reset(seed=21)
+    np.testing.assert_allclose(obs["desired_goal"][0, 3:].double().numpy(), oobs["desired_goal"][3:], atol=2e-6)
+    a, oa = obs["achieved_goal"][0].double().numpy(), oobs["achieved_goal"]
+    assert a[2] > 0.04 and oa[2] > 0.04
+    np.testing.assert_allclose(a[:3], oa[:3], atol=5e-3)
+    # env-steps from identical state
+    lay, m, s = env.backend.layout, model, orc.sim
+    rng = np.random.default_rng(5)
+    for k in range(3):
+        rec = np.zeros(lay["stride"])
+        rec[lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+        rec[lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+        rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+        rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+        rec[lay["goal"]:lay["goal"] + 7] = orc.goal
+        env.set_state(torch.as_tensor(rec[None], dtype=torch.float32))
+        act = rng.uniform(-1, 1, 20)
+        obs, rew, *_ , info = env.step(act[None].astype(np.float32))
+        oobs, orew, _, _, oinfo = orc.step(act)
+        np.testing.assert_allclose(obs["observation"][0, :24].double().numpy(), oobs["observation"][:24], atol=2e-3)
+        np.testing.assert_allclose(obs["observation"][0, 54:57].double().numpy(), oobs["observation"][54:57], atol=2e-3)
+        assert float(rew[0]) == float(orew)
+    # ignore-z goal distance: dense reward on random pose pairs against the oracle's numpy restatement
+    envd = pkg.make_vec("HandManipulatePenRotateDense-v1", num_envs=1, backend_factory=HandHostBackend, rng_mode="numpy")
+    orcd = OracleHandBlockEnv(model=model, target_position="ignore", target_rotation="xyz", reward_type="dense",
+                              randomize_initial_rotation=False, ignore_z_target_rotation=True, distance_threshold=0.05)
+    ag, dg = rng.normal(size=(32, 7)), rng.normal(size=(32, 7))
+    ag[:, 3:] /= np.linalg.norm(ag[:, 3:], axis=1, keepdims=True)
+    dg[:, 3:] /= np.linalg.norm(dg[:, 3:], axis=1, keepdims=True)
+    np.testing.assert_allclose(envd.compute_reward(ag, dg, {}), orcd.compute_reward(ag, dg, {}), atol=2e-3)
+    # the in-kernel (emulated) ignore-z distance: dense step reward against the oracle
+    envd.reset(seed=21)
+    orcd.reset(seed=21)
+    s = orcd.sim
+    rec = np.zeros(lay["stride"])
+    rec[lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+    rec[lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+    rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+    rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+    rec[lay["goal"]:lay["goal"] + 7] = orcd.goal
+    envd.set_state(torch.as_tensor(rec[None], dtype=torch.float32))
+    act = rng.uniform(-1, 1, 20)
+    _, rew, *_ = envd.step(act[None].astype(np.float32))
+    _, orew, *_ = orcd.step(act)
+    assert abs(float(rew[0]) - float(orew)) < 5e-3 and float(orew) < -0.05
