@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 # id -> (task, reward_type, max_episode_steps); only the new-binding versions (-v4) of the reference are mirrored,
 # the mujoco_py (-v1) ids are out of scope
 ENV_IDS = {}
-for _task in ("FetchReach", "FetchPush", "FetchPickAndPlace"):
+for _task in ("FetchReach", "FetchPush", "FetchSlide", "FetchPickAndPlace"):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
         ENV_IDS[f"{_task}{_suffix}-v4"] = dict(task=_task, reward_type=_rt, max_episode_steps=50)
 # AntMaze: the reference registers v3/v4/v5 x sparse/dense (__init__.py:839-958); v5 (Gymnasium Ant-v5) is mirrored
@@ -29,7 +29,8 @@ for _maze, _steps in (("UMaze", 300), ("Open", 300), ("Open_Diverse_G", 300), ("
         ENV_IDS[f"PointMaze_{_maze}{_suffix}-v3"] = dict(maze=_maze, agent="point", reward_type=_rt, max_episode_steps=_steps)
 # Shadow-Hand block manipulation, new-binding ids (-v1; __init__.py:105-395); touch-sensor variants are "next"
 for _task in ("HandManipulateBlockRotateZ", "HandManipulateBlockRotateParallel", "HandManipulateBlockRotateXYZ",
-              "HandManipulateBlockFull", "HandManipulateBlock", "HandManipulatePenRotate", "HandManipulatePenFull",
+              "HandManipulateBlockFull", "HandManipulateBlock", "HandManipulateEggRotate", "HandManipulateEggFull",
+              "HandManipulateEgg", "HandManipulatePenRotate", "HandManipulatePenFull",
               "HandManipulatePen"):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
         ENV_IDS[f"{_task}{_suffix}-v1"] = dict(hand_task=_task, reward_type=_rt, max_episode_steps=100)

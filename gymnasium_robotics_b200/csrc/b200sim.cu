@@ -106,7 +106,7 @@ __global__ void reward_kernel(const float* __restrict__ ag, const float* __restr
 
 // ---------------------------------------------------------------------------------------------------------------
 #define B200_FOR_ALL_VARIANTS(X) X(7, 14) X(7, 15) X(7, 21) X(14, 14) X(14, 15) X(14, 21) X(28, 14) X(28, 15) X(28, 21) \
-  X(7, 30) X(14, 30)
+  X(7, 22) X(14, 22) X(28, 22) X(7, 30) X(14, 30)
 
 struct b200sim {
   int N = 0, device = 0;
@@ -190,6 +190,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   h->nvp = dh->nv <= 14 ? 14 : (dh->nv == 15 ? 15 : (dh->nv <= 21 ? 21 : (dh->nv <= 30 ? 30 : 0)));  // smallest built size >= nv (identity padding)
   if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for nv > 30 yet", -8); }
   if (t.kind == TASK_HAND || t.kind == TASK_HAND_REACH) h->nvp = 30;  // the hand task code is compiled into this build only
+  if (dh->nv <= 21 && dh->any_convex_pair) h->nvp = 22;  // arm build that carries the general convex collider (FetchSlide's puck)
   if (dh->nv <= 21 && (dh->nten > 0 || dh->nfric > 0 || dh->nsensor > 0 || dh->any_round_pair)) h->nvp = 30;  // hand features live in the NVP = 30 build
   if (h->nvp == 30 && h->wpb > 14) h->wpb = 14;  // the large models' scratch does not fit 28 envs per block
   if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 14 || (w == 28 && h->nvp != 30)) h->wpb = w; }  // experiments

@@ -83,7 +83,7 @@ struct DMHead {
   int hot_words;   // leading part staged into shared memory (header + HOT arrays)
   int scr_words;   // per-env scratch size in words
   int iterations, ls_iterations, integrator, any_damping, kin_iters, ncon_max, ngrp_max, ndr_max;
-  int edges_per_con, pad5, pad6, pad7;   // pyramid edges of the widest contact (2 * (condim - 1)): line-search edge slots
+  int edges_per_con, any_convex_pair, pad6, pad7;   // pyramid edges of the widest contact (2 * (condim - 1)): line-search edge slots
   int nten, nfric, ncand_max, nsensor;   // nsensor: touch sensors (site volume + body)   // limited fixed tendons; nfric = nv when any dof has frictionloss, else 0
   int grid_len, grid_wid, ngridw, any_round_pair;   // maze wall grid (0 x 0 when the model has none)
   float grid_scale, grid_top, grid_xc, grid_yc;  // cell size, wall top height, map centre offsets
@@ -307,9 +307,12 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     I(h.o_pair_geom1, p, gmap[m.pair_geom1[sp]]); I(h.o_pair_geom2, p, pgrid[p] ? -1 : gmap[m.pair_geom2[sp]]); I(h.o_pair_condim, p, m.pair_condim[sp]);
     int t1 = m.geom_type[m.pair_geom1[sp]], t2 = m.geom_type[m.pair_geom2[sp]];
     bool r1 = t1 == B200_GEOM_SPHERE || t1 == B200_GEOM_CAPSULE, r2 = t2 == B200_GEOM_SPHERE || t2 == B200_GEOM_CAPSULE;
-    bool ok = (t1 == B200_GEOM_PLANE && (t2 == B200_GEOM_BOX || r2)) || (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) ||
-              (r1 && t2 == B200_GEOM_BOX) || (r1 && r2);
+    bool c1 = t1 == B200_GEOM_CYLINDER || t1 == B200_GEOM_ELLIPSOID, c2 = t2 == B200_GEOM_CYLINDER || t2 == B200_GEOM_ELLIPSOID;
+    bool v1 = r1 || c1 || t1 == B200_GEOM_BOX, v2 = r2 || c2 || t2 == B200_GEOM_BOX;   // convex primitives
+    bool ok = (t1 == B200_GEOM_PLANE && (t2 == B200_GEOM_BOX || r2 || c2)) || (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) ||
+              (r1 && t2 == B200_GEOM_BOX) || (r1 && r2) || ((c1 || c2) && v1 && v2);
     if (r1 && r2) h.any_round_pair = 1;
+    if (c1 || c2) h.any_convex_pair = 1;   // served by the general convex collider (kernel builds with CX)
 
     if (!ok) { err = "collision pair type not supported by the CUDA path yet"; return -1; }
     if (m.pair_condim[sp] != 1 && m.pair_condim[sp] != 3 && m.pair_condim[sp] != 4) { err = "condim must be 1, 3 or 4 on the CUDA path"; return -1; }

@@ -811,6 +811,165 @@ HDN void collide_round_round(const Ctx c, int g1, int g2, float margin, ContactO
   for (int k = 0; k < 3; k++) { o.nrm[0][k] = n[k]; o.pos[0][k] = q1[k] + n[k] * (r1 + 0.5f * dist); }
 }
 
+
+// ---- general convex pairs (a cylinder or an ellipsoid against a box / capsule / sphere / cylinder / ellipsoid): Minkowski
+// portal refinement on the support functions (Snethen's XenoCollide -- the published algorithm behind MuJoCo's convex
+// collider: tolerance 1e-6, at most 50 rounds), one contact per pair, both shapes inflated by margin / 2, dist = margin -
+// depth.  Same decision logic as oracle/oracle.c cvx_mpr; evaluated relative to the first geom's centre so that fp32
+// keeps its resolution.  A point of A - B is kept as (v, witness on A); the witness on B is a - v.
+struct CvxShape { int type; float pos[3], mat[9], size[3], infl; };
+struct CvxPt { float v[3], a[3]; };
+HD void cvx_support(const CvxShape& g, const float* d, float* out) {
+  float l[3], sl[3] = {0, 0, 0};
+  mulmtv(l, g.mat, d);
+  const float* z = g.size;
+  if (g.type == B200_GEOM_BOX) { sl[0] = l[0] >= 0 ? z[0] : -z[0]; sl[1] = l[1] >= 0 ? z[1] : -z[1]; sl[2] = l[2] >= 0 ? z[2] : -z[2]; }
+  else if (g.type == B200_GEOM_CYLINDER) {
+    float n = sqrtf(l[0] * l[0] + l[1] * l[1]);
+    if (n > 1e-12f) { float i = z[0] / n; sl[0] = i * l[0]; sl[1] = i * l[1]; }
+    sl[2] = l[2] >= 0 ? z[1] : -z[1];
+  } else if (g.type == B200_GEOM_ELLIPSOID) {
+    float a = z[0] * l[0], b = z[1] * l[1], cc = z[2] * l[2], n = sqrtf(a * a + b * b + cc * cc);
+    if (n > 0) { float i = 1.0f / n; sl[0] = z[0] * a * i; sl[1] = z[1] * b * i; sl[2] = z[2] * cc * i; }
+  } else {  // sphere, capsule
+    float n = sqrtf(dot3(l, l));
+    if (n > 0) { float i = z[0] / n; sl[0] = i * l[0]; sl[1] = i * l[1]; sl[2] = i * l[2]; }
+    if (g.type == B200_GEOM_CAPSULE) sl[2] += l[2] >= 0 ? z[1] : -z[1];
+  }
+  mulmv(out, g.mat, sl);
+  float n = sqrtf(dot3(d, d)), e = n > 0 ? g.infl / n : 0.f;
+  for (int k = 0; k < 3; k++) out[k] += g.pos[k] + e * d[k];
+}
+HD void cvx_msupport(const CvxShape& A, const CvxShape& B, const float* d, CvxPt& p) {
+  float nd[3] = {-d[0], -d[1], -d[2]}, b[3];
+  cvx_support(A, d, p.a); cvx_support(B, nd, b);
+  p.v[0] = p.a[0] - b[0]; p.v[1] = p.a[1] - b[1]; p.v[2] = p.a[2] - b[2];
+}
+HD void cvx_portal_dir(const CvxPt& o, const CvxPt& p, const CvxPt& q, float* dir) {  // normalised (p - o) x (q - o)
+  float va[3] = {p.v[0] - o.v[0], p.v[1] - o.v[1], p.v[2] - o.v[2]}, vb[3] = {q.v[0] - o.v[0], q.v[1] - o.v[1], q.v[2] - o.v[2]};
+  cross3(dir, va, vb);
+  float n = sqrtf(dot3(dir, dir)), i = n > 1e-30f ? 1.0f / n : 0.f;
+  dir[0] *= i; dir[1] *= i; dir[2] *= i;
+}
+HDN void collide_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
+  ASSUME_SHARED(c);
+  o.cnt = 0;
+  CvxShape A, B;
+  float p1[3], p2[3];
+  geom_pose(c, g1, p1, A.mat); geom_pose(c, g2, p2, B.mat);
+  A.type = MI(geom_type)[g1]; B.type = MI(geom_type)[g2];
+  for (int k = 0; k < 3; k++) { A.pos[k] = 0.f; B.pos[k] = p2[k] - p1[k]; A.size[k] = MF(geom_size)[3 * g1 + k]; B.size[k] = MF(geom_size)[3 * g2 + k]; }
+  A.infl = B.infl = 0.5f * margin;
+  const float tol = 1e-6f; const int maxit = 50;
+  CvxPt v0, v1, v2, v3, v4;
+  float dir[3], t[3];
+  for (int k = 0; k < 3; k++) { v0.a[k] = 0.f; v0.v[k] = -B.pos[k]; }
+  if (dot3(v0.v, v0.v) < 1e-24f) v0.v[0] = 1e-5f;
+  { float i = rsqrtf(dot3(v0.v, v0.v)); dir[0] = -v0.v[0] * i; dir[1] = -v0.v[1] * i; dir[2] = -v0.v[2] * i; }
+  cvx_msupport(A, B, dir, v1);
+  if (dot3(v1.v, dir) <= 0) return;
+  cross3(t, v0.v, v1.v);
+  float depth, pos[3];
+  if (dot3(t, t) < 1e-24f) {
+    // the origin lies on the ray v0 -> v1: the centres' line is the contact normal
+    depth = dot3(v1.v, dir);
+    for (int k = 0; k < 3; k++) pos[k] = v1.a[k] - 0.5f * v1.v[k];
+  } else {
+    { float i = rsqrtf(dot3(t, t)); dir[0] = t[0] * i; dir[1] = t[1] * i; dir[2] = t[2] * i; }
+    cvx_msupport(A, B, dir, v2);
+    if (dot3(v2.v, dir) <= 0) return;
+    cvx_portal_dir(v0, v1, v2, dir);
+    if (dot3(dir, v0.v) > 0) { CvxPt tmp = v1; v1 = v2; v2 = tmp; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+    for (int it = 0;; it++) {  // portal discovery
+      if (it > maxit) return;
+      cvx_msupport(A, B, dir, v3);
+      if (dot3(v3.v, dir) <= 0) return;
+      bool cont = false;
+      cross3(t, v1.v, v3.v);
+      if (dot3(t, v0.v) < 0) { v2 = v3; cont = true; }
+      else { cross3(t, v3.v, v2.v); if (dot3(t, v0.v) < 0) { v1 = v3; cont = true; } }
+      if (!cont) break;
+      cvx_portal_dir(v0, v1, v2, dir);
+    }
+    bool hit = false;
+    for (int it = 0;; it++) {  // refinement; past the origin the shapes overlap and the loop runs on to the surface
+      cvx_portal_dir(v1, v2, v3, dir);
+      if (dot3(dir, v1.v) >= 0) hit = true;
+      cvx_msupport(A, B, dir, v4);
+      float d4 = dot3(v4.v, dir);
+      if (!hit && d4 < 0) return;
+      float mn = fminf(fminf(d4 - dot3(v1.v, dir), d4 - dot3(v2.v, dir)), d4 - dot3(v3.v, dir));
+      if (mn <= tol || it >= maxit) { if (!hit) return; break; }
+      cross3(t, v4.v, v0.v);
+      if (dot3(v1.v, t) > 0) { if (dot3(v2.v, t) > 0) v1 = v4; else v3 = v4; }
+      else { if (dot3(v3.v, t) > 0) v2 = v4; else v1 = v4; }
+    }
+    depth = dot3(dir, v1.v);
+    float b0, b1, b2, b3, sum;
+    cross3(t, v1.v, v2.v); b0 = dot3(t, v3.v);
+    cross3(t, v3.v, v2.v); b1 = dot3(t, v0.v);
+    cross3(t, v0.v, v1.v); b2 = dot3(t, v3.v);
+    cross3(t, v2.v, v1.v); b3 = dot3(t, v0.v);
+    sum = b0 + b1 + b2 + b3;
+    if (sum <= 0) {
+      b0 = 0;
+      cross3(t, v2.v, v3.v); b1 = dot3(t, dir);
+      cross3(t, v3.v, v1.v); b2 = dot3(t, dir);
+      cross3(t, v1.v, v2.v); b3 = dot3(t, dir);
+      sum = b1 + b2 + b3;
+    }
+    if (!(fabsf(sum) > 0)) return;
+    float is = 1.0f / sum;
+    // midpoint of the two witnesses: a - v / 2 per portal vertex
+    for (int k = 0; k < 3; k++)
+      pos[k] = (b0 * (v0.a[k] - 0.5f * v0.v[k]) + b1 * (v1.a[k] - 0.5f * v1.v[k]) + b2 * (v2.a[k] - 0.5f * v2.v[k]) + b3 * (v3.a[k] - 0.5f * v3.v[k])) * is;
+  }
+  o.cnt = 1; o.dist[0] = margin - depth;
+  for (int k = 0; k < 3; k++) { o.nrm[0][k] = dir[k]; o.pos[0][k] = pos[k] + p1[k]; }
+}
+// plane vs cylinder / ellipsoid (same point selection as oracle/oracle.c)
+HDN void collide_plane_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
+  ASSUME_SHARED(c);
+  o.cnt = 0;
+  float pp[3], pm[9], cp[3], cm[9];
+  geom_pose(c, g1, pp, pm); geom_pose(c, g2, cp, cm);
+  float n[3] = {pm[2], pm[5], pm[8]};
+  const float* sz = MF(geom_size) + 3 * g2;
+  if (MI(geom_type)[g2] == B200_GEOM_ELLIPSOID) {
+    float l[3], nn[3] = {-n[0], -n[1], -n[2]}, sl[3] = {0, 0, 0}, p[3];
+    mulmtv(l, cm, nn);
+    float a = sz[0] * l[0], b = sz[1] * l[1], cc = sz[2] * l[2], nl = sqrtf(a * a + b * b + cc * cc);
+    if (nl > 0) { sl[0] = sz[0] * a / nl; sl[1] = sz[1] * b / nl; sl[2] = sz[2] * cc / nl; }
+    mulmv(p, cm, sl);
+    float dif[3] = {p[0] + cp[0] - pp[0], p[1] + cp[1] - pp[1], p[2] + cp[2] - pp[2]};
+    float d = dot3(dif, n);
+    if (d > margin) return;
+    o.cnt = 1; o.dist[0] = d;
+    for (int k = 0; k < 3; k++) { o.nrm[0][k] = n[k]; o.pos[0][k] = p[k] + cp[k] - 0.5f * d * n[k]; }
+    return;
+  }
+  float ax[3] = {cm[2], cm[5], cm[8]}, r = sz[0], hl = sz[1];
+  float an = dot3(ax, n);
+  if (an > 0) { ax[0] = -ax[0]; ax[1] = -ax[1]; ax[2] = -ax[2]; an = -an; }
+  float rad[3] = {-n[0] + an * ax[0], -n[1] + an * ax[1], -n[2] + an * ax[2]};
+  float rl = sqrtf(dot3(rad, rad));
+  if (rl < 1e-9f) { float y[3] = {0, 0, 0}; if (fabsf(ax[0]) < 0.5f) y[0] = 1; else y[1] = 1; cross3(rad, ax, y); rl = sqrtf(dot3(rad, rad)); }
+  { float i = 1.0f / rl; rad[0] *= i; rad[1] *= i; rad[2] *= i; }
+  float side[3];
+  cross3(side, ax, rad);
+  for (int i = 0; i < 4; i++) {
+    float cs = i < 2 ? 1.f : -0.5f, sn = i < 2 ? 0.f : (i == 2 ? 0.8660254037844386f : -0.8660254037844386f), cap = i == 1 ? -1.f : 1.f;
+    float p[3];
+    for (int k = 0; k < 3; k++) p[k] = cp[k] + cap * hl * ax[k] + r * (cs * rad[k] + sn * side[k]);
+    float dif[3] = {p[0] - pp[0], p[1] - pp[1], p[2] - pp[2]};
+    float d = dot3(dif, n);
+    if (d > margin) continue;
+    int k2 = o.cnt++;
+    o.dist[k2] = d;
+    for (int k = 0; k < 3; k++) { o.nrm[k2][k] = n[k]; o.pos[k2][k] = p[k] - 0.5f * d * n[k]; }
+  }
+}
+
 HD void make_frame(float* f) {
   float n = sqrtf(dot3(f, f)), inv = n > 1e-12f ? 1.0f / n : 0.f;
   f[0] *= inv; f[1] *= inv; f[2] *= inv;
@@ -826,7 +985,8 @@ HD void make_frame(float* f) {
 
 // HF: model family with hand features (frictionloss rows, tendon limits, round-round pairs, touch sensors); compiled out
 // of the other kernel instantiations to keep their instruction stream short
-template <bool HF>
+// CX: builds that carry the general convex collider (cylinder / ellipsoid geoms)
+template <bool HF, bool CX>
 STAGE void collision(const Ctx c) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
@@ -888,7 +1048,11 @@ STAGE void collision(const Ctx c) {
       int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
       float margin = MF(pair_margin)[p];
       int t1 = MI(geom_type)[g1], t2 = g2 < 0 ? B200_GEOM_BOX : MI(geom_type)[g2];
-      if (t1 == B200_GEOM_PLANE) {
+      const bool cv1 = t1 == B200_GEOM_CYLINDER || t1 == B200_GEOM_ELLIPSOID, cv2 = t2 == B200_GEOM_CYLINDER || t2 == B200_GEOM_ELLIPSOID;
+      if (CX && (cv1 || cv2)) {
+        if (t1 == B200_GEOM_PLANE) collide_plane_convex(c, g1, g2, margin, o);
+        else collide_convex(c, g1, g2, margin, o);
+      } else if (t1 == B200_GEOM_PLANE) {
         if (t2 == B200_GEOM_BOX) collide_plane_box(c, g1, g2, margin, o);
         else if (t2 == B200_GEOM_SPHERE) collide_plane_sphere(c, g1, g2, margin, o);
         else collide_plane_capsule(c, g1, g2, margin, o);
@@ -1672,6 +1836,7 @@ STAGE int newton_move(const Ctx c, float* improvement) {
 template <int NVP>
 HD void forward(const Ctx c, bool active) {
   constexpr bool HF = NVP >= 30;
+  constexpr bool CX = NVP == 22 || NVP >= 30;   // NVP 22 = the 21-dof arm build plus the convex collider (FetchSlide)
   constexpr int kAlign = ALIGN_LEVEL_FOR(NVP);
   TIC();
   ALIGN_AT(1); TOC(TM_BARRIER);
@@ -1679,7 +1844,7 @@ HD void forward(const Ctx c, bool active) {
   TOC(TM_KIN); ALIGN_AT(4); TOC(TM_BARRIER);
   if (active) { com_quantities(c); mass_matrix(c); }
   TOC(TM_COM_M); ALIGN_AT(2); TOC(TM_BARRIER);
-  if (active) collision<HF>(c);
+  if (active) collision<HF, CX>(c);
   TOC(TM_COLL); ALIGN_AT(2); TOC(TM_BARRIER);
   if (active) make_constraint<HF>(c);
   TOC(TM_CONSTR); ALIGN_AT(4); TOC(TM_BARRIER);

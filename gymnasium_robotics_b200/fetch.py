@@ -1,7 +1,7 @@
 """Batched Fetch environments (`gym.vector.VectorEnv`-style) on the b200sim CUDA path.
 
 Host-side mirror of the reference's Fetch stack, batched over `num_envs`:
-  * task tables              envs/fetch/{reach,push,pick_and_place}.py ctor kwargs (e.g. pick_and_place.py:139-162)
+  * task tables              envs/fetch/{reach,push,slide,pick_and_place}.py ctor kwargs (e.g. pick_and_place.py:139-162)
   * construction/_env_setup  envs/fetch/fetch_env.py:404-428, envs/robot_env.py:292-303
   * reset/_reset_sim/_sample_goal   envs/robot_env.py:154-186, envs/fetch/fetch_env.py:375-402, 153-166
   * step                     envs/robot_env.py:114-152  (runs entirely inside one CUDA kernel, csrc/fetch_task.cuh)
@@ -35,6 +35,11 @@ FETCH_TASKS = {
                               distance_threshold=0.05,
                               initial_qpos={"robot0:slide0": 0.405, "robot0:slide1": 0.48, "robot0:slide2": 0.0,
                                             "object0:joint": [1.25, 0.53, 0.4, 1.0, 0.0, 0.0, 0.0]}),
+    # envs/fetch/slide.py:160-190 (cylinder puck; target_offset = [0.4, 0, 0])
+    "FetchSlide": dict(model="fetch_slide", has_object=True, block_gripper=True, gripper_extra_height=-0.02,
+                       target_in_the_air=False, target_offset=(0.4, 0.0, 0.0), obj_range=0.1, target_range=0.3, distance_threshold=0.05,
+                       initial_qpos={"robot0:slide0": 0.05, "robot0:slide1": 0.48, "robot0:slide2": 0.0,
+                                     "object0:joint": [1.7, 1.1, 0.41, 1.0, 0.0, 0.0, 0.0]}),
 }
 N_SUBSTEPS = 20
 REF_POINT = (1.0, 0.75, 0.4)  # fixed world point the device spatial algebra is expressed about

@@ -31,6 +31,10 @@ HAND_TASKS = {
     "HandManipulateBlockRotateXYZ": dict(target_position="ignore", target_rotation="xyz"),
     "HandManipulateBlockFull": dict(target_position="random", target_rotation="xyz"),
     "HandManipulateBlock": dict(target_position="random", target_rotation="xyz"),
+    # the egg (ellipsoid object, manipulate_egg.py:214-235: same defaults as the block; ids __init__.py:453-640)
+    "HandManipulateEggRotate": dict(target_position="ignore", target_rotation="xyz", model="hand_egg", touch_model="hand_egg_touch"),
+    "HandManipulateEggFull": dict(target_position="random", target_rotation="xyz", model="hand_egg", touch_model="hand_egg_touch"),
+    "HandManipulateEgg": dict(target_position="random", target_rotation="xyz", model="hand_egg", touch_model="hand_egg_touch"),
     # the pen (manipulate_pen.py:216-235: no initial rotation randomisation, z rotation ignored, 5 cm position threshold;
     # ids __init__.py:651-780)
     "HandManipulatePenRotate": dict(target_position="ignore", target_rotation="xyz", model="hand_pen", touch_model="hand_pen_touch",

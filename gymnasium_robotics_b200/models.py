@@ -18,17 +18,20 @@ REFERENCE_ASSETS = os.environ.get("B200SIM_REFERENCE_ASSETS", "/root/reference/g
 MODEL_SOURCES = {
     "fetch_reach": "fetch/reach.xml",
     "fetch_push": "fetch/push.xml",
+    "fetch_slide": "fetch/slide.xml",
     "fetch_pick_and_place": "fetch/pick_and_place.xml",
     "hand_block": "hand/manipulate_block.xml",
     "hand_block_touch": "hand/manipulate_block_touch_sensors.xml",   # + 92 touch sensors
     "hand_reach": "hand/reach.xml",
+    "hand_egg": "hand/manipulate_egg.xml",
+    "hand_egg_touch": "hand/manipulate_egg_touch_sensors.xml",
     "hand_pen": "hand/manipulate_pen.xml",
     "hand_pen_touch": "hand/manipulate_pen_touch_sensors.xml",
 }
 # compile-time edits: the Hand's visual-only `target` free body (contype 0, never observed) is not simulated
 # and only the sensors the envs read are kept ("robot0:TS_*", manipulate_touch_sensors.py:66-79)
 _HAND = {"drop_bodies": ["target"], "sensor_prefix": "robot0:TS_"}
-MODEL_OVERRIDES = {"hand_block": _HAND, "hand_block_touch": _HAND, "hand_pen": _HAND, "hand_pen_touch": _HAND, "hand_reach": {"sensor_prefix": "robot0:TS_"}}
+MODEL_OVERRIDES = {"hand_block": _HAND, "hand_block_touch": _HAND, "hand_pen": _HAND, "hand_pen_touch": _HAND, "hand_egg": _HAND, "hand_egg_touch": _HAND, "hand_reach": {"sensor_prefix": "robot0:TS_"}}
 
 
 # maze models: in-tree legacy twin of Gymnasium's ant.xml (Gymnasium itself is un-vendored) + generated wall boxes

@@ -28,6 +28,12 @@ FETCH_TASKS = {
                               target_range=0.15, distance_threshold=0.05,
                               initial_qpos={"robot0:slide0": 0.405, "robot0:slide1": 0.48, "robot0:slide2": 0.0,
                                             "object0:joint": [1.25, 0.53, 0.4, 1.0, 0.0, 0.0, 0.0]}),
+    # envs/fetch/slide.py:160-190
+    "FetchSlide": dict(xml="fetch/slide.xml", has_object=True, block_gripper=True, gripper_extra_height=-0.02,
+                       target_in_the_air=False, target_offset=np.array([0.4, 0.0, 0.0]), obj_range=0.1, target_range=0.3,
+                       distance_threshold=0.05,
+                       initial_qpos={"robot0:slide0": 0.05, "robot0:slide1": 0.48, "robot0:slide2": 0.0,
+                                     "object0:joint": [1.7, 1.1, 0.41, 1.0, 0.0, 0.0, 0.0]}),
 }
 
 

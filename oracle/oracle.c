@@ -865,6 +865,164 @@ static void collide_round_round(oracle_sim* s, int pair, real margin) {
   add_contact(s, pair, d, pos, n);
 }
 
+
+/* ---- general convex pairs (cylinder / ellipsoid against box, capsule, sphere, cylinder, ellipsoid): Minkowski portal
+ * refinement on the support functions (Snethen, "XenoCollide", Game Programming Gems 7 -- the published algorithm that
+ * MuJoCo's convex collider wraps through libccd: tolerance opt.mpr_tolerance = 1e-6, at most opt.mpr_iterations = 50 rounds);
+ * one contact per pair, both shapes inflated by margin / 2, dist = margin - depth.  Everything is evaluated relative to the
+ * first geom's centre (the fp32 twin in csrc/sim_core.cuh needs that; here it only keeps the two implementations alike). */
+typedef struct { int type; real pos[3]; const real* mat; const double* size; real infl; } CvxShape;
+static void cvx_support(const CvxShape* g, const real* d, real* out) {
+  real l[3], sl[3] = {0, 0, 0};
+  mulmatTvec3(l, g->mat, d);
+  const double* z = g->size;
+  switch (g->type) {
+    case B200_GEOM_SPHERE: { real n = norm3(l); if (n > 0) { sl[0] = z[0] * l[0] / n; sl[1] = z[0] * l[1] / n; sl[2] = z[0] * l[2] / n; } break; }
+    case B200_GEOM_CAPSULE: { real n = norm3(l); if (n > 0) { sl[0] = z[0] * l[0] / n; sl[1] = z[0] * l[1] / n; sl[2] = z[0] * l[2] / n; } sl[2] += l[2] >= 0 ? z[1] : -z[1]; break; }
+    case B200_GEOM_CYLINDER: { real n = sqrt(l[0] * l[0] + l[1] * l[1]); if (n > 1e-12) { sl[0] = z[0] * l[0] / n; sl[1] = z[0] * l[1] / n; } sl[2] = l[2] >= 0 ? z[1] : -z[1]; break; }
+    case B200_GEOM_ELLIPSOID: { real a = z[0] * l[0], b = z[1] * l[1], c = z[2] * l[2], n = sqrt(a * a + b * b + c * c); if (n > 0) { sl[0] = z[0] * a / n; sl[1] = z[1] * b / n; sl[2] = z[2] * c / n; } break; }
+    default: /* box */ sl[0] = l[0] >= 0 ? z[0] : -z[0]; sl[1] = l[1] >= 0 ? z[1] : -z[1]; sl[2] = l[2] >= 0 ? z[2] : -z[2]; break;
+  }
+  mulmatvec3(out, g->mat, sl);
+  real n = norm3(d);
+  for (int k = 0; k < 3; k++) out[k] += g->pos[k] + (n > 0 ? g->infl * d[k] / n : 0);
+}
+typedef struct { real v[3], a[3], b[3]; } CvxPt; /* point of A - B and its witnesses */
+static void cvx_msupport(const CvxShape* A, const CvxShape* B, const real* d, CvxPt* p) {
+  real nd[3] = {-d[0], -d[1], -d[2]};
+  cvx_support(A, d, p->a); cvx_support(B, nd, p->b);
+  sub3(p->v, p->a, p->b);
+}
+/* returns 1 and (depth, dir from A to B, pos) when the inflated shapes overlap */
+static int cvx_mpr(const CvxShape* A, const CvxShape* B, real tol, int maxit, real* depth, real* dir_out, real* pos) {
+  CvxPt v0, v1, v2, v3, v4;
+  real dir[3], va[3], vb[3], t[3];
+  copy3(v0.a, A->pos); copy3(v0.b, B->pos); sub3(v0.v, v0.a, v0.b);
+  if (norm3(v0.v) < 1e-12) v0.v[0] = 1e-5;
+  for (int k = 0; k < 3; k++) dir[k] = -v0.v[k];
+  normalize3(dir);
+  cvx_msupport(A, B, dir, &v1);
+  if (dot3(v1.v, dir) <= 0) return 0;
+  cross3(dir, v0.v, v1.v);
+  if (norm3(dir) < 1e-12) {
+    /* the origin lies on the ray v0 -> v1: the centres' line is the contact normal */
+    for (int k = 0; k < 3; k++) dir_out[k] = -v0.v[k];
+    normalize3(dir_out);
+    *depth = dot3(v1.v, dir_out);
+    for (int k = 0; k < 3; k++) pos[k] = 0.5 * (v1.a[k] + v1.b[k]);
+    return 1;
+  }
+  normalize3(dir);
+  cvx_msupport(A, B, dir, &v2);
+  if (dot3(v2.v, dir) <= 0) return 0;
+  sub3(va, v1.v, v0.v); sub3(vb, v2.v, v0.v); cross3(dir, va, vb); normalize3(dir);
+  if (dot3(dir, v0.v) > 0) { CvxPt tmp = v1; v1 = v2; v2 = tmp; for (int k = 0; k < 3; k++) dir[k] = -dir[k]; }
+  /* portal discovery */
+  for (int it = 0;; it++) {
+    if (it > maxit) return 0;
+    cvx_msupport(A, B, dir, &v3);
+    if (dot3(v3.v, dir) <= 0) return 0;
+    int cont = 0;
+    cross3(t, v1.v, v3.v);
+    if (dot3(t, v0.v) < 0) { v2 = v3; cont = 1; }
+    else { cross3(t, v3.v, v2.v); if (dot3(t, v0.v) < 0) { v1 = v3; cont = 1; } }
+    if (!cont) break;
+    sub3(va, v1.v, v0.v); sub3(vb, v2.v, v0.v); cross3(dir, va, vb); normalize3(dir);
+  }
+  /* portal refinement; once the portal has passed the origin the shapes overlap and the loop continues to the surface */
+  int hit = 0;
+  for (int it = 0;; it++) {
+    sub3(va, v2.v, v1.v); sub3(vb, v3.v, v1.v); cross3(dir, va, vb); normalize3(dir);
+    if (dot3(dir, v1.v) >= 0) hit = 1;
+    cvx_msupport(A, B, dir, &v4);
+    real d4 = dot3(v4.v, dir);
+    if (!hit && d4 < 0) return 0;
+    real m1 = d4 - dot3(v1.v, dir), m2 = d4 - dot3(v2.v, dir), m3 = d4 - dot3(v3.v, dir);
+    real mn = m1 < m2 ? (m1 < m3 ? m1 : m3) : (m2 < m3 ? m2 : m3);
+    if (mn <= tol || it >= maxit) {
+      if (!hit) return 0;
+      break;
+    }
+    cross3(t, v4.v, v0.v);
+    if (dot3(v1.v, t) > 0) { if (dot3(v2.v, t) > 0) v1 = v4; else v3 = v4; }
+    else { if (dot3(v3.v, t) > 0) v2 = v4; else v1 = v4; }
+  }
+  /* depth = distance of the origin from the portal plane along its normal; witnesses by barycentric weights of the
+   * portal tetrahedron (v0 is interior, so its weight only matters before normalisation) */
+  *depth = dot3(dir, v1.v);
+  copy3(dir_out, dir);
+  real b0, b1, b2, b3, sum;
+  cross3(t, v1.v, v2.v); b0 = dot3(t, v3.v);
+  cross3(t, v3.v, v2.v); b1 = dot3(t, v0.v);
+  cross3(t, v0.v, v1.v); b2 = dot3(t, v3.v);
+  cross3(t, v2.v, v1.v); b3 = dot3(t, v0.v);
+  sum = b0 + b1 + b2 + b3;
+  if (sum <= 0) {
+    b0 = 0;
+    cross3(t, v2.v, v3.v); b1 = dot3(t, dir);
+    cross3(t, v3.v, v1.v); b2 = dot3(t, dir);
+    cross3(t, v1.v, v2.v); b3 = dot3(t, dir);
+    sum = b1 + b2 + b3;
+  }
+  if (!(fabs(sum) > 0)) return 0;
+  for (int k = 0; k < 3; k++)
+    pos[k] = 0.5 * (b0 * (v0.a[k] + v0.b[k]) + b1 * (v1.a[k] + v1.b[k]) + b2 * (v2.a[k] + v2.b[k]) + b3 * (v3.a[k] + v3.b[k])) / sum;
+  return 1;
+}
+static void collide_convex(oracle_sim* s, int pair, real margin) {
+  const b200_model_view* m = &s->m;
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  CvxShape A = {m->geom_type[g1], {0, 0, 0}, s->geom_xmat + 9 * g1, m->geom_size + 3 * g1, 0.5 * margin};
+  CvxShape B = {m->geom_type[g2], {0, 0, 0}, s->geom_xmat + 9 * g2, m->geom_size + 3 * g2, 0.5 * margin};
+  sub3(B.pos, s->geom_xpos + 3 * g2, s->geom_xpos + 3 * g1);
+  real depth, dir[3], pos[3];
+  if (!cvx_mpr(&A, &B, 1e-6, 50, &depth, dir, pos)) return;
+  add3(pos, pos, s->geom_xpos + 3 * g1);
+  add_contact(s, pair, margin - depth, pos, dir);
+}
+/* plane vs cylinder: deepest point of the lower rim, the same rim direction on the other cap, and two more points of
+ * the lower rim at +-120 degrees (own point selection; MuJoCo's mjc_PlaneCylinder picks up to four points differently) */
+static void collide_plane_cylinder(oracle_sim* s, int pair, real margin) {
+  const b200_model_view* m = &s->m;
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  const real *pp = s->geom_xpos + 3 * g1, *pm = s->geom_xmat + 9 * g1, *c = s->geom_xpos + 3 * g2, *cm = s->geom_xmat + 9 * g2;
+  real n[3] = {pm[2], pm[5], pm[8]}, ax[3] = {cm[2], cm[5], cm[8]};
+  real r = m->geom_size[3 * g2], h = m->geom_size[3 * g2 + 1];
+  real an = dot3(ax, n);
+  if (an > 0) { ax[0] = -ax[0]; ax[1] = -ax[1]; ax[2] = -ax[2]; an = -an; }   /* ax points towards the plane */
+  real rad[3] = {-n[0] + an * ax[0], -n[1] + an * ax[1], -n[2] + an * ax[2]};  /* rim direction of steepest descent */
+  real rl = norm3(rad);
+  if (rl < 1e-9) { real y[3] = {0, 0, 0}; if (fabs(ax[0]) < 0.5) y[0] = 1; else y[1] = 1; cross3(rad, ax, y); rl = norm3(rad); }
+  for (int k = 0; k < 3; k++) rad[k] /= rl;
+  real side[3];
+  cross3(side, ax, rad);
+  const real cs[4] = {1, 1, -0.5, -0.5}, sn[4] = {0, 0, 0.8660254037844386, -0.8660254037844386}, cap[4] = {1, -1, 1, 1};
+  for (int i = 0; i < 4; i++) {
+    real p[3], dif[3];
+    for (int k = 0; k < 3; k++) p[k] = c[k] + cap[i] * h * ax[k] + r * (cs[i] * rad[k] + sn[i] * side[k]);
+    sub3(dif, p, pp);
+    real d = dot3(dif, n);
+    if (d > margin) continue;
+    addscl3(p, n, -0.5 * d);
+    add_contact(s, pair, d, p, n);
+  }
+}
+/* plane vs ellipsoid: the support point of the ellipsoid against the plane normal */
+static void collide_plane_ellipsoid(oracle_sim* s, int pair, real margin) {
+  const b200_model_view* m = &s->m;
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  const real *pp = s->geom_xpos + 3 * g1, *pm = s->geom_xmat + 9 * g1;
+  real n[3] = {pm[2], pm[5], pm[8]}, nn[3] = {-n[0], -n[1], -n[2]}, p[3], dif[3];
+  CvxShape E = {B200_GEOM_ELLIPSOID, {0, 0, 0}, s->geom_xmat + 9 * g2, m->geom_size + 3 * g2, 0};
+  copy3(E.pos, s->geom_xpos + 3 * g2);
+  cvx_support(&E, nn, p);
+  sub3(dif, p, pp);
+  real d = dot3(dif, n);
+  if (d > margin) return;
+  addscl3(p, n, -0.5 * d);
+  add_contact(s, pair, d, p, n);
+}
+
 static void collision(oracle_sim* s) {
   const b200_model_view* m = &s->m;
   s->ncon = 0;
@@ -892,7 +1050,11 @@ static void collision(oracle_sim* s) {
     else if (t1 == B200_GEOM_CAPSULE && t2 == B200_GEOM_BOX) collide_capsule_box(s, p, margin);
     else if ((t1 == B200_GEOM_SPHERE || t1 == B200_GEOM_CAPSULE) && (t2 == B200_GEOM_SPHERE || t2 == B200_GEOM_CAPSULE))
       collide_round_round(s, p, margin);
-    /* other pair types: not yet restated (DESIGN.md lists them) */
+    else if (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_CYLINDER) collide_plane_cylinder(s, p, margin);
+    else if (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_ELLIPSOID) collide_plane_ellipsoid(s, p, margin);
+    else if (t1 >= B200_GEOM_SPHERE && t1 <= B200_GEOM_BOX && t2 >= B200_GEOM_SPHERE && t2 <= B200_GEOM_BOX)
+      collide_convex(s, p, margin);   /* any pair with a cylinder or an ellipsoid */
+    /* other pair types (height fields, meshes): not restated (DESIGN.md lists them) */
   }
 }
 

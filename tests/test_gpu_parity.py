@@ -456,3 +456,98 @@ def test_hand_reach_parity():
     print(f"HandReach: median {np.median(errs):.2e} max {errs.max():.2e}")
     assert np.median(errs) < 2e-5 and errs.max() < 2e-4
     env.close()
+
+
+# ------------------------------------------------------------------------------ general convex collider (cylinder, ellipsoid)
+def test_fetch_slide_parity():
+    """FetchSlide-v4: the cylinder puck runs through the portal-refinement collider (kernel build NVP = 22).  A flat
+    cylinder rocks on its single portal contact, so its Euler angles (obs 11:14) and angular velocity (obs 17:20) are
+    chaotic between fp32 and fp64; the other 19 observation entries are compared per env-step from injected states."""
+    from tests.parity_util import inject_oracle_state, oracle_env_from_model
+
+    n = 6
+    env = _mk("FetchSlide", n, rng_mode="numpy")
+    orc0 = oracle_env_from_model("FetchSlide", env.model)
+    assert np.allclose(env.initial_gripper_xpos.double().cpu().numpy(), orc0.initial_gripper_xpos, atol=1e-4)
+    assert env.height_offset == pytest.approx(orc0.height_offset, abs=5e-4)
+    obs, _ = env.reset(seed=100)
+    oracles = [oracle_env_from_model("FetchSlide", env.model) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=100 + i)
+        assert np.abs(obs["desired_goal"][i].double().cpu().numpy() - oo["desired_goal"]).max() < 5e-4
+    keep = np.array([i for i in range(25) if not 11 <= i < 14 and not 17 <= i < 20])
+    rng = np.random.default_rng(7)
+    errs = []
+    for step in range(10):
+        inject_oracle_state(env, oracles)
+        a = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        if step >= 5:   # sweep the gripper across the table towards the puck
+            a[:, 2] = -0.3
+        o, r, term, trunc, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            got = o["observation"][i].double().cpu().numpy()
+            assert np.isfinite(got).all()
+            errs.append(np.abs(got - oo["observation"])[keep].max())
+            d = np.linalg.norm(oo["achieved_goal"] - oo["desired_goal"])
+            if abs(d - 0.05) > 5e-3:
+                assert float(r[i]) == float(orr)
+    errs = np.array(errs)
+    print(f"FetchSlide: median {np.median(errs):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < OBS_TOL and np.mean(errs < 1e-3) >= 0.9 and errs.max() < 0.05
+    # batch properties at the bench size: no capacity overflow, pucks stay on the table under random actions
+    env.close()
+    env = _mk("FetchSlide", 4096, rng_mode="torch")
+    env.reset(seed=1)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    info_bits = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    for _ in range(10):
+        a = torch.rand((4096, 4), generator=g, device="cuda") * 2 - 1
+        out = env.backend.new_outputs()
+        env.backend.step(a, out, info_bits)
+        assert torch.isfinite(out["obs"]).all()
+        assert int((info_bits >> 16).max()) == 0
+    assert float(out["obs"][:, 5].min()) > 0.35
+    env.close()
+
+
+def test_hand_egg_parity():
+    """HandManipulateEggRotate-v1: the ellipsoid egg against the palm/finger capsules and boxes through the convex collider."""
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.hand_env import OracleHandBlockEnv
+
+    n = 4
+    model = load_model("hand_egg")
+    env = _mk_hand("HandManipulateEggRotate", n, rng_mode="numpy")
+    obs, _ = env.reset(seed=40)
+    oracles = [OracleHandBlockEnv(model=model) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=40 + i)
+        g = obs["desired_goal"][i].double().cpu().numpy()
+        assert np.abs(g[3:] - oo["desired_goal"][3:]).max() < 2e-6
+        a = obs["achieved_goal"][i].double().cpu().numpy()
+        assert a[2] > 0.04 and np.abs(a[:3] - oo["achieved_goal"][:3]).max() < 5e-3
+    lay, m = env.backend.layout, model
+    rng = np.random.default_rng(4)
+    errs = []
+    for step in range(8):
+        rec = np.zeros((n, lay["stride"]))
+        for i, o in enumerate(oracles):
+            s = o.sim
+            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+            rec[i, lay["goal"]:lay["goal"] + 7] = o.goal
+        env.set_state(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            got = o["observation"][i].double().cpu().numpy()
+            errs.append(max(np.abs(got[:24] - oo["observation"][:24]).max(), np.abs(got[54:57] - oo["observation"][54:57]).max()))
+            assert float(r[i]) == float(orr)
+    errs = np.array(errs)
+    print(f"HandEgg: median {np.median(errs):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < 2e-4 and np.mean(errs < 2e-3) >= 0.9
+    env.close()

@@ -220,3 +220,39 @@ def test_pen_env_matches_oracle():
     _, rew, *_ = envd.step(act[None].astype(np.float32))
     _, orew, *_ = orcd.step(act)
     assert abs(float(rew[0]) - float(orew)) < 5e-3 and float(orew) < -0.05
+
+
+def test_egg_env_matches_oracle():
+    """HandManipulateEgg*-v1 (manipulate_egg.py:214-235): ellipsoid object through the general convex collider, otherwise
+    the block env's defaults."""
+    model = load_model("hand_egg")
+    env = pkg.make_vec("HandManipulateEggRotate-v1", num_envs=1, backend_factory=HandHostBackend, rng_mode="numpy")
+    assert not env.ignore_z_target_rotation and env.distance_threshold == 0.01 and env.randomize_initial_rotation
+    orc = OracleHandBlockEnv(model=model, target_position="ignore", target_rotation="xyz")
+    obs, _ = env.reset(seed=21)
+    oobs, _ = orc.reset(seed=21)
+    np.testing.assert_allclose(obs["desired_goal"][0, 3:].double().numpy(), oobs["desired_goal"][3:], atol=2e-6)
+    a, oa = obs["achieved_goal"][0].double().numpy(), oobs["achieved_goal"]
+    assert a[2] > 0.04 and oa[2] > 0.04
+    np.testing.assert_allclose(a[:3], oa[:3], atol=5e-3)
+    lay, m, s = env.backend.layout, model, orc.sim
+    rng = np.random.default_rng(5)
+    seen_contact = False
+    for k in range(4):
+        rec = np.zeros(lay["stride"])
+        rec[lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+        rec[lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+        rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+        rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+        rec[lay["goal"]:lay["goal"] + 7] = orc.goal
+        env.set_state(torch.as_tensor(rec[None], dtype=torch.float32))
+        act = rng.uniform(-1, 1, 20)
+        obs, rew, *_ , info = env.step(act[None].astype(np.float32))
+        oobs, orew, _, _, oinfo = orc.step(act)
+        seen_contact = seen_contact or s.ncon > 0
+        np.testing.assert_allclose(obs["observation"][0, :24].double().numpy(), oobs["observation"][:24], atol=2e-4)
+        np.testing.assert_allclose(obs["observation"][0, 54:61].double().numpy(), oobs["observation"][54:61], atol=2e-4)
+        assert float(rew[0]) == float(orew)
+    assert seen_contact
+    assert {"HandManipulateEgg-v1", "HandManipulateEggFull-v1", "HandManipulateEggRotate_BooleanTouchSensors-v1",
+            "HandManipulateEgg_ContinuousTouchSensorsDense-v1"} <= set(pkg.ENV_IDS)

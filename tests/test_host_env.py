@@ -91,6 +91,35 @@ def test_step_tracks_oracle_and_reward_contract(pnp):
         assert rn.dtype == np.float32 and np.array_equal(rn, r.numpy())
 
 
+def test_fetch_slide_tracks_oracle():
+    """FetchSlide-v4 (envs/fetch/slide.py:160-190): the cylinder puck goes through the general convex collider.  A flat
+    cylinder keeps rocking on its single portal contact, so its Euler angles (obs 11:14) and angular velocity (obs
+    17:20) are chaotic between an fp32 and an fp64 run; everything else is compared."""
+    env = mk("FetchSlide", 2, rng_mode="numpy")
+    orc0 = oracle_env_from_model("FetchSlide", env.model)
+    assert np.allclose(env.initial_gripper_xpos.double().numpy(), orc0.initial_gripper_xpos, atol=5e-5)
+    assert env.height_offset == pytest.approx(orc0.height_offset, abs=5e-4)
+    assert env.height_offset == pytest.approx(0.414, abs=2e-3)       # puck resting on the table top
+    obs, _ = env.reset(seed=3)
+    oracles = [oracle_env_from_model("FetchSlide", env.model) for _ in range(2)]
+    keep = np.array([i for i in range(25) if not 11 <= i < 14 and not 17 <= i < 20])
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=3 + i)
+        assert np.abs(obs["desired_goal"][i].double().numpy() - oo["desired_goal"]).max() < 5e-4
+        assert np.abs(obs["observation"][i].double().numpy() - oo["observation"])[keep].max() < 2e-3
+        # slide.py: target_offset 0.4 in x, goal on the table
+        assert oo["desired_goal"][2] == pytest.approx(o.height_offset)
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        inject_oracle_state(env, oracles)
+        a = rng.uniform(-1, 1, (2, 4)).astype(np.float32)
+        o, r, *_ = env.step(a)
+        for i, orc in enumerate(oracles):
+            oo, orr, *_ = orc.step(a[i].astype(np.float64))
+            assert np.abs(o["observation"][i].double().numpy() - oo["observation"])[keep].max() < 5e-4
+            assert float(r[i]) == float(orr)
+
+
 def test_timelimit_and_next_step_autoreset():
     env = mk("FetchReach", 2, rng_mode="numpy", max_episode_steps=3)
     env.reset(seed=0)
@@ -121,7 +150,7 @@ def test_same_step_autoreset_reports_final_obs():
 def test_dense_reward_and_registry():
     import gymnasium_robotics_b200 as pkg
 
-    assert set(pkg.ENV_IDS) >= {"FetchReach-v4", "FetchPickAndPlace-v4", "FetchPickAndPlaceDense-v4", "FetchPush-v4"}
+    assert set(pkg.ENV_IDS) >= {"FetchReach-v4", "FetchPickAndPlace-v4", "FetchPickAndPlaceDense-v4", "FetchPush-v4", "FetchSlide-v4", "FetchSlideDense-v4"}
     assert pkg.ENV_IDS["FetchPickAndPlace-v4"]["max_episode_steps"] == 50  # reference __init__.py:47-52
     env = pkg.make_vec("FetchReachDense-v4", num_envs=1, backend_factory=HostSimBackend, rng_mode="numpy")
     obs, _ = env.reset(seed=2)

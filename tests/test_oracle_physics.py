@@ -280,3 +280,81 @@ def test_bias_force_matches_finite_difference_of_lagrangian(mjcf_file):
     Mdot = (Mp - Mm) / (2 * eps)
     pedot = (pep - pem) / (2 * eps)
     assert v @ M0 @ a + 0.5 * v @ Mdot @ v + pedot == pytest.approx(0, abs=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- general convex collider
+CONVEX_PAIR = """
+<mujoco><option timestep="0.002" gravity="0 0 0"/><worldbody>
+  <body name="a" pos="0 0 0"><freejoint/><geom type="ellipsoid" size="0.05 0.05 0.05" mass="1"/></body>
+  <body name="b" pos="0.06 0.04 0.05"><freejoint/><geom type="GEOM2" mass="1"/></body>
+</worldbody></mujoco>"""
+
+
+def test_convex_collider_reproduces_sphere_sphere(mjcf_file):
+    """An ellipsoid with three equal radii is a sphere: portal refinement must return the analytic sphere-sphere contact
+    (distance, normal from geom1 to geom2, midpoint position)."""
+    s = make(mjcf_file, CONVEX_PAIR.replace('type="GEOM2"', 'type="sphere" size="0.05"'))
+    s.forward()
+    (c,) = s.contacts()
+    d = np.array([0.06, 0.04, 0.05])
+    # pair order follows the geom types (sphere < ellipsoid): geom1 is the sphere at d, so the normal points back to 0
+    assert c["dist"] == pytest.approx(np.linalg.norm(d) - 0.1, abs=2e-6)
+    assert np.allclose(c["frame"][0], -d / np.linalg.norm(d), atol=1e-5)
+    assert np.allclose(c["pos"], d / 2, atol=1e-5)
+
+
+def test_convex_collider_capsule_against_round_ellipsoid(mjcf_file):
+    """Same check against a capsule lying along z next to the round ellipsoid: closest feature is the capsule's side."""
+    xml = CONVEX_PAIR.replace('type="GEOM2"', 'type="capsule" size="0.02 0.1"').replace('pos="0.06 0.04 0.05"', 'pos="0.065 0 0.03"')
+    s = make(mjcf_file, xml)
+    s.forward()
+    (c,) = s.contacts()
+    assert c["dist"] == pytest.approx(0.065 - 0.05 - 0.02, abs=2e-6)
+    assert np.allclose(np.abs(c["frame"][0]), [1, 0, 0], atol=1e-3)   # portal tolerance 1e-6 on the depth ~ 1e-4 on the normal
+
+
+CONVEX_ON_TABLE = """
+<mujoco><option timestep="0.002"/><worldbody>
+  <geom name="t" type="box" size="0.5 0.5 0.1" pos="0.1 0.05 0"/>
+  <body name="b" pos="0 0 ZZ"><freejoint/><geom type="GEOM" mass="2"/></body>
+</worldbody></mujoco>"""
+
+
+@pytest.mark.parametrize("geom,half", [('type="ellipsoid" size="0.04 0.03 0.02"', 0.02), ('type="cylinder" size="0.03 0.02"', 0.02)])
+def test_convex_body_rests_on_a_box_at_the_soft_contact_depth(mjcf_file, geom, half):
+    """Weight = contact force at rest, and the body sits exactly `dist` inside the table top (the constraint model
+    itself is pinned by the box-on-plane tests above; this pins the collision geometry of the new pair types)."""
+    s = make(mjcf_file, CONVEX_ON_TABLE.replace('type="GEOM"', geom).replace("ZZ", str(0.1 + half + 0.001)))
+    s.step(1500)
+    assert s.ncon == 1
+    (c,) = s.contacts()
+    f = s.efc("force")
+    # the flat cylinder keeps rocking on its single portal contact (as the published algorithm does): looser bounds
+    rocking = "cylinder" in geom
+    assert f.sum() == pytest.approx(2 * G, rel=0.2 if rocking else 2e-2)   # pyramid edges sum to the normal force
+    assert 1e-4 < -c["dist"] < 6e-3                               # soft contact: a fraction of a millimetre to millimetres
+    assert abs(s.qpos[2] - (0.1 + half + c["dist"])) < (1e-3 if rocking else 2e-4)
+    assert c["frame"][0][2] == pytest.approx(-1, abs=1e-2 if rocking else 1e-3)       # box (type 6) is geom2: normal points into the table
+
+
+PLANE_CONVEX = """
+<mujoco><option timestep="0.002"/><worldbody>
+  <geom type="plane" size="1 1 0.1"/>
+  <body name="b" pos="0 0 0.03" QUAT><freejoint/><geom type="GEOM" mass="1"/></body>
+</worldbody></mujoco>"""
+
+
+def test_plane_cylinder_and_plane_ellipsoid(mjcf_file):
+    s = make(mjcf_file, PLANE_CONVEX.replace('type="GEOM"', 'type="cylinder" size="0.05 0.03"').replace("QUAT", ""))
+    s.forward()
+    assert s.ncon == 3                                           # flat on the plane: three points of the lower rim
+    assert all(abs(c["dist"]) < 1e-9 for c in s.contacts())
+    s.step(1000)
+    assert abs(s.qpos[2] - 0.03) < 5e-3 and np.abs(s.qvel).max() < 1e-3
+    s = make(mjcf_file, PLANE_CONVEX.replace('type="GEOM"', 'type="cylinder" size="0.05 0.03"').replace("QUAT", 'quat="0.7071068 0.7071068 0 0"'))
+    s.forward()                                                  # lying on its side: the two ends of the lowest generator
+    assert s.ncon == 2 and all(abs(c["dist"] - (0.03 - 0.05)) < 1e-6 for c in s.contacts())
+    s = make(mjcf_file, PLANE_CONVEX.replace('type="GEOM"', 'type="ellipsoid" size="0.05 0.04 0.035"').replace("QUAT", ""))
+    s.forward()
+    (c,) = s.contacts()
+    assert c["dist"] == pytest.approx(0.03 - 0.035, abs=1e-12) and np.allclose(c["pos"], [0, 0, -0.0025], atol=1e-9)
