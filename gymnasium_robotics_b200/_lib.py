@@ -30,14 +30,23 @@ class FetchTaskC(ctypes.Structure):
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """nvcc-compile csrc/b200sim.cu for sm_100a into the in-tree libb200sim.so (cross-compiles without a GPU)."""
-    src = os.path.join(_HERE, "csrc", "b200sim.cu")
-    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("sim_core.cuh", "fetch_task.cuh", "dmodel.h")] + \
+    """nvcc-compile csrc/b200sim.cu and csrc/b200sim_wide.cu for sm_100a into the in-tree libb200sim.so (cross-compiles
+    without a GPU; the two translation units are compiled in parallel)."""
+    names = ("b200sim", "b200sim_wide")
+    srcs = [os.path.join(_HERE, "csrc", n + ".cu") for n in names]
+    deps = srcs + [os.path.join(_HERE, "csrc", f) for f in ("sim_core.cuh", "fetch_task.cuh", "step_kernel.cuh", "dmodel.h")] + \
            [os.path.join(_HERE, "..", "include", f) for f in ("b200sim.h", "b200sim_model.h")]
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
-    subprocess.check_call(cmd)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    objs = [os.path.join(_HERE, "csrc", n + ".o") for n in names]
+    procs = [subprocess.Popen(["nvcc"] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", o, src]) for src, o in zip(srcs, objs)]
+    rcs = [p.wait() for p in procs]
+    if any(rcs):
+        raise subprocess.CalledProcessError(max(rcs), "nvcc -c (b200sim)")
+    subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs)
+    for o in objs:
+        os.remove(o)
     return LIB_PATH
 
 

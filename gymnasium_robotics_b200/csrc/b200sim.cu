@@ -10,14 +10,13 @@
 #include <vector>
 
 #include "../../include/b200sim.h"
-#include "fetch_task.cuh"
+#include "step_kernel.cuh"
 
 // warps (= envs) per block: 28 fills an SM in one wave at 4096 envs per GPU; smaller batches use smaller blocks so
 // that every SM still gets work (e.g. the 1024-env shards of BASELINE config 4)
 #define B200_WPB_MAX 28
 
 #ifdef B200_STAGE_TIMING
-__device__ unsigned long long g_stage_cycles[TM_COUNT];
 extern "C" int b200sim_debug_stage_cycles(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, g_stage_cycles, sizeof(unsigned long long) * TM_COUNT);
@@ -25,67 +24,6 @@ extern "C" int b200sim_debug_stage_cycles(unsigned long long* out, int reset) {
   return TM_COUNT;
 }
 #endif
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int WPB, int NVP>
-__global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restrict__ model_g, FetchTask task, int mode, int nraw,
-                                                         int N, float* __restrict__ state, const float* __restrict__ actions,
-                                                         const unsigned char* __restrict__ mask, float* __restrict__ obs,
-                                                         float* __restrict__ achieved, float* __restrict__ desired,
-                                                         float* __restrict__ reward, float* __restrict__ success,
-                                                         int* __restrict__ info) {
-  extern __shared__ __align__(128) uint32_t smem[];
-  __shared__ __align__(8) unsigned long long bar;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // ---- stage the model constants: TMA 1-D bulk copy global -> shared, completion on an mbarrier
-  const int model_words = ((const DMHead*)model_g)->hot_words;  // header + HOT arrays (uniform scalar load)
-  const uint32_t bytes = (uint32_t)model_words * 4u;
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
-                 "l"(model_g), "r"(bytes), "r"(smem_u32(&bar))
-                 : "memory");
-  }
-  {
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
-                   : "=r"(done)
-                   : "r"(smem_u32(&bar))
-                   : "memory");
-    }
-  }
-  const DMHead* h = (const DMHead*)smem;
-  const int env = blockIdx.x * WPB + warp;
-  const bool active = env < N && !(mask && !mask[env]);  // warp-uniform
-  Ctx c;
-#ifdef B200_STAGE_TIMING
-  long long tim[TM_COUNT];
-  for (int k = 0; k < TM_COUNT; k++) tim[k] = 0;
-  c.tim = tim;
-  const long long t_begin = clock64();
-#endif
-  c.mg = model_g; c.mw = smem; c.h = h; c.lane = lane;
-  c.s = (float*)(smem + model_words) + (size_t)warp * h->scr_words;
-  const size_t e = active ? (size_t)env : 0;
-  const float* act = actions ? actions + e * task.nact : nullptr;  // only dereferenced in MODE_STEP by active warps
-  fetch_env_step<NVP>(c, task, active, mode, nraw, state + e * task.st_stride, act, obs + e * task.nobs, achieved + e * task.ngoal,
-                      desired + e * task.ngoal, reward + e, success + e, info ? info + e : nullptr);
-#ifdef B200_STAGE_TIMING
-  if (lane == 0 && active) {
-    long long sum = 0;
-    for (int k = 0; k < TM_OTHER; k++) sum += tim[k];
-    tim[TM_OTHER] = clock64() - t_begin - sum;
-    for (int k = 0; k < TM_COUNT; k++) atomicAdd(&g_stage_cycles[k], (unsigned long long)tim[k]);
-  }
-#endif
-}
 
 __global__ void reward_kernel(const float* __restrict__ ag, const float* __restrict__ dg, int M, int ngoal, int kind, float thr,
                               float radius, int dense, FetchTask task, float* __restrict__ out) {
@@ -107,6 +45,14 @@ __global__ void reward_kernel(const float* __restrict__ ag, const float* __restr
 // ---------------------------------------------------------------------------------------------------------------
 #define B200_FOR_ALL_VARIANTS(X) X(7, 14) X(7, 15) X(7, 21) X(14, 14) X(14, 15) X(14, 21) X(28, 14) X(28, 15) X(28, 21) \
   X(7, 22) X(14, 22) X(28, 22) X(7, 30) X(14, 30)
+
+// wide build (models with 33..40 dofs), compiled from b200sim_wide.cu with 64-bit dof masks
+extern "C" int b200sim_wide_setattr(int wpb, int smem_bytes);
+extern "C" int b200sim_wide_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
+                                   int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
+                                   float* achieved, float* desired, float* reward, float* success, int* info);
+#define B200_WIDE_NVP 36
+#define B200_WIDE_WPB 10
 
 struct b200sim {
   int N = 0, device = 0;
@@ -187,12 +133,13 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
   h->wpb = (num_envs + nsm - 1) / nsm <= 7 ? 7 : ((num_envs + nsm - 1) / nsm <= 14 ? 14 : 28);
-  h->nvp = dh->nv <= 14 ? 14 : (dh->nv == 15 ? 15 : (dh->nv <= 21 ? 21 : (dh->nv <= 30 ? 30 : 0)));  // smallest built size >= nv (identity padding)
-  if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for nv > 30 yet", -8); }
+  h->nvp = dh->nv <= 14 ? 14 : (dh->nv == 15 ? 15 : (dh->nv <= 21 ? 21 : (dh->nv <= 30 ? 30 : (dh->nv > 32 && dh->nv <= B200_WIDE_NVP ? B200_WIDE_NVP : 0))));  // smallest built size >= nv (identity padding)
+  if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for this nv (31, 32 or > 36)", -8); }
   if (t.kind == TASK_HAND || t.kind == TASK_HAND_REACH) h->nvp = 30;  // the hand task code is compiled into this build only
   if (dh->nv <= 21 && dh->any_convex_pair) h->nvp = 22;  // arm build that carries the general convex collider (FetchSlide's puck)
   if (dh->nv <= 21 && (dh->nten > 0 || dh->nfric > 0 || dh->nsensor > 0 || dh->any_round_pair)) h->nvp = 30;  // hand features live in the NVP = 30 build
   if (h->nvp == 30 && h->wpb > 14) h->wpb = 14;  // the large models' scratch does not fit 28 envs per block
+  if (h->nvp == B200_WIDE_NVP) h->wpb = h->wpb > 7 ? B200_WIDE_WPB : 7;
   if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 14 || (w == 28 && h->nvp != 30)) h->wpb = w; }  // experiments
   h->smem_bytes = ((size_t)dh->hot_words + (size_t)h->wpb * dh->scr_words) * 4;
   h->blocks = (num_envs + h->wpb - 1) / h->wpb;
@@ -200,6 +147,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
 #define B200_SETATTR(W, V) if (h->wpb == W && h->nvp == V) e = cudaFuncSetAttribute(fetch_kernel<W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   B200_FOR_ALL_VARIANTS(B200_SETATTR)
 #undef B200_SETATTR
+  if (h->nvp == B200_WIDE_NVP && b200sim_wide_setattr(h->wpb, (int)h->smem_bytes) != 0) e = cudaErrorInvalidValue;
   if (e != cudaSuccess) { std::string m = std::string("cudaFuncSetAttribute(smem=") + std::to_string(h->smem_bytes) + "): " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
   if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, (size_t)num_envs * t.st_stride * 4) != cudaSuccess) {
     delete h; return fail(nullptr, "b200sim_create: cudaMalloc failed", -9);
@@ -245,6 +193,9 @@ static int launch(b200sim* h, int mode, int nraw, const float* actions, const un
         h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info);
   B200_FOR_ALL_VARIANTS(B200_LAUNCH)
 #undef B200_LAUNCH
+  if (h->nvp == B200_WIDE_NVP)
+    b200sim_wide_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, h->state, actions, mask, obs,
+                        achieved, desired, reward, success, info);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -12,7 +12,7 @@
 #include "../../include/b200sim_model.h"
 
 #define DM_MAX_BODY 32   // one lane per body / 32-bit body masks
-#define DM_MAX_NV 32     // 32-bit dof masks
+#define DM_MAX_NV 40     // dof masks: one word per entry up to 32 dofs, two words (wide kernel build, B200_WIDE) up to 40
 #define DM_NDOFROW_MIN 8
 #define DM_NCAND_MAX 96   // broad-phase candidate slots (one byte each: pair index < 256)
 #define DM_NWELD_MAX 1
@@ -21,12 +21,12 @@
 // block; COLD arrays (per-pair contact parameters, read only when a contact is created) stay in global memory.
 #define DM_ARRAYS_HOT(X) \
   X(body_parent, 1, nb) X(body_jntadr, 1, nb) X(body_jntnum, 1, nb) X(body_dofadr, 1, nb) X(body_dofnum, 1, nb) \
-  X(body_mocapid, 1, nb) X(body_ancdof, 1, nb) X(body_sub, 1, nb) X(body_pos, 3, nb) X(body_quat, 4, nb) \
+  X(body_mocapid, 1, nb) X(body_ancdof, MW, nb) X(body_sub, 1, nb) X(body_pos, 3, nb) X(body_quat, 4, nb) \
   X(body_ipos, 3, nb) X(body_iquat, 4, nb) X(body_mass, 1, nb) X(body_inertia, 3, nb) \
   X(jnt_type, 1, njnt) X(jnt_body, 1, njnt) X(jnt_qposadr, 1, njnt) X(jnt_dofadr, 1, njnt) X(jnt_limited, 1, njnt) \
   X(jnt_pos, 3, njnt) X(jnt_axis, 3, njnt) X(jnt_range, 2, njnt) X(jnt_margin, 1, njnt) X(jnt_stiffness, 1, njnt) \
   X(jnt_solref, 2, njnt) X(jnt_solimp, 5, njnt) X(jnt_qpos0, 1, njnt) X(jnt_qspring, 1, njnt) \
-  X(dof_body, 1, nv) X(dof_jnt, 1, nv) X(dof_anc, 1, nv) X(dof_pre, 1, nv) X(dof_armature, 1, nv) \
+  X(dof_body, 1, nv) X(dof_jnt, 1, nv) X(dof_anc, MW, nv) X(dof_pre, MW, nv) X(dof_armature, 1, nv) \
   X(dof_damping, 1, nv) X(dof_frictionloss, 1, nv) X(dof_invweight0, 1, nv) \
   X(geom_type, 1, ngeom) X(geom_body, 1, ngeom) X(geom_pos, 3, ngeom) X(geom_quat, 4, ngeom) X(geom_size, 3, ngeom) \
   X(geom_rbound, 1, ngeom) \
@@ -52,7 +52,7 @@
   X(xpos, 3 * nb) X(xquat, 4 * nb) X(cdof, 6 * nv) X(M, nv * (nv + 1) / 2) X(fsmooth, nv) X(fcon, nv) \
   X(rk_q0, nrkq) X(rk_v0, nrkv) X(rk_dx, nrkv) X(rk_df, nrkv) \
   X(con, ncon_max * CON_WORDS) X(dofrow, ndr_max * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
-  X(group, ngrp_max * GRP_WORDS) X(counters, 8) X(fric, 2 * nfric) X(conx, ncx * CX_WORDS)
+  X(group, ngrp_max * grp_words) X(counters, 8) X(fric, 2 * nfric) X(conx, ncx * CX_WORDS)
 // time-shared region `uni`: kinematics {kinA, kinB} -> dynamics {cinert, b6, d6, geom_xpos, cand} -> solver {H, d6, grad,
 // search, Ma, Mv} -> observation {cvel}.  d6 keeps one offset in both phases that use it.
 #define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
@@ -73,7 +73,11 @@ enum { DR_DOF = 0, DR_COEF = 1, DR_D = 2, DR_JAR = 3, DR_JV = 4, DR_DOF2 = 5, DR
 enum { W_W = 0, W_D = 36, W_JAR = 42, W_JV = 48, W_B = 54, W_GRP = 55, WELD_WORDS = 56 };
 // group = one geom pair in contact (its contacts are contiguous) or one weld: 6x6 block K, contact range, dof mask
 // S = anc(A) xor anc(B) with sign mask (bit set: dof on the B side), and a 6-vector used for dV (J*v) and F (J^T f)
+#ifdef B200_WIDE
+enum { G_K = 0, G_START = 21, G_COUNT = 22, G_MASK = 23, G_SIGN = 25, G_V = 27, GRP_WORDS = 34 };   // two-word masks
+#else
 enum { G_K = 0, G_START = 21, G_COUNT = 22, G_MASK = 23, G_SIGN = 24, G_V = 25, GRP_WORDS = 32 };
+#endif
 enum { ROWT_EQ = 0, ROWT_FRICTION = 1, ROWT_LIMIT = 2 };
 enum { CNT_NCON = 0, CNT_NDR = 1, CNT_NGRP = 2, CNT_NCAND = 3, CNT_NWELD = 4, CNT_ITERS = 5, CNT_OVERFLOW = 6 };
 
@@ -83,7 +87,7 @@ struct DMHead {
   int hot_words;   // leading part staged into shared memory (header + HOT arrays)
   int scr_words;   // per-env scratch size in words
   int iterations, ls_iterations, integrator, any_damping, kin_iters, ncon_max, ngrp_max, ndr_max;
-  int edges_per_con, any_convex_pair, pad6, pad7;   // pyramid edges of the widest contact (2 * (condim - 1)): line-search edge slots
+  int edges_per_con, any_convex_pair, mask_words, pad7;   // mask_words: 1, or 2 when nv > 32 (wide kernel build)   // pyramid edges of the widest contact (2 * (condim - 1)): line-search edge slots
   int nten, nfric, ncand_max, nsensor;   // nsensor: touch sensors (site volume + body)   // limited fixed tendons; nfric = nv when any dof has frictionloss, else 0
   int grid_len, grid_wid, ngridw, any_round_pair;   // maze wall grid (0 x 0 when the model has none)
   float grid_scale, grid_top, grid_xc, grid_yc;  // cell size, wall top height, map centre offsets
@@ -145,7 +149,8 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   h.ncon_max = m.nmocap > 0 ? 16 : 20;   // contacts kept per env per sub-step
   h.ngrp_max = m.nmocap > 0 ? 10 : 14;   // geom pairs in contact (+ welds) per env per sub-step
   if (h.nb > DM_MAX_BODY) { err = "model has more than 32 runtime bodies"; return -1; }
-  if (h.nv > DM_MAX_NV) { err = "model has more than 32 dofs"; return -1; }
+  if (h.nv > DM_MAX_NV) { err = "model has more than 40 dofs"; return -1; }
+  h.mask_words = h.nv > 32 ? 2 : 1;
   std::vector<int> tsrc;   // limited fixed tendons (unlimited ones have no effect without springs)
   for (int t = 0; t < m.ntendon; t++) {
     if (!m.ten_limited[t]) continue;
@@ -175,7 +180,8 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   // offsets
   int nb = h.nb, njnt = h.njnt, nq = h.nq, nv = h.nv, nu = h.nu, ngeom = h.ngeom, nsite = h.nsite, nmocap = h.nmocap,
       neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max, ndr_max = h.ndr_max,
-      nten = h.nten, nfric = h.nfric, nsensor = h.nsensor, ncx = h.nsensor > 0 ? h.ncon_max : 0;
+      nten = h.nten, nfric = h.nfric, nsensor = h.nsensor, ncx = h.nsensor > 0 ? h.ncon_max : 0, MW = h.mask_words,
+      grp_words = MW == 2 ? 34 : 32;
   int nrkq = h.integrator == B200_INT_RK4 ? nq : 0, nrkv = h.integrator == B200_INT_RK4 ? nv : 0;
   int off = (int)((sizeof(DMHead) + 3) / 4);
 #define X(name, w, kind) h.o_##name = off; off += (w) * (kind);
@@ -214,16 +220,19 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   auto F = [&](int o, int i, double v) { buf[o + i] = f2w((float)v); };
   auto I = [&](int o, int i, int v) { buf[o + i] = (uint32_t)v; };
   // masks
-  std::vector<uint32_t> anc(nv, 0), pre(nv, 0), bodyanc(nb, 0), sub(nb, 0);
+  typedef unsigned long long u64;
+  std::vector<u64> anc(nv, 0), pre(nv, 0), bodyanc(nb, 0);
+  std::vector<uint32_t> sub(nb, 0);
+  auto PUTM = [&](int o, int i, u64 v) { buf[o + MW * i] = (uint32_t)v; if (MW == 2) buf[o + 2 * i + 1] = (uint32_t)(v >> 32); };
   for (int d = 0; d < nv; d++) {
     int p = m.dof_parent[d];
-    anc[d] = (p >= 0 ? anc[p] : 0u) | (1u << d);
+    anc[d] = (p >= 0 ? anc[p] : (u64)0) | ((u64)1 << d);
   }
   for (int b = 1; b < nb; b++) {
     // dofs of this body and of all ancestors
     int a = b;
     while (a > 0 && m.body_dofnum[a] == 0) a = m.body_parent[a];
-    bodyanc[b] = a > 0 ? anc[m.body_dofadr[a] + m.body_dofnum[a] - 1] : 0u;
+    bodyanc[b] = a > 0 ? anc[m.body_dofadr[a] + m.body_dofnum[a] - 1] : (u64)0;
   }
   for (int b = nb - 1; b >= 0; b--) {
     sub[b] |= 1u << b;
@@ -231,12 +240,12 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   }
   for (int d = 0; d < nv; d++) {
     int b = m.dof_body[d], j = m.dof_jnt[d];
-    uint32_t mask = bodyanc[m.body_parent[b]];  // all dofs of ancestor bodies
+    u64 mask = bodyanc[m.body_parent[b]];  // all dofs of ancestor bodies
     // earlier dofs of the same body: every earlier joint of the body; for a free joint's rotational dofs only the
     // three translational dofs (body-fixed axes: no rot-rot terms, see DESIGN.md "velocity products")
     for (int e = m.body_dofadr[b]; e < d; e++) {
-      if (m.dof_jnt[e] != j) mask |= 1u << e;
-      else if (m.jnt_type[j] == B200_JNT_FREE && d - m.jnt_dofadr[j] >= 3 && e - m.jnt_dofadr[j] < 3) mask |= 1u << e;
+      if (m.dof_jnt[e] != j) mask |= (u64)1 << e;
+      else if (m.jnt_type[j] == B200_JNT_FREE && d - m.jnt_dofadr[j] >= 3 && e - m.jnt_dofadr[j] < 3) mask |= (u64)1 << e;
     }
     pre[d] = mask;
   }
@@ -250,7 +259,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   for (int b = 0; b < nb; b++) {
     I(h.o_body_parent, b, m.body_parent[b]); I(h.o_body_jntadr, b, m.body_jntadr[b]); I(h.o_body_jntnum, b, m.body_jntnum[b]);
     I(h.o_body_dofadr, b, m.body_dofadr[b]); I(h.o_body_dofnum, b, m.body_dofnum[b]); I(h.o_body_mocapid, b, m.body_mocapid[b]);
-    buf[h.o_body_ancdof + b] = bodyanc[b]; buf[h.o_body_sub + b] = sub[b];
+    PUTM(h.o_body_ancdof, b, bodyanc[b]); buf[h.o_body_sub + b] = sub[b];
     for (int k = 0; k < 3; k++) { F(h.o_body_pos, 3 * b + k, m.body_pos[3 * b + k]); F(h.o_body_ipos, 3 * b + k, m.body_ipos[3 * b + k]);
       F(h.o_body_inertia, 3 * b + k, m.body_inertia[3 * b + k]); }
     for (int k = 0; k < 4; k++) { F(h.o_body_quat, 4 * b + k, m.body_quat[4 * b + k]); F(h.o_body_iquat, 4 * b + k, m.body_iquat[4 * b + k]); }
@@ -268,7 +277,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     if (m.jnt_type[j] == B200_JNT_FREE && m.body_jntnum[m.jnt_body[j]] != 1) { err = "free joint must be the only joint of its body"; return -1; }
   }
   for (int d = 0; d < nv; d++) {
-    I(h.o_dof_body, d, m.dof_body[d]); I(h.o_dof_jnt, d, m.dof_jnt[d]); buf[h.o_dof_anc + d] = anc[d]; buf[h.o_dof_pre + d] = pre[d];
+    I(h.o_dof_body, d, m.dof_body[d]); I(h.o_dof_jnt, d, m.dof_jnt[d]); PUTM(h.o_dof_anc, d, anc[d]); PUTM(h.o_dof_pre, d, pre[d]);
     F(h.o_dof_armature, d, m.dof_armature[d]); F(h.o_dof_damping, d, m.dof_damping[d]);
     F(h.o_dof_frictionloss, d, m.dof_frictionloss[d]); F(h.o_dof_invweight0, d, m.dof_invweight0[d]);
     if (nfric) {

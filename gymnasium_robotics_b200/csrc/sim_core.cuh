@@ -13,9 +13,10 @@
 #include "dmodel.h"
 
 #ifdef __CUDACC__
-#define HD __device__ __forceinline__
-#define HDN __device__ __noinline__
-#define STAGE __device__ __noinline__  // pipeline stages are real calls: keeps the kernel inside the instruction caches
+// internal linkage: b200sim.cu and b200sim_wide.cu compile these sources with different dof-mask widths
+#define HD static __device__ __forceinline__
+#define HDN static __device__ __noinline__
+#define STAGE static __device__ __noinline__  // pipeline stages are real calls: keeps the kernel inside the instruction caches
 #define ASSUME_SHARED_PTR(p) __builtin_assume(__isShared(p))
 #define ASSUME_SHARED(c) do { __builtin_assume(__isShared((c).s)); __builtin_assume(__isShared((c).mw)); __builtin_assume(__isShared((c).h)); } while (0)
 #define WARP_W 32
@@ -113,6 +114,34 @@ HD int ffs_pop(uint32_t& m) {  // index of lowest set bit, and clear it
   m &= m - 1;
   return b;
 }
+// dof masks: 32 bits in the ordinary builds, 64 bits in the wide build (B200_WIDE: models with 33..40 dofs, stored as two
+// words per entry in the model tables and in the group records); body masks stay 32 bits (<= 32 runtime bodies)
+#ifdef B200_WIDE
+typedef unsigned long long dmask_t;
+HD int ffs_pop(dmask_t& m) {
+#ifdef __CUDACC__
+  int b = __ffsll((long long)m) - 1;
+#else
+  int b = __builtin_ctzll(m);
+#endif
+  m &= m - 1;
+  return b;
+}
+#define DM(name, i) ((dmask_t)MU(name)[2 * (i)] | ((dmask_t)MU(name)[2 * (i) + 1] << 32))
+HD dmask_t grp_mask(const float* gr) { const uint32_t* u = (const uint32_t*)gr; return (dmask_t)u[G_MASK] | ((dmask_t)u[G_MASK + 1] << 32); }
+HD dmask_t grp_sign(const float* gr) { const uint32_t* u = (const uint32_t*)gr; return (dmask_t)u[G_SIGN] | ((dmask_t)u[G_SIGN + 1] << 32); }
+HD void grp_set_masks(int* gi, dmask_t mask, dmask_t sign) {
+  uint32_t* u = (uint32_t*)gi;
+  u[G_MASK] = (uint32_t)mask; u[G_MASK + 1] = (uint32_t)(mask >> 32); u[G_SIGN] = (uint32_t)sign; u[G_SIGN + 1] = (uint32_t)(sign >> 32);
+}
+#else
+typedef uint32_t dmask_t;
+#define DM(name, i) (MU(name)[i])
+HD dmask_t grp_mask(const float* gr) { return ((const uint32_t*)gr)[G_MASK]; }
+HD dmask_t grp_sign(const float* gr) { return ((const uint32_t*)gr)[G_SIGN]; }
+HD void grp_set_masks(int* gi, dmask_t mask, dmask_t sign) { ((uint32_t*)gi)[G_MASK] = mask; ((uint32_t*)gi)[G_SIGN] = sign; }
+#endif
+#define DBIT(m, j) ((int)(((m) >> (j)) & 1))
 
 // ---------------------------------------------------------------------------------------------------------------
 // small math
@@ -347,7 +376,7 @@ STAGE void mass_matrix(const Ctx c) {
     while (sub) { int b = ffs_pop(sub); const float* ci = SF(cinert) + 10 * b; for (int k = 0; k < 10; k++) crb[k] += ci[k]; }
     float buf[6];
     mul_inert(buf, crb, SF(cdof) + 6 * i);
-    uint32_t anc = MU(dof_anc)[i];
+    dmask_t anc = DM(dof_anc, i);
     int row = i * (i + 1) / 2;
     while (anc) { int j = ffs_pop(anc); M[row + j] = dot6(SF(cdof) + 6 * j, buf); }
     M[row + i] += MF(dof_armature)[i];
@@ -361,7 +390,7 @@ STAGE void pass_V(const Ctx c, const float* vec, float* out) {
   ASSUME_SHARED_PTR(vec); ASSUME_SHARED_PTR(out);
   LANES(b, c.h->nb) {
     float v[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t m = MU(body_ancdof)[b];
+    dmask_t m = DM(body_ancdof, b);
     while (m) { int j = ffs_pop(m); const float* cd = SF(cdof) + 6 * j; float q = vec[j]; for (int k = 0; k < 6; k++) v[k] += cd[k] * q; }
     for (int k = 0; k < 6; k++) out[6 * b + k] = v[k];
   }
@@ -376,7 +405,7 @@ STAGE void smooth_forces(const Ctx c) {
   const float *qvel = SF(qvel), *qpos = SF(qpos);
   LANES(j, nv) {
     float vp[6] = {0, 0, 0, 0, 0, 0}, vj[6];
-    uint32_t m = MU(dof_pre)[j];
+    dmask_t m = DM(dof_pre, j);
     while (m) { int i = ffs_pop(m); const float* cd = SF(cdof) + 6 * i; float q = qvel[i]; for (int k = 0; k < 6; k++) vp[k] += cd[k] * q; }
     for (int k = 0; k < 6; k++) vj[k] = SF(cdof)[6 * j + k] * qvel[j];
     cross_motion(SF(d6) + 6 * j, vp, vj);
@@ -387,7 +416,7 @@ STAGE void smooth_forces(const Ctx c) {
     if (b == 0) { for (int k = 0; k < 6; k++) f[k] = 0; continue; }
     float a[6] = {0, 0, 0, -h->gravity[0], -h->gravity[1], -h->gravity[2]};
     float v[6] = {0, 0, 0, 0, 0, 0};  // spatial velocity of this body (kept in registers)
-    uint32_t m = MU(body_ancdof)[b];
+    dmask_t m = DM(body_ancdof, b);
     while (m) {
       int j = ffs_pop(m);
       const float* d = SF(d6) + 6 * j;
@@ -1086,9 +1115,9 @@ STAGE void collision(const Ctx c) {
     if (o.cnt > 0 && gid < h->ngrp_max - DM_NWELD_MAX) {
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
       int ba = MI(geom_body)[MI(pair_geom1)[p]], bb = MI(pair_geom2)[p] < 0 ? 0 : MI(geom_body)[MI(pair_geom2)[p]];
-      uint32_t ma = MU(body_ancdof)[ba], mb = MU(body_ancdof)[bb];
+      dmask_t ma = DM(body_ancdof, ba), mb = DM(body_ancdof, bb);
       gi[G_START] = basec + slot; gi[G_COUNT] = kept;
-      ((uint32_t*)gi)[G_MASK] = ma ^ mb; ((uint32_t*)gi)[G_SIGN] = mb;
+      grp_set_masks(gi, ma ^ mb, mb);
     }
     if (c.lane == 0) {
       int nn = basec + total; if (nn > h->ncon_max) { nn = h->ncon_max; cnt[CNT_OVERFLOW] |= 2; }
@@ -1198,9 +1227,9 @@ STAGE void make_constraint(const Ctx c) {
       int gid = cnt[CNT_NGRP]++;  // one group per weld; row value = w . (V[b1] - V[b2]) => A = b2, B = b1
       ((int*)wr)[W_GRP] = gid;
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
-      uint32_t ma = MU(body_ancdof)[b2], mb = MU(body_ancdof)[b1];
+      dmask_t ma = DM(body_ancdof, b2), mb = DM(body_ancdof, b1);
       gi[G_START] = 0; gi[G_COUNT] = 0;
-      ((uint32_t*)gi)[G_MASK] = ma ^ mb; ((uint32_t*)gi)[G_SIGN] = mb;
+      grp_set_masks(gi, ma ^ mb, mb);
       cnt[CNT_NWELD]++;
     }
   }
@@ -1285,9 +1314,9 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
   LANES(idx, ngrp * 6) {
     int g = idx / 6, a = idx - 6 * g;
     float* gr = SF(group) + g * GRP_WORDS;
-    uint32_t S = ((const uint32_t*)gr)[G_MASK], sg = ((const uint32_t*)gr)[G_SIGN];
+    dmask_t S = grp_mask(gr), sg = grp_sign(gr);
     float acc = 0;
-    while (S) { int j = ffs_pop(S); float t = SF(cdof)[6 * j + a] * vec[j]; acc += ((sg >> j) & 1u) ? t : -t; }
+    while (S) { int j = ffs_pop(S); float t = SF(cdof)[6 * j + a] * vec[j]; acc += DBIT(sg, j) ? t : -t; }
     gr[G_V + a] = acc;
   }
   SYNC();
@@ -1390,10 +1419,9 @@ STAGE void pass_F(const Ctx c, float* out) {
     const float* cd = SF(cdof) + 6 * j;
     for (int g = 0; g < ngrp; g++) {
       const float* gr = SF(group) + g * GRP_WORDS;
-      uint32_t S = ((const uint32_t*)gr)[G_MASK];
-      if (!((S >> j) & 1u)) continue;
+      if (!DBIT(grp_mask(gr), j)) continue;
       float d = dot6(cd, gr + G_V);
-      q += ((((const uint32_t*)gr)[G_SIGN] >> j) & 1u) ? d : -d;
+      q += DBIT(grp_sign(gr), j) ? d : -d;
     }
     for (int i = 0; i < ndr; i++) {
       const float* dr = SF(dofrow) + i * DR_WORDS;
@@ -1475,10 +1503,9 @@ STAGE void build_H(const Ctx c) {
   // y_i = K cdof_i for dofs in the group's chains, then H_ij += sigma_i sigma_j cdof_j . y_i
   for (int g = 0; g < ngrp; g++) {
     const float* K = SF(group) + g * GRP_WORDS + G_K;
-    const uint32_t* gu = (const uint32_t*)(SF(group) + g * GRP_WORDS);
-    uint32_t S = gu[G_MASK], mb = gu[G_SIGN];
+    const dmask_t S = grp_mask(SF(group) + g * GRP_WORDS), mb = grp_sign(SF(group) + g * GRP_WORDS);
     LANES(i, nv) {
-      if (!((S >> i) & 1u)) continue;
+      if (!DBIT(S, i)) continue;
       const float* cd = SF(cdof) + 6 * i;
       float* y = SF(d6) + 6 * i;
       for (int r = 0; r < 6; r++) {
@@ -1489,14 +1516,14 @@ STAGE void build_H(const Ctx c) {
     }
     SYNC();
     LANES(i, nv) {
-      if (!((S >> i) & 1u)) continue;
-      float si = ((mb >> i) & 1u) ? 1.f : -1.f;
+      if (!DBIT(S, i)) continue;
+      float si = DBIT(mb, i) ? 1.f : -1.f;
       const float* y = SF(d6) + 6 * i;
       int row = i * (i + 1) / 2;
-      uint32_t m2 = S & ((2u << i) - 1u);  // j <= i
+      dmask_t m2 = S & (((dmask_t)2 << i) - (dmask_t)1);  // j <= i
       while (m2) {
         int j = ffs_pop(m2);
-        float sj = ((mb >> j) & 1u) ? 1.f : -1.f;
+        float sj = DBIT(mb, j) ? 1.f : -1.f;
         H[row + j] += si * sj * dot6(SF(cdof) + 6 * j, y);
       }
     }
@@ -1583,19 +1610,25 @@ STAGE void chol_solve(const Ctx c, const float* L, float* x) {
 // the full symmetric row i (lower part ends up as L, the frozen upper part gives L^T), columns travel by warp shuffle;
 // NVP is nv padded to a compile-time size (identity padding).  Host emulation: the shared-memory routines above.
 #ifdef __CUDACC__
+// Models with more than 32 dofs (wide build, NVP = 32 + KB): lane i owns row i of the leading 32 x 32 block as before and,
+// in addition, its entries of the KB border rows (c[r] = H[32 + r][i]); the KB x KB corner block is replicated in every
+// lane.  The border rows ride along the right-looking elimination (one extra shuffle per border row and step), the corner
+// becomes the Schur complement and is factorised redundantly in registers; the two triangular solves pick the border up
+// through KB warp reductions (forward) and a lane-local correction (backward).
 template <int NVP>
-__device__ __noinline__ void spd_solve(const Ctx c, const float* A, const float* dadd, float hh, float* x, float* scratchH) {
+static __device__ __noinline__ void spd_solve(const Ctx c, const float* A, const float* dadd, float hh, float* x, float* scratchH) {
   ASSUME_SHARED(c);
   __builtin_assume(__isShared(A)); __builtin_assume(__isShared(x)); if (dadd) __builtin_assume(__isShared(dadd));
   (void)scratchH;
+  constexpr int NA = NVP > 32 ? 32 : NVP, KB = NVP > 32 ? NVP - 32 : 0, KS = KB > 0 ? KB : 1;
   const int nv = c.h->nv, i = c.lane;
   const unsigned FULL = 0xffffffffu;
-  float h[NVP];
+  float h[NA];
   const int rowi = i * (i + 1) / 2;
   const bool live = i < nv;
   // branch-free loads (clamped index + select) so the warp stays converged for the shuffles below
 #pragma unroll
-  for (int j = 0; j < NVP; j++) {
+  for (int j = 0; j < NA; j++) {
     const bool in = live && j < nv;
     int idx = (j <= i) ? rowi + j : j * (j + 1) / 2 + i;
     idx = in ? idx : 0;
@@ -1603,40 +1636,99 @@ __device__ __noinline__ void spd_solve(const Ctx c, const float* A, const float*
     v = in ? v : ((i == j) ? 1.f : 0.f);
     h[j] = v;
   }
+  float cb[KS], S[KS][KS], bb[KS];   // border entries of this lane, replicated corner block, border right-hand side
+#pragma unroll
+  for (int r = 0; r < KB; r++) {
+    const int row = 32 + r, ro = row * (row + 1) / 2;
+    const bool in = row < nv;
+    cb[r] = (in && live) ? A[ro + i] : 0.f;
+#pragma unroll
+    for (int q = 0; q < KB; q++) {
+      const int col = 32 + q;
+      const bool in2 = in && col < nv;
+      float v = A[in2 ? (q <= r ? ro + col : col * (col + 1) / 2 + row) : 0];
+      S[r][q] = in2 ? v : (r == q ? 1.f : 0.f);
+    }
+    bb[r] = in ? x[row] : 0.f;
+  }
   if (dadd != nullptr) {
     float dd = hh * dadd[live ? i : 0];
 #pragma unroll
-    for (int j = 0; j < NVP; j++) h[j] += (live && i == j) ? dd : 0.f;
+    for (int j = 0; j < NA; j++) h[j] += (live && i == j) ? dd : 0.f;
+#pragma unroll
+    for (int r = 0; r < KB; r++) S[r][r] += (32 + r < nv) ? hh * dadd[32 + r < nv ? 32 + r : 0] : 0.f;
   }
   float b = 0.f;
   if (live) b = x[i];  // predicated load: idle lanes never touch x
   float dinv = 1.f;
 #pragma unroll
-  for (int k = 0; k < NVP; k++) {
+  for (int k = 0; k < NA; k++) {
     float hkk = __shfl_sync(FULL, h[k], k);
     float inv = rsqrtf(fmaxf(hkk, 1e-30f));
     float lik = (i > k) ? h[k] * inv : 0.f;
     dinv = (i == k) ? inv : dinv;
     h[k] = (i > k) ? lik : h[k];
 #pragma unroll
-    for (int j = k + 1; j < NVP; j++) { float ljk = __shfl_sync(FULL, lik, j); h[j] = fmaf(-lik, ljk, h[j]); }
+    for (int j = k + 1; j < NA; j++) { float ljk = __shfl_sync(FULL, lik, j); h[j] = fmaf(-lik, ljk, h[j]); }
+    float lr[KS];
+#pragma unroll
+    for (int r = 0; r < KB; r++) {
+      lr[r] = __shfl_sync(FULL, cb[r] * inv, k);            // L[32 + r][k]
+      cb[r] = (i == k) ? lr[r] : fmaf(-lr[r], lik, cb[r]);   // lanes <= k: lik = 0, their (final) entries stay
+    }
+#pragma unroll
+    for (int r = 0; r < KB; r++)
+#pragma unroll
+      for (int q = 0; q < KB; q++) S[r][q] = fmaf(-lr[r], lr[q], S[r][q]);
+  }
+  // corner block: S = L_S L_S^T in place (lower triangle), replicated
+  float sinv[KS];
+#pragma unroll
+  for (int k = 0; k < KB; k++) {
+    float inv = rsqrtf(fmaxf(S[k][k], 1e-30f));
+    sinv[k] = inv;
+#pragma unroll
+    for (int r = k + 1; r < KB; r++) S[r][k] *= inv;
+#pragma unroll
+    for (int r = k + 1; r < KB; r++)
+#pragma unroll
+      for (int q = k + 1; q <= r; q++) S[r][q] = fmaf(-S[r][k], S[q][k], S[r][q]);
   }
 #pragma unroll
-  for (int k = 0; k < NVP; k++) {  // L y = b
+  for (int k = 0; k < NA; k++) {  // L y = b
     float yk = __shfl_sync(FULL, b * dinv, k);
     float bn = fmaf(-h[k], yk, b);
     b = (i > k) ? bn : ((i == k) ? yk : b);
   }
+  // border: y_B = L_S^-1 (b_B - W y_A), z_B = L_S^-T y_B
+#pragma unroll
+  for (int r = 0; r < KB; r++) bb[r] -= wsum(cb[r] * b);
+#pragma unroll
+  for (int k = 0; k < KB; k++) {
+    bb[k] *= sinv[k];
+#pragma unroll
+    for (int r = k + 1; r < KB; r++) bb[r] = fmaf(-S[r][k], bb[k], bb[r]);
+  }
+#pragma unroll
+  for (int k = KB - 1; k >= 0; k--) {
+    bb[k] *= sinv[k];
+#pragma unroll
+    for (int r = 0; r < k; r++) bb[r] = fmaf(-S[k][r], bb[k], bb[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < KB; r++) b = fmaf(-cb[r], bb[r], b);   // y_A - W^T z_B
   float sacc = 0.f, z = 0.f;
 #pragma unroll
-  for (int k = NVP - 1; k >= 0; k--) {  // L^T z = y, with l_kj = h_j[k] * dinv_j for k > j
+  for (int k = NA - 1; k >= 0; k--) {  // L^T z = y, with l_kj = h_j[k] * dinv_j for k > j
     float zk = __shfl_sync(FULL, (b - dinv * sacc) * dinv, k);
     float sn = fmaf(h[k], zk, sacc);
     sacc = (i < k) ? sn : sacc;
     z = (i == k) ? zk : z;
   }
   __syncwarp();
-  if (i < nv) x[i] = z;
+  if (i < nv && i < NA) x[i] = z;
+#pragma unroll
+  for (int r = 0; r < KB; r++) if (i == r && 32 + r < nv) x[32 + r] = bb[r];
   __syncwarp();
 }
 #else
