@@ -42,6 +42,9 @@ for _task in ("HandManipulateBlockRotateZ", "HandManipulateBlockRotateParallel",
 # HandReach, new-binding version (__init__.py:90-95)
 for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
     ENV_IDS[f"HandReach{_suffix}-v3"] = dict(hand_task="HandReach", reward_type=_rt, max_episode_steps=50)
+# Adroit hand (__init__.py:1082-1101): dense reward is the plain id, `Sparse` the suffix; max_episode_steps = 200
+for _rt, _suffix in (("dense", ""), ("sparse", "Sparse")):
+    ENV_IDS[f"AdroitHandHammer{_suffix}-v2"] = dict(adroit_task="AdroitHandHammer", reward_type=_rt, max_episode_steps=200)
 
 
 def make_vec(env_id: str, num_envs: int = 1, **kwargs):
@@ -58,6 +61,10 @@ def make_vec(env_id: str, num_envs: int = 1, **kwargs):
         from .hand import make_hand_vec
 
         return make_hand_vec(spec.pop("hand_task"), num_envs=num_envs, **spec)
+    if "adroit_task" in spec:
+        from .adroit import make_adroit_vec
+
+        return make_adroit_vec(spec.pop("adroit_task"), num_envs=num_envs, **spec)
     from .fetch import FetchVectorEnv
 
     return FetchVectorEnv(num_envs=num_envs, **spec)
@@ -80,9 +87,12 @@ def register_envs():
         if env_id in registry:
             continue
         ep = "gymnasium_robotics_b200.maze:MazeVectorEnv" if "maze" in spec else \
-            ("gymnasium_robotics_b200.hand:make_hand_vec" if "hand_task" in spec else "gymnasium_robotics_b200.fetch:FetchVectorEnv")
+            ("gymnasium_robotics_b200.hand:make_hand_vec" if "hand_task" in spec else
+             ("gymnasium_robotics_b200.adroit:make_adroit_vec" if "adroit_task" in spec else "gymnasium_robotics_b200.fetch:FetchVectorEnv"))
         kw = dict(spec)
         if "hand_task" in kw:
             kw["task"] = kw.pop("hand_task")
+        if "adroit_task" in kw:
+            kw["task"] = kw.pop("adroit_task")
         register(id=env_id, vector_entry_point=ep, kwargs=kw)
     return True

@@ -26,7 +26,8 @@ class FetchTaskC(ctypes.Structure):
                 ("kind", ctypes.c_int), ("nact", ctypes.c_int), ("ngoal", ctypes.c_int), ("success_radius", ctypes.c_float),
                 ("obs_qpos_start", ctypes.c_int), ("vel_clip", ctypes.c_float),
                 ("obj_qadr", ctypes.c_int), ("obj_dadr", ctypes.c_int), ("goal_flags", ctypes.c_int),
-                ("rotation_threshold", ctypes.c_float), ("touch_mode", ctypes.c_int), ("tip_site", ctypes.c_int * 5)]
+                ("rotation_threshold", ctypes.c_float), ("touch_mode", ctypes.c_int), ("tip_site", ctypes.c_int * 5),
+                ("penv_body", ctypes.c_int)]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

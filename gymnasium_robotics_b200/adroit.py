@@ -1,0 +1,164 @@
+"""Batched Adroit hand environments on the CUDA simulator: `gym.make_vec("AdroitHandHammer-v2", num_envs=N)`.
+
+Mirrors (batched) the reference's Python around the hot path:
+  * AdroitHandHammerEnv.step / _get_obs        envs/adroit_hand/adroit_hammer.py:291-357   (inside the step kernel,
+                                               csrc/fetch_task.cuh `adroit_hammer_observe`, task kind 4)
+  * MujocoEnv.do_simulation(a, frame_skip=5)   ctrl = act_mean + clip(a) * act_rng, 5 x mj_step (un-vendored Gymnasium base)
+  * reset_model                                adroit_hammer.py:372-378: model.body_pos[nail_board].z ~ U(0.1, 0.25) per
+                                               episode (a per-env body position in the state record), init_qpos / init_qvel
+  * get_env_state / set_env_state              adroit_hammer.py:380-402
+  * registry                                   __init__.py:1082-1101: ids AdroitHandHammer-v2 (dense) / AdroitHandHammerSparse-v2,
+                                               max_episode_steps = 200
+The ctor's actuator gain / bias overwrite (adroit_hammer.py:235-262) writes the values the MJCF already holds
+(adroit_assets.xml actuator block), so the compiled model needs no edit.  The model has 33 dofs: it runs on the wide
+kernel build (64-bit dof masks, bordered register Cholesky, csrc/b200sim_wide.cu).
+Not restated: the noslip post-solver (`noslip_iterations=20`, adroit_assets.xml:3) -- listed in DESIGN.md.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ._lib import FetchTaskC
+from .fetch import CudaBackend, FetchVectorEnv
+from .models import load_model
+from .spaces import Box, batch_space
+
+ADROIT_REF_POINT = (0.0, -0.2, 0.2)   # fixed world point of the spatial algebra: inside the hand's workspace
+FRAME_SKIP = 5
+BOARD_Z_RANGE = (0.1, 0.25)           # adroit_hammer.py:374-376
+
+
+def make_hammer_task(model, reward_type, frame_skip=FRAME_SKIP):
+    """b200sim_fetch_task_t for kind 4 (ids resolved as MujocoModelNames would, adroit_hammer.py:264-270)."""
+    m = model
+    t = FetchTaskC()
+    t.kind, t.nact, t.ngoal = 4, int(m.nu), 3
+    t.n_substeps, t.reward_dense = int(frame_skip), int(reward_type == "dense")
+    t.grip_site = m.site_id("S_grasp")
+    t.obj_site = m.frame_site("Object")
+    t.frame_site = m.site_id("S_target")
+    t.tip_site[0], t.tip_site[1] = m.site_id("tool"), m.site_id("nail_goal")
+    t.penv_body = int(m.names["body_map"]["nail_board"])
+    t.nobs = int(m.nq) - 6 + 6 + 13
+    t.dt = float(m.opt[0] * frame_skip)
+    return t
+
+
+class _AdroitBackend(CudaBackend):
+    REF = ADROIT_REF_POINT
+
+
+class AdroitHammerVectorEnv(FetchVectorEnv):
+    """Observations (46), rewards and flags are float32 / bool torch tensors on `device` with a leading `num_envs` axis;
+    `info["success"]` mirrors the reference's `dict(success=goal_achieved)`."""
+
+    metadata = {"render_modes": [], "render_fps": 100, "autoreset_mode": "next_step"}
+
+    def __init__(self, num_envs: int = 1, reward_type: str = "dense", max_episode_steps: Optional[int] = 200, device="cuda:0",
+                 rng_mode: str = "auto", autoreset_mode: str = "next_step", frame_skip: int = FRAME_SKIP, backend_factory=None,
+                 model=None, **kwargs):
+        if reward_type.lower() not in ("sparse", "dense"):
+            raise ValueError(f"Unknown reward type, expected `dense` or `sparse` but got {reward_type}")   # adroit_hammer.py:224-227
+        if autoreset_mode not in ("next_step", "same_step", "disabled"):
+            raise ValueError("autoreset_mode must be next_step, same_step or disabled")
+        if kwargs.get("render_mode") is not None:
+            raise NotImplementedError("rendering is out of scope for the batched CUDA path")
+        self.task_name, self.reward_type = "AdroitHandHammer", reward_type.lower()
+        self.sparse_reward = self.reward_type == "sparse"
+        self.num_envs, self.max_episode_steps, self.autoreset_mode = int(num_envs), max_episode_steps, autoreset_mode
+        self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
+        self.n_substeps = self.frame_skip = int(frame_skip)
+        self.model = model if model is not None else load_model("adroit_hammer")
+        m = self.model
+        self.task = make_hammer_task(m, self.reward_type, frame_skip)
+        factory = backend_factory or _AdroitBackend
+        self.backend = factory(m, np.zeros((0, 11)), self.task, self.num_envs, device)
+        self.device = self.backend.device
+        self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
+            if self.rng_mode == "numpy" else None
+        self._gen = torch.Generator(device=self.device)
+        self._gen.seed()
+        lay = self.backend.layout
+        self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", m.nq), ("qvel", m.nv), ("warm", m.nv), ("ctrl", m.nu),
+                                                              ("goal", 3), ("penv", 3))}
+        self.dt = float(m.opt[0] * frame_skip)
+        self.single_action_space = Box(-1.0, 1.0, shape=(int(m.nu),), dtype=np.float32)            # adroit_hammer.py:229-232
+        self.single_observation_space = Box(-np.inf, np.inf, shape=(int(self.task.nobs),), dtype=np.float64)
+        self.action_space = batch_space(self.single_action_space, self.num_envs)
+        self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        self.init_qpos = torch.as_tensor(np.array(m.qpos0), dtype=torch.float32, device=self.device)   # MujocoEnv: data.qpos at load
+        self.init_qvel = torch.zeros(m.nv, dtype=torch.float32, device=self.device)
+        self._board_pos0 = torch.as_tensor(np.asarray(m.body_pos).reshape(-1, 3)[self.task.penv_body], dtype=torch.float32,
+                                           device=self.device)
+        cr = np.asarray(m.act_ctrlrange, dtype=np.float64).reshape(-1, 2)
+        self.act_mean, self.act_rng = cr.mean(axis=1), 0.5 * (cr[:, 1] - cr[:, 0])                      # adroit_hammer.py:271-274
+        self._last = None
+        self.closed = False
+
+    # ------------------------------------------------------------------ reset
+    def _reset_envs(self, mask, out):
+        """MujocoEnv.reset -> mj_resetData -> reset_model (adroit_hammer.py:372-378) for the envs in `mask`."""
+        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        if idx.numel() == 0:
+            return
+        n = idx.numel()
+        st, sl = self.backend.state, self._sl
+        lo, hi = BOARD_Z_RANGE
+        if self.rng_mode == "numpy":
+            z = torch.as_tensor([self._np_rngs[i].uniform(low=lo, high=hi) for i in idx.tolist()], dtype=torch.float32, device=self.device)
+        else:
+            z = lo + (hi - lo) * torch.rand(n, generator=self._gen, device=self.device)
+        rec = torch.zeros((n, st.shape[1]), dtype=torch.float32, device=self.device)   # ctrl, warm start, time <- 0
+        rec[:, sl["qpos"]] = self.init_qpos
+        rec[:, sl["qvel"]] = self.init_qvel
+        rec[:, sl["penv"]] = self._board_pos0
+        rec[:, sl["penv"].start + 2] = z
+        st[idx] = rec
+        self._elapsed[idx] = 0
+        self.backend.refresh(mask.to(torch.uint8), out)   # set_state -> mj_forward, then _get_obs
+
+    # ------------------------------------------------------------------ gymnasium API (flat observation, `success` info)
+    def _obs_dict(self, out):
+        return out["obs"]
+
+    def step(self, actions):
+        obs, reward, terminated, truncated, info = super().step(actions)
+        info["success"] = info.pop("is_success") > 0.5
+        info["_success"] = info.pop("_is_success")
+        return obs, reward, terminated, truncated, info
+
+    def compute_reward(self, *a, **k):
+        raise NotImplementedError("Adroit environments are not GoalEnvs (no compute_reward in the reference)")
+
+    # adroit_hammer.py:380-402, batched: dicts of [N, .] tensors
+    def get_env_state(self):
+        st, sl = self.backend.state, self._sl
+        return dict(qpos=st[:, sl["qpos"]].clone(), qvel=st[:, sl["qvel"]].clone(), board_pos=st[:, sl["penv"]].clone(),
+                    target_pos=self._last["achieved"].clone() if self._last is not None else None)
+
+    def set_env_state(self, state_dict):
+        st, sl = self.backend.state, self._sl
+        for key, name, width in (("qpos", "qpos", self.model.nq), ("qvel", "qvel", self.model.nv), ("board_pos", "penv", 3)):
+            v = torch.as_tensor(np.asarray(state_dict[key]) if not torch.is_tensor(state_dict[key]) else state_dict[key])
+            assert v.shape[-1] == width, f"The state dictionary entry {key} must have {width} columns"
+            st[:, sl[name]] = v.to(self.device, torch.float32).reshape(-1, width).expand(self.num_envs, width)
+        st[:, sl["warm"]] = 0
+        out = self.backend.new_outputs()
+        self.backend.refresh(None, out)   # set_state -> mj_forward
+        self._last = out
+        return out["obs"]
+
+
+ADROIT_TASKS = {"AdroitHandHammer": AdroitHammerVectorEnv}
+
+
+def make_adroit_vec(task, num_envs=1, **kwargs):
+    if task not in ADROIT_TASKS:
+        raise KeyError(f"unknown Adroit task {task!r}")
+    return ADROIT_TASKS[task](num_envs=num_envs, **kwargs)

@@ -52,7 +52,7 @@
   X(xpos, 3 * nb) X(xquat, 4 * nb) X(cdof, 6 * nv) X(M, nv * (nv + 1) / 2) X(fsmooth, nv) X(fcon, nv) \
   X(rk_q0, nrkq) X(rk_v0, nrkv) X(rk_dx, nrkv) X(rk_df, nrkv) \
   X(con, ncon_max * CON_WORDS) X(dofrow, ndr_max * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
-  X(group, ngrp_max * grp_words) X(counters, 8) X(fric, 2 * nfric) X(conx, ncx * CX_WORDS)
+  X(group, ngrp_max * grp_words) X(counters, 8) X(fric, 2 * nfric) X(conx, ncx * CX_WORDS) X(penv_pos, npenv)
 // time-shared region `uni`: kinematics {kinA, kinB} -> dynamics {cinert, b6, d6, geom_xpos, cand} -> solver {H, d6, grad,
 // search, Ma, Mv} -> observation {cvel}.  d6 keeps one offset in both phases that use it.
 #define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
@@ -87,7 +87,7 @@ struct DMHead {
   int hot_words;   // leading part staged into shared memory (header + HOT arrays)
   int scr_words;   // per-env scratch size in words
   int iterations, ls_iterations, integrator, any_damping, kin_iters, ncon_max, ngrp_max, ndr_max;
-  int edges_per_con, any_convex_pair, mask_words, pad7;   // mask_words: 1, or 2 when nv > 32 (wide kernel build)   // pyramid edges of the widest contact (2 * (condim - 1)): line-search edge slots
+  int edges_per_con, any_convex_pair, mask_words, penv_body;   // mask_words: 1, or 2 when nv > 32 (wide kernel build); penv_body: runtime body whose body_pos is per-env state (-1 = none)   // pyramid edges of the widest contact (2 * (condim - 1)): line-search edge slots
   int nten, nfric, ncand_max, nsensor;   // nsensor: touch sensors (site volume + body)   // limited fixed tendons; nfric = nv when any dof has frictionloss, else 0
   int grid_len, grid_wid, ngridw, any_round_pair;   // maze wall grid (0 x 0 when the model has none)
   float grid_scale, grid_top, grid_xc, grid_yc;  // cell size, wall top height, map centre offsets
@@ -108,7 +108,7 @@ struct DMHead {
 static inline uint32_t f2w(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
 static inline int dm_build(const b200_model_view& m, const double* eq_data_override, const float ref[3],
-                           std::vector<uint32_t>& buf, std::string& err) {
+                           std::vector<uint32_t>& buf, std::string& err, int penv_body = -1, bool force_wide = false) {
   DMHead h;
   memset(&h, 0, sizeof(h));
   h.nb = m.nbody; h.njnt = m.njnt; h.nq = m.nq; h.nv = m.nv; h.nu = m.nu; h.nsite = m.nsite;
@@ -150,7 +150,8 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   h.ngrp_max = m.nmocap > 0 ? 10 : 14;   // geom pairs in contact (+ welds) per env per sub-step
   if (h.nb > DM_MAX_BODY) { err = "model has more than 32 runtime bodies"; return -1; }
   if (h.nv > DM_MAX_NV) { err = "model has more than 40 dofs"; return -1; }
-  h.mask_words = h.nv > 32 ? 2 : 1;
+  h.mask_words = (h.nv > 32 || force_wide) ? 2 : 1;
+  h.penv_body = (penv_body > 0 && penv_body < h.nb) ? penv_body : -1;
   std::vector<int> tsrc;   // limited fixed tendons (unlimited ones have no effect without springs)
   for (int t = 0; t < m.ntendon; t++) {
     if (!m.ten_limited[t]) continue;
@@ -181,7 +182,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   int nb = h.nb, njnt = h.njnt, nq = h.nq, nv = h.nv, nu = h.nu, ngeom = h.ngeom, nsite = h.nsite, nmocap = h.nmocap,
       neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max, ndr_max = h.ndr_max,
       nten = h.nten, nfric = h.nfric, nsensor = h.nsensor, ncx = h.nsensor > 0 ? h.ncon_max : 0, MW = h.mask_words,
-      grp_words = MW == 2 ? 34 : 32;
+      grp_words = MW == 2 ? 34 : 32, npenv = h.penv_body > 0 ? 4 : 0;
   int nrkq = h.integrator == B200_INT_RK4 ? nq : 0, nrkv = h.integrator == B200_INT_RK4 ? nv : 0;
   int off = (int)((sizeof(DMHead) + 3) / 4);
 #define X(name, w, kind) h.o_##name = off; off += (w) * (kind);

@@ -27,11 +27,13 @@ struct FetchTask {
   int obj_qadr, obj_dadr, goal_flags;
   float rotation_threshold;
   int touch_mode;       // 0 = no touch observation, 1 = sensordata, 2 = boolean, 3 = log(x + 1)
-  int tip_site[5];      // HandReach: fingertip sites "robot0:S_{ff,mf,rf,lf,th}tip"
-  // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(ngoal)
-  int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride;
+  int tip_site[5];      // HandReach: fingertip sites "robot0:S_{ff,mf,rf,lf,th}tip"; Adroit hammer: [0] = "tool", [1] = "nail_goal"
+  int penv_body;        // runtime body with a per-env body_pos (-1 = none)
+  // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(ngoal) | penv body_pos(3)
+  int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride, st_penv;
 };
-enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2, TASK_HAND_REACH = 3 };  // TASK_ANTMAZE covers both maze agents (Ant, Point)
+// TASK_ANTMAZE covers both maze agents (Ant, Point)
+enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2, TASK_HAND_REACH = 3, TASK_ADROIT_HAMMER = 4 };
 enum { GOAL_USE_POS = 1, GOAL_USE_ROT = 2, GOAL_IGNORE_Z = 4 };
 
 enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
@@ -51,6 +53,7 @@ HD void load_state(const Ctx& c, const FetchTask& t, const float* st) {
   LANES(i, h->nu) SF(ctrl)[i] = st[t.st_ctrl + i];
   LANES(i, 3 * h->nmocap) SF(mocap_pos)[i] = st[t.st_mocap + i];
   LANES(i, 4 * h->nmocap) SF(mocap_quat)[i] = st[t.st_mocap + 3 + i];
+  if (h->penv_body > 0) LANES(i, 3) SF(penv_pos)[i] = st[t.st_penv + i];
   if (c.lane == 0) { SI(counters)[CNT_ITERS] = 0; SI(counters)[CNT_OVERFLOW] = 0; }
   SYNC();
 }
@@ -235,6 +238,23 @@ HD bool ray_hits_site(int type, const float* size, const float* p, const float* 
     if (cc <= 0) return true;
     return b * b - cc >= 0 && -b >= 0;
   }
+  if (type == B200_GEOM_CYLINDER) {
+    // slab |z| <= half length, then the infinite cylinder x^2 + y^2 <= r^2 over the slab's parameter interval
+    float t0 = 0, t1 = 1e30f, r = size[0], hl = size[1];
+    if (fabsf(d[2]) < 1e-12f) { if (fabsf(p[2]) > hl) return false; }
+    else {
+      float a = (-hl - p[2]) / d[2], b = (hl - p[2]) / d[2];
+      if (a > b) { float t = a; a = b; b = t; }
+      t0 = fmaxf(t0, a); t1 = fminf(t1, b);
+      if (t0 > t1) return false;
+    }
+    float A = d[0] * d[0] + d[1] * d[1], B = p[0] * d[0] + p[1] * d[1], C = p[0] * p[0] + p[1] * p[1] - r * r;
+    if (A < 1e-20f) return C <= 0;
+    float disc = B * B - A * C;
+    if (disc < 0) return false;
+    float sq = sqrtf(disc), ta = (-B - sq) / A, tb = (-B + sq) / A;
+    return fmaxf(t0, ta) <= fminf(t1, tb);
+  }
   float t0 = 0, t1 = 1e30f;
   for (int k = 0; k < 3; k++) {
     if (fabsf(d[k]) < 1e-12f) { if (fabsf(p[k]) > size[k]) return false; continue; }
@@ -245,10 +265,10 @@ HD bool ray_hits_site(int type, const float* size, const float* p, const float* 
   }
   return true;
 }
-HD void touch_observe(const Ctx& c, const FetchTask& t, float* out) {
+HD void touch_observe(const Ctx& c, const FetchTask& t, float* out, int nmax = 1 << 30) {
   const DMHead* h = c.h;
   const int ncon = SI(counters)[CNT_NCON];
-  LANES(k, h->nsensor) {
+  LANES(k, (h->nsensor < nmax ? h->nsensor : nmax)) {
     int site = GI(sensor_site)[k], body = GI(sensor_body)[k], type = GI(sensor_type)[k];
     float size[3] = {GF(sensor_size)[3 * k], GF(sensor_size)[3 * k + 1], GF(sensor_size)[3 * k + 2]};
     float total = 0.f, sp[3], sq[4];
@@ -274,6 +294,50 @@ HD void touch_observe(const Ctx& c, const FetchTask& t, float* out) {
   }
 }
 
+// AdroitHandHammer (envs/adroit_hand/adroit_hammer.py:291-357): every derived quantity is the one of the last forward pass
+// (data.xpos / site_xpos / sensordata after mj_step), qpos / qvel are the integrated ones.
+HD void adroit_hammer_observe(const Ctx& c, const FetchTask& t, float* obs, float* achieved, float* desired, float* reward,
+                              float* success) {
+  const DMHead* h = c.h;
+  const int nq = h->nq, nv = h->nv, nr = nq - 6;
+  LANES(i, nr) obs[i] = SF(qpos)[i];
+  LANES(i, 6) obs[nr + i] = fminf(fmaxf(SF(qvel)[nv - 6 + i], -1.f), 1.f);
+  float v2 = 0.f;
+  LANES(i, nv) v2 += SF(qvel)[i] * SF(qvel)[i];
+  v2 = wsum(v2);
+  float touch = 0.f;
+  if (h->nsensor > 0) {   // sensordata of "S_nail" (the model keeps only this sensor), clipped to [-1, 1]
+    float tv[1] = {0.f};
+    FetchTask tt = t; tt.touch_mode = 1;
+    touch_observe(c, tt, tv, 1);
+    touch = fminf(fmaxf(tv[0], -1.f), 1.f);
+  }
+  if (c.lane == 0) {
+    float palm[3], hamm[3], hq[4], head[3], nail[3], goal[3], e[3];
+    site_pose(c, t.grip_site, palm, nullptr);
+    site_pose(c, t.obj_site, hamm, hq);
+    site_pose(c, t.tip_site[0], head, nullptr);
+    site_pose(c, t.frame_site, nail, nullptr);
+    site_pose(c, t.tip_site[1], goal, nullptr);
+    quat_to_euler(hq, e);
+    float* o = obs + nr + 6;
+    for (int k = 0; k < 3; k++) { o[k] = palm[k]; o[3 + k] = hamm[k]; o[6 + k] = e[k]; o[9 + k] = nail[k]; achieved[k] = nail[k]; desired[k] = goal[k]; }
+    o[12] = touch;
+    float dg[3] = {nail[0] - goal[0], nail[1] - goal[1], nail[2] - goal[2]}, dp[3] = {palm[0] - hamm[0], palm[1] - hamm[1], palm[2] - hamm[2]},
+          dh[3] = {head[0] - nail[0], head[1] - nail[1], head[2] - nail[2]};
+    float gd = sqrtf(dot3(dg, dg));
+    bool ok = gd < 0.01f;
+    float r = ok ? 10.f : -0.1f;
+    if (t.reward_dense) {
+      r = -0.1f * sqrtf(dot3(dp, dp)) - sqrtf(dot3(dh, dh)) - 10.f * gd - 1e-2f * sqrtf(v2);
+      if (hamm[2] > 0.04f && head[2] > 0.04f) r += 2.f;
+      if (gd < 0.020f) r += 25.f;
+      if (gd < 0.010f) r += 75.f;
+    }
+    *reward = r; *success = ok ? 1.f : 0.f;
+  }
+}
+
 // one env, one warp.  `st` is this env's state record; outputs are this env's rows.  `active` is warp-uniform: idle
 // warps run the same control flow (for the block-wide alignment barriers) but touch no memory.
 template <int NVP>
@@ -283,7 +347,8 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   constexpr int kAlign = ALIGN_LEVEL_FOR(NVP);
   if (active) {
     load_state(c, t, st);
-    if (NVP >= 30 && mode == MODE_STEP && (t.kind == TASK_HAND || t.kind == TASK_HAND_REACH)) {
+    if (NVP >= 30 && mode == MODE_STEP && (t.kind == TASK_HAND || t.kind == TASK_HAND_REACH || t.kind == TASK_ADROIT_HAMMER)) {
+      // (Adroit: a = act_mean + clip(a) * act_rng, adroit_hammer.py:292-293 -- the same arithmetic)
       // MujocoHandEnv._set_action (hand_env.py:42-61, absolute control): ctrl = centre + clip(a) * half range, clipped
       LANES(i, h->nu) {
         float lo = MF(act_ctrlrange)[2 * i], hi = MF(act_ctrlrange)[2 * i + 1];
@@ -325,7 +390,7 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   }
   // touch sensors read the contacts and forces of the last forward pass: a refresh (no sub-step) runs one first,
   // block-uniformly (forward() contains the block-wide alignment barriers); the warm start is left untouched
-  const bool touch_fwd = NVP >= 30 && t.kind == TASK_HAND && t.touch_mode != 0 && nsub == 0;
+  const bool touch_fwd = NVP >= 30 && ((t.kind == TASK_HAND && t.touch_mode != 0) || t.kind == TASK_ADROIT_HAMMER) && nsub == 0;
   if (touch_fwd) {
     forward<NVP>(c, active);
     if (active) { LANES(i, h->nv) SF(qacc)[i] = st[t.st_warm + i]; SYNC(); }
@@ -344,6 +409,8 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   } else if (NVP >= 30 && t.kind == TASK_HAND_REACH) {
     if (nsub == 0) kinematics(c);   // refresh after a reset: site positions of the new state
     reach_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
+  } else if (NVP >= 30 && t.kind == TASK_ADROIT_HAMMER) {
+    adroit_hammer_observe(c, t, obs, achieved, desired, reward, success);
   } else if (NVP >= 30 && t.kind == TASK_HAND) {
     hand_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
     if (t.touch_mode) touch_observe(c, t, obs + t.obj_qadr + h->nv + 7);

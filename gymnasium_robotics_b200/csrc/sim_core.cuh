@@ -233,7 +233,9 @@ STAGE void kinematics(const Ctx c) {
         for (int k = 0; k < 4; k++) lq[k] = qpos[a + 3 + k];
         qnormalize(lq);
       } else {
-        for (int k = 0; k < 3; k++) lp[k] = MF(body_pos)[3 * b + k];
+        // one body may carry a per-env position (Adroit hammer: model.body_pos[nail_board] is redrawn at every reset)
+        const float* bp = (b == c.h->penv_body) ? SF(penv_pos) : MF(body_pos) + 3 * b;
+        for (int k = 0; k < 3; k++) lp[k] = bp[k];
         for (int k = 0; k < 4; k++) lq[k] = MF(body_quat)[4 * b + k];
         for (int j = ja; j < ja + jn; j++) {
           const float* jp = MF(jnt_pos) + 3 * j;
@@ -327,9 +329,34 @@ STAGE void com_quantities(const Ctx c) {
   }
   LANES(j, h->njnt) {
     int b = MI(jnt_body)[j], d = MI(jnt_dofadr)[j], t = MI(jnt_type)[j];
-    float R[9];
-    q2mat(R, SF(xquat) + 4 * b);
-    const float* xp = SF(xpos) + 3 * b;
+    float R[9], bq[4], xp[3];
+    for (int k = 0; k < 4; k++) bq[k] = SF(xquat)[4 * b + k];
+    for (int k = 0; k < 3; k++) xp[k] = SF(xpos)[3 * b + k];
+    // a body with several joints (Adroit: two arm hinges on the forearm, 3 slides + 3 hinges on the hammer): joint j acts
+    // in the frame reached before the later joints of the same body, so those are undone from the final body pose
+    for (int k = MI(body_jntadr)[b] + MI(body_jntnum)[b] - 1; k > j; k--) {
+      float dq = SF(qpos)[MI(jnt_qposadr)[k]] - MF(jnt_qpos0)[k], ax[3];
+      if (MI(jnt_type)[k] == B200_JNT_SLIDE) {
+        qrot(ax, bq, MF(jnt_axis) + 3 * k);
+        xp[0] -= ax[0] * dq; xp[1] -= ax[1] * dq; xp[2] -= ax[2] * dq;
+      } else {
+        float anc[3], tt[3], ql[4], nq[4], sn, cs;
+#ifdef __CUDACC__
+        sincosf(-0.5f * dq, &sn, &cs);
+#else
+        sn = sinf(-0.5f * dq); cs = cosf(-0.5f * dq);
+#endif
+        qrot(tt, bq, MF(jnt_pos) + 3 * k);
+        anc[0] = xp[0] + tt[0]; anc[1] = xp[1] + tt[1]; anc[2] = xp[2] + tt[2];
+        const float* ja = MF(jnt_axis) + 3 * k;
+        ql[0] = cs; ql[1] = ja[0] * sn; ql[2] = ja[1] * sn; ql[3] = ja[2] * sn;
+        qmul(nq, bq, ql);
+        bq[0] = nq[0]; bq[1] = nq[1]; bq[2] = nq[2]; bq[3] = nq[3];
+        qrot(tt, bq, MF(jnt_pos) + 3 * k);
+        xp[0] = anc[0] - tt[0]; xp[1] = anc[1] - tt[1]; xp[2] = anc[2] - tt[2];
+      }
+    }
+    q2mat(R, bq);
     float* cd = SF(cdof) + 6 * d;
     if (t == B200_JNT_FREE) {
       float off[3] = {ref[0] - xp[0], ref[1] - xp[1], ref[2] - xp[2]};

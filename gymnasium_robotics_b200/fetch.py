@@ -97,9 +97,9 @@ class CudaBackend:
         self.h = h
         self.num_envs, self.nobs = num_envs, task.nobs
         self.ngoal, self.nact = (3, 4) if task.kind == 0 else (task.ngoal, task.nact)
-        lay = (ctypes.c_int * 8)()
+        lay = (ctypes.c_int * 9)()
         self.L.b200sim_layout(h, lay)
-        self.layout = dict(zip(("qpos", "qvel", "warm", "ctrl", "mocap", "pose", "goal", "stride"), list(lay)))
+        self.layout = dict(zip(("qpos", "qvel", "warm", "ctrl", "mocap", "pose", "goal", "stride", "penv"), list(lay)))
         self.state = torch.as_tensor(_DevArray(self.L.b200sim_state(h), (num_envs, self.layout["stride"])), device=self.device)
 
     def close(self):
@@ -349,7 +349,8 @@ class FetchVectorEnv:
                 self._pending_reset = True
             elif self.autoreset_mode == "same_step":
                 if bool(done.any()):
-                    info["final_obs"] = {k: v.clone() for k, v in self._obs_dict(out).items()}
+                    fo = self._obs_dict(out)
+                    info["final_obs"] = {k: v.clone() for k, v in fo.items()} if isinstance(fo, dict) else fo.clone()
                     info["_final_obs"] = done.clone()
                     self._reset_envs(done, out)
                 self._elapsed_ub = int(self._elapsed.max())

@@ -781,7 +781,9 @@ def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None) ->
 
     # ---------------------------------------------------------------- fusing
     # runtime body = weld group, except mocap bodies which stay separate bodies (children of world)
-    keep = [b for b in range(nb) if b == 0 or body_jnts[b] or F.bodies[b]["mocap"]]
+    # `keep_bodies` (override): jointless bodies that stay runtime bodies because an env rewrites their body_pos per episode
+    keep_names = set((overrides or {}).get("keep_bodies", ()))
+    keep = [b for b in range(nb) if b == 0 or body_jnts[b] or F.bodies[b]["mocap"] or F.bodies[b]["name"] in keep_names]
     rt_of = {}
     for b in range(nb):
         a = b
@@ -1058,8 +1060,8 @@ def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None) ->
             si = sname[S["site"]]
             ss.append(si); sbod.append(rt_of[F.sites[si]["body"]]); ssz.append(F.sites[si]["size"])
             sty.append(GEOM_NAMES[F.sites[si]["type"]])
-            if sty[-1] not in (GEOM_NAMES["sphere"], GEOM_NAMES["box"]):
-                raise NotImplementedError("touch sensor sites must be spheres or boxes")
+            if sty[-1] not in (GEOM_NAMES["sphere"], GEOM_NAMES["box"], GEOM_NAMES["cylinder"]):
+                raise NotImplementedError("touch sensor sites must be spheres, boxes or cylinders")
     m.sensor_site, m.sensor_body, m.sensor_size = np.array(ss, dtype=np.int32), np.array(sbod, dtype=np.int32), np.array(ssz).reshape(-1, 3)
     m.sensor_type = np.array(sty, dtype=np.int32)
     m.key_qpos = np.zeros(0)

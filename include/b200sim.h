@@ -46,11 +46,18 @@ typedef struct b200sim_fetch_task {
   /* kind 3 = HandReach (envs/shadow_dexterous_hand/reach.py): same control as kind 2, obs = robot qpos | robot qvel |
    * 5 fingertip site positions = achieved goal (ngoal = 15), Fetch-style distance reward with distance_threshold */
   int tip_site[5];
+  /* kind 4 = AdroitHandHammer (envs/adroit_hand/adroit_hammer.py:291-357): absolute control as kind 2, frame_skip sub-steps,
+   * obs = qpos[:-6] | clip(qvel[-6:]) | palm | hammer pos | hammer euler | nail | clip(touch "S_nail") (46), dense / sparse
+   * reward, success = nail within 1 cm of its goal.  Sites: grip_site = "S_grasp", obj_site = body frame of "Object",
+   * frame_site = "S_target", tip_site[0] = "tool", tip_site[1] = "nail_goal".
+   * penv_body: runtime body whose body_pos is per-env state (nail_board, adroit_hammer.py:372-378), -1 = none; its three
+   * floats live in the state record at B200SIM_ST_PENV. */
+  int penv_body;
 } b200sim_fetch_task_t;
 
 /* indices into the layout array returned by b200sim_layout (offsets in floats inside one env's state record) */
 enum { B200SIM_ST_QPOS = 0, B200SIM_ST_QVEL, B200SIM_ST_WARM, B200SIM_ST_CTRL, B200SIM_ST_MOCAP, B200SIM_ST_POSE,
-       B200SIM_ST_GOAL, B200SIM_ST_STRIDE, B200SIM_ST_COUNT };
+       B200SIM_ST_GOAL, B200SIM_ST_STRIDE, B200SIM_ST_PENV, B200SIM_ST_COUNT };
 
 /* model_blob: include/b200sim_model.h format.  eq_data: optional [neq*11] override of the model's equality data
  * (the reference rewrites it after load: utils/mujoco_utils.py:74-80).  ref: fixed world point the spatial algebra is

@@ -1,0 +1,105 @@
+"""Single-env numpy restatement of the reference's AdroitHandHammer environment on top of the CPU oracle.
+TEST INFRASTRUCTURE ONLY (see oracle/oracle.c header; parity unpinned for the physics).
+
+Restates envs/adroit_hand/adroit_hammer.py (AdroitHandHammerEnv) on top of what Gymnasium's un-vendored `MujocoEnv` does
+(`do_simulation`: ctrl <- action, mj_step(nstep=frame_skip); `set_state`: qpos/qvel <- ..., mj_forward; `reset`:
+mj_resetData then reset_model); every method cites the lines it follows (paths relative to /root/reference/gymnasium_robotics/).
+The noslip post-solver the model asks for (adroit_assets.xml:3) is not restated.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from gymnasium_robotics_b200 import rotations
+from .oracle_sim import OracleSim
+
+
+class OracleAdroitHammerEnv:
+    def __init__(self, model, reward_type="dense", frame_skip=5):
+        self.model, self.frame_skip = model, frame_skip
+        if reward_type.lower() not in ("dense", "sparse"):   # adroit_hammer.py:219-227
+            raise ValueError(f"Unknown reward type, expected `dense` or `sparse` but got {reward_type}")
+        self.sparse_reward = reward_type.lower() == "sparse"
+        self.sim = OracleSim(model)
+        m = model
+        # adroit_hammer.py:264-270 (ids by name)
+        self.target_obj_site_id = m.site_id("S_target")
+        self.S_grasp_site_id = m.site_id("S_grasp")
+        self.obj_body_id = int(m.names["body_map"]["Object"])
+        self.tool_site_id = m.site_id("tool")
+        self.goal_site_id = m.site_id("nail_goal")
+        self.target_body_id = int(m.names["body_map"]["nail_board"])
+        cr = np.asarray(m.act_ctrlrange, dtype=np.float64).reshape(-1, 2)
+        self.act_mean = np.mean(cr, axis=1)                                  # :271
+        self.act_rng = 0.5 * (cr[:, 1] - cr[:, 0])                           # :272-274
+        self.np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(None)))
+        self.sim.forward()
+        self.init_qpos, self.init_qvel = self.sim.qpos.copy(), self.sim.qvel.copy()   # MujocoEnv.__init__
+
+    def step(self, a):  # adroit_hammer.py:291-335
+        s = self.sim
+        a = np.clip(a, -1.0, 1.0)
+        a = self.act_mean + a * self.act_rng
+        s.ctrl[:] = a                      # MujocoEnv.do_simulation
+        s.step(self.frame_skip)
+        obs = self._get_obs()
+        hamm_pos = s.xpos[self.obj_body_id].ravel()
+        palm_pos = s.site_xpos[self.S_grasp_site_id].ravel()
+        head_pos = s.site_xpos[self.tool_site_id].ravel()
+        nail_pos = s.site_xpos[self.target_obj_site_id].ravel()
+        goal_pos = s.site_xpos[self.goal_site_id].ravel()
+        goal_distance = np.linalg.norm(nail_pos - goal_pos)
+        goal_achieved = goal_distance < 0.01
+        reward = 10.0 if goal_achieved else -0.1
+        if not self.sparse_reward:
+            reward = -0.1 * np.linalg.norm(palm_pos - hamm_pos)
+            reward -= np.linalg.norm(head_pos - nail_pos)
+            reward -= 10 * np.linalg.norm(nail_pos - goal_pos)
+            reward -= 1e-2 * np.linalg.norm(s.qvel.ravel())
+            if hamm_pos[2] > 0.04 and head_pos[2] > 0.04:
+                reward += 2
+            if goal_distance < 0.020:
+                reward += 25
+            if goal_distance < 0.010:
+                reward += 75
+        return obs, reward, False, False, dict(success=goal_achieved)
+
+    def _get_obs(self):  # adroit_hammer.py:337-357
+        s = self.sim
+        qp = s.qpos.ravel()
+        qv = np.clip(s.qvel.ravel(), -1.0, 1.0)
+        obj_pos = s.xpos[self.obj_body_id].ravel()
+        obj_rot = rotations.quat2euler(s.xquat[self.obj_body_id].ravel()).ravel()
+        palm_pos = s.site_xpos[self.S_grasp_site_id].ravel()
+        target_pos = s.site_xpos[self.target_obj_site_id].ravel()
+        nail_impact = np.clip(s.sensordata[0], -1.0, 1.0)    # the compiled model keeps only "S_nail"
+        return np.concatenate([qp[:-6], qv[-6:], palm_pos, obj_pos, obj_rot, target_pos, np.array([nail_impact])])
+
+    def reset(self, *, seed=None, options=None):  # MujocoEnv.reset + adroit_hammer.py:359-370
+        if seed is not None:
+            self.np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        self.sim.reset_data()
+        obs = self.reset_model()
+        if options is not None and "initial_state_dict" in options:
+            self.set_env_state(options["initial_state_dict"])
+            obs = self._get_obs()
+        return obs, {}
+
+    def reset_model(self):  # adroit_hammer.py:372-378
+        self.sim.body_pos[self.target_body_id, 2] = self.np_random.uniform(low=0.1, high=0.25)
+        self.set_state(self.init_qpos, self.init_qvel)
+        return self._get_obs()
+
+    def set_state(self, qpos, qvel):  # MujocoEnv.set_state
+        self.sim.qpos[:] = qpos
+        self.sim.qvel[:] = qvel
+        self.sim.forward()
+
+    def get_env_state(self):  # adroit_hammer.py:380-388
+        return dict(qpos=self.sim.qpos.ravel().copy(), qvel=self.sim.qvel.ravel().copy(),
+                    board_pos=self.sim.body_pos[self.target_body_id].copy(),
+                    target_pos=self.sim.site_xpos[self.target_obj_site_id].ravel().copy())
+
+    def set_env_state(self, state_dict):  # adroit_hammer.py:390-402
+        self.sim.body_pos[self.target_body_id] = state_dict["board_pos"]
+        self.set_state(state_dict["qpos"], state_dict["qvel"])

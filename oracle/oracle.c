@@ -1501,6 +1501,23 @@ static int ray_hits_site(int type, const double* size, const real* p, const real
     real disc = b * b - c;
     return disc >= 0 && -b >= 0;       /* nearest root t = -b - sqrt(disc) >= 0 when the ray points at the sphere */
   }
+  if (type == B200_GEOM_CYLINDER) { /* slab |z| <= half length, then x^2 + y^2 <= r^2 over the slab's interval */
+    real t0 = 0, t1 = 1e30, r = size[0], hl = size[1];
+    if (fabs(d[2]) < 1e-12) { if (fabs(p[2]) > hl) return 0; }
+    else {
+      real a = (-hl - p[2]) / d[2], b = (hl - p[2]) / d[2];
+      if (a > b) { real t = a; a = b; b = t; }
+      if (a > t0) t0 = a;
+      if (b < t1) t1 = b;
+      if (t0 > t1) return 0;
+    }
+    real A = d[0] * d[0] + d[1] * d[1], B = p[0] * d[0] + p[1] * d[1], C = p[0] * p[0] + p[1] * p[1] - r * r;
+    if (A < 1e-20) return C <= 0;
+    real disc = B * B - A * C;
+    if (disc < 0) return 0;
+    real sq = sqrt(disc), ta = (-B - sq) / A, tb = (-B + sq) / A;
+    return (t0 > ta ? t0 : ta) <= (t1 < tb ? t1 : tb);
+  }
   /* box: slab test for t >= 0 */
   real t0 = 0, t1 = 1e30;
   for (int k = 0; k < 3; k++) {

@@ -9,7 +9,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
-_LIB = None
+_LIB = {}
 
 
 class FetchTaskC(ctypes.Structure):
@@ -20,27 +20,29 @@ class FetchTaskC(ctypes.Structure):
                 ("kind", ctypes.c_int), ("nact", ctypes.c_int), ("ngoal", ctypes.c_int), ("success_radius", ctypes.c_float),
                 ("obs_qpos_start", ctypes.c_int), ("vel_clip", ctypes.c_float),
                 ("obj_qadr", ctypes.c_int), ("obj_dadr", ctypes.c_int), ("goal_flags", ctypes.c_int),
-                ("rotation_threshold", ctypes.c_float), ("touch_mode", ctypes.c_int), ("tip_site", ctypes.c_int * 5)] + \
+                ("rotation_threshold", ctypes.c_float), ("touch_mode", ctypes.c_int), ("tip_site", ctypes.c_int * 5),
+                ("penv_body", ctypes.c_int)] + \
                [(n, ctypes.c_int) for n in ("st_qpos", "st_qvel", "st_warm", "st_ctrl", "st_mocap", "st_pose", "st_goal",
-                                             "st_stride")]
+                                             "st_stride", "st_penv")]
 
 
-def build(force=False):
-    out = os.path.join(_HERE, "libhostsim.so")
+def build(force=False, wide=False):
+    """wide = the 64-bit dof-mask build (models with more than 32 dofs, -DB200_WIDE as in csrc/b200sim_wide.cu)"""
+    out = os.path.join(_HERE, "libhostsim_wide.so" if wide else "libhostsim.so")
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_ROOT, "gymnasium_robotics_b200", "csrc", f)
                                                    for f in ("sim_core.cuh", "dmodel.h", "fetch_task.cuh")] + \
            [os.path.join(_ROOT, "include", "b200sim_model.h")]
     if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function", "-o", out, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function"] + (["-DB200_WIDE"] if wide else []) +
+                              ["-o", out, srcs[0]])
     return out
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        L = ctypes.CDLL(build())
+def lib(wide=False):
+    if _LIB.get(wide) is None:
+        L = ctypes.CDLL(build(wide=wide))
         L.hostsim_create.restype = ctypes.c_void_p
-        L.hostsim_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        L.hostsim_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.hostsim_scratch.restype = ctypes.POINTER(ctypes.c_float)
         L.hostsim_scratch.argtypes = [ctypes.c_void_p]
         for f in ("hostsim_destroy", "hostsim_forward", "hostsim_kinematics"):
@@ -52,21 +54,21 @@ def lib():
         L.hostsim_scr_words.argtypes = [ctypes.c_void_p]
         L.hostsim_env_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
         assert L.hostsim_task_size() == ctypes.sizeof(FetchTaskC)
-        _LIB = L
-    return _LIB
+        _LIB[wide] = L
+    return _LIB[wide]
 
 
 class HostSim:
     """fp32 single-env emulation of the kernel; arrays are views into the emulated shared-memory scratch."""
 
-    def __init__(self, model, eq_data=None, ref=(1.0, 0.75, 0.4)):
+    def __init__(self, model, eq_data=None, ref=(1.0, 0.75, 0.4), penv_body=-1):
         self.model = model
         blob = model.to_blob()
-        L = lib()
+        L = lib(wide=model.nv > 32)
         self._L = L
         eq = np.ascontiguousarray(eq_data, dtype=np.float64) if eq_data is not None else None
         r = np.asarray(ref, dtype=np.float32)
-        self._h = L.hostsim_create(blob, len(blob), eq.ctypes.data if eq is not None else None, r.ctypes.data)
+        self._h = L.hostsim_create(blob, len(blob), eq.ctypes.data if eq is not None else None, r.ctypes.data, int(penv_body))
         if not self._h:
             raise RuntimeError("hostsim_create failed")
         n = L.hostsim_scr_words(self._h)

@@ -8,6 +8,12 @@
 #include <string>
 #include "../../gymnasium_robotics_b200/csrc/fetch_task.cuh"
 
+#ifdef B200_WIDE
+static const bool kWide = true;   // 64-bit dof masks: the tables carry two words per mask
+#else
+static const bool kWide = false;
+#endif
+
 struct HostSim {
   std::vector<uint8_t> blob;
   b200_model_view view;
@@ -18,11 +24,11 @@ struct HostSim {
 };
 
 extern "C" {
-void* hostsim_create(const void* blob, size_t n, const double* eq_data, const float* ref) {
+void* hostsim_create(const void* blob, size_t n, const double* eq_data, const float* ref, int penv_body) {
   HostSim* s = new HostSim;
   s->blob.assign((const uint8_t*)blob, (const uint8_t*)blob + n);
   if (b200_model_parse(s->blob.data(), n, &s->view) != 0) { delete s; return nullptr; }
-  if (dm_build(s->view, eq_data, ref, s->model, s->err) != 0) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); delete s; return nullptr; }
+  if (dm_build(s->view, eq_data, ref, s->model, s->err, penv_body, kWide) != 0) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); delete s; return nullptr; }
   const DMHead* h = (const DMHead*)s->model.data();
   s->scratch.assign(h->scr_words, 0.f);
   s->ctx.mg = s->model.data(); s->ctx.mw = s->model.data(); s->ctx.h = h; s->ctx.s = s->scratch.data(); s->ctx.lane = 0;

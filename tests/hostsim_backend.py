@@ -15,7 +15,8 @@ class HostSimBackend:
 
         self.device = torch.device("cpu")
         self.num_envs, self.nobs = num_envs, task.nobs
-        self.sim = HostSim(model, eq_data=eq_data if len(eq_data) else None, ref=getattr(self, "REF", REF_POINT))
+        penv = int(task.penv_body) if task.kind == 4 else -1
+        self.sim = HostSim(model, eq_data=eq_data if len(eq_data) else None, ref=getattr(self, "REF", REF_POINT), penv_body=penv)
         t = HostTaskC()
         for name, _ in task._fields_:
             setattr(t, name, getattr(task, name))
@@ -26,11 +27,11 @@ class HostSimBackend:
             t.nact, t.ngoal = 4, 3
         self.ngoal, self.nact = int(t.ngoal), int(t.nact)
         for k, n in (("qpos", model.nq), ("qvel", model.nv), ("warm", model.nv), ("ctrl", model.nu), ("mocap", 7 * model.nmocap),
-                     ("pose", 7 if fetch else 0), ("goal", self.ngoal)):
+                     ("pose", 7 if fetch else 0), ("goal", self.ngoal), ("penv", 3 if penv > 0 else 0)):
             lay[k] = o
             o += n
         lay["stride"] = (o + 3) & ~3
-        for k in ("qpos", "qvel", "warm", "ctrl", "mocap", "pose", "goal", "stride"):
+        for k in ("qpos", "qvel", "warm", "ctrl", "mocap", "pose", "goal", "stride", "penv"):
             setattr(t, "st_" + k, lay[k])
         self.task, self.layout = t, lay
         self.state = torch.zeros((num_envs, lay["stride"]), dtype=torch.float32)

@@ -551,3 +551,62 @@ def test_hand_egg_parity():
     print(f"HandEgg: median {np.median(errs):.2e} max {errs.max():.2e}")
     assert np.median(errs) < 2e-4 and np.mean(errs < 2e-3) >= 0.9
     env.close()
+
+
+# ------------------------------------------------------------------------------------------------ Adroit hammer (config 5a)
+def test_adroit_hammer_parity():
+    """AdroitHandHammer-v2 on the wide kernel build (33 dofs: 64-bit dof masks, bordered register Cholesky): reset from the
+    same PCG64 draw, env-steps from injected oracle states (free motion, then the arm lowered onto the hammer), rewards."""
+    import gymnasium_robotics_b200 as pkg
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.adroit_env import OracleAdroitHammerEnv
+
+    n = 4
+    m = load_model("adroit_hammer")
+    env = pkg.make_vec("AdroitHandHammer-v2", num_envs=n, device="cuda:0", rng_mode="numpy")
+    obs, _ = env.reset(seed=30)
+    oracles = [OracleAdroitHammerEnv(m) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=30 + i)
+        assert np.abs(obs[i].double().cpu().numpy() - oo).max() < 2e-6
+    lay = env.backend.layout
+    rng = np.random.default_rng(2)
+    errs = []
+    for step in range(12):
+        rec = np.zeros((n, lay["stride"]))
+        for i, o in enumerate(oracles):
+            s = o.sim
+            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+            rec[i, lay["penv"]:lay["penv"] + 3] = s.body_pos[o.target_body_id]
+        env.backend.state.copy_(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        a = rng.uniform(-1, 1, (n, 26)).astype(np.float32)
+        if step >= 5:
+            a[:, :2] = [-1, -0.5]   # lower the arm onto the hammer
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            got = o[i].double().cpu().numpy()
+            assert np.isfinite(got).all()
+            errs.append(np.abs(got - oo).max())
+            assert abs(float(r[i]) - orr) < 1e-3 and bool(info["success"][i]) == bool(oi["success"])
+    errs = np.array(errs)
+    print(f"AdroitHammer: median {np.median(errs):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < 2e-5 and np.mean(errs < 2e-4) >= 0.9 and errs.max() < 0.05
+    env.close()
+    # bench-size batch: finite, no capacity overflow, board heights inside the sampled range
+    env = pkg.make_vec("AdroitHandHammer-v2", num_envs=2048, device="cuda:0", rng_mode="torch")
+    env.reset(seed=1)
+    z = env.get_env_state()["board_pos"][:, 2]
+    assert float(z.min()) >= 0.1 and float(z.max()) <= 0.25
+    g = torch.Generator(device="cuda").manual_seed(2)
+    info_bits = torch.zeros(2048, dtype=torch.int32, device="cuda")
+    for _ in range(10):
+        a = torch.rand((2048, 26), generator=g, device="cuda") * 2 - 1
+        out = env.backend.new_outputs()
+        env.backend.step(a, out, info_bits)
+        assert torch.isfinite(out["obs"]).all()
+        assert int((info_bits >> 16).max()) == 0, "contact / row capacity overflow"
+    env.close()

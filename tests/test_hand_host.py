@@ -256,3 +256,60 @@ def test_egg_env_matches_oracle():
     assert seen_contact
     assert {"HandManipulateEgg-v1", "HandManipulateEggFull-v1", "HandManipulateEggRotate_BooleanTouchSensors-v1",
             "HandManipulateEgg_ContinuousTouchSensorsDense-v1"} <= set(pkg.ENV_IDS)
+
+
+# ------------------------------------------------------------------------------------------------ Adroit hammer (config 5a)
+def test_adroit_hammer_env_matches_oracle():
+    """AdroitHandHammer-v2 on the wide build (33 dofs: 64-bit dof masks, bordered Cholesky; emulated here with -DB200_WIDE):
+    reset (board height from the same PCG64 draw), env-steps from injected oracle states, dense and sparse reward,
+    get/set_env_state round trip (adroit_hammer.py:291-402)."""
+    from gymnasium_robotics_b200.adroit import ADROIT_REF_POINT
+    from oracle.adroit_env import OracleAdroitHammerEnv
+
+    class AdroitHostBackend(HostSimBackend):
+        REF = ADROIT_REF_POINT
+
+    m = load_model("adroit_hammer")
+    assert m.nv == 33 and m.nu == 26
+    env = pkg.make_vec("AdroitHandHammer-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
+    assert env.single_observation_space.shape == (46,) and env.single_action_space.shape == (26,) and env.max_episode_steps == 200
+    orc = OracleAdroitHammerEnv(m)
+    obs, info = env.reset(seed=4)
+    oobs, _ = orc.reset(seed=4)
+    assert obs.shape == (1, 46) and info == {}
+    np.testing.assert_allclose(obs[0].double().numpy(), oobs, atol=1e-6)
+    board_z = float(env.get_env_state()["board_pos"][0, 2])
+    assert 0.1 <= board_z <= 0.25 and board_z == pytest.approx(orc.sim.body_pos[orc.target_body_id, 2], abs=1e-7)
+    lay, s = env.backend.layout, orc.sim
+    rng = np.random.default_rng(1)
+    errs = []
+    for k in range(8):
+        rec = np.zeros(lay["stride"])
+        rec[lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+        rec[lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+        rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+        rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+        rec[lay["penv"]:lay["penv"] + 3] = s.body_pos[orc.target_body_id]
+        env.backend.state[0] = torch.as_tensor(rec, dtype=torch.float32)
+        a = rng.uniform(-1, 1, 26)
+        if k >= 4:
+            a[:2] = [-1, -0.5]     # lower the arm onto the hammer
+        o, r, te, tr, info = env.step(a[None].astype(np.float32))
+        oo, orr, _, _, oi = orc.step(a)
+        d = np.abs(o[0].double().numpy() - oo)
+        errs.append(d.max())
+        assert d.max() < 2e-5                            # all 46 entries (measured: < 1e-6)
+        assert abs(float(r[0]) - orr) < 2e-5 and bool(info["success"][0]) == bool(oi["success"])
+        assert not bool(te.any()) and not bool(tr.any())
+    assert np.median(errs) < 5e-6
+    # sparse reward ids and the state round trip
+    envs = pkg.make_vec("AdroitHandHammerSparse-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
+    envs.reset(seed=4)
+    _, r, *_ = envs.step(np.zeros((1, 26), dtype=np.float32))
+    assert float(r[0]) == pytest.approx(-0.1)
+    st = env.get_env_state()
+    o1 = env.set_env_state(st)
+    st2 = env.get_env_state()
+    assert torch.equal(st["qpos"], st2["qpos"]) and torch.equal(st["board_pos"], st2["board_pos"]) and o1.shape == (1, 46)
+    with pytest.raises(ValueError):
+        pkg.make_vec("AdroitHandHammer-v2", num_envs=1, backend_factory=AdroitHostBackend, reward_type="shaped")
