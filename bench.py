@@ -38,6 +38,7 @@ WORKLOADS = {
     "hand_egg": ("HandManipulateEggRotate-v1", 20, 20, 2 * 4 * (31 + 60 + 20 + 0 + 7 + 1) + 80 + 4 * (61 + 14) + 10, 2048),
     # config 5a: AdroitHandHammer (33 dofs, wide kernel build); registered id is -v2 (SURVEY.md 8, config-name caveats)
     "adroit_hammer": ("AdroitHandHammer-v2", 26, 5, 2 * 4 * (33 + 66 + 26 + 0 + 3 + 1) + 104 + 4 * (46 + 6) + 10, 2048),
+    "adroit_relocate": ("AdroitHandRelocate-v2", 30, 5, 2 * 4 * (36 + 72 + 30 + 0 + 3 + 3 + 1) + 120 + 4 * (39 + 6) + 10, 2048),
     "antmaze_large": ("AntMaze_Large-v5", 8, 5, 2 * 4 * (15 + 28 + 0 + 0 + 2 + 1) + 32 + 124 + 10, 1024),  # config 4: 8192 envs over 8 GPUs
 }
 
@@ -220,14 +221,19 @@ def run_ours(args):
                 "reward": torch.empty(n, dtype=torch.float32).pin_memory(),
                 "truncated": torch.empty(n, dtype=torch.bool).pin_memory(), "terminated": torch.empty(n, dtype=torch.bool).pin_memory(),
                 "is_success": torch.empty(n, dtype=torch.float32).pin_memory()}
+    if args.workload.startswith("adroit"):
+        del host_out["achieved_goal"], host_out["desired_goal"]
     h2d = n * nact * 4
     d2h = sum(v.numel() * v.element_size() for v in host_out.values())
 
     def e2e_step(k):
         o, r, te, tr, info = env.step(host_tape[k % 8])  # FetchVectorEnv.step copies the pinned host actions to the device
-        host_out["observation"].copy_(o["observation"], non_blocking=True)
-        host_out["achieved_goal"].copy_(o["achieved_goal"], non_blocking=True)
-        host_out["desired_goal"].copy_(o["desired_goal"], non_blocking=True)
+        if isinstance(o, dict):
+            host_out["observation"].copy_(o["observation"], non_blocking=True)
+            host_out["achieved_goal"].copy_(o["achieved_goal"], non_blocking=True)
+            host_out["desired_goal"].copy_(o["desired_goal"], non_blocking=True)
+        else:   # flat observation (Adroit)
+            host_out["observation"].copy_(o, non_blocking=True)
         host_out["reward"].copy_(r, non_blocking=True)
         host_out["terminated"].copy_(te, non_blocking=True)
         host_out["truncated"].copy_(tr, non_blocking=True)

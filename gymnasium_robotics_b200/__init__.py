@@ -45,6 +45,7 @@ for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
 # Adroit hand (__init__.py:1082-1101): dense reward is the plain id, `Sparse` the suffix; max_episode_steps = 200
 for _rt, _suffix in (("dense", ""), ("sparse", "Sparse")):
     ENV_IDS[f"AdroitHandHammer{_suffix}-v2"] = dict(adroit_task="AdroitHandHammer", reward_type=_rt, max_episode_steps=200)
+    ENV_IDS[f"AdroitHandRelocate{_suffix}-v2"] = dict(adroit_task="AdroitHandRelocate", reward_type=_rt, max_episode_steps=200)
 
 
 def make_vec(env_id: str, num_envs: int = 1, **kwargs):

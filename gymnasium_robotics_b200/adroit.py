@@ -1,4 +1,5 @@
-"""Batched Adroit hand environments on the CUDA simulator: `gym.make_vec("AdroitHandHammer-v2", num_envs=N)`.
+"""Batched Adroit hand environments on the CUDA simulator: `gym.make_vec("AdroitHandHammer-v2", num_envs=N)` and
+`gym.make_vec("AdroitHandRelocate-v2", num_envs=N)`.
 
 Mirrors (batched) the reference's Python around the hot path:
   * AdroitHandHammerEnv.step / _get_obs        envs/adroit_hand/adroit_hammer.py:291-357   (inside the step kernel,
@@ -51,11 +52,27 @@ class _AdroitBackend(CudaBackend):
     REF = ADROIT_REF_POINT
 
 
+def make_relocate_task(model, reward_type, frame_skip=FRAME_SKIP):
+    """b200sim_fetch_task_t for kind 5 (adroit_relocate.py:257-259)."""
+    m = model
+    t = FetchTaskC()
+    t.kind, t.nact, t.ngoal = 5, int(m.nu), 3
+    t.n_substeps, t.reward_dense = int(frame_skip), int(reward_type == "dense")
+    t.grip_site = m.site_id("S_grasp")
+    t.obj_site = m.frame_site("Object")
+    t.penv_body = int(m.names["body_map"]["Object"])
+    t.nobs = int(m.nq) - 6 + 9
+    t.dt = float(m.opt[0] * frame_skip)
+    return t
+
+
 class AdroitHammerVectorEnv(FetchVectorEnv):
     """Observations (46), rewards and flags are float32 / bool torch tensors on `device` with a leading `num_envs` axis;
     `info["success"]` mirrors the reference's `dict(success=goal_achieved)`."""
 
     metadata = {"render_modes": [], "render_fps": 100, "autoreset_mode": "next_step"}
+    TASK_NAME, MODEL_NAME = "AdroitHandHammer", "adroit_hammer"
+    make_task = staticmethod(make_hammer_task)
 
     def __init__(self, num_envs: int = 1, reward_type: str = "dense", max_episode_steps: Optional[int] = 200, device="cuda:0",
                  rng_mode: str = "auto", autoreset_mode: str = "next_step", frame_skip: int = FRAME_SKIP, backend_factory=None,
@@ -66,14 +83,14 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
             raise ValueError("autoreset_mode must be next_step, same_step or disabled")
         if kwargs.get("render_mode") is not None:
             raise NotImplementedError("rendering is out of scope for the batched CUDA path")
-        self.task_name, self.reward_type = "AdroitHandHammer", reward_type.lower()
+        self.task_name, self.reward_type = self.TASK_NAME, reward_type.lower()
         self.sparse_reward = self.reward_type == "sparse"
         self.num_envs, self.max_episode_steps, self.autoreset_mode = int(num_envs), max_episode_steps, autoreset_mode
         self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
         self.n_substeps = self.frame_skip = int(frame_skip)
-        self.model = model if model is not None else load_model("adroit_hammer")
+        self.model = model if model is not None else load_model(self.MODEL_NAME)
         m = self.model
-        self.task = make_hammer_task(m, self.reward_type, frame_skip)
+        self.task = self.make_task(m, self.reward_type, frame_skip)
         factory = backend_factory or _AdroitBackend
         self.backend = factory(m, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device
@@ -155,7 +172,63 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         return out["obs"]
 
 
-ADROIT_TASKS = {"AdroitHandHammer": AdroitHammerVectorEnv}
+class AdroitRelocateVectorEnv(AdroitHammerVectorEnv):
+    """`gym.make_vec("AdroitHandRelocate-v2", num_envs=N)`: 36 dofs (6-dof arm + 24 hand joints + 6-dof ball) on the wide
+    build; obs 39; per-episode ball start (model.body_pos[Object] x, y) and target (model.site_pos[target]) as per-env state
+    (envs/adroit_hand/adroit_relocate.py:288-402)."""
+
+    TASK_NAME, MODEL_NAME = "AdroitHandRelocate", "adroit_relocate"
+    make_task = staticmethod(make_relocate_task)
+
+    def _reset_envs(self, mask, out):
+        """reset_model (adroit_relocate.py:354-373): five uniform draws in the reference's order."""
+        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        if idx.numel() == 0:
+            return
+        n = idx.numel()
+        st, sl = self.backend.state, self._sl
+        lo = np.array([-0.15, -0.15, -0.2, -0.2, 0.15])
+        hi = np.array([0.15, 0.3, 0.2, 0.2, 0.35])
+        if self.rng_mode == "numpy":
+            u = torch.as_tensor(np.array([[self._np_rngs[i].uniform(low=lo[k], high=hi[k]) for k in range(5)] for i in idx.tolist()]),
+                                dtype=torch.float32, device=self.device)
+        else:
+            lo_t, hi_t = (torch.as_tensor(x, dtype=torch.float32, device=self.device) for x in (lo, hi))
+            u = lo_t + (hi_t - lo_t) * torch.rand((n, 5), generator=self._gen, device=self.device)
+        rec = torch.zeros((n, st.shape[1]), dtype=torch.float32, device=self.device)
+        rec[:, sl["qpos"]] = self.init_qpos
+        rec[:, sl["qvel"]] = self.init_qvel
+        rec[:, sl["penv"]] = self._board_pos0                       # body_pos of "Object": z stays the model's
+        rec[:, sl["penv"].start:sl["penv"].start + 2] = u[:, 0:2]
+        rec[:, sl["goal"]] = u[:, 2:5]                              # site_pos of "target" (a world site)
+        st[idx] = rec
+        self._elapsed[idx] = 0
+        self.backend.refresh(mask.to(torch.uint8), out)
+
+    # adroit_relocate.py:375-402
+    def get_env_state(self):
+        st, sl = self.backend.state, self._sl
+        hand = self._last["obs"][:, -9:-6] if self._last is not None else None   # palm - ball; palm = that + ball
+        ball = self._last["achieved"] if self._last is not None else None
+        return dict(qpos=st[:, sl["qpos"]].clone(), qvel=st[:, sl["qvel"]].clone(),
+                    hand_pos=(hand + ball).clone() if hand is not None else None,
+                    obj_pos=st[:, sl["penv"]].clone(), target_pos=st[:, sl["goal"]].clone())
+
+    def set_env_state(self, state_dict):
+        st, sl = self.backend.state, self._sl
+        for key, name, width in (("qpos", "qpos", self.model.nq), ("qvel", "qvel", self.model.nv), ("obj_pos", "penv", 3),
+                                 ("target_pos", "goal", 3)):
+            v = torch.as_tensor(np.asarray(state_dict[key]) if not torch.is_tensor(state_dict[key]) else state_dict[key])
+            assert v.shape[-1] == width, f"The state dictionary entry {key} must have {width} columns"
+            st[:, sl[name]] = v.to(self.device, torch.float32).reshape(-1, width).expand(self.num_envs, width)
+        st[:, sl["warm"]] = 0
+        out = self.backend.new_outputs()
+        self.backend.refresh(None, out)
+        self._last = out
+        return out["obs"]
+
+
+ADROIT_TASKS = {"AdroitHandHammer": AdroitHammerVectorEnv, "AdroitHandRelocate": AdroitRelocateVectorEnv}
 
 
 def make_adroit_vec(task, num_envs=1, **kwargs):

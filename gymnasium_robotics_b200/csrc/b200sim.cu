@@ -97,7 +97,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   float r[3] = {0, 0, 0};
   if (ref) { r[0] = ref[0]; r[1] = ref[1]; r[2] = ref[2]; }
   std::string err;
-  if (dm_build(h->view, eq_data, r, h->model_host, err, task->kind == TASK_ADROIT_HAMMER ? task->penv_body : -1) != 0) { delete h; return fail(nullptr, "b200sim_create: " + err, -4); }
+  if (dm_build(h->view, eq_data, r, h->model_host, err, TASK_IS_ADROIT(task->kind) ? task->penv_body : -1) != 0) { delete h; return fail(nullptr, "b200sim_create: " + err, -4); }
   const DMHead* dh = (const DMHead*)h->model_host.data();
   FetchTask& t = h->task;
   memset(&t, 0, sizeof(t));
@@ -113,7 +113,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   t.obj_qadr = task->obj_qadr; t.obj_dadr = task->obj_dadr; t.goal_flags = task->goal_flags; t.rotation_threshold = task->rotation_threshold;
   t.touch_mode = task->touch_mode;
   for (int k = 0; k < 5; k++) t.tip_site[k] = task->tip_site[k];
-  t.penv_body = task->kind == TASK_ADROIT_HAMMER ? task->penv_body : -1;
+  t.penv_body = TASK_IS_ADROIT(task->kind) ? task->penv_body : -1;
   if (t.kind == TASK_FETCH) { t.nact = 4; t.ngoal = 3; }
   if (t.kind == TASK_ADROIT_HAMMER) {
     bool ok = t.nact == dh->nu && t.ngoal == 3 && t.nobs == dh->nq - 6 + 6 + 13 && dh->nsensor <= 1 && t.penv_body > 0 && t.penv_body < dh->nb;
@@ -121,7 +121,12 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
     for (int k = 0; k < 5; k++) ok = ok && sites[k] >= 0 && sites[k] < dh->nsite;
     if (!ok) { delete h; return fail(nullptr, "b200sim_create: inconsistent AdroitHandHammer task", -6); }
   }
-  if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE && t.kind != TASK_HAND && t.kind != TASK_HAND_REACH && t.kind != TASK_ADROIT_HAMMER) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
+  if (t.kind == TASK_ADROIT_RELOCATE) {
+    bool ok = t.nact == dh->nu && t.ngoal == 3 && t.nobs == dh->nq - 6 + 9 && t.penv_body > 0 && t.penv_body < dh->nb &&
+              t.grip_site >= 0 && t.grip_site < dh->nsite && t.obj_site >= 0 && t.obj_site < dh->nsite;
+    if (!ok) { delete h; return fail(nullptr, "b200sim_create: inconsistent AdroitHandRelocate task", -6); }
+  }
+  if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE && t.kind != TASK_HAND && t.kind != TASK_HAND_REACH && !TASK_IS_ADROIT(t.kind)) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
   if (t.kind == TASK_HAND && (t.nact != dh->nu || t.ngoal != 7 || t.obj_qadr != dh->nq - 7 || t.obj_dadr != dh->nv - 6 ||
                               t.touch_mode < 0 || t.touch_mode > 3 || (t.touch_mode && dh->nsensor == 0) ||
                               t.nobs != t.obj_qadr + dh->nv + 7 + (t.touch_mode ? dh->nsensor : 0))) { delete h; return fail(nullptr, "b200sim_create: inconsistent Hand task", -6); }
@@ -143,7 +148,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   h->wpb = (num_envs + nsm - 1) / nsm <= 7 ? 7 : ((num_envs + nsm - 1) / nsm <= 14 ? 14 : 28);
   h->nvp = dh->nv <= 14 ? 14 : (dh->nv == 15 ? 15 : (dh->nv <= 21 ? 21 : (dh->nv <= 30 ? 30 : (dh->nv > 32 && dh->nv <= B200_WIDE_NVP ? B200_WIDE_NVP : 0))));  // smallest built size >= nv (identity padding)
   if (h->nvp == 0) { delete h; return fail(nullptr, "b200sim_create: no kernel instantiation for this nv (31, 32 or > 36)", -8); }
-  if ((t.kind == TASK_HAND || t.kind == TASK_HAND_REACH || t.kind == TASK_ADROIT_HAMMER) && h->nvp < 30) h->nvp = 30;  // the hand task code is compiled into this build only
+  if ((t.kind == TASK_HAND || t.kind == TASK_HAND_REACH || TASK_IS_ADROIT(t.kind)) && h->nvp < 30) h->nvp = 30;  // the hand task code is compiled into this build only
   if (dh->nv <= 21 && dh->any_convex_pair) h->nvp = 22;  // arm build that carries the general convex collider (FetchSlide's puck)
   if (dh->nv <= 21 && (dh->nten > 0 || dh->nfric > 0 || dh->nsensor > 0 || dh->any_round_pair)) h->nvp = 30;  // hand features live in the NVP = 30 build
   if (h->nvp == 30 && h->wpb > 14) h->wpb = 14;  // the large models' scratch does not fit 28 envs per block

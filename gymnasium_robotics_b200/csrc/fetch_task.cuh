@@ -33,7 +33,8 @@ struct FetchTask {
   int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride, st_penv;
 };
 // TASK_ANTMAZE covers both maze agents (Ant, Point)
-enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2, TASK_HAND_REACH = 3, TASK_ADROIT_HAMMER = 4 };
+enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2, TASK_HAND_REACH = 3, TASK_ADROIT_HAMMER = 4, TASK_ADROIT_RELOCATE = 5 };
+#define TASK_IS_ADROIT(k) ((k) == TASK_ADROIT_HAMMER || (k) == TASK_ADROIT_RELOCATE)
 enum { GOAL_USE_POS = 1, GOAL_USE_ROT = 2, GOAL_IGNORE_Z = 4 };
 
 enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
@@ -338,6 +339,36 @@ HD void adroit_hammer_observe(const Ctx& c, const FetchTask& t, float* obs, floa
   }
 }
 
+// AdroitHandRelocate (envs/adroit_hand/adroit_relocate.py:288-345): obs = qpos[:-6] | palm - ball | palm - target | ball - target;
+// the target is a per-env world site position (site_pos redrawn by reset_model, :354-373) kept in the goal slot of the state
+HD void adroit_relocate_observe(const Ctx& c, const FetchTask& t, const float* goal, float* obs, float* achieved, float* desired,
+                                float* reward, float* success) {
+  const DMHead* h = c.h;
+  const int nr = h->nq - 6;
+  LANES(i, nr) obs[i] = SF(qpos)[i];
+  if (c.lane == 0) {
+    float palm[3], ball[3];
+    site_pose(c, t.grip_site, palm, nullptr);
+    site_pose(c, t.obj_site, ball, nullptr);
+    float po[3], pt[3], ot[3];
+    for (int k = 0; k < 3; k++) {
+      po[k] = palm[k] - ball[k]; pt[k] = palm[k] - goal[k]; ot[k] = ball[k] - goal[k];
+      obs[nr + k] = po[k]; obs[nr + 3 + k] = pt[k]; obs[nr + 6 + k] = ot[k];
+      achieved[k] = ball[k]; desired[k] = goal[k];
+    }
+    float gd = sqrtf(dot3(ot, ot));
+    bool ok = gd < 0.1f;
+    float r = ok ? 10.f : -0.1f;
+    if (t.reward_dense) {
+      r = -0.1f * sqrtf(dot3(po, po));
+      if (ball[2] > 0.04f) r += 1.0f - 0.5f * sqrtf(dot3(pt, pt)) - 0.5f * gd;
+      if (gd < 0.1f) r += 10.f;
+      if (gd < 0.05f) r += 20.f;
+    }
+    *reward = r; *success = ok ? 1.f : 0.f;
+  }
+}
+
 // one env, one warp.  `st` is this env's state record; outputs are this env's rows.  `active` is warp-uniform: idle
 // warps run the same control flow (for the block-wide alignment barriers) but touch no memory.
 template <int NVP>
@@ -347,7 +378,7 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   constexpr int kAlign = ALIGN_LEVEL_FOR(NVP);
   if (active) {
     load_state(c, t, st);
-    if (NVP >= 30 && mode == MODE_STEP && (t.kind == TASK_HAND || t.kind == TASK_HAND_REACH || t.kind == TASK_ADROIT_HAMMER)) {
+    if (NVP >= 30 && mode == MODE_STEP && (t.kind == TASK_HAND || t.kind == TASK_HAND_REACH || TASK_IS_ADROIT(t.kind))) {
       // (Adroit: a = act_mean + clip(a) * act_rng, adroit_hammer.py:292-293 -- the same arithmetic)
       // MujocoHandEnv._set_action (hand_env.py:42-61, absolute control): ctrl = centre + clip(a) * half range, clipped
       LANES(i, h->nu) {
@@ -411,6 +442,9 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
     reach_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   } else if (NVP >= 30 && t.kind == TASK_ADROIT_HAMMER) {
     adroit_hammer_observe(c, t, obs, achieved, desired, reward, success);
+  } else if (NVP >= 30 && t.kind == TASK_ADROIT_RELOCATE) {
+    if (nsub == 0) kinematics(c);   // refresh after a reset: body / site positions of the new state
+    adroit_relocate_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   } else if (NVP >= 30 && t.kind == TASK_HAND) {
     hand_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
     if (t.touch_mode) touch_observe(c, t, obs + t.obj_qadr + h->nv + 7);

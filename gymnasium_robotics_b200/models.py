@@ -24,6 +24,7 @@ MODEL_SOURCES = {
     "hand_block_touch": "hand/manipulate_block_touch_sensors.xml",   # + 92 touch sensors
     "hand_reach": "hand/reach.xml",
     "adroit_hammer": "adroit_hand/adroit_hammer.xml",
+    "adroit_relocate": "adroit_hand/adroit_relocate.xml",
     "hand_egg": "hand/manipulate_egg.xml",
     "hand_egg_touch": "hand/manipulate_egg_touch_sensors.xml",
     "hand_pen": "hand/manipulate_pen.xml",
@@ -35,7 +36,9 @@ _HAND = {"drop_bodies": ["target"], "sensor_prefix": "robot0:TS_"}
 # Adroit hammer: the unused mocap body is dropped (its weld is commented out, adroit_assets.xml:92-94); nail_board stays a
 # runtime body because reset_model redraws its height per episode (adroit_hammer.py:372-378); only the sensor the env reads
 _ADROIT_HAMMER = {"drop_bodies": ["vive_tracker"], "keep_bodies": ["nail_board"], "sensor_prefix": "S_nail"}
-MODEL_OVERRIDES = {"adroit_hammer": _ADROIT_HAMMER, "hand_block": _HAND, "hand_block_touch": _HAND, "hand_pen": _HAND, "hand_pen_touch": _HAND, "hand_egg": _HAND, "hand_egg_touch": _HAND, "hand_reach": {"sensor_prefix": "robot0:TS_"}}
+# relocate: no sensor is observed (the 21 "Tch_*" touch sensors of the hand model are never read by the env)
+_ADROIT_RELOCATE = {"drop_bodies": ["vive_tracker"], "sensor_prefix": "<none>"}
+MODEL_OVERRIDES = {"adroit_hammer": _ADROIT_HAMMER, "adroit_relocate": _ADROIT_RELOCATE, "hand_block": _HAND, "hand_block_touch": _HAND, "hand_pen": _HAND, "hand_pen_touch": _HAND, "hand_egg": _HAND, "hand_egg_touch": _HAND, "hand_reach": {"sensor_prefix": "robot0:TS_"}}
 
 
 # maze models: in-tree legacy twin of Gymnasium's ant.xml (Gymnasium itself is un-vendored) + generated wall boxes

@@ -52,6 +52,9 @@ typedef struct b200sim_fetch_task {
    * frame_site = "S_target", tip_site[0] = "tool", tip_site[1] = "nail_goal".
    * penv_body: runtime body whose body_pos is per-env state (nail_board, adroit_hammer.py:372-378), -1 = none; its three
    * floats live in the state record at B200SIM_ST_PENV. */
+  /* kind 5 = AdroitHandRelocate (envs/adroit_hand/adroit_relocate.py:288-373): obs = qpos[:-6] | palm - ball | palm - target |
+   * ball - target (39); grip_site = "S_grasp", obj_site = body frame of "Object", penv_body = "Object" (body_pos x, y redrawn per
+   * episode), the per-env target site position is the 3-float goal of the state record. */
   int penv_body;
 } b200sim_fetch_task_t;
 

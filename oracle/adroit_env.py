@@ -103,3 +103,73 @@ class OracleAdroitHammerEnv:
     def set_env_state(self, state_dict):  # adroit_hammer.py:390-402
         self.sim.body_pos[self.target_body_id] = state_dict["board_pos"]
         self.set_state(state_dict["qpos"], state_dict["qvel"])
+
+
+class OracleAdroitRelocateEnv(OracleAdroitHammerEnv):
+    """envs/adroit_hand/adroit_relocate.py (AdroitHandRelocateEnv).  The `target` site sits on the world body, so its
+    site_xpos is its (per-episode) site_pos: kept as `self.target_pos`."""
+
+    def __init__(self, model, reward_type="dense", frame_skip=5):
+        self.model, self.frame_skip = model, frame_skip
+        self.sparse_reward = reward_type.lower() == "sparse"
+        self.sim = OracleSim(model)
+        m = model
+        self.S_grasp_site_id = m.site_id("S_grasp")                 # adroit_relocate.py:257-259
+        self.obj_body_id = int(m.names["body_map"]["Object"])
+        self.target_pos = np.asarray(m.site_pos).reshape(-1, 3)[m.site_id("target")].copy()
+        cr = np.asarray(m.act_ctrlrange, dtype=np.float64).reshape(-1, 2)
+        self.act_mean, self.act_rng = np.mean(cr, axis=1), 0.5 * (cr[:, 1] - cr[:, 0])
+        self.np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(None)))
+        self.sim.forward()
+        self.init_qpos, self.init_qvel = self.sim.qpos.copy(), self.sim.qvel.copy()
+
+    def step(self, a):  # adroit_relocate.py:288-329
+        s = self.sim
+        a = np.clip(a, -1.0, 1.0)
+        a = self.act_mean + a * self.act_rng
+        s.ctrl[:] = a
+        s.step(self.frame_skip)
+        obs = self._get_obs()
+        obj_pos = s.xpos[self.obj_body_id].ravel()
+        palm_pos = s.site_xpos[self.S_grasp_site_id].ravel()
+        target_pos = self.target_pos
+        goal_distance = float(np.linalg.norm(obj_pos - target_pos))
+        goal_achieved = goal_distance < 0.1
+        reward = 10.0 if goal_achieved else -0.1
+        if not self.sparse_reward:
+            reward = -0.1 * np.linalg.norm(palm_pos - obj_pos)
+            if obj_pos[2] > 0.04:
+                reward += 1.0
+                reward += -0.5 * np.linalg.norm(palm_pos - target_pos)
+                reward += -0.5 * np.linalg.norm(obj_pos - target_pos)
+            if goal_distance < 0.1:
+                reward += 10.0
+            if goal_distance < 0.05:
+                reward += 20.0
+        return obs, reward, False, False, dict(success=goal_achieved)
+
+    def _get_obs(self):  # adroit_relocate.py:331-339
+        s = self.sim
+        qpos = s.qpos.ravel()
+        obj_pos = s.xpos[self.obj_body_id].ravel()
+        palm_pos = s.site_xpos[self.S_grasp_site_id].ravel()
+        return np.concatenate([qpos[:-6], palm_pos - obj_pos, palm_pos - self.target_pos, obj_pos - self.target_pos])
+
+    def reset_model(self):  # adroit_relocate.py:354-373
+        self.sim.body_pos[self.obj_body_id, 0] = self.np_random.uniform(low=-0.15, high=0.15)
+        self.sim.body_pos[self.obj_body_id, 1] = self.np_random.uniform(low=-0.15, high=0.3)
+        self.target_pos[0] = self.np_random.uniform(low=-0.2, high=0.2)
+        self.target_pos[1] = self.np_random.uniform(low=-0.2, high=0.2)
+        self.target_pos[2] = self.np_random.uniform(low=0.15, high=0.35)
+        self.set_state(self.init_qpos, self.init_qvel)
+        return self._get_obs()
+
+    def get_env_state(self):  # adroit_relocate.py:375-388
+        return dict(qpos=self.sim.qpos.ravel().copy(), qvel=self.sim.qvel.ravel().copy(),
+                    hand_pos=self.sim.site_xpos[self.S_grasp_site_id].ravel().copy(),
+                    obj_pos=self.sim.body_pos[self.obj_body_id].copy(), target_pos=self.target_pos.copy())
+
+    def set_env_state(self, state_dict):  # adroit_relocate.py:390-402
+        self.sim.body_pos[self.obj_body_id] = state_dict["obj_pos"]
+        self.target_pos[:] = state_dict["target_pos"]
+        self.set_state(state_dict["qpos"], state_dict["qvel"])

@@ -15,7 +15,7 @@ class HostSimBackend:
 
         self.device = torch.device("cpu")
         self.num_envs, self.nobs = num_envs, task.nobs
-        penv = int(task.penv_body) if task.kind == 4 else -1
+        penv = int(task.penv_body) if task.kind in (4, 5) else -1
         self.sim = HostSim(model, eq_data=eq_data if len(eq_data) else None, ref=getattr(self, "REF", REF_POINT), penv_body=penv)
         t = HostTaskC()
         for name, _ in task._fields_:

@@ -610,3 +610,47 @@ def test_adroit_hammer_parity():
         assert torch.isfinite(out["obs"]).all()
         assert int((info_bits >> 16).max()) == 0, "contact / row capacity overflow"
     env.close()
+
+
+def test_adroit_relocate_parity():
+    """AdroitHandRelocate-v2 (36 dofs: four border rows in the register Cholesky)."""
+    import gymnasium_robotics_b200 as pkg
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.adroit_env import OracleAdroitRelocateEnv
+
+    n = 4
+    m = load_model("adroit_relocate")
+    env = pkg.make_vec("AdroitHandRelocate-v2", num_envs=n, device="cuda:0", rng_mode="numpy")
+    obs, _ = env.reset(seed=30)
+    oracles = [OracleAdroitRelocateEnv(m) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=30 + i)
+        assert np.abs(obs[i].double().cpu().numpy() - oo).max() < 2e-6
+    lay = env.backend.layout
+    rng = np.random.default_rng(2)
+    errs = []
+    for step in range(10):
+        rec = np.zeros((n, lay["stride"]))
+        for i, o in enumerate(oracles):
+            s = o.sim
+            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+            rec[i, lay["penv"]:lay["penv"] + 3] = s.body_pos[o.obj_body_id]
+            rec[i, lay["goal"]:lay["goal"] + 3] = o.target_pos
+        env.backend.state.copy_(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        a = rng.uniform(-1, 1, (n, 30)).astype(np.float32)
+        if step >= 4:
+            a[:, :3] = [0, 0.5, -1]
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            got = o[i].double().cpu().numpy()
+            assert np.isfinite(got).all()
+            errs.append(np.abs(got - oo).max())
+            assert abs(float(r[i]) - orr) < 1e-3 and bool(info["success"][i]) == bool(oi["success"])
+    errs = np.array(errs)
+    print(f"AdroitRelocate: median {np.median(errs):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < 2e-5 and np.mean(errs < 2e-4) >= 0.9 and errs.max() < 0.05
+    env.close()

@@ -313,3 +313,46 @@ def test_adroit_hammer_env_matches_oracle():
     assert torch.equal(st["qpos"], st2["qpos"]) and torch.equal(st["board_pos"], st2["board_pos"]) and o1.shape == (1, 46)
     with pytest.raises(ValueError):
         pkg.make_vec("AdroitHandHammer-v2", num_envs=1, backend_factory=AdroitHostBackend, reward_type="shaped")
+
+
+def test_adroit_relocate_env_matches_oracle():
+    """AdroitHandRelocate-v2 (36 dofs, wide build): five reset draws in the reference's order (ball x, y; target x, y, z),
+    env-steps from injected oracle states, reward / success, state round trip (adroit_relocate.py:288-402)."""
+    from gymnasium_robotics_b200.adroit import ADROIT_REF_POINT
+    from oracle.adroit_env import OracleAdroitRelocateEnv
+
+    class AdroitHostBackend(HostSimBackend):
+        REF = ADROIT_REF_POINT
+
+    m = load_model("adroit_relocate")
+    assert m.nv == 36 and m.nu == 30
+    env = pkg.make_vec("AdroitHandRelocate-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
+    assert env.single_observation_space.shape == (39,) and env.single_action_space.shape == (30,)
+    orc = OracleAdroitRelocateEnv(m)
+    obs, _ = env.reset(seed=4)
+    oobs, _ = orc.reset(seed=4)
+    np.testing.assert_allclose(obs[0].double().numpy(), oobs, atol=1e-6)
+    st = env.get_env_state()
+    np.testing.assert_allclose(st["target_pos"][0].double().numpy(), orc.target_pos, atol=1e-7)
+    np.testing.assert_allclose(st["obj_pos"][0].double().numpy(), orc.sim.body_pos[orc.obj_body_id], atol=1e-7)
+    np.testing.assert_allclose(st["hand_pos"][0].double().numpy(), orc.get_env_state()["hand_pos"], atol=1e-6)
+    lay, s = env.backend.layout, orc.sim
+    rng = np.random.default_rng(1)
+    for k in range(6):
+        rec = np.zeros(lay["stride"])
+        rec[lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+        rec[lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+        rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+        rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+        rec[lay["penv"]:lay["penv"] + 3] = s.body_pos[orc.obj_body_id]
+        rec[lay["goal"]:lay["goal"] + 3] = orc.target_pos
+        env.backend.state[0] = torch.as_tensor(rec, dtype=torch.float32)
+        a = rng.uniform(-1, 1, 30)
+        if k >= 3:
+            a[:3] = [0, 0.5, -1]     # arm forward and down onto the table
+        o, r, te, tr, info = env.step(a[None].astype(np.float32))
+        oo, orr, _, _, oi = orc.step(a)
+        assert np.abs(o[0].double().numpy() - oo).max() < 2e-5
+        assert abs(float(r[0]) - orr) < 2e-5 and bool(info["success"][0]) == bool(oi["success"])
+    o1 = env.set_env_state(env.get_env_state())
+    assert o1.shape == (1, 39) and {"AdroitHandRelocate-v2", "AdroitHandRelocateSparse-v2"} <= set(pkg.ENV_IDS)
