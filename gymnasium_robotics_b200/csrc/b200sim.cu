@@ -52,7 +52,6 @@ extern "C" int b200sim_wide_launch(int wpb, int blocks, size_t smem_bytes, void*
                                    int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
                                    float* achieved, float* desired, float* reward, float* success, int* info);
 #define B200_WIDE_NVP 36
-#define B200_WIDE_WPB 10
 
 struct b200sim {
   int N = 0, device = 0;
@@ -152,8 +151,15 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   if (dh->nv <= 21 && dh->any_convex_pair) h->nvp = 22;  // arm build that carries the general convex collider (FetchSlide's puck)
   if (dh->nv <= 21 && (dh->nten > 0 || dh->nfric > 0 || dh->nsensor > 0 || dh->any_round_pair)) h->nvp = 30;  // hand features live in the NVP = 30 build
   if (h->nvp == 30 && h->wpb > 14) h->wpb = 14;  // the large models' scratch does not fit 28 envs per block
-  if (h->nvp == B200_WIDE_NVP) h->wpb = h->wpb > 7 ? B200_WIDE_WPB : 7;
-  if (h->nvp == B200_WIDE_NVP) if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 10 || w == 14) h->wpb = w; }  // experiments
+  if (h->nvp == B200_WIDE_NVP) {
+    // wide build: the largest block of {14, 13, 10, 7} warps whose scratch fits the 227 KB of shared memory (14 envs of the
+    // 33-dof hammer model, 13 of the 36-dof relocate model), 7 for small batches so that every SM still gets a block
+    const int want = h->wpb, cands[4] = {14, 13, 10, 7};
+    h->wpb = 7;
+    for (int k = 3; k >= 0; k--)
+      if (cands[k] <= (want > 7 ? 14 : 7) && ((size_t)dh->hot_words + (size_t)cands[k] * dh->scr_words) * 4 + 64 <= 232448) h->wpb = cands[k];
+    if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 10 || w == 13 || w == 14) h->wpb = w; }  // experiments
+  }
   if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 14 || (w == 28 && h->nvp != 30)) h->wpb = w; }  // experiments
   h->smem_bytes = ((size_t)dh->hot_words + (size_t)h->wpb * dh->scr_words) * 4;
   h->blocks = (num_envs + h->wpb - 1) / h->wpb;

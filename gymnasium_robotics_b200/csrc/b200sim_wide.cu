@@ -7,7 +7,7 @@
 
 #include "step_kernel.cuh"
 
-#define B200_WIDE_VARIANTS(X) X(7, 36) X(10, 36) X(14, 36)
+#define B200_WIDE_VARIANTS(X) X(7, 36) X(10, 36) X(13, 36) X(14, 36)
 
 extern "C" int b200sim_wide_setattr(int wpb, int smem_bytes) {
   cudaError_t e = cudaErrorInvalidValue;

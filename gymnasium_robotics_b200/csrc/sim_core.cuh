@@ -1121,16 +1121,19 @@ STAGE void collision(const Ctx c) {
       for (int k = 0; k < o.cnt; k++) if (o.dist[k] < inc) { if (k2 != k) { o.dist[k2] = o.dist[k]; for (int a = 0; a < 3; a++) { o.pos[k2][a] = o.pos[k][a]; o.nrm[k2][a] = o.nrm[k][a]; } } k2++; }
       o.cnt = k2;
     }
-    int total, slot = wexscan(o.cnt, c.lane, &total);
     int gtotal, gslot = wexscan(o.cnt > 0 ? 1 : 0, c.lane, &gtotal);
     int basec = cnt[CNT_NCON], baseg = cnt[CNT_NGRP];
+    int gid = baseg + gslot;
+    // a geom pair beyond the group capacity is dropped with all its contacts BEFORE the contacts are numbered: every
+    // counted contact record is then really written (a counted but unwritten record would be finalised from stale words)
+    if (o.cnt > 0 && gid >= h->ngrp_max - DM_NWELD_MAX) o.cnt = 0;
+    int total, slot = wexscan(o.cnt, c.lane, &total);
     SYNC();
     int kept = 0;
-    int gid = baseg + gslot;
     for (int k = 0; k < o.cnt; k++) {
       // raw contact (position, normal, distance, pair) parked in its record; finalised by one lane per contact below
       int id = basec + slot + k;
-      if (id >= h->ncon_max || gid >= h->ngrp_max - DM_NWELD_MAX) break;
+      if (id >= h->ncon_max) break;
       float* cr = SF(con) + id * CON_WORDS;
       cr[0] = o.pos[k][0]; cr[1] = o.pos[k][1]; cr[2] = o.pos[k][2];
       cr[3] = o.nrm[k][0]; cr[4] = o.nrm[k][1]; cr[5] = o.nrm[k][2];
@@ -1139,7 +1142,7 @@ STAGE void collision(const Ctx c) {
       ((int*)cr)[C_DIMGRP] = gid << 8;
       kept++;
     }
-    if (o.cnt > 0 && gid < h->ngrp_max - DM_NWELD_MAX) {
+    if (o.cnt > 0) {
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
       int ba = MI(geom_body)[MI(pair_geom1)[p]], bb = MI(pair_geom2)[p] < 0 ? 0 : MI(geom_body)[MI(pair_geom2)[p]];
       dmask_t ma = DM(body_ancdof, ba), mb = DM(body_ancdof, bb);

@@ -654,3 +654,20 @@ def test_adroit_relocate_parity():
     print(f"AdroitRelocate: median {np.median(errs):.2e} max {errs.max():.2e}")
     assert np.median(errs) < 2e-5 and np.mean(errs < 2e-4) >= 0.9 and errs.max() < 0.05
     env.close()
+    # bench-size batch under random actions: the arm presses the whole hand onto the table in some envs, which exceeds the
+    # 13 geom-pair groups kept per env -- flagged in the info word, never a stale contact record (regression: counted but
+    # unwritten records used to be finalised from stale words)
+    env = pkg.make_vec("AdroitHandRelocate-v2", num_envs=2048, device="cuda:0", rng_mode="torch")
+    env.reset(seed=1)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    info_bits = torch.zeros(2048, dtype=torch.int32, device="cuda")
+    flagged = 0
+    for _ in range(60):
+        a = torch.rand((2048, 30), generator=g, device="cuda") * 2 - 1
+        out = env.backend.new_outputs()
+        env.backend.step(a, out, info_bits)
+        assert torch.isfinite(out["obs"]).all()
+        flagged += int(((info_bits >> 16) != 0).sum())
+    print(f"AdroitRelocate 2048 x 60: {flagged} env-steps with a capacity flag")
+    assert flagged < 0.01 * 2048 * 60
+    env.close()
