@@ -46,6 +46,8 @@ for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
 for _rt, _suffix in (("dense", ""), ("sparse", "Sparse")):
     ENV_IDS[f"AdroitHandHammer{_suffix}-v2"] = dict(adroit_task="AdroitHandHammer", reward_type=_rt, max_episode_steps=200)
     ENV_IDS[f"AdroitHandRelocate{_suffix}-v2"] = dict(adroit_task="AdroitHandRelocate", reward_type=_rt, max_episode_steps=200)
+    ENV_IDS[f"AdroitHandDoor{_suffix}-v2"] = dict(adroit_task="AdroitHandDoor", reward_type=_rt, max_episode_steps=200)
+    ENV_IDS[f"AdroitHandPen{_suffix}-v2"] = dict(adroit_task="AdroitHandPen", reward_type=_rt, max_episode_steps=200)
 
 
 def make_vec(env_id: str, num_envs: int = 1, **kwargs):

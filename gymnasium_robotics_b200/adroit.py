@@ -1,5 +1,5 @@
 """Batched Adroit hand environments on the CUDA simulator: `gym.make_vec("AdroitHandHammer-v2", num_envs=N)` and
-`gym.make_vec("AdroitHandRelocate-v2", num_envs=N)`.
+`gym.make_vec("AdroitHandRelocate-v2", num_envs=N)`, `"AdroitHandPen-v2"`, `"AdroitHandDoor-v2"` (+ the `Sparse` ids).
 
 Mirrors (batched) the reference's Python around the hot path:
   * AdroitHandHammerEnv.step / _get_obs        envs/adroit_hand/adroit_hammer.py:291-357   (inside the step kernel,
@@ -66,6 +66,41 @@ def make_relocate_task(model, reward_type, frame_skip=FRAME_SKIP):
     return t
 
 
+def make_pen_task(model, reward_type, frame_skip=FRAME_SKIP):
+    """b200sim_fetch_task_t for kind 6 (adroit_pen.py:264-271; the two lengths of :392-399 are model constants)."""
+    m = model
+    t = FetchTaskC()
+    t.kind, t.nact, t.ngoal = 6, int(m.nu), 3
+    t.n_substeps, t.reward_dense = int(frame_skip), int(reward_type == "dense")
+    t.obj_site = m.frame_site("Object")
+    t.frame_site = m.site_id("eps_ball")
+    names = ("object_top", "object_bottom", "target_top", "target_bottom")
+    for k, n in enumerate(names):
+        t.tip_site[k] = m.site_id(n)
+    sp = np.asarray(m.site_pos).reshape(-1, 3)
+    t.distance_threshold = float(np.linalg.norm(sp[t.tip_site[0]] - sp[t.tip_site[1]]))   # pen_length
+    t.rotation_threshold = float(np.linalg.norm(sp[t.tip_site[2]] - sp[t.tip_site[3]]))   # tar_length
+    t.penv_body = int(m.names["body_map"]["target"])
+    t.nobs = int(m.nq) - 6 + 21
+    t.dt = float(m.opt[0] * frame_skip)
+    return t
+
+
+def make_door_task(model, reward_type, frame_skip=FRAME_SKIP):
+    """b200sim_fetch_task_t for kind 7 (adroit_door.py:258-263)."""
+    m = model
+    t = FetchTaskC()
+    t.kind, t.nact, t.ngoal = 7, int(m.nu), 3
+    t.n_substeps, t.reward_dense = int(frame_skip), int(reward_type == "dense")
+    t.grip_site, t.frame_site = m.site_id("S_grasp"), m.site_id("S_handle")
+    t.obj_qadr = int(m.jnt_qposadr[m.joint_id("door_hinge")])
+    assert m.names["joint"][-1] == "latch" and t.obj_qadr == int(m.nq) - 2
+    t.penv_body = int(m.names["body_map"]["frame"])
+    t.nobs = int(m.nq) - 3 + 12
+    t.dt = float(m.opt[0] * frame_skip)
+    return t
+
+
 class AdroitHammerVectorEnv(FetchVectorEnv):
     """Observations (46), rewards and flags are float32 / bool torch tensors on `device` with a leading `num_envs` axis;
     `info["success"]` mirrors the reference's `dict(success=goal_achieved)`."""
@@ -101,7 +136,7 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         self._gen.seed()
         lay = self.backend.layout
         self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", m.nq), ("qvel", m.nv), ("warm", m.nv), ("ctrl", m.nu),
-                                                              ("goal", 3), ("penv", 3))}
+                                                              ("goal", 3), ("penv", 7))}
         self.dt = float(m.opt[0] * frame_skip)
         self.single_action_space = Box(-1.0, 1.0, shape=(int(m.nu),), dtype=np.float32)            # adroit_hammer.py:229-232
         self.single_observation_space = Box(-np.inf, np.inf, shape=(int(self.task.nobs),), dtype=np.float64)
@@ -111,8 +146,10 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.init_qpos = torch.as_tensor(np.array(m.qpos0), dtype=torch.float32, device=self.device)   # MujocoEnv: data.qpos at load
         self.init_qvel = torch.zeros(m.nv, dtype=torch.float32, device=self.device)
-        self._board_pos0 = torch.as_tensor(np.asarray(m.body_pos).reshape(-1, 3)[self.task.penv_body], dtype=torch.float32,
-                                           device=self.device)
+        # model pose (position 3 + quaternion 4) of the body whose pose is per-env state
+        self._board_pos0 = torch.as_tensor(np.concatenate([np.asarray(m.body_pos).reshape(-1, 3)[self.task.penv_body],
+                                                           np.asarray(m.body_quat).reshape(-1, 4)[self.task.penv_body]]),
+                                           dtype=torch.float32, device=self.device)
         cr = np.asarray(m.act_ctrlrange, dtype=np.float64).reshape(-1, 2)
         self.act_mean, self.act_rng = cr.mean(axis=1), 0.5 * (cr[:, 1] - cr[:, 0])                      # adroit_hammer.py:271-274
         self._last = None
@@ -156,7 +193,7 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
     # adroit_hammer.py:380-402, batched: dicts of [N, .] tensors
     def get_env_state(self):
         st, sl = self.backend.state, self._sl
-        return dict(qpos=st[:, sl["qpos"]].clone(), qvel=st[:, sl["qvel"]].clone(), board_pos=st[:, sl["penv"]].clone(),
+        return dict(qpos=st[:, sl["qpos"]].clone(), qvel=st[:, sl["qvel"]].clone(), board_pos=st[:, sl["penv"]][:, :3].clone(),
                     target_pos=self._last["achieved"].clone() if self._last is not None else None)
 
     def set_env_state(self, state_dict):
@@ -164,7 +201,7 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         for key, name, width in (("qpos", "qpos", self.model.nq), ("qvel", "qvel", self.model.nv), ("board_pos", "penv", 3)):
             v = torch.as_tensor(np.asarray(state_dict[key]) if not torch.is_tensor(state_dict[key]) else state_dict[key])
             assert v.shape[-1] == width, f"The state dictionary entry {key} must have {width} columns"
-            st[:, sl[name]] = v.to(self.device, torch.float32).reshape(-1, width).expand(self.num_envs, width)
+            st[:, sl[name].start:sl[name].start + width] = v.to(self.device, torch.float32).reshape(-1, width).expand(self.num_envs, width)
         st[:, sl["warm"]] = 0
         out = self.backend.new_outputs()
         self.backend.refresh(None, out)   # set_state -> mj_forward
@@ -212,7 +249,7 @@ class AdroitRelocateVectorEnv(AdroitHammerVectorEnv):
         ball = self._last["achieved"] if self._last is not None else None
         return dict(qpos=st[:, sl["qpos"]].clone(), qvel=st[:, sl["qvel"]].clone(),
                     hand_pos=(hand + ball).clone() if hand is not None else None,
-                    obj_pos=st[:, sl["penv"]].clone(), target_pos=st[:, sl["goal"]].clone())
+                    obj_pos=st[:, sl["penv"]][:, :3].clone(), target_pos=st[:, sl["goal"]].clone())
 
     def set_env_state(self, state_dict):
         st, sl = self.backend.state, self._sl
@@ -220,7 +257,7 @@ class AdroitRelocateVectorEnv(AdroitHammerVectorEnv):
                                  ("target_pos", "goal", 3)):
             v = torch.as_tensor(np.asarray(state_dict[key]) if not torch.is_tensor(state_dict[key]) else state_dict[key])
             assert v.shape[-1] == width, f"The state dictionary entry {key} must have {width} columns"
-            st[:, sl[name]] = v.to(self.device, torch.float32).reshape(-1, width).expand(self.num_envs, width)
+            st[:, sl[name].start:sl[name].start + width] = v.to(self.device, torch.float32).reshape(-1, width).expand(self.num_envs, width)
         st[:, sl["warm"]] = 0
         out = self.backend.new_outputs()
         self.backend.refresh(None, out)
@@ -228,7 +265,110 @@ class AdroitRelocateVectorEnv(AdroitHammerVectorEnv):
         return out["obs"]
 
 
-ADROIT_TASKS = {"AdroitHandHammer": AdroitHammerVectorEnv, "AdroitHandRelocate": AdroitRelocateVectorEnv}
+class AdroitPenVectorEnv(AdroitHammerVectorEnv):
+    """`gym.make_vec("AdroitHandPen-v2", num_envs=N)`: 30 dofs (24 hand joints + 6-dof pen; the arm is fixed), obs 45; the
+    target orientation (model.body_quat[target], two Euler angles ~ U(-1, 1)) is per-env state
+    (envs/adroit_hand/adroit_pen.py:288-430)."""
+
+    TASK_NAME, MODEL_NAME = "AdroitHandPen", "adroit_pen"
+    make_task = staticmethod(make_pen_task)
+
+    def _reset_envs(self, mask, out):
+        """reset_model (adroit_pen.py:379-399)."""
+        from . import rotations
+
+        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        if idx.numel() == 0:
+            return
+        n = idx.numel()
+        st, sl = self.backend.state, self._sl
+        e = np.zeros((n, 3))
+        if self.rng_mode == "numpy":
+            for k, i in enumerate(idx.tolist()):
+                e[k, 0] = self._np_rngs[i].uniform(low=-1, high=1)
+                e[k, 1] = self._np_rngs[i].uniform(low=-1, high=1)
+        else:
+            e[:, :2] = (torch.rand((n, 2), generator=self._gen, device=self.device) * 2 - 1).double().cpu().numpy()
+        quat = torch.as_tensor(rotations.euler2quat(e), dtype=torch.float32, device=self.device)
+        rec = torch.zeros((n, st.shape[1]), dtype=torch.float32, device=self.device)
+        rec[:, sl["qpos"]] = self.init_qpos
+        rec[:, sl["qvel"]] = self.init_qvel
+        rec[:, sl["penv"]] = self._board_pos0
+        rec[:, sl["penv"].start + 3:sl["penv"].start + 7] = quat
+        st[idx] = rec
+        self._elapsed[idx] = 0
+        self.backend.refresh(mask.to(torch.uint8), out)
+
+    # adroit_pen.py:401-430
+    def get_env_state(self):
+        st, sl = self.backend.state, self._sl
+        return dict(qpos=st[:, sl["qpos"]].clone(), qvel=st[:, sl["qvel"]].clone(), desired_orien=st[:, sl["penv"]][:, 3:7].clone())
+
+    def set_env_state(self, state_dict):
+        st, sl = self.backend.state, self._sl
+        for key, start, width in (("qpos", sl["qpos"].start, self.model.nq), ("qvel", sl["qvel"].start, self.model.nv),
+                                  ("desired_orien", sl["penv"].start + 3, 4)):
+            v = torch.as_tensor(np.asarray(state_dict[key]) if not torch.is_tensor(state_dict[key]) else state_dict[key])
+            assert v.shape[-1] == width, f"The state dictionary entry {key} must have {width} columns"
+            st[:, start:start + width] = v.to(self.device, torch.float32).reshape(-1, width).expand(self.num_envs, width)
+        st[:, sl["warm"]] = 0
+        out = self.backend.new_outputs()
+        self.backend.refresh(None, out)
+        self._last = out
+        return out["obs"]
+
+
+class AdroitDoorVectorEnv(AdroitHammerVectorEnv):
+    """`gym.make_vec("AdroitHandDoor-v2", num_envs=N)`: 30 dofs (4-dof arm + 24 hand joints + door hinge + latch), obs 39; the
+    door frame position (model.body_pos[frame]) is per-env state (envs/adroit_hand/adroit_door.py:279-402)."""
+
+    TASK_NAME, MODEL_NAME = "AdroitHandDoor", "adroit_door"
+    make_task = staticmethod(make_door_task)
+
+    def _reset_envs(self, mask, out):
+        """reset_model (adroit_door.py:359-371): three uniform draws (x, y, z of the frame)."""
+        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        if idx.numel() == 0:
+            return
+        n = idx.numel()
+        st, sl = self.backend.state, self._sl
+        lo, hi = np.array([-0.3, 0.25, 0.252]), np.array([-0.2, 0.35, 0.35])
+        if self.rng_mode == "numpy":
+            u = torch.as_tensor(np.array([[self._np_rngs[i].uniform(low=lo[k], high=hi[k]) for k in range(3)] for i in idx.tolist()]),
+                                dtype=torch.float32, device=self.device)
+        else:
+            lo_t, hi_t = (torch.as_tensor(x, dtype=torch.float32, device=self.device) for x in (lo, hi))
+            u = lo_t + (hi_t - lo_t) * torch.rand((n, 3), generator=self._gen, device=self.device)
+        rec = torch.zeros((n, st.shape[1]), dtype=torch.float32, device=self.device)
+        rec[:, sl["qpos"]] = self.init_qpos
+        rec[:, sl["qvel"]] = self.init_qvel
+        rec[:, sl["penv"]] = self._board_pos0
+        rec[:, sl["penv"].start:sl["penv"].start + 3] = u
+        st[idx] = rec
+        self._elapsed[idx] = 0
+        self.backend.refresh(mask.to(torch.uint8), out)
+
+    # adroit_door.py:373-402
+    def get_env_state(self):
+        st, sl = self.backend.state, self._sl
+        return dict(qpos=st[:, sl["qpos"]].clone(), qvel=st[:, sl["qvel"]].clone(), door_body_pos=st[:, sl["penv"]][:, :3].clone())
+
+    def set_env_state(self, state_dict):
+        st, sl = self.backend.state, self._sl
+        for key, start, width in (("qpos", sl["qpos"].start, self.model.nq), ("qvel", sl["qvel"].start, self.model.nv),
+                                  ("door_body_pos", sl["penv"].start, 3)):
+            v = torch.as_tensor(np.asarray(state_dict[key]) if not torch.is_tensor(state_dict[key]) else state_dict[key])
+            assert v.shape[-1] == width, f"The state dictionary entry {key} must have {width} columns"
+            st[:, start:start + width] = v.to(self.device, torch.float32).reshape(-1, width).expand(self.num_envs, width)
+        st[:, sl["warm"]] = 0
+        out = self.backend.new_outputs()
+        self.backend.refresh(None, out)
+        self._last = out
+        return out["obs"]
+
+
+ADROIT_TASKS = {"AdroitHandHammer": AdroitHammerVectorEnv, "AdroitHandRelocate": AdroitRelocateVectorEnv,
+                "AdroitHandPen": AdroitPenVectorEnv, "AdroitHandDoor": AdroitDoorVectorEnv}
 
 
 def make_adroit_vec(task, num_envs=1, **kwargs):

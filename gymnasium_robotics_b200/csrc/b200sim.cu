@@ -120,6 +120,18 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
     for (int k = 0; k < 5; k++) ok = ok && sites[k] >= 0 && sites[k] < dh->nsite;
     if (!ok) { delete h; return fail(nullptr, "b200sim_create: inconsistent AdroitHandHammer task", -6); }
   }
+  if (t.kind == TASK_ADROIT_DOOR) {
+    bool ok = t.nact == dh->nu && t.ngoal == 3 && t.nobs == dh->nq - 3 + 12 && t.penv_body > 0 && t.penv_body < dh->nb &&
+              t.obj_qadr >= 0 && t.obj_qadr < dh->nq && t.grip_site >= 0 && t.grip_site < dh->nsite && t.frame_site >= 0 && t.frame_site < dh->nsite;
+    if (!ok) { delete h; return fail(nullptr, "b200sim_create: inconsistent AdroitHandDoor task", -6); }
+  }
+  if (t.kind == TASK_ADROIT_PEN) {
+    bool ok = t.nact == dh->nu && t.ngoal == 3 && t.nobs == dh->nq - 6 + 21 && t.penv_body > 0 && t.penv_body < dh->nb &&
+              t.distance_threshold > 0 && t.rotation_threshold > 0;
+    const int sites[6] = {t.obj_site, t.frame_site, t.tip_site[0], t.tip_site[1], t.tip_site[2], t.tip_site[3]};
+    for (int k = 0; k < 6; k++) ok = ok && sites[k] >= 0 && sites[k] < dh->nsite;
+    if (!ok) { delete h; return fail(nullptr, "b200sim_create: inconsistent AdroitHandPen task", -6); }
+  }
   if (t.kind == TASK_ADROIT_RELOCATE) {
     bool ok = t.nact == dh->nu && t.ngoal == 3 && t.nobs == dh->nq - 6 + 9 && t.penv_body > 0 && t.penv_body < dh->nb &&
               t.grip_site >= 0 && t.grip_site < dh->nsite && t.obj_site >= 0 && t.obj_site < dh->nsite;
@@ -139,7 +151,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   int o = 0;
   t.st_qpos = o; o += dh->nq; t.st_qvel = o; o += dh->nv; t.st_warm = o; o += dh->nv; t.st_ctrl = o; o += dh->nu;
   t.st_mocap = o; o += 7 * dh->nmocap; t.st_pose = o; o += (t.kind == TASK_FETCH ? 7 : 0); t.st_goal = o; o += t.ngoal;
-  t.st_penv = o; o += (t.penv_body > 0 ? 3 : 0);
+  t.st_penv = o; o += (t.penv_body > 0 ? 7 : 0);
   t.st_stride = (o + 3) & ~3;
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, "b200sim_create: cudaSetDevice failed", -7); }
   int nsm = 148;

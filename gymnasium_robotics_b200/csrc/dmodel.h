@@ -145,7 +145,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   h.nsensor = m.nsensor;
   if (m.nsensor > 0 && m.n_sensor_type != m.nsensor) { err = "model blob lacks sensor_type"; return -1; }
   h.ncand_max = DM_NCAND_MAX;
-  if (h.npair > 255) { err = "more than 255 candidate geom pairs"; return -1; }
+  if (h.npair > 65535) { err = "more than 65535 candidate geom pairs"; return -1; }
   h.ncon_max = m.nmocap > 0 ? 16 : 20;   // contacts kept per env per sub-step
   h.ngrp_max = m.nmocap > 0 ? 10 : 14;   // geom pairs in contact (+ welds) per env per sub-step
   if (h.nb > DM_MAX_BODY) { err = "model has more than 32 runtime bodies"; return -1; }
@@ -182,7 +182,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   int nb = h.nb, njnt = h.njnt, nq = h.nq, nv = h.nv, nu = h.nu, ngeom = h.ngeom, nsite = h.nsite, nmocap = h.nmocap,
       neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max, ndr_max = h.ndr_max,
       nten = h.nten, nfric = h.nfric, nsensor = h.nsensor, ncx = h.nsensor > 0 ? h.ncon_max : 0, MW = h.mask_words,
-      grp_words = MW == 2 ? 34 : 32, npenv = h.penv_body > 0 ? 4 : 0;
+      grp_words = MW == 2 ? 34 : 32, npenv = h.penv_body > 0 ? 8 : 0;
   int nrkq = h.integrator == B200_INT_RK4 ? nq : 0, nrkv = h.integrator == B200_INT_RK4 ? nv : 0;
   int off = (int)((sizeof(DMHead) + 3) / 4);
 #define X(name, w, kind) h.o_##name = off; off += (w) * (kind);
@@ -212,7 +212,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     h.s_geom_xpos = after; h.s_cand = after + 3 * ngeom;
     h.s_H = u; h.s_grad = after; h.s_search = after + nv; h.s_Ma = after + 2 * nv; h.s_Mv = after + 3 * nv;
     h.s_cvel = u;
-    int endA = after + 3 * ngeom + h.ncand_max / 4, endB = after + 4 * nv;
+    int endA = after + 3 * ngeom + (h.npair > 255 ? h.ncand_max / 2 : h.ncand_max / 4), endB = after + 4 * nv;   // candidate slots: 1 or 2 bytes
     so = endA > endB ? endA : endB;
   }
   h.scr_words = (so + 3) & ~3;

@@ -29,12 +29,13 @@ struct FetchTask {
   int touch_mode;       // 0 = no touch observation, 1 = sensordata, 2 = boolean, 3 = log(x + 1)
   int tip_site[5];      // HandReach: fingertip sites "robot0:S_{ff,mf,rf,lf,th}tip"; Adroit hammer: [0] = "tool", [1] = "nail_goal"
   int penv_body;        // runtime body with a per-env body_pos (-1 = none)
-  // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(ngoal) | penv body_pos(3)
+  // state record layout (floats, per env): qpos | qvel | warm | ctrl | mocap(7) | pose(7) | goal(ngoal) | penv body pose(3 + 4)
   int st_qpos, st_qvel, st_warm, st_ctrl, st_mocap, st_pose, st_goal, st_stride, st_penv;
 };
 // TASK_ANTMAZE covers both maze agents (Ant, Point)
-enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2, TASK_HAND_REACH = 3, TASK_ADROIT_HAMMER = 4, TASK_ADROIT_RELOCATE = 5 };
-#define TASK_IS_ADROIT(k) ((k) == TASK_ADROIT_HAMMER || (k) == TASK_ADROIT_RELOCATE)
+enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2, TASK_HAND_REACH = 3, TASK_ADROIT_HAMMER = 4, TASK_ADROIT_RELOCATE = 5,
+       TASK_ADROIT_PEN = 6, TASK_ADROIT_DOOR = 7 };
+#define TASK_IS_ADROIT(k) ((k) >= TASK_ADROIT_HAMMER && (k) <= TASK_ADROIT_DOOR)
 enum { GOAL_USE_POS = 1, GOAL_USE_ROT = 2, GOAL_IGNORE_Z = 4 };
 
 enum { MODE_STEP = 0, MODE_REFRESH = 1, MODE_RAW = 2 };
@@ -54,7 +55,7 @@ HD void load_state(const Ctx& c, const FetchTask& t, const float* st) {
   LANES(i, h->nu) SF(ctrl)[i] = st[t.st_ctrl + i];
   LANES(i, 3 * h->nmocap) SF(mocap_pos)[i] = st[t.st_mocap + i];
   LANES(i, 4 * h->nmocap) SF(mocap_quat)[i] = st[t.st_mocap + 3 + i];
-  if (h->penv_body > 0) LANES(i, 3) SF(penv_pos)[i] = st[t.st_penv + i];
+  if (h->penv_body > 0) LANES(i, 7) SF(penv_pos)[i] = st[t.st_penv + i];
   if (c.lane == 0) { SI(counters)[CNT_ITERS] = 0; SI(counters)[CNT_OVERFLOW] = 0; }
   SYNC();
 }
@@ -369,6 +370,72 @@ HD void adroit_relocate_observe(const Ctx& c, const FetchTask& t, const float* g
   }
 }
 
+// AdroitHandPen (envs/adroit_hand/adroit_pen.py:288-378): obs = qpos[:-6] | pen pos | pen qvel | pen direction | desired
+// direction | pen pos - desired pos | direction difference (45).  Directions are (top site - bottom site) / length; the two
+// lengths are measured once at reset in the reference (:392-399) and are model constants (distance_threshold = pen length,
+// rotation_threshold = target length here).  The target pen is a static body whose quaternion is per-env state.
+HD void adroit_pen_observe(const Ctx& c, const FetchTask& t, float* obs, float* achieved, float* desired, float* reward,
+                           float* success) {
+  const DMHead* h = c.h;
+  const int nr = h->nq - 6, nv = h->nv;
+  LANES(i, nr) obs[i] = SF(qpos)[i];
+  LANES(i, 6) obs[nr + 3 + i] = SF(qvel)[nv - 6 + i];
+  if (c.lane == 0) {
+    float pos[3], loc[3], ot[3], ob[3], tt[3], tb[3], oo[3], dd[3];
+    site_pose(c, t.obj_site, pos, nullptr);
+    site_pose(c, t.frame_site, loc, nullptr);
+    site_pose(c, t.tip_site[0], ot, nullptr); site_pose(c, t.tip_site[1], ob, nullptr);
+    site_pose(c, t.tip_site[2], tt, nullptr); site_pose(c, t.tip_site[3], tb, nullptr);
+    const float il = 1.0f / t.distance_threshold, it = 1.0f / t.rotation_threshold;
+    float dl[3];
+    for (int k = 0; k < 3; k++) {
+      oo[k] = (ot[k] - ob[k]) * il; dd[k] = (tt[k] - tb[k]) * it; dl[k] = pos[k] - loc[k];
+      obs[nr + k] = pos[k]; obs[nr + 9 + k] = oo[k]; obs[nr + 12 + k] = dd[k]; obs[nr + 15 + k] = dl[k]; obs[nr + 18 + k] = oo[k] - dd[k];
+      achieved[k] = oo[k]; desired[k] = dd[k];
+    }
+    float gd = sqrtf(dot3(dl, dl)), sim = dot3(oo, dd);
+    bool ok = gd < 0.075f && sim > 0.95f;
+    float r = ok ? 10.f : -0.1f;
+    if (t.reward_dense) {
+      r = -gd + sim;
+      if (gd < 0.075f && sim > 0.9f) r += 10.f;
+      if (gd < 0.075f && sim > 0.95f) r += 50.f;
+      if (pos[2] < 0.075f) r -= 5.f;
+    }
+    *reward = r; *success = ok ? 1.f : 0.f;
+  }
+}
+
+// AdroitHandDoor (envs/adroit_hand/adroit_door.py:279-344): obs = qpos[1:-2] | latch | door hinge | palm | handle | palm - handle |
+// door_open (+-1) (39); obj_qadr = qpos address of "door_hinge" (the latch is the last joint)
+HD void adroit_door_observe(const Ctx& c, const FetchTask& t, float* obs, float* achieved, float* desired, float* reward,
+                            float* success) {
+  const DMHead* h = c.h;
+  const int nq = h->nq, nv = h->nv, nr = nq - 3;
+  LANES(i, nr) obs[i] = SF(qpos)[1 + i];
+  float v2 = 0.f;
+  LANES(i, nv) v2 += SF(qvel)[i] * SF(qvel)[i];
+  v2 = wsum(v2);
+  if (c.lane == 0) {
+    float palm[3], handle[3], dp[3];
+    site_pose(c, t.grip_site, palm, nullptr);
+    site_pose(c, t.frame_site, handle, nullptr);
+    const float door = SF(qpos)[t.obj_qadr], latch = SF(qpos)[nq - 1];
+    obs[nr] = latch; obs[nr + 1] = door;
+    for (int k = 0; k < 3; k++) { dp[k] = palm[k] - handle[k]; obs[nr + 2 + k] = palm[k]; obs[nr + 5 + k] = handle[k]; obs[nr + 8 + k] = dp[k]; achieved[k] = palm[k]; desired[k] = handle[k]; }
+    obs[nr + 11] = door > 1.0f ? 1.f : -1.f;
+    bool ok = door >= 1.35f;
+    float r = ok ? 10.f : -0.1f;
+    if (t.reward_dense) {
+      r = -0.1f * sqrtf(dot3(dp, dp)) - 0.1f * (door - 1.57f) * (door - 1.57f) - 1e-5f * v2;
+      if (door > 0.2f) r += 2.f;
+      if (door > 1.0f) r += 8.f;
+      if (door > 1.35f) r += 10.f;
+    }
+    *reward = r; *success = ok ? 1.f : 0.f;
+  }
+}
+
 // one env, one warp.  `st` is this env's state record; outputs are this env's rows.  `active` is warp-uniform: idle
 // warps run the same control flow (for the block-wide alignment barriers) but touch no memory.
 template <int NVP>
@@ -442,6 +509,12 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
     reach_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   } else if (NVP >= 30 && t.kind == TASK_ADROIT_HAMMER) {
     adroit_hammer_observe(c, t, obs, achieved, desired, reward, success);
+  } else if (NVP >= 30 && t.kind == TASK_ADROIT_DOOR) {
+    if (nsub == 0) kinematics(c);
+    adroit_door_observe(c, t, obs, achieved, desired, reward, success);
+  } else if (NVP >= 30 && t.kind == TASK_ADROIT_PEN) {
+    if (nsub == 0) kinematics(c);
+    adroit_pen_observe(c, t, obs, achieved, desired, reward, success);
   } else if (NVP >= 30 && t.kind == TASK_ADROIT_RELOCATE) {
     if (nsub == 0) kinematics(c);   // refresh after a reset: body / site positions of the new state
     adroit_relocate_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);

@@ -233,10 +233,12 @@ STAGE void kinematics(const Ctx c) {
         for (int k = 0; k < 4; k++) lq[k] = qpos[a + 3 + k];
         qnormalize(lq);
       } else {
-        // one body may carry a per-env position (Adroit hammer: model.body_pos[nail_board] is redrawn at every reset)
+        // one body may carry a per-env pose (Adroit: model.body_pos[nail_board] / body_pos[Object] / body_quat[target] are
+        // redrawn at every reset): 3 + 4 floats of the state record
         const float* bp = (b == c.h->penv_body) ? SF(penv_pos) : MF(body_pos) + 3 * b;
+        const float* bqm = (b == c.h->penv_body) ? SF(penv_pos) + 3 : MF(body_quat) + 4 * b;
         for (int k = 0; k < 3; k++) lp[k] = bp[k];
-        for (int k = 0; k < 4; k++) lq[k] = MF(body_quat)[4 * b + k];
+        for (int k = 0; k < 4; k++) lq[k] = bqm[k];
         for (int j = ja; j < ja + jn; j++) {
           const float* jp = MF(jnt_pos) + 3 * j;
           const float* jax = MF(jnt_axis) + 3 * j;
@@ -1047,7 +1049,10 @@ STAGE void collision(const Ctx c) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int* cnt = SI(counters);
+  // broad-phase candidates: pair indices, one byte each (models with up to 255 candidate pairs) or two (Adroit door: 278)
   unsigned char* cand = (unsigned char*)SI(cand);
+  unsigned short* cand16 = (unsigned short*)SI(cand);
+  const bool wide_cand = h->npair > 255;
   if (c.lane == 0) { cnt[CNT_NCON] = 0; cnt[CNT_NCAND] = 0; cnt[CNT_NGRP] = 0; }
   SYNC();
   // broad phase: lanes over the static pair list, ordered compaction
@@ -1088,7 +1093,7 @@ STAGE void collision(const Ctx c) {
     int total, slot = wexscan(hit ? 1 : 0, c.lane, &total);
     int basec = cnt[CNT_NCAND];
     SYNC();
-    if (hit && basec + slot < h->ncand_max) cand[basec + slot] = (unsigned char)p;
+    if (hit && basec + slot < h->ncand_max) { if (wide_cand) cand16[basec + slot] = (unsigned short)p; else cand[basec + slot] = (unsigned char)p; }
     if (c.lane == 0) { int nn = basec + total; if (nn > h->ncand_max) { nn = h->ncand_max; cnt[CNT_OVERFLOW] |= 1; } cnt[CNT_NCAND] = nn; }
     SYNC();
   }
@@ -1100,7 +1105,7 @@ STAGE void collision(const Ctx c) {
     o.cnt = 0;
     int p = -1;
     if (ci < ncand) {
-      p = cand[ci];
+      p = wide_cand ? (int)cand16[ci] : (int)cand[ci];
       int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
       float margin = MF(pair_margin)[p];
       int t1 = MI(geom_type)[g1], t2 = g2 < 0 ? B200_GEOM_BOX : MI(geom_type)[g2];

@@ -25,6 +25,8 @@ MODEL_SOURCES = {
     "hand_reach": "hand/reach.xml",
     "adroit_hammer": "adroit_hand/adroit_hammer.xml",
     "adroit_relocate": "adroit_hand/adroit_relocate.xml",
+    "adroit_pen": "adroit_hand/adroit_pen.xml",
+    "adroit_door": "adroit_hand/adroit_door.xml",
     "hand_egg": "hand/manipulate_egg.xml",
     "hand_egg_touch": "hand/manipulate_egg_touch_sensors.xml",
     "hand_pen": "hand/manipulate_pen.xml",
@@ -38,7 +40,11 @@ _HAND = {"drop_bodies": ["target"], "sensor_prefix": "robot0:TS_"}
 _ADROIT_HAMMER = {"drop_bodies": ["vive_tracker"], "keep_bodies": ["nail_board"], "sensor_prefix": "S_nail"}
 # relocate: no sensor is observed (the 21 "Tch_*" touch sensors of the hand model are never read by the env)
 _ADROIT_RELOCATE = {"drop_bodies": ["vive_tracker"], "sensor_prefix": "<none>"}
-MODEL_OVERRIDES = {"adroit_hammer": _ADROIT_HAMMER, "adroit_relocate": _ADROIT_RELOCATE, "hand_block": _HAND, "hand_block_touch": _HAND, "hand_pen": _HAND, "hand_pen_touch": _HAND, "hand_egg": _HAND, "hand_egg_touch": _HAND, "hand_reach": {"sensor_prefix": "robot0:TS_"}}
+# pen: the static `target` pen (a colliding cylinder whose body_quat is redrawn per episode, adroit_pen.py:379-384) stays a runtime body
+_ADROIT_PEN = {"drop_bodies": ["vive_tracker"], "keep_bodies": ["target"], "sensor_prefix": "<none>"}
+# door: the static door `frame` is redrawn per episode (adroit_door.py:359-371)
+_ADROIT_DOOR = {"drop_bodies": ["vive_tracker"], "keep_bodies": ["frame"], "sensor_prefix": "<none>"}
+MODEL_OVERRIDES = {"adroit_door": _ADROIT_DOOR, "adroit_hammer": _ADROIT_HAMMER, "adroit_relocate": _ADROIT_RELOCATE, "adroit_pen": _ADROIT_PEN, "hand_block": _HAND, "hand_block_touch": _HAND, "hand_pen": _HAND, "hand_pen_touch": _HAND, "hand_egg": _HAND, "hand_egg_touch": _HAND, "hand_reach": {"sensor_prefix": "robot0:TS_"}}
 
 
 # maze models: in-tree legacy twin of Gymnasium's ant.xml (Gymnasium itself is un-vendored) + generated wall boxes

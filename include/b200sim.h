@@ -50,11 +50,16 @@ typedef struct b200sim_fetch_task {
    * obs = qpos[:-6] | clip(qvel[-6:]) | palm | hammer pos | hammer euler | nail | clip(touch "S_nail") (46), dense / sparse
    * reward, success = nail within 1 cm of its goal.  Sites: grip_site = "S_grasp", obj_site = body frame of "Object",
    * frame_site = "S_target", tip_site[0] = "tool", tip_site[1] = "nail_goal".
-   * penv_body: runtime body whose body_pos is per-env state (nail_board, adroit_hammer.py:372-378), -1 = none; its three
-   * floats live in the state record at B200SIM_ST_PENV. */
+   * penv_body: runtime body whose body_pos is per-env state (nail_board, adroit_hammer.py:372-378), -1 = none; its pose (position
+   * 3 + quaternion 4 floats) lives in the state record at B200SIM_ST_PENV. */
   /* kind 5 = AdroitHandRelocate (envs/adroit_hand/adroit_relocate.py:288-373): obs = qpos[:-6] | palm - ball | palm - target |
    * ball - target (39); grip_site = "S_grasp", obj_site = body frame of "Object", penv_body = "Object" (body_pos x, y redrawn per
    * episode), the per-env target site position is the 3-float goal of the state record. */
+  /* kind 6 = AdroitHandPen (envs/adroit_hand/adroit_pen.py:288-378): obs 45; obj_site = body frame of "Object", frame_site =
+   * "eps_ball", tip_site[0..3] = object_top, object_bottom, target_top, target_bottom; distance_threshold = pen length,
+   * rotation_threshold = target length (:392-399); penv_body = "target" (body_quat redrawn per episode, :379-384). */
+  /* kind 7 = AdroitHandDoor (envs/adroit_hand/adroit_door.py:279-371): obs 39; grip_site = "S_grasp", frame_site = "S_handle",
+   * obj_qadr = qpos address of "door_hinge", penv_body = "frame" (body_pos redrawn per episode). */
   int penv_body;
 } b200sim_fetch_task_t;
 

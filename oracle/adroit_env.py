@@ -173,3 +173,148 @@ class OracleAdroitRelocateEnv(OracleAdroitHammerEnv):
         self.sim.body_pos[self.obj_body_id] = state_dict["obj_pos"]
         self.target_pos[:] = state_dict["target_pos"]
         self.set_state(state_dict["qpos"], state_dict["qvel"])
+
+
+class OracleAdroitPenEnv(OracleAdroitHammerEnv):
+    """envs/adroit_hand/adroit_pen.py (AdroitHandPenEnv)."""
+
+    def __init__(self, model, reward_type="dense", frame_skip=5):
+        self.model, self.frame_skip = model, frame_skip
+        self.sparse_reward = reward_type.lower() == "sparse"
+        self.sim = OracleSim(model)
+        m = model
+        self.target_obj_body_id = int(m.names["body_map"]["target"])       # adroit_pen.py:264-271
+        self.obj_body_id = int(m.names["body_map"]["Object"])
+        self.eps_ball_site_id = m.site_id("eps_ball")
+        self.obj_t_site_id, self.obj_b_site_id = m.site_id("object_top"), m.site_id("object_bottom")
+        self.tar_t_site_id, self.tar_b_site_id = m.site_id("target_top"), m.site_id("target_bottom")
+        cr = np.asarray(m.act_ctrlrange, dtype=np.float64).reshape(-1, 2)
+        self.act_mean, self.act_rng = np.mean(cr, axis=1), 0.5 * (cr[:, 1] - cr[:, 0])
+        self.np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(None)))
+        self.sim.forward()
+        self.init_qpos, self.init_qvel = self.sim.qpos.copy(), self.sim.qvel.copy()
+        self.pen_length = self.tar_length = 1.0
+
+    def _orien(self):
+        s = self.sim
+        return ((s.site_xpos[self.obj_t_site_id] - s.site_xpos[self.obj_b_site_id]) / self.pen_length,
+                (s.site_xpos[self.tar_t_site_id] - s.site_xpos[self.tar_b_site_id]) / self.tar_length)
+
+    def step(self, a):  # adroit_pen.py:288-337
+        s = self.sim
+        a = np.clip(a, -1.0, 1.0)
+        a = self.act_mean + a * self.act_rng
+        s.ctrl[:] = a
+        s.step(self.frame_skip)
+        obs = self._get_obs()
+        obj_pos = s.xpos[self.obj_body_id].ravel()
+        desired_loc = s.site_xpos[self.eps_ball_site_id].ravel()
+        obj_orien, desired_orien = self._orien()
+        goal_distance = np.linalg.norm(obj_pos - desired_loc)
+        orien_similarity = np.dot(obj_orien, desired_orien)
+        goal_achieved = goal_distance < 0.075 and orien_similarity > 0.95
+        reward = 10.0 if goal_achieved else -0.1
+        if not self.sparse_reward:
+            reward = -goal_distance + orien_similarity
+            if goal_distance < 0.075 and orien_similarity > 0.9:
+                reward += 10
+            if goal_distance < 0.075 and orien_similarity > 0.95:
+                reward += 50
+            if obj_pos[2] < 0.075:
+                reward -= 5
+        return obs, reward, False, False, dict(success=goal_achieved)
+
+    def _get_obs(self):  # adroit_pen.py:339-365
+        s = self.sim
+        qpos = s.qpos.ravel()
+        obj_vel = s.qvel[-6:].ravel()
+        obj_pos = s.xpos[self.obj_body_id].ravel()
+        desired_pos = s.site_xpos[self.eps_ball_site_id].ravel()
+        obj_orien, desired_orien = self._orien()
+        return np.concatenate([qpos[:-6], obj_pos, obj_vel, obj_orien, desired_orien, obj_pos - desired_pos, obj_orien - desired_orien])
+
+    def reset_model(self):  # adroit_pen.py:379-399
+        desired_orien = np.zeros(3)
+        desired_orien[0] = self.np_random.uniform(low=-1, high=1)
+        desired_orien[1] = self.np_random.uniform(low=-1, high=1)
+        self.sim.body_quat[self.target_obj_body_id] = rotations.euler2quat(desired_orien)
+        self.set_state(self.init_qpos, self.init_qvel)
+        s = self.sim
+        self.pen_length = np.linalg.norm(s.site_xpos[self.obj_t_site_id] - s.site_xpos[self.obj_b_site_id])
+        self.tar_length = np.linalg.norm(s.site_xpos[self.tar_t_site_id] - s.site_xpos[self.tar_b_site_id])
+        return self._get_obs()
+
+    def get_env_state(self):  # adroit_pen.py:401-409
+        return dict(qpos=self.sim.qpos.ravel().copy(), qvel=self.sim.qvel.ravel().copy(),
+                    desired_orien=self.sim.body_quat[self.target_obj_body_id].ravel().copy())
+
+    def set_env_state(self, state_dict):  # adroit_pen.py:411-430
+        self.sim.body_quat[self.target_obj_body_id] = state_dict["desired_orien"]
+        self.set_state(state_dict["qpos"], state_dict["qvel"])
+
+
+class OracleAdroitDoorEnv(OracleAdroitHammerEnv):
+    """envs/adroit_hand/adroit_door.py (AdroitHandDoorEnv)."""
+
+    def __init__(self, model, reward_type="dense", frame_skip=5):
+        self.model, self.frame_skip = model, frame_skip
+        self.sparse_reward = reward_type.lower() == "sparse"
+        self.sim = OracleSim(model)
+        m = model
+        self.door_hinge_addrs = int(m.jnt_dofadr[m.joint_id("door_hinge")])      # adroit_door.py:258-263
+        self.grasp_site_id, self.handle_site_id = m.site_id("S_grasp"), m.site_id("S_handle")
+        self.door_body_id = int(m.names["body_map"]["frame"])
+        cr = np.asarray(m.act_ctrlrange, dtype=np.float64).reshape(-1, 2)
+        self.act_mean, self.act_rng = np.mean(cr, axis=1), 0.5 * (cr[:, 1] - cr[:, 0])
+        self.np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(None)))
+        self.sim.forward()
+        self.init_qpos, self.init_qvel = self.sim.qpos.copy(), self.sim.qvel.copy()
+
+    def step(self, a):  # adroit_door.py:279-316
+        s = self.sim
+        a = np.clip(a, -1.0, 1.0)
+        a = self.act_mean + a * self.act_rng
+        s.ctrl[:] = a
+        s.step(self.frame_skip)
+        obs = self._get_obs()
+        goal_distance = s.qpos[self.door_hinge_addrs]
+        goal_achieved = goal_distance >= 1.35
+        reward = 10.0 if goal_achieved else -0.1
+        if not self.sparse_reward:
+            handle_pos = s.site_xpos[self.handle_site_id].ravel()
+            palm_pos = s.site_xpos[self.grasp_site_id].ravel()
+            reward = -0.1 * np.linalg.norm(palm_pos - handle_pos)
+            reward += -0.1 * (goal_distance - 1.57) * (goal_distance - 1.57)
+            reward += -1e-5 * np.sum(s.qvel**2)
+            if goal_distance > 0.2:
+                reward += 2
+            if goal_distance > 1.0:
+                reward += 8
+            if goal_distance > 1.35:
+                reward += 10
+        return obs, reward, False, False, dict(success=goal_achieved)
+
+    def _get_obs(self):  # adroit_door.py:318-344
+        s = self.sim
+        qpos = s.qpos.ravel()
+        handle_pos = s.site_xpos[self.handle_site_id].ravel()
+        palm_pos = s.site_xpos[self.grasp_site_id].ravel()
+        door_pos = np.array([s.qpos[self.door_hinge_addrs]])
+        door_open = 1.0 if door_pos > 1.0 else -1.0
+        latch_pos = qpos[-1]
+        return np.concatenate([qpos[1:-2], [latch_pos], door_pos, palm_pos, handle_pos, palm_pos - handle_pos, [door_open]])
+
+    def reset_model(self):  # adroit_door.py:359-371
+        self.sim.body_pos[self.door_body_id, 0] = self.np_random.uniform(low=-0.3, high=-0.2)
+        self.sim.body_pos[self.door_body_id, 1] = self.np_random.uniform(low=0.25, high=0.35)
+        self.sim.body_pos[self.door_body_id, 2] = self.np_random.uniform(low=0.252, high=0.35)
+        self.set_state(self.init_qpos, self.init_qvel)
+        return self._get_obs()
+
+    def get_env_state(self):  # adroit_door.py:373-381
+        return dict(qpos=self.sim.qpos.ravel().copy(), qvel=self.sim.qvel.ravel().copy(),
+                    door_body_pos=self.sim.body_pos[self.door_body_id].ravel().copy())
+
+    def set_env_state(self, state_dict):  # adroit_door.py:383-402
+        self.sim.body_pos[self.door_body_id] = state_dict["door_body_pos"]
+        self.set_state(state_dict["qpos"], state_dict["qvel"])

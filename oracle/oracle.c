@@ -43,7 +43,7 @@ typedef struct oracle_sim {
   b200_model_view m;
   int nbody, nq, nv, nu, ngeom, nsite, nmocap;
   /* mutable model copies (the reference edits these after load) */
-  real *eq_data, *act_gainprm, *act_biasprm, *body_pos, *jnt_range;
+  real *eq_data, *act_gainprm, *act_biasprm, *body_pos, *body_quat, *jnt_range;
   /* state */
   real time;
   real *qpos, *qvel, *ctrl, *mocap_pos, *mocap_quat, *qacc_warmstart, *qacc;
@@ -175,6 +175,7 @@ oracle_sim* oracle_create(const void* blob, size_t nbytes) {
   s->act_biasprm = ddup(m->act_biasprm, (size_t)m->nu * 3);
   s->body_pos = ddup(m->body_pos, (size_t)nb * 3);
   s->jnt_range = ddup(m->jnt_range, (size_t)m->njnt * 2);
+  s->body_quat = ddup(m->body_quat, (size_t)nb * 4);
   s->qpos = dalloc(nq); s->qvel = dalloc(nv); s->ctrl = dalloc(m->nu); s->mocap_pos = dalloc(3 * m->nmocap);
   s->mocap_quat = dalloc(4 * m->nmocap); s->qacc_warmstart = dalloc(nv); s->qacc = dalloc(nv);
   s->xpos = dalloc(3 * nb); s->xquat = dalloc(4 * nb); s->xmat = dalloc(9 * nb); s->xipos = dalloc(3 * nb);
@@ -195,7 +196,7 @@ oracle_sim* oracle_create(const void* blob, size_t nbytes) {
 
 void oracle_destroy(oracle_sim* s) {
   if (!s) return;
-  real* ptrs[] = {s->eq_data, s->act_gainprm, s->act_biasprm, s->body_pos, s->jnt_range, s->qpos, s->qvel, s->ctrl, s->mocap_pos,
+  real* ptrs[] = {s->eq_data, s->act_gainprm, s->act_biasprm, s->body_pos, s->body_quat, s->jnt_range, s->qpos, s->qvel, s->ctrl, s->mocap_pos,
                   s->mocap_quat, s->qacc_warmstart, s->qacc, s->xpos, s->xquat, s->xmat, s->xipos, s->ximat, s->xanchor,
                   s->xaxis, s->geom_xpos, s->geom_xmat, s->site_xpos, s->site_xmat, s->subtree_com, s->cinert, s->crb,
                   s->cdof, s->cdof_dot, s->cvel, s->cacc, s->cfrc, s->M, s->L, s->qfrc_bias, s->qfrc_passive,
@@ -249,7 +250,7 @@ static void kinematics(oracle_sim* s) {
       real t[3];
       mulmatvec3(t, s->xmat + 9 * p, s->body_pos + 3 * b);
       add3(xp, s->xpos + 3 * p, t);
-      real bq[4] = {m->body_quat[4 * b], m->body_quat[4 * b + 1], m->body_quat[4 * b + 2], m->body_quat[4 * b + 3]};
+      real bq[4] = {s->body_quat[4 * b], s->body_quat[4 * b + 1], s->body_quat[4 * b + 2], s->body_quat[4 * b + 3]};
       mulquat(xq, s->xquat + 4 * p, bq);
       for (int j = ja; j < ja + jn; j++) {
         real jp[3] = {m->jnt_pos[3 * j], m->jnt_pos[3 * j + 1], m->jnt_pos[3 * j + 2]};
@@ -1677,7 +1678,7 @@ void oracle_step(oracle_sim* s, int nstep) {
 ACC(qpos, qpos) ACC(qvel, qvel) ACC(ctrl, ctrl) ACC(mocap_pos, mocap_pos) ACC(mocap_quat, mocap_quat)
 ACC(qacc_warmstart, qacc_warmstart) ACC(qacc, qacc) ACC(xpos, xpos) ACC(xquat, xquat) ACC(xmat, xmat)
 ACC(site_xpos, site_xpos) ACC(site_xmat, site_xmat) ACC(geom_xpos, geom_xpos) ACC(geom_xmat, geom_xmat)
-ACC(eq_data, eq_data) ACC(act_gainprm, act_gainprm) ACC(act_biasprm, act_biasprm) ACC(body_pos, body_pos)
+ACC(eq_data, eq_data) ACC(act_gainprm, act_gainprm) ACC(act_biasprm, act_biasprm) ACC(body_pos, body_pos) ACC(body_quat, body_quat)
 ACC(M, M) ACC(qfrc_bias, qfrc_bias) ACC(qfrc_smooth, qfrc_smooth) ACC(qacc_smooth, qacc_smooth)
 ACC(qfrc_constraint, qfrc_constraint) ACC(efc_J, J) ACC(efc_force, efc_force) ACC(efc_aref, efc_aref)
 ACC(efc_pos, efc_pos) ACC(efc_D, efc_D) ACC(efc_R, efc_R) ACC(sensordata, sensordata) ACC(subtree_com, subtree_com)

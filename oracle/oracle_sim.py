@@ -60,7 +60,7 @@ class OracleSim:
         "site_xpos": lambda m: (m.nsite, 3), "site_xmat": lambda m: (m.nsite, 9),
         "geom_xpos": lambda m: (m.ngeom, 3), "geom_xmat": lambda m: (m.ngeom, 9),
         "eq_data": lambda m: (m.neq, 11), "act_gainprm": lambda m: (m.nu, 3), "act_biasprm": lambda m: (m.nu, 3),
-        "body_pos": lambda m: (m.nbody, 3), "M": lambda m: (m.nv, m.nv), "qfrc_bias": lambda m: (m.nv,),
+        "body_pos": lambda m: (m.nbody, 3), "body_quat": lambda m: (m.nbody, 4), "M": lambda m: (m.nv, m.nv), "qfrc_bias": lambda m: (m.nv,),
         "qfrc_smooth": lambda m: (m.nv,), "qacc_smooth": lambda m: (m.nv,), "qfrc_constraint": lambda m: (m.nv,),
         "qfrc_actuator": lambda m: (m.nv,), "qfrc_passive": lambda m: (m.nv,),
         "sensordata": lambda m: (m.nsensor,), "subtree_com": lambda m: (m.nbody, 3), "cdof": lambda m: (m.nv, 6),

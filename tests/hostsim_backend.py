@@ -15,7 +15,7 @@ class HostSimBackend:
 
         self.device = torch.device("cpu")
         self.num_envs, self.nobs = num_envs, task.nobs
-        penv = int(task.penv_body) if task.kind in (4, 5) else -1
+        penv = int(task.penv_body) if task.kind in (4, 5, 6, 7) else -1
         self.sim = HostSim(model, eq_data=eq_data if len(eq_data) else None, ref=getattr(self, "REF", REF_POINT), penv_body=penv)
         t = HostTaskC()
         for name, _ in task._fields_:
@@ -27,7 +27,7 @@ class HostSimBackend:
             t.nact, t.ngoal = 4, 3
         self.ngoal, self.nact = int(t.ngoal), int(t.nact)
         for k, n in (("qpos", model.nq), ("qvel", model.nv), ("warm", model.nv), ("ctrl", model.nu), ("mocap", 7 * model.nmocap),
-                     ("pose", 7 if fetch else 0), ("goal", self.ngoal), ("penv", 3 if penv > 0 else 0)):
+                     ("pose", 7 if fetch else 0), ("goal", self.ngoal), ("penv", 7 if penv > 0 else 0)):
             lay[k] = o
             o += n
         lay["stride"] = (o + 3) & ~3

@@ -581,6 +581,7 @@ def test_adroit_hammer_parity():
             rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
             rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
             rec[i, lay["penv"]:lay["penv"] + 3] = s.body_pos[o.target_body_id]
+            rec[i, lay["penv"] + 3:lay["penv"] + 7] = np.asarray(m.body_quat).reshape(-1, 4)[o.target_body_id]
         env.backend.state.copy_(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
         a = rng.uniform(-1, 1, (n, 26)).astype(np.float32)
         if step >= 5:
@@ -638,6 +639,7 @@ def test_adroit_relocate_parity():
             rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
             rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
             rec[i, lay["penv"]:lay["penv"] + 3] = s.body_pos[o.obj_body_id]
+            rec[i, lay["penv"] + 3:lay["penv"] + 7] = np.asarray(m.body_quat).reshape(-1, 4)[o.obj_body_id]
             rec[i, lay["goal"]:lay["goal"] + 3] = o.target_pos
         env.backend.state.copy_(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
         a = rng.uniform(-1, 1, (n, 30)).astype(np.float32)
@@ -670,4 +672,91 @@ def test_adroit_relocate_parity():
         flagged += int(((info_bits >> 16) != 0).sum())
     print(f"AdroitRelocate 2048 x 60: {flagged} env-steps with a capacity flag")
     assert flagged < 0.01 * 2048 * 60
+    env.close()
+
+
+def test_adroit_pen_parity():
+    """AdroitHandPen-v2 (30 dofs, cylinder pen through the portal-refinement collider, per-env target quaternion)."""
+    import gymnasium_robotics_b200 as pkg
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.adroit_env import OracleAdroitPenEnv
+
+    n = 4
+    m = load_model("adroit_pen")
+    env = pkg.make_vec("AdroitHandPen-v2", num_envs=n, device="cuda:0", rng_mode="numpy")
+    obs, _ = env.reset(seed=30)
+    oracles = [OracleAdroitPenEnv(m) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=30 + i)
+        assert np.abs(obs[i].double().cpu().numpy() - oo).max() < 5e-6
+    lay = env.backend.layout
+    rng = np.random.default_rng(2)
+    errs = []
+    for step in range(10):
+        rec = np.zeros((n, lay["stride"]))
+        for i, o in enumerate(oracles):
+            s = o.sim
+            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+            rec[i, lay["penv"]:lay["penv"] + 3] = s.body_pos[o.target_obj_body_id]
+            rec[i, lay["penv"] + 3:lay["penv"] + 7] = s.body_quat[o.target_obj_body_id]
+        env.backend.state.copy_(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        a = rng.uniform(-1, 1, (n, 24)).astype(np.float32)
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            got = o[i].double().cpu().numpy()
+            assert np.isfinite(got).all()
+            d = np.abs(got - oo)
+            errs.append(np.delete(d, [30, 31, 32]).max())
+            assert d.max() < 0.05 and abs(float(r[i]) - orr) < 2e-3
+    errs = np.array(errs)
+    print(f"AdroitPen: median {np.median(errs):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < 2e-4 and np.mean(errs < 1e-3) >= 0.9
+    env.close()
+
+
+def test_adroit_door_parity():
+    """AdroitHandDoor-v2 (30 dofs, 278 candidate pairs -> two-byte candidates, per-env door frame position)."""
+    import gymnasium_robotics_b200 as pkg
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.adroit_env import OracleAdroitDoorEnv
+
+    n = 4
+    m = load_model("adroit_door")
+    env = pkg.make_vec("AdroitHandDoor-v2", num_envs=n, device="cuda:0", rng_mode="numpy")
+    obs, _ = env.reset(seed=30)
+    oracles = [OracleAdroitDoorEnv(m) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=30 + i)
+        assert np.abs(obs[i].double().cpu().numpy() - oo).max() < 5e-6
+    lay = env.backend.layout
+    rng = np.random.default_rng(2)
+    errs = []
+    for step in range(10):
+        rec = np.zeros((n, lay["stride"]))
+        for i, o in enumerate(oracles):
+            s = o.sim
+            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+            rec[i, lay["penv"]:lay["penv"] + 3] = s.body_pos[o.door_body_id]
+            rec[i, lay["penv"] + 3:lay["penv"] + 7] = s.body_quat[o.door_body_id]
+        env.backend.state.copy_(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        a = rng.uniform(-1, 1, (n, 28)).astype(np.float32)
+        if step >= 4:
+            a[:, 0] = 1.0
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            got = o[i].double().cpu().numpy()
+            assert np.isfinite(got).all()
+            errs.append(np.abs(got - oo).max())
+            assert abs(float(r[i]) - orr) < 2e-3 and bool(info["success"][i]) == bool(oi["success"])
+    errs = np.array(errs)
+    print(f"AdroitDoor: median {np.median(errs):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < 2e-5 and np.mean(errs < 1e-3) >= 0.9 and errs.max() < 0.05
     env.close()

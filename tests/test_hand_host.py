@@ -290,6 +290,7 @@ def test_adroit_hammer_env_matches_oracle():
         rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
         rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
         rec[lay["penv"]:lay["penv"] + 3] = s.body_pos[orc.target_body_id]
+        rec[lay["penv"] + 3:lay["penv"] + 7] = np.asarray(m.body_quat).reshape(-1, 4)[orc.target_body_id]
         env.backend.state[0] = torch.as_tensor(rec, dtype=torch.float32)
         a = rng.uniform(-1, 1, 26)
         if k >= 4:
@@ -345,6 +346,7 @@ def test_adroit_relocate_env_matches_oracle():
         rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
         rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
         rec[lay["penv"]:lay["penv"] + 3] = s.body_pos[orc.obj_body_id]
+        rec[lay["penv"] + 3:lay["penv"] + 7] = np.asarray(m.body_quat).reshape(-1, 4)[orc.obj_body_id]
         rec[lay["goal"]:lay["goal"] + 3] = orc.target_pos
         env.backend.state[0] = torch.as_tensor(rec, dtype=torch.float32)
         a = rng.uniform(-1, 1, 30)
@@ -356,3 +358,89 @@ def test_adroit_relocate_env_matches_oracle():
         assert abs(float(r[0]) - orr) < 2e-5 and bool(info["success"][0]) == bool(oi["success"])
     o1 = env.set_env_state(env.get_env_state())
     assert o1.shape == (1, 39) and {"AdroitHandRelocate-v2", "AdroitHandRelocateSparse-v2"} <= set(pkg.ENV_IDS)
+
+
+def test_adroit_pen_env_matches_oracle():
+    """AdroitHandPen-v2 (30 dofs): the pen is a cylinder (portal-refinement collider) and the static target pen's
+    quaternion is per-env state (two Euler draws per reset); obs 45, dense / sparse reward (adroit_pen.py:288-430)."""
+    from gymnasium_robotics_b200.adroit import ADROIT_REF_POINT
+    from oracle.adroit_env import OracleAdroitPenEnv
+
+    class AdroitHostBackend(HostSimBackend):
+        REF = ADROIT_REF_POINT
+
+    m = load_model("adroit_pen")
+    env = pkg.make_vec("AdroitHandPen-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
+    assert env.single_observation_space.shape == (45,) and env.single_action_space.shape == (24,)
+    orc = OracleAdroitPenEnv(m)
+    obs, _ = env.reset(seed=4)
+    oobs, _ = orc.reset(seed=4)
+    np.testing.assert_allclose(obs[0].double().numpy(), oobs, atol=2e-6)
+    assert orc.pen_length == pytest.approx(0.13, abs=1e-12) and env.task.distance_threshold == pytest.approx(0.13, abs=1e-7)
+    np.testing.assert_allclose(env.get_env_state()["desired_orien"][0].double().numpy(), orc.get_env_state()["desired_orien"], atol=1e-7)
+    lay, s = env.backend.layout, orc.sim
+    rng = np.random.default_rng(1)
+    errs = []
+    for k in range(8):
+        rec = np.zeros(lay["stride"])
+        rec[lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+        rec[lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+        rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+        rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+        rec[lay["penv"]:lay["penv"] + 3] = s.body_pos[orc.target_obj_body_id]
+        rec[lay["penv"] + 3:lay["penv"] + 7] = s.body_quat[orc.target_obj_body_id]
+        env.backend.state[0] = torch.as_tensor(rec, dtype=torch.float32)
+        a = rng.uniform(-1, 1, 24)
+        o, r, te, tr, info = env.step(a[None].astype(np.float32))
+        oo, orr, _, _, oi = orc.step(a)
+        d = np.abs(o[0].double().numpy() - oo)
+        errs.append(d.max())
+        assert np.delete(d, [30, 31, 32]).max() < 2e-4      # everything but the pen's angular velocity
+        assert d.max() < 2e-2                               # fp32 vs fp64 portal normals (1e-4) torque the light pen
+        assert abs(float(r[0]) - orr) < 2e-4 and bool(info["success"][0]) == bool(oi["success"])
+    assert np.median(errs) < 2e-3
+    envs = pkg.make_vec("AdroitHandPenSparse-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
+    envs.reset(seed=4)
+    _, r, *_ = envs.step(np.zeros((1, 24), dtype=np.float32))
+    assert float(r[0]) == pytest.approx(-0.1)
+    assert env.set_env_state(env.get_env_state()).shape == (1, 45)
+
+
+def test_adroit_door_env_matches_oracle():
+    """AdroitHandDoor-v2 (30 dofs, 278 candidate geom pairs -> two-byte broad-phase candidates; cylinder door posts and
+    latch through the portal-refinement collider; per-env door frame position) (adroit_door.py:279-402)."""
+    from gymnasium_robotics_b200.adroit import ADROIT_REF_POINT
+    from oracle.adroit_env import OracleAdroitDoorEnv
+
+    class AdroitHostBackend(HostSimBackend):
+        REF = ADROIT_REF_POINT
+
+    m = load_model("adroit_door")
+    assert len(m.pair_geom1) > 255
+    env = pkg.make_vec("AdroitHandDoor-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
+    assert env.single_observation_space.shape == (39,) and env.single_action_space.shape == (28,)
+    orc = OracleAdroitDoorEnv(m)
+    obs, _ = env.reset(seed=4)
+    oobs, _ = orc.reset(seed=4)
+    np.testing.assert_allclose(obs[0].double().numpy(), oobs, atol=2e-6)
+    np.testing.assert_allclose(env.get_env_state()["door_body_pos"][0].double().numpy(), orc.get_env_state()["door_body_pos"], atol=1e-7)
+    lay, s = env.backend.layout, orc.sim
+    rng = np.random.default_rng(1)
+    for k in range(8):
+        rec = np.zeros(lay["stride"])
+        rec[lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
+        rec[lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
+        rec[lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
+        rec[lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
+        rec[lay["penv"]:lay["penv"] + 3] = s.body_pos[orc.door_body_id]
+        rec[lay["penv"] + 3:lay["penv"] + 7] = s.body_quat[orc.door_body_id]
+        env.backend.state[0] = torch.as_tensor(rec, dtype=torch.float32)
+        a = rng.uniform(-1, 1, 28)
+        if k >= 4:
+            a[0] = 1.0     # push the arm towards the door
+        o, r, te, tr, info = env.step(a[None].astype(np.float32))
+        oo, orr, _, _, oi = orc.step(a)
+        assert np.abs(o[0].double().numpy() - oo).max() < 2e-4
+        assert abs(float(r[0]) - orr) < 2e-4 and bool(info["success"][0]) == bool(oi["success"])
+    assert env.set_env_state(env.get_env_state()).shape == (1, 39)
+    assert {"AdroitHandDoor-v2", "AdroitHandDoorSparse-v2", "AdroitHandPenSparse-v2"} <= set(pkg.ENV_IDS)
