@@ -37,10 +37,10 @@ WORKLOADS = {
     "fetch_slide": ("FetchSlide-v4", 4, 20, 2 * 4 * (22 + 2 * 21 + 0 + 7 + 3 + 1) + 4 * 4 + 4 * (25 + 2 * 3) + 10, 4096),
     "hand_egg": ("HandManipulateEggRotate-v1", 20, 20, 2 * 4 * (31 + 60 + 20 + 0 + 7 + 1) + 80 + 4 * (61 + 14) + 10, 2048),
     # config 5a: AdroitHandHammer (33 dofs, wide kernel build); registered id is -v2 (SURVEY.md 8, config-name caveats)
-    "adroit_hammer": ("AdroitHandHammer-v2", 26, 5, 2 * 4 * (33 + 66 + 26 + 0 + 3 + 1) + 104 + 4 * (46 + 6) + 10, 2048),
-    "adroit_relocate": ("AdroitHandRelocate-v2", 30, 5, 2 * 4 * (36 + 72 + 30 + 0 + 3 + 3 + 1) + 120 + 4 * (39 + 6) + 10, 2048),
-    "adroit_pen": ("AdroitHandPen-v2", 24, 5, 2 * 4 * (30 + 60 + 24 + 0 + 7 + 1) + 96 + 4 * (45 + 6) + 10, 2048),
-    "adroit_door": ("AdroitHandDoor-v2", 28, 5, 2 * 4 * (30 + 60 + 28 + 0 + 7 + 1) + 112 + 4 * (39 + 6) + 10, 2048),
+    "adroit_hammer": ("AdroitHandHammer-v2", 26, 5, 2 * 4 * (33 + 66 + 26 + 7 + 3 + 1) + 104 + 4 * (46 + 6) + 10, 2048),
+    "adroit_relocate": ("AdroitHandRelocate-v2", 30, 5, 2 * 4 * (36 + 72 + 30 + 7 + 3 + 1) + 120 + 4 * (39 + 6) + 10, 2048),
+    "adroit_pen": ("AdroitHandPen-v2", 24, 5, 2 * 4 * (30 + 60 + 24 + 7 + 3 + 1) + 96 + 4 * (45 + 6) + 10, 2048),
+    "adroit_door": ("AdroitHandDoor-v2", 28, 5, 2 * 4 * (30 + 60 + 28 + 7 + 3 + 1) + 112 + 4 * (39 + 6) + 10, 2048),
     "antmaze_large": ("AntMaze_Large-v5", 8, 5, 2 * 4 * (15 + 28 + 0 + 0 + 2 + 1) + 32 + 124 + 10, 1024),  # config 4: 8192 envs over 8 GPUs
 }
 

@@ -309,6 +309,13 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     int sg = gsrc[g];
     I(h.o_geom_type, g, m.geom_type[sg]); I(h.o_geom_body, g, m.geom_body[sg]);
     for (int k = 0; k < 3; k++) { F(h.o_geom_pos, 3 * g + k, m.geom_pos[3 * sg + k]); F(h.o_geom_size, 3 * g + k, m.geom_size[3 * sg + k]); }
+    if (m.geom_type[sg] == B200_GEOM_PLANE) {
+      // a plane's size is never used by the collision routines: the slot carries its world normal (planes sit on the world body)
+      if (m.geom_body[sg] != 0) { err = "plane geoms must belong to the world body"; return -1; }
+      const double* q = m.geom_quat + 4 * sg;
+      F(h.o_geom_size, 3 * g + 0, 2 * (q[1] * q[3] + q[0] * q[2])); F(h.o_geom_size, 3 * g + 1, 2 * (q[2] * q[3] - q[0] * q[1]));
+      F(h.o_geom_size, 3 * g + 2, q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3]);
+    }
     for (int k = 0; k < 4; k++) F(h.o_geom_quat, 4 * g + k, m.geom_quat[4 * sg + k]);
     F(h.o_geom_rbound, g, m.geom_rbound[sg]);
   }

@@ -1079,11 +1079,8 @@ STAGE void collision(const Ctx c) {
             }
         }
       } else if (MI(geom_type)[g1] == B200_GEOM_PLANE) {
-        int b = MI(geom_body)[g1];
-        float q[4], m[9];
-        qmul(q, SF(xquat) + 4 * b, MF(geom_quat) + 4 * g1);
-        q2mat(m, q);
-        float n[3] = {m[2], m[5], m[8]};
+        // planes live on the world body: dm_build stores the world normal in the (otherwise unused) size slot
+        const float* n = MF(geom_size) + 3 * g1;
         hit = dot3(dif, n) <= margin + MF(geom_rbound)[g2];
       } else {
         float bound = margin + MF(geom_rbound)[g1] + MF(geom_rbound)[g2];
@@ -1220,55 +1217,60 @@ STAGE void make_constraint(const Ctx c) {
   int* cnt = SI(counters);
   if (c.lane == 0) { cnt[CNT_NDR] = 0; cnt[CNT_NWELD] = 0; }
   SYNC();
-  // weld equalities (lane 0; at most DM_NWELD_MAX)
-  if (c.lane == 0) {
-    for (int e = 0; e < h->neq; e++) {
-      if (!MI(eq_active)[e] || MI(eq_type)[e] != B200_EQ_WELD) continue;
-      float* wr = SF(weld) + cnt[CNT_NWELD] * WELD_WORDS;
-      const float* data = MF(eq_data) + 11 * e;
-      int s1 = MI(eq_obj1)[e], s2 = MI(eq_obj2)[e], b1 = 0, b2 = 0;
-      float p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0}, q1[4] = {1, 0, 0, 0}, q2[4] = {1, 0, 0, 0}, t[3];
-      if (s1 >= 0) { b1 = MI(site_body)[s1]; qmul(q1, SF(xquat) + 4 * b1, MF(site_quat) + 4 * s1); qrot(t, SF(xquat) + 4 * b1, MF(site_pos) + 3 * s1); for (int k = 0; k < 3; k++) p1[k] = SF(xpos)[3 * b1 + k] + t[k]; }
-      if (s2 >= 0) { b2 = MI(site_body)[s2]; qmul(q2, SF(xquat) + 4 * b2, MF(site_quat) + 4 * s2); qrot(t, SF(xquat) + 4 * b2, MF(site_pos) + 3 * s2); for (int k = 0; k < 3; k++) p2[k] = SF(xpos)[3 * b2 + k] + t[k]; }
-      qrot(t, q1, data + 3); for (int k = 0; k < 3; k++) p1[k] += t[k];
-      qrot(t, q2, data + 0); for (int k = 0; k < 3; k++) p2[k] += t[k];
-      float cpos[6], ts = data[10];
-      for (int k = 0; k < 3; k++) cpos[k] = p1[k] - p2[k];
-      float quat[4], quat1[4] = {q2[0], -q2[1], -q2[2], -q2[3]}, quat2[4];
-      qmul(quat, q1, data + 6);
-      qmul(quat2, quat1, quat);
-      cpos[3] = ts * quat2[1]; cpos[4] = ts * quat2[2]; cpos[5] = ts * quat2[3];
-      // rows: J = J(body1 at p1) - J(body2 at p2); translational rows about the anchor of the side that carries dofs
-      const float* pm = (b1 > 0 && MU(body_ancdof)[b1]) ? p1 : p2;
-      float r[3] = {pm[0] - h->ref[0], pm[1] - h->ref[1], pm[2] - h->ref[2]};
-      for (int k = 0; k < 3; k++) {
+  // weld equalities (at most DM_NWELD_MAX): every lane evaluates the warp-uniform poses, lane k < 6 then builds row k
+  for (int e = 0; e < h->neq; e++) {
+    if (!MI(eq_active)[e] || MI(eq_type)[e] != B200_EQ_WELD) continue;
+    const int nw = cnt[CNT_NWELD], gid = cnt[CNT_NGRP];
+    float* wr = SF(weld) + nw * WELD_WORDS;
+    const float* data = MF(eq_data) + 11 * e;
+    int s1 = MI(eq_obj1)[e], s2 = MI(eq_obj2)[e], b1 = 0, b2 = 0;
+    float p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0}, q1[4] = {1, 0, 0, 0}, q2[4] = {1, 0, 0, 0}, t[3];
+    if (s1 >= 0) { b1 = MI(site_body)[s1]; qmul(q1, SF(xquat) + 4 * b1, MF(site_quat) + 4 * s1); qrot(t, SF(xquat) + 4 * b1, MF(site_pos) + 3 * s1); for (int k = 0; k < 3; k++) p1[k] = SF(xpos)[3 * b1 + k] + t[k]; }
+    if (s2 >= 0) { b2 = MI(site_body)[s2]; qmul(q2, SF(xquat) + 4 * b2, MF(site_quat) + 4 * s2); qrot(t, SF(xquat) + 4 * b2, MF(site_pos) + 3 * s2); for (int k = 0; k < 3; k++) p2[k] = SF(xpos)[3 * b2 + k] + t[k]; }
+    qrot(t, q1, data + 3); for (int k = 0; k < 3; k++) p1[k] += t[k];
+    qrot(t, q2, data + 0); for (int k = 0; k < 3; k++) p2[k] += t[k];
+    const float ts = data[10];
+    float quat[4], quat1[4] = {q2[0], -q2[1], -q2[2], -q2[3]}, quat2[4];
+    qmul(quat, q1, data + 6);
+    qmul(quat2, quat1, quat);
+    // rows: J = J(body1 at p1) - J(body2 at p2); translational rows about the anchor of the side that carries dofs
+    const bool use1 = b1 > 0 && DM(body_ancdof, b1) != 0;
+    float r[3];
+    for (int k = 0; k < 3; k++) r[k] = (use1 ? p1[k] : p2[k]) - h->ref[k];
+    float K, Bc;
+    ref_kb(c, MF(eq_solref) + 2 * e, MF(eq_solimp)[5 * e + 1], &K, &Bc);
+    LANES(k, 6) {
+      float* w = wr + W_W + 6 * k;
+      float cp;
+      if (k < 3) {
         float e3[3] = {k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
-        float* w = wr + W_W + 6 * k;
         cross3(w, r, e3); w[3] = e3[0]; w[4] = e3[1]; w[5] = e3[2];
+        cp = k == 0 ? p1[0] - p2[0] : (k == 1 ? p1[1] - p2[1] : p1[2] - p2[2]);
+      } else {
+        const int kk = k - 3;
+        for (int a = 0; a < 3; a++) {  // column a of the 3x3 map (relative angular velocity -> residual rate)
+          float qa[4] = {0, a == 0 ? 1.f : 0.f, a == 1 ? 1.f : 0.f, a == 2 ? 1.f : 0.f}, t1[4], t2[4];
+          qmul(t1, quat1, qa); qmul(t2, t1, quat);
+          w[a] = 0.5f * ts * (kk == 0 ? t2[1] : (kk == 1 ? t2[2] : t2[3])); w[3 + a] = 0;
+        }
+        cp = ts * (kk == 0 ? quat2[1] : (kk == 1 ? quat2[2] : quat2[3]));
       }
-      for (int a = 0; a < 3; a++) {  // column a of the 3x3 map (relative angular velocity -> residual rate)
-        float qa[4] = {0, a == 0 ? 1.f : 0.f, a == 1 ? 1.f : 0.f, a == 2 ? 1.f : 0.f}, t1[4], t2[4];
-        qmul(t1, quat1, qa); qmul(t2, t1, quat);
-        for (int k = 0; k < 3; k++) { float* w = wr + W_W + 6 * (3 + k); w[a] = 0.5f * ts * t2[1 + k]; w[3 + a] = 0; }
-      }
-      float K, Bc;
-      ref_kb(c, MF(eq_solref) + 2 * e, MF(eq_solimp)[5 * e + 1], &K, &Bc);
-      for (int k = 0; k < 6; k++) {
-        float imp = impedance(MF(eq_solimp) + 5 * e, cpos[k], 0.f);
-        float R = fmaxf((1 - imp) / imp * MF(eq_invweight)[2 * e + (k < 3 ? 0 : 1)], B200_MINVAL);
-        wr[W_D + k] = 1.0f / R; wr[W_JAR + k] = K * imp * cpos[k];
-      }
+      float imp = impedance(MF(eq_solimp) + 5 * e, cp, 0.f);
+      float R = fmaxf((1 - imp) / imp * MF(eq_invweight)[2 * e + (k < 3 ? 0 : 1)], B200_MINVAL);
+      wr[W_D + k] = 1.0f / R; wr[W_JAR + k] = K * imp * cp;
+    }
+    if (c.lane == 0) {
       wr[W_B] = Bc;
-      int gid = cnt[CNT_NGRP]++;  // one group per weld; row value = w . (V[b1] - V[b2]) => A = b2, B = b1
-      ((int*)wr)[W_GRP] = gid;
+      ((int*)wr)[W_GRP] = gid;  // one group per weld; row value = w . (V[b1] - V[b2]) => A = b2, B = b1
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
       dmask_t ma = DM(body_ancdof, b2), mb = DM(body_ancdof, b1);
       gi[G_START] = 0; gi[G_COUNT] = 0;
       grp_set_masks(gi, ma ^ mb, mb);
-      cnt[CNT_NWELD]++;
     }
+    SYNC();
+    if (c.lane == 0) { cnt[CNT_NGRP] = gid + 1; cnt[CNT_NWELD] = nw + 1; }
+    SYNC();
   }
-  SYNC();
   // joint limits -> dof rows (ordered compaction over joints, lower side first)
   for (int base = 0; base < h->njnt; base += WARP_W) {
     int j = base + c.lane;
@@ -1396,6 +1398,72 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
   SYNC();
 }
 
+// the two row passes that open the solver, fused: rows <- rows + B * (J qvel) + J qacc (same arithmetic and order as
+// rows_from_vec(qvel, RV_C0) followed by rows_from_vec(qacc, RV_ADD); the second group velocity is parked in the group's
+// K block, which build_H fills later)
+template <bool HF>
+STAGE void rows_begin(const Ctx c, const float* qvel, const float* qacc) {
+  ASSUME_SHARED(c);
+  ASSUME_SHARED_PTR(qvel); ASSUME_SHARED_PTR(qacc);
+  const int* cnt = SI(counters);
+  int ngrp = cnt[CNT_NGRP];
+  LANES(idx, ngrp * 6) {
+    int g = idx / 6, a = idx - 6 * g;
+    float* gr = SF(group) + g * GRP_WORDS;
+    dmask_t S = grp_mask(gr), sg = grp_sign(gr);
+    float acc = 0, acc2 = 0;
+    while (S) {
+      int j = ffs_pop(S);
+      float cd = SF(cdof)[6 * j + a], t = cd * qvel[j], t2 = cd * qacc[j];
+      bool pos = DBIT(sg, j);
+      acc += pos ? t : -t; acc2 += pos ? t2 : -t2;
+    }
+    gr[G_V + a] = acc; gr[G_K + a] = acc2;
+  }
+  SYNC();
+  LANES(i, cnt[CNT_NCON]) {
+    float* cr = SF(con) + i * CON_WORDS;
+    int dim = con_dim(cr), nbase = dim == 1 ? 1 : dim;
+    const float* gr = SF(group) + con_grp(cr) * GRP_WORDS;
+    float Bc = cr[C_JV];
+    for (int k = 0; k < nbase; k++) {
+      float w[6];
+      con_w(cr, k, w);
+      float u = cr[C_U + k];
+      u += Bc * dot6(w, gr + G_V);
+      u += dot6(w, gr + G_K);
+      cr[C_U + k] = u;
+    }
+  }
+  LANES(i, cnt[CNT_NWELD] * 6) {
+    float* wr = SF(weld) + (i / 6) * WELD_WORDS;
+    int k = i % 6;
+    const float* gr = SF(group) + ((const int*)wr)[W_GRP] * GRP_WORDS;
+    float u = wr[W_JAR + k];
+    u += wr[W_B] * dot6(wr + W_W + 6 * k, gr + G_V);
+    u += dot6(wr + W_W + 6 * k, gr + G_K);
+    wr[W_JAR + k] = u;
+  }
+  LANES(i, cnt[CNT_NDR]) {
+    float* dr = SF(dofrow) + i * DR_WORDS;
+    const int* di = (const int*)dr;
+    float v1 = dr[DR_COEF] * qvel[di[DR_DOF]], v2 = dr[DR_COEF] * qacc[di[DR_DOF]];
+    if (di[DR_DOF2] >= 0) { v1 += dr[DR_COEF2] * qvel[di[DR_DOF2]]; v2 += dr[DR_COEF2] * qacc[di[DR_DOF2]]; }
+    float u = dr[DR_JAR];
+    u += dr[DR_JV] * v1;
+    u += v2;
+    dr[DR_JAR] = u;
+  }
+  if (HF) LANES(d, c.h->nfric) {
+    float* fr = SF(fric);
+    float u = fr[d];
+    u += MF(dof_fricB)[d] * qvel[d];
+    u += qacc[d];
+    fr[d] = u;
+  }
+  SYNC();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // 8. Newton solver pieces
 // base-row generalized forces of a contact from its base-row values U (pyramid edges f = -D * min(0, u_n +- mu u_k))
@@ -1483,7 +1551,9 @@ STAGE void mulM(const Ctx c, const float* v, float* out) {
   const float* M = SF(M);
   LANES(i, nv) {
     float a = 0;
-    for (int j = 0; j < nv; j++) a += M[pidx(i, j)] * v[j];
+    const int row = i * (i + 1) / 2;
+    for (int j = 0; j <= i; j++) a += M[row + j] * v[j];                           // row part of the packed lower triangle
+    for (int j = i + 1, idx = row + 2 * i + 1; j < nv; idx += ++j) a += M[idx] * v[j];   // column part: idx = j (j + 1) / 2 + i
     out[i] = a;
   }
   SYNC();
@@ -1871,9 +1941,8 @@ template <bool HF>
 STAGE void newton_begin(const Ctx c) {
   ASSUME_SHARED(c);
   // qacc holds the warm start (previous sub-step's solution); rows become J a - aref = J a + B (J qvel) + K imp r
-  rows_from_vec<HF>(c, SF(qvel), RV_C0);
   mulM(c, SF(qacc), SF(Ma));
-  rows_from_vec<HF>(c, SF(qacc), RV_ADD);
+  rows_begin<HF>(c, SF(qvel), SF(qacc));
 }
 
 // forces, gradient and the convergence tests at the current point; returns 1 when the solver is finished

@@ -13,3 +13,10 @@ tail -2 gpurun_out/ncu_${tag}.log
 ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 6 -c 1 -o gpurun_out/prof_hand_${tag} \
     python tests/prof_hand.py 2048 8 touch > gpurun_out/ncu_hand_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_hand_${tag}.log
+# 4. the wide build (AdroitHandHammer-v2, 33 dofs, 2048 envs: BASELINE config 5a)
+ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 6 -c 1 -o gpurun_out/prof_adroit_${tag} \
+    python tests/prof_adroit.py AdroitHandHammer-v2 2048 8 > gpurun_out/ncu_adroit_${tag}.log 2>&1
+tail -2 gpurun_out/ncu_adroit_${tag}.log
+# 5. compute-sanitizer memcheck: Fetch (30 envs) and the Adroit relocate batch that overflows the contact-group capacity
+compute-sanitizer --tool memcheck python tests/sanitize_step.py > gpurun_out/memcheck_${tag}.log 2>&1; tail -3 gpurun_out/memcheck_${tag}.log
+compute-sanitizer --tool memcheck python tests/prof_adroit.py AdroitHandRelocate-v2 416 6 > gpurun_out/memcheck_adroit_${tag}.log 2>&1; tail -3 gpurun_out/memcheck_adroit_${tag}.log
