@@ -200,6 +200,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   DM_SCRATCH_PERSIST(X)
 #undef X
   {
+    so = (so + 3) & ~3;   // 16-byte aligned: the register Cholesky reads its column buffers (in the dead H region) as float4
     int nM = nv * (nv + 1) / 2, u = so;
     int d6off = 16 * nb > nM ? 16 * nb : nM;
     // the line-search edge list (x0, v, D per edge slot) overlays H and d6 after the direction solve

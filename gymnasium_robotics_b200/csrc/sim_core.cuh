@@ -1568,13 +1568,13 @@ STAGE void build_H(const Ctx c) {
   int nv = h->nv, nM = nv * (nv + 1) / 2, nweld = cnt[CNT_NWELD], ngrp = cnt[CNT_NGRP], ndr = cnt[CNT_NDR];
   float* H = SF(H);
   LANES(i, nM) H[i] = SF(M)[i];
-  // K blocks: lane e < 21 owns packed entry e of every group's 6x6
-  for (int g = 0; g < ngrp; g++) {
-    float* K = SF(group) + g * GRP_WORDS + G_K;
-    const int* gi = (const int*)(SF(group) + g * GRP_WORDS);
-    LANES(e, 21) {
-      int r = 0; while ((r + 1) * (r + 2) / 2 <= e) r++;
-      int s = e - r * (r + 1) / 2;
+  // K blocks: lane e < 21 owns packed entry e = (r, s) of every group's 6x6
+  LANES(e, 21) {
+    int r = 0; while ((r + 1) * (r + 2) / 2 <= e) r++;
+    const int s = e - r * (r + 1) / 2;
+    for (int g = 0; g < ngrp; g++) {
+      float* K = SF(group) + g * GRP_WORDS + G_K;
+      const int* gi = (const int*)(SF(group) + g * GRP_WORDS);
       float acc = 0;
       for (int i = gi[G_START]; i < gi[G_START] + gi[G_COUNT]; i++) {
         const float* cr = SF(con) + i * CON_WORDS;
@@ -1605,26 +1605,25 @@ STAGE void build_H(const Ctx c) {
     }
   }
   SYNC();
-  // y_i = K cdof_i for dofs in the group's chains, then H_ij += sigma_i sigma_j cdof_j . y_i
-  for (int g = 0; g < ngrp; g++) {
-    const float* K = SF(group) + g * GRP_WORDS + G_K;
-    const dmask_t S = grp_mask(SF(group) + g * GRP_WORDS), mb = grp_sign(SF(group) + g * GRP_WORDS);
-    LANES(i, nv) {
+  // lane i owns row i of H: for every group whose chains contain dof i, y = K cdof_i (registers), then
+  // H_ij += sigma_i sigma_j cdof_j . y for the group's dofs j <= i
+  LANES(i, nv) {
+    const float* cd = SF(cdof) + 6 * i;
+    const int row = i * (i + 1) / 2;
+    for (int g = 0; g < ngrp; g++) {
+      const float* gr = SF(group) + g * GRP_WORDS;
+      const dmask_t S = grp_mask(gr), mb = grp_sign(gr);
       if (!DBIT(S, i)) continue;
-      const float* cd = SF(cdof) + 6 * i;
-      float* y = SF(d6) + 6 * i;
+      const float* K = gr + G_K;
+      float y[6];
+#pragma unroll
       for (int r = 0; r < 6; r++) {
         float a = 0;
+#pragma unroll
         for (int s2 = 0; s2 < 6; s2++) a += K[pidx(r, s2)] * cd[s2];
         y[r] = a;
       }
-    }
-    SYNC();
-    LANES(i, nv) {
-      if (!DBIT(S, i)) continue;
       float si = DBIT(mb, i) ? 1.f : -1.f;
-      const float* y = SF(d6) + 6 * i;
-      int row = i * (i + 1) / 2;
       dmask_t m2 = S & (((dmask_t)2 << i) - (dmask_t)1);  // j <= i
       while (m2) {
         int j = ffs_pop(m2);
@@ -1632,8 +1631,8 @@ STAGE void build_H(const Ctx c) {
         H[row + j] += si * sj * dot6(SF(cdof) + 6 * j, y);
       }
     }
-    SYNC();
   }
+  SYNC();
   // dof friction rows in their quadratic zone (|x| < R * frictionloss)
   if (HF) {
     LANES(d, h->nfric) {
@@ -1724,7 +1723,7 @@ template <int NVP>
 static __device__ __noinline__ void spd_solve(const Ctx c, const float* A, const float* dadd, float hh, float* x, float* scratchH) {
   ASSUME_SHARED(c);
   __builtin_assume(__isShared(A)); __builtin_assume(__isShared(x)); if (dadd) __builtin_assume(__isShared(dadd));
-  (void)scratchH;
+  __builtin_assume(__isShared(scratchH));
   constexpr int NA = NVP > 32 ? 32 : NVP, KB = NVP > 32 ? NVP - 32 : 0, KS = KB > 0 ? KB : 1;
   const int nv = c.h->nv, i = c.lane;
   const unsigned FULL = 0xffffffffu;
@@ -1766,6 +1765,14 @@ static __device__ __noinline__ void spd_solve(const Ctx c, const float* A, const
   float b = 0.f;
   if (live) b = x[i];  // predicated load: idle lanes never touch x
   float dinv = 1.f;
+#ifdef B200_CHOL_SMEM
+  // column k of L travels through shared memory (one store per lane, 128-bit broadcast loads) instead of one shuffle per
+  // (row, column) pair; two alternating buffers in the dead `scratchH` region (A has been loaded into registers above;
+  // when A == scratchH the warp-level barrier below orders the overwrite)
+  constexpr int NA4 = (NA + 3) & ~3;
+  float* colbuf = scratchH;
+  __syncwarp();
+#endif
 #pragma unroll
   for (int k = 0; k < NA; k++) {
     float hkk = __shfl_sync(FULL, h[k], k);
@@ -1773,8 +1780,25 @@ static __device__ __noinline__ void spd_solve(const Ctx c, const float* A, const
     float lik = (i > k) ? h[k] * inv : 0.f;
     dinv = (i == k) ? inv : dinv;
     h[k] = (i > k) ? lik : h[k];
+#ifdef B200_CHOL_SMEM
+    if (k + 1 < NA) {
+      float* col = colbuf + (k & 1) * NA4;
+      if (i < NA4) col[i] = lik;
+      __syncwarp();
+      const float4* c4 = (const float4*)col;
+#pragma unroll
+      for (int q = (k + 1) / 4; q < NA4 / 4; q++) {
+        const float4 v = c4[q];
+        if (4 * q + 0 > k && 4 * q + 0 < NA) h[4 * q + 0] = fmaf(-lik, v.x, h[4 * q + 0]);
+        if (4 * q + 1 > k && 4 * q + 1 < NA) h[4 * q + 1] = fmaf(-lik, v.y, h[4 * q + 1]);
+        if (4 * q + 2 > k && 4 * q + 2 < NA) h[4 * q + 2] = fmaf(-lik, v.z, h[4 * q + 2]);
+        if (4 * q + 3 > k && 4 * q + 3 < NA) h[4 * q + 3] = fmaf(-lik, v.w, h[4 * q + 3]);
+      }
+    }
+#else
 #pragma unroll
     for (int j = k + 1; j < NA; j++) { float ljk = __shfl_sync(FULL, lik, j); h[j] = fmaf(-lik, ljk, h[j]); }
+#endif
     float lr[KS];
 #pragma unroll
     for (int r = 0; r < KB; r++) {
