@@ -158,7 +158,7 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
     # ------------------------------------------------------------------ reset
     def _reset_envs(self, mask, out):
         """MujocoEnv.reset -> mj_resetData -> reset_model (adroit_hammer.py:372-378) for the envs in `mask`."""
-        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        idx = self._mask_indices(mask)
         if idx.numel() == 0:
             return
         n = idx.numel()
@@ -219,7 +219,7 @@ class AdroitRelocateVectorEnv(AdroitHammerVectorEnv):
 
     def _reset_envs(self, mask, out):
         """reset_model (adroit_relocate.py:354-373): five uniform draws in the reference's order."""
-        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        idx = self._mask_indices(mask)
         if idx.numel() == 0:
             return
         n = idx.numel()
@@ -277,7 +277,7 @@ class AdroitPenVectorEnv(AdroitHammerVectorEnv):
         """reset_model (adroit_pen.py:379-399)."""
         from . import rotations
 
-        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        idx = self._mask_indices(mask)
         if idx.numel() == 0:
             return
         n = idx.numel()
@@ -327,7 +327,7 @@ class AdroitDoorVectorEnv(AdroitHammerVectorEnv):
 
     def _reset_envs(self, mask, out):
         """reset_model (adroit_door.py:359-371): three uniform draws (x, y, z of the frame)."""
-        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        idx = self._mask_indices(mask)
         if idx.numel() == 0:
             return
         n = idx.numel()

@@ -265,12 +265,12 @@ class FetchVectorEnv:
         u = lambda *s: torch.rand(*s, generator=self._gen, device=self.device)
         obj = None
         if cfg["has_object"]:
+            # rejection sampling (fetch_env.py:386-392) without a host round trip: 24 masked redraws leave a rejected
+            # sample with probability (pi 0.1^2 / (2 obj_range)^2)^25 < 1e-11 per env
             obj = g0[:2] + (u(n, 2) * 2 - 1) * cfg["obj_range"]
-            bad = torch.linalg.norm(obj - g0[:2], dim=1) < 0.1
-            while bool(bad.any()):
-                nb = int(bad.sum())
-                obj[bad] = g0[:2] + (u(nb, 2) * 2 - 1) * cfg["obj_range"]
+            for _ in range(24):
                 bad = torch.linalg.norm(obj - g0[:2], dim=1) < 0.1
+                obj = torch.where(bad[:, None], g0[:2] + (u(n, 2) * 2 - 1) * cfg["obj_range"], obj)
         goals = g0[:3] + (u(n, 3) * 2 - 1) * cfg["target_range"]
         if cfg["has_object"]:
             goals = goals + torch.as_tensor(off, dtype=torch.float32, device=self.device)
@@ -280,8 +280,16 @@ class FetchVectorEnv:
                 goals[:, 2] += torch.where(air, u(n) * 0.45, torch.zeros(n, device=self.device))
         return obj, goals
 
+    def _mask_indices(self, mask):
+        """Indices of the envs in `mask`; no device round trip when the caller knows that every env is due (`_reset_all`)."""
+        if getattr(self, "_reset_all", False):
+            if getattr(self, "_all_idx", None) is None or self._all_idx.numel() != self.num_envs:
+                self._all_idx = torch.arange(self.num_envs, device=self.device)
+            return self._all_idx
+        return torch.nonzero(mask, as_tuple=False).flatten()
+
     def _reset_envs(self, mask, out):
-        idx = torch.nonzero(mask, as_tuple=False).flatten()
+        idx = self._mask_indices(mask)
         if idx.numel() == 0:
             return
         st, sl = self.backend.state, self._sl
@@ -309,9 +317,14 @@ class FetchVectorEnv:
             self._gen.manual_seed(int(seeds[0]))
         out = self.backend.new_outputs()
         mask = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
-        self._reset_envs(mask, out)
+        self._reset_all = True
+        try:
+            self._reset_envs(mask, out)
+        finally:
+            self._reset_all = False
         self._needs_reset.zero_()
         self._elapsed_ub, self._pending_reset = 0, False
+        self._in_phase = True   # every env has the same step count (these envs never terminate): TimeLimit is host-known
         self._last = out
         return self._obs_dict(out), {}
 
@@ -328,9 +341,11 @@ class FetchVectorEnv:
         reward, success = out["reward"], out["success"]
         terminated = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)  # robot_env.py:106-112
         info = {"is_success": success}
+        in_phase = getattr(self, "_in_phase", False)
         if self.autoreset_mode == "next_step" and getattr(self, "_pending_reset", False):
             self._pending_reset = False
-            if bool(self._needs_reset.any()):
+            if in_phase or bool(self._needs_reset.any()):
+                self._reset_all = in_phase
                 # envs that finished on the previous call are reset now; their action is ignored (gymnasium NEXT_STEP)
                 pre = self._needs_reset.clone()
                 self._reset_envs(pre, out)
@@ -338,22 +353,27 @@ class FetchVectorEnv:
                 out["reward"] = reward
                 info["is_success"] = torch.where(pre, torch.zeros_like(success), success)
                 self._needs_reset.zero_()
-                self._elapsed_ub = int(self._elapsed.max())
+                self._reset_all = False
+                self._elapsed_ub = 0 if in_phase else int(self._elapsed.max())
         # TimeLimit: the device counters are only compared (and the host only synchronises) once the bound says an env may be due
         may_truncate = self.max_episode_steps is not None and self._elapsed_ub >= self.max_episode_steps
-        truncated = (self._elapsed >= self.max_episode_steps) if may_truncate else torch.zeros_like(terminated)
+        # in phase (all envs reset together and none terminates): the bound IS every env's step count -- no device compare
+        truncated = (torch.ones_like(terminated) if in_phase else (self._elapsed >= self.max_episode_steps)) if may_truncate \
+            else torch.zeros_like(terminated)
         done = truncated | terminated
         if may_truncate:
             if self.autoreset_mode == "next_step":
                 self._needs_reset = done
                 self._pending_reset = True
             elif self.autoreset_mode == "same_step":
-                if bool(done.any()):
+                if in_phase or bool(done.any()):
                     fo = self._obs_dict(out)
                     info["final_obs"] = {k: v.clone() for k, v in fo.items()} if isinstance(fo, dict) else fo.clone()
                     info["_final_obs"] = done.clone()
+                    self._reset_all = in_phase
                     self._reset_envs(done, out)
-                self._elapsed_ub = int(self._elapsed.max())
+                    self._reset_all = False
+                self._elapsed_ub = 0 if in_phase else int(self._elapsed.max())
         info["_is_success"] = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
         self._last = out
         return self._obs_dict(out), reward, terminated, truncated, info
@@ -384,6 +404,7 @@ class FetchVectorEnv:
         self.backend.state.copy_(state)
         if elapsed is not None:
             self._elapsed.copy_(elapsed)
+            self._in_phase = False
         self._elapsed_ub = int(self._elapsed.max())
         out = self.backend.new_outputs()
         self.backend.refresh(None, out)

@@ -1,8 +1,6 @@
+# one GPU-box round: variant A/B timing, the official bench line, the profile recipe (see profiles/README.md)
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -40) > gpurun_out/pytest_gpu5.log
-tail -6 gpurun_out/pytest_gpu5.log
-for w in fetch_pick_and_place adroit_hammer adroit_relocate adroit_pen adroit_door fetch_slide hand_egg hand_block_touch antmaze_large; do
-  timeout 200 python bench.py --workload $w --steps 60 --warmup 10 --no-cpu-baseline > gpurun_out/b5_$w.json 2> gpurun_out/b5_$w.err
-  echo $w; cut -c1-130 gpurun_out/b5_$w.json | tail -1
-done
-bash tests/variant_time.sh both 2>&1 | tee gpurun_out/variants5.log | tail -12
+bash tests/variant_time.sh both 2>&1 | tee gpurun_out/variants6.log | tail -12
+timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_r1i_n1.json 2> gpurun_out/bench_r1i_n1.err; cut -c1-200 gpurun_out/bench_r1i_n1.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1i_ref.json 2> gpurun_out/bench_r1i_ref.err; cut -c1-200 gpurun_out/bench_r1i_ref.json
+bash tests/run_profile.sh r1i 2>&1 | tail -20
