@@ -339,7 +339,10 @@ class FetchVectorEnv:
         self._elapsed += 1
         self._elapsed_ub = getattr(self, "_elapsed_ub", 0) + 1   # host-side upper bound of max(_elapsed): no sync on most steps
         reward, success = out["reward"], out["success"]
-        terminated = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)  # robot_env.py:106-112
+        if getattr(self, "_const_false", None) is None or self._const_false.numel() != self.num_envs:
+            self._const_false = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+            self._const_true = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        terminated = self._const_false  # robot_env.py:106-112 (constant tensors are shared between steps: read-only for callers)
         info = {"is_success": success}
         in_phase = getattr(self, "_in_phase", False)
         if self.autoreset_mode == "next_step" and getattr(self, "_pending_reset", False):
@@ -358,8 +361,8 @@ class FetchVectorEnv:
         # TimeLimit: the device counters are only compared (and the host only synchronises) once the bound says an env may be due
         may_truncate = self.max_episode_steps is not None and self._elapsed_ub >= self.max_episode_steps
         # in phase (all envs reset together and none terminates): the bound IS every env's step count -- no device compare
-        truncated = (torch.ones_like(terminated) if in_phase else (self._elapsed >= self.max_episode_steps)) if may_truncate \
-            else torch.zeros_like(terminated)
+        truncated = (self._const_true if in_phase else (self._elapsed >= self.max_episode_steps)) if may_truncate \
+            else self._const_false
         done = truncated | terminated
         if may_truncate:
             if self.autoreset_mode == "next_step":
@@ -374,7 +377,7 @@ class FetchVectorEnv:
                     self._reset_envs(done, out)
                     self._reset_all = False
                 self._elapsed_ub = 0 if in_phase else int(self._elapsed.max())
-        info["_is_success"] = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        info["_is_success"] = self._const_true
         self._last = out
         return self._obs_dict(out), reward, terminated, truncated, info
 
