@@ -108,7 +108,8 @@ struct DMHead {
 static inline uint32_t f2w(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
 static inline int dm_build(const b200_model_view& m, const double* eq_data_override, const float ref[3],
-                           std::vector<uint32_t>& buf, std::string& err, int penv_body = -1, bool force_wide = false) {
+                           std::vector<uint32_t>& buf, std::string& err, int penv_body = -1, bool force_wide = false,
+                           int ngrp_cap = 0 /* tests: smaller contact-group capacity to exercise the overflow path */) {
   DMHead h;
   memset(&h, 0, sizeof(h));
   h.nb = m.nbody; h.njnt = m.njnt; h.nq = m.nq; h.nv = m.nv; h.nu = m.nu; h.nsite = m.nsite;
@@ -148,6 +149,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   if (h.npair > 65535) { err = "more than 65535 candidate geom pairs"; return -1; }
   h.ncon_max = m.nmocap > 0 ? 16 : 20;   // contacts kept per env per sub-step
   h.ngrp_max = m.nmocap > 0 ? 10 : 14;   // geom pairs in contact (+ welds) per env per sub-step
+  if (ngrp_cap > DM_NWELD_MAX && ngrp_cap < h.ngrp_max) h.ngrp_max = ngrp_cap;
   if (h.nb > DM_MAX_BODY) { err = "model has more than 32 runtime bodies"; return -1; }
   if (h.nv > DM_MAX_NV) { err = "model has more than 40 dofs"; return -1; }
   h.mask_words = (h.nv > 32 || force_wide) ? 2 : 1;

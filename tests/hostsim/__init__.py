@@ -42,7 +42,7 @@ def lib(wide=False):
     if _LIB.get(wide) is None:
         L = ctypes.CDLL(build(wide=wide))
         L.hostsim_create.restype = ctypes.c_void_p
-        L.hostsim_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.hostsim_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.hostsim_scratch.restype = ctypes.POINTER(ctypes.c_float)
         L.hostsim_scratch.argtypes = [ctypes.c_void_p]
         for f in ("hostsim_destroy", "hostsim_forward", "hostsim_kinematics"):
@@ -61,14 +61,14 @@ def lib(wide=False):
 class HostSim:
     """fp32 single-env emulation of the kernel; arrays are views into the emulated shared-memory scratch."""
 
-    def __init__(self, model, eq_data=None, ref=(1.0, 0.75, 0.4), penv_body=-1):
+    def __init__(self, model, eq_data=None, ref=(1.0, 0.75, 0.4), penv_body=-1, ngrp_cap=0):
         self.model = model
         blob = model.to_blob()
         L = lib(wide=model.nv > 32)
         self._L = L
         eq = np.ascontiguousarray(eq_data, dtype=np.float64) if eq_data is not None else None
         r = np.asarray(ref, dtype=np.float32)
-        self._h = L.hostsim_create(blob, len(blob), eq.ctypes.data if eq is not None else None, r.ctypes.data, int(penv_body))
+        self._h = L.hostsim_create(blob, len(blob), eq.ctypes.data if eq is not None else None, r.ctypes.data, int(penv_body), int(ngrp_cap))
         if not self._h:
             raise RuntimeError("hostsim_create failed")
         n = L.hostsim_scr_words(self._h)

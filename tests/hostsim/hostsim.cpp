@@ -24,11 +24,11 @@ struct HostSim {
 };
 
 extern "C" {
-void* hostsim_create(const void* blob, size_t n, const double* eq_data, const float* ref, int penv_body) {
+void* hostsim_create(const void* blob, size_t n, const double* eq_data, const float* ref, int penv_body, int ngrp_cap) {
   HostSim* s = new HostSim;
   s->blob.assign((const uint8_t*)blob, (const uint8_t*)blob + n);
   if (b200_model_parse(s->blob.data(), n, &s->view) != 0) { delete s; return nullptr; }
-  if (dm_build(s->view, eq_data, ref, s->model, s->err, penv_body, kWide) != 0) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); delete s; return nullptr; }
+  if (dm_build(s->view, eq_data, ref, s->model, s->err, penv_body, kWide, ngrp_cap) != 0) { fprintf(stderr, "hostsim: %s\n", s->err.c_str()); delete s; return nullptr; }
   const DMHead* h = (const DMHead*)s->model.data();
   s->scratch.assign(h->scr_words, 0.f);
   s->ctx.mg = s->model.data(); s->ctx.mw = s->model.data(); s->ctx.h = h; s->ctx.s = s->scratch.data(); s->ctx.lane = 0;

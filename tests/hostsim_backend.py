@@ -16,7 +16,8 @@ class HostSimBackend:
         self.device = torch.device("cpu")
         self.num_envs, self.nobs = num_envs, task.nobs
         penv = int(task.penv_body) if task.kind in (4, 5, 6, 7) else -1
-        self.sim = HostSim(model, eq_data=eq_data if len(eq_data) else None, ref=getattr(self, "REF", REF_POINT), penv_body=penv)
+        self.sim = HostSim(model, eq_data=eq_data if len(eq_data) else None, ref=getattr(self, "REF", REF_POINT), penv_body=penv,
+                           ngrp_cap=getattr(self, "NGRP_CAP", 0))
         t = HostTaskC()
         for name, _ in task._fields_:
             setattr(t, name, getattr(task, name))
@@ -51,7 +52,8 @@ class HostSimBackend:
             if mask is not None and not bool(mask[i]):
                 continue
             a = actions[i].numpy() if actions is not None else np.zeros(self.nact, dtype=np.float32)
-            obs, ag, dg, rew, suc, _ = self.sim.env_step(self.task, mode, nraw, st[i], a, self.nobs, self.ngoal)
+            obs, ag, dg, rew, suc, it = self.sim.env_step(self.task, mode, nraw, st[i], a, self.nobs, self.ngoal)
+            self.overflow_bits = getattr(self, "overflow_bits", 0) | (it >> 16)   # capacity flags of the info word
             out["obs"][i] = torch.from_numpy(obs); out["achieved"][i] = torch.from_numpy(ag); out["desired"][i] = torch.from_numpy(dg)
             out["reward"][i] = rew; out["success"][i] = suc
         self.launches += 1

@@ -159,3 +159,26 @@ def test_dense_reward_and_registry():
     assert torch.allclose(r, -d)
     with pytest.raises(KeyError):
         pkg.make_vec("AdroitHandHammer-v1", num_envs=1)   # not on the CUDA path (and not a registered id of the reference)
+
+
+def test_contact_group_overflow_is_flagged_and_harmless():
+    """Regression: a geom pair beyond the per-env contact-group capacity must be dropped together with its contacts before
+    they are numbered.  (Counted-but-unwritten contact records used to be finalised from stale words: garbage pair index,
+    illegal address on the GPU with 2 048 Adroit envs pressing the hand onto the table.)  The capacity is shrunk to 3 groups
+    (weld + 2 geom pairs) so that the gripper pressed onto the table and the object overflows it at once."""
+    class TinyGroups(HostSimBackend):
+        NGRP_CAP = 4
+
+    env = FetchVectorEnv("FetchPickAndPlace", num_envs=1, backend_factory=TinyGroups, rng_mode="numpy")
+    env.reset(seed=0)
+    a = np.array([[0.0, 0.0, -1.0, -1.0]], dtype=np.float32)
+    for _ in range(12):
+        o, r, *_ = env.step(a)
+        assert torch.isfinite(o["observation"]).all()
+    assert env.backend.overflow_bits & 4, "the scenario was meant to overflow the group capacity"
+    # the same scenario with the production capacity never flags
+    env2 = mk("FetchPickAndPlace", 1, rng_mode="numpy")
+    env2.reset(seed=0)
+    for _ in range(12):
+        env2.step(a)
+    assert getattr(env2.backend, "overflow_bits", 0) == 0
