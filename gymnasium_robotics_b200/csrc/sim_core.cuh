@@ -1339,10 +1339,9 @@ STAGE void make_constraint(const Ctx c) {
   if (HF) { LANES(d, h->nfric) SF(fric)[d] = 0.f; SYNC(); }
 }
 
-// rows <- J * vec.  RV_C0: row = B * (J qvel) + row (row holds K*imp*r; B in the JV slot) ; RV_ADD: row += J a ; RV_JV: JV = J s
-enum { RV_C0 = 0, RV_ADD = 1, RV_JV = 2 };
+// JV slots of every row <- J * vec (the search direction); the opening passes J qvel / J qacc are fused in rows_begin()
 template <bool HF>
-STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
+STAGE void rows_from_vec(const Ctx c, const float* vec) {
   ASSUME_SHARED(c);
   ASSUME_SHARED_PTR(vec);
   const int* cnt = SI(counters);
@@ -1361,45 +1360,31 @@ STAGE void rows_from_vec(const Ctx c, const float* vec, int mode) {
     float* cr = SF(con) + i * CON_WORDS;
     int dim = con_dim(cr), nbase = dim == 1 ? 1 : dim;
     const float* dV = SF(group) + con_grp(cr) * GRP_WORDS + G_V;
-    float Bc = cr[C_JV];
     for (int k = 0; k < nbase; k++) {
       float w[6];
       con_w(cr, k, w);
-      float val = dot6(w, dV);
-      if (mode == RV_C0) cr[C_U + k] += Bc * val;
-      else if (mode == RV_ADD) cr[C_U + k] += val;
-      else cr[C_JV + k] = val;
+      cr[C_JV + k] = dot6(w, dV);
     }
   }
   LANES(i, cnt[CNT_NWELD] * 6) {
     float* wr = SF(weld) + (i / 6) * WELD_WORDS;
     int k = i % 6;
     const float* dV = SF(group) + ((const int*)wr)[W_GRP] * GRP_WORDS + G_V;
-    float val = dot6(wr + W_W + 6 * k, dV);
-    if (mode == RV_C0) wr[W_JAR + k] += wr[W_B] * val;
-    else if (mode == RV_ADD) wr[W_JAR + k] += val;
-    else wr[W_JV + k] = val;
+    wr[W_JV + k] = dot6(wr + W_W + 6 * k, dV);
   }
   LANES(i, cnt[CNT_NDR]) {
     float* dr = SF(dofrow) + i * DR_WORDS;
     const int* di = (const int*)dr;
     float val = dr[DR_COEF] * vec[di[DR_DOF]];
     if (di[DR_DOF2] >= 0) val += dr[DR_COEF2] * vec[di[DR_DOF2]];
-    if (mode == RV_C0) dr[DR_JAR] += dr[DR_JV] * val;
-    else if (mode == RV_ADD) dr[DR_JAR] += val;
-    else dr[DR_JV] = val;
+    dr[DR_JV] = val;
   }
-  if (HF) LANES(d, c.h->nfric) {
-    float* fr = SF(fric);
-    if (mode == RV_C0) fr[d] += MF(dof_fricB)[d] * vec[d];
-    else if (mode == RV_ADD) fr[d] += vec[d];
-    else fr[c.h->nfric + d] = vec[d];
-  }
+  if (HF) LANES(d, c.h->nfric) SF(fric)[c.h->nfric + d] = vec[d];
   SYNC();
 }
 
 // the two row passes that open the solver, fused: rows <- rows + B * (J qvel) + J qacc (same arithmetic and order as
-// rows_from_vec(qvel, RV_C0) followed by rows_from_vec(qacc, RV_ADD); the second group velocity is parked in the group's
+// two separate passes row += B * (J qvel), row += J qacc); the second group velocity is parked in the group's
 // K block, which build_H fills later)
 template <bool HF>
 STAGE void rows_begin(const Ctx c, const float* qvel, const float* qacc) {
@@ -2020,7 +2005,7 @@ STAGE int newton_move(const Ctx c, float* improvement) {
   TIC();
   mulM(c, search, Mv);
   TOC(TM_MV_MULM);
-  rows_from_vec<HF>(c, search, RV_JV);
+  rows_from_vec<HF>(c, search);
   TOC(TM_MV_ROWS);
   float q1 = 0, q2 = 0, sn = 0;
   LANES(i, nv) { q1 += search[i] * (Ma[i] - fs[i]); q2 += 0.5f * search[i] * Mv[i]; sn += search[i] * search[i]; }
