@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200SIM_LIB") or os.path.join(_HERE, "libb200sim.so")
 _LIB = None
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-DB200_BLOCK_ALIGN", "-DB200_CHOL_SMEM"] + \
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-DB200_BLOCK_ALIGN", "-DB200_CHOL_SMEM",
+              "-prec-div=false", "-prec-sqrt=false"] + \
     os.environ.get("B200SIM_NVCC_EXTRA", "").split()
 
 

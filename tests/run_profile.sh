@@ -1,7 +1,9 @@
 #!/bin/bash
 # GPU-box recipe for the committed profile summaries (see profiles/README.md).  Usage: bash tests/run_profile.sh <tag>
+# Every .ncu-rep is summarised on the box (ncu -i needs no GPU, but the reports with --import-source are ~30 MB each and
+# gpurun only brings 64 MiB back) and then removed; the text summaries are copied to gpurun_out/prof_txt/.
 tag=${1:-r1}
-mkdir -p gpurun_out
+mkdir -p gpurun_out/prof_txt
 # 1. every launch with its device time (shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv \
     python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_${tag}.log 2>&1
@@ -9,14 +11,18 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 10 -c 1 -o gpurun_out/prof_${tag} \
     python tests/prof_step.py 4096 12 > gpurun_out/ncu_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_${tag}.log
+python tests/summarize_profile.py ${tag} > gpurun_out/summarize_${tag}.log 2>&1; rm -f gpurun_out/prof_${tag}.ncu-rep
 # 3. the Shadow-Hand build of the step kernel (BASELINE config 3: 2048 envs, 92 touch sensors)
 ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 6 -c 1 -o gpurun_out/prof_hand_${tag} \
     python tests/prof_hand.py 2048 8 touch > gpurun_out/ncu_hand_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_hand_${tag}.log
+python tests/summarize_profile.py hand_${tag} > gpurun_out/summarize_hand_${tag}.log 2>&1; rm -f gpurun_out/prof_hand_${tag}.ncu-rep
 # 4. the wide build (AdroitHandHammer-v2, 33 dofs, 2048 envs: BASELINE config 5a)
 ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 6 -c 1 -o gpurun_out/prof_adroit_${tag} \
     python tests/prof_adroit.py AdroitHandHammer-v2 2048 8 > gpurun_out/ncu_adroit_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_adroit_${tag}.log
-# 5. compute-sanitizer memcheck: Fetch (30 envs) and the Adroit relocate batch that overflows the contact-group capacity
+python tests/summarize_profile.py adroit_${tag} > gpurun_out/summarize_adroit_${tag}.log 2>&1; rm -f gpurun_out/prof_adroit_${tag}.ncu-rep
+cp profiles/*${tag}* profiles/traffic*.json gpurun_out/prof_txt/ 2>/dev/null
+# 5. compute-sanitizer memcheck: Fetch (30 envs) and an Adroit relocate batch
 compute-sanitizer --tool memcheck python tests/sanitize_step.py > gpurun_out/memcheck_${tag}.log 2>&1; tail -3 gpurun_out/memcheck_${tag}.log
 compute-sanitizer --tool memcheck python tests/prof_adroit.py AdroitHandRelocate-v2 416 6 > gpurun_out/memcheck_adroit_${tag}.log 2>&1; tail -3 gpurun_out/memcheck_adroit_${tag}.log
