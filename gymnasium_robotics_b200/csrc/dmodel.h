@@ -25,7 +25,7 @@
   X(body_ipos, 3, nb) X(body_iquat, 4, nb) X(body_mass, 1, nb) X(body_inertia, 3, nb) \
   X(jnt_type, 1, njnt) X(jnt_body, 1, njnt) X(jnt_qposadr, 1, njnt) X(jnt_dofadr, 1, njnt) X(jnt_limited, 1, njnt) \
   X(jnt_pos, 3, njnt) X(jnt_axis, 3, njnt) X(jnt_range, 2, njnt) X(jnt_margin, 1, njnt) X(jnt_stiffness, 1, njnt) \
-  X(jnt_solref, 2, njnt) X(jnt_solimp, 5, njnt) X(jnt_qpos0, 1, njnt) X(jnt_qspring, 1, njnt) \
+  X(jnt_qpos0, 1, njnt) X(jnt_qspring, 1, njnt) \
   X(dof_body, 1, nv) X(dof_jnt, 1, nv) X(dof_anc, MW, nv) X(dof_pre, MW, nv) X(dof_armature, 1, nv) \
   X(dof_damping, 1, nv) X(dof_frictionloss, 1, nv) X(dof_invweight0, 1, nv) \
   X(geom_type, 1, ngeom) X(geom_body, 1, ngeom) X(geom_pos, 3, ngeom) X(geom_quat, 4, ngeom) X(geom_size, 3, ngeom) \
@@ -40,6 +40,7 @@
   X(dof_fricD, 1, nfric) X(dof_fricB, 1, nfric) \
   X(ten_dof, 2, nten) X(ten_qadr, 2, nten) X(ten_coef, 2, nten) X(ten_range, 2, nten) X(ten_margin, 1, nten)
 #define DM_ARRAYS_COLD(X) \
+  X(jnt_solref, 2, njnt) X(jnt_solimp, 5, njnt) /* read only when a limit row is created */ \
   X(pair_condim, 1, npair) X(pair_friction, 3, npair) X(pair_gap, 1, npair) X(pair_solref, 2, npair) \
   X(pair_solimp, 5, npair) X(pair_invweight, 2, npair) \
   X(ten_solref, 2, nten) X(ten_solimp, 5, nten) X(ten_invweight, 1, nten) \
@@ -68,7 +69,7 @@ enum { C_W = 0 /*18*/, C_MU = 18 /*slide, torsion*/, C_D = 20, C_U = 21 /*4*/, C
 enum { FR_JAR = 0, FR_JV = 1 };
 // contact extras kept only by models with touch sensors: world position and pair index
 enum { CX_POS = 0, CX_PAIR = 3, CX_WORDS = 4 };
-enum { DR_DOF = 0, DR_COEF = 1, DR_D = 2, DR_JAR = 3, DR_JV = 4, DR_DOF2 = 5, DR_COEF2 = 6, DR_WORDS = 8 };
+enum { DR_DOF = 0, DR_COEF = 1, DR_D = 2, DR_JAR = 3, DR_JV = 4, DR_DOF2 = 5, DR_COEF2 = 6, DR_WORDS = 7 };
 // weld: 6 rows w[6]; D[6], JAR[6] (K*imp*r during set-up), JV[6], B (one value), group
 enum { W_W = 0, W_D = 36, W_JAR = 42, W_JV = 48, W_B = 54, W_GRP = 55, WELD_WORDS = 56 };
 // group = one geom pair in contact (its contacts are contiguous) or one weld: 6x6 block K, contact range, dof mask

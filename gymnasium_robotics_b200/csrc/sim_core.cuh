@@ -1291,9 +1291,11 @@ STAGE void make_constraint(const Ctx c) {
       int* di = (int*)dr;
       int d = MI(jnt_dofadr)[j];
       float margin = MF(jnt_margin)[j];
-      float imp = impedance(MF(jnt_solimp) + 5 * j, dist[k], margin);
+      float solimp[5] = {GF(jnt_solimp)[5 * j], GF(jnt_solimp)[5 * j + 1], GF(jnt_solimp)[5 * j + 2], GF(jnt_solimp)[5 * j + 3], GF(jnt_solimp)[5 * j + 4]};
+      float solref[2] = {GF(jnt_solref)[2 * j], GF(jnt_solref)[2 * j + 1]};
+      float imp = impedance(solimp, dist[k], margin);
       float K, Bc;
-      ref_kb(c, MF(jnt_solref) + 2 * j, MF(jnt_solimp)[5 * j + 1], &K, &Bc);
+      ref_kb(c, solref, solimp[1], &K, &Bc);
       float R = fmaxf((1 - imp) / imp * MF(dof_invweight0)[d], B200_MINVAL);
       di[DR_DOF] = d; dr[DR_COEF] = sgn[k]; di[DR_DOF2] = -1; dr[DR_COEF2] = 0;
       dr[DR_D] = 1.0f / R; dr[DR_JAR] = K * imp * (dist[k] - margin); dr[DR_JV] = Bc;

@@ -1,8 +1,5 @@
-# one GPU-box round: parity tests, the official bench lines, the profile recipe (see profiles/README.md)
+# one GPU-box round: A/B variants, parity tests, bench lines
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -40) > gpurun_out/pytest_gpu7.log; tail -4 gpurun_out/pytest_gpu7.log
-timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_r1i_n1.json 2> gpurun_out/bench_r1i_n1.err; cut -c1-200 gpurun_out/bench_r1i_n1.json
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1i_ref.json 2> gpurun_out/bench_r1i_ref.err; cut -c1-200 gpurun_out/bench_r1i_ref.json
-for w in hand_block_touch adroit_hammer antmaze_large; do timeout 200 python bench.py --workload $w --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_r1i_$w.json 2> gpurun_out/b7_$w.err; cut -c1-120 gpurun_out/bench_r1i_$w.json; done
-bash tests/run_profile.sh r1i 2>&1 | tail -20
-du -sh gpurun_out
+bash tests/variant_time.sh both 2>&1 | tee gpurun_out/variants9.log | tail -14
+(timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -40) > gpurun_out/pytest_gpu9.log; tail -3 gpurun_out/pytest_gpu9.log
+for w in fetch_pick_and_place adroit_relocate adroit_hammer hand_block_touch; do timeout 200 python bench.py --workload $w --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/b9_$w.json 2> gpurun_out/b9_$w.err; cut -c1-120 gpurun_out/b9_$w.json; done
