@@ -21,6 +21,9 @@ for _maze, _steps in (("UMaze", 700), ("Open", 700), ("Open_Diverse_G", 700), ("
                       ("Large_Diverse_GR", 1000)):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
         ENV_IDS[f"AntMaze_{_maze}{_suffix}-v5"] = dict(maze=_maze, reward_type=_rt, max_episode_steps=_steps)
+        # -v4 (envs/maze/ant_maze_v4.py) is line for line the -v5 class on Gymnasium's Ant-v4 instead of Ant-v5: the same ant.xml,
+        # frame_skip, observation (use_contact_forces defaults to False in both) and maze_v4 logic -- one implementation here
+        ENV_IDS[f"AntMaze_{_maze}{_suffix}-v4"] = dict(maze=_maze, reward_type=_rt, max_episode_steps=_steps)
 # PointMaze-v3 (__init__.py:960-1080)
 for _maze, _steps in (("UMaze", 300), ("Open", 300), ("Open_Diverse_G", 300), ("Open_Diverse_GR", 300), ("Medium", 600),
                       ("Medium_Diverse_G", 600), ("Medium_Diverse_GR", 600), ("Large", 800), ("Large_Diverse_G", 800),
