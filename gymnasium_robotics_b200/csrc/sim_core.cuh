@@ -752,29 +752,38 @@ HD void sphere_box_contact(const float* center, float r, const float* bp, const 
   o.dist[k] = d;
   for (int a = 0; a < 3; a++) { o.nrm[k][a] = -nrm[a]; o.pos[k][a] = closest[a] + nrm[a] * 0.5f * d; }
 }
+// signed distance of a point given in the box frame (the distance part of point_box, no transforms)
+HD float box_sdist(const float* loc, const float* h) {
+  float dx = fabsf(loc[0]) - h[0], dy = fabsf(loc[1]) - h[1], dz = fabsf(loc[2]) - h[2];
+  if (dx <= 0 && dy <= 0 && dz <= 0) return fmaxf(dx, fmaxf(dy, dz));   // inside: minus the smallest penetration
+  float ex = fmaxf(dx, 0.f), ey = fmaxf(dy, 0.f), ez = fmaxf(dz, 0.f);
+  return sqrtf(ex * ex + ey * ey + ez * ez);
+}
 HDN void capsule_box_contacts(const float* cp, const float* ax, float r, float hl, const float* bp, const float* bm, const float* bh,
                               float margin, ContactOut& o) {
-  float e0[3] = {cp[0] - ax[0] * hl, cp[1] - ax[1] * hl, cp[2] - ax[2] * hl}, e1[3] = {cp[0] + ax[0] * hl, cp[1] + ax[1] * hl, cp[2] + ax[2] * hl};
-  float cl[3], nn[3];
-  float d0 = point_box(e0, bp, bm, bh, cl, nn) - r, d1 = point_box(e1, bp, bm, bh, cl, nn) - r;
+  // the search runs in the box frame: segment p(t) = cl + t dl, t in [-hl, hl] (rotated once; every evaluation of the convex
+  // distance function is then a handful of operations)
+  float rel[3] = {cp[0] - bp[0], cp[1] - bp[1], cp[2] - bp[2]}, cl[3], dl[3], p[3];
+  mulmtv(cl, bm, rel); mulmtv(dl, bm, ax);
+#define B200_SEG(t_) (p[0] = fmaf(dl[0], (t_), cl[0]), p[1] = fmaf(dl[1], (t_), cl[1]), p[2] = fmaf(dl[2], (t_), cl[2]), box_sdist(p, bh))
+  // no point of the segment is closer than the centre's distance minus the half length (the distance is 1-Lipschitz)
+  if (box_sdist(cl, bh) - hl - r > margin) return;
+  float d0 = B200_SEG(-hl) - r, d1 = B200_SEG(hl) - r;
   if (d0 <= margin && d1 <= margin) {
+    float e0[3] = {cp[0] - ax[0] * hl, cp[1] - ax[1] * hl, cp[2] - ax[2] * hl}, e1[3] = {cp[0] + ax[0] * hl, cp[1] + ax[1] * hl, cp[2] + ax[2] * hl};
     sphere_box_contact(e0, r, bp, bm, bh, margin, o);
     sphere_box_contact(e1, r, bp, bm, bh, margin, o);
     return;
   }
   const float gr = 0.6180339887498949f;
-  float lo = -hl, hi = hl, x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo), p[3];
-  for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * x1;
-  float f1 = point_box(p, bp, bm, bh, cl, nn);
-  for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * x2;
-  float f2 = point_box(p, bp, bm, bh, cl, nn);
+  float lo = -hl, hi = hl, x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
+  float f1 = B200_SEG(x1), f2 = B200_SEG(x2);
   for (int it = 0; it < 24; it++) {
-    if (f1 < f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * x1; f1 = point_box(p, bp, bm, bh, cl, nn); }
-    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * x2; f2 = point_box(p, bp, bm, bh, cl, nn); }
+    if (f1 < f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = B200_SEG(x1); }
+    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = B200_SEG(x2); }
   }
   float t = 0.5f * (lo + hi);
-  for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * t;
-  float fmin = point_box(p, bp, bm, bh, cl, nn);
+  float fmin = B200_SEG(t);
   if (fmin - r > margin) return;
   // flat zone {f <= fmin + tol} of the convex distance function: a capsule lying (nearly) parallel on a face gets one
   // contact at each end of the zone instead of one at an arbitrary point of it (same rule as oracle/oracle.c)
@@ -782,15 +791,14 @@ HDN void capsule_box_contacts(const float* cp, const float* ax, float r, float h
   float tz[2];
   for (int side = 0; side < 2; side++) {
     float out = side ? hl : -hl, in = t;
-    for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * out;
-    if (point_box(p, bp, bm, bh, cl, nn) <= fmin + tol) in = out;
+    if (B200_SEG(out) <= fmin + tol) in = out;
     else for (int it = 0; it < 14; it++) {
       float mid = 0.5f * (out + in);
-      for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * mid;
-      if (point_box(p, bp, bm, bh, cl, nn) <= fmin + tol) in = mid; else out = mid;
+      if (B200_SEG(mid) <= fmin + tol) in = mid; else out = mid;
     }
     tz[side] = in;
   }
+#undef B200_SEG
   if (tz[1] - tz[0] > r) {
     for (int a = 0; a < 3; a++) p[a] = cp[a] + ax[a] * tz[0];
     sphere_box_contact(p, r, bp, bm, bh, margin, o);
