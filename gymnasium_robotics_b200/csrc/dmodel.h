@@ -49,11 +49,10 @@
 
 // per-env scratch that lives for the whole sub-step (name, words expression)
 #define DM_SCRATCH_PERSIST(X) \
-  X(dofrow, ndr_max * DR_WORDS) /* first: 16-byte aligned, field-major (ndr_max is a multiple of 4) */ \
   X(qpos, nq) X(qvel, nv) X(qacc, nv) X(ctrl, nu) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) \
   X(xpos, 3 * nb) X(xquat, 4 * nb) X(cdof, 6 * nv) X(M, nv * (nv + 1) / 2) X(fsmooth, nv) X(fcon, nv) \
   X(rk_q0, nrkq) X(rk_v0, nrkv) X(rk_dx, nrkv) X(rk_df, nrkv) \
-  X(con, ncon_max * CON_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
+  X(con, ncon_max * CON_WORDS) X(dofrow, ndr_max * DR_WORDS) X(weld, DM_NWELD_MAX * WELD_WORDS) \
   X(group, ngrp_max * grp_words) X(counters, 8) X(fric, 2 * nfric) X(conx, ncx * CX_WORDS) X(penv_pos, npenv)
 // time-shared region `uni`: kinematics {kinA, kinB} -> dynamics {cinert, b6, d6, geom_xpos, cand} -> solver {H, d6, grad,
 // search, Ma, Mv} -> observation {cvel}.  d6 keeps one offset in both phases that use it.
@@ -171,7 +170,6 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     // models with tendon-coupled, friction-loaded joints (the Shadow hand) sit at many limits at once; the arm / legged
     // models keep the small table that lets 28 envs share one thread block
     h.ndr_max = (h.nten > 0 || h.nfric > 0) ? (want < DM_NDOFROW_MIN ? DM_NDOFROW_MIN : (want > 48 ? 48 : want)) : DM_NDOFROW_MIN;
-    h.ndr_max = (h.ndr_max + 3) & ~3;   // the DOF columns of the field-major row table are read four at a time
   }
   int nweld = 0;
   for (int e = 0; e < m.neq; e++) if (m.eq_type[e] == B200_EQ_WELD) nweld++;

@@ -15,7 +15,6 @@
 #ifdef __CUDACC__
 // internal linkage: b200sim.cu and b200sim_wide.cu compile these sources with different dof-mask widths
 #define HD static __device__ __forceinline__
-#define HD_INLINE __device__ __forceinline__
 #define HDN static __device__ __noinline__
 #define STAGE static __device__ __noinline__  // pipeline stages are real calls: keeps the kernel inside the instruction caches
 #define ASSUME_SHARED_PTR(p) __builtin_assume(__isShared(p))
@@ -33,7 +32,6 @@
 #endif
 #else
 #define HD static inline
-#define HD_INLINE inline
 #define HDN static
 #define STAGE static
 #define ASSUME_SHARED(c) do { } while (0)
@@ -75,8 +73,6 @@ enum { TM_KIN = 0, TM_COM_M, TM_COLL, TM_CONSTR, TM_SMOOTH, TM_NBEGIN, TM_NCHECK
 #define SF(name) (c.s + c.h->s_##name)
 #define SI(name) ((int*)(c.s + c.h->s_##name))
 #define LANES(i, n) for (int i = c.lane; i < (n); i += WARP_W)
-#define DROW(i) DRow{SF(dofrow) + (i), c.h->ndr_max}
-#define DROWI(i) DRowI{SI(dofrow) + (i), c.h->ndr_max}
 
 // ---------------------------------------------------------------------------------------------------------------
 // warp helpers
@@ -146,15 +142,6 @@ HD dmask_t grp_sign(const float* gr) { return ((const uint32_t*)gr)[G_SIGN]; }
 HD void grp_set_masks(int* gi, dmask_t mask, dmask_t sign) { ((uint32_t*)gi)[G_MASK] = mask; ((uint32_t*)gi)[G_SIGN] = sign; }
 #endif
 #define DBIT(m, j) ((int)(((m) >> (j)) & 1))
-// limit rows are stored field-major (all DOF entries, then all COEF entries, ...): the per-dof scans of pass_F / build_H
-// read the DOF / DOF2 columns contiguously.  dr[DR_x] / di[DR_x] keep their row-record syntax through these views.
-#ifdef __CUDACC__
-typedef int4 I4;   // 128-bit shared-memory loads of four consecutive DOF entries
-#else
-struct I4 { int x, y, z, w; };
-#endif
-struct DRow { float* b; int s; HD_INLINE float& operator[](int f) const { return b[f * s]; } };
-struct DRowI { int* b; int s; HD_INLINE int& operator[](int f) const { return b[f * s]; } };
 
 // ---------------------------------------------------------------------------------------------------------------
 // small math
@@ -1308,8 +1295,8 @@ STAGE void make_constraint(const Ctx c) {
     for (int k = 0; k < nrow; k++) {
       int id = basec + slot + k;
       if (id >= h->ndr_max) break;
-      const DRow dr = DROW(id);
-      const DRowI di = DROWI(id);
+      float* dr = SF(dofrow) + id * DR_WORDS;
+      int* di = (int*)dr;
       int d = MI(jnt_dofadr)[j];
       float margin = MF(jnt_margin)[j];
       float solimp[5] = {GF(jnt_solimp)[5 * j], GF(jnt_solimp)[5 * j + 1], GF(jnt_solimp)[5 * j + 2], GF(jnt_solimp)[5 * j + 3], GF(jnt_solimp)[5 * j + 4]};
@@ -1342,8 +1329,8 @@ STAGE void make_constraint(const Ctx c) {
     for (int k = 0; k < nrow; k++) {
       int id = basec + slot + k;
       if (id >= h->ndr_max) break;
-      const DRow dr = DROW(id);
-      const DRowI di = DROWI(id);
+      float* dr = SF(dofrow) + id * DR_WORDS;
+      int* di = (int*)dr;
       float margin = MF(ten_margin)[t];
       float solimp[5] = {GF(ten_solimp)[5 * t], GF(ten_solimp)[5 * t + 1], GF(ten_solimp)[5 * t + 2], GF(ten_solimp)[5 * t + 3], GF(ten_solimp)[5 * t + 4]};
       float solref[2] = {GF(ten_solref)[2 * t], GF(ten_solref)[2 * t + 1]};
@@ -1396,8 +1383,8 @@ STAGE void rows_from_vec(const Ctx c, const float* vec) {
     wr[W_JV + k] = dot6(wr + W_W + 6 * k, dV);
   }
   LANES(i, cnt[CNT_NDR]) {
-    const DRow dr = DROW(i);
-    const DRowI di = DROWI(i);
+    float* dr = SF(dofrow) + i * DR_WORDS;
+    const int* di = (const int*)dr;
     float val = dr[DR_COEF] * vec[di[DR_DOF]];
     if (di[DR_DOF2] >= 0) val += dr[DR_COEF2] * vec[di[DR_DOF2]];
     dr[DR_JV] = val;
@@ -1453,8 +1440,8 @@ STAGE void rows_begin(const Ctx c, const float* qvel, const float* qacc) {
     wr[W_JAR + k] = u;
   }
   LANES(i, cnt[CNT_NDR]) {
-    const DRow dr = DROW(i);
-    const DRowI di = DROWI(i);
+    float* dr = SF(dofrow) + i * DR_WORDS;
+    const int* di = (const int*)dr;
     float v1 = dr[DR_COEF] * qvel[di[DR_DOF]], v2 = dr[DR_COEF] * qacc[di[DR_DOF]];
     if (di[DR_DOF2] >= 0) { v1 += dr[DR_COEF2] * qvel[di[DR_DOF2]]; v2 += dr[DR_COEF2] * qacc[di[DR_DOF2]]; }
     float u = dr[DR_JAR];
@@ -1534,23 +1521,13 @@ STAGE void pass_F(const Ctx c, float* out) {
       float d = dot6(cd, gr + G_V);
       q += DBIT(grp_sign(gr), j) ? d : -d;
     }
-    {
-      // scan the DOF / DOF2 columns four rows at a time; only rows that touch dof j are opened (same accumulation order)
-      const I4* D1 = (const I4*)(SI(dofrow) + DR_DOF * h->ndr_max);
-      const I4* D2 = (const I4*)(SI(dofrow) + DR_DOF2 * h->ndr_max);
-#define B200_ROW(k_, a_, b_)                                                                          \
-      if (i4 + (k_) < ndr && ((a_) == j || (b_) == j)) {                                              \
-        const DRow dr = DROW(i4 + (k_));                                                              \
-        float x = dr[DR_JAR];                                                                         \
-        float f = x < 0 ? -dr[DR_D] * x : 0.f;                                                        \
-        if ((a_) == j) q += dr[DR_COEF] * f;                                                          \
-        if ((b_) == j) q += dr[DR_COEF2] * f;                                                         \
-      }
-      for (int i4 = 0; i4 < ndr; i4 += 4) {
-        const I4 a = D1[i4 >> 2], b = D2[i4 >> 2];
-        B200_ROW(0, a.x, b.x) B200_ROW(1, a.y, b.y) B200_ROW(2, a.z, b.z) B200_ROW(3, a.w, b.w)
-      }
-#undef B200_ROW
+    for (int i = 0; i < ndr; i++) {
+      const float* dr = SF(dofrow) + i * DR_WORDS;
+      const int* di = (const int*)dr;
+      float x = dr[DR_JAR];
+      float f = x < 0 ? -dr[DR_D] * x : 0.f;
+      if (di[DR_DOF] == j) q += dr[DR_COEF] * f;
+      if (di[DR_DOF2] == j) q += dr[DR_COEF2] * f;
     }
     if (HF && h->nfric) {
       // Huber-type friction row: force -D x clamped to +-frictionloss
@@ -1664,30 +1641,22 @@ STAGE void build_H(const Ctx c) {
     // which the lane of the larger dof owns
     LANES(j, nv) {
       float diag = 0.f;
-      const I4* D1 = (const I4*)(SI(dofrow) + DR_DOF * h->ndr_max);
-      const I4* D2 = (const I4*)(SI(dofrow) + DR_DOF2 * h->ndr_max);
-#define B200_ROW(k_, a_, b_)                                                                          \
-      if (i4 + (k_) < ndr && ((a_) == j || (b_) == j)) {                                              \
-        const DRow dr = DROW(i4 + (k_));                                                              \
-        if (dr[DR_JAR] < 0) {                                                                         \
-          const int d1 = (a_), d2 = (b_);                                                             \
-          if (d1 == j) diag += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF];                                  \
-          if (d2 == j) diag += dr[DR_D] * dr[DR_COEF2] * dr[DR_COEF2];                                \
-          if (d2 >= 0 && (d1 > d2 ? d1 : d2) == j) H[j * (j + 1) / 2 + (d1 > d2 ? d2 : d1)] += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF2]; \
-        }                                                                                             \
+      for (int i = 0; i < ndr; i++) {
+        const float* dr = SF(dofrow) + i * DR_WORDS;
+        const int* di = (const int*)dr;
+        if (!(dr[DR_JAR] < 0)) continue;
+        int d1 = di[DR_DOF], d2 = di[DR_DOF2];
+        if (d1 == j) diag += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF];
+        if (d2 == j) diag += dr[DR_D] * dr[DR_COEF2] * dr[DR_COEF2];
+        if (d2 >= 0 && (d1 > d2 ? d1 : d2) == j) H[j * (j + 1) / 2 + (d1 > d2 ? d2 : d1)] += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF2];
       }
-      for (int i4 = 0; i4 < ndr; i4 += 4) {
-        const I4 a = D1[i4 >> 2], b = D2[i4 >> 2];
-        B200_ROW(0, a.x, b.x) B200_ROW(1, a.y, b.y) B200_ROW(2, a.z, b.z) B200_ROW(3, a.w, b.w)
-      }
-#undef B200_ROW
       H[j * (j + 1) / 2 + j] += diag;
     }
   } else if (c.lane == 0) {
     // few limit rows (arm / legged models): one lane walks them
     for (int i = 0; i < ndr; i++) {
-      const DRow dr = DROW(i);
-      const DRowI di = DROWI(i);
+      const float* dr = SF(dofrow) + i * DR_WORDS;
+      const int* di = (const int*)dr;
       if (!(dr[DR_JAR] < 0)) continue;
       int d1 = di[DR_DOF], d2 = di[DR_DOF2];
       H[pidx(d1, d1)] += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF];
@@ -1929,7 +1898,7 @@ STAGE int ls_edges(const Ctx c) {
   }
   float* R = W + 3 * nweld6;
   LANES(i, ndr) {
-    const DRow dr = DROW(i);
+    const float* dr = SF(dofrow) + i * DR_WORDS;
     R[3 * i] = dr[DR_JAR]; R[3 * i + 1] = dr[DR_JV]; R[3 * i + 2] = dr[DR_D];
   }
   SYNC();
@@ -2060,7 +2029,7 @@ STAGE int newton_move(const Ctx c, float* improvement) {
   LANES(i, nv) { a[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
   LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 4; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
   LANES(i, cnt[CNT_NWELD] * 6) { float* wr = SF(weld) + (i / 6) * WELD_WORDS; wr[W_JAR + i % 6] += alpha * wr[W_JV + i % 6]; }
-  LANES(i, cnt[CNT_NDR]) { const DRow dr = DROW(i); dr[DR_JAR] += alpha * dr[DR_JV]; }
+  LANES(i, cnt[CNT_NDR]) { float* dr = SF(dofrow) + i * DR_WORDS; dr[DR_JAR] += alpha * dr[DR_JV]; }
   if (HF) LANES(d, h->nfric) SF(fric)[d] += alpha * SF(fric)[h->nfric + d];
   SYNC();
   if (c.lane == 0) cnt[CNT_ITERS] += 1;
