@@ -1,5 +1,7 @@
-# one GPU-box round: A/B variants, parity tests, bench lines
+# one GPU-box round: the official bench lines and the profile recipe of the final build (see profiles/README.md)
 mkdir -p gpurun_out
-bash tests/variant_time.sh both 2>&1 | tee gpurun_out/variants11.log | tail -10
-(timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -40) > gpurun_out/pytest_gpu11.log; tail -3 gpurun_out/pytest_gpu11.log
-for w in hand_block_touch adroit_hammer adroit_relocate adroit_pen hand_egg fetch_slide; do timeout 200 python bench.py --workload $w --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/b11_$w.json 2> gpurun_out/b11_$w.err; cut -c1-120 gpurun_out/b11_$w.json; done
+timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_r1j_n1.json 2> gpurun_out/bench_r1j_n1.err; cut -c1-200 gpurun_out/bench_r1j_n1.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1j_ref.json 2> gpurun_out/bench_r1j_ref.err; cut -c1-200 gpurun_out/bench_r1j_ref.json
+bash tests/run_profile.sh r1j 2>&1 | tail -16
+timeout 300 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_r1j_n1b.json 2> gpurun_out/bench_r1j_n1b.err; cut -c1-200 gpurun_out/bench_r1j_n1b.json
+du -sh gpurun_out
