@@ -23,9 +23,36 @@ def env_seeds(seed0: int, rank: int, world_size: int, num_envs_total: int):
 def gather_step_outputs(obs: dict, reward: torch.Tensor, dst: int = 0):
     """all_gather `observation | achieved_goal | desired_goal | reward` rows (equal local sizes) and return the
     [world*n, dim] tensor on every rank (rank `dst` is the consumer)."""
-    packed = torch.cat([obs["observation"], obs["achieved_goal"], obs["desired_goal"], reward[:, None]], dim=1).contiguous()
+    if isinstance(obs, dict):
+        packed = torch.cat([obs["observation"], obs["achieved_goal"], obs["desired_goal"], reward[:, None]], dim=1).contiguous()
+    else:   # flat observation (Adroit)
+        packed = torch.cat([obs, reward[:, None]], dim=1).contiguous()
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return packed
     out = torch.empty((dist.get_world_size() * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed)
+    return out
+
+
+def mixed_batch_assignment(env_ids, world_size: int):
+    """BASELINE config 5 style mixed batches (heterogeneous models): whole ranks per env id, split as evenly
+    as the world size allows (e.g. 4 GPUs, 2 ids -> ranks 0, 1 run the first id and ranks 2, 3 the second).  Returns the
+    env id of every rank."""
+    k = len(env_ids)
+    if world_size < k:
+        raise ValueError("a mixed batch needs at least one rank per env id")
+    return [env_ids[min(r * k // world_size, k - 1)] for r in range(world_size)]
+
+
+def gather_mixed_outputs(obs: torch.Tensor, reward: torch.Tensor, width: int):
+    """all_gather of flat observations whose width differs between ranks (one model per rank): rows are zero-padded to
+    `width` (the widest observation of the batch) and the reward is appended; [world * n, width + 1] on every rank."""
+    n, d = obs.shape
+    packed = torch.zeros((n, width + 1), dtype=obs.dtype, device=obs.device)
+    packed[:, :d] = obs
+    packed[:, width] = reward
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return packed
+    out = torch.empty((dist.get_world_size() * n, width + 1), dtype=obs.dtype, device=obs.device)
     dist.all_gather_into_tensor(out, packed)
     return out

@@ -58,3 +58,49 @@ def test_two_rank_shards_equal_single_process():
         o, r, *_ = env.step(tape[t])
     single = torch.cat([o["observation"], o["achieved_goal"], o["desired_goal"], r[:, None]], 1).numpy()
     assert gathered.shape == single.shape and np.array_equal(gathered, single)
+
+
+def _run_mixed(rank, world, port, n_local, steps, out_q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import gymnasium_robotics_b200 as pkg
+    from gymnasium_robotics_b200.adroit import ADROIT_REF_POINT
+    from gymnasium_robotics_b200.sharding import gather_mixed_outputs, mixed_batch_assignment
+    from tests.hostsim_backend import HostSimBackend
+
+    class AdroitHostBackend(HostSimBackend):
+        REF = ADROIT_REF_POINT
+
+    env_id = mixed_batch_assignment(["AdroitHandHammer-v2", "AdroitHandRelocate-v2"], world)[rank]
+    env = pkg.make_vec(env_id, num_envs=n_local, backend_factory=AdroitHostBackend, rng_mode="numpy")
+    env.reset(seed=[7 + rank * n_local + i for i in range(n_local)])
+    rng = np.random.default_rng(rank)
+    for _ in range(steps):
+        o, r, *_ = env.step(rng.uniform(-1, 1, (n_local, env.single_action_space.shape[0])).astype(np.float32))
+    g = gather_mixed_outputs(o, r, width=46)
+    if rank == 0:
+        out_q.put((g.numpy(), o.numpy(), r.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_mixed_batch_whole_ranks_per_model():
+    """BASELINE config 5 shape: heterogeneous models on one node, whole ranks per model (here Hammer on rank 0 and
+    Relocate on rank 1 -- Kitchen is not on the CUDA path yet), observations gathered zero-padded to the widest one."""
+    from gymnasium_robotics_b200.sharding import mixed_batch_assignment
+
+    assert mixed_batch_assignment(["a", "b"], 4) == ["a", "a", "b", "b"] and mixed_batch_assignment(["a", "b"], 3) == ["a", "a", "b"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_run_mixed, args=(r, 2, port, 2, 2, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    g, o0, r0 = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert g.shape == (4, 47)
+    assert np.array_equal(g[:2, :46], o0) and np.array_equal(g[:2, 46], r0)      # rank 0: hammer, 46 wide
+    assert np.all(g[2:, 39:46] == 0) and np.isfinite(g).all() and np.abs(g[2:, :39]).max() > 0   # rank 1: relocate, 39 wide, padded
