@@ -361,7 +361,7 @@ class FetchVectorEnv:
         # TimeLimit: the device counters are only compared (and the host only synchronises) once the bound says an env may be due
         may_truncate = self.max_episode_steps is not None and self._elapsed_ub >= self.max_episode_steps
         # in phase (all envs reset together and none terminates): the bound IS every env's step count -- no device compare
-        truncated = (self._const_true if in_phase else (self._elapsed >= self.max_episode_steps)) if may_truncate \
+        truncated = (self._const_true.clone() if in_phase else (self._elapsed >= self.max_episode_steps)) if may_truncate \
             else self._const_false
         done = truncated | terminated
         if may_truncate:
