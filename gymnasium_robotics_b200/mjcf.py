@@ -167,6 +167,23 @@ def geom_volume_inertia(gtype, size):
     raise ValueError(f"no inertia rule for geom type {gtype}")
 
 
+def mesh_volume_inertia(tris):
+    """Volume, centre of mass and unit-density inertia tensor (about the centre of mass, mesh frame) of a closed triangle
+    mesh [n, 3, 3] by signed tetrahedra against the origin (the exact integrals of a polyhedron)."""
+    a, b, c = tris[:, 0], tris[:, 1], tris[:, 2]
+    v6 = np.einsum("ij,ij->i", a, np.cross(b, c))          # 6 x signed volume of (0, a, b, c)
+    vol = v6.sum() / 6.0
+    if vol < 0:                                             # inward-facing winding
+        v6, vol = -v6, -vol
+    com = (v6[:, None] * (a + b + c)).sum(0) / (24.0 * vol)
+    s = a + b + c
+    S = (np.einsum("i,ij,ik->jk", v6, s, s) + np.einsum("i,ij,ik->jk", v6, a, a) + np.einsum("i,ij,ik->jk", v6, b, b) +
+         np.einsum("i,ij,ik->jk", v6, c, c)) / 120.0       # integral of x x^T over the volume
+    I0 = np.trace(S) * np.eye(3) - S                        # inertia about the origin
+    Ic = I0 - vol * (com @ com * np.eye(3) - np.outer(com, com))
+    return vol, com, Ic
+
+
 def combine_inertias(parts):
     """parts: list of (mass, com[3], R[3,3] (frame->parent), diag[3]).  Returns mass, com, quat, diag."""
     mtot = sum(p[0] for p in parts)
@@ -725,7 +742,22 @@ def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None) ->
         elif b > 0:
             parts = []
             for g in F.geoms:
-                if g["body"] != b or g["type"] in (GEOM_PLANE, GEOM_MESH, GEOM_HFIELD):
+                if g["body"] != b or g["type"] in (GEOM_PLANE, GEOM_HFIELD):
+                    continue
+                if g["type"] == GEOM_MESH:
+                    # mass properties of the triangle mesh itself (the Franka links of the kitchen model carry `mass=` on
+                    # their collision meshes and no <inertial>); visual meshes with mass="0" contribute nothing
+                    if g["mass"] is not None and g["mass"] <= 0:
+                        continue
+                    vol, cm, Ic = mesh_volume_inertia(F.meshes[g["mesh"]].reshape(-1, 3, 3))
+                    if vol < MINVAL:
+                        continue
+                    m = g["mass"] if g["mass"] is not None else g["density"] * vol
+                    w, V = np.linalg.eigh(Ic)
+                    if np.linalg.det(V) < 0:
+                        V[:, 2] = -V[:, 2]
+                    Rg = q2mat(g["quat"])
+                    parts.append((m, g["pos"] + Rg @ cm, Rg @ V, w * (m / vol)))
                     continue
                 vol, Iu = geom_volume_inertia(g["type"], g["size"])
                 m = g["mass"] if g["mass"] is not None else g["density"] * vol

@@ -27,6 +27,9 @@ MODEL_SOURCES = {
     "adroit_relocate": "adroit_hand/adroit_relocate.xml",
     "adroit_pen": "adroit_hand/adroit_pen.xml",
     "adroit_door": "adroit_hand/adroit_door.xml",
+    # Franka Kitchen: compiles (mesh-derived link inertias, 5 joint equalities, condim-6 pairs, 3 708 candidate pairs) and runs
+    # in the oracle; the CUDA builder refuses it loudly
+    "franka_kitchen": "kitchen_franka/kitchen_assets/kitchen_env_model.xml",
     "hand_egg": "hand/manipulate_egg.xml",
     "hand_egg_touch": "hand/manipulate_egg_touch_sensors.xml",
     "hand_pen": "hand/manipulate_pen.xml",
