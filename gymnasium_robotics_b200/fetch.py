@@ -373,6 +373,9 @@ class FetchVectorEnv:
                     fo = self._obs_dict(out)
                     info["final_obs"] = {k: v.clone() for k, v in fo.items()} if isinstance(fo, dict) else fo.clone()
                     info["_final_obs"] = done.clone()
+                    # gymnasium's SAME_STEP convention: the info of the finished episodes next to their last observation
+                    info["final_info"] = {"is_success": success.clone(), "_is_success": done.clone()}
+                    info["_final_info"] = done.clone()
                     self._reset_all = in_phase
                     self._reset_envs(done, out)
                     self._reset_all = False

@@ -143,6 +143,7 @@ def test_same_step_autoreset_reports_final_obs():
     env.step(a)
     o, r, te, tr, info = env.step(a)
     assert bool(tr.all()) and "final_obs" in info and bool(info["_final_obs"].all())
+    assert bool(info["_final_info"].all()) and info["final_info"]["is_success"].shape == (2,)
     assert not torch.allclose(info["final_obs"]["observation"], o["observation"])
     assert torch.allclose(o["observation"][:, :3], env.initial_gripper_xpos.expand(2, 3), atol=1e-4)
 
