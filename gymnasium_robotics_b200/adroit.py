@@ -185,6 +185,9 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         obs, reward, terminated, truncated, info = super().step(actions)
         info["success"] = info.pop("is_success") > 0.5
         info["_success"] = info.pop("_is_success")
+        if "final_info" in info:
+            fi = info["final_info"]
+            info["final_info"] = {"success": fi["is_success"] > 0.5, "_success": fi["_is_success"]}
         return obs, reward, terminated, truncated, info
 
     def compute_reward(self, *a, **k):
