@@ -172,7 +172,13 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     int want = nlim + h.nten;   // at most one side of every limit can be active at a time
     // models with tendon-coupled, friction-loaded joints (the Shadow hand) sit at many limits at once; the arm / legged
     // models keep the small table that lets 28 envs share one thread block
+#ifdef B200_KITCHEN
+    for (int e = 0; e < m.neq; e++) if (m.eq_type[e] == B200_EQ_JOINT) want++;   // one (always active) row per joint equality
+    if (want > DM_NDOFROW_MIN) h.nten = h.nten > 0 ? h.nten : 0;
+    h.ndr_max = want < DM_NDOFROW_MIN ? DM_NDOFROW_MIN : (want > 48 ? 48 : want);
+#else
     h.ndr_max = (h.nten > 0 || h.nfric > 0) ? (want < DM_NDOFROW_MIN ? DM_NDOFROW_MIN : (want > 48 ? 48 : want)) : DM_NDOFROW_MIN;
+#endif
   }
   int nweld = 0;
   for (int e = 0; e < m.neq; e++) if (m.eq_type[e] == B200_EQ_WELD) nweld++;
@@ -364,7 +370,13 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     for (int k = 0; k < 2; k++) { F(h.o_act_ctrlrange, 2 * a + k, m.act_ctrlrange[2 * a + k]); F(h.o_act_forcerange, 2 * a + k, m.act_forcerange[2 * a + k]); }
   }
   for (int e = 0; e < neq; e++) {
+#ifdef B200_KITCHEN
+    // work in progress (DESIGN.md section 7, step i): joint equalities become two-sided dof rows; only the emulation build
+    // of the Kitchen bring-up compiles this, the product library still refuses the model
+    if (m.eq_type[e] != B200_EQ_WELD && m.eq_type[e] != B200_EQ_JOINT) { err = "only weld and joint equalities are supported"; return -1; }
+#else
     if (m.eq_type[e] != B200_EQ_WELD) { err = "only weld equalities are supported by the CUDA path yet"; return -1; }
+#endif
     I(h.o_eq_type, e, m.eq_type[e]); I(h.o_eq_obj1, e, m.eq_obj1[e]); I(h.o_eq_obj2, e, m.eq_obj2[e]); I(h.o_eq_active, e, m.eq_active[e]);
     const double* data = eq_data_override ? eq_data_override + 11 * e : m.eq_data + 11 * e;
     for (int k = 0; k < 11; k++) F(h.o_eq_data, 11 * e + k, data[k]);

@@ -1345,6 +1345,36 @@ STAGE void make_constraint(const Ctx c) {
     if (c.lane == 0) { int nn = basec + total; if (nn > h->ndr_max) { nn = h->ndr_max; cnt[CNT_OVERFLOW] |= 8; } cnt[CNT_NDR] = nn; }
     SYNC();
   }
+#ifdef B200_KITCHEN
+  // joint equalities q1 - q1_0 = poly(q2 - q2_0) (oven knobs <-> burners of the kitchen model) as two-sided dof rows:
+  // coefficients (1, -poly'), D < 0 marks the row as two-sided for the solver stages  [bring-up build only]
+  if (c.lane == 0) {
+    for (int e = 0; e < h->neq; e++) {
+      if (!MI(eq_active)[e] || MI(eq_type)[e] != B200_EQ_JOINT) continue;
+      int id = cnt[CNT_NDR];
+      if (id >= h->ndr_max) { cnt[CNT_OVERFLOW] |= 8; break; }
+      const float* data = MF(eq_data) + 11 * e;
+      int j1 = MI(eq_obj1)[e], j2 = MI(eq_obj2)[e];
+      float pos = SF(qpos)[MI(jnt_qposadr)[j1]] - MF(jnt_qpos0)[j1], deriv = 0.f;
+      if (j2 >= 0) {
+        float dif = SF(qpos)[MI(jnt_qposadr)[j2]] - MF(jnt_qpos0)[j2];
+        pos -= data[0] + dif * (data[1] + dif * (data[2] + dif * (data[3] + dif * data[4])));
+        deriv = data[1] + dif * (2 * data[2] + dif * (3 * data[3] + dif * 4 * data[4]));
+      } else pos -= data[0];
+      float* dr = SF(dofrow) + id * DR_WORDS;
+      int* di = (int*)dr;
+      float imp = impedance(MF(eq_solimp) + 5 * e, pos, 0.f);
+      float K, Bc;
+      ref_kb(c, MF(eq_solref) + 2 * e, MF(eq_solimp)[5 * e + 1], &K, &Bc);
+      float R = fmaxf((1 - imp) / imp * MF(eq_invweight)[2 * e], B200_MINVAL);
+      di[DR_DOF] = MI(jnt_dofadr)[j1]; dr[DR_COEF] = 1.f;
+      di[DR_DOF2] = j2 >= 0 ? MI(jnt_dofadr)[j2] : -1; dr[DR_COEF2] = -deriv;
+      dr[DR_D] = -1.0f / R; dr[DR_JAR] = K * imp * pos; dr[DR_JV] = Bc;
+      cnt[CNT_NDR] = id + 1;
+    }
+  }
+  SYNC();
+#endif
   // dof frictionloss rows: position residual 0, so the row value starts at 0
   if (HF) { LANES(d, h->nfric) SF(fric)[d] = 0.f; SYNC(); }
 }
@@ -1525,7 +1555,11 @@ STAGE void pass_F(const Ctx c, float* out) {
       const float* dr = SF(dofrow) + i * DR_WORDS;
       const int* di = (const int*)dr;
       float x = dr[DR_JAR];
+#ifdef B200_KITCHEN
+      float f = (dr[DR_D] < 0 || x < 0) ? -fabsf(dr[DR_D]) * x : 0.f;   // D < 0: two-sided (equality) row
+#else
       float f = x < 0 ? -dr[DR_D] * x : 0.f;
+#endif
       if (di[DR_DOF] == j) q += dr[DR_COEF] * f;
       if (di[DR_DOF2] == j) q += dr[DR_COEF2] * f;
     }
@@ -1644,11 +1678,17 @@ STAGE void build_H(const Ctx c) {
       for (int i = 0; i < ndr; i++) {
         const float* dr = SF(dofrow) + i * DR_WORDS;
         const int* di = (const int*)dr;
+#ifdef B200_KITCHEN
+        if (!(dr[DR_JAR] < 0 || dr[DR_D] < 0)) continue;
+        const float Dr = fabsf(dr[DR_D]);
+#else
         if (!(dr[DR_JAR] < 0)) continue;
+        const float Dr = dr[DR_D];
+#endif
         int d1 = di[DR_DOF], d2 = di[DR_DOF2];
-        if (d1 == j) diag += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF];
-        if (d2 == j) diag += dr[DR_D] * dr[DR_COEF2] * dr[DR_COEF2];
-        if (d2 >= 0 && (d1 > d2 ? d1 : d2) == j) H[j * (j + 1) / 2 + (d1 > d2 ? d2 : d1)] += dr[DR_D] * dr[DR_COEF] * dr[DR_COEF2];
+        if (d1 == j) diag += Dr * dr[DR_COEF] * dr[DR_COEF];
+        if (d2 == j) diag += Dr * dr[DR_COEF2] * dr[DR_COEF2];
+        if (d2 >= 0 && (d1 > d2 ? d1 : d2) == j) H[j * (j + 1) / 2 + (d1 > d2 ? d2 : d1)] += Dr * dr[DR_COEF] * dr[DR_COEF2];
       }
       H[j * (j + 1) / 2 + j] += diag;
     }

@@ -27,13 +27,14 @@ class FetchTaskC(ctypes.Structure):
 
 
 def build(force=False, wide=False):
-    """wide = the 64-bit dof-mask build (models with more than 32 dofs, -DB200_WIDE as in csrc/b200sim_wide.cu)"""
-    out = os.path.join(_HERE, "libhostsim_wide.so" if wide else "libhostsim.so")
+    """wide = True: the 64-bit dof-mask build (models with more than 32 dofs, -DB200_WIDE as in csrc/b200sim_wide.cu);
+    wide = "kitchen": the bring-up build of the Franka-Kitchen kernel features (-DB200_KITCHEN)"""
+    out = os.path.join(_HERE, {True: "libhostsim_wide.so", "kitchen": "libhostsim_kitchen.so"}.get(wide, "libhostsim.so"))
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_ROOT, "gymnasium_robotics_b200", "csrc", f)
                                                    for f in ("sim_core.cuh", "dmodel.h", "fetch_task.cuh")] + \
            [os.path.join(_ROOT, "include", "b200sim_model.h")]
     if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function"] + (["-DB200_WIDE"] if wide else []) +
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function"] + (["-DB200_KITCHEN"] if wide == "kitchen" else (["-DB200_WIDE"] if wide else [])) +
                               ["-o", out, srcs[0]])
     return out
 
@@ -61,10 +62,10 @@ def lib(wide=False):
 class HostSim:
     """fp32 single-env emulation of the kernel; arrays are views into the emulated shared-memory scratch."""
 
-    def __init__(self, model, eq_data=None, ref=(1.0, 0.75, 0.4), penv_body=-1, ngrp_cap=0):
+    def __init__(self, model, eq_data=None, ref=(1.0, 0.75, 0.4), penv_body=-1, ngrp_cap=0, flavor=None):
         self.model = model
         blob = model.to_blob()
-        L = lib(wide=model.nv > 32)
+        L = lib(wide=flavor if flavor is not None else model.nv > 32)
         self._L = L
         eq = np.ascontiguousarray(eq_data, dtype=np.float64) if eq_data is not None else None
         r = np.asarray(ref, dtype=np.float32)
