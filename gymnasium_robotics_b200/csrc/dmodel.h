@@ -62,7 +62,15 @@
 // contact record (words): up to 4 base rows (normal, two tangents, torsion).  W = spatial vectors of the three
 // translational rows about `ref`; the torsional row is (W0[3:6], 0).  During row set-up JV[0] holds B of the reference
 // acceleration and U holds K*imp*r (normal row) / 0; afterwards U = J a - aref and JV = J search.
+#ifdef B200_KITCHEN
+// bring-up build (DESIGN.md section 7, step ii): condim 6 = two rolling base rows next to the torsional one; the rotational rows
+// need no extra vectors (row k >= 3 is (W[k - 3][3:6], 0)), only a third friction coefficient and six U / JV slots
+enum { C_W = 0 /*18*/, C_MU = 18 /*slide, torsion, roll*/, C_D = 21, C_U = 22 /*6*/, C_JV = 28 /*6*/, C_DIMGRP = 34, CON_WORDS = 36 };
+#define C_NB 6
+#else
 enum { C_W = 0 /*18*/, C_MU = 18 /*slide, torsion*/, C_D = 20, C_U = 21 /*4*/, C_JV = 25 /*4*/, C_DIMGRP = 29, CON_WORDS = 30 };
+#define C_NB 4
+#endif
 // dof row (joint limit or fixed-tendon limit over <= 2 dofs): JAR holds K*imp*r and JV holds B during set-up.
 // Dof frictionloss rows are always present, one per dof, with constant D and B: they live in the per-dof arrays
 // `fric` (FR_JAR, FR_JV) instead of generic rows.
@@ -345,7 +353,11 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     if (c1 || c2) h.any_convex_pair = 1;   // served by the general convex collider (kernel builds with CX)
 
     if (!ok) { err = "collision pair type not supported by the CUDA path yet"; return -1; }
+#ifdef B200_KITCHEN
+    if (m.pair_condim[sp] != 1 && m.pair_condim[sp] != 3 && m.pair_condim[sp] != 4 && m.pair_condim[sp] != 6) { err = "condim must be 1, 3, 4 or 6"; return -1; }
+#else
     if (m.pair_condim[sp] != 1 && m.pair_condim[sp] != 3 && m.pair_condim[sp] != 4) { err = "condim must be 1, 3 or 4 on the CUDA path"; return -1; }
+#endif
     F(h.o_pair_friction, 3 * p + 0, m.pair_friction[5 * sp + 0]); F(h.o_pair_friction, 3 * p + 1, m.pair_friction[5 * sp + 2]);
     F(h.o_pair_friction, 3 * p + 2, m.pair_friction[5 * sp + 3]);
     F(h.o_pair_margin, p, m.pair_margin[sp]); F(h.o_pair_gap, p, m.pair_gap[sp]);

@@ -282,7 +282,7 @@ HD void touch_observe(const Ctx& c, const FetchTask& t, float* out, int nmax = 1
       int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
       int b1 = MI(geom_body)[g1], b2 = g2 < 0 ? 0 : MI(geom_body)[g2];
       if (b1 != body && b2 != body) continue;
-      float F[4];
+      float F[C_NB];
       contact_base_forces(cr, con_dim(cr), F);
       if (!(F[0] > 0)) continue;
       if (!posed) { site_pose(c, site, sp, sq); posed = true; }

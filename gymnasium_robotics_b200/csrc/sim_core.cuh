@@ -1180,6 +1180,9 @@ STAGE void collision(const Ctx c) {
     int dim = GI(pair_condim)[p];
     float mu0 = fr[0];
     cr[C_MU] = mu0; cr[C_MU + 1] = fr[1];
+#ifdef B200_KITCHEN
+    cr[C_MU + 2] = fr[2];   // rolling friction (condim 6)
+#endif
     float incl = MF(pair_margin)[p] - GF(pair_gap)[p];
     float solimp[5] = {GF(pair_solimp)[5 * p], GF(pair_solimp)[5 * p + 1], GF(pair_solimp)[5 * p + 2], GF(pair_solimp)[5 * p + 3], GF(pair_solimp)[5 * p + 4]};
     float solref[2] = {GF(pair_solref)[2 * p], GF(pair_solref)[2 * p + 1]};
@@ -1196,6 +1199,9 @@ STAGE void collision(const Ctx c) {
     }
     cr[C_D] = 1.0f / R;
     cr[C_U] = K * imp * (dist - incl); cr[C_U + 1] = 0; cr[C_U + 2] = 0; cr[C_U + 3] = 0;
+#ifdef B200_KITCHEN
+    cr[C_U + 4] = 0; cr[C_U + 5] = 0;
+#endif
     cr[C_JV] = Bc;
     ((int*)cr)[C_DIMGRP] = dim | gid8;
     if (HF && h->nsensor > 0) {
@@ -1210,11 +1216,20 @@ STAGE void collision(const Ctx c) {
 // ---------------------------------------------------------------------------------------------------------------
 // 6. constraint rows
 // spatial vector of contact base row k (about ref): k<3 translational rows are cached in C_W, k==3 is the torsional row
+#ifdef B200_KITCHEN
+// base row k: 0..2 translational (cached), 3 torsional = (n, 0), 4 / 5 rolling = (t1, 0) / (t2, 0)
+HD void con_w(const float* cr, int k, float* w) {
+  if (k < 3) { const float* s = cr + C_W + 6 * k; w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = s[3]; w[4] = s[4]; w[5] = s[5]; }
+  else { const float* s = cr + C_W + 6 * (k - 3) + 3; w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = w[4] = w[5] = 0; }
+}
+HD float con_mu(const float* cr, int k) { return k < 3 ? cr[C_MU] : (k == 3 ? cr[C_MU + 1] : cr[C_MU + 2]); }  // base row k >= 1
+#else
 HD void con_w(const float* cr, int k, float* w) {
   if (k < 3) { const float* s = cr + C_W + 6 * k; w[0] = s[0]; w[1] = s[1]; w[2] = s[2]; w[3] = s[3]; w[4] = s[4]; w[5] = s[5]; }
   else { w[0] = cr[C_W + 3]; w[1] = cr[C_W + 4]; w[2] = cr[C_W + 5]; w[3] = w[4] = w[5] = 0; }
 }
 HD float con_mu(const float* cr, int k) { return k < 3 ? cr[C_MU] : cr[C_MU + 1]; }  // base row k >= 1
+#endif
 HD int con_dim(const float* cr) { return ((const int*)cr)[C_DIMGRP] & 0xff; }
 HD int con_grp(const float* cr) { return ((const int*)cr)[C_DIMGRP] >> 8; }
 
@@ -1494,7 +1509,7 @@ STAGE void rows_begin(const Ctx c, const float* qvel, const float* qacc) {
 // base-row generalized forces of a contact from its base-row values U (pyramid edges f = -D * min(0, u_n +- mu u_k))
 HD void contact_base_forces(const float* cr, int dim, float* F) {
   float D = cr[C_D], un = cr[C_U];
-  F[0] = F[1] = F[2] = F[3] = 0;
+  for (int k = 0; k < C_NB; k++) F[k] = 0;
   if (dim == 1) { F[0] = un < 0 ? -D * un : 0.f; return; }
   for (int k = 1; k < dim; k++) {
     float mu = con_mu(cr, k), uk = cr[C_U + k];
@@ -1516,9 +1531,12 @@ STAGE void pass_F(const Ctx c, float* out) {
   // base-row forces once per contact (parked in the JV slots, which are rewritten by the next J * search product)
   LANES(i, cnt[CNT_NCON]) {
     float* cr = SF(con) + i * CON_WORDS;
-    float F[4];
+    float F[C_NB];
     contact_base_forces(cr, con_dim(cr), F);
     cr[C_JV] = F[0]; cr[C_JV + 1] = F[1]; cr[C_JV + 2] = F[2]; cr[C_JV + 3] = F[3];
+#ifdef B200_KITCHEN
+    cr[C_JV + 4] = F[4]; cr[C_JV + 5] = F[5];
+#endif
   }
   SYNC();
   LANES(idx, ngrp * 6) {
@@ -1533,6 +1551,9 @@ STAGE void pass_F(const Ctx c, float* out) {
       acc += F[0] * cr[C_W + a];
       if (dim > 1) acc += F[1] * cr[C_W + 6 + a] + F[2] * cr[C_W + 12 + a];
       if (dim > 3 && a < 3) acc += F[3] * cr[C_W + 3 + a];
+#ifdef B200_KITCHEN
+      if (dim > 4 && a < 3) acc += F[4] * cr[C_W + 6 + 3 + a] + F[5] * cr[C_W + 12 + 3 + a];
+#endif
     }
     for (int i = 0; i < nweld; i++) {
       const float* wr = SF(weld) + i * WELD_WORDS;
@@ -1618,7 +1639,11 @@ STAGE void build_H(const Ctx c) {
           if (ap + am == 0.f) continue;
           float wkr, wks;
           if (k < 3) { wkr = cr[C_W + 6 * k + r]; wks = cr[C_W + 6 * k + s]; }
+#ifdef B200_KITCHEN
+          else { wkr = r < 3 ? cr[C_W + 6 * (k - 3) + 3 + r] : 0.f; wks = s < 3 ? cr[C_W + 6 * (k - 3) + 3 + s] : 0.f; }
+#else
           else { wkr = r < 3 ? cr[C_W + 3 + r] : 0.f; wks = s < 3 ? cr[C_W + 3 + s] : 0.f; }
+#endif
           Wnn += ap + am;
           float Wnk = mu * (ap - am), Wkk = mu * mu * (ap + am);
           acc += D * (Wnk * (wnr * wks + wkr * wns) + Wkk * wkr * wks);
@@ -2067,7 +2092,7 @@ STAGE int newton_move(const Ctx c, float* improvement) {
   TOC(TM_MV_LS);
   if (alpha == 0.f) return 1;
   LANES(i, nv) { a[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
-  LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < 4; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
+  LANES(i, cnt[CNT_NCON]) { float* cr = SF(con) + i * CON_WORDS; for (int k = 0; k < C_NB; k++) cr[C_U + k] += alpha * cr[C_JV + k]; }
   LANES(i, cnt[CNT_NWELD] * 6) { float* wr = SF(weld) + (i / 6) * WELD_WORDS; wr[W_JAR + i % 6] += alpha * wr[W_JV + i % 6]; }
   LANES(i, cnt[CNT_NDR]) { float* dr = SF(dofrow) + i * DR_WORDS; dr[DR_JAR] += alpha * dr[DR_JV]; }
   if (HF) LANES(d, h->nfric) SF(fric)[d] += alpha * SF(fric)[h->nfric + d];
