@@ -52,9 +52,18 @@ extern "C" int b200sim_wide_launch(int wpb, int blocks, size_t smem_bytes, void*
                                    int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
                                    float* achieved, float* desired, float* reward, float* success, int* info);
 #define B200_WIDE_NVP 36
+// bring-up build for models with joint equalities / condim 6 (Franka Kitchen), compiled from b200sim_kitchen.cu
+extern "C" int b200sim_kitchen_build(const b200_model_view* view, const double* eq_data, const float* ref, int penv_body,
+                                     std::vector<uint32_t>* buf, std::string* err);
+extern "C" int b200sim_kitchen_setattr(int wpb, int smem_bytes);
+extern "C" int b200sim_kitchen_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
+                                      int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
+                                      float* achieved, float* desired, float* reward, float* success, int* info);
+#define B200_KITCHEN_NVP 31   // the kitchen translation unit instantiates NVP = 31 (identity-padded; distinct kernel symbols)
 
 struct b200sim {
   int N = 0, device = 0;
+  bool kitchen = false;
   std::vector<uint8_t> blob;
   b200_model_view view;
   std::vector<uint32_t> model_host;
@@ -96,7 +105,16 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   float r[3] = {0, 0, 0};
   if (ref) { r[0] = ref[0]; r[1] = ref[1]; r[2] = ref[2]; }
   std::string err;
-  if (dm_build(h->view, eq_data, r, h->model_host, err, TASK_IS_ADROIT(task->kind) ? task->penv_body : -1) != 0) { delete h; return fail(nullptr, "b200sim_create: " + err, -4); }
+  {
+    // models with joint equalities or condim-6 pairs go to the bring-up translation unit (its contact records are larger)
+    const b200_model_view& v = h->view;
+    for (int e = 0; e < v.neq; e++) if (v.eq_type[e] == B200_EQ_JOINT) h->kitchen = true;
+    for (int p = 0; p < v.npair; p++) if (v.pair_condim[p] == 6) h->kitchen = true;
+  }
+  const int penv = TASK_IS_ADROIT(task->kind) ? task->penv_body : -1;
+  if ((h->kitchen ? b200sim_kitchen_build(&h->view, eq_data, r, penv, &h->model_host, &err) : dm_build(h->view, eq_data, r, h->model_host, err, penv)) != 0) {
+    delete h; return fail(nullptr, "b200sim_create: " + err, -4);
+  }
   const DMHead* dh = (const DMHead*)h->model_host.data();
   FetchTask& t = h->task;
   memset(&t, 0, sizeof(t));
@@ -137,7 +155,10 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
               t.grip_site >= 0 && t.grip_site < dh->nsite && t.obj_site >= 0 && t.obj_site < dh->nsite;
     if (!ok) { delete h; return fail(nullptr, "b200sim_create: inconsistent AdroitHandRelocate task", -6); }
   }
-  if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE && t.kind != TASK_HAND && t.kind != TASK_HAND_REACH && !TASK_IS_ADROIT(t.kind)) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
+  if (t.kind == TASK_KITCHEN) {
+    if (!(h->kitchen && t.nact == dh->nu && t.ngoal == dh->nq && t.nobs == dh->nq + dh->nv)) { delete h; return fail(nullptr, "b200sim_create: inconsistent FrankaKitchen task", -6); }
+  } else if (h->kitchen) { delete h; return fail(nullptr, "b200sim_create: this model needs the kitchen task kind (8)", -6); }
+  if (t.kind != TASK_FETCH && t.kind != TASK_ANTMAZE && t.kind != TASK_HAND && t.kind != TASK_HAND_REACH && !TASK_IS_ADROIT(t.kind) && t.kind != TASK_KITCHEN) { delete h; return fail(nullptr, "b200sim_create: unknown task kind", -6); }
   if (t.kind == TASK_HAND && (t.nact != dh->nu || t.ngoal != 7 || t.obj_qadr != dh->nq - 7 || t.obj_dadr != dh->nv - 6 ||
                               t.touch_mode < 0 || t.touch_mode > 3 || (t.touch_mode && dh->nsensor == 0) ||
                               t.nobs != t.obj_qadr + dh->nv + 7 + (t.touch_mode ? dh->nsensor : 0))) { delete h; return fail(nullptr, "b200sim_create: inconsistent Hand task", -6); }
@@ -163,6 +184,11 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   if (dh->nv <= 21 && dh->any_convex_pair) h->nvp = 22;  // arm build that carries the general convex collider (FetchSlide's puck)
   if (dh->nv <= 21 && (dh->nten > 0 || dh->nfric > 0 || dh->nsensor > 0 || dh->any_round_pair)) h->nvp = 30;  // hand features live in the NVP = 30 build
   if (h->nvp == 30 && h->wpb > 14) h->wpb = 14;  // the large models' scratch does not fit 28 envs per block
+  if (h->kitchen) {
+    if (dh->nv > 31) { delete h; return fail(nullptr, "b200sim_create: the kitchen build is instantiated for nv <= 31", -8); }
+    h->nvp = B200_KITCHEN_NVP;
+    h->wpb = (h->wpb > 7 && ((size_t)dh->hot_words + (size_t)10 * dh->scr_words) * 4 + 64 <= 232448) ? 10 : 7;
+  }
   if (h->nvp == B200_WIDE_NVP) {
     // wide build: the largest block of {14, 13, 10, 7} warps whose scratch fits the 227 KB of shared memory (14 envs of the
     // 33-dof hammer model, 13 of the 36-dof relocate model), 7 for small batches so that every SM still gets a block
@@ -180,6 +206,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   B200_FOR_ALL_VARIANTS(B200_SETATTR)
 #undef B200_SETATTR
   if (h->nvp == B200_WIDE_NVP && b200sim_wide_setattr(h->wpb, (int)h->smem_bytes) != 0) e = cudaErrorInvalidValue;
+  if (h->nvp == B200_KITCHEN_NVP && b200sim_kitchen_setattr(h->wpb, (int)h->smem_bytes) != 0) e = cudaErrorInvalidValue;
   if (e != cudaSuccess) { std::string m = std::string("cudaFuncSetAttribute(smem=") + std::to_string(h->smem_bytes) + "): " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
   if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, (size_t)num_envs * t.st_stride * 4) != cudaSuccess) {
     delete h; return fail(nullptr, "b200sim_create: cudaMalloc failed", -9);
@@ -225,6 +252,9 @@ static int launch(b200sim* h, int mode, int nraw, const float* actions, const un
         h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info);
   B200_FOR_ALL_VARIANTS(B200_LAUNCH)
 #undef B200_LAUNCH
+  if (h->nvp == B200_KITCHEN_NVP)
+    b200sim_kitchen_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, h->state, actions, mask, obs,
+                           achieved, desired, reward, success, info);
   if (h->nvp == B200_WIDE_NVP)
     b200sim_wide_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, h->state, actions, mask, obs,
                         achieved, desired, reward, success, info);

@@ -1,0 +1,40 @@
+// Bring-up build of the step kernel for models with joint equalities and condim-6 contacts (Franka Kitchen, BASELINE config
+// 5b): same sources as b200sim.cu compiled with -DB200_KITCHEN (two-sided dof rows, six base rows per contact, task kind 8),
+// a separate translation unit so that the validated builds stay untouched.  The device model of such a model is built here
+// too (the contact record is larger, so the scratch layout differs).  The flat candidate-pair list (3 708 pairs for the
+// kitchen) is scanned by the ordinary broad phase -- the body-level bounding-volume pass is the next step.
+#define B200_KITCHEN 1
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "step_kernel.cuh"
+
+// NVP = 31 (not 30): the instantiations must not share a symbol with the NVP = 30 kernels of b200sim.cu
+#define B200_KITCHEN_VARIANTS(X) X(7, 31) X(10, 31)
+
+extern "C" int b200sim_kitchen_build(const b200_model_view* view, const double* eq_data, const float* ref, int penv_body,
+                                     std::vector<uint32_t>* buf, std::string* err) {
+  return dm_build(*view, eq_data, ref, *buf, *err, penv_body);
+}
+
+extern "C" int b200sim_kitchen_setattr(int wpb, int smem_bytes) {
+  cudaError_t e = cudaErrorInvalidValue;
+#define B200_SETATTR(W, V) if (wpb == W) e = cudaFuncSetAttribute(fetch_kernel<W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  B200_KITCHEN_VARIANTS(B200_SETATTR)
+#undef B200_SETATTR
+  return e == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int b200sim_kitchen_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
+                                      int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
+                                      float* achieved, float* desired, float* reward, float* success, int* info) {
+#define B200_LAUNCH(W, V)                                                                                        \
+  if (wpb == W)                                                                                                  \
+    fetch_kernel<W, V><<<blocks, W * 32, smem_bytes, (cudaStream_t)stream>>>(model_dev, *task, mode, nraw, N, state, actions, mask, obs, \
+                                                                             achieved, desired, reward, success, info);
+  B200_KITCHEN_VARIANTS(B200_LAUNCH)
+#undef B200_LAUNCH
+  return 0;
+}

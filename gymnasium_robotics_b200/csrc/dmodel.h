@@ -161,6 +161,9 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   if (h.npair > 65535) { err = "more than 65535 candidate geom pairs"; return -1; }
   h.ncon_max = m.nmocap > 0 ? 16 : 20;   // contacts kept per env per sub-step
   h.ngrp_max = m.nmocap > 0 ? 10 : 14;   // geom pairs in contact (+ welds) per env per sub-step
+#ifdef B200_KITCHEN
+  h.ncon_max = 24; h.ngrp_max = 18;      // the arm sweeping through kettle, knobs and doors (emulation soak: 15 / 13 seen)
+#endif
   if (ngrp_cap > DM_NWELD_MAX && ngrp_cap < h.ngrp_max) h.ngrp_max = ngrp_cap;
   if (h.nb > DM_MAX_BODY) { err = "model has more than 32 runtime bodies"; return -1; }
   if (h.nv > DM_MAX_NV) { err = "model has more than 40 dofs"; return -1; }

@@ -34,7 +34,7 @@ struct FetchTask {
 };
 // TASK_ANTMAZE covers both maze agents (Ant, Point)
 enum { TASK_FETCH = 0, TASK_ANTMAZE = 1, TASK_HAND = 2, TASK_HAND_REACH = 3, TASK_ADROIT_HAMMER = 4, TASK_ADROIT_RELOCATE = 5,
-       TASK_ADROIT_PEN = 6, TASK_ADROIT_DOOR = 7 };
+       TASK_ADROIT_PEN = 6, TASK_ADROIT_DOOR = 7, TASK_KITCHEN = 8 };
 #define TASK_IS_ADROIT(k) ((k) >= TASK_ADROIT_HAMMER && (k) <= TASK_ADROIT_DOOR)
 enum { GOAL_USE_POS = 1, GOAL_USE_ROT = 2, GOAL_IGNORE_Z = 4 };
 
@@ -436,6 +436,24 @@ HD void adroit_door_observe(const Ctx& c, const FetchTask& t, float* obs, float*
   }
 }
 
+#ifdef B200_KITCHEN
+// FrankaKitchen-v1 (envs/franka_kitchen/franka_env.py:92-128, kitchen_env.py:371-423): the kernel runs do_simulation(ctrl, 40)
+// and returns the noise-free observation robot qpos | robot qvel | object qpos | object qvel (the first nu joints are the
+// robot's) and the full qpos as `achieved`; the position targets (from the last noisy observation), the observation noise
+// and the task bookkeeping are batched host-side tensor code (gymnasium_robotics_b200/kitchen.py), as they are Python in the
+// reference.  [bring-up build]
+HD void kitchen_observe(const Ctx& c, const FetchTask& t, float* obs, float* achieved, float* desired, float* reward, float* success) {
+  const DMHead* h = c.h;
+  const int nr = h->nu, nq = h->nq, nv = h->nv;
+  LANES(i, nr) { obs[i] = SF(qpos)[i]; obs[nr + i] = SF(qvel)[i]; }
+  LANES(i, nq - nr) obs[2 * nr + i] = SF(qpos)[nr + i];
+  LANES(i, nv - nr) obs[2 * nr + (nq - nr) + i] = SF(qvel)[nr + i];
+  LANES(i, nq) { achieved[i] = SF(qpos)[i]; desired[i] = 0.f; }
+  if (c.lane == 0) { *reward = 0.f; *success = 0.f; }
+  (void)t;
+}
+#endif
+
 // one env, one warp.  `st` is this env's state record; outputs are this env's rows.  `active` is warp-uniform: idle
 // warps run the same control flow (for the block-wide alignment barriers) but touch no memory.
 template <int NVP>
@@ -509,6 +527,10 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
     reach_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
   } else if (NVP >= 30 && t.kind == TASK_ADROIT_HAMMER) {
     adroit_hammer_observe(c, t, obs, achieved, desired, reward, success);
+#ifdef B200_KITCHEN
+  } else if (NVP >= 30 && t.kind == TASK_KITCHEN) {
+    kitchen_observe(c, t, obs, achieved, desired, reward, success);
+#endif
   } else if (NVP >= 30 && t.kind == TASK_ADROIT_DOOR) {
     if (nsub == 0) kinematics(c);
     adroit_door_observe(c, t, obs, achieved, desired, reward, success);

@@ -1093,6 +1093,20 @@ STAGE void collision(const Ctx c) {
       } else {
         float bound = margin + MF(geom_rbound)[g1] + MF(geom_rbound)[g2];
         hit = dot3(dif, dif) <= bound * bound;
+#ifdef B200_KITCHEN
+        // large boxes (counters, doors): the bounding sphere of a box is loose, so test the other geom's bounding sphere
+        // against the box itself (distance of its centre in the box frame); still conservative
+        for (int side = 0; side < 2 && hit; side++) {
+          int gb = side ? g1 : g2, go = side ? g2 : g1;
+          if (MI(geom_type)[gb] != B200_GEOM_BOX) continue;
+          float bp[3], bm[9], rel[3], loc[3];
+          geom_pose(c, gb, bp, bm);
+          const float* xo = SF(geom_xpos) + 3 * go;
+          rel[0] = xo[0] - bp[0]; rel[1] = xo[1] - bp[1]; rel[2] = xo[2] - bp[2];
+          mulmtv(loc, bm, rel);
+          hit = box_sdist(loc, MF(geom_size) + 3 * gb) <= margin + MF(geom_rbound)[go];
+        }
+#endif
       }
     }
     int total, slot = wexscan(hit ? 1 : 0, c.lane, &total);
@@ -1708,7 +1722,7 @@ STAGE void build_H(const Ctx c) {
         const float Dr = fabsf(dr[DR_D]);
 #else
         if (!(dr[DR_JAR] < 0)) continue;
-        const float Dr = dr[DR_D];
+        const float& Dr = dr[DR_D];   // (a reference: loaded where used, as before the kitchen branch existed)
 #endif
         int d1 = di[DR_DOF], d2 = di[DR_DOF2];
         if (d1 == j) diag += Dr * dr[DR_COEF] * dr[DR_COEF];

@@ -80,6 +80,7 @@ def build_models(force: bool = False):
         with open(out, "wb") as f:
             f.write(blob)
         built.append(out)
+    build_franka_config(force)
     from .maze import MAPS
 
     for name, (agent, key) in MAZE_MODELS.items():
@@ -90,6 +91,40 @@ def build_models(force: bool = False):
             f.write(compile_maze_model(agent, MAPS[key]).to_blob())
         built.append(out)
     return built
+
+
+def build_franka_config(force: bool = False):
+    """Per-dof position / velocity bounds and observation-noise amplitudes of franka_config.xml (read by FrankaRobot at
+    construction, envs/franka_kitchen/franka_env.py:172-202) as a committed JSON next to the model blobs."""
+    import json
+    import xml.etree.ElementTree as ET
+
+    out = os.path.join(MODEL_DIR, "franka_config.json")
+    src = os.path.join(REFERENCE_ASSETS, "kitchen_franka", "franka_assets", "franka_config.xml")
+    if (os.path.exists(out) and not force) or not os.path.exists(src):
+        return out
+    root = ET.parse(src).getroot()
+    cfg = {"name": root.get("name"), "pos_bound": [], "vel_bound": [], "pos_noise_amp": [], "vel_noise_amp": []}
+    i = 0
+    while root.find(f"qpos{i}") is not None:
+        n = root.find(f"qpos{i}")
+        cfg["pos_bound"].append([float(x) for x in n.get("pos_bound").split()])
+        cfg["vel_bound"].append([float(x) for x in n.get("vel_bound").split()])
+        cfg["pos_noise_amp"].append(float(n.get("pos_noise_amp").split()[0]))
+        cfg["vel_noise_amp"].append(float(n.get("vel_noise_amp").split()[0]))
+        i += 1
+    with open(out, "w") as f:
+        json.dump(cfg, f, indent=0)
+    return out
+
+
+def load_franka_config():
+    import json
+
+    path = os.path.join(MODEL_DIR, "franka_config.json")
+    if not os.path.exists(path):
+        build_franka_config()
+    return json.load(open(path))
 
 
 def load_model(name: str) -> Model:

@@ -17,7 +17,7 @@ class HostSimBackend:
         self.num_envs, self.nobs = num_envs, task.nobs
         penv = int(task.penv_body) if task.kind in (4, 5, 6, 7) else -1
         self.sim = HostSim(model, eq_data=eq_data if len(eq_data) else None, ref=getattr(self, "REF", REF_POINT), penv_body=penv,
-                           ngrp_cap=getattr(self, "NGRP_CAP", 0))
+                           ngrp_cap=getattr(self, "NGRP_CAP", 0), flavor=getattr(self, "FLAVOR", None))
         t = HostTaskC()
         for name, _ in task._fields_:
             setattr(t, name, getattr(task, name))

@@ -76,8 +76,13 @@ def test_task_completion_bookkeeping(model):
         OracleKitchenEnv(model, tasks_to_complete=["dishwasher"])
 
 
-def test_cuda_path_refuses_the_kitchen_model_loudly():
+def test_cuda_path_keeps_the_kitchen_opt_in_and_never_falls_back():
+    """The bring-up build is opt-in until it has passed on a GPU; opted in without a CUDA device it fails loudly."""
     import gymnasium_robotics_b200 as pkg
 
     with pytest.raises(NotImplementedError, match="FrankaKitchen"):
         pkg.make_vec("FrankaKitchen-v1", num_envs=2)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            pkg.make_vec("FrankaKitchen-v1", num_envs=2, experimental=True)
