@@ -41,6 +41,8 @@ WORKLOADS = {
     "adroit_relocate": ("AdroitHandRelocate-v2", 30, 5, 2 * 4 * (36 + 72 + 30 + 7 + 3 + 1) + 120 + 4 * (39 + 6) + 10, 2048),
     "adroit_pen": ("AdroitHandPen-v2", 24, 5, 2 * 4 * (30 + 60 + 24 + 7 + 3 + 1) + 96 + 4 * (45 + 6) + 10, 2048),
     "adroit_door": ("AdroitHandDoor-v2", 28, 5, 2 * 4 * (30 + 60 + 28 + 7 + 3 + 1) + 112 + 4 * (39 + 6) + 10, 2048),
+    # config 5b: FrankaKitchen-v1 (bring-up build, opt-in: csrc/b200sim_kitchen.cu); 40 sub-steps per env-step
+    "franka_kitchen": ("FrankaKitchen-v1", 9, 40, 2 * 4 * (30 + 2 * 29 + 9) + 36 + 4 * (59 + 2 * 30 + 2) + 4, 2048),
     "antmaze_large": ("AntMaze_Large-v5", 8, 5, 2 * 4 * (15 + 28 + 0 + 0 + 2 + 1) + 32 + 124 + 10, 1024),  # config 4: 8192 envs over 8 GPUs
 }
 
@@ -173,7 +175,8 @@ def run_ours(args):
     else:
         import gymnasium_robotics_b200 as grb
 
-        env = grb.make_vec(env_id, num_envs=n, device=dev, rng_mode="torch", autoreset_mode="same_step")
+        extra = {"experimental": True} if args.workload == "franka_kitchen" else {}
+        env = grb.make_vec(env_id, num_envs=n, device=dev, rng_mode="torch", autoreset_mode="same_step", **extra)
     env.reset(seed=1000 * rank)  # seeds seed0 + global env index would need numpy streams; device RNG is per rank
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     tape = torch.rand((64, n, nact), generator=g, device=dev) * 2 - 1  # pre-generated action tape (RNG outside the timed region)
@@ -223,7 +226,7 @@ def run_ours(args):
                 "reward": torch.empty(n, dtype=torch.float32).pin_memory(),
                 "truncated": torch.empty(n, dtype=torch.bool).pin_memory(), "terminated": torch.empty(n, dtype=torch.bool).pin_memory(),
                 "is_success": torch.empty(n, dtype=torch.float32).pin_memory()}
-    if args.workload.startswith("adroit"):
+    if args.workload.startswith("adroit") or args.workload == "franka_kitchen":   # flat observation / per-task goal dicts
         del host_out["achieved_goal"], host_out["desired_goal"]
     h2d = n * nact * 4
     d2h = sum(v.numel() * v.element_size() for v in host_out.values())
@@ -232,14 +235,16 @@ def run_ours(args):
         o, r, te, tr, info = env.step(host_tape[k % 8])  # FetchVectorEnv.step copies the pinned host actions to the device
         if isinstance(o, dict):
             host_out["observation"].copy_(o["observation"], non_blocking=True)
-            host_out["achieved_goal"].copy_(o["achieved_goal"], non_blocking=True)
-            host_out["desired_goal"].copy_(o["desired_goal"], non_blocking=True)
+            if "achieved_goal" in host_out:
+                host_out["achieved_goal"].copy_(o["achieved_goal"], non_blocking=True)
+                host_out["desired_goal"].copy_(o["desired_goal"], non_blocking=True)
         else:   # flat observation (Adroit)
             host_out["observation"].copy_(o, non_blocking=True)
         host_out["reward"].copy_(r, non_blocking=True)
         host_out["terminated"].copy_(te, non_blocking=True)
         host_out["truncated"].copy_(tr, non_blocking=True)
-        host_out["is_success"].copy_((info["is_success"] if "is_success" in info else info["success"]).to(torch.float32), non_blocking=True)
+        suc = info["is_success"] if "is_success" in info else (info["success"] if "success" in info else te)
+        host_out["is_success"].copy_(suc.to(torch.float32), non_blocking=True)
         torch.cuda.synchronize(dev)
 
     for k in range(args.warmup):

@@ -80,3 +80,21 @@ def test_time_limit_and_unknown_task(model):
     assert tr.all()
     with pytest.raises(ValueError):
         _make(model, 1, tasks_to_complete=["dishwasher"])
+
+
+def test_same_step_autoreset_and_device_rng(model):
+    """The configuration bench.py runs (same_step autoreset, device RNG): finished envs are reset inside the call, the
+    returned observation is the reset one and `final_obs` carries the last observation of the finished episode."""
+    env = KitchenVectorEnv(num_envs=3, backend_factory=KitchenHostBackend, device="cpu", rng_mode="torch", model=model,
+                           autoreset_mode="same_step", max_episode_steps=2)
+    obs, _ = env.reset(seed=5)
+    a = torch.zeros((3, 9))
+    obs, r, te, tr, info = env.step(a)
+    assert not tr.any() and "final_obs" not in info
+    obs, r, te, tr, info = env.step(a)
+    assert tr.all() and info["_final_obs"].all() and info["final_obs"]["observation"].shape == (3, 59)
+    assert (env._elapsed == 0).all() and torch.isfinite(obs["observation"]).all()
+    # reset observation: INIT_QPOS plus noise
+    assert float((obs["observation"][:, :9] - env.init_qpos[:9]).abs().max()) < 0.02
+    obs, r, te, tr, info = env.step(a)
+    assert not tr.any()

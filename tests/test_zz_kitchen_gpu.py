@@ -1,0 +1,84 @@
+"""GPU tests of the Franka-Kitchen bring-up build (csrc/b200sim_kitchen.cu, task kind 8), collected last on purpose.
+Status at the end of round 1: tests/kitchen_gpu_quick.py (the first test below without torch) ran on a B200 and matched the
+host emulation to 2.3e-6 (profiles/kitchen_quick_r1k.json); the env-level test and the large-batch variant (10 warps per
+block) had no GPU time left in the round, the latter is therefore a non-strict xfail."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _backend(n):
+    from gymnasium_robotics_b200.kitchen import _KitchenBackend, make_kitchen_task
+    from gymnasium_robotics_b200.models import load_model
+
+    m = load_model("franka_kitchen")
+    return m, _KitchenBackend(m, np.zeros((0, 11)), make_kitchen_task(m), n, "cuda:0")
+
+
+def test_kitchen_fixture_through_the_c_abi():
+    """tests/golden/kitchen_quick.npz (fp32 host emulation of the same kernel source): refresh + 3 env-steps of 8 envs."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "kitchen_quick.npz"))
+    state0, ctrls, exp = g["state0"], g["ctrls"], g["obs"]
+    m, be = _backend(state0.shape[0])
+    assert be.layout["stride"] == int(g["stride"])
+    be.state.copy_(torch.as_tensor(state0))
+    out = be.new_outputs()
+    be.refresh(None, out)
+    assert float((out["obs"].cpu() - torch.as_tensor(exp[0])).abs().max()) < 1e-5
+    info = torch.zeros(state0.shape[0], dtype=torch.int32, device="cuda:0")
+    pos_cols = list(range(9)) + list(range(18, 18 + m.nq - 9))
+    for k in range(ctrls.shape[0]):
+        be.step(torch.as_tensor(ctrls[k]).cuda().contiguous(), out, info)
+        err = (out["obs"].cpu() - torch.as_tensor(exp[k + 1])).abs()
+        assert float(err[:, pos_cols].max()) < 5e-4 and float(err.max()) < 5e-2
+        assert int((info >> 16).max()) == 0      # no capacity overflow
+    be.close()
+
+
+def test_kitchen_env_tracks_the_oracle_env():
+    from gymnasium_robotics_b200 import make_vec
+    from oracle.kitchen_env import OracleKitchenEnv
+
+    n, seed = 4, 21
+    env = make_vec("FrankaKitchen-v1", num_envs=n, experimental=True, rng_mode="numpy")
+    obs, info = env.reset(seed=seed)
+    orcs = [OracleKitchenEnv(env.model) for _ in range(n)]
+    for i, o in enumerate(orcs):
+        ob, _ = o.reset(seed=seed + i)
+        assert np.abs(obs["observation"][i].cpu().numpy() - ob["observation"]).max() < 1e-5
+    rng = np.random.default_rng(2)
+    for k in range(4):
+        a = rng.uniform(-1, 1, size=(n, 9))
+        obs, rew, term, trunc, info = env.step(a)
+        for i, o in enumerate(orcs):
+            ob, r, te, tr, inf = o.step(a[i])
+            e = np.abs(obs["observation"][i].cpu().numpy() - ob["observation"])
+            assert e[:9].max() < 2e-4 and e[18:39].max() < 2e-4 and e.max() < 2e-2, (k, i, e.max())
+            assert float(rew[i]) == r and bool(term[i]) == te
+    env.close()
+
+
+@pytest.mark.xfail(strict=False, reason="10-warp variant of the bring-up build: no GPU time left in round 1 to run it")
+def test_kitchen_large_batch_is_consistent():
+    """2048 noise-free envs from the same state and action stay identical to each other and to an 8-env batch (the 7-warp
+    variant validated above)."""
+    from gymnasium_robotics_b200 import make_vec
+
+    def run(n):
+        env = make_vec("FrankaKitchen-v1", num_envs=n, experimental=True, rng_mode="torch", robot_noise_ratio=0.0, object_noise_ratio=0.0)
+        env.reset(seed=1)
+        a = torch.as_tensor(np.random.default_rng(3).uniform(-1, 1, size=(1, 9)), dtype=torch.float32).expand(n, 9).contiguous()
+        for _ in range(3):
+            obs, *_ = env.step(a)
+        o = obs["observation"].cpu()
+        env.close()
+        return o
+
+    big, small = run(2048), run(8)
+    assert torch.isfinite(big).all() and float((big - big[0]).abs().max()) == 0.0
+    assert float((big[0] - small[0]).abs().max()) < 1e-5
