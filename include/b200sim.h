@@ -60,6 +60,11 @@ typedef struct b200sim_fetch_task {
    * rotation_threshold = target length (:392-399); penv_body = "target" (body_quat redrawn per episode, :379-384). */
   /* kind 7 = AdroitHandDoor (envs/adroit_hand/adroit_door.py:279-371): obs 39; grip_site = "S_grasp", frame_site = "S_handle",
    * obj_qadr = qpos address of "door_hinge", penv_body = "frame" (body_pos redrawn per episode). */
+  /* kind 8 = FrankaKitchen (envs/franka_kitchen/franka_env.py:92-128, kitchen_env.py:371-397): the action is the clipped
+   * position target of the nact = nu actuators (the caller derives it from the last noisy observation, franka_env.py:139-170),
+   * n_substeps = 40; obs = robot qpos | robot qvel | object qpos | object qvel (nq + nv, noise-free: the caller adds the
+   * observation noise), achieved = qpos (ngoal = nq; the per-task slices of kitchen_env.py:27-45 are taken by the caller),
+   * reward 0.  Chosen together with the bring-up kernel build for models with joint equalities / condim 6. */
   int penv_body;
 } b200sim_fetch_task_t;
 
