@@ -20,6 +20,7 @@ import torch
 from . import _lib
 from .mjcf import EQ_WELD, JNT_FREE
 from .models import load_model
+from .rollout import CtorPickle
 from .spaces import Box, Dict as DictSpace, batch_space
 
 FETCH_TASKS = {
@@ -156,7 +157,7 @@ class CudaBackend:
         return int(self.L.b200sim_launch_count(self.h))
 
 
-class FetchVectorEnv:
+class FetchVectorEnv(CtorPickle):
     """`gym.make_vec("FetchPickAndPlace-v4", num_envs=N)` replacement.  Observations, rewards and flags are torch
     tensors on `device` (float32 / bool) with a leading `num_envs` axis."""
 

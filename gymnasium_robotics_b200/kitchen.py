@@ -21,6 +21,7 @@ import torch
 from ._lib import FetchTaskC
 from .fetch import CudaBackend
 from .models import load_franka_config, load_model
+from .rollout import CtorPickle
 from .spaces import Box, batch_space
 
 KITCHEN_REF_POINT = (-0.2, 0.3, 1.8)   # fixed world point of the spatial algebra: inside the robot's workspace
@@ -57,7 +58,7 @@ class _KitchenBackend(CudaBackend):
     REF = KITCHEN_REF_POINT
 
 
-class KitchenVectorEnv:
+class KitchenVectorEnv(CtorPickle):
     """`gym.make_vec("FrankaKitchen-v1", num_envs=N)`.  Observation dict: `observation` [N, 59], `achieved_goal` /
     `desired_goal` dicts task -> [N, k]; reward = number of tasks completed in the step; `terminated` when every task of the
     episode is completed; info carries the bookkeeping as boolean [N, n_tasks] tensors (column order `self.tasks`)."""

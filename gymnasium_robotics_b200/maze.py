@@ -20,6 +20,7 @@ import torch
 from . import _lib
 from .fetch import CudaBackend
 from .models import load_model
+from .rollout import CtorPickle
 from .spaces import Box, Dict as DictSpace, batch_space
 
 R, G, C = "r", "g", "c"
@@ -133,7 +134,7 @@ class _AntBackend(CudaBackend):
         return out
 
 
-class MazeVectorEnv:
+class MazeVectorEnv(CtorPickle):
     """`gym.make_vec("AntMaze_Large-v5" | "PointMaze_UMaze-v3", num_envs=N)` replacement (torch CUDA tensors, leading
     `num_envs` axis).  `maze_map` may be a name from `MAPS` or (for the point agent's tests) an explicit cell list."""
 
