@@ -8,6 +8,9 @@
 #include <math.h>
 #include <vector>
 #include <string>
+#include <map>
+#include <set>
+#include <utility>
 
 #include "../../include/b200sim_model.h"
 
@@ -19,6 +22,19 @@
 
 // (name, words-per-element, kind) ; kind selects the element count.  HOT arrays are staged into shared memory by every
 // block; COLD arrays (per-pair contact parameters, read only when a contact is created) stay in global memory.
+// Kitchen build: the flat pair list (3 708 entries, 44 KB) leaves shared memory -- it is only read for the pairs of the
+// bounding-volume groups that survive the first broad-phase level -- and the group table (one bounding sphere on one body
+// against one anchor geom, a contiguous run of pairs) is staged instead.
+#ifdef B200_KITCHEN
+#define DM_PAIR_HOT(X)
+#define DM_PAIR_COLD(X) X(pair_geom1, 1, npair) X(pair_geom2, 1, npair) X(pair_margin, 1, npair)
+#define DM_BGRP_HOT(X) X(bg_body, 1, nbgrp) X(bg_anchor, 1, nbgrp) X(bg_start, 1, nbgrp) X(bg_count, 1, nbgrp) X(bg_center, 3, nbgrp) X(bg_radius, 1, nbgrp)
+#define DM_NSURV_MAX 96   // bounding-volume groups that may survive the first level per env per sub-step
+#else
+#define DM_PAIR_HOT(X) X(pair_geom1, 1, npair) X(pair_geom2, 1, npair) X(pair_margin, 1, npair)
+#define DM_PAIR_COLD(X)
+#define DM_BGRP_HOT(X)
+#endif
 #define DM_ARRAYS_HOT(X) \
   X(body_parent, 1, nb) X(body_jntadr, 1, nb) X(body_jntnum, 1, nb) X(body_dofadr, 1, nb) X(body_dofnum, 1, nb) \
   X(body_mocapid, 1, nb) X(body_ancdof, MW, nb) X(body_sub, 1, nb) X(body_pos, 3, nb) X(body_quat, 4, nb) \
@@ -30,7 +46,7 @@
   X(dof_damping, 1, nv) X(dof_frictionloss, 1, nv) X(dof_invweight0, 1, nv) \
   X(geom_type, 1, ngeom) X(geom_body, 1, ngeom) X(geom_pos, 3, ngeom) X(geom_quat, 4, ngeom) X(geom_size, 3, ngeom) \
   X(geom_rbound, 1, ngeom) \
-  X(pair_geom1, 1, npair) X(pair_geom2, 1, npair) X(pair_margin, 1, npair) \
+  DM_PAIR_HOT(X) DM_BGRP_HOT(X) \
   X(site_body, 1, nsite) X(site_pos, 3, nsite) X(site_quat, 4, nsite) \
   X(act_trnid, 1, nu) X(act_ctrllimited, 1, nu) X(act_forcelimited, 1, nu) X(act_gear, 1, nu) X(act_gain, 1, nu) \
   X(act_bias, 3, nu) X(act_ctrlrange, 2, nu) X(act_forcerange, 2, nu) \
@@ -41,6 +57,7 @@
   X(ten_dof, 2, nten) X(ten_qadr, 2, nten) X(ten_coef, 2, nten) X(ten_range, 2, nten) X(ten_margin, 1, nten)
 #define DM_ARRAYS_COLD(X) \
   X(jnt_solref, 2, njnt) X(jnt_solimp, 5, njnt) /* read only when a limit row is created */ \
+  DM_PAIR_COLD(X) \
   X(pair_condim, 1, npair) X(pair_friction, 3, npair) X(pair_gap, 1, npair) X(pair_solref, 2, npair) \
   X(pair_solimp, 5, npair) X(pair_invweight, 2, npair) \
   X(ten_solref, 2, nten) X(ten_solimp, 5, nten) X(ten_invweight, 1, nten) \
@@ -56,7 +73,11 @@
   X(group, ngrp_max * grp_words) X(counters, 8) X(fric, 2 * nfric) X(conx, ncx * CX_WORDS) X(penv_pos, npenv)
 // time-shared region `uni`: kinematics {kinA, kinB} -> dynamics {cinert, b6, d6, geom_xpos, cand} -> solver {H, d6, grad,
 // search, Ma, Mv} -> observation {cvel}.  d6 keeps one offset in both phases that use it.
+#ifdef B200_KITCHEN
+#define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(surv) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
+#else
 #define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
+#endif
 #define DM_SCRATCH(X) DM_SCRATCH_PERSIST(X)
 
 // contact record (words): up to 4 base rows (normal, two tangents, torsion).  W = spatial vectors of the three
@@ -110,6 +131,9 @@ struct DMHead {
 #define X(name) int s_##name;
   DM_SCRATCH_UNION(X)
 #undef X
+#ifdef B200_KITCHEN
+  int nbgrp;   // bounding-volume groups of the two-level broad phase (after the fields the common host code reads)
+#endif
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -134,6 +158,55 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
       else if (!seen[m.pair_geom1[p]]) { seen[m.pair_geom1[p]] = 1; psrc.push_back(p); pgrid.push_back(1); }
     }
   }
+#ifdef B200_KITCHEN
+  // Two-level broad phase: the pairs are regrouped by (body of geom1, body of geom2); inside such a bucket every geom of
+  // the anchor side (the world body's geoms, else the side with fewer geoms) gets one group = its pairs, contiguous in
+  // the device pair list, behind ONE bounding sphere fixed to the other body that encloses the bounding spheres of all
+  // its partner geoms (+ the largest pair margin).  A group whose sphere misses the anchor geom cannot hold a candidate
+  // pair, so the set of candidates is the flat scan's; only their order follows the regrouped list.
+  struct BGroup { int body, anchor, start, count; double c[3], r; };
+  std::vector<BGroup> bgs;
+  {
+    std::map<std::pair<int, int>, std::vector<int>> buckets;
+    for (size_t p = 0; p < psrc.size(); p++) {
+      if (pgrid[p]) { err = "maze-grid pairs are not part of the kitchen build"; return -1; }
+      buckets[std::make_pair(m.geom_body[m.pair_geom1[psrc[p]]], m.geom_body[m.pair_geom2[psrc[p]]])].push_back(psrc[p]);
+    }
+    std::vector<int> order;
+    for (auto& kv : buckets) {
+      const std::vector<int>& ps = kv.second;
+      std::set<int> GA, GB;
+      for (int sp : ps) { GA.insert(m.pair_geom1[sp]); GB.insert(m.pair_geom2[sp]); }
+      int ba = kv.first.first, bb = kv.first.second;
+      bool anchorB = ba == 0 ? false : (bb == 0 ? true : GB.size() <= GA.size());   // anchor side; the sphere sits on the other body
+      const std::set<int>& anchors = anchorB ? GB : GA;
+      for (int an : anchors) {
+        BGroup g;
+        g.body = anchorB ? ba : bb; g.anchor = an; g.start = (int)order.size(); g.count = 0;
+        std::vector<int> partner;
+        double mg = 0;
+        for (int sp : ps) {
+          if ((anchorB ? m.pair_geom2[sp] : m.pair_geom1[sp]) != an) continue;
+          order.push_back(sp); g.count++;
+          partner.push_back(anchorB ? m.pair_geom1[sp] : m.pair_geom2[sp]);
+          if (m.pair_margin[sp] > mg) mg = m.pair_margin[sp];
+        }
+        for (int k = 0; k < 3; k++) { g.c[k] = 0; for (int pg : partner) g.c[k] += m.geom_pos[3 * pg + k] / partner.size(); }
+        g.r = 0;
+        for (int pg : partner) {
+          double d2 = 0;
+          for (int k = 0; k < 3; k++) { double d = m.geom_pos[3 * pg + k] - g.c[k]; d2 += d * d; }
+          double rr = sqrt(d2) + m.geom_rbound[pg];
+          if (rr > g.r) g.r = rr;
+        }
+        g.r = (g.r + mg) * (1.0 + 1e-5) + 1e-6;   // fp32 slack: the group test must never reject what the pair test accepts
+        bgs.push_back(g);
+      }
+    }
+    psrc = order;
+  }
+  h.nbgrp = (int)bgs.size();
+#endif
   h.npair = (int)psrc.size();
   h.edges_per_con = 1;
   for (size_t p = 0; p < psrc.size(); p++) {
@@ -206,6 +279,9 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
       neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max, ndr_max = h.ndr_max,
       nten = h.nten, nfric = h.nfric, nsensor = h.nsensor, ncx = h.nsensor > 0 ? h.ncon_max : 0, MW = h.mask_words,
       grp_words = MW == 2 ? 34 : 32, npenv = h.penv_body > 0 ? 8 : 0;
+#ifdef B200_KITCHEN
+  int nbgrp = h.nbgrp;
+#endif
   int nrkq = h.integrator == B200_INT_RK4 ? nq : 0, nrkv = h.integrator == B200_INT_RK4 ? nv : 0;
   int off = (int)((sizeof(DMHead) + 3) / 4);
 #define X(name, w, kind) h.o_##name = off; off += (w) * (kind);
@@ -237,6 +313,9 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     h.s_H = u; h.s_grad = after; h.s_search = after + nv; h.s_Ma = after + 2 * nv; h.s_Mv = after + 3 * nv;
     h.s_cvel = u;
     int endA = after + 3 * ngeom + (h.npair > 255 ? h.ncand_max / 2 : h.ncand_max / 4), endB = after + 4 * nv;   // candidate slots: 1 or 2 bytes
+#ifdef B200_KITCHEN
+    h.s_surv = endA; endA += DM_NSURV_MAX + 1;   // surviving groups: (first pair | running pair count << 16) + one end marker
+#endif
     so = endA > endB ? endA : endB;
   }
   h.scr_words = (so + 3) & ~3;
@@ -367,6 +446,13 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     for (int k = 0; k < 2; k++) { F(h.o_pair_solref, 2 * p + k, m.pair_solref[2 * sp + k]); F(h.o_pair_invweight, 2 * p + k, m.pair_invweight[2 * sp + k]); }
     for (int k = 0; k < 5; k++) F(h.o_pair_solimp, 5 * p + k, m.pair_solimp[5 * sp + k]);
   }
+#ifdef B200_KITCHEN
+  for (int g = 0; g < nbgrp; g++) {
+    I(h.o_bg_body, g, bgs[g].body); I(h.o_bg_anchor, g, gmap[bgs[g].anchor]); I(h.o_bg_start, g, bgs[g].start); I(h.o_bg_count, g, bgs[g].count);
+    for (int k = 0; k < 3; k++) F(h.o_bg_center, 3 * g + k, bgs[g].c[k]);
+    F(h.o_bg_radius, g, bgs[g].r);
+  }
+#endif
   if (3 * (h.edges_per_con * ncon_max + 6 * DM_NWELD_MAX + ndr_max) > h.s_grad - h.s_H) { err = "line-search edge list does not fit the solver scratch"; return -1; }
   for (int k = 0; k < nsensor; k++) {
     I(h.o_sensor_site, k, m.sensor_site[k]); I(h.o_sensor_body, k, m.sensor_body[k]); I(h.o_sensor_type, k, m.sensor_type[k]);

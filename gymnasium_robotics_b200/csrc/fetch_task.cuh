@@ -279,7 +279,7 @@ HD void touch_observe(const Ctx& c, const FetchTask& t, float* out, int nmax = 1
       const float* cr = SF(con) + i * CON_WORDS;
       const float* cx = SF(conx) + i * CX_WORDS;
       int p = ((const int*)cx)[CX_PAIR];
-      int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
+      int g1 = PAIR_I(pair_geom1)[p], g2 = PAIR_I(pair_geom2)[p];
       int b1 = MI(geom_body)[g1], b2 = g2 < 0 ? 0 : MI(geom_body)[g2];
       if (b1 != body && b2 != body) continue;
       float F[C_NB];

@@ -68,6 +68,13 @@ enum { TM_KIN = 0, TM_COM_M, TM_COLL, TM_CONSTR, TM_SMOOTH, TM_NBEGIN, TM_NCHECK
 #define MI(name) ((const int*)(c.mw + c.h->o_##name))
 #define MU(name) ((const uint32_t*)(c.mw + c.h->o_##name))
 #define MF(name) ((const float*)(c.mw + c.h->o_##name))
+#ifdef B200_KITCHEN
+#define PAIR_I(name) ((const int*)(c.mg + c.h->o_##name))    // kitchen build: the pair list stays in global memory (dmodel.h)
+#define PAIR_F(name) ((const float*)(c.mg + c.h->o_##name))
+#else
+#define PAIR_I(name) MI(name)
+#define PAIR_F(name) MF(name)
+#endif
 #define GI(name) ((const int*)(c.mg + c.h->o_##name))
 #define GF(name) ((const float*)(c.mg + c.h->o_##name))
 #define SF(name) (c.s + c.h->s_##name)
@@ -1063,13 +1070,70 @@ STAGE void collision(const Ctx c) {
   const bool wide_cand = h->npair > 255;
   if (c.lane == 0) { cnt[CNT_NCON] = 0; cnt[CNT_NCAND] = 0; cnt[CNT_NGRP] = 0; }
   SYNC();
+#if defined(B200_KITCHEN) && !defined(B200_KITCHEN_FLATSCAN)
+  // broad phase, level 1: lanes over the bounding-volume groups (dmodel.h) -- one sphere fixed to a body against one anchor
+  // geom (plane / the box itself / its bounding sphere); the survivors' pair runs are listed as (first pair, running count)
+  uint32_t* surv = (uint32_t*)SI(surv);
+  int nsurv = 0, npexp = 0;   // warp-uniform
+  for (int base = 0; base < h->nbgrp; base += WARP_W) {
+    int g = base + c.lane;
+    bool hit = false;
+    int npg = 0;
+    if (g < h->nbgrp) {
+      int b = MI(bg_body)[g], an = MI(bg_anchor)[g];
+      float r = MF(bg_radius)[g], cw[3], rel[3];
+      qrot(cw, SF(xquat) + 4 * b, MF(bg_center) + 3 * g);
+      const float* xa = SF(geom_xpos) + 3 * an;
+      for (int k = 0; k < 3; k++) rel[k] = SF(xpos)[3 * b + k] + cw[k] - xa[k];
+      int ta = MI(geom_type)[an];
+      if (ta == B200_GEOM_PLANE) hit = dot3(rel, MF(geom_size) + 3 * an) <= r;
+      else if (ta == B200_GEOM_BOX) {
+        float bp[3], bm[9], loc[3];
+        geom_pose(c, an, bp, bm);
+        mulmtv(loc, bm, rel);
+        hit = box_sdist(loc, MF(geom_size) + 3 * an) <= r;
+      } else { float bound = r + MF(geom_rbound)[an]; hit = dot3(rel, rel) <= bound * bound; }
+      if (hit) npg = MI(bg_count)[g];
+    }
+    int total, slot = wexscan(hit ? 1 : 0, c.lane, &total);
+    int ptotal, poff = wexscan(npg, c.lane, &ptotal);
+    if (hit && nsurv + slot < DM_NSURV_MAX) surv[nsurv + slot] = (uint32_t)MI(bg_start)[g] | ((uint32_t)(npexp + poff) << 16);
+    if (nsurv + total > DM_NSURV_MAX) {
+      // more surviving groups than slots: the tail is dropped and flagged like a candidate overflow; the running count
+      // must end at the last kept group
+      int keep = DM_NSURV_MAX - nsurv;
+      int kept_pairs = 0;
+#ifdef __CUDACC__
+      kept_pairs = __shfl_sync(0xffffffffu, poff + npg, 31 - __clz(__ballot_sync(0xffffffffu, hit && slot < keep)));
+#else
+      kept_pairs = (hit && slot < keep) ? npg : 0;
+#endif
+      if (keep <= 0) kept_pairs = 0;
+      if (c.lane == 0) cnt[CNT_OVERFLOW] |= 1;
+      nsurv = DM_NSURV_MAX; npexp += kept_pairs;
+    } else { nsurv += total; npexp += ptotal; }
+  }
+  if (c.lane == 0) surv[nsurv] = (uint32_t)npexp << 16;   // end marker
+  SYNC();
+  // level 2: lanes over the pairs of the surviving groups (the entry holding the i-th expanded pair by bisection)
+  for (int base = 0; base < npexp; base += WARP_W) {
+    int ei = base + c.lane, p = h->npair;
+    if (ei < npexp) {
+      int lo = 0, hi = nsurv;   // surv[lo].count <= ei < surv[hi].count
+      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)(surv[mid] >> 16) <= ei) lo = mid; else hi = mid; }
+      p = (int)(surv[lo] & 0xffffu) + ei - (int)(surv[lo] >> 16);
+    }
+    bool hit = false;
+    if (p < h->npair) {
+#else
   // broad phase: lanes over the static pair list, ordered compaction
   for (int base = 0; base < h->npair; base += WARP_W) {
     int p = base + c.lane;
     bool hit = false;
     if (p < h->npair) {
-      int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
-      float margin = MF(pair_margin)[p];
+#endif
+      int g1 = PAIR_I(pair_geom1)[p], g2 = PAIR_I(pair_geom2)[p];
+      float margin = PAIR_F(pair_margin)[p];
       const float *x1 = SF(geom_xpos) + 3 * g1, *x2 = SF(geom_xpos) + 3 * g2;
       float dif[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
       if (g2 < 0) {
@@ -1125,8 +1189,8 @@ STAGE void collision(const Ctx c) {
     int p = -1;
     if (ci < ncand) {
       p = wide_cand ? (int)cand16[ci] : (int)cand[ci];
-      int g1 = MI(pair_geom1)[p], g2 = MI(pair_geom2)[p];
-      float margin = MF(pair_margin)[p];
+      int g1 = PAIR_I(pair_geom1)[p], g2 = PAIR_I(pair_geom2)[p];
+      float margin = PAIR_F(pair_margin)[p];
       int t1 = MI(geom_type)[g1], t2 = g2 < 0 ? B200_GEOM_BOX : MI(geom_type)[g2];
       const bool cv1 = t1 == B200_GEOM_CYLINDER || t1 == B200_GEOM_ELLIPSOID, cv2 = t2 == B200_GEOM_CYLINDER || t2 == B200_GEOM_ELLIPSOID;
       if (CX && (cv1 || cv2)) {
@@ -1168,7 +1232,7 @@ STAGE void collision(const Ctx c) {
     }
     if (o.cnt > 0) {
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
-      int ba = MI(geom_body)[MI(pair_geom1)[p]], bb = MI(pair_geom2)[p] < 0 ? 0 : MI(geom_body)[MI(pair_geom2)[p]];
+      int ba = MI(geom_body)[PAIR_I(pair_geom1)[p]], bb = PAIR_I(pair_geom2)[p] < 0 ? 0 : MI(geom_body)[PAIR_I(pair_geom2)[p]];
       dmask_t ma = DM(body_ancdof, ba), mb = DM(body_ancdof, bb);
       gi[G_START] = basec + slot; gi[G_COUNT] = kept;
       grp_set_masks(gi, ma ^ mb, mb);
@@ -1197,7 +1261,7 @@ STAGE void collision(const Ctx c) {
 #ifdef B200_KITCHEN
     cr[C_MU + 2] = fr[2];   // rolling friction (condim 6)
 #endif
-    float incl = MF(pair_margin)[p] - GF(pair_gap)[p];
+    float incl = PAIR_F(pair_margin)[p] - GF(pair_gap)[p];
     float solimp[5] = {GF(pair_solimp)[5 * p], GF(pair_solimp)[5 * p + 1], GF(pair_solimp)[5 * p + 2], GF(pair_solimp)[5 * p + 3], GF(pair_solimp)[5 * p + 4]};
     float solref[2] = {GF(pair_solref)[2 * p], GF(pair_solref)[2 * p + 1]};
     float imp = impedance(solimp, dist, incl);

@@ -28,13 +28,16 @@ class FetchTaskC(ctypes.Structure):
 
 def build(force=False, wide=False):
     """wide = True: the 64-bit dof-mask build (models with more than 32 dofs, -DB200_WIDE as in csrc/b200sim_wide.cu);
-    wide = "kitchen": the bring-up build of the Franka-Kitchen kernel features (-DB200_KITCHEN)"""
-    out = os.path.join(_HERE, {True: "libhostsim_wide.so", "kitchen": "libhostsim_kitchen.so"}.get(wide, "libhostsim.so"))
+    wide = "kitchen": the bring-up build of the Franka-Kitchen kernel features (-DB200_KITCHEN, DESIGN.md section 7);
+    wide = "kitchen_flat": the same with the one-level broad phase over the (regrouped) pair list, the A/B reference of the
+    two-level one (-DB200_KITCHEN_FLATSCAN)"""
+    out = os.path.join(_HERE, {True: "libhostsim_wide.so", "kitchen": "libhostsim_kitchen.so",
+                               "kitchen_flat": "libhostsim_kitchen_flat.so"}.get(wide, "libhostsim.so"))
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_ROOT, "gymnasium_robotics_b200", "csrc", f)
                                                    for f in ("sim_core.cuh", "dmodel.h", "fetch_task.cuh")] + \
            [os.path.join(_ROOT, "include", "b200sim_model.h")]
     if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function"] + (["-DB200_KITCHEN"] if wide == "kitchen" else (["-DB200_WIDE"] if wide else [])) +
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function"] + ({"kitchen": ["-DB200_KITCHEN"], "kitchen_flat": ["-DB200_KITCHEN", "-DB200_KITCHEN_FLATSCAN"]}.get(wide) or (["-DB200_WIDE"] if wide else [])) +
                               ["-o", out, srcs[0]])
     return out
 

@@ -37,6 +37,10 @@ void* hostsim_create(const void* blob, size_t n, const double* eq_data, const fl
 void hostsim_destroy(void* p) { delete (HostSim*)p; }
 float* hostsim_scratch(void* p) { return ((HostSim*)p)->scratch.data(); }
 int hostsim_scr_words(void* p) { return ((HostSim*)p)->ctx.h->scr_words; }
+int hostsim_npair(void* p) { return ((HostSim*)p)->ctx.h->npair; }
+#ifdef B200_KITCHEN
+int hostsim_nbgrp(void* p) { return ((HostSim*)p)->ctx.h->nbgrp; }
+#endif
 int hostsim_offset(void* p, const char* name) {
   const DMHead* h = ((HostSim*)p)->ctx.h;
 #define X(nm, words) if (strcmp(name, #nm) == 0) return h->s_##nm;
