@@ -29,7 +29,8 @@ unit = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}
 dram = num("dram__bytes_read.sum") * unit[vals["dram__bytes_read.sum"][1]] + num("dram__bytes_write.sum") * unit[vals["dram__bytes_write.sum"][1]]
 HAND = tag.startswith("hand")
 ADROIT = tag.startswith("adroit")
-alg_b, alg_n = (1710, 2048) if HAND else ((1410, 2048) if ADROIT else (766, 4096))
+KITCHEN = tag.startswith("kitchen")
+alg_b, alg_n = (1710, 2048) if HAND else ((1410, 2048) if ADROIT else ((1300, 2048) if KITCHEN else (766, 4096)))
 lines.append(f"dram bytes per launch (read+write): {dram:.0f}   [algorithmic: {alg_b} B x {alg_n} envs = {alg_b*alg_n}]")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 srows = list(csv.reader(src.splitlines()))
@@ -67,7 +68,7 @@ for k, n in per.most_common(25):
     lines.append(f"{k:45s} {n:12d} {100*n/ti:5.1f}%")
 open(os.path.join(out_dir, f"ncu_step_kernel_{tag}.txt"), "w").write("\n".join(lines) + "\n")
 json.dump({"dram_bytes_per_launch": dram, "source": f"profiles/ncu_step_kernel_{tag}.txt", "algorithmic_bytes_per_launch": alg_b * alg_n},
-          open(os.path.join(out_dir, "traffic_hand.json" if HAND else ("traffic_adroit.json" if ADROIT else "traffic.json")), "w"))
+          open(os.path.join(out_dir, "traffic_hand.json" if HAND else ("traffic_adroit.json" if ADROIT else ("traffic_kitchen.json" if KITCHEN else "traffic.json"))), "w"))
 # launch list
 ll = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 if os.path.exists(ll):
