@@ -31,12 +31,19 @@ class FetchTaskC(ctypes.Structure):
                 ("penv_body", ctypes.c_int)]
 
 
+class FetchResetC(ctypes.Structure):
+    """b200sim_fetch_reset_t"""
+    _fields_ = [("has_object", ctypes.c_int), ("target_in_the_air", ctypes.c_int), ("obj_qadr", ctypes.c_int),
+                ("obj_range", ctypes.c_float), ("target_range", ctypes.c_float), ("target_offset", ctypes.c_float * 3),
+                ("height_offset", ctypes.c_float), ("gripper_xpos", ctypes.c_float * 3)]
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """nvcc-compile csrc/b200sim.cu and csrc/b200sim_wide.cu for sm_100a into the in-tree libb200sim.so (cross-compiles
     without a GPU; the two translation units are compiled in parallel)."""
     names = ("b200sim", "b200sim_wide", "b200sim_kitchen")
     srcs = [os.path.join(_HERE, "csrc", n + ".cu") for n in names]
-    deps = srcs + [os.path.join(_HERE, "csrc", f) for f in ("sim_core.cuh", "fetch_task.cuh", "step_kernel.cuh", "dmodel.h")] + \
+    deps = srcs + [os.path.join(_HERE, "csrc", f) for f in ("sim_core.cuh", "fetch_task.cuh", "step_kernel.cuh", "dmodel.h", "reset_sample.cuh")] + \
            [os.path.join(_HERE, "..", "include", f) for f in ("b200sim.h", "b200sim_model.h")]
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -76,6 +83,7 @@ def lib():
     L.b200sim_raw_step.argtypes = [vp, ci] + [vp] * 6
     L.b200sim_raw_step_masked.argtypes = [vp, vp, ci] + [vp] * 6
     L.b200sim_compute_reward.argtypes = [vp, vp, vp, ci, vp, vp]
+    L.b200sim_reset.argtypes = [vp, vp, vp, ctypes.POINTER(FetchResetC), ctypes.c_ulonglong, ci, vp] + [vp] * 6
     L.b200sim_launch_count.argtypes = [vp]
     L.b200sim_launch_count.restype = ctypes.c_long
     L.b200sim_launch_config.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
@@ -84,5 +92,5 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["b200sim_create", "b200sim_destroy", "b200sim_last_error", "b200sim_num_envs", "b200sim_layout",
-                    "b200sim_state", "b200sim_step", "b200sim_refresh", "b200sim_raw_step", "b200sim_raw_step_masked", "b200sim_compute_reward",
+                    "b200sim_state", "b200sim_step", "b200sim_refresh", "b200sim_raw_step", "b200sim_raw_step_masked", "b200sim_compute_reward", "b200sim_reset",
                     "b200sim_launch_count", "b200sim_launch_config"]

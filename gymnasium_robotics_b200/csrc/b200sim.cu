@@ -11,6 +11,7 @@
 
 #include "../../include/b200sim.h"
 #include "step_kernel.cuh"
+#include "reset_sample.cuh"
 
 // warps (= envs) per block: 28 fills an SM in one wave at 4096 envs per GPU; smaller batches use smaller blocks so
 // that every SM still gets work (e.g. the 1024-env shards of BASELINE config 4)
@@ -40,6 +41,19 @@ __global__ void reward_kernel(const float* __restrict__ ag, const float* __restr
   float d = sqrtf(d2);
   if (kind == TASK_FETCH || kind == TASK_HAND_REACH) out[i] = dense ? -d : -(d > thr ? 1.f : 0.f);   // fetch_env.py:74-80, reach.py:88-93
   else out[i] = dense ? expf(-d) : (d <= radius ? 1.f : 0.f);               // maze_v4.py:381-388
+}
+
+// in-kernel reset draw (reset_sample.cuh): one thread per env writes its state record; the refresh launch that follows does
+// mj_forward + _get_obs.  32 consecutive threads write 32 consecutive records word by word (stride ~ 60 words: each record is
+// a few 128-byte lines, touched once per episode).
+__global__ void fetch_reset_kernel(b200sim_fetch_reset_t p, unsigned long long seed, int env_offset, int N, const unsigned char* __restrict__ mask,
+                                   const float* __restrict__ rest, int stride, int st_qpos, int st_goal, float* __restrict__ state,
+                                   int* __restrict__ episode) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || (mask && !mask[i])) return;
+  int ep = episode ? episode[i] : 0;
+  rs_fetch_reset_record(p, seed, (uint32_t)(i + env_offset), (uint32_t)ep, rest, stride, st_qpos, st_goal, state + (size_t)i * stride);
+  if (episode) episode[i] = ep + 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -270,6 +284,19 @@ int b200sim_step(b200sim_t* h, const float* actions, float* obs, float* achieved
 }
 int b200sim_refresh(b200sim_t* h, const unsigned char* mask, float* obs, float* achieved, float* desired, float* reward,
                     float* success, void* stream) {
+  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+}
+int b200sim_reset(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_fetch_reset_t* params,
+                  unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired, float* reward,
+                  float* success, void* stream) {
+  if (h->task.kind != TASK_FETCH) return fail(h, "b200sim_reset: the in-kernel reset draw exists for the Fetch task family only", -6);
+  if (!rest_record || !params) return fail(h, "b200sim_reset: rest_record / params is NULL", -1);
+  if (params->has_object && (params->obj_qadr < 0 || params->obj_qadr + 2 > h->task.st_qvel - h->task.st_qpos)) return fail(h, "b200sim_reset: obj_qadr outside qpos", -1);
+  CUDA_OK(cudaSetDevice(h->device));
+  fetch_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
+                                                                          h->task.st_qpos, h->task.st_goal, h->state, episode);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
   return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
 }
 int b200sim_raw_step_masked(b200sim_t* h, const unsigned char* mask, int nstep, float* obs, float* achieved, float* desired,

@@ -1,0 +1,88 @@
+// In-kernel reset sampling: the draws of the reference's reset path on the device, one counter-based
+// stream per (seed, env, episode) so that resets need no host round trip and are independent of batch size and sharding.
+//
+//   Fetch: object start xy by rejection (envs/fetch/fetch_env.py:386-392) and goal (envs/fetch/fetch_env.py:153-166).
+//
+// The generator is Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11), written out here;
+// it is the "throughput" RNG mode -- distribution-equal to the reference's numpy PCG64 stream, not value-equal (the
+// value-equal mode stays on the host: gymnasium_robotics_b200/fetch.py `_sample_reset`, rng_mode="numpy").
+// Compiles for the device (b200sim.cu) and for the host (tests/hostsim/hostsim.cpp: the CPU test backend calls the same code).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/b200sim.h"
+
+#ifdef __CUDACC__
+#define RS_HD __host__ __device__ inline
+#else
+#define RS_HD inline
+#endif
+
+RS_HD void rs_mulhilo(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
+  uint64_t p = (uint64_t)a * (uint64_t)b;
+  *hi = (uint32_t)(p >> 32); *lo = (uint32_t)p;
+}
+
+// counter c[4], key k[2] -> out[4]
+RS_HD void rs_philox4x32_10(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
+  uint32_t c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], k0 = k[0], k1 = k[1];
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0, lo0, hi1, lo1;
+    rs_mulhilo(0xD2511F53u, c0, &hi0, &lo0);
+    rs_mulhilo(0xCD9E8D57u, c2, &hi1, &lo1);
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+RS_HD float rs_u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }   // [0, 1), 24 bits
+
+// 128 candidate positions at most (the loop ends at the first accepted one, typically inside block 0 or 1): a rejected last
+// one has probability (pi 0.1^2 / (2 obj_range)^2)^128 -- 1e-58 for obj_range 0.15, 3e-14 for FetchSlide's 0.1
+#define RS_FETCH_OBJ_BLOCKS 64
+#define RS_FETCH_GOAL_BLOCK 64
+
+// draws of one Fetch reset: obj_xy (only when has_object) and goal
+RS_HD void rs_fetch_reset_draw(const b200sim_fetch_reset_t& p, unsigned long long seed, uint32_t env, uint32_t episode, float obj_xy[2],
+                               float goal[3]) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t ctr[4] = {env, episode, 0u, 0x5EEDu}, r[4];
+  if (p.has_object) {
+    // fetch_env.py:386-392: redraw until the object is at least 0.1 from the gripper in the plane
+    bool done = false;
+    for (int b = 0; b < RS_FETCH_OBJ_BLOCKS && !done; b++) {
+      ctr[2] = (uint32_t)b;
+      rs_philox4x32_10(ctr, key, r);
+      for (int h = 0; h < 2 && !done; h++) {
+        float dx = (2.0f * rs_u01(r[2 * h]) - 1.0f) * p.obj_range, dy = (2.0f * rs_u01(r[2 * h + 1]) - 1.0f) * p.obj_range;
+        obj_xy[0] = p.gripper_xpos[0] + dx; obj_xy[1] = p.gripper_xpos[1] + dy;
+        done = sqrtf(dx * dx + dy * dy) >= 0.1f;
+      }
+    }
+  }
+  ctr[2] = RS_FETCH_GOAL_BLOCK;
+  rs_philox4x32_10(ctr, key, r);
+  for (int k = 0; k < 3; k++) goal[k] = p.gripper_xpos[k] + (2.0f * rs_u01(r[k]) - 1.0f) * p.target_range;   // fetch_env.py:155-157 / :164-166
+  if (p.has_object) {
+    for (int k = 0; k < 3; k++) goal[k] += p.target_offset[k];                                                // :158
+    goal[2] = p.height_offset;                                                                                // :159
+    if (p.target_in_the_air && rs_u01(r[3]) < 0.5f) {                                                         // :160-161
+      ctr[2] = RS_FETCH_GOAL_BLOCK + 1;
+      rs_philox4x32_10(ctr, key, r);
+      goal[2] += rs_u01(r[0]) * 0.45f;
+    }
+  }
+}
+
+// one env's state record <- rest record + draws
+RS_HD void rs_fetch_reset_record(const b200sim_fetch_reset_t& p, unsigned long long seed, uint32_t env, uint32_t episode, const float* rest,
+                                 int stride, int st_qpos, int st_goal, float* rec) {
+  float xy[2] = {0.f, 0.f}, goal[3];
+  rs_fetch_reset_draw(p, seed, env, episode, xy, goal);
+  for (int k = 0; k < stride; k++) rec[k] = rest[k];
+  if (p.has_object) { rec[st_qpos + p.obj_qadr] = xy[0]; rec[st_qpos + p.obj_qadr + 1] = xy[1]; }
+  for (int k = 0; k < 3; k++) rec[st_goal + k] = goal[k];
+}

@@ -145,6 +145,13 @@ class CudaBackend:
         else:
             self._check(self.L.b200sim_raw_step_masked(self.h, mask.data_ptr(), int(nstep), *self._ptrs(out), self._stream()))
 
+    def reset_draw(self, mask, rest_record, params, seed, env_offset, episode, out):
+        """b200sim_reset: in-kernel draw of object start + goal for the masked envs (None = all), then mj_forward + _get_obs."""
+        assert rest_record.is_cuda and rest_record.dtype == torch.float32 and rest_record.numel() == self.layout["stride"]
+        assert episode.is_cuda and episode.dtype == torch.int32 and episode.numel() == self.num_envs
+        self._check(self.L.b200sim_reset(self.h, mask.data_ptr() if mask is not None else None, rest_record.data_ptr(), ctypes.byref(params),
+                                         int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), episode.data_ptr(), *self._ptrs(out), self._stream()))
+
     def compute_reward(self, ag, dg):
         ag = ag.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)
         dg = dg.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)
@@ -185,11 +192,17 @@ class FetchVectorEnv(CtorPickle):
         factory = backend_factory or CudaBackend
         self.backend = factory(self.model, eq, self.task, self.num_envs, device)
         self.device = self.backend.device
+        # "numpy": per-env PCG64 streams in the reference's draw order (value-equal resets); "torch": torch's device generator;
+        # "device": the draws happen inside the library (b200sim_reset, csrc/reset_sample.cuh) -- no host work per reset
+        if rng_mode not in ("auto", "numpy", "torch", "device"):
+            raise ValueError("rng_mode must be auto, numpy, torch or device")
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self.env_offset = int(kwargs.get("env_offset", 0))   # global index of env 0 (sharded runs, sharding.py)
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None
         self._gen = torch.Generator(device=self.device)
         self._gen.seed()
+        self._dev_seed = int(self._gen.initial_seed())
         lay = self.backend.layout
         self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", self.model.nq), ("qvel", self.model.nv), ("warm", self.model.nv),
                                                               ("ctrl", self.model.nu), ("mocap", 7), ("pose", 7), ("goal", 3))}
@@ -289,7 +302,36 @@ class FetchVectorEnv(CtorPickle):
             return self._all_idx
         return torch.nonzero(mask, as_tuple=False).flatten()
 
+    def _device_reset_params(self):
+        from ._lib import FetchResetC
+
+        cfg, p = self.cfg, FetchResetC()
+        p.has_object, p.target_in_the_air, p.obj_qadr = int(cfg["has_object"]), int(cfg["target_in_the_air"]), max(self._obj_qadr, 0)
+        p.obj_range, p.target_range = float(cfg.get("obj_range", 0.0)), float(cfg["target_range"])
+        g0 = self.initial_gripper_xpos.cpu().tolist()
+        for k in range(3):
+            p.target_offset[k] = float(np.broadcast_to(np.asarray(cfg["target_offset"], dtype=np.float64), (3,))[k])
+            p.gripper_xpos[k] = float(g0[k])
+        p.height_offset = float(self.height_offset or 0.0)
+        rest = torch.zeros(self.backend.state.shape[1], dtype=torch.float32, device=self.device)   # mj_resetData
+        rest[self._sl["qpos"]] = self.initial_qpos
+        rest[self._sl["qvel"]] = self.initial_qvel
+        rest[self._sl["mocap"]] = self._mocap_rest
+        return p, rest
+
     def _reset_envs(self, mask, out):
+        if self.rng_mode == "device":
+            if getattr(self, "_dev_reset", None) is None:
+                self._dev_reset = self._device_reset_params()
+                self._episode = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+            every = getattr(self, "_reset_all", False)
+            p, rest = self._dev_reset
+            self.backend.reset_draw(None if every else mask.to(torch.uint8), rest, p, self._dev_seed, self.env_offset, self._episode, out)
+            if every:
+                self._elapsed.zero_()
+            else:
+                self._elapsed.masked_fill_(mask, 0)
+            return
         idx = self._mask_indices(mask)
         if idx.numel() == 0:
             return
@@ -316,6 +358,10 @@ class FetchVectorEnv(CtorPickle):
             if self.rng_mode == "numpy":
                 self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(s))) for s in seeds]
             self._gen.manual_seed(int(seeds[0]))
+            if self.rng_mode == "device":   # one key for the batch; env index and episode counter select the stream
+                self._dev_seed = int(seeds[0])
+                if getattr(self, "_episode", None) is not None:
+                    self._episode.zero_()
         out = self.backend.new_outputs()
         mask = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
         self._reset_all = True

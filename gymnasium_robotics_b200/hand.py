@@ -125,6 +125,8 @@ class HandVectorEnv(FetchVectorEnv):
         factory = backend_factory or _HandBackend
         self.backend = factory(m, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device
+        if rng_mode == "device":
+            raise NotImplementedError("rng_mode='device' (in-kernel reset draws, b200sim_reset) exists for the Fetch family only")
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None
@@ -360,6 +362,8 @@ class HandReachVectorEnv(FetchVectorEnv):
         factory = backend_factory or _HandBackend
         self.backend = factory(m, np.zeros((0, 11)), t, self.num_envs, device)
         self.device = self.backend.device
+        if rng_mode == "device":
+            raise NotImplementedError("rng_mode='device' (in-kernel reset draws, b200sim_reset) exists for the Fetch family only")
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None

@@ -88,6 +88,8 @@ class KitchenVectorEnv(CtorPickle):
         self.task = make_kitchen_task(m, frame_skip)
         self.backend = (backend_factory or _KitchenBackend)(m, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = dev = self.backend.device
+        if rng_mode == "device":
+            raise NotImplementedError("rng_mode='device' (in-kernel reset draws, b200sim_reset) exists for the Fetch family only")
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None

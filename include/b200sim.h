@@ -101,6 +101,23 @@ int b200sim_raw_step(b200sim_t* h, int nstep, float* obs, float* achieved, float
  * (reference: envs/shadow_dexterous_hand/manipulate.py:213-222, 10 x mj_step(nstep=n_substeps) inside _reset_sim). */
 int b200sim_raw_step_masked(b200sim_t* h, const unsigned char* mask, int nstep, float* obs, float* achieved, float* desired,
                             float* reward, float* success, void* stream);
+/* Draw parameters of a Fetch reset (reference: envs/fetch/fetch_env.py:375-402 _reset_sim, :153-166 _sample_goal; the values the
+ * reference keeps on the env object: obj_range, target_range, target_offset, target_in_the_air, height_offset,
+ * initial_gripper_xpos); obj_qadr = qpos address of "object0:joint". */
+typedef struct b200sim_fetch_reset {
+  int has_object, target_in_the_air, obj_qadr;
+  float obj_range, target_range, target_offset[3], height_offset, gripper_xpos[3];
+} b200sim_fetch_reset_t;
+/* In-kernel reset of the envs with mask[i] != 0 (mask NULL = all), Fetch task family: the env's state record becomes
+ * `rest_record` (device, [stride] floats: mj_resetData + initial qpos / qvel / mocap, fetch_env.py:376-381) with the object start
+ * and the goal drawn on the device -- Philox4x32-10 keyed by `seed`, counter (env index + env_offset, episode[i]) -- followed by
+ * mj_forward + _get_obs exactly as b200sim_refresh.  `episode` (device, [N] int32, may be NULL = episode 0) holds per-env
+ * episode counters and is incremented for the reset envs, so that consecutive resets of an env never repeat a draw;
+ * `env_offset` is the global index of this handle's first env (sharded runs draw what one big batch would draw).
+ * Replaces the per-env np_random draws of BaseRobotEnv.reset (robot_env.py:154-186) in the throughput RNG mode. */
+int b200sim_reset(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_fetch_reset_t* params,
+                  unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired, float* reward,
+                  float* success, void* stream);
 /* GoalEnv.compute_reward on M (achieved, desired) pairs, device pointers (reference: fetch_env.py:74-80). */
 int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const float* desired, int M, float* out, void* stream);
 /* number of kernel launches issued through this handle so far */

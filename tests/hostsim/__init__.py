@@ -35,7 +35,8 @@ def build(force=False, wide=False):
                                "kitchen_flat": "libhostsim_kitchen_flat.so"}.get(wide, "libhostsim.so"))
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_ROOT, "gymnasium_robotics_b200", "csrc", f)
                                                    for f in ("sim_core.cuh", "dmodel.h", "fetch_task.cuh")] + \
-           [os.path.join(_ROOT, "include", "b200sim_model.h")]
+           [os.path.join(_ROOT, "include", "b200sim_model.h"), os.path.join(_ROOT, "include", "b200sim.h"),
+            os.path.join(_ROOT, "gymnasium_robotics_b200", "csrc", "reset_sample.cuh")]
     if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function"] + ({"kitchen": ["-DB200_KITCHEN"], "kitchen_flat": ["-DB200_KITCHEN", "-DB200_KITCHEN_FLATSCAN"]}.get(wide) or (["-DB200_WIDE"] if wide else [])) +
                               ["-o", out, srcs[0]])

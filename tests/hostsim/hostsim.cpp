@@ -62,5 +62,12 @@ int hostsim_env_step(void* p, const FetchTask* t, int mode, int nraw, float* st,
   return it;
 }
 }
+// in-kernel reset sampling (csrc/reset_sample.cuh), the same code the CUDA reset kernel runs
+#include "../../gymnasium_robotics_b200/csrc/reset_sample.cuh"
+extern "C" void hostsim_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { rs_philox4x32_10(ctr, key, out); }
+extern "C" void hostsim_fetch_reset_record(const b200sim_fetch_reset_t* p, unsigned long long seed, unsigned env, unsigned episode, const float* rest,
+                                           int stride, int st_qpos, int st_goal, float* rec) {
+  rs_fetch_reset_record(*p, seed, env, episode, rest, stride, st_qpos, st_goal, rec);
+}
 extern "C" int hostsim_model_words(void* p) { return ((HostSim*)p)->ctx.h->nwords; }
 extern "C" int hostsim_hot_words(void* p) { return ((HostSim*)p)->ctx.h->hot_words; }

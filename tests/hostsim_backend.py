@@ -67,6 +67,24 @@ class HostSimBackend:
     def raw_step(self, nstep, out, mask=None):
         self._run(2, nstep, None, mask, out)
 
+    def reset_draw(self, mask, rest_record, params, seed, env_offset, episode, out):
+        """b200sim_reset on the emulation: the same csrc/reset_sample.cuh code, env by env, then the refresh."""
+        import ctypes
+
+        L = self.sim._L
+        L.hostsim_fetch_reset_record.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.hostsim_fetch_reset_record.restype = None
+        st, rest = self.state.numpy(), rest_record.numpy()
+        for i in range(self.num_envs):
+            if mask is not None and not bool(mask[i]):
+                continue
+            L.hostsim_fetch_reset_record(ctypes.byref(params), int(seed) & 0xFFFFFFFFFFFFFFFF, i + int(env_offset), int(episode[i]), rest.ctypes.data,
+                                         self.layout["stride"], self.layout["qpos"], self.layout["goal"], st[i].ctypes.data)
+            episode[i] += 1
+        self.launches += 1
+        self.refresh(mask, out)
+
     def compute_reward(self, ag, dg):
         ag = ag.to(torch.float32).reshape(-1, self.ngoal); dg = dg.to(torch.float32).reshape(-1, self.ngoal)
         if self.task.kind == 2:  # same arithmetic as the kernel's hand_goal_distance / hand_reward (fetch_task.cuh)

@@ -1,0 +1,176 @@
+"""In-kernel reset draws (csrc/reset_sample.cuh, C-ABI b200sim_reset) on CPU: the Philox4x32-10 rounds against
+the published known answers, the draw logic against a pure-Python restatement of fetch_env.py:386-399 / :153-166 on the same
+random numbers, the distributions, and the vector env in rng_mode="device" on the host emulation backend."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import gymnasium_robotics_b200 as pkg
+from gymnasium_robotics_b200._lib import FetchResetC
+from tests import hostsim
+from tests.hostsim_backend import HostSimBackend
+
+M32 = 0xFFFFFFFF
+
+
+def philox4x32_10(ctr, key):
+    """Salmon et al. 2011, written independently of the C code (python ints)."""
+    c, k = list(ctr), list(key)
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & M32, p1 & M32, ((p0 >> 32) ^ c[3] ^ k[1]) & M32, p0 & M32]
+        k = [(k[0] + 0x9E3779B9) & M32, (k[1] + 0xBB67AE85) & M32]
+    return c
+
+
+def c_philox(ctr, key):
+    L = hostsim.lib()
+    a, b, o = (ctypes.c_uint32 * 4)(*ctr), (ctypes.c_uint32 * 2)(*key), (ctypes.c_uint32 * 4)()
+    L.hostsim_philox4x32_10(a, b, o)
+    return list(o)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors, philox4x32 10 rounds."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((M32, M32, M32, M32), (M32, M32), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(philox4x32_10(ctr, key)) == want
+        assert tuple(c_philox(ctr, key)) == want
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        ctr, key = [int(x) for x in rng.integers(0, 2 ** 32, 4)], [int(x) for x in rng.integers(0, 2 ** 32, 2)]
+        assert c_philox(ctr, key) == philox4x32_10(ctr, key)
+
+
+def u01(x):
+    return np.float32(x >> 8) * np.float32(1.0 / 16777216.0)
+
+
+def py_fetch_draw(p, seed, env, episode):
+    """fetch_env.py:386-392 and :153-166 on the generator's numbers, float32 like the kernel."""
+    f = np.float32
+    key = (seed & M32, (seed >> 32) & M32)
+    g0 = np.array(list(p.gripper_xpos), dtype=f)
+    xy = np.zeros(2, dtype=f)
+    if p.has_object:
+        done = False
+        for b in range(64):
+            r = philox4x32_10((env, episode, b, 0x5EED), key)
+            for h in range(2):
+                d = np.array([(f(2) * u01(r[2 * h]) - f(1)) * f(p.obj_range), (f(2) * u01(r[2 * h + 1]) - f(1)) * f(p.obj_range)], dtype=f)
+                xy = g0[:2] + d
+                if np.sqrt(d[0] * d[0] + d[1] * d[1]) >= f(0.1):
+                    done = True
+                    break
+            if done:
+                break
+    r = philox4x32_10((env, episode, 64, 0x5EED), key)
+    goal = np.array([g0[k] + (f(2) * u01(r[k]) - f(1)) * f(p.target_range) for k in range(3)], dtype=f)
+    if p.has_object:
+        goal = goal + np.array(list(p.target_offset), dtype=f)
+        goal[2] = f(p.height_offset)
+        if p.target_in_the_air and u01(r[3]) < f(0.5):
+            r2 = philox4x32_10((env, episode, 65, 0x5EED), key)
+            goal[2] += u01(r2[0]) * f(0.45)
+    return xy, goal
+
+
+def c_fetch_record(p, seed, env, episode, rest, st_qpos, st_goal):
+    L = hostsim.lib()
+    L.hostsim_fetch_reset_record.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.hostsim_fetch_reset_record.restype = None
+    rec = np.zeros_like(rest)
+    L.hostsim_fetch_reset_record(ctypes.byref(p), seed, env, episode, rest.ctypes.data, len(rest), st_qpos, st_goal, rec.ctypes.data)
+    return rec
+
+
+def params(has_object=True, air=True, obj_range=0.15, target_range=0.15, offset=(0.0, 0.0, 0.0)):
+    p = FetchResetC()
+    p.has_object, p.target_in_the_air, p.obj_qadr = int(has_object), int(air), 15
+    p.obj_range, p.target_range, p.height_offset = obj_range, target_range, 0.42
+    for k in range(3):
+        p.target_offset[k] = offset[k]
+        p.gripper_xpos[k] = (1.34, 0.75, 0.53)[k]
+    return p
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(air=False, obj_range=0.1, target_range=0.3, offset=(0.4, 0.0, 0.0)), dict(has_object=False)])
+def test_draw_matches_the_python_restatement_and_the_reference_distributions(cfg):
+    p = params(**cfg)
+    rest = np.arange(60, dtype=np.float32)
+    g0 = np.array(list(p.gripper_xpos))
+    xs, gs = [], []
+    for env in range(400):
+        rec = c_fetch_record(p, 0x1234567890ABCDEF, env, env % 3, rest, 0, 56)
+        xy, goal = py_fetch_draw(p, 0x1234567890ABCDEF, env, env % 3)
+        assert np.array_equal(rec[56:59], goal)
+        untouched = np.ones(60, dtype=bool)
+        untouched[56:59] = False
+        if p.has_object:
+            assert np.array_equal(rec[15:17], xy)
+            untouched[15:17] = False
+        assert np.array_equal(rec[untouched], rest[untouched])      # everything else is the rest record
+        xs.append(rec[15:17].astype(np.float64)); gs.append(rec[56:59].astype(np.float64))
+    xs, gs = np.array(xs), np.array(gs)
+    off = np.array(list(p.target_offset))
+    if p.has_object:
+        d = np.linalg.norm(xs - g0[:2], axis=1)
+        assert d.min() >= 0.1 - 1e-6 and np.abs(xs - g0[:2]).max() <= p.obj_range + 1e-6      # fetch_env.py:386-392
+        assert np.abs(gs[:, :2] - g0[:2] - off[:2]).max() <= p.target_range + 1e-6
+        lifted = gs[:, 2] > p.height_offset + 1e-9
+        if p.target_in_the_air:
+            assert 0.4 < lifted.mean() < 0.6 and gs[:, 2].max() <= p.height_offset + 0.45       # :160-161
+        else:
+            assert not lifted.any()
+        assert abs(np.mean(gs[:, 0] - g0[0] - off[0])) < 4 * p.target_range / np.sqrt(3 * 400)
+    else:
+        assert np.abs(gs - g0).max() <= p.target_range + 1e-6 and gs[:, 2].std() > 0.02
+
+
+def mk(task, n, **kw):
+    return pkg.make_vec(task, num_envs=n, backend_factory=HostSimBackend, rng_mode="device", **kw)
+
+
+def test_vector_env_with_in_kernel_resets():
+    env = mk("FetchPickAndPlace-v4", 4, max_episode_steps=3)
+    o1, _ = env.reset(seed=7)
+    g0 = env.initial_gripper_xpos.numpy()
+    st, _ = env.get_state()
+    q = st[:, :22]
+    # reset-state invariant (reference tests/test_envs.py:175-231): qpos == initial_qpos except the object's xy
+    assert torch.equal(q[:, :15], env.initial_qpos[:15].expand(4, 15)) and torch.equal(q[:, 17:], env.initial_qpos[17:].expand(4, 5))
+    assert (np.linalg.norm(q[:, 15:17].numpy() - g0[:2], axis=1) >= 0.1 - 1e-6).all()
+    assert len({tuple(r) for r in o1["desired_goal"].numpy().round(6).tolist()}) == 4          # every env its own stream
+    env2 = mk("FetchPickAndPlace-v4", 4, max_episode_steps=3)
+    o2, _ = env2.reset(seed=7)
+    assert torch.equal(o1["desired_goal"], o2["desired_goal"]) and torch.equal(o1["observation"], o2["observation"])
+    o3, _ = env2.reset(seed=8)
+    assert not torch.equal(o1["desired_goal"], o3["desired_goal"])
+    # next-step autoreset: new goals for the next episode, drawn from the episode counter
+    goals = [o1["desired_goal"].clone()]
+    for k in range(8):
+        o, r, te, tr, info = env.step(np.zeros((4, 4), dtype=np.float32))
+        if k in (3, 7):      # the call after a truncation is the reset call
+            goals.append(o["desired_goal"].clone())
+    assert not torch.equal(goals[0], goals[1]) and not torch.equal(goals[1], goals[2])
+    assert int(env._episode.min()) == 3 and int(env._episode.max()) == 3
+    # a shard that starts at global env 2 draws what envs 2, 3 of the big batch drew
+    shard = mk("FetchPickAndPlace-v4", 2, env_offset=2)
+    os_, _ = shard.reset(seed=7)
+    assert torch.equal(os_["desired_goal"], o1["desired_goal"][2:])
+    with pytest.raises(NotImplementedError):
+        pkg.make_vec("AntMaze_UMaze-v5", num_envs=1, backend_factory=HostSimBackend, rng_mode="device")
+
+
+def test_reach_has_no_object_draw():
+    env = mk("FetchReach-v4", 3)
+    o, _ = env.reset(seed=1)
+    g0 = env.initial_gripper_xpos.numpy()
+    assert np.abs(o["desired_goal"].numpy() - g0).max() <= 0.15 + 1e-6
+    st, _ = env.get_state()
+    assert torch.equal(st[:, :15], env.initial_qpos.expand(3, 15))
