@@ -171,13 +171,15 @@ def run_ours(args):
     env_id, nact, nsub, b_alg, default_n = WORKLOADS[args.workload]
     n = args.envs_per_gpu or default_n
     if args.workload == "fetch_pick_and_place":
-        env = FetchVectorEnv(TASK, num_envs=n, device=dev, rng_mode="torch", autoreset_mode="same_step")
+        # --rng-mode device: resets drawn inside the library (b200sim_reset) with seeds invariant to the world size
+        kw = dict(env_offset=rank * n) if args.rng_mode == "device" else {}
+        env = FetchVectorEnv(TASK, num_envs=n, device=dev, rng_mode=args.rng_mode, autoreset_mode="same_step", **kw)
     else:
         import gymnasium_robotics_b200 as grb
 
         extra = {"experimental": True} if args.workload == "franka_kitchen" else {}
         env = grb.make_vec(env_id, num_envs=n, device=dev, rng_mode="torch", autoreset_mode="same_step", **extra)
-    env.reset(seed=1000 * rank)  # seeds seed0 + global env index would need numpy streams; device RNG is per rank
+    env.reset(seed=0 if args.rng_mode == "device" else 1000 * rank)  # seeds seed0 + global env index would need numpy streams; device RNG is per rank
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     tape = torch.rand((64, n, nact), generator=g, device=dev) * 2 - 1  # pre-generated action tape (RNG outside the timed region)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > L2 (126 MB)
@@ -287,7 +289,8 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{env_id}, {n} envs/GPU, {nsub} sub-steps/env-step, random actions U(-1,1), TimeLimit, "
                                        "same-step autoreset", "envs_per_gpu": n, "l2": "flushed between timed iterations (256 MB fill)",
-                           "parallelism": f"env-sharded x{world}, no data-path collective"},
+                           "parallelism": f"env-sharded x{world}, no data-path collective",
+                           "reset_rng": "in-kernel Philox (b200sim_reset)" if args.rng_mode == "device" else "torch device generator"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": how, "algorithmic_bytes_per_env_step": b_alg,
                              "kernel_ms": kms,
@@ -312,6 +315,8 @@ def main():
     ap.add_argument("--workload", default="fetch_pick_and_place", choices=sorted(WORKLOADS))
     ap.add_argument("--sample-envs", type=int, default=256, help="envs per step of the CPU arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rng-mode", default="torch", choices=["torch", "device"],
+                    help="reset draws of the Fetch workload: torch's device generator (default) or in-kernel (b200sim_reset)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
