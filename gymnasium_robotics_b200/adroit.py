@@ -108,6 +108,8 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
     metadata = {"render_modes": [], "render_fps": 100, "autoreset_mode": "next_step"}
     TASK_NAME, MODEL_NAME = "AdroitHandHammer", "adroit_hammer"
     make_task = staticmethod(make_hammer_task)
+    # rng_mode="device" (b200sim_reset_uniform): (record field, offset inside it, low, high) per draw, in the reference's draw order
+    DEVICE_RESET = (("penv", 2, BOARD_Z_RANGE[0], BOARD_Z_RANGE[1]),)                                       # adroit_hammer.py:372-378
 
     def __init__(self, num_envs: int = 1, reward_type: str = "dense", max_episode_steps: Optional[int] = 200, device="cuda:0",
                  rng_mode: str = "auto", autoreset_mode: str = "next_step", frame_skip: int = FRAME_SKIP, backend_factory=None,
@@ -129,13 +131,15 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         factory = backend_factory or _AdroitBackend
         self.backend = factory(m, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device
-        if rng_mode == "device":
-            raise NotImplementedError("rng_mode='device' (in-kernel reset draws, b200sim_reset) exists for the Fetch family only")
+        if rng_mode == "device" and self.DEVICE_RESET is None:
+            raise NotImplementedError(f"rng_mode='device': {self.TASK_NAME}'s reset_model is not a plain list of uniform draws")
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self.env_offset = int(kwargs.get("env_offset", 0))
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None
         self._gen = torch.Generator(device=self.device)
         self._gen.seed()
+        self._dev_seed = int(self._gen.initial_seed())
         lay = self.backend.layout
         self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", m.nq), ("qvel", m.nv), ("warm", m.nv), ("ctrl", m.nu),
                                                               ("goal", 3), ("penv", 7))}
@@ -158,8 +162,33 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         self.closed = False
 
     # ------------------------------------------------------------------ reset
+    def _device_reset(self, mask, out):
+        """rng_mode="device": the uniform draws of reset_model happen inside the library (csrc/reset_sample.cuh)."""
+        if getattr(self, "_dev_reset", None) is None:
+            from ._lib import UniformResetC
+
+            p, sl = UniformResetC(), self._sl
+            p.n = len(self.DEVICE_RESET)
+            for k, (field, off, lo, hi) in enumerate(self.DEVICE_RESET):
+                p.slot[k], p.lo[k], p.hi[k] = sl[field].start + off, lo, hi
+            rest = torch.zeros(self.backend.state.shape[1], dtype=torch.float32, device=self.device)   # ctrl, warm start, time <- 0
+            rest[sl["qpos"]] = self.init_qpos
+            rest[sl["qvel"]] = self.init_qvel
+            rest[sl["penv"]] = self._board_pos0
+            self._dev_reset = (p, rest)
+            self._episode = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        every = getattr(self, "_reset_all", False)
+        p, rest = self._dev_reset
+        self.backend.reset_uniform(None if every else mask.to(torch.uint8), rest, p, self._dev_seed, self.env_offset, self._episode, out)
+        if every:
+            self._elapsed.zero_()
+        else:
+            self._elapsed.masked_fill_(mask, 0)
+
     def _reset_envs(self, mask, out):
         """MujocoEnv.reset -> mj_resetData -> reset_model (adroit_hammer.py:372-378) for the envs in `mask`."""
+        if self.rng_mode == "device":
+            return self._device_reset(mask, out)
         idx = self._mask_indices(mask)
         if idx.numel() == 0:
             return
@@ -221,9 +250,13 @@ class AdroitRelocateVectorEnv(AdroitHammerVectorEnv):
 
     TASK_NAME, MODEL_NAME = "AdroitHandRelocate", "adroit_relocate"
     make_task = staticmethod(make_relocate_task)
+    DEVICE_RESET = (("penv", 0, -0.15, 0.15), ("penv", 1, -0.15, 0.3), ("goal", 0, -0.2, 0.2), ("goal", 1, -0.2, 0.2),
+                    ("goal", 2, 0.15, 0.35))                                                                   # adroit_relocate.py:354-373
 
     def _reset_envs(self, mask, out):
         """reset_model (adroit_relocate.py:354-373): five uniform draws in the reference's order."""
+        if self.rng_mode == "device":
+            return self._device_reset(mask, out)
         idx = self._mask_indices(mask)
         if idx.numel() == 0:
             return
@@ -276,6 +309,7 @@ class AdroitPenVectorEnv(AdroitHammerVectorEnv):
     (envs/adroit_hand/adroit_pen.py:288-430)."""
 
     TASK_NAME, MODEL_NAME = "AdroitHandPen", "adroit_pen"
+    DEVICE_RESET = None   # the target orientation is euler2quat of two draws (adroit_pen.py:379-384): not a plain uniform slot
     make_task = staticmethod(make_pen_task)
 
     def _reset_envs(self, mask, out):
@@ -328,10 +362,13 @@ class AdroitDoorVectorEnv(AdroitHammerVectorEnv):
     door frame position (model.body_pos[frame]) is per-env state (envs/adroit_hand/adroit_door.py:279-402)."""
 
     TASK_NAME, MODEL_NAME = "AdroitHandDoor", "adroit_door"
+    DEVICE_RESET = (("penv", 0, -0.3, -0.2), ("penv", 1, 0.25, 0.35), ("penv", 2, 0.252, 0.35))              # adroit_door.py:359-371
     make_task = staticmethod(make_door_task)
 
     def _reset_envs(self, mask, out):
         """reset_model (adroit_door.py:359-371): three uniform draws (x, y, z of the frame)."""
+        if self.rng_mode == "device":
+            return self._device_reset(mask, out)
         idx = self._mask_indices(mask)
         if idx.numel() == 0:
             return

@@ -56,6 +56,15 @@ __global__ void fetch_reset_kernel(b200sim_fetch_reset_t p, unsigned long long s
   if (episode) episode[i] = ep + 1;
 }
 
+__global__ void uniform_reset_kernel(b200sim_uniform_reset_t p, unsigned long long seed, int env_offset, int N, const unsigned char* __restrict__ mask,
+                                     const float* __restrict__ rest, int stride, float* __restrict__ state, int* __restrict__ episode) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || (mask && !mask[i])) return;
+  int ep = episode ? episode[i] : 0;
+  rs_uniform_reset_record(p, seed, (uint32_t)(i + env_offset), (uint32_t)ep, rest, stride, state + (size_t)i * stride);
+  if (episode) episode[i] = ep + 1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 #define B200_FOR_ALL_VARIANTS(X) X(7, 14) X(7, 15) X(7, 21) X(14, 14) X(14, 15) X(14, 21) X(28, 14) X(28, 15) X(28, 21) \
   X(7, 22) X(14, 22) X(28, 22) X(7, 30) X(14, 30)
@@ -295,6 +304,20 @@ int b200sim_reset(b200sim_t* h, const unsigned char* mask, const float* rest_rec
   CUDA_OK(cudaSetDevice(h->device));
   fetch_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
                                                                           h->task.st_qpos, h->task.st_goal, h->state, episode);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+}
+int b200sim_reset_uniform(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_uniform_reset_t* params,
+                          unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired,
+                          float* reward, float* success, void* stream) {
+  if (!rest_record || !params) return fail(h, "b200sim_reset_uniform: rest_record / params is NULL", -1);
+  if (params->n < 0 || params->n > B200SIM_RESET_SLOTS_MAX) return fail(h, "b200sim_reset_uniform: more than 16 slots", -1);
+  for (int k = 0; k < params->n; k++)
+    if (params->slot[k] < 0 || params->slot[k] >= h->task.st_stride) return fail(h, "b200sim_reset_uniform: slot outside the state record", -1);
+  CUDA_OK(cudaSetDevice(h->device));
+  uniform_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
+                                                                            h->state, episode);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);

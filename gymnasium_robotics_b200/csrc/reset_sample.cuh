@@ -86,3 +86,17 @@ RS_HD void rs_fetch_reset_record(const b200sim_fetch_reset_t& p, unsigned long l
   if (p.has_object) { rec[st_qpos + p.obj_qadr] = xy[0]; rec[st_qpos + p.obj_qadr + 1] = xy[1]; }
   for (int k = 0; k < 3; k++) rec[st_goal + k] = goal[k];
 }
+
+// Generic form for reset_model functions that are a fixed list of uniform draws written into the env's record (the Adroit envs:
+// adroit_hammer.py:372-378 board height; adroit_relocate.py:354-373 ball xy + target xyz; adroit_door.py:359-371 frame xyz):
+// slot k of the list <- lo[k] + (hi[k] - lo[k]) * u, u = word k % 4 of Philox block k / 4 of the (seed; env, episode) stream.
+RS_HD void rs_uniform_reset_record(const b200sim_uniform_reset_t& p, unsigned long long seed, uint32_t env, uint32_t episode, const float* rest,
+                                   int stride, float* rec) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t ctr[4] = {env, episode, 0u, 0x0A11u}, r[4] = {0u, 0u, 0u, 0u};
+  for (int k = 0; k < stride; k++) rec[k] = rest[k];
+  for (int k = 0; k < p.n; k++) {
+    if ((k & 3) == 0) { ctr[2] = (uint32_t)(k >> 2); rs_philox4x32_10(ctr, key, r); }
+    rec[p.slot[k]] = p.lo[k] + (p.hi[k] - p.lo[k]) * rs_u01(r[k & 3]);
+  }
+}

@@ -152,6 +152,13 @@ class CudaBackend:
         self._check(self.L.b200sim_reset(self.h, mask.data_ptr() if mask is not None else None, rest_record.data_ptr(), ctypes.byref(params),
                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), episode.data_ptr(), *self._ptrs(out), self._stream()))
 
+    def reset_uniform(self, mask, rest_record, params, seed, env_offset, episode, out):
+        """b200sim_reset_uniform: record <- rest record + a fixed list of uniform draws, then mj_forward + _get_obs."""
+        assert rest_record.is_cuda and rest_record.dtype == torch.float32 and rest_record.numel() == self.layout["stride"]
+        assert episode.is_cuda and episode.dtype == torch.int32 and episode.numel() == self.num_envs
+        self._check(self.L.b200sim_reset_uniform(self.h, mask.data_ptr() if mask is not None else None, rest_record.data_ptr(), ctypes.byref(params),
+                                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), episode.data_ptr(), *self._ptrs(out), self._stream()))
+
     def compute_reward(self, ag, dg):
         ag = ag.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)
         dg = dg.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)

@@ -118,6 +118,17 @@ typedef struct b200sim_fetch_reset {
 int b200sim_reset(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_fetch_reset_t* params,
                   unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired, float* reward,
                   float* success, void* stream);
+/* The same for reset_model functions that are a fixed list of uniform draws (any task family; reference:
+ * adroit_hammer.py:372-378, adroit_relocate.py:354-373, adroit_door.py:359-371): record <- rest_record, then
+ * record[slot[k]] = lo[k] + (hi[k] - lo[k]) * u_k for k < n (u_k: word k % 4 of Philox block k / 4), then the refresh. */
+#define B200SIM_RESET_SLOTS_MAX 16
+typedef struct b200sim_uniform_reset {
+  int n, slot[B200SIM_RESET_SLOTS_MAX];   /* offsets in floats inside the state record (b200sim_layout) */
+  float lo[B200SIM_RESET_SLOTS_MAX], hi[B200SIM_RESET_SLOTS_MAX];
+} b200sim_uniform_reset_t;
+int b200sim_reset_uniform(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_uniform_reset_t* params,
+                          unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired,
+                          float* reward, float* success, void* stream);
 /* GoalEnv.compute_reward on M (achieved, desired) pairs, device pointers (reference: fetch_env.py:74-80). */
 int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const float* desired, int M, float* out, void* stream);
 /* number of kernel launches issued through this handle so far */

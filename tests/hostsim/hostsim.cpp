@@ -69,5 +69,9 @@ extern "C" void hostsim_fetch_reset_record(const b200sim_fetch_reset_t* p, unsig
                                            int stride, int st_qpos, int st_goal, float* rec) {
   rs_fetch_reset_record(*p, seed, env, episode, rest, stride, st_qpos, st_goal, rec);
 }
+extern "C" void hostsim_uniform_reset_record(const b200sim_uniform_reset_t* p, unsigned long long seed, unsigned env, unsigned episode, const float* rest,
+                                             int stride, float* rec) {
+  rs_uniform_reset_record(*p, seed, env, episode, rest, stride, rec);
+}
 extern "C" int hostsim_model_words(void* p) { return ((HostSim*)p)->ctx.h->nwords; }
 extern "C" int hostsim_hot_words(void* p) { return ((HostSim*)p)->ctx.h->hot_words; }

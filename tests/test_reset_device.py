@@ -174,3 +174,59 @@ def test_reach_has_no_object_draw():
     assert np.abs(o["desired_goal"].numpy() - g0).max() <= 0.15 + 1e-6
     st, _ = env.get_state()
     assert torch.equal(st[:, :15], env.initial_qpos.expand(3, 15))
+
+
+def test_uniform_slot_reset_against_python():
+    """b200sim_reset_uniform's record: slot k <- lo + (hi - lo) * u, u = word k % 4 of Philox block k / 4."""
+    from gymnasium_robotics_b200._lib import UniformResetC
+
+    L = hostsim.lib()
+    L.hostsim_uniform_reset_record.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int,
+                                               ctypes.c_void_p]
+    L.hostsim_uniform_reset_record.restype = None
+    p = UniformResetC()
+    slots, lo, hi = [3, 40, 41, 7, 12, 13], [-0.15, -0.15, -0.2, 0.1, 0.0, 5.0], [0.15, 0.3, 0.2, 0.25, 1.0, 5.0]
+    p.n = 6
+    for k in range(6):
+        p.slot[k], p.lo[k], p.hi[k] = slots[k], lo[k], hi[k]
+    rest = np.arange(48, dtype=np.float32)
+    seed = 99
+    vals = []
+    for env in range(300):
+        rec = np.zeros_like(rest)
+        L.hostsim_uniform_reset_record(ctypes.byref(p), seed, env, 2, rest.ctypes.data, 48, rec.ctypes.data)
+        f = np.float32
+        for k in range(6):
+            r = philox4x32_10((env, 2, k // 4, 0x0A11), (seed, 0))
+            want = f(lo[k]) + (f(hi[k]) - f(lo[k])) * u01(r[k % 4])
+            assert rec[slots[k]] == want
+        keep = np.ones(48, dtype=bool)
+        keep[slots] = False
+        assert np.array_equal(rec[keep], rest[keep])
+        vals.append(rec[slots])
+    vals = np.array(vals)
+    assert (vals >= np.array(lo, dtype=np.float32) - 1e-7).all() and (vals <= np.array(hi, dtype=np.float32) + 1e-7).all()
+    assert abs(vals[:, 0].mean()) < 0.03 and (vals[:, 5] == 5.0).all()
+
+
+def test_adroit_door_env_with_in_kernel_resets():
+    """adroit_door.py:359-371: the frame position is three uniform draws per episode; everything else is the model's rest state."""
+    from gymnasium_robotics_b200.adroit import ADROIT_REF_POINT
+
+    class AdroitHostBackend(HostSimBackend):
+        REF = ADROIT_REF_POINT
+
+    env = pkg.make_vec("AdroitHandDoor-v2", num_envs=3, backend_factory=AdroitHostBackend, rng_mode="device", max_episode_steps=2)
+    o, _ = env.reset(seed=5)
+    s = env.get_env_state()
+    pos = s["door_body_pos"].numpy()
+    assert ((pos >= [-0.3, 0.25, 0.252]) & (pos <= [-0.2, 0.35, 0.35])).all() and len({tuple(r) for r in pos.round(6).tolist()}) == 3
+    assert torch.equal(s["qpos"], env.init_qpos.expand(3, -1)) and torch.count_nonzero(s["qvel"]) == 0
+    env2 = pkg.make_vec("AdroitHandDoor-v2", num_envs=3, backend_factory=AdroitHostBackend, rng_mode="device")
+    o2, _ = env2.reset(seed=5)
+    assert torch.equal(o, o2)
+    for _ in range(3):     # TimeLimit 2: the third call is the next-step reset with new draws
+        o, *_ = env.step(np.zeros((3, 28), dtype=np.float32))
+    assert not np.array_equal(env.get_env_state()["door_body_pos"].numpy(), pos)
+    with pytest.raises(NotImplementedError):
+        pkg.make_vec("AdroitHandPen-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="device")

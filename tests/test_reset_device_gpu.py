@@ -57,3 +57,33 @@ def test_episodes_with_in_kernel_resets():
     # 45 step launches + 2 resets x (draw kernel + refresh)
     assert env.backend.launches - launches0 == 45 + 4
     env.close()
+
+
+def test_uniform_slot_resets_of_the_adroit_envs():
+    """b200sim_reset_uniform through the vector envs: Hammer (wide build) and Relocate draw per-env model poses on the device."""
+    import gymnasium_robotics_b200 as pkg
+    from tests.test_reset_device import philox4x32_10, u01
+
+    n, seed = 96, 11
+    env = pkg.make_vec("AdroitHandRelocate-v2", num_envs=n, rng_mode="device")
+    env.reset(seed=seed)
+    s = env.get_env_state()
+    obj, tgt = s["obj_pos"].cpu().numpy(), s["target_pos"].cpu().numpy()
+    lo, hi = np.float32([-0.15, -0.15, -0.2, -0.2, 0.15]), np.float32([0.15, 0.3, 0.2, 0.2, 0.35])
+    for i in range(n):
+        r = [philox4x32_10((i, 0, b, 0x0A11), (seed, 0)) for b in range(2)]
+        want = [lo[k] + (hi[k] - lo[k]) * u01(r[k // 4][k % 4]) for k in range(5)]
+        got = [obj[i, 0], obj[i, 1], tgt[i, 0], tgt[i, 1], tgt[i, 2]]
+        assert np.abs(np.float32(got) - np.float32(want)).max() < 1e-6, i
+    assert torch.equal(s["qpos"], env.init_qpos.expand(n, -1))
+    env.close()
+    env = pkg.make_vec("AdroitHandHammer-v2", num_envs=n, rng_mode="device", max_episode_steps=4, autoreset_mode="same_step")
+    env.reset(seed=seed)
+    z0 = env.get_env_state()["board_pos"][:, 2].clone()
+    assert float(z0.min()) >= 0.1 and float(z0.max()) <= 0.25 and float(z0.std()) > 0.02
+    for _ in range(4):
+        o, r, te, tr, info = env.step(torch.zeros((n, 26), device="cuda"))
+    assert bool(tr.all()) and torch.isfinite(o).all()
+    z1 = env.get_env_state()["board_pos"][:, 2]
+    assert not torch.equal(z0, z1) and float(z1.min()) >= 0.1 and float(z1.max()) <= 0.25
+    env.close()
