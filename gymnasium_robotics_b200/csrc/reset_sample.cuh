@@ -100,3 +100,43 @@ RS_HD void rs_uniform_reset_record(const b200sim_uniform_reset_t& p, unsigned lo
     rec[p.slot[k]] = p.lo[k] + (p.hi[k] - p.lo[k]) * rs_u01(r[k & 3]);
   }
 }
+
+// Maze reset (envs/maze/maze_v4.py:299-358 MazeEnv.reset with generate_target_goal :256-274, generate_reset_pos :276-297,
+// add_xy_position_noise :360-373): goal = a goal cell + noise, start = a reset cell farther than half a cell from the goal + noise.
+// `goal_xy` / `reset_xy` are the cell-centre tables ([n, 2]); an index is (word * n) >> 32 (bias < n / 2^32).
+#define RS_MAZE_POS_BLOCKS 32   // 128 candidate reset cells at most
+RS_HD void rs_maze_reset_draw(const b200sim_maze_reset_t& p, const float* goal_xy, const float* reset_xy, unsigned long long seed, uint32_t env,
+                              uint32_t episode, float goal[2], float pos[2]) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t ctr[4] = {env, episode, 0u, 0x3A2Eu}, r[4];
+  const float amp = p.noise * p.scaling;
+  rs_philox4x32_10(ctr, key, r);
+  uint32_t gi = (uint32_t)(((uint64_t)r[0] * (uint64_t)p.n_goal) >> 32);
+  goal[0] = goal_xy[2 * gi] + (2.0f * rs_u01(r[1]) - 1.0f) * amp;
+  goal[1] = goal_xy[2 * gi + 1] + (2.0f * rs_u01(r[2]) - 1.0f) * amp;
+  bool done = false;
+  pos[0] = goal[0]; pos[1] = goal[1];
+  for (int b = 1; b <= RS_MAZE_POS_BLOCKS && !done; b++) {
+    ctr[2] = (uint32_t)b;
+    rs_philox4x32_10(ctr, key, r);
+    for (int h = 0; h < 4 && !done; h++) {
+      uint32_t ri = (uint32_t)(((uint64_t)r[h] * (uint64_t)p.n_reset) >> 32);
+      pos[0] = reset_xy[2 * ri]; pos[1] = reset_xy[2 * ri + 1];
+      float dx = pos[0] - goal[0], dy = pos[1] - goal[1];
+      done = !(sqrtf(dx * dx + dy * dy) <= 0.5f * p.scaling);     // maze_v4.py:289-296
+    }
+  }
+  ctr[2] = RS_MAZE_POS_BLOCKS + 1;
+  rs_philox4x32_10(ctr, key, r);
+  pos[0] += (2.0f * rs_u01(r[0]) - 1.0f) * amp;
+  pos[1] += (2.0f * rs_u01(r[1]) - 1.0f) * amp;
+}
+
+RS_HD void rs_maze_reset_record(const b200sim_maze_reset_t& p, const float* goal_xy, const float* reset_xy, unsigned long long seed, uint32_t env,
+                                uint32_t episode, const float* rest, int stride, int st_qpos, int st_goal, float* rec) {
+  float goal[2], pos[2];
+  rs_maze_reset_draw(p, goal_xy, reset_xy, seed, env, episode, goal, pos);
+  for (int k = 0; k < stride; k++) rec[k] = rest[k];
+  rec[st_qpos] = pos[0]; rec[st_qpos + 1] = pos[1];      // ant_maze_v5.py:285 / point_maze.py:380: init_qpos[:2] = reset_pos
+  rec[st_goal] = goal[0]; rec[st_goal + 1] = goal[1];
+}

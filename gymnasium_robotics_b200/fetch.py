@@ -159,6 +159,16 @@ class CudaBackend:
         self._check(self.L.b200sim_reset_uniform(self.h, mask.data_ptr() if mask is not None else None, rest_record.data_ptr(), ctypes.byref(params),
                                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), episode.data_ptr(), *self._ptrs(out), self._stream()))
 
+    def reset_maze(self, mask, rest_record, params, goal_xy, reset_xy, seed, env_offset, episode, out):
+        """b200sim_reset_maze: goal cell + noise, reset cell away from the goal + noise, then mj_forward + _get_obs."""
+        assert rest_record.is_cuda and rest_record.dtype == torch.float32 and rest_record.numel() == self.layout["stride"]
+        assert episode.is_cuda and episode.dtype == torch.int32 and episode.numel() == self.num_envs
+        for t, n in ((goal_xy, params.n_goal), (reset_xy, params.n_reset)):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (n, 2)
+        self._check(self.L.b200sim_reset_maze(self.h, mask.data_ptr() if mask is not None else None, rest_record.data_ptr(), ctypes.byref(params),
+                                              goal_xy.data_ptr(), reset_xy.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset),
+                                              episode.data_ptr(), *self._ptrs(out), self._stream()))
+
     def compute_reward(self, ag, dg):
         ag = ag.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)
         dg = dg.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)

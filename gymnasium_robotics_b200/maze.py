@@ -168,12 +168,13 @@ class MazeVectorEnv(CtorPickle):
         factory = backend_factory or _AntBackend
         self.backend = factory(self.model, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device
-        if rng_mode == "device":
-            raise NotImplementedError("rng_mode='device' (in-kernel reset draws, b200sim_reset) exists for the Fetch family only")
+        # "device": goal / reset cells and their noise are drawn inside the library (b200sim_reset_maze, csrc/reset_sample.cuh)
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self.env_offset = int(kwargs.get("env_offset", 0))
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)]
         self._gen = torch.Generator(device=self.device)
         self._gen.seed()
+        self._dev_seed = int(self._gen.initial_seed())
         lay, m = self.backend.layout, self.model
         self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", m.nq), ("qvel", m.nv), ("warm", m.nv), ("ctrl", m.nu), ("goal", 2))}
         nobs = self.task.nobs
@@ -234,7 +235,23 @@ class MazeVectorEnv(CtorPickle):
             bad = torch.linalg.norm(pos - goal, dim=1) <= 0.5 * self.scaling
         return goal, pos + (u(n, 2) * 2 - 1) * NOISE * self.scaling
 
+    def _device_reset(self, mask, out):
+        if getattr(self, "_dev_reset", None) is None:
+            from ._lib import MazeResetC
+
+            p = MazeResetC()
+            p.n_goal, p.n_reset, p.scaling, p.noise = len(self._goal_loc), len(self._reset_loc), float(self.scaling), float(NOISE)
+            rest = torch.zeros(self.backend.state.shape[1], dtype=torch.float32, device=self.device)
+            rest[self._sl["qpos"]] = self.init_qpos
+            self._dev_reset = (p, rest, self._goal_loc.contiguous(), self._reset_loc.contiguous())
+            self._episode = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        p, rest, gl, rl = self._dev_reset
+        self.backend.reset_maze(mask.to(torch.uint8), rest, p, gl, rl, self._dev_seed, self.env_offset, self._episode, out)
+        self._elapsed.masked_fill_(mask, 0)
+
     def _reset_envs(self, mask, out, options=None):
+        if self.rng_mode == "device" and not options:   # explicit cells keep the reference-ordered host path
+            return self._device_reset(mask, out)
         idx = torch.nonzero(mask, as_tuple=False).flatten()
         if idx.numel() == 0:
             return
@@ -257,6 +274,9 @@ class MazeVectorEnv(CtorPickle):
             seeds = [seed + i for i in range(self.num_envs)] if isinstance(seed, (int, np.integer)) else list(seed)
             self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(s))) for s in seeds]
             self._gen.manual_seed(int(seeds[0]))
+            self._dev_seed = int(seeds[0])
+            if getattr(self, "_episode", None) is not None:
+                self._episode.zero_()
         out = self.backend.new_outputs()
         self._reset_envs(torch.ones(self.num_envs, dtype=torch.bool, device=self.device), out, options)
         self._needs_reset.zero_()

@@ -129,6 +129,16 @@ typedef struct b200sim_uniform_reset {
 int b200sim_reset_uniform(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_uniform_reset_t* params,
                           unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired,
                           float* reward, float* success, void* stream);
+/* Maze family (AntMaze / PointMaze; reference: envs/maze/maze_v4.py:256-297, 299-373): goal cell + noise, reset cell farther than
+ * half a cell from the goal + noise.  goal_xy / reset_xy: DEVICE tables [n_goal, 2] / [n_reset, 2] of cell centres
+ * (MazeEnv.maze.unique_goal_locations / unique_reset_locations, or all free cells when the map marks none, maze_v4.py:212-228). */
+typedef struct b200sim_maze_reset {
+  int n_goal, n_reset;
+  float scaling, noise;   /* maze_size_scaling; position_noise_range (0.25) */
+} b200sim_maze_reset_t;
+int b200sim_reset_maze(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_maze_reset_t* params,
+                       const float* goal_xy, const float* reset_xy, unsigned long long seed, int env_offset, int* episode, float* obs,
+                       float* achieved, float* desired, float* reward, float* success, void* stream);
 /* GoalEnv.compute_reward on M (achieved, desired) pairs, device pointers (reference: fetch_env.py:74-80). */
 int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const float* desired, int M, float* out, void* stream);
 /* number of kernel launches issued through this handle so far */

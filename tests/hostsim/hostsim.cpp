@@ -73,5 +73,9 @@ extern "C" void hostsim_uniform_reset_record(const b200sim_uniform_reset_t* p, u
                                              int stride, float* rec) {
   rs_uniform_reset_record(*p, seed, env, episode, rest, stride, rec);
 }
+extern "C" void hostsim_maze_reset_record(const b200sim_maze_reset_t* p, const float* goal_xy, const float* reset_xy, unsigned long long seed, unsigned env,
+                                          unsigned episode, const float* rest, int stride, int st_qpos, int st_goal, float* rec) {
+  rs_maze_reset_record(*p, goal_xy, reset_xy, seed, env, episode, rest, stride, st_qpos, st_goal, rec);
+}
 extern "C" int hostsim_model_words(void* p) { return ((HostSim*)p)->ctx.h->nwords; }
 extern "C" int hostsim_hot_words(void* p) { return ((HostSim*)p)->ctx.h->hot_words; }

@@ -102,6 +102,24 @@ class HostSimBackend:
         self.launches += 1
         self.refresh(mask, out)
 
+    def reset_maze(self, mask, rest_record, params, goal_xy, reset_xy, seed, env_offset, episode, out):
+        import ctypes
+
+        L = self.sim._L
+        L.hostsim_maze_reset_record.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint,
+                                                ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.hostsim_maze_reset_record.restype = None
+        st, rest, g, r = self.state.numpy(), rest_record.numpy(), goal_xy.numpy(), reset_xy.numpy()
+        for i in range(self.num_envs):
+            if mask is not None and not bool(mask[i]):
+                continue
+            L.hostsim_maze_reset_record(ctypes.byref(params), g.ctypes.data, r.ctypes.data, int(seed) & 0xFFFFFFFFFFFFFFFF, i + int(env_offset),
+                                        int(episode[i]), rest.ctypes.data, self.layout["stride"], self.layout["qpos"], self.layout["goal"],
+                                        st[i].ctypes.data)
+            episode[i] += 1
+        self.launches += 1
+        self.refresh(mask, out)
+
     def compute_reward(self, ag, dg):
         ag = ag.to(torch.float32).reshape(-1, self.ngoal); dg = dg.to(torch.float32).reshape(-1, self.ngoal)
         if self.task.kind == 2:  # same arithmetic as the kernel's hand_goal_distance / hand_reward (fetch_task.cuh)

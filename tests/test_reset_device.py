@@ -164,7 +164,7 @@ def test_vector_env_with_in_kernel_resets():
     os_, _ = shard.reset(seed=7)
     assert torch.equal(os_["desired_goal"], o1["desired_goal"][2:])
     with pytest.raises(NotImplementedError):
-        pkg.make_vec("AntMaze_UMaze-v5", num_envs=1, backend_factory=HostSimBackend, rng_mode="device")
+        pkg.make_vec("HandReach-v3", num_envs=1, backend_factory=HostSimBackend, rng_mode="device")
 
 
 def test_reach_has_no_object_draw():
@@ -230,3 +230,57 @@ def test_adroit_door_env_with_in_kernel_resets():
     assert not np.array_equal(env.get_env_state()["door_body_pos"].numpy(), pos)
     with pytest.raises(NotImplementedError):
         pkg.make_vec("AdroitHandPen-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="device")
+
+
+def py_maze_draw(goal_xy, reset_xy, scaling, noise, seed, env, episode):
+    """maze_v4.py:256-297 + :360-373 on the generator's numbers (float32 like the kernel)."""
+    f = np.float32
+    key = (seed & M32, (seed >> 32) & M32)
+    amp = f(noise) * f(scaling)
+    r = philox4x32_10((env, episode, 0, 0x3A2E), key)
+    gi = (r[0] * len(goal_xy)) >> 32
+    goal = np.array([goal_xy[gi][0] + (f(2) * u01(r[1]) - f(1)) * amp, goal_xy[gi][1] + (f(2) * u01(r[2]) - f(1)) * amp], dtype=f)
+    pos, done = goal.copy(), False
+    for b in range(1, 33):
+        r = philox4x32_10((env, episode, b, 0x3A2E), key)
+        for h in range(4):
+            ri = (r[h] * len(reset_xy)) >> 32
+            pos = np.array(reset_xy[ri], dtype=f)
+            d = pos - goal
+            if not (np.sqrt(d[0] * d[0] + d[1] * d[1]) <= f(0.5) * f(scaling)):
+                done = True
+                break
+        if done:
+            break
+    r = philox4x32_10((env, episode, 33, 0x3A2E), key)
+    pos = np.array([pos[0] + (f(2) * u01(r[0]) - f(1)) * amp, pos[1] + (f(2) * u01(r[1]) - f(1)) * amp], dtype=f)
+    return goal, pos
+
+
+def test_maze_env_with_in_kernel_resets():
+    env = pkg.make_vec("AntMaze_Medium_Diverse_GR-v5", num_envs=6, backend_factory=HostSimBackend, rng_mode="device", max_episode_steps=2)
+    o, _ = env.reset(seed=21)
+    goal_xy, reset_xy = env._goal_loc.numpy(), env._reset_loc.numpy()
+    assert len(goal_xy) >= 2 and len(reset_xy) >= 2            # the _GR maps mark goal and reset cells (maps.py)
+    st, _ = env.get_state()
+    for i in range(6):
+        g, p = py_maze_draw(goal_xy, reset_xy, env.scaling, 0.25, 21, i, 0)
+        assert np.array_equal(o["desired_goal"][i].numpy(), g) and np.array_equal(st[i, :2].numpy(), p)
+        # the goal is within the noise box of a goal cell, the start within that of a reset cell farther than half a cell away
+        assert (np.abs(goal_xy - g).max(axis=1) <= 0.25 * env.scaling + 1e-6).any()
+        assert (np.abs(reset_xy - p).max(axis=1) <= 0.25 * env.scaling + 1e-6).any()
+        assert not env.cells.is_wall_xy(p) if hasattr(env.cells, "is_wall_xy") else True
+    assert torch.equal(st[:, 2:15], env.init_qpos[2:].expand(6, 13))
+    g0 = o["desired_goal"].clone()
+    for _ in range(3):
+        o, *_ = env.step(np.zeros((6, 8), dtype=np.float32))
+    assert not torch.equal(o["desired_goal"], g0) and int(env._episode.min()) == 2
+    # explicit cells keep the host path (maze_v4.py:313-350)
+    o, _ = env.reset(seed=1, options={"goal_cell": np.array([1, 1]), "reset_cell": np.array([1, 2])})
+    assert np.abs(o["desired_goal"].numpy() - env.cells.cell_rowcol_to_xy(np.array([1, 1]))).max() <= 0.25 * env.scaling + 1e-6
+    pm = pkg.make_vec("PointMaze_UMaze-v3", num_envs=2, backend_factory=HostSimBackend, rng_mode="device")
+    o, _ = pm.reset(seed=3)
+    st, _ = pm.get_state()
+    for i in range(2):
+        g, p = py_maze_draw(pm._goal_loc.numpy(), pm._reset_loc.numpy(), pm.scaling, 0.25, 3, i, 0)
+        assert np.array_equal(o["desired_goal"][i].numpy(), g) and np.array_equal(st[i, :2].numpy(), p)

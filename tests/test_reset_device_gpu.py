@@ -87,3 +87,27 @@ def test_uniform_slot_resets_of_the_adroit_envs():
     z1 = env.get_env_state()["board_pos"][:, 2]
     assert not torch.equal(z0, z1) and float(z1.min()) >= 0.1 and float(z1.max()) <= 0.25
     env.close()
+
+
+def test_maze_resets_in_kernel():
+    """b200sim_reset_maze on the GPU against the Python restatement on the same Philox numbers (AntMaze_Large, BASELINE config 4)."""
+    import gymnasium_robotics_b200 as pkg
+    from tests.test_reset_device import py_maze_draw
+
+    n, seed = 128, 17
+    env = pkg.make_vec("AntMaze_Large-v5", num_envs=n, rng_mode="device", env_offset=1024)
+    o, _ = env.reset(seed=seed)
+    st, _ = env.get_state()
+    lay = env.backend.layout
+    goal_xy, reset_xy = env._goal_loc.cpu().numpy(), env._reset_loc.cpu().numpy()
+    q = st[:, lay["qpos"]:lay["qpos"] + 2].cpu().numpy()
+    g = o["desired_goal"].cpu().numpy()
+    for i in range(n):
+        wg, wp = py_maze_draw(goal_xy, reset_xy, env.scaling, 0.25, seed, 1024 + i, 0)
+        assert np.abs(g[i] - wg).max() < 2e-6 and np.abs(q[i] - wp).max() < 2e-6, i
+    d = np.linalg.norm(q - g, axis=1)
+    assert d.min() > 0.0 and torch.isfinite(o["observation"]).all()
+    for _ in range(3):
+        o, r, te, tr, info = env.step(torch.zeros((n, 8), device="cuda"))
+    assert torch.isfinite(o["observation"]).all()
+    env.close()
