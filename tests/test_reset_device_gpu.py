@@ -104,7 +104,7 @@ def test_maze_resets_in_kernel():
     g = o["desired_goal"].cpu().numpy()
     for i in range(n):
         wg, wp = py_maze_draw(goal_xy, reset_xy, env.scaling, 0.25, seed, 1024 + i, 0)
-        assert np.abs(g[i] - wg).max() < 2e-6 and np.abs(q[i] - wp).max() < 2e-6, i
+        assert np.abs(g[i] - wg).max() < 5e-6 and np.abs(q[i] - wp).max() < 5e-6, i   # coordinates up to 22: one fp32 ulp (FMA contraction) is 1.9e-6
     d = np.linalg.norm(q - g, axis=1)
     assert d.min() > 0.0 and torch.isfinite(o["observation"]).all()
     for _ in range(3):
