@@ -40,7 +40,8 @@ class FetchResetC(ctypes.Structure):
 
 class UniformResetC(ctypes.Structure):
     """b200sim_uniform_reset_t"""
-    _fields_ = [("n", ctypes.c_int), ("slot", ctypes.c_int * 16), ("lo", ctypes.c_float * 16), ("hi", ctypes.c_float * 16)]
+    _fields_ = [("n", ctypes.c_int), ("slot", ctypes.c_int * 16), ("lo", ctypes.c_float * 16), ("hi", ctypes.c_float * 16),
+                ("quat_slot", ctypes.c_int)]
 
 
 class MazeResetC(ctypes.Structure):

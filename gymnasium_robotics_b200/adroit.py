@@ -131,8 +131,6 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         factory = backend_factory or _AdroitBackend
         self.backend = factory(m, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device
-        if rng_mode == "device" and self.DEVICE_RESET is None:
-            raise NotImplementedError(f"rng_mode='device': {self.TASK_NAME}'s reset_model is not a plain list of uniform draws")
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
         self.env_offset = int(kwargs.get("env_offset", 0))
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
@@ -169,8 +167,13 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
 
             p, sl = UniformResetC(), self._sl
             p.n = len(self.DEVICE_RESET)
+            p.quat_slot = -1
             for k, (field, off, lo, hi) in enumerate(self.DEVICE_RESET):
-                p.slot[k], p.lo[k], p.hi[k] = sl[field].start + off, lo, hi
+                if field == "euler":      # Euler angle `off` of the orientation written to penv[3:7] (the Pen's target)
+                    p.slot[k], p.quat_slot = -1 - off, sl["penv"].start + 3
+                else:
+                    p.slot[k] = sl[field].start + off
+                p.lo[k], p.hi[k] = lo, hi
             rest = torch.zeros(self.backend.state.shape[1], dtype=torch.float32, device=self.device)   # ctrl, warm start, time <- 0
             rest[sl["qpos"]] = self.init_qpos
             rest[sl["qvel"]] = self.init_qvel
@@ -309,11 +312,13 @@ class AdroitPenVectorEnv(AdroitHammerVectorEnv):
     (envs/adroit_hand/adroit_pen.py:288-430)."""
 
     TASK_NAME, MODEL_NAME = "AdroitHandPen", "adroit_pen"
-    DEVICE_RESET = None   # the target orientation is euler2quat of two draws (adroit_pen.py:379-384): not a plain uniform slot
+    DEVICE_RESET = (("euler", 0, -1.0, 1.0), ("euler", 1, -1.0, 1.0))    # adroit_pen.py:379-384: body_quat[target] = euler2quat([u, u, 0])
     make_task = staticmethod(make_pen_task)
 
     def _reset_envs(self, mask, out):
         """reset_model (adroit_pen.py:379-399)."""
+        if self.rng_mode == "device":
+            return self._device_reset(mask, out)
         from . import rotations
 
         idx = self._mask_indices(mask)

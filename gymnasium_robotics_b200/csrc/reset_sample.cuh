@@ -95,9 +95,19 @@ RS_HD void rs_uniform_reset_record(const b200sim_uniform_reset_t& p, unsigned lo
   const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t ctr[4] = {env, episode, 0u, 0x0A11u}, r[4] = {0u, 0u, 0u, 0u};
   for (int k = 0; k < stride; k++) rec[k] = rest[k];
+  float euler[3] = {0.f, 0.f, 0.f};
   for (int k = 0; k < p.n; k++) {
     if ((k & 3) == 0) { ctr[2] = (uint32_t)(k >> 2); rs_philox4x32_10(ctr, key, r); }
-    rec[p.slot[k]] = p.lo[k] + (p.hi[k] - p.lo[k]) * rs_u01(r[k & 3]);
+    float v = p.lo[k] + (p.hi[k] - p.lo[k]) * rs_u01(r[k & 3]);
+    if (p.slot[k] >= 0) rec[p.slot[k]] = v; else euler[-1 - p.slot[k]] = v;   // slot -1 - j: Euler angle j of the orientation below
+  }
+  if (p.quat_slot >= 0) {
+    // adroit_pen.py:379-384: body_quat <- euler2quat(angles) = qx(e0) * qy(e1) * qz(e2) (utils/rotations.py:87-113)
+    float ca = cosf(0.5f * euler[0]), sa = sinf(0.5f * euler[0]), cb = cosf(0.5f * euler[1]), sb = sinf(0.5f * euler[1]);
+    float cc = cosf(0.5f * euler[2]), sc = sinf(0.5f * euler[2]);
+    float w = ca * cb, x = sa * cb, y = ca * sb, z = sa * sb;       // qx * qy
+    float* q = rec + p.quat_slot;
+    q[0] = w * cc - z * sc; q[1] = x * cc + y * sc; q[2] = y * cc - x * sc; q[3] = z * cc + w * sc;   // (* qz)
   }
 }
 

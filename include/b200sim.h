@@ -120,11 +120,14 @@ int b200sim_reset(b200sim_t* h, const unsigned char* mask, const float* rest_rec
                   float* success, void* stream);
 /* The same for reset_model functions that are a fixed list of uniform draws (any task family; reference:
  * adroit_hammer.py:372-378, adroit_relocate.py:354-373, adroit_door.py:359-371): record <- rest_record, then
- * record[slot[k]] = lo[k] + (hi[k] - lo[k]) * u_k for k < n (u_k: word k % 4 of Philox block k / 4), then the refresh. */
+ * record[slot[k]] = lo[k] + (hi[k] - lo[k]) * u_k for k < n (u_k: word k % 4 of Philox block k / 4), then the refresh.
+ * A draw with slot -1 - j (j = 0..2) is Euler angle j of an orientation instead: when quat_slot >= 0 the four floats at quat_slot
+ * become euler2quat(angles) (utils/rotations.py:87-113; adroit_pen.py:379-384 draws the target pen's orientation this way). */
 #define B200SIM_RESET_SLOTS_MAX 16
 typedef struct b200sim_uniform_reset {
   int n, slot[B200SIM_RESET_SLOTS_MAX];   /* offsets in floats inside the state record (b200sim_layout) */
   float lo[B200SIM_RESET_SLOTS_MAX], hi[B200SIM_RESET_SLOTS_MAX];
+  int quat_slot;                          /* -1 = none */
 } b200sim_uniform_reset_t;
 int b200sim_reset_uniform(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_uniform_reset_t* params,
                           unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired,

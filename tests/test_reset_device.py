@@ -186,7 +186,7 @@ def test_uniform_slot_reset_against_python():
     L.hostsim_uniform_reset_record.restype = None
     p = UniformResetC()
     slots, lo, hi = [3, 40, 41, 7, 12, 13], [-0.15, -0.15, -0.2, 0.1, 0.0, 5.0], [0.15, 0.3, 0.2, 0.25, 1.0, 5.0]
-    p.n = 6
+    p.n, p.quat_slot = 6, -1
     for k in range(6):
         p.slot[k], p.lo[k], p.hi[k] = slots[k], lo[k], hi[k]
     rest = np.arange(48, dtype=np.float32)
@@ -228,8 +228,17 @@ def test_adroit_door_env_with_in_kernel_resets():
     for _ in range(3):     # TimeLimit 2: the third call is the next-step reset with new draws
         o, *_ = env.step(np.zeros((3, 28), dtype=np.float32))
     assert not np.array_equal(env.get_env_state()["door_body_pos"].numpy(), pos)
-    with pytest.raises(NotImplementedError):
-        pkg.make_vec("AdroitHandPen-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="device")
+    # the Pen's target orientation: euler2quat of two draws (adroit_pen.py:379-384), against utils/rotations.py's restatement
+    from gymnasium_robotics_b200 import rotations
+
+    pen = pkg.make_vec("AdroitHandPen-v2", num_envs=4, backend_factory=AdroitHostBackend, rng_mode="device")
+    pen.reset(seed=9)
+    quat = pen.get_env_state()["desired_orien"].numpy()
+    for i in range(4):
+        r = philox4x32_10((i, 0, 0, 0x0A11), (9, 0))
+        e = [float(np.float32(-1) + np.float32(2) * u01(r[0])), float(np.float32(-1) + np.float32(2) * u01(r[1])), 0.0]
+        assert np.abs(quat[i] - rotations.euler2quat(np.array(e))).max() < 1e-6
+    assert abs(np.linalg.norm(quat, axis=1) - 1).max() < 1e-6
 
 
 def py_maze_draw(goal_xy, reset_xy, scaling, noise, seed, env, episode):
