@@ -37,9 +37,23 @@ def build(force=False, wide=False):
                                                    for f in ("sim_core.cuh", "dmodel.h", "fetch_task.cuh")] + \
            [os.path.join(_ROOT, "include", "b200sim_model.h"), os.path.join(_ROOT, "include", "b200sim.h"),
             os.path.join(_ROOT, "gymnasium_robotics_b200", "csrc", "reset_sample.cuh")]
-    if force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function"] + ({"kitchen": ["-DB200_KITCHEN"], "kitchen_flat": ["-DB200_KITCHEN", "-DB200_KITCHEN_FLATSCAN"]}.get(wide) or (["-DB200_WIDE"] if wide else [])) +
-                              ["-o", out, srcs[0]])
+    def stale():
+        return force or not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs)
+
+    if stale():
+        # several processes may get here at once (the 2-rank gloo tests, pytest-xdist): one compiles under a file lock into a
+        # temporary name and renames it into place, the others wait and then find the library fresh
+        import fcntl
+
+        with open(out + ".lock", "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            if stale():
+                tmp = f"{out}.{os.getpid()}.tmp"
+                subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function"] +
+                                      ({"kitchen": ["-DB200_KITCHEN"], "kitchen_flat": ["-DB200_KITCHEN", "-DB200_KITCHEN_FLATSCAN"]}.get(wide) or
+                                       (["-DB200_WIDE"] if wide else [])) + ["-o", tmp, srcs[0]])
+                os.replace(tmp, out)
+                force = False
     return out
 
 
