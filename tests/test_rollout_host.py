@@ -115,3 +115,23 @@ def test_recorder_on_flat_observations():
     eps = rec.episodes()
     assert [len(e["actions"]) for e in eps] == [3, 1]
     assert eps[0]["observations"].shape == (4, 46) and "success" in eps[0]["infos"]
+
+
+def test_recorder_on_nested_goal_dicts():
+    """FrankaKitchen-v1: achieved / desired goals are dicts task -> array (kitchen_env.py:371-397); keys are flattened as a/b."""
+    from gymnasium_robotics_b200.kitchen import KitchenVectorEnv
+
+    from tests.test_kitchen_host import KitchenHostBackend      # module-level class: picklable by reference
+
+    env = KitchenVectorEnv(num_envs=2, backend_factory=KitchenHostBackend, device="cpu", rng_mode="numpy",
+                           tasks_to_complete=["microwave", "kettle"], max_episode_steps=3)
+    rec = RolloutRecorder(env, capacity_steps=8, env_id="FrankaKitchen-v1")
+    rec.reset(seed=2)
+    for _ in range(5):
+        rec.step(np.zeros((2, 9), dtype=np.float32))
+    eps = [e for e in rec.episodes() if e["env_index"] == 0]
+    assert [len(e["actions"]) for e in eps] == [3, 1]
+    ob = eps[0]["observations"]
+    assert ob["observation"].shape == (4, 59) and ob["achieved_goal/microwave"].shape == (4, 1) and ob["desired_goal/kettle"].shape == (4, 7)
+    env2 = pickle.loads(pickle.dumps(env))
+    assert env2.tasks == ["microwave", "kettle"] and env2.max_episode_steps == 3
