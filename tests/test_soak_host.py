@@ -34,3 +34,22 @@ def test_random_action_soak_stays_finite(env_id, ref):
         assert torch.isfinite(x).all() and torch.isfinite(r).all(), f"{env_id}: non-finite output at step {k}"
     assert float(x.abs().max()) < 1e3
     assert getattr(env.backend, "overflow_bits", 0) & ~0xF == 0   # only the four documented capacity flags can ever be set
+
+
+def test_kitchen_soak_with_the_two_level_broad_phase():
+    """FrankaKitchen-v1 on the kitchen-flavor emulation (29 dofs, 3 708 pairs in 1 010 groups): saturated actions sweep the arm
+    through the scene; no capacity flag at all (a longer run of 5 600 env-steps saw none either, up to 57 candidates)."""
+    from gymnasium_robotics_b200.kitchen import KitchenVectorEnv
+    from tests.test_kitchen_host import KitchenHostBackend
+
+    env = KitchenVectorEnv(num_envs=4, backend_factory=KitchenHostBackend, device="cpu", rng_mode="torch", autoreset_mode="same_step",
+                           max_episode_steps=25)
+    env.reset(seed=0)
+    g = torch.Generator().manual_seed(3)
+    for k in range(60):
+        a = torch.rand((4, 9), generator=g) * 2 - 1
+        if k % 3 == 0:
+            a = torch.sign(a)
+        o, r, te, tr, info = env.step(a)
+        assert torch.isfinite(o["observation"]).all() and float(o["observation"].abs().max()) < 1e3, k
+    assert getattr(env.backend, "overflow_bits", 0) == 0
