@@ -75,6 +75,13 @@ __global__ void maze_reset_kernel(b200sim_maze_reset_t p, const float* __restric
   if (episode) episode[i] = ep + 1;
 }
 
+__global__ void check_state_kernel(int N, int stride, float* __restrict__ state, const float* __restrict__ rest, b200sim_keep_t keep,
+                                   unsigned char* __restrict__ bad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  bad[i] = (unsigned char)rs_check_record(state + (size_t)i * stride, stride, rest, keep);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 #define B200_FOR_ALL_VARIANTS(X) X(7, 14) X(7, 15) X(7, 21) X(14, 14) X(14, 15) X(14, 21) X(28, 14) X(28, 15) X(28, 21) \
   X(7, 22) X(14, 22) X(28, 22) X(7, 30) X(14, 30)
@@ -345,6 +352,22 @@ int b200sim_reset_maze(b200sim_t* h, const unsigned char* mask, const float* res
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+}
+int b200sim_check_state(b200sim_t* h, unsigned char* bad, const float* rest_record, const b200sim_keep_t* keep, void* stream) {
+  if (!bad) return fail(h, "b200sim_check_state: bad is NULL", -1);
+  b200sim_keep_t k;
+  k.n = 0;
+  if (keep) {
+    k = *keep;
+    if (k.n < 0 || k.n > 4) return fail(h, "b200sim_check_state: at most 4 keep ranges", -1);
+    for (int r = 0; r < k.n; r++)
+      if (k.start[r] < 0 || k.len[r] < 0 || k.start[r] + k.len[r] > h->task.st_stride) return fail(h, "b200sim_check_state: keep range outside the state record", -1);
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  check_state_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->N, h->task.st_stride, h->state, rest_record, k, bad);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
 }
 int b200sim_raw_step_masked(b200sim_t* h, const unsigned char* mask, int nstep, float* obs, float* achieved, float* desired,
                             float* reward, float* success, void* stream) {

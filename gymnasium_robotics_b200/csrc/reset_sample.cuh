@@ -150,3 +150,20 @@ RS_HD void rs_maze_reset_record(const b200sim_maze_reset_t& p, const float* goal
   rec[st_qpos] = pos[0]; rec[st_qpos + 1] = pos[1];      // ant_maze_v5.py:285 / point_maze.py:380: init_qpos[:2] = reset_pos
   rec[st_goal] = goal[0]; rec[st_goal + 1] = goal[1];
 }
+
+// Bad-state detection and recovery at env-step granularity.  mj_step checks qpos / qvel / qacc for NaN and |x| > mjMAXVAL = 1e10
+// before and after the forward pass and answers with a warning + mj_resetData ([ext] engine_forward.c mj_checkPos / mj_checkVel /
+// mj_checkAcc; SURVEY.md section 5 "failure detection"); here one thread scans its env's state record after the step and, when
+// a rest record is given, puts the env back to it except for the `keep` ranges (goal, per-episode model poses).
+RS_HD int rs_check_record(float* rec, int stride, const float* rest, const b200sim_keep_t& keep) {
+  int bad = 0;
+  for (int k = 0; k < stride; k++) { float v = rec[k]; if (!(fabsf(v) <= 1e10f)) bad = 1; }   // NaN fails the comparison too
+  if (bad && rest) {
+    for (int k = 0; k < stride; k++) {
+      bool kept = false;
+      for (int r = 0; r < keep.n; r++) if (k >= keep.start[r] && k < keep.start[r] + keep.len[r]) kept = true;
+      if (!kept || !(fabsf(rec[k]) <= 1e10f)) rec[k] = rest[k];
+    }
+  }
+  return bad;
+}

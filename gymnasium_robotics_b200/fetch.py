@@ -169,6 +169,12 @@ class CudaBackend:
                                               goal_xy.data_ptr(), reset_xy.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset),
                                               episode.data_ptr(), *self._ptrs(out), self._stream()))
 
+    def check_state(self, bad, rest_record, keep):
+        """b200sim_check_state: bad[i] = record i holds NaN / |x| > 1e10; such records are put back to `rest_record` (if given)."""
+        assert bad.is_cuda and bad.dtype == torch.uint8 and bad.numel() == self.num_envs
+        self._check(self.L.b200sim_check_state(self.h, bad.data_ptr(), rest_record.data_ptr() if rest_record is not None else None,
+                                               ctypes.byref(keep) if keep is not None else None, self._stream()))
+
     def compute_reward(self, ag, dg):
         ag = ag.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)
         dg = dg.to(self.device, torch.float32).contiguous().reshape(-1, self.ngoal)
@@ -215,6 +221,9 @@ class FetchVectorEnv(CtorPickle):
             raise ValueError("rng_mode must be auto, numpy, torch or device")
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
         self.env_offset = int(kwargs.get("env_offset", 0))   # global index of env 0 (sharded runs, sharding.py)
+        # opt-in failure detection: after every step the state records are scanned for NaN / huge values and such envs are put
+        # back to their rest state with the goal kept ([ext] mj_checkPos / mj_checkVel / mj_checkAcc + mj_resetData inside mj_step)
+        self.auto_recover = bool(kwargs.get("auto_recover", False))
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None
         self._gen = torch.Generator(device=self.device)
@@ -336,6 +345,26 @@ class FetchVectorEnv(CtorPickle):
         rest[self._sl["mocap"]] = self._mocap_rest
         return p, rest
 
+    def _recovery_record(self):
+        """(rest record, ranges of the state record a recovered env keeps) for b200sim_check_state."""
+        from ._lib import KeepC
+
+        keep = KeepC()
+        keep.n, keep.start[0], keep.len[0] = 1, self._sl["goal"].start, self._sl["goal"].stop - self._sl["goal"].start
+        return self._device_reset_params()[1], keep
+
+    def _check_and_recover(self, out, info):
+        if getattr(self, "_recovery", None) is None:
+            self._recovery = self._recovery_record()
+            self._bad = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            self.bad_state_count = torch.zeros((), dtype=torch.int64, device=self.device)
+        rest, keep = self._recovery
+        self.backend.check_state(self._bad, rest, keep)
+        self.backend.refresh(self._bad, out)          # mj_forward + _get_obs of the recovered envs (none, almost always)
+        bad = self._bad.bool()
+        self.bad_state_count += bad.sum()
+        info["bad_state"] = bad
+
     def _reset_envs(self, mask, out):
         if self.rng_mode == "device":
             if getattr(self, "_dev_reset", None) is None:
@@ -408,6 +437,10 @@ class FetchVectorEnv(CtorPickle):
             self._const_true = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
         terminated = self._const_false  # robot_env.py:106-112 (constant tensors are shared between steps: read-only for callers)
         info = {"is_success": success}
+        if getattr(self, "auto_recover", False):
+            self._check_and_recover(out, info)
+            reward, success = out["reward"], out["success"]
+            info["is_success"] = success
         in_phase = getattr(self, "_in_phase", False)
         if self.autoreset_mode == "next_step" and getattr(self, "_pending_reset", False):
             self._pending_reset = False

@@ -142,6 +142,12 @@ typedef struct b200sim_maze_reset {
 int b200sim_reset_maze(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_maze_reset_t* params,
                        const float* goal_xy, const float* reset_xy, unsigned long long seed, int env_offset, int* episode, float* obs,
                        float* achieved, float* desired, float* reward, float* success, void* stream);
+/* Failure detection ([ext] mj_checkPos / mj_checkVel / mj_checkAcc inside mj_step: NaN or |x| > 1e10 => warning + mj_resetData):
+ * bad[i] (device, [N] bytes) = 1 when env i's state record holds a non-finite or huge value, else 0.  With rest_record != NULL a bad
+ * env's record is replaced by it, except the float ranges listed in `keep` (goal, per-episode poses) whose finite values survive.
+ * The caller follows with b200sim_refresh(mask = bad) to recompute the observation of the recovered envs. */
+typedef struct b200sim_keep { int n, start[4], len[4]; } b200sim_keep_t;
+int b200sim_check_state(b200sim_t* h, unsigned char* bad, const float* rest_record, const b200sim_keep_t* keep, void* stream);
 /* GoalEnv.compute_reward on M (achieved, desired) pairs, device pointers (reference: fetch_env.py:74-80). */
 int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const float* desired, int M, float* out, void* stream);
 /* number of kernel launches issued through this handle so far */

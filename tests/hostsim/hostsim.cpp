@@ -77,5 +77,11 @@ extern "C" void hostsim_maze_reset_record(const b200sim_maze_reset_t* p, const f
                                           unsigned episode, const float* rest, int stride, int st_qpos, int st_goal, float* rec) {
   rs_maze_reset_record(*p, goal_xy, reset_xy, seed, env, episode, rest, stride, st_qpos, st_goal, rec);
 }
+extern "C" int hostsim_check_record(float* rec, int stride, const float* rest, const b200sim_keep_t* keep) {
+  b200sim_keep_t k;
+  k.n = 0;
+  if (keep) k = *keep;
+  return rs_check_record(rec, stride, rest, k);
+}
 extern "C" int hostsim_model_words(void* p) { return ((HostSim*)p)->ctx.h->nwords; }
 extern "C" int hostsim_hot_words(void* p) { return ((HostSim*)p)->ctx.h->hot_words; }

@@ -120,6 +120,18 @@ class HostSimBackend:
         self.launches += 1
         self.refresh(mask, out)
 
+    def check_state(self, bad, rest_record, keep):
+        import ctypes
+
+        L = self.sim._L
+        L.hostsim_check_record.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        st = self.state.numpy()
+        rest = rest_record.numpy() if rest_record is not None else None
+        for i in range(self.num_envs):
+            bad[i] = L.hostsim_check_record(st[i].ctypes.data, self.layout["stride"], rest.ctypes.data if rest is not None else None,
+                                            ctypes.byref(keep) if keep is not None else None)
+        self.launches += 1
+
     def compute_reward(self, ag, dg):
         ag = ag.to(torch.float32).reshape(-1, self.ngoal); dg = dg.to(torch.float32).reshape(-1, self.ngoal)
         if self.task.kind == 2:  # same arithmetic as the kernel's hand_goal_distance / hand_reward (fetch_task.cuh)

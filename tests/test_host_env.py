@@ -183,3 +183,26 @@ def test_contact_group_overflow_is_flagged_and_harmless():
     for _ in range(12):
         env2.step(a)
     assert getattr(env2.backend, "overflow_bits", 0) == 0
+
+
+def test_auto_recover_detects_and_resets_bad_states():
+    """SURVEY.md section 5 failure detection ([ext] mj_checkPos / mj_checkVel: NaN or |x| > 1e10 => mj_resetData): opt-in scan of the
+    state records after each step (C-ABI b200sim_check_state); a bad env goes back to its rest state and keeps its goal."""
+    env = mk("FetchPickAndPlace", 4, rng_mode="numpy", auto_recover=True)
+    obs, _ = env.reset(seed=3)
+    goals = obs["desired_goal"].clone()
+    o, r, te, tr, info = env.step(np.zeros((4, 4), dtype=np.float32))
+    assert not info["bad_state"].any() and int(env.bad_state_count) == 0
+    st = env.backend.state
+    st[1, env._sl["qvel"].start + 3] = float("nan")
+    st[2, env._sl["qpos"].start + 1] = 3e10
+    o, r, te, tr, info = env.step(np.full((4, 4), 0.5, dtype=np.float32))
+    assert info["bad_state"].tolist() == [False, True, True, False] and int(env.bad_state_count) == 2
+    assert torch.isfinite(o["observation"]).all() and torch.isfinite(r).all()
+    assert torch.equal(o["desired_goal"], goals)                               # the goal survives the recovery
+    rest, _ = env._recovery
+    q = env._sl["qpos"]
+    assert torch.equal(st[1, q], rest[q]) and torch.equal(st[2, q], rest[q])   # back at initial_qpos / initial_qvel
+    assert not torch.equal(st[0, q], rest[q])                                  # the healthy envs moved on
+    o, r, te, tr, info = env.step(np.zeros((4, 4), dtype=np.float32))
+    assert not info["bad_state"].any() and torch.isfinite(o["observation"]).all()

@@ -111,3 +111,25 @@ def test_maze_resets_in_kernel():
         o, r, te, tr, info = env.step(torch.zeros((n, 8), device="cuda"))
     assert torch.isfinite(o["observation"]).all()
     env.close()
+
+
+def test_check_state_recovers_bad_envs_on_the_gpu():
+    """b200sim_check_state: NaN / huge entries injected into two state records are detected, those envs go back to the rest record
+    with their goals kept, the others are untouched (opt-in `auto_recover=True`)."""
+    import gymnasium_robotics_b200 as pkg
+
+    n = 64
+    env = pkg.make_vec("FetchPickAndPlace-v4", num_envs=n, rng_mode="torch", auto_recover=True)
+    obs, _ = env.reset(seed=2)
+    goals = obs["desired_goal"].clone()
+    env.step(torch.zeros((n, 4), device="cuda"))
+    st = env.backend.state
+    st[5, env._sl["qvel"].start + 2] = float("nan")
+    st[40, env._sl["qpos"].start] = -4e10
+    o, r, te, tr, info = env.step(torch.full((n, 4), 0.3, device="cuda"))
+    bad = info["bad_state"].cpu()
+    assert bad.nonzero().flatten().tolist() == [5, 40] and int(env.bad_state_count) == 2
+    assert torch.isfinite(o["observation"]).all() and torch.equal(o["desired_goal"], goals)
+    o, r, te, tr, info = env.step(torch.zeros((n, 4), device="cuda"))
+    assert not info["bad_state"].any() and torch.isfinite(o["observation"]).all()
+    env.close()
