@@ -227,7 +227,9 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   if (h->kitchen) {
     if (dh->nv > 31) { delete h; return fail(nullptr, "b200sim_create: the kitchen build is instantiated for nv <= 31", -8); }
     h->nvp = B200_KITCHEN_NVP;
-    h->wpb = (h->wpb > 7 && ((size_t)dh->hot_words + (size_t)10 * dh->scr_words) * 4 + 64 <= 232448) ? 10 : 7;
+    auto fits = [&](int w) { return ((size_t)dh->hot_words + (size_t)w * dh->scr_words) * 4 + 64 <= 232448; };
+    h->wpb = (h->wpb > 7 && fits(10)) ? 10 : 7;
+    if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if ((w == 7 || w == 10 || w == 11) && fits(w)) h->wpb = w; }  // experiments
   }
   if (h->nvp == B200_WIDE_NVP) {
     // wide build: the largest block of {14, 13, 10, 7} warps whose scratch fits the 227 KB of shared memory (14 envs of the
@@ -238,7 +240,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
       if (cands[k] <= (want > 7 ? 14 : 7) && ((size_t)dh->hot_words + (size_t)cands[k] * dh->scr_words) * 4 + 64 <= 232448) h->wpb = cands[k];
     if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 10 || w == 13 || w == 14) h->wpb = w; }  // experiments
   }
-  if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 14 || (w == 28 && h->nvp != 30)) h->wpb = w; }  // experiments
+  if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (!h->kitchen && (w == 7 || w == 14 || (w == 28 && h->nvp != 30))) h->wpb = w; }  // experiments
   h->smem_bytes = ((size_t)dh->hot_words + (size_t)h->wpb * dh->scr_words) * 4;
   h->blocks = (num_envs + h->wpb - 1) / h->wpb;
   cudaError_t e = cudaSuccess;

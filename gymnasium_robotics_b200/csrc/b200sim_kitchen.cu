@@ -1,8 +1,8 @@
 // Bring-up build of the step kernel for models with joint equalities and condim-6 contacts (Franka Kitchen, BASELINE config
 // 5b): same sources as b200sim.cu compiled with -DB200_KITCHEN (two-sided dof rows, six base rows per contact, task kind 8),
 // a separate translation unit so that the validated builds stay untouched.  The device model of such a model is built here
-// too (the contact record is larger, so the scratch layout differs).  The flat candidate-pair list (3 708 pairs for the
-// kitchen) is scanned by the ordinary broad phase -- the body-level bounding-volume pass is the next step.
+// too (the contact record is larger, so the scratch layout differs).  The candidate-pair list (3 708 pairs for the kitchen)
+// is regrouped into bounding-volume groups there and scanned in two levels (sim_core.cuh `collision`).
 #define B200_KITCHEN 1
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,7 +12,7 @@
 #include "step_kernel.cuh"
 
 // NVP = 31 (not 30): the instantiations must not share a symbol with the NVP = 30 kernels of b200sim.cu
-#define B200_KITCHEN_VARIANTS(X) X(7, 31) X(10, 31)
+#define B200_KITCHEN_VARIANTS(X) X(7, 31) X(10, 31) X(11, 31)   // 11: fits since the pair list left shared memory; chosen only by B200SIM_WPB=11 until measured
 
 extern "C" int b200sim_kitchen_build(const b200_model_view* view, const double* eq_data, const float* ref, int penv_body,
                                      std::vector<uint32_t>* buf, std::string* err) {
