@@ -168,6 +168,17 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
+    mixed = None
+    if args.workload == "mixed_hammer_kitchen":
+        # BASELINE config 5: heterogeneous batch, whole ranks per model (sharding.mixed_batch_assignment), 1 024 envs per GPU; the
+        # line reports the aggregate over both models, the roofline object is rank 0's model (the Hammer)
+        from gymnasium_robotics_b200.sharding import mixed_batch_assignment
+
+        if world < 2:
+            raise SystemExit("--workload mixed_hammer_kitchen needs at least 2 ranks (torchrun --nproc-per-node 2|4|8)")
+        mixed = mixed_batch_assignment(["adroit_hammer", "franka_kitchen"], world)
+        args.workload = mixed[rank]
+        args.envs_per_gpu = args.envs_per_gpu or 1024
     env_id, nact, nsub, b_alg, default_n = WORKLOADS[args.workload]
     n = args.envs_per_gpu or default_n
     if args.workload == "fetch_pick_and_place":
@@ -287,9 +298,10 @@ def run_ours(args):
         line = {"metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{env_id}, {n} envs/GPU, {nsub} sub-steps/env-step, random actions U(-1,1), TimeLimit, "
+                "config": {"workload": ("AdroitHandHammer-v2 + FrankaKitchen-v1 mixed batch, whole ranks per model; rank 0: " if mixed else "") +
+                                       f"{env_id}, {n} envs/GPU, {nsub} sub-steps/env-step, random actions U(-1,1), TimeLimit, "
                                        "same-step autoreset", "envs_per_gpu": n, "l2": "flushed between timed iterations (256 MB fill)",
-                           "parallelism": f"env-sharded x{world}, no data-path collective",
+                           "parallelism": f"env-sharded x{world}, no data-path collective" + (f"; models per rank: {mixed}" if mixed else ""),
                            "reset_rng": "in-kernel Philox (b200sim_reset)" if args.rng_mode == "device" else "torch device generator"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": how, "algorithmic_bytes_per_env_step": b_alg,
@@ -312,7 +324,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=None)
-    ap.add_argument("--workload", default="fetch_pick_and_place", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="fetch_pick_and_place", choices=sorted(WORKLOADS) + ["mixed_hammer_kitchen"])
     ap.add_argument("--sample-envs", type=int, default=256, help="envs per step of the CPU arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rng-mode", default="torch", choices=["torch", "device"],

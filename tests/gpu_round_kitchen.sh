@@ -22,3 +22,9 @@ ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 
     python tests/prof_kitchen.py 2048 5 > gpurun_out/ncu_kitchen_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_kitchen_${tag}.log
 python tests/summarize_profile.py kitchen_${tag} > gpurun_out/summarize_kitchen_${tag}.log 2>&1; rm -f gpurun_out/prof_kitchen_${tag}.ncu-rep
+# 6. BASELINE config 5 (needs `gpurun --gpus 4`): 2 ranks AdroitHandHammer-v2 + 2 ranks FrankaKitchen-v1, 1 024 envs per GPU
+if [ "$(nvidia-smi -L | wc -l)" -ge 4 ]; then
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 4 \
+      --workload mixed_hammer_kitchen --steps 30 --warmup 5 > gpurun_out/bench_${tag}_mixed_n4.json 2> gpurun_out/bench_${tag}_mixed_n4.err
+  cut -c1-160 gpurun_out/bench_${tag}_mixed_n4.json
+fi
