@@ -82,6 +82,24 @@ __global__ void check_state_kernel(int N, int stride, float* __restrict__ state,
   bad[i] = (unsigned char)rs_check_record(state + (size_t)i * stride, stride, rest, keep);
 }
 
+__global__ void hand_pose_kernel(b200sim_hand_reset_t p, const float* __restrict__ parallel, unsigned long long seed, int env_offset, int N,
+                                 const unsigned char* __restrict__ mask, const float* __restrict__ rest, int stride, int st_qpos, int st_goal,
+                                 int ngoal, float* __restrict__ state, const int* __restrict__ episode, int attempt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || (mask && !mask[i])) return;
+  rs_hand_pose_record(p, parallel, seed, (uint32_t)(i + env_offset), (uint32_t)(episode ? episode[i] : 0), (uint32_t)attempt, rest, stride, st_qpos,
+                      st_goal, ngoal, state + (size_t)i * stride);
+}
+__global__ void hand_goal_kernel(b200sim_hand_reset_t p, const float* __restrict__ parallel, unsigned long long seed, int env_offset, int N,
+                                 const unsigned char* __restrict__ mask, int stride, int st_qpos, int st_goal, float* __restrict__ state,
+                                 int* __restrict__ episode) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || (mask && !mask[i])) return;
+  int ep = episode ? episode[i] : 0;
+  rs_hand_goal(p, parallel, seed, (uint32_t)(i + env_offset), (uint32_t)ep, st_qpos, st_goal, state + (size_t)i * stride);
+  if (episode) episode[i] = ep + 1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 #define B200_FOR_ALL_VARIANTS(X) X(7, 14) X(7, 15) X(7, 21) X(14, 14) X(14, 15) X(14, 21) X(28, 14) X(28, 15) X(28, 21) \
   X(7, 22) X(14, 22) X(28, 22) X(7, 30) X(14, 30)
@@ -351,6 +369,37 @@ int b200sim_reset_maze(b200sim_t* h, const unsigned char* mask, const float* res
   CUDA_OK(cudaSetDevice(h->device));
   maze_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, goal_xy, reset_xy, seed, env_offset, h->N, mask, rest_record,
                                                                          h->task.st_stride, h->task.st_qpos, h->task.st_goal, h->state, episode);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+}
+static int hand_reset_args(b200sim* h, const b200sim_hand_reset_t* p, const float* parallel) {
+  if (h->task.kind != TASK_HAND) return fail(h, "b200sim_reset_hand_*: not a Shadow-Hand manipulation task", -6);
+  if (!p || !parallel) return fail(h, "b200sim_reset_hand_*: NULL argument", -1);
+  if (p->obj_qadr != h->task.obj_qadr || h->task.ngoal != 7) return fail(h, "b200sim_reset_hand_*: obj_qadr does not match the task", -1);
+  if (p->rot_mode < 0 || p->rot_mode > 3 || p->goal_rot_mode < 0 || p->goal_rot_mode > 3) return fail(h, "b200sim_reset_hand_*: rot mode out of range", -1);
+  return 0;
+}
+int b200sim_reset_hand_pose(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_hand_reset_t* params,
+                            const float* parallel_quats, unsigned long long seed, int env_offset, const int* episode, int attempt,
+                            void* stream) {
+  if (int rc = hand_reset_args(h, params, parallel_quats)) return rc;
+  if (!rest_record) return fail(h, "b200sim_reset_hand_pose: rest_record is NULL", -1);
+  CUDA_OK(cudaSetDevice(h->device));
+  hand_pose_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, parallel_quats, seed, env_offset, h->N, mask, rest_record,
+                                                                        h->task.st_stride, h->task.st_qpos, h->task.st_goal, h->task.ngoal, h->state,
+                                                                        episode, attempt);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int b200sim_reset_hand_goal(b200sim_t* h, const unsigned char* mask, const b200sim_hand_reset_t* params, const float* parallel_quats,
+                            unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired,
+                            float* reward, float* success, void* stream) {
+  if (int rc = hand_reset_args(h, params, parallel_quats)) return rc;
+  CUDA_OK(cudaSetDevice(h->device));
+  hand_goal_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, parallel_quats, seed, env_offset, h->N, mask, h->task.st_stride,
+                                                                        h->task.st_qpos, h->task.st_goal, h->state, episode);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);

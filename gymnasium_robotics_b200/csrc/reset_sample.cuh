@@ -151,6 +151,81 @@ RS_HD void rs_maze_reset_record(const b200sim_maze_reset_t& p, const float* goal
   rec[st_goal] = goal[0]; rec[st_goal + 1] = goal[1];
 }
 
+// Shadow-Hand manipulation reset (envs/shadow_dexterous_hand/manipulate.py:154-224 _reset_sim, :226-279 _sample_goal).  The reset
+// is a loop in the reference -- draw a start pose, settle 10 x n_substeps, accept when the object rests on the palm -- so it is
+// two entry points: the pose draw of one attempt (record <- rest record + pose, goal kept) and, after the settle launches, the
+// goal draw from the settled pose.  rot modes: 0 none, 1 "z", 2 "parallel", 3 "xyz" (also the initial rotation of "ignore").
+RS_HD void rs_qmul(float* r, const float* a, const float* b) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+RS_HD void rs_qnormalize(float* q) {
+  float n = 1.0f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
+}
+// utils/rotations.py:340-346 quat_from_angle_and_axis
+RS_HD void rs_angle_axis(float* q, float angle, float ax, float ay, float az) {
+  float n = 1.0f / sqrtf(ax * ax + ay * ay + az * az), s = sinf(0.5f * angle);
+  q[0] = cosf(0.5f * angle); q[1] = s * ax * n; q[2] = s * ay * n; q[3] = s * az * n;
+  rs_qnormalize(q);
+}
+// one rotation draw in the reference's order: angle ~ U(-pi, pi), then (parallel) a table index or (xyz) an axis ~ U(-1, 1)^3
+RS_HD void rs_hand_rotation(int mode, const uint32_t r[4], const uint32_t r2[4], const float* parallel, float* q) {
+  const float PI = 3.14159265358979323846f;
+  float angle = (2.0f * rs_u01(r[0]) - 1.0f) * PI;
+  if (mode == 1) rs_angle_axis(q, angle, 0.f, 0.f, 1.f);
+  else if (mode == 2) {
+    float z[4];
+    rs_angle_axis(z, angle, 0.f, 0.f, 1.f);
+    uint32_t k = (uint32_t)(((uint64_t)r[1] * 24u) >> 32);
+    rs_qmul(q, z, parallel + 4 * k);                                   // manipulate.py:184-187 / :252-255
+  } else rs_angle_axis(q, angle, 2.0f * rs_u01(r2[0]) - 1.0f, 2.0f * rs_u01(r2[1]) - 1.0f, 2.0f * rs_u01(r2[2]) - 1.0f);
+}
+RS_HD void rs_hand_pose_record(const b200sim_hand_reset_t& p, const float* parallel, unsigned long long seed, uint32_t env, uint32_t episode,
+                               uint32_t attempt, const float* rest, int stride, int st_qpos, int st_goal, int ngoal, float* rec) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t ctr[4] = {env, episode, 4u * attempt, 0x4A2Du}, r[4], r2[4], r3[4];
+  rs_philox4x32_10(ctr, key, r);
+  ctr[2] = 4u * attempt + 1u; rs_philox4x32_10(ctr, key, r2);
+  ctr[2] = 4u * attempt + 2u; rs_philox4x32_10(ctr, key, r3);
+  float goal[8];
+  for (int k = 0; k < ngoal && k < 8; k++) goal[k] = rec[st_goal + k];
+  for (int k = 0; k < stride; k++) rec[k] = rest[k];
+  for (int k = 0; k < ngoal && k < 8; k++) rec[st_goal + k] = goal[k];
+  float* pose = rec + st_qpos + p.obj_qadr;
+  if (p.randomize_rotation && p.rot_mode != 0) {                        // manipulate.py:176-197
+    float off[4], q[4];
+    rs_hand_rotation(p.rot_mode, r, r2, parallel, off);
+    rs_qmul(q, pose + 3, off);
+    for (int k = 0; k < 4; k++) pose[3 + k] = q[k];
+  }
+  if (p.randomize_position) {                                            // :200-202: += normal(size=3, scale=0.005), Box-Muller
+    const float TWO_PI = 6.28318530717958647692f;
+    float u1 = 1.0f - rs_u01(r3[0]), u2 = rs_u01(r3[1]), u3 = 1.0f - rs_u01(r3[2]), u4 = rs_u01(r3[3]);
+    float m1 = sqrtf(-2.0f * logf(u1)), m2 = sqrtf(-2.0f * logf(u3));
+    pose[0] += 0.005f * m1 * cosf(TWO_PI * u2); pose[1] += 0.005f * m1 * sinf(TWO_PI * u2); pose[2] += 0.005f * m2 * cosf(TWO_PI * u4);
+  }
+  rs_qnormalize(pose + 3);                                               // :204
+}
+RS_HD void rs_hand_goal(const b200sim_hand_reset_t& p, const float* parallel, unsigned long long seed, uint32_t env, uint32_t episode,
+                        int st_qpos, int st_goal, float* rec) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t ctr[4] = {env, episode, 0x400u, 0x4A2Du}, r[4], r2[4], r3[4];
+  rs_philox4x32_10(ctr, key, r);
+  ctr[2] = 0x401u; rs_philox4x32_10(ctr, key, r2);
+  ctr[2] = 0x402u; rs_philox4x32_10(ctr, key, r3);
+  const float* pose = rec + st_qpos + p.obj_qadr;
+  float* g = rec + st_goal;
+  for (int k = 0; k < 3; k++) {
+    g[k] = pose[k];
+    if (p.goal_random_position) g[k] += p.pos_lo[k] + (p.pos_hi[k] - p.pos_lo[k]) * rs_u01(r3[k]);   // manipulate.py:231-241
+  }
+  if (p.goal_rot_mode == 0) for (int k = 0; k < 4; k++) g[3 + k] = pose[3 + k];                        // :269-270 ("ignore" / "fixed")
+  else rs_hand_rotation(p.goal_rot_mode, r, r2, parallel, g + 3);                                      // :247-268
+  rs_qnormalize(g + 3);                                                                                // :276
+}
+
 // Bad-state detection and recovery at env-step granularity.  mj_step checks qpos / qvel / qacc for NaN and |x| > mjMAXVAL = 1e10
 // before and after the forward pass and answers with a warning + mj_resetData ([ext] engine_forward.c mj_checkPos / mj_checkVel /
 // mj_checkAcc; SURVEY.md section 5 "failure detection"); here one thread scans its env's state record after the step and, when

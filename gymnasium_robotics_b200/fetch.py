@@ -169,6 +169,19 @@ class CudaBackend:
                                               goal_xy.data_ptr(), reset_xy.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset),
                                               episode.data_ptr(), *self._ptrs(out), self._stream()))
 
+    def reset_hand_pose(self, mask, rest_record, params, parallel, seed, env_offset, episode, attempt):
+        """b200sim_reset_hand_pose: records of the masked envs <- rest record + drawn object start pose (goal kept); no refresh."""
+        assert rest_record.is_cuda and rest_record.numel() == self.layout["stride"] and parallel.is_cuda and tuple(parallel.shape) == (24, 4)
+        self._check(self.L.b200sim_reset_hand_pose(self.h, mask.data_ptr() if mask is not None else None, rest_record.data_ptr(), ctypes.byref(params),
+                                                   parallel.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), episode.data_ptr(),
+                                                   int(attempt), self._stream()))
+
+    def reset_hand_goal(self, mask, params, parallel, seed, env_offset, episode, out):
+        """b200sim_reset_hand_goal: goal drawn from the settled object pose, episode counters incremented, then the refresh."""
+        self._check(self.L.b200sim_reset_hand_goal(self.h, mask.data_ptr() if mask is not None else None, ctypes.byref(params), parallel.data_ptr(),
+                                                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), episode.data_ptr(), *self._ptrs(out),
+                                                   self._stream()))
+
     def check_state(self, bad, rest_record, keep):
         """b200sim_check_state: bad[i] = record i holds NaN / |x| > 1e10; such records are put back to `rest_record` (if given)."""
         assert bad.is_cuda and bad.dtype == torch.uint8 and bad.numel() == self.num_envs

@@ -125,13 +125,14 @@ class HandVectorEnv(FetchVectorEnv):
         factory = backend_factory or _HandBackend
         self.backend = factory(m, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device
-        if rng_mode == "device":
-            raise NotImplementedError("rng_mode='device' (in-kernel reset draws, b200sim_reset) exists for the Fetch family only")
+        # "device": start pose and goal are drawn inside the library (b200sim_reset_hand_pose / _goal, csrc/reset_sample.cuh)
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self.env_offset = int(kwargs.get("env_offset", 0))
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None
         self._gen = torch.Generator(device=self.device)
         self._gen.seed()
+        self._dev_seed = int(self._gen.initial_seed())
         lay = self.backend.layout
         self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", m.nq), ("qvel", m.nv), ("warm", m.nv), ("ctrl", m.nu), ("goal", 7))}
         self._obj = slice(lay["qpos"] + self.task.obj_qadr, lay["qpos"] + self.task.obj_qadr + 7)
@@ -255,9 +256,48 @@ class HandVectorEnv(FetchVectorEnv):
             quat = obj[:, 3:].clone()
         return torch.cat([pos, quat / torch.linalg.norm(quat, dim=1, keepdim=True)], dim=1)
 
+    def _device_reset(self, mask, out):
+        """rng_mode="device": the same retry loop with the draws inside the library; the host only reads `pending.any()`."""
+        if getattr(self, "_dev_reset", None) is None:
+            from ._lib import HandResetC
+
+            modes = {"ignore": 0, "fixed": 0, "z": 1, "parallel": 2, "xyz": 3}
+            p = HandResetC()
+            p.obj_qadr = int(self.task.obj_qadr)
+            p.rot_mode = 3 if self.target_rotation == "ignore" else modes[self.target_rotation]     # manipulate.py:188-194
+            p.randomize_rotation = int(bool(self.randomize_initial_rotation))
+            p.randomize_position = int(bool(self.randomize_initial_position) and self.target_position != "fixed")
+            p.goal_rot_mode, p.goal_random_position = modes[self.target_rotation], int(self.target_position == "random")
+            for k in range(3):
+                p.pos_lo[k], p.pos_hi[k] = float(TARGET_POSITION_RANGE[k, 0]), float(TARGET_POSITION_RANGE[k, 1])
+            sl = self._sl
+            rest = torch.zeros(self.backend.state.shape[1], dtype=torch.float32, device=self.device)
+            rest[sl["qpos"]] = self.initial_qpos
+            rest[sl["qvel"]] = self.initial_qvel
+            rest[sl["ctrl"]] = self._ctrl_center
+            self._dev_reset = (p, rest, self._parallel.contiguous())
+            self._episode = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        p, rest, par = self._dev_reset
+        st = self.backend.state
+        pending = mask.clone()
+        for attempt in range(100):
+            if not bool(pending.any()):
+                break
+            m8 = pending.to(torch.uint8)
+            self.backend.reset_hand_pose(m8, rest, p, par, self._dev_seed, self.env_offset, self._episode, attempt)
+            self.backend.raw_step(10 * self.n_substeps, out, mask=m8)
+            self.reset_attempts += 1
+            pending = pending & ~(st[:, self._obj.start + 2] > 0.04)
+        else:
+            raise RuntimeError("hand reset did not settle on the palm within 100 attempts")
+        self.backend.reset_hand_goal(mask.to(torch.uint8), p, par, self._dev_seed, self.env_offset, self._episode, out)
+        self._elapsed.masked_fill_(mask, 0)
+
     def _reset_envs(self, mask, out):
         """BaseRobotEnv.reset (robot_env.py:154-186): retry `_reset_sim` until the block rests on the palm, then sample
         the goal.  Every attempt settles the pending envs together with one masked raw-step launch (10 x 20 sub-steps)."""
+        if self.rng_mode == "device":
+            return self._device_reset(mask, out)
         idx_all = torch.nonzero(mask, as_tuple=False).flatten()
         if idx_all.numel() == 0:
             return

@@ -142,6 +142,22 @@ typedef struct b200sim_maze_reset {
 int b200sim_reset_maze(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_maze_reset_t* params,
                        const float* goal_xy, const float* reset_xy, unsigned long long seed, int env_offset, int* episode, float* obs,
                        float* achieved, float* desired, float* reward, float* success, void* stream);
+/* Shadow-Hand manipulation (reference: envs/shadow_dexterous_hand/manipulate.py:154-224 _reset_sim, :226-279 _sample_goal).  The
+ * reference's reset is a retry loop, so the draws are two calls: `b200sim_reset_hand_pose` writes rest_record + the drawn object
+ * start pose into the masked envs' records (their goal survives) for attempt number `attempt` -- the caller then settles with
+ * b200sim_raw_step_masked and repeats for the envs whose object left the palm; `b200sim_reset_hand_goal` draws the goal from the
+ * settled object pose, increments episode[i] and refreshes.  rot modes: 0 none, 1 "z", 2 "parallel", 3 "xyz"; parallel_quats is the
+ * DEVICE table [24, 4] of rotations.get_parallel_rotations() (utils/rotations.py:349-386). */
+typedef struct b200sim_hand_reset {
+  int obj_qadr, rot_mode, randomize_rotation, randomize_position, goal_rot_mode, goal_random_position;
+  float pos_lo[3], pos_hi[3];   /* manipulate.py: target_position_range */
+} b200sim_hand_reset_t;
+int b200sim_reset_hand_pose(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_hand_reset_t* params,
+                            const float* parallel_quats, unsigned long long seed, int env_offset, const int* episode, int attempt,
+                            void* stream);
+int b200sim_reset_hand_goal(b200sim_t* h, const unsigned char* mask, const b200sim_hand_reset_t* params, const float* parallel_quats,
+                            unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired,
+                            float* reward, float* success, void* stream);
 /* Failure detection ([ext] mj_checkPos / mj_checkVel / mj_checkAcc inside mj_step: NaN or |x| > 1e10 => warning + mj_resetData):
  * bad[i] (device, [N] bytes) = 1 when env i's state record holds a non-finite or huge value, else 0.  With rest_record != NULL a bad
  * env's record is replaced by it, except the float ranges listed in `keep` (goal, per-episode poses) whose finite values survive.

@@ -77,6 +77,14 @@ extern "C" void hostsim_maze_reset_record(const b200sim_maze_reset_t* p, const f
                                           unsigned episode, const float* rest, int stride, int st_qpos, int st_goal, float* rec) {
   rs_maze_reset_record(*p, goal_xy, reset_xy, seed, env, episode, rest, stride, st_qpos, st_goal, rec);
 }
+extern "C" void hostsim_hand_pose_record(const b200sim_hand_reset_t* p, const float* parallel, unsigned long long seed, unsigned env, unsigned episode,
+                                         unsigned attempt, const float* rest, int stride, int st_qpos, int st_goal, int ngoal, float* rec) {
+  rs_hand_pose_record(*p, parallel, seed, env, episode, attempt, rest, stride, st_qpos, st_goal, ngoal, rec);
+}
+extern "C" void hostsim_hand_goal(const b200sim_hand_reset_t* p, const float* parallel, unsigned long long seed, unsigned env, unsigned episode,
+                                  int st_qpos, int st_goal, float* rec) {
+  rs_hand_goal(*p, parallel, seed, env, episode, st_qpos, st_goal, rec);
+}
 extern "C" int hostsim_check_record(float* rec, int stride, const float* rest, const b200sim_keep_t* keep) {
   b200sim_keep_t k;
   k.n = 0;

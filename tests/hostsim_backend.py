@@ -120,6 +120,37 @@ class HostSimBackend:
         self.launches += 1
         self.refresh(mask, out)
 
+    def reset_hand_pose(self, mask, rest_record, params, parallel, seed, env_offset, episode, attempt):
+        import ctypes
+
+        L = self.sim._L
+        L.hostsim_hand_pose_record.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint,
+                                               ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.hostsim_hand_pose_record.restype = None
+        st, rest, par = self.state.numpy(), rest_record.numpy(), parallel.numpy()
+        for i in range(self.num_envs):
+            if mask is None or bool(mask[i]):
+                L.hostsim_hand_pose_record(ctypes.byref(params), par.ctypes.data, int(seed) & 0xFFFFFFFFFFFFFFFF, i + int(env_offset), int(episode[i]),
+                                           int(attempt), rest.ctypes.data, self.layout["stride"], self.layout["qpos"], self.layout["goal"], self.ngoal,
+                                           st[i].ctypes.data)
+        self.launches += 1
+
+    def reset_hand_goal(self, mask, params, parallel, seed, env_offset, episode, out):
+        import ctypes
+
+        L = self.sim._L
+        L.hostsim_hand_goal.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p]
+        L.hostsim_hand_goal.restype = None
+        st, par = self.state.numpy(), parallel.numpy()
+        for i in range(self.num_envs):
+            if mask is None or bool(mask[i]):
+                L.hostsim_hand_goal(ctypes.byref(params), par.ctypes.data, int(seed) & 0xFFFFFFFFFFFFFFFF, i + int(env_offset), int(episode[i]),
+                                    self.layout["qpos"], self.layout["goal"], st[i].ctypes.data)
+                episode[i] += 1
+        self.launches += 1
+        self.refresh(mask, out)
+
     def check_state(self, bad, rest_record, keep):
         import ctypes
 

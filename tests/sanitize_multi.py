@@ -17,7 +17,7 @@ for env_id, n in (("FetchPickAndPlace-v4", 30), ("FetchSlide-v4", 10), ("HandMan
 
 # the reset-draw kernels (b200sim_reset / _uniform / _maze) and the state scan (b200sim_check_state)
 for env_id, n, kw in (("FetchPickAndPlace-v4", 33, dict(auto_recover=True)), ("AdroitHandPen-v2", 9, {}), ("AdroitHandRelocate-v2", 9, {}),
-                      ("PointMaze_Medium-v3", 17, {})):
+                      ("PointMaze_Medium-v3", 17, {}), ("HandManipulateBlockRotateParallel-v1", 9, {})):
     env = grb.make_vec(env_id, num_envs=n, rng_mode="device", max_episode_steps=2, **kw)
     env.reset(seed=1)
     nact = env.single_action_space.shape[0]

@@ -293,3 +293,90 @@ def test_maze_env_with_in_kernel_resets():
     for i in range(2):
         g, p = py_maze_draw(pm._goal_loc.numpy(), pm._reset_loc.numpy(), pm.scaling, 0.25, 3, i, 0)
         assert np.array_equal(o["desired_goal"][i].numpy(), g) and np.array_equal(st[i, :2].numpy(), p)
+
+
+def test_hand_env_with_in_kernel_resets():
+    """manipulate.py:154-279 in rng_mode="device": start pose (z-rotation / parallel / xyz offset, position noise), settle with the
+    on-palm retry, goal from the settled pose -- checked against the reference's formulas on the same Philox numbers."""
+    from gymnasium_robotics_b200 import rotations
+    from gymnasium_robotics_b200.hand import HAND_REF_POINT, TARGET_POSITION_RANGE
+
+    class HandHostBackend(HostSimBackend):
+        REF = HAND_REF_POINT
+
+    f = np.float32
+    for env_id, rot in (("HandManipulateBlockRotateZ-v1", "z"), ("HandManipulateBlockRotateParallel-v1", "parallel"),
+                        ("HandManipulateBlockFull-v1", "xyz")):
+        env = pkg.make_vec(env_id, num_envs=2, backend_factory=HandHostBackend, rng_mode="device")
+        o, _ = env.reset(seed=13)
+        assert env.reset_attempts >= 1 and int(env._episode.min()) == 1
+        st, _ = env.get_state()
+        obj = st[:, env._obj].numpy()
+        goal = o["desired_goal"].numpy()
+        assert (obj[:, 2] > 0.04).all() and np.abs(np.linalg.norm(goal[:, 3:], axis=1) - 1).max() < 1e-6
+        par = np.array(rotations.parallel_quats())
+        for i in range(2):
+            key = (13, 0)
+            r, r2, r3 = (philox4x32_10((i, 0, 0x400 + b, 0x4A2D), key) for b in range(3))
+            angle = float((f(2) * u01(r[0]) - f(1)) * f(np.pi))
+            if rot == "z":
+                want = rotations.quat_from_angle_and_axis(angle, np.array([0.0, 0.0, 1.0]))
+            elif rot == "parallel":
+                zq = rotations.quat_from_angle_and_axis(angle, np.array([0.0, 0.0, 1.0]))
+                want = rotations.quat_mul(zq, par[(r[1] * 24) >> 32])
+            else:
+                axis = np.array([float(f(2) * u01(r2[k]) - f(1)) for k in range(3)])
+                want = rotations.quat_from_angle_and_axis(angle, axis)
+            assert np.abs(goal[i, 3:] - want / np.linalg.norm(want)).max() < 2e-6, (env_id, i)
+            if env.target_position == "random":
+                off = np.array([TARGET_POSITION_RANGE[k, 0] + (TARGET_POSITION_RANGE[k, 1] - TARGET_POSITION_RANGE[k, 0]) * float(u01(r3[k]))
+                                for k in range(3)])
+                assert np.abs(goal[i, :3] - (obj[i, :3] + off)).max() < 2e-6
+            else:
+                assert np.abs(goal[i, :3] - obj[i, :3]).max() < 1e-7          # "ignore": the goal position is the settled object's
+        env2 = pkg.make_vec(env_id, num_envs=2, backend_factory=HandHostBackend, rng_mode="device")
+        o2, _ = env2.reset(seed=13)
+        assert torch.equal(o["observation"], o2["observation"]) and torch.equal(o["desired_goal"], o2["desired_goal"])
+
+
+def test_hand_start_pose_draw():
+    """One attempt's pose record against the reference's formulas: initial quat * offset, += N(0, 0.005^2) (Box-Muller)."""
+    from gymnasium_robotics_b200 import rotations
+    from gymnasium_robotics_b200._lib import HandResetC
+
+    L = hostsim.lib()
+    L.hostsim_hand_pose_record.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.hostsim_hand_pose_record.restype = None
+    par = np.array(rotations.parallel_quats(), dtype=np.float32)
+    p = HandResetC()
+    p.obj_qadr, p.randomize_rotation, p.randomize_position = 24, 1, 1
+    rest = np.zeros(100, dtype=np.float32)
+    q0 = np.array([0.3, -0.5, 0.4, 0.7]); q0 /= np.linalg.norm(q0)
+    rest[24:27], rest[27:31] = [1.0, 0.87, 0.2], q0
+    f = np.float32
+    pos = []
+    for mode in (1, 2, 3):
+        p.rot_mode = mode
+        for env in range(60):
+            rec = np.full(100, 7.0, dtype=np.float32)
+            rec[90:97] = np.arange(7)                                       # the goal must survive
+            L.hostsim_hand_pose_record(ctypes.byref(p), par.ctypes.data, 5, env, 1, 2, rest.ctypes.data, 100, 0, 90, 7, rec.ctypes.data)
+            assert np.array_equal(rec[90:97], np.arange(7, dtype=np.float32)) and np.array_equal(rec[:24], rest[:24])
+            r, r2, r3 = (philox4x32_10((env, 1, 8 + b, 0x4A2D), (5, 0)) for b in range(3))
+            angle = float((f(2) * u01(r[0]) - f(1)) * f(np.pi))
+            if mode == 1:
+                off = rotations.quat_from_angle_and_axis(angle, np.array([0.0, 0.0, 1.0]))
+            elif mode == 2:
+                off = rotations.quat_mul(rotations.quat_from_angle_and_axis(angle, np.array([0.0, 0.0, 1.0])), par[(r[1] * 24) >> 32].astype(np.float64))
+            else:
+                off = rotations.quat_from_angle_and_axis(angle, np.array([float(f(2) * u01(r2[k]) - f(1)) for k in range(3)]))
+            want = rotations.quat_mul(rest[27:31].astype(np.float64), off)
+            assert np.abs(rec[27:31] - want / np.linalg.norm(want)).max() < 2e-6
+            u1, u2, u3, u4 = 1 - float(u01(r3[0])), float(u01(r3[1])), 1 - float(u01(r3[2])), float(u01(r3[3]))
+            n = 0.005 * np.array([np.sqrt(-2 * np.log(u1)) * np.cos(2 * np.pi * u2), np.sqrt(-2 * np.log(u1)) * np.sin(2 * np.pi * u2),
+                                  np.sqrt(-2 * np.log(u3)) * np.cos(2 * np.pi * u4)])
+            assert np.abs(rec[24:27] - (rest[24:27] + n)).max() < 1e-6
+            pos.append(rec[24:27] - rest[24:27])
+    pos = np.array(pos)
+    assert 0.003 < pos.std() < 0.007 and abs(pos.mean()) < 0.002          # manipulate.py:200-202: scale 0.005

@@ -133,3 +133,25 @@ def test_check_state_recovers_bad_envs_on_the_gpu():
     o, r, te, tr, info = env.step(torch.zeros((n, 4), device="cuda"))
     assert not info["bad_state"].any() and torch.isfinite(o["observation"]).all()
     env.close()
+
+
+def test_hand_resets_in_kernel():
+    """b200sim_reset_hand_pose / _goal through HandVectorEnv (BASELINE config 3's model): every object ends on the palm, goals are unit
+    quaternions drawn per env, episodes advance the counters, same seed => same reset."""
+    import gymnasium_robotics_b200 as pkg
+
+    n = 128
+    env = pkg.make_vec("HandManipulateBlockRotateXYZ-v1", num_envs=n, rng_mode="device", max_episode_steps=5)
+    o, _ = env.reset(seed=4)
+    st, _ = env.get_state()
+    assert bool((st[:, env._obj.start + 2] > 0.04).all()) and torch.isfinite(o["observation"]).all()
+    g = o["desired_goal"]
+    assert float((g[:, 3:].norm(dim=1) - 1).abs().max()) < 1e-5 and torch.unique(g[:, 3:].round(decimals=5), dim=0).shape[0] == n
+    assert torch.equal(g[:, :3], st[:, env._obj][:, :3])              # RotateXYZ ignores the position: goal position = settled object
+    env2 = pkg.make_vec("HandManipulateBlockRotateXYZ-v1", num_envs=n, rng_mode="device", max_episode_steps=5)
+    o2, _ = env2.reset(seed=4)
+    assert torch.equal(o["desired_goal"], o2["desired_goal"]) and torch.equal(o["observation"], o2["observation"])
+    for _ in range(6):                                                # TimeLimit 5 + the next-step reset call
+        o, r, te, tr, info = env.step(torch.zeros((n, 20), device="cuda"))
+    assert int(env._episode.min()) == 2 and not torch.equal(o["desired_goal"], g) and torch.isfinite(o["observation"]).all()
+    env.close(); env2.close()
