@@ -100,6 +100,15 @@ __global__ void hand_goal_kernel(b200sim_hand_reset_t p, const float* __restrict
   if (episode) episode[i] = ep + 1;
 }
 
+__global__ void reach_reset_kernel(b200sim_reach_reset_t p, unsigned long long seed, int env_offset, int N, const unsigned char* __restrict__ mask,
+                                   const float* __restrict__ rest, int stride, int st_goal, float* __restrict__ state, int* __restrict__ episode) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || (mask && !mask[i])) return;
+  int ep = episode ? episode[i] : 0;
+  rs_reach_reset_record(p, seed, (uint32_t)(i + env_offset), (uint32_t)ep, rest, stride, st_goal, state + (size_t)i * stride);
+  if (episode) episode[i] = ep + 1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 #define B200_FOR_ALL_VARIANTS(X) X(7, 14) X(7, 15) X(7, 21) X(14, 14) X(14, 15) X(14, 21) X(28, 14) X(28, 15) X(28, 21) \
   X(7, 22) X(14, 22) X(28, 22) X(7, 30) X(14, 30)
@@ -400,6 +409,18 @@ int b200sim_reset_hand_goal(b200sim_t* h, const unsigned char* mask, const b200s
   CUDA_OK(cudaSetDevice(h->device));
   hand_goal_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, parallel_quats, seed, env_offset, h->N, mask, h->task.st_stride,
                                                                         h->task.st_qpos, h->task.st_goal, h->state, episode);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+}
+int b200sim_reset_reach(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_reach_reset_t* params,
+                        unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired, float* reward,
+                        float* success, void* stream) {
+  if (h->task.kind != TASK_HAND_REACH || h->task.ngoal != 15) return fail(h, "b200sim_reset_reach: not a HandReach task", -6);
+  if (!rest_record || !params) return fail(h, "b200sim_reset_reach: NULL argument", -1);
+  CUDA_OK(cudaSetDevice(h->device));
+  reach_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
+                                                                          h->task.st_goal, h->state, episode);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);

@@ -226,6 +226,33 @@ RS_HD void rs_hand_goal(const b200sim_hand_reset_t& p, const float* parallel, un
   rs_qnormalize(g + 3);                                                                                // :276
 }
 
+// HandReach goal (envs/shadow_dexterous_hand/reach.py:95-121): the thumb tip and one other finger tip (uniform choice of four)
+// meet at palm + (0, -0.09, 0.05) + N(0, 0.005^2): each of the two goals sits 5 mm before the meeting point on the line from its
+// initial goal; with probability 0.1 the goal is the initial finger-tip configuration.
+RS_HD void rs_reach_reset_record(const b200sim_reach_reset_t& p, unsigned long long seed, uint32_t env, uint32_t episode, const float* rest,
+                                 int stride, int st_goal, float* rec) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t ctr[4] = {env, episode, 0u, 0x2EAC4u}, r[4], r2[4];
+  rs_philox4x32_10(ctr, key, r);
+  ctr[2] = 1u; rs_philox4x32_10(ctr, key, r2);
+  for (int k = 0; k < stride; k++) rec[k] = rest[k];
+  float* g = rec + st_goal;
+  for (int k = 0; k < 15; k++) g[k] = p.initial_goal[k];
+  if (rs_u01(r[1]) < 0.1f) return;                                           // reach.py:118-120
+  const float TWO_PI = 6.28318530717958647692f;
+  float m1 = sqrtf(-2.0f * logf(1.0f - rs_u01(r2[0]))), m2 = sqrtf(-2.0f * logf(1.0f - rs_u01(r2[2])));
+  float meet[3] = {p.meeting[0] + 0.005f * m1 * cosf(TWO_PI * rs_u01(r2[1])), p.meeting[1] + 0.005f * m1 * sinf(TWO_PI * rs_u01(r2[1])),
+                   p.meeting[2] + 0.005f * m2 * cosf(TWO_PI * rs_u01(r2[3]))};
+  int finger = (int)(((uint64_t)r[0] * 4u) >> 32);                           // :99-101 (the thumb is entry 4 of the five tips)
+  const int sel[2] = {4, finger};
+  for (int j = 0; j < 2; j++) {
+    float* gj = g + 3 * sel[j];
+    float d[3] = {meet[0] - gj[0], meet[1] - gj[1], meet[2] - gj[2]};
+    float n = 0.005f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    for (int k = 0; k < 3; k++) gj[k] = meet[k] - n * d[k];                  // :111-116
+  }
+}
+
 // Bad-state detection and recovery at env-step granularity.  mj_step checks qpos / qvel / qacc for NaN and |x| > mjMAXVAL = 1e10
 // before and after the forward pass and answers with a warning + mj_resetData ([ext] engine_forward.c mj_checkPos / mj_checkVel /
 // mj_checkAcc; SURVEY.md section 5 "failure detection"); here one thread scans its env's state record after the step and, when

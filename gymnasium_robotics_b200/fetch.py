@@ -182,6 +182,12 @@ class CudaBackend:
                                                    int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), episode.data_ptr(), *self._ptrs(out),
                                                    self._stream()))
 
+    def reset_reach(self, mask, rest_record, params, seed, env_offset, episode, out):
+        """b200sim_reset_reach: HandReach goal drawn on the device, then mj_forward + _get_obs."""
+        assert rest_record.is_cuda and rest_record.numel() == self.layout["stride"] and episode.is_cuda and episode.dtype == torch.int32
+        self._check(self.L.b200sim_reset_reach(self.h, mask.data_ptr() if mask is not None else None, rest_record.data_ptr(), ctypes.byref(params),
+                                               int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), episode.data_ptr(), *self._ptrs(out), self._stream()))
+
     def check_state(self, bad, rest_record, keep):
         """b200sim_check_state: bad[i] = record i holds NaN / |x| > 1e10; such records are put back to `rest_record` (if given)."""
         assert bad.is_cuda and bad.dtype == torch.uint8 and bad.numel() == self.num_envs

@@ -402,13 +402,13 @@ class HandReachVectorEnv(FetchVectorEnv):
         factory = backend_factory or _HandBackend
         self.backend = factory(m, np.zeros((0, 11)), t, self.num_envs, device)
         self.device = self.backend.device
-        if rng_mode == "device":
-            raise NotImplementedError("rng_mode='device' (in-kernel reset draws, b200sim_reset) exists for the Fetch family only")
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
+        self.env_offset = int(kwargs.get("env_offset", 0))
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None
         self._gen = torch.Generator(device=self.device)
         self._gen.seed()
+        self._dev_seed = int(self._gen.initial_seed())
         lay = self.backend.layout
         self._sl = {k: slice(lay[k], lay[k] + n) for k, n in (("qpos", m.nq), ("qvel", m.nv), ("warm", m.nv), ("ctrl", m.nu), ("goal", 15))}
         self.dt = float(m.opt[0] * n_substeps)
@@ -471,7 +471,29 @@ class HandReachVectorEnv(FetchVectorEnv):
         goal[keep] = init_t
         return goal.reshape(n, 15)
 
+    def _device_reset(self, mask, out):
+        if getattr(self, "_dev_reset", None) is None:
+            from ._lib import ReachResetC
+
+            p = ReachResetC()
+            meeting = self.palm_xpos + np.array([0.0, -0.09, 0.05])
+            init = self.initial_goal.double().cpu().numpy()
+            for k in range(3):
+                p.meeting[k] = float(meeting[k])
+            for k in range(15):
+                p.initial_goal[k] = float(init[k])
+            rest = torch.zeros(self.backend.state.shape[1], dtype=torch.float32, device=self.device)
+            rest[self._sl["qpos"]] = self.initial_qpos
+            rest[self._sl["qvel"]] = self.initial_qvel
+            self._dev_reset = (p, rest)
+            self._episode = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        p, rest = self._dev_reset
+        self.backend.reset_reach(mask.to(torch.uint8), rest, p, self._dev_seed, self.env_offset, self._episode, out)
+        self._elapsed.masked_fill_(mask, 0)
+
     def _reset_envs(self, mask, out):
+        if self.rng_mode == "device":
+            return self._device_reset(mask, out)
         idx = torch.nonzero(mask, as_tuple=False).flatten()
         if idx.numel() == 0:
             return

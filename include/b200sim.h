@@ -158,6 +158,12 @@ int b200sim_reset_hand_pose(b200sim_t* h, const unsigned char* mask, const float
 int b200sim_reset_hand_goal(b200sim_t* h, const unsigned char* mask, const b200sim_hand_reset_t* params, const float* parallel_quats,
                             unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired,
                             float* reward, float* success, void* stream);
+/* HandReach (reference: envs/shadow_dexterous_hand/reach.py:95-130): record <- rest_record with the 15-float goal drawn on the
+ * device (meeting point of the thumb and a random other finger tip), then the refresh.  meeting = palm_xpos + (0, -0.09, 0.05). */
+typedef struct b200sim_reach_reset { float meeting[3], initial_goal[15]; } b200sim_reach_reset_t;
+int b200sim_reset_reach(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_reach_reset_t* params,
+                        unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired, float* reward,
+                        float* success, void* stream);
 /* Failure detection ([ext] mj_checkPos / mj_checkVel / mj_checkAcc inside mj_step: NaN or |x| > 1e10 => warning + mj_resetData):
  * bad[i] (device, [N] bytes) = 1 when env i's state record holds a non-finite or huge value, else 0.  With rest_record != NULL a bad
  * env's record is replaced by it, except the float ranges listed in `keep` (goal, per-episode poses) whose finite values survive.

@@ -85,6 +85,10 @@ extern "C" void hostsim_hand_goal(const b200sim_hand_reset_t* p, const float* pa
                                   int st_qpos, int st_goal, float* rec) {
   rs_hand_goal(*p, parallel, seed, env, episode, st_qpos, st_goal, rec);
 }
+extern "C" void hostsim_reach_reset_record(const b200sim_reach_reset_t* p, unsigned long long seed, unsigned env, unsigned episode, const float* rest,
+                                           int stride, int st_goal, float* rec) {
+  rs_reach_reset_record(*p, seed, env, episode, rest, stride, st_goal, rec);
+}
 extern "C" int hostsim_check_record(float* rec, int stride, const float* rest, const b200sim_keep_t* keep) {
   b200sim_keep_t k;
   k.n = 0;

@@ -151,6 +151,22 @@ class HostSimBackend:
         self.launches += 1
         self.refresh(mask, out)
 
+    def reset_reach(self, mask, rest_record, params, seed, env_offset, episode, out):
+        import ctypes
+
+        L = self.sim._L
+        L.hostsim_reach_reset_record.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_void_p]
+        L.hostsim_reach_reset_record.restype = None
+        st, rest = self.state.numpy(), rest_record.numpy()
+        for i in range(self.num_envs):
+            if mask is None or bool(mask[i]):
+                L.hostsim_reach_reset_record(ctypes.byref(params), int(seed) & 0xFFFFFFFFFFFFFFFF, i + int(env_offset), int(episode[i]), rest.ctypes.data,
+                                             self.layout["stride"], self.layout["goal"], st[i].ctypes.data)
+                episode[i] += 1
+        self.launches += 1
+        self.refresh(mask, out)
+
     def check_state(self, bad, rest_record, keep):
         import ctypes
 

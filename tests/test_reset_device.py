@@ -133,7 +133,8 @@ def test_draw_matches_the_python_restatement_and_the_reference_distributions(cfg
 
 
 def mk(task, n, **kw):
-    return pkg.make_vec(task, num_envs=n, backend_factory=HostSimBackend, rng_mode="device", **kw)
+    kw.setdefault("rng_mode", "device")
+    return pkg.make_vec(task, num_envs=n, backend_factory=HostSimBackend, **kw)
 
 
 def test_vector_env_with_in_kernel_resets():
@@ -163,8 +164,8 @@ def test_vector_env_with_in_kernel_resets():
     shard = mk("FetchPickAndPlace-v4", 2, env_offset=2)
     os_, _ = shard.reset(seed=7)
     assert torch.equal(os_["desired_goal"], o1["desired_goal"][2:])
-    with pytest.raises(NotImplementedError):
-        pkg.make_vec("HandReach-v3", num_envs=1, backend_factory=HostSimBackend, rng_mode="device")
+    with pytest.raises(ValueError):
+        mk("FetchReach-v4", 1, rng_mode="philox")
 
 
 def test_reach_has_no_object_draw():
@@ -380,3 +381,38 @@ def test_hand_start_pose_draw():
             pos.append(rec[24:27] - rest[24:27])
     pos = np.array(pos)
     assert 0.003 < pos.std() < 0.007 and abs(pos.mean()) < 0.002          # manipulate.py:200-202: scale 0.005
+
+
+def test_hand_reach_goal_draw():
+    """reach.py:95-121 on the generator's numbers: thumb + one of four fingers meet near the palm; 10 % keep the initial tips."""
+    from gymnasium_robotics_b200.hand import HAND_REF_POINT
+
+    class HandHostBackend(HostSimBackend):
+        REF = HAND_REF_POINT
+
+    env = pkg.make_vec("HandReach-v3", num_envs=40, backend_factory=HandHostBackend, rng_mode="device")
+    o, _ = env.reset(seed=6)
+    goals = o["desired_goal"].numpy().reshape(40, 5, 3)
+    init = env.initial_goal.numpy().reshape(5, 3)
+    meeting0 = env.palm_xpos + np.array([0.0, -0.09, 0.05])
+    f = np.float32
+    kept = 0
+    for i in range(40):
+        r = philox4x32_10((i, 0, 0, 0x2EAC4), (6, 0))
+        r2 = philox4x32_10((i, 0, 1, 0x2EAC4), (6, 0))
+        if u01(r[1]) < f(0.1):
+            assert np.array_equal(goals[i], init)
+            kept += 1
+            continue
+        u1, u2, u3, u4 = 1 - float(u01(r2[0])), float(u01(r2[1])), 1 - float(u01(r2[2])), float(u01(r2[3]))
+        meet = meeting0 + 0.005 * np.array([np.sqrt(-2 * np.log(u1)) * np.cos(2 * np.pi * u2), np.sqrt(-2 * np.log(u1)) * np.sin(2 * np.pi * u2),
+                                            np.sqrt(-2 * np.log(u3)) * np.cos(2 * np.pi * u4)])
+        finger = (r[0] * 4) >> 32
+        want = init.astype(np.float64).copy()
+        for j in (4, finger):
+            d = meet - want[j]
+            want[j] = meet - 0.005 * d / np.linalg.norm(d)
+        assert np.abs(goals[i] - want).max() < 1e-6, i
+    assert kept <= 12
+    st, _ = env.get_state()
+    assert torch.equal(st[:, env._sl["qpos"]], env.initial_qpos.expand(40, -1))

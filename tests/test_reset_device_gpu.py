@@ -155,3 +155,10 @@ def test_hand_resets_in_kernel():
         o, r, te, tr, info = env.step(torch.zeros((n, 20), device="cuda"))
     assert int(env._episode.min()) == 2 and not torch.equal(o["desired_goal"], g) and torch.isfinite(o["observation"]).all()
     env.close(); env2.close()
+    reach = pkg.make_vec("HandReach-v3", num_envs=64, rng_mode="device")
+    o, _ = reach.reset(seed=1)
+    init = reach.initial_goal.reshape(1, 15)
+    moved = (o["desired_goal"] - init).abs().amax(dim=1) > 0
+    assert torch.isfinite(o["observation"]).all() and 40 <= int(moved.sum()) <= 64       # ~10 % keep the initial finger tips (reach.py:118-120)
+    assert float((o["desired_goal"] - init).abs().max()) < 0.2
+    reach.close()
