@@ -133,6 +133,7 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         self.device = self.backend.device
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
         self.env_offset = int(kwargs.get("env_offset", 0))
+        self.auto_recover = bool(kwargs.get("auto_recover", False))   # opt-in NaN / huge-value scan after every step (fetch.py)
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None
         self._gen = torch.Generator(device=self.device)
@@ -187,6 +188,20 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
             self._elapsed.zero_()
         else:
             self._elapsed.masked_fill_(mask, 0)
+
+    def _recovery_record(self):
+        """A recovered env restarts from the model's rest state and keeps its per-episode model pose and target."""
+        from ._lib import KeepC
+
+        sl, keep = self._sl, KeepC()
+        keep.n = 2
+        keep.start[0], keep.len[0] = sl["goal"].start, 3
+        keep.start[1], keep.len[1] = sl["penv"].start, 7
+        rest = torch.zeros(self.backend.state.shape[1], dtype=torch.float32, device=self.device)
+        rest[sl["qpos"]] = self.init_qpos
+        rest[sl["qvel"]] = self.init_qvel
+        rest[sl["penv"]] = self._board_pos0
+        return rest, keep
 
     def _reset_envs(self, mask, out):
         """MujocoEnv.reset -> mj_resetData -> reset_model (adroit_hammer.py:372-378) for the envs in `mask`."""

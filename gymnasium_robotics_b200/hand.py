@@ -128,6 +128,7 @@ class HandVectorEnv(FetchVectorEnv):
         # "device": start pose and goal are drawn inside the library (b200sim_reset_hand_pose / _goal, csrc/reset_sample.cuh)
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
         self.env_offset = int(kwargs.get("env_offset", 0))
+        self.auto_recover = bool(kwargs.get("auto_recover", False))   # opt-in NaN / huge-value scan after every step (fetch.py)
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None
         self._gen = torch.Generator(device=self.device)
@@ -255,6 +256,18 @@ class HandVectorEnv(FetchVectorEnv):
         else:
             quat = obj[:, 3:].clone()
         return torch.cat([pos, quat / torch.linalg.norm(quat, dim=1, keepdim=True)], dim=1)
+
+    def _recovery_record(self):
+        from ._lib import KeepC
+
+        sl, keep = self._sl, KeepC()
+        keep.n, keep.start[0], keep.len[0] = 1, sl["goal"].start, sl["goal"].stop - sl["goal"].start
+        rest = torch.zeros(self.backend.state.shape[1], dtype=torch.float32, device=self.device)
+        rest[sl["qpos"]] = self.initial_qpos
+        rest[sl["qvel"]] = self.initial_qvel
+        if hasattr(self, "_ctrl_center"):
+            rest[sl["ctrl"]] = self._ctrl_center
+        return rest, keep
 
     def _device_reset(self, mask, out):
         """rng_mode="device": the same retry loop with the draws inside the library; the host only reads `pending.any()`."""
@@ -404,6 +417,7 @@ class HandReachVectorEnv(FetchVectorEnv):
         self.device = self.backend.device
         self.rng_mode = rng_mode if rng_mode != "auto" else ("numpy" if self.num_envs <= 64 else "torch")
         self.env_offset = int(kwargs.get("env_offset", 0))
+        self.auto_recover = bool(kwargs.get("auto_recover", False))   # opt-in NaN / huge-value scan after every step (fetch.py)
         self._np_rngs = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(None))) for _ in range(self.num_envs)] \
             if self.rng_mode == "numpy" else None
         self._gen = torch.Generator(device=self.device)
@@ -470,6 +484,8 @@ class HandReachVectorEnv(FetchVectorEnv):
         keep = torch.rand(n, generator=self._gen, device=dev) < 0.1
         goal[keep] = init_t
         return goal.reshape(n, 15)
+
+    _recovery_record = HandVectorEnv._recovery_record
 
     def _device_reset(self, mask, out):
         if getattr(self, "_dev_reset", None) is None:

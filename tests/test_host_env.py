@@ -206,3 +206,22 @@ def test_auto_recover_detects_and_resets_bad_states():
     assert not torch.equal(st[0, q], rest[q])                                  # the healthy envs moved on
     o, r, te, tr, info = env.step(np.zeros((4, 4), dtype=np.float32))
     assert not info["bad_state"].any() and torch.isfinite(o["observation"]).all()
+
+
+def test_auto_recover_on_other_families():
+    """The scan keeps what an episode drew: the Adroit door's frame position (per-env model pose) survives a recovery."""
+    import gymnasium_robotics_b200 as pkg
+    from gymnasium_robotics_b200.adroit import ADROIT_REF_POINT
+
+    class AdroitHostBackend(HostSimBackend):
+        REF = ADROIT_REF_POINT
+
+    env = pkg.make_vec("AdroitHandDoor-v2", num_envs=2, backend_factory=AdroitHostBackend, rng_mode="numpy", auto_recover=True)
+    env.reset(seed=1)
+    frame = env.get_env_state()["door_body_pos"].clone()
+    st = env.backend.state
+    st[1, env._sl["qvel"].start + 5] = float("inf")
+    o, r, te, tr, info = env.step(np.zeros((2, 28), dtype=np.float32))
+    assert info["bad_state"].tolist() == [False, True] and torch.isfinite(o).all()
+    s = env.get_env_state()
+    assert torch.equal(s["door_body_pos"], frame) and torch.equal(s["qpos"][1], env.init_qpos)
