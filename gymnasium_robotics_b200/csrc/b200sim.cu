@@ -123,6 +123,13 @@ extern "C" int b200sim_wide_launch(int wpb, int blocks, size_t smem_bytes, void*
 extern "C" int b200sim_kitchen_build(const b200_model_view* view, const double* eq_data, const float* ref, int penv_body,
                                      std::vector<uint32_t>* buf, std::string* err);
 extern "C" int b200sim_kitchen_setattr(int wpb, int smem_bytes);
+// the same build with the two-level broad phase, from b200sim_kitchen_groups.cu (chosen by B200SIM_KITCHEN_GROUPS=1 at create time)
+extern "C" int b200sim_kitchen_groups_build(const b200_model_view* view, const double* eq_data, const float* ref, int penv_body,
+                                            std::vector<uint32_t>* buf, std::string* err);
+extern "C" int b200sim_kitchen_groups_setattr(int wpb, int smem_bytes);
+extern "C" int b200sim_kitchen_groups_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
+                                             int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
+                                             float* achieved, float* desired, float* reward, float* success, int* info);
 extern "C" int b200sim_kitchen_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
                                       int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
                                       float* achieved, float* desired, float* reward, float* success, int* info);
@@ -130,7 +137,7 @@ extern "C" int b200sim_kitchen_launch(int wpb, int blocks, size_t smem_bytes, vo
 
 struct b200sim {
   int N = 0, device = 0;
-  bool kitchen = false;
+  bool kitchen = false, kitchen_groups = false;
   std::vector<uint8_t> blob;
   b200_model_view view;
   std::vector<uint32_t> model_host;
@@ -179,7 +186,10 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
     for (int p = 0; p < v.npair; p++) if (v.pair_condim[p] == 6) h->kitchen = true;
   }
   const int penv = TASK_IS_ADROIT(task->kind) ? task->penv_body : -1;
-  if ((h->kitchen ? b200sim_kitchen_build(&h->view, eq_data, r, penv, &h->model_host, &err) : dm_build(h->view, eq_data, r, h->model_host, err, penv)) != 0) {
+  if (h->kitchen) { const char* g = getenv("B200SIM_KITCHEN_GROUPS"); h->kitchen_groups = g && atoi(g) != 0; }
+  if ((h->kitchen ? (h->kitchen_groups ? b200sim_kitchen_groups_build(&h->view, eq_data, r, penv, &h->model_host, &err)
+                                       : b200sim_kitchen_build(&h->view, eq_data, r, penv, &h->model_host, &err))
+                  : dm_build(h->view, eq_data, r, h->model_host, err, penv)) != 0) {
     delete h; return fail(nullptr, "b200sim_create: " + err, -4);
   }
   const DMHead* dh = (const DMHead*)h->model_host.data();
@@ -256,7 +266,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
     h->nvp = B200_KITCHEN_NVP;
     auto fits = [&](int w) { return ((size_t)dh->hot_words + (size_t)w * dh->scr_words) * 4 + 64 <= 232448; };
     h->wpb = (h->wpb > 7 && fits(10)) ? 10 : 7;
-    if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if ((w == 7 || w == 10 || w == 11) && fits(w)) h->wpb = w; }  // experiments
+    if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if ((w == 7 || w == 10 || (w == 11 && h->kitchen_groups)) && fits(w)) h->wpb = w; }  // experiments
   }
   if (h->nvp == B200_WIDE_NVP) {
     // wide build: the largest block of {14, 13, 10, 7} warps whose scratch fits the 227 KB of shared memory (14 envs of the
@@ -275,7 +285,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   B200_FOR_ALL_VARIANTS(B200_SETATTR)
 #undef B200_SETATTR
   if (h->nvp == B200_WIDE_NVP && b200sim_wide_setattr(h->wpb, (int)h->smem_bytes) != 0) e = cudaErrorInvalidValue;
-  if (h->nvp == B200_KITCHEN_NVP && b200sim_kitchen_setattr(h->wpb, (int)h->smem_bytes) != 0) e = cudaErrorInvalidValue;
+  if (h->nvp == B200_KITCHEN_NVP && (h->kitchen_groups ? b200sim_kitchen_groups_setattr(h->wpb, (int)h->smem_bytes) : b200sim_kitchen_setattr(h->wpb, (int)h->smem_bytes)) != 0) e = cudaErrorInvalidValue;
   if (e != cudaSuccess) { std::string m = std::string("cudaFuncSetAttribute(smem=") + std::to_string(h->smem_bytes) + "): " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
   if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, (size_t)num_envs * t.st_stride * 4) != cudaSuccess) {
     delete h; return fail(nullptr, "b200sim_create: cudaMalloc failed", -9);
@@ -321,7 +331,10 @@ static int launch(b200sim* h, int mode, int nraw, const float* actions, const un
         h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info);
   B200_FOR_ALL_VARIANTS(B200_LAUNCH)
 #undef B200_LAUNCH
-  if (h->nvp == B200_KITCHEN_NVP)
+  if (h->nvp == B200_KITCHEN_NVP && h->kitchen_groups)
+    b200sim_kitchen_groups_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, h->state, actions, mask, obs,
+                                  achieved, desired, reward, success, info);
+  if (h->nvp == B200_KITCHEN_NVP && !h->kitchen_groups)
     b200sim_kitchen_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, h->state, actions, mask, obs,
                            achieved, desired, reward, success, info);
   if (h->nvp == B200_WIDE_NVP)

@@ -22,10 +22,11 @@
 
 // (name, words-per-element, kind) ; kind selects the element count.  HOT arrays are staged into shared memory by every
 // block; COLD arrays (per-pair contact parameters, read only when a contact is created) stay in global memory.
-// Kitchen build: the flat pair list (3 708 entries, 44 KB) leaves shared memory -- it is only read for the pairs of the
+// Kitchen build with the two-level broad phase (-DB200_KITCHEN_GROUPS on top of -DB200_KITCHEN; the plain kitchen build keeps the
+// flat scan that was validated on a B200): the flat pair list (3 708 entries, 44 KB) leaves shared memory -- it is only read for the pairs of the
 // bounding-volume groups that survive the first broad-phase level -- and the group table (one bounding sphere on one body
 // against one anchor geom, a contiguous run of pairs) is staged instead.
-#ifdef B200_KITCHEN
+#ifdef B200_KITCHEN_GROUPS
 #define DM_PAIR_HOT(X)
 #define DM_PAIR_COLD(X) X(pair_geom1, 1, npair) X(pair_geom2, 1, npair) X(pair_margin, 1, npair)
 #define DM_BGRP_HOT(X) X(bg_body, 1, nbgrp) X(bg_anchor, 1, nbgrp) X(bg_start, 1, nbgrp) X(bg_count, 1, nbgrp) X(bg_center, 3, nbgrp) X(bg_radius, 1, nbgrp)
@@ -73,7 +74,7 @@
   X(group, ngrp_max * grp_words) X(counters, 8) X(fric, 2 * nfric) X(conx, ncx * CX_WORDS) X(penv_pos, npenv)
 // time-shared region `uni`: kinematics {kinA, kinB} -> dynamics {cinert, b6, d6, geom_xpos, cand} -> solver {H, d6, grad,
 // search, Ma, Mv} -> observation {cvel}.  d6 keeps one offset in both phases that use it.
-#ifdef B200_KITCHEN
+#ifdef B200_KITCHEN_GROUPS
 #define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(surv) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
 #else
 #define DM_SCRATCH_UNION(X) X(kinA) X(kinB) X(cinert) X(b6) X(d6) X(geom_xpos) X(cand) X(H) X(grad) X(search) X(Ma) X(Mv) X(cvel)
@@ -131,7 +132,7 @@ struct DMHead {
 #define X(name) int s_##name;
   DM_SCRATCH_UNION(X)
 #undef X
-#ifdef B200_KITCHEN
+#ifdef B200_KITCHEN_GROUPS
   int nbgrp;   // bounding-volume groups of the two-level broad phase (after the fields the common host code reads)
 #endif
 };
@@ -158,7 +159,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
       else if (!seen[m.pair_geom1[p]]) { seen[m.pair_geom1[p]] = 1; psrc.push_back(p); pgrid.push_back(1); }
     }
   }
-#ifdef B200_KITCHEN
+#ifdef B200_KITCHEN_GROUPS
   // Two-level broad phase: the pairs are regrouped by (body of geom1, body of geom2); inside such a bucket every geom of
   // the anchor side (the world body's geoms, else the side with fewer geoms) gets one group = its pairs, contiguous in
   // the device pair list, behind ONE bounding sphere fixed to the other body that encloses the bounding spheres of all
@@ -279,7 +280,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
       neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max, ndr_max = h.ndr_max,
       nten = h.nten, nfric = h.nfric, nsensor = h.nsensor, ncx = h.nsensor > 0 ? h.ncon_max : 0, MW = h.mask_words,
       grp_words = MW == 2 ? 34 : 32, npenv = h.penv_body > 0 ? 8 : 0;
-#ifdef B200_KITCHEN
+#ifdef B200_KITCHEN_GROUPS
   int nbgrp = h.nbgrp;
 #endif
   int nrkq = h.integrator == B200_INT_RK4 ? nq : 0, nrkv = h.integrator == B200_INT_RK4 ? nv : 0;
@@ -313,7 +314,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     h.s_H = u; h.s_grad = after; h.s_search = after + nv; h.s_Ma = after + 2 * nv; h.s_Mv = after + 3 * nv;
     h.s_cvel = u;
     int endA = after + 3 * ngeom + (h.npair > 255 ? h.ncand_max / 2 : h.ncand_max / 4), endB = after + 4 * nv;   // candidate slots: 1 or 2 bytes
-#ifdef B200_KITCHEN
+#ifdef B200_KITCHEN_GROUPS
     h.s_surv = endA; endA += DM_NSURV_MAX + 1;   // surviving groups: (first pair | running pair count << 16) + one end marker
 #endif
     so = endA > endB ? endA : endB;
@@ -446,7 +447,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     for (int k = 0; k < 2; k++) { F(h.o_pair_solref, 2 * p + k, m.pair_solref[2 * sp + k]); F(h.o_pair_invweight, 2 * p + k, m.pair_invweight[2 * sp + k]); }
     for (int k = 0; k < 5; k++) F(h.o_pair_solimp, 5 * p + k, m.pair_solimp[5 * sp + k]);
   }
-#ifdef B200_KITCHEN
+#ifdef B200_KITCHEN_GROUPS
   for (int g = 0; g < nbgrp; g++) {
     I(h.o_bg_body, g, bgs[g].body); I(h.o_bg_anchor, g, gmap[bgs[g].anchor]); I(h.o_bg_start, g, bgs[g].start); I(h.o_bg_count, g, bgs[g].count);
     for (int k = 0; k < 3; k++) F(h.o_bg_center, 3 * g + k, bgs[g].c[k]);

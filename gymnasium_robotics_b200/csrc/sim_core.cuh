@@ -68,8 +68,8 @@ enum { TM_KIN = 0, TM_COM_M, TM_COLL, TM_CONSTR, TM_SMOOTH, TM_NBEGIN, TM_NCHECK
 #define MI(name) ((const int*)(c.mw + c.h->o_##name))
 #define MU(name) ((const uint32_t*)(c.mw + c.h->o_##name))
 #define MF(name) ((const float*)(c.mw + c.h->o_##name))
-#ifdef B200_KITCHEN
-#define PAIR_I(name) ((const int*)(c.mg + c.h->o_##name))    // kitchen build: the pair list stays in global memory (dmodel.h)
+#ifdef B200_KITCHEN_GROUPS
+#define PAIR_I(name) ((const int*)(c.mg + c.h->o_##name))    // two-level kitchen build: the pair list stays in global memory (dmodel.h)
 #define PAIR_F(name) ((const float*)(c.mg + c.h->o_##name))
 #else
 #define PAIR_I(name) MI(name)
@@ -1070,7 +1070,7 @@ STAGE void collision(const Ctx c) {
   const bool wide_cand = h->npair > 255;
   if (c.lane == 0) { cnt[CNT_NCON] = 0; cnt[CNT_NCAND] = 0; cnt[CNT_NGRP] = 0; }
   SYNC();
-#if defined(B200_KITCHEN) && !defined(B200_KITCHEN_FLATSCAN)
+#if defined(B200_KITCHEN_GROUPS) && !defined(B200_KITCHEN_FLATSCAN)
   // broad phase, level 1: lanes over the bounding-volume groups (dmodel.h) -- one sphere fixed to a body against one anchor
   // geom (plane / the box itself / its bounding sphere); the survivors' pair runs are listed as (first pair, running count)
   uint32_t* surv = (uint32_t*)SI(surv);

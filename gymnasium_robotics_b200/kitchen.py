@@ -13,6 +13,7 @@ the reference as well); the 40 sub-steps of physics are one kernel launch.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -86,7 +87,22 @@ class KitchenVectorEnv(CtorPickle):
         self.model = model if model is not None else load_model("franka_kitchen")
         m = self.model
         self.task = make_kitchen_task(m, frame_skip)
-        self.backend = (backend_factory or _KitchenBackend)(m, np.zeros((0, 11)), self.task, self.num_envs, device)
+        # broadphase="groups": the kernel build with the two-level broad phase (csrc/b200sim_kitchen_groups.cu; emulation-validated,
+        # not yet run on a B200); default "flat": the build whose first GPU parity point exists.  The library reads the choice from
+        # the environment when the handle is created.
+        broadphase = kwargs.get("broadphase", "groups" if os.environ.get("B200SIM_KITCHEN_GROUPS", "0") not in ("", "0") else "flat")
+        if broadphase not in ("flat", "groups"):
+            raise ValueError("broadphase must be 'flat' or 'groups'")
+        self.broadphase = broadphase
+        prev = os.environ.get("B200SIM_KITCHEN_GROUPS")
+        os.environ["B200SIM_KITCHEN_GROUPS"] = "1" if broadphase == "groups" else "0"
+        try:
+            self.backend = (backend_factory or _KitchenBackend)(m, np.zeros((0, 11)), self.task, self.num_envs, device)
+        finally:
+            if prev is None:
+                del os.environ["B200SIM_KITCHEN_GROUPS"]
+            else:
+                os.environ["B200SIM_KITCHEN_GROUPS"] = prev
         self.device = dev = self.backend.device
         if rng_mode == "device":
             raise NotImplementedError("rng_mode='device' (in-kernel reset draws, b200sim_reset) exists for the Fetch family only")

@@ -12,10 +12,13 @@ timeout 600 compute-sanitizer --tool memcheck python tests/prof_kitchen.py 20 2 
 timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis python tests/prof_kitchen.py 10 1 > gpurun_out/racecheck_kitchen_${tag}.log 2>&1; tail -2 gpurun_out/racecheck_kitchen_${tag}.log
 # 4. bench line (2 048 envs, 40 sub-steps per env-step)
 timeout 300 python bench.py --workload franka_kitchen --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_${tag}_franka_kitchen.json 2> gpurun_out/bench_${tag}_franka_kitchen.err; cut -c1-160 gpurun_out/bench_${tag}_franka_kitchen.json
-# 4b. A/B: 11 envs per block (fits since the pair list left shared memory), 7 envs per block
-for w in 11 7; do
-  B200SIM_WPB=$w timeout 300 python bench.py --workload franka_kitchen --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_${tag}_franka_kitchen_wpb$w.json 2>/dev/null
-  echo "wpb $w: $(cut -c1-90 gpurun_out/bench_${tag}_franka_kitchen_wpb$w.json)"
+# 4b. A/B: the two-level broad-phase build (B200SIM_KITCHEN_GROUPS=1) at 10 and 11 envs per block (11 fits since its pair list
+#     is out of shared memory), and the flat build at 7
+timeout 120 env B200SIM_KITCHEN_GROUPS=1 python tests/kitchen_gpu_quick.py > gpurun_out/kitchen_quick_groups_${tag}.log 2>&1; tail -1 gpurun_out/kitchen_quick_groups_${tag}.log
+for v in "1 10" "1 11" "0 7"; do
+  set -- $v
+  B200SIM_KITCHEN_GROUPS=$1 B200SIM_WPB=$2 timeout 300 python bench.py --workload franka_kitchen --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_${tag}_franka_kitchen_g$1_wpb$2.json 2>/dev/null
+  echo "groups $1 wpb $2: $(cut -c1-90 gpurun_out/bench_${tag}_franka_kitchen_g$1_wpb$2.json)"
 done
 # 5. one full ncu capture of the kitchen step kernel
 ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 3 -c 1 -o gpurun_out/prof_kitchen_${tag} \

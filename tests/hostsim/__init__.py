@@ -29,9 +29,10 @@ class FetchTaskC(ctypes.Structure):
 def build(force=False, wide=False):
     """wide = True: the 64-bit dof-mask build (models with more than 32 dofs, -DB200_WIDE as in csrc/b200sim_wide.cu);
     wide = "kitchen": the bring-up build of the Franka-Kitchen kernel features (-DB200_KITCHEN, DESIGN.md section 7);
-    wide = "kitchen_flat": the same with the one-level broad phase over the (regrouped) pair list, the A/B reference of the
-    two-level one (-DB200_KITCHEN_FLATSCAN)"""
-    out = os.path.join(_HERE, {True: "libhostsim_wide.so", "kitchen": "libhostsim_kitchen.so",
+    wide = "kitchen_groups": that build with the two-level broad phase (-DB200_KITCHEN_GROUPS: regrouped pair list, group table);
+    wide = "kitchen_flat": the groups build's data layout scanned in one level, the bit-exact A/B reference of the two-level scan
+    (-DB200_KITCHEN_FLATSCAN)"""
+    out = os.path.join(_HERE, {True: "libhostsim_wide.so", "kitchen": "libhostsim_kitchen.so", "kitchen_groups": "libhostsim_kitchen_groups.so",
                                "kitchen_flat": "libhostsim_kitchen_flat.so"}.get(wide, "libhostsim.so"))
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_ROOT, "gymnasium_robotics_b200", "csrc", f)
                                                    for f in ("sim_core.cuh", "dmodel.h", "fetch_task.cuh")] + \
@@ -50,7 +51,8 @@ def build(force=False, wide=False):
             if stale():
                 tmp = f"{out}.{os.getpid()}.tmp"
                 subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function"] +
-                                      ({"kitchen": ["-DB200_KITCHEN"], "kitchen_flat": ["-DB200_KITCHEN", "-DB200_KITCHEN_FLATSCAN"]}.get(wide) or
+                                      ({"kitchen": ["-DB200_KITCHEN"], "kitchen_groups": ["-DB200_KITCHEN", "-DB200_KITCHEN_GROUPS"],
+                                        "kitchen_flat": ["-DB200_KITCHEN", "-DB200_KITCHEN_GROUPS", "-DB200_KITCHEN_FLATSCAN"]}.get(wide) or
                                        (["-DB200_WIDE"] if wide else [])) + ["-o", tmp, srcs[0]])
                 os.replace(tmp, out)
                 force = False

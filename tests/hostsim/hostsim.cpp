@@ -38,7 +38,7 @@ void hostsim_destroy(void* p) { delete (HostSim*)p; }
 float* hostsim_scratch(void* p) { return ((HostSim*)p)->scratch.data(); }
 int hostsim_scr_words(void* p) { return ((HostSim*)p)->ctx.h->scr_words; }
 int hostsim_npair(void* p) { return ((HostSim*)p)->ctx.h->npair; }
-#ifdef B200_KITCHEN
+#ifdef B200_KITCHEN_GROUPS
 int hostsim_nbgrp(void* p) { return ((HostSim*)p)->ctx.h->nbgrp; }
 #endif
 int hostsim_offset(void* p, const char* name) {

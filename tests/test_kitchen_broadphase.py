@@ -1,4 +1,4 @@
-"""Two-level broad phase of the kitchen build (csrc/sim_core.cuh `collision`, csrc/dmodel.h group table), on CPU:
+"""Two-level broad phase of the kitchen build (-DB200_KITCHEN_GROUPS: csrc/sim_core.cuh `collision`, csrc/dmodel.h group table), on CPU:
 (1) the emulation of the two-level scan is bit-identical to the one-level scan over the same regrouped pair list
 (-DB200_KITCHEN_FLATSCAN), so the candidate set and order are the flat scan's; (2) a 32-lane model of the level-1 compaction
 (exclusive scans, running pair counts, the slot-overflow branch) and of the level-2 bisection against a sequential one."""
@@ -13,7 +13,7 @@ from tests.hostsim_backend import HostSimBackend
 
 
 class TwoLevel(HostSimBackend):
-    REF, FLAVOR = KITCHEN_REF_POINT, "kitchen"
+    REF, FLAVOR = KITCHEN_REF_POINT, "kitchen_groups"
 
 
 class FlatScan(HostSimBackend):
@@ -22,7 +22,7 @@ class FlatScan(HostSimBackend):
 
 def test_group_table_covers_every_pair_once():
     m = load_model("franka_kitchen")
-    s = HostSim(m, ref=KITCHEN_REF_POINT, flavor="kitchen")
+    s = HostSim(m, ref=KITCHEN_REF_POINT, flavor="kitchen_groups")
     assert s._L.hostsim_npair(s._h) == len(m.pair_geom1) == 3708
     assert 0 < s._L.hostsim_nbgrp(s._h) <= 1100          # 1 010 groups: 32 warp iterations instead of 116
     # shared-memory footprint of the staged constants: the 44 KB pair list is gone, the group table is in
@@ -111,3 +111,21 @@ def test_lane_model_of_the_compaction(nsurv_max):
         assert over == (int(hit.sum()) > nsurv_max)
         want = [p for g in kept for p in range(start[g], start[g] + count[g])]
         assert lanes_level2(surv) == want        # ascending pair order: the flat scan's candidate order
+
+
+def test_groups_build_tracks_the_validated_flat_build():
+    """The two kernel builds scan different pair orders (original list vs regrouped list), so contacts are numbered differently and
+    results agree to solver precision rather than bit for bit."""
+    from tests.test_kitchen_host import KitchenHostBackend
+
+    m = load_model("franka_kitchen")
+    ea, eb = (KitchenVectorEnv(num_envs=2, backend_factory=F, device="cpu", rng_mode="numpy", model=m) for F in (TwoLevel, KitchenHostBackend))
+    oa, _ = ea.reset(seed=4)
+    ob, _ = eb.reset(seed=4)
+    assert torch.equal(oa["observation"], ob["observation"])
+    rng = np.random.default_rng(0)
+    for k in range(6):
+        a = rng.uniform(-1, 1, size=(2, 9))
+        oa, ob = ea.step(a)[0], eb.step(a)[0]
+        e = (oa["observation"] - ob["observation"]).abs()
+        assert float(e[:, :9].max()) < 1e-4 and float(e[:, 18:39].max()) < 1e-4, k

@@ -36,11 +36,15 @@ def test_random_action_soak_stays_finite(env_id, ref):
     assert getattr(env.backend, "overflow_bits", 0) & ~0xF == 0   # only the four documented capacity flags can ever be set
 
 
-def test_kitchen_soak_with_the_two_level_broad_phase():
+@pytest.mark.parametrize("flavor", ["kitchen", "kitchen_groups"])
+def test_kitchen_soak_with_the_two_level_broad_phase(flavor):
     """FrankaKitchen-v1 on the kitchen-flavor emulation (29 dofs, 3 708 pairs in 1 010 groups): saturated actions sweep the arm
     through the scene; no capacity flag at all (a longer run of 5 600 env-steps saw none either, up to 57 candidates)."""
     from gymnasium_robotics_b200.kitchen import KitchenVectorEnv
-    from tests.test_kitchen_host import KitchenHostBackend
+    from gymnasium_robotics_b200.kitchen import KITCHEN_REF_POINT
+
+    class KitchenHostBackend(HostSimBackend):
+        REF, FLAVOR = KITCHEN_REF_POINT, flavor
 
     env = KitchenVectorEnv(num_envs=4, backend_factory=KitchenHostBackend, device="cpu", rng_mode="torch", autoreset_mode="same_step",
                            max_episode_steps=25)
