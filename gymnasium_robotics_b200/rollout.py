@@ -50,6 +50,34 @@ class CtorPickle:
         args, kwargs = getattr(self, "_ctor_call", ((), {}))
         return _rebuild, (type(self), args, kwargs)
 
+    # the rest of gymnasium.vector.VectorEnv's attribute surface that wrappers and training loops touch ([ext] gymnasium >= 1.0
+    # vector/vector_env.py: spec, render_mode, closed, unwrapped, np_random, render, close_extras, context manager)
+    spec = None
+    render_mode = None
+    is_vector_env = True
+
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def np_random(self):
+        """The per-env generators of rng_mode="numpy" (a list, one `Generator(PCG64)` per env as in the reference), else the torch generator."""
+        return getattr(self, "_np_rngs", None) or getattr(self, "_gen", None)
+
+    def render(self):
+        return None   # rendering is out of scope for the batched CUDA path (render_mode is always None)
+
+    def close_extras(self, **kwargs):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
 
 def _flatten_obs(obs, prefix="", out=None):
     """dict (possibly nested, e.g. the kitchen's goal dicts) of [N, ...] tensors -> {"a/b": tensor}; a bare tensor -> {"": t}."""

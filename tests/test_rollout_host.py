@@ -135,3 +135,13 @@ def test_recorder_on_nested_goal_dicts():
     assert ob["observation"].shape == (4, 59) and ob["achieved_goal/microwave"].shape == (4, 1) and ob["desired_goal/kettle"].shape == (4, 7)
     env2 = pickle.loads(pickle.dumps(env))
     assert env2.tasks == ["microwave", "kettle"] and env2.max_episode_steps == 3
+
+
+def test_vector_env_attribute_surface():
+    """What gymnasium.vector wrappers touch besides reset / step: unwrapped, spec, render_mode, metadata, closed, context manager."""
+    with fetch(2) as env:
+        assert env.unwrapped is env and env.spec is None and env.render_mode is None and env.render() is None
+        assert env.metadata["autoreset_mode"] == "next_step" and env.num_envs == 2 and not env.closed
+        assert len(env.np_random) == 2        # rng_mode="numpy": one PCG64 generator per env, as N reference envs would have
+        env.reset(seed=0)
+    assert env.closed
