@@ -30,7 +30,9 @@
 #define DM_PAIR_HOT(X)
 #define DM_PAIR_COLD(X) X(pair_geom1, 1, npair) X(pair_geom2, 1, npair) X(pair_margin, 1, npair)
 #define DM_BGRP_HOT(X) X(bg_body, 1, nbgrp) X(bg_anchor, 1, nbgrp) X(bg_start, 1, nbgrp) X(bg_count, 1, nbgrp) X(bg_center, 3, nbgrp) X(bg_radius, 1, nbgrp)
-#define DM_NSURV_MAX 96   // bounding-volume groups that may survive the first level per env per sub-step
+#ifndef DM_NSURV_MAX
+#define DM_NSURV_MAX 96   // bounding-volume groups that may survive the first level per env per sub-step (tests override it)
+#endif
 #else
 #define DM_PAIR_HOT(X) X(pair_geom1, 1, npair) X(pair_geom2, 1, npair) X(pair_margin, 1, npair)
 #define DM_PAIR_COLD(X)

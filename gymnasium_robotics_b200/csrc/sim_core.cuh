@@ -12,6 +12,13 @@
 #pragma once
 #include "dmodel.h"
 
+// B200_WARP_CODE: the 32-lane code paths (shuffle reductions, scans, the register Cholesky).  nvcc compiles them for the device;
+// the test-only build -DB200_HOST_WARP (tests/hostsim/hostwarp.h) compiles the same lines for the host with the warp intrinsics
+// emulated by 32 lock-step fibers, so that the CPU suite can execute the lane-parallel logic itself, not only its WARP_W == 1
+// counterpart.
+#if defined(__CUDACC__) || defined(B200_HOST_WARP)
+#define B200_WARP_CODE 1
+#endif
 #ifdef __CUDACC__
 // internal linkage: b200sim.cu and b200sim_wide.cu compile these sources with different dof-mask widths
 #define HD static __device__ __forceinline__
@@ -30,6 +37,17 @@
 #define ALIGN() do { } while (0)
 #define ALIGN_OR(p) (p)
 #endif
+#elif defined(B200_HOST_WARP)
+#define HD static inline
+#define HDN static
+#define STAGE static
+#define ASSUME_SHARED(c) do { } while (0)
+#define ASSUME_SHARED_PTR(p) do { } while (0)
+#define WARP_W 32
+#define SYNC() __syncwarp()
+#define ALIGN() __syncwarp()                          // one warp stands for the block
+#define ALIGN_OR(p) (__ballot_sync(0xffffffffu, (p)) != 0u)
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #else
 #define HD static inline
 #define HDN static
@@ -84,26 +102,26 @@ enum { TM_KIN = 0, TM_COM_M, TM_COLL, TM_CONSTR, TM_SMOOTH, TM_NBEGIN, TM_NCHECK
 // ---------------------------------------------------------------------------------------------------------------
 // warp helpers
 HD float wsum(float v) {
-#ifdef __CUDACC__
+#ifdef B200_WARP_CODE
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
 }
 HD float wmax(float v) {
-#ifdef __CUDACC__
+#ifdef B200_WARP_CODE
   for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
 #endif
   return v;
 }
 HD int wsumi(int v) {
-#ifdef __CUDACC__
+#ifdef B200_WARP_CODE
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
 }
 // exclusive prefix sum of v over lanes; *total = sum
 HD int wexscan(int v, int lane, int* total) {
-#ifdef __CUDACC__
+#ifdef B200_WARP_CODE
   int x = v;
   for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
   *total = __shfl_sync(0xffffffffu, x, 31);
@@ -1103,7 +1121,7 @@ STAGE void collision(const Ctx c) {
       // must end at the last kept group
       int keep = DM_NSURV_MAX - nsurv;
       int kept_pairs = 0;
-#ifdef __CUDACC__
+#ifdef B200_WARP_CODE
       kept_pairs = __shfl_sync(0xffffffffu, poff + npg, 31 - __clz(__ballot_sync(0xffffffffu, hit && slot < keep)));
 #else
       kept_pairs = (hit && slot < keep) ? npg : 0;
@@ -1851,7 +1869,7 @@ STAGE void chol_solve(const Ctx c, const float* L, float* x) {
 // x <- (A + hh*diag(dadd))^-1 x for the packed SPD matrix A.  CUDA: register-resident right-looking Cholesky, lane i owns
 // the full symmetric row i (lower part ends up as L, the frozen upper part gives L^T), columns travel by warp shuffle;
 // NVP is nv padded to a compile-time size (identity padding).  Host emulation: the shared-memory routines above.
-#ifdef __CUDACC__
+#ifdef B200_WARP_CODE
 // Models with more than 32 dofs (wide build, NVP = 32 + KB): lane i owns row i of the leading 32 x 32 block as before and,
 // in addition, its entries of the KB border rows (c[r] = H[32 + r][i]); the KB x KB corner block is replicated in every
 // lane.  The border rows ride along the right-looking elimination (one extra shuffle per border row and step), the corner

@@ -6,7 +6,19 @@
 #include <cstring>
 #include <vector>
 #include <string>
+#ifdef B200_HOST_WARP
+#include "hostwarp.h"   // WARP_W == 32: the lane-parallel code paths on 32 lock-step fibers
+#endif
 #include "../../gymnasium_robotics_b200/csrc/fetch_task.cuh"
+
+// run f(ctx) once (WARP_W == 1) or on the 32 lanes of the emulated warp
+template <class F> static void warp_call(const Ctx& base, F f) {
+#ifdef B200_HOST_WARP
+  hw_run([&](int lane) { Ctx c = base; c.lane = lane; f(c); });
+#else
+  f(base);
+#endif
+}
 
 #ifdef B200_WIDE
 static const bool kWide = true;   // 64-bit dof masks: the tables carry two words per mask
@@ -51,14 +63,16 @@ int hostsim_offset(void* p, const char* name) {
 #undef X
   return -1;
 }
-void hostsim_forward(void* p) { forward<32>(((HostSim*)p)->ctx, true); }
-void hostsim_step(void* p, int n) { for (int i = 0; i < n; i++) { forward<32>(((HostSim*)p)->ctx, true); euler_step<32>(((HostSim*)p)->ctx); } }
-void hostsim_kinematics(void* p) { kinematics(((HostSim*)p)->ctx); com_quantities(((HostSim*)p)->ctx); mass_matrix(((HostSim*)p)->ctx); }
+void hostsim_forward(void* p) { warp_call(((HostSim*)p)->ctx, [](const Ctx& c) { forward<32>(c, true); }); }
+void hostsim_step(void* p, int n) { warp_call(((HostSim*)p)->ctx, [n](const Ctx& c) { for (int i = 0; i < n; i++) { forward<32>(c, true); euler_step<32>(c); } }); }
+void hostsim_kinematics(void* p) { warp_call(((HostSim*)p)->ctx, [](const Ctx& c) { kinematics(c); com_quantities(c); mass_matrix(c); }); }
 int hostsim_task_size() { return (int)sizeof(FetchTask); }
 int hostsim_env_step(void* p, const FetchTask* t, int mode, int nraw, float* st, const float* action, float* obs, float* achieved,
                      float* desired, float* reward, float* success) {
   int it = 0;
-  fetch_env_step<32>(((HostSim*)p)->ctx, *t, true, mode, nraw, st, action, obs, achieved, desired, reward, success, &it);
+  warp_call(((HostSim*)p)->ctx, [&](const Ctx& c) {
+    fetch_env_step<32>(c, *t, true, mode, nraw, st, action, obs, achieved, desired, reward, success, &it);
+  });
   return it;
 }
 }
