@@ -109,5 +109,8 @@ extern "C" int hostsim_check_record(float* rec, int stride, const float* rest, c
   if (keep) k = *keep;
   return rs_check_record(rec, stride, rest, k);
 }
+#ifdef B200_HOST_WARP
+extern "C" long hostsim_collectives() { return g_hw.collectives; }   // scheduler rounds so far = warp collectives executed (2 per shuffle / ballot, 1 per __syncwarp)
+#endif
 extern "C" int hostsim_model_words(void* p) { return ((HostSim*)p)->ctx.h->nwords; }
 extern "C" int hostsim_hot_words(void* p) { return ((HostSim*)p)->ctx.h->hot_words; }
