@@ -12,8 +12,21 @@
 #include "../../gymnasium_robotics_b200/csrc/fetch_task.cuh"
 
 // run f(ctx) once (WARP_W == 1) or on the 32 lanes of the emulated warp
+#if defined(B200_HOST_WARP) && defined(B200_STAGE_TIMING)
+static long long g_stage_rounds[TM_COUNT];   // lane 0's per-stage collective counts, accumulated over calls
+extern "C" int hostsim_stage_rounds(long long* out, int reset) {
+  for (int k = 0; k < TM_COUNT; k++) { out[k] = g_stage_rounds[k]; if (reset) g_stage_rounds[k] = 0; }
+  return TM_COUNT;
+}
+#endif
 template <class F> static void warp_call(const Ctx& base, F f) {
-#ifdef B200_HOST_WARP
+#if defined(B200_HOST_WARP) && defined(B200_STAGE_TIMING)
+  hw_run([&](int lane) {
+    long long tim[TM_COUNT] = {0};
+    Ctx c = base; c.lane = lane; c.tim = tim; f(c);
+    if (lane == 0) for (int k = 0; k < TM_COUNT; k++) g_stage_rounds[k] += tim[k];
+  });
+#elif defined(B200_HOST_WARP)
   hw_run([&](int lane) { Ctx c = base; c.lane = lane; f(c); });
 #else
   f(base);

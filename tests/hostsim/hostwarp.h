@@ -99,3 +99,6 @@ static inline unsigned __ballot_sync(unsigned, bool p) {
 }
 static inline void __syncwarp() { hw_yield(); }
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+
+// -DB200_STAGE_TIMING in this build: the stage "clock" is the scheduler-round counter, so TIC / TOC attribute warp collectives to stages
+static inline long long clock64() { return g_hw.collectives; }
