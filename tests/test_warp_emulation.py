@@ -61,3 +61,25 @@ def test_32_lane_execution_matches_1_lane_execution(env_id, ref, flavor1, flavor
     assert torch.equal(o1["success"], o32["success"])
     c1, c32 = b1.sim.counters(), b32.sim.counters()
     assert c1[0] == c32[0] and c1[2] == c32[2] and c1[3] == c32[3] and c1[6] == c32[6]      # contacts, groups, candidates, flags
+
+
+def test_smoke_check_on_the_32_lane_emulation():
+    """`__graft_entry__.smoke()` -- one FetchPickAndPlace env-step against the fp64 oracle from identical state, tolerance 2e-4 -- with
+    the 32-lane emulation in the GPU's place (constructor included: `_env_setup` settles 200 sub-steps on the lane-parallel code)."""
+    from gymnasium_robotics_b200.fetch import FetchVectorEnv
+    from tests.parity_util import inject_oracle_state, oracle_env_from_model, oracle_obs_vector
+
+    class W32(HostSimBackend):
+        FLAVOR = "warp"
+
+    env = FetchVectorEnv("FetchPickAndPlace", num_envs=2, backend_factory=W32, rng_mode="numpy")
+    env.reset(seed=0)
+    orc = oracle_env_from_model("FetchPickAndPlace", env.model)
+    orc.reset(seed=0)
+    assert np.allclose(env.initial_gripper_xpos.double().numpy(), orc.initial_gripper_xpos, atol=2e-5)
+    inject_oracle_state(env, [orc] * 2)
+    a = np.tile(np.array([[0.3, -0.2, -0.5, 0.1]], dtype=np.float32), (2, 1))
+    o, r, term, trunc, info = env.step(torch.as_tensor(a))
+    oo, orr, _, _, _ = orc.step(a[0].astype(np.float64))
+    err = np.abs(o["observation"][0].double().numpy() - oracle_obs_vector(oo)).max()
+    assert err < 2e-4 and float(r[0]) == float(orr), err
