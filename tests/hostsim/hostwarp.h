@@ -57,10 +57,19 @@ static inline void hw_run(std::function<void(int)> body) {
     w.ctx[l].uc_stack.ss_sp = w.stack[l]; w.ctx[l].uc_stack.ss_size = SS; w.ctx[l].uc_link = &w.main;
     makecontext(&w.ctx[l], (void (*)())hw_entry, 1, l);
   }
+  // lane order inside a scheduler round: ascending by default; HOSTWARP_ORDER=reverse | shuffle runs the lanes of every interval
+  // between two collectives in another order -- a result that depends on it is a shared-memory race between lanes
+  static int order_mode = -1;
+  if (order_mode < 0) { const char* e = getenv("HOSTWARP_ORDER"); order_mode = !e ? 0 : (!strcmp(e, "reverse") ? 1 : (!strcmp(e, "shuffle") ? 2 : 0)); }
+  uint32_t rng = 0x9E3779B9u;
   for (;;) {
     int live = 0, ndone = 0;
     w.waiting = 0;
-    for (int l = 0; l < 32; l++) {
+    int perm[32];
+    for (int l = 0; l < 32; l++) perm[l] = order_mode == 1 ? 31 - l : l;
+    if (order_mode == 2) for (int l = 31; l > 0; l--) { rng = rng * 1664525u + 1013904223u; int j = (int)((rng >> 8) % (uint32_t)(l + 1)); int t = perm[l]; perm[l] = perm[j]; perm[j] = t; }
+    for (int li = 0; li < 32; li++) {
+      int l = perm[li];
       if (w.done[l]) { ndone++; continue; }
       w.cur = l;
       swapcontext(&w.main, &w.ctx[l]);
