@@ -228,7 +228,7 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
 
     # ------------------------------------------------------------------ gymnasium API (flat observation, `success` info)
     def _obs_dict(self, out):
-        return out["obs"]
+        return self._cast_obs(out["obs"])
 
     def step(self, actions):
         obs, reward, terminated, truncated, info = super().step(actions)

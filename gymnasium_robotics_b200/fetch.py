@@ -415,7 +415,7 @@ class FetchVectorEnv(CtorPickle):
 
     # ------------------------------------------------------------------ gymnasium API
     def _obs_dict(self, out):
-        return {"observation": out["obs"], "achieved_goal": out["achieved"], "desired_goal": out["desired"]}
+        return self._cast_obs({"observation": out["obs"], "achieved_goal": out["achieved"], "desired_goal": out["desired"]})
 
     def reset(self, *, seed=None, options=None):
         if seed is not None:

@@ -42,6 +42,9 @@ class CtorPickle:
         def wrapped(self, *args, **kwargs):
             if not hasattr(self, "_ctor_call"):  # a subclass constructor got here first: keep the outermost call
                 self._ctor_call = (args, dict(kwargs))
+                # obs_dtype=torch.float64: observations are cast to the dtype the spaces declare (the reference returns float64,
+                # robot_env.py:87-100); default None keeps the kernels' float32 tensors without a copy
+                self.obs_dtype = kwargs.get("obs_dtype", None)
             init(self, *args, **kwargs)
 
         cls.__init__ = wrapped
@@ -64,6 +67,12 @@ class CtorPickle:
     def np_random(self):
         """The per-env generators of rng_mode="numpy" (a list, one `Generator(PCG64)` per env as in the reference), else the torch generator."""
         return getattr(self, "_np_rngs", None) or getattr(self, "_gen", None)
+
+    def _cast_obs(self, obs):
+        dt = getattr(self, "obs_dtype", None)
+        if dt is None:
+            return obs
+        return {k: v.to(dt) for k, v in obs.items()} if isinstance(obs, dict) else obs.to(dt)
 
     def render(self):
         return None   # rendering is out of scope for the batched CUDA path (render_mode is always None)

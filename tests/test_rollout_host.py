@@ -145,3 +145,16 @@ def test_vector_env_attribute_surface():
         assert len(env.np_random) == 2        # rng_mode="numpy": one PCG64 generator per env, as N reference envs would have
         env.reset(seed=0)
     assert env.closed
+
+
+def test_float64_observations_on_request():
+    """The spaces declare float64 (robot_env.py:87-100); obs_dtype=torch.float64 casts the returned observations, the default stays float32."""
+    e32, e64 = fetch(2), fetch(2, obs_dtype=torch.float64)
+    o32, _ = e32.reset(seed=1)
+    o64, _ = e64.reset(seed=1)
+    assert o32["observation"].dtype == torch.float32 and all(v.dtype == torch.float64 for v in o64.values())
+    assert torch.equal(o32["observation"].double(), o64["observation"])
+    a = np.full((2, 4), 0.1, dtype=np.float32)
+    s32, s64 = e32.step(a), e64.step(a)
+    assert s64[0]["achieved_goal"].dtype == torch.float64 and torch.equal(s32[0]["achieved_goal"].double(), s64[0]["achieved_goal"])
+    assert e64.single_observation_space["observation"].dtype == np.float64
