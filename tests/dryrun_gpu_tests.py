@@ -1,6 +1,7 @@
 """Pre-flight for GPU test files on a machine without a GPU: rewrites `device="cuda"` -> "cpu" in a temporary copy and routes `make_vec`
 to the host emulation backends, then runs pytest on the copies.  It checks the tests' own logic and API usage (shapes, layouts, launch
-counts, the expected draws), not the CUDA kernels.
+counts, the expected draws), not the CUDA kernels.  Only tests that build their envs through `make_vec` can be routed; a test that
+constructs a `*VectorEnv` or a `CudaBackend` directly hits the product path's loud "no CPU fallback" error here, as it should.
     python tests/dryrun_gpu_tests.py tests/test_reset_device_gpu.py tests/test_rollout_gpu.py tests/test_zz_kitchen_gpu.py"""
 import os
 import subprocess
