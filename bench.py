@@ -211,10 +211,15 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     out = env.backend.new_outputs()
+    nvtx = torch.cuda.nvtx if args.nvtx else None   # --nvtx: ranges for ncu --nvtx / nsys filtering (tracing)
     for k in range(args.steps):
         flush.fill_(float(k))  # evict L2 between timed iterations (outside the timed interval)
         ev[k][0].record()
+        if nvtx:
+            nvtx.range_push(f"env.step {k}")
         env.step(tape[k % 64])
+        if nvtx:
+            nvtx.range_pop()
         ev[k][1].record()
     barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -327,6 +332,7 @@ def main():
     ap.add_argument("--workload", default="fetch_pick_and_place", choices=sorted(WORKLOADS) + ["mixed_hammer_kitchen"])
     ap.add_argument("--sample-envs", type=int, default=256, help="envs per step of the CPU arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nvtx", action="store_true", help="NVTX range around every timed env.step (profiling runs only)")
     ap.add_argument("--rng-mode", default="torch", choices=["torch", "device"],
                     help="reset draws of the Fetch workload: torch's device generator (default) or in-kernel (b200sim_reset)")
     args = ap.parse_args()
