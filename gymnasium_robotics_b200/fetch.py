@@ -324,10 +324,13 @@ class FetchVectorEnv(CtorPickle):
         u = lambda *s: torch.rand(*s, generator=self._gen, device=self.device)
         obj = None
         if cfg["has_object"]:
-            # rejection sampling (fetch_env.py:386-392) without a host round trip: 24 masked redraws leave a rejected
-            # sample with probability (pi 0.1^2 / (2 obj_range)^2)^25 < 1e-11 per env
+            # rejection sampling (fetch_env.py:386-392) without a host round trip: masked redraws until a rejected sample is
+            # left with probability p^(k+1) < 1e-11 per env, p = pi 0.1^2 / (2 obj_range)^2 -- 24 redraws for obj_range 0.15
+            # (p = 0.35), 105 for FetchSlide's 0.1 (p = 0.79; 24 would leave 0.2 % of its resets inside the excluded disc)
+            p_rej = min(np.pi * 0.01 / (2 * cfg["obj_range"]) ** 2, 0.999)
+            redraws = 24 if p_rej < 0.36 else int(np.ceil(np.log(1e-11) / np.log(p_rej)))
             obj = g0[:2] + (u(n, 2) * 2 - 1) * cfg["obj_range"]
-            for _ in range(24):
+            for _ in range(redraws):
                 bad = torch.linalg.norm(obj - g0[:2], dim=1) < 0.1
                 obj = torch.where(bad[:, None], g0[:2] + (u(n, 2) * 2 - 1) * cfg["obj_range"], obj)
         goals = g0[:3] + (u(n, 3) * 2 - 1) * cfg["target_range"]

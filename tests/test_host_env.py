@@ -225,3 +225,14 @@ def test_auto_recover_on_other_families():
     assert info["bad_state"].tolist() == [False, True] and torch.isfinite(o).all()
     s = env.get_env_state()
     assert torch.equal(s["door_body_pos"], frame) and torch.equal(s["qpos"][1], env.init_qpos)
+
+
+def test_torch_mode_rejection_sampling_on_fetch_slide():
+    """FetchSlide's obj_range 0.1 rejects 79 % of the candidate start positions (fetch_env.py:386-392): the masked-redraw loop of the
+    torch RNG mode must run long enough that no env keeps a rejected one."""
+    env = mk("FetchSlide", 256, rng_mode="torch")
+    env._gen.manual_seed(0)
+    obj, goals = env._sample_reset(torch.arange(256))
+    g0 = env.initial_gripper_xpos
+    d = torch.linalg.norm(obj - g0[:2], dim=1)
+    assert float(d.min()) >= 0.1 and float((obj - g0[:2]).abs().max()) <= 0.1 + 1e-6
