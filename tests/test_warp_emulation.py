@@ -20,6 +20,11 @@ CASES = [("FetchPickAndPlace-v4", REF_POINT, None, "warp", 4, 2e-4),
          ("HandManipulateBlockRotateXYZ_ContinuousTouchSensors-v1", HAND_REF_POINT, None, "warp", 1, 2e-4),   # tendons, frictionloss, touch
          ("AdroitHandHammer-v2", ADROIT_REF_POINT, True, "warp_wide", 2, 2e-4),                # 33 dofs: 64-bit masks, bordered Cholesky
          ("AntMaze_UMaze-v5", REF_POINT, None, "warp", 3, 5e-4),                               # RK4, wall grid
+         ("PointMaze_UMaze-v3", REF_POINT, None, "warp", 3, 2e-4),                             # 2 dofs, velocity clip
+         ("FetchReach-v4", REF_POINT, None, "warp", 2, 2e-4),                                  # block_gripper epilogue (kinematics refresh)
+         ("HandReach-v3", HAND_REF_POINT, None, "warp", 2, 2e-4),                              # task kind 3, 15-float goal
+         ("AdroitHandDoor-v2", ADROIT_REF_POINT, None, "warp", 2, 2e-4),                       # 278 pairs: two-byte broad-phase candidates
+         ("AdroitHandRelocate-v2", ADROIT_REF_POINT, True, "warp_wide", 2, 2e-4),              # 36 dofs: four border rows
          ("FrankaKitchen-v1", KITCHEN_REF_POINT, "kitchen_groups", "warp_kitchen_groups", 2, 2e-4)]   # two-level broad phase, condim 6
 
 
