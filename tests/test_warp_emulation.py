@@ -133,3 +133,35 @@ def test_kitchen_env_tracks_the_oracle_on_the_32_lane_emulation(flavor):
             e = np.abs(obs["observation"][i].numpy() - ob["observation"])
             assert e[:9].max() < 2e-4 and e[18:39].max() < 2e-4 and e.max() < 2e-2, (k, i, e.max())
             assert float(rew[i]) == r and bool(term[i]) == te
+
+
+def test_group_capacity_overflow_on_the_32_lane_emulation():
+    """tests/test_host_env.py::test_contact_group_overflow_is_flagged_and_harmless on the lane-parallel code: the gripper pressed onto
+    table and object with a 3-group capacity -- the over-capacity pair is dropped before its contacts are numbered (the scans and the
+    ordered compaction of the narrow phase run on 32 lanes here), the flag is raised, the observation stays finite, and the 1-lane
+    run drops the same pair (same contact / group counts)."""
+    from gymnasium_robotics_b200.fetch import FetchVectorEnv
+
+    class Tiny1(HostSimBackend):
+        NGRP_CAP = 4
+
+    class Tiny32(HostSimBackend):
+        NGRP_CAP, FLAVOR = 4, "warp"
+
+    env = FetchVectorEnv("FetchPickAndPlace", num_envs=1, backend_factory=Tiny1, rng_mode="numpy")
+    env.reset(seed=0)
+    a = np.array([[0.0, 0.0, -1.0, -1.0]], dtype=np.float32)
+    for _ in range(10):
+        env.step(a)
+    b1 = env.backend
+    b32 = Tiny32(env.model, welded_eq_data(env.model), env.task, 1, "cpu")
+    b32.state.copy_(b1.state)
+    o1, o32 = b1.new_outputs(), b32.new_outputs()
+    for _ in range(2):
+        b1.step(torch.as_tensor(a), o1)
+        b32.step(torch.as_tensor(a), o32)
+        assert torch.isfinite(o32["obs"]).all()
+        c1, c32 = b1.sim.counters(), b32.sim.counters()
+        assert c1[0] == c32[0] and c1[2] == c32[2]
+    assert b32.overflow_bits & 4 and b1.overflow_bits & 4
+    assert float((o1["obs"] - o32["obs"]).abs().max()) < 1e-3
