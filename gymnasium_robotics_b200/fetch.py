@@ -90,9 +90,15 @@ class CudaBackend:
         blob = model.to_blob()
         h = ctypes.c_void_p()
         ref = np.asarray(getattr(self, "REF", REF_POINT), dtype=np.float32)
+        # eq_data: NULL (keep the blob's equality data) or exactly neq x 11 doubles (include/b200sim.h); the C side cannot see the
+        # length, so an empty override must become NULL here -- a pointer to a zero-length array would be read out of bounds
         eq = np.ascontiguousarray(eq_data, dtype=np.float64)
-        rc = self.L.b200sim_create(blob, len(blob), eq.ctypes.data, ref.ctypes.data, ctypes.byref(task), num_envs,
-                                   self.device.index or 0, ctypes.byref(h))
+        if eq.size not in (0, 11 * int(model.neq)):
+            raise ValueError(f"eq_data must be empty or [neq = {int(model.neq)}, 11], got shape {eq.shape}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        rc = self.L.b200sim_create(blob, len(blob), eq.ctypes.data if eq.size else None, ref.ctypes.data, ctypes.byref(task), num_envs,
+                                   self.device.index, ctypes.byref(h))
         if rc != 0:
             raise RuntimeError(f"b200sim_create failed ({rc}): {self.L.b200sim_last_error(None).decode()}")
         self.h = h
