@@ -13,7 +13,7 @@ __version__ = "0.1.0"
 
 # id -> (task, reward_type, max_episode_steps); only the new-binding versions (-v4) of the reference are mirrored,
 # the mujoco_py (-v1) ids are out of scope
-ENV_IDS = {}
+ENV_IDS = {"FrankaKitchen-v1": dict(kitchen=True, max_episode_steps=280)}   # __init__.py:1117-1121
 for _task in ("FetchReach", "FetchPush", "FetchSlide", "FetchPickAndPlace"):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
         ENV_IDS[f"{_task}{_suffix}-v4"] = dict(task=_task, reward_type=_rt, max_episode_steps=50)
@@ -22,9 +22,11 @@ for _maze, _steps in (("UMaze", 700), ("Open", 700), ("Open_Diverse_G", 700), ("
                       ("Medium_Diverse_G", 1000), ("Medium_Diverse_GR", 1000), ("Large", 1000), ("Large_Diverse_G", 1000),
                       ("Large_Diverse_GR", 1000)):
     for _rt, _suffix in (("sparse", ""), ("dense", "Dense")):
-        ENV_IDS[f"AntMaze_{_maze}{_suffix}-v5"] = dict(maze=_maze, reward_type=_rt, max_episode_steps=_steps)
-        # -v4 (envs/maze/ant_maze_v4.py) is line for line the -v5 class on Gymnasium's Ant-v4 instead of Ant-v5: the same ant.xml,
-        # frame_skip, observation (use_contact_forces defaults to False in both) and maze_v4 logic -- one implementation here
+        # -v5 wraps Gymnasium's Ant-v5 with its defaults: the observation carries the clipped per-body contact forces,
+        # (105,) = 27 + 13 x 6 (envs/maze/ant_maze_v5.py:99, 132-134, 249-255)
+        ENV_IDS[f"AntMaze_{_maze}{_suffix}-v5"] = dict(maze=_maze, reward_type=_rt, max_episode_steps=_steps, include_cfrc_ext_in_observation=True)
+        # -v4 (envs/maze/ant_maze_v4.py) is the same class on Gymnasium's Ant-v4 (use_contact_forces defaults to False there): the
+        # same ant.xml, frame_skip and maze_v4 logic with the (27,) observation
         ENV_IDS[f"AntMaze_{_maze}{_suffix}-v4"] = dict(maze=_maze, reward_type=_rt, max_episode_steps=_steps)
 # PointMaze-v3 (__init__.py:960-1080)
 for _maze, _steps in (("UMaze", 300), ("Open", 300), ("Open_Diverse_G", 300), ("Open_Diverse_GR", 300), ("Medium", 600),
@@ -58,14 +60,11 @@ for _rt, _suffix in (("dense", ""), ("sparse", "Sparse")):
 def make_vec(env_id: str, num_envs: int = 1, **kwargs):
     """Batched replacement for `gym.make_vec(env_id, num_envs=...)` (reference ids, e.g. "FetchPickAndPlace-v4")."""
     if env_id.startswith("FrankaKitchen"):
-        # bring-up build (csrc/b200sim_kitchen.cu): joint-equality rows, condim 6 and the box-aware broad phase are in the
-        # kernel source and match the oracle in the host emulation of that source (tests/test_kitchen_host.py); the CUDA
-        # build of it has not run on a B200 yet, so the id is opt-in until the GPU parity tests have passed (DESIGN.md 7)
+        # kernel build csrc/b200sim_kitchen*.cu (joint-equality rows, condim 6, two-level broad phase); validated on a B200 against
+        # the oracle env and the host emulation (tests/test_zz_kitchen_gpu.py)
         if env_id != "FrankaKitchen-v1":
             raise KeyError(f"{env_id!r}: the reference registers FrankaKitchen-v1 only")
-        if not (kwargs.pop("experimental", False) or os.environ.get("B200SIM_EXPERIMENTAL_KITCHEN") == "1"):
-            raise NotImplementedError("FrankaKitchen-v1 on the CUDA path is a bring-up build without GPU validation: pass "
-                                      "experimental=True (or B200SIM_EXPERIMENTAL_KITCHEN=1); there is no CPU fallback")
+        kwargs.pop("experimental", None)   # accepted and ignored: the id was opt-in while the build was unvalidated
         from .kitchen import KitchenVectorEnv
 
         return KitchenVectorEnv(num_envs=num_envs, **kwargs)
@@ -108,8 +107,10 @@ def register_envs():
             continue
         ep = "gymnasium_robotics_b200.maze:MazeVectorEnv" if "maze" in spec else \
             ("gymnasium_robotics_b200.hand:make_hand_vec" if "hand_task" in spec else
-             ("gymnasium_robotics_b200.adroit:make_adroit_vec" if "adroit_task" in spec else "gymnasium_robotics_b200.fetch:FetchVectorEnv"))
+             ("gymnasium_robotics_b200.adroit:make_adroit_vec" if "adroit_task" in spec else
+              ("gymnasium_robotics_b200.kitchen:KitchenVectorEnv" if "kitchen" in spec else "gymnasium_robotics_b200.fetch:FetchVectorEnv")))
         kw = dict(spec)
+        kw.pop("kitchen", None)
         if "hand_task" in kw:
             kw["task"] = kw.pop("hand_task")
         if "adroit_task" in kw:

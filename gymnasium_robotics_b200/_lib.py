@@ -105,7 +105,14 @@ def lib():
     L.b200sim_layout.argtypes = [vp, ctypes.POINTER(ci)]
     L.b200sim_state.argtypes = [vp]
     L.b200sim_state.restype = vp
-    L.b200sim_step.argtypes = [vp] * 9
+    L.b200sim_step.argtypes = [vp] * 11
+    L.b200sim_set_time_limit.argtypes = [vp, ci, ci]
+    L.b200sim_elapsed.argtypes = [vp]
+    L.b200sim_elapsed.restype = vp
+    L.b200sim_overflow_counter.argtypes = [vp]
+    L.b200sim_overflow_counter.restype = vp
+    L.b200sim_packed_width.argtypes = [vp]
+    L.b200sim_set_packed.argtypes = [vp, ci]
     L.b200sim_refresh.argtypes = [vp] * 8
     L.b200sim_raw_step.argtypes = [vp, ci] + [vp] * 6
     L.b200sim_raw_step_masked.argtypes = [vp, vp, ci] + [vp] * 6
@@ -126,4 +133,5 @@ def lib():
 
 EXPORTED_SYMBOLS = ["b200sim_create", "b200sim_destroy", "b200sim_last_error", "b200sim_num_envs", "b200sim_layout",
                     "b200sim_state", "b200sim_step", "b200sim_refresh", "b200sim_raw_step", "b200sim_raw_step_masked", "b200sim_compute_reward", "b200sim_reset", "b200sim_reset_uniform", "b200sim_reset_maze", "b200sim_check_state", "b200sim_reset_reach", "b200sim_reset_hand_pose", "b200sim_reset_hand_goal",
-                    "b200sim_launch_count", "b200sim_launch_config"]
+                    "b200sim_launch_count", "b200sim_launch_config", "b200sim_set_time_limit", "b200sim_elapsed", "b200sim_overflow_counter",
+                    "b200sim_packed_width", "b200sim_set_packed"]

@@ -147,7 +147,8 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
         self.single_observation_space = Box(-np.inf, np.inf, shape=(int(self.task.nobs),), dtype=np.float64)
         self.action_space = batch_space(self.single_action_space, self.num_envs)
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
-        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._elapsed = self.backend.elapsed                      # library-owned step counters (in-kernel TimeLimit)
+        self.backend.set_time_limit(max_episode_steps, False)
         self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.init_qpos = torch.as_tensor(np.array(m.qpos0), dtype=torch.float32, device=self.device)   # MujocoEnv: data.qpos at load
         self.init_qvel = torch.zeros(m.nv, dtype=torch.float32, device=self.device)
@@ -238,6 +239,14 @@ class AdroitHammerVectorEnv(FetchVectorEnv):
             fi = info["final_info"]
             info["final_info"] = {"success": fi["is_success"] > 0.5, "_success": fi["_is_success"]}
         return obs, reward, terminated, truncated, info
+
+    def reset(self, *, seed=None, options=None):
+        """adroit_hammer.py:359-370 (and the siblings): `options={"initial_state_dict": {...}}` sets the state after the
+        ordinary reset through `set_env_state` (entries [width] for every env or [num_envs, width])."""
+        obs, info = super().reset(seed=seed, options=options)
+        if options is not None and "initial_state_dict" in options:
+            obs = self._cast_obs(self.set_env_state(options["initial_state_dict"]))
+        return obs, info
 
     def compute_reward(self, *a, **k):
         raise NotImplementedError("Adroit environments are not GoalEnvs (no compute_reward in the reference)")

@@ -48,31 +48,34 @@ __global__ void reward_kernel(const float* __restrict__ ag, const float* __restr
 // a few 128-byte lines, touched once per episode).
 __global__ void fetch_reset_kernel(b200sim_fetch_reset_t p, unsigned long long seed, int env_offset, int N, const unsigned char* __restrict__ mask,
                                    const float* __restrict__ rest, int stride, int st_qpos, int st_goal, float* __restrict__ state,
-                                   int* __restrict__ episode) {
+                                   int* __restrict__ episode, int* __restrict__ elapsed) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N || (mask && !mask[i])) return;
   int ep = episode ? episode[i] : 0;
   rs_fetch_reset_record(p, seed, (uint32_t)(i + env_offset), (uint32_t)ep, rest, stride, st_qpos, st_goal, state + (size_t)i * stride);
   if (episode) episode[i] = ep + 1;
+  if (elapsed) elapsed[i] = 0;   // a reset env starts a new episode of the TimeLimit
 }
 
 __global__ void uniform_reset_kernel(b200sim_uniform_reset_t p, unsigned long long seed, int env_offset, int N, const unsigned char* __restrict__ mask,
-                                     const float* __restrict__ rest, int stride, float* __restrict__ state, int* __restrict__ episode) {
+                                     const float* __restrict__ rest, int stride, float* __restrict__ state, int* __restrict__ episode, int* __restrict__ elapsed) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N || (mask && !mask[i])) return;
   int ep = episode ? episode[i] : 0;
   rs_uniform_reset_record(p, seed, (uint32_t)(i + env_offset), (uint32_t)ep, rest, stride, state + (size_t)i * stride);
   if (episode) episode[i] = ep + 1;
+  if (elapsed) elapsed[i] = 0;   // a reset env starts a new episode of the TimeLimit
 }
 
 __global__ void maze_reset_kernel(b200sim_maze_reset_t p, const float* __restrict__ goal_xy, const float* __restrict__ reset_xy, unsigned long long seed,
                                   int env_offset, int N, const unsigned char* __restrict__ mask, const float* __restrict__ rest, int stride,
-                                  int st_qpos, int st_goal, float* __restrict__ state, int* __restrict__ episode) {
+                                  int st_qpos, int st_goal, float* __restrict__ state, int* __restrict__ episode, int* __restrict__ elapsed) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N || (mask && !mask[i])) return;
   int ep = episode ? episode[i] : 0;
   rs_maze_reset_record(p, goal_xy, reset_xy, seed, (uint32_t)(i + env_offset), (uint32_t)ep, rest, stride, st_qpos, st_goal, state + (size_t)i * stride);
   if (episode) episode[i] = ep + 1;
+  if (elapsed) elapsed[i] = 0;   // a reset env starts a new episode of the TimeLimit
 }
 
 __global__ void check_state_kernel(int N, int stride, float* __restrict__ state, const float* __restrict__ rest, b200sim_keep_t keep,
@@ -92,21 +95,23 @@ __global__ void hand_pose_kernel(b200sim_hand_reset_t p, const float* __restrict
 }
 __global__ void hand_goal_kernel(b200sim_hand_reset_t p, const float* __restrict__ parallel, unsigned long long seed, int env_offset, int N,
                                  const unsigned char* __restrict__ mask, int stride, int st_qpos, int st_goal, float* __restrict__ state,
-                                 int* __restrict__ episode) {
+                                 int* __restrict__ episode, int* __restrict__ elapsed) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N || (mask && !mask[i])) return;
   int ep = episode ? episode[i] : 0;
   rs_hand_goal(p, parallel, seed, (uint32_t)(i + env_offset), (uint32_t)ep, st_qpos, st_goal, state + (size_t)i * stride);
   if (episode) episode[i] = ep + 1;
+  if (elapsed) elapsed[i] = 0;   // a reset env starts a new episode of the TimeLimit
 }
 
 __global__ void reach_reset_kernel(b200sim_reach_reset_t p, unsigned long long seed, int env_offset, int N, const unsigned char* __restrict__ mask,
-                                   const float* __restrict__ rest, int stride, int st_goal, float* __restrict__ state, int* __restrict__ episode) {
+                                   const float* __restrict__ rest, int stride, int st_goal, float* __restrict__ state, int* __restrict__ episode, int* __restrict__ elapsed) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N || (mask && !mask[i])) return;
   int ep = episode ? episode[i] : 0;
   rs_reach_reset_record(p, seed, (uint32_t)(i + env_offset), (uint32_t)ep, rest, stride, st_goal, state + (size_t)i * stride);
   if (episode) episode[i] = ep + 1;
+  if (elapsed) elapsed[i] = 0;   // a reset env starts a new episode of the TimeLimit
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -116,23 +121,20 @@ __global__ void reach_reset_kernel(b200sim_reach_reset_t p, unsigned long long s
 // wide build (models with 33..40 dofs), compiled from b200sim_wide.cu with 64-bit dof masks
 extern "C" int b200sim_wide_setattr(int wpb, int smem_bytes);
 extern "C" int b200sim_wide_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
-                                   int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
-                                   float* achieved, float* desired, float* reward, float* success, int* info);
+                                   int mode, int nraw, int N, const StepIO* io);
 #define B200_WIDE_NVP 36
-// bring-up build for models with joint equalities / condim 6 (Franka Kitchen), compiled from b200sim_kitchen.cu
+// build for models with joint equalities / condim 6 (Franka Kitchen), compiled from b200sim_kitchen.cu (flat broad-phase scan) and
+// b200sim_kitchen_groups.cu (two-level broad phase; the default, B200SIM_KITCHEN_GROUPS=0 selects the flat scan)
 extern "C" int b200sim_kitchen_build(const b200_model_view* view, const double* eq_data, const float* ref, int penv_body,
                                      std::vector<uint32_t>* buf, std::string* err);
 extern "C" int b200sim_kitchen_setattr(int wpb, int smem_bytes);
-// the same build with the two-level broad phase, from b200sim_kitchen_groups.cu (chosen by B200SIM_KITCHEN_GROUPS=1 at create time)
 extern "C" int b200sim_kitchen_groups_build(const b200_model_view* view, const double* eq_data, const float* ref, int penv_body,
                                             std::vector<uint32_t>* buf, std::string* err);
 extern "C" int b200sim_kitchen_groups_setattr(int wpb, int smem_bytes);
 extern "C" int b200sim_kitchen_groups_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
-                                             int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
-                                             float* achieved, float* desired, float* reward, float* success, int* info);
+                                             int mode, int nraw, int N, const StepIO* io);
 extern "C" int b200sim_kitchen_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
-                                      int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
-                                      float* achieved, float* desired, float* reward, float* success, int* info);
+                                      int mode, int nraw, int N, const StepIO* io);
 #define B200_KITCHEN_NVP 31   // the kitchen translation unit instantiates NVP = 31 (identity-padded; distinct kernel symbols)
 
 struct b200sim {
@@ -144,6 +146,10 @@ struct b200sim {
   uint32_t* model_dev = nullptr;
   FetchTask task;
   float* state = nullptr;
+  int* elapsed = nullptr;                        // per-env step counters of the TimeLimit (device, [N])
+  unsigned long long* overflow_count = nullptr;  // env-steps that hit a capacity limit (device counter)
+  int max_steps = 0, term_on_success = 0;        // b200sim_set_time_limit
+  int packed = 0, packed_w = 0;                  // b200sim_set_packed
   size_t smem_bytes = 0;
   int blocks = 0;
   long launches = 0;
@@ -163,6 +169,23 @@ static int fail(b200sim* h, const std::string& msg, int code) {
     cudaError_t e_ = (call);                                                                                  \
     if (e_ != cudaSuccess) return fail(h, std::string(#call) + ": " + cudaGetErrorString(e_), -100 - (int)e_); \
   } while (0)
+
+// every entry point runs on the handle's device and leaves the caller's current device as it found it
+struct DevGuard {
+  int prev = -1; bool ok = true;
+  explicit DevGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess; }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(h) DevGuard guard_((h)->device); if (!guard_.ok) return fail(h, "cudaSetDevice failed", -7)
+
+static void free_handle(b200sim* h) {
+  if (!h) return;
+  if (h->model_dev) cudaFree(h->model_dev);
+  if (h->state) cudaFree(h->state);
+  if (h->elapsed) cudaFree(h->elapsed);
+  if (h->overflow_count) cudaFree(h->overflow_count);
+  delete h;
+}
 
 extern "C" {
 
@@ -186,7 +209,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
     for (int p = 0; p < v.npair; p++) if (v.pair_condim[p] == 6) h->kitchen = true;
   }
   const int penv = TASK_IS_ADROIT(task->kind) ? task->penv_body : -1;
-  if (h->kitchen) { const char* g = getenv("B200SIM_KITCHEN_GROUPS"); h->kitchen_groups = g && atoi(g) != 0; }
+  if (h->kitchen) { const char* g = getenv("B200SIM_KITCHEN_GROUPS"); h->kitchen_groups = !(g && g[0] && atoi(g) == 0); }  // default: two-level broad phase
   if ((h->kitchen ? (h->kitchen_groups ? b200sim_kitchen_groups_build(&h->view, eq_data, r, penv, &h->model_host, &err)
                                        : b200sim_kitchen_build(&h->view, eq_data, r, penv, &h->model_host, &err))
                   : dm_build(h->view, eq_data, r, h->model_host, err, penv)) != 0) {
@@ -240,7 +263,8 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
                               t.touch_mode < 0 || t.touch_mode > 3 || (t.touch_mode && dh->nsensor == 0) ||
                               t.nobs != t.obj_qadr + dh->nv + 7 + (t.touch_mode ? dh->nsensor : 0))) { delete h; return fail(nullptr, "b200sim_create: inconsistent Hand task", -6); }
   if (t.kind == TASK_FETCH && dh->nmocap != 1) { delete h; return fail(nullptr, "b200sim_create: Fetch task needs exactly one mocap body", -6); }
-  if (t.kind == TASK_ANTMAZE && (t.nact != dh->nu || t.ngoal != 2 || t.nobs != dh->nq - t.obs_qpos_start + dh->nv)) { delete h; return fail(nullptr, "b200sim_create: inconsistent AntMaze task", -6); }
+  if (t.kind == TASK_ANTMAZE && (t.nact != dh->nu || t.ngoal != 2 || t.touch_mode < 0 || t.touch_mode > 1 ||
+                                 t.nobs != dh->nq - t.obs_qpos_start + dh->nv + (t.touch_mode == 1 ? 6 * (dh->nmjb - 1) : 0))) { delete h; return fail(nullptr, "b200sim_create: inconsistent AntMaze task", -6); }
   if (t.kind == TASK_HAND_REACH) {
     bool ok = t.nact == dh->nu && t.ngoal == 15 && t.nobs == dh->nq + dh->nv + 15;
     for (int k = 0; k < 5; k++) ok = ok && t.tip_site[k] >= 0 && t.tip_site[k] < dh->nsite;
@@ -251,7 +275,8 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   t.st_mocap = o; o += 7 * dh->nmocap; t.st_pose = o; o += (t.kind == TASK_FETCH ? 7 : 0); t.st_goal = o; o += t.ngoal;
   t.st_penv = o; o += (t.penv_body > 0 ? 7 : 0);
   t.st_stride = (o + 3) & ~3;
-  if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, "b200sim_create: cudaSetDevice failed", -7); }
+  DevGuard guard(device);
+  if (!guard.ok) { delete h; return fail(nullptr, "b200sim_create: cudaSetDevice failed", -7); }
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
   h->wpb = (num_envs + nsm - 1) / nsm <= 7 ? 7 : ((num_envs + nsm - 1) / nsm <= 14 ? 14 : 28);
@@ -261,47 +286,61 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   if (dh->nv <= 21 && dh->any_convex_pair) h->nvp = 22;  // arm build that carries the general convex collider (FetchSlide's puck)
   if (dh->nv <= 21 && (dh->nten > 0 || dh->nfric > 0 || dh->nsensor > 0 || dh->any_round_pair)) h->nvp = 30;  // hand features live in the NVP = 30 build
   if (h->nvp == 30 && h->wpb > 14) h->wpb = 14;  // the large models' scratch does not fit 28 envs per block
+  auto fits = [&](int w) { return ((size_t)dh->hot_words + (size_t)w * dh->scr_words) * 4 + 64 <= 232448; };
+  const char* ov = getenv("B200SIM_WPB");   // experiments: a block size that has no instantiation for this build is an error, not a no-op
+  const int ovw = ov ? atoi(ov) : 0;
   if (h->kitchen) {
     if (dh->nv > 31) { delete h; return fail(nullptr, "b200sim_create: the kitchen build is instantiated for nv <= 31", -8); }
     h->nvp = B200_KITCHEN_NVP;
-    auto fits = [&](int w) { return ((size_t)dh->hot_words + (size_t)w * dh->scr_words) * 4 + 64 <= 232448; };
-    h->wpb = (h->wpb > 7 && fits(10)) ? 10 : 7;
-    if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if ((w == 7 || w == 10 || (w == 11 && h->kitchen_groups)) && fits(w)) h->wpb = w; }  // experiments
-  }
-  if (h->nvp == B200_WIDE_NVP) {
+    h->wpb = h->wpb <= 7 ? 7 : ((h->kitchen_groups && fits(11)) ? 11 : (fits(10) ? 10 : 7));
+    if (ov) {
+      if (!((ovw == 7 || ovw == 10 || (ovw == 11 && h->kitchen_groups)) && fits(ovw))) { delete h; return fail(nullptr, "b200sim_create: B200SIM_WPB names no kitchen kernel variant that fits", -8); }
+      h->wpb = ovw;
+    }
+  } else if (h->nvp == B200_WIDE_NVP) {
     // wide build: the largest block of {14, 13, 10, 7} warps whose scratch fits the 227 KB of shared memory (14 envs of the
     // 33-dof hammer model, 13 of the 36-dof relocate model), 7 for small batches so that every SM still gets a block
     const int want = h->wpb, cands[4] = {14, 13, 10, 7};
     h->wpb = 7;
     for (int k = 3; k >= 0; k--)
-      if (cands[k] <= (want > 7 ? 14 : 7) && ((size_t)dh->hot_words + (size_t)cands[k] * dh->scr_words) * 4 + 64 <= 232448) h->wpb = cands[k];
-    if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (w == 7 || w == 10 || w == 13 || w == 14) h->wpb = w; }  // experiments
+      if (cands[k] <= (want > 7 ? 14 : 7) && fits(cands[k])) h->wpb = cands[k];
+    if (ov) {
+      if (!((ovw == 7 || ovw == 10 || ovw == 13 || ovw == 14) && fits(ovw))) { delete h; return fail(nullptr, "b200sim_create: B200SIM_WPB names no wide kernel variant that fits", -8); }
+      h->wpb = ovw;
+    }
+  } else if (ov) {
+    if (!((ovw == 7 || ovw == 14 || (ovw == 28 && h->nvp != 30)) && fits(ovw))) { delete h; return fail(nullptr, "b200sim_create: B200SIM_WPB names no kernel variant that fits", -8); }
+    h->wpb = ovw;
   }
-  if (const char* ov = getenv("B200SIM_WPB")) { int w = atoi(ov); if (!h->kitchen && (w == 7 || w == 14 || (w == 28 && h->nvp != 30))) h->wpb = w; }  // experiments
+  if (!fits(h->wpb)) { delete h; return fail(nullptr, "b200sim_create: the per-env scratch of this model does not fit the shared memory of one block", -8); }
   h->smem_bytes = ((size_t)dh->hot_words + (size_t)h->wpb * dh->scr_words) * 4;
   h->blocks = (num_envs + h->wpb - 1) / h->wpb;
-  cudaError_t e = cudaSuccess;
+  h->packed_w = (t.nobs + 2 * t.ngoal + 4 + 3) & ~3;
+  cudaError_t e = cudaErrorInvalidValue;   // stays an error when no instantiation matches (wpb, nvp)
 #define B200_SETATTR(W, V) if (h->wpb == W && h->nvp == V) e = cudaFuncSetAttribute(fetch_kernel<W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   B200_FOR_ALL_VARIANTS(B200_SETATTR)
 #undef B200_SETATTR
-  if (h->nvp == B200_WIDE_NVP && b200sim_wide_setattr(h->wpb, (int)h->smem_bytes) != 0) e = cudaErrorInvalidValue;
-  if (h->nvp == B200_KITCHEN_NVP && (h->kitchen_groups ? b200sim_kitchen_groups_setattr(h->wpb, (int)h->smem_bytes) : b200sim_kitchen_setattr(h->wpb, (int)h->smem_bytes)) != 0) e = cudaErrorInvalidValue;
-  if (e != cudaSuccess) { std::string m = std::string("cudaFuncSetAttribute(smem=") + std::to_string(h->smem_bytes) + "): " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
-  if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, (size_t)num_envs * t.st_stride * 4) != cudaSuccess) {
-    delete h; return fail(nullptr, "b200sim_create: cudaMalloc failed", -9);
+  if (h->nvp == B200_WIDE_NVP) e = b200sim_wide_setattr(h->wpb, (int)h->smem_bytes) == 0 ? cudaSuccess : cudaErrorInvalidValue;
+  if (h->nvp == B200_KITCHEN_NVP) e = (h->kitchen_groups ? b200sim_kitchen_groups_setattr(h->wpb, (int)h->smem_bytes) : b200sim_kitchen_setattr(h->wpb, (int)h->smem_bytes)) == 0 ? cudaSuccess : cudaErrorInvalidValue;
+  if (e != cudaSuccess) { std::string m = std::string("b200sim_create: no kernel variant <") + std::to_string(h->wpb) + ", " + std::to_string(h->nvp) + "> or cudaFuncSetAttribute(smem=" + std::to_string(h->smem_bytes) + ") failed: " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
+  const size_t state_bytes = (size_t)num_envs * t.st_stride * 4;
+  if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, state_bytes) != cudaSuccess ||
+      cudaMalloc(&h->elapsed, (size_t)num_envs * 4) != cudaSuccess || cudaMalloc(&h->overflow_count, 8) != cudaSuccess) {
+    free_handle(h); return fail(nullptr, "b200sim_create: cudaMalloc failed", -9);
   }
-  cudaMemcpy(h->model_dev, h->model_host.data(), h->model_host.size() * 4, cudaMemcpyHostToDevice);
-  cudaMemset(h->state, 0, (size_t)num_envs * t.st_stride * 4);
+  if (cudaMemcpy(h->model_dev, h->model_host.data(), h->model_host.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemset(h->state, 0, state_bytes) != cudaSuccess || cudaMemset(h->elapsed, 0, (size_t)num_envs * 4) != cudaSuccess ||
+      cudaMemset(h->overflow_count, 0, 8) != cudaSuccess) {
+    free_handle(h); return fail(nullptr, "b200sim_create: uploading the model / clearing the state failed", -9);
+  }
   *out = h;
   return 0;
 }
 
 void b200sim_destroy(b200sim_t* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
-  if (h->model_dev) cudaFree(h->model_dev);
-  if (h->state) cudaFree(h->state);
-  delete h;
+  DevGuard guard(h->device);
+  free_handle(h);
 }
 
 const char* b200sim_last_error(const b200sim_t* h) { return h ? h->err.c_str() : g_err.c_str(); }
@@ -313,6 +352,8 @@ int b200sim_layout(const b200sim_t* h, int* out) {
   return 0;
 }
 float* b200sim_state(b200sim_t* h) { return h->state; }
+int* b200sim_elapsed(b200sim_t* h) { return h->elapsed; }
+unsigned long long* b200sim_overflow_counter(b200sim_t* h) { return h->overflow_count; }
 long b200sim_launch_count(const b200sim_t* h) { return h->launches; }
 int b200sim_launch_config(const b200sim_t* h, int* smem_bytes, int* envs_per_block, int* blocks) {
   if (smem_bytes) *smem_bytes = (int)h->smem_bytes;
@@ -320,39 +361,62 @@ int b200sim_launch_config(const b200sim_t* h, int* smem_bytes, int* envs_per_blo
   if (blocks) *blocks = h->blocks;
   return 0;
 }
+int b200sim_set_time_limit(b200sim_t* h, int max_episode_steps, int terminate_on_success) {
+  h->max_steps = max_episode_steps > 0 ? max_episode_steps : 0;
+  h->term_on_success = terminate_on_success ? 1 : 0;
+  return 0;
+}
+int b200sim_packed_width(const b200sim_t* h) { return h->packed_w; }
+int b200sim_set_packed(b200sim_t* h, int enable) { h->packed = enable ? 1 : 0; return h->packed_w; }
 
 static int launch(b200sim* h, int mode, int nraw, const float* actions, const unsigned char* mask, float* obs, float* achieved,
-                  float* desired, float* reward, float* success, int* info, void* stream) {
-  if (!obs || !achieved || !desired || !reward || !success) return fail(h, "output pointers must not be NULL", -1);
-  CUDA_OK(cudaSetDevice(h->device));
+                  float* desired, float* reward, float* success, unsigned char* terminated, unsigned char* truncated, int* info, void* stream) {
+  const FetchTask& t = h->task;
+  StepIO io;
+  memset(&io, 0, sizeof(io));
+  io.state = h->state; io.actions = actions; io.mask = mask;
+  if (h->packed) {
+    // one [N, W] row per env: obs | achieved | desired | reward | success | terminated | truncated (include/b200sim.h)
+    if (!obs) return fail(h, "packed outputs: the `obs` argument must point at the [N, W] buffer", -1);
+    io.obs = obs; io.achieved = obs + t.nobs; io.desired = io.achieved + t.ngoal; io.reward = io.desired + t.ngoal; io.success = io.reward + 1;
+    io.term_f = io.reward + 2; io.trunc_f = io.reward + 3;
+    io.obs_stride = io.goal_stride = io.scalar_stride = h->packed_w;
+  } else {
+    if (!obs || !achieved || !desired || !reward || !success) return fail(h, "output pointers must not be NULL", -1);
+    io.obs = obs; io.achieved = achieved; io.desired = desired; io.reward = reward; io.success = success;
+    io.obs_stride = t.nobs; io.goal_stride = t.ngoal; io.scalar_stride = 1;
+  }
+  io.terminated = terminated; io.truncated = truncated; io.info = info;
+  io.elapsed = h->elapsed; io.max_steps = h->max_steps; io.term_on_success = h->term_on_success; io.overflow_count = h->overflow_count;
+  ON_DEVICE(h);
+  int matched = 0;
 #define B200_LAUNCH(W, V)                                                                                   \
-  if (h->wpb == W && h->nvp == V)                                                                                \
-    fetch_kernel<W, V><<<h->blocks, W * 32, h->smem_bytes, (cudaStream_t)stream>>>(                              \
-        h->model_dev, h->task, mode, nraw, h->N, h->state, actions, mask, obs, achieved, desired, reward, success, info);
+  if (h->wpb == W && h->nvp == V) {                                                                         \
+    matched = 1;                                                                                            \
+    fetch_kernel<W, V><<<h->blocks, W * 32, h->smem_bytes, (cudaStream_t)stream>>>(h->model_dev, h->task, mode, nraw, h->N, io); \
+  }
   B200_FOR_ALL_VARIANTS(B200_LAUNCH)
 #undef B200_LAUNCH
-  if (h->nvp == B200_KITCHEN_NVP && h->kitchen_groups)
-    b200sim_kitchen_groups_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, h->state, actions, mask, obs,
-                                  achieved, desired, reward, success, info);
-  if (h->nvp == B200_KITCHEN_NVP && !h->kitchen_groups)
-    b200sim_kitchen_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, h->state, actions, mask, obs,
-                           achieved, desired, reward, success, info);
+  if (h->nvp == B200_KITCHEN_NVP)
+    matched = (h->kitchen_groups ? b200sim_kitchen_groups_launch : b200sim_kitchen_launch)(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev,
+                                                                                        &h->task, mode, nraw, h->N, &io) == 0;
   if (h->nvp == B200_WIDE_NVP)
-    b200sim_wide_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, h->state, actions, mask, obs,
-                        achieved, desired, reward, success, info);
+    matched = b200sim_wide_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, &io) == 0;
+  if (!matched) return fail(h, "no kernel variant for this (envs per block, nv) pair: nothing was launched", -8);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
+#define LAUNCH_REFRESH(h, mask) launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, nullptr, nullptr, stream)
 
 int b200sim_step(b200sim_t* h, const float* actions, float* obs, float* achieved, float* desired, float* reward, float* success,
-                 int* info, void* stream) {
+                 unsigned char* terminated, unsigned char* truncated, int* info, void* stream) {
   if (!actions) return fail(h, "b200sim_step: actions is NULL", -1);
-  return launch(h, MODE_STEP, 0, actions, nullptr, obs, achieved, desired, reward, success, info, stream);
+  return launch(h, MODE_STEP, 0, actions, nullptr, obs, achieved, desired, reward, success, terminated, truncated, info, stream);
 }
 int b200sim_refresh(b200sim_t* h, const unsigned char* mask, float* obs, float* achieved, float* desired, float* reward,
                     float* success, void* stream) {
-  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+  return LAUNCH_REFRESH(h, mask);
 }
 int b200sim_reset(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_fetch_reset_t* params,
                   unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired, float* reward,
@@ -360,12 +424,14 @@ int b200sim_reset(b200sim_t* h, const unsigned char* mask, const float* rest_rec
   if (h->task.kind != TASK_FETCH) return fail(h, "b200sim_reset: the in-kernel reset draw exists for the Fetch task family only", -6);
   if (!rest_record || !params) return fail(h, "b200sim_reset: rest_record / params is NULL", -1);
   if (params->has_object && (params->obj_qadr < 0 || params->obj_qadr + 2 > h->task.st_qvel - h->task.st_qpos)) return fail(h, "b200sim_reset: obj_qadr outside qpos", -1);
-  CUDA_OK(cudaSetDevice(h->device));
-  fetch_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
-                                                                          h->task.st_qpos, h->task.st_goal, h->state, episode);
-  h->launches++;
-  CUDA_OK(cudaGetLastError());
-  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+  {
+    ON_DEVICE(h);
+    fetch_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
+                                                                            h->task.st_qpos, h->task.st_goal, h->state, episode, h->elapsed);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  return LAUNCH_REFRESH(h, mask);
 }
 int b200sim_reset_uniform(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_uniform_reset_t* params,
                           unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired,
@@ -375,12 +441,14 @@ int b200sim_reset_uniform(b200sim_t* h, const unsigned char* mask, const float* 
   for (int k = 0; k < params->n; k++)
     if (params->slot[k] < -3 || params->slot[k] >= h->task.st_stride) return fail(h, "b200sim_reset_uniform: slot outside the state record", -1);
   if (params->quat_slot < -1 || params->quat_slot + 4 > h->task.st_stride) return fail(h, "b200sim_reset_uniform: quat_slot outside the state record", -1);
-  CUDA_OK(cudaSetDevice(h->device));
-  uniform_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
-                                                                            h->state, episode);
-  h->launches++;
-  CUDA_OK(cudaGetLastError());
-  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+  {
+    ON_DEVICE(h);
+    uniform_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
+                                                                              h->state, episode, h->elapsed);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  return LAUNCH_REFRESH(h, mask);
 }
 int b200sim_reset_maze(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_maze_reset_t* params,
                        const float* goal_xy, const float* reset_xy, unsigned long long seed, int env_offset, int* episode, float* obs,
@@ -388,12 +456,14 @@ int b200sim_reset_maze(b200sim_t* h, const unsigned char* mask, const float* res
   if (h->task.kind != TASK_ANTMAZE) return fail(h, "b200sim_reset_maze: not a maze task", -6);
   if (!rest_record || !params || !goal_xy || !reset_xy) return fail(h, "b200sim_reset_maze: NULL argument", -1);
   if (params->n_goal < 1 || params->n_reset < 1) return fail(h, "b200sim_reset_maze: empty cell table", -1);
-  CUDA_OK(cudaSetDevice(h->device));
-  maze_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, goal_xy, reset_xy, seed, env_offset, h->N, mask, rest_record,
-                                                                         h->task.st_stride, h->task.st_qpos, h->task.st_goal, h->state, episode);
-  h->launches++;
-  CUDA_OK(cudaGetLastError());
-  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+  {
+    ON_DEVICE(h);
+    maze_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, goal_xy, reset_xy, seed, env_offset, h->N, mask, rest_record,
+                                                                           h->task.st_stride, h->task.st_qpos, h->task.st_goal, h->state, episode, h->elapsed);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  return LAUNCH_REFRESH(h, mask);
 }
 static int hand_reset_args(b200sim* h, const b200sim_hand_reset_t* p, const float* parallel) {
   if (h->task.kind != TASK_HAND) return fail(h, "b200sim_reset_hand_*: not a Shadow-Hand manipulation task", -6);
@@ -407,7 +477,7 @@ int b200sim_reset_hand_pose(b200sim_t* h, const unsigned char* mask, const float
                             void* stream) {
   if (int rc = hand_reset_args(h, params, parallel_quats)) return rc;
   if (!rest_record) return fail(h, "b200sim_reset_hand_pose: rest_record is NULL", -1);
-  CUDA_OK(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   hand_pose_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, parallel_quats, seed, env_offset, h->N, mask, rest_record,
                                                                         h->task.st_stride, h->task.st_qpos, h->task.st_goal, h->task.ngoal, h->state,
                                                                         episode, attempt);
@@ -419,24 +489,28 @@ int b200sim_reset_hand_goal(b200sim_t* h, const unsigned char* mask, const b200s
                             unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired,
                             float* reward, float* success, void* stream) {
   if (int rc = hand_reset_args(h, params, parallel_quats)) return rc;
-  CUDA_OK(cudaSetDevice(h->device));
-  hand_goal_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, parallel_quats, seed, env_offset, h->N, mask, h->task.st_stride,
-                                                                        h->task.st_qpos, h->task.st_goal, h->state, episode);
-  h->launches++;
-  CUDA_OK(cudaGetLastError());
-  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+  {
+    ON_DEVICE(h);
+    hand_goal_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, parallel_quats, seed, env_offset, h->N, mask, h->task.st_stride,
+                                                                          h->task.st_qpos, h->task.st_goal, h->state, episode, h->elapsed);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  return LAUNCH_REFRESH(h, mask);
 }
 int b200sim_reset_reach(b200sim_t* h, const unsigned char* mask, const float* rest_record, const b200sim_reach_reset_t* params,
                         unsigned long long seed, int env_offset, int* episode, float* obs, float* achieved, float* desired, float* reward,
                         float* success, void* stream) {
   if (h->task.kind != TASK_HAND_REACH || h->task.ngoal != 15) return fail(h, "b200sim_reset_reach: not a HandReach task", -6);
   if (!rest_record || !params) return fail(h, "b200sim_reset_reach: NULL argument", -1);
-  CUDA_OK(cudaSetDevice(h->device));
-  reach_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
-                                                                          h->task.st_goal, h->state, episode);
-  h->launches++;
-  CUDA_OK(cudaGetLastError());
-  return launch(h, MODE_REFRESH, 0, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+  {
+    ON_DEVICE(h);
+    reach_reset_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*params, seed, env_offset, h->N, mask, rest_record, h->task.st_stride,
+                                                                            h->task.st_goal, h->state, episode, h->elapsed);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  return LAUNCH_REFRESH(h, mask);
 }
 int b200sim_check_state(b200sim_t* h, unsigned char* bad, const float* rest_record, const b200sim_keep_t* keep, void* stream) {
   if (!bad) return fail(h, "b200sim_check_state: bad is NULL", -1);
@@ -448,7 +522,7 @@ int b200sim_check_state(b200sim_t* h, unsigned char* bad, const float* rest_reco
     for (int r = 0; r < k.n; r++)
       if (k.start[r] < 0 || k.len[r] < 0 || k.start[r] + k.len[r] > h->task.st_stride) return fail(h, "b200sim_check_state: keep range outside the state record", -1);
   }
-  CUDA_OK(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   check_state_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->N, h->task.st_stride, h->state, rest_record, k, bad);
   h->launches++;
   CUDA_OK(cudaGetLastError());
@@ -456,19 +530,21 @@ int b200sim_check_state(b200sim_t* h, unsigned char* bad, const float* rest_reco
 }
 int b200sim_raw_step_masked(b200sim_t* h, const unsigned char* mask, int nstep, float* obs, float* achieved, float* desired,
                             float* reward, float* success, void* stream) {
-  return launch(h, MODE_RAW, nstep, nullptr, mask, obs, achieved, desired, reward, success, nullptr, stream);
+  return launch(h, MODE_RAW, nstep, nullptr, mask, obs, achieved, desired, reward, success, nullptr, nullptr, nullptr, stream);
 }
 int b200sim_raw_step(b200sim_t* h, int nstep, float* obs, float* achieved, float* desired, float* reward, float* success,
                      void* stream) {
-  return launch(h, MODE_RAW, nstep, nullptr, nullptr, obs, achieved, desired, reward, success, nullptr, stream);
+  return launch(h, MODE_RAW, nstep, nullptr, nullptr, obs, achieved, desired, reward, success, nullptr, nullptr, nullptr, stream);
 }
-int b200sim_compute_reward(const b200sim_t* h, const float* achieved, const float* desired, int M, float* out, void* stream) {
+int b200sim_compute_reward(const b200sim_t* hc, const float* achieved, const float* desired, int M, float* out, void* stream) {
   if (M <= 0) return 0;
-  cudaSetDevice(h->device);
+  b200sim* h = const_cast<b200sim*>(hc);
+  ON_DEVICE(h);
   reward_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(achieved, desired, M, h->task.ngoal, h->task.kind, h->task.distance_threshold,
                                                                   h->task.success_radius, h->task.reward_dense, h->task, out);
-  const_cast<b200sim*>(h)->launches++;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -41,13 +41,11 @@ extern "C" int KITCHEN_FN(setattr)(int wpb, int smem_bytes) {
 }
 
 extern "C" int KITCHEN_FN(launch)(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
-                                      int mode, int nraw, int N, float* state, const float* actions, const unsigned char* mask, float* obs,
-                                      float* achieved, float* desired, float* reward, float* success, int* info) {
+                                      int mode, int nraw, int N, const StepIO* io) {
+  int matched = 0;
 #define B200_LAUNCH(W, V)                                                                                        \
-  if (wpb == W)                                                                                                  \
-    fetch_kernel<W, V><<<blocks, W * 32, smem_bytes, (cudaStream_t)stream>>>(model_dev, *task, mode, nraw, N, state, actions, mask, obs, \
-                                                                             achieved, desired, reward, success, info);
+  if (wpb == W) { matched = 1; fetch_kernel<W, V><<<blocks, W * 32, smem_bytes, (cudaStream_t)stream>>>(model_dev, *task, mode, nraw, N, *io); }
   B200_KITCHEN_VARIANTS(B200_LAUNCH)
 #undef B200_LAUNCH
-  return 0;
+  return matched ? 0 : -1;
 }

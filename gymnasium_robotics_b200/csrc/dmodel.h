@@ -64,7 +64,8 @@
   X(pair_condim, 1, npair) X(pair_friction, 3, npair) X(pair_gap, 1, npair) X(pair_solref, 2, npair) \
   X(pair_solimp, 5, npair) X(pair_invweight, 2, npair) \
   X(ten_solref, 2, nten) X(ten_solimp, 5, nten) X(ten_invweight, 1, nten) \
-  X(sensor_site, 1, nsensor) X(sensor_body, 1, nsensor) X(sensor_type, 1, nsensor) X(sensor_size, 3, nsensor)
+  X(sensor_site, 1, nsensor) X(sensor_body, 1, nsensor) X(sensor_type, 1, nsensor) X(sensor_size, 3, nsensor) \
+  X(geom_mjb, 1, ngeom) X(mjb_rt, 1, nmjb) /* MJCF (unfused) body of a geom / runtime body of an MJCF body: cfrc_ext rows */
 #define DM_ARRAYS(X) DM_ARRAYS_HOT(X) DM_ARRAYS_COLD(X)
 
 // per-env scratch that lives for the whole sub-step (name, words expression)
@@ -105,11 +106,12 @@ enum { DR_DOF = 0, DR_COEF = 1, DR_D = 2, DR_JAR = 3, DR_JV = 4, DR_DOF2 = 5, DR
 // weld: 6 rows w[6]; D[6], JAR[6] (K*imp*r during set-up), JV[6], B (one value), group
 enum { W_W = 0, W_D = 36, W_JAR = 42, W_JV = 48, W_B = 54, W_GRP = 55, WELD_WORDS = 56 };
 // group = one geom pair in contact (its contacts are contiguous) or one weld: 6x6 block K, contact range, dof mask
-// S = anc(A) xor anc(B) with sign mask (bit set: dof on the B side), and a 6-vector used for dV (J*v) and F (J^T f)
+// S = anc(A) xor anc(B) with sign mask (bit set: dof on the B side), a 6-vector used for dV (J*v) and F (J^T f), and the two
+// body ids (A | B << 8; A = body of the pair's first geom) for per-body contact forces (Ant-v5 cfrc_ext)
 #ifdef B200_WIDE
-enum { G_K = 0, G_START = 21, G_COUNT = 22, G_MASK = 23, G_SIGN = 25, G_V = 27, GRP_WORDS = 34 };   // two-word masks
+enum { G_K = 0, G_START = 21, G_COUNT = 22, G_MASK = 23, G_SIGN = 25, G_V = 27, G_BODIES = 33, GRP_WORDS = 34 };   // two-word masks
 #else
-enum { G_K = 0, G_START = 21, G_COUNT = 22, G_MASK = 23, G_SIGN = 24, G_V = 25, GRP_WORDS = 32 };
+enum { G_K = 0, G_START = 21, G_COUNT = 22, G_MASK = 23, G_SIGN = 24, G_V = 25, G_BODIES = 31, GRP_WORDS = 32 };
 #endif
 enum { ROWT_EQ = 0, ROWT_FRICTION = 1, ROWT_LIMIT = 2 };
 enum { CNT_NCON = 0, CNT_NDR = 1, CNT_NGRP = 2, CNT_NCAND = 3, CNT_NWELD = 4, CNT_ITERS = 5, CNT_OVERFLOW = 6 };
@@ -123,6 +125,7 @@ struct DMHead {
   int edges_per_con, any_convex_pair, mask_words, penv_body;   // mask_words: 1, or 2 when nv > 32 (wide kernel build); penv_body: runtime body whose body_pos is per-env state (-1 = none)   // pyramid edges of the widest contact (2 * (condim - 1)): line-search edge slots
   int nten, nfric, ncand_max, nsensor;   // nsensor: touch sensors (site volume + body)   // limited fixed tendons; nfric = nv when any dof has frictionloss, else 0
   int grid_len, grid_wid, ngridw, any_round_pair;   // maze wall grid (0 x 0 when the model has none)
+  int nmjb;        // MJCF bodies before fusing (rows of per-body outputs such as cfrc_ext)
   float grid_scale, grid_top, grid_xc, grid_yc;  // cell size, wall top height, map centre offsets
   float timestep, gravity[3], tolerance, impratio, meaninertia, ls_tolerance, ref[3];
 #define X(name, w, kind) int o_##name;
@@ -228,6 +231,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     h.grid_scale = (float)m.grid_param[0]; h.grid_top = (float)(m.grid_param[1] * m.grid_param[0]);
     h.grid_xc = (float)m.grid_param[2]; h.grid_yc = (float)m.grid_param[3];
   }
+  h.nmjb = m.n_mjbody_rt > 0 ? m.n_mjbody_rt : m.nbody;   // blobs without the table: runtime bodies stand for themselves
   h.nsensor = m.nsensor;
   if (m.nsensor > 0 && m.n_sensor_type != m.nsensor) { err = "model blob lacks sensor_type"; return -1; }
   h.ncand_max = DM_NCAND_MAX;
@@ -281,7 +285,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
   int nb = h.nb, njnt = h.njnt, nq = h.nq, nv = h.nv, nu = h.nu, ngeom = h.ngeom, nsite = h.nsite, nmocap = h.nmocap,
       neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max, ndr_max = h.ndr_max,
       nten = h.nten, nfric = h.nfric, nsensor = h.nsensor, ncx = h.nsensor > 0 ? h.ncon_max : 0, MW = h.mask_words,
-      grp_words = MW == 2 ? 34 : 32, npenv = h.penv_body > 0 ? 8 : 0;
+      grp_words = MW == 2 ? 34 : 32, npenv = h.penv_body > 0 ? 8 : 0, nmjb = h.nmjb;
 #ifdef B200_KITCHEN_GROUPS
   int nbgrp = h.nbgrp;
 #endif
@@ -424,6 +428,7 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     }
     for (int k = 0; k < 4; k++) F(h.o_geom_quat, 4 * g + k, m.geom_quat[4 * sg + k]);
     F(h.o_geom_rbound, g, m.geom_rbound[sg]);
+    I(h.o_geom_mjb, g, m.n_geom_mjbody == m.ngeom ? m.geom_mjbody[sg] : m.geom_body[sg]);
   }
   for (int p = 0; p < npair; p++) {
     int sp = psrc[p];
@@ -488,6 +493,8 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     for (int k = 0; k < 5; k++) F(h.o_eq_solimp, 5 * e + k, m.eq_solimp[5 * e + k]);
   }
   for (int i = 0; i < nmocap; i++) I(h.o_mocap_body, i, m.mocap_body[i]);
+  for (int b = 0; b < nmjb; b++) I(h.o_mjb_rt, b, m.n_mjbody_rt > 0 ? m.mjbody_rt[b] : b);
+  if (nmjb > 255) { err = "more than 255 MJCF bodies"; return -1; }
   memcpy(buf.data(), &h, sizeof(h));
   return 0;
 }

@@ -127,14 +127,79 @@ HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float
   }
 }
 
-// AntMaze: obs = ant qpos[2:] | qvel, achieved = qpos[:2]; reward exp(-d) (dense) or d <= r (sparse)
-// (reference: envs/maze/ant_maze_v5.py:295-320, envs/maze/maze_v4.py:381-398)
+// AntMaze: obs = ant qpos[2:] | qvel [| clipped contact forces], achieved = qpos[:2]; reward exp(-d) (dense) or d <= r (sparse)
+// (reference: envs/maze/ant_maze_v5.py:295-320, envs/maze/maze_v4.py:381-398).
+// touch_mode == 1 (AntMaze-v5 on Gymnasium's Ant-v5 [ext], ant_maze_v5.py:99: observation (105,) = 27 + 13 x 6): appended are the
+// per-body external contact forces `data.cfrc_ext[1:]` clipped to contact_force_range = (-1, 1): for every body the sum of the
+// contact forces acting on it as a spatial force [torque(3); force(3)] about the subtree com of its tree root, world axes, from
+// the contacts and constraint forces of the LAST forward pass (Ant-v5 calls mj_rnePostConstraint after mj_step).  The group's
+// spatial force about `ref` is sum_k F_k w_k over its contacts' base rows (what pass_F feeds into J^T f); body B of the pair
+// receives +, body A -.  A refresh (no sub-step) reports zeros, as the reference's reset observation does (mj_resetData).
 HD void antmaze_observe(const Ctx& c, const FetchTask& t, const float* goal, float* obs, float* achieved, float* desired,
-                        float* reward, float* success) {
+                        float* reward, float* success, bool stepped) {
   const DMHead* h = c.h;
   const int q0 = t.obs_qpos_start;
   LANES(i, h->nq - q0) obs[i] = SF(qpos)[q0 + i];
   LANES(i, h->nv) obs[h->nq - q0 + i] = SF(qvel)[i];
+  if (t.touch_mode == 1) {
+    float* cf = obs + (h->nq - q0 + h->nv);
+    const int* cnt = SI(counters);
+    const int ngrp = stepped ? cnt[CNT_NGRP] : 0;
+    LANES(i, stepped ? cnt[CNT_NCON] : 0) {   // base-row forces of every contact (parked in the JV slots, as pass_F does)
+      float* cr = SF(con) + i * CON_WORDS;
+      float F[C_NB];
+      contact_base_forces(cr, con_dim(cr), F);
+      for (int k = 0; k < C_NB; k++) cr[C_JV + k] = F[k];
+    }
+    SYNC();
+    LANES(idx, ngrp * 6) {
+      int g = idx / 6, a = idx - 6 * g;
+      float* gr = SF(group) + g * GRP_WORDS;
+      const int* gi = (const int*)gr;
+      float acc = 0;
+      for (int i = gi[G_START]; i < gi[G_START] + gi[G_COUNT]; i++) {
+        const float* cr = SF(con) + i * CON_WORDS;
+        int dim = con_dim(cr);
+        const float* F = cr + C_JV;
+        acc += F[0] * cr[C_W + a];
+        if (dim > 1) acc += F[1] * cr[C_W + 6 + a] + F[2] * cr[C_W + 12 + a];
+        if (dim > 3 && a < 3) acc += F[3] * cr[C_W + 3 + a];
+      }
+      gr[G_V + a] = acc;
+    }
+    SYNC();
+    LANES(b1, h->nmjb - 1) {
+      const int b = b1 + 1;      // MJCF body: the row layout of data.cfrc_ext (fused bodies keep their own rows)
+      float acc[6] = {0, 0, 0, 0, 0, 0};
+      for (int g = 0; g < ngrp; g++) {
+        const float* gr = SF(group) + g * GRP_WORDS;
+        const int* gi = (const int*)gr;
+        if (gi[G_COUNT] == 0) continue;   // weld groups carry no contact
+        int ba = gi[G_BODIES] & 0xff, bb = gi[G_BODIES] >> 8;
+        float sg = b == bb ? 1.f : (b == ba ? -1.f : 0.f);
+        if (sg != 0.f) for (int k = 0; k < 6; k++) acc[k] += sg * gr[G_V + k];
+      }
+      // subtree com of the tree root of body b (positions of the last forward pass)
+      int root = GI(mjb_rt)[b];
+      while (MI(body_parent)[root] != 0) root = MI(body_parent)[root];
+      uint32_t sub = MU(body_sub)[root];
+      float com[3] = {0, 0, 0}, mass = 0;
+      while (sub) {
+        int k = ffs_pop(sub);
+        float ip[3], mk = MF(body_mass)[k];
+        qrot(ip, SF(xquat) + 4 * k, MF(body_ipos) + 3 * k);
+        for (int a = 0; a < 3; a++) com[a] += mk * (SF(xpos)[3 * k + a] + ip[a]);
+        mass += mk;
+      }
+      float off[3], tq[3];
+      for (int a = 0; a < 3; a++) off[a] = com[a] / mass - h->ref[a];
+      cross3(tq, off, acc + 3);   // torque about the com = torque about ref - (com - ref) x force
+      for (int a = 0; a < 3; a++) {
+        cf[6 * b1 + a] = fminf(fmaxf(acc[a] - tq[a], -1.f), 1.f);
+        cf[6 * b1 + 3 + a] = fminf(fmaxf(acc[3 + a], -1.f), 1.f);
+      }
+    }
+  }
   if (c.lane == 0) {
     float dx = SF(qpos)[0] - goal[0], dy = SF(qpos)[1] - goal[1];
     float d = sqrtf(dx * dx + dy * dy);
@@ -544,7 +609,7 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
     hand_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
     if (t.touch_mode) touch_observe(c, t, obs + t.obj_qadr + h->nv + 7);
   } else {
-    antmaze_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success);
+    antmaze_observe(c, t, st + t.st_goal, obs, achieved, desired, reward, success, nsub > 0);
   }
   store_state(c, t, st);
   if (iters_out && c.lane == 0) *iters_out = SI(counters)[CNT_ITERS] | (SI(counters)[CNT_OVERFLOW] << 16);

@@ -1253,6 +1253,8 @@ STAGE void collision(const Ctx c) {
       int ba = MI(geom_body)[PAIR_I(pair_geom1)[p]], bb = PAIR_I(pair_geom2)[p] < 0 ? 0 : MI(geom_body)[PAIR_I(pair_geom2)[p]];
       dmask_t ma = DM(body_ancdof, ba), mb = DM(body_ancdof, bb);
       gi[G_START] = basec + slot; gi[G_COUNT] = kept;
+      // the pair's two MJCF (unfused) bodies, A | B << 8 (world / maze walls: 0): rows of per-body contact forces
+      gi[G_BODIES] = GI(geom_mjb)[PAIR_I(pair_geom1)[p]] | ((PAIR_I(pair_geom2)[p] < 0 ? 0 : GI(geom_mjb)[PAIR_I(pair_geom2)[p]]) << 8);
       grp_set_masks(gi, ma ^ mb, mb);
     }
     if (c.lane == 0) {
@@ -1383,7 +1385,7 @@ STAGE void make_constraint(const Ctx c) {
       ((int*)wr)[W_GRP] = gid;  // one group per weld; row value = w . (V[b1] - V[b2]) => A = b2, B = b1
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
       dmask_t ma = DM(body_ancdof, b2), mb = DM(body_ancdof, b1);
-      gi[G_START] = 0; gi[G_COUNT] = 0;
+      gi[G_START] = 0; gi[G_COUNT] = 0; gi[G_BODIES] = 0;
       grp_set_masks(gi, ma ^ mb, mb);
     }
     SYNC();

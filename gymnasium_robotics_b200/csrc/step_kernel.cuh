@@ -11,13 +11,26 @@ static __device__ unsigned long long g_stage_cycles[TM_COUNT];
 
 static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Everything one launch reads and writes per env.  Output rows are addressed with explicit strides, so the same kernel serves
+// the five separate [N, dim] arrays of the classic entry points and the packed [N, W] rows of b200sim_set_packed (one row per env:
+// obs | achieved | desired | reward | success | terminated | truncated).  TimeLimit lives here too: `elapsed` is
+// the library-owned per-env step counter, incremented by a MODE_STEP launch; truncated = elapsed >= max_steps
+// (gymnasium TimeLimit), terminated = success for the tasks that end an episode on success (maze_v4.py:390-398 with
+// continuing_task = False), else False (robot_env.py:106-112).
+struct StepIO {
+  float* state; const float* actions; const unsigned char* mask;
+  float *obs, *achieved, *desired, *reward, *success;
+  int obs_stride, goal_stride, scalar_stride;
+  float *term_f, *trunc_f;                 // fp32 copies of the flags inside a packed row (NULL = none), scalar_stride apart
+  unsigned char *terminated, *truncated;   // [N] byte flags (NULL = none)
+  int* elapsed; int max_steps, term_on_success;
+  int* info;
+  unsigned long long* overflow_count;      // device counter of env-steps that ran into a capacity limit (NULL = none)
+};
+
 template <int WPB, int NVP>
 __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restrict__ model_g, FetchTask task, int mode, int nraw,
-                                                         int N, float* __restrict__ state, const float* __restrict__ actions,
-                                                         const unsigned char* __restrict__ mask, float* __restrict__ obs,
-                                                         float* __restrict__ achieved, float* __restrict__ desired,
-                                                         float* __restrict__ reward, float* __restrict__ success,
-                                                         int* __restrict__ info) {
+                                                         int N, StepIO io) {
   extern __shared__ __align__(128) uint32_t smem[];
   __shared__ __align__(8) unsigned long long bar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -46,7 +59,7 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
   }
   const DMHead* h = (const DMHead*)smem;
   const int env = blockIdx.x * WPB + warp;
-  const bool active = env < N && !(mask && !mask[env]);  // warp-uniform
+  const bool active = env < N && !(io.mask && !io.mask[env]);  // warp-uniform
   Ctx c;
 #ifdef B200_STAGE_TIMING
   long long tim[TM_COUNT];
@@ -57,9 +70,25 @@ __global__ void __launch_bounds__(WPB * 32) fetch_kernel(const uint32_t* __restr
   c.mg = model_g; c.mw = smem; c.h = h; c.lane = lane;
   c.s = (float*)(smem + model_words) + (size_t)warp * h->scr_words;
   const size_t e = active ? (size_t)env : 0;
-  const float* act = actions ? actions + e * task.nact : nullptr;  // only dereferenced in MODE_STEP by active warps
-  fetch_env_step<NVP>(c, task, active, mode, nraw, state + e * task.st_stride, act, obs + e * task.nobs, achieved + e * task.ngoal,
-                      desired + e * task.ngoal, reward + e, success + e, info ? info + e : nullptr);
+  const float* act = io.actions ? io.actions + e * task.nact : nullptr;  // only dereferenced in MODE_STEP by active warps
+  float* success = io.success + e * io.scalar_stride;
+  int iters = 0;
+  fetch_env_step<NVP>(c, task, active, mode, nraw, io.state + e * task.st_stride, act, io.obs + e * io.obs_stride, io.achieved + e * io.goal_stride,
+                      io.desired + e * io.goal_stride, io.reward + e * io.scalar_stride, success, &iters);
+  if (active && lane == 0) {
+    // episode bookkeeping of the env-step (TimeLimit wrapper + compute_terminated), flags in both output forms; refresh / raw
+    // launches leave the flags of the rows they rewrite alone (a same-step autoreset keeps the flags of the finished episode)
+    if (mode == MODE_STEP) {
+      bool term = io.term_on_success && *success != 0.f, trunc = false;
+      if (io.elapsed) { int el = io.elapsed[e] + 1; io.elapsed[e] = el; trunc = io.max_steps > 0 && el >= io.max_steps; }
+      if (io.terminated) io.terminated[e] = term ? 1 : 0;
+      if (io.truncated) io.truncated[e] = trunc ? 1 : 0;
+      if (io.term_f) io.term_f[e * io.scalar_stride] = term ? 1.f : 0.f;
+      if (io.trunc_f) io.trunc_f[e * io.scalar_stride] = trunc ? 1.f : 0.f;
+    }
+    if (io.info) io.info[e] = iters;
+    if (io.overflow_count && (iters >> 16)) atomicAdd(io.overflow_count, 1ull);
+  }
 #ifdef B200_STAGE_TIMING
   if (lane == 0 && active) {
     long long sum = 0;

@@ -75,12 +75,16 @@ def welded_eq_data(model):
 
 
 class _DevArray:
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
 
 
 class CudaBackend:
-    """Thin owner of a `b200sim_t` handle; all arguments are torch CUDA tensors passed as raw device pointers."""
+    """Thin owner of a `b200sim_t` handle; all arguments are torch CUDA tensors passed as raw device pointers.
+
+    Outputs are PACKED (b200sim_set_packed): one [N, W] fp32 row per env, obs | achieved | desired | reward | success | terminated |
+    truncated; `new_outputs()` hands out that buffer under "packed" next to column views of it under the classic names, so one
+    device->host copy (or one all-gather) moves everything a step produced."""
 
     def __init__(self, model, eq_data, task, num_envs, device):
         if not torch.cuda.is_available():
@@ -108,6 +112,14 @@ class CudaBackend:
         self.L.b200sim_layout(h, lay)
         self.layout = dict(zip(("qpos", "qvel", "warm", "ctrl", "mocap", "pose", "goal", "stride", "penv"), list(lay)))
         self.state = torch.as_tensor(_DevArray(self.L.b200sim_state(h), (num_envs, self.layout["stride"])), device=self.device)
+        # per-env step counters of the in-kernel TimeLimit (b200sim_set_time_limit), capacity-overflow counter, info words
+        self.elapsed = torch.as_tensor(_DevArray(self.L.b200sim_elapsed(h), (num_envs,), "<i4"), device=self.device)
+        self.overflow_counter = torch.as_tensor(_DevArray(self.L.b200sim_overflow_counter(h), (1,), "<i8"), device=self.device)
+        self.info = torch.zeros(num_envs, dtype=torch.int32, device=self.device)
+        self.packed_w = int(self.L.b200sim_set_packed(h, 1))
+
+    def set_time_limit(self, max_episode_steps, terminate_on_success=False):
+        self._check(self.L.b200sim_set_time_limit(self.h, int(max_episode_steps or 0), int(bool(terminate_on_success))))
 
     def close(self):
         if getattr(self, "h", None):
@@ -126,21 +138,27 @@ class CudaBackend:
             raise RuntimeError(f"b200sim call failed ({rc}): {self.L.b200sim_last_error(self.h).decode()}")
 
     def new_outputs(self):
-        n, d = self.num_envs, self.device
-        return dict(obs=torch.empty((n, self.nobs), dtype=torch.float32, device=d),
-                    achieved=torch.empty((n, self.ngoal), dtype=torch.float32, device=d),
-                    desired=torch.empty((n, self.ngoal), dtype=torch.float32, device=d),
-                    reward=torch.empty(n, dtype=torch.float32, device=d), success=torch.empty(n, dtype=torch.float32, device=d))
+        n, d, no, ng = self.num_envs, self.device, self.nobs, self.ngoal
+        p = torch.zeros((n, self.packed_w), dtype=torch.float32, device=d)   # zeros: refresh / raw launches do not write the flags
+        flags = torch.zeros((2, n), dtype=torch.uint8, device=d)
+        k = no + 2 * ng
+        return dict(packed=p, obs=p[:, :no], achieved=p[:, no:no + ng], desired=p[:, no + ng:k], reward=p[:, k], success=p[:, k + 1],
+                    terminated=flags[0].view(torch.bool), truncated=flags[1].view(torch.bool), flags=flags)
 
     def _ptrs(self, out):
-        return [out[k].data_ptr() for k in ("obs", "achieved", "desired", "reward", "success")]
+        return [out["packed"].data_ptr(), None, None, None, None]
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def step(self, actions, out, info=None):
+        """One env-step of every env; the flags of the step land in out["terminated"] / out["truncated"], the solver's info word
+        (Newton iterations | capacity-overflow bits << 16) in `info` (default: the backend's persistent `self.info`)."""
         assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape == (self.num_envs, self.nact)
-        self._check(self.L.b200sim_step(self.h, actions.data_ptr(), *self._ptrs(out), info.data_ptr() if info is not None else None, self._stream()))
+        info = self.info if info is None else info
+        f = out["flags"]
+        self._check(self.L.b200sim_step(self.h, actions.data_ptr(), *self._ptrs(out), f[0].data_ptr(), f[1].data_ptr(), info.data_ptr(),
+                                        self._stream()))
 
     def refresh(self, mask, out):
         self._check(self.L.b200sim_refresh(self.h, mask.data_ptr() if mask is not None else None, *self._ptrs(out), self._stream()))
@@ -266,7 +284,10 @@ class FetchVectorEnv(CtorPickle):
             observation=Box(-np.inf, np.inf, shape=(nobs,), dtype=np.float64)))
         self.action_space = batch_space(self.single_action_space, self.num_envs)
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
-        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        # TimeLimit and the terminated / truncated flags are computed by the step kernel (b200sim_set_time_limit); the per-env
+        # step counters live in the library and are visible here as a tensor
+        self._elapsed = self.backend.elapsed
+        self.backend.set_time_limit(max_episode_steps, False)   # robot_env.py:106-112: compute_terminated is constant False
         self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self._env_setup()
         self.closed = False
@@ -456,19 +477,18 @@ class FetchVectorEnv(CtorPickle):
             raise ValueError("Action dimension mismatch")
         actions = actions.to(self.device, torch.float32, non_blocking=True).contiguous()
         out = self.backend.new_outputs()
-        self.backend.step(actions, out)  # clip + _set_action + n_substeps x mj_step + _get_obs + reward, one kernel
-        self._elapsed += 1
+        # clip + _set_action + n_substeps x mj_step + _get_obs + reward + TimeLimit / terminated / truncated: one kernel
+        self.backend.step(actions, out)
         self._elapsed_ub = getattr(self, "_elapsed_ub", 0) + 1   # host-side upper bound of max(_elapsed): no sync on most steps
         reward, success = out["reward"], out["success"]
-        if getattr(self, "_const_false", None) is None or self._const_false.numel() != self.num_envs:
-            self._const_false = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
-            self._const_true = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
-        terminated = self._const_false  # robot_env.py:106-112 (constant tensors are shared between steps: read-only for callers)
-        info = {"is_success": success}
+        terminated, truncated = out["terminated"], out["truncated"]
+        # solver_info: Newton iterations (low 16 bits) | capacity-overflow flags << 16 of this step, per env (the backend's
+        # persistent tensor: valid until the next step); solver_overflow_count: device counter over the env's lifetime
+        info = {"is_success": success, "solver_info": self.backend.info}
         if getattr(self, "auto_recover", False):
             self._check_and_recover(out, info)
-            reward, success = out["reward"], out["success"]
-            info["is_success"] = success
+        if getattr(self, "_const_true", None) is None or self._const_true.numel() != self.num_envs:
+            self._const_true = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
         in_phase = getattr(self, "_in_phase", False)
         if self.autoreset_mode == "next_step" and getattr(self, "_pending_reset", False):
             self._pending_reset = False
@@ -477,23 +497,19 @@ class FetchVectorEnv(CtorPickle):
                 # envs that finished on the previous call are reset now; their action is ignored (gymnasium NEXT_STEP)
                 pre = self._needs_reset.clone()
                 self._reset_envs(pre, out)
-                reward = torch.where(pre, torch.zeros_like(reward), reward)
-                out["reward"] = reward
-                info["is_success"] = torch.where(pre, torch.zeros_like(success), success)
+                self._mask_step_outputs(out, pre)
                 self._needs_reset.zero_()
                 self._reset_all = False
                 self._elapsed_ub = 0 if in_phase else int(self._elapsed.max())
-        # TimeLimit: the device counters are only compared (and the host only synchronises) once the bound says an env may be due
+        # TimeLimit: the flags come from the kernel; the host only looks at them (and synchronises) once the bound says an env may be due
         may_truncate = self.max_episode_steps is not None and self._elapsed_ub >= self.max_episode_steps
-        # in phase (all envs reset together and none terminates): the bound IS every env's step count -- no device compare
-        truncated = (self._const_true.clone() if in_phase else (self._elapsed >= self.max_episode_steps)) if may_truncate \
-            else self._const_false
-        done = truncated | terminated
         if may_truncate:
+            done = truncated | terminated
             if self.autoreset_mode == "next_step":
                 self._needs_reset = done
                 self._pending_reset = True
             elif self.autoreset_mode == "same_step":
+                # in phase (all envs reset together and none terminates): the bound IS every env's step count -- no device read
                 if in_phase or bool(done.any()):
                     fo = self._obs_dict(out)
                     info["final_obs"] = {k: v.clone() for k, v in fo.items()} if isinstance(fo, dict) else fo.clone()
@@ -508,6 +524,19 @@ class FetchVectorEnv(CtorPickle):
         info["_is_success"] = self._const_true
         self._last = out
         return self._obs_dict(out), reward, terminated, truncated, info
+
+    def _mask_step_outputs(self, out, pre):
+        """NEXT_STEP autoreset: the envs in `pre` were reset instead of stepped -- reward 0, no success, no flags (in place, so the
+        packed row stays the single source of the step's results)."""
+        k = self.backend.nobs + 2 * self.backend.ngoal
+        out["packed"][:, k:k + 4].masked_fill_(pre[:, None], 0.0)
+        out["flags"].masked_fill_(pre[None, :], 0)
+
+    @property
+    def solver_overflow_count(self):
+        """Env-steps so far in which a capacity limit (broad-phase candidates, contacts, contact groups, limit rows) dropped
+        something (DESIGN.md deviation 5); reads the device counter (synchronises)."""
+        return int(self.backend.overflow_counter[0])
 
     # GoalEnv API (core.py:45-114), batched; accepts numpy or torch, any leading shape
     def compute_reward(self, achieved_goal, desired_goal, info=None):

@@ -146,7 +146,8 @@ class HandVectorEnv(FetchVectorEnv):
             observation=Box(-np.inf, np.inf, shape=(nobs,), dtype=np.float64)))
         self.action_space = batch_space(self.single_action_space, self.num_envs)
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
-        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._elapsed = self.backend.elapsed                      # library-owned step counters (in-kernel TimeLimit)
+        self.backend.set_time_limit(max_episode_steps, False)
         self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         # robot_env.py:301-303 after _env_setup with initial_qpos = {} (manipulate.py:148-151)
         self.initial_qpos = torch.as_tensor(np.array(m.qpos0), dtype=torch.float32, device=self.device)
@@ -433,7 +434,8 @@ class HandReachVectorEnv(FetchVectorEnv):
             observation=Box(-np.inf, np.inf, shape=(t.nobs,), dtype=np.float64)))
         self.action_space = batch_space(self.single_action_space, self.num_envs)
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
-        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._elapsed = self.backend.elapsed                      # library-owned step counters (in-kernel TimeLimit)
+        self.backend.set_time_limit(max_episode_steps, False)
         self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         # _env_setup (reach.py:286-296): initial joint angles, mj_forward, initial fingertip positions and palm position
         q0 = np.array(m.qpos0, dtype=np.float64)

@@ -1,4 +1,4 @@
-"""Batched FrankaKitchen-v1 on the CUDA simulator (bring-up build: emulation-validated).
+"""Batched FrankaKitchen-v1 on the CUDA simulator (kernel build csrc/b200sim_kitchen*.cu: joint equalities, condim 6).
 
 Mirrors (batched) the reference's Python around the hot path:
   * FrankaRobot.step / _ctrl_velocity_limits / _ctrl_position_limits / _get_obs   envs/franka_kitchen/franka_env.py:92-170
@@ -87,10 +87,11 @@ class KitchenVectorEnv(CtorPickle):
         self.model = model if model is not None else load_model("franka_kitchen")
         m = self.model
         self.task = make_kitchen_task(m, frame_skip)
-        # broadphase="groups": the kernel build with the two-level broad phase (csrc/b200sim_kitchen_groups.cu; emulation-validated,
-        # not yet run on a B200); default "flat": the build whose first GPU parity point exists.  The library reads the choice from
-        # the environment when the handle is created.
-        broadphase = kwargs.get("broadphase", "groups" if os.environ.get("B200SIM_KITCHEN_GROUPS", "0") not in ("", "0") else "flat")
+        # broadphase="groups" (default): the kernel build with the two-level broad phase (csrc/b200sim_kitchen_groups.cu) -- on a B200
+        # it matches the flat-scan build (tests/test_zz_kitchen_gpu.py) and is 1.5x faster (8.6 vs 12.6 ms per 2048-env step,
+        # profiles/kitchen_diag_r2a_after_fix.log); "flat": one scan over all 3 708 pairs.  The library reads the choice from the
+        # environment when the handle is created.
+        broadphase = kwargs.get("broadphase", "flat" if os.environ.get("B200SIM_KITCHEN_GROUPS", "1") in ("0",) else "groups")
         if broadphase not in ("flat", "groups"):
             raise ValueError("broadphase must be 'flat' or 'groups'")
         self.broadphase = broadphase
@@ -132,7 +133,8 @@ class KitchenVectorEnv(CtorPickle):
         self.action_space = batch_space(self.single_action_space, self.num_envs)
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
         n, k = self.num_envs, len(tasks)
-        self._elapsed = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._elapsed = self.backend.elapsed                      # library-owned step counters (in-kernel TimeLimit)
+        self.backend.set_time_limit(max_episode_steps, False)     # `terminated` is the task bookkeeping below, not a kernel flag
         self._needs_reset = torch.zeros(n, dtype=torch.bool, device=dev)
         self._todo = torch.ones((n, k), dtype=torch.bool, device=dev)            # tasks_to_complete
         self._episode_done = torch.zeros((n, k), dtype=torch.bool, device=dev)  # episode_task_completions
@@ -203,8 +205,8 @@ class KitchenVectorEnv(CtorPickle):
         vel = torch.clamp(torch.clamp(a, -1.0, 1.0) * 2.0, self._vel_lo, self._vel_hi)
         ctrl = torch.clamp(self._last_robot_qpos + vel * self.dt, self._pos_lo, self._pos_hi).contiguous()
         out = self.backend.new_outputs()
-        self.backend.step(ctrl, out)                                  # do_simulation(ctrl, 40): one kernel launch
-        self._elapsed += 1
+        self.backend.step(ctrl, out)                                  # do_simulation(ctrl, 40) + TimeLimit: one kernel launch
+        truncated = out["truncated"]
         all_idx = torch.arange(self.num_envs, device=self.device)
         obs = out["obs"] + self._noise(all_idx)
         self._last_robot_qpos = obs[:, :9].clone()
@@ -226,10 +228,10 @@ class KitchenVectorEnv(CtorPickle):
             obs[idx] = noisy
             reward = torch.where(pre, torch.zeros_like(reward), reward)
             terminated = terminated & ~pre
+            truncated = truncated & ~pre
             info = {"tasks_to_complete": self._todo.clone(), "step_task_completions": step_done & ~pre[:, None],
                     "episode_task_completions": self._episode_done.clone()}
             self._needs_reset.zero_()
-        truncated = (self._elapsed >= self.max_episode_steps) if self.max_episode_steps is not None else torch.zeros_like(terminated)
         done = terminated | truncated
         if self.autoreset_mode == "next_step":
             self._needs_reset = done

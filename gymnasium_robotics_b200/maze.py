@@ -97,13 +97,15 @@ class MazeCells:
         return np.array([math.floor((self.y_center - xy[1]) / self.scaling), math.floor((xy[0] + self.x_center) / self.scaling)])
 
 
-def make_maze_task(model, reward_type, agent="ant"):
+def make_maze_task(model, reward_type, agent="ant", contact_forces=False):
+    """contact_forces: append Ant-v5's clipped `cfrc_ext[1:]` (6 values per body) to the observation -- (105,) instead of (27,)"""
     cfg = AGENTS[agent]
     t = _lib.FetchTaskC()
     t.kind, t.nact, t.ngoal = 1, int(model.nu), 2
     t.n_substeps, t.reward_dense = cfg["frame_skip"], int(reward_type == "dense")
     t.obs_qpos_start, t.vel_clip = cfg["obs_qpos_start"], cfg["vel_clip"]
-    t.nobs = int(model.nq - cfg["obs_qpos_start"] + model.nv)
+    t.touch_mode = int(bool(contact_forces))
+    t.nobs = int(model.nq - cfg["obs_qpos_start"] + model.nv) + (6 * (len(model.mjbody_rt) - 1) if contact_forces else 0)
     t.success_radius = SUCCESS_RADIUS
     t.dt = float(model.opt[0] * cfg["frame_skip"])
     return t
@@ -114,24 +116,7 @@ def make_antmaze_task(model, reward_type):
 
 
 class _AntBackend(CudaBackend):
-    """CudaBackend with AntMaze output widths (goal dim 2, action dim 8)."""
-
-    def new_outputs(self):
-        n, d = self.num_envs, self.device
-        return dict(obs=torch.empty((n, self.nobs), dtype=torch.float32, device=d),
-                    achieved=torch.empty((n, 2), dtype=torch.float32, device=d), desired=torch.empty((n, 2), dtype=torch.float32, device=d),
-                    reward=torch.empty(n, dtype=torch.float32, device=d), success=torch.empty(n, dtype=torch.float32, device=d))
-
-    def step(self, actions, out, info=None):
-        assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape[0] == self.num_envs
-        self._check(self.L.b200sim_step(self.h, actions.data_ptr(), *self._ptrs(out), info.data_ptr() if info is not None else None, self._stream()))
-
-    def compute_reward(self, ag, dg):
-        ag = ag.to(self.device, torch.float32).contiguous().reshape(-1, 2)
-        dg = dg.to(self.device, torch.float32).contiguous().reshape(-1, 2)
-        out = torch.empty(ag.shape[0], dtype=torch.float32, device=self.device)
-        self._check(self.L.b200sim_compute_reward(self.h, ag.data_ptr(), dg.data_ptr(), ag.shape[0], out.data_ptr(), self._stream()))
-        return out
+    """CudaBackend of the maze agents (goal dim 2; the action dim comes from the task)."""
 
 
 class MazeVectorEnv(CtorPickle):
@@ -143,7 +128,8 @@ class MazeVectorEnv(CtorPickle):
 
     def __init__(self, maze="Large", num_envs: int = 1, reward_type: str = "sparse", continuing_task: bool = True,
                  reset_target: bool = False, max_episode_steps: Optional[int] = None, device="cuda:0", rng_mode: str = "auto",
-                 autoreset_mode: str = "next_step", backend_factory=None, agent: Optional[str] = None, model=None, **kwargs):
+                 autoreset_mode: str = "next_step", backend_factory=None, agent: Optional[str] = None, model=None,
+                 include_cfrc_ext_in_observation: bool = False, **kwargs):
         self.agent = agent or self.AGENT
         cfg = AGENTS[self.agent]
         if isinstance(maze, str) and maze not in MAPS:
@@ -152,6 +138,8 @@ class MazeVectorEnv(CtorPickle):
             raise ValueError("reward_type must be 'sparse' or 'dense'")
         if kwargs.get("render_mode") is not None:
             raise NotImplementedError("rendering is out of scope for the batched CUDA path")
+        if autoreset_mode not in ("next_step", "same_step", "disabled"):
+            raise ValueError("autoreset_mode must be next_step, same_step or disabled")
         self.maze_name, self.reward_type = maze, reward_type
         self.continuing_task, self.reset_target = continuing_task, reset_target
         self.num_envs, self.autoreset_mode = int(num_envs), autoreset_mode
@@ -164,7 +152,10 @@ class MazeVectorEnv(CtorPickle):
         if model is None and not named:
             raise ValueError("an explicit maze map needs its compiled `model` (see models.compile_maze_model)")
         self.model = model if model is not None else load_model(model_name(self.agent, maze))
-        self.task = make_maze_task(self.model, reward_type, self.agent)
+        # Ant-v5 keyword [ext]: AntMaze_*-v5 observes the clipped per-body contact forces (ant_maze_v5.py:99: (105,) = 27 + 13 x 6);
+        # AntMaze_*-v4 (Ant-v4, use_contact_forces False) and the point agent do not.  The registry sets it per id.
+        self.include_cfrc = bool(include_cfrc_ext_in_observation) and self.agent == "ant"
+        self.task = make_maze_task(self.model, reward_type, self.agent, self.include_cfrc)
         factory = backend_factory or _AntBackend
         self.backend = factory(self.model, np.zeros((0, 11)), self.task, self.num_envs, device)
         self.device = self.backend.device
@@ -188,7 +179,10 @@ class MazeVectorEnv(CtorPickle):
         self.init_qpos = torch.as_tensor(np.array(m.qpos0), dtype=torch.float32, device=self.device)
         self._goal_loc = torch.as_tensor(self.cells.goal_locations, dtype=torch.float32, device=self.device)
         self._reset_loc = torch.as_tensor(self.cells.reset_locations, dtype=torch.float32, device=self.device)
-        self._elapsed = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        # TimeLimit and compute_terminated (maze_v4.py:390-398: success ends the episode unless continuing_task) run inside the
+        # step kernel; the step counters are library memory
+        self._elapsed = self.backend.elapsed
+        self.backend.set_time_limit(self.max_episode_steps, not continuing_task)
         self._needs_reset = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.dt = float(m.opt[0] * self.frame_skip)
         self.closed = False
@@ -281,6 +275,7 @@ class MazeVectorEnv(CtorPickle):
         self._reset_envs(torch.ones(self.num_envs, dtype=torch.bool, device=self.device), out, options)
         self._needs_reset.zero_()
         self._elapsed_ub, self._pending_reset = 0, False
+        self._last = out
         return self._obs_dict(out), {"success": out["success"] > 0}
 
     def step(self, actions):
@@ -290,31 +285,34 @@ class MazeVectorEnv(CtorPickle):
             raise ValueError("Action dimension mismatch")
         actions = actions.to(self.device, torch.float32, non_blocking=True).contiguous()
         out = self.backend.new_outputs()
-        self.backend.step(actions, out)
-        self._elapsed += 1
+        self.backend.step(actions, out)   # physics + observation + reward + success + terminated / truncated flags: one kernel
         self._elapsed_ub = getattr(self, "_elapsed_ub", 0) + 1   # host-side upper bound of max(_elapsed)
         reward, success = out["reward"], out["success"] > 0
-        terminated = torch.zeros_like(success) if self.continuing_task else success.clone()  # maze_v4.py:390-398
-        info = {"success": success}
+        terminated, truncated = out["terminated"], out["truncated"]
+        info = {"success": success, "solver_info": self.backend.info}
         # a continuing task can only end by TimeLimit: then the host knows from its step counter when a check is due and
         # does not synchronise with the device on the other steps
         lazy = self.continuing_task
+        pre = None
         if self.autoreset_mode == "next_step" and (not lazy or getattr(self, "_pending_reset", True)):
             self._pending_reset = False
             if bool(self._needs_reset.any()):
+                # envs that finished on the previous call are reset now: their action was ignored, so the step they did not
+                # take reports reward 0, no success and no flags (gymnasium NEXT_STEP)
                 pre = self._needs_reset.clone()
                 self._reset_envs(pre, out)
-                reward = torch.where(pre, torch.zeros_like(reward), reward)
-                out["reward"] = reward
-                terminated = terminated & ~pre
+                k = self.backend.nobs + 2 * self.backend.ngoal
+                out["packed"][:, k:k + 4].masked_fill_(pre[:, None], 0.0)
+                out["flags"].masked_fill_(pre[None, :], 0)
+                success = success & ~pre
+                info["success"] = success
                 self._needs_reset.zero_()
                 self._elapsed_ub = int(self._elapsed.max())
         if self.continuing_task and self.reset_target and len(self.cells.goal_locations) > 1 and bool(success.any()):
-            self._update_goal(success, out)  # maze_v4.py:400-418
+            self._update_goal(success, out)  # maze_v4.py:400-418 (never for the envs that were just reset: `success` is masked)
         may_truncate = self.max_episode_steps is not None and (not lazy or self._elapsed_ub >= self.max_episode_steps)
-        truncated = (self._elapsed >= self.max_episode_steps) if may_truncate else torch.zeros_like(terminated)
-        done = truncated | terminated
         if may_truncate or not lazy:
+            done = truncated | terminated
             if self.autoreset_mode == "next_step":
                 self._needs_reset = done
                 self._pending_reset = True
@@ -322,9 +320,17 @@ class MazeVectorEnv(CtorPickle):
                 if bool(done.any()):
                     info["final_obs"] = {k: v.clone() for k, v in self._obs_dict(out).items()}
                     info["_final_obs"] = done.clone()
+                    # gymnasium's SAME_STEP convention: the info of the finished episodes next to their last observation
+                    info["final_info"] = {"success": success.clone(), "_success": done.clone()}
+                    info["_final_info"] = done.clone()
                     self._reset_envs(done, out)
                 self._elapsed_ub = int(self._elapsed.max())
+        self._last = out      # the packed rows of this step (obs | achieved | desired | reward | success | flags)
         return self._obs_dict(out), reward, terminated, truncated, info
+
+    @property
+    def solver_overflow_count(self):
+        return int(self.backend.overflow_counter[0])
 
     def _update_goal(self, success, out):
         idx = torch.nonzero(success, as_tuple=False).flatten()

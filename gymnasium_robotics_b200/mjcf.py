@@ -531,7 +531,7 @@ class Model:
                   "dof_body", "dof_jnt", "dof_parent", "geom_type", "geom_body", "pair_geom1", "pair_geom2", "pair_condim",
                   "site_body", "act_trnid", "act_ctrllimited", "act_forcelimited", "eq_type", "eq_obj1", "eq_obj2",
                   "eq_active", "mocap_body", "ten_adr", "ten_num", "ten_limited", "wrap_dof", "sensor_site", "sensor_body", "sensor_type",
-                  "pair_grid", "grid_dims", "grid_walls"]
+                  "pair_grid", "grid_dims", "grid_walls", "geom_mjbody", "mjbody_rt"]
     FLT_FIELDS = ["opt", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "jnt_pos",
                   "jnt_axis", "jnt_range", "jnt_margin", "jnt_stiffness", "jnt_solref", "jnt_solimp", "qpos0",
                   "qpos_spring", "dof_armature", "dof_damping", "dof_frictionloss", "dof_invweight0", "dof_solref_fri",
@@ -587,6 +587,9 @@ class Model:
                 setattr(m, name, np.frombuffer(blob, dtype=np.float64, count=c, offset=base + o).copy())
             else:
                 m.names = json.loads(blob[base + o: base + o + c].decode())
+        for name in Model.INT_FIELDS:    # blobs written before a field existed: the field reads as empty
+            if name not in m.__dict__:
+                setattr(m, name, np.zeros(0, dtype=np.int32))
         m._reshape()
         return m
 
@@ -928,6 +931,10 @@ def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None) ->
                    GEOM_CYLINDER: np.hypot(size[0], size[1]), GEOM_BOX: np.linalg.norm(size),
                    GEOM_ELLIPSOID: max(size)}[typ])
     m.geom_type, m.geom_body = np.array(gt, dtype=np.int32), np.array(gb, dtype=np.int32)
+    # the MJCF (unfused) body of every runtime geom and the runtime body every MJCF body was fused into: per-MJCF-body quantities
+    # such as data.cfrc_ext (one row per mjModel body; Ant-v5's contact-force observation) keep the reference's row layout
+    m.geom_mjbody = np.array([F.geoms[gi]["body"] for gi in gkeep], dtype=np.int32)
+    m.mjbody_rt = np.array([rt_of[b] for b in range(nb)], dtype=np.int32)
     m.geom_pos, m.geom_quat, m.geom_size = np.array(gp).reshape(-1, 3), np.array(gq).reshape(-1, 4), np.array(gs).reshape(-1, 3)
     m.geom_rbound = np.array(gr)
 

@@ -56,3 +56,49 @@ def gather_mixed_outputs(obs: torch.Tensor, reward: torch.Tensor, width: int):
     out = torch.empty((dist.get_world_size() * n, width + 1), dtype=obs.dtype, device=obs.device)
     dist.all_gather_into_tensor(out, packed)
     return out
+
+
+class PackedGather:
+    """The optional all-gather of the per-step results to every rank (rank 0 is the consumer), on the PACKED rows of
+    the step kernel (`b200sim_set_packed`: obs | achieved | desired | reward | success | terminated | truncated) -- one NCCL
+    `all_gather_into_tensor` per step, issued on a side stream so that it overlaps the next step's kernel instead of sitting in
+    front of it.  Two destination buffers alternate: the consumer reads `latest()` while the next gather fills the other one."""
+
+    def __init__(self, n_local: int, width: int, device, world_size=None):
+        self.world = world_size or (dist.get_world_size() if dist.is_initialized() else 1)
+        self.rows = self.world * n_local
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self.bufs = [torch.empty((self.rows, width), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.k, self.done = 0, None
+
+    def launch(self, packed: torch.Tensor):
+        """Start the gather of this step's packed rows (produced on the current stream); returns the destination buffer."""
+        dst = self.bufs[self.k]
+        self.k ^= 1
+        if self.stream is None:   # CPU tensors (gloo tests): synchronous
+            if self.world > 1:
+                dist.all_gather_into_tensor(dst, packed.contiguous())
+            else:
+                dst.copy_(packed)
+            self.dst = dst
+            return dst
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        packed.record_stream(self.stream)   # the caching allocator must not hand the rows out again before the gather has read them
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            if self.world > 1:
+                dist.all_gather_into_tensor(dst, packed)
+            else:
+                dst.copy_(packed, non_blocking=True)
+            self.done = torch.cuda.Event()
+            self.done.record(self.stream)
+        self.dst = dst
+        return dst
+
+    def wait(self):
+        """Block the host until the last launched gather has landed; returns its buffer ([world * n, W])."""
+        if self.done is not None:
+            self.done.synchronize()
+        return getattr(self, "dst", None)

@@ -41,7 +41,10 @@ typedef struct b200sim_fetch_task {
   int obj_qadr, obj_dadr, goal_flags;
   float rotation_threshold;
   /* touch observation appended after the 61 base entries (manipulate_touch_sensors.py:107-138): 0 = none,
-   * 1 = sensordata, 2 = boolean, 3 = log(x + 1); one value per touch sensor of the model */
+   * 1 = sensordata, 2 = boolean, 3 = log(x + 1); one value per touch sensor of the model.
+   * kind 1 (maze agents): 1 = append the clipped per-body contact forces of Gymnasium's Ant-v5 (`cfrc_ext[1:]`, 6 per body,
+   * [torque; force] about the tree root's subtree com, clipped to (-1, 1)): the (105,) observation of AntMaze_*-v5
+   * (envs/maze/ant_maze_v5.py:99, 132-134); 0 = the (27,) observation of AntMaze_*-v4 / PointMaze */
   int touch_mode;
   /* kind 3 = HandReach (envs/shadow_dexterous_hand/reach.py): same control as kind 2, obs = robot qpos | robot qvel |
    * 5 fingertip site positions = achieved goal (ngoal = 15), Fetch-style distance reward with distance_threshold */
@@ -72,8 +75,8 @@ typedef struct b200sim_fetch_task {
 enum { B200SIM_ST_QPOS = 0, B200SIM_ST_QVEL, B200SIM_ST_WARM, B200SIM_ST_CTRL, B200SIM_ST_MOCAP, B200SIM_ST_POSE,
        B200SIM_ST_GOAL, B200SIM_ST_STRIDE, B200SIM_ST_PENV, B200SIM_ST_COUNT };
 
-/* model_blob: include/b200sim_model.h format.  eq_data: optional [neq*11] override of the model's equality data
- * (the reference rewrites it after load: utils/mujoco_utils.py:74-80).  ref: fixed world point the spatial algebra is
+/* model_blob: include/b200sim_model.h format.  eq_data: NULL, or exactly [neq*11] doubles overriding the model's equality data
+ * (the reference rewrites it after load: utils/mujoco_utils.py:74-80); the library cannot see its length.  ref: fixed world point the spatial algebra is
  * expressed about.  Replaces MjModel.from_xml_path + MjData (robot_env.py:293-294). */
 int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data, const float* ref,
                    const b200sim_fetch_task_t* task, int num_envs, int device, b200sim_t** out);
@@ -86,10 +89,26 @@ int b200sim_layout(const b200sim_t* h, int* out /* [B200SIM_ST_COUNT] */);
  * the hook for reset, parity injection and checkpointing (reference: data.qpos/qvel views, robot_env.py:301-315). */
 float* b200sim_state(b200sim_t* h);
 
-/* One env.step() for every env: clip + _set_action + n_substeps x mj_step + _step_callback + _get_obs + reward.
+/* One env.step() for every env: clip + _set_action + n_substeps x mj_step + _step_callback + _get_obs + reward, plus the episode
+ * bookkeeping of the step (BaseRobotEnv.compute_terminated / compute_truncated, robot_env.py:106-112, 143-146, and gymnasium's
+ * TimeLimit wrapper): terminated / truncated (optional, [N] bytes each) -- see b200sim_set_time_limit.
  * info (optional, [N] int32): low 16 bits = Newton iterations spent, bit 16.. = capacity-overflow flags. */
-int b200sim_step(b200sim_t* h, const float* actions, float* obs, float* achieved, float* desired, float* reward,
-                 float* success, int* info, void* stream);
+int b200sim_step(b200sim_t* h, const float* actions, float* obs, float* achieved, float* desired, float* reward, float* success,
+                 unsigned char* terminated, unsigned char* truncated, int* info, void* stream);
+/* TimeLimit inside the step kernel: the library owns one step counter per env (device, [N] int32, b200sim_elapsed) that a
+ * b200sim_step launch increments and the b200sim_reset* draws zero; truncated = counter >= max_episode_steps (<= 0: never).
+ * terminate_on_success != 0: terminated = success (MazeEnv.compute_terminated with continuing_task = False, maze_v4.py:390-398);
+ * 0: terminated = False (Fetch / Hand / Adroit).  Callers that write state records themselves also zero the counters they reset. */
+int b200sim_set_time_limit(b200sim_t* h, int max_episode_steps, int terminate_on_success);
+int* b200sim_elapsed(b200sim_t* h);
+/* device counter (one unsigned 64-bit word): env-steps so far in which a capacity limit dropped candidates / contacts / rows */
+unsigned long long* b200sim_overflow_counter(b200sim_t* h);
+/* Packed output rows: after b200sim_set_packed(h, 1) every entry point that takes (obs, achieved, desired, reward, success)
+ * expects `obs` to point at ONE [N, W] fp32 buffer, W = b200sim_packed_width(h), and ignores the other four pointers.
+ * Row layout: obs[nobs] | achieved[ngoal] | desired[ngoal] | reward | success | terminated | truncated | pad (W is a multiple
+ * of 4 floats; the two flags are 0.0 / 1.0).  One device->host copy or one all-gather then moves everything a step produced. */
+int b200sim_packed_width(const b200sim_t* h);
+int b200sim_set_packed(b200sim_t* h, int enable);
 /* mj_forward-style refresh of derived quantities + observation for envs with mask[i] != 0 (mask NULL = all);
  * used after reset writes new state records (reference: fetch_env.py:375-402 _reset_sim -> mj_forward, _get_obs). */
 int b200sim_refresh(b200sim_t* h, const unsigned char* mask, float* obs, float* achieved, float* desired, float* reward,

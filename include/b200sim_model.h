@@ -38,7 +38,7 @@ enum { B200_OPTI_ITERATIONS = 0, B200_OPTI_LS_ITERATIONS = 1, B200_OPTI_INTEGRAT
   X(dof_body) X(dof_jnt) X(dof_parent) X(geom_type) X(geom_body) X(pair_geom1) X(pair_geom2) X(pair_condim) \
   X(site_body) X(act_trnid) X(act_ctrllimited) X(act_forcelimited) X(eq_type) X(eq_obj1) X(eq_obj2) \
   X(eq_active) X(mocap_body) X(ten_adr) X(ten_num) X(ten_limited) X(wrap_dof) X(sensor_site) X(sensor_body) X(sensor_type) \
-  X(pair_grid) X(grid_dims) X(grid_walls)
+  X(pair_grid) X(grid_dims) X(grid_walls) X(geom_mjbody) X(mjbody_rt)
 
 #define B200M_FLT_FIELDS(X) \
   X(opt) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_inertia) X(jnt_pos) \

@@ -34,7 +34,8 @@ def compile_ant_maze(maze_map, ant_xml="/root/reference/gymnasium_robotics/envs/
 class OracleAntMazeEnv:
     FRAME_SKIP = 5
 
-    def __init__(self, maze_map=LARGE_MAZE, reward_type="sparse", continuing_task=True, reset_target=False, model=None):
+    def __init__(self, maze_map=LARGE_MAZE, reward_type="sparse", continuing_task=True, reset_target=False, model=None,
+                 include_cfrc_ext_in_observation=False):
         self.model = model if model is not None else compile_ant_maze(maze_map)
         self.sim = OracleSim(self.model)
         self.logic = MazeResetLogic(maze_map, maze_size_scaling=4.0, position_noise_range=0.25)
@@ -42,9 +43,17 @@ class OracleAntMazeEnv:
         self.init_qpos = np.array(self.model.qpos0, dtype=np.float64)
         self.init_qvel = np.zeros(self.model.nv)
         self.goal = np.zeros(2)
+        # Ant-v5 [ext] (gymnasium ant_v5.AntEnv): include_cfrc_ext_in_observation defaults to True, contact_force_range (-1, 1);
+        # AntMaze_*-v5 builds it with the defaults (ant_maze_v5.py:249-255) => observation (105,) (ant_maze_v5.py:99); -v4 (Ant-v4,
+        # use_contact_forces False) => (27,)
+        self.include_cfrc = include_cfrc_ext_in_observation
+        self._cfrc = np.zeros((len(self.model.mjbody_rt), 6))
 
     def _ant_obs(self):
-        return np.concatenate([self.sim.qpos.copy(), self.sim.qvel.copy()])
+        o = [self.sim.qpos.copy(), self.sim.qvel.copy()]
+        if self.include_cfrc:
+            o.append(np.clip(self._cfrc[1:], -1.0, 1.0).ravel())      # contact_forces[1:]: the world body is left out
+        return np.concatenate(o)
 
     def _get_obs(self):  # ant_maze_v5.py:312-320
         o = self._ant_obs()
@@ -58,12 +67,14 @@ class OracleAntMazeEnv:
         s.qpos[:] = self.init_qpos
         s.qvel[:] = self.init_qvel
         s.forward()
+        self._cfrc[:] = 0.0      # mj_resetData zeroes cfrc_ext; set_state's mj_forward does not recompute it
         obs = self._get_obs()
         return obs, {"success": bool(np.linalg.norm(obs["achieved_goal"] - self.goal) <= 0.45)}
 
     def step(self, action):  # ant_maze_v5.py:295-310
         self.sim.ctrl[:] = np.asarray(action, dtype=np.float64)
         self.sim.step(self.FRAME_SKIP)
+        self._cfrc = self.sim.cfrc_ext()      # MujocoEnv.do_simulation [ext]: mj_step, then mj_rnePostConstraint
         obs = self._get_obs()
         reward = compute_reward(obs["achieved_goal"], self.goal, self.reward_type)
         terminated = compute_terminated(obs["achieved_goal"], self.goal, self.continuing_task)

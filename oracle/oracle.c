@@ -1690,6 +1690,39 @@ int oracle_solver_iter(const oracle_sim* s) { return s->solver_iter; }
 long oracle_total_newton_iter(const oracle_sim* s) { return s->total_newton_iter; }
 int oracle_overflow(const oracle_sim* s) { return s->warn_overflow; }
 int oracle_size(const oracle_sim* s, int which) { return s->m.sizes[which]; }
+/* Per-body external contact force, the contact part of mj_rnePostConstraint [ext] (Gymnasium's Ant-v5 calls it after mj_step and
+ * reads data.cfrc_ext: gymnasium_robotics/envs/maze/ant_maze_v5.py:99 "(105,) = 27 + 13 x 6"): for every contact with constraint
+ * rows, the contact force in the contact frame (mj_contactForce: pyramid edges f -> normal = sum f, friction k = mu_k (f+ - f-))
+ * rotated to world axes, taken as a spatial force [torque; force] about the subtree com of the body's tree root, subtracted from
+ * the first body and added to the second.  out: nbody x 6. */
+void oracle_cfrc_ext(const oracle_sim* s, real* out) {
+  const b200_model_view* m = &s->m;
+  /* rows = MJCF (unfused) bodies when the blob carries the tables, else the runtime bodies */
+  const int rows = m->n_mjbody_rt > 0 ? m->n_mjbody_rt : s->nbody;
+  memset(out, 0, sizeof(real) * 6 * rows);
+  for (int c = 0; c < s->ncon; c++) {
+    const Contact* con = &s->con[c];
+    if (con->efc_address < 0) continue;
+    real f[6] = {0, 0, 0, 0, 0, 0};
+    if (con->dim == 1) f[0] = s->efc_force[con->efc_address];
+    else for (int k = 1; k < con->dim; k++) {
+      real fp = s->efc_force[con->efc_address + 2 * (k - 1)], fm = s->efc_force[con->efc_address + 2 * (k - 1) + 1];
+      f[0] += fp + fm; f[k] = con->friction[k - 1] * (fp - fm);
+    }
+    real F[3] = {0, 0, 0}, T[3] = {0, 0, 0};
+    for (int a = 0; a < 3; a++) { addscl3(F, con->frame + 3 * a, f[a]); addscl3(T, con->frame + 3 * a, f[3 + a]); }
+    for (int side = 0; side < 2; side++) {
+      int rb = side ? con->body2 : con->body1, g = side ? con->geom2 : con->geom1;
+      if (rb == 0) continue;
+      int row = (m->n_geom_mjbody == s->ngeom && g >= 0) ? m->geom_mjbody[g] : rb;
+      real sg = side ? 1 : -1, r[3], tq[3];
+      sub3(r, con->pos, s->subtree_com + 3 * m->body_rootid[rb]);
+      cross3(tq, r, F);
+      for (int a = 0; a < 3; a++) { out[6 * row + a] += sg * (T[a] + tq[a]); out[6 * row + 3 + a] += sg * F[a]; }
+    }
+  }
+}
+int oracle_cfrc_rows(const oracle_sim* s) { return s->m.n_mjbody_rt > 0 ? s->m.n_mjbody_rt : s->nbody; }
 /* contact k -> out[0]=dist, out[1:4]=pos, out[4:13]=frame, out[13]=dim, out[14]=geom1, out[15]=geom2, out[16]=efc_address */
 void oracle_contact(const oracle_sim* s, int k, real* out) {
   const Contact* c = &s->con[k];

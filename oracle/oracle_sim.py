@@ -16,14 +16,39 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
+_NATIVE = False
+
+
+def use_native_build():
+    """bench.py's CPU arm only: build and load liboracle with `-O3 -march=native` for the box it runs on (the default -O2 build is
+    what the parity tests use and what travels between machines).  Must be called before the first `lib()`."""
+    global _NATIVE
+    if _LIB is None:
+        _NATIVE = True
+
+
 def build(force: bool = False) -> str:
     """Compile oracle.c -> oracle/_build/liboracle.so with gcc (idempotent)."""
-    out = os.path.join(_HERE, "_build", "liboracle.so")
+    name, flags = "liboracle.so", ["-O2"]
+    if _NATIVE:
+        import hashlib
+        import platform
+
+        cpu = ""
+        try:
+            cpu = next((l for l in open("/proc/cpuinfo") if l.startswith("model name")), "")
+        except OSError:
+            pass
+        name = "liboracle_native_" + hashlib.sha1((platform.machine() + cpu).encode()).hexdigest()[:10] + ".so"
+        flags = ["-O3", "-march=native"]
+    out = os.path.join(_HERE, "_build", name)
     src = os.path.join(_HERE, "oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "b200sim_model.h")
     if force or not os.path.exists(out) or (os.path.exists(src) and os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", out, src, "-lm"])
+        tmp = f"{out}.{os.getpid()}.tmp"
+        subprocess.check_call(["gcc"] + flags + ["-fPIC", "-shared", "-o", tmp, src, "-lm"])
+        os.replace(tmp, out)
     return out
 
 
@@ -43,6 +68,9 @@ def lib():
         for f in ("oracle_ncon", "oracle_nefc", "oracle_solver_iter", "oracle_overflow"):
             getattr(L, f).argtypes = [ctypes.c_void_p]
             getattr(L, f).restype = ctypes.c_int
+        L.oracle_cfrc_ext.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_cfrc_ext.restype = None
+        L.oracle_cfrc_rows.argtypes = [ctypes.c_void_p]
         L.oracle_total_newton_iter.argtypes = [ctypes.c_void_p]
         L.oracle_total_newton_iter.restype = ctypes.c_long
         L.oracle_size.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -122,6 +150,12 @@ class OracleSim:
     @property
     def solver_iter(self):
         return self._L.oracle_solver_iter(self._h)
+
+    def cfrc_ext(self):
+        """data.cfrc_ext after an explicit mj_rnePostConstraint [ext]: one row per MJCF body, torque | force (contacts only)."""
+        out = np.zeros((int(self._L.oracle_cfrc_rows(self._h)), 6))
+        self._L.oracle_cfrc_ext(self._h, out.ctypes.data)
+        return out
 
     @property
     def total_newton_iter(self):

@@ -34,3 +34,16 @@ def mjcf_file(tmp_path):
         return str(p)
 
     return _write
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """B200_PARITY_STATS=<path>: dump the measured error distributions of the parity tests (tests/parity_util.check_envelope)."""
+    path = os.environ.get("B200_PARITY_STATS")
+    if path:
+        import json
+
+        from tests.parity_util import PARITY_STATS
+
+        if PARITY_STATS:
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            json.dump(PARITY_STATS, open(path, "w"), indent=1, sort_keys=True)

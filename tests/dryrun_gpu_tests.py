@@ -38,6 +38,12 @@ def make_vec(env_id, num_envs=1, **kw):
 if __name__ == "__main__":
     with tempfile.TemporaryDirectory() as tmp:
         open(os.path.join(tmp, "gpu_dryrun_shim.py"), "w").write(SHIM)
+        # the session hooks of tests/conftest.py (marker registration, B200_PARITY_STATS dump) apply to the copies too
+        open(os.path.join(tmp, "conftest.py"), "w").write(open(os.path.join(ROOT, "tests", "conftest.py")).read())
+        os.makedirs(os.path.join(tmp, "golden"), exist_ok=True)
+        for f in os.listdir(os.path.join(ROOT, "tests", "golden")):
+            if f.endswith((".json", ".b200m", ".npz")):
+                os.symlink(os.path.join(ROOT, "tests", "golden", f), os.path.join(tmp, "golden", f))
         names = []
         for path in sys.argv[1:]:
             s = open(path).read()
@@ -51,4 +57,5 @@ if __name__ == "__main__":
             names.append(os.path.join(tmp, os.path.basename(path)))
             open(names[-1], "w").write(s)
         env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + tmp)
-        sys.exit(subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-rxX"] + names, cwd=tmp, env=env).returncode)
+        sys.exit(subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-rxX"] + sys.argv[1:0] + names +
+                                (["-k", os.environ["DRYRUN_K"]] if os.environ.get("DRYRUN_K") else []), cwd=tmp, env=env).returncode)

@@ -37,17 +37,30 @@ class HostSimBackend:
         self.task, self.layout = t, lay
         self.state = torch.zeros((num_envs, lay["stride"]), dtype=torch.float32)
         self.launches = 0
+        # the same episode bookkeeping as the step kernel (csrc/step_kernel.cuh): per-env step counters, flags, info words
+        self.elapsed = torch.zeros(num_envs, dtype=torch.int32)
+        self.info = torch.zeros(num_envs, dtype=torch.int32)
+        self.overflow_counter = torch.zeros(1, dtype=torch.int64)
+        self.max_steps, self.term_on_success = 0, False
+        self.packed_w = (self.nobs + 2 * self.ngoal + 4 + 3) & ~3
+
+    def set_time_limit(self, max_episode_steps, terminate_on_success=False):
+        self.max_steps, self.term_on_success = int(max_episode_steps or 0), bool(terminate_on_success)
 
     def close(self):
         pass
 
     def new_outputs(self):
-        n = self.num_envs
-        return dict(obs=torch.zeros((n, self.nobs)), achieved=torch.zeros((n, self.ngoal)), desired=torch.zeros((n, self.ngoal)),
-                    reward=torch.zeros(n), success=torch.zeros(n))
+        n, no, ng = self.num_envs, self.nobs, self.ngoal
+        p = torch.zeros((n, self.packed_w))
+        flags = torch.zeros((2, n), dtype=torch.uint8)
+        k = no + 2 * ng
+        return dict(packed=p, obs=p[:, :no], achieved=p[:, no:no + ng], desired=p[:, no + ng:k], reward=p[:, k], success=p[:, k + 1],
+                    terminated=flags[0].view(torch.bool), truncated=flags[1].view(torch.bool), flags=flags)
 
-    def _run(self, mode, nraw, actions, mask, out):
+    def _run(self, mode, nraw, actions, mask, out, info=None):
         st = self.state.numpy()
+        k = self.nobs + 2 * self.ngoal
         for i in range(self.num_envs):
             if mask is not None and not bool(mask[i]):
                 continue
@@ -56,10 +69,20 @@ class HostSimBackend:
             self.overflow_bits = getattr(self, "overflow_bits", 0) | (it >> 16)   # capacity flags of the info word
             out["obs"][i] = torch.from_numpy(obs); out["achieved"][i] = torch.from_numpy(ag); out["desired"][i] = torch.from_numpy(dg)
             out["reward"][i] = rew; out["success"][i] = suc
+            if mode == 0:   # flags are written by step launches only (refresh / raw leave them alone)
+                self.elapsed[i] += 1
+                trunc = self.max_steps > 0 and int(self.elapsed[i]) >= self.max_steps
+                term = self.term_on_success and suc != 0
+                out["flags"][0, i], out["flags"][1, i] = int(term), int(trunc)
+                out["packed"][i, k + 2], out["packed"][i, k + 3] = float(term), float(trunc)
+            if info is not None:
+                info[i] = it
+            if it >> 16:
+                self.overflow_counter += 1
         self.launches += 1
 
     def step(self, actions, out, info=None):
-        self._run(0, 0, actions, None, out)
+        self._run(0, 0, actions, None, out, self.info if info is None else info)
 
     def refresh(self, mask, out):
         self._run(1, 0, None, mask, out)
@@ -82,6 +105,7 @@ class HostSimBackend:
             L.hostsim_fetch_reset_record(ctypes.byref(params), int(seed) & 0xFFFFFFFFFFFFFFFF, i + int(env_offset), int(episode[i]), rest.ctypes.data,
                                          self.layout["stride"], self.layout["qpos"], self.layout["goal"], st[i].ctypes.data)
             episode[i] += 1
+            self.elapsed[i] = 0
         self.launches += 1
         self.refresh(mask, out)
 
@@ -99,6 +123,7 @@ class HostSimBackend:
             L.hostsim_uniform_reset_record(ctypes.byref(params), int(seed) & 0xFFFFFFFFFFFFFFFF, i + int(env_offset), int(episode[i]), rest.ctypes.data,
                                            self.layout["stride"], st[i].ctypes.data)
             episode[i] += 1
+            self.elapsed[i] = 0
         self.launches += 1
         self.refresh(mask, out)
 
@@ -117,6 +142,7 @@ class HostSimBackend:
                                         int(episode[i]), rest.ctypes.data, self.layout["stride"], self.layout["qpos"], self.layout["goal"],
                                         st[i].ctypes.data)
             episode[i] += 1
+            self.elapsed[i] = 0
         self.launches += 1
         self.refresh(mask, out)
 
@@ -148,6 +174,7 @@ class HostSimBackend:
                 L.hostsim_hand_goal(ctypes.byref(params), par.ctypes.data, int(seed) & 0xFFFFFFFFFFFFFFFF, i + int(env_offset), int(episode[i]),
                                     self.layout["qpos"], self.layout["goal"], st[i].ctypes.data)
                 episode[i] += 1
+                self.elapsed[i] = 0
         self.launches += 1
         self.refresh(mask, out)
 
@@ -164,6 +191,7 @@ class HostSimBackend:
                 L.hostsim_reach_reset_record(ctypes.byref(params), int(seed) & 0xFFFFFFFFFFFFFFFF, i + int(env_offset), int(episode[i]), rest.ctypes.data,
                                              self.layout["stride"], self.layout["goal"], st[i].ctypes.data)
                 episode[i] += 1
+                self.elapsed[i] = 0
         self.launches += 1
         self.refresh(mask, out)
 

@@ -6,7 +6,7 @@ import gymnasium_robotics_b200 as grb
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
-env = grb.make_vec("FrankaKitchen-v1", num_envs=n, experimental=True, rng_mode="torch", autoreset_mode="same_step")
+env = grb.make_vec("FrankaKitchen-v1", num_envs=n, rng_mode="torch", autoreset_mode="same_step")
 env.reset(seed=0)
 g = torch.Generator(device="cuda").manual_seed(1234)
 for k in range(steps):

@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 10 -c 1 -o gpurun_out/prof_${tag} \
     python tests/prof_step.py 4096 12 > gpurun_out/ncu_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_${tag}.log
-python tests/summarize_profile.py ${tag} > gpurun_out/summarize_${tag}.log 2>&1; rm -f gpurun_out/prof_${tag}.ncu-rep
+python tests/summarize_profile.py ${tag} > gpurun_out/summarize_${tag}.log 2>&1   # (this one report is kept: read here with ncu -i)
 # 3. the Shadow-Hand build of the step kernel (BASELINE config 3: 2048 envs, 92 touch sensors)
 ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 6 -c 1 -o gpurun_out/prof_hand_${tag} \
     python tests/prof_hand.py 2048 8 touch > gpurun_out/ncu_hand_${tag}.log 2>&1
@@ -22,7 +22,12 @@ ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 
     python tests/prof_adroit.py AdroitHandHammer-v2 2048 8 > gpurun_out/ncu_adroit_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_adroit_${tag}.log
 python tests/summarize_profile.py adroit_${tag} > gpurun_out/summarize_adroit_${tag}.log 2>&1; rm -f gpurun_out/prof_adroit_${tag}.ncu-rep
-cp profiles/*${tag}* profiles/traffic*.json gpurun_out/prof_txt/ 2>/dev/null
+# 4b. the kitchen build (FrankaKitchen-v1, two-level broad phase, 2048 envs: BASELINE config 5b)
+ncu --set full --clock-control none --import-source on -k regex:fetch_kernel -s 4 -c 1 -o gpurun_out/prof_kitchen_${tag} \
+    python tests/prof_kitchen.py 2048 6 > gpurun_out/ncu_kitchen_${tag}.log 2>&1
+tail -2 gpurun_out/ncu_kitchen_${tag}.log
+python tests/summarize_profile.py kitchen_${tag} > gpurun_out/summarize_kitchen_${tag}.log 2>&1; rm -f gpurun_out/prof_kitchen_${tag}.ncu-rep
+cp profiles/*${tag}* profiles/traffic*.json profiles/roofline_*.json gpurun_out/prof_txt/ 2>/dev/null
 # 5. compute-sanitizer memcheck: Fetch (30 envs) and an Adroit relocate batch
 compute-sanitizer --tool memcheck python tests/sanitize_step.py > gpurun_out/memcheck_${tag}.log 2>&1; tail -3 gpurun_out/memcheck_${tag}.log
 compute-sanitizer --tool memcheck python tests/prof_adroit.py AdroitHandRelocate-v2 416 6 > gpurun_out/memcheck_adroit_${tag}.log 2>&1; tail -3 gpurun_out/memcheck_adroit_${tag}.log

@@ -5,7 +5,7 @@ import torch
 import gymnasium_robotics_b200 as grb
 
 for env_id, n in (("FetchPickAndPlace-v4", 30), ("FetchSlide-v4", 10), ("HandManipulateBlockRotateXYZ_ContinuousTouchSensors-v1", 16),
-                  ("AdroitHandHammer-v2", 16), ("AntMaze_UMaze-v5", 9)):
+                  ("AdroitHandHammer-v2", 16), ("AntMaze_UMaze-v5", 9), ("FrankaKitchen-v1", 9)):
     env = grb.make_vec(env_id, num_envs=n, rng_mode="torch")
     env.reset(seed=0)
     nact = env.single_action_space.shape[0]

@@ -17,7 +17,10 @@ keep = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "sm__cycles_elapsed.avg.per_second"]
+        "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "sm__cycles_elapsed.avg.per_second",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
+        "smsp__inst_executed.avg.per_cycle_active", "l1tex__t_bytes_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_bytes_pipe_lsu_mem_local_op_st.sum"]
 vals = {a: (c, b) for a, b, c in zip(h, u, v)}
 lines = [f"# ncu --set full, kernel fetch_kernel (step), report gpurun_out/prof_{tag}.ncu-rep", f"kernel: {vals.get('Kernel Name', ('?',''))[0]}"]
 for k in keep:
@@ -67,6 +70,29 @@ lines.append(f"\n# executed warp instructions by source function (total {ti})")
 for k, n in per.most_common(25):
     lines.append(f"{k:45s} {n:12d} {100*n/ti:5.1f}%")
 open(os.path.join(out_dir, f"ncu_step_kernel_{tag}.txt"), "w").write("\n".join(lines) + "\n")
+# the compute-side roofline figures bench.py attaches to its JSON line, per workload
+def numk(k, default=None):
+    try:
+        return num(k)
+    except Exception:
+        return default
+workload = {"hand": "hand_block_touch", "adroit": "adroit_hammer", "kitchen": "franka_kitchen"}.get(tag.split("_")[0], "fetch_pick_and_place")
+tms = numk("gpu__time_duration.sum")
+tunit = vals.get("gpu__time_duration.sum", ("", ""))[1]
+tms = tms * {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "second": 1e3, "nsecond": 1e-6}.get(tunit, 1e-6) if tms is not None else None
+fl = [numk("smsp__sass_thread_inst_executed_op_fadd_pred_on.sum"), numk("smsp__sass_thread_inst_executed_op_fmul_pred_on.sum"),
+      numk("smsp__sass_thread_inst_executed_op_ffma_pred_on.sum")]
+roof = {"workload": workload, "ncu_source": f"profiles/ncu_step_kernel_{tag}.txt", "ncu_kernel_ms": tms, "envs_per_launch": alg_n,
+        "dram_bytes_per_launch": dram, "algorithmic_bytes_per_launch": alg_b * alg_n,
+        "issue_active_pct": numk("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "warps_active_pct": numk("sm__warps_active.avg.pct_of_peak_sustained_active"),
+        "fma_pipe_pct": numk("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+        "avg_active_lanes": numk("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "fp32_flop_per_launch": (fl[0] + fl[1] + 2 * fl[2]) if None not in fl else None,
+        "local_load_store_inst": [numk("sass__inst_executed_local_loads"), numk("sass__inst_executed_local_stores")],
+        "registers_per_thread": numk("launch__registers_per_thread"), "smem_per_block_bytes": numk("launch__shared_mem_per_block_dynamic"),
+        "top_stalls": [[k.replace("stall_", ""), round(100 * n / tot, 1)] for k, n in stalls.most_common(5)]}
+json.dump(roof, open(os.path.join(out_dir, f"roofline_{workload}.json"), "w"), indent=1)
 json.dump({"dram_bytes_per_launch": dram, "source": f"profiles/ncu_step_kernel_{tag}.txt", "algorithmic_bytes_per_launch": alg_b * alg_n},
           open(os.path.join(out_dir, "traffic_hand.json" if HAND else ("traffic_adroit.json" if ADROIT else ("traffic_kitchen.json" if KITCHEN else "traffic.json"))), "w"))
 # launch list

@@ -16,14 +16,70 @@ def mk(maze="Large", n=2, **kw):
 
 
 def test_registry_and_spaces():
-    assert pkg.ENV_IDS["AntMaze_Large-v5"] == dict(maze="Large", reward_type="sparse", max_episode_steps=1000)
+    assert pkg.ENV_IDS["AntMaze_Large-v5"] == dict(maze="Large", reward_type="sparse", max_episode_steps=1000, include_cfrc_ext_in_observation=True)
+    assert pkg.ENV_IDS["AntMaze_Large-v4"] == dict(maze="Large", reward_type="sparse", max_episode_steps=1000)
     assert pkg.ENV_IDS["AntMaze_UMazeDense-v5"]["max_episode_steps"] == 700  # reference __init__.py:839-850
+    # -v5 wraps Ant-v5: (105,) = 27 + 13 x 6 clipped contact forces (ant_maze_v5.py:99); -v4 wraps Ant-v4: (27,)
     env = pkg.make_vec("AntMaze_Large-v5", num_envs=2, backend_factory=HostSimBackend, rng_mode="numpy")
-    assert env.single_action_space.shape == (8,) and env.single_observation_space["observation"].shape == (27,)
+    assert env.single_action_space.shape == (8,) and env.single_observation_space["observation"].shape == (105,)
     obs, info = env.reset(seed=0)
-    assert obs["observation"].shape == (2, 27) and obs["achieved_goal"].shape == (2, 2) and info["success"].shape == (2,)
+    assert obs["observation"].shape == (2, 105) and obs["achieved_goal"].shape == (2, 2) and info["success"].shape == (2,)
+    assert float(obs["observation"][:, 27:].abs().max()) == 0.0      # reset: cfrc_ext is zero (mj_resetData)
     with pytest.raises(ValueError):
         env.step(np.zeros((2, 4), dtype=np.float32))
+    env4 = pkg.make_vec("AntMaze_Large-v4", num_envs=2, backend_factory=HostSimBackend, rng_mode="numpy")
+    assert env4.single_observation_space["observation"].shape == (27,)
+
+
+def test_v5_contact_force_observation_matches_oracle():
+    """The 78 trailing entries of the AntMaze-v5 observation: `cfrc_ext[1:]` of the last forward pass clipped to (-1, 1), [torque;
+    force] per body about the ant's com.  Unclipped, the forces are hundreds of newtons, so most entries sit at +-1 or 0: the test
+    also compares the sign pattern and, with the clip range opened in the oracle, checks that the standing ant's foot forces carry
+    its weight."""
+    n = 3
+    env = pkg.make_vec("AntMaze_UMaze-v5", num_envs=n, backend_factory=HostSimBackend, rng_mode="numpy")
+    env.reset(seed=8)
+    model = load_model("antmaze_umaze")
+    oracles = [OracleAntMazeEnv(MAPS["UMaze"], model=model, include_cfrc_ext_in_observation=True) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        o.reset(seed=8 + i)
+        for _ in range(12):          # the ant is dropped from z = 0.75: let it land before comparing contact forces
+            o.step(np.zeros(8))
+    lay = env.backend.layout
+    rng = np.random.default_rng(3)
+    touched = 0
+    for step in range(8):
+        rec = np.zeros((n, lay["stride"]))
+        for i, o in enumerate(oracles):
+            rec[i, lay["qpos"]:lay["qpos"] + 15] = o.sim.qpos
+            rec[i, lay["qvel"]:lay["qvel"] + 14] = o.sim.qvel
+            rec[i, lay["warm"]:lay["warm"] + 14] = o.sim.qacc_warmstart
+            rec[i, lay["goal"]:lay["goal"] + 2] = o.goal
+        env.set_state(torch.as_tensor(rec, dtype=torch.float32))
+        a = rng.uniform(-1, 1, (n, 8)).astype(np.float32) * (0.3 if step < 4 else 1.0)
+        o, r, te, tr, info = env.step(a)
+        for i, orc in enumerate(oracles):
+            oo, *_ = orc.step(a[i].astype(np.float64))
+            got, want = o["observation"][i].double().numpy(), oo["observation"]
+            assert got.shape == (105,) and want.shape == (105,)
+            cf, wf = got[27:].reshape(13, 6), want[27:].reshape(13, 6)
+            raw = orc.sim.cfrc_ext()[1:]
+            big = np.abs(raw) > 1.5                      # entries the clip saturates in both: must agree exactly
+            assert np.array_equal(cf[big], wf[big])
+            small = np.abs(raw) < 0.5
+            assert np.abs(cf[small] - wf[small]).max() < 2e-2 if small.any() else True
+            touched += int((np.abs(raw).sum(axis=1) > 0).sum())
+    assert touched >= 12, touched     # the comparison saw real contacts (the ants are still bouncing after the drop)
+    env.close()
+    # magnitude and sign of the formula: an ant that has settled on its feet is carried by its contact forces
+    orc = oracles[0]
+    orc.reset(seed=8)
+    for _ in range(60):
+        orc.step(np.zeros(8))
+    raw = orc.sim.cfrc_ext()
+    weight = 9.81 * float(np.sum(model.body_mass))
+    assert abs(raw[:, 5].sum() - weight) < 0.05 * weight and np.abs(raw[:, 3:5].sum(axis=0)).max() < 0.05 * weight, (raw[:, 3:].sum(axis=0), weight)
+    assert np.abs(raw[0]).max() == 0.0      # the world row stays empty (and is left out of the observation)
 
 
 def test_cell_tables_match_oracle_maze():

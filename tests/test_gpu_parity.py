@@ -10,15 +10,38 @@ import numpy as np
 import pytest
 import torch
 
+import gymnasium_robotics_b200 as pkg
+from tests.parity_util import check_envelope, inject_records
+
 pytestmark = pytest.mark.gpu
 
 OBS_TOL = 2e-4
+# Stated fp32-vs-fp64 envelopes: (median, 99th percentile, maximum) of max |obs_gpu - obs_oracle| over the entries of an
+# observation group, one sample per (env, env-step) from identical injected states; ALL THREE are asserted, every observation
+# entry belongs to a group unless the test lists it as excluded with the reason.  Positions in m / rad, Fetch velocities are
+# scaled by dt = 0.04 (fetch_env.py:121-128), Hand / Adroit / Ant velocities are raw rad/s or m/s.  Measured values of the
+# B200 run that calibrated them: profiles/parity_stats_r2*.json (the limits leave a factor >= 3 over the measured values).
+ENVELOPE = {
+    # free motion: nothing touches, every entry
+    "fetch_free/FetchReach": (2e-6, 2e-5, 5e-5), "fetch_free/FetchPush": (2e-6, 5e-5, 2e-4), "fetch_free/FetchPickAndPlace": (2e-6, 5e-5, 2e-4),
+    # gripper driven onto the table / the object: impacts amplify fp32 round-off inside one env-step
+    "fetch_contact/FetchReach": (2e-6, 2e-4, 5e-3), "fetch_contact/FetchPush": (5e-6, 5e-2, 0.2), "fetch_contact/FetchPickAndPlace": (5e-6, 5e-2, 0.2),
+    # the object held between the closing fingers (contact-heavy variant of SURVEY.md 8d)
+    "fetch_grasp/pos": (2e-5, 5e-3, 2e-2), "fetch_grasp/vel": (5e-5, 2e-2, 5e-2),
+    "fetch_slide": (2e-5, 2e-3, 5e-2),
+    "antmaze/pos": (2e-5, 2e-3, 5e-2), "antmaze/vel": (5e-4, 0.2, 1.0), "antmaze/cfrc": (1e-3, 0.5, 2.0),
+    "hand_block/pos": (2e-5, 5e-4, 5e-3), "hand_block/vel": (2e-3, 0.2, 1.0), "hand_block/quat": (2e-5, 2e-3, 2e-2),
+    "hand_egg/pos": (2e-5, 5e-4, 5e-3), "hand_egg/vel": (2e-3, 0.2, 1.0), "hand_egg/quat": (2e-5, 2e-3, 2e-2),
+    "hand_pen/pos": (2e-5, 5e-4, 5e-3), "hand_pen/vel": (2e-3, 0.2, 1.0), "hand_pen/quat": (2e-5, 2e-3, 2e-2),
+    "hand_touch": (2e-3, 5e-2, 0.2),
+    "hand_reach": (5e-6, 1e-4, 2e-4),
+    "adroit_hammer": (5e-6, 5e-3, 5e-2), "adroit_relocate": (5e-6, 5e-3, 5e-2), "adroit_door": (5e-6, 5e-3, 5e-2),
+    "adroit_pen/pos": (5e-5, 5e-3, 5e-2), "adroit_pen/angvel": (5e-3, 5e-2, 0.1),
+}
 
 
 def _mk(task, n, **kw):
-    from gymnasium_robotics_b200.fetch import FetchVectorEnv
-
-    return FetchVectorEnv(task, num_envs=n, device="cuda:0", **kw)
+    return pkg.make_vec(f"{task}-v4", num_envs=n, device="cuda:0", **kw)
 
 
 @pytest.mark.parametrize("task", ["FetchReach", "FetchPush", "FetchPickAndPlace"])
@@ -60,17 +83,14 @@ def test_step_parity_from_identical_state(task):
             err = np.abs(got - oo["observation"]).max()
             (free_errs if step < 6 else errs).append(err)
             assert np.isfinite(got).all()
+            assert not bool(term[i]) and not bool(trunc[i])
             # reward/success must agree unless the distance sits within tolerance of the threshold
             d = np.linalg.norm(oo["achieved_goal"] - oo["desired_goal"])
             if abs(d - 0.05) > 5e-3:
                 assert float(r[i]) == float(orr) and float(info["is_success"][i]) == float(oi["is_success"])
-    free_errs, errs = np.array(free_errs), np.array(errs)
-    print(f"{task}: free-motion max {free_errs.max():.2e}; contact phase median {np.median(errs):.2e} max {errs.max():.2e}")
-    # free motion (object at rest, arm moving): every sample within tolerance
-    assert free_errs.max() < OBS_TOL
-    # contact-driving phase: impacts amplify fp32/fp64 differences within a single env-step (SURVEY.md 7 "contact-rich
-    # chaos"): at least 90% of the samples within tolerance, none wildly off
-    assert np.mean(errs < OBS_TOL) >= 0.9 and errs.max() < 0.2
+    # every one of the 10 / 25 observation entries is compared; terminated / truncated are constant False (robot_env.py:106-112)
+    check_envelope(f"fetch_free/{task}", free_errs, *ENVELOPE[f"fetch_free/{task}"])
+    check_envelope(f"fetch_contact/{task}", errs, *ENVELOPE[f"fetch_contact/{task}"])
     env.close()
 
 
@@ -89,6 +109,62 @@ def test_free_running_rollout_tracks_oracle():
         o, r, *_ = env.step(torch.as_tensor(a))
         oo, *_ = orc.step(a[0].astype(np.float64))
         assert np.abs(o["observation"][0].double().cpu().numpy() - oo["observation"]).max() < 1e-3
+    env.close()
+
+
+def test_fetch_grasp_contact_heavy_parity():
+    """Contact-heavy variant: the object starts between the open fingers, the gripper closes on it and lifts.  Finger
+    pads against the box are box-box pairs with friction pyramids whose active edges change while the grip tightens, so the
+    Newton solver needs more than one move per sub-step -- asserted on both sides (the oracle's iteration counter and the kernel's
+    info word).  Per env-step from injected states; positions and (dt-scaled) velocities have their own envelopes."""
+    from tests.parity_util import inject_oracle_state, oracle_env_from_model
+
+    n = 6
+    env = _mk("FetchPickAndPlace", n, rng_mode="numpy")
+    env.reset(seed=300)
+    oracles = [oracle_env_from_model("FetchPickAndPlace", env.model) for _ in range(n)]
+    rng = np.random.default_rng(11)
+    for i, o in enumerate(oracles):
+        o.reset(seed=300 + i)
+        s, m = o.sim, o.model
+        a = m.jnt_qposadr[m.joint_id("object0:joint")]
+        grip = s.site_xpos[o._grip_site].copy()
+        s.qpos[a:a + 3] = grip + np.array([0.002 * (i - 2.5), 0.0, -0.004 * (i % 3)])   # between the fingers, slightly off centre
+        yaw = 0.05 * (i - 2.5)
+        s.qpos[a + 3:a + 7] = [np.cos(yaw / 2), 0.0, 0.0, np.sin(yaw / 2)]
+        for fq in o._finger_q:
+            s.qpos[fq] = 0.045                                                      # fingers open wider than the 5 cm box
+        s.qvel[:] = 0.0
+        s.forward()
+    pos, vel = [], []
+    gpu_iters, orc_iters = 0, 0
+    for step in range(10):
+        inject_oracle_state(env, oracles)
+        a = rng.uniform(-0.2, 0.2, (n, 4)).astype(np.float32)
+        a[:, 3] = -1.0                                     # close
+        if step >= 4:
+            a[:, 2] = 0.6                                  # and lift
+        it0 = [o.sim.total_newton_iter for o in oracles]
+        o, r, term, trunc, info = env.step(torch.as_tensor(a))
+        gpu_iters = max(gpu_iters, int((info["solver_info"] & 0xffff).max()))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            orc_iters = max(orc_iters, orc.sim.total_newton_iter - it0[i])
+            got = o["observation"][i].double().cpu().numpy()
+            assert np.isfinite(got).all()
+            d = np.abs(got - oo["observation"])
+            pos.append(max(d[:14].max(), 0.0))             # grip pos, object pos, relative pos, finger widths, object Euler angles
+            vel.append(d[14:25].max())                     # object velp / velr, grip velp, finger velocities (x dt)
+            dgoal = np.linalg.norm(oo["achieved_goal"] - oo["desired_goal"])
+            if abs(dgoal - 0.05) > 5e-3:
+                assert float(r[i]) == float(orr)
+    # 20 sub-steps per env-step: more than 20 (30) Newton moves means the active set changed inside sub-steps
+    assert orc_iters > 30 and gpu_iters > 30, (orc_iters, gpu_iters)
+    # the object is really held: it went up with the gripper in at least half of the envs
+    lifted = sum(1 for orc in oracles if orc.sim.site_xpos[orc._obj_site][2] > orc.height_offset + 0.02)
+    assert lifted >= n // 2, lifted
+    check_envelope("fetch_grasp/pos", pos, *ENVELOPE["fetch_grasp/pos"])
+    check_envelope("fetch_grasp/vel", vel, *ENVELOPE["fetch_grasp/vel"])
     env.close()
 
 
@@ -167,9 +243,7 @@ def test_missing_device_is_loud():
 
 # ------------------------------------------------------------------------------------------------ AntMaze (config 4)
 def _mk_ant(maze, n, **kw):
-    from gymnasium_robotics_b200.maze import AntMazeVectorEnv
-
-    return AntMazeVectorEnv(maze, num_envs=n, device="cuda:0", **kw)
+    return pkg.make_vec(f"AntMaze_{maze}-v5", num_envs=n, device="cuda:0", **kw)
 
 
 def test_antmaze_step_parity_from_identical_state():
@@ -182,33 +256,32 @@ def test_antmaze_step_parity_from_identical_state():
     env = _mk_ant("Large", n, rng_mode="numpy")
     obs, info = env.reset(seed=20)
     model = load_model("antmaze_large")
-    oracles = [OracleAntMazeEnv(MAPS["Large"], model=model) for _ in range(n)]
+    oracles = [OracleAntMazeEnv(MAPS["Large"], model=model, include_cfrc_ext_in_observation=True) for _ in range(n)]
+    assert obs["observation"].shape == (n, 105)      # AntMaze-v5: 27 + 13 x 6 clipped contact forces (ant_maze_v5.py:99)
     for i, o in enumerate(oracles):
         oo, _ = o.reset(seed=20 + i)
         assert np.abs(obs["desired_goal"][i].double().cpu().numpy() - oo["desired_goal"]).max() < 2e-6  # same PCG64 stream
-    lay = env.backend.layout
+        assert np.abs(obs["observation"][i].double().cpu().numpy() - oo["observation"]).max() < 2e-6
     rng = np.random.default_rng(2)
-    errs = []
+    epos, evel, ecf = [], [], []
     for step in range(12):
-        rec = np.zeros((n, lay["stride"]))
-        for i, o in enumerate(oracles):
-            rec[i, lay["qpos"]:lay["qpos"] + 15] = o.sim.qpos
-            rec[i, lay["qvel"]:lay["qvel"] + 14] = o.sim.qvel
-            rec[i, lay["warm"]:lay["warm"] + 14] = o.sim.qacc_warmstart
-            rec[i, lay["goal"]:lay["goal"] + 2] = o.goal
-        env.set_state(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        env.set_state(inject_records(env, oracles, lambda i, o, rec, lay: rec.__setitem__(slice(lay["goal"], lay["goal"] + 2), o.goal)))
         a = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
         o, r, te, tr, info = env.step(torch.as_tensor(a))
         for i, orc in enumerate(oracles):
-            oo, orr, ote, _, oi = orc.step(a[i].astype(np.float64))
+            oo, orr, ote, otr, oi = orc.step(a[i].astype(np.float64))
             got = o["observation"][i].double().cpu().numpy()
             assert np.isfinite(got).all()
-            errs.append(np.abs(got - oo["observation"]).max())
+            d = np.abs(got - oo["observation"])
+            epos.append(d[:13].max())      # torso height, torso quaternion, 8 joint angles (qpos[2:])
+            evel.append(d[13:27].max())    # qvel, raw: tens of rad/s under +-150 N m random torques
+            ecf.append(d[27:].max())       # cfrc_ext[1:] clipped to (-1, 1): forces of hundreds of newtons sit at the clip bounds
             assert float(r[i]) == float(orr) and bool(info["success"][i]) == oi["success"]
-    errs = np.array(errs)
-    print(f"AntMaze: median {np.median(errs):.2e} p90 {np.quantile(errs, 0.9):.2e} max {errs.max():.2e}")
-    # velocities reach tens of rad/s under +-150 N.m random torques; contact events amplify fp32/fp64 differences
-    assert np.median(errs) < 2e-4 and np.mean(errs < 2e-3) >= 0.9 and errs.max() < 1.0
+            assert bool(te[i]) == bool(ote) and bool(tr[i]) == bool(otr)      # terminated / truncated flags of the step kernel
+    check_envelope("antmaze/pos", epos, *ENVELOPE["antmaze/pos"])
+    check_envelope("antmaze/vel", evel, *ENVELOPE["antmaze/vel"])
+    check_envelope("antmaze/cfrc", ecf, *ENVELOPE["antmaze/cfrc"])
+    env.close()
 
 
 def test_antmaze_shard_size_batch_properties():
@@ -286,9 +359,17 @@ def test_pointmaze_rollout_tracks_oracle():
 
 # ------------------------------------------------------------------------------------------------ Shadow Hand (config 3)
 def _mk_hand(task, n, **kw):
-    from gymnasium_robotics_b200.hand import HandVectorEnv
+    return pkg.make_vec(f"{task}-v1", num_envs=n, device="cuda:0", **kw)
 
-    return HandVectorEnv(task, num_envs=n, device="cuda:0", **kw)
+
+def _hand_groups(got, want, name, pos, vel, quat):
+    """The 61 entries of the manipulation observation (manipulate.py:298-314) in three groups: robot joint angles [0:24] + object
+    position [54:57] (`pos`), robot joint velocities [24:48] + object velocity [48:54] (`vel`, raw rad/s and m/s), object
+    quaternion [57:61] (`quat`)."""
+    d = np.abs(got - want)
+    pos.append(max(d[:24].max(), d[54:57].max()))
+    vel.append(d[24:54].max())
+    quat.append(d[57:61].max())
 
 
 def test_hand_reset_and_step_parity():
@@ -309,31 +390,21 @@ def test_hand_reset_and_step_parity():
         assert np.abs(g[3:] - oo["desired_goal"][3:]).max() < 2e-6
         a = obs["achieved_goal"][i].double().cpu().numpy()
         assert a[2] > 0.04 and np.abs(a[:3] - oo["achieved_goal"][:3]).max() < 5e-3
-    lay, m = env.backend.layout, model
     rng = np.random.default_rng(4)
-    errs = []
+    pos, vel, quat = [], [], []
     for step in range(10):
-        rec = np.zeros((n, lay["stride"]))
-        for i, o in enumerate(oracles):
-            s = o.sim
-            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
-            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
-            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
-            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
-            rec[i, lay["goal"]:lay["goal"] + 7] = o.goal
-        env.set_state(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        env.set_state(inject_records(env, oracles, lambda i, o, rec, lay: rec.__setitem__(slice(lay["goal"], lay["goal"] + 7), o.goal)))
         a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
-        info_bits = torch.zeros(n, dtype=torch.int32, device="cuda")
         o, r, te, tr, info = env.step(torch.as_tensor(a))
         for i, orc in enumerate(oracles):
             oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
             got = o["observation"][i].double().cpu().numpy()
             assert np.isfinite(got).all()
-            errs.append(max(np.abs(got[:24] - oo["observation"][:24]).max(), np.abs(got[54:57] - oo["observation"][54:57]).max()))
+            _hand_groups(got, oo["observation"], "hand_block", pos, vel, quat)     # all 61 entries
             assert float(r[i]) == float(orr) and float(info["is_success"][i]) == float(oi["is_success"])
-    errs = np.array(errs)
-    print(f"Hand: median {np.median(errs):.2e} p90 {np.quantile(errs, 0.9):.2e} max {errs.max():.2e}")
-    assert np.median(errs) < 2e-4 and np.mean(errs < 2e-3) >= 0.9 and errs.max() < 0.1
+            assert not bool(te[i]) and not bool(tr[i])
+    for g, e in (("pos", pos), ("vel", vel), ("quat", quat)):
+        check_envelope(f"hand_block/{g}", e, *ENVELOPE[f"hand_block/{g}"])
     env.close()
 
 
@@ -387,33 +458,27 @@ def test_hand_touch_sensors_parity():
     assert env.single_observation_space["observation"].shape == (153,)
     obs, _ = env.reset(seed=60)
     oracles = [OracleHandBlockEnv(model=model, touch_get_obs="sensordata") for _ in range(n)]
-    lay, m = env.backend.layout, model
     rng = np.random.default_rng(6)
-    agree, total = 0, 0
     for i, o in enumerate(oracles):
         oo, _ = o.reset(seed=60 + i)
         t, ot = obs["observation"][i, 61:].double().cpu().numpy(), oo["observation"][61:]
         assert ot.sum() > 0.3 and abs(t.sum() - ot.sum()) < 0.1 * ot.sum()   # the block's weight is carried by the hand
+    terr, fired_same, fired_total = [], 0, 0
     for step in range(6):
-        rec = np.zeros((n, lay["stride"]))
-        for i, o in enumerate(oracles):
-            s = o.sim
-            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
-            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
-            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
-            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
-            rec[i, lay["goal"]:lay["goal"] + 7] = o.goal
-        env.set_state(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        env.set_state(inject_records(env, oracles, lambda i, o, rec, lay: rec.__setitem__(slice(lay["goal"], lay["goal"] + 7), o.goal)))
         a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
         o, r, te, tr, info = env.step(torch.as_tensor(a))
         for i, orc in enumerate(oracles):
             oo, *_ = orc.step(a[i].astype(np.float64))
             t, ot = o["observation"][i, 61:].double().cpu().numpy(), oo["observation"][61:]
             assert np.isfinite(t).all() and (t >= 0).all()
-            total += 1
-            agree += int(np.abs(t - ot).max() <= 0.05 * max(1.0, ot.max()))
-    print(f"Hand touch: {agree}/{total} env-steps with all 92 sensors within 5 % of the force scale")
-    assert agree >= 0.8 * total
+            # error of the 92 sensor values relative to the force scale of the sample (N; >= 1 N so that idle hands count too)
+            terr.append(np.abs(t - ot).max() / max(1.0, ot.max()))
+            fired_same += int(((t > 1e-3) == (ot > 1e-3)).sum())
+            fired_total += t.size
+    check_envelope("hand_touch", terr, *ENVELOPE["hand_touch"])
+    print(f"Hand touch: {fired_same}/{fired_total} sensor readings agree on firing")
+    assert fired_same >= 0.98 * fired_total
     env.close()
 
 
@@ -433,28 +498,18 @@ def test_hand_reach_parity():
         oo, _ = o.reset(seed=70 + i)
         assert np.abs(obs["desired_goal"][i].double().cpu().numpy() - oo["desired_goal"]).max() < 2e-6
         assert np.abs(obs["observation"][i].double().cpu().numpy() - oo["observation"]).max() < 2e-6
-    lay, m = env.backend.layout, model
     rng = np.random.default_rng(7)
     errs = []
     for step in range(8):
-        rec = np.zeros((n, lay["stride"]))
-        for i, o in enumerate(oracles):
-            s = o.sim
-            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
-            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
-            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
-            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
-            rec[i, lay["goal"]:lay["goal"] + 15] = o.goal
-        env.set_state(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        env.set_state(inject_records(env, oracles, lambda i, o, rec, lay: rec.__setitem__(slice(lay["goal"], lay["goal"] + 15), o.goal)))
         a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
         o, r, te, tr, info = env.step(torch.as_tensor(a))
         for i, orc in enumerate(oracles):
             oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
-            errs.append(np.abs(o["achieved_goal"][i].double().cpu().numpy() - oo["achieved_goal"]).max())
+            errs.append(np.abs(o["achieved_goal"][i].double().cpu().numpy() - oo["achieved_goal"]).max())   # the 5 fingertip positions
             assert float(r[i]) == float(orr) and float(info["is_success"][i]) == float(oi["is_success"])
-    errs = np.array(errs)
-    print(f"HandReach: median {np.median(errs):.2e} max {errs.max():.2e}")
-    assert np.median(errs) < 2e-5 and errs.max() < 2e-4
+            assert not bool(te[i]) and not bool(tr[i])
+    check_envelope("hand_reach", errs, *ENVELOPE["hand_reach"])
     env.close()
 
 
@@ -492,9 +547,9 @@ def test_fetch_slide_parity():
             d = np.linalg.norm(oo["achieved_goal"] - oo["desired_goal"])
             if abs(d - 0.05) > 5e-3:
                 assert float(r[i]) == float(orr)
-    errs = np.array(errs)
-    print(f"FetchSlide: median {np.median(errs):.2e} max {errs.max():.2e}")
-    assert np.median(errs) < OBS_TOL and np.mean(errs < 1e-3) >= 0.9 and errs.max() < 0.05
+    # excluded, with the reason: entries 11:14 (puck Euler angles) and 17:20 (puck angular velocity) -- a flat cylinder rocks on the
+    # single contact point the portal-refinement collider returns, which is chaotic between fp32 and fp64 (DESIGN.md deviation 11)
+    check_envelope("fetch_slide", errs, *ENVELOPE["fetch_slide"])
     # batch properties at the bench size: no capacity overflow, pucks stay on the table under random actions
     env.close()
     env = _mk("FetchSlide", 4096, rng_mode="torch")
@@ -527,30 +582,82 @@ def test_hand_egg_parity():
         assert np.abs(g[3:] - oo["desired_goal"][3:]).max() < 2e-6
         a = obs["achieved_goal"][i].double().cpu().numpy()
         assert a[2] > 0.04 and np.abs(a[:3] - oo["achieved_goal"][:3]).max() < 5e-3
-    lay, m = env.backend.layout, model
     rng = np.random.default_rng(4)
-    errs = []
+    pos, vel, quat = [], [], []
     for step in range(8):
-        rec = np.zeros((n, lay["stride"]))
-        for i, o in enumerate(oracles):
-            s = o.sim
-            rec[i, lay["qpos"]:lay["qpos"] + m.nq] = s.qpos
-            rec[i, lay["qvel"]:lay["qvel"] + m.nv] = s.qvel
-            rec[i, lay["warm"]:lay["warm"] + m.nv] = s.qacc_warmstart
-            rec[i, lay["ctrl"]:lay["ctrl"] + m.nu] = s.ctrl
-            rec[i, lay["goal"]:lay["goal"] + 7] = o.goal
-        env.set_state(torch.as_tensor(rec, dtype=torch.float32, device="cuda"))
+        env.set_state(inject_records(env, oracles, lambda i, o, rec, lay: rec.__setitem__(slice(lay["goal"], lay["goal"] + 7), o.goal)))
         a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
         o, r, te, tr, info = env.step(torch.as_tensor(a))
         for i, orc in enumerate(oracles):
             oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
             got = o["observation"][i].double().cpu().numpy()
-            errs.append(max(np.abs(got[:24] - oo["observation"][:24]).max(), np.abs(got[54:57] - oo["observation"][54:57]).max()))
+            _hand_groups(got, oo["observation"], "hand_egg", pos, vel, quat)
             assert float(r[i]) == float(orr)
-    errs = np.array(errs)
-    print(f"HandEgg: median {np.median(errs):.2e} max {errs.max():.2e}")
-    assert np.median(errs) < 2e-4 and np.mean(errs < 2e-3) >= 0.9
+    for g, e in (("pos", pos), ("vel", vel), ("quat", quat)):
+        check_envelope(f"hand_egg/{g}", e, *ENVELOPE[f"hand_egg/{g}"])
     env.close()
+
+
+def test_hand_pen_parity():
+    """HandManipulatePenRotate-v1 (envs/shadow_dexterous_hand/manipulate_pen.py:216-235): capsule object, no initial rotation
+    randomisation, 5 cm position threshold, and `ignore_z_target_rotation` in the goal distance (manipulate.py:88-115: both
+    quaternions to Euler angles, the achieved z angle replaced by the goal's, back to a quaternion) -- on the GPU through the
+    C-ABI: reset draws, env-steps from injected oracle states (all 61 observation entries), sparse rewards exact, and the dense
+    reward (which IS the ignore-z distance) against the oracle on the stepped states and on random pose pairs."""
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.hand_env import OracleHandBlockEnv
+
+    n = 4
+    model = load_model("hand_pen")
+    kw = dict(model=model, target_position="ignore", target_rotation="xyz", randomize_initial_rotation=False, ignore_z_target_rotation=True,
+              distance_threshold=0.05)
+    env = _mk_hand("HandManipulatePenRotate", n, rng_mode="numpy")
+    assert env.ignore_z_target_rotation and env.distance_threshold == 0.05 and not env.randomize_initial_rotation
+    obs, _ = env.reset(seed=21)
+    oracles = [OracleHandBlockEnv(**kw) for _ in range(n)]
+    for i, o in enumerate(oracles):
+        oo, _ = o.reset(seed=21 + i)
+        assert np.abs(obs["desired_goal"][i, 3:].double().cpu().numpy() - oo["desired_goal"][3:]).max() < 2e-6
+        a = obs["achieved_goal"][i].double().cpu().numpy()
+        assert a[2] > 0.04 and np.abs(a[:3] - oo["achieved_goal"][:3]).max() < 5e-3
+    rng = np.random.default_rng(5)
+    pos, vel, quat = [], [], []
+    for step in range(8):
+        env.set_state(inject_records(env, oracles, lambda i, o, rec, lay: rec.__setitem__(slice(lay["goal"], lay["goal"] + 7), o.goal)))
+        a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
+        o, r, te, tr, info = env.step(torch.as_tensor(a))
+        for i, orc in enumerate(oracles):
+            oo, orr, _, _, oi = orc.step(a[i].astype(np.float64))
+            got = o["observation"][i].double().cpu().numpy()
+            assert np.isfinite(got).all()
+            _hand_groups(got, oo["observation"], "hand_pen", pos, vel, quat)
+            assert float(r[i]) == float(orr) and float(info["is_success"][i]) == float(oi["is_success"])
+            assert not bool(te[i]) and not bool(tr[i])
+    for g, e in (("pos", pos), ("vel", vel), ("quat", quat)):
+        check_envelope(f"hand_pen/{g}", e, *ENVELOPE[f"hand_pen/{g}"])
+    env.close()
+    # the ignore-z distance itself: dense reward of the step kernel and of b200sim_compute_reward against the oracle
+    envd = _mk_hand("HandManipulatePenRotateDense", n, rng_mode="numpy")
+    orcd = [OracleHandBlockEnv(reward_type="dense", **kw) for _ in range(n)]
+    envd.reset(seed=21)
+    for i, o in enumerate(orcd):
+        o.reset(seed=21 + i)
+    for step in range(3):
+        envd.set_state(inject_records(envd, orcd, lambda i, o, rec, lay: rec.__setitem__(slice(lay["goal"], lay["goal"] + 7), o.goal)))
+        a = rng.uniform(-1, 1, (n, 20)).astype(np.float32)
+        o, r, *_ = envd.step(torch.as_tensor(a))
+        for i, orc in enumerate(orcd):
+            _, orr, *_ = orc.step(a[i].astype(np.float64))
+            assert abs(float(r[i]) - float(orr)) < 5e-3 and float(orr) < -0.05    # d_rot of a few tenths of a radian, to 5e-3
+    ag, dg = rng.normal(size=(4096, 7)), rng.normal(size=(4096, 7))
+    ag[:, 3:] /= np.linalg.norm(ag[:, 3:], axis=1, keepdims=True)
+    dg[:, 3:] /= np.linalg.norm(dg[:, 3:], axis=1, keepdims=True)
+    want = orcd[0].compute_reward(ag, dg, {})
+    got = envd.compute_reward(torch.as_tensor(ag, dtype=torch.float32), torch.as_tensor(dg, dtype=torch.float32), {}).double().cpu().numpy()
+    # acos near |w| = 1 and the Euler round trip near gimbal lock lose digits in fp32: 99 % of random pairs to 2e-3, all to 5e-2
+    e = np.abs(got - want)
+    assert np.quantile(e, 0.99) < 2e-3 and e.max() < 5e-2, (np.quantile(e, 0.99), e.max())
+    envd.close()
 
 
 # ------------------------------------------------------------------------------------------------ Adroit hammer (config 5a)
@@ -593,9 +700,8 @@ def test_adroit_hammer_parity():
             assert np.isfinite(got).all()
             errs.append(np.abs(got - oo).max())
             assert abs(float(r[i]) - orr) < 1e-3 and bool(info["success"][i]) == bool(oi["success"])
-    errs = np.array(errs)
-    print(f"AdroitHammer: median {np.median(errs):.2e} max {errs.max():.2e}")
-    assert np.median(errs) < 2e-5 and np.mean(errs < 2e-4) >= 0.9 and errs.max() < 0.05
+            assert not bool(te[i]) and not bool(tr[i])      # adroit_hammer.py:296-301: never terminated, TimeLimit 200 not reached
+    check_envelope("adroit_hammer", errs, *ENVELOPE["adroit_hammer"])     # all 46 observation entries
     env.close()
     # bench-size batch: finite, no capacity overflow, board heights inside the sampled range
     env = pkg.make_vec("AdroitHandHammer-v2", num_envs=2048, device="cuda:0", rng_mode="torch")
@@ -652,9 +758,8 @@ def test_adroit_relocate_parity():
             assert np.isfinite(got).all()
             errs.append(np.abs(got - oo).max())
             assert abs(float(r[i]) - orr) < 1e-3 and bool(info["success"][i]) == bool(oi["success"])
-    errs = np.array(errs)
-    print(f"AdroitRelocate: median {np.median(errs):.2e} max {errs.max():.2e}")
-    assert np.median(errs) < 2e-5 and np.mean(errs < 2e-4) >= 0.9 and errs.max() < 0.05
+            assert not bool(te[i]) and not bool(tr[i])      # adroit_hammer.py:296-301: never terminated, TimeLimit 200 not reached
+    check_envelope("adroit_relocate", errs, *ENVELOPE["adroit_relocate"])   # all 39 observation entries
     env.close()
     # bench-size batch under random actions: the arm presses the whole hand onto the table in some envs, which exceeds the
     # 13 geom-pair groups kept per env -- flagged in the info word, never a stale contact record (regression: counted but
@@ -691,7 +796,7 @@ def test_adroit_pen_parity():
         assert np.abs(obs[i].double().cpu().numpy() - oo).max() < 5e-6
     lay = env.backend.layout
     rng = np.random.default_rng(2)
-    errs = []
+    errs, angvel = [], []
     for step in range(10):
         rec = np.zeros((n, lay["stride"]))
         for i, o in enumerate(oracles):
@@ -711,10 +816,12 @@ def test_adroit_pen_parity():
             assert np.isfinite(got).all()
             d = np.abs(got - oo)
             errs.append(np.delete(d, [30, 31, 32]).max())
-            assert d.max() < 0.05 and abs(float(r[i]) - orr) < 2e-3
-    errs = np.array(errs)
-    print(f"AdroitPen: median {np.median(errs):.2e} max {errs.max():.2e}")
-    assert np.median(errs) < 2e-4 and np.mean(errs < 1e-3) >= 0.9
+            angvel.append(d[30:33].max())
+            assert abs(float(r[i]) - orr) < 2e-3 and not bool(te[i]) and not bool(tr[i])
+    # all 45 entries, in two groups: the pen's angular velocity (entries 30:33, raw rad/s) is torqued by the 1e-4 rad difference of
+    # the fp32 / fp64 portal normals on a 15 g pen (DESIGN.md deviation 11) and gets its own, wider envelope
+    check_envelope("adroit_pen/pos", errs, *ENVELOPE["adroit_pen/pos"])
+    check_envelope("adroit_pen/angvel", angvel, *ENVELOPE["adroit_pen/angvel"])
     env.close()
 
 
@@ -756,7 +863,29 @@ def test_adroit_door_parity():
             assert np.isfinite(got).all()
             errs.append(np.abs(got - oo).max())
             assert abs(float(r[i]) - orr) < 2e-3 and bool(info["success"][i]) == bool(oi["success"])
-    errs = np.array(errs)
-    print(f"AdroitDoor: median {np.median(errs):.2e} max {errs.max():.2e}")
-    assert np.median(errs) < 2e-5 and np.mean(errs < 1e-3) >= 0.9 and errs.max() < 0.05
+    check_envelope("adroit_door", errs, *ENVELOPE["adroit_door"])       # all 39 observation entries
+    env.close()
+
+
+def test_packed_row_and_kernel_flags_on_gpu():
+    """include/b200sim.h b200sim_set_packed / b200sim_set_time_limit through the C-ABI: the classic outputs are views of one packed
+    row per env, terminated / truncated come from the step kernel, the library's step counters follow resets, one D2H copy of the
+    packed buffer carries everything step() returned."""
+    n = 300
+    env = _mk("FetchPickAndPlace", n, rng_mode="torch", autoreset_mode="same_step", max_episode_steps=4)
+    env.reset(seed=2)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    host = torch.empty((n, env.backend.packed_w), dtype=torch.float32).pin_memory()
+    for k in range(9):
+        a = torch.rand((n, 4), generator=g, device="cuda") * 2 - 1
+        o, r, te, tr, info = env.step(a)
+        host.copy_(env._last["packed"], non_blocking=True)
+        torch.cuda.synchronize()
+        assert torch.equal(host[:, :25], o["observation"].cpu()) and torch.equal(host[:, 25:28], o["achieved_goal"].cpu())
+        assert torch.equal(host[:, 31], r.cpu()) and torch.equal(host[:, 32], info["is_success"].cpu())
+        assert torch.equal(host[:, 33] > 0, te.cpu()) and torch.equal(host[:, 34] > 0, tr.cpu())
+        assert bool(tr.all()) == (k % 4 == 3) and not bool(te.any())
+        assert int(env._elapsed.max()) == (k + 1) % 4
+        assert int((info["solver_info"] & 0xffff).max()) >= 1      # Newton iterations were spent
+    assert env.solver_overflow_count >= 0
     env.close()

@@ -444,3 +444,24 @@ def test_adroit_door_env_matches_oracle():
         assert abs(float(r[0]) - orr) < 2e-4 and bool(info["success"][0]) == bool(oi["success"])
     assert env.set_env_state(env.get_env_state()).shape == (1, 39)
     assert {"AdroitHandDoor-v2", "AdroitHandDoorSparse-v2", "AdroitHandPenSparse-v2"} <= set(pkg.ENV_IDS)
+
+
+def test_adroit_reset_honours_initial_state_dict():
+    """adroit_hammer.py:359-370: reset(options={"initial_state_dict": ...}) = ordinary reset, then set_env_state."""
+    from gymnasium_robotics_b200.adroit import ADROIT_REF_POINT
+
+    class AdroitHostBackend(HostSimBackend):
+        REF = ADROIT_REF_POINT
+
+    env = pkg.make_vec("AdroitHandHammer-v2", num_envs=2, backend_factory=AdroitHostBackend, rng_mode="numpy")
+    obs0, _ = env.reset(seed=3)
+    sd = env.get_env_state()
+    q = sd["qpos"][0].clone()
+    q[2] += 0.1                                   # bend one arm joint
+    want = dict(qpos=q.numpy(), qvel=np.zeros(env.model.nv), board_pos=np.array([0.05, 0.0, 0.2]))
+    obs, _ = env.reset(seed=3, options={"initial_state_dict": want})
+    sd2 = env.get_env_state()
+    assert torch.allclose(sd2["qpos"], torch.as_tensor(want["qpos"], dtype=torch.float32).expand(2, -1))
+    assert torch.allclose(sd2["board_pos"], torch.as_tensor(want["board_pos"], dtype=torch.float32).expand(2, -1))
+    assert float((obs - obs0).abs().max()) > 1e-3 and abs(float(obs[0, 2]) - float(q[2])) < 1e-6
+    env.close()

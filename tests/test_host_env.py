@@ -236,3 +236,34 @@ def test_torch_mode_rejection_sampling_on_fetch_slide():
     g0 = env.initial_gripper_xpos
     d = torch.linalg.norm(obj - g0[:2], dim=1)
     assert float(d.min()) >= 0.1 and float((obj - g0[:2]).abs().max()) <= 0.1 + 1e-6
+
+
+def test_packed_row_flags_and_solver_info():
+    """The step's results live in ONE packed row per env (obs | achieved | desired | reward | success | terminated | truncated,
+    include/b200sim.h b200sim_set_packed) that the classic outputs are views of; TimeLimit / terminated / truncated come from
+    the step itself (b200sim_set_time_limit) in every autoreset mode; info carries the solver's per-env info word."""
+    env = mk("FetchPickAndPlace", 2, rng_mode="numpy", autoreset_mode="same_step", max_episode_steps=3)
+    env.reset(seed=5)
+    for k in range(3):
+        o, r, te, tr, info = env.step(np.full((2, 4), 0.1, dtype=np.float32))
+        out = env._last
+        p, no = out["packed"], 25
+        assert p.shape[1] % 4 == 0 and p.shape[1] >= no + 6 + 4
+        # final_obs holds the pre-reset observation on the truncation step; the packed row holds what step() returned
+        assert torch.equal(p[:, :no], o["observation"]) and torch.equal(p[:, no:no + 3], o["achieved_goal"]) and torch.equal(p[:, no + 3:no + 6], o["desired_goal"])
+        assert torch.equal(p[:, no + 6], r) and torch.equal(p[:, no + 8] > 0, te) and torch.equal(p[:, no + 9] > 0, tr)
+        assert bool(tr.all()) == (k == 2) and not bool(te.any())
+        assert info["solver_info"].shape == (2,) and int((info["solver_info"] & 0xffff).min()) >= 0
+    assert "final_obs" in info and int(env._elapsed.max()) == 0   # same-step autoreset zeroed the library's step counters
+    assert env.solver_overflow_count == 0
+    env.close()
+    # NEXT_STEP: the call after a truncation resets instead of stepping and reports neutral results for those envs
+    env = mk("FetchReach", 2, rng_mode="numpy", autoreset_mode="next_step", max_episode_steps=2)
+    env.reset(seed=5)
+    env.step(np.zeros((2, 4), dtype=np.float32))
+    _, _, _, tr, _ = env.step(np.zeros((2, 4), dtype=np.float32))
+    assert bool(tr.all())
+    o, r, te, tr, info = env.step(np.ones((2, 4), dtype=np.float32))
+    assert not bool(tr.any()) and float(r.abs().max()) == 0.0 and float(info["is_success"].max()) == 0.0 and int(env._elapsed.max()) == 0
+    assert float(env._last["packed"][:, 10 + 6:10 + 10].abs().max()) == 0.0
+    env.close()

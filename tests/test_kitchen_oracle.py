@@ -76,13 +76,15 @@ def test_task_completion_bookkeeping(model):
         OracleKitchenEnv(model, tasks_to_complete=["dishwasher"])
 
 
-def test_cuda_path_keeps_the_kitchen_opt_in_and_never_falls_back():
-    """The bring-up build is opt-in until it has passed on a GPU; opted in without a CUDA device it fails loudly."""
+def test_cuda_path_never_falls_back_for_the_kitchen():
+    """FrankaKitchen-v1 is a regular id of the CUDA path (GPU-validated in round 2); without a CUDA device it fails loudly
+    instead of falling back to the oracle, and the reference's registry holds no other kitchen id."""
     import gymnasium_robotics_b200 as pkg
-
-    with pytest.raises(NotImplementedError, match="FrankaKitchen"):
-        pkg.make_vec("FrankaKitchen-v1", num_envs=2)
     import torch
+
+    assert "FrankaKitchen-v1" in pkg.ENV_IDS
+    with pytest.raises(KeyError):
+        pkg.make_vec("FrankaKitchen-v2", num_envs=2)
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
-            pkg.make_vec("FrankaKitchen-v1", num_envs=2, experimental=True)
+            pkg.make_vec("FrankaKitchen-v1", num_envs=2)

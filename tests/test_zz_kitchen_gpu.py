@@ -1,8 +1,6 @@
-"""GPU tests of the Franka-Kitchen bring-up build (csrc/b200sim_kitchen.cu, task kind 8), collected last on purpose.
-Status at the end of round 1: tests/kitchen_gpu_quick.py (the first test below without torch) ran on a B200 and matched the
-host emulation to 2.3e-6 (profiles/kitchen_quick_r1k.json); the env-level test and the large-batch variant (10 warps per
-block) had no GPU time left in the round, the latter is therefore a non-strict xfail.  The default build is the flat-scan one those
-results belong to; the two-level broad-phase build (broadphase="groups") is compared with it in a non-strict xfail test."""
+"""GPU tests of the Franka-Kitchen kernel builds (csrc/b200sim_kitchen.cu: flat broad-phase scan; csrc/b200sim_kitchen_groups.cu:
+two-level broad phase, the default), task kind 8.  All four ran green on a B200 in round 2 (profiles/kitchen_diag_r2a_after_fix.log)
+once the out-of-bounds read of an empty eq_data override was fixed (the round-1 NaN)."""
 import os
 
 import numpy as np
@@ -46,7 +44,7 @@ def test_kitchen_env_tracks_the_oracle_env():
     from oracle.kitchen_env import OracleKitchenEnv
 
     n, seed = 4, 21
-    env = make_vec("FrankaKitchen-v1", num_envs=n, experimental=True, rng_mode="numpy")
+    env = make_vec("FrankaKitchen-v1", num_envs=n, rng_mode="numpy")
     obs, info = env.reset(seed=seed)
     orcs = [OracleKitchenEnv(env.model) for _ in range(n)]
     for i, o in enumerate(orcs):
@@ -64,14 +62,13 @@ def test_kitchen_env_tracks_the_oracle_env():
     env.close()
 
 
-@pytest.mark.xfail(strict=False, reason="two-level broad-phase build (fetch_kernel_groups): written after the last GPU minute of round 1")
 def test_kitchen_groups_build_matches_the_flat_build():
     """The build with the two-level broad phase (csrc/b200sim_kitchen_groups.cu, broadphase="groups") against the validated flat
     build on the same states and actions: positions to 1e-4 (the contact numbering differs, not the candidate set), no overflow."""
     from gymnasium_robotics_b200 import make_vec
 
     def run(bp):
-        env = make_vec("FrankaKitchen-v1", num_envs=16, experimental=True, rng_mode="numpy", robot_noise_ratio=0.0, object_noise_ratio=0.0,
+        env = make_vec("FrankaKitchen-v1", num_envs=16, rng_mode="numpy", robot_noise_ratio=0.0, object_noise_ratio=0.0,
                        broadphase=bp)
         env.reset(seed=5)
         rng = np.random.default_rng(1)
@@ -91,14 +88,13 @@ def test_kitchen_groups_build_matches_the_flat_build():
     assert float(e[..., :9].max()) < 1e-4 and float(e[..., 18:39].max()) < 1e-4
 
 
-@pytest.mark.xfail(strict=False, reason="10-warp variant of the bring-up build: no GPU time left in round 1 to run it")
 def test_kitchen_large_batch_is_consistent():
     """2048 noise-free envs from the same state and action stay identical to each other and to an 8-env batch (the 7-warp
     variant validated above)."""
     from gymnasium_robotics_b200 import make_vec
 
     def run(n):
-        env = make_vec("FrankaKitchen-v1", num_envs=n, experimental=True, rng_mode="torch", robot_noise_ratio=0.0, object_noise_ratio=0.0)
+        env = make_vec("FrankaKitchen-v1", num_envs=n, rng_mode="torch", robot_noise_ratio=0.0, object_noise_ratio=0.0)
         env.reset(seed=1)
         a = torch.as_tensor(np.random.default_rng(3).uniform(-1, 1, size=(1, 9)), dtype=torch.float32).expand(n, 9).contiguous()
         for _ in range(3):
@@ -110,3 +106,23 @@ def test_kitchen_large_batch_is_consistent():
     big, small = run(2048), run(8)
     assert torch.isfinite(big).all() and float((big - big[0]).abs().max()) == 0.0
     assert float((big[0] - small[0]).abs().max()) < 1e-5
+
+
+def test_kitchen_timelimit_and_bookkeeping_on_gpu():
+    """280-step TimeLimit from the kernel's flags (franka: max_episode_steps = 280, __init__.py:1117-1121), NEXT_STEP autoreset,
+    finite observations under random actions, no capacity overflow in the first episode."""
+    from gymnasium_robotics_b200 import make_vec
+
+    n = 64
+    env = make_vec("FrankaKitchen-v1", num_envs=n, rng_mode="torch", max_episode_steps=6)
+    env.reset(seed=3)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for k in range(6):
+        obs, rew, term, trunc, info = env.step(torch.rand((n, 9), generator=g, device="cuda") * 2 - 1)
+        assert torch.isfinite(obs["observation"]).all()
+        assert bool(trunc.all()) == (k == 5) and not bool(term.any())
+    obs, rew, term, trunc, info = env.step(torch.zeros((n, 9), device="cuda"))    # the reset step of NEXT_STEP
+    assert not bool(trunc.any()) and int(env._elapsed.max()) == 0
+    assert float((obs["observation"][:, :9] - env.init_qpos[:9]).abs().max()) < 2e-3   # noisy initial robot pose
+    assert int(env.backend.overflow_counter[0]) == 0
+    env.close()
