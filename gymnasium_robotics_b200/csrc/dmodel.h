@@ -19,6 +19,11 @@
 #define DM_NDOFROW_MIN 8
 #define DM_NCAND_MAX 96   // broad-phase candidate slots (one byte each: pair index < 256)
 #define DM_NWELD_MAX 1
+// narrow-phase result slot of one lane in shared memory (sim_core.cuh `ContactOut`): 29 result words + the clipping buffers of
+// the box-box routine (8 x 2 + 8 x 3), padded to an even count.  The slots overlay scratch that is dead while the narrow phase
+// runs: region A = the body-force / dof-term buffers of the smooth-force stage (b6 .. d6), region B = the contact records that
+// the narrow phase itself is about to fill (the lanes park their results in registers before the records are written).
+#define DM_CSLOT_WORDS 70
 
 // (name, words-per-element, kind) ; kind selects the element count.  HOT arrays are staged into shared memory by every
 // block; COLD arrays (per-pair contact parameters, read only when a contact is created) stay in global memory.
@@ -126,6 +131,7 @@ struct DMHead {
   int nten, nfric, ncand_max, nsensor;   // nsensor: touch sensors (site volume + body)   // limited fixed tendons; nfric = nv when any dof has frictionloss, else 0
   int grid_len, grid_wid, ngridw, any_round_pair;   // maze wall grid (0 x 0 when the model has none)
   int nmjb;        // MJCF bodies before fusing (rows of per-body outputs such as cfrc_ext)
+  int s_cslotA, ncslotA, s_cslotB, ncslotB;   // narrow-phase lane slots (DM_CSLOT_WORDS each): two scratch regions, ncslotA + ncslotB <= 32
   float grid_scale, grid_top, grid_xc, grid_yc;  // cell size, wall top height, map centre offsets
   float timestep, gravity[3], tolerance, impratio, meaninertia, ls_tolerance, ref[3];
 #define X(name, w, kind) int o_##name;
@@ -324,6 +330,12 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     h.s_surv = endA; endA += DM_NSURV_MAX + 1;   // surviving groups: (first pair | running pair count << 16) + one end marker
 #endif
     so = endA > endB ? endA : endB;
+    h.s_cslotA = h.s_b6; h.ncslotA = (h.s_d6 + 6 * nv - h.s_b6) / DM_CSLOT_WORDS;
+    h.s_cslotB = h.s_con; h.ncslotB = (ncon_max * CON_WORDS) / DM_CSLOT_WORDS;
+
+    if (h.ncslotA > 32) h.ncslotA = 32;
+    if (h.ncslotA + h.ncslotB > 32) h.ncslotB = 32 - h.ncslotA;
+    if (h.ncslotA < 1) { err = "no scratch for a narrow-phase lane slot"; return -1; }
   }
   h.scr_words = (so + 3) & ~3;
   (void)nq;

@@ -87,7 +87,9 @@ HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float
                       float* reward, float* success) {
   pass_V(c, SF(qvel), SF(cvel));  // site velocities: Jacobian of the last forward pass times the current qvel
   if (c.lane == 0) {
-    float grip[3], gvel[3], o[32];
+    // (written straight to the observation row: a local staging array indexed by a running count would be local memory)
+    float grip[3], gvel[3];
+    float* o = obs;
     int n = 0;
     site_pose(c, t.grip_site, grip, nullptr);
     site_vel(c, t.grip_site, grip, gvel, nullptr);
@@ -118,7 +120,6 @@ HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float
     } else { o[n++] = gstate[0]; o[n++] = gstate[1]; }
     for (int k = 0; k < 3; k++) o[n++] = gvel[k];
     o[n++] = gv[0]; o[n++] = gv[1];
-    for (int k = 0; k < n; k++) obs[k] = o[k];
     float d2 = 0;
     for (int k = 0; k < 3; k++) { achieved[k] = ag[k]; desired[k] = goal[k]; float e = ag[k] - goal[k]; d2 += e * e; }
     float d = sqrtf(d2);
@@ -562,11 +563,12 @@ HD void fetch_env_step(const Ctx& c, const FetchTask& t, bool active, int mode, 
   }
   int nsub = mode == MODE_STEP ? t.n_substeps : (mode == MODE_RAW ? nraw : 0);
   for (int s = 0; s < nsub; s++) {
-    forward<NVP>(c, active);
+    bool solved = false;
+    forward<NVP>(c, active, h->integrator == B200_INT_RK4 ? nullptr : &solved);
     TIC();
     ALIGN_AT(4); TOC(TM_BARRIER);
     if (h->integrator == B200_INT_RK4) rk4_substep<NVP>(c, active);
-    else if (active) euler_step<NVP>(c);
+    else if (active) euler_step<NVP>(c, solved);
     TOC(TM_INTEG);
   }
   // touch sensors read the contacts and forces of the last forward pass: a refresh (no sub-step) runs one first,

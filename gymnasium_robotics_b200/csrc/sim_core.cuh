@@ -31,8 +31,13 @@
 // block-wide alignment points: keep the warps of a block inside the same code window (instruction-cache locality)
 #ifdef B200_BLOCK_ALIGN
 // the alignment group is the whole block
+#ifdef B200_ALIGN_SYNCWARP
+#define ALIGN() do { __syncwarp(); __syncthreads(); } while (0)
+#define ALIGN_OR(p) (__syncwarp(), __syncthreads_or(p))
+#else
 #define ALIGN() __syncthreads()
 #define ALIGN_OR(p) __syncthreads_or(p)
+#endif
 #else
 #define ALIGN() do { } while (0)
 #define ALIGN_OR(p) (p)
@@ -61,6 +66,16 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #endif
 
+// Address-space hint for the narrow-phase lane slots.  Measured on a B200 (profiles/bisect_r2c.log): with the hint on the slot
+// reference inside collision() the kernel reads garbage addresses (compute-sanitizer: invalid __shared__ read in the NEXT broad
+// phase; the 32-lane host emulation under ASan / UBSan is clean, the same build without the hint is clean on the GPU) -- the
+// slot address is a per-lane select between two scratch regions and nvcc 12.9 mis-handles the assumption there.  collision()
+// therefore reaches its slot through generic loads / stores; the hint inside the callees is opt-in (-DB200_SLOT_ASSUME).
+#ifdef B200_SLOT_ASSUME
+#define ASSUME_SHARED_SLOT(p) ASSUME_SHARED_PTR(p)
+#else
+#define ASSUME_SHARED_SLOT(p) do { } while (0)
+#endif
 #define B200_MINVAL 1e-15f
 #define B200_MINIMP 0.0001f
 #define B200_MAXIMP 0.9999f
@@ -513,9 +528,10 @@ STAGE void smooth_forces(const Ctx c) {
 }
 
 // impedance and reference-acceleration constants of the soft-constraint model (used when rows are created)
-HDN float impedance(const float* solimp, float pos, float margin) {
-  float d0 = fminf(fmaxf(solimp[0], B200_MINIMP), B200_MAXIMP), d1 = fminf(fmaxf(solimp[1], B200_MINIMP), B200_MAXIMP);
-  float width = fmaxf(solimp[2], 0.f), mid = fminf(fmaxf(solimp[3], B200_MINIMP), B200_MAXIMP), power = fmaxf(solimp[4], 1.f);
+// (the five solimp numbers travel by value: a pointer to a caller's local array would force that array into local memory)
+HDN float impedance5(float s0, float s1, float s2, float s3, float s4, float pos, float margin) {
+  float d0 = fminf(fmaxf(s0, B200_MINIMP), B200_MAXIMP), d1 = fminf(fmaxf(s1, B200_MINIMP), B200_MAXIMP);
+  float width = fmaxf(s2, 0.f), mid = fminf(fmaxf(s3, B200_MINIMP), B200_MAXIMP), power = fmaxf(s4, 1.f);
   if (d0 == d1 || width <= B200_MINVAL) return 0.5f * (d0 + d1);
   float x = fabsf((pos - margin) / width);
   if (x >= 1) return d1;
@@ -525,6 +541,9 @@ HDN float impedance(const float* solimp, float pos, float margin) {
   else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
   else y = x <= mid ? powf(x, power) / powf(mid, power - 1) : 1 - powf(1 - x, power) / powf(1 - mid, power - 1);
   return d0 + y * (d1 - d0);
+}
+HD float impedance(const float* solimp, float pos, float margin) {
+  return impedance5(solimp[0], solimp[1], solimp[2], solimp[3], solimp[4], pos, margin);
 }
 // K and B of the reference acceleration (refsafe), given solref and dmax = solimp[1]
 HD void ref_kb(const Ctx& c, const float* solref, float dmax_in, float* K, float* B) {
@@ -538,7 +557,11 @@ HD void ref_kb(const Ctx& c, const float* solref, float dmax_in, float* K, float
 
 // ---------------------------------------------------------------------------------------------------------------
 // 5. collision (plane-box, box-box; same decision logic as oracle/oracle.c, fp32)
-struct ContactOut { float pos[4][3]; float nrm[4][3]; float dist[4]; int cnt; };
+// Result of one candidate pair (at most 4 contacts) plus the clipping buffers of collide_box_box.  The narrow phase keeps one
+// such slot per working lane in SHARED memory (dmodel.h DM_CSLOT_WORDS): a slot on the thread's stack would be local memory,
+// i.e. L2 / DRAM traffic (229 KB of shared memory per block leave no L1), which the round-1 profile showed as 350 MB per launch.
+struct ContactOut { float pos[4][3]; float nrm[4][3]; float dist[4]; int cnt; float poly[8][2]; float tmp[8][3]; };
+static_assert(sizeof(ContactOut) <= DM_CSLOT_WORDS * 4, "ContactOut must fit a narrow-phase lane slot");
 
 HD void geom_pose(const Ctx& c, int g, float* pos, float* mat) {
   int b = MI(geom_body)[g];
@@ -568,6 +591,7 @@ HD void collide_plane_box(const Ctx& c, int g1, int g2, float margin, ContactOut
 }
 
 HD int clip_poly(const float (*in)[2], int n, float (*out)[2], int axis, float bound, float sign) {
+  ASSUME_SHARED_SLOT(in); ASSUME_SHARED_SLOT(out);
   int k = 0;
   for (int i = 0; i < n; i++) {
     const float* a = in[i];
@@ -582,6 +606,8 @@ HD int clip_poly(const float (*in)[2], int n, float (*out)[2], int axis, float b
   return k;
 }
 
+#ifdef B200_BOXBOX_OLD
+// A/B variant: working arrays on the lane's stack, indexed face axes (the round-1 form)
 HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
   ASSUME_SHARED(c);
   float pa[3], Ra[9], pb[3], Rb[9];
@@ -715,6 +741,167 @@ HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& 
     for (int a = 0; a < 3; a++) o.pos[k][a] = pr[a] + au[a] * cd[0] + av[a] * cd[1] + nr[a] * (hr[ax] + 0.5f * cd[2]);
   }
 }
+#else
+HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
+  ASSUME_SHARED(c);
+  ASSUME_SHARED_SLOT(&o);
+  float pa[3], Ra[9], pb[3], Rb[9];
+  geom_pose(c, g1, pa, Ra); geom_pose(c, g2, pb, Rb);
+  const float* ha = MF(geom_size) + 3 * g1;
+  const float* hb = MF(geom_size) + 3 * g2;
+  o.cnt = 0;
+  float d[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]}, da[3], db[3];
+  mulmtv(da, Ra, d); mulmtv(db, Rb, d);
+  float C[3][3], Q[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) { C[i][j] = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j]; Q[i][j] = fabsf(C[i][j]); }
+  float best = -1e30f, bestsign = 1; int code = -1;
+  for (int i = 0; i < 3; i++) {
+    float sep = fabsf(da[i]) - (ha[i] + hb[0] * Q[i][0] + hb[1] * Q[i][1] + hb[2] * Q[i][2]);
+    if (sep > margin) return;
+    if (sep > best) { best = sep; code = i; bestsign = da[i] < 0 ? -1.f : 1.f; }
+  }
+  for (int j = 0; j < 3; j++) {
+    float sep = fabsf(db[j]) - (hb[j] + ha[0] * Q[0][j] + ha[1] * Q[1][j] + ha[2] * Q[2][j]);
+    if (sep > margin) return;
+    if (sep > best) { best = sep; code = 3 + j; bestsign = db[j] < 0 ? -1.f : 1.f; }
+  }
+  float ebest = -1e30f; int ecode = -1; float eaxis[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      float ai[3] = {Ra[i], Ra[3 + i], Ra[6 + i]}, bj[3] = {Rb[j], Rb[3 + j], Rb[6 + j]}, ax[3];
+      cross3(ax, ai, bj);
+      float l = sqrtf(dot3(ax, ax));
+      if (l < 1e-6f) continue;
+      float il = 1.0f / l;
+      ax[0] *= il; ax[1] *= il; ax[2] *= il;
+      float ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) {
+        float ak[3] = {Ra[k], Ra[3 + k], Ra[6 + k]}, bk[3] = {Rb[k], Rb[3 + k], Rb[6 + k]};
+        ra += ha[k] * fabsf(dot3(ak, ax)); rb += hb[k] * fabsf(dot3(bk, ax));
+      }
+      float dd = dot3(d, ax), sep = fabsf(dd) - (ra + rb);
+      if (sep > margin) return;
+      if (sep > ebest) { ebest = sep; ecode = 3 * i + j; float sg = dd < 0 ? -1.f : 1.f; eaxis[0] = sg * ax[0]; eaxis[1] = sg * ax[1]; eaxis[2] = sg * ax[2]; }
+    }
+  // (runtime-indexed columns / entries are picked with selects so that the matrices stay in registers: an array indexed by a
+  // runtime value, or reached through a pointer chosen at run time, would live in local memory)
+#define B200_SEL3(a0, a1, a2, i) ((i) == 0 ? (a0) : ((i) == 1 ? (a1) : (a2)))
+#define B200_COL(out, R, i) do { out[0] = B200_SEL3(R[0], R[1], R[2], i); out[1] = B200_SEL3(R[3], R[4], R[5], i); out[2] = B200_SEL3(R[6], R[7], R[8], i); } while (0)
+  if (ecode >= 0 && ebest > best + 1e-3f * (fabsf(best) + 1e-3f) && ebest > 0.95f * best && ebest > best) {
+    int i = ecode / 3, j = ecode - 3 * i;
+    float n[3] = {eaxis[0], eaxis[1], eaxis[2]};
+    float ea[3], eb[3];
+    B200_COL(ea, Ra, i); B200_COL(eb, Rb, j);
+    float PA[3] = {pa[0], pa[1], pa[2]}, PB[3] = {pb[0], pb[1], pb[2]};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float ak[3] = {Ra[k], Ra[3 + k], Ra[6 + k]}, bk[3] = {Rb[k], Rb[3 + k], Rb[6 + k]};
+      if (k != i) { float sg = (dot3(n, ak) > 0 ? 1.f : -1.f) * ha[k]; PA[0] += ak[0] * sg; PA[1] += ak[1] * sg; PA[2] += ak[2] * sg; }
+      if (k != j) { float sg = (dot3(n, bk) > 0 ? -1.f : 1.f) * hb[k]; PB[0] += bk[0] * sg; PB[1] += bk[1] * sg; PB[2] += bk[2] * sg; }
+    }
+    float w[3] = {PA[0] - PB[0], PA[1] - PB[1], PA[2] - PB[2]};
+    float b = dot3(ea, eb), dd = dot3(ea, w), e = dot3(eb, w), den = 1 - b * b;
+    float sp = den > 1e-12f ? (b * e - dd) / den : 0, tp = den > 1e-12f ? (e - b * dd) / den : 0;
+    sp = fminf(fmaxf(sp, -ha[i]), ha[i]); tp = fminf(fmaxf(tp, -hb[j]), hb[j]);
+    o.cnt = 1; o.dist[0] = ebest; o.nrm[0][0] = n[0]; o.nrm[0][1] = n[1]; o.nrm[0][2] = n[2];
+    for (int k = 0; k < 3; k++) o.pos[0][k] = 0.5f * (PA[k] + ea[k] * sp + PB[k] + eb[k] * tp);
+    return;
+  }
+  // reference box (owner of the separating face) and incident box, copied with selects
+  const bool flipb = code >= 3;
+  const int ax = flipb ? code - 3 : code, flip = flipb ? 1 : 0;
+  const float sgn = flipb ? -bestsign : bestsign;
+  float pr[3], pi[3], Rr[9], Ri[9];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { pr[k] = flipb ? pb[k] : pa[k]; pi[k] = flipb ? pa[k] : pb[k]; }
+#pragma unroll
+  for (int k = 0; k < 9; k++) { Rr[k] = flipb ? Rb[k] : Ra[k]; Ri[k] = flipb ? Ra[k] : Rb[k]; }
+  const float* hr = flipb ? hb : ha;   // half sizes: shared-memory tables, runtime indices are fine there
+  const float* hi = flipb ? ha : hb;
+  float nr[3];
+  B200_COL(nr, Rr, ax);
+  nr[0] *= sgn; nr[1] *= sgn; nr[2] *= sgn;
+  float nloc[3];
+  mulmtv(nloc, Ri, nr);
+  int iax = 0; float bestd = -1;
+#pragma unroll
+  for (int k = 0; k < 3; k++) if (fabsf(nloc[k]) > bestd) { bestd = fabsf(nloc[k]); iax = k; }
+  float isgn = B200_SEL3(nloc[0], nloc[1], nloc[2], iax) > 0 ? -1.f : 1.f;
+  int u = (iax + 1) % 3, v = (iax + 2) % 3, ru = (ax + 1) % 3, rv = (ax + 2) % 3;
+  float au[3], av[3], iu[3], iv[3], ia[3];
+  B200_COL(au, Rr, ru); B200_COL(av, Rr, rv); B200_COL(iu, Ri, u); B200_COL(iv, Ri, v); B200_COL(ia, Ri, iax);
+  const float hia = hi[iax] * isgn, hiu = hi[u], hiv = hi[v], hrax = hr[ax];
+  float fc[3] = {pi[0] + ia[0] * hia, pi[1] + ia[1] * hia, pi[2] + ia[2] * hia};
+  float (*poly)[2] = o.poly;
+  float (*tmp)[2] = (float (*)[2])o.tmp;
+  float zc[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float su = (k == 0 || k == 3) ? 1.f : -1.f, sv = (k < 2) ? 1.f : -1.f;
+    float rel[3];
+    for (int a = 0; a < 3; a++) rel[a] = fc[a] + iu[a] * su * hiu + iv[a] * sv * hiv - pr[a];
+    poly[k][0] = dot3(rel, au); poly[k][1] = dot3(rel, av);
+    zc[k] = dot3(rel, nr) - hrax;
+  }
+  float h0, hx, hy;
+  {
+    float x0 = poly[0][0], y0 = poly[0][1], x1 = poly[1][0], y1 = poly[1][1], x3 = poly[3][0], y3 = poly[3][1];
+    float z0 = zc[0], z1 = zc[1], z3 = zc[3];
+    float det = (x1 - x0) * (y3 - y0) - (x3 - x0) * (y1 - y0);
+    if (fabsf(det) < 1e-14f) { hx = hy = 0; h0 = z0; }
+    else {
+      hx = ((z1 - z0) * (y3 - y0) - (z3 - z0) * (y1 - y0)) / det;
+      hy = ((x1 - x0) * (z3 - z0) - (x3 - x0) * (z1 - z0)) / det;
+      h0 = z0 - hx * x0 - hy * y0;
+    }
+  }
+  int n = 4;
+  n = clip_poly(poly, n, tmp, 0, hr[ru], 1.f);
+  n = clip_poly(tmp, n, poly, 0, hr[ru], -1.f);
+  n = clip_poly(poly, n, tmp, 1, hr[rv], 1.f);
+  n = clip_poly(tmp, n, poly, 1, hr[rv], -1.f);
+  float (*cand)[3] = o.tmp;   // the clipping result is in `poly`: `tmp` is free again
+  int nc = 0;
+  for (int k = 0; k < n && k < 8; k++) {
+    float z = h0 + hx * poly[k][0] + hy * poly[k][1];
+    if (z > margin) continue;
+    cand[nc][0] = poly[k][0]; cand[nc][1] = poly[k][1]; cand[nc][2] = z; nc++;
+  }
+  if (nc == 0) return;
+  // at most four of the candidates, in ascending candidate order: kept as a bit mask (no index array)
+  uint32_t keep = (1u << nc) - 1u;
+  if (nc > 4) {
+    int i0 = 0;
+    for (int k = 1; k < nc; k++) if (cand[k][2] < cand[i0][2]) i0 = k;
+    int i1 = -1; float bd = -1;
+    for (int k = 0; k < nc; k++) { float dx = cand[k][0] - cand[i0][0], dy = cand[k][1] - cand[i0][1], q = dx * dx + dy * dy; if (k != i0 && q > bd) { bd = q; i1 = k; } }
+    float ex = cand[i1][0] - cand[i0][0], ey = cand[i1][1] - cand[i0][1];
+    int i2 = -1, i3 = -1; float bp = 0, bn = 0;
+    for (int k = 0; k < nc; k++) {
+      if (k == i0 || k == i1) continue;
+      float cr = ex * (cand[k][1] - cand[i0][1]) - ey * (cand[k][0] - cand[i0][0]);
+      if (cr > bp) { bp = cr; i2 = k; }
+      if (cr < bn) { bn = cr; i3 = k; }
+    }
+    keep = (1u << i0) | (1u << i1);
+    if (i2 >= 0) keep |= 1u << i2;
+    if (i3 >= 0) keep |= 1u << i3;
+  }
+  float fs = flip ? -1.f : 1.f;
+  int ns = 0;
+  while (keep) {
+    const float* cd = cand[ffs_pop(keep)];
+    o.dist[ns] = cd[2];
+    o.nrm[ns][0] = fs * nr[0]; o.nrm[ns][1] = fs * nr[1]; o.nrm[ns][2] = fs * nr[2];
+    for (int a = 0; a < 3; a++) o.pos[ns][a] = pr[a] + au[a] * cd[0] + av[a] * cd[1] + nr[a] * (hrax + 0.5f * cd[2]);
+    ns++;
+  }
+  o.cnt = ns;
+#undef B200_COL
+#undef B200_SEL3
+}
+#endif
 
 // ---- sphere / capsule against planes and boxes (same decision logic as oracle/oracle.c)
 HD void collide_plane_sphere(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
@@ -786,6 +973,7 @@ HD float box_sdist(const float* loc, const float* h) {
 }
 HDN void capsule_box_contacts(const float* cp, const float* ax, float r, float hl, const float* bp, const float* bm, const float* bh,
                               float margin, ContactOut& o) {
+  ASSUME_SHARED_SLOT(&o);
   // the search runs in the box frame: segment p(t) = cl + t dl, t in [-hl, hl] (rotated once; every evaluation of the convex
   // distance function is then a handful of operations)
   float rel[3] = {cp[0] - bp[0], cp[1] - bp[1], cp[2] - bp[2]}, cl[3], dl[3], p[3];
@@ -870,6 +1058,7 @@ HD void collide_round_box(const Ctx& c, int g1, int g2, float margin, ContactOut
 // (same decision logic as oracle/oracle.c collide_round_round)
 HDN void collide_round_round(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
   ASSUME_SHARED(c);
+  ASSUME_SHARED_SLOT(&o);
   o.cnt = 0;
   float p1[3], m1[9], p2[3], m2[9];
   geom_pose(c, g1, p1, m1); geom_pose(c, g2, p2, m2);
@@ -944,6 +1133,7 @@ HD void cvx_portal_dir(const CvxPt& o, const CvxPt& p, const CvxPt& q, float* di
 }
 HDN void collide_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
   ASSUME_SHARED(c);
+  ASSUME_SHARED_SLOT(&o);
   o.cnt = 0;
   CvxShape A, B;
   float p1[3], p2[3];
@@ -1021,6 +1211,7 @@ HDN void collide_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o
 // plane vs cylinder / ellipsoid (same point selection as oracle/oracle.c)
 HDN void collide_plane_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
   ASSUME_SHARED(c);
+  ASSUME_SHARED_SLOT(&o);
   o.cnt = 0;
   float pp[3], pm[9], cp[3], cm[9];
   geom_pose(c, g1, pp, pm); geom_pose(c, g2, cp, cm);
@@ -1198,14 +1389,21 @@ STAGE void collision(const Ctx c) {
     if (c.lane == 0) { int nn = basec + total; if (nn > h->ncand_max) { nn = h->ncand_max; cnt[CNT_OVERFLOW] |= 1; } cnt[CNT_NCAND] = nn; }
     SYNC();
   }
-  // narrow phase: one lane per candidate pair (lock-step over identical pair types in the common case)
+  // narrow phase: one lane per candidate pair (lock-step over identical pair types in the common case), `nslot` pairs per
+  // round: every working lane owns a result slot in shared memory (see ContactOut)
   int ncand = cnt[CNT_NCAND];
-  for (int base = 0; base < ncand; base += WARP_W) {
+  const int nslotA = h->ncslotA, nslotAB = nslotA + h->ncslotB;
+  ContactOut& o = *(ContactOut*)(c.lane < nslotA ? c.s + h->s_cslotA + c.lane * DM_CSLOT_WORDS
+                                                 : c.s + h->s_cslotB + ((c.lane < nslotAB ? c.lane : nslotA) - nslotA) * DM_CSLOT_WORDS);
+  for (int base = 0, nslot = 0; base < ncand; base += nslot) {
+    // region B is the contact-record array itself: usable as long as no record has been written (always in the first round)
+    nslot = cnt[CNT_NCON] == 0 ? nslotAB : nslotA;
+    if (nslot > WARP_W) nslot = WARP_W;   // (the one-lane host emulation walks the candidates one by one)
     int ci = base + c.lane;
-    ContactOut o;
-    o.cnt = 0;
+    int ocnt = 0;
     int p = -1;
-    if (ci < ncand) {
+    if (c.lane < nslot && ci < ncand) {
+      o.cnt = 0;
       p = wide_cand ? (int)cand16[ci] : (int)cand[ci];
       int g1 = PAIR_I(pair_geom1)[p], g2 = PAIR_I(pair_geom2)[p];
       float margin = PAIR_F(pair_margin)[p];
@@ -1226,29 +1424,38 @@ STAGE void collision(const Ctx c) {
       int k2 = 0;
       for (int k = 0; k < o.cnt; k++) if (o.dist[k] < inc) { if (k2 != k) { o.dist[k2] = o.dist[k]; for (int a = 0; a < 3; a++) { o.pos[k2][a] = o.pos[k][a]; o.nrm[k2][a] = o.nrm[k][a]; } } k2++; }
       o.cnt = k2;
+      ocnt = k2;
     }
-    int gtotal, gslot = wexscan(o.cnt > 0 ? 1 : 0, c.lane, &gtotal);
+    int gtotal, gslot = wexscan(ocnt > 0 ? 1 : 0, c.lane, &gtotal);
     int basec = cnt[CNT_NCON], baseg = cnt[CNT_NGRP];
     int gid = baseg + gslot;
     // a geom pair beyond the group capacity is dropped with all its contacts BEFORE the contacts are numbered: every
     // counted contact record is then really written (a counted but unwritten record would be finalised from stale words)
-    if (o.cnt > 0 && gid >= h->ngrp_max - DM_NWELD_MAX) o.cnt = 0;
-    int total, slot = wexscan(o.cnt, c.lane, &total);
+    if (ocnt > 0 && gid >= h->ngrp_max - DM_NWELD_MAX) ocnt = 0;
+    int total, slot = wexscan(ocnt, c.lane, &total);
+    // the slots of region B overlay the contact records written below: every lane parks its contacts in registers first
+    float P[4][7];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (k < ocnt) {
+      P[k][0] = o.pos[k][0]; P[k][1] = o.pos[k][1]; P[k][2] = o.pos[k][2];
+      P[k][3] = o.nrm[k][0]; P[k][4] = o.nrm[k][1]; P[k][5] = o.nrm[k][2]; P[k][6] = o.dist[k];
+    }
     SYNC();
     int kept = 0;
-    for (int k = 0; k < o.cnt; k++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
       // raw contact (position, normal, distance, pair) parked in its record; finalised by one lane per contact below
       int id = basec + slot + k;
-      if (id >= h->ncon_max) break;
+      if (k >= ocnt || id >= h->ncon_max) continue;
       float* cr = SF(con) + id * CON_WORDS;
-      cr[0] = o.pos[k][0]; cr[1] = o.pos[k][1]; cr[2] = o.pos[k][2];
-      cr[3] = o.nrm[k][0]; cr[4] = o.nrm[k][1]; cr[5] = o.nrm[k][2];
-      cr[6] = o.dist[k];
+      cr[0] = P[k][0]; cr[1] = P[k][1]; cr[2] = P[k][2];
+      cr[3] = P[k][3]; cr[4] = P[k][4]; cr[5] = P[k][5];
+      cr[6] = P[k][6];
       ((int*)cr)[7] = p;
       ((int*)cr)[C_DIMGRP] = gid << 8;
       kept++;
     }
-    if (o.cnt > 0) {
+    if (ocnt > 0) {
       int* gi = (int*)(SF(group) + gid * GRP_WORDS);
       int ba = MI(geom_body)[PAIR_I(pair_geom1)[p]], bb = PAIR_I(pair_geom2)[p] < 0 ? 0 : MI(geom_body)[PAIR_I(pair_geom2)[p]];
       dmask_t ma = DM(body_ancdof, ba), mb = DM(body_ancdof, bb);
@@ -1395,31 +1602,34 @@ STAGE void make_constraint(const Ctx c) {
   // joint limits -> dof rows (ordered compaction over joints, lower side first)
   for (int base = 0; base < h->njnt; base += WARP_W) {
     int j = base + c.lane;
-    int nrow = 0; float dist[2] = {0, 0}; float sgn[2] = {0, 0};
+    // (the lower-side row first, then the upper-side one: two scalars each instead of runtime-indexed arrays)
+    int nrow = 0; float dist0 = 0, dist1 = 0, sgn0 = 0, sgn1 = 0;
     if (j < h->njnt && MI(jnt_limited)[j] && MI(jnt_type)[j] != B200_JNT_FREE) {
       float q = SF(qpos)[MI(jnt_qposadr)[j]], margin = MF(jnt_margin)[j];
       float dl = q - MF(jnt_range)[2 * j], du = MF(jnt_range)[2 * j + 1] - q;
-      if (dl < margin) { dist[nrow] = dl; sgn[nrow] = 1.f; nrow++; }
-      if (du < margin) { dist[nrow] = du; sgn[nrow] = -1.f; nrow++; }
+      if (dl < margin) { dist0 = dl; sgn0 = 1.f; nrow = 1; }
+      if (du < margin) { if (nrow) { dist1 = du; sgn1 = -1.f; } else { dist0 = du; sgn0 = -1.f; } nrow++; }
     }
     int total, slot = wexscan(nrow, c.lane, &total);
     int basec = cnt[CNT_NDR];
     SYNC();
-    for (int k = 0; k < nrow; k++) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
       int id = basec + slot + k;
-      if (id >= h->ndr_max) break;
+      if (k >= nrow || id >= h->ndr_max) continue;
+      const float distk = k ? dist1 : dist0, sgnk = k ? sgn1 : sgn0;
       float* dr = SF(dofrow) + id * DR_WORDS;
       int* di = (int*)dr;
       int d = MI(jnt_dofadr)[j];
       float margin = MF(jnt_margin)[j];
       float solimp[5] = {GF(jnt_solimp)[5 * j], GF(jnt_solimp)[5 * j + 1], GF(jnt_solimp)[5 * j + 2], GF(jnt_solimp)[5 * j + 3], GF(jnt_solimp)[5 * j + 4]};
       float solref[2] = {GF(jnt_solref)[2 * j], GF(jnt_solref)[2 * j + 1]};
-      float imp = impedance(solimp, dist[k], margin);
+      float imp = impedance(solimp, distk, margin);
       float K, Bc;
       ref_kb(c, solref, solimp[1], &K, &Bc);
       float R = fmaxf((1 - imp) / imp * MF(dof_invweight0)[d], B200_MINVAL);
-      di[DR_DOF] = d; dr[DR_COEF] = sgn[k]; di[DR_DOF2] = -1; dr[DR_COEF2] = 0;
-      dr[DR_D] = 1.0f / R; dr[DR_JAR] = K * imp * (dist[k] - margin); dr[DR_JV] = Bc;
+      di[DR_DOF] = d; dr[DR_COEF] = sgnk; di[DR_DOF2] = -1; dr[DR_COEF2] = 0;
+      dr[DR_D] = 1.0f / R; dr[DR_JAR] = K * imp * (distk - margin); dr[DR_JV] = Bc;
     }
     if (c.lane == 0) { int nn = basec + total; if (nn > h->ndr_max) { nn = h->ndr_max; cnt[CNT_OVERFLOW] |= 8; } cnt[CNT_NDR] = nn; }
     SYNC();
@@ -1427,33 +1637,35 @@ STAGE void make_constraint(const Ctx c) {
   // limits of fixed tendons (length = sum coef * qpos over <= 2 joints) -> dof rows, lower side first
   if (HF) for (int base = 0; base < h->nten; base += WARP_W) {
     int t = base + c.lane;
-    int nrow = 0; float dist[2] = {0, 0}; float sgn[2] = {0, 0};
+    int nrow = 0; float dist0 = 0, dist1 = 0, sgn0 = 0, sgn1 = 0;
     if (t < h->nten) {
       float len = MF(ten_coef)[2 * t] * SF(qpos)[MI(ten_qadr)[2 * t]];
       if (MI(ten_dof)[2 * t + 1] >= 0) len += MF(ten_coef)[2 * t + 1] * SF(qpos)[MI(ten_qadr)[2 * t + 1]];
       float margin = MF(ten_margin)[t];
       float dl = len - MF(ten_range)[2 * t], du = MF(ten_range)[2 * t + 1] - len;
-      if (dl < margin) { dist[nrow] = dl; sgn[nrow] = 1.f; nrow++; }
-      if (du < margin) { dist[nrow] = du; sgn[nrow] = -1.f; nrow++; }
+      if (dl < margin) { dist0 = dl; sgn0 = 1.f; nrow = 1; }
+      if (du < margin) { if (nrow) { dist1 = du; sgn1 = -1.f; } else { dist0 = du; sgn0 = -1.f; } nrow++; }
     }
     int total, slot = wexscan(nrow, c.lane, &total);
     int basec = cnt[CNT_NDR];
     SYNC();
-    for (int k = 0; k < nrow; k++) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
       int id = basec + slot + k;
-      if (id >= h->ndr_max) break;
+      if (k >= nrow || id >= h->ndr_max) continue;
+      const float distk = k ? dist1 : dist0, sgnk = k ? sgn1 : sgn0;
       float* dr = SF(dofrow) + id * DR_WORDS;
       int* di = (int*)dr;
       float margin = MF(ten_margin)[t];
       float solimp[5] = {GF(ten_solimp)[5 * t], GF(ten_solimp)[5 * t + 1], GF(ten_solimp)[5 * t + 2], GF(ten_solimp)[5 * t + 3], GF(ten_solimp)[5 * t + 4]};
       float solref[2] = {GF(ten_solref)[2 * t], GF(ten_solref)[2 * t + 1]};
-      float imp = impedance(solimp, dist[k], margin);
+      float imp = impedance(solimp, distk, margin);
       float K, Bc;
       ref_kb(c, solref, solimp[1], &K, &Bc);
       float R = fmaxf((1 - imp) / imp * GF(ten_invweight)[t], B200_MINVAL);
-      di[DR_DOF] = MI(ten_dof)[2 * t]; dr[DR_COEF] = sgn[k] * MF(ten_coef)[2 * t];
-      di[DR_DOF2] = MI(ten_dof)[2 * t + 1]; dr[DR_COEF2] = sgn[k] * MF(ten_coef)[2 * t + 1];
-      dr[DR_D] = 1.0f / R; dr[DR_JAR] = K * imp * (dist[k] - margin); dr[DR_JV] = Bc;
+      di[DR_DOF] = MI(ten_dof)[2 * t]; dr[DR_COEF] = sgnk * MF(ten_coef)[2 * t];
+      di[DR_DOF2] = MI(ten_dof)[2 * t + 1]; dr[DR_COEF2] = sgnk * MF(ten_coef)[2 * t + 1];
+      dr[DR_D] = 1.0f / R; dr[DR_JAR] = K * imp * (distk - margin); dr[DR_JV] = Bc;
     }
     if (c.lane == 0) { int nn = basec + total; if (nn > h->ndr_max) { nn = h->ndr_max; cnt[CNT_OVERFLOW] |= 8; } cnt[CNT_NDR] = nn; }
     SYNC();
@@ -1607,9 +1819,12 @@ STAGE void rows_begin(const Ctx c, const float* qvel, const float* qacc) {
 // base-row generalized forces of a contact from its base-row values U (pyramid edges f = -D * min(0, u_n +- mu u_k))
 HD void contact_base_forces(const float* cr, int dim, float* F) {
   float D = cr[C_D], un = cr[C_U];
+#pragma unroll
   for (int k = 0; k < C_NB; k++) F[k] = 0;
   if (dim == 1) { F[0] = un < 0 ? -D * un : 0.f; return; }
-  for (int k = 1; k < dim; k++) {
+#pragma unroll
+  for (int k = 1; k < C_NB; k++) {   // (statically indexed so that F stays in registers)
+    if (k >= dim) continue;
     float mu = con_mu(cr, k), uk = cr[C_U + k];
     float xp = un + mu * uk, xm = un - mu * uk;
     float fp = xp < 0 ? -D * xp : 0.f, fm = xm < 0 ? -D * xm : 0.f;
@@ -2200,6 +2415,17 @@ STAGE int newton_move(const Ctx c, float* improvement) {
   return 0;
 }
 
+// the solve of the implicit-damping Euler step: SF(search) <- (M + h B)^-1 (f_smooth + f_constraint)
+template <int NVP>
+STAGE void euler_solve(const Ctx c) {
+  ASSUME_SHARED(c);
+  const DMHead* h = c.h;
+  float* x = SF(search);
+  LANES(i, h->nv) x[i] = SF(fsmooth)[i] + SF(fcon)[i];
+  SYNC();
+  spd_solve<NVP>(c, SF(M), MF(dof_damping), h->timestep, x, SF(H));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // forward dynamics (mj_forward) and one Euler sub-step
 // One forward pass.  `active` is warp-uniform; idle warps (no env, or masked out) only take part in the block-wide
@@ -2211,8 +2437,12 @@ STAGE int newton_move(const Ctx c, float* improvement) {
 // alignment density per kernel build: the hand build (NVP = 30, 14 warps per block) gains from the finest level
 #define ALIGN_LEVEL_FOR(NVP) ((NVP) >= 30 ? 4 : B200_ALIGN_LEVEL)
 #define ALIGN_AT(level) do { if (kAlign >= (level)) ALIGN(); } while (0)
+// `euler_solved` (optional): the caller integrates with the implicit-damping Euler step right after this pass.  A warp whose
+// Newton solve has converged then runs the (M + h B) solve of that step while the other warps of the block run their next
+// Newton direction solve -- the same routine (spd_solve<NVP>), i.e. the same code window -- instead of idling at the barrier;
+// *euler_solved tells euler_step that SF(search) already holds the solution.
 template <int NVP>
-HD void forward(const Ctx c, bool active) {
+HD void forward(const Ctx c, bool active, bool* euler_solved = nullptr) {
   constexpr bool HF = NVP >= 30;
   constexpr bool CX = NVP == 22 || NVP >= 30;   // NVP 22 = the 21-dof arm build plus the convex collider (FetchSlide)
   constexpr int kAlign = ALIGN_LEVEL_FOR(NVP);
@@ -2243,6 +2473,9 @@ HD void forward(const Ctx c, bool active) {
       if (!done) build_H<HF>(c);
       TOC(TM_BUILDH); ALIGN_AT(4); TOC(TM_BARRIER);
       if (!done) newton_direction<NVP>(c);
+#ifdef B200_EULER_PIGGYBACK
+      else if (euler_solved && active && !*euler_solved && c.h->any_damping) { euler_solve<NVP>(c); *euler_solved = true; }
+#endif
       TOC(TM_NDIR); ALIGN(); TOC(TM_BARRIER);
       if (!done) done = newton_move<HF>(c, &improvement) ? 2 : 0;
       TOC(TM_NMOVE);
@@ -2285,17 +2518,14 @@ STAGE void integrate_pos(const Ctx c, float* qpos, const float* qvel, float hh) 
 }
 
 template <int NVP>
-STAGE void euler_step(const Ctx c) {
+STAGE void euler_step(const Ctx c, bool solved = false) {
   ASSUME_SHARED(c);
   const DMHead* h = c.h;
   int nv = h->nv;
   float hh = h->timestep;
-  float* H = SF(H);
   float* x = SF(search);  // qacc itself is next sub-step's warm start
   if (h->any_damping) {
-    LANES(i, nv) x[i] = SF(fsmooth)[i] + SF(fcon)[i];
-    SYNC();
-    spd_solve<NVP>(c, SF(M), MF(dof_damping), hh, x, H);
+    if (!solved) euler_solve<NVP>(c);
   } else {
     LANES(i, nv) x[i] = SF(qacc)[i];
     SYNC();

@@ -15,12 +15,15 @@ from .oracle_sim import OracleSim
 
 
 class OracleAdroitHammerEnv:
-    def __init__(self, model, reward_type="dense", frame_skip=5):
+    def __init__(self, model, reward_type="dense", frame_skip=5, noslip=True):
         self.model, self.frame_skip = model, frame_skip
         if reward_type.lower() not in ("dense", "sparse"):   # adroit_hammer.py:219-227
             raise ValueError(f"Unknown reward type, expected `dense` or `sparse` but got {reward_type}")
         self.sparse_reward = reward_type.lower() == "sparse"
         self.sim = OracleSim(model)
+        # adroit_assets.xml:3 noslip_iterations="20": on, as in the reference; the CUDA path does not run the pass (DESIGN.md deviation
+        # 12), so its parity tests build the oracle env with noslip=False and a separate test bounds the difference
+        self.sim.set_noslip(noslip)
         m = model
         # adroit_hammer.py:264-270 (ids by name)
         self.target_obj_site_id = m.site_id("S_target")
@@ -109,10 +112,13 @@ class OracleAdroitRelocateEnv(OracleAdroitHammerEnv):
     """envs/adroit_hand/adroit_relocate.py (AdroitHandRelocateEnv).  The `target` site sits on the world body, so its
     site_xpos is its (per-episode) site_pos: kept as `self.target_pos`."""
 
-    def __init__(self, model, reward_type="dense", frame_skip=5):
+    def __init__(self, model, reward_type="dense", frame_skip=5, noslip=True):
         self.model, self.frame_skip = model, frame_skip
         self.sparse_reward = reward_type.lower() == "sparse"
         self.sim = OracleSim(model)
+        # adroit_assets.xml:3 noslip_iterations="20": on, as in the reference; the CUDA path does not run the pass (DESIGN.md deviation
+        # 12), so its parity tests build the oracle env with noslip=False and a separate test bounds the difference
+        self.sim.set_noslip(noslip)
         m = model
         self.S_grasp_site_id = m.site_id("S_grasp")                 # adroit_relocate.py:257-259
         self.obj_body_id = int(m.names["body_map"]["Object"])
@@ -178,10 +184,13 @@ class OracleAdroitRelocateEnv(OracleAdroitHammerEnv):
 class OracleAdroitPenEnv(OracleAdroitHammerEnv):
     """envs/adroit_hand/adroit_pen.py (AdroitHandPenEnv)."""
 
-    def __init__(self, model, reward_type="dense", frame_skip=5):
+    def __init__(self, model, reward_type="dense", frame_skip=5, noslip=True):
         self.model, self.frame_skip = model, frame_skip
         self.sparse_reward = reward_type.lower() == "sparse"
         self.sim = OracleSim(model)
+        # adroit_assets.xml:3 noslip_iterations="20": on, as in the reference; the CUDA path does not run the pass (DESIGN.md deviation
+        # 12), so its parity tests build the oracle env with noslip=False and a separate test bounds the difference
+        self.sim.set_noslip(noslip)
         m = model
         self.target_obj_body_id = int(m.names["body_map"]["target"])       # adroit_pen.py:264-271
         self.obj_body_id = int(m.names["body_map"]["Object"])
@@ -256,10 +265,13 @@ class OracleAdroitPenEnv(OracleAdroitHammerEnv):
 class OracleAdroitDoorEnv(OracleAdroitHammerEnv):
     """envs/adroit_hand/adroit_door.py (AdroitHandDoorEnv)."""
 
-    def __init__(self, model, reward_type="dense", frame_skip=5):
+    def __init__(self, model, reward_type="dense", frame_skip=5, noslip=True):
         self.model, self.frame_skip = model, frame_skip
         self.sparse_reward = reward_type.lower() == "sparse"
         self.sim = OracleSim(model)
+        # adroit_assets.xml:3 noslip_iterations="20": on, as in the reference; the CUDA path does not run the pass (DESIGN.md deviation
+        # 12), so its parity tests build the oracle env with noslip=False and a separate test bounds the difference
+        self.sim.set_noslip(noslip)
         m = model
         self.door_hinge_addrs = int(m.jnt_dofadr[m.joint_id("door_hinge")])      # adroit_door.py:258-263
         self.grasp_site_id, self.handle_site_id = m.site_id("S_grasp"), m.site_id("S_handle")

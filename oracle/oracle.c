@@ -62,7 +62,7 @@ typedef struct oracle_sim {
       efc_force[MAXEFC], efc_floss[MAXEFC], efc_diagA[MAXEFC], efc_KBIP[MAXEFC][4];
   int efc_type[MAXEFC], efc_id[MAXEFC];
   /* solver stats */
-  int solver_iter, warn_overflow;
+  int solver_iter, warn_overflow, noslip_enabled, noslip_iter;
   long total_newton_iter, total_substeps;
   real solver_fwdinv;
 } oracle_sim;
@@ -191,6 +191,7 @@ oracle_sim* oracle_create(const void* blob, size_t nbytes) {
   s->sensordata = dalloc(m->nsensor);
   s->J = dalloc((size_t)MAXEFC * nv);
   oracle_reset_data(s);
+  s->noslip_enabled = 1;   /* honours <option noslip_iterations>; oracle_set_noslip(s, 0) switches the pass off */
   return s;
 }
 
@@ -1492,6 +1493,93 @@ static void solve_newton(oracle_sim* s) {
 #undef MULJ
 }
 
+/* 8b. Noslip post-pass [ext: mj_solNoSlip, enabled by <option noslip_iterations="N"> -- the Adroit models ask for 20,
+ * gymnasium_robotics/envs/assets/adroit_hand/adroit_assets.xml:3].  After the main solve the forces of the FRICTION dimensions are
+ * re-solved by projected Gauss-Seidel on the UNREGULARISED dual problem min_f 1/2 f^T A f + f^T b, A = J M^-1 J^T (no R on the
+ * diagonal), b = J qacc_smooth - aref, everything else held fixed:
+ *   - dof frictionloss rows: one-dimensional Newton step, clamped to [-frictionloss, +frictionloss];
+ *   - pyramidal contacts: for every pair of opposing edges (f+, f-) of a friction direction the sum f+ + f- (their share of the
+ *     normal force) is kept and the difference is re-solved on the segment |y| <= mid, f+ = mid + y, f- = mid - y
+ *     (K1 = A++ + A-- - 2 A+-, K0 = mid (A++ - A--) + bc+ - bc-, y = -K0 / K1);
+ *   - limit rows, equality rows and frictionless contacts are not touched.
+ * Stops after N sweeps or when the cost decrease of a sweep, scaled by 1 / (meaninertia max(1, nv)), falls under noslip_tolerance
+ * (1e-6, MuJoCo's default).  Restated from memory of the published algorithm (SURVEY.md Appendix B.1 grades it LOW confidence);
+ * pinned here by a closed-form stick test (tests/test_oracle_physics.py).  `oracle_set_noslip(s, 0)` switches it off so that
+ * the CUDA path, which does not run the pass (DESIGN.md deviation 12), can be compared like for like. */
+static void solve_noslip(oracle_sim* s) {
+  const b200_model_view* m = &s->m;
+  int nv = s->nv, ne = s->nefc, niter = m->opt_int[B200_OPTI_NOSLIP_ITERATIONS];
+  if (niter <= 0 || ne == 0 || !s->noslip_enabled) return;
+  int any = 0;
+  for (int i = 0; i < ne; i++) if (s->efc_type[i] == ROW_FRICTION) any = 1;
+  for (int c = 0; c < s->ncon; c++) if (s->con[c].efc_address >= 0 && s->con[c].dim > 1) any = 1;
+  if (!any) return;
+  real *X = dalloc((size_t)ne * nv), *A = dalloc((size_t)ne * ne), *b = dalloc(ne), *f = dalloc(ne);
+  for (int i = 0; i < ne; i++) chol_solve(X + (size_t)i * nv, s->L, s->J + (size_t)i * nv, nv);   /* X_i = M^-1 J_i^T */
+  for (int i = 0; i < ne; i++)
+    for (int j = 0; j < ne; j++) {
+      real a = 0;
+      for (int d = 0; d < nv; d++) a += s->J[(size_t)i * nv + d] * X[(size_t)j * nv + d];
+      A[(size_t)i * ne + j] = a;
+    }
+  for (int i = 0; i < ne; i++) {
+    real a = -s->efc_aref[i];
+    for (int d = 0; d < nv; d++) a += s->J[(size_t)i * nv + d] * s->qacc_smooth[d];
+    b[i] = a; f[i] = s->efc_force[i];
+  }
+  real scale = 1.0 / (m->opt[B200_OPT_MEANINERTIA] * (nv > 1 ? nv : 1));
+#define RES(i) ({ real r_ = b[i]; for (int j_ = 0; j_ < ne; j_++) r_ += A[(size_t)(i) * ne + j_] * f[j_]; r_; })
+  int it = 0;
+  for (; it < niter; it++) {
+    real improvement = 0;
+    for (int i = 0; i < ne; i++) {
+      if (s->efc_type[i] != ROW_FRICTION) continue;
+      real Aii = A[(size_t)i * ne + i];
+      if (Aii < MINVAL) continue;
+      real res = RES(i), old = f[i], fl = s->efc_floss[i];
+      real nw = old - res / Aii;
+      if (nw < -fl) nw = -fl; else if (nw > fl) nw = fl;
+      real d = nw - old;
+      f[i] = nw;
+      improvement -= 0.5 * d * d * Aii + d * res;
+    }
+    for (int c = 0; c < s->ncon; c++) {
+      const Contact* con = &s->con[c];
+      if (con->efc_address < 0 || con->dim == 1) continue;
+      for (int k = 1; k < con->dim; k++) {
+        int j = con->efc_address + 2 * (k - 1);
+        real A00 = A[(size_t)j * ne + j], A11 = A[(size_t)(j + 1) * ne + j + 1], A01 = A[(size_t)j * ne + j + 1];
+        real r0 = RES(j), r1 = RES(j + 1), o0 = f[j], o1 = f[j + 1];
+        real bc0 = r0 - A00 * o0 - A01 * o1, bc1 = r1 - A01 * o0 - A11 * o1;
+        real mid = 0.5 * (o0 + o1), K1 = A00 + A11 - 2 * A01, K0 = mid * (A00 - A11) + bc0 - bc1;
+        real n0, n1;
+        if (K1 < MINVAL) { n0 = n1 = mid; }
+        else {
+          real y = -K0 / K1;
+          if (y < -mid) { n0 = 0; n1 = 2 * mid; } else if (y > mid) { n0 = 2 * mid; n1 = 0; } else { n0 = mid + y; n1 = mid - y; }
+        }
+        real d0 = n0 - o0, d1 = n1 - o1;
+        f[j] = n0; f[j + 1] = n1;
+        improvement -= 0.5 * (d0 * d0 * A00 + d1 * d1 * A11 + 2 * d0 * d1 * A01) + d0 * r0 + d1 * r1;
+      }
+    }
+    if (improvement * scale < 1e-6) { it++; break; }
+  }
+#undef RES
+  s->noslip_iter = it;
+  memcpy(s->efc_force, f, sizeof(real) * ne);
+  for (int d = 0; d < nv; d++) {
+    real a = 0;
+    for (int r = 0; r < ne; r++) a += s->J[(size_t)r * nv + d] * f[r];
+    s->qfrc_constraint[d] = a;
+  }
+  /* qacc = qacc_smooth + M^-1 qfrc_constraint */
+  real* t = dalloc(nv);
+  chol_solve(t, s->L, s->qfrc_constraint, nv);
+  for (int d = 0; d < nv; d++) s->qacc[d] = s->qacc_smooth[d] + t[d];
+  free(t); free(X); free(A); free(b); free(f);
+}
+
 /* 9. touch sensors (public MuJoCo semantics): sum of the normal forces of the active contacts that involve the sensor's
  * body and whose ray -- from the contact point along the contact normal, flipped when the sensor's body is the second
  * body -- hits the site volume (always true for a contact point inside the volume).  Site shapes: sphere, box. */
@@ -1587,6 +1675,7 @@ void oracle_forward(oracle_sim* s) {
       s->efc_aref[i] = -s->efc_KBIP[i][1] * v - s->efc_KBIP[i][0] * s->efc_KBIP[i][2] * (s->efc_pos[i] - s->efc_margin[i]);
     }
     solve_newton(s);
+    solve_noslip(s);
   }
   sensors(s);
   (void)m;
@@ -1689,6 +1778,8 @@ int oracle_nefc(const oracle_sim* s) { return s->nefc; }
 int oracle_solver_iter(const oracle_sim* s) { return s->solver_iter; }
 long oracle_total_newton_iter(const oracle_sim* s) { return s->total_newton_iter; }
 int oracle_overflow(const oracle_sim* s) { return s->warn_overflow; }
+void oracle_set_noslip(oracle_sim* s, int on) { s->noslip_enabled = on ? 1 : 0; }
+int oracle_noslip_iter(const oracle_sim* s) { return s->noslip_iter; }
 int oracle_size(const oracle_sim* s, int which) { return s->m.sizes[which]; }
 /* Per-body external contact force, the contact part of mj_rnePostConstraint [ext] (Gymnasium's Ant-v5 calls it after mj_step and
  * reads data.cfrc_ext: gymnasium_robotics/envs/maze/ant_maze_v5.py:99 "(105,) = 27 + 13 x 6"): for every contact with constraint

@@ -68,6 +68,9 @@ def lib():
         for f in ("oracle_ncon", "oracle_nefc", "oracle_solver_iter", "oracle_overflow"):
             getattr(L, f).argtypes = [ctypes.c_void_p]
             getattr(L, f).restype = ctypes.c_int
+        L.oracle_set_noslip.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.oracle_set_noslip.restype = None
+        L.oracle_noslip_iter.argtypes = [ctypes.c_void_p]
         L.oracle_cfrc_ext.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_cfrc_ext.restype = None
         L.oracle_cfrc_rows.argtypes = [ctypes.c_void_p]
@@ -150,6 +153,14 @@ class OracleSim:
     @property
     def solver_iter(self):
         return self._L.oracle_solver_iter(self._h)
+
+    def set_noslip(self, on: bool):
+        """Switch the noslip post-pass (models with <option noslip_iterations>) on or off; on by default."""
+        self._L.oracle_set_noslip(self._h, int(bool(on)))
+
+    @property
+    def noslip_iter(self):
+        return self._L.oracle_noslip_iter(self._h)
 
     def cfrc_ext(self):
         """data.cfrc_ext after an explicit mj_rnePostConstraint [ext]: one row per MJCF body, torque | force (contacts only)."""

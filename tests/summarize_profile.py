@@ -90,7 +90,8 @@ roof = {"workload": workload, "ncu_source": f"profiles/ncu_step_kernel_{tag}.txt
         "avg_active_lanes": numk("smsp__thread_inst_executed_per_inst_executed.ratio"),
         "fp32_flop_per_launch": (fl[0] + fl[1] + 2 * fl[2]) if None not in fl else None,
         "local_load_store_inst": [numk("sass__inst_executed_local_loads"), numk("sass__inst_executed_local_stores")],
-        "registers_per_thread": numk("launch__registers_per_thread"), "smem_per_block_bytes": numk("launch__shared_mem_per_block_dynamic"),
+        "registers_per_thread": numk("launch__registers_per_thread"),
+        "smem_per_block_bytes": (numk("launch__shared_mem_per_block_dynamic") or 0) * unit.get(vals.get("launch__shared_mem_per_block_dynamic", ("", "byte"))[1].split("/")[0], 1),
         "top_stalls": [[k.replace("stall_", ""), round(100 * n / tot, 1)] for k, n in stalls.most_common(5)]}
 json.dump(roof, open(os.path.join(out_dir, f"roofline_{workload}.json"), "w"), indent=1)
 json.dump({"dram_bytes_per_launch": dram, "source": f"profiles/ncu_step_kernel_{tag}.txt", "algorithmic_bytes_per_launch": alg_b * alg_n},

@@ -273,7 +273,7 @@ def test_adroit_hammer_env_matches_oracle():
     assert m.nv == 33 and m.nu == 26
     env = pkg.make_vec("AdroitHandHammer-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
     assert env.single_observation_space.shape == (46,) and env.single_action_space.shape == (26,) and env.max_episode_steps == 200
-    orc = OracleAdroitHammerEnv(m)
+    orc = OracleAdroitHammerEnv(m, noslip=False)
     obs, info = env.reset(seed=4)
     oobs, _ = orc.reset(seed=4)
     assert obs.shape == (1, 46) and info == {}
@@ -329,7 +329,7 @@ def test_adroit_relocate_env_matches_oracle():
     assert m.nv == 36 and m.nu == 30
     env = pkg.make_vec("AdroitHandRelocate-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
     assert env.single_observation_space.shape == (39,) and env.single_action_space.shape == (30,)
-    orc = OracleAdroitRelocateEnv(m)
+    orc = OracleAdroitRelocateEnv(m, noslip=False)
     obs, _ = env.reset(seed=4)
     oobs, _ = orc.reset(seed=4)
     np.testing.assert_allclose(obs[0].double().numpy(), oobs, atol=1e-6)
@@ -372,7 +372,7 @@ def test_adroit_pen_env_matches_oracle():
     m = load_model("adroit_pen")
     env = pkg.make_vec("AdroitHandPen-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
     assert env.single_observation_space.shape == (45,) and env.single_action_space.shape == (24,)
-    orc = OracleAdroitPenEnv(m)
+    orc = OracleAdroitPenEnv(m, noslip=False)
     obs, _ = env.reset(seed=4)
     oobs, _ = orc.reset(seed=4)
     np.testing.assert_allclose(obs[0].double().numpy(), oobs, atol=2e-6)
@@ -419,7 +419,7 @@ def test_adroit_door_env_matches_oracle():
     assert len(m.pair_geom1) > 255
     env = pkg.make_vec("AdroitHandDoor-v2", num_envs=1, backend_factory=AdroitHostBackend, rng_mode="numpy")
     assert env.single_observation_space.shape == (39,) and env.single_action_space.shape == (28,)
-    orc = OracleAdroitDoorEnv(m)
+    orc = OracleAdroitDoorEnv(m, noslip=False)
     obs, _ = env.reset(seed=4)
     oobs, _ = orc.reset(seed=4)
     np.testing.assert_allclose(obs[0].double().numpy(), oobs, atol=2e-6)

@@ -267,3 +267,46 @@ def test_packed_row_flags_and_solver_info():
     assert not bool(tr.any()) and float(r.abs().max()) == 0.0 and float(info["is_success"].max()) == 0.0 and int(env._elapsed.max()) == 0
     assert float(env._last["packed"][:, 10 + 6:10 + 10].abs().max()) == 0.0
     env.close()
+
+
+def test_register_envs_against_a_gymnasium_stub(monkeypatch):
+    """`register_envs()` (gymnasium is absent from this image): executed against a stub of `gymnasium.envs.registration` -- every
+    id of the reference's registry that the CUDA path provides is registered once with a `vector_entry_point` that resolves to a
+    constructor of this package and kwargs that constructor accepts (checked by building two of them on the host emulation)."""
+    import importlib
+    import sys
+    import types
+
+    import gymnasium_robotics_b200 as pkg
+
+    calls, registry = [], {}
+    gym = types.ModuleType("gymnasium")
+    envs = types.ModuleType("gymnasium.envs")
+    reg = types.ModuleType("gymnasium.envs.registration")
+
+    def register(id, vector_entry_point=None, kwargs=None, **kw):
+        calls.append((id, vector_entry_point, dict(kwargs or {})))
+        registry[id] = vector_entry_point
+
+    reg.register, reg.registry = register, registry
+    gym.envs, envs.registration = envs, reg
+    for name, mod in (("gymnasium", gym), ("gymnasium.envs", envs), ("gymnasium.envs.registration", reg)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    assert pkg.register_envs() is True
+    ids = [c[0] for c in calls]
+    assert len(ids) == len(set(ids)) == len(pkg.ENV_IDS)
+    assert {"FetchPickAndPlace-v4", "AntMaze_Large-v5", "HandManipulateBlockRotateXYZ_ContinuousTouchSensors-v1", "AdroitHandHammer-v2",
+            "FrankaKitchen-v1", "PointMaze_UMaze-v3"} <= set(ids)
+    n0 = len(calls)
+    assert pkg.register_envs() is True and len(calls) == n0           # idempotent: ids already in the registry are skipped
+    by_id = {c[0]: c for c in calls}
+    for env_id in ids:                                                # every entry point resolves
+        mod, attr = by_id[env_id][1].split(":")
+        assert callable(getattr(importlib.import_module(mod), attr)), env_id
+    # gymnasium.make_vec(id, num_envs=N, vectorization_mode="vector_entry_point") calls entry_point(num_envs=N, **kwargs)
+    for env_id in ("FetchReach-v4", "AntMaze_UMaze-v4"):
+        mod, attr = by_id[env_id][1].split(":")
+        env = getattr(importlib.import_module(mod), attr)(num_envs=2, backend_factory=HostSimBackend, rng_mode="numpy", **by_id[env_id][2])
+        obs, _ = env.reset(seed=0)
+        assert obs["observation"].shape[0] == 2 and env.max_episode_steps == pkg.ENV_IDS[env_id]["max_episode_steps"]
+        env.close()

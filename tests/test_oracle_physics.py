@@ -155,6 +155,54 @@ def test_friction_cone_stick_and_slip(mjcf_file):
             assert s.qvel[0] == pytest.approx(a * 1.0, rel=0.03)
 
 
+def test_noslip_post_pass_removes_the_soft_contact_creep(mjcf_file):
+    """<option noslip_iterations="20"> (the Adroit models, adroit_assets.xml:3): a box on an incline below the friction angle.
+    The soft friction rows alone let it creep downhill (tangential force = -D x with finite D); the noslip pass re-solves the
+    friction dimensions WITHOUT regularisation, so the tangential reference acceleration -B v_t is met exactly and a box that
+    starts at rest stays at rest: closed form v_t = 0.  Above the friction angle the pass must not stop the slide (cone clamp):
+    a = g (sin(theta) - mu cos(theta)).  A frictionloss joint below its stiction force does not move either."""
+    mu = 0.5
+    # slope 0.1: well inside the friction pyramid.  (The pass keeps the normal-force share of every pair of opposing edges, so a
+    # single friction direction can supply at most mu x its pair's share -- at slope mu / 2 = 0.25 that bound is reached and the
+    # box creeps again; the main solver's pyramid has no such per-pair bound.)
+    th = np.arctan(0.1)
+    g = np.array([G * np.sin(th), 0, -G * np.cos(th)])
+    creep = {}
+    for noslip in (0, 20):
+        xml = BOX_ON_PLANE.replace('timestep="0.002"', f'timestep="0.002" gravity="{g[0]} {g[1]} {g[2]}" noslip_iterations="{noslip}"')
+        xml = xml.replace('type="plane"', f'type="plane" friction="{mu} 0.005 0.0001"').replace('type="box"', f'type="box" friction="{mu} 0.005 0.0001"')
+        s = make(mjcf_file, xml)
+        s.step(1000)
+        x1 = s.qpos[0]
+        s.step(1000)
+        creep[noslip] = (abs(s.qvel[0]), abs(s.qpos[0] - x1) / 2.0)      # slip velocity, mean creep rate over the last 2 s
+        if noslip:
+            assert s.noslip_iter >= 1
+    assert creep[0][0] > 1e-4 and creep[0][1] > 1e-4        # the soft model creeps at 0.3 mm/s ...
+    assert creep[20][0] < 1e-6 and creep[20][1] < 1e-6       # ... the noslip pass holds the box: closed form, no slip
+    # switching the pass off on a model that asks for it reproduces the soft answer (what the CUDA-path parity tests compare against)
+    s.reset_data(); s.set_noslip(False); s.step(2000)
+    assert abs(s.qvel[0]) == pytest.approx(creep[0][0], rel=1e-6)
+    # above the friction angle: the clamp to the friction pyramid keeps the sliding acceleration
+    th2 = np.arctan(1.0)
+    g2 = np.array([G * np.sin(th2), 0, -G * np.cos(th2)])
+    xml = BOX_ON_PLANE.replace('timestep="0.002"', f'timestep="0.002" gravity="{g2[0]} {g2[1]} {g2[2]}" noslip_iterations="20"')
+    xml = xml.replace('type="plane"', f'type="plane" friction="{mu} 0.005 0.0001"').replace('type="box"', f'type="box" friction="{mu} 0.005 0.0001"')
+    s = make(mjcf_file, xml)
+    s.step(500)
+    assert s.qvel[0] == pytest.approx(G * (np.sin(th2) - mu * np.cos(th2)), rel=0.03)
+    # dry joint friction: a slider pulled with 0.8 x frictionloss does not creep with the pass, and does without it
+    for noslip, moves in ((0, True), (20, False)):
+        xml = f"""
+        <mujoco><option timestep="0.002" gravity="0 0 0" noslip_iterations="{noslip}"/>
+        <worldbody><body name="m"><joint name="s" type="slide" axis="1 0 0" frictionloss="2.0"/><geom type="sphere" size="0.05" mass="1"/></body></worldbody>
+        <actuator><motor joint="s" gear="1"/></actuator></mujoco>"""
+        s = make(mjcf_file, xml)
+        s.ctrl[0] = 1.6
+        s.step(500)
+        assert (abs(s.qvel[0]) > 1e-5) == moves, (noslip, s.qvel[0])
+
+
 LIMIT = """
 <mujoco><option timestep="0.002"/>
 <worldbody>
@@ -358,3 +406,32 @@ def test_plane_cylinder_and_plane_ellipsoid(mjcf_file):
     s.forward()
     (c,) = s.contacts()
     assert c["dist"] == pytest.approx(0.03 - 0.035, abs=1e-12) and np.allclose(c["pos"], [0, 0, -0.0025], atol=1e-9)
+
+
+def test_noslip_changes_the_adroit_hammer_scenario_by_a_bounded_amount():
+    """What deviation 12 (the CUDA path runs no noslip pass) costs on the reference's own model: the oracle's
+    AdroitHandHammer env with the pass on (as the reference's adroit_assets.xml:3 asks) against the same env with the pass off,
+    same seed and actions, the arm lowered onto the hammer.  The observation difference per env-step is the bound a user of the
+    CUDA path gets with respect to a noslip-enabled simulator; it is measured, printed and asserted to stay small."""
+    from gymnasium_robotics_b200.models import load_model
+    from oracle.adroit_env import OracleAdroitHammerEnv
+
+    m = load_model("adroit_hammer")
+    on, off = OracleAdroitHammerEnv(m), OracleAdroitHammerEnv(m, noslip=False)
+    on.reset(seed=30)
+    off.reset(seed=30)
+    rng = np.random.default_rng(2)
+    worst, iters = 0.0, 0
+    for step in range(12):
+        a = rng.uniform(-1, 1, 26)
+        if step >= 5:
+            a[:2] = [-1, -0.5]           # lower the arm onto the hammer
+        # per-step difference from IDENTICAL states: the noslip env is re-synchronised to the soft one before every step
+        on.sim.qpos[:] = off.sim.qpos; on.sim.qvel[:] = off.sim.qvel; on.sim.qacc_warmstart[:] = off.sim.qacc_warmstart
+        oo, *_ = on.step(a)
+        of, *_ = off.step(a)
+        iters = max(iters, on.sim.noslip_iter)
+        worst = max(worst, float(np.abs(np.asarray(oo) - np.asarray(of)).max()))
+    print(f"noslip on vs off, AdroitHandHammer, 12 env-steps from identical states: max |obs difference| = {worst:.2e}, sweeps <= {iters}")
+    assert iters >= 1            # the pass ran (frictionloss rows are always there)
+    assert worst < 5e-2
