@@ -19,11 +19,10 @@
 #define DM_NDOFROW_MIN 8
 #define DM_NCAND_MAX 96   // broad-phase candidate slots (one byte each: pair index < 256)
 #define DM_NWELD_MAX 1
-// narrow-phase result slot of one lane in shared memory (sim_core.cuh `ContactOut`): 29 result words + the clipping buffers of
-// the box-box routine (8 x 2 + 8 x 3), padded to an even count.  The slots overlay scratch that is dead while the narrow phase
-// runs: region A = the body-force / dof-term buffers of the smooth-force stage (b6 .. d6), region B = the contact records that
-// the narrow phase itself is about to fill (the lanes park their results in registers before the records are written).
-#define DM_CSLOT_WORDS 70
+// box-box working set of one narrow-phase lane in shared memory (sim_core.cuh `BoxScratch`: the clipping polygons, 8 x 2 + 8 x 3
+// words).  The slots overlay scratch that is dead while the narrow phase runs: region A = the body-force / dof-term buffers of the
+// smooth-force stage (b6 .. d6), region B = the contact records, as long as the narrow phase has not written one.
+#define DM_CSLOT_WORDS 40
 
 // (name, words-per-element, kind) ; kind selects the element count.  HOT arrays are staged into shared memory by every
 // block; COLD arrays (per-pair contact parameters, read only when a contact is created) stay in global memory.

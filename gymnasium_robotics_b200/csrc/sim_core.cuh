@@ -34,6 +34,16 @@
 #ifdef B200_ALIGN_SYNCWARP
 #define ALIGN() do { __syncwarp(); __syncthreads(); } while (0)
 #define ALIGN_OR(p) (__syncwarp(), __syncthreads_or(p))
+#elif defined(B200_ALIGN_NONALIGNED)
+// A/B variant: PTX `barrier.sync` WITHOUT `.aligned` -- the form that tolerates a warp arriving in several convergence groups
+static __device__ __forceinline__ void b200_bar_na() { asm volatile("barrier.sync 0;" ::: "memory"); }
+static __device__ __forceinline__ bool b200_bar_or_na(bool p) {
+  int r;
+  asm volatile("{ .reg .pred q, r; setp.ne.s32 q, %1, 0; barrier.red.or.pred r, 0, q; selp.s32 %0, 1, 0, r; }" : "=r"(r) : "r"((int)p) : "memory");
+  return r != 0;
+}
+#define ALIGN() b200_bar_na()
+#define ALIGN_OR(p) b200_bar_or_na(p)
 #else
 #define ALIGN() __syncthreads()
 #define ALIGN_OR(p) __syncthreads_or(p)
@@ -557,11 +567,15 @@ HD void ref_kb(const Ctx& c, const float* solref, float dmax_in, float* K, float
 
 // ---------------------------------------------------------------------------------------------------------------
 // 5. collision (plane-box, box-box; same decision logic as oracle/oracle.c, fp32)
-// Result of one candidate pair (at most 4 contacts) plus the clipping buffers of collide_box_box.  The narrow phase keeps one
-// such slot per working lane in SHARED memory (dmodel.h DM_CSLOT_WORDS): a slot on the thread's stack would be local memory,
-// i.e. L2 / DRAM traffic (229 KB of shared memory per block leave no L1), which the round-1 profile showed as 350 MB per launch.
-struct ContactOut { float pos[4][3]; float nrm[4][3]; float dist[4]; int cnt; float poly[8][2]; float tmp[8][3]; };
-static_assert(sizeof(ContactOut) <= DM_CSLOT_WORDS * 4, "ContactOut must fit a narrow-phase lane slot");
+// Result of one candidate pair (at most 4 contacts): 29 words on the lane's stack.  Measured on a B200 (profiles/variants_r2e.log):
+// keeping the result in a shared-memory slot forces the lanes to park it in 28 registers before the contact records -- which the
+// slots overlay -- are written, and that costs 0.48 ms of the 3.7 ms step in the 72-register build.  What does move to shared memory is
+// the box-box routine's working set (BoxScratch): it is dead when the routine returns, so no parking is needed, and with it the
+// stack frame -- whose size x 132 k threads is what the local-memory write-back traffic scales with -- shrinks.
+struct ContactOut { float pos[4][3]; float nrm[4][3]; float dist[4]; int cnt; };
+// clipping buffers of collide_box_box: one slot per working lane in SHARED memory (dmodel.h DM_CSLOT_WORDS)
+struct BoxScratch { float poly[8][2]; float tmp[8][3]; };
+static_assert(sizeof(BoxScratch) <= DM_CSLOT_WORDS * 4, "BoxScratch must fit a narrow-phase lane slot");
 
 HD void geom_pose(const Ctx& c, int g, float* pos, float* mat) {
   int b = MI(geom_body)[g];
@@ -606,145 +620,9 @@ HD int clip_poly(const float (*in)[2], int n, float (*out)[2], int axis, float b
   return k;
 }
 
-#ifdef B200_BOXBOX_OLD
-// A/B variant: working arrays on the lane's stack, indexed face axes (the round-1 form)
-HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
+HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& o, BoxScratch& bs) {
   ASSUME_SHARED(c);
-  float pa[3], Ra[9], pb[3], Rb[9];
-  geom_pose(c, g1, pa, Ra); geom_pose(c, g2, pb, Rb);
-  const float* ha = MF(geom_size) + 3 * g1;
-  const float* hb = MF(geom_size) + 3 * g2;
-  o.cnt = 0;
-  float d[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]}, da[3], db[3];
-  mulmtv(da, Ra, d); mulmtv(db, Rb, d);
-  float C[3][3], Q[3][3];
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) { C[i][j] = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j]; Q[i][j] = fabsf(C[i][j]); }
-  float best = -1e30f, bestsign = 1; int code = -1;
-  for (int i = 0; i < 3; i++) {
-    float sep = fabsf(da[i]) - (ha[i] + hb[0] * Q[i][0] + hb[1] * Q[i][1] + hb[2] * Q[i][2]);
-    if (sep > margin) return;
-    if (sep > best) { best = sep; code = i; bestsign = da[i] < 0 ? -1.f : 1.f; }
-  }
-  for (int j = 0; j < 3; j++) {
-    float sep = fabsf(db[j]) - (hb[j] + ha[0] * Q[0][j] + ha[1] * Q[1][j] + ha[2] * Q[2][j]);
-    if (sep > margin) return;
-    if (sep > best) { best = sep; code = 3 + j; bestsign = db[j] < 0 ? -1.f : 1.f; }
-  }
-  float ebest = -1e30f; int ecode = -1; float eaxis[3] = {0, 0, 0};
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
-      float ai[3] = {Ra[i], Ra[3 + i], Ra[6 + i]}, bj[3] = {Rb[j], Rb[3 + j], Rb[6 + j]}, ax[3];
-      cross3(ax, ai, bj);
-      float l = sqrtf(dot3(ax, ax));
-      if (l < 1e-6f) continue;
-      float il = 1.0f / l;
-      ax[0] *= il; ax[1] *= il; ax[2] *= il;
-      float ra = 0, rb = 0;
-      for (int k = 0; k < 3; k++) {
-        float ak[3] = {Ra[k], Ra[3 + k], Ra[6 + k]}, bk[3] = {Rb[k], Rb[3 + k], Rb[6 + k]};
-        ra += ha[k] * fabsf(dot3(ak, ax)); rb += hb[k] * fabsf(dot3(bk, ax));
-      }
-      float dd = dot3(d, ax), sep = fabsf(dd) - (ra + rb);
-      if (sep > margin) return;
-      if (sep > ebest) { ebest = sep; ecode = 3 * i + j; float sg = dd < 0 ? -1.f : 1.f; eaxis[0] = sg * ax[0]; eaxis[1] = sg * ax[1]; eaxis[2] = sg * ax[2]; }
-    }
-  if (ecode >= 0 && ebest > best + 1e-3f * (fabsf(best) + 1e-3f) && ebest > 0.95f * best && ebest > best) {
-    int i = ecode / 3, j = ecode % 3;
-    float n[3] = {eaxis[0], eaxis[1], eaxis[2]};
-    float ea[3] = {Ra[i], Ra[3 + i], Ra[6 + i]}, eb[3] = {Rb[j], Rb[3 + j], Rb[6 + j]};
-    float PA[3] = {pa[0], pa[1], pa[2]}, PB[3] = {pb[0], pb[1], pb[2]};
-    for (int k = 0; k < 3; k++) {
-      float ak[3] = {Ra[k], Ra[3 + k], Ra[6 + k]}, bk[3] = {Rb[k], Rb[3 + k], Rb[6 + k]};
-      if (k != i) { float sg = (dot3(n, ak) > 0 ? 1.f : -1.f) * ha[k]; PA[0] += ak[0] * sg; PA[1] += ak[1] * sg; PA[2] += ak[2] * sg; }
-      if (k != j) { float sg = (dot3(n, bk) > 0 ? -1.f : 1.f) * hb[k]; PB[0] += bk[0] * sg; PB[1] += bk[1] * sg; PB[2] += bk[2] * sg; }
-    }
-    float w[3] = {PA[0] - PB[0], PA[1] - PB[1], PA[2] - PB[2]};
-    float b = dot3(ea, eb), dd = dot3(ea, w), e = dot3(eb, w), den = 1 - b * b;
-    float sp = den > 1e-12f ? (b * e - dd) / den : 0, tp = den > 1e-12f ? (e - b * dd) / den : 0;
-    sp = fminf(fmaxf(sp, -ha[i]), ha[i]); tp = fminf(fmaxf(tp, -hb[j]), hb[j]);
-    o.cnt = 1; o.dist[0] = ebest; o.nrm[0][0] = n[0]; o.nrm[0][1] = n[1]; o.nrm[0][2] = n[2];
-    for (int k = 0; k < 3; k++) o.pos[0][k] = 0.5f * (PA[k] + ea[k] * sp + PB[k] + eb[k] * tp);
-    return;
-  }
-  const float *pr, *Rr, *pi, *Ri; const float *hr, *hi; int ax; float sgn; int flip;
-  if (code < 3) { pr = pa; Rr = Ra; pi = pb; Ri = Rb; hr = ha; hi = hb; ax = code; sgn = bestsign; flip = 0; }
-  else { pr = pb; Rr = Rb; pi = pa; Ri = Ra; hr = hb; hi = ha; ax = code - 3; sgn = -bestsign; flip = 1; }
-  float nr[3] = {Rr[ax] * sgn, Rr[3 + ax] * sgn, Rr[6 + ax] * sgn};
-  float nloc[3];
-  mulmtv(nloc, Ri, nr);
-  int iax = 0; float bestd = -1;
-  for (int k = 0; k < 3; k++) if (fabsf(nloc[k]) > bestd) { bestd = fabsf(nloc[k]); iax = k; }
-  float isgn = nloc[iax] > 0 ? -1.f : 1.f;
-  int u = (iax + 1) % 3, v = (iax + 2) % 3, ru = (ax + 1) % 3, rv = (ax + 2) % 3;
-  float au[3] = {Rr[ru], Rr[3 + ru], Rr[6 + ru]}, av[3] = {Rr[rv], Rr[3 + rv], Rr[6 + rv]};
-  float fc[3] = {pi[0] + Ri[iax] * isgn * hi[iax], pi[1] + Ri[3 + iax] * isgn * hi[iax], pi[2] + Ri[6 + iax] * isgn * hi[iax]};
-  float iu[3] = {Ri[u], Ri[3 + u], Ri[6 + u]}, iv[3] = {Ri[v], Ri[3 + v], Ri[6 + v]};
-  float poly[8][2], tmp[8][2], zc[4];
-  for (int k = 0; k < 4; k++) {
-    float su = (k == 0 || k == 3) ? 1.f : -1.f, sv = (k < 2) ? 1.f : -1.f;
-    float rel[3];
-    for (int a = 0; a < 3; a++) rel[a] = fc[a] + iu[a] * su * hi[u] + iv[a] * sv * hi[v] - pr[a];
-    poly[k][0] = dot3(rel, au); poly[k][1] = dot3(rel, av);
-    zc[k] = dot3(rel, nr) - hr[ax];
-  }
-  float h0, hx, hy;
-  {
-    float x0 = poly[0][0], y0 = poly[0][1], x1 = poly[1][0], y1 = poly[1][1], x3 = poly[3][0], y3 = poly[3][1];
-    float z0 = zc[0], z1 = zc[1], z3 = zc[3];
-    float det = (x1 - x0) * (y3 - y0) - (x3 - x0) * (y1 - y0);
-    if (fabsf(det) < 1e-14f) { hx = hy = 0; h0 = z0; }
-    else {
-      hx = ((z1 - z0) * (y3 - y0) - (z3 - z0) * (y1 - y0)) / det;
-      hy = ((x1 - x0) * (z3 - z0) - (x3 - x0) * (z1 - z0)) / det;
-      h0 = z0 - hx * x0 - hy * y0;
-    }
-  }
-  int n = 4;
-  n = clip_poly(poly, n, tmp, 0, hr[ru], 1.f);
-  n = clip_poly(tmp, n, poly, 0, hr[ru], -1.f);
-  n = clip_poly(poly, n, tmp, 1, hr[rv], 1.f);
-  n = clip_poly(tmp, n, poly, 1, hr[rv], -1.f);
-  float cand[8][3]; int nc = 0;
-  for (int k = 0; k < n && k < 8; k++) {
-    float z = h0 + hx * poly[k][0] + hy * poly[k][1];
-    if (z > margin) continue;
-    cand[nc][0] = poly[k][0]; cand[nc][1] = poly[k][1]; cand[nc][2] = z; nc++;
-  }
-  if (nc == 0) return;
-  int sel[4], ns = 0;
-  if (nc <= 4) { for (int k = 0; k < nc; k++) sel[ns++] = k; }
-  else {
-    int i0 = 0;
-    for (int k = 1; k < nc; k++) if (cand[k][2] < cand[i0][2]) i0 = k;
-    int i1 = -1; float bd = -1;
-    for (int k = 0; k < nc; k++) { float dx = cand[k][0] - cand[i0][0], dy = cand[k][1] - cand[i0][1], q = dx * dx + dy * dy; if (k != i0 && q > bd) { bd = q; i1 = k; } }
-    float ex = cand[i1][0] - cand[i0][0], ey = cand[i1][1] - cand[i0][1];
-    int i2 = -1, i3 = -1; float bp = 0, bn = 0;
-    for (int k = 0; k < nc; k++) {
-      if (k == i0 || k == i1) continue;
-      float cr = ex * (cand[k][1] - cand[i0][1]) - ey * (cand[k][0] - cand[i0][0]);
-      if (cr > bp) { bp = cr; i2 = k; }
-      if (cr < bn) { bn = cr; i3 = k; }
-    }
-    sel[ns++] = i0; sel[ns++] = i1;
-    if (i2 >= 0) sel[ns++] = i2;
-    if (i3 >= 0) sel[ns++] = i3;
-    for (int a = 0; a < ns; a++) for (int b = a + 1; b < ns; b++) if (sel[b] < sel[a]) { int t = sel[a]; sel[a] = sel[b]; sel[b] = t; }
-  }
-  float fs = flip ? -1.f : 1.f;
-  o.cnt = ns;
-  for (int k = 0; k < ns; k++) {
-    const float* cd = cand[sel[k]];
-    o.dist[k] = cd[2];
-    o.nrm[k][0] = fs * nr[0]; o.nrm[k][1] = fs * nr[1]; o.nrm[k][2] = fs * nr[2];
-    for (int a = 0; a < 3; a++) o.pos[k][a] = pr[a] + au[a] * cd[0] + av[a] * cd[1] + nr[a] * (hr[ax] + 0.5f * cd[2]);
-  }
-}
-#else
-HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
-  ASSUME_SHARED(c);
-  ASSUME_SHARED_SLOT(&o);
+  ASSUME_SHARED_SLOT(&bs);
   float pa[3], Ra[9], pb[3], Rb[9];
   geom_pose(c, g1, pa, Ra); geom_pose(c, g2, pb, Rb);
   const float* ha = MF(geom_size) + 3 * g1;
@@ -833,8 +711,8 @@ HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& 
   B200_COL(au, Rr, ru); B200_COL(av, Rr, rv); B200_COL(iu, Ri, u); B200_COL(iv, Ri, v); B200_COL(ia, Ri, iax);
   const float hia = hi[iax] * isgn, hiu = hi[u], hiv = hi[v], hrax = hr[ax];
   float fc[3] = {pi[0] + ia[0] * hia, pi[1] + ia[1] * hia, pi[2] + ia[2] * hia};
-  float (*poly)[2] = o.poly;
-  float (*tmp)[2] = (float (*)[2])o.tmp;
+  float (*poly)[2] = bs.poly;
+  float (*tmp)[2] = (float (*)[2])bs.tmp;
   float zc[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -861,7 +739,7 @@ HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& 
   n = clip_poly(tmp, n, poly, 0, hr[ru], -1.f);
   n = clip_poly(poly, n, tmp, 1, hr[rv], 1.f);
   n = clip_poly(tmp, n, poly, 1, hr[rv], -1.f);
-  float (*cand)[3] = o.tmp;   // the clipping result is in `poly`: `tmp` is free again
+  float (*cand)[3] = bs.tmp;   // the clipping result is in `poly`: `tmp` is free again
   int nc = 0;
   for (int k = 0; k < n && k < 8; k++) {
     float z = h0 + hx * poly[k][0] + hy * poly[k][1];
@@ -901,7 +779,6 @@ HDN void collide_box_box(const Ctx c, int g1, int g2, float margin, ContactOut& 
 #undef B200_COL
 #undef B200_SEL3
 }
-#endif
 
 // ---- sphere / capsule against planes and boxes (same decision logic as oracle/oracle.c)
 HD void collide_plane_sphere(const Ctx& c, int g1, int g2, float margin, ContactOut& o) {
@@ -973,7 +850,6 @@ HD float box_sdist(const float* loc, const float* h) {
 }
 HDN void capsule_box_contacts(const float* cp, const float* ax, float r, float hl, const float* bp, const float* bm, const float* bh,
                               float margin, ContactOut& o) {
-  ASSUME_SHARED_SLOT(&o);
   // the search runs in the box frame: segment p(t) = cl + t dl, t in [-hl, hl] (rotated once; every evaluation of the convex
   // distance function is then a handful of operations)
   float rel[3] = {cp[0] - bp[0], cp[1] - bp[1], cp[2] - bp[2]}, cl[3], dl[3], p[3];
@@ -1058,7 +934,6 @@ HD void collide_round_box(const Ctx& c, int g1, int g2, float margin, ContactOut
 // (same decision logic as oracle/oracle.c collide_round_round)
 HDN void collide_round_round(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
   ASSUME_SHARED(c);
-  ASSUME_SHARED_SLOT(&o);
   o.cnt = 0;
   float p1[3], m1[9], p2[3], m2[9];
   geom_pose(c, g1, p1, m1); geom_pose(c, g2, p2, m2);
@@ -1133,7 +1008,6 @@ HD void cvx_portal_dir(const CvxPt& o, const CvxPt& p, const CvxPt& q, float* di
 }
 HDN void collide_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
   ASSUME_SHARED(c);
-  ASSUME_SHARED_SLOT(&o);
   o.cnt = 0;
   CvxShape A, B;
   float p1[3], p2[3];
@@ -1211,7 +1085,6 @@ HDN void collide_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o
 // plane vs cylinder / ellipsoid (same point selection as oracle/oracle.c)
 HDN void collide_plane_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o) {
   ASSUME_SHARED(c);
-  ASSUME_SHARED_SLOT(&o);
   o.cnt = 0;
   float pp[3], pm[9], cp[3], cm[9];
   geom_pose(c, g1, pp, pm); geom_pose(c, g2, cp, cm);
@@ -1390,20 +1263,20 @@ STAGE void collision(const Ctx c) {
     SYNC();
   }
   // narrow phase: one lane per candidate pair (lock-step over identical pair types in the common case), `nslot` pairs per
-  // round: every working lane owns a result slot in shared memory (see ContactOut)
+  // round: every working lane owns a BoxScratch slot in shared memory (the result record itself stays on the lane's stack)
   int ncand = cnt[CNT_NCAND];
   const int nslotA = h->ncslotA, nslotAB = nslotA + h->ncslotB;
-  ContactOut& o = *(ContactOut*)(c.lane < nslotA ? c.s + h->s_cslotA + c.lane * DM_CSLOT_WORDS
-                                                 : c.s + h->s_cslotB + ((c.lane < nslotAB ? c.lane : nslotA) - nslotA) * DM_CSLOT_WORDS);
+  BoxScratch& bs = *(BoxScratch*)(c.lane < nslotA ? c.s + h->s_cslotA + c.lane * DM_CSLOT_WORDS
+                                                  : c.s + h->s_cslotB + ((c.lane < nslotAB ? c.lane : nslotA) - nslotA) * DM_CSLOT_WORDS);
   for (int base = 0, nslot = 0; base < ncand; base += nslot) {
     // region B is the contact-record array itself: usable as long as no record has been written (always in the first round)
     nslot = cnt[CNT_NCON] == 0 ? nslotAB : nslotA;
     if (nslot > WARP_W) nslot = WARP_W;   // (the one-lane host emulation walks the candidates one by one)
     int ci = base + c.lane;
-    int ocnt = 0;
+    ContactOut o;
+    o.cnt = 0;
     int p = -1;
     if (c.lane < nslot && ci < ncand) {
-      o.cnt = 0;
       p = wide_cand ? (int)cand16[ci] : (int)cand[ci];
       int g1 = PAIR_I(pair_geom1)[p], g2 = PAIR_I(pair_geom2)[p];
       float margin = PAIR_F(pair_margin)[p];
@@ -1416,7 +1289,7 @@ STAGE void collision(const Ctx c) {
         if (t2 == B200_GEOM_BOX) collide_plane_box(c, g1, g2, margin, o);
         else if (t2 == B200_GEOM_SPHERE) collide_plane_sphere(c, g1, g2, margin, o);
         else collide_plane_capsule(c, g1, g2, margin, o);
-      } else if (t1 == B200_GEOM_BOX) collide_box_box(c, g1, g2, margin, o);
+      } else if (t1 == B200_GEOM_BOX) collide_box_box(c, g1, g2, margin, o, bs);
       else if (t2 == B200_GEOM_BOX) collide_round_box(c, g1, g2, margin, o);
       else if (HF) collide_round_round(c, g1, g2, margin, o);
       // contacts beyond the gap are not turned into constraints
@@ -1424,8 +1297,8 @@ STAGE void collision(const Ctx c) {
       int k2 = 0;
       for (int k = 0; k < o.cnt; k++) if (o.dist[k] < inc) { if (k2 != k) { o.dist[k2] = o.dist[k]; for (int a = 0; a < 3; a++) { o.pos[k2][a] = o.pos[k][a]; o.nrm[k2][a] = o.nrm[k][a]; } } k2++; }
       o.cnt = k2;
-      ocnt = k2;
     }
+    int ocnt = o.cnt;
     int gtotal, gslot = wexscan(ocnt > 0 ? 1 : 0, c.lane, &gtotal);
     int basec = cnt[CNT_NCON], baseg = cnt[CNT_NGRP];
     int gid = baseg + gslot;
@@ -1433,24 +1306,17 @@ STAGE void collision(const Ctx c) {
     // counted contact record is then really written (a counted but unwritten record would be finalised from stale words)
     if (ocnt > 0 && gid >= h->ngrp_max - DM_NWELD_MAX) ocnt = 0;
     int total, slot = wexscan(ocnt, c.lane, &total);
-    // the slots of region B overlay the contact records written below: every lane parks its contacts in registers first
-    float P[4][7];
-#pragma unroll
-    for (int k = 0; k < 4; k++) if (k < ocnt) {
-      P[k][0] = o.pos[k][0]; P[k][1] = o.pos[k][1]; P[k][2] = o.pos[k][2];
-      P[k][3] = o.nrm[k][0]; P[k][4] = o.nrm[k][1]; P[k][5] = o.nrm[k][2]; P[k][6] = o.dist[k];
-    }
+    // (the slots of region B overlay the contact records written below: BoxScratch is dead by now)
     SYNC();
     int kept = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < ocnt; k++) {
       // raw contact (position, normal, distance, pair) parked in its record; finalised by one lane per contact below
       int id = basec + slot + k;
-      if (k >= ocnt || id >= h->ncon_max) continue;
+      if (id >= h->ncon_max) break;
       float* cr = SF(con) + id * CON_WORDS;
-      cr[0] = P[k][0]; cr[1] = P[k][1]; cr[2] = P[k][2];
-      cr[3] = P[k][3]; cr[4] = P[k][4]; cr[5] = P[k][5];
-      cr[6] = P[k][6];
+      cr[0] = o.pos[k][0]; cr[1] = o.pos[k][1]; cr[2] = o.pos[k][2];
+      cr[3] = o.nrm[k][0]; cr[4] = o.nrm[k][1]; cr[5] = o.nrm[k][2];
+      cr[6] = o.dist[k];
       ((int*)cr)[7] = p;
       ((int*)cr)[C_DIMGRP] = gid << 8;
       kept++;

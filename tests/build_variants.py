@@ -13,7 +13,12 @@ NAMES = ("b200sim", "b200sim_wide", "b200sim_kitchen", "b200sim_kitchen_groups")
 def build(name, src, extra):
     out = os.path.join(ROOT, "gpurun_variants", f"lib{name}.so")
     objs, procs = [], []
+    only = os.environ.get("B200_VARIANT_ONLY")            # e.g. "b200sim": compile that unit only ...
+    reuse = os.environ.get("B200_VARIANT_REUSE")          # ... and link the other units' objects of an earlier variant
     for n in NAMES:
+        if only and n != only:
+            objs.append(os.path.join("/tmp", f"var_{reuse}_{n}.o"))
+            continue
         o = os.path.join("/tmp", f"var_{name}_{n}.o")
         objs.append(o)
         procs.append(subprocess.Popen(["nvcc"] + BASE + extra + ["-c", "-o", o, os.path.join(src, "gymnasium_robotics_b200", "csrc", n + ".cu")],
