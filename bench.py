@@ -22,6 +22,17 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE JSON line: NCCL's own banner ("NCCL version ...", printed on stdout when NCCL_DEBUG is set) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# ... and whatever else a library writes to file descriptor 1 ends up on stderr too: the JSON line is written to a duplicate of the
+# original stdout
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -150,7 +161,7 @@ def run_reference(args, quiet=False):
                              "median": value, "min": min(rates), "max": max(rates), "per_core": value / cores, "repetitions": reps},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if not quiet:
-        print(json.dumps(line))
+        emit(line)
     return line
 
 
@@ -452,7 +463,7 @@ def run_ours(args):
                 "roofline": roofline_object(res, args.steps), "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": res["launches"], "resets_in_timed_region": int(resets), "solver_overflow_env_steps": int(overflow),
                 "clocks": res["clocks"], "configs": configs}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         H.dist.destroy_process_group()
 

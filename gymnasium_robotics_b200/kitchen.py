@@ -128,6 +128,21 @@ class KitchenVectorEnv(CtorPickle):
         self.init_qpos, self.init_qvel = f32(INIT_QPOS), torch.zeros(nv, dtype=torch.float32, device=dev)
         self._idx = {t: torch.as_tensor(OBS_ELEMENT_INDICES[t], device=dev) for t in tasks}
         self._goal = {t: f32(OBS_ELEMENT_GOALS[t]) for t in tasks}
+        # every task's qpos entries are one contiguous run (kitchen_env.py:20-38): `achieved_goal[t]` is a view, not a gather
+        self._run = {}
+        for t in tasks:
+            ii = [int(i) for i in OBS_ELEMENT_INDICES[t]]
+            self._run[t] = slice(ii[0], ii[-1] + 1) if ii == list(range(ii[0], ii[-1] + 1)) else None
+        # all tasks' distance tests in one pass: entries padded to the longest task, padding masked out of the squared distance
+        kmax = max(len(OBS_ELEMENT_INDICES[t]) for t in tasks)
+        idx_pad = np.zeros((len(tasks), kmax), dtype=np.int64)
+        goal_pad, live = np.zeros((len(tasks), kmax)), np.zeros((len(tasks), kmax))
+        for j, t in enumerate(tasks):
+            k = len(OBS_ELEMENT_INDICES[t])
+            idx_pad[j, :k], goal_pad[j, :k], live[j, :k] = OBS_ELEMENT_INDICES[t], OBS_ELEMENT_GOALS[t], 1.0
+        self._idx_pad = torch.as_tensor(idx_pad.reshape(-1), device=dev)
+        self._goal_pad, self._live_pad = f32(goal_pad), f32(live)
+        self._all_idx = torch.arange(self.num_envs, device=dev)
         self.single_action_space = Box(-1.0, 1.0, shape=(9,), dtype=np.float64)  # franka_env.py:90
         self.single_observation_space = Box(-np.inf, np.inf, shape=(int(self.task.nobs),), dtype=np.float64)
         self.action_space = batch_space(self.single_action_space, self.num_envs)
@@ -156,7 +171,8 @@ class KitchenVectorEnv(CtorPickle):
 
     def _obs_dict(self, out, obs):
         q = out["achieved"]
-        return {"observation": obs, "achieved_goal": {t: q[:, self._idx[t]] for t in self.tasks},
+        return {"observation": obs,
+                "achieved_goal": {t: (q[:, self._run[t]] if self._run[t] is not None else q[:, self._idx[t]]) for t in self.tasks},
                 "desired_goal": {t: self._goal[t].expand(self.num_envs, -1) for t in self.tasks}}
 
     # ------------------------------------------------------------------ reset
@@ -207,12 +223,13 @@ class KitchenVectorEnv(CtorPickle):
         out = self.backend.new_outputs()
         self.backend.step(ctrl, out)                                  # do_simulation(ctrl, 40) + TimeLimit: one kernel launch
         truncated = out["truncated"]
-        all_idx = torch.arange(self.num_envs, device=self.device)
-        obs = out["obs"] + self._noise(all_idx)
+        obs = out["obs"] + self._noise(self._all_idx)
         self._last_robot_qpos = obs[:, :9].clone()
         q = out["achieved"]
         # kitchen_env.py:356-369, 399-423
-        close = torch.stack([torch.linalg.norm(q[:, self._idx[t]] - self._goal[t], dim=1) < BONUS_THRESH for t in self.tasks], dim=1)
+        # (|| q[task] - goal || < BONUS_THRESH for every task at once; the norm itself, as the reference compares it)
+        diff = (q[:, self._idx_pad].view(self.num_envs, len(self.tasks), -1) - self._goal_pad) * self._live_pad
+        close = torch.linalg.norm(diff, dim=2) < BONUS_THRESH
         step_done = close & self._todo
         reward = step_done.sum(dim=1).to(torch.float32)
         if self.remove_task_when_completed:
