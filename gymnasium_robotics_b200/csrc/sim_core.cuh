@@ -2313,11 +2313,15 @@ HD void forward(const Ctx c, bool active, bool* euler_solved = nullptr) {
   constexpr bool CX = NVP == 22 || NVP >= 30;   // NVP 22 = the 21-dof arm build plus the convex collider (FetchSlide)
   constexpr int kAlign = ALIGN_LEVEL_FOR(NVP);
   TIC();
+#ifndef B200_NO_ALIGN_FIRST
   ALIGN_AT(1); TOC(TM_BARRIER);
+#endif
   if (active) kinematics(c);
   TOC(TM_KIN); ALIGN_AT(4); TOC(TM_BARRIER);
   if (active) { com_quantities(c); mass_matrix(c); }
+#ifndef B200_NO_ALIGN_PRECOLL
   TOC(TM_COM_M); ALIGN_AT(2); TOC(TM_BARRIER);
+#endif
   if (active) collision<HF, CX>(c);
   TOC(TM_COLL); ALIGN_AT(2); TOC(TM_BARRIER);
   if (active) make_constraint<HF>(c);
