@@ -1035,10 +1035,12 @@ HDN void collide_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o
     if (dot3(v2.v, dir) <= 0) return;
     cvx_portal_dir(v0, v1, v2, dir);
     if (dot3(dir, v0.v) > 0) { CvxPt tmp = v1; v1 = v2; v2 = tmp; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+    // (the two search loops leave through `break` only -- a miss is a flag tested after the loop, not a return from inside it)
+    bool miss = false;
     for (int it = 0;; it++) {  // portal discovery
-      if (it > maxit) return;
+      if (it > maxit) { miss = true; break; }
       cvx_msupport(A, B, dir, v3);
-      if (dot3(v3.v, dir) <= 0) return;
+      if (dot3(v3.v, dir) <= 0) { miss = true; break; }
       bool cont = false;
       cross3(t, v1.v, v3.v);
       if (dot3(t, v0.v) < 0) { v2 = v3; cont = true; }
@@ -1046,19 +1048,21 @@ HDN void collide_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o
       if (!cont) break;
       cvx_portal_dir(v0, v1, v2, dir);
     }
+    if (miss) return;
     bool hit = false;
     for (int it = 0;; it++) {  // refinement; past the origin the shapes overlap and the loop runs on to the surface
       cvx_portal_dir(v1, v2, v3, dir);
       if (dot3(dir, v1.v) >= 0) hit = true;
       cvx_msupport(A, B, dir, v4);
       float d4 = dot3(v4.v, dir);
-      if (!hit && d4 < 0) return;
+      if (!hit && d4 < 0) { miss = true; break; }
       float mn = fminf(fminf(d4 - dot3(v1.v, dir), d4 - dot3(v2.v, dir)), d4 - dot3(v3.v, dir));
-      if (mn <= tol || it >= maxit) { if (!hit) return; break; }
+      if (mn <= tol || it >= maxit) { miss = !hit; break; }
       cross3(t, v4.v, v0.v);
       if (dot3(v1.v, t) > 0) { if (dot3(v2.v, t) > 0) v1 = v4; else v3 = v4; }
       else { if (dot3(v3.v, t) > 0) v2 = v4; else v1 = v4; }
     }
+    if (miss) return;
     depth = dot3(dir, v1.v);
     float b0, b1, b2, b3, sum;
     cross3(t, v1.v, v2.v); b0 = dot3(t, v3.v);
