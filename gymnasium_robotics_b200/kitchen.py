@@ -210,16 +210,19 @@ class KitchenVectorEnv(CtorPickle):
         return self._obs_dict(out, noisy), info
 
     # ------------------------------------------------------------------ step
+    def control_targets(self, a):
+        """franka_env.py:92-100, 139-170: clip, act_mid + a * act_rng (0, 2), velocity bounds, position target from the last noisy
+        robot observation, position bounds -- the `ctrl` the step kernel receives."""
+        vel = torch.clamp(torch.clamp(a, -1.0, 1.0) * 2.0, self._vel_lo, self._vel_hi)
+        return torch.clamp(self._last_robot_qpos + vel * self.dt, self._pos_lo, self._pos_hi).contiguous()
+
     def step(self, actions):
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
         if tuple(actions.shape) != (self.num_envs, 9):
             raise ValueError("Action dimension mismatch")
         a = actions.to(self.device, torch.float32, non_blocking=True)
-        # franka_env.py:92-100, 139-170: clip, act_mid + a * act_rng (0, 2), velocity bounds, target from the last noisy
-        # robot observation, position bounds
-        vel = torch.clamp(torch.clamp(a, -1.0, 1.0) * 2.0, self._vel_lo, self._vel_hi)
-        ctrl = torch.clamp(self._last_robot_qpos + vel * self.dt, self._pos_lo, self._pos_hi).contiguous()
+        ctrl = self.control_targets(a)
         out = self.backend.new_outputs()
         self.backend.step(ctrl, out)                                  # do_simulation(ctrl, 40) + TimeLimit: one kernel launch
         truncated = out["truncated"]
