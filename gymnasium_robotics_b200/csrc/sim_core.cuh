@@ -34,6 +34,17 @@
 #ifdef B200_ALIGN_SYNCWARP
 #define ALIGN() do { __syncwarp(); __syncthreads(); } while (0)
 #define ALIGN_OR(p) (__syncwarp(), __syncthreads_or(p))
+#elif defined(B200_AG)
+// A/B variant: alignment groups of B200_AG warps inside the block (named barriers 1 + group): fewer warps wait for one straggler, at the
+// price of as many code windows per SM as there are groups
+static __device__ __forceinline__ void b200_bar_g(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+static __device__ __forceinline__ bool b200_bar_or_g(int id, int nthreads, bool p) {
+  int r;
+  asm volatile("{ .reg .pred q, r; setp.ne.s32 q, %3, 0; bar.red.or.pred r, %1, %2, q; selp.s32 %0, 1, 0, r; }" : "=r"(r) : "r"(id), "r"(nthreads), "r"((int)p) : "memory");
+  return r != 0;
+}
+#define ALIGN() b200_bar_g(1 + (int)(threadIdx.x >> 5) / B200_AG, B200_AG * 32)
+#define ALIGN_OR(p) b200_bar_or_g(1 + (int)(threadIdx.x >> 5) / B200_AG, B200_AG * 32, (p))
 #elif defined(B200_ALIGN_NONALIGNED)
 // A/B variant: PTX `barrier.sync` WITHOUT `.aligned` -- the form that tolerates a warp arriving in several convergence groups
 static __device__ __forceinline__ void b200_bar_na() { asm volatile("barrier.sync 0;" ::: "memory"); }
