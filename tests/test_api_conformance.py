@@ -115,6 +115,11 @@ def test_api_conformance(env_id, goal_env, nact, nobs):
         assert tuple(r.shape) == (n,) and r.dtype == torch.float32 and bool(torch.isfinite(r).all())
         assert tuple(te.shape) == (n,) and te.dtype == torch.bool and tuple(tr.shape) == (n,) and tr.dtype == torch.bool
         assert isinstance(inf, dict)
+        # the reference's info keys: robot_env.py:139-141 `is_success`; adroit_hammer.py:319 / maze_v4.py:401 `success`;
+        # kitchen_env.py:399-423 the three task-bookkeeping entries
+        want = ("is_success",) if env_id.startswith(("Fetch", "Hand")) else (("success",) if not env_id.startswith("Franka") else
+                ("tasks_to_complete", "step_task_completions", "episode_task_completions"))
+        assert all(k in inf for k in want), sorted(inf)
         if goal_env and not env_id.startswith("Franka"):
             # GoalEnv contract (core.py:45-62): the reward is a function of the goals in the observation
             rr = torch.as_tensor(env.compute_reward(o["achieved_goal"], o["desired_goal"], inf), dtype=torch.float32).reshape(n)
