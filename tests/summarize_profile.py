@@ -33,7 +33,8 @@ dram = num("dram__bytes_read.sum") * unit[vals["dram__bytes_read.sum"][1]] + num
 HAND = tag.startswith("hand")
 ADROIT = tag.startswith("adroit")
 KITCHEN = tag.startswith("kitchen")
-alg_b, alg_n = (1710, 2048) if HAND else ((1410, 2048) if ADROIT else ((1300, 2048) if KITCHEN else (766, 4096)))
+ANT = tag.startswith("ant")
+alg_b, alg_n = (1710, 2048) if HAND else ((1410, 2048) if ADROIT else ((1300, 2048) if KITCHEN else ((846, 1024) if ANT else (766, 4096))))
 lines.append(f"dram bytes per launch (read+write): {dram:.0f}   [algorithmic: {alg_b} B x {alg_n} envs = {alg_b*alg_n}]")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 srows = list(csv.reader(src.splitlines()))
@@ -76,7 +77,7 @@ def numk(k, default=None):
         return num(k)
     except Exception:
         return default
-workload = {"hand": "hand_block_touch", "adroit": "adroit_hammer", "kitchen": "franka_kitchen"}.get(tag.split("_")[0], "fetch_pick_and_place")
+workload = {"hand": "hand_block_touch", "adroit": "adroit_hammer", "kitchen": "franka_kitchen", "ant": "antmaze_large"}.get(tag.split("_")[0], "fetch_pick_and_place")
 tms = numk("gpu__time_duration.sum")
 tunit = vals.get("gpu__time_duration.sum", ("", ""))[1]
 tms = tms * {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "second": 1e3, "nsecond": 1e-6}.get(tunit, 1e-6) if tms is not None else None
@@ -95,7 +96,7 @@ roof = {"workload": workload, "ncu_source": f"profiles/ncu_step_kernel_{tag}.txt
         "top_stalls": [[k.replace("stall_", ""), round(100 * n / tot, 1)] for k, n in stalls.most_common(5)]}
 json.dump(roof, open(os.path.join(out_dir, f"roofline_{workload}.json"), "w"), indent=1)
 json.dump({"dram_bytes_per_launch": dram, "source": f"profiles/ncu_step_kernel_{tag}.txt", "algorithmic_bytes_per_launch": alg_b * alg_n},
-          open(os.path.join(out_dir, "traffic_hand.json" if HAND else ("traffic_adroit.json" if ADROIT else ("traffic_kitchen.json" if KITCHEN else "traffic.json"))), "w"))
+          open(os.path.join(out_dir, "traffic_hand.json" if HAND else ("traffic_adroit.json" if ADROIT else ("traffic_kitchen.json" if KITCHEN else ("traffic_ant.json" if ANT else "traffic.json")))), "w"))
 # launch list
 ll = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 if os.path.exists(ll):
