@@ -83,6 +83,13 @@ HD void site_vel(const Ctx& c, int site, const float* pos, float* velp, float* v
   if (velr) { velr[0] = V[0]; velr[1] = V[1]; velr[2] = V[2]; }
 }
 
+// squared-distance accumulation with ONE rounding sequence on the device (round-to-nearest fused multiply-add per term), the same in the
+// step kernel and in reward_kernel: `reward == compute_reward(achieved_goal, desired_goal)` bit for bit
+#ifdef __CUDA_ARCH__
+#define B200_SQACC(d2, e) d2 = fmaf((e), (e), d2)
+#else
+#define B200_SQACC(d2, e) d2 += (e) * (e)
+#endif
 HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float* obs, float* achieved, float* desired,
                       float* reward, float* success) {
   pass_V(c, SF(qvel), SF(cvel));  // site velocities: Jacobian of the last forward pass times the current qvel
@@ -121,7 +128,7 @@ HD void fetch_observe(const Ctx& c, const FetchTask& t, const float* goal, float
     for (int k = 0; k < 3; k++) o[n++] = gvel[k];
     o[n++] = gv[0]; o[n++] = gv[1];
     float d2 = 0;
-    for (int k = 0; k < 3; k++) { achieved[k] = ag[k]; desired[k] = goal[k]; float e = ag[k] - goal[k]; d2 += e * e; }
+    for (int k = 0; k < 3; k++) { achieved[k] = ag[k]; desired[k] = goal[k]; float e = ag[k] - goal[k]; B200_SQACC(d2, e); }
     float d = sqrtf(d2);
     *reward = t.reward_dense ? -d : -(d > t.distance_threshold ? 1.f : 0.f);
     *success = d < t.distance_threshold ? 1.f : 0.f;
@@ -203,7 +210,13 @@ HD void antmaze_observe(const Ctx& c, const FetchTask& t, const float* goal, flo
   }
   if (c.lane == 0) {
     float dx = SF(qpos)[0] - goal[0], dy = SF(qpos)[1] - goal[1];
+    // the same rounding sequence as reward_kernel's loop over the goal entries (b200sim.cu): round(dx^2), then one fused multiply-add --
+    // `reward == compute_reward(achieved_goal, desired_goal)` holds bit for bit (core.py:61-62), dense exp(-d) rewards included
+#ifdef __CUDA_ARCH__
+    float d = sqrtf(fmaf(dy, dy, __fmul_rn(dx, dx)));
+#else
     float d = sqrtf(dx * dx + dy * dy);
+#endif
     achieved[0] = SF(qpos)[0]; achieved[1] = SF(qpos)[1]; desired[0] = goal[0]; desired[1] = goal[1];
     *reward = t.reward_dense ? expf(-d) : (d <= t.success_radius ? 1.f : 0.f);
     *success = d <= t.success_radius ? 1.f : 0.f;
@@ -286,7 +299,7 @@ HD void reach_observe(const Ctx& c, const FetchTask& t, const float* goal, float
     for (int a = 0; a < 3; a++) {
       obs[h->nq + h->nv + 3 * k + a] = p[a]; achieved[3 * k + a] = p[a]; desired[3 * k + a] = goal[3 * k + a];
       float e = p[a] - goal[3 * k + a];
-      d2 += e * e;
+      B200_SQACC(d2, e);
     }
   }
   float d = sqrtf(wsum(d2));
