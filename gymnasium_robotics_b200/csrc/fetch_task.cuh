@@ -293,6 +293,22 @@ HD void reach_observe(const Ctx& c, const FetchTask& t, const float* goal, float
   LANES(i, h->nq) obs[i] = SF(qpos)[i];
   LANES(i, h->nv) obs[h->nq + i] = SF(qvel)[i];
   float d2 = 0.f;
+#ifdef B200_WARP_CODE
+  // lane k < 5 holds the error of finger tip k; the squared distance is then accumulated over the 15 entries IN ORDER by every lane
+  // (15 shuffles, once per env-step): the rounding sequence of reward_kernel's loop, so that the dense reward equals compute_reward bit for bit
+  float e3[3] = {0.f, 0.f, 0.f};
+  LANES(k, 5) {
+    float p[3];
+    site_pose(c, t.tip_site[k], p, nullptr);
+    for (int a = 0; a < 3; a++) {
+      obs[h->nq + h->nv + 3 * k + a] = p[a]; achieved[3 * k + a] = p[a]; desired[3 * k + a] = goal[3 * k + a];
+      e3[a] = p[a] - goal[3 * k + a];
+    }
+  }
+  for (int k = 0; k < 5; k++)
+    for (int a = 0; a < 3; a++) { float e = __shfl_sync(0xffffffffu, e3[a], k); B200_SQACC(d2, e); }
+  float d = sqrtf(d2);
+#else
   LANES(k, 5) {
     float p[3];
     site_pose(c, t.tip_site[k], p, nullptr);
@@ -303,6 +319,7 @@ HD void reach_observe(const Ctx& c, const FetchTask& t, const float* goal, float
     }
   }
   float d = sqrtf(wsum(d2));
+#endif
   if (c.lane == 0) {
     *reward = t.reward_dense ? -d : -(d > t.distance_threshold ? 1.f : 0.f);
     *success = d < t.distance_threshold ? 1.f : 0.f;

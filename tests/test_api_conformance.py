@@ -46,7 +46,7 @@ def _factory(env_id):
 # (id, goal-env?, action dim, observation dim)
 CASES = [
     ("FetchReach-v4", True, 4, 10), ("FetchPushDense-v4", True, 4, 25), ("FetchSlide-v4", True, 4, 25), ("FetchPickAndPlace-v4", True, 4, 25),
-    ("HandReach-v3", True, 20, 63), ("HandManipulateBlockRotateZ-v1", True, 20, 61),
+    ("HandReach-v3", True, 20, 63), ("HandReachDense-v3", True, 20, 63), ("HandManipulateBlockRotateZ-v1", True, 20, 61),
     ("HandManipulateBlockRotateXYZ_ContinuousTouchSensors-v1", True, 20, 153), ("HandManipulateEggFull-v1", True, 20, 61),
     ("HandManipulatePenRotateDense-v1", True, 20, 61),
     ("AdroitHandHammer-v2", False, 26, 46), ("AdroitHandRelocateSparse-v2", False, 30, 39), ("AdroitHandPen-v2", False, 24, 45),

@@ -10,6 +10,10 @@ from tests.test_api_conformance import CASES, _leaves, _same
 
 pytestmark = pytest.mark.gpu
 
+# more dense-reward ids on the product path (the GoalEnv contract is the point here)
+CASES = CASES + [("AntMaze_UMazeDense-v5", True, 8, 105), ("PointMaze_MediumDense-v3", True, 2, 4), ("FetchPickAndPlaceDense-v4", True, 4, 25),
+                 ("HandManipulateBlockRotateXYZDense-v1", True, 20, 61), ("HandManipulateEggRotateDense-v1", True, 20, 61)]
+
 
 @pytest.mark.parametrize("env_id,goal_env,nact,nobs", CASES, ids=[c[0] for c in CASES])
 def test_api_conformance_on_gpu(env_id, goal_env, nact, nobs):
