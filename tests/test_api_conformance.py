@@ -162,3 +162,22 @@ def test_same_seed_rollouts_are_bit_identical_and_pickle_round_trips(env_id):
     assert any(not torch.equal(la[k], lb[k]) for k in la)
     for e in (e1, e2, e3):
         e.close()
+
+
+@pytest.mark.parametrize("env_id", ["FetchReach-v4", "FetchPush-v4", "FetchSlide-v4", "FetchPickAndPlace-v4", "HandReach-v3"])
+def test_robot_env_reset_state(env_id):
+    """tests/test_envs.py:175-231 `test_robot_env_reset`: after reset, qpos == initial_qpos (the object's xy, qpos[-7:-5], excluded for
+    the tasks that draw it) and qvel == initial_qvel, for two seeds."""
+    n = 3
+    env = _make(env_id, n)
+    sl = env._sl
+    for seed in (24, 10):
+        env.reset(seed=seed)
+        st = env.backend.state
+        qpos, qvel = st[:, sl["qpos"]].clone(), st[:, sl["qvel"]].clone()
+        iq, iv = env.initial_qpos.clone().expand(n, -1), env.initial_qvel.clone().expand(n, -1)
+        if any(t in env_id for t in ("FetchPush", "FetchPickAndPlace", "FetchSlide")):
+            keep = [i for i in range(qpos.shape[1]) if i not in (qpos.shape[1] - 7, qpos.shape[1] - 6)]
+            qpos, iq = qpos[:, keep], iq[:, keep]
+        assert torch.equal(qpos, iq) and torch.equal(qvel, iv)
+    env.close()
