@@ -68,7 +68,7 @@ class KeepC(ctypes.Structure):
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """nvcc-compile csrc/b200sim.cu and csrc/b200sim_wide.cu for sm_100a into the in-tree libb200sim.so (cross-compiles
     without a GPU; the two translation units are compiled in parallel)."""
-    names = ("b200sim", "b200sim_wide", "b200sim_kitchen", "b200sim_kitchen_groups")
+    names = ("b200sim", "b200sim_wide", "b200sim_kitchen", "b200sim_kitchen_groups", "b200sim_kitchen_hull")
     srcs = [os.path.join(_HERE, "csrc", n + ".cu") for n in names]
     deps = srcs + [os.path.join(_HERE, "csrc", f) for f in ("sim_core.cuh", "fetch_task.cuh", "step_kernel.cuh", "dmodel.h", "reset_sample.cuh")] + \
            [os.path.join(_HERE, "..", "include", f) for f in ("b200sim.h", "b200sim_model.h")]

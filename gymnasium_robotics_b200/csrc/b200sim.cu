@@ -133,13 +133,19 @@ extern "C" int b200sim_kitchen_groups_build(const b200_model_view* view, const d
 extern "C" int b200sim_kitchen_groups_setattr(int wpb, int smem_bytes);
 extern "C" int b200sim_kitchen_groups_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
                                              int mode, int nraw, int N, const StepIO* io);
+// b200sim_kitchen_hull.cu: the groups build + support-map narrow phase for MESH geoms (models compiled with mesh_hull)
+extern "C" int b200sim_kitchen_hull_build(const b200_model_view* view, const double* eq_data, const float* ref, int penv_body,
+                                          std::vector<uint32_t>* buf, std::string* err);
+extern "C" int b200sim_kitchen_hull_setattr(int wpb, int smem_bytes);
+extern "C" int b200sim_kitchen_hull_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
+                                             int mode, int nraw, int N, const StepIO* io);
 extern "C" int b200sim_kitchen_launch(int wpb, int blocks, size_t smem_bytes, void* stream, const uint32_t* model_dev, const FetchTask* task,
                                       int mode, int nraw, int N, const StepIO* io);
 #define B200_KITCHEN_NVP 31   // the kitchen translation unit instantiates NVP = 31 (identity-padded; distinct kernel symbols)
 
 struct b200sim {
   int N = 0, device = 0;
-  bool kitchen = false, kitchen_groups = false;
+  bool kitchen = false, kitchen_groups = false, hull = false;
   std::vector<uint8_t> blob;
   b200_model_view view;
   std::vector<uint32_t> model_host;
@@ -210,8 +216,13 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   }
   const int penv = TASK_IS_ADROIT(task->kind) ? task->penv_body : -1;
   if (h->kitchen) { const char* g = getenv("B200SIM_KITCHEN_GROUPS"); h->kitchen_groups = !(g && g[0] && atoi(g) == 0); }  // default: two-level broad phase
-  if ((h->kitchen ? (h->kitchen_groups ? b200sim_kitchen_groups_build(&h->view, eq_data, r, penv, &h->model_host, &err)
-                                       : b200sim_kitchen_build(&h->view, eq_data, r, penv, &h->model_host, &err))
+  // MESH geoms (a model compiled with mesh_hull: hull vertex tables instead of box proxies) exist in the hull build only; that build
+  // is the kitchen groups build plus the support-map narrow phase, so it serves any model the kitchen build serves
+  for (int g = 0; g < h->view.ngeom; g++) if (h->view.geom_type[g] == B200_GEOM_MESH) h->hull = true;
+  if (h->hull) { h->kitchen = true; h->kitchen_groups = true; }
+  if ((h->kitchen ? (h->hull ? b200sim_kitchen_hull_build(&h->view, eq_data, r, penv, &h->model_host, &err)
+                             : (h->kitchen_groups ? b200sim_kitchen_groups_build(&h->view, eq_data, r, penv, &h->model_host, &err)
+                                                  : b200sim_kitchen_build(&h->view, eq_data, r, penv, &h->model_host, &err)))
                   : dm_build(h->view, eq_data, r, h->model_host, err, penv)) != 0) {
     delete h; return fail(nullptr, "b200sim_create: " + err, -4);
   }
@@ -321,7 +332,7 @@ int b200sim_create(const void* model_blob, size_t nbytes, const double* eq_data,
   B200_FOR_ALL_VARIANTS(B200_SETATTR)
 #undef B200_SETATTR
   if (h->nvp == B200_WIDE_NVP) e = b200sim_wide_setattr(h->wpb, (int)h->smem_bytes) == 0 ? cudaSuccess : cudaErrorInvalidValue;
-  if (h->nvp == B200_KITCHEN_NVP) e = (h->kitchen_groups ? b200sim_kitchen_groups_setattr(h->wpb, (int)h->smem_bytes) : b200sim_kitchen_setattr(h->wpb, (int)h->smem_bytes)) == 0 ? cudaSuccess : cudaErrorInvalidValue;
+  if (h->nvp == B200_KITCHEN_NVP) e = (h->hull ? b200sim_kitchen_hull_setattr(h->wpb, (int)h->smem_bytes) : (h->kitchen_groups ? b200sim_kitchen_groups_setattr(h->wpb, (int)h->smem_bytes) : b200sim_kitchen_setattr(h->wpb, (int)h->smem_bytes))) == 0 ? cudaSuccess : cudaErrorInvalidValue;
   if (e != cudaSuccess) { std::string m = std::string("b200sim_create: no kernel variant <") + std::to_string(h->wpb) + ", " + std::to_string(h->nvp) + "> or cudaFuncSetAttribute(smem=" + std::to_string(h->smem_bytes) + ") failed: " + cudaGetErrorString(e); delete h; return fail(nullptr, m, -8); }
   const size_t state_bytes = (size_t)num_envs * t.st_stride * 4;
   if (cudaMalloc(&h->model_dev, h->model_host.size() * 4) != cudaSuccess || cudaMalloc(&h->state, state_bytes) != cudaSuccess ||
@@ -398,7 +409,7 @@ static int launch(b200sim* h, int mode, int nraw, const float* actions, const un
   B200_FOR_ALL_VARIANTS(B200_LAUNCH)
 #undef B200_LAUNCH
   if (h->nvp == B200_KITCHEN_NVP)
-    matched = (h->kitchen_groups ? b200sim_kitchen_groups_launch : b200sim_kitchen_launch)(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev,
+    matched = (h->hull ? b200sim_kitchen_hull_launch : (h->kitchen_groups ? b200sim_kitchen_groups_launch : b200sim_kitchen_launch))(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev,
                                                                                         &h->task, mode, nraw, h->N, &io) == 0;
   if (h->nvp == B200_WIDE_NVP)
     matched = b200sim_wide_launch(h->wpb, h->blocks, h->smem_bytes, stream, h->model_dev, &h->task, mode, nraw, h->N, &io) == 0;

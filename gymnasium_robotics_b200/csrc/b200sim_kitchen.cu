@@ -7,7 +7,10 @@
 // (dmodel.h / sim_core.cuh); its kernels and entry points carry the suffix _groups so that both builds live in one library and
 // `b200sim_create` can pick either (B200SIM_KITCHEN_GROUPS=1; the plain build is the one validated on a B200 so far).
 #define B200_KITCHEN 1
-#ifdef B200_KITCHEN_GROUPS
+#if defined(B200_HULL)
+#define fetch_kernel fetch_kernel_hull
+#define KITCHEN_FN(name) b200sim_kitchen_hull_##name
+#elif defined(B200_KITCHEN_GROUPS)
 #define fetch_kernel fetch_kernel_groups
 #define KITCHEN_FN(name) b200sim_kitchen_groups_##name
 #else

@@ -42,6 +42,13 @@
 #define DM_PAIR_COLD(X)
 #define DM_BGRP_HOT(X)
 #endif
+// builds with the support-map narrow phase for mesh geoms (-DB200_HULL): per geom (first vertex, count) into the reduced-hull vertex
+// table of the blob (mjcf.py hull_vertices); read only by the narrow phase of a pair with such a geom
+#ifdef B200_HULL
+#define DM_HULL_COLD(X) X(geom_hull, 2, ngeom) X(hull_vert, 3, nhullv)
+#else
+#define DM_HULL_COLD(X)
+#endif
 #define DM_ARRAYS_HOT(X) \
   X(body_parent, 1, nb) X(body_jntadr, 1, nb) X(body_jntnum, 1, nb) X(body_dofadr, 1, nb) X(body_dofnum, 1, nb) \
   X(body_mocapid, 1, nb) X(body_ancdof, MW, nb) X(body_sub, 1, nb) X(body_pos, 3, nb) X(body_quat, 4, nb) \
@@ -69,7 +76,8 @@
   X(pair_solimp, 5, npair) X(pair_invweight, 2, npair) \
   X(ten_solref, 2, nten) X(ten_solimp, 5, nten) X(ten_invweight, 1, nten) \
   X(sensor_site, 1, nsensor) X(sensor_body, 1, nsensor) X(sensor_type, 1, nsensor) X(sensor_size, 3, nsensor) \
-  X(geom_mjb, 1, ngeom) X(mjb_rt, 1, nmjb) /* MJCF (unfused) body of a geom / runtime body of an MJCF body: cfrc_ext rows */
+  X(geom_mjb, 1, ngeom) X(mjb_rt, 1, nmjb) /* MJCF (unfused) body of a geom / runtime body of an MJCF body: cfrc_ext rows */ \
+  DM_HULL_COLD(X)
 #define DM_ARRAYS(X) DM_ARRAYS_HOT(X) DM_ARRAYS_COLD(X)
 
 // per-env scratch that lives for the whole sub-step (name, words expression)
@@ -291,6 +299,10 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
       neq = h.neq, npair = h.npair, ngridw = h.ngridw, ncon_max = h.ncon_max, ngrp_max = h.ngrp_max, ndr_max = h.ndr_max,
       nten = h.nten, nfric = h.nfric, nsensor = h.nsensor, ncx = h.nsensor > 0 ? h.ncon_max : 0, MW = h.mask_words,
       grp_words = MW == 2 ? 34 : 32, npenv = h.penv_body > 0 ? 8 : 0, nmjb = h.nmjb;
+#ifdef B200_HULL
+  int nhullv = m.n_hull_vert / 3;
+  if (m.n_geom_hull != 2 * m.ngeom) { err = "model blob lacks the hull vertex table (compile with mesh_hull)"; return -1; }
+#endif
 #ifdef B200_KITCHEN_GROUPS
   int nbgrp = h.nbgrp;
 #endif
@@ -440,7 +452,16 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     for (int k = 0; k < 4; k++) F(h.o_geom_quat, 4 * g + k, m.geom_quat[4 * sg + k]);
     F(h.o_geom_rbound, g, m.geom_rbound[sg]);
     I(h.o_geom_mjb, g, m.n_geom_mjbody == m.ngeom ? m.geom_mjbody[sg] : m.geom_body[sg]);
+#ifdef B200_HULL
+    I(h.o_geom_hull, 2 * g, m.geom_hull[2 * sg]); I(h.o_geom_hull, 2 * g + 1, m.geom_hull[2 * sg + 1]);
+    if (m.geom_type[sg] == B200_GEOM_MESH && m.geom_hull[2 * sg + 1] < 4) { err = "mesh geom without a hull vertex table"; return -1; }
+#else
+    if (m.geom_type[sg] == B200_GEOM_MESH) { err = "mesh geoms need the hull build of the library (models compiled without mesh_hull carry box proxies)"; return -1; }
+#endif
   }
+#ifdef B200_HULL
+  for (int i = 0; i < 3 * nhullv; i++) F(h.o_hull_vert, i, m.hull_vert[i]);
+#endif
   for (int p = 0; p < npair; p++) {
     int sp = psrc[p];
     I(h.o_pair_geom1, p, gmap[m.pair_geom1[sp]]); I(h.o_pair_geom2, p, pgrid[p] ? -1 : gmap[m.pair_geom2[sp]]); I(h.o_pair_condim, p, m.pair_condim[sp]);
@@ -450,6 +471,12 @@ static inline int dm_build(const b200_model_view& m, const double* eq_data_overr
     bool v1 = r1 || c1 || t1 == B200_GEOM_BOX, v2 = r2 || c2 || t2 == B200_GEOM_BOX;   // convex primitives
     bool ok = (t1 == B200_GEOM_PLANE && (t2 == B200_GEOM_BOX || r2 || c2)) || (t1 == B200_GEOM_BOX && t2 == B200_GEOM_BOX) ||
               (r1 && t2 == B200_GEOM_BOX) || (r1 && r2) || ((c1 || c2) && v1 && v2);
+#ifdef B200_HULL
+    {  // hull geoms: plane-hull has its own routine, every other pair with a hull goes through the portal-refinement collider
+      bool m1 = t1 == B200_GEOM_MESH, m2 = t2 == B200_GEOM_MESH;
+      if ((t1 == B200_GEOM_PLANE && m2) || ((m1 || m2) && (v1 || m1) && (v2 || m2))) { ok = true; c1 = c1 || m1; c2 = c2 || m2; }
+    }
+#endif
     if (r1 && r2) h.any_round_pair = 1;
     if (c1 || c2) h.any_convex_pair = 1;   // served by the general convex collider (kernel builds with CX)
 

@@ -983,13 +983,24 @@ HDN void collide_round_round(const Ctx c, int g1, int g2, float margin, ContactO
 // collider: tolerance 1e-6, at most 50 rounds), one contact per pair, both shapes inflated by margin / 2, dist = margin -
 // depth.  Same decision logic as oracle/oracle.c cvx_mpr; evaluated relative to the first geom's centre so that fp32
 // keeps its resolution.  A point of A - B is kept as (v, witness on A); the witness on B is a - v.
+#ifdef B200_HULL
+struct CvxShape { int type; float pos[3], mat[9], size[3], infl; const float* hv; int nhv; };   // hv: hull vertices (global memory)
+#else
 struct CvxShape { int type; float pos[3], mat[9], size[3], infl; };
+#endif
 struct CvxPt { float v[3], a[3]; };
 HD void cvx_support(const CvxShape& g, const float* d, float* out) {
   float l[3], sl[3] = {0, 0, 0};
   mulmtv(l, g.mat, d);
   const float* z = g.size;
   if (g.type == B200_GEOM_BOX) { sl[0] = l[0] >= 0 ? z[0] : -z[0]; sl[1] = l[1] >= 0 ? z[1] : -z[1]; sl[2] = l[2] >= 0 ? z[2] : -z[2]; }
+#ifdef B200_HULL
+  else if (g.type == B200_GEOM_MESH) {   // reduced convex hull: the vertex farthest along l, the first one on ties (as oracle/oracle.c)
+    int best = 0; float bd = -3.0e38f;
+    for (int i = 0; i < g.nhv; i++) { float dd = g.hv[3 * i] * l[0] + g.hv[3 * i + 1] * l[1] + g.hv[3 * i + 2] * l[2]; if (dd > bd) { bd = dd; best = i; } }
+    if (g.nhv > 0) { sl[0] = g.hv[3 * best]; sl[1] = g.hv[3 * best + 1]; sl[2] = g.hv[3 * best + 2]; }
+  }
+#endif
   else if (g.type == B200_GEOM_CYLINDER) {
     float n = sqrtf(l[0] * l[0] + l[1] * l[1]);
     if (n > 1e-12f) { float i = z[0] / n; sl[0] = i * l[0]; sl[1] = i * l[1]; }
@@ -1024,6 +1035,10 @@ HDN void collide_convex(const Ctx c, int g1, int g2, float margin, ContactOut& o
   float p1[3], p2[3];
   geom_pose(c, g1, p1, A.mat); geom_pose(c, g2, p2, B.mat);
   A.type = MI(geom_type)[g1]; B.type = MI(geom_type)[g2];
+#ifdef B200_HULL
+  A.hv = GF(hull_vert) + 3 * GI(geom_hull)[2 * g1]; A.nhv = GI(geom_hull)[2 * g1 + 1];
+  B.hv = GF(hull_vert) + 3 * GI(geom_hull)[2 * g2]; B.nhv = GI(geom_hull)[2 * g2 + 1];
+#endif
   for (int k = 0; k < 3; k++) { A.pos[k] = 0.f; B.pos[k] = p2[k] - p1[k]; A.size[k] = MF(geom_size)[3 * g1 + k]; B.size[k] = MF(geom_size)[3 * g2 + k]; }
   A.infl = B.infl = 0.5f * margin;
   const float tol = 1e-6f; const int maxit = 50;
@@ -1105,6 +1120,32 @@ HDN void collide_plane_convex(const Ctx c, int g1, int g2, float margin, Contact
   geom_pose(c, g1, pp, pm); geom_pose(c, g2, cp, cm);
   float n[3] = {pm[2], pm[5], pm[8]};
   const float* sz = MF(geom_size) + 3 * g2;
+#ifdef B200_HULL
+  if (MI(geom_type)[g2] == B200_GEOM_MESH) {
+    // plane vs hull: the hull vertices within the margin of the plane, the deepest first, at most four ((distance, index) order)
+    const float* hv = GF(hull_vert) + 3 * GI(geom_hull)[2 * g2];
+    const int nhv = GI(geom_hull)[2 * g2 + 1];
+    float last = -3.0e38f; int lasti = -1;
+    for (int k = 0; k < 4; k++) {
+      int best = -1; float bd = 3.0e38f;
+      for (int i = 0; i < nhv; i++) {
+        float p[3];
+        mulmv(p, cm, hv + 3 * i);
+        float dif[3] = {p[0] + cp[0] - pp[0], p[1] + cp[1] - pp[1], p[2] + cp[2] - pp[2]};
+        float d = dot3(dif, n);
+        if ((d > last || (d == last && i > lasti)) && d < bd) { bd = d; best = i; }
+      }
+      if (best < 0 || bd > margin) break;
+      float p[3];
+      mulmv(p, cm, hv + 3 * best);
+      int k2 = o.cnt++;
+      o.dist[k2] = bd;
+      for (int a = 0; a < 3; a++) { o.nrm[k2][a] = n[a]; o.pos[k2][a] = p[a] + cp[a] - 0.5f * bd * n[a]; }
+      last = bd; lasti = best;
+    }
+    return;
+  }
+#endif
   if (MI(geom_type)[g2] == B200_GEOM_ELLIPSOID) {
     float l[3], nn[3] = {-n[0], -n[1], -n[2]}, sl[3] = {0, 0, 0}, p[3];
     mulmtv(l, cm, nn);
@@ -1296,7 +1337,12 @@ STAGE void collision(const Ctx c) {
       int g1 = PAIR_I(pair_geom1)[p], g2 = PAIR_I(pair_geom2)[p];
       float margin = PAIR_F(pair_margin)[p];
       int t1 = MI(geom_type)[g1], t2 = g2 < 0 ? B200_GEOM_BOX : MI(geom_type)[g2];
+#ifdef B200_HULL
+      const bool cv1 = t1 == B200_GEOM_CYLINDER || t1 == B200_GEOM_ELLIPSOID || t1 == B200_GEOM_MESH,
+                 cv2 = t2 == B200_GEOM_CYLINDER || t2 == B200_GEOM_ELLIPSOID || t2 == B200_GEOM_MESH;
+#else
       const bool cv1 = t1 == B200_GEOM_CYLINDER || t1 == B200_GEOM_ELLIPSOID, cv2 = t2 == B200_GEOM_CYLINDER || t2 == B200_GEOM_ELLIPSOID;
+#endif
       if (CX && (cv1 || cv2)) {
         if (t1 == B200_GEOM_PLANE) collide_plane_convex(c, g1, g2, margin, o);
         else collide_convex(c, g1, g2, margin, o);

@@ -84,7 +84,13 @@ class KitchenVectorEnv(CtorPickle):
         self.num_envs, self.max_episode_steps, self.autoreset_mode = int(num_envs), max_episode_steps, autoreset_mode
         self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
         self.frame_skip = self.n_substeps = int(frame_skip)
-        self.model = model if model is not None else load_model("franka_kitchen")
+        # mesh_collision="hull": the nine Franka collision meshes collide through support maps on their reduced convex hulls (32 vertices
+        # each; blob franka_kitchen_hull, kernels of csrc/b200sim_kitchen_hull.cu) instead of box proxies (DESIGN.md deviation 1)
+        mesh_collision = kwargs.get("mesh_collision", "box")
+        if mesh_collision not in ("box", "hull"):
+            raise ValueError("mesh_collision must be 'box' or 'hull'")
+        self.mesh_collision = mesh_collision
+        self.model = model if model is not None else load_model("franka_kitchen_hull" if mesh_collision == "hull" else "franka_kitchen")
         m = self.model
         self.task = make_kitchen_task(m, frame_skip)
         # broadphase="groups" (default): the kernel build with the two-level broad phase (csrc/b200sim_kitchen_groups.cu) -- on a B200
@@ -94,6 +100,8 @@ class KitchenVectorEnv(CtorPickle):
         broadphase = kwargs.get("broadphase", "flat" if os.environ.get("B200SIM_KITCHEN_GROUPS", "1") in ("0",) else "groups")
         if broadphase not in ("flat", "groups"):
             raise ValueError("broadphase must be 'flat' or 'groups'")
+        if mesh_collision == "hull" and broadphase != "groups":
+            raise ValueError("mesh_collision='hull' exists for the two-level broad phase only")
         self.broadphase = broadphase
         prev = os.environ.get("B200SIM_KITCHEN_GROUPS")
         os.environ["B200SIM_KITCHEN_GROUPS"] = "1" if broadphase == "groups" else "0"

@@ -167,6 +167,40 @@ def geom_volume_inertia(gtype, size):
     raise ValueError(f"no inertia rule for geom type {gtype}")
 
 
+HULL_MAX_VERTS = 32
+
+
+def hull_vertices(points, kmax=HULL_MAX_VERTS):
+    """At most `kmax` vertices of the convex hull of `points` [n, 3]: the hull's own vertices (scipy / qhull) when there are few,
+    otherwise the support points of a fixed direction set (axes, cube diagonals, a Fibonacci sphere) thinned by farthest-point
+    selection -- an inner approximation whose support function is exact in the sampled directions.  Deterministic."""
+    from scipy.spatial import ConvexHull
+
+    pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    hv = pts[np.sort(ConvexHull(pts).vertices)]
+    if len(hv) <= kmax:
+        return hv
+    dirs = [np.array(d, dtype=np.float64) for d in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1))]
+    dirs += [np.array((a, b, c), dtype=np.float64) for a in (-1, 1) for b in (-1, 1) for c in (-1, 1)]
+    n, ga = 96, np.pi * (3.0 - np.sqrt(5.0))
+    for i in range(n):
+        z = 1.0 - 2.0 * (i + 0.5) / n
+        r = np.sqrt(max(0.0, 1.0 - z * z))
+        dirs.append(np.array((r * np.cos(ga * i), r * np.sin(ga * i), z)))
+    idx = sorted({int(np.argmax(hv @ (d / np.linalg.norm(d)))) for d in dirs})
+    cand = hv[idx]
+    if len(cand) <= kmax:
+        return cand
+    # farthest-point thinning, seeded with the six axis extremes
+    keep = sorted({int(np.argmax(cand @ d)) for d in dirs[:6]})
+    dist = np.min(np.linalg.norm(cand[:, None, :] - cand[keep][None, :, :], axis=2), axis=1)
+    while len(keep) < kmax:
+        j = int(np.argmax(dist))
+        keep.append(j)
+        dist = np.minimum(dist, np.linalg.norm(cand - cand[j], axis=1))
+    return cand[sorted(keep)]
+
+
 def mesh_volume_inertia(tris):
     """Volume, centre of mass and unit-density inertia tensor (about the centre of mass, mesh frame) of a closed triangle
     mesh [n, 3, 3] by signed tetrahedra against the origin (the exact integrals of a polyhedron)."""
@@ -359,8 +393,12 @@ class _Parser:
         for a in r.findall("asset"):
             for m in a.findall("mesh"):
                 ma = self.attrs(m, None)
-                name = ma.get("name") or os.path.splitext(os.path.basename(ma["file"]))[0]
-                v = load_stl(os.path.join(self.dir, self.compiler["meshdir"], ma["file"]))
+                if "vertex" in ma:     # MJCF: vertex coordinates given inline (the hull of the points is the mesh)
+                    name = ma["name"]
+                    v = floats(ma["vertex"]).reshape(-1, 3)
+                else:
+                    name = ma.get("name") or os.path.splitext(os.path.basename(ma["file"]))[0]
+                    v = load_stl(os.path.join(self.dir, self.compiler["meshdir"], ma["file"]))
                 v = v * floats(ma.get("scale"), 3, [1, 1, 1])
                 self.full.meshes[name] = v
         # world body (id 0)
@@ -531,7 +569,7 @@ class Model:
                   "dof_body", "dof_jnt", "dof_parent", "geom_type", "geom_body", "pair_geom1", "pair_geom2", "pair_condim",
                   "site_body", "act_trnid", "act_ctrllimited", "act_forcelimited", "eq_type", "eq_obj1", "eq_obj2",
                   "eq_active", "mocap_body", "ten_adr", "ten_num", "ten_limited", "wrap_dof", "sensor_site", "sensor_body", "sensor_type",
-                  "pair_grid", "grid_dims", "grid_walls", "geom_mjbody", "mjbody_rt"]
+                  "pair_grid", "grid_dims", "grid_walls", "geom_mjbody", "mjbody_rt", "geom_hull"]
     FLT_FIELDS = ["opt", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "jnt_pos",
                   "jnt_axis", "jnt_range", "jnt_margin", "jnt_stiffness", "jnt_solref", "jnt_solimp", "qpos0",
                   "qpos_spring", "dof_armature", "dof_damping", "dof_frictionloss", "dof_invweight0", "dof_solref_fri",
@@ -539,7 +577,9 @@ class Model:
                   "geom_size", "geom_rbound", "pair_friction", "pair_margin", "pair_gap", "pair_solref", "pair_solimp",
                   "pair_invweight", "site_pos", "site_quat", "act_gear", "act_gainprm", "act_biasprm", "act_ctrlrange",
                   "act_forcerange", "eq_data", "eq_solref", "eq_solimp", "eq_invweight", "ten_range", "ten_margin",
-                  "ten_solref", "ten_solimp", "ten_invweight0", "wrap_coef", "sensor_size", "key_qpos", "grid_param"]
+                  "ten_solref", "ten_solimp", "ten_invweight0", "wrap_coef", "sensor_size", "key_qpos", "grid_param", "hull_vert"]
+    # written only when non-empty, read as empty when absent: blobs of models without such data are byte-identical to older ones
+    OPTIONAL_FIELDS = ("geom_hull", "hull_vert")
 
     def __init__(self):
         self.names = {}
@@ -557,11 +597,15 @@ class Model:
         entries, payload = [], b""
         for name in self.INT_FIELDS:
             arr = np.ascontiguousarray(getattr(self, name), dtype=np.int32).ravel()
+            if name in self.OPTIONAL_FIELDS and arr.size == 0:
+                continue
             entries.append((name, 0, arr.size, len(payload)))
             payload += arr.tobytes()
             payload += b"\0" * ((-len(payload)) % 8)
         for name in self.FLT_FIELDS:
             arr = np.ascontiguousarray(getattr(self, name), dtype=np.float64).ravel()
+            if name in self.OPTIONAL_FIELDS and arr.size == 0:
+                continue
             entries.append((name, 1, arr.size, len(payload)))
             payload += arr.tobytes()
         meta = json.dumps(self.names).encode()
@@ -590,6 +634,9 @@ class Model:
         for name in Model.INT_FIELDS:    # blobs written before a field existed: the field reads as empty
             if name not in m.__dict__:
                 setattr(m, name, np.zeros(0, dtype=np.int32))
+        for name in Model.OPTIONAL_FIELDS:
+            if name not in m.__dict__:
+                setattr(m, name, np.zeros(0, dtype=np.float64 if name in Model.FLT_FIELDS else np.int32))
         m._reshape()
         return m
 
@@ -598,7 +645,7 @@ class Model:
                "geom_pos": 3, "geom_quat": 4, "geom_size": 3,
                "pair_friction": 5, "pair_solref": 2, "pair_solimp": 5, "pair_invweight": 2, "site_pos": 3, "site_quat": 4,
                "act_gainprm": 3, "act_biasprm": 3, "act_ctrlrange": 2, "act_forcerange": 2, "eq_data": 11, "eq_solref": 2,
-               "eq_solimp": 5, "eq_invweight": 2, "ten_range": 2, "ten_solref": 2, "ten_solimp": 5, "sensor_size": 3}
+               "eq_solimp": 5, "eq_invweight": 2, "ten_range": 2, "ten_solref": 2, "ten_solimp": 5, "sensor_size": 3, "hull_vert": 3}
 
     def _reshape(self):
         for k, w in self._SHAPES.items():
@@ -718,11 +765,12 @@ def make_maze_xml(agent_xml_path, maze_map, maze_size_scaling, maze_height):
     return root, grid
 
 
-def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None) -> Model:
+def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None, mesh_hull=False) -> Model:
     """Compile an MJCF file to the runtime :class:`Model`.
 
     ``overrides`` may carry ``{"opt": {...}, "actuator_gainprm": {name: [...]}, ...}`` for
-    constructor-time edits the reference performs on the loaded model.
+    constructor-time edits the reference performs on the loaded model.  ``mesh_hull``: mesh geoms keep the type MESH and carry a
+    reduced convex-hull vertex table (`hull_vertices`) for a support-map narrow phase instead of becoming box proxies.
     """
     P = _Parser(path, overrides, root=root)
     F = P.parse()
@@ -915,13 +963,24 @@ def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None) ->
     gkeep = [i for i, g in enumerate(F.geoms) if geom_can_collide(g) or g["name"] in pair_geoms]
     gidx = {g: i for i, g in enumerate(gkeep)}
     gt, gb, gp, gq, gs, gr = [], [], [], [], [], []
+    ghull, hverts = [], []
     for gi in gkeep:
         g = F.geoms[gi]
         b = g["body"]
         pos, quat, size, typ = g["pos"], g["quat"], g["size"], g["type"]
+        hull = None
         if typ == GEOM_MESH:
             pos = pos + qrot(quat, g["mesh_center"])
-            size, typ = g["mesh_half"], GEOM_BOX
+            size = g["mesh_half"]
+            if mesh_hull:
+                # support-map narrow phase: hull vertices in the geom frame (= mesh frame re-centred on the bounding box); the box
+                # half extents stay in geom_size as the bounding volume of the broad phase
+                hull = hull_vertices(F.meshes[g["mesh"]].reshape(-1, 3) - g["mesh_center"])
+            else:
+                typ = GEOM_BOX
+        ghull.append((len(hverts), 0 if hull is None else len(hull)))
+        if hull is not None:
+            hverts.extend(hull.tolist())
         gt.append(typ)
         gb.append(rt_of[b])
         gp.append(rel_pos[b] + qrot(rel_quat[b], pos))
@@ -929,8 +988,13 @@ def compile_mjcf(path, overrides=None, mesh_mesh=False, root=None, grid=None) ->
         gs.append(size)
         gr.append({GEOM_PLANE: 0.0, GEOM_SPHERE: size[0], GEOM_CAPSULE: size[0] + size[1],
                    GEOM_CYLINDER: np.hypot(size[0], size[1]), GEOM_BOX: np.linalg.norm(size),
-                   GEOM_ELLIPSOID: max(size)}[typ])
+                   GEOM_ELLIPSOID: max(size),
+                   GEOM_MESH: (float(np.linalg.norm(hull, axis=1).max()) if hull is not None else 0.0)}[typ])
     m.geom_type, m.geom_body = np.array(gt, dtype=np.int32), np.array(gb, dtype=np.int32)
+    if hverts:     # optional blob fields (absent from models without hull geoms: their blobs do not change)
+        m.geom_hull, m.hull_vert = np.array(ghull, dtype=np.int32).reshape(-1, 2), np.array(hverts, dtype=np.float64).reshape(-1, 3)
+    else:
+        m.geom_hull, m.hull_vert = np.zeros((0, 2), dtype=np.int32), np.zeros((0, 3))
     # the MJCF (unfused) body of every runtime geom and the runtime body every MJCF body was fused into: per-MJCF-body quantities
     # such as data.cfrc_ext (one row per mjModel body; Ant-v5's contact-force observation) keep the reference's row layout
     m.geom_mjbody = np.array([F.geoms[gi]["body"] for gi in gkeep], dtype=np.int32)

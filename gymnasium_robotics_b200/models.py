@@ -50,6 +50,11 @@ _ADROIT_DOOR = {"drop_bodies": ["vive_tracker"], "keep_bodies": ["frame"], "sens
 MODEL_OVERRIDES = {"adroit_door": _ADROIT_DOOR, "adroit_hammer": _ADROIT_HAMMER, "adroit_relocate": _ADROIT_RELOCATE, "adroit_pen": _ADROIT_PEN, "hand_block": _HAND, "hand_block_touch": _HAND, "hand_pen": _HAND, "hand_pen_touch": _HAND, "hand_egg": _HAND, "hand_egg_touch": _HAND, "hand_reach": {"sensor_prefix": "robot0:TS_"}}
 
 
+# models compiled a second time with hull vertex tables for their mesh geoms (mjcf.py compile_mjcf(mesh_hull=True)): blob name -> source
+# model; served by the hull build of the library (csrc/b200sim_kitchen_hull.cu), opt-in through `mesh_collision="hull"`
+MODEL_HULL = {"franka_kitchen_hull": "franka_kitchen"}
+
+
 # maze models: in-tree legacy twin of Gymnasium's ant.xml (Gymnasium itself is un-vendored) + generated wall boxes
 ANT_XML = "../mujoco/assets/ant.xml"
 POINT_XML = "point/point.xml"
@@ -77,6 +82,14 @@ def build_models(force: bool = False):
         if os.path.exists(out) and not force:
             continue
         blob = compile_mjcf(os.path.join(REFERENCE_ASSETS, rel), overrides=MODEL_OVERRIDES.get(name)).to_blob()
+        with open(out, "wb") as f:
+            f.write(blob)
+        built.append(out)
+    for name, src in MODEL_HULL.items():
+        out = os.path.join(MODEL_DIR, name + ".b200m")
+        if os.path.exists(out) and not force:
+            continue
+        blob = compile_mjcf(os.path.join(REFERENCE_ASSETS, MODEL_SOURCES[src]), overrides=MODEL_OVERRIDES.get(src), mesh_hull=True).to_blob()
         with open(out, "wb") as f:
             f.write(blob)
         built.append(out)

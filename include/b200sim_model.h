@@ -6,6 +6,8 @@
  * Blob = { u32 magic, u32 version, u32 nentries, u32 pad } + nentries * { char name[32]; u32 dtype;
  * u32 count; u64 offset } + payload.  dtype 0 = int32, 1 = float64, 2 = bytes (JSON name tables).
  * Offsets are relative to the start of the payload; float64 arrays are 8-byte aligned.
+ * Optional entries (absent = empty): geom_hull [ngeom][2] = (first vertex, count) into hull_vert [n][3], the reduced convex hull of a
+ * MESH geom in its geom frame (support-map narrow phase); models compiled without `mesh_hull` carry meshes as BOX proxies instead.
  */
 #ifndef B200SIM_MODEL_H
 #define B200SIM_MODEL_H
@@ -38,7 +40,7 @@ enum { B200_OPTI_ITERATIONS = 0, B200_OPTI_LS_ITERATIONS = 1, B200_OPTI_INTEGRAT
   X(dof_body) X(dof_jnt) X(dof_parent) X(geom_type) X(geom_body) X(pair_geom1) X(pair_geom2) X(pair_condim) \
   X(site_body) X(act_trnid) X(act_ctrllimited) X(act_forcelimited) X(eq_type) X(eq_obj1) X(eq_obj2) \
   X(eq_active) X(mocap_body) X(ten_adr) X(ten_num) X(ten_limited) X(wrap_dof) X(sensor_site) X(sensor_body) X(sensor_type) \
-  X(pair_grid) X(grid_dims) X(grid_walls) X(geom_mjbody) X(mjbody_rt)
+  X(pair_grid) X(grid_dims) X(grid_walls) X(geom_mjbody) X(mjbody_rt) X(geom_hull)
 
 #define B200M_FLT_FIELDS(X) \
   X(opt) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass) X(body_inertia) X(jnt_pos) \
@@ -48,7 +50,7 @@ enum { B200_OPTI_ITERATIONS = 0, B200_OPTI_LS_ITERATIONS = 1, B200_OPTI_INTEGRAT
   X(pair_gap) X(pair_solref) X(pair_solimp) X(pair_invweight) X(site_pos) X(site_quat) X(act_gear) \
   X(act_gainprm) X(act_biasprm) X(act_ctrlrange) X(act_forcerange) X(eq_data) X(eq_solref) X(eq_solimp) \
   X(eq_invweight) X(ten_range) X(ten_margin) X(ten_solref) X(ten_solimp) X(ten_invweight0) X(wrap_coef) \
-  X(sensor_size) X(key_qpos) X(grid_param)
+  X(sensor_size) X(key_qpos) X(grid_param) X(hull_vert)
 
 typedef struct b200_model_view {
   int nbody, njnt, nq, nv, nu, ngeom, nsite, nmocap, neq, npair, ntendon, nwrap, nsensor, nM;

@@ -873,7 +873,7 @@ static void collide_round_round(oracle_sim* s, int pair, real margin) {
  * MuJoCo's convex collider wraps through libccd: tolerance opt.mpr_tolerance = 1e-6, at most opt.mpr_iterations = 50 rounds);
  * one contact per pair, both shapes inflated by margin / 2, dist = margin - depth.  Everything is evaluated relative to the
  * first geom's centre (the fp32 twin in csrc/sim_core.cuh needs that; here it only keeps the two implementations alike). */
-typedef struct { int type; real pos[3]; const real* mat; const double* size; real infl; } CvxShape;
+typedef struct { int type; real pos[3]; const real* mat; const double* size; real infl; const double* hv; int nhv; } CvxShape;
 static void cvx_support(const CvxShape* g, const real* d, real* out) {
   real l[3], sl[3] = {0, 0, 0};
   mulmatTvec3(l, g->mat, d);
@@ -883,6 +883,12 @@ static void cvx_support(const CvxShape* g, const real* d, real* out) {
     case B200_GEOM_CAPSULE: { real n = norm3(l); if (n > 0) { sl[0] = z[0] * l[0] / n; sl[1] = z[0] * l[1] / n; sl[2] = z[0] * l[2] / n; } sl[2] += l[2] >= 0 ? z[1] : -z[1]; break; }
     case B200_GEOM_CYLINDER: { real n = sqrt(l[0] * l[0] + l[1] * l[1]); if (n > 1e-12) { sl[0] = z[0] * l[0] / n; sl[1] = z[0] * l[1] / n; } sl[2] = l[2] >= 0 ? z[1] : -z[1]; break; }
     case B200_GEOM_ELLIPSOID: { real a = z[0] * l[0], b = z[1] * l[1], c = z[2] * l[2], n = sqrt(a * a + b * b + c * c); if (n > 0) { sl[0] = z[0] * a / n; sl[1] = z[1] * b / n; sl[2] = z[2] * c / n; } break; }
+    case B200_GEOM_MESH: {   /* reduced convex hull (mjcf.py hull_vertices): the vertex that is farthest along l, first one on ties */
+      int best = 0; real bd = -1e300;
+      for (int i = 0; i < g->nhv; i++) { real dd = g->hv[3 * i] * l[0] + g->hv[3 * i + 1] * l[1] + g->hv[3 * i + 2] * l[2]; if (dd > bd) { bd = dd; best = i; } }
+      if (g->nhv > 0) { sl[0] = g->hv[3 * best]; sl[1] = g->hv[3 * best + 1]; sl[2] = g->hv[3 * best + 2]; }
+      break;
+    }
     default: /* box */ sl[0] = l[0] >= 0 ? z[0] : -z[0]; sl[1] = l[1] >= 0 ? z[1] : -z[1]; sl[2] = l[2] >= 0 ? z[2] : -z[2]; break;
   }
   mulmatvec3(out, g->mat, sl);
@@ -974,8 +980,10 @@ static int cvx_mpr(const CvxShape* A, const CvxShape* B, real tol, int maxit, re
 static void collide_convex(oracle_sim* s, int pair, real margin) {
   const b200_model_view* m = &s->m;
   int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
-  CvxShape A = {m->geom_type[g1], {0, 0, 0}, s->geom_xmat + 9 * g1, m->geom_size + 3 * g1, 0.5 * margin};
-  CvxShape B = {m->geom_type[g2], {0, 0, 0}, s->geom_xmat + 9 * g2, m->geom_size + 3 * g2, 0.5 * margin};
+  CvxShape A = {m->geom_type[g1], {0, 0, 0}, s->geom_xmat + 9 * g1, m->geom_size + 3 * g1, 0.5 * margin, NULL, 0};
+  CvxShape B = {m->geom_type[g2], {0, 0, 0}, s->geom_xmat + 9 * g2, m->geom_size + 3 * g2, 0.5 * margin, NULL, 0};
+  if (A.type == B200_GEOM_MESH) { A.hv = m->hull_vert + 3 * m->geom_hull[2 * g1]; A.nhv = m->geom_hull[2 * g1 + 1]; }
+  if (B.type == B200_GEOM_MESH) { B.hv = m->hull_vert + 3 * m->geom_hull[2 * g2]; B.nhv = m->geom_hull[2 * g2 + 1]; }
   sub3(B.pos, s->geom_xpos + 3 * g2, s->geom_xpos + 3 * g1);
   real depth, dir[3], pos[3];
   if (!cvx_mpr(&A, &B, 1e-6, 50, &depth, dir, pos)) return;
@@ -1015,7 +1023,7 @@ static void collide_plane_ellipsoid(oracle_sim* s, int pair, real margin) {
   int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
   const real *pp = s->geom_xpos + 3 * g1, *pm = s->geom_xmat + 9 * g1;
   real n[3] = {pm[2], pm[5], pm[8]}, nn[3] = {-n[0], -n[1], -n[2]}, p[3], dif[3];
-  CvxShape E = {B200_GEOM_ELLIPSOID, {0, 0, 0}, s->geom_xmat + 9 * g2, m->geom_size + 3 * g2, 0};
+  CvxShape E = {B200_GEOM_ELLIPSOID, {0, 0, 0}, s->geom_xmat + 9 * g2, m->geom_size + 3 * g2, 0, NULL, 0};
   copy3(E.pos, s->geom_xpos + 3 * g2);
   cvx_support(&E, nn, p);
   sub3(dif, p, pp);
@@ -1023,6 +1031,36 @@ static void collide_plane_ellipsoid(oracle_sim* s, int pair, real margin) {
   if (d > margin) return;
   addscl3(p, n, -0.5 * d);
   add_contact(s, pair, d, p, n);
+}
+
+/* plane vs hull (mesh geoms compiled with mesh_hull): the hull vertices within the margin of the plane, the deepest first, at most four
+ * (own point selection; ties keep the lower vertex index) */
+static void collide_plane_hull(oracle_sim* s, int pair, real margin) {
+  const b200_model_view* m = &s->m;
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  const real *pp = s->geom_xpos + 3 * g1, *pm = s->geom_xmat + 9 * g1, *c = s->geom_xpos + 3 * g2, *cm = s->geom_xmat + 9 * g2;
+  real n[3] = {pm[2], pm[5], pm[8]};
+  const double* hv = m->hull_vert + 3 * m->geom_hull[2 * g2];
+  int nhv = m->geom_hull[2 * g2 + 1];
+  real last = -1e300; int lasti = -1;
+  for (int k = 0; k < 4; k++) {
+    /* the next vertex in (distance, index) order after (last, lasti) */
+    int best = -1; real bd = 1e300;
+    for (int i = 0; i < nhv; i++) {
+      real p[3], dif[3];
+      mulmatvec3(p, cm, hv + 3 * i);
+      for (int a = 0; a < 3; a++) dif[a] = p[a] + c[a] - pp[a];
+      real d = dot3(dif, n);
+      if ((d > last || (d == last && i > lasti)) && d < bd) { bd = d; best = i; }
+    }
+    if (best < 0 || bd > margin) break;
+    real p[3];
+    mulmatvec3(p, cm, hv + 3 * best);
+    for (int a = 0; a < 3; a++) p[a] += c[a];
+    addscl3(p, n, -0.5 * bd);
+    add_contact(s, pair, bd, p, n);
+    last = bd; lasti = best;
+  }
 }
 
 static void collision(oracle_sim* s) {
@@ -1054,9 +1092,11 @@ static void collision(oracle_sim* s) {
       collide_round_round(s, p, margin);
     else if (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_CYLINDER) collide_plane_cylinder(s, p, margin);
     else if (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_ELLIPSOID) collide_plane_ellipsoid(s, p, margin);
-    else if (t1 >= B200_GEOM_SPHERE && t1 <= B200_GEOM_BOX && t2 >= B200_GEOM_SPHERE && t2 <= B200_GEOM_BOX)
-      collide_convex(s, p, margin);   /* any pair with a cylinder or an ellipsoid */
-    /* other pair types (height fields, meshes): not restated (DESIGN.md lists them) */
+    else if (t1 == B200_GEOM_PLANE && t2 == B200_GEOM_MESH && m->n_geom_hull > 0) collide_plane_hull(s, p, margin);
+    else if (t1 >= B200_GEOM_SPHERE && t1 <= B200_GEOM_MESH && t2 >= B200_GEOM_SPHERE && t2 <= B200_GEOM_MESH &&
+             ((t1 != B200_GEOM_MESH && t2 != B200_GEOM_MESH) || m->n_geom_hull > 0))
+      collide_convex(s, p, margin);   /* any pair with a cylinder, an ellipsoid or a hull (mesh geom with a vertex table) */
+    /* other pair types (height fields): not restated (DESIGN.md lists them) */
   }
 }
 

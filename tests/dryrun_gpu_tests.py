@@ -25,7 +25,7 @@ def make_vec(env_id, num_envs=1, **kw):
     elif env_id.startswith("Hand"):
         ref = HAND_REF_POINT
     elif env_id.startswith("Franka"):
-        ref, flavor = KITCHEN_REF_POINT, "kitchen"
+        ref, flavor = KITCHEN_REF_POINT, ("kitchen_hull" if kw.get("mesh_collision") == "hull" else "kitchen")
         kw.setdefault("device", "cpu")
 
     class B(HostSimBackend):

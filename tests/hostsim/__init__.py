@@ -34,7 +34,8 @@ def build(force=False, wide=False):
     (-DB200_KITCHEN_FLATSCAN)"""
     out = os.path.join(_HERE, {True: "libhostsim_wide.so", "kitchen": "libhostsim_kitchen.so", "kitchen_groups": "libhostsim_kitchen_groups.so",
                                "kitchen_flat": "libhostsim_kitchen_flat.so", "warp": "libhostsim_warp.so", "warp_wide": "libhostsim_warp_wide.so",
-                               "warp_kitchen_groups": "libhostsim_warp_kitchen_groups.so", "warp_kitchen": "libhostsim_warp_kitchen.so", "warp_timing": "libhostsim_warp_timing.so"}.get(wide, "libhostsim.so"))
+                               "warp_kitchen_groups": "libhostsim_warp_kitchen_groups.so", "warp_kitchen": "libhostsim_warp_kitchen.so", "warp_timing": "libhostsim_warp_timing.so",
+                               "kitchen_hull": "libhostsim_kitchen_hull.so", "warp_kitchen_hull": "libhostsim_warp_kitchen_hull.so"}.get(wide, "libhostsim.so"))
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_ROOT, "gymnasium_robotics_b200", "csrc", f)
                                                    for f in ("sim_core.cuh", "dmodel.h", "fetch_task.cuh")] + \
            [os.path.join(_ROOT, "include", "b200sim_model.h"), os.path.join(_ROOT, "include", "b200sim.h"), os.path.join(_HERE, "hostwarp.h"),
@@ -60,7 +61,11 @@ def build(force=False, wide=False):
                                         "warp_timing": ["-DB200_HOST_WARP", "-DB200_CHOL_SMEM", "-DB200_STAGE_TIMING", "-Wno-unknown-pragmas"],
                                         "warp_kitchen": ["-DB200_HOST_WARP", "-DB200_CHOL_SMEM", "-DB200_KITCHEN", "-Wno-unknown-pragmas"],
                                         "warp_kitchen_groups": ["-DB200_HOST_WARP", "-DB200_CHOL_SMEM", "-DB200_KITCHEN", "-DB200_KITCHEN_GROUPS",
-                                                                "-Wno-unknown-pragmas"]}.get(wide) or
+                                                                "-Wno-unknown-pragmas"],
+                                        # the kitchen groups build + the support-map narrow phase for mesh geoms (csrc/b200sim_kitchen_hull.cu)
+                                        "kitchen_hull": ["-DB200_KITCHEN", "-DB200_KITCHEN_GROUPS", "-DB200_HULL"],
+                                        "warp_kitchen_hull": ["-DB200_HOST_WARP", "-DB200_CHOL_SMEM", "-DB200_KITCHEN", "-DB200_KITCHEN_GROUPS",
+                                                              "-DB200_HULL", "-Wno-unknown-pragmas"]}.get(wide) or
                                        (["-DB200_WIDE"] if wide else [])) + ["-o", tmp, srcs[0]])
                 os.replace(tmp, out)
                 force = False

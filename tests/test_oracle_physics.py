@@ -435,3 +435,74 @@ def test_noslip_changes_the_adroit_hammer_scenario_by_a_bounded_amount():
     print(f"noslip on vs off, AdroitHandHammer, 12 env-steps from identical states: max |obs difference| = {worst:.2e}, sweeps <= {iters}")
     assert iters >= 1            # the pass ran (frictionloss rows are always there)
     assert worst < 5e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# hull support maps for mesh geoms (compile_mjcf(mesh_hull=True)): the mesh keeps its type and a vertex table
+HULL_XML = """
+<mujoco>
+  <option timestep="0.002"/>
+  <asset>
+    <mesh name="cube" vertex="-0.05 -0.05 -0.05  0.05 -0.05 -0.05  -0.05 0.05 -0.05  0.05 0.05 -0.05
+                               -0.05 -0.05 0.05   0.05 -0.05 0.05   -0.05 0.05 0.05   0.05 0.05 0.05  0 0 0"/>
+  </asset>
+  <worldbody>
+    <geom name="floor" type="plane" size="1 1 0.1"/>
+    <body name="b" pos="0 0 0.0502">
+      <freejoint/>
+      <inertial pos="0 0 0" mass="1" diaginertia="0.0016667 0.0016667 0.0016667"/>
+      <geom name="g" type="GTYPE" GSPEC/>
+    </body>
+    EXTRA
+  </worldbody>
+</mujoco>
+"""
+
+
+def _hull_sim(mjcf_file, gtype, extra="", floor=True):
+    spec = 'mesh="cube"' if gtype == "mesh" else 'size="0.05 0.05 0.05"'
+    xml = HULL_XML.replace("GTYPE", gtype).replace("GSPEC", spec).replace("EXTRA", extra)
+    if not floor:
+        xml = xml.replace('<geom name="floor" type="plane" size="1 1 0.1"/>', "")
+    return OracleSim(compile_mjcf(mjcf_file(xml), mesh_hull=True))
+
+
+def test_hull_vertices_of_a_cube_and_thinning():
+    from gymnasium_robotics_b200.mjcf import hull_vertices
+
+    c = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], dtype=float)
+    hv = hull_vertices(np.vstack([c, [[0, 0, 0], [0.5, 0.2, 0.1]]]))           # interior points are dropped
+    assert sorted(map(tuple, hv)) == sorted(map(tuple, c))
+    rng = np.random.default_rng(0)
+    p = rng.normal(size=(400, 3)); p /= np.linalg.norm(p, axis=1)[:, None]     # 400 points on the unit sphere: all are hull vertices
+    hv = hull_vertices(p)
+    assert len(hv) == 32 and np.allclose(np.linalg.norm(hv, axis=1), 1.0)
+    d = rng.normal(size=(200, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+    assert float(((hv @ d.T).max(axis=0)).min()) > 0.85                        # inner approximation: the support stays close to 1
+
+
+def test_mesh_hull_cube_rests_like_the_box_primitive(mjcf_file):
+    """A cube given as a mesh (hull support map, plane-hull contacts at the 4 lowest vertices) settles at the same height as the box
+    primitive of the same size (plane-box: the 4 lowest corners)."""
+    zs = []
+    for gtype in ("mesh", "box"):
+        sim = _hull_sim(mjcf_file, gtype)
+        assert (7 in [int(t) for t in sim.model.geom_type]) == (gtype == "mesh")
+        sim.step(1500)
+        zs.append(float(sim.qpos[2]))
+        assert sim.ncon == 4
+    assert abs(zs[0] - zs[1]) < 1e-9, zs
+
+
+def test_mesh_hull_against_a_box_rests_on_one_portal_contact(mjcf_file):
+    """Hull cube resting on a fixed box: portal refinement gives ONE contact that carries the weight; the box primitive on the same
+    table rests on the four points of the box-box routine.  Same weight through one soft contact instead of four: the hull sits deeper,
+    by less than a millimetre, and both come to rest."""
+    extra = '<body name="table" pos="0 0 -0.1"><geom name="t" type="box" size="0.3 0.3 0.1"/></body>'
+    zs = []
+    for gtype in ("mesh", "box"):
+        sim = _hull_sim(mjcf_file, gtype, extra, floor=False)
+        sim.step(1500)
+        zs.append(float(sim.qpos[2]))
+        assert sim.ncon >= 1 and abs(float(sim.qvel[2])) < 1e-4
+    assert 0.049 < zs[0] < zs[1] + 1e-9 and zs[1] - zs[0] < 1e-3, zs

@@ -25,6 +25,9 @@ from tests.parity_util import check_envelope
 KITCHEN_ENVELOPE = {
     "kitchen/pos": (4e-6, 7e-6, 7e-6),      # 7.4e-7 / 1.3e-6 / 1.3e-6  (profiles/parity_stats_r2n.json)
     "kitchen/vel": (2.5e-5, 8e-5, 8e-5),    # 4.5e-6 / 1.6e-5 / 1.6e-5
+    # mesh_collision="hull" (support-map narrow phase, csrc/b200sim_kitchen_hull.cu): free motion, then an arm link's hull on the kitchen
+    "kitchen_hull/pos": (2e-5, 5e-4, 5e-4),
+    "kitchen_hull/vel": (2e-4, 2e-2, 2e-2),
 }
 
 
@@ -139,4 +142,40 @@ def test_kitchen_timelimit_and_bookkeeping_on_gpu():
     assert not bool(trunc.any()) and int(env._elapsed.max()) == 0
     assert float((obs["observation"][:, :9] - env.init_qpos[:9]).abs().max()) < 2e-3   # noisy initial robot pose
     assert int(env.backend.overflow_counter[0]) == 0
+    env.close()
+
+
+def test_kitchen_hull_build_tracks_the_oracle_env():
+    """FrankaKitchen-v1 with mesh_collision="hull": the nine Franka collision meshes collide through their reduced convex hulls (kernels
+    fetch_kernel_hull<W, 31>).  Env 0..2: random actions; env 3: the constant action that presses a link's hull onto the kitchen from
+    env-step 7 on (tests/test_mesh_hull.py) -- the oracle env on the same hull model, same seeds and actions."""
+    from gymnasium_robotics_b200 import make_vec
+    from oracle.kitchen_env import OracleKitchenEnv
+
+    n, seed = 4, 41
+    env = make_vec("FrankaKitchen-v1", num_envs=n, rng_mode="numpy", mesh_collision="hull")
+    assert int((np.asarray(env.model.geom_type) == 7).sum()) == 9
+    obs, info = env.reset(seed=seed)
+    orcs = [OracleKitchenEnv(env.model) for _ in range(n)]
+    for i, o in enumerate(orcs):
+        ob, _ = o.reset(seed=seed + i)
+        assert np.abs(obs["observation"][i].cpu().numpy() - ob["observation"]).max() < 1e-5
+    rng = np.random.default_rng(6)
+    press = np.array([1.0, 1.0, 1.0, -1.0, -1.0, 1.0, -1.0, 0.0, 0.0])
+    pos_err, vel_err, mesh_hits = [], [], 0
+    for k in range(12):
+        a = rng.uniform(-1, 1, size=(n, 9))
+        a[3] = press
+        obs, rew, term, trunc, info = env.step(a)
+        for i, o in enumerate(orcs):
+            ob, r, te, tr, inf = o.step(a[i])
+            e = np.abs(obs["observation"][i].cpu().numpy() - ob["observation"])
+            pos_err.append(max(e[:9].max(), e[18:39].max()))
+            vel_err.append(max(e[9:18].max(), e[39:].max()))
+            assert float(rew[i]) == r and bool(term[i]) == te and bool(trunc[i]) == tr
+        gt = env.model.geom_type
+        mesh_hits += int(any(gt[int(c["geom1"])] == 7 or (int(c["geom2"]) >= 0 and gt[int(c["geom2"])] == 7) for c in orcs[3].sim.contacts()))
+    assert mesh_hits >= 3, "no hull geom in contact: the test would not exercise the hull narrow phase"
+    check_envelope("kitchen_hull/pos", pos_err, *KITCHEN_ENVELOPE["kitchen_hull/pos"])
+    check_envelope("kitchen_hull/vel", vel_err, *KITCHEN_ENVELOPE["kitchen_hull/vel"])
     env.close()
