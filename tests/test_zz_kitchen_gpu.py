@@ -26,8 +26,8 @@ KITCHEN_ENVELOPE = {
     "kitchen/pos": (4e-6, 7e-6, 7e-6),      # 7.4e-7 / 1.3e-6 / 1.3e-6  (profiles/parity_stats_r2n.json)
     "kitchen/vel": (2.5e-5, 8e-5, 8e-5),    # 4.5e-6 / 1.6e-5 / 1.6e-5
     # mesh_collision="hull" (support-map narrow phase, csrc/b200sim_kitchen_hull.cu): free motion, then an arm link's hull on the kitchen
-    "kitchen_hull/pos": (2e-5, 5e-4, 5e-4),
-    "kitchen_hull/vel": (2e-4, 2e-2, 2e-2),
+    "kitchen_hull/pos": (5e-6, 2.2e-5, 2.5e-5),     # 9.9e-7 / 4.4e-6 / 4.7e-6  (profiles/parity_stats_r2w.json)
+    "kitchen_hull/vel": (9e-5, 3e-4, 4e-4),         # 1.8e-5 / 2.8e-5 / 3.3e-5  (the host emulation of the same source reaches 2.1e-4)
 }
 
 
